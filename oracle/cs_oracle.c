@@ -1,0 +1,1168 @@
+/*============================================================================
+ * oracle/cs_oracle.c -- TEST INFRASTRUCTURE, not product code.
+ *
+ * Plain-C, single-threaded CPU restatement of the reference (code_saturne)
+ * src/alge linear-solve hot path, used ONLY as the parity checker by tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline leg.  The product
+ * (code_saturne_b200/csrc) never includes, links or calls this file.
+ *
+ * Parity status: PINNED.  Every function here is checked against the
+ * reference's own compiled code (oracle/_ref/libcsref.so, built from
+ * /root/reference by oracle/Makefile.ref) in tests/test_oracle_vs_ref.py,
+ * and against the committed fixtures in tests/golden/ (generated from that
+ * same reference build by tests/golden/make_golden.py).  The reference tree
+ * itself holds no golden vectors for this path.
+ *
+ * Arithmetic: plain IEEE double mul/add in the reference's evaluation order
+ * (compile with -ffp-contract=off; the reference build has no FMA either).
+ * All of this restates the reference behaviour with OMP_NUM_THREADS=1, except
+ * where a "n_threads" argument restates cs_parall_thread_range blocking.
+ *============================================================================*/
+
+#include <math.h>
+#include <float.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+#include "cs_oracle.h"
+
+#define ORA_CL_SIZE 64            /* CS_CL_SIZE, src/base/cs_defs.h:491 */
+#define ORA_SBLOCK 60             /* CS_SBLOCK_BLOCK_SIZE, src/alge/cs_blas.cpp:81 */
+
+/*----------------------------------------------------------------------------
+ * cs_parall_thread_range (src/base/cs_parall.h:571-590) for thread t_id of n_t
+ *----------------------------------------------------------------------------*/
+
+static int _align(int i, int m) { return ((i + m - 1) / m) * m; }
+
+void
+ora_thread_range(int n, int type_size, int t_id, int n_t, int *s_id, int *e_id)
+{
+  const int t_n = (n + n_t - 1) / n_t;
+  const int cl_m = ORA_CL_SIZE / type_size;
+  *s_id = t_id * t_n;
+  *e_id = (t_id + 1) * t_n;
+  *s_id = _align(*s_id, cl_m);
+  *e_id = _align(*e_id, cl_m);
+  if (*e_id > n) *e_id = n;
+  if (*s_id > n) *s_id = n;
+}
+
+/*----------------------------------------------------------------------------
+ * y = A.x, scalar MSR: _mat_vec_p_l_msr (src/alge/cs_matrix_spmv.cpp:2103-2165)
+ * off-diagonal sum in CSR order first, diagonal term added last.
+ *----------------------------------------------------------------------------*/
+
+void
+ora_spmv_msr(int n_rows, const int *row_index, const int *col_id,
+             const double *d_val, const double *x_val, int exclude_diag,
+             const double *x, double *y)
+{
+  for (int ii = 0; ii < n_rows; ii++) {
+    double sii = 0.0;
+    for (int jj = row_index[ii]; jj < row_index[ii+1]; jj++)
+      sii += (x_val[jj] * x[col_id[jj]]);
+    if (!exclude_diag && d_val != NULL)
+      y[ii] = sii + d_val[ii] * x[ii];
+    else
+      y[ii] = sii;
+  }
+}
+
+/*----------------------------------------------------------------------------
+ * Superblock dot products: _cs_dot_*_superblock (src/alge/cs_blas.cpp:173-640)
+ * blocks of 60, sqrt(n_blocks) superblocks (_sbloc_sizes :173-184).
+ *----------------------------------------------------------------------------*/
+
+static void
+_sbloc_sizes(int n, int *n_sblocks, int *blocks_in_sblocks)
+{
+  int n_blocks = (n + ORA_SBLOCK - 1) / ORA_SBLOCK;
+  *n_sblocks = (n_blocks > 1) ? (int)sqrt((double)n_blocks) : 1;
+  int n_b = ORA_SBLOCK * *n_sblocks;
+  *blocks_in_sblocks = (n + n_b - 1) / n_b;
+}
+
+/* generic up-to-3-way: s[0]=x.x (or x.y when mode says so) ... see callers */
+#define ORA_SB_LOOP(BODY_DECL, BODY_ACC, BODY_SB, BODY_TOT)                  \
+  int n_sblocks, blocks_in_sblocks;                                          \
+  _sbloc_sizes(n, &n_sblocks, &blocks_in_sblocks);                           \
+  for (int sid = 0; sid < n_sblocks; sid++) {                                \
+    BODY_DECL(s)                                                             \
+    for (int bid = 0; bid < blocks_in_sblocks; bid++) {                      \
+      int start_id = ORA_SBLOCK * (blocks_in_sblocks*sid + bid);             \
+      int end_id = ORA_SBLOCK * (blocks_in_sblocks*sid + bid + 1);           \
+      if (end_id > n) end_id = n;                                            \
+      BODY_DECL(c)                                                           \
+      for (int i = start_id; i < end_id; i++) { BODY_ACC }                   \
+      BODY_SB                                                                \
+    }                                                                        \
+    BODY_TOT                                                                 \
+  }
+
+double
+ora_dot(int n, const double *x, const double *y)
+{
+  double dot = 0.0;
+#define D1(p) double p##0 = 0.0;
+  ORA_SB_LOOP(D1, c0 += x[i]*y[i];, s0 += c0;, dot += s0;)
+  return dot;
+}
+
+double
+ora_dot_xx(int n, const double *x)
+{
+  double dot = 0.0;
+  ORA_SB_LOOP(D1, c0 += x[i]*x[i];, s0 += c0;, dot += s0;)
+  return dot;
+}
+
+void
+ora_dot_xx_xy(int n, const double *x, const double *y, double *xx, double *xy)
+{
+  double d0 = 0.0, d1 = 0.0;
+#define D2(p) double p##0 = 0.0, p##1 = 0.0;
+  ORA_SB_LOOP(D2, c0 += x[i]*x[i]; c1 += x[i]*y[i];,
+              s0 += c0; s1 += c1;, d0 += s0; d1 += s1;)
+  *xx = d0; *xy = d1;
+}
+
+void
+ora_dot_xy_yz(int n, const double *x, const double *y, const double *z,
+              double *xy, double *yz)
+{
+  double d0 = 0.0, d1 = 0.0;
+  ORA_SB_LOOP(D2, c0 += x[i]*y[i]; c1 += y[i]*z[i];,
+              s0 += c0; s1 += c1;, d0 += s0; d1 += s1;)
+  *xy = d0; *yz = d1;
+}
+
+void
+ora_dot_xx_xy_yz(int n, const double *x, const double *y, const double *z,
+                 double *xx, double *xy, double *yz)
+{
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+#define D3(p) double p##0 = 0.0, p##1 = 0.0, p##2 = 0.0;
+  ORA_SB_LOOP(D3, c0 += x[i]*x[i]; c1 += x[i]*y[i]; c2 += y[i]*z[i];,
+              s0 += c0; s1 += c1; s2 += c2;, d0 += s0; d1 += s1; d2 += s2;)
+  *xx = d0; *xy = d1; *yz = d2;
+}
+
+/*----------------------------------------------------------------------------
+ * Convergence test: _convergence_test (src/alge/cs_sles_it.cpp:243-325)
+ *----------------------------------------------------------------------------*/
+
+typedef struct {
+  double precision, r_norm, initial_residual;
+  int    n_iterations_max;
+  int    n_iterations;
+  double residual;
+  double *history;   /* optional: residual per test */
+  int     history_size, history_n;
+} ora_cvg_t;
+
+static int
+_cvg_test(ora_cvg_t *c, int n_iter, double residual)
+{
+  c->n_iterations = n_iter;
+  c->residual = residual;
+  if (c->history != NULL && c->history_n < c->history_size)
+    c->history[c->history_n++] = residual;
+
+  if (c->precision > 0 && residual < c->precision * c->r_norm)
+    return ORA_CONVERGED;
+  else if (n_iter >= c->n_iterations_max)
+    return ORA_MAX_ITERATION;
+  else if (residual > c->initial_residual * 10000.0 && residual > 100.)
+    return ORA_DIVERGED;
+  if (isnan(residual) || isinf(residual))
+    return ORA_DIVERGED;
+  return ORA_ITERATING;
+}
+
+/*----------------------------------------------------------------------------
+ * PCG + Jacobi, single reduction: _conjugate_gradient_sr_p0
+ * (src/alge/cs_sles_it.cpp:1441-1645).  Residual sign r = A.x - b.
+ * out[0]=n_iter out[1]=residual out[2]=initial_residual
+ *----------------------------------------------------------------------------*/
+
+int
+ora_pcg_sr_p0(int n_rows, const int *row_index, const int *col_id,
+              const double *d_val, const double *x_val,
+              int n_max_iter, double precision, double r_norm,
+              const double *rhs, double *vx, int use_vx_ini,
+              double *out, double *history, int history_size)
+{
+  const int n = n_rows;
+  double *rk = malloc(sizeof(double)*n*6);
+  double *dk = rk + n, *gk = rk + 2*n, *zk = rk + 3*n, *sk = rk + 4*n;
+  double *ad_inv = rk + 5*n;
+  for (int i = 0; i < n; i++) ad_inv[i] = 1.0 / d_val[i]; /* cs_sles_pc.cpp:376 */
+
+  ora_cvg_t cv = {precision, r_norm, -1, n_max_iter, 0, -1,
+                  history, history_size, 0};
+  int cvg = ORA_ITERATING;
+  int n_iter = 0;
+  const int update_residual = (precision > 0.);
+
+  if (use_vx_ini) {
+    ora_spmv_msr(n, row_index, col_id, d_val, x_val, 0, vx, rk);
+    for (int ii = 0; ii < n; ii++) {
+      rk[ii] -= rhs[ii];
+      dk[ii] = rk[ii] * ad_inv[ii];
+    }
+  }
+  else {
+    for (int ii = 0; ii < n; ii++) {
+      vx[ii] = 0;
+      rk[ii] = -rhs[ii];
+      dk[ii] = rk[ii] * ad_inv[ii];
+    }
+  }
+
+  ora_spmv_msr(n, row_index, col_id, d_val, x_val, 0, dk, zk);
+
+  double ro_0 = 0, ro_1 = 0;
+  double rk_gkm1 = 0, residual = -1, rk_gk = 0, gk_sk = 0;
+
+  if (update_residual) {
+    ora_dot_xx_xy_yz(n, rk, dk, zk, &residual, &ro_0, &ro_1);
+    residual = sqrt(residual);
+  }
+  else
+    ora_dot_xy_yz(n, rk, dk, zk, &ro_0, &ro_1);
+
+  cv.initial_residual = residual;
+  cvg = _cvg_test(&cv, n_iter, residual);
+
+  if (cvg == ORA_ITERATING) {
+    n_iter = 1;
+    double d_ro_1 = (fabs(ro_1) > DBL_MIN) ? 1. / ro_1 : 0.;
+    double alpha = - ro_0 * d_ro_1;
+    rk_gkm1 = ro_0;
+
+    /* parallel_for_reduce_sum: same superblock order (cs_dispatch.h:369-420) */
+    for (int ii = 0; ii < n; ii++) {
+      vx[ii] += (alpha * dk[ii]);
+      rk[ii] += (alpha * zk[ii]);
+      gk[ii] = rk[ii] * ad_inv[ii];
+    }
+    if (update_residual)
+      residual = sqrt(ora_dot_xx(n, rk));
+
+    cvg = _cvg_test(&cv, n_iter, residual);
+  }
+
+  while (cvg == ORA_ITERATING) {
+    ora_spmv_msr(n, row_index, col_id, d_val, x_val, 0, gk, sk);
+
+    if (update_residual) {
+      ora_dot_xx_xy_yz(n, rk, gk, sk, &residual, &rk_gk, &gk_sk);
+      residual = sqrt(residual);
+    }
+    else
+      ora_dot_xy_yz(n, rk, gk, sk, &rk_gk, &gk_sk);
+
+    if (n_iter > 1)
+      cvg = _cvg_test(&cv, n_iter, residual);
+    if (cvg != ORA_ITERATING)
+      break;
+
+    n_iter += 1;
+
+    double beta = (fabs(rk_gkm1) > DBL_MIN) ? rk_gk / rk_gkm1 : 0.;
+    rk_gkm1 = rk_gk;
+    ro_1 = gk_sk - beta*beta*ro_1;
+    ro_0 = rk_gk;
+    double d_ro_1 = (fabs(ro_1) > DBL_MIN) ? 1. / ro_1 : 0.;
+    double alpha = - ro_0 * d_ro_1;
+
+    for (int ii = 0; ii < n; ii++) {
+      dk[ii] = gk[ii] + (beta * dk[ii]);
+      vx[ii] += alpha * dk[ii];
+      zk[ii] = sk[ii] + (beta * zk[ii]);
+      rk[ii] += alpha * zk[ii];
+      gk[ii] = rk[ii] * ad_inv[ii];
+    }
+  }
+
+  out[0] = cv.n_iterations;
+  out[1] = cv.residual;
+  out[2] = cv.initial_residual;
+  out[3] = cv.history_n;
+  free(rk);
+  return cvg;
+}
+
+/*----------------------------------------------------------------------------
+ * Jacobi: _jacobi (src/alge/cs_sles_it.cpp:2098-2270)
+ *----------------------------------------------------------------------------*/
+
+int
+ora_jacobi(int n_rows, const int *row_index, const int *col_id,
+           const double *d_val, const double *x_val,
+           int n_max_iter, double precision, double r_norm,
+           const double *rhs, double *vx, int use_vx_ini,
+           double *out, double *history, int history_size)
+{
+  const int n = n_rows;
+  double *rk = malloc(sizeof(double)*n*2);
+  double *ad_inv = rk + n;
+  for (int i = 0; i < n; i++) ad_inv[i] = 1.0 / d_val[i];
+
+  ora_cvg_t cv = {precision, r_norm, -1, n_max_iter, 0, -1,
+                  history, history_size, 0};
+  int cvg = ORA_ITERATING;
+  int n_iter = 0;
+  double residual = -1;
+
+  if (!use_vx_ini) {
+    n_iter += 1;
+    double res2 = 0.0;
+    for (int ii = 0; ii < n; ii++) {
+      vx[ii] = rhs[ii]*ad_inv[ii];
+      double r = rhs[ii];
+      res2 += (r*r);
+      rk[ii] = vx[ii];
+    }
+    if (precision > 0.)
+      residual = sqrt(res2);
+    if (n_iter == 1) cv.initial_residual = residual;
+    cvg = _cvg_test(&cv, n_iter, residual);
+  }
+  else {
+    for (int ii = 0; ii < n; ii++) rk[ii] = vx[ii];
+  }
+
+  while (cvg == ORA_ITERATING) {
+    n_iter += 1;
+    ora_spmv_msr(n, row_index, col_id, d_val, x_val, 1, rk, vx);
+    double res2 = 0.0;
+    for (int ii = 0; ii < n; ii++) {
+      vx[ii] = (rhs[ii]-vx[ii])*ad_inv[ii];
+      double r = d_val[ii] * (vx[ii]-rk[ii]);
+      res2 += (r*r);
+      rk[ii] = vx[ii];
+    }
+    if (precision > 0.)
+      residual = sqrt(res2);
+    if (n_iter == 1) cv.initial_residual = residual;
+    cvg = _cvg_test(&cv, n_iter, residual);
+  }
+
+  out[0] = cv.n_iterations;
+  out[1] = cv.residual;
+  out[2] = cv.initial_residual;
+  out[3] = cv.history_n;
+  free(rk);
+  return cvg;
+}
+
+/*----------------------------------------------------------------------------
+ * BiCGStab + Jacobi preconditioner: _bi_cgstab (src/alge/cs_sles_it.cpp:2693-2880)
+ * with pc_apply = x*ad_inv (src/alge/cs_sles_pc.cpp:502-535).
+ *----------------------------------------------------------------------------*/
+
+int
+ora_bicgstab(int n_rows, const int *row_index, const int *col_id,
+             const double *d_val, const double *x_val,
+             int n_max_iter, double precision, double r_norm,
+             const double *rhs, double *vx, int use_vx_ini,
+             double *out, double *history, int history_size)
+{
+  const int n = n_rows;
+  const double epzero = 1.e-30;   /* _epzero, cs_sles_it.cpp:169 */
+  double *res0 = malloc(sizeof(double)*n*7);
+  double *rk = res0 + n, *pk = res0 + 2*n, *zk = res0 + 3*n;
+  double *uk = res0 + 4*n, *vk = res0 + 5*n, *ad_inv = res0 + 6*n;
+  for (int i = 0; i < n; i++) ad_inv[i] = 1.0 / d_val[i];
+
+  ora_cvg_t cv = {precision, r_norm, -1, n_max_iter, 0, -1,
+                  history, history_size, 0};
+  int cvg = ORA_ITERATING;
+  int n_iter = 0;
+  double ro_0, ro_1, alpha, beta = 0, betam1, gamma, omega, ukres0;
+  double residual = -1;
+
+  for (int ii = 0; ii < n; ii++) { pk[ii] = 0.0; uk[ii] = 0.0; }
+
+  if (use_vx_ini) {
+    ora_spmv_msr(n, row_index, col_id, d_val, x_val, 0, vx, res0);
+    for (int ii = 0; ii < n; ii++) {
+      res0[ii] = -res0[ii] + rhs[ii];
+      rk[ii] = res0[ii];
+    }
+  }
+  else {
+    for (int ii = 0; ii < n; ii++) {
+      vx[ii] = 0; res0[ii] = rhs[ii]; rk[ii] = rhs[ii];
+    }
+  }
+
+  alpha = 1.0; betam1 = 1.0; gamma = 1.0;
+
+  while (cvg == ORA_ITERATING) {
+    if (n_iter == 0) {
+      beta = ora_dot_xx(n, rk);
+      residual = sqrt(beta);
+      cv.initial_residual = residual;
+    }
+    else {
+      ora_dot_xx_xy(n, rk, res0, &residual, &beta);
+      residual = sqrt(residual);
+    }
+    cvg = _cvg_test(&cv, n_iter, residual);
+    if (cvg != ORA_ITERATING) break;
+
+    n_iter += 1;
+
+    if (fabs(beta) < epzero) { cvg = ORA_BREAKDOWN; break; }
+    if (fabs(alpha) < epzero) { cvg = ORA_BREAKDOWN; break; }
+
+    omega = beta*gamma / (alpha*betam1);
+    betam1 = beta;
+
+    for (int ii = 0; ii < n; ii++)
+      pk[ii] = rk[ii] + omega*(pk[ii] - alpha*uk[ii]);
+    for (int ii = 0; ii < n; ii++)
+      zk[ii] = pk[ii] * ad_inv[ii];
+    ora_spmv_msr(n, row_index, col_id, d_val, x_val, 0, zk, uk);
+    ukres0 = ora_dot(n, uk, res0);
+    gamma = beta / ukres0;
+    for (int ii = 0; ii < n; ii++) {
+      vx[ii] += (gamma * zk[ii]);
+      rk[ii] -= (gamma * uk[ii]);
+    }
+    for (int ii = 0; ii < n; ii++)
+      zk[ii] = rk[ii] * ad_inv[ii];
+    ora_spmv_msr(n, row_index, col_id, d_val, x_val, 0, zk, vk);
+    ora_dot_xx_xy(n, vk, rk, &ro_1, &ro_0);
+    if (fabs(ro_1) < epzero) { cvg = ORA_BREAKDOWN; break; }
+    double d_ro_1 = (fabs(ro_1) > DBL_MIN) ? 1. / ro_1 : 0.;
+    alpha = ro_0 * d_ro_1;
+    for (int ii = 0; ii < n; ii++) {
+      vx[ii] += (alpha * zk[ii]);
+      rk[ii] -= (alpha * vk[ii]);
+    }
+  }
+
+  out[0] = cv.n_iterations;
+  out[1] = cv.residual;
+  out[2] = cv.initial_residual;
+  out[3] = cv.history_n;
+  free(res0);
+  return cvg;
+}
+
+/*============================================================================
+ * Grid hierarchy (cs_grid.cpp)
+ *============================================================================*/
+
+/* _reorder_f_c_row (src/alge/cs_grid.cpp:1638-1664) */
+static void
+_reorder_f_c_row(int f_n_rows, int c_n_rows, int *c_o2n, int *f_c_row)
+{
+  for (int i = 0; i < c_n_rows; i++) c_o2n[i] = -1;
+  int c_count = 0;
+  for (int i = 0; i < f_n_rows; i++) {
+    int c_row = f_c_row[i];
+    if (c_row > -1) {
+      if (c_o2n[c_row] < 0) {
+        c_o2n[c_row] = c_count;
+        f_c_row[i] = c_count;
+        c_count++;
+      }
+      else
+        f_c_row[i] = c_o2n[c_row];
+    }
+  }
+}
+
+/*----------------------------------------------------------------------------
+ * _automatic_aggregation_dx_msr (src/alge/cs_grid.cpp:4282-4767), symmetric
+ * scalar case (isym = 1, CS_GRID_COARSENING_SPD_DX).  n_threads restates the
+ * per-thread row blocks (aggregation never crosses a block, :4374-4376,
+ * :4492) followed by _scan_f_c_row (:1686-1716).
+ * f_c_row (size n_rows) is written; returns the number of coarse rows.
+ *----------------------------------------------------------------------------*/
+
+int
+ora_aggregation_dx_msr(int level, int f_n_rows, const int *row_index,
+                       const int *col_id, const double *d_val,
+                       const double *x_val, int max_aggregation,
+                       int n_threads, int *f_c_row)
+{
+  const int npass_max = 10;
+  const double epsilon = 1.e-6;
+  const double penalization_threshold = 1e4;  /* cs_grid.cpp:165 */
+  const int f_nnz = row_index[f_n_rows];
+
+  int n_loc_threads = n_threads;
+  { /* cs_parall_n_threads(f_n_rows, CS_THR_MIN) (cs_parall.h:549-565) */
+    int n_t_l = f_n_rows / 128;
+    if (n_t_l < n_loc_threads) n_loc_threads = n_t_l;
+    if (n_loc_threads < 1) n_loc_threads = 1;
+  }
+
+  for (int ii = 0; ii < f_n_rows; ii++) f_c_row[ii] = -2;  /* _coarse_init :520 */
+
+  short *c_cardinality = malloc(sizeof(short)*(f_n_rows > 0 ? f_n_rows : 1));
+  short *c_aggr_count = malloc(sizeof(short)*(f_n_rows > 0 ? f_n_rows : 1));
+  const int ag_queue_stride = 2;
+  int ag_work_size = f_nnz*ag_queue_stride;
+  if (ag_work_size < f_n_rows) ag_work_size = f_n_rows;
+  int *ag_work = malloc(sizeof(int)*(ag_work_size > 0 ? ag_work_size : 1));
+  int *ag_queue = ag_work;
+  int *t_c_scan = calloc(n_loc_threads, sizeof(int));
+  int *t_range = malloc(sizeof(int)*2*n_loc_threads);
+  int c_n_rows = 0;
+
+  for (int t_id = 0; t_id < n_loc_threads; t_id++) {
+    int t_s_id, t_e_id;
+    ora_thread_range(f_n_rows, 8, t_id, n_loc_threads, &t_s_id, &t_e_id);
+    t_range[2*t_id] = t_s_id; t_range[2*t_id+1] = t_e_id;
+
+    int ncoarse = 8, inc_nei = 0;
+    int _max_aggregation = 1;
+
+    if (level == 0) {
+      for (int ii = t_s_id; ii < t_e_id; ii++) {
+        c_cardinality[ii] = row_index[ii+1] - row_index[ii];
+        c_aggr_count[ii] = 1;
+        double sum = 0.0;
+        for (int jj = row_index[ii]; jj < row_index[ii+1]; jj++) {
+          const double xv = x_val[jj];
+          if (xv < 0.) sum -= xv; else sum += xv;
+        }
+        if (d_val[ii] > penalization_threshold * sum) {
+          f_c_row[ii] = -1;
+          c_aggr_count[ii] = 0;
+        }
+      }
+    }
+    else {
+      for (int ii = t_s_id; ii < t_e_id; ii++) {
+        c_cardinality[ii] = row_index[ii+1] - row_index[ii];
+        c_aggr_count[ii] = 1;
+      }
+    }
+
+    const int t_r_s_id = row_index[t_s_id] * ag_queue_stride;
+    int t_r_e_id = t_r_s_id;
+    int t_c_n_rows = 0;
+    int r_n_faces = 0;
+
+    /* First pass */
+    {
+      if (_max_aggregation < max_aggregation) _max_aggregation++;
+      const double ag_threshold = 1. - epsilon;
+
+      for (int ii = t_s_id; ii < t_e_id; ii++) {
+        for (int ix0 = row_index[ii]; ix0 < row_index[ii+1]; ix0++) {
+          int jj = col_id[ix0];
+          if (jj < ii || jj >= t_e_id) continue;
+          int ii_c = f_c_row[ii];
+          int jj_c = f_c_row[jj];
+          if (ii_c == -1 || jj_c == -1 || (ii_c >= 0 && jj_c >= 0)) continue;
+          int ix1 = ix0;
+
+          double f_da0_da1_inv = (c_cardinality[ii]*c_cardinality[jj])
+                                 / (d_val[ii] * d_val[jj]);
+          double f_xa0_xa1 = x_val[ix0] * x_val[ix1];
+          double aggr_crit = f_da0_da1_inv * f_xa0_xa1;
+
+          int count = 0;
+          if (aggr_crit > ag_threshold) {
+            if (ii_c > -1 && jj_c < -1) {
+              if (c_aggr_count[t_s_id + ii_c] < _max_aggregation + 1) {
+                f_c_row[jj] = ii_c;
+                c_aggr_count[t_s_id + ii_c] += 1;
+                count++;
+              }
+            }
+            else if (ii_c < -1 && jj_c > -1) {
+              if (c_aggr_count[t_s_id + jj_c] < _max_aggregation + 1) {
+                f_c_row[ii] = jj_c;
+                c_aggr_count[t_s_id + jj_c] += 1;
+                count++;
+              }
+            }
+            else if (ii_c < -1 && jj_c < -1) {
+              f_c_row[ii] = t_c_n_rows;
+              f_c_row[jj] = t_c_n_rows;
+              c_aggr_count[t_s_id + t_c_n_rows] += 1;
+              t_c_n_rows++;
+              count++;
+            }
+          }
+          if (count == 0) {
+            ag_queue[t_r_e_id] = ii;
+            ag_queue[t_r_e_id+1] = ix0;
+            t_r_e_id += ag_queue_stride;
+            r_n_faces++;
+          }
+        }
+      }
+    }
+
+    /* Other passes */
+    for (int npass = 2; npass <= npass_max; npass++) {
+      int aggr_count = 0;
+      for (int ii = t_s_id; ii < t_e_id; ii++)
+        if (f_c_row[ii] < -1) aggr_count++;
+
+      if (   aggr_count == 0
+          || (t_c_n_rows + aggr_count)*ncoarse < (t_e_id - t_s_id)
+          || r_n_faces == 0)
+        break;
+
+      if (_max_aggregation < max_aggregation) _max_aggregation++;
+      r_n_faces = 0;
+      inc_nei += 1;
+      int r_idx_n = t_r_s_id;
+
+      for (int r_idx = t_r_s_id; r_idx < t_r_e_id; r_idx += ag_queue_stride) {
+        const double ag_threshold = 1. - epsilon;
+        int ii = ag_queue[r_idx];
+        int ix0 = ag_queue[r_idx+1];
+        int ix1 = ix0;
+        int jj = col_id[ix0];
+        int ii_c = f_c_row[ii];
+        int jj_c = f_c_row[jj];
+        if (ii_c >= 0 && jj_c >= 0) continue;
+        int count = 0;
+
+        double f_da0_da1_inv = (  (c_cardinality[ii]+inc_nei)
+                                * (c_cardinality[jj]+inc_nei))
+                               / (d_val[ii] * d_val[jj]);
+        double f_xa0_xa1 = x_val[ix0] * x_val[ix1];
+        double aggr_crit = f_da0_da1_inv * f_xa0_xa1;
+
+        if (aggr_crit > ag_threshold) {
+          if (ii_c > -1 && jj_c < -1) {
+            if (c_aggr_count[t_s_id + ii_c] < _max_aggregation + 1) {
+              f_c_row[jj] = ii_c;
+              c_aggr_count[t_s_id + ii_c] += 1;
+              count++;
+            }
+          }
+          else if (ii_c < -1 && jj_c > -1) {
+            if (c_aggr_count[t_s_id + jj_c] < _max_aggregation + 1) {
+              f_c_row[ii] = jj_c;
+              c_aggr_count[t_s_id + jj_c] += 1;
+              count++;
+            }
+          }
+          else if (ii_c < -1 && jj_c < -1) {
+            f_c_row[ii] = t_c_n_rows;
+            f_c_row[jj] = t_c_n_rows;
+            c_aggr_count[t_s_id + t_c_n_rows] += 1;
+            t_c_n_rows++;
+            count++;
+          }
+        }
+        if (count == 0) {
+          ag_queue[r_idx_n] = ii;
+          ag_queue[r_idx_n+1] = ix0;
+          r_idx_n += ag_queue_stride;
+          r_n_faces++;
+        }
+      }
+      t_r_e_id = r_idx_n;
+    }
+
+    for (int ii = t_s_id; ii < t_e_id; ii++) {
+      if (f_c_row[ii] < -1) {
+        f_c_row[ii] = t_c_n_rows;
+        t_c_n_rows++;
+      }
+    }
+    t_c_scan[t_id] = t_c_n_rows;
+  }
+
+  /* after the barrier (:4706): per-block reordering using ag_work */
+  for (int t_id = 0; t_id < n_loc_threads; t_id++) {
+    int t_s_id = t_range[2*t_id], t_e_id = t_range[2*t_id+1];
+    _reorder_f_c_row(t_e_id - t_s_id, t_c_scan[t_id],
+                     ag_work + t_s_id, f_c_row + t_s_id);
+  }
+
+  /* _scan_f_c_row */
+  for (int t_id = 0; t_id < n_loc_threads; t_id++) {
+    int n_t_rows = t_c_scan[t_id];
+    t_c_scan[t_id] = c_n_rows;
+    c_n_rows += n_t_rows;
+  }
+  for (int t_id = 1; t_id < n_loc_threads; t_id++) {
+    int r_shift = t_c_scan[t_id];
+    if (r_shift != 0)
+      for (int ii = t_range[2*t_id]; ii < t_range[2*t_id+1]; ii++)
+        if (f_c_row[ii] > -1) f_c_row[ii] += r_shift;
+  }
+
+  free(ag_work); free(c_cardinality); free(c_aggr_count);
+  free(t_c_scan); free(t_range);
+  return c_n_rows;
+}
+
+/* cs_sort_lnum restated only as "ascending order" (result is order-unique) */
+static int _cmp_int(const void *a, const void *b)
+{ int x = *(const int *)a, y = *(const int *)b; return (x > y) - (x < y); }
+
+/* _l_id_binary_search (src/alge/cs_grid.cpp:277-300) */
+static int
+_bsearch_id(int size, int id, const int *a)
+{
+  if (size < 1) return -1;
+  int start_id = 0, end_id = size - 1;
+  int mid_id = (end_id - start_id) / 2;
+  while (start_id < end_id) {
+    if (a[mid_id] < id) start_id = mid_id + 1;
+    else if (a[mid_id] > id) end_id = mid_id - 1;
+    else break;
+    mid_id = start_id + ((end_id - start_id) / 2);
+  }
+  if (a[mid_id] != id) mid_id = -1;
+  return mid_id;
+}
+
+void
+ora_grid_free(ora_grid_t *g)
+{
+  if (g == NULL) return;
+  free(g->row_index); free(g->col_id); free(g->d_val); free(g->x_val);
+  free(g->coarse_row); free(g->cell_face); free(g->cell_face_sgn);
+  free(g->cell_cen); free(g->cell_vol); free(g->face_normal);
+  free(g->face_u_normal); free(g->face_surf); free(g->xa0); free(g->xa0ij);
+  free(g);
+}
+
+static void *_dup(const void *p, size_t s)
+{ if (p == NULL) return NULL; void *q = malloc(s > 0 ? s : 1); memcpy(q, p, s); return q; }
+
+/* Level-0 grid from MSR arrays + mesh association
+   (cs_grid_create_from_shared, src/alge/cs_grid.cpp:7425-7562). */
+ora_grid_t *
+ora_grid_create_fine(int n_rows, const int *row_index, const int *col_id,
+                     const double *d_val, const double *x_val,
+                     int n_faces, const int *c2f, const short *c2f_sgn,
+                     const double *cell_cen, const double *cell_vol,
+                     const double *face_u_normal, const double *face_surf)
+{
+  ora_grid_t *g = calloc(1, sizeof(ora_grid_t));
+  const int nnz = row_index[n_rows];
+  g->level = 0; g->n_rows = n_rows; g->nnz = nnz; g->n_faces = n_faces;
+  g->row_index = _dup(row_index, sizeof(int)*(n_rows+1));
+  g->col_id = _dup(col_id, sizeof(int)*nnz);
+  g->d_val = _dup(d_val, sizeof(double)*n_rows);
+  g->x_val = _dup(x_val, sizeof(double)*nnz);
+  g->cell_face = _dup(c2f, sizeof(int)*nnz);
+  g->cell_face_sgn = _dup(c2f_sgn, sizeof(short)*nnz);
+  g->cell_cen = _dup(cell_cen, sizeof(double)*3*n_rows);
+  g->cell_vol = _dup(cell_vol, sizeof(double)*n_rows);
+  g->face_u_normal = _dup(face_u_normal, sizeof(double)*3*n_faces);
+  g->face_surf = _dup(face_surf, sizeof(double)*n_faces);
+  return g;
+}
+
+/*----------------------------------------------------------------------------
+ * One coarsening step on the live path for a symmetric MSR matrix with mesh
+ * association ("msr_gather", src/alge/cs_grid.cpp:8019-8022):
+ *   aggregation      _automatic_aggregation_dx_msr            (:4282)
+ *   adjacency        _coarse_to_fine_adjacency_msr(_serial)   (:2860)
+ *   structure        _coarse_msr_struct                       (:3020)
+ *   coarse faces     _msr_face_adjacency                      (:3751)
+ *   quantities       _coarse_quantities_msr_with_faces_stage_1 (:6226)
+ *   values           _compute_coarse_quantities_msr_with_faces (:6841-6897)
+ *----------------------------------------------------------------------------*/
+
+ora_grid_t *
+ora_grid_coarsen(const ora_grid_t *f, int max_aggregation, double relax_param,
+                 int n_threads)
+{
+  const int f_n_rows = f->n_rows;
+  const int *f_row_index = f->row_index, *f_col_id = f->col_id;
+  const double *f_d_val = f->d_val, *f_x_val = f->x_val;
+
+  ora_grid_t *c = calloc(1, sizeof(ora_grid_t));
+  c->level = f->level + 1;
+  c->coarse_row = malloc(sizeof(int)*(f_n_rows > 0 ? f_n_rows : 1));
+  int *f_c_row = c->coarse_row;
+
+  const int c_n_rows
+    = ora_aggregation_dx_msr(f->level, f_n_rows, f_row_index, f_col_id,
+                             f_d_val, f_x_val, max_aggregation, n_threads,
+                             f_c_row);
+  c->n_rows = c_n_rows;
+
+  /* coarse -> fine adjacency, ascending fine row order (serial variant) */
+  int *c_f_row_index = calloc(c_n_rows + 1, sizeof(int));
+  int *c_f_row_ids = malloc(sizeof(int)*(f_n_rows > 0 ? f_n_rows : 1));
+  for (int ii = 0; ii < f_n_rows; ii++)
+    if (f_c_row[ii] > -1) c_f_row_index[f_c_row[ii] + 1] += 1;
+  for (int i = 0; i < c_n_rows; i++) c_f_row_index[i+1] += c_f_row_index[i];
+  {
+    int *shift = calloc(c_n_rows > 0 ? c_n_rows : 1, sizeof(int));
+    for (int ii = 0; ii < f_n_rows; ii++) {
+      int jj = f_c_row[ii];
+      if (jj > -1) c_f_row_ids[c_f_row_index[jj] + shift[jj]++] = ii;
+    }
+    free(shift);
+  }
+
+  /* coarse MSR structure: sorted unique coarse columns per coarse row */
+  int *c_row_index = calloc(c_n_rows + 1, sizeof(int));
+  int c_nnz_0 = 0;
+  for (int ic = 0; ic < c_n_rows; ic++)
+    for (int r = c_f_row_index[ic]; r < c_f_row_index[ic+1]; r++) {
+      int ii = c_f_row_ids[r];
+      c_nnz_0 += f_row_index[ii+1] - f_row_index[ii];
+    }
+  int *c_col_id = malloc(sizeof(int)*(c_nnz_0 > 0 ? c_nnz_0 : 1));
+  int c_nnz = 0;
+  for (int ic = 0; ic < c_n_rows; ic++) {
+    int *l_buf = c_col_id + c_nnz;
+    int b_e = 0;
+    for (int r = c_f_row_index[ic]; r < c_f_row_index[ic+1]; r++) {
+      int ii = c_f_row_ids[r];
+      for (int jj = f_row_index[ii]; jj < f_row_index[ii+1]; jj++) {
+        int kk = f_c_row[f_col_id[jj]];
+        if (kk > -1 && kk != ic) l_buf[b_e++] = kk;
+      }
+    }
+    qsort(l_buf, b_e, sizeof(int), _cmp_int);
+    int r_count = 0;
+    if (b_e > 0) {
+      r_count = 1;
+      for (int jj = 1; jj < b_e; jj++)
+        if (l_buf[jj] > l_buf[jj-1]) l_buf[r_count++] = l_buf[jj];
+    }
+    c_nnz += r_count;
+    c_row_index[ic+1] = c_nnz;
+  }
+  c->nnz = c_nnz;
+
+  /* coarse faces: upper-triangle entries in (row, col) order */
+  int *c_cell_face = malloc(sizeof(int)*(c_nnz > 0 ? c_nnz : 1));
+  short *c_cell_face_sgn = malloc(sizeof(short)*(c_nnz > 0 ? c_nnz : 1));
+  int c_n_faces = 0;
+  for (int ic = 0; ic < c_n_rows; ic++)
+    for (int idx = c_row_index[ic]; idx < c_row_index[ic+1]; idx++) {
+      if (c_col_id[idx] < ic) {
+        c_cell_face[idx] = -1; c_cell_face_sgn[idx] = -1;
+      }
+      else {
+        c_cell_face[idx] = c_n_faces++; c_cell_face_sgn[idx] = 1;
+      }
+    }
+  for (int ic = 0; ic < c_n_rows; ic++)
+    for (int idx = c_row_index[ic]; idx < c_row_index[ic+1]; idx++)
+      if (c_cell_face[idx] == -1) {
+        int ia = c_col_id[idx];
+        int k = _bsearch_id(c_row_index[ia+1] - c_row_index[ia], ic,
+                            c_col_id + c_row_index[ia]);
+        c_cell_face[idx] = c_cell_face[c_row_index[ia] + k];
+      }
+  c->n_faces = c_n_faces;
+
+  /* stage 1 */
+  double *c_d_val = malloc(sizeof(double)*(c_n_rows > 0 ? c_n_rows : 1));
+  double *c_x_val = malloc(sizeof(double)*(c_nnz > 0 ? c_nnz : 1));
+  double *c_cell_cen = malloc(sizeof(double)*3*(c_n_rows > 0 ? c_n_rows : 1));
+  double *c_cell_vol = malloc(sizeof(double)*(c_n_rows > 0 ? c_n_rows : 1));
+  double *c_face_normal = calloc(3*(c_n_faces > 0 ? c_n_faces : 1), sizeof(double));
+  double *c_xa0 = calloc(c_n_faces > 0 ? c_n_faces : 1, sizeof(double));
+  double *c_xa0ij = calloc(3*(c_n_faces > 0 ? c_n_faces : 1), sizeof(double));
+
+  const double *f_cell_cen = f->cell_cen, *f_cell_vol = f->cell_vol;
+  const int *f_cell_face = f->cell_face;
+  const short *f_cell_face_sgn = f->cell_face_sgn;
+
+  for (int ii_c = 0; ii_c < c_n_rows; ii_c++) {
+    const int c_s_idx = c_row_index[ii_c];
+    const int n_c_cols = c_row_index[ii_c+1] - c_s_idx;
+    double *_cen = c_cell_cen + 3*ii_c;
+    _cen[0] = 0.; _cen[1] = 0.; _cen[2] = 0.;
+    c_cell_vol[ii_c] = 0;
+    c_d_val[ii_c] = 0;
+
+    for (int r_idx = c_f_row_index[ii_c]; r_idx < c_f_row_index[ii_c+1]; r_idx++) {
+      int ii = c_f_row_ids[r_idx];
+      for (int k = 0; k < 3; k++)
+        _cen[k] += f_cell_cen[ii*3+k]*f_cell_vol[ii];
+      c_cell_vol[ii_c] += f_cell_vol[ii];
+      c_d_val[ii_c] += f_d_val[ii];
+
+      for (int f_idx = f_row_index[ii]; f_idx < f_row_index[ii+1]; f_idx++) {
+        int jj = f_col_id[f_idx];
+        int jj_c = f_c_row[jj];
+        c_d_val[ii_c] += f_x_val[f_idx];
+
+        if (jj_c > -1 && jj_c != ii_c) {
+          int k = _bsearch_id(n_c_cols, jj_c, c_col_id + c_s_idx);
+          int c_idx = c_s_idx + k;
+          if (jj_c > ii_c) {
+            int sgn = f_cell_face_sgn[f_idx];
+            int f_face_id = f_cell_face[f_idx];
+            int c_face_id = c_cell_face[c_idx];
+            if (f->level == 0) {
+              double sgn_surf = sgn * f->face_surf[f_face_id];
+              for (int q = 0; q < 3; q++)
+                c_face_normal[c_face_id*3+q]
+                  += sgn_surf * f->face_u_normal[f_face_id*3+q];
+              const double f_xa0_f = f_x_val[f_idx];
+              c_xa0[c_face_id] += f_xa0_f;
+              for (int q = 0; q < 3; q++)
+                c_xa0ij[c_face_id*3+q]
+                  += f_xa0_f * (f_cell_cen[jj*3+q] - f_cell_cen[ii*3+q]);
+            }
+            else {
+              for (int q = 0; q < 3; q++)
+                c_face_normal[c_face_id*3+q]
+                  += sgn * f->face_normal[f_face_id*3+q];
+              c_xa0[c_face_id] += f->xa0[f_face_id];
+              for (int q = 0; q < 3; q++)
+                c_xa0ij[c_face_id*3+q] += sgn * f->xa0ij[f_face_id*3+q];
+            }
+          }
+        }
+      }
+    }
+    for (int k = 0; k < 3; k++) _cen[k] /= c_cell_vol[ii_c];
+  }
+
+  /* values: P0 restriction relaxed with P1 (:6848-6895) */
+  for (int ic = 0; ic < c_n_rows; ic++) {
+    const double *cen_ic = c_cell_cen + 3*ic;
+    for (int r_idx = c_row_index[ic]; r_idx < c_row_index[ic+1]; r_idx++) {
+      const int jc = c_col_id[r_idx];
+      const int c_face_id = c_cell_face[r_idx];
+      const double sgn = (double)c_cell_face_sgn[r_idx];
+      const double *cen_jc = c_cell_cen + 3*jc;
+      const double *nrm = c_face_normal + 3*c_face_id;
+      const double *xij = c_xa0ij + 3*c_face_id;
+
+      const double dsigjg
+        = sgn * (  (cen_jc[0] - cen_ic[0])*nrm[0]
+                 + (cen_jc[1] - cen_ic[1])*nrm[1]
+                 + (cen_jc[2] - cen_ic[2])*nrm[2]);
+
+      double c_x_val_c = c_xa0[c_face_id];
+
+      if (fabs(dsigjg) > 1e-12) {
+        const double dsxaij = xij[0]*nrm[0] + xij[1]*nrm[1] + xij[2]*nrm[2];
+        const double agij = dsxaij/dsigjg;
+        if (agij >= c_x_val_c && agij <= 0.)
+          c_x_val_c = agij;
+      }
+      c_x_val_c =         relax_param *c_x_val_c
+                  + (1. - relax_param)*c_xa0[c_face_id];
+      c_x_val[r_idx] = c_x_val_c;
+      c_d_val[ic] -= c_x_val_c;
+    }
+  }
+
+  free(c_f_row_index); free(c_f_row_ids);
+
+  c->row_index = c_row_index;
+  c->col_id = realloc(c_col_id, sizeof(int)*(c_nnz > 0 ? c_nnz : 1));
+  c->d_val = c_d_val; c->x_val = c_x_val;
+  c->cell_face = c_cell_face; c->cell_face_sgn = c_cell_face_sgn;
+  c->cell_cen = c_cell_cen; c->cell_vol = c_cell_vol;
+  c->face_normal = c_face_normal; c->xa0 = c_xa0; c->xa0ij = c_xa0ij;
+  return c;
+}
+
+/*----------------------------------------------------------------------------
+ * Hierarchy: _setup_hierarchy stop criteria (src/alge/cs_multigrid.cpp:2454-2584)
+ *----------------------------------------------------------------------------*/
+
+ora_mg_t *
+ora_mg_setup(ora_grid_t *fine, int aggregation_limit, int n_levels_max,
+             int n_g_rows_min, double p0p1_relax, int n_threads)
+{
+  ora_mg_t *mg = calloc(1, sizeof(ora_mg_t));
+  mg->grids = calloc(n_levels_max > 0 ? n_levels_max : 1, sizeof(ora_grid_t *));
+  mg->grids[0] = fine;
+  mg->n_levels = 1;
+  ora_grid_t *g = fine;
+  long n_g_rows = g->n_rows, n_g_rows_prev;
+
+  while (1) {
+    n_g_rows_prev = n_g_rows;
+    if (mg->n_levels >= n_levels_max) break;
+    ora_grid_t *c = ora_grid_coarsen(g, aggregation_limit, p0p1_relax, n_threads);
+    n_g_rows = c->n_rows;
+    int add = 1;
+    if (n_g_rows == 0) add = 0;
+    else if (mg->n_levels > 1) {
+      if (n_g_rows < n_g_rows_min || n_g_rows > (0.8 * n_g_rows_prev)) add = 0;
+    }
+    if (!add) { ora_grid_free(c); break; }
+    mg->grids[mg->n_levels++] = c;
+    g = c;
+  }
+  return mg;
+}
+
+void
+ora_mg_free(ora_mg_t *mg, int free_fine)
+{
+  if (mg == NULL) return;
+  for (int i = (free_fine ? 0 : 1); i < mg->n_levels; i++)
+    ora_grid_free(mg->grids[i]);
+  free(mg->grids);
+  free(mg);
+}
+
+/* cs_grid_restrict_row_var, CS_DISPATCH_SUM_SIMPLE (src/alge/cs_grid.cpp:8987-9040) */
+void
+ora_restrict(int f_n_rows, int c_n_rows, const int *coarse_row,
+             const double *f_var, double *c_var)
+{
+  for (int ii = 0; ii < c_n_rows; ii++) c_var[ii] = 0.;
+  for (int ii = 0; ii < f_n_rows; ii++) {
+    int i = coarse_row[ii];
+    if (i >= 0) c_var[i] += f_var[ii];
+  }
+}
+
+/* cs_grid_prolong_row_var, increment mode (src/alge/cs_grid.cpp:9156-9166) */
+void
+ora_prolong_inc(int f_n_rows, const int *coarse_row,
+                const double *c_var, double *f_var)
+{
+  for (int ii = 0; ii < f_n_rows; ii++) {
+    int ic = coarse_row[ii];
+    if (ic >= 0) f_var[ii] += c_var[ic];
+  }
+}
+
+/*----------------------------------------------------------------------------
+ * Multigrid solve, V-cycle in solver mode with cs_sles_it PCG(+Jacobi)
+ * smoothers and coarse solver:
+ *   cs_multigrid_solve  (src/alge/cs_multigrid.cpp:5362-5588)
+ *   _multigrid_v_cycle  (:3127-3542),  _convergence_test (:2927-3035)
+ * opt: n_max_cycles, n_max_iter[3] (descent, ascent, coarse),
+ *      precision_mult[3].
+ * out[0]=n_equiv_iter out[1]=residual out[2]=n_cycles
+ * cycle_res (size >= n_max_cycles+1): fine residual norm at each cycle start.
+ *----------------------------------------------------------------------------*/
+
+int
+ora_mg_solve(const ora_mg_t *mg, const ora_mg_opt_t *opt,
+             double precision, double r_norm,
+             const double *rhs, double *vx, int use_vx_ini,
+             double *out, double *cycle_res)
+{
+  const int n_levels = mg->n_levels;
+  const int coarsest_level = n_levels - 1;
+  const ora_grid_t *g0 = mg->grids[0];
+  const double denom_n_g_rows_0 = 1.0 / g0->n_rows;
+
+  /* rhs_vx work arrays (cs_multigrid.cpp:1888-1935) */
+  double **rhs_l = calloc(n_levels, sizeof(double *));
+  double **vx_l = calloc(n_levels, sizeof(double *));
+  int wr_size = g0->n_rows;
+  for (int l = 1; l < n_levels; l++) {
+    int n = mg->grids[l]->n_rows;
+    rhs_l[l] = calloc(n > 0 ? n : 1, sizeof(double));
+    vx_l[l] = calloc(n > 0 ? n : 1, sizeof(double));
+    if (n > wr_size) wr_size = n;
+  }
+  vx_l[0] = vx;
+  double *wr = malloc(sizeof(double)*(wr_size > 0 ? wr_size : 1));
+
+  int cvg = ORA_ITERATING;
+  int n_equiv_iter = 0;
+  double initial_residual = -1, residual = -1;
+  int n_cycles = 0;
+  double sout[4];
+
+  for (n_cycles = 0; cvg == ORA_ITERATING; n_cycles++) {
+    const int cycle_id = n_cycles + 1;
+    const int vx_ini_nonzero = (n_cycles > 0) ? 1 : use_vx_ini;
+    int end_cycle = 0;
+    int c_cvg = ORA_ITERATING;
+    int level;
+
+    /* Descent */
+    for (level = 0; level < coarsest_level; level++) {
+      const ora_grid_t *f = mg->grids[level];
+      const ora_grid_t *c = mg->grids[level+1];
+      const double *rhs_lv = (level == 0) ? rhs : rhs_l[level];
+      double *vx_lv = vx_l[level];
+      const int ini = (level == 0) ? vx_ini_nonzero : 0;
+
+      c_cvg = ora_pcg_sr_p0(f->n_rows, f->row_index, f->col_id, f->d_val,
+                            f->x_val, opt->n_max_iter[0],
+                            precision*opt->precision_mult[0], r_norm,
+                            rhs_lv, vx_lv, ini, sout, NULL, 0);
+      int n_iter = (int)sout[0];
+      if (level == 0 && cycle_id == 1) initial_residual = sout[2];
+      if (c_cvg < ORA_BREAKDOWN) { end_cycle = 1; break; }
+
+      ora_spmv_msr(f->n_rows, f->row_index, f->col_id, f->d_val, f->x_val,
+                   0, vx_lv, wr);
+      for (int ii = 0; ii < f->n_rows; ii++) wr[ii] = rhs_lv[ii] - wr[ii];
+
+      if (level == 0) {
+        double r2 = ora_dot_xx(f->n_rows, wr);
+        residual = sqrt(r2);
+        /* initial_residual is passed by value to _convergence_test (:2937,
+           :2967-2968): cycle 1 compares against itself, later cycles against
+           the level-0 smoother's initial residual of cycle 1 (:3278-3279) */
+        const double ir = (cycle_id == 1) ? residual : initial_residual;
+        if (cycle_res != NULL) cycle_res[cycle_id - 1] = residual;
+        if (residual < precision*r_norm) cvg = ORA_CONVERGED;
+        else if (cycle_id > opt->n_max_cycles) cvg = ORA_MAX_ITERATION;
+        else if (residual > ir * 10000.0 && residual > 100.)
+          cvg = ORA_DIVERGED;
+        else if (isnan(residual) || isinf(residual)) cvg = ORA_DIVERGED;
+        if (cvg != 0) {
+          c_cvg = cvg; end_cycle = 1;
+          n_equiv_iter += n_iter * f->n_rows * denom_n_g_rows_0;
+          break;
+        }
+      }
+      n_equiv_iter += n_iter * f->n_rows * denom_n_g_rows_0;
+
+      ora_restrict(f->n_rows, c->n_rows, c->coarse_row, wr, rhs_l[level+1]);
+    }
+
+    if (!end_cycle) {
+      const ora_grid_t *c = mg->grids[coarsest_level];
+      const double *rhs_lv = (coarsest_level == 0) ? rhs : rhs_l[coarsest_level];
+      c_cvg = ora_pcg_sr_p0(c->n_rows, c->row_index, c->col_id, c->d_val,
+                            c->x_val, opt->n_max_iter[2],
+                            precision*opt->precision_mult[2], r_norm,
+                            rhs_lv, vx_l[coarsest_level], 0, sout, NULL, 0);
+      n_equiv_iter += (int)sout[0] * c->n_rows * denom_n_g_rows_0;
+      if (c_cvg < ORA_BREAKDOWN) end_cycle = 1;
+    }
+
+    if (!end_cycle) {
+      for (level = coarsest_level - 1; level > -1; level--) {
+        const ora_grid_t *f = mg->grids[level];
+        const ora_grid_t *c = mg->grids[level+1];
+        ora_prolong_inc(f->n_rows, c->coarse_row, vx_l[level+1], vx_l[level]);
+        if (level > 0) {
+          c_cvg = ora_pcg_sr_p0(f->n_rows, f->row_index, f->col_id, f->d_val,
+                                f->x_val, opt->n_max_iter[1],
+                                precision*opt->precision_mult[1], r_norm,
+                                rhs_l[level], vx_l[level], 1, sout, NULL, 0);
+          n_equiv_iter += (int)sout[0] * f->n_rows * denom_n_g_rows_0;
+          if (c_cvg < ORA_BREAKDOWN) break;
+        }
+      }
+    }
+  }
+
+  out[0] = n_equiv_iter;
+  out[1] = residual;
+  out[2] = n_cycles;
+  for (int l = 1; l < n_levels; l++) { free(rhs_l[l]); free(vx_l[l]); }
+  free(rhs_l); free(vx_l); free(wr);
+  return cvg;
+}

@@ -1,0 +1,104 @@
+/* oracle/cs_oracle.h -- TEST INFRASTRUCTURE (see cs_oracle.c header).
+ * CPU restatement of the reference's src/alge hot path; parity pinned against
+ * the reference's own compiled code (oracle/_ref). Never used by the product. */
+#ifndef CS_ORACLE_H
+#define CS_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* cs_sles_convergence_state_t (src/alge/cs_sles.h:57-68) */
+#define ORA_DIVERGED      -3
+#define ORA_BREAKDOWN     -2
+#define ORA_MAX_ITERATION -1
+#define ORA_ITERATING      0
+#define ORA_CONVERGED      1
+
+/* One level of the hierarchy: subset of cs_grid_t (src/alge/cs_grid_priv.h:53-162) */
+typedef struct {
+  int      level, n_rows, nnz, n_faces;
+  int     *row_index, *col_id;
+  double  *d_val, *x_val;
+  int     *coarse_row;      /* parent rows -> rows of this level (level > 0) */
+  int     *cell_face;       /* per off-diagonal entry */
+  short   *cell_face_sgn;
+  double  *cell_cen, *cell_vol;
+  double  *face_normal;     /* level > 0 */
+  double  *face_u_normal, *face_surf;  /* level 0 */
+  double  *xa0, *xa0ij;     /* level > 0 */
+} ora_grid_t;
+
+typedef struct {
+  int          n_levels;
+  ora_grid_t **grids;
+} ora_mg_t;
+
+typedef struct {
+  int     n_max_cycles;
+  int     n_max_iter[3];      /* descent, ascent, coarse */
+  double  precision_mult[3];
+} ora_mg_opt_t;
+
+void   ora_thread_range(int n, int type_size, int t_id, int n_t, int *s_id, int *e_id);
+
+void   ora_spmv_msr(int n_rows, const int *row_index, const int *col_id,
+                    const double *d_val, const double *x_val, int exclude_diag,
+                    const double *x, double *y);
+
+double ora_dot(int n, const double *x, const double *y);
+double ora_dot_xx(int n, const double *x);
+void   ora_dot_xx_xy(int n, const double *x, const double *y, double *xx, double *xy);
+void   ora_dot_xy_yz(int n, const double *x, const double *y, const double *z,
+                     double *xy, double *yz);
+void   ora_dot_xx_xy_yz(int n, const double *x, const double *y, const double *z,
+                        double *xx, double *xy, double *yz);
+
+int    ora_pcg_sr_p0(int n_rows, const int *row_index, const int *col_id,
+                     const double *d_val, const double *x_val,
+                     int n_max_iter, double precision, double r_norm,
+                     const double *rhs, double *vx, int use_vx_ini,
+                     double *out, double *history, int history_size);
+int    ora_jacobi(int n_rows, const int *row_index, const int *col_id,
+                  const double *d_val, const double *x_val,
+                  int n_max_iter, double precision, double r_norm,
+                  const double *rhs, double *vx, int use_vx_ini,
+                  double *out, double *history, int history_size);
+int    ora_bicgstab(int n_rows, const int *row_index, const int *col_id,
+                    const double *d_val, const double *x_val,
+                    int n_max_iter, double precision, double r_norm,
+                    const double *rhs, double *vx, int use_vx_ini,
+                    double *out, double *history, int history_size);
+
+int    ora_aggregation_dx_msr(int level, int f_n_rows, const int *row_index,
+                              const int *col_id, const double *d_val,
+                              const double *x_val, int max_aggregation,
+                              int n_threads, int *f_c_row);
+
+ora_grid_t *ora_grid_create_fine(int n_rows, const int *row_index, const int *col_id,
+                                 const double *d_val, const double *x_val,
+                                 int n_faces, const int *c2f, const short *c2f_sgn,
+                                 const double *cell_cen, const double *cell_vol,
+                                 const double *face_u_normal, const double *face_surf);
+ora_grid_t *ora_grid_coarsen(const ora_grid_t *f, int max_aggregation,
+                             double relax_param, int n_threads);
+void        ora_grid_free(ora_grid_t *g);
+
+ora_mg_t   *ora_mg_setup(ora_grid_t *fine, int aggregation_limit, int n_levels_max,
+                         int n_g_rows_min, double p0p1_relax, int n_threads);
+void        ora_mg_free(ora_mg_t *mg, int free_fine);
+
+void   ora_restrict(int f_n_rows, int c_n_rows, const int *coarse_row,
+                    const double *f_var, double *c_var);
+void   ora_prolong_inc(int f_n_rows, const int *coarse_row,
+                       const double *c_var, double *f_var);
+
+int    ora_mg_solve(const ora_mg_t *mg, const ora_mg_opt_t *opt,
+                    double precision, double r_norm,
+                    const double *rhs, double *vx, int use_vx_ini,
+                    double *out, double *cycle_res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

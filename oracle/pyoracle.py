@@ -1,0 +1,336 @@
+"""ctypes bindings for the CPU checkers -- TEST INFRASTRUCTURE ONLY.
+
+* ``Oracle``  : oracle/libcs_oracle.so, the plain-C restatement (oracle/cs_oracle.c)
+* ``RefLib``  : oracle/_ref/libcsref.so, the reference's own compiled CPU code
+                driven by oracle/ref_harness.cpp (built by oracle/Makefile.ref)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module.  The product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+
+c_int_p = C.POINTER(C.c_int)
+c_dbl_p = C.POINTER(C.c_double)
+c_short_p = C.POINTER(C.c_short)
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(c_int_p)
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(c_dbl_p)
+
+
+def _sp(a):
+    return None if a is None else a.ctypes.data_as(c_short_p)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def build_oracle(force: bool = False) -> str:
+    """Compile oracle/cs_oracle.c into oracle/libcs_oracle.so (gcc, seconds)."""
+    so = os.path.join(_HERE, "libcs_oracle.so")
+    src = os.path.join(_HERE, "cs_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-f", "oracle/Makefile"], cwd=_ROOT,
+                              stdout=subprocess.DEVNULL)
+    return so
+
+
+def ref_available() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libcsref.so"))
+
+
+class OraGrid(C.Structure):
+    _fields_ = [("level", C.c_int), ("n_rows", C.c_int), ("nnz", C.c_int),
+                ("n_faces", C.c_int),
+                ("row_index", c_int_p), ("col_id", c_int_p),
+                ("d_val", c_dbl_p), ("x_val", c_dbl_p),
+                ("coarse_row", c_int_p), ("cell_face", c_int_p),
+                ("cell_face_sgn", c_short_p),
+                ("cell_cen", c_dbl_p), ("cell_vol", c_dbl_p),
+                ("face_normal", c_dbl_p), ("face_u_normal", c_dbl_p),
+                ("face_surf", c_dbl_p), ("xa0", c_dbl_p), ("xa0ij", c_dbl_p)]
+
+
+class OraMg(C.Structure):
+    _fields_ = [("n_levels", C.c_int), ("grids", C.POINTER(C.POINTER(OraGrid)))]
+
+
+class OraMgOpt(C.Structure):
+    _fields_ = [("n_max_cycles", C.c_int), ("n_max_iter", C.c_int * 3),
+                ("precision_mult", C.c_double * 3)]
+
+
+def _np_from(ptr, n, dtype):
+    if n <= 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+class Oracle:
+    """The C restatement (oracle/cs_oracle.c)."""
+
+    def __init__(self):
+        self.lib = C.CDLL(build_oracle())
+        L = self.lib
+        L.ora_dot.restype = C.c_double
+        L.ora_dot_xx.restype = C.c_double
+        L.ora_grid_create_fine.restype = C.POINTER(OraGrid)
+        L.ora_grid_coarsen.restype = C.POINTER(OraGrid)
+        L.ora_mg_setup.restype = C.POINTER(OraMg)
+        L.ora_grid_coarsen.argtypes = [C.POINTER(OraGrid), C.c_int, C.c_double, C.c_int]
+        L.ora_mg_setup.argtypes = [C.POINTER(OraGrid), C.c_int, C.c_int, C.c_int,
+                                   C.c_double, C.c_int]
+        L.ora_mg_solve.argtypes = [C.POINTER(OraMg), C.POINTER(OraMgOpt), C.c_double,
+                                   C.c_double, c_dbl_p, c_dbl_p, C.c_int, c_dbl_p, c_dbl_p]
+
+    # -- kernels ----------------------------------------------------------
+    def spmv(self, ri, ci, d, x_val, x, exclude_diag=False):
+        ri, ci, d, x_val, x = _i32(ri), _i32(ci), _f64(d), _f64(x_val), _f64(x)
+        y = np.empty(len(ri) - 1)
+        self.lib.ora_spmv_msr(C.c_int(len(ri) - 1), _ip(ri), _ip(ci), _dp(d), _dp(x_val),
+                              C.c_int(int(exclude_diag)), _dp(x), _dp(y))
+        return y
+
+    def dot(self, x, y):
+        x, y = _f64(x), _f64(y)
+        return self.lib.ora_dot(C.c_int(len(x)), _dp(x), _dp(y))
+
+    def dot_xx(self, x):
+        x = _f64(x)
+        return self.lib.ora_dot_xx(C.c_int(len(x)), _dp(x))
+
+    def dot_xx_xy_yz(self, x, y, z):
+        x, y, z = _f64(x), _f64(y), _f64(z)
+        r = (C.c_double * 3)()
+        self.lib.ora_dot_xx_xy_yz(C.c_int(len(x)), _dp(x), _dp(y), _dp(z),
+                                  C.byref(r, 0), C.byref(r, 8), C.byref(r, 16))
+        return tuple(r)
+
+    def _solve(self, fn, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0):
+        ri, ci, d, xv, rhs = _i32(ri), _i32(ci), _f64(d), _f64(xv), _f64(rhs)
+        n = len(ri) - 1
+        vx = np.zeros(n) if vx0 is None else _f64(vx0).copy()
+        out = np.zeros(4)
+        hist = np.zeros(n_max_iter + 8)
+        cvg = fn(C.c_int(n), _ip(ri), _ip(ci), _dp(d), _dp(xv), C.c_int(n_max_iter),
+                 C.c_double(precision), C.c_double(r_norm), _dp(rhs), _dp(vx),
+                 C.c_int(0 if vx0 is None else 1), _dp(out), _dp(hist), C.c_int(len(hist)))
+        return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], initial_residual=out[2],
+                    history=hist[:int(out[3])].copy(), vx=vx)
+
+    def pcg(self, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0=None):
+        return self._solve(self.lib.ora_pcg_sr_p0, ri, ci, d, xv, rhs, n_max_iter,
+                           precision, r_norm, vx0)
+
+    def jacobi(self, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0=None):
+        return self._solve(self.lib.ora_jacobi, ri, ci, d, xv, rhs, n_max_iter,
+                           precision, r_norm, vx0)
+
+    def bicgstab(self, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0=None):
+        return self._solve(self.lib.ora_bicgstab, ri, ci, d, xv, rhs, n_max_iter,
+                           precision, r_norm, vx0)
+
+    def aggregation(self, level, ri, ci, d, xv, max_aggregation=3, n_threads=1):
+        ri, ci, d, xv = _i32(ri), _i32(ci), _f64(d), _f64(xv)
+        n = len(ri) - 1
+        f_c_row = np.empty(n, dtype=np.int32)
+        nc = self.lib.ora_aggregation_dx_msr(C.c_int(level), C.c_int(n), _ip(ri), _ip(ci),
+                                             _dp(d), _dp(xv), C.c_int(max_aggregation),
+                                             C.c_int(n_threads), _ip(f_c_row))
+        return nc, f_c_row
+
+    # -- hierarchy ---------------------------------------------------------
+    def fine_grid(self, s):
+        ri, ci = _i32(s.row_index), _i32(s.col_id)
+        args = [_f64(s.d_val), _f64(s.x_val)]
+        c2f, sgn = _i32(s.c2f), np.ascontiguousarray(s.c2f_sgn, dtype=np.int16)
+        cen, vol = _f64(s.cell_cen), _f64(s.cell_vol)
+        fun, fs = _f64(s.face_u_normal), _f64(s.face_surf)
+        return self.lib.ora_grid_create_fine(
+            C.c_int(s.n_rows), _ip(ri), _ip(ci), _dp(args[0]), _dp(args[1]),
+            C.c_int(s.n_faces), _ip(c2f), _sp(sgn), _dp(cen), _dp(vol), _dp(fun), _dp(fs))
+
+    def mg_setup(self, s, aggregation_limit=3, n_levels_max=25, n_g_rows_min=30,
+                 p0p1_relax=0.95, n_threads=1):
+        g = self.fine_grid(s)
+        return self.lib.ora_mg_setup(g, aggregation_limit, n_levels_max, n_g_rows_min,
+                                     p0p1_relax, n_threads)
+
+    @staticmethod
+    def mg_levels(mg):
+        """Copy every level out as numpy arrays."""
+        out = []
+        for l in range(mg.contents.n_levels):
+            g = mg.contents.grids[l].contents
+            parent_n = mg.contents.grids[l - 1].contents.n_rows if l > 0 else 0
+            out.append(dict(
+                n_rows=g.n_rows, nnz=g.nnz, n_faces=g.n_faces,
+                row_index=_np_from(g.row_index, g.n_rows + 1, np.int32),
+                col_id=_np_from(g.col_id, g.nnz, np.int32),
+                d_val=_np_from(g.d_val, g.n_rows, np.float64),
+                x_val=_np_from(g.x_val, g.nnz, np.float64),
+                coarse_row=_np_from(g.coarse_row, parent_n, np.int32),
+                cell_cen=_np_from(g.cell_cen, 3 * g.n_rows, np.float64),
+                cell_vol=_np_from(g.cell_vol, g.n_rows, np.float64)))
+        return out
+
+    def mg_solve(self, mg, rhs, precision, r_norm, n_max_cycles=100, n_max_iter=(2, 10, 500),
+                 precision_mult=(1., 1., 1.), vx0=None):
+        rhs = _f64(rhs)
+        n = len(rhs)
+        vx = np.zeros(n) if vx0 is None else _f64(vx0).copy()
+        opt = OraMgOpt()
+        opt.n_max_cycles = n_max_cycles
+        for i in range(3):
+            opt.n_max_iter[i] = n_max_iter[i]
+            opt.precision_mult[i] = precision_mult[i]
+        out = np.zeros(4)
+        cyc = np.zeros(n_max_cycles + 2)
+        cvg = self.lib.ora_mg_solve(mg, C.byref(opt), precision, r_norm, _dp(rhs), _dp(vx),
+                                    0 if vx0 is None else 1, _dp(out), _dp(cyc))
+        nc = int(out[2])
+        return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], n_cycles=nc,
+                    cycle_residuals=cyc[:nc].copy(), vx=vx)
+
+    def mg_free(self, mg):
+        self.lib.ora_mg_free(mg, 1)
+
+
+class RefLib:
+    """The reference's own CPU code (oracle/_ref/libcsref.so)."""
+
+    PCG, FCG, IPCG, JACOBI, BICGSTAB = 0, 1, 2, 3, 4
+
+    def __init__(self, n_threads=1, quiet=True):
+        path = os.path.join(_HERE, "_ref", "libcsref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} missing: run `make -f oracle/Makefile.ref -j8` where "
+                "/root/reference is mounted")
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.csref_system_create.restype = C.c_void_p
+        L.csref_hierarchy_build.restype = C.c_void_p
+        L.csref_dot.restype = C.c_double
+        L.csref_dot_xx.restype = C.c_double
+        self.n_threads = L.csref_init(C.c_int(n_threads), C.c_int(int(quiet)))
+
+    def set_threads(self, n):
+        self.n_threads = self.lib.csref_init(C.c_int(n), C.c_int(1))
+
+    def system(self, s, d_val=None, x_val=None, symmetric=True, with_mesh=True):
+        ri, ci = _i32(s.row_index), _i32(s.col_id)
+        d = _f64(s.d_val if d_val is None else d_val)
+        xv = _f64(s.x_val if x_val is None else x_val)
+        h = C.c_void_p(self.lib.csref_system_create(C.c_int(s.n_rows), _ip(ri), _ip(ci),
+                                                    _dp(d), _dp(xv), C.c_int(int(symmetric))))
+        if with_mesh and s.n_faces > 0:
+            fc, c2f = _i32(s.face_cells), _i32(s.c2f)
+            sgn = np.ascontiguousarray(s.c2f_sgn, dtype=np.int16)
+            cen, vol = _f64(s.cell_cen), _f64(s.cell_vol)
+            fun, fs = _f64(s.face_u_normal), _f64(s.face_surf)
+            self.lib.csref_system_set_mesh(h, C.c_int(s.n_faces), _ip(fc), _ip(c2f), _sp(sgn),
+                                           _dp(cen), _dp(vol), _dp(fun), _dp(fs))
+        return h
+
+    def destroy(self, h):
+        self.lib.csref_system_destroy(h)
+
+    def spmv(self, h, x, n_rows, exclude_diag=False):
+        x = _f64(x).copy()
+        y = np.empty(n_rows)
+        self.lib.csref_spmv(h, C.c_int(int(exclude_diag)), _dp(x), _dp(y))
+        return y
+
+    def dot(self, x, y):
+        x, y = _f64(x), _f64(y)
+        return self.lib.csref_dot(C.c_int(len(x)), _dp(x), _dp(y))
+
+    def dot_xx(self, x):
+        x = _f64(x)
+        return self.lib.csref_dot_xx(C.c_int(len(x)), _dp(x))
+
+    def dot_xx_xy_yz(self, x, y, z):
+        x, y, z = _f64(x), _f64(y), _f64(z)
+        r = np.zeros(3)
+        self.lib.csref_dot_xx_xy_yz(C.c_int(len(x)), _dp(x), _dp(y), _dp(z), _dp(r))
+        return tuple(r)
+
+    def sles_it(self, h, solver, rhs, n_max_iter, precision, r_norm, vx0=None, poly_degree=0):
+        rhs = _f64(rhs)
+        vx = np.zeros(len(rhs)) if vx0 is None else _f64(vx0).copy()
+        out = np.zeros(5)
+        cvg = self.lib.csref_sles_it_solve(h, C.c_int(solver), C.c_int(poly_degree),
+                                           C.c_int(n_max_iter), C.c_double(precision),
+                                           C.c_double(r_norm), _dp(rhs), _dp(vx),
+                                           C.c_int(0 if vx0 is None else 1), _dp(out))
+        return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], initial_residual=out[2],
+                    t_setup=out[3], t_solve=out[4], vx=vx)
+
+    def multigrid(self, h, rhs, precision, r_norm, n_max_cycles=100, n_max_iter=(2, 10, 500),
+                  types=(0, 0, 0), poly_degree=(0, 0, 0), precision_mult=(1., 1., 1.),
+                  aggregation_limit=3, coarsening_type=0, n_levels_max=25, n_g_rows_min=30,
+                  p0p1_relax=0.95, vx0=None, verbosity=0):
+        rhs = _f64(rhs)
+        vx = np.zeros(len(rhs)) if vx0 is None else _f64(vx0).copy()
+        iopt = np.array(list(types) + [n_max_cycles] + list(n_max_iter) + list(poly_degree)
+                        + [aggregation_limit, coarsening_type, n_levels_max, n_g_rows_min],
+                        dtype=np.int32)
+        dopt = np.array(list(precision_mult) + [p0p1_relax], dtype=np.float64)
+        out = np.zeros(4)
+        cvg = self.lib.csref_multigrid_solve(h, _ip(iopt), _dp(dopt), C.c_double(precision),
+                                             C.c_double(r_norm), _dp(rhs), _dp(vx),
+                                             C.c_int(0 if vx0 is None else 1),
+                                             C.c_int(verbosity), _dp(out))
+        return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], t_setup=out[2],
+                    t_solve=out[3], vx=vx)
+
+    def hierarchy(self, h, aggregation_limit=3, coarsening_type=0, n_levels_max=25,
+                  n_g_rows_min=30, p0p1_relax=0.95, verbosity=0):
+        hh = C.c_void_p(self.lib.csref_hierarchy_build(h, C.c_int(aggregation_limit),
+                                                       C.c_int(coarsening_type),
+                                                       C.c_int(n_levels_max),
+                                                       C.c_int(n_g_rows_min),
+                                                       C.c_double(p0p1_relax),
+                                                       C.c_int(verbosity)))
+        n_levels = self.lib.csref_hierarchy_n_levels(hh)
+        levels = []
+        parent_n = 0
+        for l in range(n_levels):
+            info = np.zeros(3, dtype=np.int32)
+            self.lib.csref_hierarchy_level_info(hh, C.c_int(l), _ip(info))
+            n, nnz = int(info[0]), int(info[1])
+            cr = np.zeros(max(parent_n, 1), dtype=np.int32)
+            ri = np.zeros(n + 1, dtype=np.int32)
+            ci = np.zeros(max(nnz, 1), dtype=np.int32)
+            d = np.zeros(max(n, 1))
+            xv = np.zeros(max(nnz, 1))
+            cen = np.zeros(3 * max(n, 1))
+            vol = np.zeros(max(n, 1))
+            self.lib.csref_hierarchy_level_copy(hh, C.c_int(l), _ip(cr), _ip(ri), _ip(ci),
+                                                _dp(d), _dp(xv), _dp(cen), _dp(vol))
+            levels.append(dict(n_rows=n, nnz=nnz, n_faces=int(info[2]),
+                               row_index=ri, col_id=ci[:nnz], d_val=d[:n], x_val=xv[:nnz],
+                               coarse_row=cr[:parent_n], cell_cen=cen[:3 * n],
+                               cell_vol=vol[:n]))
+            parent_n = n
+        self.lib.csref_hierarchy_destroy(hh)
+        return levels

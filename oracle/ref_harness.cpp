@@ -1,0 +1,438 @@
+/*============================================================================
+ * oracle/ref_harness.cpp -- TEST INFRASTRUCTURE, not product code.
+ *
+ * Thin extern "C" driver around the UNMODIFIED reference (code_saturne)
+ * CPU implementation of the src/alge linear-solve path, linked from the
+ * objects oracle/Makefile.ref compiles in place from /root/reference.
+ *
+ * It only calls the reference's public (and cs_grid_priv.h) API:
+ *   cs_matrix_structure_create_msr_shared / cs_matrix_create /
+ *   cs_matrix_transfer_coefficients_msr / cs_matrix_set_mesh_association
+ *     (src/alge/cs_matrix.cpp:4518, :4682, :5451, :6328)
+ *   cs_matrix_vector_multiply            (src/alge/cs_matrix.cpp:6405)
+ *   cs_sles_it_create/_setup/_solve      (src/alge/cs_sles_it.cpp:4659,:4964,:5194)
+ *   cs_multigrid_create/_setup/_solve    (src/alge/cs_multigrid.cpp:4644,:5275,:5362)
+ *   cs_grid_create_from_shared / cs_grid_coarsen
+ *                                        (src/alge/cs_grid.cpp:7425, :7980)
+ *   cs_dot_xx, cs_dot_xx_xy_yz ...       (src/alge/cs_blas.cpp:1629-1905)
+ *
+ * Used (a) to pin oracle/*.c restatements and generate tests/golden fixtures,
+ * (b) as the CPU baseline of bench.py ("kind": "reference").
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load the resulting oracle/_ref/libcsref.so.
+ *============================================================================*/
+
+#include "base/cs_defs.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <chrono>
+#include <omp.h>
+
+#include "bft/bft_error.h"
+#include "bft/bft_printf.h"
+#include "base/cs_mem.h"
+#include "base/cs_halo.h"
+#include "base/cs_timer.h"
+#include "mesh/cs_mesh.h"
+#include "alge/cs_blas.h"
+#include "alge/cs_matrix.h"
+#include "alge/cs_matrix_default.h"
+#include "alge/cs_sles.h"
+#include "alge/cs_sles_it.h"
+#include "alge/cs_sles_pc.h"
+#include "alge/cs_multigrid.h"
+#include "alge/cs_grid.h"
+#include "alge/cs_grid_priv.h"
+
+namespace {
+
+struct ref_system {
+  cs_lnum_t  n_rows = 0;
+  cs_lnum_t  n_faces = 0;
+  bool       symmetric = true;
+  cs_lnum_t *row_index = nullptr;
+  cs_lnum_t *col_id = nullptr;
+  cs_matrix_structure_t *ms = nullptr;
+  cs_matrix_t           *m = nullptr;
+  /* mesh association (owned copies) */
+  cs_lnum_t    *c2f = nullptr;
+  short int    *c2f_sgn = nullptr;
+  cs_real_3_t  *cell_cen = nullptr;
+  cs_real_t    *cell_vol = nullptr;
+  cs_nreal_3_t *face_u_normal = nullptr;
+  cs_real_t    *face_surf = nullptr;
+};
+
+struct ref_hierarchy {
+  std::vector<cs_grid_t *> grids;
+};
+
+bool g_initialized = false;
+bool g_quiet = true;
+
+int _printf_quiet(const char *const format, va_list arg_ptr)
+{
+  if (g_quiet) return 0;
+  return vprintf(format, arg_ptr);
+}
+
+double _now()
+{
+  return std::chrono::duration<double>(
+    std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+void _set_glob_mesh_faces(const ref_system *s, const cs_lnum_t *face_cells)
+{
+  /* cs_multigrid_setup reads cs_glob_mesh->n_i_faces / i_face_cells
+     (src/alge/cs_multigrid.cpp:5283,:5312). */
+  if (cs_glob_mesh == nullptr)
+    cs_glob_mesh = cs_mesh_create();
+  cs_mesh_t *mesh = cs_glob_mesh;
+  CS_FREE(mesh->i_face_cells);
+  mesh->n_cells = s->n_rows;
+  mesh->n_cells_with_ghosts = s->n_rows;
+  mesh->n_i_faces = s->n_faces;
+  CS_MALLOC(mesh->i_face_cells, (s->n_faces > 0) ? s->n_faces : 1, cs_lnum_2_t);
+  if (face_cells != nullptr)
+    memcpy(mesh->i_face_cells, face_cells, sizeof(cs_lnum_2_t)*s->n_faces);
+}
+
+} // namespace
+
+extern "C" {
+
+/* Initialise reference globals; n_threads <= 0 keeps the OpenMP default. */
+int
+csref_init(int n_threads, int quiet)
+{
+  if (n_threads > 0)
+    omp_set_num_threads(n_threads);
+  cs_glob_n_threads = omp_get_max_threads();
+  g_quiet = (quiet != 0);
+  if (!g_initialized) {
+    bft_printf_proxy_set(_printf_quiet);
+    g_initialized = true;
+  }
+  return cs_glob_n_threads;
+}
+
+/* Build a reference MSR cs_matrix_t from plain arrays (values are copied). */
+void *
+csref_system_create(int            n_rows,
+                    const int     *row_index,
+                    const int     *col_id,
+                    const double  *d_val,
+                    const double  *x_val,
+                    int            symmetric)
+{
+  ref_system *s = new ref_system;
+  s->n_rows = n_rows;
+  s->symmetric = (symmetric != 0);
+  const cs_lnum_t nnz = row_index[n_rows];
+
+  CS_MALLOC(s->row_index, n_rows+1, cs_lnum_t);
+  CS_MALLOC(s->col_id, (nnz > 0) ? nnz : 1, cs_lnum_t);
+  memcpy(s->row_index, row_index, sizeof(cs_lnum_t)*(n_rows+1));
+  memcpy(s->col_id, col_id, sizeof(cs_lnum_t)*nnz);
+
+  s->ms = cs_matrix_structure_create_msr_shared(true, n_rows, n_rows,
+                                                s->row_index, s->col_id,
+                                                nullptr, nullptr);
+  s->m = cs_matrix_create(s->ms);
+
+  cs_real_t *d, *x;
+  CS_MALLOC(d, n_rows, cs_real_t);
+  CS_MALLOC(x, (nnz > 0) ? nnz : 1, cs_real_t);
+  memcpy(d, d_val, sizeof(cs_real_t)*n_rows);
+  memcpy(x, x_val, sizeof(cs_real_t)*nnz);
+  cs_matrix_transfer_coefficients_msr(s->m, s->symmetric, 1, 1,
+                                      s->row_index, s->col_id, &d, &x);
+  return s;
+}
+
+/* Associate mesh data (same role as src/alge/cs_sles_default.cpp:826-838). */
+void
+csref_system_set_mesh(void          *sys,
+                      int            n_faces,
+                      const int     *face_cells,    /* 2*n_faces */
+                      const int     *c2f,           /* nnz: face id per entry */
+                      const short   *c2f_sgn,       /* nnz */
+                      const double  *cell_cen,      /* 3*n_rows */
+                      const double  *cell_vol,      /* n_rows */
+                      const double  *face_u_normal, /* 3*n_faces */
+                      const double  *face_surf)     /* n_faces */
+{
+  ref_system *s = static_cast<ref_system *>(sys);
+  const cs_lnum_t nnz = s->row_index[s->n_rows];
+  s->n_faces = n_faces;
+
+  CS_MALLOC(s->c2f, nnz, cs_lnum_t);
+  CS_MALLOC(s->c2f_sgn, nnz, short int);
+  CS_MALLOC(s->cell_cen, s->n_rows, cs_real_3_t);
+  CS_MALLOC(s->cell_vol, s->n_rows, cs_real_t);
+  CS_MALLOC(s->face_u_normal, n_faces, cs_nreal_3_t);
+  CS_MALLOC(s->face_surf, n_faces, cs_real_t);
+  memcpy(s->c2f, c2f, sizeof(cs_lnum_t)*nnz);
+  memcpy(s->c2f_sgn, c2f_sgn, sizeof(short int)*nnz);
+  memcpy(s->cell_cen, cell_cen, sizeof(cs_real_3_t)*s->n_rows);
+  memcpy(s->cell_vol, cell_vol, sizeof(cs_real_t)*s->n_rows);
+  for (cs_lnum_t i = 0; i < n_faces; i++) {
+    for (int k = 0; k < 3; k++)
+      s->face_u_normal[i][k] = face_u_normal[i*3+k];
+    s->face_surf[i] = face_surf[i];
+  }
+
+  cs_matrix_set_mesh_association(s->m, s->row_index, s->c2f, s->c2f_sgn,
+                                 s->cell_cen, s->cell_vol,
+                                 s->face_u_normal, s->face_surf);
+  _set_glob_mesh_faces(s, face_cells);
+}
+
+void
+csref_system_destroy(void *sys)
+{
+  ref_system *s = static_cast<ref_system *>(sys);
+  if (s == nullptr) return;
+  cs_matrix_destroy(&(s->m));
+  cs_matrix_structure_destroy(&(s->ms));
+  CS_FREE(s->row_index); CS_FREE(s->col_id);
+  CS_FREE(s->c2f); CS_FREE(s->c2f_sgn);
+  CS_FREE(s->cell_cen); CS_FREE(s->cell_vol);
+  CS_FREE(s->face_u_normal); CS_FREE(s->face_surf);
+  delete s;
+}
+
+/* y = A.x (or (A-D).x): reference _mat_vec_p_l_msr through the public entry. */
+void
+csref_spmv(void *sys, int exclude_diag, double *x, double *y)
+{
+  ref_system *s = static_cast<ref_system *>(sys);
+  if (exclude_diag)
+    cs_matrix_vector_multiply_partial(s->m, CS_MATRIX_SPMV_E, x, y);
+  else
+    cs_matrix_vector_multiply(s->m, x, y);
+}
+
+double csref_dot(int n, const double *x, const double *y)
+{ return cs_dot(n, x, y); }
+
+double csref_dot_xx(int n, const double *x)
+{ return cs_dot_xx(n, x); }
+
+void csref_dot_xx_xy_yz(int n, const double *x, const double *y,
+                        const double *z, double *r)
+{ cs_dot_xx_xy_yz(n, x, y, z, r, r+1, r+2); }
+
+void csref_dot_xx_xy(int n, const double *x, const double *y, double *r)
+{ cs_dot_xx_xy(n, x, y, r, r+1); }
+
+void csref_dot_xy_yz(int n, const double *x, const double *y,
+                     const double *z, double *r)
+{ cs_dot_xy_yz(n, x, y, z, r, r+1); }
+
+/* cs_sles_it solve. type: cs_sles_it_type_t value (0 PCG, 3 Jacobi, 4 BiCGStab
+   ...). vx holds the initial guess when use_vx_ini != 0 and the result.
+   out[0] = n_iter, out[1] = residual, out[2] = initial residual,
+   out[3] = setup seconds, out[4] = solve seconds. Returns convergence state. */
+int
+csref_sles_it_solve(void          *sys,
+                    int            type,
+                    int            poly_degree,
+                    int            n_max_iter,
+                    double         precision,
+                    double         r_norm,
+                    const double  *rhs,
+                    double        *vx,
+                    int            use_vx_ini,
+                    double        *out)
+{
+  ref_system *s = static_cast<ref_system *>(sys);
+  void *c = cs_sles_it_create((cs_sles_it_type_t)type, poly_degree,
+                              n_max_iter, false);
+  double t0 = _now();
+  cs_sles_it_setup(c, "csref", s->m, 0);
+  double t1 = _now();
+  int n_iter = 0;
+  double residual = -1;
+  cs_sles_convergence_state_t cvg
+    = cs_sles_it_solve(c, "csref", s->m, -1, precision, r_norm,
+                       &n_iter, &residual, rhs,
+                       use_vx_ini ? vx : nullptr, vx, 0, nullptr);
+  double t2 = _now();
+  out[0] = n_iter;
+  out[1] = residual;
+  out[2] = cs_sles_it_get_last_initial_residual((const cs_sles_it_t *)c);
+  out[3] = t1 - t0;
+  out[4] = t2 - t1;
+  cs_sles_it_free(c);
+  cs_sles_it_destroy(&c);
+  return (int)cvg;
+}
+
+/* cs_multigrid V-cycle solve (solver mode).
+   iopt: [0..2] descent/ascent/coarse solver type, [3] n_max_cycles,
+         [4..6] n_max_iter, [7..9] poly_degree, [10] aggregation_limit,
+         [11] coarsening_type, [12] n_max_levels, [13] min_g_rows
+   dopt: [0..2] precision_mult, [3] p0p1_relax
+   out : [0] n_equiv_iter, [1] residual, [2] setup s, [3] solve s */
+int
+csref_multigrid_solve(void          *sys,
+                      const int     *iopt,
+                      const double  *dopt,
+                      double         precision,
+                      double         r_norm,
+                      const double  *rhs,
+                      double        *vx,
+                      int            use_vx_ini,
+                      int            verbosity,
+                      double        *out)
+{
+  ref_system *s = static_cast<ref_system *>(sys);
+  cs_multigrid_t *mg = cs_multigrid_create(CS_MULTIGRID_V_CYCLE, nullptr);
+  cs_multigrid_set_solver_options(mg,
+                                  (cs_sles_it_type_t)iopt[0],
+                                  (cs_sles_it_type_t)iopt[1],
+                                  (cs_sles_it_type_t)iopt[2],
+                                  iopt[3], iopt[4], iopt[5], iopt[6],
+                                  iopt[7], iopt[8], iopt[9],
+                                  dopt[0], dopt[1], dopt[2]);
+  cs_multigrid_set_coarsening_options(mg, iopt[10],
+                                      (cs_grid_coarsening_t)iopt[11],
+                                      iopt[12], (cs_gnum_t)iopt[13],
+                                      dopt[3], 0);
+  bool q = g_quiet;
+  if (verbosity > 0) g_quiet = false;
+  double t0 = _now();
+  cs_multigrid_setup(mg, "csref", s->m, verbosity);
+  double t1 = _now();
+  int n_iter = 0;
+  double residual = -1;
+  cs_sles_convergence_state_t cvg
+    = cs_multigrid_solve(mg, "csref", s->m, verbosity, precision, r_norm,
+                         &n_iter, &residual, rhs,
+                         use_vx_ini ? vx : nullptr, vx, 0, nullptr);
+  double t2 = _now();
+  g_quiet = q;
+  out[0] = n_iter;
+  out[1] = residual;
+  out[2] = t1 - t0;
+  out[3] = t2 - t1;
+  cs_multigrid_free(mg);
+  void *ctx = mg;
+  cs_multigrid_destroy(&ctx);
+  return (int)cvg;
+}
+
+/* Build the grid hierarchy with the reference's cs_grid_coarsen, following
+   the stop criteria of _setup_hierarchy (src/alge/cs_multigrid.cpp:2454-2584). */
+void *
+csref_hierarchy_build(void   *sys,
+                      int     aggregation_limit,
+                      int     coarsening_type,
+                      int     n_levels_max,
+                      int     n_g_rows_min,
+                      double  p0p1_relax,
+                      int     verbosity)
+{
+  ref_system *s = static_cast<ref_system *>(sys);
+  ref_hierarchy *h = new ref_hierarchy;
+  bool q = g_quiet;
+  if (verbosity > 0) g_quiet = false;
+
+  cs_grid_t *f
+    = cs_grid_create_from_shared(cs_glob_mesh ? cs_glob_mesh->n_i_faces : 0,
+                                 1, 1,
+                                 cs_glob_mesh ? cs_glob_mesh->i_face_cells
+                                              : nullptr,
+                                 s->m, false);
+  h->grids.push_back(f);
+  cs_grid_t *g = f;
+  cs_gnum_t n_g_rows = g->n_g_rows, n_g_rows_prev = 0;
+
+  while (true) {
+    n_g_rows_prev = n_g_rows;
+    if ((int)h->grids.size() >= n_levels_max)
+      break;
+    cs_grid_t *c = cs_grid_coarsen(g, CS_ALLOC_HOST,
+                                   (cs_grid_coarsening_t)coarsening_type,
+                                   aggregation_limit, verbosity,
+                                   1, 300, 500, p0p1_relax);
+    n_g_rows = c->n_g_rows;
+    bool add = true;
+    if (n_g_rows == 0)
+      add = false;
+    else if (h->grids.size() > 1) {
+      if (   n_g_rows < (cs_gnum_t)n_g_rows_min
+          || n_g_rows > (0.8 * n_g_rows_prev))
+        add = false;
+    }
+    if (!add) {
+      cs_grid_destroy(&c);
+      break;
+    }
+    h->grids.push_back(c);
+    g = c;
+  }
+  g_quiet = q;
+  return h;
+}
+
+int
+csref_hierarchy_n_levels(void *hier)
+{ return (int)static_cast<ref_hierarchy *>(hier)->grids.size(); }
+
+/* info: [0] n_rows, [1] nnz (off-diagonal), [2] n_faces */
+void
+csref_hierarchy_level_info(void *hier, int level, int *info)
+{
+  cs_grid_t *g = static_cast<ref_hierarchy *>(hier)->grids[level];
+  const cs_lnum_t *ri, *ci; const cs_real_t *d, *x;
+  cs_matrix_get_msr_arrays(g->matrix, &ri, &ci, &d, &x);
+  info[0] = g->n_rows;
+  info[1] = ri[g->n_rows];
+  info[2] = g->n_faces;
+}
+
+/* Copy a level out. coarse_row (size: parent's n_rows) is the fine->coarse
+   map FROM the parent level TO this level (level >= 1), NULL to skip. */
+void
+csref_hierarchy_level_copy(void    *hier,
+                           int      level,
+                           int     *coarse_row,
+                           int     *row_index,
+                           int     *col_id,
+                           double  *d_val,
+                           double  *x_val,
+                           double  *cell_cen,
+                           double  *cell_vol)
+{
+  ref_hierarchy *h = static_cast<ref_hierarchy *>(hier);
+  cs_grid_t *g = h->grids[level];
+  const cs_lnum_t *ri, *ci; const cs_real_t *d, *x;
+  cs_matrix_get_msr_arrays(g->matrix, &ri, &ci, &d, &x);
+  const cs_lnum_t n = g->n_rows, nnz = ri[n];
+  if (coarse_row != nullptr && level > 0)
+    memcpy(coarse_row, g->coarse_row,
+           sizeof(cs_lnum_t)*h->grids[level-1]->n_rows);
+  if (row_index) memcpy(row_index, ri, sizeof(cs_lnum_t)*(n+1));
+  if (col_id) memcpy(col_id, ci, sizeof(cs_lnum_t)*nnz);
+  if (d_val) memcpy(d_val, d, sizeof(cs_real_t)*n);
+  if (x_val) memcpy(x_val, x, sizeof(cs_real_t)*nnz);
+  if (cell_cen && g->cell_cen) memcpy(cell_cen, g->cell_cen, sizeof(cs_real_3_t)*n);
+  if (cell_vol && g->cell_vol) memcpy(cell_vol, g->cell_vol, sizeof(cs_real_t)*n);
+}
+
+void
+csref_hierarchy_destroy(void *hier)
+{
+  ref_hierarchy *h = static_cast<ref_hierarchy *>(hier);
+  for (size_t i = h->grids.size(); i > 0; i--)
+    cs_grid_destroy(&(h->grids[i-1]));
+  delete h;
+}
+
+} /* extern "C" */
