@@ -1,0 +1,502 @@
+"""Python mirror of the reference's cs_matrix / cs_sles_it / cs_multigrid interface,
+bound with ctypes to the C-ABI of ``csrc/libcsb200.so`` (include/csb200.h).
+
+This is what the parity tests and bench.py call; it adds no arithmetic of its
+own.  Names and argument meaning follow the reference:
+
+* ``Matrix``            cs_matrix_t (MSR)          src/alge/cs_matrix.cpp:4518,:5451,:6328,:6405
+* ``SlesIt``            cs_sles_it_t               src/alge/cs_sles_it.cpp:4659,:4964,:5194
+* ``Multigrid``         cs_multigrid_t             src/alge/cs_multigrid.cpp:4644,:5032,:5275,:5362
+* ``ConvergenceState``  cs_sles_convergence_state_t  src/alge/cs_sles.h:57-68
+
+The library has no CPU fallback: importing works anywhere (so that the symbol
+table can be checked), but ``init()`` raises unless a CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "csrc", "libcsb200.so")
+HEADER_PATH = os.path.join(_ROOT, "include", "csb200.h")
+
+
+class CsbError(RuntimeError):
+    pass
+
+
+class ConvergenceState(enum.IntEnum):
+    DIVERGED = -3
+    BREAKDOWN = -2
+    MAX_ITERATION = -1
+    ITERATING = 0
+    CONVERGED = 1
+
+
+class SlesItType(enum.IntEnum):
+    PCG = 0
+    JACOBI = 3
+    BICGSTAB = 4
+
+
+_lib = None
+
+
+def header_symbols() -> list[str]:
+    """Every function name declared in include/csb200.h."""
+    txt = open(HEADER_PATH).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(csb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def load_library() -> C.CDLL:
+    """dlopen libcsb200.so and declare prototypes.  Fails loudly if missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CsbError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, ci, cd, cs = C.c_void_p, C.c_int, C.c_double, C.c_size_t
+    L.csb_last_error.restype = C.c_char_p
+    L.csb_version.restype = C.c_char_p
+    L.csb_init.argtypes = [ci]
+    L.csb_set_stream.argtypes = [vp]
+    L.csb_malloc_device.restype = vp
+    L.csb_malloc_device.argtypes = [cs]
+    L.csb_free_device.argtypes = [vp]
+    L.csb_copy_h2d.argtypes = [vp, vp, cs]
+    L.csb_copy_d2h.argtypes = [vp, vp, cs]
+    L.csb_malloc_pinned.restype = vp
+    L.csb_malloc_pinned.argtypes = [cs]
+    L.csb_free_pinned.argtypes = [vp]
+    L.csb_launch_count.restype = C.c_longlong
+    L.csb_launch_count.argtypes = [ci]
+    L.csb_matrix_create_msr.restype = vp
+    L.csb_matrix_create_msr.argtypes = [ci, ci, vp, vp, vp, vp, ci]
+    L.csb_matrix_set_coefficients.argtypes = [vp, ci, vp, vp]
+    L.csb_matrix_set_mesh_association.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp]
+    L.csb_matrix_set_halo.argtypes = [vp, vp]
+    L.csb_matrix_destroy.argtypes = [C.POINTER(vp)]
+    for f in (L.csb_matrix_get_n_rows, L.csb_matrix_get_n_columns, L.csb_matrix_get_n_entries):
+        f.argtypes = [vp]
+    L.csb_matrix_vector_multiply.argtypes = [vp, vp, vp]
+    L.csb_matrix_vector_multiply_exdiag.argtypes = [vp, vp, vp]
+    L.csb_matrix_spmv_bytes.restype = cd
+    L.csb_matrix_spmv_bytes.argtypes = [vp]
+    L.csb_dot.restype = cd
+    L.csb_dot.argtypes = [ci, vp, vp]
+    L.csb_dot_xx.restype = cd
+    L.csb_dot_xx.argtypes = [ci, vp]
+    L.csb_dot_xx_xy_yz.argtypes = [ci, vp, vp, vp, vp, vp, vp]
+    L.csb_comm_get_unique_id.argtypes = [vp]
+    L.csb_comm_init_rank.restype = vp
+    L.csb_comm_init_rank.argtypes = [vp, ci, ci]
+    L.csb_comm_destroy.argtypes = [vp]
+    L.csb_halo_create.restype = vp
+    L.csb_halo_create.argtypes = [vp, ci, ci, vp, ci, vp, vp, vp]
+    L.csb_halo_destroy.argtypes = [C.POINTER(vp)]
+    L.csb_halo_sync_var.argtypes = [vp, vp]
+    L.csb_sles_it_create.restype = vp
+    L.csb_sles_it_create.argtypes = [ci, ci, ci, ci]
+    L.csb_sles_it_set_reduce_comm.argtypes = [vp, vp]
+    L.csb_sles_it_setup.argtypes = [vp, C.c_char_p, vp, ci]
+    L.csb_sles_it_setup.restype = None
+    solve_args = [vp, C.c_char_p, vp, ci, cd, cd, C.POINTER(ci), C.POINTER(cd), vp, vp, vp,
+                  cs, vp]
+    L.csb_sles_it_solve.argtypes = solve_args
+    L.csb_sles_it_free.argtypes = [vp]
+    L.csb_sles_it_free.restype = None
+    L.csb_sles_it_destroy.argtypes = [C.POINTER(vp)]
+    L.csb_sles_it_destroy.restype = None
+    L.csb_sles_it_get_last_initial_residual.restype = cd
+    L.csb_sles_it_get_last_initial_residual.argtypes = [vp]
+    L.csb_sles_it_get_residual_history.argtypes = [vp, vp, ci]
+    L.csb_sles_it_log.argtypes = [vp, ci]
+    L.csb_sles_it_log.restype = None
+    L.csb_sles_it_copy.restype = vp
+    L.csb_sles_it_copy.argtypes = [vp]
+    L.csb_multigrid_create.restype = vp
+    L.csb_multigrid_create.argtypes = [ci]
+    L.csb_multigrid_set_solver_options.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci,
+                                                   cd, cd, cd]
+    L.csb_multigrid_set_solver_options.restype = None
+    L.csb_multigrid_set_coarsening_options.argtypes = [vp, ci, ci, ci, C.c_ulonglong, cd, ci]
+    L.csb_multigrid_set_coarsening_options.restype = None
+    L.csb_multigrid_set_aggregation_blocks.argtypes = [vp, ci]
+    L.csb_multigrid_set_aggregation_blocks.restype = None
+    L.csb_multigrid_set_reduce_comm.argtypes = [vp, vp]
+    L.csb_multigrid_setup.argtypes = [vp, C.c_char_p, vp, ci]
+    L.csb_multigrid_setup.restype = None
+    L.csb_multigrid_solve.argtypes = solve_args
+    L.csb_multigrid_free.argtypes = [vp]
+    L.csb_multigrid_free.restype = None
+    L.csb_multigrid_destroy.argtypes = [C.POINTER(vp)]
+    L.csb_multigrid_destroy.restype = None
+    L.csb_multigrid_get_n_levels.argtypes = [vp]
+    L.csb_multigrid_get_n_cycles.argtypes = [vp]
+    L.csb_multigrid_get_level_info.argtypes = [vp, ci, vp]
+    L.csb_multigrid_get_level_arrays.argtypes = [vp, ci, vp, vp, vp, vp, vp]
+    L.csb_multigrid_get_cycle_residuals.argtypes = [vp, vp, ci]
+    L.csb_multigrid_get_setup_times.argtypes = [vp, vp]
+    L.csb_multigrid_log.argtypes = [vp, ci]
+    L.csb_multigrid_log.restype = None
+    L.csb_multigrid_copy.restype = vp
+    L.csb_multigrid_copy.argtypes = [vp]
+    L.csb_host_aggregate_dx_msr.argtypes = [ci, ci, vp, vp, vp, vp, ci, ci, vp]
+    L.csb_host_coarse_structure.argtypes = [ci, vp, vp, vp, ci, vp, vp, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def _err(what: str):
+    L = load_library()
+    raise CsbError(f"{what}: {L.csb_last_error().decode()}")
+
+
+def init(device: int = 0) -> None:
+    """csb_init: select the device.  Raises without a CUDA device (no fallback)."""
+    if load_library().csb_init(device) != 0:
+        _err("csb_init")
+
+
+def finalize() -> None:
+    load_library().csb_finalize()
+
+
+def set_stream(cuda_stream: int | None) -> None:
+    """Run all kernels on the given cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+    if load_library().csb_set_stream(C.c_void_p(cuda_stream or 0)) != 0:
+        _err("csb_set_stream")
+
+
+def synchronize() -> None:
+    if load_library().csb_stream_synchronize() != 0:
+        _err("csb_stream_synchronize")
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(load_library().csb_launch_count(1 if reset else 0))
+
+
+def _ptr(a):
+    """Address of a numpy array, a torch tensor (host or device), an int or None."""
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(f"unsupported buffer type {type(a)}")
+
+
+def _i32(a):
+    return a if not isinstance(a, np.ndarray) else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return a if not isinstance(a, np.ndarray) else np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Matrix:
+    """cs_matrix_t in MSR format, resident in HBM."""
+
+    def __init__(self, n_rows, row_index, col_id, d_val, x_val, symmetric=True,
+                 n_cols_ext=None):
+        L = load_library()
+        self.n_rows = int(n_rows)
+        self.n_cols_ext = int(n_cols_ext if n_cols_ext is not None else n_rows)
+        ri, ci, d, x = _i32(row_index), _i32(col_id), _f64(d_val), _f64(x_val)
+        self._h = L.csb_matrix_create_msr(self.n_rows, self.n_cols_ext, _ptr(ri), _ptr(ci),
+                                          _ptr(d), _ptr(x), int(bool(symmetric)))
+        if not self._h:
+            _err("csb_matrix_create_msr")
+        self.nnz = int(L.csb_matrix_get_n_entries(self._h)) - self.n_rows
+        self._halo = None
+
+    @classmethod
+    def from_system(cls, s, with_mesh=True):
+        """Build from a mesh_cartesian.CubeSystem (host arrays)."""
+        m = cls(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val, True)
+        if with_mesh and s.n_faces > 0:
+            m.set_mesh_association(s.n_faces, s.c2f, s.c2f_sgn, s.cell_cen, s.cell_vol,
+                                   s.face_u_normal, s.face_surf)
+        return m
+
+    @property
+    def handle(self):
+        return C.c_void_p(self._h)
+
+    def set_coefficients(self, d_val, x_val, symmetric=True):
+        d, x = _f64(d_val), _f64(x_val)
+        if load_library().csb_matrix_set_coefficients(self.handle, int(bool(symmetric)),
+                                                      _ptr(d), _ptr(x)) != 0:
+            _err("csb_matrix_set_coefficients")
+
+    def set_mesh_association(self, n_faces, c2f, c2f_sgn, cell_cen, cell_vol, face_u_normal,
+                             face_surf):
+        c2f = _i32(c2f)
+        sgn = np.ascontiguousarray(c2f_sgn, dtype=np.int16)
+        cen, vol = _f64(cell_cen), _f64(cell_vol)
+        fun, fs = _f64(face_u_normal), _f64(face_surf)
+        if load_library().csb_matrix_set_mesh_association(self.handle, int(n_faces), _ptr(c2f),
+                                                          _ptr(sgn), _ptr(cen), _ptr(vol),
+                                                          _ptr(fun), _ptr(fs)) != 0:
+            _err("csb_matrix_set_mesh_association")
+
+    def set_halo(self, halo):
+        self._halo = halo
+        load_library().csb_matrix_set_halo(self.handle, halo.handle if halo else None)
+
+    def vector_multiply(self, x, y=None, exclude_diag=False):
+        """y = A.x (cs_matrix_vector_multiply).  numpy in -> numpy out; torch device
+        tensors are used in place."""
+        L = load_library()
+        fn = L.csb_matrix_vector_multiply_exdiag if exclude_diag else L.csb_matrix_vector_multiply
+        if isinstance(x, np.ndarray):
+            x = _f64(x)
+            if y is None:
+                y = np.empty(self.n_rows, dtype=np.float64)
+        elif y is None:
+            raise ValueError("y is required with device buffers")
+        if fn(self.handle, _ptr(x), _ptr(y)) != 0:
+            _err("csb_matrix_vector_multiply")
+        return y
+
+    def spmv_bytes(self) -> float:
+        return float(load_library().csb_matrix_spmv_bytes(self.handle))
+
+    def destroy(self):
+        if self._h:
+            h = C.c_void_p(self._h)
+            load_library().csb_matrix_destroy(C.byref(h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def dot(x, y) -> float:
+    x, y = _f64(x), _f64(y)
+    return float(load_library().csb_dot(len(x), _ptr(x), _ptr(y)))
+
+
+def dot_xx(x) -> float:
+    x = _f64(x)
+    return float(load_library().csb_dot_xx(len(x), _ptr(x)))
+
+
+def dot_xx_xy_yz(x, y, z):
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    r = (C.c_double * 3)()
+    if load_library().csb_dot_xx_xy_yz(len(x), _ptr(x), _ptr(y), _ptr(z), C.byref(r, 0),
+                                       C.byref(r, 8), C.byref(r, 16)) != 0:
+        _err("csb_dot_xx_xy_yz")
+    return tuple(r)
+
+
+def host_aggregate(level, row_index, col_id, d_val, x_val, max_aggregation=3, n_blocks=1):
+    """Host-side DX aggregation used by Multigrid.setup (no GPU needed)."""
+    ri, ci, d, x = _i32(row_index), _i32(col_id), _f64(d_val), _f64(x_val)
+    n = len(ri) - 1
+    f_c_row = np.empty(max(n, 1), dtype=np.int32)
+    nc = load_library().csb_host_aggregate_dx_msr(level, n, _ptr(ri), _ptr(ci), _ptr(d), _ptr(x),
+                                                  max_aggregation, n_blocks, _ptr(f_c_row))
+    return nc, f_c_row[:n]
+
+
+def host_coarse_structure(row_index, col_id, f_c_row, c_n_rows):
+    """Host-side coarse MSR structure + coarse face numbering (no GPU needed)."""
+    ri, ci, fc = _i32(row_index), _i32(col_id), _i32(f_c_row)
+    n = len(ri) - 1
+    nnz = int(ri[-1])
+    c_ri = np.zeros(c_n_rows + 1, dtype=np.int32)
+    c_ci = np.zeros(max(nnz, 1), dtype=np.int32)
+    c_cf = np.zeros(max(nnz, 1), dtype=np.int32)
+    c_sg = np.zeros(max(nnz, 1), dtype=np.int16)
+    nf = C.c_int(0)
+    c_nnz = load_library().csb_host_coarse_structure(n, _ptr(ri), _ptr(ci), _ptr(fc), c_n_rows,
+                                                     _ptr(c_ri), _ptr(c_ci), _ptr(c_cf),
+                                                     _ptr(c_sg), C.byref(nf))
+    return dict(row_index=c_ri, col_id=c_ci[:c_nnz], cell_face=c_cf[:c_nnz],
+                cell_face_sgn=c_sg[:c_nnz], n_faces=nf.value)
+
+
+class _SolverBase:
+    _solve_name = ""
+
+    def _solve(self, a: Matrix, rhs, precision, r_norm, vx=None, use_vx_ini=False,
+               verbosity=0, name="system"):
+        L = load_library()
+        fn = getattr(L, self._solve_name)
+        host = isinstance(rhs, np.ndarray)
+        if host:
+            rhs = _f64(rhs)
+            if vx is None:
+                vx = np.zeros(a.n_cols_ext, dtype=np.float64)
+                use_vx_ini = False
+            else:
+                vx = _f64(vx)
+        elif vx is None:
+            raise ValueError("vx is required with device buffers")
+        n_iter = C.c_int(0)
+        residual = C.c_double(0.)
+        cvg = fn(C.c_void_p(self._h), name.encode(), a.handle, verbosity, float(precision),
+                 float(r_norm), C.byref(n_iter), C.byref(residual), _ptr(rhs),
+                 _ptr(vx) if use_vx_ini else None, _ptr(vx), 0, None)
+        if cvg == ConvergenceState.BREAKDOWN and L.csb_last_error():
+            msg = L.csb_last_error().decode()
+            if msg:
+                raise CsbError(f"{self._solve_name}: {msg}")
+        return dict(cvg=ConvergenceState(cvg), n_iter=n_iter.value, residual=residual.value,
+                    vx=vx)
+
+
+class SlesIt(_SolverBase):
+    """cs_sles_it_t: PCG / Jacobi / BiCGStab with Jacobi preconditioning."""
+
+    _solve_name = "csb_sles_it_solve"
+
+    def __init__(self, solver_type, n_max_iter, poly_degree=0, update_stats=False):
+        self._h = load_library().csb_sles_it_create(int(solver_type), int(poly_degree),
+                                                    int(n_max_iter), int(update_stats))
+        if not self._h:
+            _err("csb_sles_it_create")
+
+    def setup(self, a: Matrix, name="system", verbosity=0):
+        load_library().csb_sles_it_setup(C.c_void_p(self._h), name.encode(), a.handle, verbosity)
+
+    def solve(self, a, rhs, precision, r_norm, vx=None, use_vx_ini=False, verbosity=0):
+        out = self._solve(a, rhs, precision, r_norm, vx, use_vx_ini, verbosity)
+        out["initial_residual"] = float(
+            load_library().csb_sles_it_get_last_initial_residual(C.c_void_p(self._h)))
+        out["history"] = self.residual_history()
+        return out
+
+    def residual_history(self):
+        buf = np.zeros(2048)
+        n = load_library().csb_sles_it_get_residual_history(C.c_void_p(self._h), _ptr(buf), 2048)
+        return buf[:n].copy()
+
+    def free(self):
+        load_library().csb_sles_it_free(C.c_void_p(self._h))
+
+    def log(self):
+        load_library().csb_sles_it_log(C.c_void_p(self._h), 0)
+
+    def destroy(self):
+        if self._h:
+            h = C.c_void_p(self._h)
+            load_library().csb_sles_it_destroy(C.byref(h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Multigrid(_SolverBase):
+    """cs_multigrid_t, V-cycle (solver mode defaults of cs_multigrid_define)."""
+
+    _solve_name = "csb_multigrid_solve"
+
+    def __init__(self):
+        self._h = load_library().csb_multigrid_create(0)
+        if not self._h:
+            _err("csb_multigrid_create")
+
+    def set_solver_options(self, descent=SlesItType.PCG, ascent=SlesItType.PCG,
+                           coarse=SlesItType.PCG, n_max_cycles=100, n_max_iter_descent=2,
+                           n_max_iter_ascent=10, n_max_iter_coarse=500, poly_degree=(0, 0, 0),
+                           precision_mult=(1., 1., 1.)):
+        load_library().csb_multigrid_set_solver_options(
+            C.c_void_p(self._h), int(descent), int(ascent), int(coarse), n_max_cycles,
+            n_max_iter_descent, n_max_iter_ascent, n_max_iter_coarse, *[int(p) for p in poly_degree],
+            *[float(p) for p in precision_mult])
+
+    def set_coarsening_options(self, aggregation_limit=3, coarsening_type=0, n_max_levels=25,
+                               min_g_rows=30, p0p1_relax=0.95):
+        load_library().csb_multigrid_set_coarsening_options(
+            C.c_void_p(self._h), aggregation_limit, coarsening_type, n_max_levels, min_g_rows,
+            p0p1_relax, 0)
+
+    def set_aggregation_blocks(self, n_blocks):
+        load_library().csb_multigrid_set_aggregation_blocks(C.c_void_p(self._h), int(n_blocks))
+
+    def setup(self, a: Matrix, name="system", verbosity=0):
+        L = load_library()
+        L.csb_multigrid_setup(C.c_void_p(self._h), name.encode(), a.handle, verbosity)
+        if L.csb_multigrid_get_n_levels(C.c_void_p(self._h)) < 1:
+            _err("csb_multigrid_setup")
+
+    def solve(self, a, rhs, precision, r_norm, vx=None, use_vx_ini=False, verbosity=0):
+        out = self._solve(a, rhs, precision, r_norm, vx, use_vx_ini, verbosity)
+        L = load_library()
+        out["n_cycles"] = L.csb_multigrid_get_n_cycles(C.c_void_p(self._h))
+        buf = np.zeros(512)
+        n = L.csb_multigrid_get_cycle_residuals(C.c_void_p(self._h), _ptr(buf), 512)
+        out["cycle_residuals"] = buf[:n].copy()
+        return out
+
+    def n_levels(self):
+        return load_library().csb_multigrid_get_n_levels(C.c_void_p(self._h))
+
+    def setup_times(self):
+        t = np.zeros(4)
+        load_library().csb_multigrid_get_setup_times(C.c_void_p(self._h), _ptr(t))
+        return dict(total=t[0], aggregation=t[1], assembly=t[2], transfers=t[3])
+
+    def levels(self):
+        """Copy the hierarchy to host arrays (for the parity tests)."""
+        L = load_library()
+        out = []
+        parent_n = 0
+        for l in range(self.n_levels()):
+            info = np.zeros(3, dtype=np.int32)
+            L.csb_multigrid_get_level_info(C.c_void_p(self._h), l, _ptr(info))
+            n, nnz = int(info[0]), int(info[2])
+            cr = np.zeros(max(parent_n, 1), dtype=np.int32)
+            ri = np.zeros(n + 1, dtype=np.int32)
+            ci = np.zeros(max(nnz, 1), dtype=np.int32)
+            d = np.zeros(max(n, 1))
+            xv = np.zeros(max(nnz, 1))
+            if L.csb_multigrid_get_level_arrays(C.c_void_p(self._h), l, _ptr(cr), _ptr(ri),
+                                                _ptr(ci), _ptr(d), _ptr(xv)) != 0:
+                _err("csb_multigrid_get_level_arrays")
+            out.append(dict(n_rows=n, nnz=nnz, coarse_row=cr[:parent_n], row_index=ri,
+                            col_id=ci[:nnz], d_val=d[:n], x_val=xv[:nnz]))
+            parent_n = n
+        return out
+
+    def free(self):
+        load_library().csb_multigrid_free(C.c_void_p(self._h))
+
+    def log(self):
+        load_library().csb_multigrid_log(C.c_void_p(self._h), 0)
+
+    def destroy(self):
+        if self._h:
+            h = C.c_void_p(self._h)
+            load_library().csb_multigrid_destroy(C.byref(h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass

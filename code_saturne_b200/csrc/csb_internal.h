@@ -1,0 +1,266 @@
+/* csb_internal.h -- internal C++ declarations of libcsb200 (not part of the C-ABI). */
+#ifndef CSB_INTERNAL_H
+#define CSB_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "csb200.h"
+
+namespace csb {
+
+/*--------------------------------------------------------------------------
+ * Runtime context: one per process (one process per GPU).
+ *--------------------------------------------------------------------------*/
+
+struct Context {
+  bool          ready = false;
+  int           device = -1;
+  int           sm_count = 148;
+  cudaStream_t  own_stream = nullptr;
+  cudaStream_t  stream = nullptr;       /* stream all kernels are launched on */
+  cudaStream_t  comm_stream = nullptr;  /* halo exchange */
+  cudaEvent_t   ev_a = nullptr, ev_b = nullptr;
+  /* 2-stage deterministic reduction workspace */
+  double       *partials = nullptr;     /* [RED_MAX_BLOCKS * RED_MAX_Q] */
+  unsigned     *ticket = nullptr;       /* self-resetting atomicInc counter */
+  double       *red_out = nullptr;      /* device scalars for plain csb_dot* */
+  double       *red_out_h = nullptr;    /* pinned mirror */
+  long long     launches = 0;
+  std::string   err;
+};
+
+Context &ctx();
+void set_error(const char *fmt, ...);
+bool cuda_ok(cudaError_t e, const char *what, const char *file, int line);
+
+#define CSB_CUDA(call) ::csb::cuda_ok((call), #call, __FILE__, __LINE__)
+
+constexpr int RED_MAX_BLOCKS = 4096;
+constexpr int RED_MAX_Q = 4;
+constexpr int HIST_MAX = 2048;
+constexpr int CYCLE_MAX = 512;
+
+/* true if p is a device (or managed) pointer */
+bool is_device_ptr(const void *p);
+
+/* RAII device buffer */
+template <typename T>
+struct DevBuf {
+  T      *p = nullptr;
+  size_t  n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
+  bool alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) count = 1;
+    return CSB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  /* copy from host or device pointer */
+  bool upload(const T *src, size_t count) {
+    if (!alloc(count)) return false;
+    if (count == 0) return true;
+    return CSB_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyDefault,
+                                    ctx().stream));
+  }
+  bool download(T *dst) const {
+    if (n == 0) return true;
+    bool ok = CSB_CUDA(cudaMemcpyAsync(dst, p, n * sizeof(T), cudaMemcpyDeviceToHost,
+                                       ctx().stream));
+    return ok && CSB_CUDA(cudaStreamSynchronize(ctx().stream));
+  }
+};
+
+/*--------------------------------------------------------------------------
+ * Device-resident solver state (no host round trip per iteration)
+ *--------------------------------------------------------------------------*/
+
+/* cs_sles_it convergence + Krylov scalars; lives in device memory. */
+struct ItState {
+  double precision, r_norm;
+  double residual, initial_residual;
+  double ro_0, ro_1, rk_gkm1, alpha, beta;
+  double gamma, omega, betam1;           /* BiCGStab */
+  int    n_iter, n_max_iter;
+  int    cvg;                            /* csb_sles_convergence_state_t, 2 = skipped */
+  int    n_hist;
+  double hist[HIST_MAX];
+};
+
+/* cs_multigrid cycle state; lives in device memory. */
+struct MgState {
+  double precision, r_norm;
+  double residual, initial_residual;
+  int    cvg;              /* gate: != 0 turns the rest of the cycle into no-ops */
+  int    cycle_id, n_max_cycles;
+  int    n_equiv_iter;
+  int    n_cycles_res;
+  int    diverged_level;
+  double cycle_res[CYCLE_MAX];
+};
+
+/*--------------------------------------------------------------------------
+ * Halo
+ *--------------------------------------------------------------------------*/
+
+} // namespace csb
+
+struct _csb_halo_t {
+  void              *nccl_comm = nullptr;
+  int                local_rank = 0;
+  int                n_c_domains = 0;
+  csb_lnum_t         n_local_elts = 0;
+  csb_lnum_t         n_send = 0, n_ghost = 0;
+  std::vector<int>         c_domain_rank;
+  std::vector<csb_lnum_t>  send_index, index;   /* host copies */
+  csb::DevBuf<csb_lnum_t>  send_list;
+  csb::DevBuf<double>      send_buf;
+};
+
+/*--------------------------------------------------------------------------
+ * Matrix
+ *--------------------------------------------------------------------------*/
+
+struct _csb_matrix_t {
+  csb_lnum_t  n_rows = 0, n_cols_ext = 0, nnz = 0;
+  bool        symmetric = true;
+  csb::DevBuf<csb_lnum_t>  row_index, col_id;
+  csb::DevBuf<double>      d_val, x_val;
+  /* host mirrors of the structure and values (needed by the host-side
+     aggregation, like the reference which always aggregates on the host,
+     src/alge/cs_grid.cpp:8035-8041) */
+  std::vector<csb_lnum_t>  h_row_index, h_col_id;
+  std::vector<double>      h_d_val, h_x_val;
+  bool        h_vals_valid = false;
+  /* SpMV launch geometry */
+  int         spmv_rows_per_block = 256;
+  size_t      spmv_smem = 0;           /* bytes of staged products per block */
+  bool        spmv_stream_ok = true;   /* false -> scalar fallback kernel */
+  /* mesh association (device) */
+  csb_lnum_t  n_faces = 0;
+  csb::DevBuf<csb_lnum_t>  c2f;
+  csb::DevBuf<short>       c2f_sgn;
+  csb::DevBuf<double>      cell_cen, cell_vol, face_u_normal, face_surf;
+  bool        has_mesh = false;
+  _csb_halo_t *halo = nullptr;
+};
+
+namespace csb {
+
+/*--------------------------------------------------------------------------
+ * Kernel launch wrappers (kernels.cu)
+ *--------------------------------------------------------------------------*/
+
+enum SpmvEpilogue {
+  EPI_STORE = 0,        /* y = A.x                                        */
+  EPI_RESIDUAL,         /* y = b - A.x  (V-cycle residual, cs_multigrid.cpp:3296-3301) */
+  EPI_RESIDUAL_NORM,    /* same + sum(y^2) -> mg finalize (level 0)       */
+  EPI_PCG_INIT,         /* rk = A.x - b ; dk = rk*ad_inv  (cs_sles_it.cpp:1503-1508) */
+  EPI_PCG_DOT3          /* y = A.x ; sums (rk.rk, rk.x, x.y) -> pcg finalize */
+};
+
+struct SpmvArgs {
+  const _csb_matrix_t *m;
+  bool          exclude_diag = false;
+  const double *x = nullptr;
+  double       *y = nullptr;
+  const double *b = nullptr;       /* rhs for residual / init epilogues */
+  const double *ad_inv = nullptr;
+  double       *rk = nullptr;      /* PCG vectors for fused epilogues */
+  double       *dk = nullptr;
+  ItState      *st = nullptr;
+  MgState      *mg = nullptr;
+  int           phase = 0;         /* PCG_DOT3: 0 = first (ro_0, ro_1), 1 = iteration */
+};
+
+bool launch_spmv(SpmvEpilogue epi, const SpmvArgs &a);
+
+/* setup of SpMV launch geometry after (re)building a structure */
+void matrix_plan_spmv(_csb_matrix_t *m);
+
+/* ad_inv = 1/d  (cs_sles_pc.cpp:376) */
+bool launch_ad_inv(int n, const double *d, double *ad_inv);
+
+/* plain reductions -> ctx().red_out[0..q) */
+bool launch_dot(int n, const double *x, const double *y, const double *z, int mode);
+
+/* device-state PCG pieces (cs_sles_it.cpp:1441-1645) */
+bool launch_it_state_init(ItState *st, const MgState *gate, double precision,
+                          double r_norm, int n_max_iter);
+bool launch_pcg_init_zero(int n, ItState *st, const double *rhs, const double *ad_inv,
+                          double *vx, double *rk, double *dk);
+bool launch_pcg_update_first(int n, ItState *st, const double *ad_inv, const double *dk,
+                             const double *zk, double *vx, double *rk, double *gk);
+bool launch_pcg_update(int n, ItState *st, const double *ad_inv, const double *sk,
+                       double *dk, double *gk, double *zk, double *rk, double *vx);
+/* whole PCG in one thread block for small systems */
+bool launch_pcg_single_block(const _csb_matrix_t *m, ItState *st, const MgState *gate,
+                             double precision, double r_norm, int n_max_iter,
+                             const double *ad_inv, const double *rhs, double *vx,
+                             int vx_ini_nonzero, double *work /* 5*n */);
+
+/* Jacobi (cs_sles_it.cpp:2098-2270) */
+bool launch_jacobi_first(int n, ItState *st, const double *rhs, const double *ad_inv,
+                         double *vx, double *rk);
+bool launch_jacobi_sweep(const _csb_matrix_t *m, ItState *st, const double *rhs,
+                         const double *ad_inv, double *vx, double *rk);
+bool launch_copy(int n, const double *src, double *dst, const ItState *st);
+
+/* BiCGStab (cs_sles_it.cpp:2693-2880) */
+bool launch_bicg_init(int n, ItState *st, const double *rhs, double *vx, double *res0,
+                      double *rk, double *pk, double *uk, bool have_ax);
+bool launch_bicg_dots_a(int n, ItState *st, const double *rk, const double *res0);
+bool launch_bicg_pk_zk(int n, ItState *st, const double *rk, const double *uk,
+                       const double *ad_inv, double *pk, double *zk);
+bool launch_bicg_spmv_b(const _csb_matrix_t *m, ItState *st, const double *zk, double *uk,
+                        const double *res0);
+bool launch_bicg_upd1(int n, ItState *st, const double *ad_inv, double *vx, double *rk,
+                      double *zk, const double *uk);
+bool launch_bicg_spmv_c(const _csb_matrix_t *m, ItState *st, const double *zk, double *vk,
+                        const double *rk);
+bool launch_bicg_upd2(int n, ItState *st, double *vx, double *rk, const double *zk,
+                      const double *vk, const double *res0);
+
+/* multigrid transfer operators (cs_grid.cpp:8987-9210) */
+bool launch_restrict(int c_n_rows, const int *c_f_row_index, const int *c_f_row_ids,
+                     const double *f_var, double *c_var, const MgState *gate);
+bool launch_prolong_inc(int f_n_rows, const int *coarse_row, const double *c_var,
+                        double *f_var, const MgState *gate);
+bool launch_mg_state_init(MgState *mg, double precision, double r_norm, int n_max_cycles);
+bool launch_mg_cycle_begin(MgState *mg, int cycle_id);
+bool launch_mg_accum_iter(MgState *mg, const ItState *st, int level, double n_rows_ratio,
+                          int take_initial_residual);
+
+/* coarse level assembly (cs_grid.cpp:6226-6590, :6841-6897) */
+struct CoarseAssemblyArgs {
+  int  f_level;
+  int  f_n_rows, c_n_rows, c_n_faces;
+  const int *f_row_index, *f_col_id;
+  const double *f_d_val, *f_x_val;
+  const int *f_c_row;                    /* fine -> coarse */
+  const int *c_f_row_index, *c_f_row_ids;
+  const int *c_row_index, *c_col_id;
+  const int *f_cell_face; const short *f_cell_face_sgn;
+  const int *c_cell_face; const short *c_cell_face_sgn;
+  const double *f_cell_cen, *f_cell_vol;
+  const double *f_face_u_normal, *f_face_surf;   /* level 0 */
+  const double *f_face_normal, *f_xa0, *f_xa0ij; /* level > 0 */
+  double *c_d_val, *c_x_val;
+  double *c_cell_cen, *c_cell_vol, *c_face_normal, *c_xa0, *c_xa0ij;
+  double relax;
+};
+bool launch_coarse_assembly(const CoarseAssemblyArgs &a);
+
+bool launch_halo_pack(int n_send, const int *send_list, const double *var, double *buf);
+
+} // namespace csb
+
+#endif

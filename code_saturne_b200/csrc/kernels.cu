@@ -1,0 +1,1410 @@
+/*============================================================================
+ * kernels.cu -- hand-written sm_100a kernels of the linear-solve hot path.
+ *
+ * All arithmetic is FP64, compiled with -fmad=false so that every per-entry
+ * operation (products, in-row sums, vector updates, coarse-matrix assembly)
+ * is the same IEEE mul/add sequence as the reference's CPU path; only the
+ * order of the global reductions differs (fixed-shape 2-stage trees, so they
+ * are deterministic run to run).
+ *
+ * Everything here is HBM-bandwidth bound: no tensor cores.
+ *   - SpMV: "CSR-stream": a CTA streams the contiguous off-diagonal entries
+ *     of 256 consecutive rows with fully coalesced loads, stages the products
+ *     x_val[k]*x[col_id[k]] in shared memory, then each thread sums its own
+ *     row in CSR order (same order as _mat_vec_p_l_msr,
+ *     src/alge/cs_matrix_spmv.cpp:2130-2142) and runs a fused epilogue
+ *     (residual, PCG initialisation, the 3 PCG dot products ...).
+ *   - dots: block tree + "last CTA reduces the partials" (one launch, result
+ *     and all Krylov scalars stay on the device: no host sync per iteration).
+ *============================================================================*/
+
+#include "csb_internal.h"
+
+#include <cfloat>
+#include <cmath>
+
+namespace csb {
+
+namespace {
+
+constexpr int TPB = 256;           /* threads per CTA for streaming kernels */
+constexpr int SB_TPB = 1024;       /* single-CTA solver */
+
+inline int vec_grid(int n)
+{
+  int g = (n + TPB*4 - 1) / (TPB*4);
+  int gmax = ctx().sm_count * 8;
+  if (g > gmax) g = gmax;
+  if (g > RED_MAX_BLOCKS) g = RED_MAX_BLOCKS;
+  if (g < 1) g = 1;
+  return g;
+}
+
+inline bool post_launch(const char *name)
+{
+  ctx().launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("kernel %s launch failed: %s", name, cudaGetErrorString(e));
+    return false;
+  }
+  return true;
+}
+
+/*--------------------------------------------------------------------------
+ * Reductions
+ *--------------------------------------------------------------------------*/
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+/* Sum Q values over the CTA; result valid in thread 0. s_red: Q*32 doubles. */
+template <int Q>
+__device__ __forceinline__ void block_sum(double (&v)[Q], double *s_red)
+{
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int n_warps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    double w = warp_sum(v[q]);
+    if (lane == 0) s_red[q*32 + wid] = w;
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      double w = (lane < n_warps) ? s_red[q*32 + lane] : 0.0;
+      v[q] = warp_sum(w);
+    }
+  }
+  __syncthreads();
+}
+
+/* Grid-wide sum of Q values; the last CTA to arrive reduces the per-CTA
+   partials in a fixed order and thread 0 of it calls fin(sums). */
+template <int Q, class Fin>
+__device__ __forceinline__ void grid_sum_finalize(double (&v)[Q], double *partials,
+                                                  unsigned *ticket, Fin fin)
+{
+  __shared__ double s_red[Q*32];
+  __shared__ int s_last;
+  block_sum<Q>(v, s_red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < Q; q++)
+      partials[q*gridDim.x + blockIdx.x] = v[q];
+    __threadfence();
+    unsigned t = atomicInc(ticket, gridDim.x - 1);   /* wraps back to 0 */
+    s_last = (t == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double w[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      w[q] = 0.0;
+      for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x)
+        w[q] += __ldcg(partials + q*gridDim.x + i);
+    }
+    block_sum<Q>(w, s_red);
+    if (threadIdx.x == 0) fin(w);
+  }
+}
+
+/*--------------------------------------------------------------------------
+ * Device-side solver logic
+ *--------------------------------------------------------------------------*/
+
+/* _convergence_test, src/alge/cs_sles_it.cpp:243-325 */
+__device__ __forceinline__ int it_cvg_test(ItState *st, int n_iter, double residual)
+{
+  st->residual = residual;
+  if (st->n_hist < HIST_MAX) st->hist[st->n_hist++] = residual;
+  if (st->precision > 0 && residual < st->precision * st->r_norm)
+    return CSB_SLES_CONVERGED;
+  else if (n_iter >= st->n_max_iter)
+    return CSB_SLES_MAX_ITERATION;
+  else if (residual > st->initial_residual * 10000.0 && residual > 100.)
+    return CSB_SLES_DIVERGED;
+  if (isnan(residual) || isinf(residual))
+    return CSB_SLES_DIVERGED;
+  return CSB_SLES_ITERATING;
+}
+
+/* cs_sles_it.cpp:1529-1548 */
+__device__ __forceinline__ void pcg_finalize_first(ItState *st, const double *s)
+{
+  double residual = sqrt(s[0]);
+  st->ro_0 = s[1];
+  st->ro_1 = s[2];
+  st->initial_residual = residual;
+  int cvg = it_cvg_test(st, 0, residual);
+  if (cvg == CSB_SLES_ITERATING) {
+    st->n_iter = 1;
+    double d_ro_1 = (fabs(st->ro_1) > DBL_MIN) ? 1. / st->ro_1 : 0.;
+    st->alpha = - st->ro_0 * d_ro_1;
+    st->rk_gkm1 = st->ro_0;
+  }
+  st->cvg = cvg;
+}
+
+/* cs_sles_it.cpp:1595-1621 */
+__device__ __forceinline__ void pcg_finalize_iter(ItState *st, const double *s)
+{
+  double residual = sqrt(s[0]);
+  const double rk_gk = s[1], gk_sk = s[2];
+  int cvg = CSB_SLES_ITERATING;
+  if (st->n_iter > 1)
+    cvg = it_cvg_test(st, st->n_iter, residual);
+  if (cvg == CSB_SLES_ITERATING) {
+    st->n_iter += 1;
+    double beta = (fabs(st->rk_gkm1) > DBL_MIN) ? rk_gk / st->rk_gkm1 : 0.;
+    st->rk_gkm1 = rk_gk;
+    st->ro_1 = gk_sk - beta*beta*st->ro_1;
+    st->ro_0 = rk_gk;
+    double d_ro_1 = (fabs(st->ro_1) > DBL_MIN) ? 1. / st->ro_1 : 0.;
+    st->alpha = - st->ro_0 * d_ro_1;
+    st->beta = beta;
+  }
+  st->cvg = cvg;
+}
+
+/* _convergence_test, src/alge/cs_multigrid.cpp:2927-3035 */
+__device__ __forceinline__ void mg_finalize_residual(MgState *mg, const double *s)
+{
+  double residual = sqrt(s[0]);
+  mg->residual = residual;
+  const int cycle_id = mg->cycle_id;
+  if (mg->n_cycles_res < CYCLE_MAX) mg->cycle_res[mg->n_cycles_res++] = residual;
+  const double ir = (cycle_id == 1) ? residual : mg->initial_residual;
+  int cvg = CSB_SLES_ITERATING;
+  if (residual < mg->precision * mg->r_norm)
+    cvg = CSB_SLES_CONVERGED;
+  else if (cycle_id > mg->n_max_cycles)
+    cvg = CSB_SLES_MAX_ITERATION;
+  else if (residual > ir * 10000.0 && residual > 100.)
+    cvg = CSB_SLES_DIVERGED;
+  else if (isnan(residual) || isinf(residual))
+    cvg = CSB_SLES_DIVERGED;
+  mg->cvg = cvg;
+}
+
+/*--------------------------------------------------------------------------
+ * SpMV, CSR-stream with fused epilogues
+ *--------------------------------------------------------------------------*/
+
+struct SpmvK {
+  int           n_rows;
+  const int    *row_index;
+  const int    *col_id;
+  const double *d_val;     /* nullptr: exclude diagonal */
+  const double *x_val;
+  const double *x;
+  double       *y;
+  const double *b;
+  const double *ad_inv;
+  double       *rk;
+  double       *dk;
+  ItState      *st;
+  MgState      *mg;
+  int           phase;
+  double       *partials;
+  unsigned     *ticket;
+};
+
+template <int EPI>
+__device__ __forceinline__ bool spmv_gated_off(const SpmvK &a)
+{
+  if (EPI == EPI_PCG_INIT || EPI == EPI_PCG_DOT3)
+    return (a.st->cvg != CSB_SLES_ITERATING);
+  if (EPI == EPI_RESIDUAL || EPI == EPI_RESIDUAL_NORM)
+    return (a.mg != nullptr && a.mg->cvg != CSB_SLES_ITERATING);
+  if (EPI == EPI_STORE)
+    return (a.st != nullptr && a.st->cvg != CSB_SLES_ITERATING);
+  return false;
+}
+
+template <int EPI>
+__device__ __forceinline__ void spmv_epilogue(const SpmvK &a, int r, bool active,
+                                              double sii)
+{
+  /* sii = sum of off-diagonal products in CSR order; diagonal added last
+     (src/alge/cs_matrix_spmv.cpp:2138-2142) */
+  double v[3] = {0., 0., 0.};
+  if (active) {
+    const double xr = (a.d_val != nullptr || EPI == EPI_PCG_DOT3) ? a.x[r] : 0.;
+    const double yr = (a.d_val != nullptr) ? sii + a.d_val[r]*xr : sii;
+    if (EPI == EPI_STORE) {
+      a.y[r] = yr;
+    }
+    else if (EPI == EPI_RESIDUAL || EPI == EPI_RESIDUAL_NORM) {
+      const double w = a.b[r] - yr;
+      a.y[r] = w;
+      v[0] = w*w;
+    }
+    else if (EPI == EPI_PCG_INIT) {
+      const double rr = yr - a.b[r];
+      a.rk[r] = rr;
+      a.dk[r] = rr * a.ad_inv[r];
+    }
+    else if (EPI == EPI_PCG_DOT3) {
+      a.y[r] = yr;
+      const double rr = a.rk[r];
+      v[0] = rr*rr;
+      v[1] = rr*xr;
+      v[2] = xr*yr;
+    }
+  }
+  if (EPI == EPI_RESIDUAL_NORM) {
+    double w[1] = {v[0]};
+    MgState *mg = a.mg;
+    grid_sum_finalize<1>(w, a.partials, a.ticket,
+                         [mg](const double *s) { mg_finalize_residual(mg, s); });
+  }
+  else if (EPI == EPI_PCG_DOT3) {
+    ItState *st = a.st;
+    if (a.phase == 0)
+      grid_sum_finalize<3>(v, a.partials, a.ticket,
+                           [st](const double *s) { pcg_finalize_first(st, s); });
+    else
+      grid_sum_finalize<3>(v, a.partials, a.ticket,
+                           [st](const double *s) { pcg_finalize_iter(st, s); });
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(TPB)
+k_spmv_stream(const SpmvK a)
+{
+  extern __shared__ double s_prod[];
+  if (spmv_gated_off<EPI>(a)) return;
+
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * TPB;
+  const int r1 = min(r0 + TPB, a.n_rows);
+  const int k0 = __ldg(a.row_index + r0);
+  const int k1 = __ldg(a.row_index + r1);
+  const int nk = k1 - k0;
+
+  const int    *__restrict__ ci = a.col_id + k0;
+  const double *__restrict__ xv = a.x_val + k0;
+  const double *__restrict__ x = a.x;
+
+  /* coalesced streaming of the CTA's entries, 4 independent loads in flight */
+  int i = tid;
+  for (; i + 3*TPB < nk; i += 4*TPB) {
+    const int c0 = __ldg(ci + i),         c1 = __ldg(ci + i + TPB);
+    const int c2 = __ldg(ci + i + 2*TPB), c3 = __ldg(ci + i + 3*TPB);
+    const double m0 = __ldg(xv + i),         m1 = __ldg(xv + i + TPB);
+    const double m2 = __ldg(xv + i + 2*TPB), m3 = __ldg(xv + i + 3*TPB);
+    const double x0 = __ldg(x + c0), x1 = __ldg(x + c1);
+    const double x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+    s_prod[i]         = m0*x0;
+    s_prod[i + TPB]   = m1*x1;
+    s_prod[i + 2*TPB] = m2*x2;
+    s_prod[i + 3*TPB] = m3*x3;
+  }
+  for (; i < nk; i += TPB)
+    s_prod[i] = __ldg(xv + i) * __ldg(x + __ldg(ci + i));
+  __syncthreads();
+
+  const int r = r0 + tid;
+  const bool active = (r < r1);
+  double sii = 0.0;
+  if (active) {
+    const int ks = __ldg(a.row_index + r) - k0;
+    const int ke = __ldg(a.row_index + r + 1) - k0;
+    for (int k = ks; k < ke; k++)
+      sii += s_prod[k];
+  }
+  spmv_epilogue<EPI>(a, r, active, sii);
+}
+
+/* Fallback when a 256-row slab does not fit in shared memory: thread per row */
+template <int EPI>
+__global__ void __launch_bounds__(TPB)
+k_spmv_scalar(const SpmvK a)
+{
+  if (spmv_gated_off<EPI>(a)) return;
+  const int r = blockIdx.x * TPB + threadIdx.x;
+  const bool active = (r < a.n_rows);
+  double sii = 0.0;
+  if (active) {
+    const int ks = a.row_index[r], ke = a.row_index[r+1];
+    for (int k = ks; k < ke; k++)
+      sii += a.x_val[k] * a.x[a.col_id[k]];
+  }
+  spmv_epilogue<EPI>(a, r, active, sii);
+}
+
+template <int EPI>
+bool spmv_dispatch(const SpmvK &k, const _csb_matrix_t *m)
+{
+  const int grid = (m->n_rows + TPB - 1) / TPB;
+  if (grid < 1) return true;
+  if (grid > RED_MAX_BLOCKS && (EPI == EPI_RESIDUAL_NORM || EPI == EPI_PCG_DOT3)) {
+    /* partials buffer is sized at csb_init from the largest matrix seen */
+  }
+  if (m->spmv_stream_ok) {
+    static bool attr_set = false;
+    static size_t attr_bytes = 0;
+    if (m->spmv_smem > 48*1024 && (!attr_set || m->spmv_smem > attr_bytes)) {
+      cudaFuncSetAttribute(k_spmv_stream<EPI>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)m->spmv_smem);
+      attr_set = true; attr_bytes = m->spmv_smem;
+    }
+    k_spmv_stream<EPI><<<grid, TPB, m->spmv_smem, ctx().stream>>>(k);
+  }
+  else
+    k_spmv_scalar<EPI><<<grid, TPB, 0, ctx().stream>>>(k);
+  return post_launch("spmv");
+}
+
+} // anonymous namespace
+
+void matrix_plan_spmv(_csb_matrix_t *m)
+{
+  /* largest number of off-diagonal entries in any slab of 256 rows */
+  size_t max_nk = 0;
+  const std::vector<csb_lnum_t> &ri = m->h_row_index;
+  for (csb_lnum_t r0 = 0; r0 < m->n_rows; r0 += TPB) {
+    csb_lnum_t r1 = r0 + TPB;
+    if (r1 > m->n_rows) r1 = m->n_rows;
+    size_t nk = (size_t)(ri[r1] - ri[r0]);
+    if (nk > max_nk) max_nk = nk;
+  }
+  m->spmv_rows_per_block = TPB;
+  m->spmv_smem = max_nk * sizeof(double);
+  if (m->spmv_smem < 16) m->spmv_smem = 16;
+  m->spmv_stream_ok = (m->spmv_smem <= 200*1024);
+}
+
+bool ensure_partials(int n_blocks);
+
+bool launch_spmv(SpmvEpilogue epi, const SpmvArgs &a)
+{
+  const _csb_matrix_t *m = a.m;
+  SpmvK k;
+  k.n_rows = m->n_rows;
+  k.row_index = m->row_index.p;
+  k.col_id = m->col_id.p;
+  k.d_val = a.exclude_diag ? nullptr : m->d_val.p;
+  k.x_val = m->x_val.p;
+  k.x = a.x; k.y = a.y; k.b = a.b; k.ad_inv = a.ad_inv;
+  k.rk = a.rk; k.dk = a.dk; k.st = a.st; k.mg = a.mg; k.phase = a.phase;
+  k.partials = ctx().partials; k.ticket = ctx().ticket;
+  if (epi == EPI_RESIDUAL_NORM || epi == EPI_PCG_DOT3)
+    if (!ensure_partials((m->n_rows + TPB - 1) / TPB)) return false;
+  switch (epi) {
+  case EPI_STORE:         return spmv_dispatch<EPI_STORE>(k, m);
+  case EPI_RESIDUAL:      return spmv_dispatch<EPI_RESIDUAL>(k, m);
+  case EPI_RESIDUAL_NORM: return spmv_dispatch<EPI_RESIDUAL_NORM>(k, m);
+  case EPI_PCG_INIT:      return spmv_dispatch<EPI_PCG_INIT>(k, m);
+  case EPI_PCG_DOT3:      return spmv_dispatch<EPI_PCG_DOT3>(k, m);
+  }
+  return false;
+}
+
+/* partials buffer grows with the largest reduction grid seen */
+static int g_partials_blocks = 0;
+
+bool ensure_partials(int n_blocks)
+{
+  if (n_blocks <= g_partials_blocks) return true;
+  Context &c = ctx();
+  if (c.partials) {
+    cudaStreamSynchronize(c.stream);
+    cudaFree(c.partials);
+    c.partials = nullptr;
+  }
+  int nb = n_blocks + n_blocks/4 + 1024;
+  if (!CSB_CUDA(cudaMalloc((void **)&c.partials, sizeof(double)*RED_MAX_Q*(size_t)nb)))
+    return false;
+  g_partials_blocks = nb;
+  return true;
+}
+
+void reset_partials()
+{
+  g_partials_blocks = 0;
+}
+
+/*--------------------------------------------------------------------------
+ * Elementwise / BLAS-1
+ *--------------------------------------------------------------------------*/
+
+namespace {
+
+__global__ void __launch_bounds__(TPB)
+k_ad_inv(int n, const double *__restrict__ d, double *__restrict__ ad_inv)
+{
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB)
+    ad_inv[i] = 1.0 / d[i];
+}
+
+/* mode 0: x.y ; 1: x.x ; 2: (x.x, x.y, y.z) ; 3: (x.x, x.y) */
+template <int MODE>
+__global__ void __launch_bounds__(TPB)
+k_dot(int n, const double *__restrict__ x, const double *__restrict__ y,
+      const double *__restrict__ z, double *partials, unsigned *ticket, double *out)
+{
+  double v[3] = {0., 0., 0.};
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    if (MODE == 0) v[0] += x[i]*y[i];
+    else if (MODE == 1) v[0] += x[i]*x[i];
+    else if (MODE == 2) { v[0] += x[i]*x[i]; v[1] += x[i]*y[i]; v[2] += y[i]*z[i]; }
+    else { v[0] += x[i]*x[i]; v[1] += x[i]*y[i]; }
+  }
+  grid_sum_finalize<3>(v, partials, ticket,
+                       [out](const double *s) { out[0] = s[0]; out[1] = s[1]; out[2] = s[2]; });
+}
+
+__global__ void
+k_it_state_init(ItState *st, const MgState *gate, double precision, double r_norm,
+                int n_max_iter)
+{
+  st->precision = precision;
+  st->r_norm = r_norm;
+  st->residual = -1.;
+  st->initial_residual = -1.;
+  st->ro_0 = 0.; st->ro_1 = 0.; st->rk_gkm1 = 0.; st->alpha = 0.; st->beta = 0.;
+  st->gamma = 1.; st->omega = 0.; st->betam1 = 1.;
+  st->n_iter = 0;
+  st->n_max_iter = n_max_iter;
+  st->n_hist = 0;
+  st->cvg = (gate != nullptr && gate->cvg != CSB_SLES_ITERATING) ? 2 : CSB_SLES_ITERATING;
+}
+
+/* cs_sles_it.cpp:1511-1515 */
+__global__ void __launch_bounds__(TPB)
+k_pcg_init_zero(int n, const ItState *st, const double *__restrict__ rhs,
+                const double *__restrict__ ad_inv, double *__restrict__ vx,
+                double *__restrict__ rk, double *__restrict__ dk)
+{
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    vx[i] = 0;
+    const double r = -rhs[i];
+    rk[i] = r;
+    dk[i] = r * ad_inv[i];
+  }
+}
+
+/* cs_sles_it.cpp:1550-1582 */
+__global__ void __launch_bounds__(TPB)
+k_pcg_update_first(int n, ItState *st, const double *__restrict__ ad_inv,
+                   const double *__restrict__ dk, const double *__restrict__ zk,
+                   double *__restrict__ vx, double *__restrict__ rk,
+                   double *__restrict__ gk, double *partials, unsigned *ticket)
+{
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  const double alpha = st->alpha;
+  double v[1] = {0.};
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    vx[i] += (alpha * dk[i]);
+    const double r = rk[i] + (alpha * zk[i]);
+    rk[i] = r;
+    gk[i] = r * ad_inv[i];
+    v[0] += r*r;
+  }
+  grid_sum_finalize<1>(v, partials, ticket, [st](const double *s) {
+    st->cvg = it_cvg_test(st, st->n_iter, sqrt(s[0]));
+  });
+}
+
+/* cs_sles_it.cpp:1623-1631 */
+__global__ void __launch_bounds__(TPB)
+k_pcg_update(int n, const ItState *st, const double *__restrict__ ad_inv,
+             const double *__restrict__ sk, double *__restrict__ dk,
+             double *__restrict__ gk, double *__restrict__ zk,
+             double *__restrict__ rk, double *__restrict__ vx)
+{
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  const double alpha = st->alpha, beta = st->beta;
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    const double d = gk[i] + (beta * dk[i]);
+    dk[i] = d;
+    vx[i] += alpha * d;
+    const double z = sk[i] + (beta * zk[i]);
+    zk[i] = z;
+    const double r = rk[i] + alpha * z;
+    rk[i] = r;
+    gk[i] = r * ad_inv[i];
+  }
+}
+
+} // anonymous namespace
+
+bool launch_ad_inv(int n, const double *d, double *ad_inv)
+{
+  if (n < 1) return true;
+  k_ad_inv<<<vec_grid(n), TPB, 0, ctx().stream>>>(n, d, ad_inv);
+  return post_launch("ad_inv");
+}
+
+bool launch_dot(int n, const double *x, const double *y, const double *z, int mode)
+{
+  Context &c = ctx();
+  const int g = vec_grid(n);
+  if (!ensure_partials(g)) return false;
+  switch (mode) {
+  case 0: k_dot<0><<<g, TPB, 0, c.stream>>>(n, x, y, z, c.partials, c.ticket, c.red_out); break;
+  case 1: k_dot<1><<<g, TPB, 0, c.stream>>>(n, x, y, z, c.partials, c.ticket, c.red_out); break;
+  case 2: k_dot<2><<<g, TPB, 0, c.stream>>>(n, x, y, z, c.partials, c.ticket, c.red_out); break;
+  default: k_dot<3><<<g, TPB, 0, c.stream>>>(n, x, y, z, c.partials, c.ticket, c.red_out); break;
+  }
+  return post_launch("dot");
+}
+
+bool launch_it_state_init(ItState *st, const MgState *gate, double precision,
+                          double r_norm, int n_max_iter)
+{
+  k_it_state_init<<<1, 1, 0, ctx().stream>>>(st, gate, precision, r_norm, n_max_iter);
+  return post_launch("it_state_init");
+}
+
+bool launch_pcg_init_zero(int n, ItState *st, const double *rhs, const double *ad_inv,
+                          double *vx, double *rk, double *dk)
+{
+  if (n < 1) return true;
+  k_pcg_init_zero<<<vec_grid(n), TPB, 0, ctx().stream>>>(n, st, rhs, ad_inv, vx, rk, dk);
+  return post_launch("pcg_init_zero");
+}
+
+bool launch_pcg_update_first(int n, ItState *st, const double *ad_inv, const double *dk,
+                             const double *zk, double *vx, double *rk, double *gk)
+{
+  Context &c = ctx();
+  const int g = vec_grid(n);
+  if (!ensure_partials(g)) return false;
+  k_pcg_update_first<<<g, TPB, 0, c.stream>>>(n, st, ad_inv, dk, zk, vx, rk, gk,
+                                              c.partials, c.ticket);
+  return post_launch("pcg_update_first");
+}
+
+bool launch_pcg_update(int n, ItState *st, const double *ad_inv, const double *sk,
+                       double *dk, double *gk, double *zk, double *rk, double *vx)
+{
+  if (n < 1) return true;
+  k_pcg_update<<<vec_grid(n), TPB, 0, ctx().stream>>>(n, st, ad_inv, sk, dk, gk, zk, rk, vx);
+  return post_launch("pcg_update");
+}
+
+/*--------------------------------------------------------------------------
+ * Whole PCG(+Jacobi) solve in ONE thread block, for the small levels of the
+ * hierarchy and the coarsest solve (up to 500 iterations in the reference,
+ * cs_multigrid.cpp:4762): avoids 2 launches per iteration on latency-bound
+ * levels.  Same algorithm as the multi-kernel path.
+ *--------------------------------------------------------------------------*/
+
+namespace {
+
+__device__ __forceinline__ double sb_row(const int *__restrict__ ri,
+                                         const int *__restrict__ ci,
+                                         const double *__restrict__ xv,
+                                         const double *__restrict__ dv,
+                                         const double *x, int r)
+{
+  double sii = 0.0;
+  const int ks = ri[r], ke = ri[r+1];
+  for (int k = ks; k < ke; k++)
+    sii += xv[k] * x[ci[k]];
+  return sii + dv[r]*x[r];
+}
+
+__global__ void __launch_bounds__(SB_TPB)
+k_pcg_single_block(int n, const int *__restrict__ ri, const int *__restrict__ ci,
+                   const double *__restrict__ dv, const double *__restrict__ xv,
+                   ItState *st, const MgState *gate, double precision, double r_norm,
+                   int n_max_iter, const double *__restrict__ ad_inv,
+                   const double *__restrict__ rhs, double *vx, int vx_ini_nonzero,
+                   double *work)
+{
+  __shared__ double s_red[3*32];
+  __shared__ int s_cvg;
+  __shared__ double s_alpha, s_beta;
+
+  const int tid = threadIdx.x;
+  double *rk = work, *dk = work + n, *gk = work + 2*n, *zk = work + 3*n, *sk = work + 4*n;
+
+  if (tid == 0) {
+    st->precision = precision; st->r_norm = r_norm;
+    st->residual = -1.; st->initial_residual = -1.;
+    st->ro_0 = 0.; st->ro_1 = 0.; st->rk_gkm1 = 0.; st->alpha = 0.; st->beta = 0.;
+    st->n_iter = 0; st->n_max_iter = n_max_iter; st->n_hist = 0;
+    st->cvg = (gate != nullptr && gate->cvg != CSB_SLES_ITERATING) ? 2 : CSB_SLES_ITERATING;
+    s_cvg = st->cvg;
+  }
+  __syncthreads();
+  if (s_cvg != CSB_SLES_ITERATING) return;
+
+  /* residual and descent direction */
+  if (vx_ini_nonzero) {
+    for (int r = tid; r < n; r += SB_TPB) {
+      const double rr = sb_row(ri, ci, xv, dv, vx, r) - rhs[r];
+      rk[r] = rr;
+      dk[r] = rr * ad_inv[r];
+    }
+  }
+  else {
+    for (int r = tid; r < n; r += SB_TPB) {
+      vx[r] = 0;
+      const double rr = -rhs[r];
+      rk[r] = rr;
+      dk[r] = rr * ad_inv[r];
+    }
+  }
+  __syncthreads();
+
+  double v[3] = {0., 0., 0.};
+  for (int r = tid; r < n; r += SB_TPB) {
+    const double z = sb_row(ri, ci, xv, dv, dk, r);
+    zk[r] = z;
+    const double rr = rk[r], d = dk[r];
+    v[0] += rr*rr; v[1] += rr*d; v[2] += d*z;
+  }
+  block_sum<3>(v, s_red);
+  if (tid == 0) {
+    pcg_finalize_first(st, v);
+    s_cvg = st->cvg; s_alpha = st->alpha;
+  }
+  __syncthreads();
+
+  if (s_cvg == CSB_SLES_ITERATING) {
+    const double alpha = s_alpha;
+    double w[1] = {0.};
+    for (int r = tid; r < n; r += SB_TPB) {
+      vx[r] += (alpha * dk[r]);
+      const double rr = rk[r] + (alpha * zk[r]);
+      rk[r] = rr;
+      gk[r] = rr * ad_inv[r];
+      w[0] += rr*rr;
+    }
+    block_sum<1>(w, s_red);
+    if (tid == 0) {
+      st->cvg = it_cvg_test(st, st->n_iter, sqrt(w[0]));
+      s_cvg = st->cvg;
+    }
+    __syncthreads();
+  }
+
+  while (s_cvg == CSB_SLES_ITERATING) {
+    v[0] = 0.; v[1] = 0.; v[2] = 0.;
+    for (int r = tid; r < n; r += SB_TPB) {
+      const double s = sb_row(ri, ci, xv, dv, gk, r);
+      sk[r] = s;
+      const double rr = rk[r], g = gk[r];
+      v[0] += rr*rr; v[1] += rr*g; v[2] += g*s;
+    }
+    block_sum<3>(v, s_red);
+    if (tid == 0) {
+      pcg_finalize_iter(st, v);
+      s_cvg = st->cvg; s_alpha = st->alpha; s_beta = st->beta;
+    }
+    __syncthreads();
+    if (s_cvg != CSB_SLES_ITERATING) break;
+    const double alpha = s_alpha, beta = s_beta;
+    for (int r = tid; r < n; r += SB_TPB) {
+      const double d = gk[r] + (beta * dk[r]);
+      dk[r] = d;
+      vx[r] += alpha * d;
+      const double z = sk[r] + (beta * zk[r]);
+      zk[r] = z;
+      const double rr = rk[r] + alpha * z;
+      rk[r] = rr;
+      gk[r] = rr * ad_inv[r];
+    }
+    __syncthreads();
+  }
+}
+
+} // anonymous namespace
+
+bool launch_pcg_single_block(const _csb_matrix_t *m, ItState *st, const MgState *gate,
+                             double precision, double r_norm, int n_max_iter,
+                             const double *ad_inv, const double *rhs, double *vx,
+                             int vx_ini_nonzero, double *work)
+{
+  k_pcg_single_block<<<1, SB_TPB, 0, ctx().stream>>>(
+    m->n_rows, m->row_index.p, m->col_id.p, m->d_val.p, m->x_val.p, st, gate,
+    precision, r_norm, n_max_iter, ad_inv, rhs, vx, vx_ini_nonzero, work);
+  return post_launch("pcg_single_block");
+}
+
+/*--------------------------------------------------------------------------
+ * Jacobi (src/alge/cs_sles_it.cpp:2098-2270)
+ *--------------------------------------------------------------------------*/
+
+namespace {
+
+__global__ void __launch_bounds__(TPB)
+k_jacobi_first(int n, ItState *st, const double *__restrict__ rhs,
+               const double *__restrict__ ad_inv, double *__restrict__ vx,
+               double *__restrict__ rk, double *partials, unsigned *ticket)
+{
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  double v[1] = {0.};
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    const double r = rhs[i];
+    const double x = r * ad_inv[i];
+    vx[i] = x;
+    rk[i] = x;
+    v[0] += (r*r);
+  }
+  grid_sum_finalize<1>(v, partials, ticket, [st](const double *s) {
+    st->n_iter = 1;
+    double residual = (st->precision > 0.) ? sqrt(s[0]) : -1.;
+    st->initial_residual = residual;
+    st->cvg = it_cvg_test(st, 1, residual);
+  });
+}
+
+__global__ void __launch_bounds__(TPB)
+k_copy_gated(int n, const double *__restrict__ src, double *__restrict__ dst,
+             const ItState *st)
+{
+  if (st != nullptr && st->cvg != CSB_SLES_ITERATING) return;
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB)
+    dst[i] = src[i];
+}
+
+/* one sweep: vx <- (rhs - (A-D).rk)/D ; res2 = sum (D (vx-rk))^2 ; rk <- vx */
+__global__ void __launch_bounds__(TPB)
+k_jacobi_sweep(SpmvK a)
+{
+  extern __shared__ double s_prod[];
+  ItState *st = a.st;
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * TPB;
+  const int r1 = min(r0 + TPB, a.n_rows);
+  const int k0 = __ldg(a.row_index + r0);
+  const int nk = __ldg(a.row_index + r1) - k0;
+  const int *__restrict__ ci = a.col_id + k0;
+  const double *__restrict__ xv = a.x_val + k0;
+  const double *__restrict__ x = a.x;        /* rk (previous iterate) */
+  for (int i = tid; i < nk; i += TPB)
+    s_prod[i] = __ldg(xv + i) * __ldg(x + __ldg(ci + i));
+  __syncthreads();
+  const int r = r0 + tid;
+  double v[1] = {0.};
+  if (r < r1) {
+    const int ks = __ldg(a.row_index + r) - k0;
+    const int ke = __ldg(a.row_index + r + 1) - k0;
+    double sii = 0.0;
+    for (int k = ks; k < ke; k++) sii += s_prod[k];
+    const double xn = (a.b[r] - sii) * a.ad_inv[r];
+    const double d = a.d_val[r] * (xn - x[r]);
+    a.y[r] = xn;              /* vx */
+    v[0] = d*d;
+  }
+  grid_sum_finalize<1>(v, a.partials, a.ticket, [st](const double *s) {
+    st->n_iter += 1;
+    double residual = (st->precision > 0.) ? sqrt(s[0]) : -1.;
+    if (st->n_iter == 1) st->initial_residual = residual;
+    st->cvg = it_cvg_test(st, st->n_iter, residual);
+  });
+}
+
+} // anonymous namespace
+
+bool launch_jacobi_first(int n, ItState *st, const double *rhs, const double *ad_inv,
+                         double *vx, double *rk)
+{
+  Context &c = ctx();
+  const int g = vec_grid(n);
+  if (!ensure_partials(g)) return false;
+  k_jacobi_first<<<g, TPB, 0, c.stream>>>(n, st, rhs, ad_inv, vx, rk, c.partials, c.ticket);
+  return post_launch("jacobi_first");
+}
+
+namespace {
+/* latest Jacobi iterate lives in rk when the iteration count is odd */
+__global__ void __launch_bounds__(TPB)
+k_jacobi_finish(int n, const ItState *st, const double *__restrict__ rk,
+                double *__restrict__ vx)
+{
+  if ((st->n_iter & 1) == 0) return;
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB)
+    vx[i] = rk[i];
+}
+}
+
+bool launch_jacobi_finish(int n, const ItState *st, const double *rk, double *vx)
+{
+  if (n < 1) return true;
+  k_jacobi_finish<<<vec_grid(n), TPB, 0, ctx().stream>>>(n, st, rk, vx);
+  return post_launch("jacobi_finish");
+}
+
+bool launch_copy(int n, const double *src, double *dst, const ItState *st)
+{
+  if (n < 1) return true;
+  k_copy_gated<<<vec_grid(n), TPB, 0, ctx().stream>>>(n, src, dst, st);
+  return post_launch("copy");
+}
+
+bool launch_jacobi_sweep(const _csb_matrix_t *m, ItState *st, const double *rhs,
+                         const double *ad_inv, double *vx, double *rk)
+{
+  /* reads rk (previous iterate), writes vx; caller swaps/copies */
+  SpmvK k;
+  k.n_rows = m->n_rows; k.row_index = m->row_index.p; k.col_id = m->col_id.p;
+  k.d_val = m->d_val.p; k.x_val = m->x_val.p; k.x = rk; k.y = vx; k.b = rhs;
+  k.ad_inv = ad_inv; k.rk = nullptr; k.dk = nullptr; k.st = st; k.mg = nullptr;
+  k.phase = 0; k.partials = ctx().partials; k.ticket = ctx().ticket;
+  const int grid = (m->n_rows + TPB - 1) / TPB;
+  if (grid < 1) return true;
+  if (!ensure_partials(grid)) return false;
+  k.partials = ctx().partials;
+  if (!m->spmv_stream_ok) {
+    set_error("jacobi sweep: row slab exceeds shared memory");
+    return false;
+  }
+  static size_t attr_bytes = 0;
+  if (m->spmv_smem > 48*1024 && m->spmv_smem > attr_bytes) {
+    cudaFuncSetAttribute(k_jacobi_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)m->spmv_smem);
+    attr_bytes = m->spmv_smem;
+  }
+  k_jacobi_sweep<<<grid, TPB, m->spmv_smem, ctx().stream>>>(k);
+  return post_launch("jacobi_sweep");
+}
+
+/*--------------------------------------------------------------------------
+ * BiCGStab + Jacobi preconditioner (src/alge/cs_sles_it.cpp:2693-2880)
+ *--------------------------------------------------------------------------*/
+
+namespace {
+
+constexpr double BICG_EPZERO = 1.e-30;   /* _epzero, cs_sles_it.cpp:169 */
+
+/* dots (rk.rk, rk.res0) -> residual, beta, convergence test, omega
+   (cs_sles_it.cpp:2780-2812) */
+__device__ __forceinline__ void bicg_finalize_a(ItState *st, const double *s)
+{
+  double residual, beta;
+  if (st->n_iter == 0) {
+    beta = s[0];
+    residual = sqrt(beta);
+    st->initial_residual = residual;
+  }
+  else {
+    residual = sqrt(s[0]);
+    beta = s[1];
+  }
+  int cvg = it_cvg_test(st, st->n_iter, residual);
+  if (cvg == CSB_SLES_ITERATING) {
+    st->n_iter += 1;
+    if (fabs(beta) < BICG_EPZERO || fabs(st->alpha) < BICG_EPZERO)
+      cvg = CSB_SLES_BREAKDOWN;
+    else {
+      st->omega = beta*st->gamma / (st->alpha*st->betam1);
+      st->betam1 = beta;
+      st->beta = beta;
+    }
+  }
+  st->cvg = cvg;
+}
+
+__global__ void __launch_bounds__(TPB)
+k_bicg_init(int n, ItState *st, const double *__restrict__ rhs, double *__restrict__ vx,
+            double *__restrict__ res0, double *__restrict__ rk, double *__restrict__ pk,
+            double *__restrict__ uk, int have_ax)
+{
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    pk[i] = 0.0;
+    uk[i] = 0.0;
+    double r;
+    if (have_ax)
+      r = -res0[i] + rhs[i];     /* res0 holds A.vx on entry */
+    else {
+      vx[i] = 0;
+      r = rhs[i];
+    }
+    res0[i] = r;
+    rk[i] = r;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st->alpha = 1.0; st->betam1 = 1.0; st->gamma = 1.0;
+  }
+}
+
+__global__ void __launch_bounds__(TPB)
+k_bicg_dots_a(int n, ItState *st, const double *__restrict__ rk,
+              const double *__restrict__ res0, double *partials, unsigned *ticket)
+{
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  double v[2] = {0., 0.};
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    const double r = rk[i];
+    v[0] += r*r;
+    v[1] += r*res0[i];
+  }
+  grid_sum_finalize<2>(v, partials, ticket,
+                       [st](const double *s) { bicg_finalize_a(st, s); });
+}
+
+__global__ void __launch_bounds__(TPB)
+k_bicg_pk_zk(int n, const ItState *st, const double *__restrict__ rk,
+             const double *__restrict__ uk, const double *__restrict__ ad_inv,
+             double *__restrict__ pk, double *__restrict__ zk)
+{
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  const double omega = st->omega, alpha = st->alpha;
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    const double p = rk[i] + omega*(pk[i] - alpha*uk[i]);
+    pk[i] = p;
+    zk[i] = p * ad_inv[i];
+  }
+}
+
+/* y = A.x with one or two fused dots; MODE 0: (y.b) -> gamma ; 1: (y.y, y.b) -> alpha */
+template <int MODE>
+__global__ void __launch_bounds__(TPB)
+k_bicg_spmv(SpmvK a)
+{
+  extern __shared__ double s_prod[];
+  ItState *st = a.st;
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * TPB;
+  const int r1 = min(r0 + TPB, a.n_rows);
+  const int k0 = __ldg(a.row_index + r0);
+  const int nk = __ldg(a.row_index + r1) - k0;
+  const int *__restrict__ ci = a.col_id + k0;
+  const double *__restrict__ xv = a.x_val + k0;
+  const double *__restrict__ x = a.x;
+  for (int i = tid; i < nk; i += TPB)
+    s_prod[i] = __ldg(xv + i) * __ldg(x + __ldg(ci + i));
+  __syncthreads();
+  const int r = r0 + tid;
+  double v[2] = {0., 0.};
+  if (r < r1) {
+    const int ks = __ldg(a.row_index + r) - k0;
+    const int ke = __ldg(a.row_index + r + 1) - k0;
+    double sii = 0.0;
+    for (int k = ks; k < ke; k++) sii += s_prod[k];
+    const double yr = sii + a.d_val[r]*x[r];
+    a.y[r] = yr;
+    if (MODE == 0) v[0] = yr * a.b[r];
+    else { v[0] = yr*yr; v[1] = yr * a.b[r]; }
+  }
+  if (MODE == 0)
+    grid_sum_finalize<2>(v, a.partials, a.ticket, [st](const double *s) {
+      st->gamma = st->beta / s[0];          /* cs_sles_it.cpp:2830-2832 */
+    });
+  else
+    grid_sum_finalize<2>(v, a.partials, a.ticket, [st](const double *s) {
+      const double ro_1 = s[0], ro_0 = s[1]; /* cs_sles_it.cpp:2847-2855 */
+      if (fabs(ro_1) < BICG_EPZERO) { st->cvg = CSB_SLES_BREAKDOWN; return; }
+      double d_ro_1 = (fabs(ro_1) > DBL_MIN) ? 1. / ro_1 : 0.;
+      st->alpha = ro_0 * d_ro_1;
+    });
+}
+
+__global__ void __launch_bounds__(TPB)
+k_bicg_upd1(int n, const ItState *st, const double *__restrict__ ad_inv,
+            double *__restrict__ vx, double *__restrict__ rk, double *__restrict__ zk,
+            const double *__restrict__ uk)
+{
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  const double gamma = st->gamma;
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    vx[i] += (gamma * zk[i]);
+    const double r = rk[i] - (gamma * uk[i]);
+    rk[i] = r;
+    zk[i] = r * ad_inv[i];
+  }
+}
+
+/* final update of the iteration fused with next iteration's (rk.rk, rk.res0) */
+__global__ void __launch_bounds__(TPB)
+k_bicg_upd2(int n, ItState *st, double *__restrict__ vx, double *__restrict__ rk,
+            const double *__restrict__ zk, const double *__restrict__ vk,
+            const double *__restrict__ res0, double *partials, unsigned *ticket)
+{
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  const double alpha = st->alpha;
+  double v[2] = {0., 0.};
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    vx[i] += (alpha * zk[i]);
+    const double r = rk[i] - (alpha * vk[i]);
+    rk[i] = r;
+    v[0] += r*r;
+    v[1] += r*res0[i];
+  }
+  grid_sum_finalize<2>(v, partials, ticket,
+                       [st](const double *s) { bicg_finalize_a(st, s); });
+}
+
+bool bicg_spmv_launch(int mode, const _csb_matrix_t *m, ItState *st, const double *x,
+                      double *y, const double *b)
+{
+  SpmvK k;
+  k.n_rows = m->n_rows; k.row_index = m->row_index.p; k.col_id = m->col_id.p;
+  k.d_val = m->d_val.p; k.x_val = m->x_val.p; k.x = x; k.y = y; k.b = b;
+  k.ad_inv = nullptr; k.rk = nullptr; k.dk = nullptr; k.st = st; k.mg = nullptr;
+  k.phase = 0;
+  const int grid = (m->n_rows + TPB - 1) / TPB;
+  if (grid < 1) return true;
+  if (!ensure_partials(grid)) return false;
+  k.partials = ctx().partials; k.ticket = ctx().ticket;
+  if (!m->spmv_stream_ok) {
+    set_error("bicgstab spmv: row slab exceeds shared memory");
+    return false;
+  }
+  static size_t attr_bytes[2] = {0, 0};
+  if (m->spmv_smem > 48*1024 && m->spmv_smem > attr_bytes[mode]) {
+    if (mode == 0)
+      cudaFuncSetAttribute(k_bicg_spmv<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)m->spmv_smem);
+    else
+      cudaFuncSetAttribute(k_bicg_spmv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)m->spmv_smem);
+    attr_bytes[mode] = m->spmv_smem;
+  }
+  if (mode == 0)
+    k_bicg_spmv<0><<<grid, TPB, m->spmv_smem, ctx().stream>>>(k);
+  else
+    k_bicg_spmv<1><<<grid, TPB, m->spmv_smem, ctx().stream>>>(k);
+  return post_launch("bicg_spmv");
+}
+
+} // anonymous namespace
+
+bool launch_bicg_init(int n, ItState *st, const double *rhs, double *vx, double *res0,
+                      double *rk, double *pk, double *uk, bool have_ax)
+{
+  if (n < 1) return true;
+  k_bicg_init<<<vec_grid(n), TPB, 0, ctx().stream>>>(n, st, rhs, vx, res0, rk, pk, uk,
+                                                     have_ax ? 1 : 0);
+  return post_launch("bicg_init");
+}
+
+bool launch_bicg_dots_a(int n, ItState *st, const double *rk, const double *res0)
+{
+  Context &c = ctx();
+  const int g = vec_grid(n);
+  if (!ensure_partials(g)) return false;
+  k_bicg_dots_a<<<g, TPB, 0, c.stream>>>(n, st, rk, res0, c.partials, c.ticket);
+  return post_launch("bicg_dots_a");
+}
+
+bool launch_bicg_pk_zk(int n, ItState *st, const double *rk, const double *uk,
+                       const double *ad_inv, double *pk, double *zk)
+{
+  if (n < 1) return true;
+  k_bicg_pk_zk<<<vec_grid(n), TPB, 0, ctx().stream>>>(n, st, rk, uk, ad_inv, pk, zk);
+  return post_launch("bicg_pk_zk");
+}
+
+bool launch_bicg_spmv_b(const _csb_matrix_t *m, ItState *st, const double *zk, double *uk,
+                        const double *res0)
+{ return bicg_spmv_launch(0, m, st, zk, uk, res0); }
+
+bool launch_bicg_upd1(int n, ItState *st, const double *ad_inv, double *vx, double *rk,
+                      double *zk, const double *uk)
+{
+  if (n < 1) return true;
+  k_bicg_upd1<<<vec_grid(n), TPB, 0, ctx().stream>>>(n, st, ad_inv, vx, rk, zk, uk);
+  return post_launch("bicg_upd1");
+}
+
+bool launch_bicg_spmv_c(const _csb_matrix_t *m, ItState *st, const double *zk, double *vk,
+                        const double *rk)
+{ return bicg_spmv_launch(1, m, st, zk, vk, rk); }
+
+bool launch_bicg_upd2(int n, ItState *st, double *vx, double *rk, const double *zk,
+                      const double *vk, const double *res0)
+{
+  Context &c = ctx();
+  const int g = vec_grid(n);
+  if (!ensure_partials(g)) return false;
+  k_bicg_upd2<<<g, TPB, 0, c.stream>>>(n, st, vx, rk, zk, vk, res0, c.partials, c.ticket);
+  return post_launch("bicg_upd2");
+}
+
+/*--------------------------------------------------------------------------
+ * Multigrid transfer operators and cycle bookkeeping
+ *--------------------------------------------------------------------------*/
+
+namespace {
+
+/* Deterministic restriction: coarse row = sum of its fine rows in ascending
+   fine-row order, i.e. exactly the order of the reference's sequential
+   "simple sum" loop (src/alge/cs_grid.cpp:9025-9030); the reference's own
+   device path uses atomics and is not reproducible. */
+__global__ void __launch_bounds__(TPB)
+k_restrict(int c_n_rows, const int *__restrict__ c_f_row_index,
+           const int *__restrict__ c_f_row_ids, const double *__restrict__ f_var,
+           double *__restrict__ c_var, const MgState *gate)
+{
+  if (gate != nullptr && gate->cvg != CSB_SLES_ITERATING) return;
+  for (int ic = blockIdx.x*TPB + threadIdx.x; ic < c_n_rows; ic += gridDim.x*TPB) {
+    double s = 0.;
+    const int rs = c_f_row_index[ic], re = c_f_row_index[ic+1];
+    for (int r = rs; r < re; r++)
+      s += f_var[c_f_row_ids[r]];
+    c_var[ic] = s;
+  }
+}
+
+/* src/alge/cs_grid.cpp:9156-9166 */
+__global__ void __launch_bounds__(TPB)
+k_prolong_inc(int f_n_rows, const int *__restrict__ coarse_row,
+              const double *__restrict__ c_var, double *__restrict__ f_var,
+              const MgState *gate)
+{
+  if (gate != nullptr && gate->cvg != CSB_SLES_ITERATING) return;
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < f_n_rows; i += gridDim.x*TPB) {
+    const int ic = coarse_row[i];
+    if (ic >= 0) f_var[i] += c_var[ic];
+  }
+}
+
+__global__ void
+k_mg_state_init(MgState *mg, double precision, double r_norm, int n_max_cycles)
+{
+  mg->precision = precision; mg->r_norm = r_norm;
+  mg->residual = -1.; mg->initial_residual = -1.;
+  mg->cvg = CSB_SLES_ITERATING;
+  mg->cycle_id = 0; mg->n_max_cycles = n_max_cycles;
+  mg->n_equiv_iter = 0; mg->n_cycles_res = 0; mg->diverged_level = -1;
+}
+
+__global__ void
+k_mg_cycle_begin(MgState *mg, int cycle_id)
+{
+  if (mg->cvg == CSB_SLES_ITERATING) mg->cycle_id = cycle_id;
+}
+
+/* *n_equiv_iter += n_iter * n_g_rows * denom_n_g_rows_0 (cs_multigrid.cpp:3341,
+   :3414, :3514), int += double truncation included; a diverged smoother ends
+   the cycle (:3285-3288). */
+__global__ void
+k_mg_accum_iter(MgState *mg, const ItState *st, int level, double n_rows_ratio,
+                int take_initial_residual)
+{
+  if (st->cvg == 2) return;   /* skipped */
+  /* gate already closed by the level-0 residual test: the reference still
+     counts the level-0 descent smoother of that cycle (:3324-3333) */
+  mg->n_equiv_iter = (int)((double)mg->n_equiv_iter + st->n_iter * n_rows_ratio);
+  if (take_initial_residual && mg->cycle_id == 1)
+    mg->initial_residual = st->initial_residual;
+  if (st->cvg < CSB_SLES_BREAKDOWN && mg->cvg == CSB_SLES_ITERATING) {
+    mg->cvg = CSB_SLES_DIVERGED;
+    mg->diverged_level = level;
+  }
+}
+
+} // anonymous namespace
+
+bool launch_restrict(int c_n_rows, const int *c_f_row_index, const int *c_f_row_ids,
+                     const double *f_var, double *c_var, const MgState *gate)
+{
+  if (c_n_rows < 1) return true;
+  k_restrict<<<vec_grid(c_n_rows*4), TPB, 0, ctx().stream>>>(c_n_rows, c_f_row_index,
+                                                            c_f_row_ids, f_var, c_var, gate);
+  return post_launch("restrict");
+}
+
+bool launch_prolong_inc(int f_n_rows, const int *coarse_row, const double *c_var,
+                        double *f_var, const MgState *gate)
+{
+  if (f_n_rows < 1) return true;
+  k_prolong_inc<<<vec_grid(f_n_rows*4), TPB, 0, ctx().stream>>>(f_n_rows, coarse_row, c_var,
+                                                               f_var, gate);
+  return post_launch("prolong");
+}
+
+bool launch_mg_state_init(MgState *mg, double precision, double r_norm, int n_max_cycles)
+{
+  k_mg_state_init<<<1, 1, 0, ctx().stream>>>(mg, precision, r_norm, n_max_cycles);
+  return post_launch("mg_state_init");
+}
+
+bool launch_mg_cycle_begin(MgState *mg, int cycle_id)
+{
+  k_mg_cycle_begin<<<1, 1, 0, ctx().stream>>>(mg, cycle_id);
+  return post_launch("mg_cycle_begin");
+}
+
+bool launch_mg_accum_iter(MgState *mg, const ItState *st, int level, double n_rows_ratio,
+                          int take_initial_residual)
+{
+  k_mg_accum_iter<<<1, 1, 0, ctx().stream>>>(mg, st, level, n_rows_ratio,
+                                             take_initial_residual);
+  return post_launch("mg_accum_iter");
+}
+
+/*--------------------------------------------------------------------------
+ * Coarse level assembly: one thread per coarse row, same loop order as the
+ * reference's row-parallel host/device lambdas
+ * (src/alge/cs_grid.cpp:6347-6435, :6446-6530, :6848-6895), so values are
+ * bit-identical to the CPU path (compiled with -fmad=false).
+ *--------------------------------------------------------------------------*/
+
+namespace {
+
+__device__ __forceinline__ int l_id_search(int size, int id, const int *__restrict__ a)
+{
+  int lo = 0, hi = size - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const int v = a[mid];
+    if (v < id) lo = mid + 1;
+    else if (v > id) hi = mid - 1;
+    else return mid;
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(128)
+k_coarse_stage_1(const CoarseAssemblyArgs a)
+{
+  const int ii_c = blockIdx.x*blockDim.x + threadIdx.x;
+  if (ii_c >= a.c_n_rows) return;
+
+  const int c_s_idx = a.c_row_index[ii_c];
+  const int n_c_cols = a.c_row_index[ii_c+1] - c_s_idx;
+
+  double cen0 = 0., cen1 = 0., cen2 = 0., vol = 0., dsum = 0.;
+
+  const int r_s = a.c_f_row_index[ii_c], r_e = a.c_f_row_index[ii_c+1];
+  for (int r_idx = r_s; r_idx < r_e; r_idx++) {
+    const int ii = a.c_f_row_ids[r_idx];
+    const double fv = a.f_cell_vol[ii];
+    const double fc0 = a.f_cell_cen[ii*3], fc1 = a.f_cell_cen[ii*3+1],
+                 fc2 = a.f_cell_cen[ii*3+2];
+    cen0 += fc0*fv; cen1 += fc1*fv; cen2 += fc2*fv;
+    vol += fv;
+    dsum += a.f_d_val[ii];
+
+    const int f_s = a.f_row_index[ii], f_e = a.f_row_index[ii+1];
+    for (int f_idx = f_s; f_idx < f_e; f_idx++) {
+      const int jj = a.f_col_id[f_idx];
+      const int jj_c = a.f_c_row[jj];
+      const double fx = a.f_x_val[f_idx];
+      dsum += fx;
+
+      if (jj_c > -1 && jj_c != ii_c && jj_c > ii_c) {
+        const int k = l_id_search(n_c_cols, jj_c, a.c_col_id + c_s_idx);
+        const int c_face_id = a.c_cell_face[c_s_idx + k];
+        const int sgn = a.f_cell_face_sgn[f_idx];
+        const int f_face_id = a.f_cell_face[f_idx];
+        double *nrm = a.c_face_normal + 3*(size_t)c_face_id;
+        double *xij = a.c_xa0ij + 3*(size_t)c_face_id;
+        if (a.f_level == 0) {
+          const double sgn_surf = sgn * a.f_face_surf[f_face_id];
+          nrm[0] += sgn_surf * a.f_face_u_normal[f_face_id*3];
+          nrm[1] += sgn_surf * a.f_face_u_normal[f_face_id*3+1];
+          nrm[2] += sgn_surf * a.f_face_u_normal[f_face_id*3+2];
+          a.c_xa0[c_face_id] += fx;
+          xij[0] += fx * (a.f_cell_cen[jj*3]   - fc0);
+          xij[1] += fx * (a.f_cell_cen[jj*3+1] - fc1);
+          xij[2] += fx * (a.f_cell_cen[jj*3+2] - fc2);
+        }
+        else {
+          nrm[0] += sgn * a.f_face_normal[f_face_id*3];
+          nrm[1] += sgn * a.f_face_normal[f_face_id*3+1];
+          nrm[2] += sgn * a.f_face_normal[f_face_id*3+2];
+          a.c_xa0[c_face_id] += a.f_xa0[f_face_id];
+          xij[0] += sgn * a.f_xa0ij[f_face_id*3];
+          xij[1] += sgn * a.f_xa0ij[f_face_id*3+1];
+          xij[2] += sgn * a.f_xa0ij[f_face_id*3+2];
+        }
+      }
+    }
+  }
+  a.c_cell_cen[ii_c*3]   = cen0 / vol;
+  a.c_cell_cen[ii_c*3+1] = cen1 / vol;
+  a.c_cell_cen[ii_c*3+2] = cen2 / vol;
+  a.c_cell_vol[ii_c] = vol;
+  a.c_d_val[ii_c] = dsum;
+}
+
+__global__ void __launch_bounds__(128)
+k_coarse_stage_2(const CoarseAssemblyArgs a)
+{
+  const int ic = blockIdx.x*blockDim.x + threadIdx.x;
+  if (ic >= a.c_n_rows) return;
+  const double ci0 = a.c_cell_cen[ic*3], ci1 = a.c_cell_cen[ic*3+1],
+               ci2 = a.c_cell_cen[ic*3+2];
+  double d = a.c_d_val[ic];
+  const int s = a.c_row_index[ic], e = a.c_row_index[ic+1];
+  for (int r_idx = s; r_idx < e; r_idx++) {
+    const int jc = a.c_col_id[r_idx];
+    const int c_face_id = a.c_cell_face[r_idx];
+    const double sgn = (double)a.c_cell_face_sgn[r_idx];
+    const double *nrm = a.c_face_normal + 3*(size_t)c_face_id;
+    const double *xij = a.c_xa0ij + 3*(size_t)c_face_id;
+    const double n0 = nrm[0], n1 = nrm[1], n2 = nrm[2];
+    const double dsigjg
+      = sgn * (  (a.c_cell_cen[jc*3]   - ci0)*n0
+               + (a.c_cell_cen[jc*3+1] - ci1)*n1
+               + (a.c_cell_cen[jc*3+2] - ci2)*n2);
+    const double xa0 = a.c_xa0[c_face_id];
+    double c_x_val_c = xa0;
+    if (fabs(dsigjg) > 1e-12) {          /* cs_math_epzero */
+      const double dsxaij = xij[0]*n0 + xij[1]*n1 + xij[2]*n2;
+      const double agij = dsxaij/dsigjg;
+      if (agij >= c_x_val_c && agij <= 0.)
+        c_x_val_c = agij;
+    }
+    c_x_val_c = a.relax*c_x_val_c + (1. - a.relax)*xa0;
+    a.c_x_val[r_idx] = c_x_val_c;
+    d -= c_x_val_c;
+  }
+  a.c_d_val[ic] = d;
+}
+
+} // anonymous namespace
+
+bool launch_coarse_assembly(const CoarseAssemblyArgs &a)
+{
+  Context &c = ctx();
+  if (a.c_n_rows < 1) return true;
+  if (a.c_n_faces > 0) {
+    if (!CSB_CUDA(cudaMemsetAsync(a.c_face_normal, 0, sizeof(double)*3*(size_t)a.c_n_faces, c.stream))) return false;
+    if (!CSB_CUDA(cudaMemsetAsync(a.c_xa0, 0, sizeof(double)*(size_t)a.c_n_faces, c.stream))) return false;
+    if (!CSB_CUDA(cudaMemsetAsync(a.c_xa0ij, 0, sizeof(double)*3*(size_t)a.c_n_faces, c.stream))) return false;
+  }
+  const int grid = (a.c_n_rows + 127) / 128;
+  k_coarse_stage_1<<<grid, 128, 0, c.stream>>>(a);
+  if (!post_launch("coarse_stage_1")) return false;
+  k_coarse_stage_2<<<grid, 128, 0, c.stream>>>(a);
+  return post_launch("coarse_stage_2");
+}
+
+/*--------------------------------------------------------------------------
+ * Halo packing (cs_halo_sync_pack, src/base/cs_halo.cpp:1739-1834;
+ * _gather_full_cu, src/base/cs_halo_cuda.cu:74-160)
+ *--------------------------------------------------------------------------*/
+
+namespace {
+__global__ void __launch_bounds__(TPB)
+k_halo_pack(int n_send, const int *__restrict__ send_list, const double *__restrict__ var,
+            double *__restrict__ buf)
+{
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n_send; i += gridDim.x*TPB)
+    buf[i] = var[send_list[i]];
+}
+}
+
+bool launch_halo_pack(int n_send, const int *send_list, const double *var, double *buf)
+{
+  if (n_send < 1) return true;
+  k_halo_pack<<<vec_grid(n_send*4), TPB, 0, ctx().stream>>>(n_send, send_list, var, buf);
+  return post_launch("halo_pack");
+}
+
+} // namespace csb

@@ -1,0 +1,344 @@
+/*============================================================================
+ * runtime.cu -- context, memory helpers, matrix object, BLAS-1 entry points.
+ *============================================================================*/
+
+#include "csb_internal.h"
+
+#include <cstdarg>
+
+namespace csb {
+
+static Context g_ctx;
+
+Context &ctx() { return g_ctx; }
+
+void set_error(const char *fmt, ...)
+{
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_ctx.err = buf;
+  if (getenv("CSB_VERBOSE_ERRORS") != nullptr)
+    fprintf(stderr, "[csb200] error: %s\n", buf);
+}
+
+bool cuda_ok(cudaError_t e, const char *what, const char *file, int line)
+{
+  if (e == cudaSuccess) return true;
+  set_error("%s failed at %s:%d: %s", what, file, line, cudaGetErrorString(e));
+  return false;
+}
+
+bool is_device_ptr(const void *p)
+{
+  if (p == nullptr) return false;
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
+}
+
+void reset_partials();
+
+} // namespace csb
+
+using namespace csb;
+
+extern "C" {
+
+const char *csb_version(void) { return "csb200 0.1 (sm_100a, FP64)"; }
+
+const char *csb_last_error(void) { return ctx().err.c_str(); }
+
+int csb_init(int device_id)
+{
+  Context &c = ctx();
+  if (c.ready && c.device == device_id) return 0;
+  if (c.ready) csb_finalize();
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1) {
+    cudaGetLastError();
+    set_error("csb_init: no CUDA device available (this library has no CPU fallback)");
+    return -1;
+  }
+  if (device_id < 0 || device_id >= n_dev) {
+    set_error("csb_init: device %d out of range (%d devices)", device_id, n_dev);
+    return -1;
+  }
+  if (!CSB_CUDA(cudaSetDevice(device_id))) return -1;
+  cudaDeviceProp prop;
+  if (!CSB_CUDA(cudaGetDeviceProperties(&prop, device_id))) return -1;
+  c.sm_count = prop.multiProcessorCount;
+  c.device = device_id;
+  if (!CSB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking))) return -1;
+  if (!CSB_CUDA(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking))) return -1;
+  c.stream = c.own_stream;
+  if (!CSB_CUDA(cudaEventCreateWithFlags(&c.ev_a, cudaEventDisableTiming))) return -1;
+  if (!CSB_CUDA(cudaEventCreateWithFlags(&c.ev_b, cudaEventDisableTiming))) return -1;
+  if (!CSB_CUDA(cudaMalloc((void **)&c.ticket, sizeof(unsigned)))) return -1;
+  if (!CSB_CUDA(cudaMemset(c.ticket, 0, sizeof(unsigned)))) return -1;
+  if (!CSB_CUDA(cudaMalloc((void **)&c.red_out, sizeof(double)*8))) return -1;
+  if (!CSB_CUDA(cudaMallocHost((void **)&c.red_out_h, sizeof(double)*8))) return -1;
+  c.partials = nullptr;
+  reset_partials();
+  c.launches = 0;
+  c.ready = true;
+  c.err.clear();
+  return 0;
+}
+
+void csb_finalize(void)
+{
+  Context &c = ctx();
+  if (!c.ready) return;
+  cudaDeviceSynchronize();
+  if (c.partials) cudaFree(c.partials);
+  if (c.ticket) cudaFree(c.ticket);
+  if (c.red_out) cudaFree(c.red_out);
+  if (c.red_out_h) cudaFreeHost(c.red_out_h);
+  if (c.ev_a) cudaEventDestroy(c.ev_a);
+  if (c.ev_b) cudaEventDestroy(c.ev_b);
+  if (c.own_stream) cudaStreamDestroy(c.own_stream);
+  if (c.comm_stream) cudaStreamDestroy(c.comm_stream);
+  c = Context();
+  reset_partials();
+}
+
+int csb_set_stream(void *cuda_stream)
+{
+  Context &c = ctx();
+  if (!c.ready) { set_error("csb_set_stream: csb_init not called"); return -1; }
+  c.stream = (cuda_stream != nullptr) ? (cudaStream_t)cuda_stream : c.own_stream;
+  return 0;
+}
+
+int csb_stream_synchronize(void)
+{
+  return CSB_CUDA(cudaStreamSynchronize(ctx().stream)) ? 0 : -1;
+}
+
+void *csb_malloc_device(size_t n_bytes)
+{
+  void *p = nullptr;
+  if (!CSB_CUDA(cudaMalloc(&p, n_bytes > 0 ? n_bytes : 1))) return nullptr;
+  return p;
+}
+
+void csb_free_device(void *p) { if (p) cudaFree(p); }
+
+int csb_copy_h2d(void *dst_d, const void *src_h, size_t n_bytes)
+{
+  if (!CSB_CUDA(cudaMemcpyAsync(dst_d, src_h, n_bytes, cudaMemcpyHostToDevice, ctx().stream)))
+    return -1;
+  return CSB_CUDA(cudaStreamSynchronize(ctx().stream)) ? 0 : -1;
+}
+
+int csb_copy_d2h(void *dst_h, const void *src_d, size_t n_bytes)
+{
+  if (!CSB_CUDA(cudaMemcpyAsync(dst_h, src_d, n_bytes, cudaMemcpyDeviceToHost, ctx().stream)))
+    return -1;
+  return CSB_CUDA(cudaStreamSynchronize(ctx().stream)) ? 0 : -1;
+}
+
+void *csb_malloc_pinned(size_t n_bytes)
+{
+  void *p = nullptr;
+  if (!CSB_CUDA(cudaMallocHost(&p, n_bytes > 0 ? n_bytes : 1))) return nullptr;
+  return p;
+}
+
+void csb_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+
+long long csb_launch_count(int reset)
+{
+  long long n = ctx().launches;
+  if (reset) ctx().launches = 0;
+  return n;
+}
+
+/*----------------------------------------------------------------------------
+ * Matrix
+ *----------------------------------------------------------------------------*/
+
+csb_matrix_t *
+csb_matrix_create_msr(csb_lnum_t n_rows, csb_lnum_t n_cols_ext,
+                      const csb_lnum_t *row_index, const csb_lnum_t *col_id,
+                      const csb_real_t *d_val, const csb_real_t *x_val, int symmetric)
+{
+  Context &c = ctx();
+  if (!c.ready) { set_error("csb_matrix_create_msr: csb_init not called"); return nullptr; }
+  if (n_rows < 0 || n_cols_ext < n_rows || row_index == nullptr) {
+    set_error("csb_matrix_create_msr: invalid sizes"); return nullptr;
+  }
+  csb_matrix_t *m = new csb_matrix_t;
+  m->n_rows = n_rows;
+  m->n_cols_ext = n_cols_ext;
+  m->symmetric = (symmetric != 0);
+
+  m->h_row_index.resize((size_t)n_rows + 1);
+  if (is_device_ptr(row_index)) {
+    if (!CSB_CUDA(cudaMemcpy(m->h_row_index.data(), row_index,
+                             sizeof(csb_lnum_t)*((size_t)n_rows+1), cudaMemcpyDeviceToHost))) {
+      delete m; return nullptr;
+    }
+  }
+  else
+    memcpy(m->h_row_index.data(), row_index, sizeof(csb_lnum_t)*((size_t)n_rows+1));
+  m->nnz = m->h_row_index[n_rows];
+
+  bool ok = m->row_index.upload(row_index, (size_t)n_rows + 1)
+         && m->col_id.upload(col_id, (size_t)m->nnz)
+         && m->d_val.upload(d_val, (size_t)n_rows)
+         && m->x_val.upload(x_val, (size_t)m->nnz)
+         && CSB_CUDA(cudaStreamSynchronize(c.stream));
+  if (!ok) { delete m; return nullptr; }
+  matrix_plan_spmv(m);
+  return m;
+}
+
+int csb_matrix_set_coefficients(csb_matrix_t *m, int symmetric,
+                                const csb_real_t *d_val, const csb_real_t *x_val)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  m->symmetric = (symmetric != 0);
+  Context &c = ctx();
+  bool ok = CSB_CUDA(cudaMemcpyAsync(m->d_val.p, d_val, sizeof(double)*(size_t)m->n_rows,
+                                     cudaMemcpyDefault, c.stream))
+         && CSB_CUDA(cudaMemcpyAsync(m->x_val.p, x_val, sizeof(double)*(size_t)m->nnz,
+                                     cudaMemcpyDefault, c.stream))
+         && CSB_CUDA(cudaStreamSynchronize(c.stream));
+  m->h_vals_valid = false;
+  return ok ? 0 : -1;
+}
+
+int csb_matrix_set_mesh_association(csb_matrix_t *m, csb_lnum_t n_faces,
+                                    const csb_lnum_t *c2f, const short *c2f_sgn,
+                                    const csb_real_t *cell_cen, const csb_real_t *cell_vol,
+                                    const csb_real_t *face_u_normal,
+                                    const csb_real_t *face_surf)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (c2f == nullptr || c2f_sgn == nullptr || cell_cen == nullptr || cell_vol == nullptr
+      || face_u_normal == nullptr || face_surf == nullptr) {
+    set_error("csb_matrix_set_mesh_association: all arrays are required");
+    return -1;
+  }
+  m->n_faces = n_faces;
+  bool ok = m->c2f.upload(c2f, (size_t)m->nnz)
+         && m->c2f_sgn.upload(c2f_sgn, (size_t)m->nnz)
+         && m->cell_cen.upload(cell_cen, 3*(size_t)m->n_cols_ext)
+         && m->cell_vol.upload(cell_vol, (size_t)m->n_cols_ext)
+         && m->face_u_normal.upload(face_u_normal, 3*(size_t)n_faces)
+         && m->face_surf.upload(face_surf, (size_t)n_faces)
+         && CSB_CUDA(cudaStreamSynchronize(ctx().stream));
+  m->has_mesh = ok;
+  return ok ? 0 : -1;
+}
+
+int csb_matrix_set_halo(csb_matrix_t *m, csb_halo_t *halo)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  m->halo = halo;
+  return 0;
+}
+
+void csb_matrix_destroy(csb_matrix_t **m)
+{
+  if (m == nullptr || *m == nullptr) return;
+  delete *m;
+  *m = nullptr;
+}
+
+csb_lnum_t csb_matrix_get_n_rows(const csb_matrix_t *m) { return m ? m->n_rows : 0; }
+csb_lnum_t csb_matrix_get_n_columns(const csb_matrix_t *m) { return m ? m->n_cols_ext : 0; }
+csb_lnum_t csb_matrix_get_n_entries(const csb_matrix_t *m) { return m ? m->nnz + m->n_rows : 0; }
+
+double csb_matrix_spmv_bytes(const csb_matrix_t *m)
+{
+  if (m == nullptr) return 0.;
+  return 12.0*m->nnz + 4.0*(m->n_rows + 1.0) + 8.0*m->n_rows + 8.0*m->n_cols_ext
+         + 8.0*m->n_rows;
+}
+
+static int _spmv_api(const csb_matrix_t *m, csb_real_t *x, csb_real_t *y, bool exdiag)
+{
+  Context &c = ctx();
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  const bool xd = is_device_ptr(x), yd = is_device_ptr(y);
+  DevBuf<double> tx, ty;
+  double *x_d = x, *y_d = y;
+  if (!xd) {
+    if (!tx.upload(x, (size_t)m->n_cols_ext)) return -1;
+    x_d = tx.p;
+  }
+  if (!yd) {
+    if (!ty.alloc((size_t)m->n_rows)) return -1;
+    y_d = ty.p;
+  }
+  if (m->halo != nullptr)
+    if (csb_halo_sync_var(m->halo, x_d) != 0) return -1;
+  SpmvArgs a;
+  a.m = m; a.exclude_diag = exdiag; a.x = x_d; a.y = y_d;
+  if (!launch_spmv(EPI_STORE, a)) return -1;
+  if (!yd) {
+    if (!CSB_CUDA(cudaMemcpyAsync(y, y_d, sizeof(double)*(size_t)m->n_rows,
+                                  cudaMemcpyDeviceToHost, c.stream))) return -1;
+  }
+  if (!xd || !yd)
+    if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return -1;
+  return 0;
+}
+
+int csb_matrix_vector_multiply(const csb_matrix_t *m, csb_real_t *x, csb_real_t *y)
+{ return _spmv_api(m, x, y, false); }
+
+int csb_matrix_vector_multiply_exdiag(const csb_matrix_t *m, csb_real_t *x, csb_real_t *y)
+{ return _spmv_api(m, x, y, true); }
+
+/*----------------------------------------------------------------------------
+ * BLAS-1
+ *----------------------------------------------------------------------------*/
+
+static int _dot_api(csb_lnum_t n, const double *x, const double *y, const double *z,
+                    int mode, double *out, int n_out)
+{
+  Context &c = ctx();
+  DevBuf<double> tx, ty, tz;
+  const double *xd = x, *yd = y, *zd = z;
+  if (x && !is_device_ptr(x)) { if (!tx.upload(x, n)) return -1; xd = tx.p; }
+  if (y && !is_device_ptr(y)) { if (!ty.upload(y, n)) return -1; yd = ty.p; }
+  if (z && !is_device_ptr(z)) { if (!tz.upload(z, n)) return -1; zd = tz.p; }
+  if (!launch_dot(n, xd, yd, zd, mode)) return -1;
+  if (!CSB_CUDA(cudaMemcpyAsync(c.red_out_h, c.red_out, sizeof(double)*3,
+                                cudaMemcpyDeviceToHost, c.stream))) return -1;
+  if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return -1;
+  for (int i = 0; i < n_out; i++) out[i] = c.red_out_h[i];
+  return 0;
+}
+
+double csb_dot(csb_lnum_t n, const csb_real_t *x, const csb_real_t *y)
+{
+  double r[1] = {NAN};
+  _dot_api(n, x, y, nullptr, 0, r, 1);
+  return r[0];
+}
+
+double csb_dot_xx(csb_lnum_t n, const csb_real_t *x)
+{
+  double r[1] = {NAN};
+  _dot_api(n, x, nullptr, nullptr, 1, r, 1);
+  return r[0];
+}
+
+int csb_dot_xx_xy_yz(csb_lnum_t n, const csb_real_t *x, const csb_real_t *y,
+                     const csb_real_t *z, double *xx, double *xy, double *yz)
+{
+  double r[3];
+  if (_dot_api(n, x, y, z, 2, r, 3) != 0) return -1;
+  *xx = r[0]; *xy = r[1]; *yz = r[2];
+  return 0;
+}
+
+} /* extern "C" */

@@ -1,0 +1,1001 @@
+/*============================================================================
+ * sles.cu -- host drivers of the device-resident solvers:
+ *   cs_sles_it  (PCG+Jacobi single-reduction, Jacobi, BiCGStab)
+ *   cs_multigrid V-cycle over the aggregation hierarchy
+ *
+ * The host only enqueues kernels.  Krylov scalars, convergence tests and the
+ * multigrid cycle gate live in device memory (ItState / MgState), so there is
+ * no host<->device round trip per iteration (the reference's device path does
+ * a stream sync + D2H of 1-5 doubles per dot product,
+ * src/alge/cs_sles_it_cuda.cu:1049-1095).  Once a solver converges the
+ * remaining enqueued kernels of that solve return immediately.
+ *============================================================================*/
+
+#include "csb_internal.h"
+#include "grid_host.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstddef>
+#include <algorithm>
+
+using namespace csb;
+
+namespace {
+
+double wall()
+{
+  return std::chrono::duration<double>(
+    std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int env_int(const char *name, int dflt)
+{
+  const char *s = getenv(name);
+  return (s != nullptr) ? atoi(s) : dflt;
+}
+
+/* stage a host vector on the device when needed */
+struct StagedVec {
+  double         *d = nullptr;
+  double         *h = nullptr;
+  DevBuf<double>  tmp;
+  size_t          n = 0;
+  bool init(double *p, size_t count, bool copy_in) {
+    n = count;
+    if (is_device_ptr(p)) { d = p; return true; }
+    h = p;
+    if (copy_in) { if (!tmp.upload(p, count)) return false; }
+    else if (!tmp.alloc(count)) return false;
+    d = tmp.p;
+    return true;
+  }
+  bool copy_back(size_t count) {
+    if (h == nullptr) return true;
+    return CSB_CUDA(cudaMemcpyAsync(h, d, sizeof(double)*count, cudaMemcpyDeviceToHost,
+                                    ctx().stream));
+  }
+};
+
+const size_t IT_HEAD = offsetof(ItState, hist);
+const size_t MG_HEAD = offsetof(MgState, cycle_res);
+
+} // anonymous namespace
+
+/*----------------------------------------------------------------------------
+ * cs_sles_it
+ *----------------------------------------------------------------------------*/
+
+struct _csb_sles_it_t {
+  csb_sles_it_type_t  type = CSB_SLES_PCG;
+  int                 poly_degree = 0;
+  int                 n_max_iter = 10000;
+  bool                update_stats = false;
+  void               *nccl_comm = nullptr;
+  /* setup data (cs_sles_it_setup_t, src/alge/cs_sles_it_priv.h) */
+  const csb_matrix_t *a = nullptr;
+  bool                setup_done = false;
+  DevBuf<double>      ad_inv;
+  DevBuf<double>      work;
+  DevBuf<ItState>     st;
+  ItState            *h_st = nullptr;     /* pinned mirror */
+  /* stats (cs_sles_it_priv.h:177-190) */
+  unsigned n_setups = 0, n_solves = 0;
+  unsigned n_iterations_last = 0, n_iterations_min = 0, n_iterations_max = 0;
+  unsigned long long n_iterations_tot = 0;
+  double t_setup = 0, t_solve = 0;
+  ~_csb_sles_it_t() { if (h_st) cudaFreeHost(h_st); }
+};
+
+namespace {
+
+int sb_rows_threshold()
+{
+  static int v = env_int("CSB_SB_ROWS", 2048);
+  return v;
+}
+
+/* Enqueue a PCG+Jacobi solve (cs_sles_it.cpp:1441-1645).
+   smoother = true: fixed-sweep use inside the V-cycle; the SpMV + dots whose
+   only purpose is the convergence test after the last iteration are not
+   issued (they do not change vx).
+   Returns false on launch error.  work: 5*n_cols_ext doubles. */
+bool pcg_enqueue(const csb_matrix_t *m, ItState *st, const MgState *gate,
+                 const double *ad_inv, double precision, double r_norm, int n_max_iter,
+                 const double *rhs, double *vx, bool vx_ini_nonzero, bool smoother,
+                 double *work, ItState *h_st)
+{
+  const int n = m->n_rows;
+  const size_t ws = (size_t)m->n_cols_ext;
+  Context &c = ctx();
+
+  if (n <= sb_rows_threshold() && m->halo == nullptr)
+    return launch_pcg_single_block(m, st, gate, precision, r_norm, n_max_iter, ad_inv,
+                                   rhs, vx, vx_ini_nonzero ? 1 : 0, work);
+
+  double *rk = work, *dk = work + ws, *gk = work + 2*ws, *zk = work + 3*ws,
+         *sk = work + 4*ws;
+
+  if (!launch_it_state_init(st, gate, precision, r_norm, n_max_iter)) return false;
+
+  SpmvArgs a;
+  a.m = m; a.st = st; a.ad_inv = ad_inv; a.rk = rk; a.dk = dk; a.b = rhs;
+  if (vx_ini_nonzero) {
+    a.x = vx; a.y = nullptr;
+    if (!launch_spmv(EPI_PCG_INIT, a)) return false;
+  }
+  else if (!launch_pcg_init_zero(n, st, rhs, ad_inv, vx, rk, dk)) return false;
+
+  a.x = dk; a.y = zk; a.phase = 0;
+  if (!launch_spmv(EPI_PCG_DOT3, a)) return false;
+  if (!launch_pcg_update_first(n, st, ad_inv, dk, zk, vx, rk, gk)) return false;
+
+  a.x = gk; a.y = sk; a.phase = 1;
+  const int poll = 16;
+  for (int it = 1; ; it++) {
+    /* iteration "it" is complete on the device here */
+    if (smoother && it >= n_max_iter) break;
+    if (!launch_spmv(EPI_PCG_DOT3, a)) return false;
+    if (it >= n_max_iter) break;     /* that was the final convergence test */
+    if (!launch_pcg_update(n, st, ad_inv, sk, dk, gk, zk, rk, vx)) return false;
+    if (!smoother && h_st != nullptr && (it % poll) == 0) {
+      if (!CSB_CUDA(cudaMemcpyAsync(h_st, st, IT_HEAD, cudaMemcpyDeviceToHost, c.stream)))
+        return false;
+      if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return false;
+      if (h_st->cvg != CSB_SLES_ITERATING) break;
+    }
+  }
+  return true;
+}
+
+/* Jacobi (cs_sles_it.cpp:2098-2270); iterate t lives in vx when t is even,
+   in rk when t is odd (ping-pong instead of the reference's rk <- vx copy). */
+bool jacobi_enqueue(const csb_matrix_t *m, ItState *st, const double *ad_inv,
+                    double precision, double r_norm, int n_max_iter, const double *rhs,
+                    double *vx, bool vx_ini_nonzero, double *rk, ItState *h_st);
+
+bool bicgstab_enqueue(const csb_matrix_t *m, ItState *st, const double *ad_inv,
+                      double precision, double r_norm, int n_max_iter, const double *rhs,
+                      double *vx, bool vx_ini_nonzero, double *work, ItState *h_st);
+
+} // anonymous namespace
+
+namespace csb {
+bool launch_jacobi_finish(int n, const ItState *st, const double *rk, double *vx);
+}
+
+namespace {
+
+bool jacobi_enqueue(const csb_matrix_t *m, ItState *st, const double *ad_inv,
+                    double precision, double r_norm, int n_max_iter, const double *rhs,
+                    double *vx, bool vx_ini_nonzero, double *rk, ItState *h_st)
+{
+  const int n = m->n_rows;
+  Context &c = ctx();
+  if (!launch_it_state_init(st, nullptr, precision, r_norm, n_max_iter)) return false;
+  int t = 0;
+  if (!vx_ini_nonzero) {
+    if (!launch_jacobi_first(n, st, rhs, ad_inv, vx, rk)) return false;
+    t = 1;
+  }
+  const int poll = 16;
+  while (t < n_max_iter) {
+    t += 1;
+    double *src = ((t - 1) % 2 == 0) ? vx : rk;
+    double *dst = (t % 2 == 0) ? vx : rk;
+    if (t == 2 && !vx_ini_nonzero) src = rk;   /* iterate 1 is in both */
+    if (!launch_jacobi_sweep(m, st, rhs, ad_inv, dst, src)) return false;
+    if (h_st != nullptr && (t % poll) == 0) {
+      if (!CSB_CUDA(cudaMemcpyAsync(h_st, st, IT_HEAD, cudaMemcpyDeviceToHost, c.stream)))
+        return false;
+      if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return false;
+      if (h_st->cvg != CSB_SLES_ITERATING) break;
+    }
+  }
+  return launch_jacobi_finish(n, st, rk, vx);
+}
+
+bool bicgstab_enqueue(const csb_matrix_t *m, ItState *st, const double *ad_inv,
+                      double precision, double r_norm, int n_max_iter, const double *rhs,
+                      double *vx, bool vx_ini_nonzero, double *work, ItState *h_st)
+{
+  const int n = m->n_rows;
+  const size_t ws = (size_t)m->n_cols_ext;
+  Context &c = ctx();
+  double *res0 = work, *rk = work + ws, *pk = work + 2*ws, *zk = work + 3*ws,
+         *uk = work + 4*ws, *vk = work + 5*ws;
+  if (!launch_it_state_init(st, nullptr, precision, r_norm, n_max_iter)) return false;
+  if (vx_ini_nonzero) {
+    SpmvArgs a; a.m = m; a.x = vx; a.y = res0;
+    if (!launch_spmv(EPI_STORE, a)) return false;
+  }
+  if (!launch_bicg_init(n, st, rhs, vx, res0, rk, pk, uk, vx_ini_nonzero)) return false;
+  if (!launch_bicg_dots_a(n, st, rk, res0)) return false;
+  const int poll = 8;
+  for (int it = 1; it <= n_max_iter; it++) {
+    if (!launch_bicg_pk_zk(n, st, rk, uk, ad_inv, pk, zk)) return false;
+    if (!launch_bicg_spmv_b(m, st, zk, uk, res0)) return false;
+    if (!launch_bicg_upd1(n, st, ad_inv, vx, rk, zk, uk)) return false;
+    if (!launch_bicg_spmv_c(m, st, zk, vk, rk)) return false;
+    if (!launch_bicg_upd2(n, st, vx, rk, zk, vk, res0)) return false;
+    if (h_st != nullptr && (it % poll) == 0) {
+      if (!CSB_CUDA(cudaMemcpyAsync(h_st, st, IT_HEAD, cudaMemcpyDeviceToHost, c.stream)))
+        return false;
+      if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return false;
+      if (h_st->cvg != CSB_SLES_ITERATING) break;
+    }
+  }
+  return true;
+}
+
+} // anonymous namespace
+
+extern "C" {
+
+csb_sles_it_t *
+csb_sles_it_create(csb_sles_it_type_t solver_type, int poly_degree, int n_max_iter,
+                   int update_stats)
+{
+  if (!ctx().ready) { set_error("csb_sles_it_create: csb_init not called"); return nullptr; }
+  if (solver_type != CSB_SLES_PCG && solver_type != CSB_SLES_JACOBI
+      && solver_type != CSB_SLES_BICGSTAB) {
+    set_error("csb_sles_it_create: solver type %d is not available on this path",
+              (int)solver_type);
+    return nullptr;
+  }
+  if (solver_type != CSB_SLES_JACOBI && poly_degree != 0) {
+    set_error("csb_sles_it_create: only the Jacobi preconditioner (poly_degree 0) "
+              "is available on this path");
+    return nullptr;
+  }
+  csb_sles_it_t *c = new csb_sles_it_t;
+  c->type = solver_type;
+  c->poly_degree = poly_degree;
+  c->n_max_iter = n_max_iter;
+  c->update_stats = (update_stats != 0);
+  return c;
+}
+
+int csb_sles_it_set_reduce_comm(csb_sles_it_t *c, void *nccl_comm)
+{
+  if (c == nullptr) return -1;
+  c->nccl_comm = nccl_comm;
+  return 0;
+}
+
+void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, int verbosity)
+{
+  (void)name; (void)verbosity;
+  csb_sles_it_t *c = static_cast<csb_sles_it_t *>(context);
+  if (c == nullptr || a == nullptr) { set_error("csb_sles_it_setup: null argument"); return; }
+  double t0 = wall();
+  c->a = a;
+  c->setup_done = false;
+  const size_t n_wa = (c->type == CSB_SLES_BICGSTAB) ? 6 : ((c->type == CSB_SLES_PCG) ? 5 : 1);
+  if (!c->ad_inv.alloc((size_t)a->n_rows)) return;
+  if (!launch_ad_inv(a->n_rows, a->d_val.p, c->ad_inv.p)) return;
+  if (!c->work.alloc(n_wa * (size_t)a->n_cols_ext)) return;
+  if (!c->st.alloc(1)) return;
+  if (c->h_st == nullptr)
+    if (!CSB_CUDA(cudaMallocHost((void **)&c->h_st, sizeof(ItState)))) return;
+  c->setup_done = true;
+  c->n_setups += 1;
+  c->t_setup += wall() - t0;
+}
+
+csb_sles_convergence_state_t
+csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int verbosity,
+                  double precision, double r_norm, int *n_iter, double *residual,
+                  const csb_real_t *rhs, csb_real_t *vx_ini, csb_real_t *vx,
+                  size_t aux_size, void *aux_vectors)
+{
+  (void)aux_size; (void)aux_vectors;
+  csb_sles_it_t *c = static_cast<csb_sles_it_t *>(context);
+  Context &cx = ctx();
+  cx.err.clear();
+  if (n_iter) *n_iter = 0;
+  if (c == nullptr || a == nullptr || rhs == nullptr || vx == nullptr) {
+    set_error("csb_sles_it_solve: null argument");
+    return CSB_SLES_BREAKDOWN;
+  }
+  if (vx_ini != nullptr && vx_ini != vx) {
+    set_error("csb_sles_it_solve: vx_ini must be vx or NULL (cs_sles_it.cpp:5182-5184)");
+    return CSB_SLES_BREAKDOWN;
+  }
+  if (!c->setup_done || c->a != a)
+    csb_sles_it_setup(c, name, a, verbosity);
+  if (!c->setup_done) return CSB_SLES_BREAKDOWN;
+
+  double t0 = wall();
+  const bool ini = (vx_ini == vx);
+  StagedVec s_rhs, s_vx;
+  if (!s_rhs.init(const_cast<double *>(rhs), (size_t)a->n_rows, true)) return CSB_SLES_BREAKDOWN;
+  if (!s_vx.init(vx, (size_t)a->n_cols_ext, ini)) return CSB_SLES_BREAKDOWN;
+
+  bool ok = false;
+  switch (c->type) {
+  case CSB_SLES_PCG:
+    ok = pcg_enqueue(a, c->st.p, nullptr, c->ad_inv.p, precision, r_norm, c->n_max_iter,
+                     s_rhs.d, s_vx.d, ini, false, c->work.p, c->h_st);
+    break;
+  case CSB_SLES_JACOBI:
+    ok = jacobi_enqueue(a, c->st.p, c->ad_inv.p, precision, r_norm, c->n_max_iter,
+                        s_rhs.d, s_vx.d, ini, c->work.p, c->h_st);
+    break;
+  case CSB_SLES_BICGSTAB:
+    ok = bicgstab_enqueue(a, c->st.p, c->ad_inv.p, precision, r_norm, c->n_max_iter,
+                          s_rhs.d, s_vx.d, ini, c->work.p, c->h_st);
+    break;
+  }
+  if (!ok) return CSB_SLES_BREAKDOWN;
+
+  if (!CSB_CUDA(cudaMemcpyAsync(c->h_st, c->st.p, sizeof(ItState), cudaMemcpyDeviceToHost,
+                                cx.stream))) return CSB_SLES_BREAKDOWN;
+  if (!s_vx.copy_back((size_t)a->n_rows)) return CSB_SLES_BREAKDOWN;
+  if (!CSB_CUDA(cudaStreamSynchronize(cx.stream))) return CSB_SLES_BREAKDOWN;
+
+  int cvg = c->h_st->cvg;
+  if (cvg == CSB_SLES_ITERATING) cvg = CSB_SLES_MAX_ITERATION;
+  /* reported iteration count = value at the last convergence test */
+  int n_it = c->h_st->n_iter;
+  if (n_iter) *n_iter = n_it;
+  if (residual) *residual = c->h_st->residual;
+
+  c->n_solves += 1;
+  if (c->n_iterations_tot == 0 || c->n_iterations_min > (unsigned)n_it)
+    c->n_iterations_min = n_it;
+  if (c->n_iterations_max < (unsigned)n_it) c->n_iterations_max = n_it;
+  c->n_iterations_last = n_it;
+  c->n_iterations_tot += n_it;
+  c->t_solve += wall() - t0;
+  return (csb_sles_convergence_state_t)cvg;
+}
+
+void csb_sles_it_free(void *context)
+{
+  csb_sles_it_t *c = static_cast<csb_sles_it_t *>(context);
+  if (c == nullptr) return;
+  c->ad_inv.release();
+  c->work.release();
+  c->a = nullptr;
+  c->setup_done = false;
+}
+
+void csb_sles_it_destroy(void **context)
+{
+  if (context == nullptr || *context == nullptr) return;
+  csb_sles_it_t *c = static_cast<csb_sles_it_t *>(*context);
+  delete c;
+  *context = nullptr;
+}
+
+double csb_sles_it_get_last_initial_residual(const csb_sles_it_t *c)
+{
+  return (c != nullptr && c->h_st != nullptr) ? c->h_st->initial_residual : -1.;
+}
+
+int csb_sles_it_get_residual_history(const csb_sles_it_t *c, double *hist, int max_n)
+{
+  if (c == nullptr || c->h_st == nullptr) return 0;
+  int n = c->h_st->n_hist;
+  if (n > max_n) n = max_n;
+  for (int i = 0; i < n; i++) hist[i] = c->h_st->hist[i];
+  return n;
+}
+
+void csb_sles_it_log(const void *context, int log_type)
+{
+  (void)log_type;
+  const csb_sles_it_t *c = static_cast<const csb_sles_it_t *>(context);
+  if (c == nullptr) return;
+  const char *tn = (c->type == CSB_SLES_PCG) ? "Conjugate Gradient"
+                 : (c->type == CSB_SLES_JACOBI) ? "Jacobi" : "BiCGstab";
+  printf("  Solver type:                       %s (B200 device)\n"
+         "  Number of setups:                  %12u\n"
+         "  Number of calls:                   %12u\n"
+         "  Minimum number of iterations:      %12u\n"
+         "  Maximum number of iterations:      %12u\n"
+         "  Total number of iterations:        %12llu\n"
+         "  Total setup time:                  %12.3f\n"
+         "  Total solution time:               %12.3f\n",
+         tn, c->n_setups, c->n_solves, c->n_iterations_min, c->n_iterations_max,
+         c->n_iterations_tot, c->t_setup, c->t_solve);
+}
+
+void *csb_sles_it_copy(const void *context)
+{
+  const csb_sles_it_t *c = static_cast<const csb_sles_it_t *>(context);
+  if (c == nullptr) return nullptr;
+  csb_sles_it_t *d = csb_sles_it_create(c->type, c->poly_degree, c->n_max_iter,
+                                        c->update_stats ? 1 : 0);
+  if (d) d->nccl_comm = c->nccl_comm;
+  return d;
+}
+
+} /* extern "C" */
+
+/*----------------------------------------------------------------------------
+ * cs_multigrid
+ *----------------------------------------------------------------------------*/
+
+namespace {
+
+struct MgLevel {
+  const csb_matrix_t *m = nullptr;
+  csb_matrix_t       *owned = nullptr;
+  /* towards the next (coarser) level */
+  DevBuf<int>         coarse_row;                 /* this level's rows -> next level */
+  DevBuf<int>         c_f_row_index, c_f_row_ids; /* next level rows -> this level's rows */
+  std::vector<int>    h_coarse_row;
+  /* solve data */
+  DevBuf<double>      ad_inv, rhs, vx;
+  /* geometry of this level used to coarsen it (level > 0; level 0 uses the
+     matrix's mesh association) */
+  DevBuf<int>         cell_face;
+  DevBuf<short>       cell_face_sgn;
+  DevBuf<double>      cell_cen, cell_vol, face_normal, xa0, xa0ij;
+  int                 n_faces = 0;
+  ~MgLevel() { if (owned) csb_matrix_destroy(&owned); }
+};
+
+} // anonymous namespace
+
+struct _csb_multigrid_t {
+  csb_multigrid_type_t type = CSB_MULTIGRID_V_CYCLE;
+  /* settings, defaults of cs_multigrid_create (cs_multigrid.cpp:4689-4764) */
+  int     aggregation_limit = 3;
+  int     coarsening_type = 0;
+  int     n_levels_max = 25;
+  unsigned long long n_g_rows_min = 30;
+  double  p0p1_relax = 0.95;
+  int     n_blocks = 1;
+  csb_sles_it_type_t solver_type[3] = {CSB_SLES_PCG, CSB_SLES_PCG, CSB_SLES_PCG};
+  int     n_max_cycles = 100;
+  int     n_max_iter[3] = {2, 10, 500};
+  int     poly_degree[3] = {0, 0, 0};
+  double  precision_mult[3] = {1., 1., 1.};
+  void   *nccl_comm = nullptr;
+  /* setup data */
+  std::vector<MgLevel *> levels;
+  DevBuf<ItState>  it_states;   /* 2 per level */
+  DevBuf<MgState>  mg_state;
+  MgState         *h_mg = nullptr;   /* pinned */
+  DevBuf<double>   wr, aux;
+  bool             setup_done = false;
+  const csb_matrix_t *a = nullptr;
+  /* results / stats */
+  int      n_cycles_last = 0;
+  unsigned n_setups = 0, n_solves = 0;
+  unsigned long long n_cycles_tot = 0;
+  double   t_setup_tot = 0, t_solve_tot = 0;
+  double   t_setup[4] = {0, 0, 0, 0};
+  ~_csb_multigrid_t() {
+    for (MgLevel *l : levels) delete l;
+    if (h_mg) cudaFreeHost(h_mg);
+  }
+};
+
+namespace {
+
+void mg_clear_hierarchy(csb_multigrid_t *mg)
+{
+  for (MgLevel *l : mg->levels) delete l;
+  mg->levels.clear();
+  mg->wr.release();
+  mg->aux.release();
+  mg->it_states.release();
+  mg->setup_done = false;
+  mg->a = nullptr;
+}
+
+/* make sure the host mirrors of a matrix are available for aggregation */
+bool matrix_host_mirror(csb_matrix_t *m)
+{
+  Context &c = ctx();
+  if (m->h_col_id.size() != (size_t)m->nnz) {
+    m->h_col_id.resize(std::max<size_t>((size_t)m->nnz, 1));
+    if (m->nnz > 0 &&
+        !CSB_CUDA(cudaMemcpyAsync(m->h_col_id.data(), m->col_id.p, sizeof(int)*(size_t)m->nnz,
+                                  cudaMemcpyDeviceToHost, c.stream))) return false;
+  }
+  if (!m->h_vals_valid) {
+    m->h_d_val.resize(std::max<size_t>((size_t)m->n_rows, 1));
+    m->h_x_val.resize(std::max<size_t>((size_t)m->nnz, 1));
+    if (m->n_rows > 0 &&
+        !CSB_CUDA(cudaMemcpyAsync(m->h_d_val.data(), m->d_val.p, sizeof(double)*(size_t)m->n_rows,
+                                  cudaMemcpyDeviceToHost, c.stream))) return false;
+    if (m->nnz > 0 &&
+        !CSB_CUDA(cudaMemcpyAsync(m->h_x_val.data(), m->x_val.p, sizeof(double)*(size_t)m->nnz,
+                                  cudaMemcpyDeviceToHost, c.stream))) return false;
+    m->h_vals_valid = true;
+  }
+  return CSB_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+} // anonymous namespace
+
+extern "C" {
+
+csb_multigrid_t *csb_multigrid_create(csb_multigrid_type_t mg_type)
+{
+  if (!ctx().ready) { set_error("csb_multigrid_create: csb_init not called"); return nullptr; }
+  if (mg_type != CSB_MULTIGRID_V_CYCLE) {
+    set_error("csb_multigrid_create: only the V-cycle is available on this path");
+    return nullptr;
+  }
+  return new csb_multigrid_t;
+}
+
+void
+csb_multigrid_set_solver_options(csb_multigrid_t *mg,
+                                 csb_sles_it_type_t descent_smoother_type,
+                                 csb_sles_it_type_t ascent_smoother_type,
+                                 csb_sles_it_type_t coarse_solver_type,
+                                 int n_max_cycles, int n_max_iter_descent,
+                                 int n_max_iter_ascent, int n_max_iter_coarse,
+                                 int poly_degree_descent, int poly_degree_ascent,
+                                 int poly_degree_coarse, double precision_mult_descent,
+                                 double precision_mult_ascent, double precision_mult_coarse)
+{
+  if (mg == nullptr) return;
+  mg->solver_type[0] = descent_smoother_type;
+  mg->solver_type[1] = ascent_smoother_type;
+  mg->solver_type[2] = coarse_solver_type;
+  mg->n_max_cycles = n_max_cycles;
+  mg->n_max_iter[0] = n_max_iter_descent;
+  mg->n_max_iter[1] = n_max_iter_ascent;
+  mg->n_max_iter[2] = n_max_iter_coarse;
+  mg->poly_degree[0] = poly_degree_descent;
+  mg->poly_degree[1] = poly_degree_ascent;
+  mg->poly_degree[2] = poly_degree_coarse;
+  mg->precision_mult[0] = precision_mult_descent;
+  mg->precision_mult[1] = precision_mult_ascent;
+  mg->precision_mult[2] = precision_mult_coarse;
+}
+
+void
+csb_multigrid_set_coarsening_options(csb_multigrid_t *mg, int aggregation_limit,
+                                     int coarsening_type, int n_max_levels,
+                                     unsigned long long min_g_rows, double p0p1_relax,
+                                     int postprocess_block_size)
+{
+  (void)postprocess_block_size;
+  if (mg == nullptr) return;
+  mg->aggregation_limit = aggregation_limit;
+  mg->coarsening_type = coarsening_type;
+  mg->n_levels_max = n_max_levels;
+  mg->n_g_rows_min = min_g_rows;
+  mg->p0p1_relax = p0p1_relax;
+}
+
+void csb_multigrid_set_aggregation_blocks(csb_multigrid_t *mg, int n_blocks)
+{
+  if (mg != nullptr) mg->n_blocks = (n_blocks > 0) ? n_blocks : 1;
+}
+
+int csb_multigrid_set_reduce_comm(csb_multigrid_t *mg, void *nccl_comm)
+{
+  if (mg == nullptr) return -1;
+  mg->nccl_comm = nccl_comm;
+  return 0;
+}
+
+void csb_multigrid_free(void *context)
+{
+  csb_multigrid_t *mg = static_cast<csb_multigrid_t *>(context);
+  if (mg != nullptr) mg_clear_hierarchy(mg);
+}
+
+void csb_multigrid_destroy(void **context)
+{
+  if (context == nullptr || *context == nullptr) return;
+  delete static_cast<csb_multigrid_t *>(*context);
+  *context = nullptr;
+}
+
+/* Hierarchy construction: cs_multigrid_setup -> _setup_hierarchy ->
+   cs_grid_coarsen (cs_multigrid.cpp:5275, :2407; cs_grid.cpp:7980) on the
+   reference's live path for a symmetric MSR matrix with mesh association
+   ("msr_gather", cs_grid.cpp:8019-8022). */
+void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
+                         int verbosity)
+{
+  (void)name;
+  csb_multigrid_t *mg = static_cast<csb_multigrid_t *>(context);
+  Context &c = ctx();
+  if (mg == nullptr || a == nullptr) { set_error("csb_multigrid_setup: null argument"); return; }
+  if (mg->setup_done) mg_clear_hierarchy(mg);
+
+  if (!a->symmetric || !a->has_mesh) {
+    set_error("csb_multigrid_setup: this path needs a symmetric MSR matrix with mesh "
+              "association (cs_matrix_set_mesh_association), as the reference's "
+              "pressure solve provides");
+    return;
+  }
+  if (mg->coarsening_type != 0 && mg->coarsening_type != 1) {
+    set_error("csb_multigrid_setup: only CS_GRID_COARSENING_DEFAULT / SPD_DX are available");
+    return;
+  }
+  for (int i = 0; i < 3; i++)
+    if (mg->solver_type[i] != CSB_SLES_PCG || mg->poly_degree[i] != 0) {
+      set_error("csb_multigrid_setup: smoothers / coarse solver must be PCG + Jacobi "
+                "(cs_multigrid_create defaults)");
+      return;
+    }
+  if (a->halo != nullptr) {
+    set_error("csb_multigrid_setup: distributed hierarchy not available yet");
+    return;
+  }
+
+  const double t_start = wall();
+  double t_aggr = 0, t_asm = 0, t_xfer = 0;
+
+  MgLevel *l0 = new MgLevel;
+  l0->m = a;
+  mg->levels.push_back(l0);
+  mg->a = a;
+
+  unsigned long long n_g_rows = (unsigned long long)a->n_rows, n_g_rows_prev;
+
+  while (true) {
+    n_g_rows_prev = n_g_rows;
+    if ((int)mg->levels.size() >= mg->n_levels_max) break;
+
+    MgLevel *f = mg->levels.back();
+    csb_matrix_t *fm = const_cast<csb_matrix_t *>(f->m);
+    const int f_level = (int)mg->levels.size() - 1;
+
+    double t0 = wall();
+    if (!matrix_host_mirror(fm)) return;
+    t_xfer += wall() - t0;
+
+    /* aggregation on the host */
+    t0 = wall();
+    f->h_coarse_row.resize(std::max(fm->n_rows, 1));
+    const int c_n_rows
+      = aggregate_dx_msr(f_level, fm->n_rows, fm->h_row_index.data(), fm->h_col_id.data(),
+                         fm->h_d_val.data(), fm->h_x_val.data(), mg->aggregation_limit,
+                         mg->n_blocks, f->h_coarse_row.data());
+    t_aggr += wall() - t0;
+
+    /* stop criteria of _setup_hierarchy (cs_multigrid.cpp:2518-2529); they
+       only depend on the row count, so the rejected level is never assembled */
+    n_g_rows = (unsigned long long)c_n_rows;
+    bool add = true;
+    if (n_g_rows == 0) add = false;
+    else if (mg->levels.size() > 1) {
+      if (n_g_rows < mg->n_g_rows_min || (double)n_g_rows > (0.8 * (double)n_g_rows_prev))
+        add = false;
+    }
+    if (!add) { f->h_coarse_row.clear(); break; }
+
+    t0 = wall();
+    CoarseStructure cs;
+    build_coarse_structure(fm->n_rows, fm->h_row_index.data(), fm->h_col_id.data(),
+                           f->h_coarse_row.data(), c_n_rows, cs);
+    t_aggr += wall() - t0;
+    const int c_nnz = cs.c_row_index[c_n_rows];
+
+    t0 = wall();
+    MgLevel *cl = new MgLevel;
+    csb_matrix_t *cm = new csb_matrix_t;
+    cl->owned = cm; cl->m = cm;
+    cm->n_rows = c_n_rows; cm->n_cols_ext = c_n_rows; cm->nnz = c_nnz;
+    cm->symmetric = true;
+    bool ok = f->coarse_row.upload(f->h_coarse_row.data(), (size_t)fm->n_rows)
+           && f->c_f_row_index.upload(cs.c_f_row_index.data(), (size_t)c_n_rows + 1)
+           && f->c_f_row_ids.upload(cs.c_f_row_ids.data(), (size_t)fm->n_rows)
+           && cm->row_index.upload(cs.c_row_index.data(), (size_t)c_n_rows + 1)
+           && cm->col_id.upload(cs.c_col_id.data(), (size_t)c_nnz)
+           && cl->cell_face.upload(cs.c_cell_face.data(), (size_t)c_nnz)
+           && cl->cell_face_sgn.upload(cs.c_cell_face_sgn.data(), (size_t)c_nnz)
+           && cm->d_val.alloc((size_t)c_n_rows) && cm->x_val.alloc((size_t)c_nnz)
+           && cl->cell_cen.alloc(3*(size_t)c_n_rows) && cl->cell_vol.alloc((size_t)c_n_rows)
+           && cl->face_normal.alloc(3*(size_t)cs.c_n_faces)
+           && cl->xa0.alloc((size_t)cs.c_n_faces) && cl->xa0ij.alloc(3*(size_t)cs.c_n_faces)
+           && CSB_CUDA(cudaStreamSynchronize(c.stream));  /* cs.* vectors die below */
+    if (!ok) { delete cl; return; }
+    cl->n_faces = cs.c_n_faces;
+    cm->h_row_index.swap(cs.c_row_index);
+    cm->h_col_id.swap(cs.c_col_id);
+    t_xfer += wall() - t0;
+
+    /* floating-point assembly on the device */
+    t0 = wall();
+    CoarseAssemblyArgs ca;
+    ca.f_level = f_level;
+    ca.f_n_rows = fm->n_rows; ca.c_n_rows = c_n_rows; ca.c_n_faces = cl->n_faces;
+    ca.f_row_index = fm->row_index.p; ca.f_col_id = fm->col_id.p;
+    ca.f_d_val = fm->d_val.p; ca.f_x_val = fm->x_val.p;
+    ca.f_c_row = f->coarse_row.p;
+    ca.c_f_row_index = f->c_f_row_index.p; ca.c_f_row_ids = f->c_f_row_ids.p;
+    ca.c_row_index = cm->row_index.p; ca.c_col_id = cm->col_id.p;
+    ca.c_cell_face = cl->cell_face.p; ca.c_cell_face_sgn = cl->cell_face_sgn.p;
+    if (f_level == 0) {
+      ca.f_cell_face = fm->c2f.p; ca.f_cell_face_sgn = fm->c2f_sgn.p;
+      ca.f_cell_cen = fm->cell_cen.p; ca.f_cell_vol = fm->cell_vol.p;
+      ca.f_face_u_normal = fm->face_u_normal.p; ca.f_face_surf = fm->face_surf.p;
+      ca.f_face_normal = nullptr; ca.f_xa0 = nullptr; ca.f_xa0ij = nullptr;
+    }
+    else {
+      ca.f_cell_face = f->cell_face.p; ca.f_cell_face_sgn = f->cell_face_sgn.p;
+      ca.f_cell_cen = f->cell_cen.p; ca.f_cell_vol = f->cell_vol.p;
+      ca.f_face_u_normal = nullptr; ca.f_face_surf = nullptr;
+      ca.f_face_normal = f->face_normal.p; ca.f_xa0 = f->xa0.p; ca.f_xa0ij = f->xa0ij.p;
+    }
+    ca.c_d_val = cm->d_val.p; ca.c_x_val = cm->x_val.p;
+    ca.c_cell_cen = cl->cell_cen.p; ca.c_cell_vol = cl->cell_vol.p;
+    ca.c_face_normal = cl->face_normal.p; ca.c_xa0 = cl->xa0.p; ca.c_xa0ij = cl->xa0ij.p;
+    ca.relax = mg->p0p1_relax;
+    if (!launch_coarse_assembly(ca)) { delete cl; return; }
+    if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) { delete cl; return; }
+    t_asm += wall() - t0;
+
+    matrix_plan_spmv(cm);
+    mg->levels.push_back(cl);
+
+    if (verbosity > 2)
+      printf("   building level %2d grid\n     number of rows:      %10d\n"
+             "     number of entries:   %10d\n",
+             (int)mg->levels.size() - 1, c_n_rows, c_nnz + c_n_rows);
+  }
+
+  /* solve-time data */
+  const int n_levels = (int)mg->levels.size();
+  size_t wr_size = 1, aux_size = 1;
+  for (int l = 0; l < n_levels; l++) {
+    MgLevel *lv = mg->levels[l];
+    const csb_matrix_t *m = lv->m;
+    wr_size = std::max(wr_size, (size_t)m->n_cols_ext);
+    aux_size = std::max(aux_size, 5*(size_t)m->n_cols_ext);
+    if (!lv->ad_inv.alloc((size_t)m->n_rows)) return;
+    if (!launch_ad_inv(m->n_rows, m->d_val.p, lv->ad_inv.p)) return;
+    if (l > 0) {
+      if (!lv->rhs.alloc((size_t)m->n_cols_ext) || !lv->vx.alloc((size_t)m->n_cols_ext)) return;
+    }
+  }
+  if (!mg->wr.alloc(wr_size) || !mg->aux.alloc(aux_size)) return;
+  if (!mg->it_states.alloc(2*(size_t)n_levels)) return;
+  if (!mg->mg_state.p && !mg->mg_state.alloc(1)) return;
+  if (mg->h_mg == nullptr)
+    if (!CSB_CUDA(cudaMallocHost((void **)&mg->h_mg, sizeof(MgState)))) return;
+  if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return;
+
+  mg->setup_done = true;
+  mg->n_setups += 1;
+  mg->t_setup[0] = wall() - t_start;
+  mg->t_setup[1] = t_aggr; mg->t_setup[2] = t_asm; mg->t_setup[3] = t_xfer;
+  mg->t_setup_tot += mg->t_setup[0];
+}
+
+/* cs_multigrid_solve (cs_multigrid.cpp:5362-5588) driving _multigrid_v_cycle
+   (:3127-3542). One host sync per cycle (to read the gate); everything else
+   is enqueued ahead. */
+csb_sles_convergence_state_t
+csb_multigrid_solve(void *context, const char *name, const csb_matrix_t *a, int verbosity,
+                    double precision, double r_norm, int *n_iter, double *residual,
+                    const csb_real_t *rhs, csb_real_t *vx_ini, csb_real_t *vx,
+                    size_t aux_size, void *aux_vectors)
+{
+  (void)aux_size; (void)aux_vectors;
+  csb_multigrid_t *mg = static_cast<csb_multigrid_t *>(context);
+  Context &c = ctx();
+  c.err.clear();
+  if (n_iter) *n_iter = 0;
+  if (residual) *residual = -1.;
+  if (mg == nullptr || a == nullptr || rhs == nullptr || vx == nullptr) {
+    set_error("csb_multigrid_solve: null argument");
+    return CSB_SLES_BREAKDOWN;
+  }
+  if (vx_ini != nullptr && vx_ini != vx) {
+    set_error("csb_multigrid_solve: vx_ini must be vx or NULL");
+    return CSB_SLES_BREAKDOWN;
+  }
+  if (!mg->setup_done || mg->a != a)
+    csb_multigrid_setup(mg, name, a, verbosity);
+  if (!mg->setup_done) return CSB_SLES_BREAKDOWN;
+
+  const double t0 = wall();
+  const int n_levels = (int)mg->levels.size();
+  const int coarsest = n_levels - 1;
+  const double denom = 1.0 / (double)a->n_rows;
+
+  StagedVec s_rhs, s_vx;
+  if (!s_rhs.init(const_cast<double *>(rhs), (size_t)a->n_rows, true)) return CSB_SLES_BREAKDOWN;
+  if (!s_vx.init(vx, (size_t)a->n_cols_ext, vx_ini == vx)) return CSB_SLES_BREAKDOWN;
+
+  MgState *ms = mg->mg_state.p;
+  if (!launch_mg_state_init(ms, precision, r_norm, mg->n_max_cycles)) return CSB_SLES_BREAKDOWN;
+
+  int cvg = CSB_SLES_ITERATING;
+  int n_cycles = 0;
+  for (n_cycles = 0; cvg == CSB_SLES_ITERATING; n_cycles++) {
+    const int cycle_id = n_cycles + 1;
+    bool ok = launch_mg_cycle_begin(ms, cycle_id);
+
+    /* descent */
+    for (int level = 0; ok && level < coarsest; level++) {
+      MgLevel *f = mg->levels[level], *cl = mg->levels[level+1];
+      const double *rhs_lv = (level == 0) ? s_rhs.d : f->rhs.p;
+      double *vx_lv = (level == 0) ? s_vx.d : f->vx.p;
+      const bool ini = (level == 0) ? ((n_cycles > 0) || (vx_ini == vx)) : false;
+      ItState *st = mg->it_states.p + 2*level;
+
+      ok = ok && pcg_enqueue(f->m, st, ms, f->ad_inv.p, precision*mg->precision_mult[0],
+                             r_norm, mg->n_max_iter[0], rhs_lv, vx_lv, ini, true,
+                             mg->aux.p, nullptr);
+      ok = ok && launch_mg_accum_iter(ms, st, level, (double)f->m->n_rows * denom,
+                                      level == 0 ? 1 : 0);
+      SpmvArgs sa;
+      sa.m = f->m; sa.x = vx_lv; sa.y = mg->wr.p; sa.b = rhs_lv; sa.mg = ms;
+      ok = ok && launch_spmv(level == 0 ? EPI_RESIDUAL_NORM : EPI_RESIDUAL, sa);
+      ok = ok && launch_restrict(cl->m->n_rows, f->c_f_row_index.p, f->c_f_row_ids.p,
+                                 mg->wr.p, cl->rhs.p, ms);
+    }
+
+    /* coarsest level solve */
+    if (ok) {
+      MgLevel *cl = mg->levels[coarsest];
+      const double *rhs_lv = (coarsest == 0) ? s_rhs.d : cl->rhs.p;
+      double *vx_lv = (coarsest == 0) ? s_vx.d : cl->vx.p;
+      ItState *st = mg->it_states.p + 2*coarsest;
+      ok = ok && pcg_enqueue(cl->m, st, ms, cl->ad_inv.p, precision*mg->precision_mult[2],
+                             r_norm, mg->n_max_iter[2], rhs_lv, vx_lv, false, true,
+                             mg->aux.p, nullptr);
+      ok = ok && launch_mg_accum_iter(ms, st, coarsest, (double)cl->m->n_rows * denom, 0);
+    }
+
+    /* ascent */
+    for (int level = coarsest - 1; ok && level > -1; level--) {
+      MgLevel *f = mg->levels[level], *cl = mg->levels[level+1];
+      double *vx_lv = (level == 0) ? s_vx.d : f->vx.p;
+      ok = ok && launch_prolong_inc(f->m->n_rows, f->coarse_row.p, cl->vx.p, vx_lv, ms);
+      if (level > 0) {
+        ItState *st = mg->it_states.p + 2*level + 1;
+        ok = ok && pcg_enqueue(f->m, st, ms, f->ad_inv.p, precision*mg->precision_mult[1],
+                               r_norm, mg->n_max_iter[1], f->rhs.p, vx_lv, true, true,
+                               mg->aux.p, nullptr);
+        ok = ok && launch_mg_accum_iter(ms, st, level, (double)f->m->n_rows * denom, 0);
+      }
+    }
+    if (!ok) return CSB_SLES_BREAKDOWN;
+
+    if (!CSB_CUDA(cudaMemcpyAsync(mg->h_mg, ms, MG_HEAD, cudaMemcpyDeviceToHost, c.stream)))
+      return CSB_SLES_BREAKDOWN;
+    if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return CSB_SLES_BREAKDOWN;
+    cvg = mg->h_mg->cvg;
+    if (verbosity > 2)
+      printf("     %4d  |               %6d  |  %12.4e\n", cycle_id, mg->h_mg->n_equiv_iter,
+             mg->h_mg->residual / r_norm);
+  }
+
+  if (!CSB_CUDA(cudaMemcpyAsync(mg->h_mg, ms, sizeof(MgState), cudaMemcpyDeviceToHost,
+                                c.stream))) return CSB_SLES_BREAKDOWN;
+  if (!s_vx.copy_back((size_t)a->n_rows)) return CSB_SLES_BREAKDOWN;
+  if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return CSB_SLES_BREAKDOWN;
+
+  if (n_iter) *n_iter = mg->h_mg->n_equiv_iter;
+  if (residual) *residual = mg->h_mg->residual;
+  mg->n_cycles_last = n_cycles;
+  mg->n_cycles_tot += n_cycles;
+  mg->n_solves += 1;
+  mg->t_solve_tot += wall() - t0;
+  return (csb_sles_convergence_state_t)cvg;
+}
+
+/* host-only helpers (no device needed): the aggregation and coarse structure
+   used by csb_multigrid_setup, exposed for CPU-side parity tests */
+int csb_host_aggregate_dx_msr(int level, csb_lnum_t n_rows, const csb_lnum_t *row_index,
+                              const csb_lnum_t *col_id, const csb_real_t *d_val,
+                              const csb_real_t *x_val, int max_aggregation, int n_blocks,
+                              csb_lnum_t *f_c_row)
+{
+  return aggregate_dx_msr(level, n_rows, row_index, col_id, d_val, x_val, max_aggregation,
+                          n_blocks, f_c_row);
+}
+
+int csb_host_coarse_structure(csb_lnum_t f_n_rows, const csb_lnum_t *f_row_index,
+                              const csb_lnum_t *f_col_id, const csb_lnum_t *f_c_row,
+                              csb_lnum_t c_n_rows, csb_lnum_t *c_row_index,
+                              csb_lnum_t *c_col_id, csb_lnum_t *c_cell_face,
+                              short *c_cell_face_sgn, csb_lnum_t *c_n_faces)
+{
+  CoarseStructure cs;
+  build_coarse_structure(f_n_rows, f_row_index, f_col_id, f_c_row, c_n_rows, cs);
+  const int c_nnz = cs.c_row_index[c_n_rows];
+  if (c_row_index) memcpy(c_row_index, cs.c_row_index.data(), sizeof(int)*((size_t)c_n_rows+1));
+  if (c_col_id) memcpy(c_col_id, cs.c_col_id.data(), sizeof(int)*(size_t)c_nnz);
+  if (c_cell_face) memcpy(c_cell_face, cs.c_cell_face.data(), sizeof(int)*(size_t)c_nnz);
+  if (c_cell_face_sgn) memcpy(c_cell_face_sgn, cs.c_cell_face_sgn.data(), sizeof(short)*(size_t)c_nnz);
+  if (c_n_faces) *c_n_faces = cs.c_n_faces;
+  return c_nnz;
+}
+
+int csb_multigrid_get_n_levels(const csb_multigrid_t *mg)
+{ return (mg != nullptr) ? (int)mg->levels.size() : 0; }
+
+int csb_multigrid_get_n_cycles(const csb_multigrid_t *mg)
+{ return (mg != nullptr) ? mg->n_cycles_last : 0; }
+
+int csb_multigrid_get_level_info(const csb_multigrid_t *mg, int level, csb_lnum_t info[3])
+{
+  if (mg == nullptr || level < 0 || level >= (int)mg->levels.size()) return -1;
+  const csb_matrix_t *m = mg->levels[level]->m;
+  info[0] = m->n_rows; info[1] = m->n_cols_ext; info[2] = m->nnz;
+  return 0;
+}
+
+int csb_multigrid_get_level_arrays(const csb_multigrid_t *mg, int level,
+                                   csb_lnum_t *coarse_row, csb_lnum_t *row_index,
+                                   csb_lnum_t *col_id, csb_real_t *d_val, csb_real_t *x_val)
+{
+  if (mg == nullptr || level < 0 || level >= (int)mg->levels.size()) return -1;
+  const csb_matrix_t *m = mg->levels[level]->m;
+  if (coarse_row != nullptr && level > 0) {
+    const MgLevel *p = mg->levels[level-1];
+    memcpy(coarse_row, p->h_coarse_row.data(), sizeof(int)*(size_t)p->m->n_rows);
+  }
+  bool ok = true;
+  if (row_index) ok = ok && m->row_index.download(row_index);
+  if (col_id) ok = ok && m->col_id.download(col_id);
+  if (d_val) ok = ok && m->d_val.download(d_val);
+  if (x_val) ok = ok && m->x_val.download(x_val);
+  return ok ? 0 : -1;
+}
+
+int csb_multigrid_get_cycle_residuals(const csb_multigrid_t *mg, double *res, int max_n)
+{
+  if (mg == nullptr || mg->h_mg == nullptr) return 0;
+  int n = mg->h_mg->n_cycles_res;
+  if (n > max_n) n = max_n;
+  for (int i = 0; i < n; i++) res[i] = mg->h_mg->cycle_res[i];
+  return n;
+}
+
+int csb_multigrid_get_setup_times(const csb_multigrid_t *mg, double t[4])
+{
+  if (mg == nullptr) return -1;
+  for (int i = 0; i < 4; i++) t[i] = mg->t_setup[i];
+  return 0;
+}
+
+void csb_multigrid_log(const void *context, int log_type)
+{
+  (void)log_type;
+  const csb_multigrid_t *mg = static_cast<const csb_multigrid_t *>(context);
+  if (mg == nullptr) return;
+  printf("  Solver type:                       Multigrid V-cycle (B200 device)\n"
+         "  Number of setups:                  %12u\n"
+         "  Number of calls:                   %12u\n"
+         "  Number of levels (last):           %12d\n"
+         "  Total number of cycles:            %12llu\n"
+         "  Total setup time:                  %12.3f\n"
+         "  Total solution time:               %12.3f\n",
+         mg->n_setups, mg->n_solves, (int)mg->levels.size(), mg->n_cycles_tot,
+         mg->t_setup_tot, mg->t_solve_tot);
+}
+
+void *csb_multigrid_copy(const void *context)
+{
+  const csb_multigrid_t *s = static_cast<const csb_multigrid_t *>(context);
+  if (s == nullptr) return nullptr;
+  csb_multigrid_t *d = csb_multigrid_create(s->type);
+  if (d == nullptr) return nullptr;
+  d->aggregation_limit = s->aggregation_limit;
+  d->coarsening_type = s->coarsening_type;
+  d->n_levels_max = s->n_levels_max;
+  d->n_g_rows_min = s->n_g_rows_min;
+  d->p0p1_relax = s->p0p1_relax;
+  d->n_blocks = s->n_blocks;
+  d->n_max_cycles = s->n_max_cycles;
+  for (int i = 0; i < 3; i++) {
+    d->solver_type[i] = s->solver_type[i];
+    d->n_max_iter[i] = s->n_max_iter[i];
+    d->poly_degree[i] = s->poly_degree[i];
+    d->precision_mult[i] = s->precision_mult[i];
+  }
+  d->nccl_comm = s->nccl_comm;
+  return d;
+}
+
+} /* extern "C" */

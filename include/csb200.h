@@ -1,0 +1,348 @@
+/*============================================================================
+ * csb200.h -- C-ABI of the B200-native linear-solve path for code_saturne.
+ *
+ * Drop-in boundary for the reference's src/alge hot path (SpMV -> Krylov ->
+ * multigrid V-cycle -> halo exchange).  Every entry point below replaces the
+ * reference interface cited next to it; argument meaning, return values and
+ * error behaviour follow that interface.  Plain pointers and sizes only.
+ *
+ * Conventions (src/base/cs_defs.h:317-335): cs_lnum_t = int32, cs_real_t =
+ * double.  Pointers named *_h must be host pointers; rhs/vx/x/y arguments may
+ * be host OR device pointers (detected with cudaPointerGetAttributes, like
+ * cs_check_device_ptr in src/alge/cs_sles_it.cpp:5300-5332): host arrays are
+ * staged to the device and copied back inside the call.
+ *
+ * Error convention: functions returning int give 0 on success, < 0 on error
+ * (csb_last_error() returns the message); solve functions return the
+ * reference's cs_sles_convergence_state_t values.  There is NO CPU fallback:
+ * without a usable CUDA device csb_init() fails and nothing else works.
+ *============================================================================*/
+
+#ifndef CSB200_H
+#define CSB200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int    csb_lnum_t;   /* cs_lnum_t */
+typedef double csb_real_t;   /* cs_real_t */
+
+/* cs_sles_convergence_state_t, src/alge/cs_sles.h:57-68 */
+typedef enum {
+  CSB_SLES_DIVERGED      = -3,
+  CSB_SLES_BREAKDOWN     = -2,
+  CSB_SLES_MAX_ITERATION = -1,
+  CSB_SLES_ITERATING     =  0,
+  CSB_SLES_CONVERGED     =  1
+} csb_sles_convergence_state_t;
+
+/* cs_sles_it_type_t, src/alge/cs_sles_it.h:55-77 (same numeric values) */
+typedef enum {
+  CSB_SLES_PCG      = 0,
+  CSB_SLES_JACOBI   = 3,
+  CSB_SLES_BICGSTAB = 4
+} csb_sles_it_type_t;
+
+/* cs_multigrid_type_t, src/alge/cs_multigrid.h:58-65 */
+typedef enum {
+  CSB_MULTIGRID_V_CYCLE = 0
+} csb_multigrid_type_t;
+
+typedef struct _csb_matrix_t     csb_matrix_t;      /* cs_matrix_t (MSR) */
+typedef struct _csb_halo_t       csb_halo_t;        /* cs_halo_t */
+typedef struct _csb_sles_it_t    csb_sles_it_t;     /* cs_sles_it_t */
+typedef struct _csb_multigrid_t  csb_multigrid_t;   /* cs_multigrid_t */
+
+/*----------------------------------------------------------------------------
+ * Runtime (replaces cs_base_cuda_select_default_device / stream table,
+ * src/base/cs_base_cuda.cu:732-815)
+ *----------------------------------------------------------------------------*/
+
+/* Select CUDA device (>= 0) and create the library stream. < 0 on failure. */
+int          csb_init(int device_id);
+void         csb_finalize(void);
+const char  *csb_last_error(void);
+const char  *csb_version(void);
+
+/* Use an externally owned cudaStream_t (passed as void *) for all work;
+   NULL restores the library's own stream
+   (cs_matrix_spmv_cuda_set_stream, src/alge/cs_matrix_spmv_cuda.cu). */
+int          csb_set_stream(void *cuda_stream);
+int          csb_stream_synchronize(void);
+
+/* Device memory helpers (CS_MALLOC_HD / cs_copy_h2d / cs_copy_d2h,
+   src/base/cs_mem.h:48-55) */
+void        *csb_malloc_device(size_t n_bytes);
+void         csb_free_device(void *p);
+int          csb_copy_h2d(void *dst_d, const void *src_h, size_t n_bytes);
+int          csb_copy_d2h(void *dst_h, const void *src_d, size_t n_bytes);
+void        *csb_malloc_pinned(size_t n_bytes);
+void         csb_free_pinned(void *p);
+
+/* Number of kernel launches issued by this library since the last reset
+   (bench.py "gpu_launches"). */
+long long    csb_launch_count(int reset);
+
+/*----------------------------------------------------------------------------
+ * Matrix (cs_matrix_t, MSR)
+ *----------------------------------------------------------------------------*/
+
+/* cs_matrix_structure_create_msr_shared + cs_matrix_create +
+   cs_matrix_transfer_coefficients_msr  (src/alge/cs_matrix.cpp:4518, :4682,
+   :5451).  Arrays may be host or device pointers; they are copied to HBM.
+   n_cols_ext = n_rows + number of ghost columns (halo). */
+csb_matrix_t *csb_matrix_create_msr(csb_lnum_t         n_rows,
+                                    csb_lnum_t         n_cols_ext,
+                                    const csb_lnum_t  *row_index,
+                                    const csb_lnum_t  *col_id,
+                                    const csb_real_t  *d_val,
+                                    const csb_real_t  *x_val,
+                                    int                symmetric);
+
+/* Replace coefficient values only (cs_matrix_set_coefficients on an existing
+   structure, src/alge/cs_matrix.cpp:5315). */
+int  csb_matrix_set_coefficients(csb_matrix_t      *m,
+                                 int                symmetric,
+                                 const csb_real_t  *d_val,
+                                 const csb_real_t  *x_val);
+
+/* cs_matrix_set_mesh_association (src/alge/cs_matrix.cpp:6328): cell -> face
+   adjacency aligned with the MSR entries (c2f_idx == row_index), geometry
+   used by the P0/P1-relaxed coarse matrices.  Host or device pointers. */
+int  csb_matrix_set_mesh_association(csb_matrix_t      *m,
+                                     csb_lnum_t         n_faces,
+                                     const csb_lnum_t  *c2f,
+                                     const short       *c2f_sgn,
+                                     const csb_real_t  *cell_cen,      /* [n_cols_ext][3] */
+                                     const csb_real_t  *cell_vol,      /* [n_cols_ext] */
+                                     const csb_real_t  *face_u_normal, /* [n_faces][3] */
+                                     const csb_real_t  *face_surf);    /* [n_faces] */
+
+/* Attach a halo (cs_matrix_structure_create_msr_shared "halo" argument). */
+int  csb_matrix_set_halo(csb_matrix_t *m, csb_halo_t *halo);
+
+void csb_matrix_destroy(csb_matrix_t **m);
+
+csb_lnum_t csb_matrix_get_n_rows(const csb_matrix_t *m);     /* cs_matrix.cpp:4976 */
+csb_lnum_t csb_matrix_get_n_columns(const csb_matrix_t *m);  /* cs_matrix.cpp:4957 */
+csb_lnum_t csb_matrix_get_n_entries(const csb_matrix_t *m);  /* cs_matrix.cpp:4998 */
+
+/* y = A.x  -- cs_matrix_vector_multiply (src/alge/cs_matrix.cpp:6405);
+   x has n_cols_ext entries (ghosts are updated through the halo first),
+   y has n_rows.  Host or device pointers. */
+int  csb_matrix_vector_multiply(const csb_matrix_t *m, csb_real_t *x, csb_real_t *y);
+
+/* y = (A - D).x -- cs_matrix_vector_multiply_partial(CS_MATRIX_SPMV_E)
+   (src/alge/cs_matrix.cpp:6593) */
+int  csb_matrix_vector_multiply_exdiag(const csb_matrix_t *m, csb_real_t *x, csb_real_t *y);
+
+/* Algorithmic HBM bytes of one SpMV launch: 12*nnz + 4*(n+1) + 8n + 8n_cols + 8n
+   (SURVEY.md section 8(d)). */
+double csb_matrix_spmv_bytes(const csb_matrix_t *m);
+
+/*----------------------------------------------------------------------------
+ * BLAS-1 reductions (cs_dot, cs_dot_xx, cs_dot_xx_xy_yz;
+ * src/alge/cs_blas.cpp:1629-1905); device-resident 2-stage deterministic sums.
+ *----------------------------------------------------------------------------*/
+
+double csb_dot(csb_lnum_t n, const csb_real_t *x, const csb_real_t *y);
+double csb_dot_xx(csb_lnum_t n, const csb_real_t *x);
+int    csb_dot_xx_xy_yz(csb_lnum_t n, const csb_real_t *x, const csb_real_t *y,
+                        const csb_real_t *z, double *xx, double *xy, double *yz);
+
+/*----------------------------------------------------------------------------
+ * Halo (cs_halo_t, src/base/cs_halo.h:74-171): ghost cells exchanged with
+ * neighbour ranks.  One process per GPU; exchange = grouped ncclSend/ncclRecv
+ * (src/base/cs_halo.cpp:518-587) on the library's communication stream.
+ *----------------------------------------------------------------------------*/
+
+/* Communicator bootstrap (ncclGetUniqueId on rank 0, broadcast of the 128-byte
+   id by the caller, ncclCommInitRank on every rank;
+   src/base/cs_base_cuda.cu:201-262). NCCL is resolved with dlopen. */
+int         csb_comm_get_unique_id(void *id_128_bytes);
+void       *csb_comm_init_rank(const void *id_128_bytes, int n_ranks, int rank);
+void        csb_comm_destroy(void *nccl_comm);
+
+/* nccl_comm: an ncclComm_t (as void *) spanning all ranks, or NULL for a
+   single-rank (periodic/self) halo.
+   c_domain_rank[n_c_domains]; send_index[n_c_domains+1] into send_list;
+   index[n_c_domains+1] = ghost sections (offsets from n_local_elts). */
+csb_halo_t *csb_halo_create(void              *nccl_comm,
+                            int                local_rank,
+                            int                n_c_domains,
+                            const int         *c_domain_rank,
+                            csb_lnum_t         n_local_elts,
+                            const csb_lnum_t  *send_index,
+                            const csb_lnum_t  *send_list,
+                            const csb_lnum_t  *index);
+void        csb_halo_destroy(csb_halo_t **halo);
+
+/* cs_halo_sync_var (pack + start + wait, src/base/cs_halo.cpp:1739,:1957,:2130)
+   on a device array of n_local_elts + n_ghost doubles. */
+int         csb_halo_sync_var(const csb_halo_t *halo, csb_real_t *var_d);
+
+/*----------------------------------------------------------------------------
+ * Iterative solvers (cs_sles_it_t)
+ *----------------------------------------------------------------------------*/
+
+/* cs_sles_it_create (src/alge/cs_sles_it.cpp:4659): poly_degree 0 = Jacobi
+   preconditioner (the only one on this path), < 0 = none. */
+csb_sles_it_t *csb_sles_it_create(csb_sles_it_type_t  solver_type,
+                                  int                 poly_degree,
+                                  int                 n_max_iter,
+                                  int                 update_stats);
+
+/* Global-sum communicator for dot products (cs_sles_it_set_mpi_reduce_comm,
+   src/alge/cs_sles_it.cpp:5669): ncclComm_t as void *, NULL = single rank. */
+int  csb_sles_it_set_reduce_comm(csb_sles_it_t *c, void *nccl_comm);
+
+/* cs_sles_setup_t (src/alge/cs_sles.h:91-101) -> cs_sles_it_setup (:4964) */
+void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a,
+                       int verbosity);
+
+/* cs_sles_solve_t (src/alge/cs_sles.h:121-142) -> cs_sles_it_solve (:5194).
+   vx_ini == vx: nonzero initial guess in vx; vx_ini == NULL: start from 0. */
+csb_sles_convergence_state_t
+csb_sles_it_solve(void                *context,
+                  const char          *name,
+                  const csb_matrix_t  *a,
+                  int                  verbosity,
+                  double               precision,
+                  double               r_norm,
+                  int                 *n_iter,
+                  double              *residual,
+                  const csb_real_t    *rhs,
+                  csb_real_t          *vx_ini,
+                  csb_real_t          *vx,
+                  size_t               aux_size,
+                  void                *aux_vectors);
+
+void csb_sles_it_free(void *context);                 /* cs_sles_it_free :5436 */
+void csb_sles_it_destroy(void **context);             /* cs_sles_it_destroy :4764 */
+double csb_sles_it_get_last_initial_residual(const csb_sles_it_t *c);  /* :5505 */
+
+/* Residual norm after each convergence test of the last solve (the data the
+   reference plots through cs_time_plot, src/alge/cs_sles_it.cpp:264-274).
+   Returns the number of values written (<= max_n). */
+int  csb_sles_it_get_residual_history(const csb_sles_it_t *c, double *hist, int max_n);
+
+/*----------------------------------------------------------------------------
+ * Multigrid (cs_multigrid_t)
+ *----------------------------------------------------------------------------*/
+
+/* cs_multigrid_create (src/alge/cs_multigrid.cpp:4644) with the V-cycle
+   defaults of :4693-4764. */
+csb_multigrid_t *csb_multigrid_create(csb_multigrid_type_t mg_type);
+
+/* cs_multigrid_set_solver_options (src/alge/cs_multigrid.cpp:5032) */
+void csb_multigrid_set_solver_options(csb_multigrid_t    *mg,
+                                      csb_sles_it_type_t  descent_smoother_type,
+                                      csb_sles_it_type_t  ascent_smoother_type,
+                                      csb_sles_it_type_t  coarse_solver_type,
+                                      int                 n_max_cycles,
+                                      int                 n_max_iter_descent,
+                                      int                 n_max_iter_ascent,
+                                      int                 n_max_iter_coarse,
+                                      int                 poly_degree_descent,
+                                      int                 poly_degree_ascent,
+                                      int                 poly_degree_coarse,
+                                      double              precision_mult_descent,
+                                      double              precision_mult_ascent,
+                                      double              precision_mult_coarse);
+
+/* cs_multigrid_set_coarsening_options (src/alge/cs_multigrid.cpp:4945);
+   coarsening_type 0 (default) / 1 = CS_GRID_COARSENING_SPD_DX. */
+void csb_multigrid_set_coarsening_options(csb_multigrid_t  *mg,
+                                          int               aggregation_limit,
+                                          int               coarsening_type,
+                                          int               n_max_levels,
+                                          unsigned long long min_g_rows,
+                                          double            p0p1_relax,
+                                          int               postprocess_block_size);
+
+/* Number of row blocks the greedy aggregation is confined to; restates the
+   reference's per-OpenMP-thread blocks (src/alge/cs_grid.cpp:4374-4393).
+   1 (default) == reference with OMP_NUM_THREADS=1. */
+void csb_multigrid_set_aggregation_blocks(csb_multigrid_t *mg, int n_blocks);
+
+int  csb_multigrid_set_reduce_comm(csb_multigrid_t *mg, void *nccl_comm);
+
+void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
+                         int verbosity);               /* cs_multigrid_setup :5275 */
+
+csb_sles_convergence_state_t
+csb_multigrid_solve(void                *context,      /* cs_multigrid_solve :5362 */
+                    const char          *name,
+                    const csb_matrix_t  *a,
+                    int                  verbosity,
+                    double               precision,
+                    double               r_norm,
+                    int                 *n_iter,
+                    double              *residual,
+                    const csb_real_t    *rhs,
+                    csb_real_t          *vx_ini,
+                    csb_real_t          *vx,
+                    size_t               aux_size,
+                    void                *aux_vectors);
+
+void csb_multigrid_free(void *context);                /* cs_multigrid_free :5604 */
+void csb_multigrid_destroy(void **context);            /* cs_multigrid_destroy :4793 */
+
+/* Hierarchy inspection (what cs_grid_get_info / cs_grid_dump expose,
+   src/alge/cs_grid.cpp:7740, :8839): used by the parity tests. */
+int  csb_multigrid_get_n_levels(const csb_multigrid_t *mg);
+int  csb_multigrid_get_n_cycles(const csb_multigrid_t *mg);
+/* info[0] = n_rows, info[1] = n_cols_ext, info[2] = n_entries (off-diagonal) */
+int  csb_multigrid_get_level_info(const csb_multigrid_t *mg, int level, csb_lnum_t info[3]);
+/* Copy level data to host arrays (any pointer may be NULL).  coarse_row has
+   the parent level's n_rows entries and maps parent rows -> rows of `level`. */
+int  csb_multigrid_get_level_arrays(const csb_multigrid_t *mg, int level,
+                                    csb_lnum_t *coarse_row, csb_lnum_t *row_index,
+                                    csb_lnum_t *col_id, csb_real_t *d_val,
+                                    csb_real_t *x_val);
+/* Fine-level residual norm at the start of each cycle of the last solve. */
+int  csb_multigrid_get_cycle_residuals(const csb_multigrid_t *mg, double *res, int max_n);
+/* Seconds spent in the last setup, split: [0] total, [1] aggregation (host),
+   [2] coarse matrix assembly, [3] transfers. */
+int  csb_multigrid_get_setup_times(const csb_multigrid_t *mg, double t[4]);
+
+/* Host-only pieces of the hierarchy construction (no device needed), exposed
+   so that CPU-side tests can check them: the DX aggregation map
+   (_automatic_aggregation_dx_msr, src/alge/cs_grid.cpp:4282) and the coarse MSR
+   structure + coarse face numbering (_coarse_msr_struct :3020,
+   _msr_face_adjacency :3751).  csb_host_coarse_structure returns the number of
+   coarse off-diagonal entries; output arrays must hold at least the fine nnz. */
+int  csb_host_aggregate_dx_msr(int level, csb_lnum_t n_rows, const csb_lnum_t *row_index,
+                               const csb_lnum_t *col_id, const csb_real_t *d_val,
+                               const csb_real_t *x_val, int max_aggregation, int n_blocks,
+                               csb_lnum_t *f_c_row);
+int  csb_host_coarse_structure(csb_lnum_t f_n_rows, const csb_lnum_t *f_row_index,
+                               const csb_lnum_t *f_col_id, const csb_lnum_t *f_c_row,
+                               csb_lnum_t c_n_rows, csb_lnum_t *c_row_index,
+                               csb_lnum_t *c_col_id, csb_lnum_t *c_cell_face,
+                               short *c_cell_face_sgn, csb_lnum_t *c_n_faces);
+
+/*----------------------------------------------------------------------------
+ * cs_sles_t registry boundary (src/alge/cs_sles.cpp:1385-1425): these are the
+ * six callbacks a maintainer passes to cs_sles_define(); see INTEGRATION.md.
+ *   setup  : csb_multigrid_setup   / csb_sles_it_setup
+ *   solve  : csb_multigrid_solve   / csb_sles_it_solve
+ *   free   : csb_multigrid_free    / csb_sles_it_free
+ *   log    : csb_multigrid_log     / csb_sles_it_log
+ *   copy   : csb_multigrid_copy    / csb_sles_it_copy
+ *   destroy: csb_multigrid_destroy / csb_sles_it_destroy
+ *----------------------------------------------------------------------------*/
+
+void  csb_sles_it_log(const void *context, int log_type);
+void *csb_sles_it_copy(const void *context);
+void  csb_multigrid_log(const void *context, int log_type);
+void *csb_multigrid_copy(const void *context);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CSB200_H */

@@ -1,0 +1,339 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI (ctypes), against
+the oracle on the same seeded inputs, against the committed golden fixtures
+(outputs of the reference's own CPU code) and, at large sizes, through
+size-independent properties.
+
+Tolerances (BASELINE.json north_star):
+  * index / integer data (aggregation maps, coarse structures)   bit-exact
+  * per-row arithmetic (SpMV, coarse matrix values)               bit-exact
+    (same IEEE op sequence as the reference, kernels built with -fmad=false)
+  * reductions (dots, norms): reduction-order rounding            rel 1e-13
+  * converged solutions                                           rel L2 <= 1e-10
+  * iteration counts                                              +-2
+"""
+import numpy as np
+import pytest
+
+from code_saturne_b200.mesh_cartesian import cube_poisson, matrix_check_coefficients
+from conftest import golden_cases, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+RED_TOL = 1e-13      # reduction-order rounding
+SOL_TOL = 1e-10      # converged solution, relative L2
+
+
+# ---------------------------------------------------------------- SpMV / dots
+
+@pytest.mark.parametrize("N,bc,path", golden_cases())
+def test_spmv_and_dots_match_golden(csb, N, bc, path):
+    g = np.load(path)
+    s = cube_poisson(N, bc)
+    d, xv, x = matrix_check_coefficients(s)
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, d, xv)
+    y = m.vector_multiply(x)
+    ye = m.vector_multiply(x, exclude_diag=True)
+    assert np.array_equal(y, g["spmv_y"])             # bit-exact
+    assert np.array_equal(ye, g["spmv_y_exdiag"])
+    assert abs(csb.dot_xx(x) - float(g["dot_xx"])) <= RED_TOL * abs(float(g["dot_xx"]))
+    assert abs(csb.dot(x, y) - float(g["dot_xy"])) <= RED_TOL * np.linalg.norm(x) * np.linalg.norm(y)
+    r = np.array(csb.dot_xx_xy_yz(x, y, ye))
+    scale = np.array([np.dot(x, x), np.linalg.norm(x) * np.linalg.norm(y),
+                      np.linalg.norm(y) * np.linalg.norm(ye)])
+    assert np.all(np.abs(r - g["dot_xx_xy_yz"]) <= RED_TOL * scale)
+    m.destroy()
+
+
+@pytest.mark.parametrize("N", [2, 3, 7, 33, 64, 100])
+def test_spmv_bit_exact_vs_oracle(csb, oracle, N):
+    """Ragged sizes: rows per CTA not a multiple of 256, last slab partial."""
+    s = cube_poisson(N, with_mesh=False)
+    for sym in (True, False):
+        d, xv, x = matrix_check_coefficients(s, symmetric=sym)
+        m = csb.Matrix(s.n_rows, s.row_index, s.col_id, d, xv, symmetric=sym)
+        assert np.array_equal(m.vector_multiply(x),
+                              oracle.spmv(s.row_index, s.col_id, d, xv, x))
+        assert np.array_equal(m.vector_multiply(x, exclude_diag=True),
+                              oracle.spmv(s.row_index, s.col_id, d, xv, x, True))
+        m.destroy()
+
+
+def test_spmv_irregular_rows_and_empty_rows(csb, oracle):
+    """Random sparsity with empty rows and a few long rows (scalar fallback not
+    needed, but the slab size is non-uniform)."""
+    rng = np.random.default_rng(1234)
+    n = 5000
+    counts = rng.integers(0, 12, size=n)
+    counts[rng.integers(0, n, size=200)] = 0
+    counts[[17, 2500, 4999]] = [300, 511, 64]
+    ri = np.zeros(n + 1, dtype=np.int32)
+    np.cumsum(counts, out=ri[1:])
+    ci = np.concatenate([np.sort(rng.choice(n, size=c, replace=False)) for c in counts]).astype(np.int32)
+    xv = rng.standard_normal(ri[-1])
+    d = rng.standard_normal(n)
+    x = rng.standard_normal(n)
+    m = csb.Matrix(n, ri, ci, d, xv, symmetric=False)
+    assert np.array_equal(m.vector_multiply(x), oracle.spmv(ri, ci, d, xv, x))
+    m.destroy()
+
+
+def test_spmv_diagonal_only_and_single_row(csb, oracle):
+    for n in (1, 257):
+        ri = np.zeros(n + 1, dtype=np.int32)
+        d = np.arange(1, n + 1, dtype=np.float64)
+        x = np.ones(n)
+        m = csb.Matrix(n, ri, np.zeros(0, dtype=np.int32), d, np.zeros(0))
+        assert np.array_equal(m.vector_multiply(x), d)
+        m.destroy()
+
+
+def test_spmv_linearity_large(csb):
+    """128^3 (config 2 size): A(ax+by) = aAx + bAy to rounding; A.1 = row sums."""
+    s = cube_poisson(128, with_mesh=False)
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+    rng = np.random.default_rng(7)
+    x, y = rng.standard_normal(s.n_rows), rng.standard_normal(s.n_rows)
+    lhs = m.vector_multiply(2.0 * x - 3.0 * y)
+    rhs = 2.0 * m.vector_multiply(x) - 3.0 * m.vector_multiply(y)
+    assert rel_l2(lhs, rhs) < 1e-14
+    ones = m.vector_multiply(np.ones(s.n_rows))
+    rowsum = s.d_val + np.add.reduceat(s.x_val, s.row_index[:-1])
+    assert np.allclose(ones, rowsum, rtol=0, atol=1e-15)
+    m.destroy()
+
+
+@pytest.mark.parametrize("n", [1, 5, 255, 256, 257, 100003, 3000000])
+def test_dots_vs_oracle(csb, oracle, n):
+    rng = np.random.default_rng(n)
+    x, y, z = (rng.standard_normal(n) for _ in range(3))
+    assert abs(csb.dot(x, y) - oracle.dot(x, y)) <= RED_TOL * np.linalg.norm(x) * np.linalg.norm(y)
+    assert abs(csb.dot_xx(x) - oracle.dot_xx(x)) <= RED_TOL * np.dot(x, x)
+    a, b = np.array(csb.dot_xx_xy_yz(x, y, z)), np.array(oracle.dot_xx_xy_yz(x, y, z))
+    scale = np.array([np.dot(x, x), np.linalg.norm(x) * np.linalg.norm(y),
+                      np.linalg.norm(y) * np.linalg.norm(z)])
+    assert np.all(np.abs(a - b) <= RED_TOL * scale)
+    # run-to-run determinism (fixed-shape reduction tree)
+    assert csb.dot(x, y) == csb.dot(x, y)
+
+
+# ---------------------------------------------------------------- cs_sles_it
+
+SOLVERS = [("pcg", "PCG", 1000), ("jacobi", "JACOBI", 40), ("bicgstab", "BICGSTAB", 1000)]
+
+
+@pytest.mark.parametrize("N,bc,path", golden_cases())
+@pytest.mark.parametrize("name,tname,nmax", SOLVERS)
+def test_sles_it_matches_golden(csb, N, bc, path, name, tname, nmax):
+    g = np.load(path)
+    s = cube_poisson(N, bc)
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+    c = csb.SlesIt(csb.SlesItType[tname], nmax)
+    r = c.solve(m, s.rhs, 1e-8, float(g["r_norm"]))
+    assert int(r["cvg"]) == int(g[f"{name}_cvg"])
+    assert abs(r["n_iter"] - int(g[f"{name}_n_iter"])) <= 2
+    assert rel_l2(r["vx"][:s.n_rows], g[f"{name}_vx"]) <= (SOL_TOL if name != "jacobi" else 1e-12)
+    # residual history within reduction-order rounding (early part: before
+    # rounding differences are amplified by the Krylov recurrence)
+    hist_ref = g[f"{name}_history"]
+    h = r["history"]
+    if name == "jacobi":
+        k = min(len(h), len(hist_ref))
+        assert np.allclose(h[:k], hist_ref[:k], rtol=1e-11, atol=0)
+    else:
+        # golden[k-1] = residual at the test made with n_iter = k; device history
+        # has one extra leading entry (the n_iter = 0 test)
+        k = min(len(h) - 1, len(hist_ref), 8)
+        assert np.allclose(h[1:1 + k], hist_ref[:k], rtol=1e-9, atol=0)
+    assert abs(r["initial_residual"] - float(g[f"{name}_initial_residual"])) \
+        <= 1e-12 * abs(float(g[f"{name}_initial_residual"]))
+    c.destroy()
+    m.destroy()
+
+
+@pytest.mark.parametrize("N,bc", [(24, "neumann"), (40, "dirichlet"), (64, "neumann")])
+@pytest.mark.parametrize("name,tname,nmax", SOLVERS)
+def test_sles_it_vs_oracle(csb, oracle, N, bc, name, tname, nmax):
+    """Multi-CTA sizes (> single-block threshold)."""
+    s = cube_poisson(N, bc, with_mesh=False)
+    r_norm = float(np.sqrt(oracle.dot_xx(s.rhs)))
+    o = getattr(oracle, name)(s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, nmax, 1e-8, r_norm)
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+    c = csb.SlesIt(csb.SlesItType[tname], nmax)
+    r = c.solve(m, s.rhs, 1e-8, r_norm)
+    assert int(r["cvg"]) == o["cvg"]
+    assert abs(r["n_iter"] - o["n_iter"]) <= 2
+    if o["cvg"] == 1:
+        assert rel_l2(r["vx"][:s.n_rows], o["vx"]) <= 1e-8   # both only converged to 1e-8
+        # true residual check, independent of the oracle
+        res = np.linalg.norm(oracle.spmv(s.row_index, s.col_id, s.d_val, s.x_val,
+                                         r["vx"][:s.n_rows]) - s.rhs)
+        assert res <= 1.5e-8 * r_norm
+    else:
+        assert rel_l2(r["vx"][:s.n_rows], o["vx"]) <= 1e-11  # same fixed number of sweeps
+    k = min(len(r["history"]), len(o["history"]), 6)
+    assert np.allclose(r["history"][:k], o["history"][:k], rtol=1e-10, atol=0)
+    c.destroy()
+    m.destroy()
+
+
+def test_pcg_tight_tolerance_solution_parity(csb, oracle):
+    """Converged-solution parity at the north-star tolerance: both solved to 1e-13."""
+    s = cube_poisson(32, "dirichlet", with_mesh=False)
+    r_norm = float(np.sqrt(oracle.dot_xx(s.rhs)))
+    o = oracle.pcg(s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, 5000, 1e-13, r_norm)
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+    c = csb.SlesIt(csb.SlesItType.PCG, 5000)
+    r = c.solve(m, s.rhs, 1e-13, r_norm)
+    assert int(r["cvg"]) == 1 and o["cvg"] == 1
+    assert abs(r["n_iter"] - o["n_iter"]) <= 2
+    assert rel_l2(r["vx"][:s.n_rows], o["vx"]) <= SOL_TOL
+    c.destroy()
+    m.destroy()
+
+
+def test_pcg_warm_start_and_zero_rhs(csb, oracle):
+    g = np.load([p.values[2] for p in golden_cases() if p.id == "cube_N10_neumann"][0])
+    s = cube_poisson(10, "neumann")
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+    c = csb.SlesIt(csb.SlesItType.PCG, 1000)
+    vx = g["jacobi_vx"].copy()
+    r = c.solve(m, s.rhs, 1e-10, float(g["r_norm"]), vx=vx, use_vx_ini=True)
+    assert abs(r["n_iter"] - int(g["pcg_warm_n_iter"])) <= 2
+    assert rel_l2(r["vx"], g["pcg_warm_vx"]) <= SOL_TOL
+    # zero right-hand side: converged at once with a zero solution
+    r = c.solve(m, np.zeros(s.n_rows), 1e-8, 1.0)
+    assert int(r["cvg"]) == 1 and r["n_iter"] == 0 and not r["vx"].any()
+    # max-iteration exit reports the reference's state and count
+    r = c2 = None
+    c2 = csb.SlesIt(csb.SlesItType.PCG, 3)
+    r = c2.solve(m, s.rhs, 1e-12, float(g["r_norm"]))
+    o = oracle.pcg(s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, 3, 1e-12, float(g["r_norm"]))
+    assert int(r["cvg"]) == -1 == o["cvg"] and r["n_iter"] == o["n_iter"] == 3
+    assert rel_l2(r["vx"], o["vx"]) <= 1e-12
+    c.destroy(); c2.destroy(); m.destroy()
+
+
+def test_device_buffers_are_used_in_place(csb):
+    """rhs / vx given as device pointers (torch tensors): no staging copies."""
+    import torch
+    s = cube_poisson(20, "dirichlet", with_mesh=False)
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+    c = csb.SlesIt(csb.SlesItType.PCG, 1000)
+    rhs_d = torch.from_numpy(s.rhs).cuda()
+    vx_d = torch.zeros(s.n_rows, dtype=torch.float64, device="cuda")
+    r_norm = float(np.linalg.norm(s.rhs))
+    r = c.solve(m, rhs_d, 1e-9, r_norm, vx=vx_d)
+    host = c.solve(m, s.rhs, 1e-9, r_norm)
+    assert int(r["cvg"]) == 1
+    assert np.array_equal(vx_d.cpu().numpy(), host["vx"])   # deterministic: identical
+    y_d = torch.empty_like(vx_d)
+    m.vector_multiply(vx_d, y_d)
+    assert np.linalg.norm(y_d.cpu().numpy() - s.rhs) <= 2e-9 * r_norm
+    c.destroy(); m.destroy()
+
+
+# ---------------------------------------------------------------- multigrid
+
+@pytest.mark.parametrize("N,bc,path", golden_cases())
+def test_multigrid_matches_golden(csb, N, bc, path):
+    g = np.load(path)
+    s = cube_poisson(N, bc)
+    m = csb.Matrix.from_system(s)
+    mg = csb.Multigrid()
+    mg.setup(m)
+    lv = mg.levels()
+    assert len(lv) == int(g["mg_n_levels"])
+    for l in range(1, len(lv)):
+        for k in ("coarse_row", "row_index", "col_id"):        # index data: bit-exact
+            assert np.array_equal(lv[l][k], g[f"mg_l{l}_{k}"]), (l, k)
+        for k in ("d_val", "x_val"):                           # assembled on device: bit-exact
+            assert np.array_equal(lv[l][k], g[f"mg_l{l}_{k}"]), (l, k)
+    r = mg.solve(m, s.rhs, 1e-8, float(g["r_norm"]))
+    assert int(r["cvg"]) == int(g["mg_cvg"])
+    assert abs(r["n_iter"] - int(g["mg_n_iter"])) <= 2
+    assert rel_l2(r["vx"][:s.n_rows], g["mg_vx"]) <= 1e-8      # both converged to 1e-8 only
+    cyc = g["mg_cycle_residuals_from3"]
+    k = min(len(cyc), len(r["cycle_residuals"]) - 2, 6)
+    assert np.allclose(r["cycle_residuals"][2:2 + k], cyc[:k], rtol=1e-7, atol=0)
+    mg.destroy(); m.destroy()
+
+
+@pytest.mark.parametrize("N,bc,n_blocks", [(24, "neumann", 1), (40, "dirichlet", 1),
+                                           (48, "neumann", 4), (64, "neumann", 1)])
+def test_multigrid_vs_oracle(csb, oracle, N, bc, n_blocks):
+    s = cube_poisson(N, bc)
+    r_norm = float(np.sqrt(oracle.dot_xx(s.rhs)))
+    omg = oracle.mg_setup(s, n_threads=n_blocks)
+    olv = oracle.mg_levels(omg)
+    m = csb.Matrix.from_system(s)
+    mg = csb.Multigrid()
+    mg.set_aggregation_blocks(n_blocks)
+    mg.setup(m)
+    lv = mg.levels()
+    assert [g["n_rows"] for g in lv] == [g["n_rows"] for g in olv]
+    for l in range(1, len(lv)):
+        for k in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
+            assert np.array_equal(lv[l][k], olv[l][k]), (l, k)
+    o = oracle.mg_solve(omg, s.rhs, 1e-8, r_norm)
+    r = mg.solve(m, s.rhs, 1e-8, r_norm)
+    assert int(r["cvg"]) == o["cvg"] == 1
+    assert abs(r["n_cycles"] - o["n_cycles"]) <= 1
+    assert abs(r["n_iter"] - o["n_iter"]) <= max(2, o["n_iter"] // 20)
+    k = min(len(r["cycle_residuals"]), len(o["cycle_residuals"]), 5)
+    assert np.allclose(r["cycle_residuals"][:k], o["cycle_residuals"][:k], rtol=1e-7, atol=0)
+    res = np.linalg.norm(oracle.spmv(s.row_index, s.col_id, s.d_val, s.x_val,
+                                     r["vx"][:s.n_rows]) - s.rhs)
+    assert res <= 1.0001e-8 * r_norm
+    oracle.mg_free(omg)
+    mg.destroy(); m.destroy()
+
+
+def test_multigrid_tight_tolerance_solution_parity(csb, oracle):
+    """North-star tolerance: converged solutions within 1e-10 relative L2."""
+    s = cube_poisson(32, "dirichlet")
+    r_norm = float(np.sqrt(oracle.dot_xx(s.rhs)))
+    omg = oracle.mg_setup(s)
+    o = oracle.mg_solve(omg, s.rhs, 1e-13, r_norm)
+    m = csb.Matrix.from_system(s)
+    mg = csb.Multigrid()
+    r = mg.solve(m, s.rhs, 1e-13, r_norm)       # lazy setup inside solve, like the reference
+    assert int(r["cvg"]) == o["cvg"] == 1
+    assert abs(r["n_cycles"] - o["n_cycles"]) <= 2
+    assert rel_l2(r["vx"][:s.n_rows], o["vx"]) <= SOL_TOL
+    oracle.mg_free(omg)
+    mg.destroy(); m.destroy()
+
+
+def test_multigrid_requires_mesh_association(csb):
+    s = cube_poisson(8, with_mesh=False)
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+    mg = csb.Multigrid()
+    with pytest.raises(csb.CsbError):
+        mg.setup(m)
+    mg.destroy(); m.destroy()
+
+
+def test_multigrid_128_properties(csb):
+    """Config-2 size (128^3, 2.1 M rows): hierarchy shape and true residual."""
+    s = cube_poisson(128, "neumann")
+    m = csb.Matrix.from_system(s)
+    mg = csb.Multigrid()
+    mg.setup(m)
+    lv = mg.levels()
+    rows = [g["n_rows"] for g in lv]
+    assert rows[0] == 128 ** 3 and all(a > b for a, b in zip(rows, rows[1:])) and rows[-1] >= 30
+    for l in range(1, len(lv)):
+        cr = lv[l]["coarse_row"]
+        assert cr.min() == 0 and cr.max() == rows[l] - 1          # onto
+        assert np.bincount(cr).max() <= 4                          # aggregation limit 3 (+1)
+        assert np.all(lv[l]["x_val"] <= 0) and np.all(lv[l]["d_val"] > 0)
+        # constants stay (nearly) in the kernel: row sums ~ regularisation only
+        rs = lv[l]["d_val"] + np.add.reduceat(lv[l]["x_val"], lv[l]["row_index"][:-1])
+        assert np.all(rs > -1e-12) and rs.sum() < 1.01 * (1e-6 / 128) * 128 ** 3
+    r_norm = float(np.linalg.norm(s.rhs))
+    r = mg.solve(m, s.rhs, 1e-8, r_norm)
+    assert int(r["cvg"]) == 1
+    y = m.vector_multiply(r["vx"])
+    assert np.linalg.norm(y - s.rhs) <= 1.0001e-8 * r_norm
+    assert np.all(np.diff(r["cycle_residuals"]) < 0)               # monotone convergence
+    mg.destroy(); m.destroy()

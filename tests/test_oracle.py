@@ -1,0 +1,108 @@
+"""CPU tests of the checker itself: the C restatement (oracle/cs_oracle.c) against
+(1) the committed golden fixtures generated from the reference's own compiled
+code and (2) that code directly when oracle/_ref/libcsref.so is present.
+Integer/index data must match bit-exactly; floating-point data too, since the
+restatement keeps the reference's evaluation order."""
+import numpy as np
+import pytest
+
+from code_saturne_b200.mesh_cartesian import cube_poisson, matrix_check_coefficients
+from conftest import golden_cases
+
+
+@pytest.mark.parametrize("N,bc,path", golden_cases())
+def test_oracle_kernels_match_golden(oracle, N, bc, path):
+    g = np.load(path)
+    s = cube_poisson(N, bc)
+    d, xv, x = matrix_check_coefficients(s)
+    y = oracle.spmv(s.row_index, s.col_id, d, xv, x)
+    ye = oracle.spmv(s.row_index, s.col_id, d, xv, x, True)
+    assert np.array_equal(y, g["spmv_y"])
+    assert np.array_equal(ye, g["spmv_y_exdiag"])
+    assert oracle.dot_xx(x) == float(g["dot_xx"])
+    assert oracle.dot(x, y) == float(g["dot_xy"])
+    assert np.array_equal(np.array(oracle.dot_xx_xy_yz(x, y, ye)), g["dot_xx_xy_yz"])
+
+
+@pytest.mark.parametrize("N,bc,path", golden_cases())
+@pytest.mark.parametrize("solver,nmax", [("pcg", 1000), ("jacobi", 40), ("bicgstab", 1000)])
+def test_oracle_solvers_match_golden(oracle, N, bc, path, solver, nmax):
+    g = np.load(path)
+    s = cube_poisson(N, bc)
+    r = getattr(oracle, solver)(s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, nmax, 1e-8,
+                                float(g["r_norm"]))
+    assert r["cvg"] == int(g[f"{solver}_cvg"])
+    assert r["n_iter"] == int(g[f"{solver}_n_iter"])
+    assert r["residual"] == float(g[f"{solver}_residual"])
+    assert r["initial_residual"] == float(g[f"{solver}_initial_residual"])
+    assert np.array_equal(r["vx"], g[f"{solver}_vx"])
+    # history: golden[k-1] = residual reported with n_max_iter = k
+    hist = g[f"{solver}_history"]
+    for k in (1, 2, len(hist) // 2, len(hist)):
+        if k < 1:
+            continue
+        rk = getattr(oracle, solver)(s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, k, 1e-8,
+                                     float(g["r_norm"]))
+        assert rk["residual"] == hist[k - 1]
+
+
+@pytest.mark.parametrize("N,bc,path", golden_cases())
+def test_oracle_pcg_warm_start_matches_golden(oracle, N, bc, path):
+    g = np.load(path)
+    s = cube_poisson(N, bc)
+    r = oracle.pcg(s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, 1000, 1e-10,
+                   float(g["r_norm"]), vx0=g["jacobi_vx"])
+    assert r["n_iter"] == int(g["pcg_warm_n_iter"])
+    assert np.array_equal(r["vx"], g["pcg_warm_vx"])
+
+
+@pytest.mark.parametrize("N,bc,path", golden_cases())
+def test_oracle_hierarchy_matches_golden(oracle, N, bc, path):
+    g = np.load(path)
+    s = cube_poisson(N, bc)
+    mg = oracle.mg_setup(s)
+    lv = oracle.mg_levels(mg)
+    assert len(lv) == int(g["mg_n_levels"])
+    for l in range(1, len(lv)):
+        for k in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
+            assert np.array_equal(lv[l][k], g[f"mg_l{l}_{k}"]), (l, k)
+    r = oracle.mg_solve(mg, s.rhs, 1e-8, float(g["r_norm"]))
+    assert r["cvg"] == int(g["mg_cvg"])
+    assert r["n_iter"] == int(g["mg_n_iter"])
+    assert r["residual"] == float(g["mg_residual"])
+    assert np.array_equal(r["vx"], g["mg_vx"])
+    cyc = g["mg_cycle_residuals_from3"]
+    assert np.array_equal(r["cycle_residuals"][2:2 + len(cyc)], cyc[:len(r["cycle_residuals"]) - 2])
+    oracle.mg_free(mg)
+
+
+@pytest.mark.parametrize("N,bc,n_threads", [(12, "neumann", 1), (20, "dirichlet", 1),
+                                            (24, "neumann", 4), (30, "dirichlet", 3)])
+def test_oracle_vs_reference_direct(oracle, reflib, N, bc, n_threads):
+    """Same comparison against the live reference build, incl. the per-thread
+    aggregation blocks (cs_grid.cpp:4374-4393)."""
+    reflib.set_threads(n_threads)
+    try:
+        s = cube_poisson(N, bc)
+        h = reflib.system(s)
+        lv_ref = reflib.hierarchy(h)
+        mg = oracle.mg_setup(s, n_threads=n_threads)
+        lv = oracle.mg_levels(mg)
+        assert [g["n_rows"] for g in lv] == [g["n_rows"] for g in lv_ref]
+        for l in range(1, len(lv)):
+            for k in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
+                assert np.array_equal(lv[l][k], lv_ref[l][k]), (l, k)
+        if n_threads == 1:
+            r_norm = float(np.sqrt(oracle.dot_xx(s.rhs)))
+            a = reflib.multigrid(h, s.rhs, 1e-8, r_norm)
+            b = oracle.mg_solve(mg, s.rhs, 1e-8, r_norm)
+            assert (a["cvg"], a["n_iter"], a["residual"]) == (b["cvg"], b["n_iter"], b["residual"])
+            assert np.array_equal(a["vx"], b["vx"])
+            a = reflib.sles_it(h, reflib.PCG, s.rhs, 2000, 1e-9, r_norm)
+            b = oracle.pcg(s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, 2000, 1e-9, r_norm)
+            assert (a["n_iter"], a["residual"]) == (b["n_iter"], b["residual"])
+            assert np.array_equal(a["vx"], b["vx"])
+        oracle.mg_free(mg)
+        reflib.destroy(h)
+    finally:
+        reflib.set_threads(1)
