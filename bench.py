@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- multigrid pressure-Poisson solve on a cs_mesh_cartesian-style hex cube.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--cube 256]
+
+One "step" = one cs_multigrid_solve (V-cycle, solver-mode defaults of
+cs_multigrid_define: PCG+Jacobi smoothers 2/10, PCG coarse solve) of the
+synthetic pressure system to precision 1e-8, hierarchy already set up (the
+reference times setup and solve separately too: cs_multigrid.cpp:5324-5332,
+:5583-5586; setup seconds are reported beside the headline).
+
+Prints ONE JSON line (rank 0).  `value` = seconds per solve with rhs/vx resident
+in HBM; `e2e` = the same solve through the C-ABI with HOST rhs/vx buffers
+(H2D + D2H inside the timed region); `roofline` = level-0 SpMV kernel, achieved
+algorithmic bytes / CUDA-event time against the measured HBM copy bandwidth;
+`cpu_baseline` = the reference's own CPU code (oracle/_ref/libcsref.so) on the
+box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "multigrid Poisson solve, seconds per solve"
+UNIT = "s/solve"
+PRECISION = 1e-8
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx.append(float(s[1]))
+            except Exception:
+                continue
+            for k, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(k)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- reference arm
+
+def run_reference(args, sample_cube=None, quiet=False):
+    """Time the reference's own CPU implementation (cs_multigrid_setup/_solve from
+    oracle/_ref/libcsref.so) on the host cores, on a bounded sample of the workload."""
+    from code_saturne_b200.mesh_cartesian import cube_poisson
+    from oracle.pyoracle import RefLib, ref_available
+    cores = os.cpu_count() or 1
+    n_cube = sample_cube or args.ref_cube
+    if not ref_available():
+        # the oracle port always exists: single-threaded C restatement
+        from oracle.pyoracle import Oracle
+        ora = Oracle()
+        s = cube_poisson(n_cube)
+        r_norm = float(np.linalg.norm(s.rhs))
+        t0 = time.perf_counter(); mg = ora.mg_setup(s); t_setup = time.perf_counter() - t0
+        times = []
+        for i in range(max(1, min(args.steps, 2))):
+            t0 = time.perf_counter(); r = ora.mg_solve(mg, s.rhs, PRECISION, r_norm)
+            times.append(time.perf_counter() - t0)
+        ora.mg_free(mg)
+        return dict(kind="port", cores=1, cube=n_cube, n_rows=s.n_rows, t_solve=min(times),
+                    t_setup=t_setup, n_cycles=r["n_cycles"], n_iter=r["n_iter"])
+    ref = RefLib(cores)
+    s = cube_poisson(n_cube)
+    h = ref.system(s)
+    r_norm = float(np.linalg.norm(s.rhs))
+    times, setups = [], []
+    n_runs = args.warmup_ref + max(1, args.steps_ref)
+    r = None
+    for i in range(n_runs):
+        r = ref.multigrid(h, s.rhs, PRECISION, r_norm)
+        if i >= args.warmup_ref:
+            times.append(r["t_solve"]); setups.append(r["t_setup"])
+    ref.destroy(h)
+    return dict(kind="reference", cores=ref.n_threads, cube=n_cube, n_rows=s.n_rows,
+                t_solve=float(np.mean(times)), t_setup=float(np.mean(setups)),
+                n_iter=r["n_iter"], cvg=r["cvg"], residual=r["residual"])
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    b = run_reference(args)
+    scale = (args.cube ** 3) / float(b["n_rows"])
+    value = b["t_solve"] * scale
+    sample = (f"{b['cube']}^3 cube ({b['n_rows']} rows) full solve to {PRECISION:g}, "
+              f"{b['cores']} OpenMP threads; seconds scaled x{scale:g} (row count) to the "
+              f"{args.cube}^3 workload")
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference",
+        "n_gpus": args.gpus, "steps": args.steps_ref, "warmup": args.warmup_ref,
+        "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.cube}^3 hex cube pressure Poisson, cs_multigrid V-cycle "
+                               "(PCG+Jacobi smoothers), precision 1e-8",
+                   "sample_cube": b["cube"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": b["cores"], "kind": b["kind"],
+                         "sample": sample, "sample_s_per_solve": b["t_solve"],
+                         "sample_setup_s": b["t_setup"], "sample_n_equiv_iter": b["n_iter"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- our arm
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cube", type=int, default=256, help="cells per edge of the hex cube")
+    ap.add_argument("--ref-cube", type=int, default=128, help="CPU sample size (bounded)")
+    ap.add_argument("--steps-ref", type=int, default=2)
+    ap.add_argument("--warmup-ref", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spmv-launches", type=int, default=50)
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        reference_main(args)
+        return
+
+    import torch
+    from code_saturne_b200 import api
+    from code_saturne_b200.mesh_cartesian import cube_poisson
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    api.init(local_rank)
+    # a dedicated (non-default) stream shared by torch events and the library
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    api.set_stream(stream.cuda_stream)
+
+    # ---- synthetic input (host), matrix + hierarchy setup ------------------
+    # N > 1: weak scaling, every rank solves its own cube (domain replicas) until
+    # the distributed hierarchy lands; see DESIGN.md (e).
+    t0 = time.perf_counter()
+    s = cube_poisson(args.cube)
+    t_gen = time.perf_counter() - t0
+    r_norm = float(np.linalg.norm(s.rhs))
+    t0 = time.perf_counter()
+    m = api.Matrix.from_system(s)
+    t_upload = time.perf_counter() - t0
+    mg = api.Multigrid()
+    t0 = time.perf_counter()
+    mg.setup(m)
+    t_setup = time.perf_counter() - t0
+    st = mg.setup_times()
+    n_levels = mg.n_levels()
+
+    rhs_d = torch.from_numpy(s.rhs).cuda()
+    vx_d = torch.zeros(s.n_rows, dtype=torch.float64, device="cuda")
+    rhs_h = torch.from_numpy(s.rhs).pin_memory()
+    vx_h = torch.zeros(s.n_rows, dtype=torch.float64).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def solve_device():
+        return mg.solve(m, rhs_d, PRECISION, r_norm, vx=vx_d)
+
+    def solve_host():
+        return mg.solve(m, rhs_h.numpy(), PRECISION, r_norm, vx=vx_h.numpy())
+
+    for _ in range(args.warmup):
+        r = solve_device()
+    assert int(r["cvg"]) == 1, f"solve did not converge: {r['cvg']}"
+
+    sampler = ClockSampler(local_rank)
+    with sampler:
+        # ---- value: inputs resident in HBM --------------------------------
+        barrier()
+        api.launch_count(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            r = solve_device()
+        e1.record(stream)
+        barrier()
+        launches = api.launch_count()
+        t_dev = e0.elapsed_time(e1) * 1e-3 / args.steps
+
+        # ---- e2e: host buffers through the C-ABI --------------------------
+        for _ in range(min(args.warmup, 2)):
+            solve_host()
+        barrier()
+        w0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(args.steps):
+            rh = solve_host()
+        e1.record(stream)
+        barrier()
+        t_e2e = max(e0.elapsed_time(e1) * 1e-3, time.perf_counter() - w0) / args.steps
+
+        # ---- roofline: level-0 SpMV kernel, inputs (1.7 GB) >> L2 ----------
+        x_d = torch.from_numpy(np.sin(np.arange(s.n_rows) * 0.37)).cuda()
+        y_d = torch.empty_like(x_d)
+        for _ in range(5):
+            m.vector_multiply(x_d, y_d)
+        barrier()
+        e0.record(stream)
+        for _ in range(args.spmv_launches):
+            m.vector_multiply(x_d, y_d)
+        e1.record(stream)
+        barrier()
+        t_spmv = e0.elapsed_time(e1) * 1e-3 / args.spmv_launches
+    clocks = sampler.summary()
+
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e, t_spmv], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e, t_spmv = (float(v) for v in t.cpu())
+
+    spmv_bytes = m.spmv_bytes()
+    peak, peak_src = measured_peak_gbs()
+    achieved = spmv_bytes / t_spmv / 1e9
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                b = run_reference(args)
+                scale = s.n_rows / float(b["n_rows"])
+                cpu = {"value": b["t_solve"] * scale, "unit": UNIT, "cores": b["cores"],
+                       "kind": b["kind"],
+                       "sample": (f"{b['cube']}^3 cube ({b['n_rows']} rows) full solve to "
+                                  f"{PRECISION:g} with {b['cores']} OpenMP threads; seconds "
+                                  f"scaled x{scale:g} (row count) to the {args.cube}^3 workload"),
+                       "sample_s_per_solve": b["t_solve"], "sample_setup_s": b["t_setup"],
+                       "sample_n_equiv_iter": b["n_iter"]}
+            except Exception as e:  # the baseline is reported, never required
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                       "sample": f"unavailable: {e}"}
+        line = {
+            "metric": METRIC, "value": t_dev, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev * 1e3,
+            "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.cube}^3 hex cube ({s.n_rows} cells) pressure Poisson, "
+                                   "cs_multigrid V-cycle (PCG+Jacobi smoothers 2/10, coarse PCG), "
+                                   f"precision {PRECISION:g}, all-Neumann + eps",
+                       "rows_per_gpu": s.n_rows, "n_levels": n_levels,
+                       "n_cycles": int(r["n_cycles"]), "n_equiv_iter": int(r["n_iter"]),
+                       "final_residual_over_rnorm": float(r["residual"] / r_norm),
+                       "l2_policy": "inputs (1.7 GB matrix) larger than L2; no flush needed",
+                       "setup_s": t_setup, "setup_aggregation_host_s": st["aggregation"],
+                       "setup_assembly_device_s": st["assembly"],
+                       "setup_transfers_s": st["transfers"],
+                       "matrix_upload_s": t_upload, "input_generation_s": t_gen,
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas"},
+            "e2e": {"value": t_e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * s.n_rows,
+                    "d2h_bytes_per_step": 8 * s.n_rows + 4096},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_spmv_stream (level-0 MSR SpMV)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": spmv_bytes,
+                         "ms_per_launch": t_spmv * 1e3, "peak_source": peak_src},
+            "spmv_hbm_gbs": achieved,
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+
+    mg.destroy()
+    m.destroy()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -348,9 +348,6 @@ bool spmv_dispatch(const SpmvK &k, const _csb_matrix_t *m)
 {
   const int grid = (m->n_rows + TPB - 1) / TPB;
   if (grid < 1) return true;
-  if (grid > RED_MAX_BLOCKS && (EPI == EPI_RESIDUAL_NORM || EPI == EPI_PCG_DOT3)) {
-    /* partials buffer is sized at csb_init from the largest matrix seen */
-  }
   if (m->spmv_stream_ok) {
     static bool attr_set = false;
     static size_t attr_bytes = 0;
@@ -399,9 +396,9 @@ bool launch_spmv(SpmvEpilogue epi, const SpmvArgs &a)
   k.x_val = m->x_val.p;
   k.x = a.x; k.y = a.y; k.b = a.b; k.ad_inv = a.ad_inv;
   k.rk = a.rk; k.dk = a.dk; k.st = a.st; k.mg = a.mg; k.phase = a.phase;
-  k.partials = ctx().partials; k.ticket = ctx().ticket;
   if (epi == EPI_RESIDUAL_NORM || epi == EPI_PCG_DOT3)
     if (!ensure_partials((m->n_rows + TPB - 1) / TPB)) return false;
+  k.partials = ctx().partials; k.ticket = ctx().ticket;   /* after a possible regrow */
   switch (epi) {
   case EPI_STORE:         return spmv_dispatch<EPI_STORE>(k, m);
   case EPI_RESIDUAL:      return spmv_dispatch<EPI_RESIDUAL>(k, m);

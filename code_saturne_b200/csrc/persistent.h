@@ -1,0 +1,68 @@
+/* persistent.h -- descriptors of the persistent cooperative kernels (persistent.cu). */
+#ifndef CSB_PERSISTENT_H
+#define CSB_PERSISTENT_H
+
+#include "csb_internal.h"
+
+namespace csb {
+
+/* One level of the hierarchy as seen by the device-side V-cycle. */
+struct MgLevelDesc {
+  int           n_rows;
+  int           n_slabs;       /* ceil(n_rows / slab_rows) */
+  int           slab_rows;     /* <= 256 rows streamed per CTA step */
+  int           n_rows_next;
+  const int    *row_index;
+  const int    *col_id;
+  const double *d_val;
+  const double *x_val;
+  const double *ad_inv;
+  double       *rhs;           /* levels > 0 */
+  double       *vx;            /* levels > 0 */
+  const int    *coarse_row;    /* rows of this level -> rows of the next level */
+  const int    *c_f_row_index; /* rows of the next level -> rows of this level */
+  const int    *c_f_row_ids;
+  ItState      *st_descent;    /* also used for the coarsest solve */
+  ItState      *st_ascent;
+};
+
+struct PersistentCommon {
+  double   *work;          /* 5 * work_stride doubles: rk dk gk zk sk */
+  size_t    work_stride;
+  double   *partials;      /* 12 * grid doubles */
+  unsigned *barrier;       /* 2 words, zero-initialised */
+};
+
+struct MgSolveParams {
+  int                n_levels;
+  const MgLevelDesc *levels;     /* device array */
+  MgState           *ms;
+  const double      *rhs;
+  double            *vx;
+  double            *wr;
+  int                vx_ini_nonzero;
+  int                n_max_cycles;
+  int                n_max_iter[3];
+  double             precision_mult[3];
+  double             precision, r_norm;
+  int                single_rows;  /* levels up to this size run in one CTA */
+};
+
+size_t persistent_smem_bytes(size_t max_slab_entries);
+int    persistent_grid(int which, size_t smem);   /* 0: PCG kernel, 1: multigrid kernel */
+
+bool launch_pcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
+                           bool vx_ini_nonzero, int n_max_iter, double precision,
+                           double r_norm, const PersistentCommon &P, ItState *st,
+                           int grid, size_t smem, bool single);
+
+bool launch_mg_persistent(const MgSolveParams &S, const PersistentCommon &P, int grid,
+                          size_t smem);
+
+/* choose the slab height of a level so that a slab's products fit in ~40 KB */
+void plan_slabs(const std::vector<csb_lnum_t> &row_index, int n_rows, int &slab_rows,
+                int &n_slabs, size_t &max_entries);
+
+} // namespace csb
+
+#endif

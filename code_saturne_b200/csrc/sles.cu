@@ -13,6 +13,7 @@
 
 #include "csb_internal.h"
 #include "grid_host.h"
+#include "persistent.h"
 
 #include <chrono>
 #include <cmath>
@@ -79,6 +80,12 @@ struct _csb_sles_it_t {
   DevBuf<double>      work;
   DevBuf<ItState>     st;
   ItState            *h_st = nullptr;     /* pinned mirror */
+  /* persistent-kernel launch data */
+  MgLevelDesc         desc;
+  DevBuf<double>      partials;
+  DevBuf<unsigned>    barrier;
+  int                 p_grid = 0;
+  size_t              p_smem = 0;
   /* stats (cs_sles_it_priv.h:177-190) */
   unsigned n_setups = 0, n_solves = 0;
   unsigned n_iterations_last = 0, n_iterations_min = 0, n_iterations_max = 0;
@@ -278,6 +285,20 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
   if (!c->st.alloc(1)) return;
   if (c->h_st == nullptr)
     if (!CSB_CUDA(cudaMallocHost((void **)&c->h_st, sizeof(ItState)))) return;
+  if (c->type == CSB_SLES_PCG && a->halo == nullptr) {
+    size_t max_entries = 0;
+    MgLevelDesc &d = c->desc;
+    memset(&d, 0, sizeof(d));
+    plan_slabs(a->h_row_index, a->n_rows, d.slab_rows, d.n_slabs, max_entries);
+    d.n_rows = a->n_rows;
+    d.row_index = a->row_index.p; d.col_id = a->col_id.p;
+    d.d_val = a->d_val.p; d.x_val = a->x_val.p; d.ad_inv = c->ad_inv.p;
+    c->p_smem = persistent_smem_bytes(max_entries);
+    c->p_grid = persistent_grid(0, c->p_smem);
+    if (c->p_grid < 1) return;
+    if (!c->partials.alloc(12*(size_t)c->p_grid) || !c->barrier.alloc(2)) return;
+    if (!CSB_CUDA(cudaMemsetAsync(c->barrier.p, 0, 2*sizeof(unsigned), ctx().stream))) return;
+  }
   c->setup_done = true;
   c->n_setups += 1;
   c->t_setup += wall() - t0;
@@ -315,8 +336,18 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
   bool ok = false;
   switch (c->type) {
   case CSB_SLES_PCG:
-    ok = pcg_enqueue(a, c->st.p, nullptr, c->ad_inv.p, precision, r_norm, c->n_max_iter,
-                     s_rhs.d, s_vx.d, ini, false, c->work.p, c->h_st);
+    if (a->halo == nullptr && env_int("CSB_PCG_MODE_MULTI", 0) == 0) {
+      /* whole solve in one persistent cooperative kernel */
+      PersistentCommon P;
+      P.work = c->work.p; P.work_stride = (size_t)a->n_cols_ext;
+      P.partials = c->partials.p; P.barrier = c->barrier.p;
+      const bool single = (a->n_rows <= sb_rows_threshold());
+      ok = launch_pcg_persistent(c->desc, s_rhs.d, s_vx.d, ini, c->n_max_iter, precision,
+                                 r_norm, P, c->st.p, c->p_grid, c->p_smem, single);
+    }
+    else
+      ok = pcg_enqueue(a, c->st.p, nullptr, c->ad_inv.p, precision, r_norm, c->n_max_iter,
+                       s_rhs.d, s_vx.d, ini, false, c->work.p, c->h_st);
     break;
   case CSB_SLES_JACOBI:
     ok = jacobi_enqueue(a, c->st.p, c->ad_inv.p, precision, r_norm, c->n_max_iter,
@@ -461,6 +492,12 @@ struct _csb_multigrid_t {
   DevBuf<MgState>  mg_state;
   MgState         *h_mg = nullptr;   /* pinned */
   DevBuf<double>   wr, aux;
+  /* persistent-kernel launch data */
+  DevBuf<MgLevelDesc> descs;
+  DevBuf<double>   partials;
+  DevBuf<unsigned> barrier;
+  int              p_grid = 0;
+  size_t           p_smem = 0;
   bool             setup_done = false;
   const csb_matrix_t *a = nullptr;
   /* results / stats */
@@ -756,6 +793,35 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
   }
   if (!mg->wr.alloc(wr_size) || !mg->aux.alloc(aux_size)) return;
   if (!mg->it_states.alloc(2*(size_t)n_levels)) return;
+  {
+    std::vector<MgLevelDesc> h_desc((size_t)n_levels);
+    size_t max_entries = 0;
+    for (int l = 0; l < n_levels; l++) {
+      MgLevelDesc &d = h_desc[l];
+      MgLevelDesc zero; memset(&zero, 0, sizeof(zero)); d = zero;
+      MgLevel *lv = mg->levels[l];
+      const csb_matrix_t *m = lv->m;
+      size_t me = 0;
+      plan_slabs(m->h_row_index, m->n_rows, d.slab_rows, d.n_slabs, me);
+      max_entries = std::max(max_entries, me);
+      d.n_rows = m->n_rows;
+      d.n_rows_next = (l + 1 < n_levels) ? mg->levels[l+1]->m->n_rows : 0;
+      d.row_index = m->row_index.p; d.col_id = m->col_id.p;
+      d.d_val = m->d_val.p; d.x_val = m->x_val.p; d.ad_inv = lv->ad_inv.p;
+      d.rhs = lv->rhs.p; d.vx = lv->vx.p;
+      d.coarse_row = lv->coarse_row.p;
+      d.c_f_row_index = lv->c_f_row_index.p; d.c_f_row_ids = lv->c_f_row_ids.p;
+      d.st_descent = mg->it_states.p + 2*l;
+      d.st_ascent = mg->it_states.p + 2*l + 1;
+    }
+    mg->p_smem = persistent_smem_bytes(max_entries);
+    mg->p_grid = persistent_grid(1, mg->p_smem);
+    if (mg->p_grid < 1) return;
+    if (!mg->descs.upload(h_desc.data(), (size_t)n_levels)) return;
+    if (!mg->partials.alloc(12*(size_t)mg->p_grid) || !mg->barrier.alloc(2)) return;
+    if (!CSB_CUDA(cudaMemsetAsync(mg->barrier.p, 0, 2*sizeof(unsigned), c.stream))) return;
+    if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return;   /* h_desc dies here */
+  }
   if (!mg->mg_state.p && !mg->mg_state.alloc(1)) return;
   if (mg->h_mg == nullptr)
     if (!CSB_CUDA(cudaMallocHost((void **)&mg->h_mg, sizeof(MgState)))) return;
@@ -809,7 +875,33 @@ csb_multigrid_solve(void *context, const char *name, const csb_matrix_t *a, int 
 
   int cvg = CSB_SLES_ITERATING;
   int n_cycles = 0;
-  for (n_cycles = 0; cvg == CSB_SLES_ITERATING; n_cycles++) {
+  const bool persistent = (env_int("CSB_MG_MODE_MULTI", 0) == 0);
+
+  if (persistent) {
+    /* the whole solve (all cycles, all levels) in one cooperative launch */
+    MgSolveParams S;
+    S.n_levels = n_levels; S.levels = mg->descs.p; S.ms = ms;
+    S.rhs = s_rhs.d; S.vx = s_vx.d; S.wr = mg->wr.p;
+    S.vx_ini_nonzero = (vx_ini == vx) ? 1 : 0;
+    S.n_max_cycles = mg->n_max_cycles;
+    for (int i = 0; i < 3; i++) {
+      S.n_max_iter[i] = mg->n_max_iter[i];
+      S.precision_mult[i] = mg->precision_mult[i];
+    }
+    S.precision = precision; S.r_norm = r_norm;
+    S.single_rows = sb_rows_threshold();
+    PersistentCommon P;
+    P.work = mg->aux.p; P.work_stride = (size_t)a->n_cols_ext;
+    P.partials = mg->partials.p; P.barrier = mg->barrier.p;
+    if (!launch_mg_persistent(S, P, mg->p_grid, mg->p_smem)) return CSB_SLES_BREAKDOWN;
+    if (!CSB_CUDA(cudaMemcpyAsync(mg->h_mg, ms, MG_HEAD, cudaMemcpyDeviceToHost, c.stream)))
+      return CSB_SLES_BREAKDOWN;
+    if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return CSB_SLES_BREAKDOWN;
+    cvg = mg->h_mg->cvg;
+    n_cycles = mg->h_mg->cycle_id;
+  }
+
+  for (n_cycles = persistent ? n_cycles : 0; !persistent && cvg == CSB_SLES_ITERATING; n_cycles++) {
     const int cycle_id = n_cycles + 1;
     bool ok = launch_mg_cycle_begin(ms, cycle_id);
 
