@@ -147,6 +147,7 @@ def load_library() -> C.CDLL:
     L.csb_multigrid_get_level_arrays.argtypes = [vp, ci, vp, vp, vp, vp, vp]
     L.csb_multigrid_get_cycle_residuals.argtypes = [vp, vp, ci]
     L.csb_multigrid_get_setup_times.argtypes = [vp, vp]
+    L.csb_multigrid_get_phase_times.argtypes = [vp, vp, ci]
     L.csb_multigrid_log.argtypes = [vp, ci]
     L.csb_multigrid_log.restype = None
     L.csb_multigrid_copy.restype = vp
@@ -460,6 +461,14 @@ class Multigrid(_SolverBase):
         t = np.zeros(4)
         load_library().csb_multigrid_get_setup_times(C.c_void_p(self._h), _ptr(t))
         return dict(total=t[0], aggregation=t[1], assembly=t[2], transfers=t[3])
+
+    def phase_times(self):
+        """Seconds per (level, phase) of the last solve, from the device-side timers of
+        the persistent kernel.  Columns: descent, residual, restrict, coarsest, prolong,
+        ascent."""
+        buf = np.zeros((32, 6))
+        n = load_library().csb_multigrid_get_phase_times(C.c_void_p(self._h), _ptr(buf), 32)
+        return buf[:n].copy()
 
     def levels(self):
         """Copy the hierarchy to host arrays (for the parity tests)."""

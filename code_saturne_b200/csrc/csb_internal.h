@@ -44,6 +44,10 @@ constexpr int RED_MAX_BLOCKS = 4096;
 constexpr int RED_MAX_Q = 4;
 constexpr int HIST_MAX = 2048;
 constexpr int CYCLE_MAX = 512;
+constexpr int PROF_LEVELS = 32;
+constexpr int PROF_PHASES = 6;
+enum { MG_PROF_DESCENT = 0, MG_PROF_RESIDUAL, MG_PROF_RESTRICT, MG_PROF_COARSEST,
+       MG_PROF_PROLONG, MG_PROF_ASCENT };
 
 /* true if p is a device (or managed) pointer */
 bool is_device_ptr(const void *p);
@@ -105,6 +109,10 @@ struct MgState {
   int    n_cycles_res;
   int    diverged_level;
   double cycle_res[CYCLE_MAX];
+  /* device-side phase timers of the persistent V-cycle kernel: nanoseconds
+     (%globaltimer, lead thread, after the phase's closing grid barrier) summed
+     over the cycles of the last solve; [level][phase], phases = MG_PROF_* */
+  unsigned long long prof[PROF_LEVELS][PROF_PHASES];
 };
 
 /*--------------------------------------------------------------------------

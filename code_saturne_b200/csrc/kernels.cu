@@ -1176,6 +1176,9 @@ k_mg_state_init(MgState *mg, double precision, double r_norm, int n_max_cycles)
   mg->cvg = CSB_SLES_ITERATING;
   mg->cycle_id = 0; mg->n_max_cycles = n_max_cycles;
   mg->n_equiv_iter = 0; mg->n_cycles_res = 0; mg->diverged_level = -1;
+  for (int l = 0; l < PROF_LEVELS; l++)
+    for (int p = 0; p < PROF_PHASES; p++)
+      mg->prof[l][p] = 0ull;
 }
 
 __global__ void

@@ -200,6 +200,22 @@ __device__ __forceinline__ int it_cvg_eval(double precision, double r_norm, int 
   return CSB_SLES_ITERATING;
 }
 
+__device__ __forceinline__ unsigned long long global_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+/* lead thread only: add the time since the previous mark to prof[level][phase] */
+__device__ __forceinline__ void prof_mark(MgState *ms, unsigned long long &t_last, int level,
+                                          int phase)
+{
+  const unsigned long long t = global_ns();
+  if (level < PROF_LEVELS) ms->prof[level][phase] += t - t_last;
+  t_last = t;
+}
+
 struct PcgResult { int n_iter; int cvg; double residual; double initial_residual; };
 
 /*--------------------------------------------------------------------------
@@ -386,6 +402,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
   int n_equiv_iter = 0;
   double initial_residual = -1., residual = -1.;
   int n_cycles = 0;
+  unsigned long long t_last = lead ? global_ns() : 0ull;
 
   for (n_cycles = 0; cvg == CSB_SLES_ITERATING; n_cycles++) {
     const int cycle_id = n_cycles + 1;
@@ -418,6 +435,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
                            L.st_descent, s_prod, s_red);
         grid_barrier(P.barrier);
       }
+      if (lead) prof_mark(ms, t_last, level, MG_PROF_DESCENT);
       if (level == 0 && cycle_id == 1) initial_residual = R.initial_residual;
       if (R.cvg < CSB_SLES_BREAKDOWN) { end_cycle = true; cvg = CSB_SLES_DIVERGED; break; }
 
@@ -445,6 +463,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
       }
       else
         grid_barrier(P.barrier);
+      if (lead) prof_mark(ms, t_last, level, MG_PROF_RESIDUAL);
 
       n_equiv_iter = (int)((double)n_equiv_iter
                            + R.n_iter * ((double)L.n_rows * denom_n_rows_0));
@@ -465,6 +484,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
         });
       }
       grid_barrier(P.barrier);
+      if (lead) prof_mark(ms, t_last, level, MG_PROF_RESTRICT);
     }
 
     /* ---------------- coarsest level (:3367-3429) ---------------- */
@@ -489,6 +509,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
                            L.st_descent, s_prod, s_red);
         grid_barrier(P.barrier);
       }
+      if (lead) prof_mark(ms, t_last, coarsest, MG_PROF_COARSEST);
       n_equiv_iter = (int)((double)n_equiv_iter
                            + R.n_iter * ((double)L.n_rows * denom_n_rows_0));
       if (R.cvg < CSB_SLES_BREAKDOWN) { end_cycle = true; cvg = CSB_SLES_DIVERGED; }
@@ -513,6 +534,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
           });
         }
         grid_barrier(P.barrier);
+        if (lead) prof_mark(ms, t_last, level, MG_PROF_PROLONG);
         if (level > 0) {
           const bool single = (L.n_rows <= S.single_rows);
           PcgResult R;
@@ -531,6 +553,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
                                L.st_ascent, s_prod, s_red);
             grid_barrier(P.barrier);
           }
+          if (lead) prof_mark(ms, t_last, level, MG_PROF_ASCENT);
           n_equiv_iter = (int)((double)n_equiv_iter
                                + R.n_iter * ((double)L.n_rows * denom_n_rows_0));
           if (R.cvg < CSB_SLES_BREAKDOWN) { cvg = CSB_SLES_DIVERGED; break; }

@@ -1044,6 +1044,18 @@ int csb_multigrid_get_cycle_residuals(const csb_multigrid_t *mg, double *res, in
   return n;
 }
 
+int csb_multigrid_get_phase_times(const csb_multigrid_t *mg, double *seconds, int max_levels)
+{
+  if (mg == nullptr || mg->h_mg == nullptr) return 0;
+  int n = (int)mg->levels.size();
+  if (n > max_levels) n = max_levels;
+  if (n > PROF_LEVELS) n = PROF_LEVELS;
+  for (int l = 0; l < n; l++)
+    for (int p = 0; p < PROF_PHASES; p++)
+      seconds[l*PROF_PHASES + p] = 1e-9 * (double)mg->h_mg->prof[l][p];
+  return n;
+}
+
 int csb_multigrid_get_setup_times(const csb_multigrid_t *mg, double t[4])
 {
   if (mg == nullptr) return -1;

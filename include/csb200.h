@@ -309,6 +309,13 @@ int  csb_multigrid_get_cycle_residuals(const csb_multigrid_t *mg, double *res, i
    [2] coarse matrix assembly, [3] transfers. */
 int  csb_multigrid_get_setup_times(const csb_multigrid_t *mg, double t[4]);
 
+/* Device-side phase timers of the last solve (persistent V-cycle kernel):
+   seconds[level*6 + phase], phase = 0 descent smoother, 1 residual, 2 restrict,
+   3 coarsest solve, 4 prolong, 5 ascent smoother; the instrument the reference
+   offers through its per-level timers (src/alge/cs_multigrid.cpp:170-205).
+   Returns the number of levels written (<= max_levels). */
+int  csb_multigrid_get_phase_times(const csb_multigrid_t *mg, double *seconds, int max_levels);
+
 /* Host-only pieces of the hierarchy construction (no device needed), exposed
    so that CPU-side tests can check them: the DX aggregation map
    (_automatic_aggregation_dx_msr, src/alge/cs_grid.cpp:4282) and the coarse MSR

@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""Per-level / per-phase breakdown of one multigrid solve (device-side timers of the
+persistent V-cycle kernel) against each phase's algorithmic HBM bytes (DESIGN.md,
+"algorithmic bytes").  Usage: python scripts/mg_phases.py [--cube 256] [--out file.md]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def phase_bytes(n, nnz, nc, n_desc, n_asc, level, coarsest):
+    """Algorithmic bytes of each phase of one cycle at one level."""
+    M = 12.0 * nnz + 12.0 * n            # col_id + x_val + row_index + d_val
+
+    def pcg(n_it, ini):
+        b = (M + 32 * n) if ini else 40 * n          # residual / zero start
+        b += M + 24 * n                               # zk = A.dk + 3 dots
+        if n_it >= 1:
+            b += 64 * n                               # first update
+        b += max(n_it - 1, 0) * (M + 24 * n)          # sk = A.gk + 3 dots
+        b += max(n_it - 2, 0) * 96 * n                # fused 5-vector update
+        if n_it >= 2:
+            b += 32 * n                               # last update of a smoother: vx only
+        return b
+
+    out = np.zeros(6)
+    if level < coarsest:
+        out[0] = pcg(n_desc, level == 0)
+        out[1] = M + 24 * n
+        out[2] = 12 * n + 12 * nc
+        out[4] = 20 * n + 8 * nc
+        if level > 0:
+            out[5] = pcg(n_asc, True)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cube", type=int, default=256)
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+
+    from code_saturne_b200 import api
+    from code_saturne_b200.mesh_cartesian import cube_poisson
+    import torch
+
+    api.init(0)
+    s = cube_poisson(args.cube)
+    r_norm = float(np.linalg.norm(s.rhs))
+    m = api.Matrix.from_system(s)
+    mg = api.Multigrid()
+    mg.setup(m)
+    rhs_d = torch.from_numpy(s.rhs).cuda()
+    vx_d = torch.zeros(s.n_rows, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        r = mg.solve(m, rhs_d, 1e-8, r_norm, vx=vx_d)
+    pt = mg.phase_times()
+    n_cycles = r["n_cycles"]
+    info = []
+    L = api.load_library()
+    import ctypes as C
+    for l in range(mg.n_levels()):
+        a = np.zeros(3, dtype=np.int32)
+        L.csb_multigrid_get_level_info(C.c_void_p(mg._h), l, a.ctypes.data_as(C.c_void_p))
+        info.append((int(a[0]), int(a[2])))
+    peak = 6543.4
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        peak = float(json.load(open(p))["hbm_gbs"])
+    names = ["descent", "residual", "restrict", "coarsest", "prolong", "ascent"]
+    lines = [f"# multigrid phase breakdown, {args.cube}^3, {n_cycles} cycles, "
+             f"kernel time {pt.sum()*1e3:.1f} ms ({pt.sum()/n_cycles*1e3:.3f} ms/cycle); "
+             f"peak {peak:.0f} GB/s (measured copy)", "",
+             "| level | rows | nnz | " + " | ".join(f"{n} us/cyc (GB/s, frac)" for n in names)
+             + " | level total us/cyc |", "|---|---|---|" + "---|" * 7]
+    coarsest = len(info) - 1
+    tot_bytes = 0.0
+    for l, (n, nnz) in enumerate(info):
+        nc = info[l + 1][0] if l < coarsest else 0
+        b = phase_bytes(n, nnz, nc, 2, 10, l, coarsest)
+        tot_bytes += b.sum()
+        cells = []
+        for k in range(6):
+            us = pt[l, k] / n_cycles * 1e6
+            if us <= 0:
+                cells.append("-")
+            elif b[k] > 0:
+                gbs = b[k] / (pt[l, k] / n_cycles) / 1e9
+                cells.append(f"{us:.1f} ({gbs:.0f}, {gbs/peak:.2f})")
+            else:
+                cells.append(f"{us:.1f}")
+        lines.append(f"| {l} | {n} | {nnz} | " + " | ".join(cells)
+                     + f" | {pt[l].sum()/n_cycles*1e6:.1f} |")
+    ach = tot_bytes / (pt.sum() / n_cycles) / 1e9
+    lines += ["", f"algorithmic bytes per cycle (levels above the coarsest): {tot_bytes/1e9:.2f} GB; "
+              f"whole-cycle achieved {ach:.0f} GB/s = {ach/peak:.3f} of measured peak"]
+    txt = "\n".join(lines)
+    print(txt)
+    if args.out:
+        os.makedirs(os.path.dirname(args.out), exist_ok=True)
+        open(args.out, "w").write(txt + "\n")
+
+
+if __name__ == "__main__":
+    main()
