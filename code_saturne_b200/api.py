@@ -105,6 +105,26 @@ def load_library() -> C.CDLL:
     L.csb_halo_create.argtypes = [vp, ci, ci, vp, ci, vp, vp, vp]
     L.csb_halo_destroy.argtypes = [C.POINTER(vp)]
     L.csb_halo_sync_var.argtypes = [vp, vp]
+    L.csb_pcomm_create.restype = vp
+    L.csb_pcomm_create.argtypes = [ci, ci, cs, cs]
+    L.csb_pcomm_get_ipc_handle.argtypes = [vp, vp]
+    L.csb_pcomm_open_peers.argtypes = [vp, vp]
+    L.csb_pcomm_group_create.restype = vp
+    L.csb_pcomm_group_create.argtypes = [ci]
+    L.csb_pcomm_group_destroy.argtypes = [C.POINTER(vp)]
+    L.csb_pcomm_group_destroy.restype = None
+    L.csb_pcomm_create_in_group.restype = vp
+    L.csb_pcomm_create_in_group.argtypes = [vp, ci, cs, cs]
+    L.csb_pcomm_destroy.argtypes = [C.POINTER(vp)]
+    L.csb_pcomm_destroy.restype = None
+    L.csb_pcomm_rank.argtypes = [vp]
+    L.csb_pcomm_n_ranks.argtypes = [vp]
+    L.csb_pcomm_allreduce_sum.argtypes = [vp, vp, ci]
+    L.csb_pcomm_barrier.argtypes = [vp]
+    L.csb_halo_set_pcomm.argtypes = [vp, vp]
+    L.csb_sles_it_set_pcomm.argtypes = [vp, vp]
+    L.csb_multigrid_set_pcomm.argtypes = [vp, vp]
+    L.csb_multigrid_get_level_halo.argtypes = [vp, ci, vp, vp, vp, vp, vp]
     L.csb_sles_it_create.restype = vp
     L.csb_sles_it_create.argtypes = [ci, ci, ci, ci]
     L.csb_sles_it_set_reduce_comm.argtypes = [vp, vp]
@@ -142,6 +162,7 @@ def load_library() -> C.CDLL:
     L.csb_multigrid_destroy.argtypes = [C.POINTER(vp)]
     L.csb_multigrid_destroy.restype = None
     L.csb_multigrid_get_n_levels.argtypes = [vp]
+    L.csb_multigrid_is_setup.argtypes = [vp]
     L.csb_multigrid_get_n_cycles.argtypes = [vp]
     L.csb_multigrid_get_level_info.argtypes = [vp, ci, vp]
     L.csb_multigrid_get_level_arrays.argtypes = [vp, ci, vp, vp, vp, vp, vp]
@@ -188,6 +209,119 @@ def launch_count(reset: bool = False) -> int:
     return int(load_library().csb_launch_count(1 if reset else 0))
 
 
+class PComm:
+    """Peer-memory communicator (csb_pcomm_t): ghost exchange and global sums between
+    the GPUs of one box without MPI/NCCL calls.  Build it with `from_handles` (one
+    process per GPU) or `in_group` (ranks as threads of one process)."""
+
+    def __init__(self, handle, n_ranks, rank):
+        self._h = handle
+        self.n_ranks = n_ranks
+        self.rank = rank
+
+    @property
+    def handle(self):
+        return C.c_void_p(self._h)
+
+    @staticmethod
+    def default_sizes(n_ghost, n_levels=25):
+        """(arena_bytes, window_bytes) large enough for a hierarchy whose finest level
+        has n_ghost ghost rows (ghost buffers shrink ~2x per level)."""
+        return 64 * (n_ghost + 64) + 8192 * n_levels, 32 * (n_ghost + 64)
+
+    @classmethod
+    def from_handles(cls, n_ranks, rank, arena_bytes, window_bytes, all_gather):
+        """One process per GPU.  `all_gather(bytes64) -> list of n_ranks bytes objects`
+        exchanges the cudaIpc handles (torch.distributed.all_gather_object, MPI_Allgather)."""
+        L = load_library()
+        h = L.csb_pcomm_create(n_ranks, rank, arena_bytes, window_bytes)
+        if not h:
+            _err("csb_pcomm_create")
+        self = cls(h, n_ranks, rank)
+        if n_ranks > 1:
+            buf = C.create_string_buffer(64)
+            if L.csb_pcomm_get_ipc_handle(self.handle, buf) != 0:
+                _err("csb_pcomm_get_ipc_handle")
+            handles = all_gather(buf.raw)
+            blob = b"".join(handles)
+            assert len(blob) == 64 * n_ranks
+            if L.csb_pcomm_open_peers(self.handle, blob) != 0:
+                _err("csb_pcomm_open_peers")
+        return self
+
+    @classmethod
+    def in_group(cls, group, n_ranks, rank, arena_bytes, window_bytes):
+        """Collective over the threads of `group` (an int from `PComm.group_create`)."""
+        h = load_library().csb_pcomm_create_in_group(C.c_void_p(group), rank, arena_bytes,
+                                                     window_bytes)
+        if not h:
+            _err("csb_pcomm_create_in_group")
+        return cls(h, n_ranks, rank)
+
+    @staticmethod
+    def group_create(n_ranks):
+        g = load_library().csb_pcomm_group_create(n_ranks)
+        if not g:
+            raise CsbError("csb_pcomm_group_create failed")
+        return g
+
+    @staticmethod
+    def group_destroy(group):
+        g = C.c_void_p(group)
+        load_library().csb_pcomm_group_destroy(C.byref(g))
+
+    def allreduce_sum(self, vals):
+        a = np.ascontiguousarray(vals, dtype=np.float64).copy()
+        if load_library().csb_pcomm_allreduce_sum(self.handle, _ptr(a), len(a)) != 0:
+            _err("csb_pcomm_allreduce_sum")
+        return a
+
+    def barrier(self):
+        if load_library().csb_pcomm_barrier(self.handle) != 0:
+            _err("csb_pcomm_barrier")
+
+    def destroy(self):
+        if self._h:
+            h = C.c_void_p(self._h)
+            load_library().csb_pcomm_destroy(C.byref(h))
+            self._h = None
+
+
+class Halo:
+    """cs_halo_t: ghost sections and send lists of one rank (mesh_cartesian.HaloDesc)."""
+
+    def __init__(self, desc, rank, pcomm=None, nccl_comm=None):
+        L = load_library()
+        ranks = np.ascontiguousarray(desc.c_domain_rank, dtype=np.int32)
+        si = np.ascontiguousarray(desc.send_index, dtype=np.int32)
+        sl = np.ascontiguousarray(desc.send_list, dtype=np.int32)
+        gi = np.ascontiguousarray(desc.index, dtype=np.int32)
+        self.n_ghost = int(gi[-1])
+        self.n_local = int(desc.n_local_elts)
+        self._h = L.csb_halo_create(C.c_void_p(nccl_comm or 0), rank, len(ranks), _ptr(ranks),
+                                    self.n_local, _ptr(si), _ptr(sl), _ptr(gi))
+        if not self._h:
+            _err("csb_halo_create")
+        if pcomm is not None:
+            if L.csb_halo_set_pcomm(C.c_void_p(self._h), pcomm.handle) != 0:
+                _err("csb_halo_set_pcomm")
+
+    @property
+    def handle(self):
+        return C.c_void_p(self._h)
+
+    def sync_var(self, var_d):
+        """cs_halo_sync_var on a device array of n_local + n_ghost doubles (torch tensor)."""
+        if load_library().csb_halo_sync_var(self.handle, _ptr(var_d)) != 0:
+            _err("csb_halo_sync_var")
+
+    def destroy(self):
+        if self._h:
+            h = C.c_void_p(self._h)
+            load_library().csb_halo_destroy(C.byref(h))
+            self._h = None
+
+
 def _ptr(a):
     """Address of a numpy array, a torch tensor (host or device), an int or None."""
     if a is None:
@@ -228,7 +362,8 @@ class Matrix:
     @classmethod
     def from_system(cls, s, with_mesh=True):
         """Build from a mesh_cartesian.CubeSystem (host arrays)."""
-        m = cls(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val, True)
+        m = cls(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val, True,
+                n_cols_ext=s.meta.get("n_cols_ext", s.n_rows))
         if with_mesh and s.n_faces > 0:
             m.set_mesh_association(s.n_faces, s.c2f, s.c2f_sgn, s.cell_cen, s.cell_vol,
                                    s.face_u_normal, s.face_surf)
@@ -377,6 +512,9 @@ class SlesIt(_SolverBase):
         if not self._h:
             _err("csb_sles_it_create")
 
+    def set_pcomm(self, pcomm):
+        load_library().csb_sles_it_set_pcomm(C.c_void_p(self._h), pcomm.handle)
+
     def setup(self, a: Matrix, name="system", verbosity=0):
         load_library().csb_sles_it_setup(C.c_void_p(self._h), name.encode(), a.handle, verbosity)
 
@@ -436,13 +574,33 @@ class Multigrid(_SolverBase):
             C.c_void_p(self._h), aggregation_limit, coarsening_type, n_max_levels, min_g_rows,
             p0p1_relax, 0)
 
+    def set_pcomm(self, pcomm):
+        load_library().csb_multigrid_set_pcomm(C.c_void_p(self._h), pcomm.handle)
+
+    def level_halo(self, level):
+        """Halo of one level of a distributed hierarchy, or None."""
+        L = load_library()
+        sizes = np.zeros(3, dtype=np.int32)
+        if L.csb_multigrid_get_level_halo(C.c_void_p(self._h), level, _ptr(sizes), None, None,
+                                          None, None) != 0:
+            return None
+        nd, ns = int(sizes[0]), int(sizes[1])
+        ranks = np.zeros(max(nd, 1), dtype=np.int32)
+        si = np.zeros(nd + 1, dtype=np.int32)
+        gi = np.zeros(nd + 1, dtype=np.int32)
+        sl = np.zeros(max(ns, 1), dtype=np.int32)
+        L.csb_multigrid_get_level_halo(C.c_void_p(self._h), level, _ptr(sizes), _ptr(ranks),
+                                       _ptr(si), _ptr(sl), _ptr(gi))
+        return dict(ranks=ranks[:nd], send_index=si, send_list=sl[:ns], index=gi)
+
     def set_aggregation_blocks(self, n_blocks):
         load_library().csb_multigrid_set_aggregation_blocks(C.c_void_p(self._h), int(n_blocks))
 
     def setup(self, a: Matrix, name="system", verbosity=0):
         L = load_library()
         L.csb_multigrid_setup(C.c_void_p(self._h), name.encode(), a.handle, verbosity)
-        if L.csb_multigrid_get_n_levels(C.c_void_p(self._h)) < 1:
+        if (L.csb_multigrid_get_n_levels(C.c_void_p(self._h)) < 1
+                or not L.csb_multigrid_is_setup(C.c_void_p(self._h))):
             _err("csb_multigrid_setup")
 
     def solve(self, a, rhs, precision, r_norm, vx=None, use_vx_ini=False, verbosity=0):
@@ -478,7 +636,7 @@ class Multigrid(_SolverBase):
         for l in range(self.n_levels()):
             info = np.zeros(3, dtype=np.int32)
             L.csb_multigrid_get_level_info(C.c_void_p(self._h), l, _ptr(info))
-            n, nnz = int(info[0]), int(info[2])
+            n, nce, nnz = int(info[0]), int(info[1]), int(info[2])
             cr = np.zeros(max(parent_n, 1), dtype=np.int32)
             ri = np.zeros(n + 1, dtype=np.int32)
             ci = np.zeros(max(nnz, 1), dtype=np.int32)
@@ -487,9 +645,9 @@ class Multigrid(_SolverBase):
             if L.csb_multigrid_get_level_arrays(C.c_void_p(self._h), l, _ptr(cr), _ptr(ri),
                                                 _ptr(ci), _ptr(d), _ptr(xv)) != 0:
                 _err("csb_multigrid_get_level_arrays")
-            out.append(dict(n_rows=n, nnz=nnz, coarse_row=cr[:parent_n], row_index=ri,
-                            col_id=ci[:nnz], d_val=d[:n], x_val=xv[:nnz]))
-            parent_n = n
+            out.append(dict(n_rows=n, n_cols_ext=nce, nnz=nnz, coarse_row=cr[:parent_n],
+                            row_index=ri, col_id=ci[:nnz], d_val=d[:n], x_val=xv[:nnz]))
+            parent_n = nce      # the map covers the parent's ghost rows too
         return out
 
     def free(self):

@@ -31,6 +31,8 @@ struct Context {
   double       *red_out = nullptr;      /* device scalars for plain csb_dot* */
   double       *red_out_h = nullptr;    /* pinned mirror */
   long long     launches = 0;
+  int           partials_blocks = 0;    /* capacity of `partials` in CTAs */
+  int           device_share = 1;       /* ranks sharing this device (in-process groups) */
   std::string   err;
 };
 
@@ -116,22 +118,151 @@ struct MgState {
 };
 
 /*--------------------------------------------------------------------------
- * Halo
+ * Peer-memory communicator (comm.cu): one arena per rank, mapped by every
+ * other rank (cudaIpc between processes, plain pointers between host threads).
  *--------------------------------------------------------------------------*/
+
+constexpr int COMM_MAX_RANKS = 16;
+constexpr int COMM_MAX_DOM = 16;       /* neighbour ranks of one halo */
+
+/* At arena offset 0 on every rank; written by peers. */
+struct CommHeader {
+  unsigned  xflag[2][COMM_MAX_RANKS];      /* all-reduce: epoch published by rank r */
+  double    xsum[2][COMM_MAX_RANKS][8];    /* all-reduce: partial sums of rank r */
+  unsigned  mflag[COMM_MAX_RANKS];         /* mailbox: message count from rank r */
+  unsigned  mack[COMM_MAX_RANKS];          /* mailbox: my messages consumed by rank r */
+  long long mbox[COMM_MAX_RANKS][8];
+  unsigned  wflag[COMM_MAX_RANKS];         /* window exchange: message count from rank r */
+  unsigned  wack[COMM_MAX_RANKS];
+};
+
+/* Rank-private device state. */
+struct CommLocal {
+  unsigned x_epoch;
+  unsigned m_sent[COMM_MAX_RANKS], m_recv[COMM_MAX_RANKS];
+  unsigned w_sent[COMM_MAX_RANKS], w_recv[COMM_MAX_RANKS];
+};
+
+/* What kernels need of the communicator (lives in device memory). */
+struct CommDev {
+  int        n_ranks, rank;
+  char      *peer[COMM_MAX_RANKS];         /* arena base of every rank (own included) */
+  CommLocal *local;
+  size_t     window_off, window_bytes;     /* staging window inside the arena */
+  unsigned long long timeout_ns;           /* a flag not seen for this long traps the kernel */
+};
+
+/* Halo as seen by the window-exchange kernel. */
+struct HaloDev {
+  int        n_dom;
+  int        rank_of[COMM_MAX_DOM];
+  int        send_index[COMM_MAX_DOM + 1];
+  int        ghost_index[COMM_MAX_DOM + 1];
+  int        peer_ghost_index[COMM_MAX_DOM];   /* where my section starts at the neighbour */
+  const int *send_list;                        /* nullptr: source already in send order */
+};
+
+/* One level's ghost exchange inside the persistent kernels: CTAs store the send
+   list straight into the neighbour's ghost buffer (double-buffered by exchange
+   parity), the last CTA to finish publishes the exchange count in the
+   neighbour's flag word. */
+struct DistLevel {
+  int        n_dom, n_send, n_ghost;
+  int        send_index[COMM_MAX_DOM + 1];
+  const int *send_list;
+  double    *gbuf[2];                      /* local ghost values (arena) */
+  double    *push_dst[COMM_MAX_DOM][2];    /* neighbour's gbuf[p] + its section for me */
+  unsigned  *flag_local;                   /* [n_dom] arena words written by neighbours */
+  unsigned  *flag_remote[COMM_MAX_DOM];    /* neighbour's flag word for me */
+  unsigned  *count;                        /* exchanges done so far (rank-private) */
+  unsigned  *ticket;                       /* CTA arrival counter (rank-private) */
+  unsigned long long timeout_ns;
+};
+
+#ifdef __CUDACC__
+/* device-side helpers shared by comm.cu and persistent.cu */
+__device__ __forceinline__ unsigned long long gtime_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+/* wait until *flag >= expect (flags only grow); trap instead of hanging forever */
+__device__ __forceinline__ void spin_until_ge(const unsigned *flag, unsigned expect,
+                                              unsigned long long timeout_ns, int what)
+{
+  const volatile unsigned *f = flag;
+  if ((int)(*f - expect) >= 0) return;
+  const unsigned long long t0 = gtime_ns();
+  unsigned n = 0;
+  while ((int)(*f - expect) < 0) {
+    __nanosleep(64);
+    if ((++n & 1023u) == 0 && gtime_ns() - t0 > timeout_ns) {
+      printf("[csb200] peer flag timeout (wait %d, block %d thread %d): have %u, expect %u\n",
+             what, blockIdx.x, threadIdx.x, *f, expect);
+      __trap();
+    }
+  }
+}
+#endif
 
 } // namespace csb
 
+struct CommGroup;
+
+struct _csb_pcomm_t {
+  csb::CommDev   h;                 /* host copy */
+  csb::CommDev  *d = nullptr;       /* device copy */
+  char          *arena = nullptr;
+  size_t         arena_bytes = 0, arena_used = 0;
+  CommGroup     *group = nullptr;   /* in-process ranks (host threads) */
+  bool           ipc_open[csb::COMM_MAX_RANKS] = {false};
+  double        *scratch = nullptr; /* 16 doubles, device */
+  double        *scratch_h = nullptr;
+};
+typedef struct _csb_pcomm_t csb_pcomm_t;
+
+namespace csb {
+
+void  *pcomm_arena_alloc(csb_pcomm_t *c, size_t bytes);   /* zero-filled, 256-byte aligned */
+size_t pcomm_arena_mark(const csb_pcomm_t *c);
+void   pcomm_arena_release(csb_pcomm_t *c, size_t mark);
+void   pcomm_host_barrier(csb_pcomm_t *c);
+/* sum of n (<= 8) doubles over all ranks, in place, result on the host */
+bool   pcomm_allreduce(csb_pcomm_t *c, double *vals, int n);
+/* send 8 values to / receive 8 values from each listed neighbour */
+bool   pcomm_mailbox(csb_pcomm_t *c, int n_nbr, const int *nbr, const long long *send,
+                     long long *recv);
+/* ghost section of dst <- neighbours' send lists of src; device arrays */
+bool   pcomm_window_exchange(csb_pcomm_t *c, const HaloDev &h, int elem_bytes, int stride,
+                             const void *src_d, void *ghost_dst_d);
+
+} // namespace csb
+
+/*--------------------------------------------------------------------------
+ * Halo
+ *--------------------------------------------------------------------------*/
+
 struct _csb_halo_t {
   void              *nccl_comm = nullptr;
+  csb_pcomm_t       *pcomm = nullptr;
+  std::vector<int>   peer_ghost_index;   /* set by csb_halo_set_pcomm */
   int                local_rank = 0;
   int                n_c_domains = 0;
   csb_lnum_t         n_local_elts = 0;
   csb_lnum_t         n_send = 0, n_ghost = 0;
   std::vector<int>         c_domain_rank;
   std::vector<csb_lnum_t>  send_index, index;   /* host copies */
+  std::vector<csb_lnum_t>  h_send_list;         /* host copy (coarsening) */
   csb::DevBuf<csb_lnum_t>  send_list;
   csb::DevBuf<double>      send_buf;
 };
+
+namespace csb {
+/* fill the kernel view of a halo; false if it has too many neighbours */
+bool halo_dev_view(const _csb_halo_t *h, HaloDev &v);
+}
 
 /*--------------------------------------------------------------------------
  * Matrix
@@ -265,7 +396,7 @@ struct CoarseAssemblyArgs {
   double *c_cell_cen, *c_cell_vol, *c_face_normal, *c_xa0, *c_xa0ij;
   double relax;
 };
-bool launch_coarse_assembly(const CoarseAssemblyArgs &a);
+bool launch_coarse_assembly(const CoarseAssemblyArgs &a, int stages /* 1 | 2 */);
 
 bool launch_halo_pack(int n_send, const int *send_list, const double *var, double *buf);
 

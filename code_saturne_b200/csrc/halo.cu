@@ -143,6 +143,15 @@ csb_halo_create(void *nccl_comm, int local_rank, int n_c_domains, const int *c_d
   h->index.assign(index, index + n_c_domains + 1);
   h->n_send = (n_c_domains > 0) ? h->send_index[n_c_domains] : 0;
   h->n_ghost = (n_c_domains > 0) ? h->index[n_c_domains] : 0;
+  h->h_send_list.resize((size_t)h->n_send);
+  if (h->n_send > 0) {
+    if (is_device_ptr(send_list)) {
+      if (!CSB_CUDA(cudaMemcpy(h->h_send_list.data(), send_list, sizeof(csb_lnum_t)*(size_t)h->n_send,
+                               cudaMemcpyDeviceToHost))) { delete h; return nullptr; }
+    }
+    else
+      memcpy(h->h_send_list.data(), send_list, sizeof(csb_lnum_t)*(size_t)h->n_send);
+  }
   if (!h->send_list.upload(send_list, (size_t)h->n_send) ||
       !h->send_buf.alloc((size_t)h->n_send) ||
       !CSB_CUDA(cudaStreamSynchronize(ctx().stream))) {
@@ -159,11 +168,40 @@ void csb_halo_destroy(csb_halo_t **halo)
   *halo = nullptr;
 }
 
+/* Collective over the neighbour ranks: each side learns where its section
+   starts among the neighbour's ghosts (the offset the reference's receiver
+   passes to MPI_Irecv, src/base/cs_halo.cpp:1985-1996). */
+int csb_halo_set_pcomm(csb_halo_t *h, csb_pcomm_t *comm)
+{
+  if (h == nullptr || comm == nullptr) { set_error("csb_halo_set_pcomm: null argument"); return -1; }
+  const int nd = h->n_c_domains;
+  for (int i = 0; i < nd; i++)
+    if (h->c_domain_rank[i] < 0 || h->c_domain_rank[i] >= comm->h.n_ranks
+        || h->c_domain_rank[i] == comm->h.rank) {
+      set_error("csb_halo_set_pcomm: neighbour rank %d invalid for rank %d of %d",
+                h->c_domain_rank[i], comm->h.rank, comm->h.n_ranks);
+      return -1;
+    }
+  std::vector<long long> snd((size_t)nd*8 + 8, 0), rcv((size_t)nd*8 + 8, 0);
+  for (int i = 0; i < nd; i++) snd[(size_t)i*8] = h->index[i];
+  if (!pcomm_mailbox(comm, nd, h->c_domain_rank.data(), snd.data(), rcv.data())) return -1;
+  h->peer_ghost_index.resize(nd);
+  for (int i = 0; i < nd; i++) h->peer_ghost_index[i] = (int)rcv[(size_t)i*8];
+  h->pcomm = comm;
+  return 0;
+}
+
 int csb_halo_sync_var(const csb_halo_t *halo, csb_real_t *var_d)
 {
   if (halo == nullptr) return 0;
   Context &c = ctx();
   csb_halo_t *h = const_cast<csb_halo_t *>(halo);
+  if (h->pcomm != nullptr) {
+    /* peer-memory exchange: gather + remote stores + flags in one kernel */
+    HaloDev v;
+    if (!halo_dev_view(h, v)) return -1;
+    return pcomm_window_exchange(h->pcomm, v, 8, 1, var_d, var_d + h->n_local_elts) ? 0 : -1;
+  }
   if (h->n_c_domains == 0) return 0;
   if (!launch_halo_pack(h->n_send, h->send_list.p, var_d, h->send_buf.p)) return -1;
 

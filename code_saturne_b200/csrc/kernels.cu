@@ -410,12 +410,10 @@ bool launch_spmv(SpmvEpilogue epi, const SpmvArgs &a)
 }
 
 /* partials buffer grows with the largest reduction grid seen */
-static int g_partials_blocks = 0;
-
 bool ensure_partials(int n_blocks)
 {
-  if (n_blocks <= g_partials_blocks) return true;
   Context &c = ctx();
+  if (n_blocks <= c.partials_blocks) return true;
   if (c.partials) {
     cudaStreamSynchronize(c.stream);
     cudaFree(c.partials);
@@ -424,13 +422,13 @@ bool ensure_partials(int n_blocks)
   int nb = n_blocks + n_blocks/4 + 1024;
   if (!CSB_CUDA(cudaMalloc((void **)&c.partials, sizeof(double)*RED_MAX_Q*(size_t)nb)))
     return false;
-  g_partials_blocks = nb;
+  c.partials_blocks = nb;
   return true;
 }
 
 void reset_partials()
 {
-  g_partials_blocks = 0;
+  ctx().partials_blocks = 0;
 }
 
 /*--------------------------------------------------------------------------
@@ -1369,18 +1367,26 @@ k_coarse_stage_2(const CoarseAssemblyArgs a)
 
 } // anonymous namespace
 
-bool launch_coarse_assembly(const CoarseAssemblyArgs &a)
+/* stages: 1 = sums over fine rows (cell centres, volumes, faces, diagonal),
+   2 = extra-diagonal values; ghost cell centres / volumes of a distributed
+   level are synchronised between the two (cs_grid.cpp:6561-6581) */
+bool launch_coarse_assembly(const CoarseAssemblyArgs &a, int stages)
 {
   Context &c = ctx();
   if (a.c_n_rows < 1) return true;
+  const int grid = (a.c_n_rows + 127) / 128;
+  if (!(stages & 1)) {
+    k_coarse_stage_2<<<grid, 128, 0, c.stream>>>(a);
+    return post_launch("coarse_stage_2");
+  }
   if (a.c_n_faces > 0) {
     if (!CSB_CUDA(cudaMemsetAsync(a.c_face_normal, 0, sizeof(double)*3*(size_t)a.c_n_faces, c.stream))) return false;
     if (!CSB_CUDA(cudaMemsetAsync(a.c_xa0, 0, sizeof(double)*(size_t)a.c_n_faces, c.stream))) return false;
     if (!CSB_CUDA(cudaMemsetAsync(a.c_xa0ij, 0, sizeof(double)*3*(size_t)a.c_n_faces, c.stream))) return false;
   }
-  const int grid = (a.c_n_rows + 127) / 128;
   k_coarse_stage_1<<<grid, 128, 0, c.stream>>>(a);
   if (!post_launch("coarse_stage_1")) return false;
+  if (!(stages & 2)) return true;
   k_coarse_stage_2<<<grid, 128, 0, c.stream>>>(a);
   return post_launch("coarse_stage_2");
 }

@@ -102,28 +102,118 @@ __device__ __forceinline__ void cta_sum_bcast(double (&v)[Q], double *s_red /* Q
   __syncthreads();
 }
 
-/* Grid-wide deterministic sum, result identical in every thread of every CTA.
-   SINGLE: only this CTA takes part. */
+/* Deterministic sum over the grid and, with a communicator, over all ranks:
+   the result is identical in every thread of every CTA of every rank.
+   SINGLE: only this CTA takes part on this rank.
+   Cross-rank stage: block 0 stores the rank's totals into slot [parity][rank]
+   of every peer's header and publishes the epoch in the matching flag; every
+   CTA polls the (local) flags of all ranks and adds the totals in rank order.
+   Two slots suffice: a rank cannot start all-reduce e+2 before every rank has
+   contributed to e+1, i.e. has finished reading e. */
 template <bool SINGLE, int Q>
 __device__ __forceinline__ void all_sum(double (&v)[Q], double *partials, unsigned *bar,
-                                        double *s_red)
+                                        double *s_red, const CommDev *C)
 {
+  unsigned e = 0;
+  if (C != nullptr)      /* read before the grid barrier: block 0 bumps it after */
+    e = *(volatile unsigned *)&C->local->x_epoch + 1;
   cta_sum_bcast<Q>(v, s_red);
-  if (SINGLE) return;
-  const unsigned G = gridDim.x;
-  if (threadIdx.x == 0) {
+  if (!SINGLE) {
+    const unsigned G = gridDim.x;
+    if (threadIdx.x == 0) {
 #pragma unroll
-    for (int q = 0; q < Q; q++) partials[q*G + blockIdx.x] = v[q];
+      for (int q = 0; q < Q; q++) partials[q*G + blockIdx.x] = v[q];
+    }
+    grid_barrier(bar);
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      double w = 0.0;
+      for (unsigned i = threadIdx.x; i < G; i += PT)
+        w += __ldcg(partials + q*G + i);
+      v[q] = w;
+    }
+    cta_sum_bcast<Q>(v, s_red);
   }
-  grid_barrier(bar);
+  if (C == nullptr) return;
+
+  const int R = C->n_ranks, me = C->rank, par = e & 1;
+  CommHeader *H = (CommHeader *)C->peer[me];
+  if ((SINGLE || blockIdx.x == 0) && threadIdx.x == 0) {
+    *(volatile unsigned *)&C->local->x_epoch = e;
+    for (int r = 0; r < R; r++) {
+      CommHeader *P = (CommHeader *)C->peer[r];
+#pragma unroll
+      for (int q = 0; q < Q; q++) P->xsum[par][me][q] = v[q];
+    }
+    __threadfence_system();
+    for (int r = 0; r < R; r++)
+      *(volatile unsigned *)&((CommHeader *)C->peer[r])->xflag[par][me] = e;
+  }
+  double *s_x = s_red + 40;        /* [Q][COMM_MAX_RANKS] */
+  if (threadIdx.x < R) {
+    spin_until_ge(&H->xflag[par][threadIdx.x], e, C->timeout_ns, 6);
+    __threadfence();
+#pragma unroll
+    for (int q = 0; q < Q; q++)
+      s_x[q*COMM_MAX_RANKS + threadIdx.x] = __ldcg(&H->xsum[par][threadIdx.x][q]);
+  }
+  __syncthreads();
 #pragma unroll
   for (int q = 0; q < Q; q++) {
     double w = 0.0;
-    for (unsigned i = threadIdx.x; i < G; i += PT)
-      w += __ldcg(partials + q*G + i);
+    for (int r = 0; r < R; r++) w += s_x[q*COMM_MAX_RANKS + r];
     v[q] = w;
   }
-  cta_sum_bcast<Q>(v, s_red);
+  __syncthreads();
+}
+
+/*--------------------------------------------------------------------------
+ * Ghost exchange of one level, fused into the solver kernel
+ * (cs_halo_sync_var: pack + send/recv + wait, src/base/cs_halo.cpp:1739-2220).
+ * Every CTA gathers its share of the send list and stores it straight into the
+ * neighbours' ghost buffers; the last CTA to finish publishes the exchange
+ * count in each neighbour's flag word; then every CTA waits for the flags of
+ * its own neighbours.  Returns the buffer holding this exchange's ghost values
+ * (ghost column c is at [c - n_rows]); nullptr when there is nothing to wait for.
+ * x must be complete (call after a grid barrier).
+ *--------------------------------------------------------------------------*/
+
+template <bool SINGLE>
+__device__ __forceinline__ const double *halo_exchange(const MgLevelDesc &L, const double *x)
+{
+  const DistLevel *D = L.dist;
+  if (D == nullptr) return nullptr;
+  const int n_dom = D->n_dom;
+  if (n_dom == 0) return nullptr;
+  const unsigned k = *(volatile unsigned *)D->count + 1;
+  const int par = k & 1;
+  const int first = SINGLE ? threadIdx.x : blockIdx.x*PT + threadIdx.x;
+  const int step = SINGLE ? PT : gridDim.x*PT;
+  const int *__restrict__ send_list = D->send_list;
+  for (int i = 0; i < n_dom; i++) {
+    const int s0 = D->send_index[i], s1 = D->send_index[i+1];
+    double *dst = D->push_dst[i][par];
+    for (int e = s0 + first; e < s1; e += step)
+      dst[e - s0] = x[send_list[e]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bool last = true;
+    if (!SINGLE) last = (atomicInc(D->ticket, gridDim.x - 1) == gridDim.x - 1);
+    if (last) {
+      *(volatile unsigned *)D->count = k;
+      __threadfence_system();
+      for (int i = 0; i < n_dom; i++)
+        *(volatile unsigned *)D->flag_remote[i] = k;
+    }
+  }
+  if (threadIdx.x < n_dom) {
+    spin_until_ge(D->flag_local + threadIdx.x, k, D->timeout_ns, 7);
+    __threadfence();
+  }
+  __syncthreads();
+  return D->gbuf[par];
 }
 
 /*--------------------------------------------------------------------------
@@ -136,8 +226,10 @@ __device__ __forceinline__ void all_sum(double (&v)[Q], double *partials, unsign
 
 template <bool SINGLE, class Epi>
 __device__ __forceinline__ void spmv_slabs(const MgLevelDesc &L, const double *x,
-                                           double *s_prod, Epi epi)
+                                           const double *ghost, double *s_prod, Epi epi)
 {
+  /* column c < n_rows: x[c]; ghost column: ghost[c - n_rows] */
+  const double *xg = (ghost != nullptr) ? ghost - L.n_rows : x;
   const int tid = threadIdx.x;
   const int first = SINGLE ? 0 : blockIdx.x;
   const int step = SINGLE ? 1 : gridDim.x;
@@ -158,14 +250,17 @@ __device__ __forceinline__ void spmv_slabs(const MgLevelDesc &L, const double *x
       const int c2 = __ldg(ci + i + 2*PT), c3 = __ldg(ci + i + 3*PT);
       const double m0 = __ldg(xv + i),        m1 = __ldg(xv + i + PT);
       const double m2 = __ldg(xv + i + 2*PT), m3 = __ldg(xv + i + 3*PT);
-      const double x0 = x[c0], x1 = x[c1], x2 = x[c2], x3 = x[c3];
+      const double x0 = (c0 < n_rows) ? x[c0] : xg[c0], x1 = (c1 < n_rows) ? x[c1] : xg[c1];
+      const double x2 = (c2 < n_rows) ? x[c2] : xg[c2], x3 = (c3 < n_rows) ? x[c3] : xg[c3];
       s_prod[i]        = m0*x0;
       s_prod[i + PT]   = m1*x1;
       s_prod[i + 2*PT] = m2*x2;
       s_prod[i + 3*PT] = m3*x3;
     }
-    for (; i < nk; i += PT)
-      s_prod[i] = __ldg(xv + i) * x[__ldg(ci + i)];
+    for (; i < nk; i += PT) {
+      const int c = __ldg(ci + i);
+      s_prod[i] = __ldg(xv + i) * ((c < n_rows) ? x[c] : xg[c]);
+    }
     __syncthreads();
     const int r = r0 + tid;
     if (r < r1) {
@@ -246,8 +341,10 @@ __device__ __noinline__ PcgResult pcg_run(const MgLevelDesc &L, const double *rh
   if (rec) st->n_hist = 0;
 
   /* residual and descent direction (:1502-1516) */
+  const CommDev *comm = P.comm;
   if (vx_ini_nonzero) {
-    spmv_slabs<SINGLE>(L, vx, s_prod, [&](int r, double sii) {
+    const double *gh = halo_exchange<SINGLE>(L, vx);
+    spmv_slabs<SINGLE>(L, vx, gh, s_prod, [&](int r, double sii) {
       const double rr = (sii + d_val[r]*vx[r]) - rhs[r];
       rk[r] = rr;
       dk[r] = rr * ad_inv[r];
@@ -265,14 +362,15 @@ __device__ __noinline__ PcgResult pcg_run(const MgLevelDesc &L, const double *rh
 
   /* zk = A.dk and the first 3 dots (:1521-1535) */
   double v[3] = {0., 0., 0.};
-  spmv_slabs<SINGLE>(L, dk, s_prod, [&](int r, double sii) {
+  const double *gh_d = halo_exchange<SINGLE>(L, dk);
+  spmv_slabs<SINGLE>(L, dk, gh_d, s_prod, [&](int r, double sii) {
     const double d = dk[r];
     const double z = sii + d_val[r]*d;
     zk[r] = z;
     const double rr = rk[r];
     v[0] += rr*rr; v[1] += rr*d; v[2] += d*z;
   });
-  all_sum<SINGLE, 3>(v, part0, P.barrier, s_red);
+  all_sum<SINGLE, 3>(v, part0, P.barrier, s_red, comm);
 
   double ro_0 = v[1], ro_1 = v[2], rk_gkm1 = 0., alpha = 0., beta = 0.;
   R.residual = sqrt(v[0]);
@@ -293,7 +391,7 @@ __device__ __noinline__ PcgResult pcg_run(const MgLevelDesc &L, const double *rh
       gk[i] = rr * ad_inv[i];
       w[0] += rr*rr;
     });
-    all_sum<SINGLE, 1>(w, part1, P.barrier, s_red);
+    all_sum<SINGLE, 1>(w, part1, P.barrier, s_red, comm);
     if (SINGLE) __syncthreads();
     R.residual = sqrt(w[0]);
     R.cvg = it_cvg_eval(precision, r_norm, n_max_iter, R.initial_residual, 1, R.residual);
@@ -303,14 +401,15 @@ __device__ __noinline__ PcgResult pcg_run(const MgLevelDesc &L, const double *rh
   while (R.cvg == CSB_SLES_ITERATING) {
     if (smoother && R.n_iter >= n_max_iter) break;
     v[0] = 0.; v[1] = 0.; v[2] = 0.;
-    spmv_slabs<SINGLE>(L, gk, s_prod, [&](int r, double sii) {   /* :1591-1600 */
+    const double *gh_g = halo_exchange<SINGLE>(L, gk);
+    spmv_slabs<SINGLE>(L, gk, gh_g, s_prod, [&](int r, double sii) {   /* :1591-1600 */
       const double g = gk[r];
       const double s = sii + d_val[r]*g;
       sk[r] = s;
       const double rr = rk[r];
       v[0] += rr*rr; v[1] += rr*g; v[2] += g*s;
     });
-    all_sum<SINGLE, 3>(v, part0, P.barrier, s_red);
+    all_sum<SINGLE, 3>(v, part0, P.barrier, s_red, comm);
     const double residual = sqrt(v[0]);
     const double rk_gk = v[1], gk_sk = v[2];
     R.residual = residual;
@@ -369,8 +468,8 @@ k_pcg_persistent(const MgLevelDesc L, const double *rhs, double *vx, int vx_ini_
                  const PersistentCommon P, ItState *st, int single)
 {
   extern __shared__ double s_dyn[];
-  double *s_red = s_dyn;             /* 40 doubles */
-  double *s_prod = s_dyn + 40;
+  double *s_red = s_dyn;
+  double *s_prod = s_dyn + PERSISTENT_S_RED;
   if (single) {
     if (blockIdx.x == 0)
       pcg_run<true>(L, rhs, vx, vx_ini_nonzero != 0, n_max_iter, precision, r_norm, false,
@@ -390,13 +489,13 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
 {
   extern __shared__ double s_dyn[];
   double *s_red = s_dyn;
-  double *s_prod = s_dyn + 40;
+  double *s_prod = s_dyn + PERSISTENT_S_RED;
 
   const MgLevelDesc *__restrict__ LV = S.levels;
   MgState *ms = S.ms;
   const bool lead = (blockIdx.x == 0 && threadIdx.x == 0);
   const int coarsest = S.n_levels - 1;
-  const double denom_n_rows_0 = 1.0 / (double)LV[0].n_rows;
+  const double denom_n_rows_0 = 1.0 / LV[0].n_g_rows;     /* global rows (:3341) */
 
   int cvg = CSB_SLES_ITERATING;
   int n_equiv_iter = 0;
@@ -444,7 +543,8 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
       {
         const double *__restrict__ d_val = L.d_val;
         double *wr = S.wr;
-        spmv_slabs<false>(L, vx_lv, s_prod, [&](int r, double sii) {
+        const double *gh = halo_exchange<false>(L, vx_lv);
+        spmv_slabs<false>(L, vx_lv, gh, s_prod, [&](int r, double sii) {
           const double y = sii + d_val[r]*vx_lv[r];
           const double t = rhs_lv[r] - y;
           wr[r] = t;
@@ -452,7 +552,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
         });
       }
       if (level == 0) {
-        all_sum<false, 1>(w, P.partials + 8*(size_t)gridDim.x, P.barrier, s_red);
+        all_sum<false, 1>(w, P.partials + 8*(size_t)gridDim.x, P.barrier, s_red, P.comm);
         residual = sqrt(w[0]);
         const double ir = (cycle_id == 1) ? residual : initial_residual;   /* :2967 */
         if (lead && ms->n_cycles_res < CYCLE_MAX) ms->cycle_res[ms->n_cycles_res++] = residual;
@@ -466,7 +566,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
       if (lead) prof_mark(ms, t_last, level, MG_PROF_RESIDUAL);
 
       n_equiv_iter = (int)((double)n_equiv_iter
-                           + R.n_iter * ((double)L.n_rows * denom_n_rows_0));
+                           + R.n_iter * (L.n_g_rows * denom_n_rows_0));
       if (cvg != CSB_SLES_ITERATING) { end_cycle = true; break; }
 
       /* restriction: coarse row = sum of its fine rows, ascending fine order
@@ -511,7 +611,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
       }
       if (lead) prof_mark(ms, t_last, coarsest, MG_PROF_COARSEST);
       n_equiv_iter = (int)((double)n_equiv_iter
-                           + R.n_iter * ((double)L.n_rows * denom_n_rows_0));
+                           + R.n_iter * (L.n_g_rows * denom_n_rows_0));
       if (R.cvg < CSB_SLES_BREAKDOWN) { end_cycle = true; cvg = CSB_SLES_DIVERGED; }
       if (coarsest == 0) {   /* degenerate one-level hierarchy: plain PCG solve */
         residual = *((volatile double *)&L.st_descent->residual);
@@ -555,7 +655,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
           }
           if (lead) prof_mark(ms, t_last, level, MG_PROF_ASCENT);
           n_equiv_iter = (int)((double)n_equiv_iter
-                               + R.n_iter * ((double)L.n_rows * denom_n_rows_0));
+                               + R.n_iter * (L.n_g_rows * denom_n_rows_0));
           if (R.cvg < CSB_SLES_BREAKDOWN) { cvg = CSB_SLES_DIVERGED; break; }
         }
       }
@@ -592,7 +692,7 @@ void plan_slabs(const std::vector<csb_lnum_t> &ri, int n_rows, int &slab_rows, i
 
 size_t persistent_smem_bytes(size_t max_slab_entries)
 {
-  return (40 + (max_slab_entries > 2 ? max_slab_entries : 2)) * sizeof(double);
+  return (PERSISTENT_S_RED + (max_slab_entries > 2 ? max_slab_entries : 2)) * sizeof(double);
 }
 
 /* number of co-resident CTAs for the given dynamic shared memory size */
@@ -622,20 +722,26 @@ int persistent_grid(int which, size_t smem)
     cap = (s != nullptr) ? atoi(s) : 4;
   }
   if (occ > cap && cap > 0) occ = cap;
-  return occ * c.sm_count;
+  int g = occ * c.sm_count / (c.device_share > 1 ? c.device_share : 1);
+  return (g > 0) ? g : 1;
 }
 
 bool launch_pcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
                            bool vx_ini_nonzero, int n_max_iter, double precision,
                            double r_norm, const PersistentCommon &P, ItState *st,
-                           int grid, size_t smem, bool single)
+                           int grid, size_t smem, bool single, bool cooperative)
 {
   int ini = vx_ini_nonzero ? 1 : 0;
   int sgl = single ? 1 : 0;
   void *args[] = {(void *)&L, (void *)&rhs, (void *)&vx, (void *)&ini, (void *)&n_max_iter,
                   (void *)&precision, (void *)&r_norm, (void *)&P, (void *)&st, (void *)&sgl};
-  cudaError_t e = cudaLaunchCooperativeKernel((void *)k_pcg_persistent, dim3(grid), dim3(PT),
-                                              args, smem, ctx().stream);
+  /* ranks sharing one device (in-process test groups) cannot both launch
+     cooperatively; their grids are sized to be co-resident together */
+  cudaError_t e = cooperative
+    ? cudaLaunchCooperativeKernel((void *)k_pcg_persistent, dim3(grid), dim3(PT), args, smem,
+                                  ctx().stream)
+    : cudaLaunchKernel((void *)k_pcg_persistent, dim3(grid), dim3(PT), args, smem,
+                       ctx().stream);
   ctx().launches += 1;
   if (e != cudaSuccess) {
     set_error("cooperative launch of k_pcg_persistent failed: %s", cudaGetErrorString(e));
@@ -645,11 +751,14 @@ bool launch_pcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
 }
 
 bool launch_mg_persistent(const MgSolveParams &S, const PersistentCommon &P, int grid,
-                          size_t smem)
+                          size_t smem, bool cooperative)
 {
   void *args[] = {(void *)&S, (void *)&P};
-  cudaError_t e = cudaLaunchCooperativeKernel((void *)k_mg_persistent, dim3(grid), dim3(PT),
-                                              args, smem, ctx().stream);
+  cudaError_t e = cooperative
+    ? cudaLaunchCooperativeKernel((void *)k_mg_persistent, dim3(grid), dim3(PT), args, smem,
+                                  ctx().stream)
+    : cudaLaunchKernel((void *)k_mg_persistent, dim3(grid), dim3(PT), args, smem,
+                       ctx().stream);
   ctx().launches += 1;
   if (e != cudaSuccess) {
     set_error("cooperative launch of k_mg_persistent failed: %s", cudaGetErrorString(e));

@@ -24,6 +24,8 @@ struct MgLevelDesc {
   const int    *c_f_row_ids;
   ItState      *st_descent;    /* also used for the coarsest solve */
   ItState      *st_ascent;
+  double        n_g_rows;      /* rows of this level over all ranks */
+  const DistLevel *dist;       /* ghost exchange of this level; nullptr on one rank */
 };
 
 struct PersistentCommon {
@@ -31,7 +33,10 @@ struct PersistentCommon {
   size_t    work_stride;
   double   *partials;      /* 12 * grid doubles */
   unsigned *barrier;       /* 2 words, zero-initialised */
+  const CommDev *comm;     /* nullptr on one rank */
 };
+
+constexpr int PERSISTENT_S_RED = 104;   /* doubles of reduction scratch ahead of the slab */
 
 struct MgSolveParams {
   int                n_levels;
@@ -54,10 +59,10 @@ int    persistent_grid(int which, size_t smem);   /* 0: PCG kernel, 1: multigrid
 bool launch_pcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
                            bool vx_ini_nonzero, int n_max_iter, double precision,
                            double r_norm, const PersistentCommon &P, ItState *st,
-                           int grid, size_t smem, bool single);
+                           int grid, size_t smem, bool single, bool cooperative);
 
 bool launch_mg_persistent(const MgSolveParams &S, const PersistentCommon &P, int grid,
-                          size_t smem);
+                          size_t smem, bool cooperative);
 
 /* choose the slab height of a level so that a slab's products fit in ~40 KB */
 void plan_slabs(const std::vector<csb_lnum_t> &row_index, int n_rows, int &slab_rows,

@@ -8,7 +8,8 @@
 
 namespace csb {
 
-static Context g_ctx;
+/* one context per host thread: a rank is a process, or a thread of one */
+static thread_local Context g_ctx;
 
 Context &ctx() { return g_ctx; }
 

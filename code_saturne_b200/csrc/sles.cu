@@ -61,6 +61,63 @@ struct StagedVec {
 const size_t IT_HEAD = offsetof(ItState, hist);
 const size_t MG_HEAD = offsetof(MgState, cycle_res);
 
+/* Ghost-exchange descriptor of one matrix/level for the persistent kernels:
+   ghost buffers and flag words in the arena, the neighbours' matching
+   addresses obtained through the mailbox.  Collective over all ranks. */
+struct DistLevelHost {
+  DistLevel           h;
+  DevBuf<unsigned>    words;      /* count, ticket */
+  DevBuf<DistLevel>   d;          /* device copy */
+};
+
+bool build_dist_level(csb_pcomm_t *pc, const csb_halo_t *halo, DistLevelHost &out)
+{
+  Context &c = ctx();
+  DistLevel &D = out.h;
+  memset(&D, 0, sizeof(D));
+  const int nd = (halo != nullptr) ? halo->n_c_domains : 0;
+  if (nd > COMM_MAX_DOM) {
+    set_error("halo with %d neighbour ranks: at most %d supported", nd, COMM_MAX_DOM);
+    return false;
+  }
+  if (halo != nullptr && halo->pcomm != pc) {
+    set_error("matrix halo is not attached to the solver's communicator (csb_halo_set_pcomm)");
+    return false;
+  }
+  D.n_dom = nd;
+  D.n_send = (halo != nullptr) ? halo->n_send : 0;
+  D.n_ghost = (halo != nullptr) ? halo->n_ghost : 0;
+  D.send_list = (halo != nullptr) ? halo->send_list.p : nullptr;
+  for (int i = 0; i <= nd && halo != nullptr; i++) D.send_index[i] = halo->send_index[i];
+  const size_t gb = sizeof(double) * (size_t)(D.n_ghost > 0 ? D.n_ghost : 1);
+  D.gbuf[0] = (double *)pcomm_arena_alloc(pc, gb);
+  D.gbuf[1] = (double *)pcomm_arena_alloc(pc, gb);
+  D.flag_local = (unsigned *)pcomm_arena_alloc(pc, sizeof(unsigned)*COMM_MAX_DOM);
+  if (D.gbuf[0] == nullptr || D.gbuf[1] == nullptr || D.flag_local == nullptr) return false;
+  if (!out.words.alloc(2)) return false;
+  if (!CSB_CUDA(cudaMemsetAsync(out.words.p, 0, 2*sizeof(unsigned), c.stream))) return false;
+  D.count = out.words.p;
+  D.ticket = out.words.p + 1;
+  D.timeout_ns = pc->h.timeout_ns;
+
+  std::vector<long long> snd((size_t)nd*8 + 8, 0), rcv((size_t)nd*8 + 8, 0);
+  for (int i = 0; i < nd; i++) {
+    snd[(size_t)i*8 + 0] = ((char *)D.gbuf[0] - pc->arena) + 8ll*halo->index[i];
+    snd[(size_t)i*8 + 1] = ((char *)D.gbuf[1] - pc->arena) + 8ll*halo->index[i];
+    snd[(size_t)i*8 + 2] = ((char *)D.flag_local - pc->arena) + 4ll*i;
+  }
+  if (!pcomm_mailbox(pc, nd, nd > 0 ? halo->c_domain_rank.data() : nullptr, snd.data(),
+                     rcv.data())) return false;
+  for (int i = 0; i < nd; i++) {
+    char *base = pc->h.peer[halo->c_domain_rank[i]];
+    D.push_dst[i][0] = (double *)(base + rcv[(size_t)i*8 + 0]);
+    D.push_dst[i][1] = (double *)(base + rcv[(size_t)i*8 + 1]);
+    D.flag_remote[i] = (unsigned *)(base + rcv[(size_t)i*8 + 2]);
+  }
+  if (!out.d.upload(&D, 1)) return false;
+  return CSB_CUDA(cudaStreamSynchronize(c.stream));
+}
+
 } // anonymous namespace
 
 /*----------------------------------------------------------------------------
@@ -73,6 +130,10 @@ struct _csb_sles_it_t {
   int                 n_max_iter = 10000;
   bool                update_stats = false;
   void               *nccl_comm = nullptr;
+  csb_pcomm_t        *pcomm = nullptr;
+  DistLevelHost       dist;
+  size_t              arena_mark = 0;
+  bool                arena_used = false;
   /* setup data (cs_sles_it_setup_t, src/alge/cs_sles_it_priv.h) */
   const csb_matrix_t *a = nullptr;
   bool                setup_done = false;
@@ -270,6 +331,13 @@ int csb_sles_it_set_reduce_comm(csb_sles_it_t *c, void *nccl_comm)
   return 0;
 }
 
+int csb_sles_it_set_pcomm(csb_sles_it_t *c, csb_pcomm_t *comm)
+{
+  if (c == nullptr) return -1;
+  c->pcomm = comm;
+  return 0;
+}
+
 void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, int verbosity)
 {
   (void)name; (void)verbosity;
@@ -285,10 +353,24 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
   if (!c->st.alloc(1)) return;
   if (c->h_st == nullptr)
     if (!CSB_CUDA(cudaMallocHost((void **)&c->h_st, sizeof(ItState)))) return;
-  if (c->type == CSB_SLES_PCG && a->halo == nullptr) {
+  if (a->halo != nullptr && (c->type != CSB_SLES_PCG || c->pcomm == nullptr)) {
+    set_error("csb_sles_it_setup: a matrix with a halo needs CSB_SLES_PCG and a peer "
+              "communicator (csb_sles_it_set_pcomm) on this path");
+    return;
+  }
+  if (c->type == CSB_SLES_PCG) {
     size_t max_entries = 0;
     MgLevelDesc &d = c->desc;
     memset(&d, 0, sizeof(d));
+    d.n_g_rows = (double)a->n_rows;
+    if (a->halo != nullptr) {
+      if (c->arena_used) pcomm_arena_release(c->pcomm, c->arena_mark);
+      c->arena_mark = pcomm_arena_mark(c->pcomm);
+      c->arena_used = true;
+      if (!build_dist_level(c->pcomm, a->halo, c->dist)) return;
+      d.dist = c->dist.d.p;
+      if (!pcomm_allreduce(c->pcomm, &d.n_g_rows, 1)) return;
+    }
     plan_slabs(a->h_row_index, a->n_rows, d.slab_rows, d.n_slabs, max_entries);
     d.n_rows = a->n_rows;
     d.row_index = a->row_index.p; d.col_id = a->col_id.p;
@@ -336,14 +418,18 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
   bool ok = false;
   switch (c->type) {
   case CSB_SLES_PCG:
-    if (a->halo == nullptr && env_int("CSB_PCG_MODE_MULTI", 0) == 0) {
-      /* whole solve in one persistent cooperative kernel */
+    if (a->halo != nullptr || env_int("CSB_PCG_MODE_MULTI", 0) == 0) {
+      /* whole solve in one persistent cooperative kernel (per rank) */
       PersistentCommon P;
       P.work = c->work.p; P.work_stride = (size_t)a->n_cols_ext;
       P.partials = c->partials.p; P.barrier = c->barrier.p;
+      P.comm = (a->halo != nullptr) ? c->pcomm->d : nullptr;
       const bool single = (a->n_rows <= sb_rows_threshold());
+      if (a->halo != nullptr) pcomm_host_barrier(c->pcomm);
       ok = launch_pcg_persistent(c->desc, s_rhs.d, s_vx.d, ini, c->n_max_iter, precision,
-                                 r_norm, P, c->st.p, c->p_grid, c->p_smem, single);
+                                 r_norm, P, c->st.p, c->p_grid, c->p_smem, single,
+                                 cx.device_share <= 1);
+      if (a->halo != nullptr) pcomm_host_barrier(c->pcomm);   /* all ranks launched */
     }
     else
       ok = pcg_enqueue(a, c->st.p, nullptr, c->ad_inv.p, precision, r_norm, c->n_max_iter,
@@ -388,6 +474,10 @@ void csb_sles_it_free(void *context)
   if (c == nullptr) return;
   c->ad_inv.release();
   c->work.release();
+  if (c->arena_used && c->pcomm != nullptr) {
+    pcomm_arena_release(c->pcomm, c->arena_mark);
+    c->arena_used = false;
+  }
   c->a = nullptr;
   c->setup_done = false;
 }
@@ -439,7 +529,7 @@ void *csb_sles_it_copy(const void *context)
   if (c == nullptr) return nullptr;
   csb_sles_it_t *d = csb_sles_it_create(c->type, c->poly_degree, c->n_max_iter,
                                         c->update_stats ? 1 : 0);
-  if (d) d->nccl_comm = c->nccl_comm;
+  if (d) { d->nccl_comm = c->nccl_comm; d->pcomm = c->pcomm; }
   return d;
 }
 
@@ -466,7 +556,15 @@ struct MgLevel {
   DevBuf<short>       cell_face_sgn;
   DevBuf<double>      cell_cen, cell_vol, face_normal, xa0, xa0ij;
   int                 n_faces = 0;
-  ~MgLevel() { if (owned) csb_matrix_destroy(&owned); }
+  /* distributed hierarchy */
+  csb_halo_t         *halo = nullptr;       /* this level's halo (owned when level > 0) */
+  bool                halo_owned = false;
+  double              n_g_rows = 0.;        /* rows over all ranks */
+  DistLevelHost       dist;
+  ~MgLevel() {
+    if (owned) csb_matrix_destroy(&owned);
+    if (halo_owned && halo) csb_halo_destroy(&halo);
+  }
 };
 
 } // anonymous namespace
@@ -486,6 +584,9 @@ struct _csb_multigrid_t {
   int     poly_degree[3] = {0, 0, 0};
   double  precision_mult[3] = {1., 1., 1.};
   void   *nccl_comm = nullptr;
+  csb_pcomm_t *pcomm = nullptr;
+  size_t  arena_mark = 0;
+  bool    arena_used = false;
   /* setup data */
   std::vector<MgLevel *> levels;
   DevBuf<ItState>  it_states;   /* 2 per level */
@@ -518,6 +619,10 @@ void mg_clear_hierarchy(csb_multigrid_t *mg)
 {
   for (MgLevel *l : mg->levels) delete l;
   mg->levels.clear();
+  if (mg->arena_used && mg->pcomm != nullptr) {
+    pcomm_arena_release(mg->pcomm, mg->arena_mark);
+    mg->arena_used = false;
+  }
   mg->wr.release();
   mg->aux.release();
   mg->it_states.release();
@@ -547,6 +652,88 @@ bool matrix_host_mirror(csb_matrix_t *m)
     m->h_vals_valid = true;
   }
   return CSB_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+/* Coarse halo of a distributed level: _coarsen_halo (src/alge/cs_grid.cpp:924-1329).
+   f_c_row has f_n_cols_ext entries; the local part is the aggregation map, the
+   ghost part is filled here with coarse ghost column ids (c_n_rows + position in
+   the coarse ghost sections).  Collective over the neighbour ranks. */
+csb_halo_t *coarsen_halo(csb_pcomm_t *pc, const csb_halo_t *fh, int f_n_rows, int c_n_rows,
+                         std::vector<int> &f_c_row)
+{
+  Context &c = ctx();
+  const int nd = fh->n_c_domains;
+  const int n_f_send = fh->n_send, n_f_ghost = fh->n_ghost;
+  for (int ii = f_n_rows; ii < f_n_rows + n_f_ghost; ii++) f_c_row[ii] = -1;      /* :960-962 */
+
+  /* sub_num shifted by 1 so that penalised rows (-1) map to slot 0 (:971-977) */
+  std::vector<int> sub_num((size_t)c_n_rows + 1, -1), coarse_send((size_t)std::max(n_f_send, 1), -1);
+  std::vector<int> c_send_list, c_send_index((size_t)nd + 1, 0);
+  sub_num[0] = -2;
+  const int *send_list = fh->h_send_list.data();
+  for (int d = 0; d < nd; d++) {                                                   /* :988-1061 */
+    int sub_count = 0;
+    for (int ii = fh->send_index[d]; ii < fh->send_index[d+1]; ii++) {
+      const int jj = f_c_row[send_list[ii]] + 1;
+      if (sub_num[jj] == -1) {
+        sub_num[jj] = sub_count++;
+        c_send_list.push_back(jj - 1);                                             /* :1188-1197 */
+      }
+      coarse_send[ii] = sub_num[jj];
+    }
+    for (int ii = fh->send_index[d]; ii < fh->send_index[d+1]; ii++)
+      sub_num[f_c_row[send_list[ii]] + 1] = -1;
+    sub_num[0] = -2;
+    c_send_index[d+1] = (int)c_send_list.size();
+  }
+
+  /* _exchange_halo_coarsening (:802-910): ids travel in send-list order */
+  {
+    DevBuf<int> d_send, d_ghost;
+    HaloDev v;
+    if (!halo_dev_view(fh, v)) return nullptr;
+    v.send_list = nullptr;
+    if (!d_send.upload(coarse_send.data(), (size_t)std::max(n_f_send, 1))
+        || !d_ghost.alloc((size_t)std::max(n_f_ghost, 1))) return nullptr;
+    if (!pcomm_window_exchange(pc, v, 4, 1, d_send.p, d_ghost.p)) return nullptr;
+    if (n_f_ghost > 0 &&
+        !CSB_CUDA(cudaMemcpyAsync(f_c_row.data() + f_n_rows, d_ghost.p, sizeof(int)*(size_t)n_f_ghost,
+                                  cudaMemcpyDeviceToHost, c.stream))) return nullptr;
+    if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return nullptr;
+  }
+
+  /* coarse ghost numbering, section by section (:1076-1140) */
+  std::vector<int> c_index((size_t)nd + 1, 0);
+  int n_elts = 0;
+  for (int d = 0; d < nd; d++) {
+    int jj = -1;
+    for (int ii = f_n_rows + fh->index[d]; ii < f_n_rows + fh->index[d+1]; ii++) {
+      if (f_c_row[ii] > -1) {
+        if (f_c_row[ii] > jj) jj += 1;
+        f_c_row[ii] += c_n_rows + n_elts;
+      }
+    }
+    n_elts += jj + 1;
+    c_index[d+1] = n_elts;
+  }
+
+  /* drop neighbours with nothing left to exchange (:1218-1304) */
+  std::vector<int> ranks, idx(1, 0), sidx(1, 0), sl;
+  for (int d = 0; d < nd; d++) {
+    const int n_r = c_index[d+1] - c_index[d], n_s = c_send_index[d+1] - c_send_index[d];
+    if (n_r + n_s == 0) continue;
+    ranks.push_back(fh->c_domain_rank[d]);
+    idx.push_back(c_index[d+1]);
+    sl.insert(sl.end(), c_send_list.begin() + c_send_index[d], c_send_list.begin() + c_send_index[d+1]);
+    sidx.push_back((int)sl.size());
+  }
+  int dummy = 0;
+  csb_halo_t *ch = csb_halo_create(nullptr, fh->local_rank, (int)ranks.size(),
+                                   ranks.empty() ? &dummy : ranks.data(), c_n_rows, sidx.data(),
+                                   sl.empty() ? &dummy : sl.data(), idx.data());
+  if (ch == nullptr) return nullptr;
+  if (csb_halo_set_pcomm(ch, pc) != 0) { csb_halo_destroy(&ch); return nullptr; }
+  return ch;
 }
 
 } // anonymous namespace
@@ -617,6 +804,13 @@ int csb_multigrid_set_reduce_comm(csb_multigrid_t *mg, void *nccl_comm)
   return 0;
 }
 
+int csb_multigrid_set_pcomm(csb_multigrid_t *mg, csb_pcomm_t *comm)
+{
+  if (mg == nullptr) return -1;
+  mg->pcomm = comm;
+  return 0;
+}
+
 void csb_multigrid_free(void *context)
 {
   csb_multigrid_t *mg = static_cast<csb_multigrid_t *>(context);
@@ -659,9 +853,16 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
                 "(cs_multigrid_create defaults)");
       return;
     }
-  if (a->halo != nullptr) {
-    set_error("csb_multigrid_setup: distributed hierarchy not available yet");
+  const bool dist = (a->halo != nullptr);
+  csb_pcomm_t *pc = dist ? mg->pcomm : nullptr;
+  if (dist && (pc == nullptr || a->halo->pcomm != pc)) {
+    set_error("csb_multigrid_setup: a matrix with a halo needs csb_multigrid_set_pcomm and "
+              "a halo attached to the same communicator (csb_halo_set_pcomm)");
     return;
+  }
+  if (dist) {
+    mg->arena_mark = pcomm_arena_mark(pc);
+    mg->arena_used = true;
   }
 
   const double t_start = wall();
@@ -669,10 +870,15 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
 
   MgLevel *l0 = new MgLevel;
   l0->m = a;
+  l0->halo = a->halo;
   mg->levels.push_back(l0);
   mg->a = a;
 
-  unsigned long long n_g_rows = (unsigned long long)a->n_rows, n_g_rows_prev;
+  /* global row counts drive the stop criteria (cs_grid.cpp:1364-1374) */
+  double g_rows = (double)a->n_rows;
+  if (dist && !pcomm_allreduce(pc, &g_rows, 1)) return;
+  l0->n_g_rows = g_rows;
+  unsigned long long n_g_rows = (unsigned long long)g_rows, n_g_rows_prev;
 
   while (true) {
     n_g_rows_prev = n_g_rows;
@@ -688,7 +894,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
 
     /* aggregation on the host */
     t0 = wall();
-    f->h_coarse_row.resize(std::max(fm->n_rows, 1));
+    f->h_coarse_row.assign((size_t)std::max(fm->n_cols_ext, 1), -1);
     const int c_n_rows
       = aggregate_dx_msr(f_level, fm->n_rows, fm->h_row_index.data(), fm->h_col_id.data(),
                          fm->h_d_val.data(), fm->h_x_val.data(), mg->aggregation_limit,
@@ -696,8 +902,11 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     t_aggr += wall() - t0;
 
     /* stop criteria of _setup_hierarchy (cs_multigrid.cpp:2518-2529); they
-       only depend on the row count, so the rejected level is never assembled */
-    n_g_rows = (unsigned long long)c_n_rows;
+       only depend on the (global) row count, so the rejected level is never
+       assembled */
+    g_rows = (double)c_n_rows;
+    if (dist && !pcomm_allreduce(pc, &g_rows, 1)) return;
+    n_g_rows = (unsigned long long)g_rows;
     bool add = true;
     if (n_g_rows == 0) add = false;
     else if (mg->levels.size() > 1) {
@@ -705,6 +914,17 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
         add = false;
     }
     if (!add) { f->h_coarse_row.clear(); break; }
+
+    /* coarse halo and coarse ids of the ghost rows */
+    csb_halo_t *ch = nullptr;
+    if (dist) {
+      t0 = wall();
+      ch = coarsen_halo(pc, f->halo, fm->n_rows, c_n_rows, f->h_coarse_row);
+      if (ch == nullptr) return;
+      t_xfer += wall() - t0;
+    }
+    const int c_n_ghost = (ch != nullptr) ? ch->n_ghost : 0;
+    const size_t c_n_cols_ext = (size_t)c_n_rows + (size_t)c_n_ghost;
 
     t0 = wall();
     CoarseStructure cs;
@@ -717,9 +937,12 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     MgLevel *cl = new MgLevel;
     csb_matrix_t *cm = new csb_matrix_t;
     cl->owned = cm; cl->m = cm;
-    cm->n_rows = c_n_rows; cm->n_cols_ext = c_n_rows; cm->nnz = c_nnz;
+    cl->halo = ch; cl->halo_owned = (ch != nullptr);
+    cl->n_g_rows = g_rows;
+    cm->halo = ch;
+    cm->n_rows = c_n_rows; cm->n_cols_ext = (csb_lnum_t)c_n_cols_ext; cm->nnz = c_nnz;
     cm->symmetric = true;
-    bool ok = f->coarse_row.upload(f->h_coarse_row.data(), (size_t)fm->n_rows)
+    bool ok = f->coarse_row.upload(f->h_coarse_row.data(), (size_t)fm->n_cols_ext)
            && f->c_f_row_index.upload(cs.c_f_row_index.data(), (size_t)c_n_rows + 1)
            && f->c_f_row_ids.upload(cs.c_f_row_ids.data(), (size_t)fm->n_rows)
            && cm->row_index.upload(cs.c_row_index.data(), (size_t)c_n_rows + 1)
@@ -727,7 +950,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
            && cl->cell_face.upload(cs.c_cell_face.data(), (size_t)c_nnz)
            && cl->cell_face_sgn.upload(cs.c_cell_face_sgn.data(), (size_t)c_nnz)
            && cm->d_val.alloc((size_t)c_n_rows) && cm->x_val.alloc((size_t)c_nnz)
-           && cl->cell_cen.alloc(3*(size_t)c_n_rows) && cl->cell_vol.alloc((size_t)c_n_rows)
+           && cl->cell_cen.alloc(3*c_n_cols_ext) && cl->cell_vol.alloc(c_n_cols_ext)
            && cl->face_normal.alloc(3*(size_t)cs.c_n_faces)
            && cl->xa0.alloc((size_t)cs.c_n_faces) && cl->xa0ij.alloc(3*(size_t)cs.c_n_faces)
            && CSB_CUDA(cudaStreamSynchronize(c.stream));  /* cs.* vectors die below */
@@ -764,7 +987,17 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     ca.c_cell_cen = cl->cell_cen.p; ca.c_cell_vol = cl->cell_vol.p;
     ca.c_face_normal = cl->face_normal.p; ca.c_xa0 = cl->xa0.p; ca.c_xa0ij = cl->xa0ij.p;
     ca.relax = mg->p0p1_relax;
-    if (!launch_coarse_assembly(ca)) { delete cl; return; }
+    if (!launch_coarse_assembly(ca, 1)) { delete cl; return; }
+    if (dist) {
+      /* ghost cell centres and volumes (cs_grid.cpp:6561-6581) */
+      HaloDev hv;
+      if (!halo_dev_view(ch, hv)
+          || !pcomm_window_exchange(pc, hv, 8, 3, cl->cell_cen.p, cl->cell_cen.p + 3*(size_t)c_n_rows)
+          || !pcomm_window_exchange(pc, hv, 8, 1, cl->cell_vol.p, cl->cell_vol.p + c_n_rows)) {
+        delete cl; return;
+      }
+    }
+    if (!launch_coarse_assembly(ca, 2)) { delete cl; return; }
     if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) { delete cl; return; }
     t_asm += wall() - t0;
 
@@ -790,6 +1023,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     if (l > 0) {
       if (!lv->rhs.alloc((size_t)m->n_cols_ext) || !lv->vx.alloc((size_t)m->n_cols_ext)) return;
     }
+    if (dist && !build_dist_level(pc, lv->halo, lv->dist)) return;
   }
   if (!mg->wr.alloc(wr_size) || !mg->aux.alloc(aux_size)) return;
   if (!mg->it_states.alloc(2*(size_t)n_levels)) return;
@@ -813,6 +1047,8 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
       d.c_f_row_index = lv->c_f_row_index.p; d.c_f_row_ids = lv->c_f_row_ids.p;
       d.st_descent = mg->it_states.p + 2*l;
       d.st_ascent = mg->it_states.p + 2*l + 1;
+      d.n_g_rows = dist ? lv->n_g_rows : (double)m->n_rows;
+      d.dist = dist ? lv->dist.d.p : nullptr;
     }
     mg->p_smem = persistent_smem_bytes(max_entries);
     mg->p_grid = persistent_grid(1, mg->p_smem);
@@ -864,7 +1100,7 @@ csb_multigrid_solve(void *context, const char *name, const csb_matrix_t *a, int 
   const double t0 = wall();
   const int n_levels = (int)mg->levels.size();
   const int coarsest = n_levels - 1;
-  const double denom = 1.0 / (double)a->n_rows;
+  const double denom = 1.0 / (double)a->n_rows;   /* kernel-per-phase path: one rank only */
 
   StagedVec s_rhs, s_vx;
   if (!s_rhs.init(const_cast<double *>(rhs), (size_t)a->n_rows, true)) return CSB_SLES_BREAKDOWN;
@@ -875,7 +1111,8 @@ csb_multigrid_solve(void *context, const char *name, const csb_matrix_t *a, int 
 
   int cvg = CSB_SLES_ITERATING;
   int n_cycles = 0;
-  const bool persistent = (env_int("CSB_MG_MODE_MULTI", 0) == 0);
+  const bool dist = (a->halo != nullptr);
+  const bool persistent = dist || (env_int("CSB_MG_MODE_MULTI", 0) == 0);
 
   if (persistent) {
     /* the whole solve (all cycles, all levels) in one cooperative launch */
@@ -893,7 +1130,12 @@ csb_multigrid_solve(void *context, const char *name, const csb_matrix_t *a, int 
     PersistentCommon P;
     P.work = mg->aux.p; P.work_stride = (size_t)a->n_cols_ext;
     P.partials = mg->partials.p; P.barrier = mg->barrier.p;
-    if (!launch_mg_persistent(S, P, mg->p_grid, mg->p_smem)) return CSB_SLES_BREAKDOWN;
+    P.comm = dist ? mg->pcomm->d : nullptr;
+    if (dist) pcomm_host_barrier(mg->pcomm);   /* no rank is inside cudaFree while kernels spin */
+    const bool launched_ok = launch_mg_persistent(S, P, mg->p_grid, mg->p_smem,
+                                                  c.device_share <= 1);
+    if (dist) pcomm_host_barrier(mg->pcomm);   /* all ranks launched before anyone blocks */
+    if (!launched_ok) return CSB_SLES_BREAKDOWN;
     if (!CSB_CUDA(cudaMemcpyAsync(mg->h_mg, ms, MG_HEAD, cudaMemcpyDeviceToHost, c.stream)))
       return CSB_SLES_BREAKDOWN;
     if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return CSB_SLES_BREAKDOWN;
@@ -1006,6 +1248,9 @@ int csb_host_coarse_structure(csb_lnum_t f_n_rows, const csb_lnum_t *f_row_index
 int csb_multigrid_get_n_levels(const csb_multigrid_t *mg)
 { return (mg != nullptr) ? (int)mg->levels.size() : 0; }
 
+int csb_multigrid_is_setup(const csb_multigrid_t *mg)
+{ return (mg != nullptr && mg->setup_done) ? 1 : 0; }
+
 int csb_multigrid_get_n_cycles(const csb_multigrid_t *mg)
 { return (mg != nullptr) ? mg->n_cycles_last : 0; }
 
@@ -1025,7 +1270,7 @@ int csb_multigrid_get_level_arrays(const csb_multigrid_t *mg, int level,
   const csb_matrix_t *m = mg->levels[level]->m;
   if (coarse_row != nullptr && level > 0) {
     const MgLevel *p = mg->levels[level-1];
-    memcpy(coarse_row, p->h_coarse_row.data(), sizeof(int)*(size_t)p->m->n_rows);
+    memcpy(coarse_row, p->h_coarse_row.data(), sizeof(int)*(size_t)p->m->n_cols_ext);
   }
   bool ok = true;
   if (row_index) ok = ok && m->row_index.download(row_index);
@@ -1033,6 +1278,22 @@ int csb_multigrid_get_level_arrays(const csb_multigrid_t *mg, int level,
   if (d_val) ok = ok && m->d_val.download(d_val);
   if (x_val) ok = ok && m->x_val.download(x_val);
   return ok ? 0 : -1;
+}
+
+int csb_multigrid_get_level_halo(const csb_multigrid_t *mg, int level, int sizes[3],
+                                 int *c_domain_rank, csb_lnum_t *send_index,
+                                 csb_lnum_t *send_list, csb_lnum_t *index)
+{
+  if (mg == nullptr || level < 0 || level >= (int)mg->levels.size()) return -1;
+  const csb_halo_t *h = mg->levels[level]->halo;
+  if (h == nullptr) return -1;
+  if (sizes) { sizes[0] = h->n_c_domains; sizes[1] = h->n_send; sizes[2] = h->n_ghost; }
+  const int nd = h->n_c_domains;
+  if (c_domain_rank) for (int i = 0; i < nd; i++) c_domain_rank[i] = h->c_domain_rank[i];
+  if (send_index) for (int i = 0; i <= nd; i++) send_index[i] = h->send_index[i];
+  if (index) for (int i = 0; i <= nd; i++) index[i] = h->index[i];
+  if (send_list) for (int i = 0; i < h->n_send; i++) send_list[i] = h->h_send_list[i];
+  return 0;
 }
 
 int csb_multigrid_get_cycle_residuals(const csb_multigrid_t *mg, double *res, int max_n)
@@ -1099,6 +1360,7 @@ void *csb_multigrid_copy(const void *context)
     d->precision_mult[i] = s->precision_mult[i];
   }
   d->nccl_comm = s->nccl_comm;
+  d->pcomm = s->pcomm;
   return d;
 }
 

@@ -187,3 +187,176 @@ def matrix_check_coefficients(sys: CubeSystem, symmetric: bool = True):
         x_val = np.where(cols > rows, x_val, -x_val)
     x = np.sin(g * 0.37 + 0.2)
     return d_val, x_val, x
+
+
+# --------------------------------------------------------------------------- partitioning
+
+@dataclass
+class HaloDesc:
+    """cs_halo_t content for one rank (src/base/cs_halo.h:74-171, CS_HALO_STANDARD only,
+    no periodicity): neighbour ranks ascending, one ghost section and one send section
+    per neighbour.  Ghost g of section i is column n_local_elts + index[i] + g."""
+
+    n_local_elts: int
+    c_domain_rank: np.ndarray   # int32 [n_c_domains]
+    index: np.ndarray           # int32 [n_c_domains + 1]  ghost sections
+    send_index: np.ndarray      # int32 [n_c_domains + 1]
+    send_list: np.ndarray       # int32 [n_send]  local ids
+
+    @property
+    def n_c_domains(self) -> int:
+        return len(self.c_domain_rank)
+
+    @property
+    def n_ghost(self) -> int:
+        return int(self.index[-1])
+
+
+def partition_dims(n_ranks: int):
+    """Bricks per direction (px, py, pz).  Powers of two split z, then y, then x, which
+    is what the reference's default Morton-box partitioning (src/mesh/cs_partition.cpp:
+    2947-2948) yields on a cube: halves, quarter bricks, octants."""
+    p = [1, 1, 1]
+    n, d = n_ranks, 2
+    while n > 1:
+        f = 2 if n % 2 == 0 else n
+        p[d] *= f
+        n //= f
+        d = (d - 1) % 3
+    return tuple(p)
+
+
+def _bounds(N, p):
+    return [(N * r) // p for r in range(p + 1)]
+
+
+def cube_poisson_local(N: int, n_ranks: int, rank: int, bc: str = "neumann",
+                       eps_factor: float = 1e-6):
+    """The rows of cube_poisson(N, bc) owned by `rank` out of `n_ranks` bricks, in the
+    layout an MPI run of the reference would hold them: local cells numbered in global
+    order, ghost cells appended (grouped by owner rank ascending, global order inside a
+    section), local MSR column ids, local interior-face numbering (faces on a parallel
+    boundary included, numbered in global face order).  Returns (CubeSystem, HaloDesc,
+    global_ids) where global_ids[n_cols_ext] maps local columns to global cell ids."""
+    px, py, pz = partition_dims(n_ranks)
+    bx, by, bz = _bounds(N, px), _bounds(N, py), _bounds(N, pz)
+    rx, ry, rz = rank % px, (rank // px) % py, rank // (px * py)
+    x0, x1, y0, y1, z0, z1 = bx[rx], bx[rx + 1], by[ry], by[ry + 1], bz[rz], bz[rz + 1]
+    nx, ny, nz = x1 - x0, y1 - y0, z1 - z0
+    n = nx * ny * nz
+    h = 1.0 / N
+
+    lid = np.arange(n, dtype=np.int64)
+    I = x0 + lid % nx
+    J = y0 + (lid // nx) % ny
+    K = z0 + lid // (nx * ny)
+    gid = I + J * N + K * N * N
+
+    def owner_of(ii, jj, kk):
+        ox = np.searchsorted(bx, ii, side="right") - 1
+        oy = np.searchsorted(by, jj, side="right") - 1
+        oz = np.searchsorted(bz, kk, side="right") - 1
+        return ox + oy * px + oz * px * py
+
+    n_fx = (N - 1) * N * N
+    n_fy = n_fx
+    dirs = [(0, 0, -1), (0, -1, 0), (-1, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)]
+    rows, cols_g, own, fgid, sgn = [], [], [], [], []
+    for (dx, dy, dz) in dirs:
+        ii, jj, kk = I + dx, J + dy, K + dz
+        ok = (ii >= 0) & (ii < N) & (jj >= 0) & (jj < N) & (kk >= 0) & (kk < N)
+        s = np.nonzero(ok)[0]
+        ii, jj, kk = ii[s], jj[s], kk[s]
+        rows.append(s)
+        cols_g.append(ii + jj * N + kk * N * N)
+        own.append(owner_of(ii, jj, kk))
+        # global interior face id between the two cells (cs_mesh_cartesian ordering)
+        hi_i, hi_j, hi_k = np.maximum(ii, I[s]), np.maximum(jj, J[s]), np.maximum(kk, K[s])
+        if dx != 0:
+            f = (hi_i - 1) + hi_j * (N - 1) + hi_k * (N - 1) * N
+        elif dy != 0:
+            f = n_fx + hi_i + (hi_j - 1) * N + hi_k * N * (N - 1)
+        else:
+            f = n_fx + n_fy + hi_i + hi_j * N + (hi_k - 1) * N * N
+        fgid.append(f)
+        sgn.append(np.full(len(s), 1 if (dx + dy + dz) > 0 else -1, dtype=np.int16))
+    rows = np.concatenate(rows)
+    cols_g = np.concatenate(cols_g)
+    own = np.concatenate(own)
+    fgid = np.concatenate(fgid)
+    sgn = np.concatenate(sgn)
+
+    # ghosts: unique (owner, global id), owner ascending then global id ascending
+    is_ghost = own != rank
+    gkey = own[is_ghost] * (N ** 3) + cols_g[is_ghost]
+    ukey = np.unique(gkey)
+    g_owner = (ukey // (N ** 3)).astype(np.int32)
+    g_gid = ukey % (N ** 3)
+    n_ghost = len(ukey)
+    c_domain_rank = np.unique(g_owner).astype(np.int32)
+    index = np.concatenate([[0], np.cumsum([np.count_nonzero(g_owner == r)
+                                            for r in c_domain_rank])]).astype(np.int32)
+
+    # local column ids
+    col_l = np.empty(len(rows), dtype=np.int64)
+    loc = ~is_ghost
+    ci, cj, ck = cols_g[loc] % N, (cols_g[loc] // N) % N, cols_g[loc] // (N * N)
+    col_l[loc] = (ci - x0) + (cj - y0) * nx + (ck - z0) * nx * ny
+    col_l[is_ghost] = n + np.searchsorted(ukey, gkey)
+
+    order = np.lexsort((col_l, rows))
+    rows, col_l, fgid, sgn = rows[order], col_l[order], fgid[order], sgn[order]
+    counts = np.bincount(rows, minlength=n)
+    row_index = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(counts, out=row_index[1:])
+
+    # send lists: my cells that are ghosts of neighbour d, in global (= local) order
+    send_list, send_index = [], [0]
+    entry_own = own[order]
+    for d in c_domain_rank:
+        cells = np.unique(rows[entry_own == d])
+        send_list.append(cells)
+        send_index.append(send_index[-1] + len(cells))
+    send_list = (np.concatenate(send_list) if send_list else np.zeros(0)).astype(np.int32)
+
+    # local faces in global face order
+    ufaces, c2f = np.unique(fgid, return_inverse=True)
+    n_faces = len(ufaces)
+    face_u_normal = np.zeros((n_faces, 3), dtype=np.float64)
+    face_u_normal[ufaces < n_fx, 0] = 1.0
+    face_u_normal[(ufaces >= n_fx) & (ufaces < n_fx + n_fy), 1] = 1.0
+    face_u_normal[ufaces >= n_fx + n_fy, 2] = 1.0
+    face_cells = np.zeros((n_faces, 2), dtype=np.int32)
+    face_cells[c2f[sgn > 0], 0] = rows[sgn > 0]
+    face_cells[c2f[sgn > 0], 1] = col_l[sgn > 0]
+    face_cells[c2f[sgn < 0], 1] = rows[sgn < 0]
+    face_cells[c2f[sgn < 0], 0] = col_l[sgn < 0]
+
+    x_val = np.full(len(rows), -h, dtype=np.float64)
+    d_val = counts.astype(np.float64) * h
+    if bc == "dirichlet":
+        d_val = d_val + (6 - counts).astype(np.float64) * (2.0 * h)
+    elif bc == "neumann":
+        d_val = d_val + eps_factor * h
+    else:
+        raise ValueError("bc must be 'neumann' or 'dirichlet'")
+
+    gids = np.concatenate([gid, g_gid])
+    cen = np.empty((n + n_ghost, 3), dtype=np.float64)
+    cen[:, 0] = (gids % N + 0.5) * h
+    cen[:, 1] = ((gids // N) % N + 0.5) * h
+    cen[:, 2] = (gids // (N * N) + 0.5) * h
+    rhs = (np.sin(2 * np.pi * cen[:n, 0]) * np.sin(2 * np.pi * cen[:n, 1])
+           * np.sin(2 * np.pi * cen[:n, 2])) * (h ** 3)
+
+    s = CubeSystem(
+        N=N, n_rows=n, n_faces=n_faces, row_index=row_index.astype(np.int32),
+        col_id=col_l.astype(np.int32), d_val=d_val, x_val=x_val, face_cells=face_cells,
+        c2f=c2f.astype(np.int32), c2f_sgn=sgn.astype(np.int16), cell_cen=cen,
+        cell_vol=np.full(n + n_ghost, h ** 3, dtype=np.float64),
+        face_u_normal=face_u_normal, face_surf=np.full(n_faces, h * h, dtype=np.float64),
+        rhs=rhs, meta={"bc": bc, "eps_factor": eps_factor, "h": h, "rank": rank,
+                       "n_ranks": n_ranks, "n_cols_ext": n + n_ghost})
+    halo = HaloDesc(n_local_elts=n, c_domain_rank=c_domain_rank, index=index,
+                    send_index=np.array(send_index, dtype=np.int32), send_list=send_list)
+    return s, halo, gids

@@ -55,6 +55,8 @@ typedef struct _csb_matrix_t     csb_matrix_t;      /* cs_matrix_t (MSR) */
 typedef struct _csb_halo_t       csb_halo_t;        /* cs_halo_t */
 typedef struct _csb_sles_it_t    csb_sles_it_t;     /* cs_sles_it_t */
 typedef struct _csb_multigrid_t  csb_multigrid_t;   /* cs_multigrid_t */
+typedef struct _csb_pcomm_t      csb_pcomm_t;       /* peer-memory communicator */
+typedef struct _csb_pcomm_group_t csb_pcomm_group_t; /* ranks as threads of one process */
 
 /*----------------------------------------------------------------------------
  * Runtime (replaces cs_base_cuda_select_default_device / stream table,
@@ -185,6 +187,47 @@ void        csb_halo_destroy(csb_halo_t **halo);
 int         csb_halo_sync_var(const csb_halo_t *halo, csb_real_t *var_d);
 
 /*----------------------------------------------------------------------------
+ * Peer-memory communicator: what the solvers use instead of MPI / NCCL calls
+ * for the ghost exchange (cs_halo_sync_var, src/base/cs_halo.cpp:1739-2220),
+ * the global sums of dot products (MPI_Allreduce, src/alge/cs_sles_it.cpp:
+ * 372-378; ncclAllReduce, src/alge/cs_sles_it_cuda.cu:1000-1006) and the
+ * exchanges of the hierarchy construction (src/alge/cs_grid.cpp:802-910,
+ * :1366-1374, :6561-6581).  Each rank owns an arena in its GPU's memory that
+ * every other rank of the NVSwitch domain maps; kernels store into peers'
+ * arenas and publish counters (see csrc/comm.cu).  n_ranks <= 16.
+ *
+ * One process per GPU (the reference's model, src/base/cs_base_cuda.cu:752):
+ *     c = csb_pcomm_create(n_ranks, rank, arena_bytes, window_bytes);
+ *     csb_pcomm_get_ipc_handle(c, h);   MPI_Allgather / all_gather the 64 bytes
+ *     csb_pcomm_open_peers(c, all_handles);
+ * Ranks as host threads of one process (each thread calls csb_init first):
+ *     g = csb_pcomm_group_create(n_ranks);               once
+ *     c = csb_pcomm_create_in_group(g, rank, ...);       every thread (collective)
+ * arena_bytes: room for the solvers' ghost buffers (16 bytes per ghost row and
+ * level is enough); window_bytes: staging window, >= 24 bytes per ghost row.
+ *----------------------------------------------------------------------------*/
+
+csb_pcomm_t *csb_pcomm_create(int n_ranks, int rank, size_t arena_bytes, size_t window_bytes);
+int          csb_pcomm_get_ipc_handle(csb_pcomm_t *c, void *handle_64_bytes);
+int          csb_pcomm_open_peers(csb_pcomm_t *c, const void *all_handles /* n_ranks x 64 */);
+csb_pcomm_group_t *csb_pcomm_group_create(int n_ranks);
+void         csb_pcomm_group_destroy(csb_pcomm_group_t **group);
+csb_pcomm_t *csb_pcomm_create_in_group(csb_pcomm_group_t *group, int rank, size_t arena_bytes,
+                                       size_t window_bytes);
+void         csb_pcomm_destroy(csb_pcomm_t **c);
+int          csb_pcomm_rank(const csb_pcomm_t *c);
+int          csb_pcomm_n_ranks(const csb_pcomm_t *c);
+/* collective: in-place sum of n <= 8 host doubles over all ranks (rank order,
+   identical result everywhere); csb_pcomm_barrier = the same with no payload */
+int          csb_pcomm_allreduce_sum(csb_pcomm_t *c, double *vals, int n);
+int          csb_pcomm_barrier(csb_pcomm_t *c);
+
+/* Attach a halo to the communicator (collective over the neighbour ranks):
+   c_domain_rank values are ranks of `c`.  csb_halo_sync_var and the solvers
+   then exchange ghosts through peer memory instead of NCCL. */
+int          csb_halo_set_pcomm(csb_halo_t *halo, csb_pcomm_t *c);
+
+/*----------------------------------------------------------------------------
  * Iterative solvers (cs_sles_it_t)
  *----------------------------------------------------------------------------*/
 
@@ -198,6 +241,9 @@ csb_sles_it_t *csb_sles_it_create(csb_sles_it_type_t  solver_type,
 /* Global-sum communicator for dot products (cs_sles_it_set_mpi_reduce_comm,
    src/alge/cs_sles_it.cpp:5669): ncclComm_t as void *, NULL = single rank. */
 int  csb_sles_it_set_reduce_comm(csb_sles_it_t *c, void *nccl_comm);
+/* Same role with the peer-memory communicator (PCG: the whole distributed
+   solve then runs as one persistent kernel per rank). */
+int  csb_sles_it_set_pcomm(csb_sles_it_t *c, csb_pcomm_t *comm);
 
 /* cs_sles_setup_t (src/alge/cs_sles.h:91-101) -> cs_sles_it_setup (:4964) */
 void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a,
@@ -269,6 +315,9 @@ void csb_multigrid_set_coarsening_options(csb_multigrid_t  *mg,
 void csb_multigrid_set_aggregation_blocks(csb_multigrid_t *mg, int n_blocks);
 
 int  csb_multigrid_set_reduce_comm(csb_multigrid_t *mg, void *nccl_comm);
+/* Communicator of a distributed hierarchy: required when the matrix has a halo
+   (the reference takes cs_glob_mpi_comm, src/alge/cs_multigrid.cpp:4720). */
+int  csb_multigrid_set_pcomm(csb_multigrid_t *mg, csb_pcomm_t *comm);
 
 void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
                          int verbosity);               /* cs_multigrid_setup :5275 */
@@ -294,9 +343,18 @@ void csb_multigrid_destroy(void **context);            /* cs_multigrid_destroy :
 /* Hierarchy inspection (what cs_grid_get_info / cs_grid_dump expose,
    src/alge/cs_grid.cpp:7740, :8839): used by the parity tests. */
 int  csb_multigrid_get_n_levels(const csb_multigrid_t *mg);
+/* 1 when the last csb_multigrid_setup completed (setup returns void like
+   cs_multigrid_setup; on failure the message is in csb_last_error()) */
+int  csb_multigrid_is_setup(const csb_multigrid_t *mg);
 int  csb_multigrid_get_n_cycles(const csb_multigrid_t *mg);
 /* info[0] = n_rows, info[1] = n_cols_ext, info[2] = n_entries (off-diagonal) */
 int  csb_multigrid_get_level_info(const csb_multigrid_t *mg, int level, csb_lnum_t info[3]);
+/* Halo of a level of a distributed hierarchy (cs_grid_get_halo, src/alge/cs_grid.cpp:
+   7724): sizes[0] = n_c_domains, sizes[1] = n_send, sizes[2] = n_ghost; any array
+   pointer may be NULL.  Returns -1 when the level has no halo. */
+int  csb_multigrid_get_level_halo(const csb_multigrid_t *mg, int level, int sizes[3],
+                                  int *c_domain_rank, csb_lnum_t *send_index,
+                                  csb_lnum_t *send_list, csb_lnum_t *index);
 /* Copy level data to host arrays (any pointer may be NULL).  coarse_row has
    the parent level's n_rows entries and maps parent rows -> rows of `level`. */
 int  csb_multigrid_get_level_arrays(const csb_multigrid_t *mg, int level,

@@ -763,6 +763,27 @@ ora_grid_create_fine(int n_rows, const int *row_index, const int *col_id,
   g->cell_vol = _dup(cell_vol, sizeof(double)*n_rows);
   g->face_u_normal = _dup(face_u_normal, sizeof(double)*3*n_faces);
   g->face_surf = _dup(face_surf, sizeof(double)*n_faces);
+  g->n_cols_ext = n_rows;
+  return g;
+}
+
+/* Same for one rank of a distributed matrix: columns >= n_rows are ghost rows
+   (cs_grid_create_from_shared reads n_cols_ext from the matrix, :7470-7480);
+   cell_cen / cell_vol hold n_cols_ext entries (ghost values already synced). */
+ora_grid_t *
+ora_grid_create_fine_ext(int n_rows, int n_cols_ext, const int *row_index, const int *col_id,
+                         const double *d_val, const double *x_val,
+                         int n_faces, const int *c2f, const short *c2f_sgn,
+                         const double *cell_cen, const double *cell_vol,
+                         const double *face_u_normal, const double *face_surf)
+{
+  ora_grid_t *g = ora_grid_create_fine(n_rows, row_index, col_id, d_val, x_val, n_faces,
+                                       c2f, c2f_sgn, cell_cen, cell_vol, face_u_normal,
+                                       face_surf);
+  free(g->cell_cen); free(g->cell_vol);
+  g->cell_cen = _dup(cell_cen, sizeof(double)*3*n_cols_ext);
+  g->cell_vol = _dup(cell_vol, sizeof(double)*n_cols_ext);
+  g->n_cols_ext = n_cols_ext;
   return g;
 }
 
@@ -777,24 +798,27 @@ ora_grid_create_fine(int n_rows, const int *row_index, const int *col_id,
  *   values           _compute_coarse_quantities_msr_with_faces (:6841-6897)
  *----------------------------------------------------------------------------*/
 
+/* Structure + stage 1 for a given fine -> coarse map.  f_c_row has f->n_cols_ext
+   entries (ghost entries = coarse ghost ids from _coarsen_halo, or absent when
+   n_cols_ext == n_rows); it is copied.  Coarse cell_cen / cell_vol get
+   c_n_cols_ext entries; the ghost part is to be filled by the caller (halo sync,
+   cs_grid.cpp:6561-6581) before ora_grid_coarsen_finish. */
 ora_grid_t *
-ora_grid_coarsen(const ora_grid_t *f, int max_aggregation, double relax_param,
-                 int n_threads)
+ora_grid_coarsen_begin(const ora_grid_t *f, const int *f_c_row_in, int c_n_rows,
+                       int c_n_cols_ext)
 {
   const int f_n_rows = f->n_rows;
+  const int f_n_cols_ext = (f->n_cols_ext > f_n_rows) ? f->n_cols_ext : f_n_rows;
   const int *f_row_index = f->row_index, *f_col_id = f->col_id;
   const double *f_d_val = f->d_val, *f_x_val = f->x_val;
 
   ora_grid_t *c = calloc(1, sizeof(ora_grid_t));
   c->level = f->level + 1;
-  c->coarse_row = malloc(sizeof(int)*(f_n_rows > 0 ? f_n_rows : 1));
+  c->coarse_row = malloc(sizeof(int)*(f_n_cols_ext > 0 ? f_n_cols_ext : 1));
+  memcpy(c->coarse_row, f_c_row_in, sizeof(int)*f_n_cols_ext);
   int *f_c_row = c->coarse_row;
-
-  const int c_n_rows
-    = ora_aggregation_dx_msr(f->level, f_n_rows, f_row_index, f_col_id,
-                             f_d_val, f_x_val, max_aggregation, n_threads,
-                             f_c_row);
   c->n_rows = c_n_rows;
+  c->n_cols_ext = c_n_cols_ext;
 
   /* coarse -> fine adjacency, ascending fine row order (serial variant) */
   int *c_f_row_index = calloc(c_n_rows + 1, sizeof(int));
@@ -869,8 +893,8 @@ ora_grid_coarsen(const ora_grid_t *f, int max_aggregation, double relax_param,
   /* stage 1 */
   double *c_d_val = malloc(sizeof(double)*(c_n_rows > 0 ? c_n_rows : 1));
   double *c_x_val = malloc(sizeof(double)*(c_nnz > 0 ? c_nnz : 1));
-  double *c_cell_cen = malloc(sizeof(double)*3*(c_n_rows > 0 ? c_n_rows : 1));
-  double *c_cell_vol = malloc(sizeof(double)*(c_n_rows > 0 ? c_n_rows : 1));
+  double *c_cell_cen = calloc(3*(c_n_cols_ext > 0 ? c_n_cols_ext : 1), sizeof(double));
+  double *c_cell_vol = calloc(c_n_cols_ext > 0 ? c_n_cols_ext : 1, sizeof(double));
   double *c_face_normal = calloc(3*(c_n_faces > 0 ? c_n_faces : 1), sizeof(double));
   double *c_xa0 = calloc(c_n_faces > 0 ? c_n_faces : 1, sizeof(double));
   double *c_xa0ij = calloc(3*(c_n_faces > 0 ? c_n_faces : 1), sizeof(double));
@@ -932,6 +956,29 @@ ora_grid_coarsen(const ora_grid_t *f, int max_aggregation, double relax_param,
     for (int k = 0; k < 3; k++) _cen[k] /= c_cell_vol[ii_c];
   }
 
+  free(c_f_row_index); free(c_f_row_ids);
+
+  c->row_index = c_row_index;
+  c->col_id = realloc(c_col_id, sizeof(int)*(c_nnz > 0 ? c_nnz : 1));
+  c->d_val = c_d_val; c->x_val = c_x_val;
+  c->cell_face = c_cell_face; c->cell_face_sgn = c_cell_face_sgn;
+  c->cell_cen = c_cell_cen; c->cell_vol = c_cell_vol;
+  c->face_normal = c_face_normal; c->xa0 = c_xa0; c->xa0ij = c_xa0ij;
+  return c;
+}
+
+/* Stage 2: coarse extra-diagonal values and final diagonal. */
+void
+ora_grid_coarsen_finish(ora_grid_t *c, double relax_param)
+{
+  const int c_n_rows = c->n_rows;
+  const int *c_row_index = c->row_index, *c_col_id = c->col_id;
+  const int *c_cell_face = c->cell_face;
+  const short *c_cell_face_sgn = c->cell_face_sgn;
+  const double *c_cell_cen = c->cell_cen, *c_face_normal = c->face_normal;
+  const double *c_xa0 = c->xa0, *c_xa0ij = c->xa0ij;
+  double *c_d_val = c->d_val, *c_x_val = c->x_val;
+
   /* values: P0 restriction relaxed with P1 (:6848-6895) */
   for (int ic = 0; ic < c_n_rows; ic++) {
     const double *cen_ic = c_cell_cen + 3*ic;
@@ -963,14 +1010,23 @@ ora_grid_coarsen(const ora_grid_t *f, int max_aggregation, double relax_param,
     }
   }
 
-  free(c_f_row_index); free(c_f_row_ids);
+}
 
-  c->row_index = c_row_index;
-  c->col_id = realloc(c_col_id, sizeof(int)*(c_nnz > 0 ? c_nnz : 1));
-  c->d_val = c_d_val; c->x_val = c_x_val;
-  c->cell_face = c_cell_face; c->cell_face_sgn = c_cell_face_sgn;
-  c->cell_cen = c_cell_cen; c->cell_vol = c_cell_vol;
-  c->face_normal = c_face_normal; c->xa0 = c_xa0; c->xa0ij = c_xa0ij;
+ora_grid_t *
+ora_grid_coarsen(const ora_grid_t *f, int max_aggregation, double relax_param,
+                 int n_threads)
+{
+  const int f_n_rows = f->n_rows;
+  const int f_n_cols_ext = (f->n_cols_ext > f_n_rows) ? f->n_cols_ext : f_n_rows;
+  int *f_c_row = malloc(sizeof(int)*(f_n_cols_ext > 0 ? f_n_cols_ext : 1));
+  for (int i = f_n_rows; i < f_n_cols_ext; i++) f_c_row[i] = -1;
+  const int c_n_rows
+    = ora_aggregation_dx_msr(f->level, f_n_rows, f->row_index, f->col_id,
+                             f->d_val, f->x_val, max_aggregation, n_threads,
+                             f_c_row);
+  ora_grid_t *c = ora_grid_coarsen_begin(f, f_c_row, c_n_rows, c_n_rows);
+  free(f_c_row);
+  ora_grid_coarsen_finish(c, relax_param);
   return c;
 }
 

@@ -27,6 +27,7 @@ typedef struct {
   double  *face_normal;     /* level > 0 */
   double  *face_u_normal, *face_surf;  /* level 0 */
   double  *xa0, *xa0ij;     /* level > 0 */
+  int      n_cols_ext;      /* n_rows + ghost rows (== n_rows on one rank) */
 } ora_grid_t;
 
 typedef struct {
@@ -80,6 +81,15 @@ ora_grid_t *ora_grid_create_fine(int n_rows, const int *row_index, const int *co
                                  int n_faces, const int *c2f, const short *c2f_sgn,
                                  const double *cell_cen, const double *cell_vol,
                                  const double *face_u_normal, const double *face_surf);
+ora_grid_t *ora_grid_create_fine_ext(int n_rows, int n_cols_ext, const int *row_index,
+                                     const int *col_id, const double *d_val,
+                                     const double *x_val, int n_faces, const int *c2f,
+                                     const short *c2f_sgn, const double *cell_cen,
+                                     const double *cell_vol, const double *face_u_normal,
+                                     const double *face_surf);
+ora_grid_t *ora_grid_coarsen_begin(const ora_grid_t *f, const int *f_c_row, int c_n_rows,
+                                   int c_n_cols_ext);
+void        ora_grid_coarsen_finish(ora_grid_t *c, double relax_param);
 ora_grid_t *ora_grid_coarsen(const ora_grid_t *f, int max_aggregation,
                              double relax_param, int n_threads);
 void        ora_grid_free(ora_grid_t *g);

@@ -66,7 +66,8 @@ class OraGrid(C.Structure):
                 ("cell_face_sgn", c_short_p),
                 ("cell_cen", c_dbl_p), ("cell_vol", c_dbl_p),
                 ("face_normal", c_dbl_p), ("face_u_normal", c_dbl_p),
-                ("face_surf", c_dbl_p), ("xa0", c_dbl_p), ("xa0ij", c_dbl_p)]
+                ("face_surf", c_dbl_p), ("xa0", c_dbl_p), ("xa0ij", c_dbl_p),
+                ("n_cols_ext", C.c_int)]
 
 
 class OraMg(C.Structure):

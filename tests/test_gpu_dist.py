@@ -1,0 +1,39 @@
+"""Multi-rank parity on the GPU: R ranks (host threads, one context and stream each)
+run the distributed kernels -- fused ghost exchange through peer stores + flags,
+cross-rank all-reduce, distributed hierarchy construction -- against the multi-rank
+oracle on the same partition.  Each scenario is a subprocess (tests/dist_worker.py) so
+that a hung rank cannot hang the suite."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run(*args, timeout=420):
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), *map(str, args)],
+                       capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    assert p.returncode == 0 and "OK" in p.stdout, f"{args}:\n{p.stdout[-2000:]}\n{p.stderr[-4000:]}"
+    return p.stdout
+
+
+@pytest.mark.parametrize("R", [2, 4, 8])
+def test_pcomm_allreduce_and_halo_sync(R):
+    run("comm", R)
+
+
+@pytest.mark.parametrize("N,R,bc", [(16, 2, "dirichlet"), (24, 4, "neumann"), (32, 8, "dirichlet"),
+                                    (20, 3, "dirichlet")])
+def test_distributed_pcg(N, R, bc):
+    run("pcg", N, R, bc)
+
+
+@pytest.mark.parametrize("N,R,bc,prec", [(16, 2, "dirichlet", 1e-8), (24, 4, "neumann", 1e-8),
+                                         (32, 8, "dirichlet", 1e-13), (48, 2, "neumann", 1e-8),
+                                         (24, 1, "dirichlet", 1e-8)])
+def test_distributed_multigrid(N, R, bc, prec):
+    run("mg", N, R, bc, prec)
