@@ -202,16 +202,37 @@ def main():
     api.set_stream(stream.cuda_stream)
 
     # ---- synthetic input (host), matrix + hierarchy setup ------------------
-    # N > 1: weak scaling, every rank solves its own cube (domain replicas) until
-    # the distributed hierarchy lands; see DESIGN.md (e).
+    # N > 1: the SAME cube is partitioned into N bricks (what the reference's Morton-box
+    # partitioning yields, cs_partition.cpp:2947), one brick per GPU: strong scaling.
+    # Ghost exchange and dot products run inside the persistent solver kernel over
+    # NVLink peer memory; torch.distributed only bootstraps.
     t0 = time.perf_counter()
-    s = cube_poisson(args.cube)
+    ro = None
+    if world > 1:
+        from code_saturne_b200.dist import RankObjects, pcomm_from_torch_dist
+        from code_saturne_b200.mesh_cartesian import cube_poisson_local
+        s, halo_desc, gids = cube_poisson_local(args.cube, world, rank)
+        n_cols_ext = s.meta["n_cols_ext"]
+    else:
+        s = cube_poisson(args.cube)
+        n_cols_ext = s.n_rows
     t_gen = time.perf_counter() - t0
-    r_norm = float(np.linalg.norm(s.rhs))
+    rr = torch.tensor([float(np.dot(s.rhs, s.rhs)), float(s.n_rows)], dtype=torch.float64,
+                      device="cuda")
+    if world > 1:
+        dist.all_reduce(rr)
+    r_norm = float(torch.sqrt(rr[0]).item())
+    n_rows_global = int(rr[1].item())
     t0 = time.perf_counter()
-    m = api.Matrix.from_system(s)
+    if world > 1:
+        pc = pcomm_from_torch_dist(halo_desc.n_ghost)
+        ro = RankObjects(s, halo_desc, gids, pc, rank)
+        m = ro.matrix
+        mg = ro.multigrid()
+    else:
+        m = api.Matrix.from_system(s)
+        mg = api.Multigrid()
     t_upload = time.perf_counter() - t0
-    mg = api.Multigrid()
     t0 = time.perf_counter()
     mg.setup(m)
     t_setup = time.perf_counter() - t0
@@ -219,9 +240,9 @@ def main():
     n_levels = mg.n_levels()
 
     rhs_d = torch.from_numpy(s.rhs).cuda()
-    vx_d = torch.zeros(s.n_rows, dtype=torch.float64, device="cuda")
+    vx_d = torch.zeros(n_cols_ext, dtype=torch.float64, device="cuda")
     rhs_h = torch.from_numpy(s.rhs).pin_memory()
-    vx_h = torch.zeros(s.n_rows, dtype=torch.float64).pin_memory()
+    vx_h = torch.zeros(n_cols_ext, dtype=torch.float64).pin_memory()
 
     def barrier():
         if world > 1:
@@ -265,8 +286,8 @@ def main():
         t_e2e = max(e0.elapsed_time(e1) * 1e-3, time.perf_counter() - w0) / args.steps
 
         # ---- roofline: level-0 SpMV kernel, inputs (1.7 GB) >> L2 ----------
-        x_d = torch.from_numpy(np.sin(np.arange(s.n_rows) * 0.37)).cuda()
-        y_d = torch.empty_like(x_d)
+        x_d = torch.from_numpy(np.sin(np.arange(n_cols_ext) * 0.37)).cuda()
+        y_d = torch.empty(s.n_rows, dtype=torch.float64, device="cuda")
         for _ in range(5):
             m.vector_multiply(x_d, y_d)
         barrier()
@@ -283,7 +304,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_e2e, t_spmv = (float(v) for v in t.cpu())
 
-    spmv_bytes = m.spmv_bytes()
+    spmv_bytes = m.spmv_bytes()          # this rank's brick; all bricks are equal
     peak, peak_src = measured_peak_gbs()
     achieved = spmv_bytes / t_spmv / 1e9
 
@@ -306,12 +327,12 @@ def main():
         line = {
             "metric": METRIC, "value": t_dev, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev * 1e3,
-            "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.cube}^3 hex cube ({s.n_rows} cells) pressure Poisson, "
+            "config": {"workload": f"{args.cube}^3 hex cube ({n_rows_global} cells) pressure Poisson, "
                                    "cs_multigrid V-cycle (PCG+Jacobi smoothers 2/10, coarse PCG), "
                                    f"precision {PRECISION:g}, all-Neumann + eps",
-                       "rows_per_gpu": s.n_rows, "n_levels": n_levels,
+                       "rows_per_gpu": n_rows_global // world, "n_levels": n_levels,
                        "n_cycles": int(r["n_cycles"]), "n_equiv_iter": int(r["n_iter"]),
                        "final_residual_over_rnorm": float(r["residual"] / r_norm),
                        "l2_policy": "inputs (1.7 GB matrix) larger than L2; no flush needed",
@@ -319,11 +340,14 @@ def main():
                        "setup_assembly_device_s": st["assembly"],
                        "setup_transfers_s": st["transfers"],
                        "matrix_upload_s": t_upload, "input_generation_s": t_gen,
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas"},
-            "e2e": {"value": t_e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * s.n_rows,
-                    "d2h_bytes_per_step": 8 * s.n_rows + 4096},
+                       "parallelism": "1 GPU" if world == 1 else
+                       f"{world} bricks (Morton-box partition), one per GPU; ghost exchange + "
+                       "all-reduce fused in the persistent kernel over NVLink peer memory"},
+            "e2e": {"value": t_e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n_rows_global,
+                    "d2h_bytes_per_step": 8 * n_rows_global + 4096 * world},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_spmv_stream (level-0 MSR SpMV)",
+            "roofline": {"bound": "hbm", "kernel": "k_spmv_stream (level-0 MSR SpMV"
+                         + (", per GPU, incl. ghost exchange)" if world > 1 else ")"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None,
                          "algorithmic_bytes_per_launch": spmv_bytes,
@@ -335,8 +359,14 @@ def main():
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
 
+    if world > 1:
+        dist.barrier()
     mg.destroy()
-    m.destroy()
+    if ro is not None:
+        ro.destroy()
+        pc.destroy()
+    else:
+        m.destroy()
     if world > 1:
         dist.destroy_process_group()
 

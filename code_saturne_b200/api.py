@@ -24,6 +24,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "csrc", "libcsb200.so")
+if os.environ.get("CSB_LIB"):       # tuning experiments: a variant build of the same library
+    LIB_PATH = os.path.abspath(os.environ["CSB_LIB"])
 HEADER_PATH = os.path.join(_ROOT, "include", "csb200.h")
 
 
@@ -169,6 +171,7 @@ def load_library() -> C.CDLL:
     L.csb_multigrid_get_cycle_residuals.argtypes = [vp, vp, ci]
     L.csb_multigrid_get_setup_times.argtypes = [vp, vp]
     L.csb_multigrid_get_phase_times.argtypes = [vp, vp, ci]
+    L.csb_multigrid_get_smoother_times.argtypes = [vp, vp, ci]
     L.csb_multigrid_log.argtypes = [vp, ci]
     L.csb_multigrid_log.restype = None
     L.csb_multigrid_copy.restype = vp
@@ -626,6 +629,13 @@ class Multigrid(_SolverBase):
         ascent."""
         buf = np.zeros((32, 6))
         n = load_library().csb_multigrid_get_phase_times(C.c_void_p(self._h), _ptr(buf), 32)
+        return buf[:n].copy()
+
+    def smoother_times(self):
+        """Seconds per (level, kind) inside the PCG smoothers of the last solve.  Columns:
+        residual SpMV, SpMV + 3 dots, vector updates."""
+        buf = np.zeros((32, 3))
+        n = load_library().csb_multigrid_get_smoother_times(C.c_void_p(self._h), _ptr(buf), 32)
         return buf[:n].copy()
 
     def levels(self):

@@ -48,6 +48,7 @@ constexpr int HIST_MAX = 2048;
 constexpr int CYCLE_MAX = 512;
 constexpr int PROF_LEVELS = 32;
 constexpr int PROF_PHASES = 6;
+constexpr int PROF_IT_PHASES = 3;
 enum { MG_PROF_DESCENT = 0, MG_PROF_RESIDUAL, MG_PROF_RESTRICT, MG_PROF_COARSEST,
        MG_PROF_PROLONG, MG_PROF_ASCENT };
 
@@ -67,7 +68,8 @@ struct DevBuf {
     release();
     n = count;
     if (count == 0) count = 1;
-    return CSB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+    /* 64 bytes of slack: bulk copies (cp.async.bulk) read whole 16-byte units */
+    return CSB_CUDA(cudaMalloc((void **)&p, count * sizeof(T) + 64));
   }
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
   /* copy from host or device pointer */
@@ -115,6 +117,9 @@ struct MgState {
      (%globaltimer, lead thread, after the phase's closing grid barrier) summed
      over the cycles of the last solve; [level][phase], phases = MG_PROF_* */
   unsigned long long prof[PROF_LEVELS][PROF_PHASES];
+  /* inside the smoothers: [level][0 residual SpMV, 1 SpMV + 3 dots, 2 vector updates],
+     each including the grid barrier / reduction that closes it */
+  unsigned long long prof_it[PROF_LEVELS][PROF_IT_PHASES];
 };
 
 /*--------------------------------------------------------------------------

@@ -1177,6 +1177,9 @@ k_mg_state_init(MgState *mg, double precision, double r_norm, int n_max_cycles)
   for (int l = 0; l < PROF_LEVELS; l++)
     for (int p = 0; p < PROF_PHASES; p++)
       mg->prof[l][p] = 0ull;
+  for (int l = 0; l < PROF_LEVELS; l++)
+    for (int p = 0; p < PROF_IT_PHASES; p++)
+      mg->prof_it[l][p] = 0ull;
 }
 
 __global__ void

@@ -32,10 +32,39 @@ namespace csb {
 
 namespace {
 
-constexpr int PT = 256;   /* threads per CTA */
-#ifndef CSB_MIN_CTAS
-#define CSB_MIN_CTAS 3
+/* CTA shape.  The kernels are HBM-latency bound unless every SM keeps ~45 KB of
+   loads in flight (6.5 TB/s x ~1 us / 148 SMs); registers are what holds them, so
+   the shape is "few fat CTAs": PT threads x MIN_CTAS per SM at <= 64 registers,
+   each thread batching SLAB_E matrix entries (96 B) or 2-4 rows of every vector
+   of an elementwise phase before it consumes anything. */
+#ifndef CSB_PT
+#define CSB_PT 256
 #endif
+#ifndef CSB_MIN_CTAS
+#define CSB_MIN_CTAS 2
+#endif
+constexpr int PT = CSB_PT;         /* threads per CTA */
+constexpr int NW = PT / 32;        /* warps per CTA */
+#ifndef CSB_STAGES
+#define CSB_STAGES 3
+#endif
+constexpr int NS = CSB_STAGES;     /* shared memory stages of the bulk-copy pipeline */
+static_assert(NS >= 2 && NS <= 4, "pipeline depth");
+/* In the streaming phases the last warp of the CTA is the producer (it only issues bulk
+   copies); the other NWC warps consume: one row (SpMV) or two rows (elementwise) per lane. */
+constexpr int NWC = NW - 1;
+constexpr int SLAB_ROWS_MAX = NWC*32;
+#ifndef CSB_SLAB_CAP
+#define CSB_SLAB_CAP 2432
+#endif
+constexpr int SLAB_CAP = CSB_SLAB_CAP;   /* matrix entries of a slab (shared memory budget) */
+static_assert(SLAB_CAP % 4 == 0, "slab capacity");
+#ifndef CSB_GATHER
+#define CSB_GATHER 12
+#endif
+constexpr int NG = CSB_GATHER;     /* x[col] gathers a lane keeps in flight for its next row */
+static_assert(PT % 32 == 0 && NW <= 32, "CTA shape");
+static_assert(3*NW + 3 <= 56 && 56 + 3*COMM_MAX_RANKS <= PERSISTENT_S_RED, "s_red layout");
 
 /*--------------------------------------------------------------------------
  * Grid-wide barrier (all CTAs are co-resident: cooperative launch).
@@ -79,26 +108,26 @@ __device__ __forceinline__ double warp_sum(double v)
 
 /* CTA-wide sum of Q values, result broadcast to every thread. */
 template <int Q>
-__device__ __forceinline__ void cta_sum_bcast(double (&v)[Q], double *s_red /* Q*8 + Q */)
+__device__ __forceinline__ void cta_sum_bcast(double (&v)[Q], double *s_red /* Q*NW + Q */)
 {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int q = 0; q < Q; q++) {
     const double w = warp_sum(v[q]);
-    if (lane == 0) s_red[q*8 + wid] = w;
+    if (lane == 0) s_red[q*NW + wid] = w;
   }
   __syncthreads();
   if (wid == 0) {
 #pragma unroll
     for (int q = 0; q < Q; q++) {
-      double w = (lane < PT/32) ? s_red[q*8 + lane] : 0.0;
+      double w = (lane < NW) ? s_red[q*NW + lane] : 0.0;
       w = warp_sum(w);
-      if (lane == 0) s_red[Q*8 + q] = w;
+      if (lane == 0) s_red[Q*NW + q] = w;
     }
   }
   __syncthreads();
 #pragma unroll
-  for (int q = 0; q < Q; q++) v[q] = s_red[Q*8 + q];
+  for (int q = 0; q < Q; q++) v[q] = s_red[Q*NW + q];
   __syncthreads();
 }
 
@@ -149,7 +178,7 @@ __device__ __forceinline__ void all_sum(double (&v)[Q], double *partials, unsign
     for (int r = 0; r < R; r++)
       *(volatile unsigned *)&((CommHeader *)C->peer[r])->xflag[par][me] = e;
   }
-  double *s_x = s_red + 40;        /* [Q][COMM_MAX_RANKS] */
+  double *s_x = s_red + 56;        /* [Q][COMM_MAX_RANKS] */
   if (threadIdx.x < R) {
     spin_until_ge(&H->xflag[par][threadIdx.x], e, C->timeout_ns, 6);
     __threadfence();
@@ -217,70 +246,542 @@ __device__ __forceinline__ const double *halo_exchange(const MgLevelDesc &L, con
 }
 
 /*--------------------------------------------------------------------------
- * SpMV over the slabs owned by this CTA.
- * A slab = L.slab_rows (<= 256) consecutive rows; its off-diagonal entries
- * are contiguous in memory: streamed with coalesced loads, products staged in
- * shared memory, then one thread per row sums its products in CSR order and
- * calls epi(row, off_diagonal_sum).
+ * Shared memory of a CTA and the bulk-copy (TMA) pipeline.
+ *
+ * Everything that is *streamed* (matrix entries, row index, the vector
+ * operands of an epilogue or of an elementwise update) reaches the SM through
+ * cp.async.bulk copies issued by one thread into an NS-stage ring of shared
+ * memory buffers, each guarded by an mbarrier (complete_tx byte counting): the
+ * copies need no registers and no scoreboard, so NS-1 slabs per CTA are in
+ * flight while one is consumed.  Only the x[col] gathers (L2 hits) go through
+ * registers, issued one slab ahead of their use.
+ *
+ *   [ s_red: PERSISTENT_S_RED doubles | PipeState | NS x stage_bytes ]
+ *   SpMV stage : col_id (cap+4 int) | x_val (cap+2 double) | row_index (PT+4 int)
+ *                | 4 operand vectors (PT doubles each)
+ *   row stage  : up to 7 operand vectors of ROW_CH doubles each
+ * Bulk copies need 16-byte aligned addresses and sizes: a slab's entry range is
+ * widened to the enclosing aligned range (k0 & ~3 ints, k0 & ~1 doubles) and
+ * sizes are rounded up; device arrays are allocated with 64 bytes of slack.
  *--------------------------------------------------------------------------*/
 
-template <bool SINGLE, class Epi>
-__device__ __forceinline__ void spmv_slabs(const MgLevelDesc &L, const double *x,
-                                           const double *ghost, double *s_prod, Epi epi)
+struct PipeState {
+  unsigned long long full[4];   /* stage filled: 1 arrival (expect_tx) + the copied bytes */
+  unsigned long long empty[4];  /* stage consumed: one arrival per consumer warp */
+  unsigned           base;      /* stages filled so far by this CTA (stage = count % NS) */
+  unsigned           pad[15];
+};
+
+constexpr int SMEM_HDR = (PERSISTENT_S_RED*8 + (int)sizeof(PipeState) + 127) / 128 * 128;
+constexpr int ST_RI_BYTES = ((SLAB_ROWS_MAX + 1 + 3)*4 + 15) / 16 * 16;
+constexpr int ST_OP_STRIDE = SLAB_ROWS_MAX;          /* doubles between staged operand vectors */
+constexpr int ST_FIXED = 16 + 16 + ST_RI_BYTES + 4*ST_OP_STRIDE*8;
+constexpr int ROW_CH = 2*SLAB_ROWS_MAX;              /* rows per chunk of an elementwise phase */
+constexpr int ROW_STAGE_BYTES = 7*ROW_CH*8;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p)
+{ return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory"); }
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+  const unsigned addr = smem_u32(bar);
+  unsigned done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+
+/* global -> shared bulk copy; bytes > 0, multiple of 16; both addresses 16-byte aligned */
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned bytes,
+                                          unsigned long long *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+/* generic-proxy accesses (other CTAs' global stores seen through the grid barrier, this
+   CTA's shared memory reads) are ordered before the async-proxy copies that follow */
+__device__ __forceinline__ void fence_proxy_async()
+{ asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned dyn_smem_bytes()
+{
+  unsigned v;
+  asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(v));
+  return v;
+}
+
+struct SmemView {
+  PipeState     *pipe;
+  unsigned char *stages;
+  int            stage_bytes;
+  int            cap;            /* entries of a SpMV stage */
+};
+
+__device__ __forceinline__ SmemView smem_view(unsigned char *s_raw)
+{
+  SmemView v;
+  v.pipe = (PipeState *)(s_raw + PERSISTENT_S_RED*8);
+  v.stages = s_raw + SMEM_HDR;
+  v.stage_bytes = (int)((dyn_smem_bytes() - SMEM_HDR) / NS) & ~127;
+  v.cap = ((v.stage_bytes - ST_FIXED) / 12) & ~3;
+  return v;
+}
+
+/* once per kernel */
+__device__ __forceinline__ void pipe_init(unsigned char *s_raw)
+{
+  PipeState *pipe = (PipeState *)(s_raw + PERSISTENT_S_RED*8);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; i++) { mbar_init(&pipe->full[i], 1); mbar_init(&pipe->empty[i], NWC); }
+    pipe->base = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+}
+
+/* Fill number q (counted per CTA over the whole kernel) goes to stage q % NS and is the
+   (q / NS)-th use of it: the producer first waits until use q/NS - 1 has been released
+   by all consumer warps; consumers wait for the fill, read, then release. */
+__device__ __forceinline__ void producer_acquire(const SmemView &sv, unsigned q)
+{
+  const unsigned u = q / NS;
+  if (u > 0) mbar_wait(&sv.pipe->empty[q % NS], (u - 1) & 1u);
+  fence_proxy_async();
+}
+__device__ __forceinline__ void consumer_wait(const SmemView &sv, unsigned q)
+{ mbar_wait(&sv.pipe->full[q % NS], (q / NS) & 1u); }
+__device__ __forceinline__ void consumer_release(const SmemView &sv, unsigned q)
+{
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(&sv.pipe->empty[q % NS]);
+}
+
+/*--------------------------------------------------------------------------
+ * SpMV over the slabs owned by this CTA, fused with an epilogue.
+ * A slab = L.slab_rows (<= SLAB_ROWS_MAX) consecutive rows; its off-diagonal
+ * entries are contiguous in memory.  Warp-specialised, no CTA-wide barrier
+ * inside the loop:
+ *   producer warp  - for every slab: wait until the stage is released, then bulk-copy
+ *                    col_id / x_val / row_index / the epilogue's vector operands;
+ *   consumer warps - lane = row.  The x[col] gathers of the lane's row in the NEXT
+ *                    slab are issued (L2 hits; consecutive rows read consecutive x on
+ *                    a structured mesh: coalesced) before the row of THIS slab is
+ *                    summed **in CSR order** (the reference's order,
+ *                    cs_matrix_spmv.cpp:2138-2142) and passed to the epilogue.
+ * F (by value) supplies NV (staged vectors), src(j) (their base pointers) and
+ *   void epi(int row, double off_diagonal_sum, const double *op, double (&acc)[3])
+ * where op[j*ST_OP_STRIDE] is the value of staged vector j at this row.
+ * acc_out[0..2] receives this thread's partial sums.
+ *--------------------------------------------------------------------------*/
+
+template <bool SINGLE, bool GHOST, class F>
+__device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
+                                          const double *ghost, unsigned char *s_raw,
+                                          const F f, double *acc_out)
 {
   /* column c < n_rows: x[c]; ghost column: ghost[c - n_rows] */
-  const double *xg = (ghost != nullptr) ? ghost - L.n_rows : x;
+  const double *xg = GHOST ? ghost - L.n_rows : x;
   const int tid = threadIdx.x;
   const int first = SINGLE ? 0 : blockIdx.x;
   const int step = SINGLE ? 1 : gridDim.x;
   const int n_slabs = L.n_slabs, slab_rows = L.slab_rows, n_rows = L.n_rows;
-  const int    *__restrict__ row_index = L.row_index;
-  const int    *__restrict__ col_id = L.col_id;
-  const double *__restrict__ x_val = L.x_val;
-  for (int slab = first; slab < n_slabs; slab += step) {
-    const int r0 = slab * slab_rows;
-    const int r1 = min(r0 + slab_rows, n_rows);
-    const int k0 = __ldg(row_index + r0);
-    const int nk = __ldg(row_index + r1) - k0;
-    const int    *__restrict__ ci = col_id + k0;
-    const double *__restrict__ xv = x_val + k0;
-    int i = tid;
-    for (; i + 3*PT < nk; i += 4*PT) {
-      const int c0 = __ldg(ci + i),        c1 = __ldg(ci + i + PT);
-      const int c2 = __ldg(ci + i + 2*PT), c3 = __ldg(ci + i + 3*PT);
-      const double m0 = __ldg(xv + i),        m1 = __ldg(xv + i + PT);
-      const double m2 = __ldg(xv + i + 2*PT), m3 = __ldg(xv + i + 3*PT);
-      const double x0 = (c0 < n_rows) ? x[c0] : xg[c0], x1 = (c1 < n_rows) ? x[c1] : xg[c1];
-      const double x2 = (c2 < n_rows) ? x[c2] : xg[c2], x3 = (c3 < n_rows) ? x[c3] : xg[c3];
-      s_prod[i]        = m0*x0;
-      s_prod[i + PT]   = m1*x1;
-      s_prod[i + 2*PT] = m2*x2;
-      s_prod[i + 3*PT] = m3*x3;
+  const SmemView sv = smem_view(s_raw);
+  const int n_my = (first < n_slabs) ? (n_slabs - first + step - 1) / step : 0;
+  const unsigned base = sv.pipe->base;
+  const int off_val = 4*(sv.cap + 4), off_ri = off_val + 8*(sv.cap + 2),
+            off_ops = off_ri + ST_RI_BYTES;
+  double acc[3] = {0., 0., 0.};
+
+  if (n_my > 0) {
+    if (tid >= NWC*32) {
+      /* ---------------- producer ---------------- */
+      if (tid == NWC*32) {
+        const int    *__restrict__ row_index = L.row_index;
+        const int    *col_id = L.col_id;
+        const double *x_val = L.x_val;
+        int k0 = __ldg(row_index + first*slab_rows);
+        int k1 = __ldg(row_index + min(first*slab_rows + slab_rows, n_rows));
+        for (int j = 0; j < n_my; j++) {
+          const int r0 = (first + j*step) * slab_rows;
+          int k0n = 0, k1n = 0;
+          if (j + 1 < n_my) {
+            const int r0n = r0 + step*slab_rows;
+            k0n = __ldg(row_index + r0n);
+            k1n = __ldg(row_index + min(r0n + slab_rows, n_rows));
+          }
+          const unsigned q = base + (unsigned)j;
+          unsigned char *sb = sv.stages + (q % NS)*sv.stage_bytes;
+          unsigned long long *bar = &sv.pipe->full[q % NS];
+          const int rows = min(slab_rows, n_rows - r0);
+          const int ka = k0 & ~3, nc = (k1 - ka + 3) & ~3;
+          const int kb = k0 & ~1, nv = (k1 - kb + 1) & ~1;
+          const unsigned ri_b = (unsigned)(((rows + 1)*4 + 15) & ~15);
+          const unsigned v_b = (unsigned)((rows*8 + 15) & ~15);
+          producer_acquire(sv, q);
+          mbar_expect_tx(bar, 4u*nc + 8u*nv + ri_b + (unsigned)F::NV*v_b);
+          if (nc > 0) bulk_load(sb, col_id + ka, 4u*nc, bar);
+          if (nv > 0) bulk_load(sb + off_val, x_val + kb, 8u*nv, bar);
+          bulk_load(sb + off_ri, row_index + r0, ri_b, bar);
+#pragma unroll
+          for (int v = 0; v < F::NV; v++)
+            bulk_load(sb + off_ops + v*ST_OP_STRIDE*8, f.src(v) + r0, v_b, bar);
+          k0 = k0n; k1 = k1n;
+        }
+      }
+      __syncwarp();
     }
-    for (; i < nk; i += PT) {
-      const int c = __ldg(ci + i);
-      s_prod[i] = __ldg(xv + i) * ((c < n_rows) ? x[c] : xg[c]);
+    else {
+      /* ---------------- consumers: lane = row ---------------- */
+      /* Two register sets (A, B) alternate between "being gathered for the next slab" and
+         "being consumed": the loop body handles two slabs, so no set is ever copied and
+         every element is indexed by a compile-time constant (they stay in registers). */
+      double gA[NG], gB[NG];
+      int ksA = 0, keA = 0, ksB = 0, keB = 0;   /* entries of the lane's row, relative to the
+                                                   start of the staged x_val */
+      /* row bounds of local iteration j and the first NG gathers of the lane's row */
+      auto prefetch = [&](int j, double (&gg)[NG], int &pks, int &pke) {
+        const unsigned q = base + (unsigned)j;
+        const unsigned char *sb = sv.stages + (q % NS)*sv.stage_bytes;
+        consumer_wait(sv, q);
+        const int *s_ri = (const int *)(sb + off_ri);
+        const int rows = min(slab_rows, n_rows - (first + j*step)*slab_rows);
+        const int k0 = s_ri[0];
+        int ks = 0, ke = 0;
+        if (tid < rows) { ks = s_ri[tid] - k0; ke = s_ri[tid + 1] - k0; }
+        const int *s_col = (const int *)sb + (k0 & 3);
+#pragma unroll
+        for (int e = 0; e < NG; e++) {
+          double v = 0.;
+          if (ks + e < ke) {
+            const int c = s_col[ks + e];
+            const double *px = (!GHOST || c < n_rows) ? x : xg;   /* one load, selected base */
+            v = px[c];
+          }
+          gg[e] = v;
+        }
+        pks = ks + (k0 & 1);        /* x_val is staged from an even entry */
+        pke = ke + (k0 & 1);
+      };
+      auto consume = [&](int j, const double (&gg)[NG], int ks, int ke) {
+        const unsigned q = base + (unsigned)j;
+        const unsigned char *sb = sv.stages + (q % NS)*sv.stage_bytes;
+        const int r0 = (first + j*step)*slab_rows;
+        if (tid < min(slab_rows, n_rows - r0)) {
+          const double *s_val = (const double *)(sb + off_val);
+          double sii = 0.0;
+#pragma unroll
+          for (int e = 0; e < NG; e++)
+            if (ks + e < ke) sii += s_val[ks + e] * gg[e];
+          if (ks + NG < ke) {       /* row longer than the gather pipeline */
+            const int k0 = ((const int *)(sb + off_ri))[0];
+            const int *s_col = (const int *)sb + (k0 & 3) - (k0 & 1);
+#pragma unroll 1
+            for (int k = ks + NG; k < ke; k++) {
+              const int c = s_col[k];
+              const double *px = (!GHOST || c < n_rows) ? x : xg;
+              sii += s_val[k] * px[c];
+            }
+          }
+          f.epi(r0 + tid, sii, (const double *)(sb + off_ops) + tid, acc);
+        }
+        consumer_release(sv, q);
+      };
+
+      /* (a prefetch past the last slab repeats the last one: its stage is still full) */
+      const int j_last = n_my - 1;
+      prefetch(0, gA, ksA, keA);
+      for (int j = 0; j < n_my; j += 2) {
+        prefetch(min(j + 1, j_last), gB, ksB, keB);
+        consume(j, gA, ksA, keA);
+        if (j + 1 < n_my) {
+          prefetch(min(j + 2, j_last), gA, ksA, keA);
+          consume(j + 1, gB, ksB, keB);
+        }
+      }
     }
     __syncthreads();
-    const int r = r0 + tid;
-    if (r < r1) {
-      const int ks = __ldg(row_index + r) - k0;
-      const int ke = __ldg(row_index + r + 1) - k0;
-      double sii = 0.0;
-      for (int k = ks; k < ke; k++) sii += s_prod[k];
-      epi(r, sii);
+    if (tid == 0) sv.pipe->base = base + (unsigned)n_my;
+    __syncthreads();
+  }
+  if (acc_out != nullptr) { acc_out[0] = acc[0]; acc_out[1] = acc[1]; acc_out[2] = acc[2]; }
+}
+
+template <bool SINGLE, class F>
+__device__ __forceinline__ void spmv_phase(const MgLevelDesc &L, const double *x,
+                                           const double *ghost, unsigned char *s_raw,
+                                           const F &f, double *acc_out)
+{
+  if (ghost != nullptr) spmv_phase_g<SINGLE, true>(L, x, ghost, s_raw, f, acc_out);
+  else spmv_phase_g<SINGLE, false>(L, x, ghost, s_raw, f, acc_out);
+}
+
+/* r = (A.vx - rhs), dk = r * ad_inv            (cs_sles_it.cpp:1502-1516) */
+struct EpiInitResidual {
+  static constexpr int NV = 4;
+  const double *d_val, *vx, *rhs, *ad_inv;
+  double *rk, *dk;
+  __device__ __forceinline__ const double *src(int v) const
+  { return (v == 0) ? d_val : (v == 1) ? vx : (v == 2) ? rhs : ad_inv; }
+  __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&)[3]) const
+  {
+    const double rr = (sii + op[0]*op[ST_OP_STRIDE]) - op[2*ST_OP_STRIDE];
+    rk[r] = rr;
+    dk[r] = rr * op[3*ST_OP_STRIDE];
+  }
+};
+
+/* out = A.p and the three dots rk.rk, rk.p, p.out      (:1521-1535, :1591-1600) */
+struct EpiDots {
+  static constexpr int NV = 3;
+  const double *d_val, *p, *rk;
+  double *out;
+  __device__ __forceinline__ const double *src(int v) const
+  { return (v == 0) ? d_val : (v == 1) ? p : rk; }
+  __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&acc)[3]) const
+  {
+    const double d = op[ST_OP_STRIDE];
+    const double z = sii + op[0]*d;
+    out[r] = z;
+    const double rr = op[2*ST_OP_STRIDE];
+    acc[0] += rr*rr; acc[1] += rr*d; acc[2] += d*z;
+  }
+};
+
+/* wr = rhs - A.vx and its squared norm          (cs_multigrid.cpp:3296-3301) */
+struct EpiResidual {
+  static constexpr int NV = 3;
+  const double *d_val, *vx, *rhs;
+  double *wr;
+  __device__ __forceinline__ const double *src(int v) const
+  { return (v == 0) ? d_val : (v == 1) ? vx : rhs; }
+  __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&acc)[3]) const
+  {
+    const double y = sii + op[0]*op[ST_OP_STRIDE];
+    const double t = op[2*ST_OP_STRIDE] - y;
+    wr[r] = t;
+    acc[0] += t*t;
+  }
+};
+
+/*--------------------------------------------------------------------------
+ * Elementwise phases over chunks of ROW_CH rows, same producer / consumer
+ * split: the F::NV input vectors of a chunk are bulk-copied into a stage; a
+ * consumer lane handles rows t and t + ROW_CH/2 of the chunk:
+ * F::st(row, op, acc) with op[v*ROW_CH] = input vector v at this row.
+ *--------------------------------------------------------------------------*/
+
+template <bool SINGLE, class F>
+__device__ __noinline__ void row_phase(int n, unsigned char *s_raw, const F f, double *acc_out)
+{
+  const int tid = threadIdx.x;
+  const int first = SINGLE ? 0 : blockIdx.x;
+  const int step = SINGLE ? 1 : gridDim.x;
+  const SmemView sv = smem_view(s_raw);
+  const int n_chunks = (n + ROW_CH - 1) / ROW_CH;
+  const int n_my = (first < n_chunks) ? (n_chunks - first + step - 1) / step : 0;
+  const unsigned base = sv.pipe->base;
+  double acc = 0.;
+
+  if (n_my > 0) {
+    if (tid >= NWC*32) {
+      if (tid == NWC*32) {
+        for (int j = 0; j < n_my; j++) {
+          const unsigned q = base + (unsigned)j;
+          unsigned char *sb = sv.stages + (q % NS)*sv.stage_bytes;
+          unsigned long long *bar = &sv.pipe->full[q % NS];
+          const int c0 = (first + j*step) * ROW_CH;
+          const int rows = min(ROW_CH, n - c0);
+          const unsigned v_b = (unsigned)((rows*8 + 15) & ~15);
+          producer_acquire(sv, q);
+          mbar_expect_tx(bar, (unsigned)F::NV*v_b);
+#pragma unroll
+          for (int v = 0; v < F::NV; v++)
+            bulk_load(sb + v*ROW_CH*8, f.src(v) + c0, v_b, bar);
+        }
+      }
+      __syncwarp();
+    }
+    else {
+      for (int j = 0; j < n_my; j++) {
+        const unsigned q = base + (unsigned)j;
+        const double *sb = (const double *)(sv.stages + (q % NS)*sv.stage_bytes);
+        consumer_wait(sv, q);
+        const int c0 = (first + j*step) * ROW_CH;
+        const int rows = min(ROW_CH, n - c0);
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const int i = tid + u*(ROW_CH/2);
+          if (i < rows) f.st(c0 + i, sb + i, acc);
+        }
+        consumer_release(sv, q);
+      }
     }
     __syncthreads();
+    if (tid == 0) sv.pipe->base = base + (unsigned)n_my;
+    __syncthreads();
+  }
+  if (acc_out != nullptr) *acc_out = acc;
+}
+
+/* vx = 0, rk = -rhs, dk = rk * ad_inv                     (:1502-1516, vx = 0) */
+struct RowInitZero {
+  static constexpr int NV = 2;
+  const double *rhs, *ad_inv;
+  double *vx, *rk, *dk;
+  __device__ __forceinline__ const double *src(int v) const { return (v == 0) ? rhs : ad_inv; }
+  __device__ __forceinline__ void st(int i, const double *op, double &) const
+  {
+    vx[i] = 0;
+    const double rr = -op[0];
+    rk[i] = rr;
+    dk[i] = rr * op[ROW_CH];
+  }
+};
+
+/* first update of the single-reduction variant                   (:1550-1558) */
+struct RowFirstUpdate {
+  static constexpr int NV = 5;
+  double alpha;
+  const double *dk, *zk, *ad_inv;
+  double *rk, *vx, *gk;
+  __device__ __forceinline__ const double *src(int v) const
+  { return (v == 0) ? dk : (v == 1) ? zk : (v == 2) ? rk : (v == 3) ? vx : ad_inv; }
+  __device__ __forceinline__ void st(int i, const double *op, double &acc) const
+  {
+    vx[i] = op[3*ROW_CH] + (alpha * op[0]);
+    const double rr = op[2*ROW_CH] + (alpha * op[ROW_CH]);
+    rk[i] = rr;
+    gk[i] = rr * op[4*ROW_CH];
+    acc += rr*rr;
+  }
+};
+
+/* the 5-vector update of an iteration                            (:1623-1631) */
+struct RowUpdate {
+  static constexpr int NV = 7;
+  double alpha, beta;
+  const double *sk, *ad_inv;
+  double *gk, *dk, *vx, *zk, *rk;
+  __device__ __forceinline__ const double *src(int v) const
+  {
+    return (v == 0) ? gk : (v == 1) ? dk : (v == 2) ? vx : (v == 3) ? sk : (v == 4) ? zk
+         : (v == 5) ? rk : ad_inv;
+  }
+  __device__ __forceinline__ void st(int i, const double *op, double &) const
+  {
+    const double d = op[0] + (beta * op[ROW_CH]);
+    dk[i] = d;
+    vx[i] = op[2*ROW_CH] + alpha * d;
+    const double z = op[3*ROW_CH] + (beta * op[4*ROW_CH]);
+    zk[i] = z;
+    const double rr = op[5*ROW_CH] + alpha * z;
+    rk[i] = rr;
+    gk[i] = rr * op[6*ROW_CH];
+  }
+};
+
+/* last sweep of a smoother: only vx is used afterwards */
+struct RowLastUpdate {
+  static constexpr int NV = 3;
+  double alpha, beta;
+  const double *gk, *dk;
+  double *vx;
+  __device__ __forceinline__ const double *src(int v) const
+  { return (v == 0) ? gk : (v == 1) ? dk : vx; }
+  __device__ __forceinline__ void st(int i, const double *op, double &) const
+  {
+    const double d = op[0] + (beta * op[ROW_CH]);
+    vx[i] = op[2*ROW_CH] + alpha * d;
+  }
+};
+
+/* Prolongation f[i] += c[coarse_row[i]] (cs_grid.cpp:9156-9166): the coarse
+   values are gathered for all U rows before the first store. */
+template <bool SINGLE>
+__device__ __noinline__ void prolong_rows(int n, const int *__restrict__ coarse_row,
+                                          const double *c_vx, double *vx)
+{
+  constexpr int U = 4;
+  const int first = SINGLE ? threadIdx.x : blockIdx.x*PT + threadIdx.x;
+  const int step = SINGLE ? PT : gridDim.x*PT;
+  for (int base = first; base < n; base += U*step) {
+    int ic[U];
+    double v[U], c[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int i = base + u*step;
+      ic[u] = -1;
+      if (i < n) { ic[u] = __ldg(coarse_row + i); v[u] = vx[i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (ic[u] >= 0) c[u] = c_vx[ic[u]];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (ic[u] >= 0) vx[base + u*step] = v[u] + c[u];
   }
 }
 
-/* elementwise loop over the rows owned by this CTA */
-template <bool SINGLE, class F>
-__device__ __forceinline__ void row_loop(int n, F f)
+/* Restriction: coarse row = sum of its fine rows in ascending fine order
+   (== the sequential loop of cs_grid.cpp:9025-9030).  Three dependent loads
+   (row range -> fine row ids -> values); each level is issued for U coarse
+   rows x up to 4 fine rows before the next one is touched. */
+template <bool SINGLE>
+__device__ __noinline__ void restrict_rows(int nc, const int *__restrict__ cfi,
+                                           const int *__restrict__ cfr,
+                                           const double *wr, double *c_rhs)
 {
+  constexpr int U = 2, J = 4;
   const int first = SINGLE ? threadIdx.x : blockIdx.x*PT + threadIdx.x;
   const int step = SINGLE ? PT : gridDim.x*PT;
-  for (int i = first; i < n; i += step) f(i);
+  for (int base = first; base < nc; base += U*step) {
+    int rs[U], cnt[U], id[U][J];
+    double w[U][J];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int ic = base + u*step;
+      rs[u] = 0; cnt[u] = 0;
+      if (ic < nc) { rs[u] = __ldg(cfi + ic); cnt[u] = __ldg(cfi + ic + 1) - rs[u]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int j = 0; j < J; j++)
+        if (j < cnt[u]) id[u][j] = __ldg(cfr + rs[u] + j);
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int j = 0; j < J; j++)
+        if (j < cnt[u]) w[u][j] = wr[id[u][j]];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int ic = base + u*step;
+      if (ic < nc) {
+        double s = 0.;
+#pragma unroll
+        for (int j = 0; j < J; j++)
+          if (j < cnt[u]) s += w[u][j];
+        for (int q = J; q < cnt[u]; q++) s += wr[__ldg(cfr + rs[u] + q)];
+        c_rhs[ic] = s;
+      }
+    }
+  }
 }
 
 /* _convergence_test, src/alge/cs_sles_it.cpp:276-324 (pure part) */
@@ -325,8 +826,15 @@ template <bool SINGLE>
 __device__ __noinline__ PcgResult pcg_run(const MgLevelDesc &L, const double *rhs, double *vx,
                              bool vx_ini_nonzero, int n_max_iter, double precision,
                              double r_norm, bool smoother, const PersistentCommon &P,
-                             ItState *st, double *s_prod, double *s_red)
+                             ItState *st, unsigned char *s_raw,
+                             unsigned long long *prof_it = nullptr)
 {
+  /* lead thread: time spent per kind of phase, closing barrier / reduction included */
+  const bool timed = (prof_it != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
+  unsigned long long t_mark = timed ? global_ns() : 0ull;
+  auto mark = [&](int kind) {
+    if (timed) { const unsigned long long t = global_ns(); prof_it[kind] += t - t_mark; t_mark = t; }
+  };
   const int n = L.n_rows;
   const size_t ws = P.work_stride;
   double *rk = P.work, *dk = P.work + ws, *gk = P.work + 2*ws, *zk = P.work + 3*ws,
@@ -335,6 +843,7 @@ __device__ __noinline__ PcgResult pcg_run(const MgLevelDesc &L, const double *rh
   const double *__restrict__ d_val = L.d_val;
   const bool rec = (st != nullptr) && (SINGLE || blockIdx.x == 0) && threadIdx.x == 0;
   double *part0 = P.partials, *part1 = P.partials + 4*(size_t)gridDim.x;
+  double *s_red = (double *)s_raw;
 
   PcgResult R;
   R.n_iter = 0; R.cvg = CSB_SLES_ITERATING; R.residual = -1.; R.initial_residual = -1.;
@@ -344,33 +853,28 @@ __device__ __noinline__ PcgResult pcg_run(const MgLevelDesc &L, const double *rh
   const CommDev *comm = P.comm;
   if (vx_ini_nonzero) {
     const double *gh = halo_exchange<SINGLE>(L, vx);
-    spmv_slabs<SINGLE>(L, vx, gh, s_prod, [&](int r, double sii) {
-      const double rr = (sii + d_val[r]*vx[r]) - rhs[r];
-      rk[r] = rr;
-      dk[r] = rr * ad_inv[r];
-    });
+    EpiInitResidual f;
+    f.d_val = d_val; f.vx = vx; f.rhs = rhs; f.ad_inv = ad_inv; f.rk = rk; f.dk = dk;
+    spmv_phase<SINGLE>(L, vx, gh, s_raw, f, nullptr);
   }
   else {
-    row_loop<SINGLE>(n, [&](int i) {
-      vx[i] = 0;
-      const double rr = -rhs[i];
-      rk[i] = rr;
-      dk[i] = rr * ad_inv[i];
-    });
+    RowInitZero f;
+    f.rhs = rhs; f.ad_inv = ad_inv; f.vx = vx; f.rk = rk; f.dk = dk;
+    row_phase<SINGLE>(n, s_raw, f, nullptr);
   }
   phase_barrier<SINGLE>(P.barrier);
+  mark(vx_ini_nonzero ? 0 : 2);
 
   /* zk = A.dk and the first 3 dots (:1521-1535) */
   double v[3] = {0., 0., 0.};
   const double *gh_d = halo_exchange<SINGLE>(L, dk);
-  spmv_slabs<SINGLE>(L, dk, gh_d, s_prod, [&](int r, double sii) {
-    const double d = dk[r];
-    const double z = sii + d_val[r]*d;
-    zk[r] = z;
-    const double rr = rk[r];
-    v[0] += rr*rr; v[1] += rr*d; v[2] += d*z;
-  });
+  {
+    EpiDots f;
+    f.d_val = d_val; f.p = dk; f.rk = rk; f.out = zk;
+    spmv_phase<SINGLE>(L, dk, gh_d, s_raw, f, v);
+  }
   all_sum<SINGLE, 3>(v, part0, P.barrier, s_red, comm);
+  mark(1);
 
   double ro_0 = v[1], ro_1 = v[2], rk_gkm1 = 0., alpha = 0., beta = 0.;
   R.residual = sqrt(v[0]);
@@ -384,15 +888,14 @@ __device__ __noinline__ PcgResult pcg_run(const MgLevelDesc &L, const double *rh
     alpha = - ro_0 * d_ro_1;
     rk_gkm1 = ro_0;
     double w[1] = {0.};
-    row_loop<SINGLE>(n, [&](int i) {      /* :1550-1558 */
-      vx[i] += (alpha * dk[i]);
-      const double rr = rk[i] + (alpha * zk[i]);
-      rk[i] = rr;
-      gk[i] = rr * ad_inv[i];
-      w[0] += rr*rr;
-    });
+    {
+      RowFirstUpdate f;                                /* :1550-1558 */
+      f.alpha = alpha; f.dk = dk; f.zk = zk; f.ad_inv = ad_inv; f.rk = rk; f.vx = vx; f.gk = gk;
+      row_phase<SINGLE>(n, s_raw, f, w);
+    }
     all_sum<SINGLE, 1>(w, part1, P.barrier, s_red, comm);
     if (SINGLE) __syncthreads();
+    mark(2);
     R.residual = sqrt(w[0]);
     R.cvg = it_cvg_eval(precision, r_norm, n_max_iter, R.initial_residual, 1, R.residual);
     if (rec && st->n_hist < HIST_MAX) st->hist[st->n_hist++] = R.residual;
@@ -402,14 +905,13 @@ __device__ __noinline__ PcgResult pcg_run(const MgLevelDesc &L, const double *rh
     if (smoother && R.n_iter >= n_max_iter) break;
     v[0] = 0.; v[1] = 0.; v[2] = 0.;
     const double *gh_g = halo_exchange<SINGLE>(L, gk);
-    spmv_slabs<SINGLE>(L, gk, gh_g, s_prod, [&](int r, double sii) {   /* :1591-1600 */
-      const double g = gk[r];
-      const double s = sii + d_val[r]*g;
-      sk[r] = s;
-      const double rr = rk[r];
-      v[0] += rr*rr; v[1] += rr*g; v[2] += g*s;
-    });
+    {
+      EpiDots f;                                                       /* :1591-1600 */
+      f.d_val = d_val; f.p = gk; f.rk = rk; f.out = sk;
+      spmv_phase<SINGLE>(L, gk, gh_g, s_raw, f, v);
+    }
     all_sum<SINGLE, 3>(v, part0, P.barrier, s_red, comm);
+    mark(1);
     const double residual = sqrt(v[0]);
     const double rk_gk = v[1], gk_sk = v[2];
     R.residual = residual;
@@ -428,24 +930,18 @@ __device__ __noinline__ PcgResult pcg_run(const MgLevelDesc &L, const double *rh
     alpha = - ro_0 * d_ro_1;
     if (smoother && R.n_iter >= n_max_iter) {
       /* last sweep of a smoother: only vx is used afterwards */
-      row_loop<SINGLE>(n, [&](int i) {
-        const double d = gk[i] + (beta * dk[i]);
-        vx[i] += alpha * d;
-      });
+      RowLastUpdate f;
+      f.alpha = alpha; f.beta = beta; f.gk = gk; f.dk = dk; f.vx = vx;
+      row_phase<SINGLE>(n, s_raw, f, nullptr);
     }
     else {
-      row_loop<SINGLE>(n, [&](int i) {        /* :1623-1631 */
-        const double d = gk[i] + (beta * dk[i]);
-        dk[i] = d;
-        vx[i] += alpha * d;
-        const double z = sk[i] + (beta * zk[i]);
-        zk[i] = z;
-        const double rr = rk[i] + alpha * z;
-        rk[i] = rr;
-        gk[i] = rr * ad_inv[i];
-      });
+      RowUpdate f;                              /* :1623-1631 */
+      f.alpha = alpha; f.beta = beta; f.sk = sk; f.ad_inv = ad_inv;
+      f.gk = gk; f.dk = dk; f.vx = vx; f.zk = zk; f.rk = rk;
+      row_phase<SINGLE>(n, s_raw, f, nullptr);
     }
     phase_barrier<SINGLE>(P.barrier);
+    mark(2);
   }
 
   if (rec) {
@@ -467,17 +963,16 @@ k_pcg_persistent(const MgLevelDesc L, const double *rhs, double *vx, int vx_ini_
                  int n_max_iter, double precision, double r_norm,
                  const PersistentCommon P, ItState *st, int single)
 {
-  extern __shared__ double s_dyn[];
-  double *s_red = s_dyn;
-  double *s_prod = s_dyn + PERSISTENT_S_RED;
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  pipe_init(s_raw);
   if (single) {
     if (blockIdx.x == 0)
       pcg_run<true>(L, rhs, vx, vx_ini_nonzero != 0, n_max_iter, precision, r_norm, false,
-                    P, st, s_prod, s_red);
+                    P, st, s_raw);
   }
   else
     pcg_run<false>(L, rhs, vx, vx_ini_nonzero != 0, n_max_iter, precision, r_norm, false,
-                   P, st, s_prod, s_red);
+                   P, st, s_raw);
 }
 
 /*--------------------------------------------------------------------------
@@ -487,9 +982,9 @@ k_pcg_persistent(const MgLevelDesc L, const double *rhs, double *vx, int vx_ini_
 __global__ void __launch_bounds__(PT, CSB_MIN_CTAS)
 k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
 {
-  extern __shared__ double s_dyn[];
-  double *s_red = s_dyn;
-  double *s_prod = s_dyn + PERSISTENT_S_RED;
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  double *s_red = (double *)s_raw;
+  pipe_init(s_raw);
 
   const MgLevelDesc *__restrict__ LV = S.levels;
   MgState *ms = S.ms;
@@ -521,7 +1016,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
         if (blockIdx.x == 0)
           R = pcg_run<true>(L, rhs_lv, vx_lv, ini, S.n_max_iter[0],
                             S.precision*S.precision_mult[0], S.r_norm, true, P,
-                            L.st_descent, s_prod, s_red);
+                            L.st_descent, s_raw, ms->prof_it[level < PROF_LEVELS ? level : PROF_LEVELS-1]);
         grid_barrier(P.barrier);
         /* other CTAs need the iteration count for n_equiv_iter */
         R.n_iter = *((volatile int *)&L.st_descent->n_iter);
@@ -531,7 +1026,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
       else {
         R = pcg_run<false>(L, rhs_lv, vx_lv, ini, S.n_max_iter[0],
                            S.precision*S.precision_mult[0], S.r_norm, true, P,
-                           L.st_descent, s_prod, s_red);
+                           L.st_descent, s_raw, ms->prof_it[level < PROF_LEVELS ? level : PROF_LEVELS-1]);
         grid_barrier(P.barrier);
       }
       if (lead) prof_mark(ms, t_last, level, MG_PROF_DESCENT);
@@ -544,12 +1039,11 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
         const double *__restrict__ d_val = L.d_val;
         double *wr = S.wr;
         const double *gh = halo_exchange<false>(L, vx_lv);
-        spmv_slabs<false>(L, vx_lv, gh, s_prod, [&](int r, double sii) {
-          const double y = sii + d_val[r]*vx_lv[r];
-          const double t = rhs_lv[r] - y;
-          wr[r] = t;
-          w[0] += t*t;
-        });
+        EpiResidual f;
+        f.d_val = d_val; f.vx = vx_lv; f.rhs = rhs_lv; f.wr = wr;
+        double acc[3];
+        spmv_phase<false>(L, vx_lv, gh, s_raw, f, acc);
+        w[0] = acc[0];
       }
       if (level == 0) {
         all_sum<false, 1>(w, P.partials + 8*(size_t)gridDim.x, P.barrier, s_red, P.comm);
@@ -571,18 +1065,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
 
       /* restriction: coarse row = sum of its fine rows, ascending fine order
          (== the sequential loop of cs_grid.cpp:9025-9030) */
-      {
-        const int *__restrict__ cfi = L.c_f_row_index;
-        const int *__restrict__ cfr = L.c_f_row_ids;
-        const double *wr = S.wr;
-        double *c_rhs = C.rhs;
-        row_loop<false>(C.n_rows, [&](int ic) {
-          double s = 0.;
-          const int rs = cfi[ic], re = cfi[ic+1];
-          for (int q = rs; q < re; q++) s += wr[cfr[q]];
-          c_rhs[ic] = s;
-        });
-      }
+      restrict_rows<false>(C.n_rows, L.c_f_row_index, L.c_f_row_ids, S.wr, C.rhs);
       grid_barrier(P.barrier);
       if (lead) prof_mark(ms, t_last, level, MG_PROF_RESTRICT);
     }
@@ -598,7 +1081,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
         if (blockIdx.x == 0)
           R = pcg_run<true>(L, rhs_lv, vx_lv, false, S.n_max_iter[2],
                             S.precision*S.precision_mult[2], S.r_norm, true, P,
-                            L.st_descent, s_prod, s_red);
+                            L.st_descent, s_raw, ms->prof_it[coarsest < PROF_LEVELS ? coarsest : PROF_LEVELS-1]);
         grid_barrier(P.barrier);
         R.n_iter = *((volatile int *)&L.st_descent->n_iter);
         R.cvg = *((volatile int *)&L.st_descent->cvg);
@@ -606,7 +1089,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
       else {
         R = pcg_run<false>(L, rhs_lv, vx_lv, false, S.n_max_iter[2],
                            S.precision*S.precision_mult[2], S.r_norm, true, P,
-                           L.st_descent, s_prod, s_red);
+                           L.st_descent, s_raw, ms->prof_it[coarsest < PROF_LEVELS ? coarsest : PROF_LEVELS-1]);
         grid_barrier(P.barrier);
       }
       if (lead) prof_mark(ms, t_last, coarsest, MG_PROF_COARSEST);
@@ -628,10 +1111,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
         {
           const int *__restrict__ coarse_row = L.coarse_row;
           const double *c_vx = C.vx;
-          row_loop<false>(L.n_rows, [&](int i) {       /* cs_grid.cpp:9156-9166 */
-            const int ic = coarse_row[i];
-            if (ic >= 0) vx_lv[i] += c_vx[ic];
-          });
+          prolong_rows<false>(L.n_rows, coarse_row, c_vx, vx_lv);
         }
         grid_barrier(P.barrier);
         if (lead) prof_mark(ms, t_last, level, MG_PROF_PROLONG);
@@ -642,7 +1122,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
             if (blockIdx.x == 0)
               R = pcg_run<true>(L, L.rhs, vx_lv, true, S.n_max_iter[1],
                                 S.precision*S.precision_mult[1], S.r_norm, true, P,
-                                L.st_ascent, s_prod, s_red);
+                                L.st_ascent, s_raw, ms->prof_it[level < PROF_LEVELS ? level : PROF_LEVELS-1]);
             grid_barrier(P.barrier);
             R.n_iter = *((volatile int *)&L.st_ascent->n_iter);
             R.cvg = *((volatile int *)&L.st_ascent->cvg);
@@ -650,7 +1130,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
           else {
             R = pcg_run<false>(L, L.rhs, vx_lv, true, S.n_max_iter[1],
                                S.precision*S.precision_mult[1], S.r_norm, true, P,
-                               L.st_ascent, s_prod, s_red);
+                               L.st_ascent, s_raw, ms->prof_it[level < PROF_LEVELS ? level : PROF_LEVELS-1]);
             grid_barrier(P.barrier);
           }
           if (lead) prof_mark(ms, t_last, level, MG_PROF_ASCENT);
@@ -676,7 +1156,9 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
 void plan_slabs(const std::vector<csb_lnum_t> &ri, int n_rows, int &slab_rows, int &n_slabs,
                 size_t &max_entries)
 {
-  slab_rows = PT;
+  /* Tallest slab (whole consumer warps: SLAB_ROWS_MAX, -32, ...) whose widest instance
+     fits a pipeline stage of SLAB_CAP entries. */
+  slab_rows = SLAB_ROWS_MAX;
   while (true) {
     max_entries = 0;
     for (int r0 = 0; r0 < n_rows; r0 += slab_rows) {
@@ -684,15 +1166,23 @@ void plan_slabs(const std::vector<csb_lnum_t> &ri, int n_rows, int &slab_rows, i
       const size_t nk = (size_t)(ri[r1] - ri[r0]);
       if (nk > max_entries) max_entries = nk;
     }
-    if (max_entries * sizeof(double) <= 40*1024 || slab_rows <= 32) break;
-    slab_rows /= 2;
+    if (max_entries <= (size_t)SLAB_CAP || slab_rows <= 4) break;
+    slab_rows = (slab_rows > 32) ? slab_rows - 32 : slab_rows / 2;
   }
   n_slabs = (n_rows + slab_rows - 1) / slab_rows;
 }
 
 size_t persistent_smem_bytes(size_t max_slab_entries)
 {
-  return (PERSISTENT_S_RED + (max_slab_entries > 2 ? max_slab_entries : 2)) * sizeof(double);
+  /* header (reduction scratch + mbarriers) + NS stages; a stage holds the widest slab
+     (entries rounded up to 4; see the layout in the kernel) or a chunk of an
+     elementwise phase, whichever is larger */
+  size_t cap = (max_slab_entries + 3) / 4 * 4;
+  if (cap < 4) cap = 4;
+  size_t stage = 12*cap + ST_FIXED;
+  if (stage < (size_t)ROW_STAGE_BYTES) stage = ROW_STAGE_BYTES;
+  stage = (stage + 127) / 128 * 128;
+  return SMEM_HDR + NS*stage;
 }
 
 /* number of co-resident CTAs for the given dynamic shared memory size */
@@ -719,7 +1209,7 @@ int persistent_grid(int which, size_t smem)
   static int cap = -1;
   if (cap < 0) {
     const char *s = getenv("CSB_CTAS_PER_SM");
-    cap = (s != nullptr) ? atoi(s) : 4;
+    cap = (s != nullptr) ? atoi(s) : CSB_MIN_CTAS;
   }
   if (occ > cap && cap > 0) occ = cap;
   int g = occ * c.sm_count / (c.device_share > 1 ? c.device_share : 1);

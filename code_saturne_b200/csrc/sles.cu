@@ -39,12 +39,14 @@ int env_int(const char *name, int dflt)
 /* stage a host vector on the device when needed */
 struct StagedVec {
   double         *d = nullptr;
-  double         *h = nullptr;
+  double         *h = nullptr;     /* caller's buffer when it is not used in place */
   DevBuf<double>  tmp;
   size_t          n = 0;
+  /* A device buffer is used in place when the bulk copies of the persistent kernels
+     can read it: 16-byte aligned, and an even length (they read whole 16-byte units). */
   bool init(double *p, size_t count, bool copy_in) {
     n = count;
-    if (is_device_ptr(p)) { d = p; return true; }
+    if (is_device_ptr(p) && ((uintptr_t)p & 15) == 0 && (count & 1) == 0) { d = p; return true; }
     h = p;
     if (copy_in) { if (!tmp.upload(p, count)) return false; }
     else if (!tmp.alloc(count)) return false;
@@ -53,10 +55,14 @@ struct StagedVec {
   }
   bool copy_back(size_t count) {
     if (h == nullptr) return true;
-    return CSB_CUDA(cudaMemcpyAsync(h, d, sizeof(double)*count, cudaMemcpyDeviceToHost,
+    return CSB_CUDA(cudaMemcpyAsync(h, d, sizeof(double)*count, cudaMemcpyDefault,
                                     ctx().stream));
   }
 };
+
+/* distance between the work vectors of the persistent kernels: even, so that every
+   vector starts on a 16-byte boundary */
+inline size_t work_stride_of(size_t n_cols_ext) { return (n_cols_ext + 1) & ~(size_t)1; }
 
 const size_t IT_HEAD = offsetof(ItState, hist);
 const size_t MG_HEAD = offsetof(MgState, cycle_res);
@@ -349,7 +355,7 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
   const size_t n_wa = (c->type == CSB_SLES_BICGSTAB) ? 6 : ((c->type == CSB_SLES_PCG) ? 5 : 1);
   if (!c->ad_inv.alloc((size_t)a->n_rows)) return;
   if (!launch_ad_inv(a->n_rows, a->d_val.p, c->ad_inv.p)) return;
-  if (!c->work.alloc(n_wa * (size_t)a->n_cols_ext)) return;
+  if (!c->work.alloc(n_wa * work_stride_of((size_t)a->n_cols_ext))) return;
   if (!c->st.alloc(1)) return;
   if (c->h_st == nullptr)
     if (!CSB_CUDA(cudaMallocHost((void **)&c->h_st, sizeof(ItState)))) return;
@@ -421,7 +427,7 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
     if (a->halo != nullptr || env_int("CSB_PCG_MODE_MULTI", 0) == 0) {
       /* whole solve in one persistent cooperative kernel (per rank) */
       PersistentCommon P;
-      P.work = c->work.p; P.work_stride = (size_t)a->n_cols_ext;
+      P.work = c->work.p; P.work_stride = work_stride_of((size_t)a->n_cols_ext);
       P.partials = c->partials.p; P.barrier = c->barrier.p;
       P.comm = (a->halo != nullptr) ? c->pcomm->d : nullptr;
       const bool single = (a->n_rows <= sb_rows_threshold());
@@ -1017,7 +1023,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     MgLevel *lv = mg->levels[l];
     const csb_matrix_t *m = lv->m;
     wr_size = std::max(wr_size, (size_t)m->n_cols_ext);
-    aux_size = std::max(aux_size, 5*(size_t)m->n_cols_ext);
+    aux_size = std::max(aux_size, 5*work_stride_of((size_t)m->n_cols_ext));
     if (!lv->ad_inv.alloc((size_t)m->n_rows)) return;
     if (!launch_ad_inv(m->n_rows, m->d_val.p, lv->ad_inv.p)) return;
     if (l > 0) {
@@ -1128,7 +1134,7 @@ csb_multigrid_solve(void *context, const char *name, const csb_matrix_t *a, int 
     S.precision = precision; S.r_norm = r_norm;
     S.single_rows = sb_rows_threshold();
     PersistentCommon P;
-    P.work = mg->aux.p; P.work_stride = (size_t)a->n_cols_ext;
+    P.work = mg->aux.p; P.work_stride = work_stride_of((size_t)a->n_cols_ext);
     P.partials = mg->partials.p; P.barrier = mg->barrier.p;
     P.comm = dist ? mg->pcomm->d : nullptr;
     if (dist) pcomm_host_barrier(mg->pcomm);   /* no rank is inside cudaFree while kernels spin */
@@ -1314,6 +1320,18 @@ int csb_multigrid_get_phase_times(const csb_multigrid_t *mg, double *seconds, in
   for (int l = 0; l < n; l++)
     for (int p = 0; p < PROF_PHASES; p++)
       seconds[l*PROF_PHASES + p] = 1e-9 * (double)mg->h_mg->prof[l][p];
+  return n;
+}
+
+int csb_multigrid_get_smoother_times(const csb_multigrid_t *mg, double *seconds, int max_levels)
+{
+  if (mg == nullptr || mg->h_mg == nullptr) return 0;
+  int n = (int)mg->levels.size();
+  if (n > max_levels) n = max_levels;
+  if (n > PROF_LEVELS) n = PROF_LEVELS;
+  for (int l = 0; l < n; l++)
+    for (int p = 0; p < PROF_IT_PHASES; p++)
+      seconds[l*PROF_IT_PHASES + p] = 1e-9 * (double)mg->h_mg->prof_it[l][p];
   return n;
 }
 

@@ -373,6 +373,10 @@ int  csb_multigrid_get_setup_times(const csb_multigrid_t *mg, double t[4]);
    offers through its per-level timers (src/alge/cs_multigrid.cpp:170-205).
    Returns the number of levels written (<= max_levels). */
 int  csb_multigrid_get_phase_times(const csb_multigrid_t *mg, double *seconds, int max_levels);
+/* The same timers inside the PCG smoothers (descent + ascent + coarsest solve):
+   seconds[level*3 + k], k = 0 residual SpMV (r = A.vx - rhs), 1 SpMV + 3 dots,
+   2 fused vector updates. */
+int  csb_multigrid_get_smoother_times(const csb_multigrid_t *mg, double *seconds, int max_levels);
 
 /* Host-only pieces of the hierarchy construction (no device needed), exposed
    so that CPU-side tests can check them: the DX aggregation map

@@ -100,6 +100,25 @@ def main():
     ach = tot_bytes / (pt.sum() / n_cycles) / 1e9
     lines += ["", f"algorithmic bytes per cycle (levels above the coarsest): {tot_bytes/1e9:.2f} GB; "
               f"whole-cycle achieved {ach:.0f} GB/s = {ach/peak:.3f} of measured peak"]
+    # inside the PCG smoothers: residual SpMV / SpMV + 3 dots / vector updates
+    stt = mg.smoother_times()
+    lines += ["", "| level | r = A.vx - rhs: us/cyc (us each, GB/s, frac) | A.p + 3 dots: us/cyc (us each, "
+              "GB/s, frac) | vector updates us/cyc (GB/s, frac) |", "|---|---|---|---|"]
+    for l, (n, nnz) in enumerate(info):
+        if l == coarsest:
+            break
+        M = 12.0 * nnz + 12.0 * n
+        n0, n1 = 1, (2 if l == 0 else 12)
+        b0, b1 = M + 32 * n, M + 24 * n
+        upd = (64 + 32) * n if l == 0 else (40 + 64 + 32 + 64 + 8 * 96 + 32) * n
+        t0, t1, t2 = (stt[l, k] / n_cycles for k in range(3))
+        def cell(t, cnt, b):
+            if t <= 0:
+                return "-"
+            g = cnt * b / t / 1e9
+            return f"{t*1e6:.1f} ({t/cnt*1e6:.1f}, {g:.0f}, {g/peak:.2f})"
+        g2 = upd / t2 / 1e9 if t2 > 0 else 0.0
+        lines.append(f"| {l} | {cell(t0, n0, b0)} | {cell(t1, n1, b1)} | {t2*1e6:.1f} ({g2:.0f}, {g2/peak:.2f}) |")
     txt = "\n".join(lines)
     print(txt)
     if args.out:

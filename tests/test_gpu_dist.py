@@ -37,3 +37,28 @@ def test_distributed_pcg(N, R, bc):
                                          (24, 1, "dirichlet", 1e-8)])
 def test_distributed_multigrid(N, R, bc, prec):
     run("mg", N, R, bc, prec)
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("N,R,bc", [(32, 2, "dirichlet"), (48, 4, "neumann"), (64, 8, "dirichlet")])
+def test_one_process_per_gpu_multigrid(N, R, bc):
+    """torchrun, one process per GPU, arenas mapped with cudaIpc: needs R visible GPUs."""
+    if _n_gpus() < R:
+        pytest.skip(f"needs {R} GPUs")
+    import socket
+    with socket.socket() as so:
+        so.bind(("127.0.0.1", 0))
+        port = so.getsockname()[1]
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                        f"--nproc-per-node={R}", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port),
+                        os.path.join(ROOT, "tests", "dist_proc_worker.py"), str(N), bc],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0 and "OK proc-mg" in p.stdout, f"{p.stdout[-2000:]}\n{p.stderr[-4000:]}"
