@@ -43,6 +43,7 @@ class ConvergenceState(enum.IntEnum):
 
 class SlesItType(enum.IntEnum):
     PCG = 0
+    FCG = 1
     JACOBI = 3
     BICGSTAB = 4
 

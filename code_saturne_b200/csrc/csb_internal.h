@@ -100,6 +100,7 @@ struct ItState {
   int    n_iter, n_max_iter;
   int    cvg;                            /* csb_sles_convergence_state_t, 2 = skipped */
   int    n_hist;
+  int    n_halo;                         /* ghost exchanges done by the last run */
   double hist[HIST_MAX];
 };
 

@@ -64,7 +64,7 @@ static_assert(SLAB_CAP % 4 == 0, "slab capacity");
 #endif
 constexpr int NG = CSB_GATHER;     /* x[col] gathers a lane keeps in flight for its next row */
 static_assert(PT % 32 == 0 && NW <= 32, "CTA shape");
-static_assert(3*NW + 3 <= 56 && 56 + 3*COMM_MAX_RANKS <= PERSISTENT_S_RED, "s_red layout");
+static_assert(4*NW + 4 <= 56 && 56 + 4*COMM_MAX_RANKS <= PERSISTENT_S_RED, "s_red layout");
 
 /*--------------------------------------------------------------------------
  * Grid-wide barrier (all CTAs are co-resident: cooperative launch).
@@ -207,6 +207,12 @@ __device__ __forceinline__ void all_sum(double (&v)[Q], double *partials, unsign
  * x must be complete (call after a grid barrier).
  *--------------------------------------------------------------------------*/
 
+/* Exchanges done so far, per level: a copy private to the CTA (shared memory), loaded
+   from DistLevel::count at kernel start (halo_counts_init) so that a CTA that reaches an
+   exchange late cannot read a count that the packing CTAs have already advanced. */
+constexpr int HALO_K_OFF = PERSISTENT_S_RED*8;     /* unsigned[PROF_LEVELS] ahead of PipeState */
+extern __shared__ __align__(128) unsigned char s_raw_base[];
+
 template <bool SINGLE>
 __device__ __forceinline__ const double *halo_exchange(const MgLevelDesc &L, const double *x)
 {
@@ -214,27 +220,36 @@ __device__ __forceinline__ const double *halo_exchange(const MgLevelDesc &L, con
   if (D == nullptr) return nullptr;
   const int n_dom = D->n_dom;
   if (n_dom == 0) return nullptr;
-  const unsigned k = *(volatile unsigned *)D->count + 1;
+  unsigned *s_hk = (unsigned *)(s_raw_base + HALO_K_OFF) + L.level_id;
+  const unsigned k = *s_hk + 1;
   const int par = k & 1;
-  const int first = SINGLE ? threadIdx.x : blockIdx.x*PT + threadIdx.x;
-  const int step = SINGLE ? PT : gridDim.x*PT;
-  const int *__restrict__ send_list = D->send_list;
-  for (int i = 0; i < n_dom; i++) {
-    const int s0 = D->send_index[i], s1 = D->send_index[i+1];
-    double *dst = D->push_dst[i][par];
-    for (int e = s0 + first; e < s1; e += step)
-      dst[e - s0] = x[send_list[e]];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    bool last = true;
-    if (!SINGLE) last = (atomicInc(D->ticket, gridDim.x - 1) == gridDim.x - 1);
-    if (last) {
-      *(volatile unsigned *)D->count = k;
-      __threadfence_system();
-      for (int i = 0; i < n_dom; i++)
-        *(volatile unsigned *)D->flag_remote[i] = k;
+  /* only as many CTAs as the send list needs pack, fence and take a ticket: on the
+     coarse levels that is one or two, and the exchange costs one NVLink round trip
+     instead of a grid-wide ticket */
+  const int n_send = D->send_index[n_dom];
+  const unsigned n_pack = SINGLE ? 1u
+    : (unsigned)min((int)gridDim.x, max(1, (n_send + PT - 1) / PT));
+  if (SINGLE || blockIdx.x < n_pack) {
+    const int first = SINGLE ? threadIdx.x : blockIdx.x*PT + threadIdx.x;
+    const int step = SINGLE ? PT : (int)n_pack*PT;
+    const int *__restrict__ send_list = D->send_list;
+    for (int i = 0; i < n_dom; i++) {
+      const int s0 = D->send_index[i], s1 = D->send_index[i+1];
+      double *dst = D->push_dst[i][par];
+      for (int e = s0 + first; e < s1; e += step)
+        dst[e - s0] = x[send_list[e]];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bool last = true;
+      if (!SINGLE) last = (atomicInc(D->ticket, n_pack - 1) == n_pack - 1);
+      if (last) {
+        *(volatile unsigned *)D->count = k;
+        __threadfence_system();
+        for (int i = 0; i < n_dom; i++)
+          *(volatile unsigned *)D->flag_remote[i] = k;
+      }
     }
   }
   if (threadIdx.x < n_dom) {
@@ -242,7 +257,41 @@ __device__ __forceinline__ const double *halo_exchange(const MgLevelDesc &L, con
     __threadfence();
   }
   __syncthreads();
+  if (threadIdx.x == 0) *s_hk = k;      /* read again only after further CTA barriers */
   return D->gbuf[par];
+}
+
+__device__ __forceinline__ unsigned halo_count(const MgLevelDesc &L)
+{
+  return (L.dist != nullptr) ? ((const unsigned *)(s_raw_base + HALO_K_OFF))[L.level_id] : 0u;
+}
+
+/* After a level was run by CTA 0 alone (grid barrier passed): the other CTAs advance
+   their exchange count of the level by what CTA 0 did. */
+__device__ __forceinline__ void halo_count_follow(const MgLevelDesc &L, const ItState *st)
+{
+  if (L.dist == nullptr) return;
+  if (blockIdx.x != 0 && threadIdx.x == 0)
+    ((unsigned *)(s_raw_base + HALO_K_OFF))[L.level_id] += (unsigned)*((volatile int *)&st->n_halo);
+  __syncthreads();
+}
+
+/* kernel start, levels with a ghost exchange: load the exchange counts, then a grid
+   barrier (no CTA starts an exchange before every CTA holds its copy) */
+__device__ __forceinline__ void halo_counts_init(const MgLevelDesc *levels, int n_levels,
+                                                 unsigned *bar)
+{
+  unsigned *s_hk = (unsigned *)(s_raw_base + HALO_K_OFF);
+  bool any = false;
+  for (int l = 0; l < n_levels && l < PROF_LEVELS; l++) {
+    const DistLevel *D = levels[l].dist;
+    if (D != nullptr) {
+      any = true;
+      if (threadIdx.x == 0) s_hk[levels[l].level_id] = *(volatile unsigned *)D->count;
+    }
+  }
+  if (any) grid_barrier(bar);
+  else __syncthreads();
 }
 
 /*--------------------------------------------------------------------------
@@ -272,7 +321,8 @@ struct PipeState {
   unsigned           pad[15];
 };
 
-constexpr int SMEM_HDR = (PERSISTENT_S_RED*8 + (int)sizeof(PipeState) + 127) / 128 * 128;
+constexpr int PIPE_OFF = HALO_K_OFF + PROF_LEVELS*4;
+constexpr int SMEM_HDR = (PIPE_OFF + (int)sizeof(PipeState) + 127) / 128 * 128;
 constexpr int ST_RI_BYTES = ((SLAB_ROWS_MAX + 1 + 3)*4 + 15) / 16 * 16;
 constexpr int ST_OP_STRIDE = SLAB_ROWS_MAX;          /* doubles between staged operand vectors */
 constexpr int ST_FIXED = 16 + 16 + ST_RI_BYTES + 4*ST_OP_STRIDE*8;
@@ -336,7 +386,7 @@ struct SmemView {
 __device__ __forceinline__ SmemView smem_view(unsigned char *s_raw)
 {
   SmemView v;
-  v.pipe = (PipeState *)(s_raw + PERSISTENT_S_RED*8);
+  v.pipe = (PipeState *)(s_raw + PIPE_OFF);
   v.stages = s_raw + SMEM_HDR;
   v.stage_bytes = (int)((dyn_smem_bytes() - SMEM_HDR) / NS) & ~127;
   v.cap = ((v.stage_bytes - ST_FIXED) / 12) & ~3;
@@ -346,7 +396,7 @@ __device__ __forceinline__ SmemView smem_view(unsigned char *s_raw)
 /* once per kernel */
 __device__ __forceinline__ void pipe_init(unsigned char *s_raw)
 {
-  PipeState *pipe = (PipeState *)(s_raw + PERSISTENT_S_RED*8);
+  PipeState *pipe = (PipeState *)(s_raw + PIPE_OFF);
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; i++) { mbar_init(&pipe->full[i], 1); mbar_init(&pipe->empty[i], NWC); }
     pipe->base = 0;
@@ -385,9 +435,9 @@ __device__ __forceinline__ void consumer_release(const SmemView &sv, unsigned q)
  *                    summed **in CSR order** (the reference's order,
  *                    cs_matrix_spmv.cpp:2138-2142) and passed to the epilogue.
  * F (by value) supplies NV (staged vectors), src(j) (their base pointers) and
- *   void epi(int row, double off_diagonal_sum, const double *op, double (&acc)[3])
+ *   void epi(int row, double off_diagonal_sum, const double *op, double (&acc)[4])
  * where op[j*ST_OP_STRIDE] is the value of staged vector j at this row.
- * acc_out[0..2] receives this thread's partial sums.
+ * acc_out[0..3] receives this thread's partial sums.
  *--------------------------------------------------------------------------*/
 
 template <bool SINGLE, bool GHOST, class F>
@@ -406,7 +456,7 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
   const unsigned base = sv.pipe->base;
   const int off_val = 4*(sv.cap + 4), off_ri = off_val + 8*(sv.cap + 2),
             off_ops = off_ri + ST_RI_BYTES;
-  double acc[3] = {0., 0., 0.};
+  double acc[4] = {0., 0., 0., 0.};
 
   if (n_my > 0) {
     if (tid >= NWC*32) {
@@ -519,7 +569,9 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
     if (tid == 0) sv.pipe->base = base + (unsigned)n_my;
     __syncthreads();
   }
-  if (acc_out != nullptr) { acc_out[0] = acc[0]; acc_out[1] = acc[1]; acc_out[2] = acc[2]; }
+  if (acc_out != nullptr) {
+    acc_out[0] = acc[0]; acc_out[1] = acc[1]; acc_out[2] = acc[2]; acc_out[3] = acc[3];
+  }
 }
 
 template <bool SINGLE, class F>
@@ -538,7 +590,7 @@ struct EpiInitResidual {
   double *rk, *dk;
   __device__ __forceinline__ const double *src(int v) const
   { return (v == 0) ? d_val : (v == 1) ? vx : (v == 2) ? rhs : ad_inv; }
-  __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&)[3]) const
+  __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&)[4]) const
   {
     const double rr = (sii + op[0]*op[ST_OP_STRIDE]) - op[2*ST_OP_STRIDE];
     rk[r] = rr;
@@ -553,7 +605,7 @@ struct EpiDots {
   double *out;
   __device__ __forceinline__ const double *src(int v) const
   { return (v == 0) ? d_val : (v == 1) ? p : rk; }
-  __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&acc)[3]) const
+  __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&acc)[4]) const
   {
     const double d = op[ST_OP_STRIDE];
     const double z = sii + op[0]*d;
@@ -570,7 +622,7 @@ struct EpiResidual {
   double *wr;
   __device__ __forceinline__ const double *src(int v) const
   { return (v == 0) ? d_val : (v == 1) ? vx : rhs; }
-  __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&acc)[3]) const
+  __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&acc)[4]) const
   {
     const double y = sii + op[0]*op[ST_OP_STRIDE];
     const double t = op[2*ST_OP_STRIDE] - y;
@@ -848,6 +900,7 @@ __device__ __noinline__ PcgResult pcg_run(const MgLevelDesc &L, const double *rh
   PcgResult R;
   R.n_iter = 0; R.cvg = CSB_SLES_ITERATING; R.residual = -1.; R.initial_residual = -1.;
   if (rec) st->n_hist = 0;
+  const unsigned hk0 = halo_count(L);
 
   /* residual and descent direction (:1502-1516) */
   const CommDev *comm = P.comm;
@@ -866,14 +919,14 @@ __device__ __noinline__ PcgResult pcg_run(const MgLevelDesc &L, const double *rh
   mark(vx_ini_nonzero ? 0 : 2);
 
   /* zk = A.dk and the first 3 dots (:1521-1535) */
-  double v[3] = {0., 0., 0.};
+  double v[4] = {0., 0., 0., 0.};
   const double *gh_d = halo_exchange<SINGLE>(L, dk);
   {
     EpiDots f;
     f.d_val = d_val; f.p = dk; f.rk = rk; f.out = zk;
     spmv_phase<SINGLE>(L, dk, gh_d, s_raw, f, v);
   }
-  all_sum<SINGLE, 3>(v, part0, P.barrier, s_red, comm);
+  { double v3[3] = {v[0], v[1], v[2]}; all_sum<SINGLE, 3>(v3, part0, P.barrier, s_red, comm); v[0] = v3[0]; v[1] = v3[1]; v[2] = v3[2]; }
   mark(1);
 
   double ro_0 = v[1], ro_1 = v[2], rk_gkm1 = 0., alpha = 0., beta = 0.;
@@ -910,7 +963,7 @@ __device__ __noinline__ PcgResult pcg_run(const MgLevelDesc &L, const double *rh
       f.d_val = d_val; f.p = gk; f.rk = rk; f.out = sk;
       spmv_phase<SINGLE>(L, gk, gh_g, s_raw, f, v);
     }
-    all_sum<SINGLE, 3>(v, part0, P.barrier, s_red, comm);
+    { double v3[3] = {v[0], v[1], v[2]}; all_sum<SINGLE, 3>(v3, part0, P.barrier, s_red, comm); v[0] = v3[0]; v[1] = v3[1]; v[2] = v3[2]; }
     mark(1);
     const double residual = sqrt(v[0]);
     const double rk_gk = v[1], gk_sk = v[2];
@@ -950,8 +1003,189 @@ __device__ __noinline__ PcgResult pcg_run(const MgLevelDesc &L, const double *rh
     st->n_iter = R.n_iter; st->n_max_iter = n_max_iter; st->cvg = R.cvg;
     st->alpha = alpha; st->beta = beta; st->ro_0 = ro_0; st->ro_1 = ro_1;
     st->rk_gkm1 = rk_gkm1;
+    st->n_halo = (int)(halo_count(L) - hk0);
   }
   return R;
+}
+
+/*--------------------------------------------------------------------------
+ * Flexible CG + Jacobi (_flexible_conjugate_gradient, cs_sles_it.cpp:832-985):
+ * per iteration ONE SpMV phase (wk = A.vk with the four dots of
+ * _dot_products_vr_vw_vq_rr, :693-724) and ONE vector phase (the two update
+ * loops :939-951 fused with the next preconditioning vk = rk * ad_inv, :906).
+ * Work vectors: rk vk wk dk qk.  Residual sign r = b - A.x.
+ *--------------------------------------------------------------------------*/
+
+/* rk = rhs - A.vx, qk = 0, vk = rk * ad_inv                    (:874-906) */
+struct EpiFcgInit {
+  static constexpr int NV = 4;
+  const double *d_val, *vx, *rhs, *ad_inv;
+  double *rk, *qk, *vk;
+  __device__ __forceinline__ const double *src(int v) const
+  { return (v == 0) ? d_val : (v == 1) ? vx : (v == 2) ? rhs : ad_inv; }
+  __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&)[4]) const
+  {
+    const double rr = op[2*ST_OP_STRIDE] - (sii + op[0]*op[ST_OP_STRIDE]);
+    rk[r] = rr;
+    qk[r] = 0;
+    vk[r] = rr * op[3*ST_OP_STRIDE];
+  }
+};
+
+/* wk = A.vk; alpha = vk.rk, beta = vk.wk, gamma = vk.qk, rr = rk.rk     (:908-918) */
+struct EpiFcg {
+  static constexpr int NV = 4;
+  const double *d_val, *vk, *rk, *qk;
+  double *wk;
+  __device__ __forceinline__ const double *src(int v) const
+  { return (v == 0) ? d_val : (v == 1) ? vk : (v == 2) ? rk : qk; }
+  __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&acc)[4]) const
+  {
+    const double v = op[ST_OP_STRIDE];
+    const double w = sii + op[0]*v;
+    wk[r] = w;
+    const double rr = op[2*ST_OP_STRIDE];
+    acc[0] += rr*v; acc[1] += w*v; acc[2] += v*op[3*ST_OP_STRIDE]; acc[3] += rr*rr;
+  }
+};
+
+/* vx = 0, rk = rhs, qk = 0, vk = rk * ad_inv                     (:880-893) */
+struct RowFcgInitZero {
+  static constexpr int NV = 2;
+  const double *rhs, *ad_inv;
+  double *vx, *rk, *qk, *vk;
+  __device__ __forceinline__ const double *src(int v) const { return (v == 0) ? rhs : ad_inv; }
+  __device__ __forceinline__ void st(int i, const double *op, double &) const
+  {
+    vx[i] = 0;
+    rk[i] = op[0];
+    qk[i] = 0;
+    vk[i] = op[0] * op[ROW_CH];
+  }
+};
+
+/* dk, vx, qk, rk updates (:939-951; first iteration :960-972) + vk = rk * ad_inv */
+struct RowFcgUpdate {
+  static constexpr int NV = 7;
+  double gk_rk1, ak_rk;
+  int first;
+  const double *wk, *ad_inv;
+  double *vk, *dk, *vx, *qk, *rk;
+  __device__ __forceinline__ const double *src(int v) const
+  {
+    return (v == 0) ? vk : (v == 1) ? dk : (v == 2) ? vx : (v == 3) ? wk : (v == 4) ? qk
+         : (v == 5) ? rk : ad_inv;
+  }
+  __device__ __forceinline__ void st(int i, const double *op, double &) const
+  {
+    const double d = first ? op[0] : op[0] - gk_rk1 * op[ROW_CH];
+    dk[i] = d;
+    vx[i] = op[2*ROW_CH] + ak_rk * d;
+    const double q = first ? op[3*ROW_CH] : op[3*ROW_CH] - gk_rk1 * op[4*ROW_CH];
+    qk[i] = q;
+    const double rr = op[5*ROW_CH] - ak_rk * q;
+    rk[i] = rr;
+    vk[i] = rr * op[6*ROW_CH];
+  }
+};
+
+template <bool SINGLE>
+__device__ __noinline__ PcgResult fcg_run(const MgLevelDesc &L, const double *rhs, double *vx,
+                             bool vx_ini_nonzero, int n_max_iter, double precision,
+                             double r_norm, const PersistentCommon &P, ItState *st,
+                             unsigned char *s_raw)
+{
+  const int n = L.n_rows;
+  const size_t ws = P.work_stride;
+  double *rk = P.work, *vk = P.work + ws, *wk = P.work + 2*ws, *dk = P.work + 3*ws,
+         *qk = P.work + 4*ws;
+  const bool rec = (st != nullptr) && (SINGLE || blockIdx.x == 0) && threadIdx.x == 0;
+  double *s_red = (double *)s_raw;
+  const CommDev *comm = P.comm;
+
+  PcgResult R;
+  R.n_iter = 0; R.cvg = CSB_SLES_ITERATING; R.residual = -1.; R.initial_residual = -1.;
+  if (rec) st->n_hist = 0;
+
+  if (vx_ini_nonzero) {
+    const double *gh = halo_exchange<SINGLE>(L, vx);
+    EpiFcgInit f;
+    f.d_val = L.d_val; f.vx = vx; f.rhs = rhs; f.ad_inv = L.ad_inv; f.rk = rk; f.qk = qk; f.vk = vk;
+    spmv_phase<SINGLE>(L, vx, gh, s_raw, f, nullptr);
+  }
+  else {
+    RowFcgInitZero f;
+    f.rhs = rhs; f.ad_inv = L.ad_inv; f.vx = vx; f.rk = rk; f.qk = qk; f.vk = vk;
+    row_phase<SINGLE>(n, s_raw, f, nullptr);
+  }
+  phase_barrier<SINGLE>(P.barrier);
+
+  double rho_km1 = 0., ak_rk = 0., gk_rk1 = 0.;
+  while (R.cvg == CSB_SLES_ITERATING) {
+    double v[4] = {0., 0., 0., 0.};
+    const double *gh = halo_exchange<SINGLE>(L, vk);
+    {
+      EpiFcg f;
+      f.d_val = L.d_val; f.vk = vk; f.rk = rk; f.qk = qk; f.wk = wk;
+      spmv_phase<SINGLE>(L, vk, gh, s_raw, f, v);
+    }
+    all_sum<SINGLE, 4>(v, P.partials, P.barrier, s_red, comm);
+    const double alpha_k = v[0], beta_k = v[1], gamma_k = v[2];
+    R.residual = sqrt(v[3]);
+    if (R.n_iter > 0)
+      R.cvg = it_cvg_eval(precision, r_norm, n_max_iter, R.initial_residual, R.n_iter,
+                          R.residual);
+    else
+      R.initial_residual = R.residual;
+    if (rec && st->n_hist < HIST_MAX) st->hist[st->n_hist++] = R.residual;
+    if (R.cvg != CSB_SLES_ITERATING) break;
+
+    double rho_k;
+    if (R.n_iter > 0) {
+      gk_rk1 = (fabs(rho_km1) > DBL_MIN) ? gamma_k / rho_km1 : 0.;
+      rho_k = beta_k - gamma_k * gk_rk1;
+    }
+    else {
+      gk_rk1 = 0.;
+      rho_k = beta_k;
+    }
+    ak_rk = (fabs(rho_k) > DBL_MIN) ? alpha_k / rho_k : 0.;
+    {
+      RowFcgUpdate f;
+      f.gk_rk1 = gk_rk1; f.ak_rk = ak_rk; f.first = (R.n_iter == 0) ? 1 : 0;
+      f.wk = wk; f.ad_inv = L.ad_inv; f.vk = vk; f.dk = dk; f.vx = vx; f.qk = qk; f.rk = rk;
+      row_phase<SINGLE>(n, s_raw, f, nullptr);
+    }
+    phase_barrier<SINGLE>(P.barrier);
+    rho_km1 = rho_k;
+    R.n_iter += 1;
+  }
+
+  if (rec) {
+    st->precision = precision; st->r_norm = r_norm;
+    st->residual = R.residual; st->initial_residual = R.initial_residual;
+    st->n_iter = R.n_iter; st->n_max_iter = n_max_iter; st->cvg = R.cvg;
+    st->alpha = ak_rk; st->beta = gk_rk1; st->ro_0 = rho_km1; st->ro_1 = 0.; st->rk_gkm1 = 0.;
+  }
+  return R;
+}
+
+__global__ void __launch_bounds__(PT, CSB_MIN_CTAS)
+k_fcg_persistent(const MgLevelDesc L, const double *rhs, double *vx, int vx_ini_nonzero,
+                 int n_max_iter, double precision, double r_norm,
+                 const PersistentCommon P, ItState *st, int single)
+{
+  unsigned char *s_raw = s_raw_base;
+  pipe_init(s_raw);
+  halo_counts_init(&L, 1, P.barrier);
+  if (single) {
+    if (blockIdx.x == 0)
+      fcg_run<true>(L, rhs, vx, vx_ini_nonzero != 0, n_max_iter, precision, r_norm, P, st,
+                    s_raw);
+  }
+  else
+    fcg_run<false>(L, rhs, vx, vx_ini_nonzero != 0, n_max_iter, precision, r_norm, P, st,
+                   s_raw);
 }
 
 /*--------------------------------------------------------------------------
@@ -963,8 +1197,9 @@ k_pcg_persistent(const MgLevelDesc L, const double *rhs, double *vx, int vx_ini_
                  int n_max_iter, double precision, double r_norm,
                  const PersistentCommon P, ItState *st, int single)
 {
-  extern __shared__ __align__(128) unsigned char s_raw[];
+  unsigned char *s_raw = s_raw_base;
   pipe_init(s_raw);
+  halo_counts_init(&L, 1, P.barrier);
   if (single) {
     if (blockIdx.x == 0)
       pcg_run<true>(L, rhs, vx, vx_ini_nonzero != 0, n_max_iter, precision, r_norm, false,
@@ -982,9 +1217,10 @@ k_pcg_persistent(const MgLevelDesc L, const double *rhs, double *vx, int vx_ini_
 __global__ void __launch_bounds__(PT, CSB_MIN_CTAS)
 k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
 {
-  extern __shared__ __align__(128) unsigned char s_raw[];
+  unsigned char *s_raw = s_raw_base;
   double *s_red = (double *)s_raw;
   pipe_init(s_raw);
+  halo_counts_init(S.levels, S.n_levels, P.barrier);
 
   const MgLevelDesc *__restrict__ LV = S.levels;
   MgState *ms = S.ms;
@@ -1022,6 +1258,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
         R.n_iter = *((volatile int *)&L.st_descent->n_iter);
         R.cvg = *((volatile int *)&L.st_descent->cvg);
         R.initial_residual = *((volatile double *)&L.st_descent->initial_residual);
+        halo_count_follow(L, L.st_descent);
       }
       else {
         R = pcg_run<false>(L, rhs_lv, vx_lv, ini, S.n_max_iter[0],
@@ -1041,7 +1278,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
         const double *gh = halo_exchange<false>(L, vx_lv);
         EpiResidual f;
         f.d_val = d_val; f.vx = vx_lv; f.rhs = rhs_lv; f.wr = wr;
-        double acc[3];
+        double acc[4];
         spmv_phase<false>(L, vx_lv, gh, s_raw, f, acc);
         w[0] = acc[0];
       }
@@ -1085,6 +1322,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
         grid_barrier(P.barrier);
         R.n_iter = *((volatile int *)&L.st_descent->n_iter);
         R.cvg = *((volatile int *)&L.st_descent->cvg);
+        halo_count_follow(L, L.st_descent);
       }
       else {
         R = pcg_run<false>(L, rhs_lv, vx_lv, false, S.n_max_iter[2],
@@ -1126,6 +1364,7 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
             grid_barrier(P.barrier);
             R.n_iter = *((volatile int *)&L.st_ascent->n_iter);
             R.cvg = *((volatile int *)&L.st_ascent->cvg);
+            halo_count_follow(L, L.st_ascent);
           }
           else {
             R = pcg_run<false>(L, L.rhs, vx_lv, true, S.n_max_iter[1],
@@ -1190,18 +1429,24 @@ int persistent_grid(int which, size_t smem)
 {
   Context &c = ctx();
   int occ = 0;
-  if (which == 0) {
-    if (smem > 48*1024)
-      cudaFuncSetAttribute(k_pcg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)smem);
+  /* opt in to the device maximum once, not to this call's size: the attribute belongs to
+     the (shared) context, and ranks living in one process ask for different sizes */
+  int optin = 0;
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device);
+  if ((size_t)optin < smem) {
+    set_error("persistent kernel needs %zu bytes of shared memory, the device offers %d",
+              smem, optin);
+    return 0;
+  }
+  const void *k = (which == 0) ? (const void *)k_pcg_persistent
+                : (which == 2) ? (const void *)k_fcg_persistent : (const void *)k_mg_persistent;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  if (which == 0)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pcg_persistent, PT, smem);
-  }
-  else {
-    if (smem > 48*1024)
-      cudaFuncSetAttribute(k_mg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)smem);
+  else if (which == 2)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fcg_persistent, PT, smem);
+  else
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mg_persistent, PT, smem);
-  }
   if (occ < 1) {
     set_error("persistent kernel does not fit on an SM with %zu bytes of shared memory", smem);
     return 0;
@@ -1235,6 +1480,28 @@ bool launch_pcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
   ctx().launches += 1;
   if (e != cudaSuccess) {
     set_error("cooperative launch of k_pcg_persistent failed: %s", cudaGetErrorString(e));
+    return false;
+  }
+  return true;
+}
+
+bool launch_fcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
+                           bool vx_ini_nonzero, int n_max_iter, double precision,
+                           double r_norm, const PersistentCommon &P, ItState *st,
+                           int grid, size_t smem, bool single, bool cooperative)
+{
+  int ini = vx_ini_nonzero ? 1 : 0;
+  int sgl = single ? 1 : 0;
+  void *args[] = {(void *)&L, (void *)&rhs, (void *)&vx, (void *)&ini, (void *)&n_max_iter,
+                  (void *)&precision, (void *)&r_norm, (void *)&P, (void *)&st, (void *)&sgl};
+  cudaError_t e = cooperative
+    ? cudaLaunchCooperativeKernel((void *)k_fcg_persistent, dim3(grid), dim3(PT), args, smem,
+                                  ctx().stream)
+    : cudaLaunchKernel((void *)k_fcg_persistent, dim3(grid), dim3(PT), args, smem,
+                       ctx().stream);
+  ctx().launches += 1;
+  if (e != cudaSuccess) {
+    set_error("cooperative launch of k_fcg_persistent failed: %s", cudaGetErrorString(e));
     return false;
   }
   return true;

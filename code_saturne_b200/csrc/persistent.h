@@ -12,6 +12,7 @@ struct MgLevelDesc {
   int           n_slabs;       /* ceil(n_rows / slab_rows) */
   int           slab_rows;     /* <= 256 rows streamed per CTA step */
   int           n_rows_next;
+  int           level_id;      /* index of the level (slot of its exchange counter) */
   const int    *row_index;
   const int    *col_id;
   const double *d_val;
@@ -36,7 +37,7 @@ struct PersistentCommon {
   const CommDev *comm;     /* nullptr on one rank */
 };
 
-constexpr int PERSISTENT_S_RED = 104;   /* doubles of reduction scratch ahead of the slab */
+constexpr int PERSISTENT_S_RED = 136;   /* doubles of reduction scratch ahead of the slab */
 
 struct MgSolveParams {
   int                n_levels;
@@ -54,7 +55,7 @@ struct MgSolveParams {
 };
 
 size_t persistent_smem_bytes(size_t max_slab_entries);
-int    persistent_grid(int which, size_t smem);   /* 0: PCG kernel, 1: multigrid kernel */
+int    persistent_grid(int which, size_t smem);   /* 0: PCG, 1: multigrid, 2: FCG kernel */
 
 bool launch_pcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
                            bool vx_ini_nonzero, int n_max_iter, double precision,
@@ -63,6 +64,12 @@ bool launch_pcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
 
 bool launch_mg_persistent(const MgSolveParams &S, const PersistentCommon &P, int grid,
                           size_t smem, bool cooperative);
+
+/* flexible CG (cs_sles_it.cpp:832-985): same arguments as the PCG kernel */
+bool launch_fcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
+                           bool vx_ini_nonzero, int n_max_iter, double precision,
+                           double r_norm, const PersistentCommon &P, ItState *st,
+                           int grid, size_t smem, bool single, bool cooperative);
 
 /* choose the slab height of a level so that a slab's products fit in ~40 KB */
 void plan_slabs(const std::vector<csb_lnum_t> &row_index, int n_rows, int &slab_rows,

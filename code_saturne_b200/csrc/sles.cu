@@ -311,8 +311,8 @@ csb_sles_it_create(csb_sles_it_type_t solver_type, int poly_degree, int n_max_it
                    int update_stats)
 {
   if (!ctx().ready) { set_error("csb_sles_it_create: csb_init not called"); return nullptr; }
-  if (solver_type != CSB_SLES_PCG && solver_type != CSB_SLES_JACOBI
-      && solver_type != CSB_SLES_BICGSTAB) {
+  if (solver_type != CSB_SLES_PCG && solver_type != CSB_SLES_FCG
+      && solver_type != CSB_SLES_JACOBI && solver_type != CSB_SLES_BICGSTAB) {
     set_error("csb_sles_it_create: solver type %d is not available on this path",
               (int)solver_type);
     return nullptr;
@@ -352,19 +352,21 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
   double t0 = wall();
   c->a = a;
   c->setup_done = false;
-  const size_t n_wa = (c->type == CSB_SLES_BICGSTAB) ? 6 : ((c->type == CSB_SLES_PCG) ? 5 : 1);
+  const size_t n_wa = (c->type == CSB_SLES_BICGSTAB) ? 6
+    : ((c->type == CSB_SLES_PCG || c->type == CSB_SLES_FCG) ? 5 : 1);
   if (!c->ad_inv.alloc((size_t)a->n_rows)) return;
   if (!launch_ad_inv(a->n_rows, a->d_val.p, c->ad_inv.p)) return;
   if (!c->work.alloc(n_wa * work_stride_of((size_t)a->n_cols_ext))) return;
   if (!c->st.alloc(1)) return;
   if (c->h_st == nullptr)
     if (!CSB_CUDA(cudaMallocHost((void **)&c->h_st, sizeof(ItState)))) return;
-  if (a->halo != nullptr && (c->type != CSB_SLES_PCG || c->pcomm == nullptr)) {
-    set_error("csb_sles_it_setup: a matrix with a halo needs CSB_SLES_PCG and a peer "
+  if (a->halo != nullptr && ((c->type != CSB_SLES_PCG && c->type != CSB_SLES_FCG)
+                             || c->pcomm == nullptr)) {
+    set_error("csb_sles_it_setup: a matrix with a halo needs CSB_SLES_PCG / _FCG and a peer "
               "communicator (csb_sles_it_set_pcomm) on this path");
     return;
   }
-  if (c->type == CSB_SLES_PCG) {
+  if (c->type == CSB_SLES_PCG || c->type == CSB_SLES_FCG) {
     size_t max_entries = 0;
     MgLevelDesc &d = c->desc;
     memset(&d, 0, sizeof(d));
@@ -382,7 +384,7 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
     d.row_index = a->row_index.p; d.col_id = a->col_id.p;
     d.d_val = a->d_val.p; d.x_val = a->x_val.p; d.ad_inv = c->ad_inv.p;
     c->p_smem = persistent_smem_bytes(max_entries);
-    c->p_grid = persistent_grid(0, c->p_smem);
+    c->p_grid = persistent_grid(c->type == CSB_SLES_FCG ? 2 : 0, c->p_smem);
     if (c->p_grid < 1) return;
     if (!c->partials.alloc(12*(size_t)c->p_grid) || !c->barrier.alloc(2)) return;
     if (!CSB_CUDA(cudaMemsetAsync(c->barrier.p, 0, 2*sizeof(unsigned), ctx().stream))) return;
@@ -440,6 +442,21 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
     else
       ok = pcg_enqueue(a, c->st.p, nullptr, c->ad_inv.p, precision, r_norm, c->n_max_iter,
                        s_rhs.d, s_vx.d, ini, false, c->work.p, c->h_st);
+    break;
+  case CSB_SLES_FCG:
+    {
+      /* whole solve in one persistent cooperative kernel (per rank) */
+      PersistentCommon P;
+      P.work = c->work.p; P.work_stride = work_stride_of((size_t)a->n_cols_ext);
+      P.partials = c->partials.p; P.barrier = c->barrier.p;
+      P.comm = (a->halo != nullptr) ? c->pcomm->d : nullptr;
+      const bool single = (a->n_rows <= sb_rows_threshold());
+      if (a->halo != nullptr) pcomm_host_barrier(c->pcomm);
+      ok = launch_fcg_persistent(c->desc, s_rhs.d, s_vx.d, ini, c->n_max_iter, precision,
+                                 r_norm, P, c->st.p, c->p_grid, c->p_smem, single,
+                                 cx.device_share <= 1);
+      if (a->halo != nullptr) pcomm_host_barrier(c->pcomm);
+    }
     break;
   case CSB_SLES_JACOBI:
     ok = jacobi_enqueue(a, c->st.p, c->ad_inv.p, precision, r_norm, c->n_max_iter,
@@ -516,6 +533,7 @@ void csb_sles_it_log(const void *context, int log_type)
   const csb_sles_it_t *c = static_cast<const csb_sles_it_t *>(context);
   if (c == nullptr) return;
   const char *tn = (c->type == CSB_SLES_PCG) ? "Conjugate Gradient"
+                 : (c->type == CSB_SLES_FCG) ? "Flexible Conjugate Gradient"
                  : (c->type == CSB_SLES_JACOBI) ? "Jacobi" : "BiCGstab";
   printf("  Solver type:                       %s (B200 device)\n"
          "  Number of setups:                  %12u\n"
@@ -1046,6 +1064,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
       max_entries = std::max(max_entries, me);
       d.n_rows = m->n_rows;
       d.n_rows_next = (l + 1 < n_levels) ? mg->levels[l+1]->m->n_rows : 0;
+      d.level_id = l;
       d.row_index = m->row_index.p; d.col_id = m->col_id.p;
       d.d_val = m->d_val.p; d.x_val = m->x_val.p; d.ad_inv = lv->ad_inv.p;
       d.rhs = lv->rhs.p; d.vx = lv->vx.p;

@@ -42,6 +42,7 @@ typedef enum {
 /* cs_sles_it_type_t, src/alge/cs_sles_it.h:55-77 (same numeric values) */
 typedef enum {
   CSB_SLES_PCG      = 0,
+  CSB_SLES_FCG      = 1,   /* flexible CG, cs_sles_it.cpp:832-985 */
   CSB_SLES_JACOBI   = 3,
   CSB_SLES_BICGSTAB = 4
 } csb_sles_it_type_t;

@@ -182,6 +182,99 @@ _cvg_test(ora_cvg_t *c, int n_iter, double residual)
 }
 
 /*----------------------------------------------------------------------------
+ * Flexible conjugate gradient with Jacobi preconditioning:
+ * _flexible_conjugate_gradient (src/alge/cs_sles_it.cpp:832-985), the default
+ * outer solver of the pressure system.  Residual sign r = b - A.x.
+ * Dots as in _dot_products_vr_vw_vq_rr (:693-724): cs_dot_xy_yz(w, v, q) then
+ * cs_dot_xx_xy(r, v).  pc_apply = ad_inv scaling (cs_sles_pc.cpp:502-535).
+ * out[0]=n_iter out[1]=residual out[2]=initial_residual
+ *----------------------------------------------------------------------------*/
+
+int
+ora_fcg(int n_rows, const int *row_index, const int *col_id,
+        const double *d_val, const double *x_val,
+        int n_max_iter, double precision, double r_norm,
+        const double *rhs, double *vx, int use_vx_ini,
+        double *out, double *history, int history_size)
+{
+  const int n = n_rows;
+  double *rk = malloc(sizeof(double)*n*6);
+  double *vk = rk + n, *wk = rk + 2*n, *dk = rk + 3*n, *qk = rk + 4*n;
+  double *ad_inv = rk + 5*n;
+  for (int i = 0; i < n; i++) ad_inv[i] = 1.0 / d_val[i];
+
+  ora_cvg_t cv = {precision, r_norm, -1, n_max_iter, 0, -1,
+                  history, history_size, 0};
+  int cvg = ORA_ITERATING;
+  int n_iter = 0;
+  double residual = -1;
+
+  if (use_vx_ini) {
+    ora_spmv_msr(n, row_index, col_id, d_val, x_val, 0, vx, rk);
+    for (int ii = 0; ii < n; ii++) rk[ii] = rhs[ii] - rk[ii];
+  }
+  else {
+    for (int ii = 0; ii < n; ii++) { vx[ii] = 0; rk[ii] = rhs[ii]; }
+  }
+  for (int ii = 0; ii < n; ii++) qk[ii] = 0;
+
+  double rho_km1 = 0;
+
+  while (cvg == ORA_ITERATING) {
+    for (int ii = 0; ii < n; ii++) vk[ii] = rk[ii] * ad_inv[ii];
+    ora_spmv_msr(n, row_index, col_id, d_val, x_val, 0, vk, wk);
+
+    double alpha_k, beta_k, gamma_k;
+    ora_dot_xy_yz(n, wk, vk, qk, &beta_k, &gamma_k);
+    ora_dot_xx_xy(n, rk, vk, &residual, &alpha_k);
+    residual = sqrt(residual);
+
+    if (n_iter > 0)
+      cvg = _cvg_test(&cv, n_iter, residual);
+    else {
+      cv.initial_residual = residual;
+      if (history != NULL && cv.history_n < history_size)
+        history[cv.history_n++] = residual;
+    }
+    if (cvg != ORA_ITERATING) break;
+
+    if (n_iter > 0) {
+      const double gk_rk1 = (fabs(rho_km1) > DBL_MIN) ? gamma_k / rho_km1 : 0.;
+      const double rho_k = beta_k - gamma_k * gk_rk1;
+      const double ak_rk = (fabs(rho_k) > DBL_MIN) ? alpha_k / rho_k : 0.;
+      for (int ii = 0; ii < n; ii++) {
+        dk[ii] = vk[ii] - gk_rk1 * dk[ii];
+        vx[ii] = vx[ii] + ak_rk * dk[ii];
+      }
+      for (int ii = 0; ii < n; ii++) {
+        qk[ii] = wk[ii] - gk_rk1 * qk[ii];
+        rk[ii] = rk[ii] - ak_rk * qk[ii];
+      }
+      rho_km1 = rho_k;
+    }
+    else {
+      const double rho_k = beta_k;
+      const double ak_rk = (fabs(rho_k) > DBL_MIN) ? alpha_k / rho_k : 0.;
+      for (int ii = 0; ii < n; ii++) {
+        dk[ii] = vk[ii];
+        vx[ii] = vx[ii] + ak_rk * vk[ii];
+      }
+      for (int ii = 0; ii < n; ii++) {
+        qk[ii] = wk[ii];
+        rk[ii] = rk[ii] - ak_rk * wk[ii];
+      }
+      rho_km1 = rho_k;
+    }
+    n_iter += 1;
+  }
+
+  out[0] = n_iter; out[1] = residual; out[2] = cv.initial_residual;
+  out[3] = cv.history_n;
+  free(rk);
+  return cvg;
+}
+
+/*----------------------------------------------------------------------------
  * PCG + Jacobi, single reduction: _conjugate_gradient_sr_p0
  * (src/alge/cs_sles_it.cpp:1441-1645).  Residual sign r = A.x - b.
  * out[0]=n_iter out[1]=residual out[2]=initial_residual

@@ -141,6 +141,10 @@ class Oracle:
         return self._solve(self.lib.ora_pcg_sr_p0, ri, ci, d, xv, rhs, n_max_iter,
                            precision, r_norm, vx0)
 
+    def fcg(self, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0=None):
+        return self._solve(self.lib.ora_fcg, ri, ci, d, xv, rhs, n_max_iter,
+                           precision, r_norm, vx0)
+
     def jacobi(self, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0=None):
         return self._solve(self.lib.ora_jacobi, ri, ci, d, xv, rhs, n_max_iter,
                            precision, r_norm, vx0)

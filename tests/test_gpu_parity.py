@@ -341,3 +341,65 @@ def test_multigrid_128_properties(csb):
     assert np.linalg.norm(y - s.rhs) <= 1.0001e-8 * r_norm
     assert np.all(np.diff(r["cycle_residuals"][1:]) < 0)           # monotone after cycle 1
     mg.destroy(); m.destroy()
+
+
+# --------------------------------------------------------------------------- flexible CG
+
+@pytest.mark.parametrize("N,bc", [(8, "neumann"), (12, "dirichlet"), (16, "neumann")])
+def test_fcg_matches_reference_golden(csb, N, bc):
+    """CSB_SLES_FCG (persistent kernel: one SpMV phase + one vector phase per iteration)
+    against the reference's _flexible_conjugate_gradient output (tests/golden/fcg_*.npz):
+    iteration count +-2, residual history to reduction-order rounding, solution <= 1e-10
+    where both are converged; warm start with a max-iteration exit."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"fcg_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    r_norm = float(g["r_norm"])
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+    c = csb.SlesIt(csb.SlesItType.FCG, 1000)
+    r = c.solve(m, s.rhs, 1e-9, r_norm)
+    assert int(r["cvg"]) == int(g["cvg"]) == 1
+    assert abs(r["n_iter"] - int(g["n_iter"])) <= 2
+    assert abs(r["initial_residual"] - float(g["initial_residual"])) <= RED_TOL * float(g["initial_residual"])
+    k = min(len(r["history"]) - 1, len(g["history"]), 8)
+    assert np.allclose(r["history"][1:1 + k], g["history"][:k], rtol=1e-9, atol=0)
+    # both stopped at 1e-9: the solutions agree to the solver tolerance times the conditioning
+    assert rel_l2(r["vx"][:s.n_rows], g["vx"]) <= (1e-7 if bc == "dirichlet" else 1e-3)
+    w = c.solve(m, s.rhs, 1e-12, r_norm, vx=0.5 * g["vx"], use_vx_ini=True)
+    assert w["n_iter"] >= 5
+    c5 = csb.SlesIt(csb.SlesItType.FCG, 5)
+    w = c5.solve(m, s.rhs, 1e-12, r_norm, vx=0.5 * g["vx"], use_vx_ini=True)
+    assert (int(w["cvg"]), w["n_iter"]) == (int(g["warm_cvg"]), int(g["warm_n_iter"]))
+    assert abs(w["residual"] - float(g["warm_residual"])) <= 1e-9 * float(g["warm_residual"])
+    assert rel_l2(w["vx"][:s.n_rows], g["warm_vx"]) <= 1e-11
+    c.destroy(); c5.destroy(); m.destroy()
+
+
+def test_fcg_tight_tolerance_solution_parity(csb, oracle):
+    """Converged-solution parity at the north-star tolerance (both solved to 1e-13)."""
+    s = cube_poisson(32, "dirichlet", with_mesh=False)
+    r_norm = float(np.sqrt(oracle.dot_xx(s.rhs)))
+    o = oracle.fcg(s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, 5000, 1e-13, r_norm)
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+    c = csb.SlesIt(csb.SlesItType.FCG, 5000)
+    r = c.solve(m, s.rhs, 1e-13, r_norm)
+    assert int(r["cvg"]) == 1 and o["cvg"] == 1
+    assert abs(r["n_iter"] - o["n_iter"]) <= 2
+    assert rel_l2(r["vx"][:s.n_rows], o["vx"]) <= SOL_TOL
+    # zero right-hand side: nothing to do
+    z = c.solve(m, np.zeros(s.n_rows), 1e-8, 1.0)
+    assert not z["vx"].any()
+    c.destroy(); m.destroy()
+
+
+def test_fcg_128_true_residual(csb, oracle):
+    """Config-2 size (128^3): the returned residual is the true one, ||b - A.x|| <= eps.||b||."""
+    s = cube_poisson(128, "dirichlet", with_mesh=False)
+    r_norm = float(np.linalg.norm(s.rhs))
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+    c = csb.SlesIt(csb.SlesItType.FCG, 5000)
+    r = c.solve(m, s.rhs, 1e-8, r_norm)
+    assert int(r["cvg"]) == 1
+    res = np.linalg.norm(s.rhs - m.vector_multiply(r["vx"][:s.n_rows].copy()))
+    assert res <= 1.01e-8 * r_norm and abs(res - r["residual"]) <= 1e-2 * res
+    c.destroy(); m.destroy()

@@ -102,7 +102,40 @@ def test_oracle_vs_reference_direct(oracle, reflib, N, bc, n_threads):
             b = oracle.pcg(s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, 2000, 1e-9, r_norm)
             assert (a["n_iter"], a["residual"]) == (b["n_iter"], b["residual"])
             assert np.array_equal(a["vx"], b["vx"])
+            # flexible CG (cs_sles_it.cpp:832-985), cold and warm start
+            a = reflib.sles_it(h, reflib.FCG, s.rhs, 2000, 1e-9, r_norm)
+            b = oracle.fcg(s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, 2000, 1e-9, r_norm)
+            assert (a["cvg"], a["n_iter"], a["residual"], a["initial_residual"]) \
+                == (b["cvg"], b["n_iter"], b["residual"], b["initial_residual"])
+            assert np.array_equal(a["vx"], b["vx"])
+            vx0 = 0.5 * a["vx"]
+            a = reflib.sles_it(h, reflib.FCG, s.rhs, 7, 1e-12, r_norm, vx0=vx0)
+            b = oracle.fcg(s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, 7, 1e-12, r_norm, vx0=vx0)
+            assert (a["cvg"], a["n_iter"], a["residual"]) == (b["cvg"], b["n_iter"], b["residual"])
+            assert np.array_equal(a["vx"], b["vx"])
         oracle.mg_free(mg)
         reflib.destroy(h)
     finally:
         reflib.set_threads(1)
+
+
+@pytest.mark.parametrize("N,bc", [(8, "neumann"), (12, "dirichlet"), (16, "neumann")])
+def test_oracle_fcg_matches_golden(oracle, N, bc):
+    """Flexible CG restatement against fixtures produced by the reference build
+    (tests/golden/make_golden_fcg.py): bit-exact solution, counts and residuals."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"fcg_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    r_norm = float(g["r_norm"])
+    o = oracle.fcg(s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, 1000, 1e-9, r_norm)
+    assert (o["cvg"], o["n_iter"]) == (int(g["cvg"]), int(g["n_iter"]))
+    assert o["residual"] == float(g["residual"])
+    assert o["initial_residual"] == float(g["initial_residual"])
+    assert np.array_equal(o["vx"], g["vx"])
+    # history[0] is the initial residual, then one entry per convergence test
+    assert np.array_equal(o["history"][1:1 + len(g["history"])], g["history"])
+    w = oracle.fcg(s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, 5, 1e-12, r_norm,
+                   vx0=0.5 * g["vx"])
+    assert (w["cvg"], w["n_iter"], w["residual"]) \
+        == (int(g["warm_cvg"]), int(g["warm_n_iter"]), float(g["warm_residual"]))
+    assert np.array_equal(w["vx"], g["warm_vx"])
