@@ -306,7 +306,25 @@ def main():
 
     spmv_bytes = m.spmv_bytes()          # this rank's brick; all bricks are equal
     peak, peak_src = measured_peak_gbs()
-    achieved = spmv_bytes / t_spmv / 1e9
+    spmv_gbs = spmv_bytes / t_spmv / 1e9
+    # dominant kernel = k_mg_persistent, ONE launch per solve: algorithmic bytes of the
+    # cycles it ran (code_saturne_b200/traffic.py) over its CUDA-event time
+    from code_saturne_b200.traffic import cycle_bytes, level_sizes
+    info = level_sizes(mg)
+    solve_bytes = cycle_bytes(info) * int(r["n_cycles"])       # per rank
+    achieved = solve_bytes / t_dev / 1e9
+    # in-solve SpMV + 3 dots phase of the finest level, from the device-side timers
+    stt = mg.smoother_times()
+    n0, nnz0 = info[0]
+    t_sp = stt[0, 1] / max(int(r["n_cycles"]), 1) / 2.0
+    in_solve_spmv = ((12.0 * nnz0 + 36.0 * n0) / t_sp / 1e9) if t_sp > 0 else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01", "ncu_mg_persistent_traffic.json")
+    if world == 1 and args.cube == 256 and os.path.exists(tp):
+        try:      # dram__bytes_read+write of one ncu --set full capture, per cycle
+            traffic = float(json.load(open(tp))["dram_bytes_per_cycle"]) * int(r["n_cycles"])
+        except Exception:
+            traffic = None
 
     if rank == 0:
         cpu = None
@@ -346,13 +364,21 @@ def main():
             "e2e": {"value": t_e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n_rows_global,
                     "d2h_bytes_per_step": 8 * n_rows_global + 4096 * world},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_spmv_stream (level-0 MSR SpMV"
-                         + (", per GPU, incl. ghost exchange)" if world > 1 else ")"),
+            "roofline": {"bound": "hbm",
+                         "kernel": "k_mg_persistent (whole V-cycle solve: all cycles and levels "
+                                   "in one launch" + (", per GPU)" if world > 1 else ")"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
-                         "algorithmic_bytes_per_launch": spmv_bytes,
-                         "ms_per_launch": t_spmv * 1e3, "peak_source": peak_src},
-            "spmv_hbm_gbs": achieved,
+                         "frac": achieved / peak, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": solve_bytes,
+                         "ms_per_launch": t_dev * 1e3, "peak_source": peak_src,
+                         "launches_timed": args.steps},
+            "spmv": {"kernel": "k_spmv_stream (level-0 MSR SpMV, stand-alone"
+                               + (", per GPU, incl. ghost exchange)" if world > 1 else ")"),
+                     "achieved": spmv_gbs, "frac": spmv_gbs / peak, "unit": "GB/s",
+                     "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": t_spmv * 1e3,
+                     "in_solve_spmv_3dots_gbs": in_solve_spmv,
+                     "in_solve_spmv_3dots_frac": (in_solve_spmv / peak) if in_solve_spmv else None},
+            "spmv_hbm_gbs": spmv_gbs,
             "clocks": clocks,
         }
         if cpu is not None:

@@ -1,0 +1,68 @@
+"""Algorithmic HBM bytes of the hot path.
+
+"Algorithmic" = every array an operation has to read or write once, nothing more:
+MSR SpMV  12*nnz (col_id + x_val) + 4*(n+1) (row_index) + 8n (d_val) + 8n (x) + 8n (y).
+The figures are per level of the hierarchy and per phase of one V-cycle with the
+solver-mode defaults (PCG+Jacobi smoothers, 2 descent / 10 ascent sweeps); bench.py and
+scripts/mg_phases.py divide them by device-side times.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+PHASES = ("descent", "residual", "restrict", "coarsest", "prolong", "ascent")
+
+
+def spmv_bytes(n, nnz):
+    return 12.0 * nnz + 4.0 * (n + 1) + 24.0 * n
+
+
+def phase_bytes(n, nnz, nc, n_desc, n_asc, level, coarsest):
+    """Bytes of each phase (PHASES order) of one cycle at one level."""
+    M = 12.0 * nnz + 12.0 * n            # col_id + x_val + row_index + d_val
+
+    def pcg(n_it, ini):
+        b = (M + 32 * n) if ini else 40 * n          # residual / zero start
+        b += M + 24 * n                               # zk = A.dk + 3 dots
+        if n_it >= 1:
+            b += 64 * n                               # first update
+        b += max(n_it - 1, 0) * (M + 24 * n)          # sk = A.gk + 3 dots
+        b += max(n_it - 2, 0) * 96 * n                # fused 5-vector update
+        if n_it >= 2:
+            b += 32 * n                               # last update of a smoother: vx only
+        return b
+
+    out = np.zeros(6)
+    if level < coarsest:
+        out[0] = pcg(n_desc, level == 0)
+        out[1] = M + 24 * n
+        out[2] = 12 * n + 12 * nc
+        out[4] = 20 * n + 8 * nc
+        if level > 0:
+            out[5] = pcg(n_asc, True)
+    return out
+
+
+def level_sizes(mg):
+    """[(n_rows, nnz)] of every level of an api.Multigrid after setup."""
+    from . import api
+    L = api.load_library()
+    info = []
+    for l in range(mg.n_levels()):
+        a = np.zeros(3, dtype=np.int32)
+        L.csb_multigrid_get_level_info(C.c_void_p(mg._h), l, a.ctypes.data_as(C.c_void_p))
+        info.append((int(a[0]), int(a[2])))
+    return info
+
+
+def cycle_bytes(info, n_desc=2, n_asc=10):
+    """Algorithmic bytes of one V-cycle over the hierarchy `info` (levels above the coarsest;
+    the coarsest solve is latency-, not bandwidth-bound)."""
+    coarsest = len(info) - 1
+    tot = 0.0
+    for l, (n, nnz) in enumerate(info):
+        nc = info[l + 1][0] if l < coarsest else 0
+        tot += phase_bytes(n, nnz, nc, n_desc, n_asc, l, coarsest).sum()
+    return tot

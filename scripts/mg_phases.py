@@ -14,30 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def phase_bytes(n, nnz, nc, n_desc, n_asc, level, coarsest):
-    """Algorithmic bytes of each phase of one cycle at one level."""
-    M = 12.0 * nnz + 12.0 * n            # col_id + x_val + row_index + d_val
-
-    def pcg(n_it, ini):
-        b = (M + 32 * n) if ini else 40 * n          # residual / zero start
-        b += M + 24 * n                               # zk = A.dk + 3 dots
-        if n_it >= 1:
-            b += 64 * n                               # first update
-        b += max(n_it - 1, 0) * (M + 24 * n)          # sk = A.gk + 3 dots
-        b += max(n_it - 2, 0) * 96 * n                # fused 5-vector update
-        if n_it >= 2:
-            b += 32 * n                               # last update of a smoother: vx only
-        return b
-
-    out = np.zeros(6)
-    if level < coarsest:
-        out[0] = pcg(n_desc, level == 0)
-        out[1] = M + 24 * n
-        out[2] = 12 * n + 12 * nc
-        out[4] = 20 * n + 8 * nc
-        if level > 0:
-            out[5] = pcg(n_asc, True)
-    return out
+from code_saturne_b200.traffic import level_sizes, phase_bytes  # noqa: E402
 
 
 def main():
@@ -62,13 +39,7 @@ def main():
         r = mg.solve(m, rhs_d, 1e-8, r_norm, vx=vx_d)
     pt = mg.phase_times()
     n_cycles = r["n_cycles"]
-    info = []
-    L = api.load_library()
-    import ctypes as C
-    for l in range(mg.n_levels()):
-        a = np.zeros(3, dtype=np.int32)
-        L.csb_multigrid_get_level_info(C.c_void_p(mg._h), l, a.ctypes.data_as(C.c_void_p))
-        info.append((int(a[0]), int(a[2])))
+    info = level_sizes(mg)
     peak = 6543.4
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
