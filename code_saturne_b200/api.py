@@ -83,6 +83,8 @@ def load_library() -> C.CDLL:
     L.csb_free_pinned.argtypes = [vp]
     L.csb_launch_count.restype = C.c_longlong
     L.csb_launch_count.argtypes = [ci]
+    L.csb_matrix_create_csr.restype = vp
+    L.csb_matrix_create_csr.argtypes = [ci, ci, vp, vp, vp, ci]
     L.csb_matrix_create_msr.restype = vp
     L.csb_matrix_create_msr.argtypes = [ci, ci, vp, vp, vp, vp, ci]
     L.csb_matrix_set_coefficients.argtypes = [vp, ci, vp, vp]
@@ -362,6 +364,23 @@ class Matrix:
             _err("csb_matrix_create_msr")
         self.nnz = int(L.csb_matrix_get_n_entries(self._h)) - self.n_rows
         self._halo = None
+
+    @classmethod
+    def from_csr(cls, n_rows, row_index, col_id, val, symmetric=True, n_cols_ext=None):
+        """CS_MATRIX_CSR (diagonal stored as an ordinary entry): vector_multiply sums in CSR
+        order like _mat_vec_p_l_csr; the solvers use the MSR split made at creation."""
+        L = load_library()
+        self = cls.__new__(cls)
+        self.n_rows = int(n_rows)
+        self.n_cols_ext = int(n_cols_ext if n_cols_ext is not None else n_rows)
+        ri, ci, v = _i32(row_index), _i32(col_id), _f64(val)
+        self._h = L.csb_matrix_create_csr(self.n_rows, self.n_cols_ext, _ptr(ri), _ptr(ci),
+                                          _ptr(v), int(bool(symmetric)))
+        if not self._h:
+            _err("csb_matrix_create_csr")
+        self.nnz = int(L.csb_matrix_get_n_entries(self._h)) - self.n_rows
+        self._halo = None
+        return self
 
     @classmethod
     def from_system(cls, s, with_mesh=True):

@@ -289,6 +289,10 @@ struct _csb_matrix_t {
   int         spmv_rows_per_block = 256;
   size_t      spmv_smem = 0;           /* bytes of staged products per block */
   bool        spmv_stream_ok = true;   /* false -> scalar fallback kernel */
+  /* slab plan of the bulk-copy pipeline kernel (k_spmv_pipeline), made on first use */
+  mutable int    pl_state = 0;         /* 0 not planned, 1 usable, -1 not usable */
+  mutable int    pl_slab_rows = 0, pl_n_slabs = 0, pl_grid = 0;
+  mutable size_t pl_smem = 0;
   /* mesh association (device) */
   csb_lnum_t  n_faces = 0;
   csb::DevBuf<csb_lnum_t>  c2f;
@@ -296,6 +300,11 @@ struct _csb_matrix_t {
   csb::DevBuf<double>      cell_cen, cell_vol, face_u_normal, face_surf;
   bool        has_mesh = false;
   _csb_halo_t *halo = nullptr;
+  /* matrix created from CSR arrays (cs_matrix_type_t CS_MATRIX_CSR): the CSR arrays are
+     kept for cs_matrix_vector_multiply in CSR order (_mat_vec_p_l_csr); this object holds
+     the MSR split (diagonal extracted) the solvers and the hierarchy work on */
+  _csb_matrix_t *csr = nullptr;
+  ~_csb_matrix_t() { delete csr; }
 };
 
 namespace csb {
@@ -327,6 +336,7 @@ struct SpmvArgs {
 };
 
 bool launch_spmv(SpmvEpilogue epi, const SpmvArgs &a);
+bool launch_spmv_csr_exdiag(const _csb_matrix_t *m, const double *x, double *y);
 
 /* setup of SpMV launch geometry after (re)building a structure */
 void matrix_plan_spmv(_csb_matrix_t *m);

@@ -27,6 +27,8 @@
 
 #include <cfloat>
 #include <cmath>
+#include <cstdint>
+#include <cstring>
 
 namespace csb {
 
@@ -1189,6 +1191,45 @@ k_fcg_persistent(const MgLevelDesc L, const double *rhs, double *vx, int vx_ini_
 }
 
 /*--------------------------------------------------------------------------
+ * Stand-alone SpMV (cs_matrix_vector_multiply, _mat_vec_p_l_msr
+ * cs_matrix_spmv.cpp:2103-2165) through the same pipeline.
+ *--------------------------------------------------------------------------*/
+
+struct EpiStore {            /* y = E.x + d*x  (diagonal last, :2138-2142) */
+  static constexpr int NV = 2;
+  const double *d_val, *x;
+  double *y;
+  __device__ __forceinline__ const double *src(int v) const { return (v == 0) ? d_val : x; }
+  __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&)[4]) const
+  { y[r] = sii + op[0]*op[ST_OP_STRIDE]; }
+};
+
+struct EpiStoreExDiag {      /* y = E.x */
+  static constexpr int NV = 0;
+  double *y;
+  __device__ __forceinline__ const double *src(int) const { return nullptr; }
+  __device__ __forceinline__ void epi(int r, double sii, const double *, double (&)[4]) const
+  { y[r] = sii; }
+};
+
+__global__ void __launch_bounds__(PT, CSB_MIN_CTAS)
+k_spmv_pipeline(const MgLevelDesc L, const double *x, double *y, int exclude_diag)
+{
+  unsigned char *s_raw = s_raw_base;
+  pipe_init(s_raw);
+  if (exclude_diag) {
+    EpiStoreExDiag f;
+    f.y = y;
+    spmv_phase_g<false, false>(L, x, nullptr, s_raw, f, nullptr);
+  }
+  else {
+    EpiStore f;
+    f.d_val = L.d_val; f.x = x; f.y = y;
+    spmv_phase_g<false, false>(L, x, nullptr, s_raw, f, nullptr);
+  }
+}
+
+/*--------------------------------------------------------------------------
  * Kernel 1: one PCG solve (cs_sles_it_solve with CS_SLES_PCG + Jacobi)
  *--------------------------------------------------------------------------*/
 
@@ -1459,6 +1500,51 @@ int persistent_grid(int which, size_t smem)
   if (occ > cap && cap > 0) occ = cap;
   int g = occ * c.sm_count / (c.device_share > 1 ? c.device_share : 1);
   return (g > 0) ? g : 1;
+}
+
+bool launch_spmv_pipeline(const _csb_matrix_t *m, const double *x, double *y, bool exclude_diag,
+                          bool *launched)
+{
+  *launched = false;
+  Context &c = ctx();
+  if (m->pl_state == 0) {
+    m->pl_state = -1;
+    if ((size_t)m->h_row_index.size() == (size_t)m->n_rows + 1 && m->n_rows > 0) {
+      size_t max_entries = 0;
+      plan_slabs(m->h_row_index, m->n_rows, m->pl_slab_rows, m->pl_n_slabs, max_entries);
+      m->pl_smem = persistent_smem_bytes(max_entries);
+      int optin = 0, occ = 0;
+      cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device);
+      if ((size_t)optin >= m->pl_smem && max_entries <= (size_t)SLAB_CAP) {
+        cudaFuncSetAttribute(k_spmv_pipeline, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_pipeline, PT, m->pl_smem);
+        if (occ > CSB_MIN_CTAS) occ = CSB_MIN_CTAS;
+        if (occ >= 1) {
+          m->pl_grid = occ * c.sm_count;
+          if (m->pl_grid > m->pl_n_slabs) m->pl_grid = m->pl_n_slabs;
+          m->pl_state = 1;
+        }
+      }
+    }
+  }
+  /* the diagonal epilogue bulk-copies x: 16-byte aligned, whole 16-byte units */
+  if (m->pl_state != 1) return true;
+  if (!exclude_diag && ((((uintptr_t)x) & 15) != 0
+                        || ((m->n_rows & 1) != 0 && m->n_cols_ext == m->n_rows))) return true;
+  MgLevelDesc L;
+  memset(&L, 0, sizeof(L));
+  L.n_rows = m->n_rows; L.n_slabs = m->pl_n_slabs; L.slab_rows = m->pl_slab_rows;
+  L.row_index = m->row_index.p; L.col_id = m->col_id.p;
+  L.d_val = m->d_val.p; L.x_val = m->x_val.p;
+  k_spmv_pipeline<<<m->pl_grid, PT, m->pl_smem, c.stream>>>(L, x, y, exclude_diag ? 1 : 0);
+  c.launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("kernel k_spmv_pipeline launch failed: %s", cudaGetErrorString(e));
+    return false;
+  }
+  *launched = true;
+  return true;
 }
 
 bool launch_pcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,

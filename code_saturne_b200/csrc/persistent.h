@@ -71,6 +71,13 @@ bool launch_fcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
                            double r_norm, const PersistentCommon &P, ItState *st,
                            int grid, size_t smem, bool single, bool cooperative);
 
+/* y = A.x (or E.x) through the bulk-copy pipeline of the persistent kernels, as a
+   stand-alone launch (cs_matrix_vector_multiply).  Returns false with no error set when
+   the pipeline cannot take these buffers (alignment, odd length): the caller falls back
+   to k_spmv_stream. */
+bool launch_spmv_pipeline(const _csb_matrix_t *m, const double *x, double *y, bool exclude_diag,
+                          bool *launched);
+
 /* choose the slab height of a level so that a slab's products fit in ~40 KB */
 void plan_slabs(const std::vector<csb_lnum_t> &row_index, int n_rows, int &slab_rows,
                 int &n_slabs, size_t &max_entries);

@@ -199,6 +199,45 @@ csb_matrix_create_msr(csb_lnum_t n_rows, csb_lnum_t n_cols_ext,
   return m;
 }
 
+csb_matrix_t *
+csb_matrix_create_csr(csb_lnum_t n_rows, csb_lnum_t n_cols_ext,
+                      const csb_lnum_t *row_index, const csb_lnum_t *col_id,
+                      const csb_real_t *val, int symmetric)
+{
+  Context &c = ctx();
+  if (!c.ready) { set_error("csb_matrix_create_csr: csb_init not called"); return nullptr; }
+  if (n_rows < 0 || n_cols_ext < n_rows || row_index == nullptr) {
+    set_error("csb_matrix_create_csr: invalid sizes"); return nullptr;
+  }
+  if (is_device_ptr(row_index) || is_device_ptr(col_id) || is_device_ptr(val)) {
+    set_error("csb_matrix_create_csr: host arrays expected (the MSR split is made on the host)");
+    return nullptr;
+  }
+  /* MSR split: diagonal out, the other entries keep their order */
+  const size_t nnz = (size_t)row_index[n_rows];
+  std::vector<csb_lnum_t> ri((size_t)n_rows + 1, 0), ci;
+  std::vector<double> dv((size_t)n_rows, 0.0), xv;
+  ci.reserve(nnz); xv.reserve(nnz);
+  for (csb_lnum_t i = 0; i < n_rows; i++) {
+    for (csb_lnum_t k = row_index[i]; k < row_index[i+1]; k++) {
+      if (col_id[k] == i) dv[i] += val[k];
+      else { ci.push_back(col_id[k]); xv.push_back(val[k]); }
+    }
+    ri[(size_t)i + 1] = (csb_lnum_t)ci.size();
+  }
+  csb_lnum_t dummy_i = 0; double dummy_d = 0.;
+  csb_matrix_t *m = csb_matrix_create_msr(n_rows, n_cols_ext, ri.data(),
+                                          ci.empty() ? &dummy_i : ci.data(), dv.data(),
+                                          xv.empty() ? &dummy_d : xv.data(), symmetric);
+  if (m == nullptr) return nullptr;
+  /* the CSR arrays as an "off-diagonal only" matrix: E.x of it is the CSR product */
+  std::vector<double> zero((size_t)n_rows, 0.0);
+  m->csr = csb_matrix_create_msr(n_rows, n_cols_ext, row_index, col_id, zero.data(), val,
+                                 symmetric);
+  if (m->csr == nullptr) { delete m; return nullptr; }
+  return m;
+}
+
 int csb_matrix_set_coefficients(csb_matrix_t *m, int symmetric,
                                 const csb_real_t *d_val, const csb_real_t *x_val)
 {
@@ -280,9 +319,20 @@ static int _spmv_api(const csb_matrix_t *m, csb_real_t *x, csb_real_t *y, bool e
   }
   if (m->halo != nullptr)
     if (csb_halo_sync_var(m->halo, x_d) != 0) return -1;
-  SpmvArgs a;
-  a.m = m; a.exclude_diag = exdiag; a.x = x_d; a.y = y_d;
-  if (!launch_spmv(EPI_STORE, a)) return -1;
+  if (m->csr != nullptr) {
+    /* CSR order: every entry (diagonal included) in place; exclude_diag skips col == row */
+    if (exdiag) { if (!launch_spmv_csr_exdiag(m->csr, x_d, y_d)) return -1; }
+    else {
+      SpmvArgs a;
+      a.m = m->csr; a.exclude_diag = true; a.x = x_d; a.y = y_d;
+      if (!launch_spmv(EPI_STORE, a)) return -1;
+    }
+  }
+  else {
+    SpmvArgs a;
+    a.m = m; a.exclude_diag = exdiag; a.x = x_d; a.y = y_d;
+    if (!launch_spmv(EPI_STORE, a)) return -1;
+  }
   if (!yd) {
     if (!CSB_CUDA(cudaMemcpyAsync(y, y_d, sizeof(double)*(size_t)m->n_rows,
                                   cudaMemcpyDeviceToHost, c.stream))) return -1;

@@ -40,17 +40,20 @@ int env_int(const char *name, int dflt)
 struct StagedVec {
   double         *d = nullptr;
   double         *h = nullptr;     /* caller's buffer when it is not used in place */
-  DevBuf<double>  tmp;
   size_t          n = 0;
   /* A device buffer is used in place when the bulk copies of the persistent kernels
-     can read it: 16-byte aligned, and an even length (they read whole 16-byte units). */
-  bool init(double *p, size_t count, bool copy_in) {
+     can read it: 16-byte aligned, and an even length (they read whole 16-byte units).
+     Otherwise the vector is staged in `keep`, a buffer that lives with the solver object
+     (no cudaMalloc / cudaFree per solve). */
+  bool init(double *p, size_t count, bool copy_in, DevBuf<double> &keep) {
     n = count;
     if (is_device_ptr(p) && ((uintptr_t)p & 15) == 0 && (count & 1) == 0) { d = p; return true; }
     h = p;
-    if (copy_in) { if (!tmp.upload(p, count)) return false; }
-    else if (!tmp.alloc(count)) return false;
-    d = tmp.p;
+    if (keep.n < count && !keep.alloc(count)) return false;
+    d = keep.p;
+    if (copy_in && count > 0)
+      return CSB_CUDA(cudaMemcpyAsync(d, p, sizeof(double)*count, cudaMemcpyDefault,
+                                      ctx().stream));
     return true;
   }
   bool copy_back(size_t count) {
@@ -150,6 +153,7 @@ struct _csb_sles_it_t {
   /* persistent-kernel launch data */
   MgLevelDesc         desc;
   DevBuf<double>      partials;
+  DevBuf<double>      stage_rhs, stage_vx;   /* host rhs / vx staged here, kept across solves */
   DevBuf<unsigned>    barrier;
   int                 p_grid = 0;
   size_t              p_smem = 0;
@@ -420,8 +424,9 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
   double t0 = wall();
   const bool ini = (vx_ini == vx);
   StagedVec s_rhs, s_vx;
-  if (!s_rhs.init(const_cast<double *>(rhs), (size_t)a->n_rows, true)) return CSB_SLES_BREAKDOWN;
-  if (!s_vx.init(vx, (size_t)a->n_cols_ext, ini)) return CSB_SLES_BREAKDOWN;
+  if (!s_rhs.init(const_cast<double *>(rhs), (size_t)a->n_rows, true, c->stage_rhs))
+    return CSB_SLES_BREAKDOWN;
+  if (!s_vx.init(vx, (size_t)a->n_cols_ext, ini, c->stage_vx)) return CSB_SLES_BREAKDOWN;
 
   bool ok = false;
   switch (c->type) {
@@ -620,6 +625,7 @@ struct _csb_multigrid_t {
   /* persistent-kernel launch data */
   DevBuf<MgLevelDesc> descs;
   DevBuf<double>   partials;
+  DevBuf<double>   stage_rhs, stage_vx;      /* host rhs / vx staged here, kept across solves */
   DevBuf<unsigned> barrier;
   int              p_grid = 0;
   size_t           p_smem = 0;
@@ -1128,8 +1134,10 @@ csb_multigrid_solve(void *context, const char *name, const csb_matrix_t *a, int 
   const double denom = 1.0 / (double)a->n_rows;   /* kernel-per-phase path: one rank only */
 
   StagedVec s_rhs, s_vx;
-  if (!s_rhs.init(const_cast<double *>(rhs), (size_t)a->n_rows, true)) return CSB_SLES_BREAKDOWN;
-  if (!s_vx.init(vx, (size_t)a->n_cols_ext, vx_ini == vx)) return CSB_SLES_BREAKDOWN;
+  if (!s_rhs.init(const_cast<double *>(rhs), (size_t)a->n_rows, true, mg->stage_rhs))
+    return CSB_SLES_BREAKDOWN;
+  if (!s_vx.init(vx, (size_t)a->n_cols_ext, vx_ini == vx, mg->stage_vx))
+    return CSB_SLES_BREAKDOWN;
 
   MgState *ms = mg->mg_state.p;
   if (!launch_mg_state_init(ms, precision, r_norm, mg->n_max_cycles)) return CSB_SLES_BREAKDOWN;

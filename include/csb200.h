@@ -105,6 +105,18 @@ csb_matrix_t *csb_matrix_create_msr(csb_lnum_t         n_rows,
                                     const csb_real_t  *x_val,
                                     int                symmetric);
 
+/* CS_MATRIX_CSR (cs_matrix_struct_csr_t, src/alge/cs_matrix_priv.h:143-160): the
+   diagonal is an ordinary entry of (row_index, col_id, val).  csb_matrix_vector_multiply
+   on such a matrix sums every row in CSR order like _mat_vec_p_l_csr
+   (src/alge/cs_matrix_spmv.cpp:1890-1955, exclude_diag skips col_id == row); the solvers
+   work on the MSR split made at creation (host arrays only). */
+csb_matrix_t *csb_matrix_create_csr(csb_lnum_t         n_rows,
+                                    csb_lnum_t         n_cols_ext,
+                                    const csb_lnum_t  *row_index,
+                                    const csb_lnum_t  *col_id,
+                                    const csb_real_t  *val,
+                                    int                symmetric);
+
 /* Replace coefficient values only (cs_matrix_set_coefficients on an existing
    structure, src/alge/cs_matrix.cpp:5315). */
 int  csb_matrix_set_coefficients(csb_matrix_t      *m,

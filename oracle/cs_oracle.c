@@ -150,6 +150,31 @@ ora_dot_xx_xy_yz(int n, const double *x, const double *y, const double *z,
 }
 
 /*----------------------------------------------------------------------------
+ * CSR SpMV: _mat_vec_p_l_csr (src/alge/cs_matrix_spmv.cpp:1890-1955).  The
+ * diagonal is an ordinary entry; exclude_diag skips col_id == row.
+ *----------------------------------------------------------------------------*/
+
+void
+ora_spmv_csr(int n_rows, const int *row_index, const int *col_id, const double *val,
+             int exclude_diag, const double *x, double *y)
+{
+  for (int ii = 0; ii < n_rows; ii++) {
+    const int *restrict c = col_id + row_index[ii];
+    const double *restrict m_row = val + row_index[ii];
+    const int n_cols = row_index[ii+1] - row_index[ii];
+    double sii = 0.0;
+    if (!exclude_diag) {
+      for (int jj = 0; jj < n_cols; jj++) sii += (m_row[jj]*x[c[jj]]);
+    }
+    else {
+      for (int jj = 0; jj < n_cols; jj++)
+        if (c[jj] != ii) sii += (m_row[jj]*x[c[jj]]);
+    }
+    y[ii] = sii;
+  }
+}
+
+/*----------------------------------------------------------------------------
  * Convergence test: _convergence_test (src/alge/cs_sles_it.cpp:243-325)
  *----------------------------------------------------------------------------*/
 

@@ -47,6 +47,8 @@ void   ora_spmv_msr(int n_rows, const int *row_index, const int *col_id,
                     const double *d_val, const double *x_val, int exclude_diag,
                     const double *x, double *y);
 
+void   ora_spmv_csr(int n_rows, const int *row_index, const int *col_id, const double *val,
+                    int exclude_diag, const double *x, double *y);
 double ora_dot(int n, const double *x, const double *y);
 double ora_dot_xx(int n, const double *x);
 void   ora_dot_xx_xy(int n, const double *x, const double *y, double *xx, double *xy);

@@ -110,6 +110,13 @@ class Oracle:
                               C.c_int(int(exclude_diag)), _dp(x), _dp(y))
         return y
 
+    def spmv_csr(self, ri, ci, val, x, exclude_diag=False):
+        ri, ci, val, x = _i32(ri), _i32(ci), _f64(val), _f64(x)
+        y = np.empty(len(ri) - 1)
+        self.lib.ora_spmv_csr(C.c_int(len(ri) - 1), _ip(ri), _ip(ci), _dp(val),
+                              C.c_int(int(exclude_diag)), _dp(x), _dp(y))
+        return y
+
     def dot(self, x, y):
         x, y = _f64(x), _f64(y)
         return self.lib.ora_dot(C.c_int(len(x)), _dp(x), _dp(y))
@@ -255,6 +262,22 @@ class RefLib:
             self.lib.csref_system_set_mesh(h, C.c_int(s.n_faces), _ip(fc), _ip(c2f), _sp(sgn),
                                            _dp(cen), _dp(vol), _dp(fun), _dp(fs))
         return h
+
+    def system_csr(self, n_rows, edges, da, xa, symmetric=True):
+        """CS_MATRIX_CSR built by the reference from an edge list; returns (handle,
+        row_index, col_id, val) with the arrays the reference holds."""
+        edges = np.ascontiguousarray(edges, dtype=np.int32)
+        da, xa = _f64(da), _f64(xa)
+        self.lib.csref_system_create_csr.restype = C.c_void_p
+        h = C.c_void_p(self.lib.csref_system_create_csr(C.c_int(n_rows), C.c_int(len(edges)),
+                                                        _ip(edges), _dp(da), _dp(xa),
+                                                        C.c_int(int(symmetric))))
+        nnz = self.lib.csref_get_csr_arrays(h, None, None, None)
+        ri = np.empty(n_rows + 1, dtype=np.int32)
+        ci = np.empty(nnz, dtype=np.int32)
+        val = np.empty(nnz)
+        self.lib.csref_get_csr_arrays(h, _ip(ri), _ip(ci), _dp(val))
+        return h, ri, ci, val
 
     def destroy(self, h):
         self.lib.csref_system_destroy(h)

@@ -154,6 +154,47 @@ csref_system_create(int            n_rows,
   return s;
 }
 
+/* CS_MATRIX_CSR from an edge list (the reference's native way to a CSR matrix:
+   cs_matrix_structure_create + cs_matrix_set_coefficients, cs_matrix.cpp:4328, :5315).
+   xa: one value per edge (symmetric) or two (lower-to-upper, upper-to-lower). */
+void *
+csref_system_create_csr(int            n_rows,
+                        int            n_edges,
+                        const int     *edges,
+                        const double  *da,
+                        const double  *xa,
+                        int            symmetric)
+{
+  ref_system *s = new ref_system;
+  s->n_rows = n_rows;
+  s->symmetric = (symmetric != 0);
+  s->row_index = nullptr;
+  s->col_id = nullptr;
+  s->ms = cs_matrix_structure_create(CS_MATRIX_CSR, n_rows, n_rows, n_edges,
+                                     (const cs_lnum_2_t *)edges, nullptr, nullptr);
+  s->m = cs_matrix_create(s->ms);
+  cs_matrix_set_coefficients(s->m, s->symmetric, 1, 1, n_edges,
+                             (const cs_lnum_2_t *)edges, da, xa);
+  return s;
+}
+
+/* Copy the CSR arrays out; returns the number of entries (call with null pointers
+   first to size the buffers). */
+int
+csref_get_csr_arrays(void *sys, int *row_index, int *col_id, double *val)
+{
+  ref_system *s = static_cast<ref_system *>(sys);
+  const cs_lnum_t *ri = nullptr, *ci = nullptr;
+  const cs_real_t *v = nullptr;
+  cs_matrix_get_csr_arrays(s->m, &ri, &ci, &v);
+  if (ri == nullptr) return -1;
+  const int nnz = ri[s->n_rows];
+  if (row_index != nullptr) memcpy(row_index, ri, sizeof(int)*(s->n_rows + 1));
+  if (col_id != nullptr) memcpy(col_id, ci, sizeof(int)*nnz);
+  if (val != nullptr) memcpy(val, v, sizeof(double)*nnz);
+  return nnz;
+}
+
 /* Associate mesh data (same role as src/alge/cs_sles_default.cpp:826-838). */
 void
 csref_system_set_mesh(void          *sys,

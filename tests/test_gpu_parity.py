@@ -11,6 +11,8 @@ Tolerances (BASELINE.json north_star):
   * converged solutions                                           rel L2 <= 1e-10
   * iteration counts                                              +-2
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -402,4 +404,80 @@ def test_fcg_128_true_residual(csb, oracle):
     assert int(r["cvg"]) == 1
     res = np.linalg.norm(s.rhs - m.vector_multiply(r["vx"][:s.n_rows].copy()))
     assert res <= 1.01e-8 * r_norm and abs(res - r["residual"]) <= 1e-2 * res
+    c.destroy(); m.destroy()
+
+
+def test_spmv_pipeline_kernel_bit_exact():
+    """k_spmv_pipeline (the persistent kernels' bulk-copy pipeline as a stand-alone SpMV,
+    CSB_SPMV_PIPELINE=1) is bit-identical to the oracle, diagonal included and excluded,
+    on a cube and on a matrix with irregular and empty rows."""
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np
+from code_saturne_b200 import api
+from code_saturne_b200.mesh_cartesian import cube_poisson, matrix_check_coefficients
+from oracle.pyoracle import Oracle
+api.init(0)
+ora = Oracle()
+s = cube_poisson(40, with_mesh=False)
+d, xv, x = matrix_check_coefficients(s)
+m = api.Matrix(s.n_rows, s.row_index, s.col_id, d, xv)
+assert np.array_equal(m.vector_multiply(x), ora.spmv(s.row_index, s.col_id, d, xv, x))
+assert np.array_equal(m.vector_multiply(x, exclude_diag=True),
+                      ora.spmv(s.row_index, s.col_id, d, xv, x, exclude_diag=True))
+rng = np.random.default_rng(1234)
+n = 5000
+cnt = rng.integers(0, 40, n); cnt[::7] = 0
+ri = np.zeros(n + 1, dtype=np.int32); np.cumsum(cnt, out=ri[1:])
+ci = np.concatenate([np.sort(rng.choice(n, c, replace=False)) for c in cnt]).astype(np.int32)
+xv = rng.standard_normal(len(ci)); d = rng.standard_normal(n); x = rng.standard_normal(n)
+m2 = api.Matrix(n, ri, ci, d, xv)
+assert np.array_equal(m2.vector_multiply(x), ora.spmv(ri, ci, d, xv, x))
+assert api.launch_count() > 0
+print("OK pipeline spmv")
+'''
+    env = dict(os.environ, CSB_SPMV_PIPELINE="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
+                       cwd=root, env=env)
+    assert p.returncode == 0 and "OK pipeline spmv" in p.stdout, p.stdout[-2000:] + p.stderr[-3000:]
+
+
+# --------------------------------------------------------------------------- CSR format
+
+@pytest.mark.parametrize("name", ["csr_N6_sym", "csr_N10_nonsym", "csr_N14_sym"])
+def test_csr_spmv_bit_exact_vs_reference_golden(csb, name):
+    """csb_matrix_create_csr + csb_matrix_vector_multiply against the reference's
+    _mat_vec_p_l_csr output (tests/golden/csr_*.npz): bit-exact, with and without diagonal."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    n = len(g["row_index"]) - 1
+    m = csb.Matrix.from_csr(n, g["row_index"], g["col_id"], g["val"], symmetric="nonsym" not in name)
+    assert np.array_equal(m.vector_multiply(g["x"]), g["y"])
+    assert np.array_equal(m.vector_multiply(g["x"], exclude_diag=True), g["y_exdiag"])
+    m.destroy()
+
+
+def test_csr_matrix_solves_like_its_msr_split(csb, oracle):
+    """A CSR-created matrix is solvable: PCG on it equals PCG on the MSR form of the same
+    system (the MSR split is what the solvers run on), and matches the oracle."""
+    s = cube_poisson(16, "dirichlet", with_mesh=False)
+    n = s.n_rows
+    # CSR with the diagonal merged in sorted position
+    rows = np.repeat(np.arange(n), np.diff(s.row_index))
+    r_all = np.concatenate([rows, np.arange(n)])
+    c_all = np.concatenate([s.col_id, np.arange(n)])
+    v_all = np.concatenate([s.x_val, s.d_val])
+    order = np.lexsort((c_all, r_all))
+    ri = np.zeros(n + 1, dtype=np.int32)
+    np.cumsum(np.bincount(r_all, minlength=n), out=ri[1:])
+    m = csb.Matrix.from_csr(n, ri, c_all[order].astype(np.int32), v_all[order])
+    r_norm = float(np.linalg.norm(s.rhs))
+    c = csb.SlesIt(csb.SlesItType.PCG, 2000)
+    r = c.solve(m, s.rhs, 1e-12, r_norm)
+    o = oracle.pcg(s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, 2000, 1e-12, r_norm)
+    assert int(r["cvg"]) == 1 == o["cvg"] and abs(r["n_iter"] - o["n_iter"]) <= 2
+    assert rel_l2(r["vx"][:n], o["vx"]) <= SOL_TOL
+    y = m.vector_multiply(o["vx"])
+    assert np.allclose(y, s.rhs, rtol=0, atol=2e-12 * r_norm)
     c.destroy(); m.destroy()

@@ -3,6 +3,8 @@
 code and (2) that code directly when oracle/_ref/libcsref.so is present.
 Integer/index data must match bit-exactly; floating-point data too, since the
 restatement keeps the reference's evaluation order."""
+import os
+
 import numpy as np
 import pytest
 
@@ -139,3 +141,31 @@ def test_oracle_fcg_matches_golden(oracle, N, bc):
     assert (w["cvg"], w["n_iter"], w["residual"]) \
         == (int(g["warm_cvg"]), int(g["warm_n_iter"]), float(g["warm_residual"]))
     assert np.array_equal(w["vx"], g["warm_vx"])
+
+
+@pytest.mark.parametrize("name", ["csr_N6_sym", "csr_N10_nonsym", "csr_N14_sym"])
+def test_oracle_csr_spmv_matches_golden(oracle, name):
+    """_mat_vec_p_l_csr restatement against arrays and products of the reference build
+    (tests/golden/make_golden_csr.py): bit-exact, diagonal included and excluded."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    y = oracle.spmv_csr(g["row_index"], g["col_id"], g["val"], g["x"])
+    assert np.array_equal(y, g["y"])
+    y = oracle.spmv_csr(g["row_index"], g["col_id"], g["val"], g["x"], exclude_diag=True)
+    assert np.array_equal(y, g["y_exdiag"])
+
+
+def test_oracle_csr_vs_reference_direct(oracle, reflib):
+    sys_path = os.path.join(os.path.dirname(__file__), "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(sys_path, "make_golden_csr.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    for N, symmetric in ((9, True), (12, False)):
+        s = cube_poisson(N, "dirichlet")
+        edges, da, xa, x = mk.coefficients(s, symmetric)
+        h, ri, ci, val = reflib.system_csr(s.n_rows, edges, da, xa, symmetric)
+        assert np.array_equal(reflib.spmv(h, x, s.n_rows), oracle.spmv_csr(ri, ci, val, x))
+        assert np.array_equal(reflib.spmv(h, x, s.n_rows, True),
+                              oracle.spmv_csr(ri, ci, val, x, exclude_diag=True))
+        reflib.destroy(h)
