@@ -83,6 +83,8 @@ def load_library() -> C.CDLL:
     L.csb_free_pinned.argtypes = [vp]
     L.csb_launch_count.restype = C.c_longlong
     L.csb_launch_count.argtypes = [ci]
+    L.csb_matrix_create_msr_block.restype = vp
+    L.csb_matrix_create_msr_block.argtypes = [ci, ci, ci, vp, vp, vp, vp, ci]
     L.csb_matrix_create_csr.restype = vp
     L.csb_matrix_create_csr.argtypes = [ci, ci, vp, vp, vp, ci]
     L.csb_matrix_create_msr.restype = vp
@@ -365,6 +367,28 @@ class Matrix:
         self.nnz = int(L.csb_matrix_get_n_entries(self._h)) - self.n_rows
         self._halo = None
 
+    db = 1      # diagonal block size (3 for from_block matrices)
+
+    @classmethod
+    def from_block(cls, n_rows, db, row_index, col_id, d_val, x_val, symmetric=False,
+                   n_cols_ext=None):
+        """MSR with db x db diagonal blocks (d_val: n_rows*db*db) and scalar extra-diagonal
+        entries (CS_MATRIX_BLOCK_D); vectors hold db values per row."""
+        L = load_library()
+        self = cls.__new__(cls)
+        self.n_rows = int(n_rows)
+        self.db = int(db)
+        self.n_cols_ext = int(n_cols_ext if n_cols_ext is not None else n_rows)
+        ri, ci, d, x = _i32(row_index), _i32(col_id), _f64(d_val), _f64(x_val)
+        assert d.size == self.n_rows * self.db * self.db
+        self._h = L.csb_matrix_create_msr_block(self.n_rows, self.n_cols_ext, self.db, _ptr(ri),
+                                                _ptr(ci), _ptr(d), _ptr(x), int(bool(symmetric)))
+        if not self._h:
+            _err("csb_matrix_create_msr_block")
+        self.nnz = int(L.csb_matrix_get_n_entries(self._h)) - self.n_rows
+        self._halo = None
+        return self
+
     @classmethod
     def from_csr(cls, n_rows, row_index, col_id, val, symmetric=True, n_cols_ext=None):
         """CS_MATRIX_CSR (diagonal stored as an ordinary entry): vector_multiply sums in CSR
@@ -425,7 +449,7 @@ class Matrix:
         if isinstance(x, np.ndarray):
             x = _f64(x)
             if y is None:
-                y = np.empty(self.n_rows, dtype=np.float64)
+                y = np.empty(self.n_rows * self.db, dtype=np.float64)
         elif y is None:
             raise ValueError("y is required with device buffers")
         if fn(self.handle, _ptr(x), _ptr(y)) != 0:
@@ -505,7 +529,7 @@ class _SolverBase:
         if host:
             rhs = _f64(rhs)
             if vx is None:
-                vx = np.zeros(a.n_cols_ext, dtype=np.float64)
+                vx = np.zeros(a.n_cols_ext * a.db, dtype=np.float64)
                 use_vx_ini = False
             else:
                 vx = _f64(vx)

@@ -276,6 +276,7 @@ bool halo_dev_view(const _csb_halo_t *h, HaloDev &v);
 
 struct _csb_matrix_t {
   csb_lnum_t  n_rows = 0, n_cols_ext = 0, nnz = 0;
+  int         db = 1;                  /* diagonal block size: 1, or 3 (CS_MATRIX_BLOCK_D) */
   bool        symmetric = true;
   csb::DevBuf<csb_lnum_t>  row_index, col_id;
   csb::DevBuf<double>      d_val, x_val;
@@ -337,6 +338,10 @@ struct SpmvArgs {
 
 bool launch_spmv(SpmvEpilogue epi, const SpmvArgs &a);
 bool launch_spmv_csr_exdiag(const _csb_matrix_t *m, const double *x, double *y);
+bool launch_spmv_b3(const _csb_matrix_t *m, const double *x, double *y, bool exclude_diag);
+bool launch_ad_inv_block(int n_rows, int db, const double *d_val, double *ad_inv);
+bool launch_bicg_spmv_b3(int mode, const _csb_matrix_t *m, ItState *st, const double *x,
+                         double *y, const double *b);
 
 /* setup of SpMV launch geometry after (re)building a structure */
 void matrix_plan_spmv(_csb_matrix_t *m);

@@ -391,6 +391,112 @@ bool launch_spmv_csr_exdiag(const _csb_matrix_t *m, const double *x, double *y)
   return post_launch("spmv_csr_exdiag");
 }
 
+/*--------------------------------------------------------------------------
+ * 3x3 block-diagonal MSR (CS_MATRIX_BLOCK_D): _b_mat_vec_p_l_msr_3
+ * (cs_matrix_spmv.cpp:2394-2455).  Thread per block row: y_i = D_i.x_i
+ * (_dense_3_3_ax, :590-607) FIRST, then += e_ij * x_j in CSR order.
+ * MODE -1: store only; 0: + (y.b) -> gamma; 1: + (y.y, y.b) -> alpha (BiCGStab).
+ * Algorithmic bytes: 12 nnz + 4 n + 72 n (D) + 24 n (x) + 24 n (y).
+ *--------------------------------------------------------------------------*/
+
+template <int MODE>
+__global__ void __launch_bounds__(TPB)
+k_spmv_b3(int n_rows, const int *__restrict__ row_index, const int *__restrict__ col_id,
+          const double *__restrict__ d_val, const double *__restrict__ x_val,
+          const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ b,
+          ItState *st, double *partials, unsigned *ticket)
+{
+  if (MODE >= 0 && st->cvg != CSB_SLES_ITERATING) return;
+  const int ii = blockIdx.x*TPB + threadIdx.x;
+  double v[2] = {0., 0.};
+  if (ii < n_rows) {
+    double y0, y1, y2;
+    if (d_val != nullptr) {
+      const double *a = d_val + (size_t)ii*9;
+      const double x0 = x[ii*3], x1 = x[ii*3 + 1], x2 = x[ii*3 + 2];
+      y0 = a[0]*x0 + a[1]*x1 + a[2]*x2;
+      y1 = a[3]*x0 + a[4]*x1 + a[5]*x2;
+      y2 = a[6]*x0 + a[7]*x1 + a[8]*x2;
+    }
+    else { y0 = 0.; y1 = 0.; y2 = 0.; }
+    const int ks = row_index[ii], ke = row_index[ii+1];
+    for (int jj = ks; jj < ke; jj++) {
+      const double e = x_val[jj];
+      const double *xc = x + (size_t)col_id[jj]*3;
+      y0 += (e*xc[0]);
+      y1 += (e*xc[1]);
+      y2 += (e*xc[2]);
+    }
+    y[ii*3] = y0; y[ii*3 + 1] = y1; y[ii*3 + 2] = y2;
+    if (MODE == 0)
+      v[0] = y0*b[ii*3] + y1*b[ii*3 + 1] + y2*b[ii*3 + 2];
+    else if (MODE == 1) {
+      v[0] = y0*y0 + y1*y1 + y2*y2;
+      v[1] = y0*b[ii*3] + y1*b[ii*3 + 1] + y2*b[ii*3 + 2];
+    }
+  }
+  if (MODE == 0)
+    grid_sum_finalize<2>(v, partials, ticket, [st](const double *s) {
+      st->gamma = st->beta / s[0];          /* cs_sles_it.cpp:2830-2832 */
+    });
+  else if (MODE == 1)
+    grid_sum_finalize<2>(v, partials, ticket, [st](const double *s) {
+      const double ro_1 = s[0], ro_0 = s[1]; /* cs_sles_it.cpp:2847-2855 */
+      if (fabs(ro_1) < 1.e-30) { st->cvg = CSB_SLES_BREAKDOWN; return; }
+      double d_ro_1 = (fabs(ro_1) > DBL_MIN) ? 1. / ro_1 : 0.;
+      st->alpha = ro_0 * d_ro_1;
+    });
+}
+
+bool launch_spmv_b3(const _csb_matrix_t *m, const double *x, double *y, bool exclude_diag)
+{
+  const int grid = (m->n_rows + TPB - 1) / TPB;
+  if (grid < 1) return true;
+  k_spmv_b3<-1><<<grid, TPB, 0, ctx().stream>>>(m->n_rows, m->row_index.p, m->col_id.p,
+                                                exclude_diag ? nullptr : m->d_val.p,
+                                                m->x_val.p, x, y, nullptr, nullptr, nullptr,
+                                                nullptr);
+  return post_launch("spmv_b3");
+}
+
+bool ensure_partials(int n_blocks);
+
+bool launch_bicg_spmv_b3(int mode, const _csb_matrix_t *m, ItState *st, const double *x,
+                         double *y, const double *b)
+{
+  const int grid = (m->n_rows + TPB - 1) / TPB;
+  if (grid < 1) return true;
+  if (!ensure_partials(grid)) return false;
+  Context &c = ctx();
+  if (mode == 0)
+    k_spmv_b3<0><<<grid, TPB, 0, c.stream>>>(m->n_rows, m->row_index.p, m->col_id.p,
+                                             m->d_val.p, m->x_val.p, x, y, b, st, c.partials,
+                                             c.ticket);
+  else
+    k_spmv_b3<1><<<grid, TPB, 0, c.stream>>>(m->n_rows, m->row_index.p, m->col_id.p,
+                                             m->d_val.p, m->x_val.p, x, y, b, st, c.partials,
+                                             c.ticket);
+  return post_launch("bicg_spmv_b3");
+}
+
+/* point Jacobi of a block matrix: ad_inv[i] = 1 / ad[i*db + i%db]  (cs_sles_pc.cpp:383-388) */
+__global__ void __launch_bounds__(TPB)
+k_ad_inv_block(int n, int db, const double *__restrict__ d, double *__restrict__ ad_inv)
+{
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB)
+    ad_inv[i] = 1.0 / d[(size_t)i*db + (i % db)];
+}
+
+bool launch_ad_inv_block(int n_rows, int db, const double *d_val, double *ad_inv)
+{
+  const int n = n_rows*db;
+  if (n < 1) return true;
+  int g = (n + TPB - 1) / TPB;
+  if (g > 65535) g = 65535;
+  k_ad_inv_block<<<g, TPB, 0, ctx().stream>>>(n, db, d_val, ad_inv);
+  return post_launch("ad_inv_block");
+}
+
 void matrix_plan_spmv(_csb_matrix_t *m)
 {
   /* largest number of off-diagonal entries in any slab of 256 rows */
@@ -1086,6 +1192,7 @@ k_bicg_upd2(int n, ItState *st, double *__restrict__ vx, double *__restrict__ rk
 bool bicg_spmv_launch(int mode, const _csb_matrix_t *m, ItState *st, const double *x,
                       double *y, const double *b)
 {
+  if (m->db == 3) return launch_bicg_spmv_b3(mode, m, st, x, y, b);
   SpmvK k;
   k.n_rows = m->n_rows; k.row_index = m->row_index.p; k.col_id = m->col_id.p;
   k.d_val = m->d_val.p; k.x_val = m->x_val.p; k.x = x; k.y = y; k.b = b;

@@ -200,6 +200,50 @@ csb_matrix_create_msr(csb_lnum_t n_rows, csb_lnum_t n_cols_ext,
 }
 
 csb_matrix_t *
+csb_matrix_create_msr_block(csb_lnum_t n_rows, csb_lnum_t n_cols_ext, int db_size,
+                            const csb_lnum_t *row_index, const csb_lnum_t *col_id,
+                            const csb_real_t *d_val, const csb_real_t *x_val, int symmetric)
+{
+  if (db_size == 1)
+    return csb_matrix_create_msr(n_rows, n_cols_ext, row_index, col_id, d_val, x_val, symmetric);
+  Context &c = ctx();
+  if (!c.ready) { set_error("csb_matrix_create_msr_block: csb_init not called"); return nullptr; }
+  if (db_size != 3) {
+    set_error("csb_matrix_create_msr_block: diagonal block size %d (1 and 3 are available)",
+              db_size);
+    return nullptr;
+  }
+  if (n_rows < 0 || n_cols_ext < n_rows || row_index == nullptr) {
+    set_error("csb_matrix_create_msr_block: invalid sizes"); return nullptr;
+  }
+  csb_matrix_t *m = new csb_matrix_t;
+  m->n_rows = n_rows;
+  m->n_cols_ext = n_cols_ext;
+  m->db = db_size;
+  m->symmetric = (symmetric != 0);
+  m->h_row_index.resize((size_t)n_rows + 1);
+  if (is_device_ptr(row_index)) {
+    if (!CSB_CUDA(cudaMemcpy(m->h_row_index.data(), row_index,
+                             sizeof(csb_lnum_t)*((size_t)n_rows+1), cudaMemcpyDeviceToHost))) {
+      delete m; return nullptr;
+    }
+  }
+  else
+    memcpy(m->h_row_index.data(), row_index, sizeof(csb_lnum_t)*((size_t)n_rows+1));
+  m->nnz = m->h_row_index[n_rows];
+  bool ok = m->row_index.upload(row_index, (size_t)n_rows + 1)
+         && m->col_id.upload(col_id, (size_t)m->nnz)
+         && m->d_val.upload(d_val, (size_t)n_rows*db_size*db_size)
+         && m->x_val.upload(x_val, (size_t)m->nnz)
+         && CSB_CUDA(cudaStreamSynchronize(c.stream));
+  if (!ok) { delete m; return nullptr; }
+  matrix_plan_spmv(m);
+  return m;
+}
+
+int csb_matrix_get_diag_block_size(const csb_matrix_t *m) { return m ? m->db : 0; }
+
+csb_matrix_t *
 csb_matrix_create_csr(csb_lnum_t n_rows, csb_lnum_t n_cols_ext,
                       const csb_lnum_t *row_index, const csb_lnum_t *col_id,
                       const csb_real_t *val, int symmetric)
@@ -310,12 +354,20 @@ static int _spmv_api(const csb_matrix_t *m, csb_real_t *x, csb_real_t *y, bool e
   DevBuf<double> tx, ty;
   double *x_d = x, *y_d = y;
   if (!xd) {
-    if (!tx.upload(x, (size_t)m->n_cols_ext)) return -1;
+    if (!tx.upload(x, (size_t)m->n_cols_ext*m->db)) return -1;
     x_d = tx.p;
   }
   if (!yd) {
-    if (!ty.alloc((size_t)m->n_rows)) return -1;
+    if (!ty.alloc((size_t)m->n_rows*m->db)) return -1;
     y_d = ty.p;
+  }
+  if (m->db == 3) {
+    if (m->halo != nullptr) { set_error("block matrices: no halo on this path yet"); return -1; }
+    if (!launch_spmv_b3(m, x_d, y_d, exdiag)) return -1;
+    if (!yd && !CSB_CUDA(cudaMemcpyAsync(y, y_d, sizeof(double)*(size_t)m->n_rows*3,
+                                         cudaMemcpyDeviceToHost, c.stream))) return -1;
+    if ((!xd || !yd) && !CSB_CUDA(cudaStreamSynchronize(c.stream))) return -1;
+    return 0;
   }
   if (m->halo != nullptr)
     if (csb_halo_sync_var(m->halo, x_d) != 0) return -1;

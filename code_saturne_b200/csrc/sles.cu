@@ -277,15 +277,18 @@ bool bicgstab_enqueue(const csb_matrix_t *m, ItState *st, const double *ad_inv,
                       double precision, double r_norm, int n_max_iter, const double *rhs,
                       double *vx, bool vx_ini_nonzero, double *work, ItState *h_st)
 {
-  const int n = m->n_rows;
-  const size_t ws = (size_t)m->n_cols_ext;
+  const int n = m->n_rows*m->db;                      /* cs_sles_it_priv.cpp: n_rows*db */
+  const size_t ws = work_stride_of((size_t)m->n_cols_ext*m->db);
   Context &c = ctx();
   double *res0 = work, *rk = work + ws, *pk = work + 2*ws, *zk = work + 3*ws,
          *uk = work + 4*ws, *vk = work + 5*ws;
   if (!launch_it_state_init(st, nullptr, precision, r_norm, n_max_iter)) return false;
   if (vx_ini_nonzero) {
-    SpmvArgs a; a.m = m; a.x = vx; a.y = res0;
-    if (!launch_spmv(EPI_STORE, a)) return false;
+    if (m->db == 3) { if (!launch_spmv_b3(m, vx, res0, false)) return false; }
+    else {
+      SpmvArgs a; a.m = m; a.x = vx; a.y = res0;
+      if (!launch_spmv(EPI_STORE, a)) return false;
+    }
   }
   if (!launch_bicg_init(n, st, rhs, vx, res0, rk, pk, uk, vx_ini_nonzero)) return false;
   if (!launch_bicg_dots_a(n, st, rk, res0)) return false;
@@ -358,9 +361,15 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
   c->setup_done = false;
   const size_t n_wa = (c->type == CSB_SLES_BICGSTAB) ? 6
     : ((c->type == CSB_SLES_PCG || c->type == CSB_SLES_FCG) ? 5 : 1);
-  if (!c->ad_inv.alloc((size_t)a->n_rows)) return;
-  if (!launch_ad_inv(a->n_rows, a->d_val.p, c->ad_inv.p)) return;
-  if (!c->work.alloc(n_wa * work_stride_of((size_t)a->n_cols_ext))) return;
+  if (a->db != 1 && c->type != CSB_SLES_BICGSTAB) {
+    set_error("csb_sles_it_setup: block matrices (db %d) are solved with CSB_SLES_BICGSTAB "
+              "on this path", a->db);
+    return;
+  }
+  if (!c->ad_inv.alloc((size_t)a->n_rows*a->db)) return;
+  if (a->db == 1) { if (!launch_ad_inv(a->n_rows, a->d_val.p, c->ad_inv.p)) return; }
+  else if (!launch_ad_inv_block(a->n_rows, a->db, a->d_val.p, c->ad_inv.p)) return;
+  if (!c->work.alloc(n_wa * work_stride_of((size_t)a->n_cols_ext*a->db))) return;
   if (!c->st.alloc(1)) return;
   if (c->h_st == nullptr)
     if (!CSB_CUDA(cudaMallocHost((void **)&c->h_st, sizeof(ItState)))) return;
@@ -424,9 +433,9 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
   double t0 = wall();
   const bool ini = (vx_ini == vx);
   StagedVec s_rhs, s_vx;
-  if (!s_rhs.init(const_cast<double *>(rhs), (size_t)a->n_rows, true, c->stage_rhs))
+  if (!s_rhs.init(const_cast<double *>(rhs), (size_t)a->n_rows*a->db, true, c->stage_rhs))
     return CSB_SLES_BREAKDOWN;
-  if (!s_vx.init(vx, (size_t)a->n_cols_ext, ini, c->stage_vx)) return CSB_SLES_BREAKDOWN;
+  if (!s_vx.init(vx, (size_t)a->n_cols_ext*a->db, ini, c->stage_vx)) return CSB_SLES_BREAKDOWN;
 
   bool ok = false;
   switch (c->type) {
@@ -476,7 +485,7 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
 
   if (!CSB_CUDA(cudaMemcpyAsync(c->h_st, c->st.p, sizeof(ItState), cudaMemcpyDeviceToHost,
                                 cx.stream))) return CSB_SLES_BREAKDOWN;
-  if (!s_vx.copy_back((size_t)a->n_rows)) return CSB_SLES_BREAKDOWN;
+  if (!s_vx.copy_back((size_t)a->n_rows*a->db)) return CSB_SLES_BREAKDOWN;
   if (!CSB_CUDA(cudaStreamSynchronize(cx.stream))) return CSB_SLES_BREAKDOWN;
 
   int cvg = c->h_st->cvg;
@@ -902,6 +911,11 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
   l0->m = a;
   l0->halo = a->halo;
   mg->levels.push_back(l0);
+  if (a->db != 1) {
+    set_error("csb_multigrid_setup: block matrices (db %d) are not handled by the multigrid "
+              "path yet", a->db);
+    return;
+  }
   mg->a = a;
 
   /* global row counts drive the stop criteria (cs_grid.cpp:1364-1374) */

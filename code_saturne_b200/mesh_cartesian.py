@@ -360,3 +360,32 @@ def cube_poisson_local(N: int, n_ranks: int, rank: int, bc: str = "neumann",
     halo = HaloDesc(n_local_elts=n, c_domain_rank=c_domain_rank, index=index,
                     send_index=np.array(send_index, dtype=np.int32), send_list=send_list)
     return s, halo, gids
+
+
+# --------------------------------------------------------------------------- config 4
+
+def cube_block3_convection_diffusion(N: int, seed: int = 1234):
+    """Non-symmetric 3x3 block-diagonal system on the hex cube (BASELINE config 4 in the
+    small: velocity convection-diffusion).  Extra-diagonal entries are scalars
+    `xa = -h +- 0.5*phi_f` (upwind-like, two values per face => non-symmetric), diagonal
+    blocks are `(sum of -xa + eps) I + small dense coupling` (diagonally dominant).
+    Returns (row_index, col_id, d_val[n,3,3], x_val, rhs[3n])."""
+    s = cube_poisson(N, "dirichlet", with_mesh=False)
+    n = s.n_rows
+    ri = s.row_index.astype(np.int64)
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(ri))
+    cols = s.col_id.astype(np.int64)
+    h = 1.0 / N
+    lo, hi = np.minimum(rows, cols), np.maximum(rows, cols)
+    phi = 0.6 * h * np.cos(0.37 * lo + 0.11 * hi)          # face mass flux, same for both sides
+    x_val = -h + np.where(cols > rows, 0.5, -0.5) * phi
+    row_sum = np.zeros(n)
+    np.add.at(row_sum, rows, -x_val)
+    rng = np.random.default_rng(seed)
+    d_val = np.zeros((n, 3, 3))
+    for k in range(3):
+        d_val[:, k, k] = row_sum + (0.05 + 0.02 * k) * h + (6 - np.diff(ri)) * 2.0 * h
+    d_val += 0.02 * h * rng.standard_normal((n, 3, 3))
+    g = np.arange(3 * n, dtype=np.float64)
+    rhs = np.sin(0.013 * g + 0.4) * h ** 3
+    return s.row_index, s.col_id, d_val, x_val, rhs

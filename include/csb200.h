@@ -105,6 +105,22 @@ csb_matrix_t *csb_matrix_create_msr(csb_lnum_t         n_rows,
                                     const csb_real_t  *x_val,
                                     int                symmetric);
 
+/* MSR with db_size x db_size diagonal blocks and scalar extra-diagonal entries (fill type
+   CS_MATRIX_BLOCK_D: cs_matrix_transfer_coefficients_msr with db_size = 3, eb_size = 1; the
+   velocity systems).  d_val: n_rows*db_size*db_size, row-major blocks; vectors hold db_size
+   values per row.  SpMV = _b_mat_vec_p_l_msr_3 (src/alge/cs_matrix_spmv.cpp:2394-2455);
+   solver on such matrices: CSB_SLES_BICGSTAB with the point-Jacobi preconditioner of
+   cs_sles_pc.cpp:383-388.  db_size 1 and 3. */
+csb_matrix_t *csb_matrix_create_msr_block(csb_lnum_t         n_rows,
+                                          csb_lnum_t         n_cols_ext,
+                                          int                db_size,
+                                          const csb_lnum_t  *row_index,
+                                          const csb_lnum_t  *col_id,
+                                          const csb_real_t  *d_val,
+                                          const csb_real_t  *x_val,
+                                          int                symmetric);
+int  csb_matrix_get_diag_block_size(const csb_matrix_t *m);
+
 /* CS_MATRIX_CSR (cs_matrix_struct_csr_t, src/alge/cs_matrix_priv.h:143-160): the
    diagonal is an ordinary entry of (row_index, col_id, val).  csb_matrix_vector_multiply
    on such a matrix sums every row in CSR order like _mat_vec_p_l_csr

@@ -478,23 +478,65 @@ ora_jacobi(int n_rows, const int *row_index, const int *col_id,
 }
 
 /*----------------------------------------------------------------------------
+ * Block-diagonal MSR SpMV, 3x3 blocks: _b_mat_vec_p_l_msr_3
+ * (src/alge/cs_matrix_spmv.cpp:2394-2455) with _dense_3_3_ax (:590-607):
+ * y_i = D_i.x_i first, then += e_ij * x_j in CSR order, per component.
+ *----------------------------------------------------------------------------*/
+
+void
+ora_spmv_msr_b3(int n_rows, const int *row_index, const int *col_id,
+                const double *d_val, const double *x_val, int exclude_diag,
+                const double *x, double *y)
+{
+  for (int ii = 0; ii < n_rows; ii++) {
+    const int *restrict c = col_id + row_index[ii];
+    const double *restrict m_row = x_val + row_index[ii];
+    const int n_cols = row_index[ii+1] - row_index[ii];
+    if (!exclude_diag) {
+      const double *a = d_val;
+      y[ii*3]     =   a[ii*9]         * x[ii*3]
+                    + a[ii*9 + 1]     * x[ii*3 + 1]
+                    + a[ii*9 + 2]     * x[ii*3 + 2];
+      y[ii*3 + 1] =   a[ii*9 + 3]     * x[ii*3]
+                    + a[ii*9 + 3 + 1] * x[ii*3 + 1]
+                    + a[ii*9 + 3 + 2] * x[ii*3 + 2];
+      y[ii*3 + 2] =   a[ii*9 + 6]     * x[ii*3]
+                    + a[ii*9 + 6 + 1] * x[ii*3 + 1]
+                    + a[ii*9 + 6 + 2] * x[ii*3 + 2];
+    }
+    else {
+      for (int kk = 0; kk < 3; kk++) y[ii*3 + kk] = 0.;
+    }
+    for (int jj = 0; jj < n_cols; jj++)
+      for (int kk = 0; kk < 3; kk++)
+        y[ii*3 + kk] += (m_row[jj]*x[c[jj]*3 + kk]);
+  }
+}
+
+/*----------------------------------------------------------------------------
  * BiCGStab + Jacobi preconditioner: _bi_cgstab (src/alge/cs_sles_it.cpp:2693-2880)
  * with pc_apply = x*ad_inv (src/alge/cs_sles_pc.cpp:502-535).
+ * db = 1 (scalar) or 3 (block-diagonal matrix: vectors of n_rows*3, point
+ * Jacobi ad_inv[i] = 1/ad[i*db + i%db], cs_sles_pc.cpp:383-388).
  *----------------------------------------------------------------------------*/
 
 int
-ora_bicgstab(int n_rows, const int *row_index, const int *col_id,
-             const double *d_val, const double *x_val,
-             int n_max_iter, double precision, double r_norm,
-             const double *rhs, double *vx, int use_vx_ini,
-             double *out, double *history, int history_size)
+ora_bicgstab_b(int n_rows, int db, const int *row_index, const int *col_id,
+               const double *d_val, const double *x_val,
+               int n_max_iter, double precision, double r_norm,
+               const double *rhs, double *vx, int use_vx_ini,
+               double *out, double *history, int history_size)
 {
-  const int n = n_rows;
+  const int n = n_rows*db;
   const double epzero = 1.e-30;   /* _epzero, cs_sles_it.cpp:169 */
   double *res0 = malloc(sizeof(double)*n*7);
   double *rk = res0 + n, *pk = res0 + 2*n, *zk = res0 + 3*n;
   double *uk = res0 + 4*n, *vk = res0 + 5*n, *ad_inv = res0 + 6*n;
-  for (int i = 0; i < n; i++) ad_inv[i] = 1.0 / d_val[i];
+  for (int i = 0; i < n; i++) ad_inv[i] = 1.0 / d_val[(size_t)i*db + (i % db)];
+
+#define ORA_SPMV(xx, yy) \
+  do { if (db == 1) ora_spmv_msr(n_rows, row_index, col_id, d_val, x_val, 0, xx, yy); \
+       else ora_spmv_msr_b3(n_rows, row_index, col_id, d_val, x_val, 0, xx, yy); } while (0)
 
   ora_cvg_t cv = {precision, r_norm, -1, n_max_iter, 0, -1,
                   history, history_size, 0};
@@ -506,7 +548,7 @@ ora_bicgstab(int n_rows, const int *row_index, const int *col_id,
   for (int ii = 0; ii < n; ii++) { pk[ii] = 0.0; uk[ii] = 0.0; }
 
   if (use_vx_ini) {
-    ora_spmv_msr(n, row_index, col_id, d_val, x_val, 0, vx, res0);
+    ORA_SPMV(vx, res0);
     for (int ii = 0; ii < n; ii++) {
       res0[ii] = -res0[ii] + rhs[ii];
       rk[ii] = res0[ii];
@@ -545,7 +587,7 @@ ora_bicgstab(int n_rows, const int *row_index, const int *col_id,
       pk[ii] = rk[ii] + omega*(pk[ii] - alpha*uk[ii]);
     for (int ii = 0; ii < n; ii++)
       zk[ii] = pk[ii] * ad_inv[ii];
-    ora_spmv_msr(n, row_index, col_id, d_val, x_val, 0, zk, uk);
+    ORA_SPMV(zk, uk);
     ukres0 = ora_dot(n, uk, res0);
     gamma = beta / ukres0;
     for (int ii = 0; ii < n; ii++) {
@@ -554,7 +596,7 @@ ora_bicgstab(int n_rows, const int *row_index, const int *col_id,
     }
     for (int ii = 0; ii < n; ii++)
       zk[ii] = rk[ii] * ad_inv[ii];
-    ora_spmv_msr(n, row_index, col_id, d_val, x_val, 0, zk, vk);
+    ORA_SPMV(zk, vk);
     ora_dot_xx_xy(n, vk, rk, &ro_1, &ro_0);
     if (fabs(ro_1) < epzero) { cvg = ORA_BREAKDOWN; break; }
     double d_ro_1 = (fabs(ro_1) > DBL_MIN) ? 1. / ro_1 : 0.;
@@ -564,6 +606,7 @@ ora_bicgstab(int n_rows, const int *row_index, const int *col_id,
       rk[ii] -= (alpha * vk[ii]);
     }
   }
+#undef ORA_SPMV
 
   out[0] = cv.n_iterations;
   out[1] = cv.residual;
@@ -571,6 +614,17 @@ ora_bicgstab(int n_rows, const int *row_index, const int *col_id,
   out[3] = cv.history_n;
   free(res0);
   return cvg;
+}
+
+int
+ora_bicgstab(int n_rows, const int *row_index, const int *col_id,
+             const double *d_val, const double *x_val,
+             int n_max_iter, double precision, double r_norm,
+             const double *rhs, double *vx, int use_vx_ini,
+             double *out, double *history, int history_size)
+{
+  return ora_bicgstab_b(n_rows, 1, row_index, col_id, d_val, x_val, n_max_iter, precision,
+                        r_norm, rhs, vx, use_vx_ini, out, history, history_size);
 }
 
 /*============================================================================

@@ -110,6 +110,28 @@ class Oracle:
                               C.c_int(int(exclude_diag)), _dp(x), _dp(y))
         return y
 
+    def spmv_b3(self, ri, ci, d, x_val, x, exclude_diag=False):
+        ri, ci, d, x_val, x = _i32(ri), _i32(ci), _f64(d), _f64(x_val), _f64(x)
+        n = len(ri) - 1
+        y = np.empty(3 * n)
+        self.lib.ora_spmv_msr_b3(C.c_int(n), _ip(ri), _ip(ci), _dp(d), _dp(x_val),
+                                 C.c_int(int(exclude_diag)), _dp(x), _dp(y))
+        return y
+
+    def bicgstab_b3(self, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0=None):
+        ri, ci, d, xv, rhs = _i32(ri), _i32(ci), _f64(d), _f64(xv), _f64(rhs)
+        n = len(ri) - 1
+        vx = np.zeros(3 * n) if vx0 is None else _f64(vx0).copy()
+        out = np.zeros(4)
+        hist = np.zeros(n_max_iter + 8)
+        cvg = self.lib.ora_bicgstab_b(C.c_int(n), C.c_int(3), _ip(ri), _ip(ci), _dp(d), _dp(xv),
+                                      C.c_int(n_max_iter), C.c_double(precision),
+                                      C.c_double(r_norm), _dp(rhs), _dp(vx),
+                                      C.c_int(0 if vx0 is None else 1), _dp(out), _dp(hist),
+                                      C.c_int(len(hist)))
+        return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], initial_residual=out[2],
+                    history=hist[:int(out[3])].copy(), vx=vx)
+
     def spmv_csr(self, ri, ci, val, x, exclude_diag=False):
         ri, ci, val, x = _i32(ri), _i32(ci), _f64(val), _f64(x)
         y = np.empty(len(ri) - 1)
@@ -262,6 +284,14 @@ class RefLib:
             self.lib.csref_system_set_mesh(h, C.c_int(s.n_faces), _ip(fc), _ip(c2f), _sp(sgn),
                                            _dp(cen), _dp(vol), _dp(fun), _dp(fs))
         return h
+
+    def system_block(self, n_rows, db, ri, ci, d_val, x_val, symmetric=False):
+        """MSR matrix with db x db diagonal blocks (d_val: n_rows*db*db) built by the reference."""
+        ri, ci, d, xv = _i32(ri), _i32(ci), _f64(d_val), _f64(x_val)
+        self.lib.csref_system_create_block.restype = C.c_void_p
+        return C.c_void_p(self.lib.csref_system_create_block(
+            C.c_int(n_rows), C.c_int(db), _ip(ri), _ip(ci), _dp(d), _dp(xv),
+            C.c_int(int(symmetric))))
 
     def system_csr(self, n_rows, edges, da, xa, symmetric=True):
         """CS_MATRIX_CSR built by the reference from an edge list; returns (handle,

@@ -154,6 +154,43 @@ csref_system_create(int            n_rows,
   return s;
 }
 
+/* MSR matrix with db x db diagonal blocks and scalar extra-diagonal entries
+   (cs_matrix_transfer_coefficients_msr with db_size = db, eb_size = 1; fill type
+   CS_MATRIX_BLOCK_D).  d_val: n_rows*db*db, row-major blocks. */
+void *
+csref_system_create_block(int            n_rows,
+                          int            db,
+                          const int     *row_index,
+                          const int     *col_id,
+                          const double  *d_val,
+                          const double  *x_val,
+                          int            symmetric)
+{
+  ref_system *s = new ref_system;
+  s->n_rows = n_rows;
+  s->symmetric = (symmetric != 0);
+  const cs_lnum_t nnz = row_index[n_rows];
+
+  CS_MALLOC(s->row_index, n_rows+1, cs_lnum_t);
+  CS_MALLOC(s->col_id, (nnz > 0) ? nnz : 1, cs_lnum_t);
+  memcpy(s->row_index, row_index, sizeof(cs_lnum_t)*(n_rows+1));
+  memcpy(s->col_id, col_id, sizeof(cs_lnum_t)*nnz);
+
+  s->ms = cs_matrix_structure_create_msr_shared(true, n_rows, n_rows,
+                                                s->row_index, s->col_id,
+                                                nullptr, nullptr);
+  s->m = cs_matrix_create(s->ms);
+
+  cs_real_t *d, *x;
+  CS_MALLOC(d, (size_t)n_rows*db*db, cs_real_t);
+  CS_MALLOC(x, (nnz > 0) ? nnz : 1, cs_real_t);
+  memcpy(d, d_val, sizeof(cs_real_t)*(size_t)n_rows*db*db);
+  memcpy(x, x_val, sizeof(cs_real_t)*nnz);
+  cs_matrix_transfer_coefficients_msr(s->m, s->symmetric, db, 1,
+                                      s->row_index, s->col_id, &d, &x);
+  return s;
+}
+
 /* CS_MATRIX_CSR from an edge list (the reference's native way to a CSR matrix:
    cs_matrix_structure_create + cs_matrix_set_coefficients, cs_matrix.cpp:4328, :5315).
    xa: one value per edge (symmetric) or two (lower-to-upper, upper-to-lower). */

@@ -481,3 +481,52 @@ def test_csr_matrix_solves_like_its_msr_split(csb, oracle):
     y = m.vector_multiply(o["vx"])
     assert np.allclose(y, s.rhs, rtol=0, atol=2e-12 * r_norm)
     c.destroy(); m.destroy()
+
+
+# --------------------------------------------------------------------------- 3x3 blocks
+
+@pytest.mark.parametrize("N", [6, 10, 14])
+def test_block3_spmv_and_bicgstab_match_reference_golden(csb, N):
+    """Config 4 in the small: CS_MATRIX_BLOCK_D matrix (3x3 diagonal blocks, non-symmetric
+    scalar extra-diagonal), SpMV bit-exact vs _b_mat_vec_p_l_msr_3 and BiCGStab + point
+    Jacobi vs _bi_cgstab of the reference build (tests/golden/block3_*.npz)."""
+    from code_saturne_b200.mesh_cartesian import cube_block3_convection_diffusion
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"block3_N{N}.npz"))
+    ri, ci, d, xv, rhs = cube_block3_convection_diffusion(N)
+    n = len(ri) - 1
+    m = csb.Matrix.from_block(n, 3, ri, ci, d.ravel(), xv)
+    assert np.array_equal(m.vector_multiply(g["x"]), g["y"])
+    assert np.array_equal(m.vector_multiply(g["x"], exclude_diag=True), g["y_exdiag"])
+    c = csb.SlesIt(csb.SlesItType.BICGSTAB, 1000)
+    r_norm = float(g["r_norm"])
+    r = c.solve(m, rhs, 1e-10, r_norm)
+    assert int(r["cvg"]) == int(g["bicg_cvg"]) == 1
+    assert abs(r["n_iter"] - int(g["bicg_n_iter"])) <= 2
+    k = min(len(r["history"]) - 1, len(g["bicg_history"]), 6)
+    assert np.allclose(r["history"][1:1 + k], g["bicg_history"][:k], rtol=1e-8, atol=0)
+    assert rel_l2(r["vx"], g["bicg_vx"]) <= 1e-7          # both stopped at 1e-10
+    res = np.linalg.norm(rhs - m.vector_multiply(r["vx"].copy()))
+    assert res <= 1.05e-10 * r_norm
+    c.destroy(); m.destroy()
+
+
+def test_block3_tight_tolerance_and_warm_start(csb, oracle):
+    from code_saturne_b200.mesh_cartesian import cube_block3_convection_diffusion
+    ri, ci, d, xv, rhs = cube_block3_convection_diffusion(20, seed=5)
+    n = len(ri) - 1
+    rhs = rhs * 1e5      # keep |vk.vk| away from the absolute breakdown threshold (1e-30,
+    #                      cs_sles_it.cpp:169) when converging to 1e-13
+    r_norm = float(np.linalg.norm(rhs))
+    o = oracle.bicgstab_b3(ri, ci, d.ravel(), xv, rhs, 2000, 1e-13, r_norm)
+    m = csb.Matrix.from_block(n, 3, ri, ci, d.ravel(), xv)
+    c = csb.SlesIt(csb.SlesItType.BICGSTAB, 2000)
+    r = c.solve(m, rhs, 1e-13, r_norm)
+    assert int(r["cvg"]) == 1 == o["cvg"] and abs(r["n_iter"] - o["n_iter"]) <= 2
+    assert rel_l2(r["vx"], o["vx"]) <= SOL_TOL
+    w = c.solve(m, rhs, 1e-10, r_norm, vx=o["vx"].copy(), use_vx_ini=True)
+    assert int(w["cvg"]) == 1 and w["n_iter"] <= 1
+    # only BiCGStab takes block matrices on this path: loud refusal otherwise
+    p = csb.SlesIt(csb.SlesItType.PCG, 10)
+    with pytest.raises(Exception):
+        p.solve(m, rhs, 1e-8, r_norm)
+    p.destroy(); c.destroy(); m.destroy()

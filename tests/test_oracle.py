@@ -169,3 +169,37 @@ def test_oracle_csr_vs_reference_direct(oracle, reflib):
         assert np.array_equal(reflib.spmv(h, x, s.n_rows, True),
                               oracle.spmv_csr(ri, ci, val, x, exclude_diag=True))
         reflib.destroy(h)
+
+
+@pytest.mark.parametrize("N", [6, 10, 14])
+def test_oracle_block3_matches_golden(oracle, N):
+    """3x3 block-diagonal SpMV and BiCGStab restatements against the reference build's
+    outputs (tests/golden/make_golden_block3.py): bit-exact."""
+    from code_saturne_b200.mesh_cartesian import cube_block3_convection_diffusion
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"block3_N{N}.npz"))
+    ri, ci, d, xv, rhs = cube_block3_convection_diffusion(N)
+    assert np.array_equal(oracle.spmv_b3(ri, ci, d.ravel(), xv, g["x"]), g["y"])
+    assert np.array_equal(oracle.spmv_b3(ri, ci, d.ravel(), xv, g["x"], True), g["y_exdiag"])
+    o = oracle.bicgstab_b3(ri, ci, d.ravel(), xv, rhs, 1000, 1e-10, float(g["r_norm"]))
+    assert (o["cvg"], o["n_iter"], o["residual"]) \
+        == (int(g["bicg_cvg"]), int(g["bicg_n_iter"]), float(g["bicg_residual"]))
+    assert np.array_equal(o["vx"], g["bicg_vx"])
+
+
+def test_oracle_block3_vs_reference_direct(oracle, reflib):
+    import ctypes as C
+    from code_saturne_b200.mesh_cartesian import cube_block3_convection_diffusion
+    from oracle.pyoracle import _dp
+    ri, ci, d, xv, rhs = cube_block3_convection_diffusion(9, seed=7)
+    n = len(ri) - 1
+    h = reflib.system_block(n, 3, ri, ci, d.ravel(), xv, False)
+    x = np.sin(0.3 * np.arange(3 * n))
+    y = np.empty(3 * n)
+    reflib.lib.csref_spmv(h, C.c_int(0), _dp(x.copy()), _dp(y))
+    assert np.array_equal(y, oracle.spmv_b3(ri, ci, d.ravel(), xv, x))
+    r_norm = float(np.linalg.norm(rhs))
+    a = reflib.sles_it(h, reflib.BICGSTAB, rhs, 7, 1e-12, r_norm, vx0=0.1 * x)
+    b = oracle.bicgstab_b3(ri, ci, d.ravel(), xv, rhs, 7, 1e-12, r_norm, vx0=0.1 * x)
+    assert (a["cvg"], a["n_iter"], a["residual"]) == (b["cvg"], b["n_iter"], b["residual"])
+    assert np.array_equal(a["vx"], b["vx"])
+    reflib.destroy(h)
