@@ -44,6 +44,7 @@ class ConvergenceState(enum.IntEnum):
 class SlesItType(enum.IntEnum):
     PCG = 0
     FCG = 1
+    IPCG = 2
     JACOBI = 3
     BICGSTAB = 4
 

@@ -637,7 +637,8 @@ struct EpiResidual {
  * Elementwise phases over chunks of ROW_CH rows, same producer / consumer
  * split: the F::NV input vectors of a chunk are bulk-copied into a stage; a
  * consumer lane handles rows t and t + ROW_CH/2 of the chunk:
- * F::st(row, op, acc) with op[v*ROW_CH] = input vector v at this row.
+ * F::st(row, op, acc) with op[v*ROW_CH] = input vector v at this row; acc_out[0..3]
+ * receives this thread's partial sums.
  *--------------------------------------------------------------------------*/
 
 template <bool SINGLE, class F>
@@ -650,7 +651,7 @@ __device__ __noinline__ void row_phase(int n, unsigned char *s_raw, const F f, d
   const int n_chunks = (n + ROW_CH - 1) / ROW_CH;
   const int n_my = (first < n_chunks) ? (n_chunks - first + step - 1) / step : 0;
   const unsigned base = sv.pipe->base;
-  double acc = 0.;
+  double acc[4] = {0., 0., 0., 0.};
 
   if (n_my > 0) {
     if (tid >= NWC*32) {
@@ -690,7 +691,9 @@ __device__ __noinline__ void row_phase(int n, unsigned char *s_raw, const F f, d
     if (tid == 0) sv.pipe->base = base + (unsigned)n_my;
     __syncthreads();
   }
-  if (acc_out != nullptr) *acc_out = acc;
+  if (acc_out != nullptr) {
+    acc_out[0] = acc[0]; acc_out[1] = acc[1]; acc_out[2] = acc[2]; acc_out[3] = acc[3];
+  }
 }
 
 /* vx = 0, rk = -rhs, dk = rk * ad_inv                     (:1502-1516, vx = 0) */
@@ -699,7 +702,7 @@ struct RowInitZero {
   const double *rhs, *ad_inv;
   double *vx, *rk, *dk;
   __device__ __forceinline__ const double *src(int v) const { return (v == 0) ? rhs : ad_inv; }
-  __device__ __forceinline__ void st(int i, const double *op, double &) const
+  __device__ __forceinline__ void st(int i, const double *op, double (&)[4]) const
   {
     vx[i] = 0;
     const double rr = -op[0];
@@ -716,13 +719,13 @@ struct RowFirstUpdate {
   double *rk, *vx, *gk;
   __device__ __forceinline__ const double *src(int v) const
   { return (v == 0) ? dk : (v == 1) ? zk : (v == 2) ? rk : (v == 3) ? vx : ad_inv; }
-  __device__ __forceinline__ void st(int i, const double *op, double &acc) const
+  __device__ __forceinline__ void st(int i, const double *op, double (&acc)[4]) const
   {
     vx[i] = op[3*ROW_CH] + (alpha * op[0]);
     const double rr = op[2*ROW_CH] + (alpha * op[ROW_CH]);
     rk[i] = rr;
     gk[i] = rr * op[4*ROW_CH];
-    acc += rr*rr;
+    acc[0] += rr*rr;
   }
 };
 
@@ -737,7 +740,7 @@ struct RowUpdate {
     return (v == 0) ? gk : (v == 1) ? dk : (v == 2) ? vx : (v == 3) ? sk : (v == 4) ? zk
          : (v == 5) ? rk : ad_inv;
   }
-  __device__ __forceinline__ void st(int i, const double *op, double &) const
+  __device__ __forceinline__ void st(int i, const double *op, double (&)[4]) const
   {
     const double d = op[0] + (beta * op[ROW_CH]);
     dk[i] = d;
@@ -758,7 +761,7 @@ struct RowLastUpdate {
   double *vx;
   __device__ __forceinline__ const double *src(int v) const
   { return (v == 0) ? gk : (v == 1) ? dk : vx; }
-  __device__ __forceinline__ void st(int i, const double *op, double &) const
+  __device__ __forceinline__ void st(int i, const double *op, double (&)[4]) const
   {
     const double d = op[0] + (beta * op[ROW_CH]);
     vx[i] = op[2*ROW_CH] + alpha * d;
@@ -942,13 +945,13 @@ __device__ __noinline__ PcgResult pcg_run(const MgLevelDesc &L, const double *rh
     const double d_ro_1 = (fabs(ro_1) > DBL_MIN) ? 1. / ro_1 : 0.;
     alpha = - ro_0 * d_ro_1;
     rk_gkm1 = ro_0;
-    double w[1] = {0.};
+    double w[4] = {0., 0., 0., 0.};
     {
       RowFirstUpdate f;                                /* :1550-1558 */
       f.alpha = alpha; f.dk = dk; f.zk = zk; f.ad_inv = ad_inv; f.rk = rk; f.vx = vx; f.gk = gk;
       row_phase<SINGLE>(n, s_raw, f, w);
     }
-    all_sum<SINGLE, 1>(w, part1, P.barrier, s_red, comm);
+    { double w1[1] = {w[0]}; all_sum<SINGLE, 1>(w1, part1, P.barrier, s_red, comm); w[0] = w1[0]; }
     if (SINGLE) __syncthreads();
     mark(2);
     R.residual = sqrt(w[0]);
@@ -1057,7 +1060,7 @@ struct RowFcgInitZero {
   const double *rhs, *ad_inv;
   double *vx, *rk, *qk, *vk;
   __device__ __forceinline__ const double *src(int v) const { return (v == 0) ? rhs : ad_inv; }
-  __device__ __forceinline__ void st(int i, const double *op, double &) const
+  __device__ __forceinline__ void st(int i, const double *op, double (&)[4]) const
   {
     vx[i] = 0;
     rk[i] = op[0];
@@ -1078,7 +1081,7 @@ struct RowFcgUpdate {
     return (v == 0) ? vk : (v == 1) ? dk : (v == 2) ? vx : (v == 3) ? wk : (v == 4) ? qk
          : (v == 5) ? rk : ad_inv;
   }
-  __device__ __forceinline__ void st(int i, const double *op, double &) const
+  __device__ __forceinline__ void st(int i, const double *op, double (&)[4]) const
   {
     const double d = first ? op[0] : op[0] - gk_rk1 * op[ROW_CH];
     dk[i] = d;
@@ -1188,6 +1191,211 @@ k_fcg_persistent(const MgLevelDesc L, const double *rhs, double *vx, int vx_ini_
   else
     fcg_run<false>(L, rhs, vx, vx_ini_nonzero != 0, n_max_iter, precision, r_norm, P, st,
                    s_raw);
+}
+
+/*--------------------------------------------------------------------------
+ * Inexact-preconditioning CG + Jacobi (_conjugate_gradient_ip,
+ * cs_sles_it.cpp:1016-1203).  Work vectors: rk rkm1 dk gk zk.  Per iteration:
+ * vector phase (gk = rk*ad_inv + 3 dots), vector phase (dk = gk + beta*dk),
+ * SpMV phase (zk = A.dk + 2 dots), vector phase (vx, rkm1, rk).
+ *--------------------------------------------------------------------------*/
+
+/* rk = A.vx - rhs, gk = rk*ad_inv, dk = gk; dots rk.rk, rk.gk            (:1060-1092) */
+struct EpiIpcgInit {
+  static constexpr int NV = 4;
+  const double *d_val, *vx, *rhs, *ad_inv;
+  double *rk, *gk, *dk;
+  __device__ __forceinline__ const double *src(int v) const
+  { return (v == 0) ? d_val : (v == 1) ? vx : (v == 2) ? rhs : ad_inv; }
+  __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&acc)[4]) const
+  {
+    const double rr = (sii + op[0]*op[ST_OP_STRIDE]) - op[2*ST_OP_STRIDE];
+    const double g = rr * op[3*ST_OP_STRIDE];
+    rk[r] = rr; gk[r] = g; dk[r] = g;
+    acc[0] += rr*rr; acc[1] += rr*g;
+  }
+};
+
+struct RowIpcgInitZero {     /* vx = 0, rk = -rhs, gk = dk = rk*ad_inv */
+  static constexpr int NV = 2;
+  const double *rhs, *ad_inv;
+  double *vx, *rk, *gk, *dk;
+  __device__ __forceinline__ const double *src(int v) const { return (v == 0) ? rhs : ad_inv; }
+  __device__ __forceinline__ void st(int i, const double *op, double (&acc)[4]) const
+  {
+    vx[i] = 0;
+    const double rr = -op[0];
+    const double g = rr * op[ROW_CH];
+    rk[i] = rr; gk[i] = g; dk[i] = g;
+    acc[0] += rr*rr; acc[1] += rr*g;
+  }
+};
+
+struct RowIpcgPc {           /* gk = rk*ad_inv; dots rk.rk, rk.gk, rkm1.gk     (:1133-1139) */
+  static constexpr int NV = 3;
+  const double *rk, *ad_inv, *rkm1;
+  double *gk;
+  __device__ __forceinline__ const double *src(int v) const
+  { return (v == 0) ? rk : (v == 1) ? ad_inv : rkm1; }
+  __device__ __forceinline__ void st(int i, const double *op, double (&acc)[4]) const
+  {
+    const double g = op[0] * op[ROW_CH];
+    gk[i] = g;
+    acc[0] += op[0]*op[0]; acc[1] += op[0]*g; acc[2] += g*op[2*ROW_CH];
+  }
+};
+
+struct RowIpcgDir {          /* dk = gk + beta*dk                               (:1158-1160) */
+  static constexpr int NV = 2;
+  double beta;
+  const double *gk;
+  double *dk;
+  __device__ __forceinline__ const double *src(int v) const { return (v == 0) ? gk : dk; }
+  __device__ __forceinline__ void st(int i, const double *op, double (&)[4]) const
+  { dk[i] = op[0] + (beta * op[ROW_CH]); }
+};
+
+struct RowIpcgUpdate {       /* vx += alpha*dk; rkm1 = rk; rk += alpha*zk; dot rk.rk */
+  static constexpr int NV = 4;
+  double alpha;
+  const double *dk, *zk;
+  double *vx, *rk, *rkm1;
+  __device__ __forceinline__ const double *src(int v) const
+  { return (v == 0) ? dk : (v == 1) ? zk : (v == 2) ? vx : rk; }
+  __device__ __forceinline__ void st(int i, const double *op, double (&acc)[4]) const
+  {
+    vx[i] = op[2*ROW_CH] + (alpha * op[0]);
+    rkm1[i] = op[3*ROW_CH];
+    const double rr = op[3*ROW_CH] + (alpha * op[ROW_CH]);
+    rk[i] = rr;
+    acc[0] += rr*rr;
+  }
+};
+
+template <bool SINGLE>
+__device__ __noinline__ PcgResult ipcg_run(const MgLevelDesc &L, const double *rhs, double *vx,
+                             bool vx_ini_nonzero, int n_max_iter, double precision,
+                             double r_norm, const PersistentCommon &P, ItState *st,
+                             unsigned char *s_raw)
+{
+  const int n = L.n_rows;
+  const size_t ws = P.work_stride;
+  double *rk = P.work, *rkm1 = P.work + ws, *dk = P.work + 2*ws, *gk = P.work + 3*ws,
+         *zk = P.work + 4*ws;
+  const bool rec = (st != nullptr) && (SINGLE || blockIdx.x == 0) && threadIdx.x == 0;
+  double *s_red = (double *)s_raw;
+  const CommDev *comm = P.comm;
+
+  PcgResult R;
+  R.n_iter = 0; R.cvg = CSB_SLES_ITERATING; R.residual = -1.; R.initial_residual = -1.;
+  if (rec) st->n_hist = 0;
+  double v[4] = {0., 0., 0., 0.};
+  double alpha = 0., beta = 0., rk_gk_m1 = 0.;
+  /* three regions of per-CTA partials: two reductions that follow each other without a
+     grid barrier in between never share one (a fast CTA would overwrite what a slow one
+     is still reading) */
+  double *part0 = P.partials, *part1 = P.partials + 4*(size_t)gridDim.x,
+         *part2 = P.partials + 8*(size_t)gridDim.x;
+
+  auto spmv_dk = [&]() {      /* zk = A.dk; v[1] = rk.dk, v[2] = dk.zk */
+    const double *gh = halo_exchange<SINGLE>(L, dk);
+    EpiDots f;
+    f.d_val = L.d_val; f.p = dk; f.rk = rk; f.out = zk;
+    spmv_phase<SINGLE>(L, dk, gh, s_raw, f, v);
+    all_sum<SINGLE, 4>(v, part0, P.barrier, s_red, comm);
+  };
+  auto update = [&]() {       /* v[0] = rk.rk after the update */
+    RowIpcgUpdate f;
+    f.alpha = alpha; f.dk = dk; f.zk = zk; f.vx = vx; f.rk = rk; f.rkm1 = rkm1;
+    row_phase<SINGLE>(n, s_raw, f, v);
+  };
+
+  if (vx_ini_nonzero) {
+    const double *gh = halo_exchange<SINGLE>(L, vx);
+    EpiIpcgInit f;
+    f.d_val = L.d_val; f.vx = vx; f.rhs = rhs; f.ad_inv = L.ad_inv; f.rk = rk; f.gk = gk; f.dk = dk;
+    spmv_phase<SINGLE>(L, vx, gh, s_raw, f, v);
+  }
+  else {
+    RowIpcgInitZero f;
+    f.rhs = rhs; f.ad_inv = L.ad_inv; f.vx = vx; f.rk = rk; f.gk = gk; f.dk = dk;
+    row_phase<SINGLE>(n, s_raw, f, v);
+  }
+  all_sum<SINGLE, 4>(v, part2, P.barrier, s_red, comm);
+  R.residual = sqrt(v[0]);
+  rk_gk_m1 = v[1];
+  R.initial_residual = R.residual;
+  R.cvg = it_cvg_eval(precision, r_norm, n_max_iter, R.initial_residual, 0, R.residual);
+  if (rec && st->n_hist < HIST_MAX) st->hist[st->n_hist++] = R.residual;
+
+  if (R.cvg == CSB_SLES_ITERATING) {
+    R.n_iter = 1;
+    spmv_dk();
+    const double d_ro_1 = (fabs(v[2]) > DBL_MIN) ? 1. / v[2] : 0.;
+    alpha = - v[1] * d_ro_1;
+    update();
+    all_sum<SINGLE, 4>(v, part1, P.barrier, s_red, comm);
+    R.residual = sqrt(v[0]);
+    R.cvg = it_cvg_eval(precision, r_norm, n_max_iter, R.initial_residual, 1, R.residual);
+    if (rec && st->n_hist < HIST_MAX) st->hist[st->n_hist++] = R.residual;
+  }
+
+  while (R.cvg == CSB_SLES_ITERATING) {
+    {
+      RowIpcgPc f;
+      f.rk = rk; f.ad_inv = L.ad_inv; f.rkm1 = rkm1; f.gk = gk;
+      row_phase<SINGLE>(n, s_raw, f, v);
+    }
+    all_sum<SINGLE, 4>(v, part2, P.barrier, s_red, comm);
+    const double rk_gk = v[1], rkm1_gk = v[2];
+    R.residual = sqrt(v[0]);
+    if (R.n_iter > 1) {
+      R.cvg = it_cvg_eval(precision, r_norm, n_max_iter, R.initial_residual, R.n_iter,
+                          R.residual);
+      if (rec && st->n_hist < HIST_MAX) st->hist[st->n_hist++] = R.residual;
+    }
+    if (R.cvg != CSB_SLES_ITERATING) break;
+    R.n_iter += 1;
+    beta = (fabs(rk_gk_m1) > DBL_MIN) ? (rk_gk - rkm1_gk) / rk_gk_m1 : 0.;
+    rk_gk_m1 = rk_gk;
+    {
+      RowIpcgDir f;
+      f.beta = beta; f.gk = gk; f.dk = dk;
+      row_phase<SINGLE>(n, s_raw, f, nullptr);
+    }
+    phase_barrier<SINGLE>(P.barrier);
+    spmv_dk();
+    const double d_ro_1 = (fabs(v[2]) > DBL_MIN) ? 1. / v[2] : 0.;
+    alpha = - v[1] * d_ro_1;
+    update();
+    phase_barrier<SINGLE>(P.barrier);
+  }
+
+  if (rec) {
+    st->precision = precision; st->r_norm = r_norm;
+    st->residual = R.residual; st->initial_residual = R.initial_residual;
+    st->n_iter = R.n_iter; st->n_max_iter = n_max_iter; st->cvg = R.cvg;
+    st->alpha = alpha; st->beta = beta; st->ro_0 = 0.; st->ro_1 = 0.; st->rk_gkm1 = rk_gk_m1;
+  }
+  return R;
+}
+
+__global__ void __launch_bounds__(PT, CSB_MIN_CTAS)
+k_ipcg_persistent(const MgLevelDesc L, const double *rhs, double *vx, int vx_ini_nonzero,
+                  int n_max_iter, double precision, double r_norm,
+                  const PersistentCommon P, ItState *st, int single)
+{
+  unsigned char *s_raw = s_raw_base;
+  pipe_init(s_raw);
+  halo_counts_init(&L, 1, P.barrier);
+  if (single) {
+    if (blockIdx.x == 0)
+      ipcg_run<true>(L, rhs, vx, vx_ini_nonzero != 0, n_max_iter, precision, r_norm, P, st,
+                     s_raw);
+  }
+  else
+    ipcg_run<false>(L, rhs, vx, vx_ini_nonzero != 0, n_max_iter, precision, r_norm, P, st,
+                    s_raw);
 }
 
 /*--------------------------------------------------------------------------
@@ -1480,12 +1688,15 @@ int persistent_grid(int which, size_t smem)
     return 0;
   }
   const void *k = (which == 0) ? (const void *)k_pcg_persistent
-                : (which == 2) ? (const void *)k_fcg_persistent : (const void *)k_mg_persistent;
+                : (which == 2) ? (const void *)k_fcg_persistent
+                : (which == 3) ? (const void *)k_ipcg_persistent : (const void *)k_mg_persistent;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   if (which == 0)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pcg_persistent, PT, smem);
   else if (which == 2)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fcg_persistent, PT, smem);
+  else if (which == 3)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ipcg_persistent, PT, smem);
   else
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mg_persistent, PT, smem);
   if (occ < 1) {
@@ -1574,20 +1785,20 @@ bool launch_pcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
 bool launch_fcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
                            bool vx_ini_nonzero, int n_max_iter, double precision,
                            double r_norm, const PersistentCommon &P, ItState *st,
-                           int grid, size_t smem, bool single, bool cooperative)
+                           int grid, size_t smem, bool single, bool cooperative, bool ipcg)
 {
   int ini = vx_ini_nonzero ? 1 : 0;
   int sgl = single ? 1 : 0;
   void *args[] = {(void *)&L, (void *)&rhs, (void *)&vx, (void *)&ini, (void *)&n_max_iter,
                   (void *)&precision, (void *)&r_norm, (void *)&P, (void *)&st, (void *)&sgl};
+  void *kern = ipcg ? (void *)k_ipcg_persistent : (void *)k_fcg_persistent;
   cudaError_t e = cooperative
-    ? cudaLaunchCooperativeKernel((void *)k_fcg_persistent, dim3(grid), dim3(PT), args, smem,
-                                  ctx().stream)
-    : cudaLaunchKernel((void *)k_fcg_persistent, dim3(grid), dim3(PT), args, smem,
-                       ctx().stream);
+    ? cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(PT), args, smem, ctx().stream)
+    : cudaLaunchKernel(kern, dim3(grid), dim3(PT), args, smem, ctx().stream);
   ctx().launches += 1;
   if (e != cudaSuccess) {
-    set_error("cooperative launch of k_fcg_persistent failed: %s", cudaGetErrorString(e));
+    set_error("cooperative launch of k_%s_persistent failed: %s", ipcg ? "ipcg" : "fcg",
+              cudaGetErrorString(e));
     return false;
   }
   return true;

@@ -55,7 +55,7 @@ struct MgSolveParams {
 };
 
 size_t persistent_smem_bytes(size_t max_slab_entries);
-int    persistent_grid(int which, size_t smem);   /* 0: PCG, 1: multigrid, 2: FCG kernel */
+int    persistent_grid(int which, size_t smem);   /* 0: PCG, 1: multigrid, 2: FCG, 3: IPCG kernel */
 
 bool launch_pcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
                            bool vx_ini_nonzero, int n_max_iter, double precision,
@@ -69,7 +69,8 @@ bool launch_mg_persistent(const MgSolveParams &S, const PersistentCommon &P, int
 bool launch_fcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
                            bool vx_ini_nonzero, int n_max_iter, double precision,
                            double r_norm, const PersistentCommon &P, ItState *st,
-                           int grid, size_t smem, bool single, bool cooperative);
+                           int grid, size_t smem, bool single, bool cooperative,
+                           bool ipcg = false);   /* true: _conjugate_gradient_ip (:1016-1203) */
 
 /* y = A.x (or E.x) through the bulk-copy pipeline of the persistent kernels, as a
    stand-alone launch (cs_matrix_vector_multiply).  Returns false with no error set when

@@ -319,6 +319,7 @@ csb_sles_it_create(csb_sles_it_type_t solver_type, int poly_degree, int n_max_it
 {
   if (!ctx().ready) { set_error("csb_sles_it_create: csb_init not called"); return nullptr; }
   if (solver_type != CSB_SLES_PCG && solver_type != CSB_SLES_FCG
+      && solver_type != CSB_SLES_IPCG
       && solver_type != CSB_SLES_JACOBI && solver_type != CSB_SLES_BICGSTAB) {
     set_error("csb_sles_it_create: solver type %d is not available on this path",
               (int)solver_type);
@@ -360,7 +361,7 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
   c->a = a;
   c->setup_done = false;
   const size_t n_wa = (c->type == CSB_SLES_BICGSTAB) ? 6
-    : ((c->type == CSB_SLES_PCG || c->type == CSB_SLES_FCG) ? 5 : 1);
+    : ((c->type == CSB_SLES_PCG || c->type == CSB_SLES_FCG || c->type == CSB_SLES_IPCG) ? 5 : 1);
   if (a->db != 1 && c->type != CSB_SLES_BICGSTAB) {
     set_error("csb_sles_it_setup: block matrices (db %d) are solved with CSB_SLES_BICGSTAB "
               "on this path", a->db);
@@ -373,13 +374,13 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
   if (!c->st.alloc(1)) return;
   if (c->h_st == nullptr)
     if (!CSB_CUDA(cudaMallocHost((void **)&c->h_st, sizeof(ItState)))) return;
-  if (a->halo != nullptr && ((c->type != CSB_SLES_PCG && c->type != CSB_SLES_FCG)
+  if (a->halo != nullptr && ((c->type != CSB_SLES_PCG && c->type != CSB_SLES_FCG && c->type != CSB_SLES_IPCG)
                              || c->pcomm == nullptr)) {
     set_error("csb_sles_it_setup: a matrix with a halo needs CSB_SLES_PCG / _FCG and a peer "
               "communicator (csb_sles_it_set_pcomm) on this path");
     return;
   }
-  if (c->type == CSB_SLES_PCG || c->type == CSB_SLES_FCG) {
+  if (c->type == CSB_SLES_PCG || c->type == CSB_SLES_FCG || c->type == CSB_SLES_IPCG) {
     size_t max_entries = 0;
     MgLevelDesc &d = c->desc;
     memset(&d, 0, sizeof(d));
@@ -397,7 +398,7 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
     d.row_index = a->row_index.p; d.col_id = a->col_id.p;
     d.d_val = a->d_val.p; d.x_val = a->x_val.p; d.ad_inv = c->ad_inv.p;
     c->p_smem = persistent_smem_bytes(max_entries);
-    c->p_grid = persistent_grid(c->type == CSB_SLES_FCG ? 2 : 0, c->p_smem);
+    c->p_grid = persistent_grid(c->type == CSB_SLES_FCG ? 2 : (c->type == CSB_SLES_IPCG ? 3 : 0), c->p_smem);
     if (c->p_grid < 1) return;
     if (!c->partials.alloc(12*(size_t)c->p_grid) || !c->barrier.alloc(2)) return;
     if (!CSB_CUDA(cudaMemsetAsync(c->barrier.p, 0, 2*sizeof(unsigned), ctx().stream))) return;
@@ -458,6 +459,7 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
                        s_rhs.d, s_vx.d, ini, false, c->work.p, c->h_st);
     break;
   case CSB_SLES_FCG:
+  case CSB_SLES_IPCG:
     {
       /* whole solve in one persistent cooperative kernel (per rank) */
       PersistentCommon P;
@@ -468,7 +470,7 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
       if (a->halo != nullptr) pcomm_host_barrier(c->pcomm);
       ok = launch_fcg_persistent(c->desc, s_rhs.d, s_vx.d, ini, c->n_max_iter, precision,
                                  r_norm, P, c->st.p, c->p_grid, c->p_smem, single,
-                                 cx.device_share <= 1);
+                                 cx.device_share <= 1, c->type == CSB_SLES_IPCG);
       if (a->halo != nullptr) pcomm_host_barrier(c->pcomm);
     }
     break;
@@ -548,6 +550,7 @@ void csb_sles_it_log(const void *context, int log_type)
   if (c == nullptr) return;
   const char *tn = (c->type == CSB_SLES_PCG) ? "Conjugate Gradient"
                  : (c->type == CSB_SLES_FCG) ? "Flexible Conjugate Gradient"
+                 : (c->type == CSB_SLES_IPCG) ? "Inexact Conjugate Gradient"
                  : (c->type == CSB_SLES_JACOBI) ? "Jacobi" : "BiCGstab";
   printf("  Solver type:                       %s (B200 device)\n"
          "  Number of setups:                  %12u\n"

@@ -43,6 +43,7 @@ typedef enum {
 typedef enum {
   CSB_SLES_PCG      = 0,
   CSB_SLES_FCG      = 1,   /* flexible CG, cs_sles_it.cpp:832-985 */
+  CSB_SLES_IPCG     = 2,   /* inexact-preconditioning CG, cs_sles_it.cpp:1016-1203 */
   CSB_SLES_JACOBI   = 3,
   CSB_SLES_BICGSTAB = 4
 } csb_sles_it_type_t;

@@ -300,6 +300,84 @@ ora_fcg(int n_rows, const int *row_index, const int *col_id,
 }
 
 /*----------------------------------------------------------------------------
+ * Inexact-preconditioning CG with Jacobi preconditioning:
+ * _conjugate_gradient_ip (src/alge/cs_sles_it.cpp:1016-1203).
+ * Residual sign r = A.x - b; beta = (rk.gk - rkm1.gk) / rkm1.gkm1.
+ * out[0]=n_iter out[1]=residual out[2]=initial_residual out[3]=history count
+ *----------------------------------------------------------------------------*/
+
+int
+ora_ipcg(int n_rows, const int *row_index, const int *col_id,
+         const double *d_val, const double *x_val,
+         int n_max_iter, double precision, double r_norm,
+         const double *rhs, double *vx, int use_vx_ini,
+         double *out, double *history, int history_size)
+{
+  const int n = n_rows;
+  double *rk = malloc(sizeof(double)*n*6);
+  double *rkm1 = rk + n, *dk = rk + 2*n, *gk = rk + 3*n, *zk = rk + 4*n;
+  double *ad_inv = rk + 5*n;
+  for (int i = 0; i < n; i++) ad_inv[i] = 1.0 / d_val[i];
+
+  ora_cvg_t cv = {precision, r_norm, -1, n_max_iter, 0, -1,
+                  history, history_size, 0};
+  int cvg;
+  int n_iter = 0;
+  double ro_0, ro_1, alpha, rk_gk_m1, rkm1_gk, rk_gk, beta, residual;
+
+  if (use_vx_ini) {
+    ora_spmv_msr(n, row_index, col_id, d_val, x_val, 0, vx, rk);
+    for (int ii = 0; ii < n; ii++) rk[ii] -= rhs[ii];
+  }
+  else {
+    for (int ii = 0; ii < n; ii++) { vx[ii] = 0; rk[ii] = -rhs[ii]; }
+  }
+  for (int ii = 0; ii < n; ii++) gk[ii] = rk[ii] * ad_inv[ii];
+  for (int ii = 0; ii < n; ii++) dk[ii] = gk[ii];
+
+  ora_dot_xx_xy(n, rk, gk, &residual, &rk_gk_m1);
+  residual = sqrt(residual);
+  cv.initial_residual = residual;
+  cvg = _cvg_test(&cv, n_iter, residual);
+
+  if (cvg == ORA_ITERATING) {
+    n_iter = 1;
+    ora_spmv_msr(n, row_index, col_id, d_val, x_val, 0, dk, zk);
+    ora_dot_xy_yz(n, rk, dk, zk, &ro_0, &ro_1);
+    double d_ro_1 = (fabs(ro_1) > DBL_MIN) ? 1. / ro_1 : 0.;
+    alpha = - ro_0 * d_ro_1;
+    for (int ii = 0; ii < n; ii++) vx[ii] += (alpha * dk[ii]);
+    for (int ii = 0; ii < n; ii++) { rkm1[ii] = rk[ii]; rk[ii] += (alpha * zk[ii]); }
+    residual = sqrt(ora_dot_xx(n, rk));
+    cvg = _cvg_test(&cv, n_iter, residual);
+  }
+
+  while (cvg == ORA_ITERATING) {
+    for (int ii = 0; ii < n; ii++) gk[ii] = rk[ii] * ad_inv[ii];
+    ora_dot_xx_xy_yz(n, rk, gk, rkm1, &residual, &rk_gk, &rkm1_gk);
+    residual = sqrt(residual);
+    if (n_iter > 1)
+      cvg = _cvg_test(&cv, n_iter, residual);
+    if (cvg != ORA_ITERATING) break;
+    n_iter += 1;
+    beta = (fabs(rk_gk_m1) > DBL_MIN) ? (rk_gk - rkm1_gk) / rk_gk_m1 : 0.;
+    rk_gk_m1 = rk_gk;
+    for (int ii = 0; ii < n; ii++) dk[ii] = gk[ii] + (beta * dk[ii]);
+    ora_spmv_msr(n, row_index, col_id, d_val, x_val, 0, dk, zk);
+    ora_dot_xy_yz(n, rk, dk, zk, &ro_0, &ro_1);
+    double d_ro_1 = (fabs(ro_1) > DBL_MIN) ? 1. / ro_1 : 0.;
+    alpha = - ro_0 * d_ro_1;
+    for (int ii = 0; ii < n; ii++) vx[ii] += (alpha * dk[ii]);
+    for (int ii = 0; ii < n; ii++) { rkm1[ii] = rk[ii]; rk[ii] += (alpha * zk[ii]); }
+  }
+
+  out[0] = cv.n_iterations; out[1] = cv.residual; out[2] = cv.initial_residual;
+  out[3] = cv.history_n;
+  free(rk);
+  return cvg;
+}
+
+/*----------------------------------------------------------------------------
  * PCG + Jacobi, single reduction: _conjugate_gradient_sr_p0
  * (src/alge/cs_sles_it.cpp:1441-1645).  Residual sign r = A.x - b.
  * out[0]=n_iter out[1]=residual out[2]=initial_residual

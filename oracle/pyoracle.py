@@ -174,6 +174,10 @@ class Oracle:
         return self._solve(self.lib.ora_fcg, ri, ci, d, xv, rhs, n_max_iter,
                            precision, r_norm, vx0)
 
+    def ipcg(self, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0=None):
+        return self._solve(self.lib.ora_ipcg, ri, ci, d, xv, rhs, n_max_iter,
+                           precision, r_norm, vx0)
+
     def jacobi(self, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0=None):
         return self._solve(self.lib.ora_jacobi, ri, ci, d, xv, rhs, n_max_iter,
                            precision, r_norm, vx0)

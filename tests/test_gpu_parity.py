@@ -530,3 +530,34 @@ def test_block3_tight_tolerance_and_warm_start(csb, oracle):
     with pytest.raises(Exception):
         p.solve(m, rhs, 1e-8, r_norm)
     p.destroy(); c.destroy(); m.destroy()
+
+
+# --------------------------------------------------------------------------- inexact CG
+
+@pytest.mark.parametrize("N,bc", [(8, "neumann"), (12, "dirichlet"), (16, "neumann")])
+def test_ipcg_matches_reference_golden(csb, oracle, N, bc):
+    """CSB_SLES_IPCG (persistent kernel) against _conjugate_gradient_ip of the reference build
+    (tests/golden/ipcg_*.npz): iteration count +-2, residuals to reduction-order rounding,
+    max-iteration exit after a warm start, tight-tolerance solution parity."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"ipcg_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    r_norm = float(g["r_norm"])
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+    c = csb.SlesIt(csb.SlesItType.IPCG, 1000)
+    r = c.solve(m, s.rhs, 1e-9, r_norm)
+    assert int(r["cvg"]) == int(g["cvg"]) == 1
+    assert abs(r["n_iter"] - int(g["n_iter"])) <= 2
+    assert abs(r["initial_residual"] - float(g["initial_residual"])) <= RED_TOL * float(g["initial_residual"])
+    k = min(len(r["history"]) - 1, len(g["history"]), 8)
+    assert np.allclose(r["history"][1:1 + k], g["history"][:k], rtol=1e-9, atol=0)
+    c5 = csb.SlesIt(csb.SlesItType.IPCG, 5)
+    w = c5.solve(m, s.rhs, 1e-12, r_norm, vx=0.5 * g["vx"], use_vx_ini=True)
+    assert (int(w["cvg"]), w["n_iter"]) == (int(g["warm_cvg"]), int(g["warm_n_iter"]))
+    assert abs(w["residual"] - float(g["warm_residual"])) <= 1e-9 * float(g["warm_residual"])
+    assert rel_l2(w["vx"][:s.n_rows], g["warm_vx"]) <= 1e-11
+    if bc == "dirichlet":
+        o = oracle.ipcg(s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, 5000, 1e-13, r_norm)
+        t = c.solve(m, s.rhs, 1e-13, r_norm)
+        assert int(t["cvg"]) == 1 == o["cvg"] and abs(t["n_iter"] - o["n_iter"]) <= 2
+        assert rel_l2(t["vx"][:s.n_rows], o["vx"]) <= SOL_TOL
+    c.destroy(); c5.destroy(); m.destroy()

@@ -203,3 +203,20 @@ def test_oracle_block3_vs_reference_direct(oracle, reflib):
     assert (a["cvg"], a["n_iter"], a["residual"]) == (b["cvg"], b["n_iter"], b["residual"])
     assert np.array_equal(a["vx"], b["vx"])
     reflib.destroy(h)
+
+
+@pytest.mark.parametrize("N,bc", [(8, "neumann"), (12, "dirichlet"), (16, "neumann")])
+def test_oracle_ipcg_matches_golden(oracle, N, bc):
+    """_conjugate_gradient_ip restatement against fixtures produced by the reference build."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"ipcg_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    r_norm = float(g["r_norm"])
+    o = oracle.ipcg(s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, 1000, 1e-9, r_norm)
+    assert (o["cvg"], o["n_iter"], o["residual"], o["initial_residual"]) \
+        == (int(g["cvg"]), int(g["n_iter"]), float(g["residual"]), float(g["initial_residual"]))
+    assert np.array_equal(o["vx"], g["vx"])
+    w = oracle.ipcg(s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, 5, 1e-12, r_norm,
+                    vx0=0.5 * g["vx"])
+    assert (w["cvg"], w["n_iter"], w["residual"]) \
+        == (int(g["warm_cvg"]), int(g["warm_n_iter"]), float(g["warm_residual"]))
+    assert np.array_equal(w["vx"], g["warm_vx"])
