@@ -348,6 +348,7 @@ void matrix_plan_spmv(_csb_matrix_t *m);
 
 /* ad_inv = 1/d  (cs_sles_pc.cpp:376) */
 bool launch_ad_inv(int n, const double *d, double *ad_inv);
+bool launch_fill(int n, double v, double *x);
 
 /* plain reductions -> ctx().red_out[0..q) */
 bool launch_dot(int n, const double *x, const double *y, const double *z, int mode);

@@ -685,6 +685,19 @@ k_pcg_update(int n, const ItState *st, const double *__restrict__ ad_inv,
 
 } // anonymous namespace
 
+__global__ void __launch_bounds__(TPB)
+k_fill(int n, double v, double *__restrict__ x)
+{
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) x[i] = v;
+}
+
+bool launch_fill(int n, double v, double *x)
+{
+  if (n < 1) return true;
+  k_fill<<<vec_grid(n), TPB, 0, ctx().stream>>>(n, v, x);
+  return post_launch("fill");
+}
+
 bool launch_ad_inv(int n, const double *d, double *ad_inv)
 {
   if (n < 1) return true;

@@ -325,9 +325,12 @@ csb_sles_it_create(csb_sles_it_type_t solver_type, int poly_degree, int n_max_it
               (int)solver_type);
     return nullptr;
   }
-  if (solver_type != CSB_SLES_JACOBI && poly_degree != 0) {
-    set_error("csb_sles_it_create: only the Jacobi preconditioner (poly_degree 0) "
-              "is available on this path");
+  /* poly_degree 0: Jacobi; < 0 with PCG: no preconditioner (_conjugate_gradient_sr_npc,
+     cs_sles_it.cpp:1673-1860) */
+  if (solver_type != CSB_SLES_JACOBI && poly_degree != 0
+      && !(solver_type == CSB_SLES_PCG && poly_degree < 0)) {
+    set_error("csb_sles_it_create: poly_degree %d: Jacobi (0), or none (< 0, PCG only), "
+              "are the preconditioners available on this path", poly_degree);
     return nullptr;
   }
   csb_sles_it_t *c = new csb_sles_it_t;
@@ -368,7 +371,12 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
     return;
   }
   if (!c->ad_inv.alloc((size_t)a->n_rows*a->db)) return;
-  if (a->db == 1) { if (!launch_ad_inv(a->n_rows, a->d_val.p, c->ad_inv.p)) return; }
+  if (a->db == 1 && c->type == CSB_SLES_PCG && c->poly_degree < 0) {
+    /* no preconditioner: gk = rk * 1 is rk, the single-reduction recurrences are those of
+       _conjugate_gradient_sr_npc term for term */
+    if (!launch_fill(a->n_rows, 1.0, c->ad_inv.p)) return;
+  }
+  else if (a->db == 1) { if (!launch_ad_inv(a->n_rows, a->d_val.p, c->ad_inv.p)) return; }
   else if (!launch_ad_inv_block(a->n_rows, a->db, a->d_val.p, c->ad_inv.p)) return;
   if (!c->work.alloc(n_wa * work_stride_of((size_t)a->n_cols_ext*a->db))) return;
   if (!c->st.alloc(1)) return;

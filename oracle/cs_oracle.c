@@ -378,6 +378,86 @@ ora_ipcg(int n_rows, const int *row_index, const int *col_id,
 }
 
 /*----------------------------------------------------------------------------
+ * Unpreconditioned CG, single reduction: _conjugate_gradient_sr_npc
+ * (src/alge/cs_sles_it.cpp:1673-1860; selected when poly_degree < 0).
+ * out[0]=n_iter out[1]=residual out[2]=initial_residual out[3]=history count
+ *----------------------------------------------------------------------------*/
+
+int
+ora_pcg_sr_npc(int n_rows, const int *row_index, const int *col_id,
+               const double *d_val, const double *x_val,
+               int n_max_iter, double precision, double r_norm,
+               const double *rhs, double *vx, int use_vx_ini,
+               double *out, double *history, int history_size)
+{
+  const int n = n_rows;
+  double *rk = malloc(sizeof(double)*n*4);
+  double *dk = rk + n, *zk = rk + 2*n, *sk = rk + 3*n;
+
+  ora_cvg_t cv = {precision, r_norm, -1, n_max_iter, 0, -1,
+                  history, history_size, 0};
+  int cvg = ORA_ITERATING;
+  int n_iter = 0;
+
+  if (use_vx_ini) {
+    ora_spmv_msr(n, row_index, col_id, d_val, x_val, 0, vx, rk);
+    for (int ii = 0; ii < n; ii++) { rk[ii] = rk[ii] - rhs[ii]; dk[ii] = rk[ii]; }
+  }
+  else {
+    for (int ii = 0; ii < n; ii++) { vx[ii] = 0; rk[ii] = - rhs[ii]; dk[ii] = rk[ii]; }
+  }
+  ora_spmv_msr(n, row_index, col_id, d_val, x_val, 0, dk, zk);
+
+  double ro_0 = 0, ro_1 = 0;
+  double rk_rkm1 = 0, residual = -1, rk_rk = 0, rk_sk = 0;
+  ora_dot_xx_xy_yz(n, rk, dk, zk, &residual, &ro_0, &ro_1);
+  residual = sqrt(residual);
+  cv.initial_residual = residual;
+  cvg = _cvg_test(&cv, n_iter, residual);
+
+  if (cvg == ORA_ITERATING) {
+    n_iter = 1;
+    double d_ro_1 = (fabs(ro_1) > DBL_MIN) ? 1. / ro_1 : 0.;
+    double alpha = - ro_0 * d_ro_1;
+    rk_rkm1 = ro_0;
+    for (int ii = 0; ii < n; ii++) {
+      vx[ii] += (alpha * dk[ii]);
+      rk[ii] += (alpha * zk[ii]);
+    }
+    residual = sqrt(ora_dot_xx(n, rk));
+    cvg = _cvg_test(&cv, n_iter, residual);
+  }
+
+  while (cvg == ORA_ITERATING) {
+    ora_spmv_msr(n, row_index, col_id, d_val, x_val, 0, rk, sk);
+    ora_dot_xx_xy(n, rk, sk, &residual, &rk_sk);
+    rk_rk = residual;
+    residual = sqrt(residual);
+    if (n_iter > 1)
+      cvg = _cvg_test(&cv, n_iter, residual);
+    if (cvg != ORA_ITERATING) break;
+    n_iter += 1;
+    double beta = (fabs(rk_rkm1) > DBL_MIN) ? rk_rk / rk_rkm1 : 0.;
+    rk_rkm1 = rk_rk;
+    ro_1 = rk_sk - beta*beta*ro_1;
+    ro_0 = rk_rk;
+    double d_ro_1 = (fabs(ro_1) > DBL_MIN) ? 1. / ro_1 : 0.;
+    double alpha = - ro_0 * d_ro_1;
+    for (int ii = 0; ii < n; ii++) {
+      dk[ii] = rk[ii] + (beta * dk[ii]);
+      vx[ii] += alpha * dk[ii];
+      zk[ii] = sk[ii] + (beta * zk[ii]);
+      rk[ii] += alpha * zk[ii];
+    }
+  }
+
+  out[0] = cv.n_iterations; out[1] = cv.residual; out[2] = cv.initial_residual;
+  out[3] = cv.history_n;
+  free(rk);
+  return cvg;
+}
+
+/*----------------------------------------------------------------------------
  * PCG + Jacobi, single reduction: _conjugate_gradient_sr_p0
  * (src/alge/cs_sles_it.cpp:1441-1645).  Residual sign r = A.x - b.
  * out[0]=n_iter out[1]=residual out[2]=initial_residual

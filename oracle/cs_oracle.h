@@ -72,6 +72,11 @@ int    ora_ipcg(int n_rows, const int *row_index, const int *col_id,
                 int n_max_iter, double precision, double r_norm,
                 const double *rhs, double *vx, int use_vx_ini,
                 double *out, double *history, int history_size);
+int    ora_pcg_sr_npc(int n_rows, const int *row_index, const int *col_id,
+                      const double *d_val, const double *x_val,
+                      int n_max_iter, double precision, double r_norm,
+                      const double *rhs, double *vx, int use_vx_ini,
+                      double *out, double *history, int history_size);
 int    ora_jacobi(int n_rows, const int *row_index, const int *col_id,
                   const double *d_val, const double *x_val,
                   int n_max_iter, double precision, double r_norm,

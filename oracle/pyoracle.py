@@ -178,6 +178,10 @@ class Oracle:
         return self._solve(self.lib.ora_ipcg, ri, ci, d, xv, rhs, n_max_iter,
                            precision, r_norm, vx0)
 
+    def pcg_npc(self, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0=None):
+        return self._solve(self.lib.ora_pcg_sr_npc, ri, ci, d, xv, rhs, n_max_iter,
+                           precision, r_norm, vx0)
+
     def jacobi(self, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0=None):
         return self._solve(self.lib.ora_jacobi, ri, ci, d, xv, rhs, n_max_iter,
                            precision, r_norm, vx0)

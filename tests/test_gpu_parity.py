@@ -561,3 +561,22 @@ def test_ipcg_matches_reference_golden(csb, oracle, N, bc):
         assert int(t["cvg"]) == 1 == o["cvg"] and abs(t["n_iter"] - o["n_iter"]) <= 2
         assert rel_l2(t["vx"][:s.n_rows], o["vx"]) <= SOL_TOL
     c.destroy(); c5.destroy(); m.destroy()
+
+
+def test_pcg_without_preconditioner_matches_oracle(csb, oracle):
+    """poly_degree < 0: _conjugate_gradient_sr_npc (cs_sles_it.cpp:1673-1860); the oracle
+    restatement is bit-exact against the reference build (tests/test_oracle.py)."""
+    s = cube_poisson(16, "dirichlet", with_mesh=False)                # well conditioned
+    d = s.d_val * (1.0 + 0.3 * np.cos(0.2 * np.arange(s.n_rows)))     # non-uniform diagonal
+    r_norm = float(np.linalg.norm(s.rhs))
+    o = oracle.pcg_npc(s.row_index, s.col_id, d, s.x_val, s.rhs, 2000, 1e-10, r_norm)
+    op = oracle.pcg(s.row_index, s.col_id, d, s.x_val, s.rhs, 2000, 1e-10, r_norm)
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, d, s.x_val)
+    c = csb.SlesIt(csb.SlesItType.PCG, 2000, poly_degree=-1)
+    r = c.solve(m, s.rhs, 1e-10, r_norm)
+    assert int(r["cvg"]) == 1 == o["cvg"] and abs(r["n_iter"] - o["n_iter"]) <= 2
+    assert o["n_iter"] != op["n_iter"]                  # really a different algorithm
+    k = min(len(r["history"]), len(o["history"]), 8)
+    assert np.allclose(r["history"][:k], o["history"][:k], rtol=1e-10, atol=0)
+    assert rel_l2(r["vx"][:s.n_rows], o["vx"]) <= 1e-7   # both stopped at 1e-10
+    c.destroy(); m.destroy()

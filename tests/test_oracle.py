@@ -220,3 +220,21 @@ def test_oracle_ipcg_matches_golden(oracle, N, bc):
     assert (w["cvg"], w["n_iter"], w["residual"]) \
         == (int(g["warm_cvg"]), int(g["warm_n_iter"]), float(g["warm_residual"]))
     assert np.array_equal(w["vx"], g["warm_vx"])
+
+
+def test_oracle_pcg_npc_vs_reference_direct(oracle, reflib):
+    """_conjugate_gradient_sr_npc (poly_degree < 0) restatement against the live reference."""
+    for N, bc in ((10, "neumann"), (13, "dirichlet")):
+        s = cube_poisson(N, bc)
+        d = s.d_val * (1.0 + 0.3 * np.cos(0.2 * np.arange(s.n_rows)))
+        h = reflib.system(s, d_val=d, with_mesh=False)
+        r_norm = float(np.sqrt(oracle.dot_xx(s.rhs)))
+        a = reflib.sles_it(h, reflib.PCG, s.rhs, 2000, 1e-9, r_norm, poly_degree=-1)
+        b = oracle.pcg_npc(s.row_index, s.col_id, d, s.x_val, s.rhs, 2000, 1e-9, r_norm)
+        assert (a["cvg"], a["n_iter"], a["residual"]) == (b["cvg"], b["n_iter"], b["residual"])
+        assert np.array_equal(a["vx"], b["vx"])
+        a = reflib.sles_it(h, reflib.PCG, s.rhs, 4, 1e-12, r_norm, vx0=0.2 * a["vx"], poly_degree=-1)
+        b = oracle.pcg_npc(s.row_index, s.col_id, d, s.x_val, s.rhs, 4, 1e-12, r_norm, vx0=0.2 * b["vx"])
+        assert (a["cvg"], a["n_iter"], a["residual"]) == (b["cvg"], b["n_iter"], b["residual"])
+        assert np.array_equal(a["vx"], b["vx"])
+        reflib.destroy(h)
