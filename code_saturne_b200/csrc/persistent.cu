@@ -68,27 +68,58 @@ constexpr int NG = CSB_GATHER;     /* x[col] gathers a lane keeps in flight for 
 static_assert(PT % 32 == 0 && NW <= 32, "CTA shape");
 static_assert(4*NW + 4 <= 56 && 56 + 4*COMM_MAX_RANKS <= PERSISTENT_S_RED, "s_red layout");
 
+#ifdef CSB_PHASE_TRACE
+/* Debug build only (scripts/build_variants.sh "trace:-DCSB_PHASE_TRACE"): where the time of
+   a small-level SpMV + dots phase goes, seen by lane 0 of CTA 0 on levels with
+   TRACE_LO < n_rows <= TRACE_HI.  Sums of nanoseconds: [0] entry -> first stage full,
+   [1] -> first gathers back, [2] -> own slabs consumed, [3] -> CTA joined, [4] reduction
+   (all_sum), [5] whole phase; [15] number of phases. */
+__device__ unsigned long long g_trace[16];
+#ifndef TRACE_LO
+#define TRACE_LO 5000
+#endif
+#ifndef TRACE_HI
+#define TRACE_HI 10000
+#endif
+__device__ __forceinline__ unsigned long long trace_now()
+{ unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+
+/* Layout of the head of a CTA's dynamic shared memory (the stages follow, see below). */
+extern __shared__ __align__(128) unsigned char s_raw_base[];
+constexpr int HALO_K_OFF = PERSISTENT_S_RED*8;        /* unsigned[PROF_LEVELS]: exchange counts */
+constexpr int BAR_TGT_OFF = HALO_K_OFF + PROF_LEVELS*4;   /* unsigned: arrivals at the next barrier */
+constexpr int PIPE_OFF = BAR_TGT_OFF + 16;            /* PipeState */
+
 /*--------------------------------------------------------------------------
  * Grid-wide barrier (all CTAs are co-resident: cooperative launch).
- * bar[0] = arrival counter, bar[1] = generation.
+ * bar[0] is an arrival counter that only grows (reset to 0 by the host before every
+ * launch): barrier k is passed when it reaches k*gridDim.x.  One atomic per CTA and one
+ * word to poll -- no "last CTA resets and bumps a generation" hop, no sleep in the poll.
+ * Every CTA keeps the target of its next barrier in shared memory (all CTAs execute the
+ * same sequence of barriers).
  *--------------------------------------------------------------------------*/
+
+/* Release / acquire fences of the message-passing patterns below.  __threadfence() is a
+   sequentially-consistent fence (SASS MEMBAR.SC + ERRBAR); everything here is "publish data,
+   then a flag / read the flag, then the data", for which acq_rel (MEMBAR.ALL) is enough. */
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 
 __device__ __forceinline__ void grid_barrier(unsigned *bar)
 {
   __syncthreads();
   if (threadIdx.x == 0) {
-    volatile unsigned *gen = bar + 1;
-    const unsigned my_gen = *gen;
-    __threadfence();
-    if (atomicAdd(bar, 1u) == gridDim.x - 1) {
-      bar[0] = 0;
-      __threadfence();
-      atomicAdd(bar + 1, 1u);
-    }
-    else {
-      while (*gen == my_gen) { __nanosleep(20); }
-    }
-    __threadfence();      /* acquire; also invalidates this SM's L1 */
+    unsigned *tgt = (unsigned *)(s_raw_base + BAR_TGT_OFF);
+    const unsigned target = *tgt + gridDim.x;
+    *tgt = target;
+    fence_gpu();                     /* release: this CTA's stores (bar.sync-cumulative) */
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" :: "l"(bar) : "memory");
+    unsigned seen;
+    do {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+    } while ((int)(seen - target) < 0);
+    fence_gpu();                     /* acquire */
   }
   __syncthreads();
 }
@@ -133,6 +164,27 @@ __device__ __forceinline__ void cta_sum_bcast(double (&v)[Q], double *s_red /* Q
   __syncthreads();
 }
 
+/* CTA-wide sum of Q values, result in thread 0 only (one barrier). */
+template <int Q>
+__device__ __forceinline__ void cta_sum_t0(double (&v)[Q], double *s_red /* Q*NW */)
+{
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    const double w = warp_sum(v[q]);
+    if (lane == 0) s_red[q*NW + wid] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      double w = 0.;
+      for (int i = 0; i < NW; i++) w += s_red[q*NW + i];
+      v[q] = w;
+    }
+  }
+}
+
 /* Deterministic sum over the grid and, with a communicator, over all ranks:
    the result is identical in every thread of every CTA of every rank.
    SINGLE: only this CTA takes part on this rank.
@@ -148,20 +200,34 @@ __device__ __forceinline__ void all_sum(double (&v)[Q], double *partials, unsign
   unsigned e = 0;
   if (C != nullptr)      /* read before the grid barrier: block 0 bumps it after */
     e = *(volatile unsigned *)&C->local->x_epoch + 1;
-  cta_sum_bcast<Q>(v, s_red);
-  if (!SINGLE) {
+  if (SINGLE) cta_sum_bcast<Q>(v, s_red);
+  else {
     const unsigned G = gridDim.x;
+    cta_sum_t0<Q>(v, s_red);
     if (threadIdx.x == 0) {
 #pragma unroll
       for (int q = 0; q < Q; q++) partials[q*G + blockIdx.x] = v[q];
     }
     grid_barrier(bar);
+    /* all loads of a thread are issued before the first add (one L2 latency, not
+       one per term); thread t sums partials t, t + PT, ... in that order */
+    {
+      double w[Q];
 #pragma unroll
-    for (int q = 0; q < Q; q++) {
-      double w = 0.0;
-      for (unsigned i = threadIdx.x; i < G; i += PT)
-        w += __ldcg(partials + q*G + i);
-      v[q] = w;
+      for (int q = 0; q < Q; q++) w[q] = 0.0;
+      for (unsigned i0 = threadIdx.x; i0 < G; i0 += 2*PT) {
+        double a[Q], b[Q];
+        const unsigned i1 = i0 + PT;
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+          a[q] = __ldcg(partials + q*G + i0);
+          b[q] = (i1 < G) ? __ldcg(partials + q*G + i1) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < Q; q++) { w[q] += a[q]; if (i1 < G) w[q] += b[q]; }
+      }
+#pragma unroll
+      for (int q = 0; q < Q; q++) v[q] = w[q];
     }
     cta_sum_bcast<Q>(v, s_red);
   }
@@ -176,14 +242,14 @@ __device__ __forceinline__ void all_sum(double (&v)[Q], double *partials, unsign
 #pragma unroll
       for (int q = 0; q < Q; q++) P->xsum[par][me][q] = v[q];
     }
-    __threadfence_system();
+    fence_sys();
     for (int r = 0; r < R; r++)
       *(volatile unsigned *)&((CommHeader *)C->peer[r])->xflag[par][me] = e;
   }
   double *s_x = s_red + 56;        /* [Q][COMM_MAX_RANKS] */
   if (threadIdx.x < R) {
     spin_until_ge(&H->xflag[par][threadIdx.x], e, C->timeout_ns, 6);
-    __threadfence();
+    fence_gpu();
 #pragma unroll
     for (int q = 0; q < Q; q++)
       s_x[q*COMM_MAX_RANKS + threadIdx.x] = __ldcg(&H->xsum[par][threadIdx.x][q]);
@@ -212,8 +278,6 @@ __device__ __forceinline__ void all_sum(double (&v)[Q], double *partials, unsign
 /* Exchanges done so far, per level: a copy private to the CTA (shared memory), loaded
    from DistLevel::count at kernel start (halo_counts_init) so that a CTA that reaches an
    exchange late cannot read a count that the packing CTAs have already advanced. */
-constexpr int HALO_K_OFF = PERSISTENT_S_RED*8;     /* unsigned[PROF_LEVELS] ahead of PipeState */
-extern __shared__ __align__(128) unsigned char s_raw_base[];
 
 template <bool SINGLE>
 __device__ __forceinline__ const double *halo_exchange(const MgLevelDesc &L, const double *x)
@@ -241,14 +305,14 @@ __device__ __forceinline__ const double *halo_exchange(const MgLevelDesc &L, con
       for (int e = s0 + first; e < s1; e += step)
         dst[e - s0] = x[send_list[e]];
     }
-    __threadfence_system();
+    fence_sys();
     __syncthreads();
     if (threadIdx.x == 0) {
       bool last = true;
       if (!SINGLE) last = (atomicInc(D->ticket, n_pack - 1) == n_pack - 1);
       if (last) {
         *(volatile unsigned *)D->count = k;
-        __threadfence_system();
+        fence_sys();
         for (int i = 0; i < n_dom; i++)
           *(volatile unsigned *)D->flag_remote[i] = k;
       }
@@ -256,7 +320,7 @@ __device__ __forceinline__ const double *halo_exchange(const MgLevelDesc &L, con
   }
   if (threadIdx.x < n_dom) {
     spin_until_ge(D->flag_local + threadIdx.x, k, D->timeout_ns, 7);
-    __threadfence();
+    fence_gpu();
   }
   __syncthreads();
   if (threadIdx.x == 0) *s_hk = k;      /* read again only after further CTA barriers */
@@ -323,7 +387,6 @@ struct PipeState {
   unsigned           pad[15];
 };
 
-constexpr int PIPE_OFF = HALO_K_OFF + PROF_LEVELS*4;
 constexpr int SMEM_HDR = (PIPE_OFF + (int)sizeof(PipeState) + 127) / 128 * 128;
 constexpr int ST_RI_BYTES = ((SLAB_ROWS_MAX + 1 + 3)*4 + 15) / 16 * 16;
 constexpr int ST_OP_STRIDE = SLAB_ROWS_MAX;          /* doubles between staged operand vectors */
@@ -402,6 +465,7 @@ __device__ __forceinline__ void pipe_init(unsigned char *s_raw)
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; i++) { mbar_init(&pipe->full[i], 1); mbar_init(&pipe->empty[i], NWC); }
     pipe->base = 0;
+    *(unsigned *)(s_raw + BAR_TGT_OFF) = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -540,14 +604,29 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
 #pragma unroll
           for (int e = 0; e < NG; e++)
             if (ks + e < ke) sii += s_val[ks + e] * gg[e];
-          if (ks + NG < ke) {       /* row longer than the gather pipeline */
+          if (ks + NG < ke) {
+            /* row longer than the gather pipeline: the rest is gathered NT at a time
+               (one L2 latency per batch, not per entry), in registers the first NG
+               values no longer need */
+            constexpr int NT = 8;
             const int k0 = ((const int *)(sb + off_ri))[0];
             const int *s_col = (const int *)sb + (k0 & 3) - (k0 & 1);
 #pragma unroll 1
-            for (int k = ks + NG; k < ke; k++) {
-              const int c = s_col[k];
-              const double *px = (!GHOST || c < n_rows) ? x : xg;
-              sii += s_val[k] * px[c];
+            for (int kb = ks + NG; kb < ke; kb += NT) {
+              double gt[NT];
+#pragma unroll
+              for (int e = 0; e < NT; e++) {
+                double v = 0.;
+                if (kb + e < ke) {
+                  const int c = s_col[kb + e];
+                  const double *px = (!GHOST || c < n_rows) ? x : xg;
+                  v = px[c];
+                }
+                gt[e] = v;
+              }
+#pragma unroll
+              for (int e = 0; e < NT; e++)
+                if (kb + e < ke) sii += s_val[kb + e] * gt[e];
             }
           }
           f.epi(r0 + tid, sii, (const double *)(sb + off_ops) + tid, acc);
@@ -557,7 +636,18 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
 
       /* (a prefetch past the last slab repeats the last one: its stage is still full) */
       const int j_last = n_my - 1;
+#ifdef CSB_PHASE_TRACE
+      const bool tr = (!SINGLE && blockIdx.x == 0 && tid == 0 && n_rows > TRACE_LO
+                       && n_rows <= TRACE_HI);
+      const unsigned long long tr0 = trace_now();
+      if (tr) consumer_wait(sv, base);
+      const unsigned long long tr1 = trace_now();
+#endif
       prefetch(0, gA, ksA, keA);
+#ifdef CSB_PHASE_TRACE
+      if (tr && gA[0] == 1.2345e300) g_trace[14] += 1;      /* wait for the gathers */
+      const unsigned long long tr2 = trace_now();
+#endif
       for (int j = 0; j < n_my; j += 2) {
         prefetch(min(j + 1, j_last), gB, ksB, keB);
         consume(j, gA, ksA, keA);
@@ -566,8 +656,17 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
           consume(j + 1, gB, ksB, keB);
         }
       }
+#ifdef CSB_PHASE_TRACE
+      const unsigned long long tr3 = trace_now();
+      if (tr) { g_trace[0] += tr1 - tr0; g_trace[1] += tr2 - tr1; g_trace[2] += tr3 - tr2;
+                g_trace[13] = tr3; }
+#endif
     }
     __syncthreads();
+#ifdef CSB_PHASE_TRACE
+    if (!SINGLE && blockIdx.x == 0 && tid == 0 && n_rows > TRACE_LO && n_rows <= TRACE_HI)
+      g_trace[3] += trace_now() - g_trace[13];
+#endif
     if (tid == 0) sv.pipe->base = base + (unsigned)n_my;
     __syncthreads();
   }
@@ -962,13 +1061,25 @@ __device__ __noinline__ PcgResult pcg_run(const MgLevelDesc &L, const double *rh
   while (R.cvg == CSB_SLES_ITERATING) {
     if (smoother && R.n_iter >= n_max_iter) break;
     v[0] = 0.; v[1] = 0.; v[2] = 0.;
+#ifdef CSB_PHASE_TRACE
+    const bool tr = (!SINGLE && blockIdx.x == 0 && threadIdx.x == 0 && L.n_rows > TRACE_LO
+                     && L.n_rows <= TRACE_HI);
+    const unsigned long long trp0 = trace_now();
+#endif
     const double *gh_g = halo_exchange<SINGLE>(L, gk);
     {
       EpiDots f;                                                       /* :1591-1600 */
       f.d_val = d_val; f.p = gk; f.rk = rk; f.out = sk;
       spmv_phase<SINGLE>(L, gk, gh_g, s_raw, f, v);
     }
+#ifdef CSB_PHASE_TRACE
+    const unsigned long long trp1 = trace_now();
+#endif
     { double v3[3] = {v[0], v[1], v[2]}; all_sum<SINGLE, 3>(v3, part0, P.barrier, s_red, comm); v[0] = v3[0]; v[1] = v3[1]; v[2] = v3[2]; }
+#ifdef CSB_PHASE_TRACE
+    if (tr) { const unsigned long long t = trace_now();
+              g_trace[4] += t - trp1; g_trace[5] += t - trp0; g_trace[15] += 1; }
+#endif
     mark(1);
     const double residual = sqrt(v[0]);
     const double rk_gk = v[1], gk_sk = v[2];
@@ -1713,6 +1824,81 @@ int persistent_grid(int which, size_t smem)
   return (g > 0) ? g : 1;
 }
 
+#ifdef CSB_PHASE_TRACE
+namespace {
+/* Debug build only: latency of n grid barriers / n grid reductions in a row. */
+__global__ void __launch_bounds__(PT, CSB_MIN_CTAS)
+k_barrier_bench(unsigned *bar, double *partials, int n, int what, unsigned long long *out)
+{
+  unsigned char *s_raw = s_raw_base;
+  pipe_init(s_raw);
+  double *s_red = (double *)s_raw;
+  grid_barrier(bar);
+  const unsigned long long t0 = trace_now();
+  double acc = 0.;
+  for (int i = 0; i < n; i++) {
+    if (what == 0) grid_barrier(bar);
+    else {
+      double v[3] = {1.0 + threadIdx.x, 2.0, 3.0 + i};
+      all_sum<false, 3>(v, partials + ((i & 1) ? 4*(size_t)gridDim.x : 0), bar, s_red, nullptr);
+      acc += v[0];
+    }
+  }
+  const unsigned long long t1 = trace_now();
+  if (blockIdx.x == 0 && threadIdx.x == 0) { out[0] = t1 - t0; out[1] = (unsigned long long)acc; }
+}
+}
+#endif
+
+} // namespace csb
+extern "C" double csb_debug_barrier_bench(int n, int what)
+{
+#ifdef CSB_PHASE_TRACE
+  using namespace csb;
+  Context &c = ctx();
+  int optin = 0, occ = 0;
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device);
+  const size_t smem = persistent_smem_bytes(1344);
+  cudaFuncSetAttribute(k_barrier_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_barrier_bench, PT, smem);
+  if (occ > CSB_MIN_CTAS) occ = CSB_MIN_CTAS;
+  const int grid = occ * c.sm_count;
+  unsigned *bar; double *partials; unsigned long long *out;
+  cudaMalloc(&bar, 8); cudaMalloc(&partials, sizeof(double)*12*grid); cudaMalloc(&out, 16);
+  cudaMemset(bar, 0, 8);
+  void *args[] = {(void *)&bar, (void *)&partials, (void *)&n, (void *)&what, (void *)&out};
+  cudaLaunchCooperativeKernel((void *)k_barrier_bench, dim3(grid), dim3(PT), args, smem, c.stream);
+  unsigned long long h[2] = {0, 0};
+  cudaStreamSynchronize(c.stream);
+  cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
+  cudaFree(bar); cudaFree(partials); cudaFree(out);
+  return (double)h[0] / n * 1e-3;      /* microseconds each */
+#else
+  (void)n; (void)what;
+  return -1.;
+#endif
+}
+extern "C" int csb_debug_phase_trace(double *out16, int reset)
+{
+#ifdef CSB_PHASE_TRACE
+  unsigned long long h[16];
+  if (cudaMemcpyFromSymbol(h, csb::g_trace, sizeof(h)) != cudaSuccess) return -1;
+  for (int i = 0; i < 16; i++) out16[i] = (double)h[i];
+  if (reset) { memset(h, 0, sizeof(h)); cudaMemcpyToSymbol(csb::g_trace, h, sizeof(h)); }
+  return 1;
+#else
+  (void)out16; (void)reset;
+  return 0;
+#endif
+}
+namespace csb {
+
+/* the arrival counter of the grid barrier starts every launch at 0 */
+static bool reset_barrier(const PersistentCommon &P)
+{
+  return CSB_CUDA(cudaMemsetAsync(P.barrier, 0, 2*sizeof(unsigned), ctx().stream));
+}
+
 bool launch_spmv_pipeline(const _csb_matrix_t *m, const double *x, double *y, bool exclude_diag,
                           bool *launched)
 {
@@ -1767,6 +1953,7 @@ bool launch_pcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
   int sgl = single ? 1 : 0;
   void *args[] = {(void *)&L, (void *)&rhs, (void *)&vx, (void *)&ini, (void *)&n_max_iter,
                   (void *)&precision, (void *)&r_norm, (void *)&P, (void *)&st, (void *)&sgl};
+  if (!reset_barrier(P)) return false;
   /* ranks sharing one device (in-process test groups) cannot both launch
      cooperatively; their grids are sized to be co-resident together */
   cudaError_t e = cooperative
@@ -1792,6 +1979,7 @@ bool launch_fcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
   void *args[] = {(void *)&L, (void *)&rhs, (void *)&vx, (void *)&ini, (void *)&n_max_iter,
                   (void *)&precision, (void *)&r_norm, (void *)&P, (void *)&st, (void *)&sgl};
   void *kern = ipcg ? (void *)k_ipcg_persistent : (void *)k_fcg_persistent;
+  if (!reset_barrier(P)) return false;
   cudaError_t e = cooperative
     ? cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(PT), args, smem, ctx().stream)
     : cudaLaunchKernel(kern, dim3(grid), dim3(PT), args, smem, ctx().stream);
@@ -1808,6 +1996,7 @@ bool launch_mg_persistent(const MgSolveParams &S, const PersistentCommon &P, int
                           size_t smem, bool cooperative)
 {
   void *args[] = {(void *)&S, (void *)&P};
+  if (!reset_barrier(P)) return false;
   cudaError_t e = cooperative
     ? cudaLaunchCooperativeKernel((void *)k_mg_persistent, dim3(grid), dim3(PT), args, smem,
                                   ctx().stream)
