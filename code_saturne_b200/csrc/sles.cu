@@ -169,7 +169,7 @@ namespace {
 
 int sb_rows_threshold()
 {
-  static int v = env_int("CSB_SB_ROWS", 2048);
+  static int v = env_int("CSB_SB_ROWS", 512);   /* measured: 796-row level faster on the grid, 263-row level in one CTA */
   return v;
 }
 
