@@ -35,10 +35,10 @@ namespace csb {
 namespace {
 
 /* CTA shape.  The kernels are HBM-latency bound unless every SM keeps ~45 KB of
-   loads in flight (6.5 TB/s x ~1 us / 148 SMs); registers are what holds them, so
-   the shape is "few fat CTAs": PT threads x MIN_CTAS per SM at <= 64 registers,
-   each thread batching SLAB_E matrix entries (96 B) or 2-4 rows of every vector
-   of an elementwise phase before it consumes anything. */
+   loads in flight (6.5 TB/s x ~1 us / 148 SMs).  Streams are kept in flight by
+   bulk copies into a shared memory ring (no registers, no scoreboard), so the
+   shape is "few fat CTAs": PT threads x MIN_CTAS per SM, 128 registers each for
+   the two alternating sets of x[col] gathers, ~113 KB of shared memory per CTA. */
 #ifndef CSB_PT
 #define CSB_PT 256
 #endif
