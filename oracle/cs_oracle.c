@@ -1552,3 +1552,308 @@ ora_mg_solve(const ora_mg_t *mg, const ora_mg_opt_t *opt,
   free(rhs_l); free(vx_l); free(wr);
   return cvg;
 }
+
+/*----------------------------------------------------------------------------
+ * Multigrid smoothers without convergence test (fixed sweep counts):
+ *   _jacobi          (src/alge/cs_multigrid_smoother.cpp:143-226)
+ *   _relaxed_jacobi  (:244-373): w = 2/3; RJ2 {1.7319, 0.5695};
+ *                    RJ3 {2.2473, 0.8573, 0.5296}, w_k = w[n_iter % M]
+ *   _l1_jacobi       (:804-905) with l1_inv = 1/(d_i + sum_j |x_ij|)
+ *                    (_setup_ad_l1_inv, src/alge/cs_sles_it_priv.cpp:231-262)
+ * Sweep count rounded up to a multiple of M for the scheduled variants
+ * (cs_multigrid_smoother_setup, :1888-1898).
+ * type: cs_sles_it_type_t value.  out[0] = number of sweeps done.
+ * Returns ORA_MAX_ITERATION like the reference, -100 for an unknown type.
+ *----------------------------------------------------------------------------*/
+
+int
+ora_smoother(int type, int n_rows, const int *row_index, const int *col_id,
+             const double *d_val, const double *x_val, int n_max_iter,
+             const double *rhs, double *vx, int use_vx_ini, double *out)
+{
+  const int n = n_rows;
+  if (   type != ORA_SLES_JACOBI && type != ORA_SLES_L1_JACOBI
+      && type != ORA_SLES_R_JACOBI && type != ORA_SLES_RJ2 && type != ORA_SLES_RJ3)
+    return -100;
+
+  double *tmp = malloc(sizeof(double)*(2*(size_t)n + 2));
+  double *ad_inv = tmp + n;
+
+  if (type == ORA_SLES_L1_JACOBI) {
+    for (int i = 0; i < n; i++) {
+      double s1 = d_val[i];
+      for (int j = row_index[i]; j < row_index[i+1]; j++)
+        s1 += fabs(x_val[j]);
+      ad_inv[i] = 1.0 / s1;
+    }
+  }
+  else
+    for (int i = 0; i < n; i++) ad_inv[i] = 1.0 / d_val[i];
+
+  int n_iter = 0;
+
+  if (type == ORA_SLES_JACOBI) {
+    double *rk = tmp;
+    int iter_ini = 0;
+    if (!use_vx_ini) {
+      for (int ii = 0; ii < n; ii++) vx[ii] = rhs[ii]*ad_inv[ii];
+      iter_ini = 1;
+    }
+    for (n_iter = iter_ini; n_iter < n_max_iter; n_iter++) {
+      for (int ii = 0; ii < n; ii++) rk[ii] = vx[ii];
+      ora_spmv_msr(n, row_index, col_id, d_val, x_val, 1, rk, vx);
+      for (int ii = 0; ii < n; ii++) vx[ii] = (rhs[ii]-vx[ii])*ad_inv[ii];
+    }
+  }
+
+  else if (type == ORA_SLES_L1_JACOBI) {
+    double *vx_n = vx, *vx_np = tmp;
+    int iter_ini = 0;
+    if (!use_vx_ini) {
+      for (int ii = 0; ii < n; ii++) vx_n[ii] = rhs[ii]*ad_inv[ii];
+      iter_ini = 1;
+    }
+    for (n_iter = iter_ini; n_iter < n_max_iter; n_iter++) {
+      double *t = vx_n; vx_n = vx_np; vx_np = t;
+      ora_spmv_msr(n, row_index, col_id, d_val, x_val, 0, vx_np, vx_n);
+      for (int ii = 0; ii < n; ii++)
+        vx_n[ii] = vx_np[ii] + (rhs[ii]-vx_n[ii]) * ad_inv[ii];
+    }
+    if (vx_n != vx)
+      for (int ii = 0; ii < n; ii++) vx[ii] = vx_n[ii];
+  }
+
+  else {
+    double w[3] = {2./3., 1.0, 1.0};
+    int wk_m = 1;
+    if (type == ORA_SLES_RJ2) { w[0] = 1.7319; w[1] = 0.5695; wk_m = 2; }
+    if (type == ORA_SLES_RJ3) { w[0] = 2.2473; w[1] = 0.8573; w[2] = 0.5296; wk_m = 3; }
+    if (n_max_iter % wk_m) n_max_iter += wk_m - (n_max_iter % wk_m);
+
+    double *vx_n = vx, *vx_np = tmp;
+    int iter_ini = 0;
+    if (!use_vx_ini) {
+      const double wk = w[0];
+      for (int ii = 0; ii < n; ii++) vx_n[ii] = wk * rhs[ii]*ad_inv[ii];
+      iter_ini = 1;
+    }
+    for (n_iter = iter_ini; n_iter < n_max_iter; n_iter++) {
+      const double wk = w[n_iter % wk_m];
+      const double o_m_wk = 1.0 - wk;
+      double *t = vx_n; vx_n = vx_np; vx_np = t;
+      ora_spmv_msr(n, row_index, col_id, d_val, x_val, 1, vx_np, vx_n);
+      for (int ii = 0; ii < n; ii++)
+        vx_n[ii] = o_m_wk*vx_np[ii] + wk*(rhs[ii]-vx_n[ii])*ad_inv[ii];
+    }
+    if (vx_n != vx)
+      for (int ii = 0; ii < n; ii++) vx[ii] = vx_n[ii];
+  }
+
+  if (out != NULL) out[0] = n_iter;
+  free(tmp);
+  return ORA_MAX_ITERATION;
+}
+
+/* One level's smoother / solver as _multigrid_setup_sles builds it
+   (src/alge/cs_multigrid.cpp:2150-2175): precision_mult < 0 and a smoother-capable
+   type -> cs_multigrid_smoother_*; otherwise cs_sles_it (PCG + Jacobi here). */
+
+static int
+_mg_level_solve(int type, double precision_mult, const ora_grid_t *g, int n_max_iter,
+                double precision, double r_norm, const double *rhs, double *vx,
+                int use_vx_ini, double *sout)
+{
+  if (precision_mult < 0 && type != ORA_SLES_PCG) {
+    sout[2] = HUGE_VAL;
+    return ora_smoother(type, g->n_rows, g->row_index, g->col_id, g->d_val, g->x_val,
+                        n_max_iter, rhs, vx, use_vx_ini, sout);
+  }
+  if (type == ORA_SLES_PCG)
+    return ora_pcg_sr_p0(g->n_rows, g->row_index, g->col_id, g->d_val, g->x_val,
+                         n_max_iter, precision*precision_mult, r_norm,
+                         rhs, vx, use_vx_ini, sout, NULL, 0);
+  return -100;
+}
+
+/*----------------------------------------------------------------------------
+ * Single V-cycle without convergence tests, the form used when the multigrid
+ * is a preconditioner (n_max_cycles == 1):
+ *   _multigrid_v_cycle_pc (src/alge/cs_multigrid.cpp:3569-4000), reached from
+ *   cs_multigrid_solve (:5484-5499) and _multigrid_pc_apply (:1500-1600).
+ * Descent: smoother from 0 (or vx at level 0 when use_vx_ini), residual,
+ * restriction; coarsest solve from 0; ascent: prolongation (increment), then
+ * the ascent smoother on EVERY level including 0.
+ * out[0] = n_equiv_iter.  Returns ORA_ITERATING like the reference, or the
+ * failing level solver's state (< ORA_BREAKDOWN).
+ *----------------------------------------------------------------------------*/
+
+int
+ora_mg_cycle_pc(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt,
+                double precision, double r_norm,
+                const double *rhs, double *vx, int use_vx_ini, double *out)
+{
+  const int n_levels = mg->n_levels;
+  const int coarsest_level = n_levels - 1;
+  const ora_grid_t *g0 = mg->grids[0];
+  const double denom_n_g_rows_0 = 1.0 / g0->n_rows;
+
+  double **rhs_l = calloc(n_levels, sizeof(double *));
+  double **vx_l = calloc(n_levels, sizeof(double *));
+  int wr_size = g0->n_rows;
+  for (int l = 1; l < n_levels; l++) {
+    int n = mg->grids[l]->n_rows;
+    rhs_l[l] = calloc(n > 0 ? n : 1, sizeof(double));
+    vx_l[l] = calloc(n > 0 ? n : 1, sizeof(double));
+    if (n > wr_size) wr_size = n;
+  }
+  vx_l[0] = vx;
+  double *wr = malloc(sizeof(double)*(wr_size > 0 ? wr_size : 1));
+
+  int n_equiv_iter = 0;
+  int c_cvg = ORA_ITERATING;
+  int end_cycle = 0;
+  int ret = ORA_ITERATING;
+  double sout[4];
+  int level;
+
+  for (level = 0; level < coarsest_level; level++) {
+    const ora_grid_t *f = mg->grids[level];
+    const ora_grid_t *c = mg->grids[level+1];
+    const double *rhs_lv = (level == 0) ? rhs : rhs_l[level];
+    double *vx_lv = vx_l[level];
+    const int ini = (level == 0) ? use_vx_ini : 0;
+
+    c_cvg = _mg_level_solve(opt->type[0], opt->precision_mult[0], f, opt->n_max_iter[0],
+                            precision, r_norm, rhs_lv, vx_lv, ini, sout);
+    if (c_cvg < ORA_BREAKDOWN) { end_cycle = 1; ret = c_cvg; break; }
+
+    ora_spmv_msr(f->n_rows, f->row_index, f->col_id, f->d_val, f->x_val, 0, vx_lv, wr);
+    for (int ii = 0; ii < f->n_rows; ii++) wr[ii] = rhs_lv[ii] - wr[ii];
+
+    n_equiv_iter += (int)sout[0] * f->n_rows * denom_n_g_rows_0;
+    ora_restrict(f->n_rows, c->n_rows, c->coarse_row, wr, rhs_l[level+1]);
+  }
+
+  if (!end_cycle) {
+    const ora_grid_t *c = mg->grids[coarsest_level];
+    const double *rhs_lv = (coarsest_level == 0) ? rhs : rhs_l[coarsest_level];
+    c_cvg = _mg_level_solve(opt->type[2], opt->precision_mult[2], c, opt->n_max_iter[2],
+                            precision, r_norm, rhs_lv, vx_l[coarsest_level], 0, sout);
+    n_equiv_iter += (int)sout[0] * c->n_rows * denom_n_g_rows_0;
+    if (c_cvg < ORA_BREAKDOWN) { end_cycle = 1; ret = c_cvg; }
+  }
+
+  if (!end_cycle) {
+    for (level = coarsest_level - 1; level > -1; level--) {
+      const ora_grid_t *f = mg->grids[level];
+      const ora_grid_t *c = mg->grids[level+1];
+      const double *rhs_lv = (level == 0) ? rhs : rhs_l[level];
+      ora_prolong_inc(f->n_rows, c->coarse_row, vx_l[level+1], vx_l[level]);
+      c_cvg = _mg_level_solve(opt->type[1], opt->precision_mult[1], f, opt->n_max_iter[1],
+                              precision, r_norm, rhs_lv, vx_l[level], 1, sout);
+      n_equiv_iter += (int)sout[0] * f->n_rows * denom_n_g_rows_0;
+      if (c_cvg < ORA_BREAKDOWN) { ret = c_cvg; break; }
+    }
+  }
+
+  if (out != NULL) out[0] = n_equiv_iter;
+  for (int l = 1; l < n_levels; l++) { free(rhs_l[l]); free(vx_l[l]); }
+  free(rhs_l); free(vx_l); free(wr);
+  return ret;
+}
+
+/*----------------------------------------------------------------------------
+ * Flexible CG preconditioned by one multigrid V-cycle -- the reference's
+ * production pressure solver (cs_sles_default.cpp: FCG + cs_multigrid_pc):
+ *   _flexible_conjugate_gradient (src/alge/cs_sles_it.cpp:832-985) with
+ *   pc_apply = _multigrid_pc_apply (src/alge/cs_multigrid.cpp:1500-1600);
+ *   the pc tolerance is the outer solver's (cs_sles_it_solve ->
+ *   cs_sles_pc_set_tolerance, _multigrid_pc_tolerance_t :1473-1481).
+ * A one-level hierarchy makes the preconditioner the identity (:1518-1541).
+ * out[0]=n_iter out[1]=residual out[2]=initial_residual out[3]=history count
+ *----------------------------------------------------------------------------*/
+
+int
+ora_fcg_mgpc(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt,
+             int n_max_iter, double precision, double r_norm,
+             const double *rhs, double *vx, int use_vx_ini,
+             double *out, double *history, int history_size)
+{
+  const ora_grid_t *g = mg->grids[0];
+  const int n = g->n_rows;
+  double *rk = malloc(sizeof(double)*((size_t)n*5 + 1));
+  double *vk = rk + n, *wk = rk + 2*n, *dk = rk + 3*n, *qk = rk + 4*n;
+
+  ora_cvg_t cv = {precision, r_norm, -1, n_max_iter, 0, -1,
+                  history, history_size, 0};
+  int cvg = ORA_ITERATING;
+  int n_iter = 0;
+  double residual = -1;
+
+  if (use_vx_ini) {
+    ora_spmv_msr(n, g->row_index, g->col_id, g->d_val, g->x_val, 0, vx, rk);
+    for (int ii = 0; ii < n; ii++) rk[ii] = rhs[ii] - rk[ii];
+  }
+  else {
+    for (int ii = 0; ii < n; ii++) { vx[ii] = 0; rk[ii] = rhs[ii]; }
+  }
+  for (int ii = 0; ii < n; ii++) qk[ii] = 0;
+
+  double rho_km1 = 0;
+
+  while (cvg == ORA_ITERATING) {
+    if (mg->n_levels == 1)
+      for (int ii = 0; ii < n; ii++) vk[ii] = rk[ii];
+    else
+      ora_mg_cycle_pc(mg, opt, precision, r_norm, rk, vk, 0, NULL);
+    ora_spmv_msr(n, g->row_index, g->col_id, g->d_val, g->x_val, 0, vk, wk);
+
+    double alpha_k, beta_k, gamma_k;
+    ora_dot_xy_yz(n, wk, vk, qk, &beta_k, &gamma_k);
+    ora_dot_xx_xy(n, rk, vk, &residual, &alpha_k);
+    residual = sqrt(residual);
+
+    if (n_iter > 0)
+      cvg = _cvg_test(&cv, n_iter, residual);
+    else {
+      cv.initial_residual = residual;
+      if (history != NULL && cv.history_n < history_size)
+        history[cv.history_n++] = residual;
+    }
+    if (cvg != ORA_ITERATING) break;
+
+    if (n_iter > 0) {
+      const double gk_rk1 = (fabs(rho_km1) > DBL_MIN) ? gamma_k / rho_km1 : 0.;
+      const double rho_k = beta_k - gamma_k * gk_rk1;
+      const double ak_rk = (fabs(rho_k) > DBL_MIN) ? alpha_k / rho_k : 0.;
+      for (int ii = 0; ii < n; ii++) {
+        dk[ii] = vk[ii] - gk_rk1 * dk[ii];
+        vx[ii] = vx[ii] + ak_rk * dk[ii];
+      }
+      for (int ii = 0; ii < n; ii++) {
+        qk[ii] = wk[ii] - gk_rk1 * qk[ii];
+        rk[ii] = rk[ii] - ak_rk * qk[ii];
+      }
+      rho_km1 = rho_k;
+    }
+    else {
+      const double rho_k = beta_k;
+      const double ak_rk = (fabs(rho_k) > DBL_MIN) ? alpha_k / rho_k : 0.;
+      for (int ii = 0; ii < n; ii++) {
+        dk[ii] = vk[ii];
+        vx[ii] = vx[ii] + ak_rk * vk[ii];
+      }
+      for (int ii = 0; ii < n; ii++) {
+        qk[ii] = wk[ii];
+        rk[ii] = rk[ii] - ak_rk * wk[ii];
+      }
+      rho_km1 = rho_k;
+    }
+    n_iter += 1;
+  }
+
+  out[0] = n_iter; out[1] = residual; out[2] = cv.initial_residual;
+  out[3] = cv.history_n;
+  free(rk);
+  return cvg;
+}

@@ -41,6 +41,21 @@ typedef struct {
   double  precision_mult[3];
 } ora_mg_opt_t;
 
+/* cs_sles_it_type_t values used on this path (src/alge/cs_sles_it.h:55-87) */
+#define ORA_SLES_PCG        0
+#define ORA_SLES_JACOBI     3
+#define ORA_SLES_L1_JACOBI 13
+#define ORA_SLES_R_JACOBI  14
+#define ORA_SLES_RJ2       15
+#define ORA_SLES_RJ3       16
+
+/* options of the single-cycle (preconditioner) form of the V-cycle */
+typedef struct {
+  int     type[3];            /* descent, ascent, coarse: cs_sles_it_type_t */
+  int     n_max_iter[3];
+  double  precision_mult[3];  /* < 0: cs_multigrid_smoother (no convergence test) */
+} ora_mg_pc_opt_t;
+
 void   ora_thread_range(int n, int type_size, int t_id, int n_t, int *s_id, int *e_id);
 
 void   ora_spmv_msr(int n_rows, const int *row_index, const int *col_id,
@@ -132,6 +147,17 @@ int    ora_mg_solve(const ora_mg_t *mg, const ora_mg_opt_t *opt,
                     double precision, double r_norm,
                     const double *rhs, double *vx, int use_vx_ini,
                     double *out, double *cycle_res);
+
+int    ora_smoother(int type, int n_rows, const int *row_index, const int *col_id,
+                    const double *d_val, const double *x_val, int n_max_iter,
+                    const double *rhs, double *vx, int use_vx_ini, double *out);
+int    ora_mg_cycle_pc(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt,
+                       double precision, double r_norm,
+                       const double *rhs, double *vx, int use_vx_ini, double *out);
+int    ora_fcg_mgpc(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt,
+                    int n_max_iter, double precision, double r_norm,
+                    const double *rhs, double *vx, int use_vx_ini,
+                    double *out, double *history, int history_size);
 
 #ifdef __cplusplus
 }

@@ -79,6 +79,16 @@ class OraMgOpt(C.Structure):
                 ("precision_mult", C.c_double * 3)]
 
 
+class OraMgPcOpt(C.Structure):
+    _fields_ = [("type", C.c_int * 3), ("n_max_iter", C.c_int * 3),
+                ("precision_mult", C.c_double * 3)]
+
+
+# cs_sles_it_type_t values (src/alge/cs_sles_it.h:55-87)
+SLES_PCG, SLES_FCG, SLES_IPCG, SLES_JACOBI, SLES_BICGSTAB = 0, 1, 2, 3, 4
+SLES_L1_JACOBI, SLES_R_JACOBI, SLES_RJ2, SLES_RJ3 = 13, 14, 15, 16
+
+
 def _np_from(ptr, n, dtype):
     if n <= 0 or not ptr:
         return np.zeros(0, dtype=dtype)
@@ -255,6 +265,56 @@ class Oracle:
     def mg_free(self, mg):
         self.lib.ora_mg_free(mg, 1)
 
+    # -- smoothers, single-cycle (preconditioner) V-cycle, FCG + multigrid pc --------
+    def smoother(self, stype, ri, ci, d, xv, rhs, n_max_iter, vx0=None):
+        ri, ci, d, xv, rhs = _i32(ri), _i32(ci), _f64(d), _f64(xv), _f64(rhs)
+        n = len(ri) - 1
+        vx = np.zeros(n) if vx0 is None else _f64(vx0).copy()
+        out = np.zeros(4)
+        cvg = self.lib.ora_smoother(C.c_int(stype), C.c_int(n), _ip(ri), _ip(ci), _dp(d),
+                                    _dp(xv), C.c_int(n_max_iter), _dp(rhs), _dp(vx),
+                                    C.c_int(0 if vx0 is None else 1), _dp(out))
+        return dict(cvg=cvg, n_iter=int(out[0]), vx=vx)
+
+    @staticmethod
+    def _pc_opt(types, n_max_iter, precision_mult):
+        opt = OraMgPcOpt()
+        for i in range(3):
+            opt.type[i] = types[i]
+            opt.n_max_iter[i] = n_max_iter[i]
+            opt.precision_mult[i] = precision_mult[i]
+        return opt
+
+    def mg_cycle_pc(self, mg, rhs, precision, r_norm, types=(SLES_RJ3, SLES_RJ3, SLES_PCG),
+                    n_max_iter=(3, 3, 500), precision_mult=(-1., -1., 1.), vx0=None):
+        rhs = _f64(rhs)
+        vx = np.zeros(len(rhs)) if vx0 is None else _f64(vx0).copy()
+        opt = self._pc_opt(types, n_max_iter, precision_mult)
+        out = np.zeros(4)
+        self.lib.ora_mg_cycle_pc.argtypes = [C.POINTER(OraMg), C.POINTER(OraMgPcOpt),
+                                             C.c_double, C.c_double, c_dbl_p, c_dbl_p,
+                                             C.c_int, c_dbl_p]
+        cvg = self.lib.ora_mg_cycle_pc(mg, C.byref(opt), precision, r_norm, _dp(rhs),
+                                       _dp(vx), 0 if vx0 is None else 1, _dp(out))
+        return dict(cvg=cvg, n_iter=int(out[0]), vx=vx)
+
+    def fcg_mgpc(self, mg, rhs, n_max_iter, precision, r_norm,
+                 types=(SLES_RJ3, SLES_RJ3, SLES_PCG), mg_n_max_iter=(3, 3, 500),
+                 precision_mult=(-1., -1., 1.), vx0=None):
+        rhs = _f64(rhs)
+        vx = np.zeros(len(rhs)) if vx0 is None else _f64(vx0).copy()
+        opt = self._pc_opt(types, mg_n_max_iter, precision_mult)
+        out = np.zeros(4)
+        hist = np.zeros(n_max_iter + 8)
+        self.lib.ora_fcg_mgpc.argtypes = [C.POINTER(OraMg), C.POINTER(OraMgPcOpt), C.c_int,
+                                          C.c_double, C.c_double, c_dbl_p, c_dbl_p, C.c_int,
+                                          c_dbl_p, c_dbl_p, C.c_int]
+        cvg = self.lib.ora_fcg_mgpc(mg, C.byref(opt), n_max_iter, precision, r_norm,
+                                    _dp(rhs), _dp(vx), 0 if vx0 is None else 1, _dp(out),
+                                    _dp(hist), len(hist))
+        return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], initial_residual=out[2],
+                    history=hist[:int(out[3])].copy(), vx=vx)
+
 
 class RefLib:
     """The reference's own CPU code (oracle/_ref/libcsref.so)."""
@@ -368,6 +428,33 @@ class RefLib:
                                              C.c_int(verbosity), _dp(out))
         return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], t_setup=out[2],
                     t_solve=out[3], vx=vx)
+
+    def smoother(self, h, stype, rhs, n_max_iter, vx0=None):
+        rhs = _f64(rhs)
+        vx = np.zeros(len(rhs)) if vx0 is None else _f64(vx0).copy()
+        out = np.zeros(4)
+        cvg = self.lib.csref_smoother_solve(h, C.c_int(stype), C.c_int(n_max_iter), _dp(rhs),
+                                            _dp(vx), C.c_int(0 if vx0 is None else 1),
+                                            _dp(out))
+        return dict(cvg=cvg, n_iter=int(out[0]), vx=vx)
+
+    def fcg_mgpc(self, h, rhs, n_max_iter, precision, r_norm, types=(16, 16, 0),
+                 mg_n_max_iter=(3, 3, 500), poly_degree=(0, 0, 0),
+                 precision_mult=(-1., -1., 1.), aggregation_limit=3, coarsening_type=0,
+                 n_levels_max=25, n_g_rows_min=30, p0p1_relax=0.95, vx0=None):
+        rhs = _f64(rhs)
+        vx = np.zeros(len(rhs)) if vx0 is None else _f64(vx0).copy()
+        iopt = np.array(list(types) + [1] + list(mg_n_max_iter) + list(poly_degree)
+                        + [aggregation_limit, coarsening_type, n_levels_max, n_g_rows_min],
+                        dtype=np.int32)
+        dopt = np.array(list(precision_mult) + [p0p1_relax], dtype=np.float64)
+        out = np.zeros(5)
+        cvg = self.lib.csref_fcg_mgpc_solve(h, _ip(iopt), _dp(dopt), C.c_int(n_max_iter),
+                                            C.c_double(precision), C.c_double(r_norm),
+                                            _dp(rhs), _dp(vx),
+                                            C.c_int(0 if vx0 is None else 1), _dp(out))
+        return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], initial_residual=out[2],
+                    t_setup=out[3], t_solve=out[4], vx=vx)
 
     def hierarchy(self, h, aggregation_limit=3, coarsening_type=0, n_levels_max=25,
                   n_g_rows_min=30, p0p1_relax=0.95, verbosity=0):

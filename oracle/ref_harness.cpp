@@ -15,6 +15,10 @@
  *   cs_grid_create_from_shared / cs_grid_coarsen
  *                                        (src/alge/cs_grid.cpp:7425, :7980)
  *   cs_dot_xx, cs_dot_xx_xy_yz ...       (src/alge/cs_blas.cpp:1629-1905)
+ *   cs_multigrid_smoother_create/_setup/_solve
+ *                                        (src/alge/cs_multigrid_smoother.cpp:1726,:1825,:2008)
+ *   cs_multigrid_pc_create, cs_sles_it_transfer_pc
+ *                                        (src/alge/cs_multigrid.cpp:5682, cs_sles_it.cpp)
  *
  * Used (a) to pin oracle/*.c restatements and generate tests/golden fixtures,
  * (b) as the CPU baseline of bench.py ("kind": "reference").
@@ -44,6 +48,7 @@
 #include "alge/cs_sles_it.h"
 #include "alge/cs_sles_pc.h"
 #include "alge/cs_multigrid.h"
+#include "alge/cs_multigrid_smoother.h"
 #include "alge/cs_grid.h"
 #include "alge/cs_grid_priv.h"
 
@@ -402,6 +407,90 @@ csref_multigrid_solve(void          *sys,
   cs_multigrid_free(mg);
   void *ctx = mg;
   cs_multigrid_destroy(&ctx);
+  return (int)cvg;
+}
+
+/* cs_multigrid_smoother solve (fixed sweep count, no convergence test).
+   type: cs_sles_it_type_t value (3 Jacobi, 13 L1 Jacobi, 14 relaxed Jacobi,
+   15 RJ2, 16 RJ3).  out[0] = n_iter.  Returns the convergence state. */
+int
+csref_smoother_solve(void          *sys,
+                     int            type,
+                     int            n_max_iter,
+                     const double  *rhs,
+                     double        *vx,
+                     int            use_vx_ini,
+                     double        *out)
+{
+  ref_system *s = static_cast<ref_system *>(sys);
+  cs_sles_it_t *c = cs_multigrid_smoother_create((cs_sles_it_type_t)type, 0,
+                                                 n_max_iter);
+  if (c == nullptr)
+    return -100;
+  cs_multigrid_smoother_setup(c, "csref", s->m, 0);
+  int n_iter = 0;
+  double residual = -1;
+  cs_sles_convergence_state_t cvg
+    = cs_multigrid_smoother_solve(c, "csref", s->m, -1, 0., 1.,
+                                  &n_iter, &residual, rhs,
+                                  use_vx_ini ? vx : nullptr, vx, 0, nullptr);
+  out[0] = n_iter;
+  void *ctx = c;
+  cs_sles_it_free(ctx);
+  cs_sles_it_destroy(&ctx);
+  return (int)cvg;
+}
+
+/* FCG preconditioned by one V-cycle (cs_multigrid_pc_create + cs_sles_it_transfer_pc),
+   the reference's production pressure solver layout.
+   iopt/dopt as csref_multigrid_solve ([3] n_max_cycles is forced to 1).
+   out: [0] n_iter, [1] residual, [2] initial residual, [3] setup s, [4] solve s */
+int
+csref_fcg_mgpc_solve(void          *sys,
+                     const int     *iopt,
+                     const double  *dopt,
+                     int            n_max_iter,
+                     double         precision,
+                     double         r_norm,
+                     const double  *rhs,
+                     double        *vx,
+                     int            use_vx_ini,
+                     double        *out)
+{
+  ref_system *s = static_cast<ref_system *>(sys);
+  cs_sles_it_t *c = cs_sles_it_create(CS_SLES_FCG, -1, n_max_iter, false);
+  cs_sles_pc_t *pc = cs_multigrid_pc_create(CS_MULTIGRID_V_CYCLE);
+  cs_multigrid_t *mg = (cs_multigrid_t *)cs_sles_pc_get_context(pc);
+  cs_multigrid_set_solver_options(mg,
+                                  (cs_sles_it_type_t)iopt[0],
+                                  (cs_sles_it_type_t)iopt[1],
+                                  (cs_sles_it_type_t)iopt[2],
+                                  1, iopt[4], iopt[5], iopt[6],
+                                  iopt[7], iopt[8], iopt[9],
+                                  dopt[0], dopt[1], dopt[2]);
+  cs_multigrid_set_coarsening_options(mg, iopt[10],
+                                      (cs_grid_coarsening_t)iopt[11],
+                                      iopt[12], (cs_gnum_t)iopt[13],
+                                      dopt[3], 0);
+  cs_sles_it_transfer_pc(c, &pc);
+  double t0 = _now();
+  cs_sles_it_setup(c, "csref", s->m, 0);
+  double t1 = _now();
+  int n_iter = 0;
+  double residual = -1;
+  cs_sles_convergence_state_t cvg
+    = cs_sles_it_solve(c, "csref", s->m, -1, precision, r_norm,
+                       &n_iter, &residual, rhs,
+                       use_vx_ini ? vx : nullptr, vx, 0, nullptr);
+  double t2 = _now();
+  out[0] = n_iter;
+  out[1] = residual;
+  out[2] = cs_sles_it_get_last_initial_residual(c);
+  out[3] = t1 - t0;
+  out[4] = t2 - t1;
+  void *ctx = c;
+  cs_sles_it_free(ctx);
+  cs_sles_it_destroy(&ctx);
   return (int)cvg;
 }
 

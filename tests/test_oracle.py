@@ -238,3 +238,80 @@ def test_oracle_pcg_npc_vs_reference_direct(oracle, reflib):
         assert (a["cvg"], a["n_iter"], a["residual"]) == (b["cvg"], b["n_iter"], b["residual"])
         assert np.array_equal(a["vx"], b["vx"])
         reflib.destroy(h)
+
+
+# ---- multigrid smoothers, single-cycle V-cycle (preconditioner form), FCG + multigrid pc ----
+
+MGPC_CASES = [(8, "neumann"), (12, "dirichlet")]
+SMOOTHERS = {"jacobi": 3, "l1_jacobi": 13, "r_jacobi": 14, "rj2": 15, "rj3": 16}
+MGPC_CYCLES = {"rj3": ((16, 16, 0), (3, 3, 500)), "rj2": ((15, 15, 0), (2, 4, 500)),
+               "r_jacobi": ((14, 14, 0), (2, 2, 500)), "l1_jacobi": ((13, 13, 0), (2, 2, 500)),
+               "jacobi": ((3, 3, 0), (2, 3, 500))}
+
+
+@pytest.mark.parametrize("N,bc", MGPC_CASES)
+def test_oracle_smoothers_match_golden(oracle, N, bc):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"mgpc_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    for name, st in SMOOTHERS.items():
+        for nit in (1, 3):
+            r = oracle.smoother(st, s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, nit)
+            assert np.array_equal(r["vx"], g[f"sm_{name}_{nit}_zero"]), (name, nit)
+            r = oracle.smoother(st, s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, nit, g["vx0"])
+            assert np.array_equal(r["vx"], g[f"sm_{name}_{nit}_warm"]), (name, nit)
+            assert r["n_iter"] == int(g[f"sm_{name}_{nit}_n_iter"])
+
+
+@pytest.mark.parametrize("N,bc", MGPC_CASES)
+def test_oracle_cycle_pc_and_fcg_mgpc_match_golden(oracle, N, bc):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"mgpc_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    r_norm = float(g["r_norm"])
+    mg = oracle.mg_setup(s)
+    for name, (types, nmi) in MGPC_CYCLES.items():
+        r = oracle.mg_cycle_pc(mg, s.rhs, 1e-8, r_norm, types, nmi)
+        assert np.array_equal(r["vx"], g[f"cyc_{name}_vx"]), name
+        assert r["n_iter"] == int(g[f"cyc_{name}_n_iter"])
+        r = oracle.fcg_mgpc(mg, s.rhs, 200, 1e-8, r_norm, types, nmi)
+        assert r["cvg"] == int(g[f"fcg_{name}_cvg"]) == 1
+        assert r["n_iter"] == int(g[f"fcg_{name}_n_iter"])
+        assert r["residual"] == float(g[f"fcg_{name}_residual"])
+        assert r["initial_residual"] == float(g[f"fcg_{name}_initial_residual"])
+        assert np.array_equal(r["vx"], g[f"fcg_{name}_vx"])
+        hist = g[f"fcg_{name}_history"]
+        assert np.array_equal(r["history"][1:], hist)     # history[0] = initial residual
+    oracle.mg_free(mg)
+
+
+def test_oracle_mgpc_vs_reference_direct(oracle, reflib):
+    """Sizes beyond the fixtures, warm starts and every sweep count, against the reference's
+    own code when it is built here."""
+    rng = np.random.default_rng(11)
+    for N, bc in ((10, "dirichlet"), (21, "neumann")):
+        s = cube_poisson(N, bc)
+        h = reflib.system(s)
+        r_norm = float(np.linalg.norm(s.rhs))
+        vx0 = rng.standard_normal(s.n_rows)
+        for st in SMOOTHERS.values():
+            for nit in (1, 2, 4, 7):
+                for v0 in (None, vx0):
+                    a = oracle.smoother(st, s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, nit, v0)
+                    b = reflib.smoother(h, st, s.rhs, nit, v0)
+                    assert a["n_iter"] == b["n_iter"] and a["cvg"] == b["cvg"]
+                    assert np.array_equal(a["vx"], b["vx"]), (N, st, nit)
+        mg = oracle.mg_setup(s)
+        for types, nmi in MGPC_CYCLES.values():
+            for v0 in (None, vx0):
+                a = oracle.mg_cycle_pc(mg, s.rhs, 1e-8, r_norm, types, nmi, vx0=v0)
+                b = reflib.multigrid(h, s.rhs, 1e-8, r_norm, n_max_cycles=1, n_max_iter=nmi,
+                                     types=types, precision_mult=(-1., -1., 1.), vx0=v0)
+                assert np.array_equal(a["vx"], b["vx"]) and a["n_iter"] == b["n_iter"]
+            a = oracle.fcg_mgpc(mg, s.rhs, 200, 1e-8, r_norm, types, nmi)
+            b = reflib.fcg_mgpc(h, s.rhs, 200, 1e-8, r_norm, types, nmi)
+            assert (a["cvg"], a["n_iter"], a["residual"]) == (b["cvg"], b["n_iter"], b["residual"])
+            assert np.array_equal(a["vx"], b["vx"])
+            a = oracle.fcg_mgpc(mg, s.rhs, 3, 1e-12, r_norm, types, nmi, vx0=0.5 * a["vx"])
+            b = reflib.fcg_mgpc(h, s.rhs, 3, 1e-12, r_norm, types, nmi, vx0=0.5 * b["vx"])
+            assert a["cvg"] == b["cvg"] == -1 and np.array_equal(a["vx"], b["vx"])
+        oracle.mg_free(mg)
+        reflib.destroy(h)
