@@ -47,6 +47,11 @@ class SlesItType(enum.IntEnum):
     IPCG = 2
     JACOBI = 3
     BICGSTAB = 4
+    # multigrid smoothers (cs_sles_it.h:79-83)
+    L1_JACOBI = 13
+    R_JACOBI = 14
+    RJ2 = 15
+    RJ3 = 16
 
 
 _lib = None
@@ -182,6 +187,16 @@ def load_library() -> C.CDLL:
     L.csb_multigrid_log.restype = None
     L.csb_multigrid_copy.restype = vp
     L.csb_multigrid_copy.argtypes = [vp]
+    L.csb_multigrid_pc_create.restype = vp
+    L.csb_multigrid_pc_create.argtypes = [ci]
+    L.csb_sles_it_transfer_pc.argtypes = [vp, C.POINTER(vp)]
+    L.csb_sles_it_get_pc.restype = vp
+    L.csb_sles_it_get_pc.argtypes = [vp]
+    L.csb_multigrid_smoother_create.restype = vp
+    L.csb_multigrid_smoother_create.argtypes = [ci, ci, ci]
+    L.csb_multigrid_smoother_setup.argtypes = [vp, C.c_char_p, vp, ci]
+    L.csb_multigrid_smoother_setup.restype = None
+    L.csb_multigrid_smoother_solve.argtypes = solve_args
     L.csb_host_aggregate_dx_msr.argtypes = [ci, ci, vp, vp, vp, vp, ci, ci, vp]
     L.csb_host_coarse_structure.argtypes = [ci, vp, vp, vp, ci, vp, vp, vp, vp, vp]
     _lib = L
@@ -563,6 +578,14 @@ class SlesIt(_SolverBase):
     def set_pcomm(self, pcomm):
         load_library().csb_sles_it_set_pcomm(C.c_void_p(self._h), pcomm.handle)
 
+    def transfer_pc(self, mg: "Multigrid"):
+        """cs_sles_it_transfer_pc: the solver takes ownership of the multigrid preconditioner
+        (FCG created with poly_degree < 0)."""
+        h = C.c_void_p(mg._h)
+        if load_library().csb_sles_it_transfer_pc(C.c_void_p(self._h), C.byref(h)) != 0:
+            _err("csb_sles_it_transfer_pc")
+        mg._h = None
+
     def setup(self, a: Matrix, name="system", verbosity=0):
         load_library().csb_sles_it_setup(C.c_void_p(self._h), name.encode(), a.handle, verbosity)
 
@@ -597,13 +620,34 @@ class SlesIt(_SolverBase):
             pass
 
 
+class Smoother(SlesIt):
+    """cs_multigrid_smoother_*: a fixed number of Jacobi-family sweeps, no convergence test."""
+
+    _solve_name = "csb_multigrid_smoother_solve"
+
+    def __init__(self, smoother_type, n_iter, poly_degree=0):
+        self._h = load_library().csb_multigrid_smoother_create(int(smoother_type),
+                                                               int(poly_degree), int(n_iter))
+        if not self._h:
+            _err("csb_multigrid_smoother_create")
+
+    def setup(self, a: Matrix, name="system", verbosity=0):
+        load_library().csb_multigrid_smoother_setup(C.c_void_p(self._h), name.encode(),
+                                                    a.handle, verbosity)
+
+    def solve(self, a, rhs, vx=None, use_vx_ini=False, verbosity=0):
+        return self._solve(a, rhs, 0., 1., vx, use_vx_ini, verbosity)
+
+
 class Multigrid(_SolverBase):
-    """cs_multigrid_t, V-cycle (solver mode defaults of cs_multigrid_define)."""
+    """cs_multigrid_t, V-cycle (solver mode defaults of cs_multigrid_define);
+    ``Multigrid(pc=True)`` = cs_multigrid_pc_create (single cycle, device smoother settings)."""
 
     _solve_name = "csb_multigrid_solve"
 
-    def __init__(self):
-        self._h = load_library().csb_multigrid_create(0)
+    def __init__(self, pc=False):
+        L = load_library()
+        self._h = L.csb_multigrid_pc_create(0) if pc else L.csb_multigrid_create(0)
         if not self._h:
             _err("csb_multigrid_create")
 

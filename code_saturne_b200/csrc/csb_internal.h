@@ -319,7 +319,18 @@ enum SpmvEpilogue {
   EPI_RESIDUAL,         /* y = b - A.x  (V-cycle residual, cs_multigrid.cpp:3296-3301) */
   EPI_RESIDUAL_NORM,    /* same + sum(y^2) -> mg finalize (level 0)       */
   EPI_PCG_INIT,         /* rk = A.x - b ; dk = rk*ad_inv  (cs_sles_it.cpp:1503-1508) */
-  EPI_PCG_DOT3          /* y = A.x ; sums (rk.rk, rk.x, x.y) -> pcg finalize */
+  EPI_PCG_DOT3,         /* y = A.x ; sums (rk.rk, rk.x, x.y) -> pcg finalize */
+  EPI_SMOOTH,           /* one fused Jacobi-family smoother sweep: y = S(x, b, A.x)
+                           (cs_multigrid_smoother.cpp:205-213, :345-352, :880-887) */
+  EPI_FCG_DOT4          /* y = A.x ; sums (rk.rk, rk.x, y.x, x.qk) -> fcg finalize
+                           (_dot_products_vr_vw_vq_rr, cs_sles_it.cpp:693-724) */
+};
+
+/* EPI_SMOOTH variants (SpmvArgs::smooth_mode) */
+enum SmoothMode {
+  SMOOTH_JACOBI = 0,    /* y = (b - E.x) * ad_inv                            */
+  SMOOTH_RELAXED,       /* y = w1*x + w0*(b - E.x)*ad_inv, w1 = 1 - w0      */
+  SMOOTH_L1             /* y = x + (b - A.x) * l1_inv  (full product)        */
 };
 
 struct SpmvArgs {
@@ -334,6 +345,9 @@ struct SpmvArgs {
   ItState      *st = nullptr;
   MgState      *mg = nullptr;
   int           phase = 0;         /* PCG_DOT3: 0 = first (ro_0, ro_1), 1 = iteration */
+  int           smooth_mode = 0;   /* EPI_SMOOTH */
+  double        w0 = 1., w1 = 0.;  /* EPI_SMOOTH relaxation weights */
+  const double *qk = nullptr;      /* EPI_FCG_DOT4 */
 };
 
 bool launch_spmv(SpmvEpilogue epi, const SpmvArgs &a);
@@ -390,6 +404,21 @@ bool launch_bicg_spmv_c(const _csb_matrix_t *m, ItState *st, const double *zk, d
 bool launch_bicg_upd2(int n, ItState *st, double *vx, double *rk, const double *zk,
                       const double *vk, const double *res0);
 
+/* Multigrid smoothers without convergence test (cs_multigrid_smoother.cpp) */
+bool launch_l1_inv(const _csb_matrix_t *m, double *l1_inv);   /* cs_sles_it_priv.cpp:231-262 */
+/* first sweep from a zero start: vx = rhs*ad_inv, or w0*rhs*ad_inv when relaxed */
+bool launch_smoother_first(int n, int smooth_mode, double w0, const double *rhs,
+                           const double *ad_inv, double *vx, const MgState *gate);
+bool launch_copy_gated(int n, const double *src, double *dst, const MgState *gate);
+/* mirror the outer Krylov solver's state into the gate of its multigrid preconditioner */
+bool launch_gate_from_it(MgState *gate, const ItState *st);
+
+/* FCG with a general preconditioner, kernel per phase (cs_sles_it.cpp:832-985) */
+bool launch_fcg_init(int n, ItState *st, const double *rhs, double *vx, double *rk,
+                     double *qk, bool have_residual);
+bool launch_fcg_update(int n, ItState *st, const double *vk, const double *wk, double *dk,
+                       double *qk, double *rk, double *vx);
+
 /* multigrid transfer operators (cs_grid.cpp:8987-9210) */
 bool launch_restrict(int c_n_rows, const int *c_f_row_index, const int *c_f_row_ids,
                      const double *f_var, double *c_var, const MgState *gate);
@@ -399,6 +428,8 @@ bool launch_mg_state_init(MgState *mg, double precision, double r_norm, int n_ma
 bool launch_mg_cycle_begin(MgState *mg, int cycle_id);
 bool launch_mg_accum_iter(MgState *mg, const ItState *st, int level, double n_rows_ratio,
                           int take_initial_residual);
+/* same for a smoother whose sweep count is known: += n_iter * n_rows * denom */
+bool launch_mg_accum_n(MgState *mg, int n_iter, int n_rows, double denom_n_g_rows_0);
 
 /* coarse level assembly (cs_grid.cpp:6226-6590, :6841-6897) */
 struct CoarseAssemblyArgs {

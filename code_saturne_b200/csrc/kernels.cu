@@ -176,6 +176,37 @@ __device__ __forceinline__ void pcg_finalize_iter(ItState *st, const double *s)
   st->cvg = cvg;
 }
 
+/* Scalar part of one FCG iteration (cs_sles_it.cpp:926-980), s = (rk.rk, rk.vk = alpha_k,
+   wk.vk = beta_k, vk.qk = gamma_k).  Leaves gk_rk1 in st->beta, ak_rk in st->alpha,
+   rho_k in st->ro_0 and counts the iteration; the update kernel tests n_iter == 1 for the
+   first-iteration form. */
+__device__ __forceinline__ void fcg_finalize(ItState *st, const double *s)
+{
+  const double residual = sqrt(s[0]);
+  const double alpha_k = s[1], beta_k = s[2], gamma_k = s[3];
+  int cvg = CSB_SLES_ITERATING;
+  if (st->n_iter > 0)
+    cvg = it_cvg_test(st, st->n_iter, residual);
+  else {
+    st->initial_residual = residual;
+    st->residual = residual;
+    if (st->n_hist < HIST_MAX) st->hist[st->n_hist++] = residual;
+  }
+  if (cvg == CSB_SLES_ITERATING) {
+    double gk_rk1 = 0., rho_k = beta_k;
+    if (st->n_iter > 0) {
+      const double rho_km1 = st->ro_0;
+      gk_rk1 = (fabs(rho_km1) > DBL_MIN) ? gamma_k / rho_km1 : 0.;
+      rho_k = beta_k - gamma_k * gk_rk1;
+    }
+    st->alpha = (fabs(rho_k) > DBL_MIN) ? alpha_k / rho_k : 0.;
+    st->beta = gk_rk1;
+    st->ro_0 = rho_k;
+    st->n_iter += 1;
+  }
+  st->cvg = cvg;
+}
+
 /* _convergence_test, src/alge/cs_multigrid.cpp:2927-3035 */
 __device__ __forceinline__ void mg_finalize_residual(MgState *mg, const double *s)
 {
@@ -217,6 +248,9 @@ struct SpmvK {
   int           phase;
   double       *partials;
   unsigned     *ticket;
+  int           smooth_mode;
+  double        w0, w1;
+  const double *qk;
 };
 
 template <int EPI>
@@ -228,6 +262,10 @@ __device__ __forceinline__ bool spmv_gated_off(const SpmvK &a)
     return (a.mg != nullptr && a.mg->cvg != CSB_SLES_ITERATING);
   if (EPI == EPI_STORE)
     return (a.st != nullptr && a.st->cvg != CSB_SLES_ITERATING);
+  if (EPI == EPI_SMOOTH)
+    return (a.mg != nullptr && a.mg->cvg != CSB_SLES_ITERATING);
+  if (EPI == EPI_FCG_DOT4)
+    return (a.st->cvg != CSB_SLES_ITERATING);
   return false;
 }
 
@@ -238,8 +276,10 @@ __device__ __forceinline__ void spmv_epilogue(const SpmvK &a, int r, bool active
   /* sii = sum of off-diagonal products in CSR order; diagonal added last
      (src/alge/cs_matrix_spmv.cpp:2138-2142) */
   double v[3] = {0., 0., 0.};
+  double v3 = 0.;     /* 4th sum of EPI_FCG_DOT4 */
   if (active) {
-    const double xr = (a.d_val != nullptr || EPI == EPI_PCG_DOT3) ? a.x[r] : 0.;
+    const double xr = (a.d_val != nullptr || EPI == EPI_PCG_DOT3 || EPI == EPI_SMOOTH
+                       || EPI == EPI_FCG_DOT4) ? a.x[r] : 0.;
     const double yr = (a.d_val != nullptr) ? sii + a.d_val[r]*xr : sii;
     if (EPI == EPI_STORE) {
       a.y[r] = yr;
@@ -261,6 +301,30 @@ __device__ __forceinline__ void spmv_epilogue(const SpmvK &a, int r, bool active
       v[1] = rr*xr;
       v[2] = xr*yr;
     }
+    else if (EPI == EPI_SMOOTH) {
+      /* yr = E.x (diagonal excluded) for the Jacobi variants, A.x for L1 */
+      const double t = a.b[r] - yr;
+      if (a.smooth_mode == SMOOTH_JACOBI)
+        a.y[r] = t * a.ad_inv[r];
+      else if (a.smooth_mode == SMOOTH_RELAXED)
+        a.y[r] = a.w1*xr + a.w0*t*a.ad_inv[r];
+      else
+        a.y[r] = xr + t * a.ad_inv[r];
+    }
+    else if (EPI == EPI_FCG_DOT4) {
+      a.y[r] = yr;
+      const double rr = a.rk[r];
+      v[0] = rr*rr;
+      v[1] = rr*xr;
+      v[2] = yr*xr;
+      v3 = xr*a.qk[r];
+    }
+  }
+  if (EPI == EPI_FCG_DOT4) {
+    double w[4] = {v[0], v[1], v[2], v3};
+    ItState *st = a.st;
+    grid_sum_finalize<4>(w, a.partials, a.ticket,
+                         [st](const double *s) { fcg_finalize(st, s); });
   }
   if (EPI == EPI_RESIDUAL_NORM) {
     double w[1] = {v[0]};
@@ -537,7 +601,8 @@ bool launch_spmv(SpmvEpilogue epi, const SpmvArgs &a)
   k.x_val = m->x_val.p;
   k.x = a.x; k.y = a.y; k.b = a.b; k.ad_inv = a.ad_inv;
   k.rk = a.rk; k.dk = a.dk; k.st = a.st; k.mg = a.mg; k.phase = a.phase;
-  if (epi == EPI_RESIDUAL_NORM || epi == EPI_PCG_DOT3)
+  k.smooth_mode = a.smooth_mode; k.w0 = a.w0; k.w1 = a.w1; k.qk = a.qk;
+  if (epi == EPI_RESIDUAL_NORM || epi == EPI_PCG_DOT3 || epi == EPI_FCG_DOT4)
     if (!ensure_partials((m->n_rows + TPB - 1) / TPB)) return false;
   k.partials = ctx().partials; k.ticket = ctx().ticket;   /* after a possible regrow */
   if (epi == EPI_STORE && spmv_pipeline_enabled()) {
@@ -553,6 +618,8 @@ bool launch_spmv(SpmvEpilogue epi, const SpmvArgs &a)
   case EPI_RESIDUAL_NORM: return spmv_dispatch<EPI_RESIDUAL_NORM>(k, m);
   case EPI_PCG_INIT:      return spmv_dispatch<EPI_PCG_INIT>(k, m);
   case EPI_PCG_DOT3:      return spmv_dispatch<EPI_PCG_DOT3>(k, m);
+  case EPI_SMOOTH:        return spmv_dispatch<EPI_SMOOTH>(k, m);
+  case EPI_FCG_DOT4:      return spmv_dispatch<EPI_FCG_DOT4>(k, m);
   }
   return false;
 }
@@ -1554,6 +1621,172 @@ bool launch_coarse_assembly(const CoarseAssemblyArgs &a, int stages)
   if (!(stages & 2)) return true;
   k_coarse_stage_2<<<grid, 128, 0, c.stream>>>(a);
   return post_launch("coarse_stage_2");
+}
+
+/*--------------------------------------------------------------------------
+ * Multigrid smoothers without convergence test (cs_multigrid_smoother.cpp:143-373,
+ * :804-905): the sweeps themselves are k_spmv_stream<EPI_SMOOTH> (product and update
+ * fused, one pass over the matrix per sweep); these are the pieces around them.
+ *--------------------------------------------------------------------------*/
+
+namespace {
+
+/* _setup_ad_l1_inv, MSR (src/alge/cs_sles_it_priv.cpp:236-251) */
+__global__ void __launch_bounds__(TPB)
+k_l1_inv(int n, const int *__restrict__ row_index, const double *__restrict__ d_val,
+         const double *__restrict__ x_val, double *__restrict__ l1_inv)
+{
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    double s1 = d_val[i];
+    const int ks = row_index[i], ke = row_index[i+1];
+    for (int k = ks; k < ke; k++)
+      s1 += fabs(x_val[k]);
+    l1_inv[i] = 1.0 / s1;
+  }
+}
+
+/* first sweep from vx = 0 (cs_multigrid_smoother.cpp:196-199, :322-327, :858-861) */
+__global__ void __launch_bounds__(TPB)
+k_smoother_first(int n, int relaxed, double w0, const double *__restrict__ rhs,
+                 const double *__restrict__ ad_inv, double *__restrict__ vx,
+                 const MgState *gate)
+{
+  if (gate != nullptr && gate->cvg != CSB_SLES_ITERATING) return;
+  if (relaxed) {
+    for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB)
+      vx[i] = w0 * rhs[i]*ad_inv[i];
+  }
+  else {
+    for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB)
+      vx[i] = rhs[i]*ad_inv[i];
+  }
+}
+
+__global__ void __launch_bounds__(TPB)
+k_copy_mg_gated(int n, const double *__restrict__ src, double *__restrict__ dst,
+                const MgState *gate)
+{
+  if (gate != nullptr && gate->cvg != CSB_SLES_ITERATING) return;
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB)
+    dst[i] = src[i];
+}
+
+/* *n_equiv_iter += n_iter * n_g_rows * denom_n_g_rows_0 (cs_multigrid.cpp:3700, :3790, :3905):
+   integer product, then double, then the int += double truncation */
+__global__ void
+k_mg_accum_n(MgState *mg, int n_iter, int n_rows, double denom)
+{
+  if (mg->cvg != CSB_SLES_ITERATING) return;
+  const double x = (double)((unsigned long long)n_iter * (unsigned long long)n_rows) * denom;
+  mg->n_equiv_iter = (int)((double)mg->n_equiv_iter + x);
+}
+
+__global__ void
+k_gate_from_it(MgState *gate, const ItState *st)
+{
+  gate->cvg = (st->cvg == CSB_SLES_ITERATING) ? CSB_SLES_ITERATING : CSB_SLES_CONVERGED;
+}
+
+/* FCG start (cs_sles_it.cpp:880-905): rk holds A.vx on entry when have_residual */
+__global__ void __launch_bounds__(TPB)
+k_fcg_init(int n, const double *__restrict__ rhs, double *__restrict__ vx,
+           double *__restrict__ rk, double *__restrict__ qk, int have_residual)
+{
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    if (have_residual)
+      rk[i] = rhs[i] - rk[i];
+    else {
+      vx[i] = 0.;
+      rk[i] = rhs[i];
+    }
+    qk[i] = 0.;
+  }
+}
+
+/* FCG vector updates (cs_sles_it.cpp:940-978); st->n_iter was already counted by
+   fcg_finalize, so n_iter == 1 is the first iteration (dk, qk not yet defined) */
+__global__ void __launch_bounds__(TPB)
+k_fcg_update(int n, const ItState *st, const double *__restrict__ vk,
+             const double *__restrict__ wk, double *__restrict__ dk,
+             double *__restrict__ qk, double *__restrict__ rk, double *__restrict__ vx)
+{
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  const double ak_rk = st->alpha, gk_rk1 = st->beta;
+  if (st->n_iter == 1) {
+    for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+      const double v = vk[i], w = wk[i];
+      dk[i] = v;
+      vx[i] = vx[i] + ak_rk * v;
+      qk[i] = w;
+      rk[i] = rk[i] - ak_rk * w;
+    }
+  }
+  else {
+    for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+      const double d = vk[i] - gk_rk1 * dk[i];
+      dk[i] = d;
+      vx[i] = vx[i] + ak_rk * d;
+      const double q = wk[i] - gk_rk1 * qk[i];
+      qk[i] = q;
+      rk[i] = rk[i] - ak_rk * q;
+    }
+  }
+}
+
+} // anonymous namespace
+
+bool launch_l1_inv(const _csb_matrix_t *m, double *l1_inv)
+{
+  if (m->n_rows < 1) return true;
+  k_l1_inv<<<vec_grid(m->n_rows*4), TPB, 0, ctx().stream>>>(m->n_rows, m->row_index.p,
+                                                           m->d_val.p, m->x_val.p, l1_inv);
+  return post_launch("l1_inv");
+}
+
+bool launch_smoother_first(int n, int smooth_mode, double w0, const double *rhs,
+                           const double *ad_inv, double *vx, const MgState *gate)
+{
+  if (n < 1) return true;
+  k_smoother_first<<<vec_grid(n), TPB, 0, ctx().stream>>>(
+    n, smooth_mode == SMOOTH_RELAXED ? 1 : 0, w0, rhs, ad_inv, vx, gate);
+  return post_launch("smoother_first");
+}
+
+bool launch_copy_gated(int n, const double *src, double *dst, const MgState *gate)
+{
+  if (n < 1) return true;
+  k_copy_mg_gated<<<vec_grid(n), TPB, 0, ctx().stream>>>(n, src, dst, gate);
+  return post_launch("copy_gated");
+}
+
+bool launch_mg_accum_n(MgState *mg, int n_iter, int n_rows, double denom_n_g_rows_0)
+{
+  k_mg_accum_n<<<1, 1, 0, ctx().stream>>>(mg, n_iter, n_rows, denom_n_g_rows_0);
+  return post_launch("mg_accum_n");
+}
+
+bool launch_gate_from_it(MgState *gate, const ItState *st)
+{
+  k_gate_from_it<<<1, 1, 0, ctx().stream>>>(gate, st);
+  return post_launch("gate_from_it");
+}
+
+bool launch_fcg_init(int n, ItState *st, const double *rhs, double *vx, double *rk,
+                     double *qk, bool have_residual)
+{
+  (void)st;
+  if (n < 1) return true;
+  k_fcg_init<<<vec_grid(n), TPB, 0, ctx().stream>>>(n, rhs, vx, rk, qk,
+                                                    have_residual ? 1 : 0);
+  return post_launch("fcg_init");
+}
+
+bool launch_fcg_update(int n, ItState *st, const double *vk, const double *wk, double *dk,
+                       double *qk, double *rk, double *vx)
+{
+  if (n < 1) return true;
+  k_fcg_update<<<vec_grid(n), TPB, 0, ctx().stream>>>(n, st, vk, wk, dk, qk, rk, vx);
+  return post_launch("fcg_update");
 }
 
 /*--------------------------------------------------------------------------

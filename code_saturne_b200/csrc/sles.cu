@@ -143,6 +143,10 @@ struct _csb_sles_it_t {
   DistLevelHost       dist;
   size_t              arena_mark = 0;
   bool                arena_used = false;
+  /* preconditioner handed over by csb_sles_it_transfer_pc (owned), FCG only:
+     cs_sles_it_t::_pc, src/alge/cs_sles_it_priv.h */
+  csb_multigrid_t    *pc_mg = nullptr;
+  bool                is_smoother = false;   /* created by csb_multigrid_smoother_create */
   /* setup data (cs_sles_it_setup_t, src/alge/cs_sles_it_priv.h) */
   const csb_matrix_t *a = nullptr;
   bool                setup_done = false;
@@ -162,7 +166,7 @@ struct _csb_sles_it_t {
   unsigned n_iterations_last = 0, n_iterations_min = 0, n_iterations_max = 0;
   unsigned long long n_iterations_tot = 0;
   double t_setup = 0, t_solve = 0;
-  ~_csb_sles_it_t() { if (h_st) cudaFreeHost(h_st); }
+  ~_csb_sles_it_t();
 };
 
 namespace {
@@ -171,6 +175,69 @@ int sb_rows_threshold()
 {
   static int v = env_int("CSB_SB_ROWS", 512);   /* measured: 796-row level faster on the grid, 263-row level in one CTA */
   return v;
+}
+
+bool is_smoother_type(int t)
+{
+  return (t == CSB_SLES_JACOBI || t == CSB_SLES_L1_JACOBI || t == CSB_SLES_R_JACOBI
+          || t == CSB_SLES_RJ2 || t == CSB_SLES_RJ3);
+}
+
+/* Sweep schedule of the Jacobi-family smoothers: relaxation weights
+   (cs_multigrid_smoother.cpp:259-281) and the sweep count rounded up to a multiple of the
+   schedule length (cs_multigrid_smoother_setup, :1888-1898). */
+struct SmootherPlan {
+  int    mode = SMOOTH_JACOBI;
+  int    wk_m = 1;
+  double w[3] = {1., 1., 1.};
+  int    n_iter = 0;
+};
+
+SmootherPlan smoother_plan(int type, int n_max_iter)
+{
+  SmootherPlan p;
+  p.n_iter = n_max_iter;
+  if (type == CSB_SLES_L1_JACOBI) p.mode = SMOOTH_L1;
+  else if (type != CSB_SLES_JACOBI) {
+    p.mode = SMOOTH_RELAXED;
+    p.w[0] = 2./3.;
+    if (type == CSB_SLES_RJ2) { p.w[0] = 1.7319; p.w[1] = 0.5695; p.wk_m = 2; }
+    if (type == CSB_SLES_RJ3) { p.w[0] = 2.2473; p.w[1] = 0.8573; p.w[2] = 0.5296; p.wk_m = 3; }
+    if (p.n_iter % p.wk_m) p.n_iter += p.wk_m - (p.n_iter % p.wk_m);
+  }
+  return p;
+}
+
+/* Fixed number of Jacobi-family sweeps without convergence test (_jacobi, _relaxed_jacobi,
+   _l1_jacobi: cs_multigrid_smoother.cpp:143-226, :244-373, :804-905).  Each sweep is ONE
+   kernel: the (diagonal-excluded, or full for L1) product in CSR order with the update in
+   its epilogue, ping-ponging between vx and tmp like the reference's vx_n / vx_np.
+   inv: 1/d, or the L1 inverse for CSB_SLES_L1_JACOBI.  tmp: n_cols_ext doubles. */
+bool smoother_enqueue(const csb_matrix_t *m, int type, int n_max_iter, const double *inv,
+                      const double *rhs, double *vx, bool vx_ini_nonzero, double *tmp,
+                      const MgState *gate)
+{
+  const SmootherPlan p = smoother_plan(type, n_max_iter);
+  const int n = m->n_rows;
+  double *vx_n = vx, *vx_np = tmp;
+  int iter_ini = 0;
+  if (!vx_ini_nonzero) {
+    if (!launch_smoother_first(n, p.mode, p.w[0], rhs, inv, vx_n, gate)) return false;
+    iter_ini = 1;
+  }
+  for (int it = iter_ini; it < p.n_iter; it++) {
+    const double wk = p.w[it % p.wk_m];
+    double *t = vx_n; vx_n = vx_np; vx_np = t;
+    SpmvArgs sa;
+    sa.m = m; sa.exclude_diag = (p.mode != SMOOTH_L1);
+    sa.x = vx_np; sa.y = vx_n; sa.b = rhs; sa.ad_inv = inv;
+    sa.mg = const_cast<MgState *>(gate);
+    sa.smooth_mode = p.mode; sa.w0 = wk; sa.w1 = 1.0 - wk;
+    if (!launch_spmv(EPI_SMOOTH, sa)) return false;
+  }
+  if (vx_n != vx)
+    if (!launch_copy_gated(n, vx_n, vx, gate)) return false;
+  return true;
 }
 
 /* Enqueue a PCG+Jacobi solve (cs_sles_it.cpp:1441-1645).
@@ -309,6 +376,59 @@ bool bicgstab_enqueue(const csb_matrix_t *m, ItState *st, const double *ad_inv,
   return true;
 }
 
+/* _multigrid_v_cycle_pc as a sequence of launches (defined with the multigrid below) */
+bool mg_cycle_pc_enqueue(csb_multigrid_t *mg, double precision, double r_norm,
+                         const double *rhs_d, double *vx_d, bool vx_ini_nonzero);
+int  mg_n_levels(const csb_multigrid_t *mg);
+MgState *mg_gate(csb_multigrid_t *mg);
+
+/* FCG with a general preconditioner (_flexible_conjugate_gradient, cs_sles_it.cpp:832-985;
+   pc_apply = one multigrid V-cycle, _multigrid_pc_apply cs_multigrid.cpp:1500-1600, or the
+   identity).  Per iteration: the preconditioner's launches, one SpMV with the 4 dot products
+   and the scalar recurrences in its epilogue, one fused 6-vector update; Krylov scalars and
+   the convergence state stay on the device, the host only polls the state every few
+   iterations.  Launches issued after convergence are gated off on the device. */
+bool fcg_pc_enqueue(csb_sles_it_t *c, const csb_matrix_t *a, double precision, double r_norm,
+                    const double *rhs, double *vx, bool vx_ini_nonzero)
+{
+  const int n = a->n_rows;
+  const size_t ws = work_stride_of((size_t)a->n_cols_ext);
+  Context &cx = ctx();
+  double *rk = c->work.p, *vk = rk + ws, *wk = rk + 2*ws, *dk = rk + 3*ws, *qk = rk + 4*ws;
+  ItState *st = c->st.p;
+  csb_multigrid_t *mg = c->pc_mg;
+  const bool identity = (mg == nullptr || mg_n_levels(mg) == 1);   /* cs_multigrid.cpp:1518 */
+
+  if (!launch_it_state_init(st, nullptr, precision, r_norm, c->n_max_iter)) return false;
+  if (vx_ini_nonzero) {
+    SpmvArgs sa; sa.m = a; sa.x = vx; sa.y = rk;
+    if (!launch_spmv(EPI_STORE, sa)) return false;
+  }
+  if (!launch_fcg_init(n, st, rhs, vx, rk, qk, vx_ini_nonzero)) return false;
+  if (!identity && !launch_mg_state_init(mg_gate(mg), precision, r_norm, 1)) return false;
+
+  const int poll = identity ? 16 : 2;
+  for (int it = 0; it <= c->n_max_iter; it++) {
+    if (identity) {
+      if (!launch_copy(n, rk, vk, st)) return false;
+    }
+    else if (!mg_cycle_pc_enqueue(mg, precision, r_norm, rk, vk, false))
+      return false;
+    SpmvArgs sa;
+    sa.m = a; sa.x = vk; sa.y = wk; sa.rk = rk; sa.qk = qk; sa.st = st;
+    if (!launch_spmv(EPI_FCG_DOT4, sa)) return false;
+    if (!identity && !launch_gate_from_it(mg_gate(mg), st)) return false;
+    if (!launch_fcg_update(n, st, vk, wk, dk, qk, rk, vx)) return false;
+    if ((it + 1) % poll == 0) {
+      if (!CSB_CUDA(cudaMemcpyAsync(c->h_st, st, IT_HEAD, cudaMemcpyDeviceToHost, cx.stream)))
+        return false;
+      if (!CSB_CUDA(cudaStreamSynchronize(cx.stream))) return false;
+      if (c->h_st->cvg != CSB_SLES_ITERATING) break;
+    }
+  }
+  return true;
+}
+
 } // anonymous namespace
 
 extern "C" {
@@ -327,10 +447,13 @@ csb_sles_it_create(csb_sles_it_type_t solver_type, int poly_degree, int n_max_it
   }
   /* poly_degree 0: Jacobi; < 0 with PCG: no preconditioner (_conjugate_gradient_sr_npc,
      cs_sles_it.cpp:1673-1860) */
+  /* FCG with poly_degree < 0: the preconditioner is handed over afterwards
+     (csb_sles_it_transfer_pc: one multigrid V-cycle), identity if none is */
   if (solver_type != CSB_SLES_JACOBI && poly_degree != 0
-      && !(solver_type == CSB_SLES_PCG && poly_degree < 0)) {
-    set_error("csb_sles_it_create: poly_degree %d: Jacobi (0), or none (< 0, PCG only), "
-              "are the preconditioners available on this path", poly_degree);
+      && !((solver_type == CSB_SLES_PCG || solver_type == CSB_SLES_FCG) && poly_degree < 0)) {
+    set_error("csb_sles_it_create: poly_degree %d: Jacobi (0), or none / transferred "
+              "(< 0, PCG and FCG only), are the preconditioners available on this path",
+              poly_degree);
     return nullptr;
   }
   csb_sles_it_t *c = new csb_sles_it_t;
@@ -382,6 +505,22 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
   if (!c->st.alloc(1)) return;
   if (c->h_st == nullptr)
     if (!CSB_CUDA(cudaMallocHost((void **)&c->h_st, sizeof(ItState)))) return;
+  if (c->type == CSB_SLES_FCG && c->poly_degree < 0) {
+    /* general-preconditioner FCG, kernel per phase (fcg_pc_enqueue) */
+    if (a->halo != nullptr) {
+      set_error("csb_sles_it_setup: FCG with a transferred preconditioner runs on one rank "
+                "on this path");
+      return;
+    }
+    if (c->pc_mg != nullptr) {
+      csb_multigrid_setup(c->pc_mg, name, a, verbosity);
+      if (!csb_multigrid_is_setup(c->pc_mg)) return;
+    }
+    c->setup_done = true;
+    c->n_setups += 1;
+    c->t_setup += wall() - t0;
+    return;
+  }
   if (a->halo != nullptr && ((c->type != CSB_SLES_PCG && c->type != CSB_SLES_FCG && c->type != CSB_SLES_IPCG)
                              || c->pcomm == nullptr)) {
     set_error("csb_sles_it_setup: a matrix with a halo needs CSB_SLES_PCG / _FCG and a peer "
@@ -468,6 +607,10 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
     break;
   case CSB_SLES_FCG:
   case CSB_SLES_IPCG:
+    if (c->type == CSB_SLES_FCG && c->poly_degree < 0) {
+      ok = fcg_pc_enqueue(c, a, precision, r_norm, s_rhs.d, s_vx.d, ini);
+      break;
+    }
     {
       /* whole solve in one persistent cooperative kernel (per rank) */
       PersistentCommon P;
@@ -521,6 +664,7 @@ void csb_sles_it_free(void *context)
   if (c == nullptr) return;
   c->ad_inv.release();
   c->work.release();
+  if (c->pc_mg != nullptr) csb_multigrid_free(c->pc_mg);
   if (c->arena_used && c->pcomm != nullptr) {
     pcomm_arena_release(c->pcomm, c->arena_mark);
     c->arena_used = false;
@@ -559,7 +703,11 @@ void csb_sles_it_log(const void *context, int log_type)
   const char *tn = (c->type == CSB_SLES_PCG) ? "Conjugate Gradient"
                  : (c->type == CSB_SLES_FCG) ? "Flexible Conjugate Gradient"
                  : (c->type == CSB_SLES_IPCG) ? "Inexact Conjugate Gradient"
-                 : (c->type == CSB_SLES_JACOBI) ? "Jacobi" : "BiCGstab";
+                 : (c->type == CSB_SLES_JACOBI) ? "Jacobi"
+                 : (c->type == CSB_SLES_L1_JACOBI) ? "L1 Jacobi"
+                 : (c->type == CSB_SLES_R_JACOBI) ? "Relaxed Jacobi"
+                 : (c->type == CSB_SLES_RJ2) ? "Scheduled relaxed Jacobi (M=2)"
+                 : (c->type == CSB_SLES_RJ3) ? "Scheduled relaxed Jacobi (M=3)" : "BiCGstab";
   printf("  Solver type:                       %s (B200 device)\n"
          "  Number of setups:                  %12u\n"
          "  Number of calls:                   %12u\n"
@@ -576,9 +724,15 @@ void *csb_sles_it_copy(const void *context)
 {
   const csb_sles_it_t *c = static_cast<const csb_sles_it_t *>(context);
   if (c == nullptr) return nullptr;
-  csb_sles_it_t *d = csb_sles_it_create(c->type, c->poly_degree, c->n_max_iter,
-                                        c->update_stats ? 1 : 0);
-  if (d) { d->nccl_comm = c->nccl_comm; d->pcomm = c->pcomm; }
+  csb_sles_it_t *d = c->is_smoother
+    ? csb_multigrid_smoother_create(c->type, c->poly_degree, c->n_max_iter)
+    : csb_sles_it_create(c->type, c->poly_degree, c->n_max_iter, c->update_stats ? 1 : 0);
+  if (d) {
+    d->nccl_comm = c->nccl_comm; d->pcomm = c->pcomm;
+    /* the preconditioner is cloned with its settings (cs_sles_pc_clone, cs_sles_it.cpp:4920) */
+    if (c->pc_mg != nullptr)
+      d->pc_mg = static_cast<csb_multigrid_t *>(csb_multigrid_copy(c->pc_mg));
+  }
   return d;
 }
 
@@ -599,6 +753,7 @@ struct MgLevel {
   std::vector<int>    h_coarse_row;
   /* solve data */
   DevBuf<double>      ad_inv, rhs, vx;
+  DevBuf<double>      l1_inv;                     /* L1 Jacobi smoother only */
   /* geometry of this level used to coarsen it (level > 0; level 0 uses the
      matrix's mesh association) */
   DevBuf<int>         cell_face;
@@ -663,7 +818,86 @@ struct _csb_multigrid_t {
   }
 };
 
+_csb_sles_it_t::~_csb_sles_it_t()
+{
+  if (h_st) cudaFreeHost(h_st);
+  delete pc_mg;
+}
+
 namespace {
+
+int mg_n_levels(const csb_multigrid_t *mg) { return (int)mg->levels.size(); }
+MgState *mg_gate(csb_multigrid_t *mg) { return mg->mg_state.p; }
+
+/* One level's descent (which = 0) or ascent (1) smoother of the single-cycle form, as
+   _multigrid_setup_sles builds it (cs_multigrid.cpp:2150-2175): a cs_multigrid_smoother
+   when precision_mult < 0 and the type is one, cs_sles_it PCG + Jacobi otherwise. */
+bool mg_level_smooth(csb_multigrid_t *mg, int which, int level, const double *rhs_lv,
+                     double *vx_lv, bool ini, double precision, double r_norm)
+{
+  MgLevel *f = mg->levels[level];
+  MgState *ms = mg->mg_state.p;
+  const int type = (int)mg->solver_type[which];
+  const double ratio = (double)f->m->n_rows / (double)mg->levels[0]->m->n_rows;
+  if (type == CSB_SLES_PCG) {
+    ItState *st = mg->it_states.p + 2*level + which;
+    return pcg_enqueue(f->m, st, ms, f->ad_inv.p, precision*mg->precision_mult[which], r_norm,
+                       mg->n_max_iter[which], rhs_lv, vx_lv, ini, true, mg->aux.p, nullptr)
+           && launch_mg_accum_iter(ms, st, level, ratio, 0);
+  }
+  const double *inv = (type == CSB_SLES_L1_JACOBI) ? f->l1_inv.p : f->ad_inv.p;
+  return smoother_enqueue(f->m, type, mg->n_max_iter[which], inv, rhs_lv, vx_lv, ini,
+                          mg->aux.p, ms)
+         && launch_mg_accum_n(ms, smoother_plan(type, mg->n_max_iter[which]).n_iter,
+                              f->m->n_rows, 1.0 / (double)mg->levels[0]->m->n_rows);
+}
+
+/* _multigrid_v_cycle_pc (cs_multigrid.cpp:3569-4000): one V-cycle without convergence
+   tests -- descent smoother from zero (from vx at level 0 when vx_ini_nonzero), residual,
+   restriction; coarsest-level PCG; prolongation and the ascent smoother on every level,
+   level 0 included.  A sequence of launches, no host synchronisation; every launch is
+   gated on mg_state.cvg (closed by the outer solver once it has converged). */
+bool mg_cycle_pc_enqueue(csb_multigrid_t *mg, double precision, double r_norm,
+                         const double *rhs_d, double *vx_d, bool vx_ini_nonzero)
+{
+  const int n_levels = (int)mg->levels.size();
+  const int coarsest = n_levels - 1;
+  MgState *ms = mg->mg_state.p;
+  const double denom = 1.0 / (double)mg->levels[0]->m->n_rows;
+  bool ok = true;
+
+  for (int level = 0; ok && level < coarsest; level++) {
+    MgLevel *f = mg->levels[level], *cl = mg->levels[level+1];
+    const double *rhs_lv = (level == 0) ? rhs_d : f->rhs.p;
+    double *vx_lv = (level == 0) ? vx_d : f->vx.p;
+    ok = mg_level_smooth(mg, 0, level, rhs_lv, vx_lv, (level == 0) ? vx_ini_nonzero : false,
+                         precision, r_norm);
+    SpmvArgs sa;
+    sa.m = f->m; sa.x = vx_lv; sa.y = mg->wr.p; sa.b = rhs_lv; sa.mg = ms;
+    ok = ok && launch_spmv(EPI_RESIDUAL, sa);
+    ok = ok && launch_restrict(cl->m->n_rows, f->c_f_row_index.p, f->c_f_row_ids.p,
+                               mg->wr.p, cl->rhs.p, ms);
+  }
+
+  if (ok) {
+    MgLevel *cl = mg->levels[coarsest];
+    const double *rhs_lv = (coarsest == 0) ? rhs_d : cl->rhs.p;
+    double *vx_lv = (coarsest == 0) ? vx_d : cl->vx.p;
+    ItState *st = mg->it_states.p + 2*coarsest;
+    ok = pcg_enqueue(cl->m, st, ms, cl->ad_inv.p, precision*mg->precision_mult[2], r_norm,
+                     mg->n_max_iter[2], rhs_lv, vx_lv, false, true, mg->aux.p, nullptr);
+    ok = ok && launch_mg_accum_iter(ms, st, coarsest, (double)cl->m->n_rows * denom, 0);
+  }
+
+  for (int level = coarsest - 1; ok && level > -1; level--) {
+    MgLevel *f = mg->levels[level], *cl = mg->levels[level+1];
+    const double *rhs_lv = (level == 0) ? rhs_d : f->rhs.p;
+    double *vx_lv = (level == 0) ? vx_d : f->vx.p;
+    ok = launch_prolong_inc(f->m->n_rows, f->coarse_row.p, cl->vx.p, vx_lv, ms);
+    ok = ok && mg_level_smooth(mg, 1, level, rhs_lv, vx_lv, true, precision, r_norm);
+  }
+  return ok;
+}
 
 void mg_clear_hierarchy(csb_multigrid_t *mg)
 {
@@ -897,12 +1131,24 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     set_error("csb_multigrid_setup: only CS_GRID_COARSENING_DEFAULT / SPD_DX are available");
     return;
   }
-  for (int i = 0; i < 3; i++)
-    if (mg->solver_type[i] != CSB_SLES_PCG || mg->poly_degree[i] != 0) {
-      set_error("csb_multigrid_setup: smoothers / coarse solver must be PCG + Jacobi "
-                "(cs_multigrid_create defaults)");
+  /* smoothers: cs_sles_it PCG + Jacobi (cs_multigrid_create defaults), or -- in the
+     single-cycle (preconditioner) form, precision_mult < 0 -- the Jacobi-family
+     cs_multigrid_smoother types the reference's device settings select
+     (cs_multigrid_set_solver_options, cs_multigrid.cpp:5070-5090); coarse solver: PCG */
+  bool any_l1 = false;
+  for (int i = 0; i < 3; i++) {
+    const bool pcg = (mg->solver_type[i] == CSB_SLES_PCG && mg->poly_degree[i] == 0);
+    const bool smoother = (i < 2 && is_smoother_type((int)mg->solver_type[i])
+                           && mg->precision_mult[i] < 0 && mg->n_max_cycles == 1
+                           && a->halo == nullptr);
+    if (!pcg && !smoother) {
+      set_error("csb_multigrid_setup: smoothers must be PCG + Jacobi, or (n_max_cycles 1, "
+                "precision_mult < 0, one rank) Jacobi / L1 / relaxed / RJ2 / RJ3 smoothers; "
+                "the coarse solver PCG + Jacobi");
       return;
     }
+    if (mg->solver_type[i] == CSB_SLES_L1_JACOBI) any_l1 = true;
+  }
   const bool dist = (a->halo != nullptr);
   csb_pcomm_t *pc = dist ? mg->pcomm : nullptr;
   if (dist && (pc == nullptr || a->halo->pcomm != pc)) {
@@ -1075,6 +1321,9 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     aux_size = std::max(aux_size, 5*work_stride_of((size_t)m->n_cols_ext));
     if (!lv->ad_inv.alloc((size_t)m->n_rows)) return;
     if (!launch_ad_inv(m->n_rows, m->d_val.p, lv->ad_inv.p)) return;
+    if (any_l1) {
+      if (!lv->l1_inv.alloc((size_t)m->n_rows) || !launch_l1_inv(m, lv->l1_inv.p)) return;
+    }
     if (l > 0) {
       if (!lv->rhs.alloc((size_t)m->n_cols_ext) || !lv->vx.alloc((size_t)m->n_cols_ext)) return;
     }
@@ -1166,6 +1415,24 @@ csb_multigrid_solve(void *context, const char *name, const csb_matrix_t *a, int 
 
   MgState *ms = mg->mg_state.p;
   if (!launch_mg_state_init(ms, precision, r_norm, mg->n_max_cycles)) return CSB_SLES_BREAKDOWN;
+
+  if (mg->n_max_cycles == 1 && a->halo == nullptr) {
+    /* cs_multigrid_solve :5484-5499: a single cycle is the form without convergence
+       tests (_multigrid_v_cycle_pc); the reference returns CS_SLES_ITERATING from it */
+    if (!mg_cycle_pc_enqueue(mg, precision, r_norm, s_rhs.d, s_vx.d, vx_ini == vx))
+      return CSB_SLES_BREAKDOWN;
+    if (!CSB_CUDA(cudaMemcpyAsync(mg->h_mg, ms, MG_HEAD, cudaMemcpyDeviceToHost, c.stream)))
+      return CSB_SLES_BREAKDOWN;
+    if (!s_vx.copy_back((size_t)a->n_rows)) return CSB_SLES_BREAKDOWN;
+    if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return CSB_SLES_BREAKDOWN;
+    if (n_iter) *n_iter = mg->h_mg->n_equiv_iter;
+    mg->n_cycles_last = 1;
+    mg->n_cycles_tot += 1;
+    mg->n_solves += 1;
+    mg->t_solve_tot += wall() - t0;
+    return (mg->h_mg->cvg < CSB_SLES_BREAKDOWN) ? (csb_sles_convergence_state_t)mg->h_mg->cvg
+                                                 : CSB_SLES_ITERATING;
+  }
 
   int cvg = CSB_SLES_ITERATING;
   int n_cycles = 0;
@@ -1432,6 +1699,134 @@ void *csb_multigrid_copy(const void *context)
   d->nccl_comm = s->nccl_comm;
   d->pcomm = s->pcomm;
   return d;
+}
+
+/*----------------------------------------------------------------------------
+ * Multigrid as a preconditioner, and the multigrid smoothers as objects
+ *----------------------------------------------------------------------------*/
+
+/* cs_multigrid_pc_create (cs_multigrid.cpp:5682) -> _multigrid_pc_create (:1616-1640) with the
+   device settings cs_multigrid_set_solver_options derives from them (:5070-5090): the
+   symmetric Gauss-Seidel smoothers of the host path become RJ3 with twice the sweeps
+   (1 -> 2, rounded up to the schedule length 3 at setup), PCG coarse solver, one cycle. */
+csb_multigrid_t *csb_multigrid_pc_create(csb_multigrid_type_t mg_type)
+{
+  csb_multigrid_t *mg = csb_multigrid_create(mg_type);
+  if (mg == nullptr) return nullptr;
+  csb_multigrid_set_solver_options(mg, CSB_SLES_RJ3, CSB_SLES_RJ3, CSB_SLES_PCG,
+                                   1, 2, 2, 500, 0, 0, 0, -1., -1., 1.);
+  return mg;
+}
+
+/* cs_sles_it_transfer_pc (cs_sles_it.cpp:5612): the solver takes ownership, *pc is set to
+   NULL.  Available for CSB_SLES_FCG created with poly_degree < 0. */
+int csb_sles_it_transfer_pc(csb_sles_it_t *c, csb_multigrid_t **pc)
+{
+  if (c == nullptr || pc == nullptr) return -1;
+  if (c->type != CSB_SLES_FCG || c->poly_degree >= 0) {
+    set_error("csb_sles_it_transfer_pc: needs CSB_SLES_FCG created with poly_degree < 0");
+    return -1;
+  }
+  delete c->pc_mg;
+  c->pc_mg = *pc;
+  *pc = nullptr;
+  c->setup_done = false;
+  return 0;
+}
+
+csb_multigrid_t *csb_sles_it_get_pc(csb_sles_it_t *c)     /* cs_sles_it_get_pc :5590 */
+{
+  return (c != nullptr) ? c->pc_mg : nullptr;
+}
+
+/* cs_multigrid_smoother_create (cs_multigrid_smoother.cpp:1726-1812) */
+csb_sles_it_t *
+csb_multigrid_smoother_create(csb_sles_it_type_t smoother_type, int poly_degree, int n_iter)
+{
+  (void)poly_degree;
+  if (!ctx().ready) { set_error("csb_multigrid_smoother_create: csb_init not called"); return nullptr; }
+  if (!is_smoother_type((int)smoother_type)) {
+    set_error("csb_multigrid_smoother_create: type %d is not a smoother available on this "
+              "path (Jacobi, L1 Jacobi, relaxed Jacobi, RJ2, RJ3)", (int)smoother_type);
+    return nullptr;
+  }
+  csb_sles_it_t *c = new csb_sles_it_t;
+  c->type = smoother_type;
+  c->n_max_iter = n_iter;
+  c->is_smoother = true;
+  return c;
+}
+
+/* cs_multigrid_smoother_setup (cs_multigrid_smoother.cpp:1825-1985) */
+void csb_multigrid_smoother_setup(void *context, const char *name, const csb_matrix_t *a,
+                                  int verbosity)
+{
+  (void)name; (void)verbosity;
+  csb_sles_it_t *c = static_cast<csb_sles_it_t *>(context);
+  if (c == nullptr || a == nullptr || !c->is_smoother) {
+    set_error("csb_multigrid_smoother_setup: not a smoother context");
+    return;
+  }
+  const double t0 = wall();
+  c->a = a;
+  c->setup_done = false;
+  if (a->db != 1 || a->halo != nullptr) {
+    set_error("csb_multigrid_smoother_setup: scalar matrices on one rank on this path");
+    return;
+  }
+  if (!c->ad_inv.alloc((size_t)a->n_rows)) return;
+  if (c->type == CSB_SLES_L1_JACOBI) { if (!launch_l1_inv(a, c->ad_inv.p)) return; }
+  else if (!launch_ad_inv(a->n_rows, a->d_val.p, c->ad_inv.p)) return;
+  if (!c->work.alloc(work_stride_of((size_t)a->n_cols_ext))) return;
+  /* the scheduled variants run whole schedules (:1888-1898) */
+  c->n_max_iter = smoother_plan((int)c->type, c->n_max_iter).n_iter;
+  c->setup_done = true;
+  c->n_setups += 1;
+  c->t_setup += wall() - t0;
+}
+
+/* cs_multigrid_smoother_solve (cs_multigrid_smoother.cpp:2008-2090): fixed sweep count,
+   *residual = -1 (not computed), returns CSB_SLES_MAX_ITERATION like the reference. */
+csb_sles_convergence_state_t
+csb_multigrid_smoother_solve(void *context, const char *name, const csb_matrix_t *a,
+                             int verbosity, double precision, double r_norm, int *n_iter,
+                             double *residual, const csb_real_t *rhs, csb_real_t *vx_ini,
+                             csb_real_t *vx, size_t aux_size, void *aux_vectors)
+{
+  (void)precision; (void)r_norm; (void)aux_size; (void)aux_vectors;
+  csb_sles_it_t *c = static_cast<csb_sles_it_t *>(context);
+  Context &cx = ctx();
+  cx.err.clear();
+  if (n_iter) *n_iter = 0;
+  if (residual) *residual = -1.;
+  if (c == nullptr || !c->is_smoother || a == nullptr || rhs == nullptr || vx == nullptr) {
+    set_error("csb_multigrid_smoother_solve: null argument or not a smoother context");
+    return CSB_SLES_BREAKDOWN;
+  }
+  if (vx_ini != nullptr && vx_ini != vx) {
+    set_error("csb_multigrid_smoother_solve: vx_ini must be vx or NULL");
+    return CSB_SLES_BREAKDOWN;
+  }
+  if (!c->setup_done || c->a != a)
+    csb_multigrid_smoother_setup(c, name, a, verbosity);
+  if (!c->setup_done) return CSB_SLES_BREAKDOWN;
+
+  const double t0 = wall();
+  const bool ini = (vx_ini == vx);
+  StagedVec s_rhs, s_vx;
+  if (!s_rhs.init(const_cast<double *>(rhs), (size_t)a->n_rows, true, c->stage_rhs))
+    return CSB_SLES_BREAKDOWN;
+  if (!s_vx.init(vx, (size_t)a->n_cols_ext, ini, c->stage_vx)) return CSB_SLES_BREAKDOWN;
+  if (!smoother_enqueue(a, (int)c->type, c->n_max_iter, c->ad_inv.p, s_rhs.d, s_vx.d, ini,
+                        c->work.p, nullptr)) return CSB_SLES_BREAKDOWN;
+  if (!s_vx.copy_back((size_t)a->n_rows)) return CSB_SLES_BREAKDOWN;
+  if (!CSB_CUDA(cudaStreamSynchronize(cx.stream))) return CSB_SLES_BREAKDOWN;
+  if (n_iter) *n_iter = c->n_max_iter;
+  c->n_solves += 1;
+  c->n_iterations_last = c->n_max_iter;
+  c->n_iterations_tot += c->n_max_iter;
+  c->t_solve += wall() - t0;
+  return CSB_SLES_MAX_ITERATION;
 }
 
 } /* extern "C" */

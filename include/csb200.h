@@ -45,7 +45,14 @@ typedef enum {
   CSB_SLES_FCG      = 1,   /* flexible CG, cs_sles_it.cpp:832-985 */
   CSB_SLES_IPCG     = 2,   /* inexact-preconditioning CG, cs_sles_it.cpp:1016-1203 */
   CSB_SLES_JACOBI   = 3,
-  CSB_SLES_BICGSTAB = 4
+  CSB_SLES_BICGSTAB = 4,
+  /* multigrid smoothers without convergence test (cs_sles_it.h:79-83,
+     src/alge/cs_multigrid_smoother.cpp); created with csb_multigrid_smoother_create or
+     selected through csb_multigrid_set_solver_options with precision_mult < 0 */
+  CSB_SLES_L1_JACOBI = 13,  /* _l1_jacobi       :804-905 */
+  CSB_SLES_R_JACOBI  = 14,  /* _relaxed_jacobi  :244-373, w = 2/3 */
+  CSB_SLES_RJ2       = 15,  /* scheduled relaxation {1.7319, 0.5695} */
+  CSB_SLES_RJ3       = 16   /* scheduled relaxation {2.2473, 0.8573, 0.5296} */
 } csb_sles_it_type_t;
 
 /* cs_multigrid_type_t, src/alge/cs_multigrid.h:58-65 */
@@ -423,6 +430,53 @@ int  csb_host_coarse_structure(csb_lnum_t f_n_rows, const csb_lnum_t *f_row_inde
                                csb_lnum_t c_n_rows, csb_lnum_t *c_row_index,
                                csb_lnum_t *c_col_id, csb_lnum_t *c_cell_face,
                                short *c_cell_face_sgn, csb_lnum_t *c_n_faces);
+
+/*----------------------------------------------------------------------------
+ * Multigrid as a preconditioner (cs_multigrid_pc_create, src/alge/cs_multigrid.cpp:5682;
+ * _multigrid_pc_apply :1500-1600; _multigrid_v_cycle_pc :3569-4000) and the multigrid
+ * smoothers (src/alge/cs_multigrid_smoother.h:77-165).
+ *
+ * The reference's production pressure solver is FCG preconditioned by one V-cycle:
+ *   c  = csb_sles_it_create(CSB_SLES_FCG, -1, n_max_iter, 1);
+ *   pc = csb_multigrid_pc_create(CSB_MULTIGRID_V_CYCLE);
+ *   csb_sles_it_transfer_pc(c, &pc);              // cs_sles_it_transfer_pc, cs_sles_it.h:379
+ * csb_multigrid_solve with n_max_cycles == 1 runs the same single cycle without
+ * convergence tests (cs_multigrid_solve, cs_multigrid.cpp:5484-5499) and returns
+ * CSB_SLES_ITERATING like the reference.
+ *----------------------------------------------------------------------------*/
+
+/* V-cycle with the reference's device settings for a preconditioner: RJ3 smoothers
+   (3 sweeps), PCG coarse solver (500), one cycle, precision_mult (-1, -1, 1). */
+csb_multigrid_t *csb_multigrid_pc_create(csb_multigrid_type_t mg_type);
+
+/* The solver takes ownership of the preconditioner; *pc is set to NULL.
+   CSB_SLES_FCG created with poly_degree < 0 only; with no preconditioner transferred such
+   a solver runs unpreconditioned (identity).  Returns 0, or -1 (see csb_last_error). */
+int  csb_sles_it_transfer_pc(csb_sles_it_t *c, csb_multigrid_t **pc);
+csb_multigrid_t *csb_sles_it_get_pc(csb_sles_it_t *c);   /* cs_sles_it_get_pc */
+
+/* cs_multigrid_smoother_create / _setup / _solve (cs_multigrid_smoother.cpp:1726, :1825,
+   :2008): n_iter sweeps (rounded up to whole schedules for RJ2 / RJ3 at setup), no
+   convergence test, *residual = -1, returns CSB_SLES_MAX_ITERATION.  Free / destroy / log /
+   copy: csb_sles_it_free, _destroy, _log, _copy (the reference uses cs_sles_it_destroy). */
+csb_sles_it_t *csb_multigrid_smoother_create(csb_sles_it_type_t smoother_type,
+                                             int poly_degree, int n_iter);
+void csb_multigrid_smoother_setup(void *context, const char *name, const csb_matrix_t *a,
+                                  int verbosity);
+csb_sles_convergence_state_t
+csb_multigrid_smoother_solve(void                *context,
+                             const char          *name,
+                             const csb_matrix_t  *a,
+                             int                  verbosity,
+                             double               precision,
+                             double               r_norm,
+                             int                 *n_iter,
+                             double              *residual,
+                             const csb_real_t    *rhs,
+                             csb_real_t          *vx_ini,
+                             csb_real_t          *vx,
+                             size_t               aux_size,
+                             void                *aux_vectors);
 
 /*----------------------------------------------------------------------------
  * cs_sles_t registry boundary (src/alge/cs_sles.cpp:1385-1425): these are the

@@ -1,0 +1,229 @@
+"""GPU parity of the rows added after the first V-cycle path (a14/a15 FCG with a
+general preconditioner, a24 _multigrid_v_cycle_pc, a26 Jacobi-family multigrid smoothers),
+through the C-ABI, against the reference-built golden fixtures (tests/golden/mgpc_*.npz) and
+the oracle.
+
+Tolerances: the smoothers are per-row arithmetic with no reduction -> bit-exact.  The
+single-cycle V-cycle contains a coarsest-level PCG whose dot products are summed in another
+order -> agreement to the coarse solver's tolerance; FCG + multigrid: iteration counts +-2,
+solutions <= 1e-10 relative L2 when both are solved tightly.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from code_saturne_b200.mesh_cartesian import cube_poisson
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+SOL_TOL = 1e-10
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+MGPC_CASES = [(8, "neumann"), (12, "dirichlet")]
+SMOOTHERS = {"jacobi": 3, "l1_jacobi": 13, "r_jacobi": 14, "rj2": 15, "rj3": 16}
+CYCLES = {"rj3": ((16, 16, 0), (3, 3, 500)), "rj2": ((15, 15, 0), (2, 4, 500)),
+          "r_jacobi": ((14, 14, 0), (2, 2, 500)), "l1_jacobi": ((13, 13, 0), (2, 2, 500)),
+          "jacobi": ((3, 3, 0), (2, 3, 500))}
+
+
+def _mg(csb, types, nmi, precision_mult=(-1., -1., 1.)):
+    mg = csb.Multigrid()
+    mg.set_solver_options(descent=types[0], ascent=types[1], coarse=types[2], n_max_cycles=1,
+                          n_max_iter_descent=nmi[0], n_max_iter_ascent=nmi[1],
+                          n_max_iter_coarse=nmi[2], precision_mult=precision_mult)
+    return mg
+
+
+# ------------------------------------------------------------------------------ smoothers
+
+@pytest.mark.parametrize("N,bc", MGPC_CASES)
+def test_smoothers_bit_exact_vs_reference_golden(csb, N, bc):
+    """cs_multigrid_smoother_solve: every Jacobi-family type, from zero and from a given
+    iterate; one fused kernel per sweep, same IEEE operations as the reference -> identical."""
+    g = np.load(os.path.join(GOLD, f"mgpc_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+    for name, st in SMOOTHERS.items():
+        for nit in (1, 3):
+            sm = csb.Smoother(st, nit)
+            r = sm.solve(m, s.rhs)
+            assert int(r["cvg"]) == -1                       # CS_SLES_MAX_ITERATION
+            assert r["residual"] == -1.0
+            assert np.array_equal(r["vx"][:s.n_rows], g[f"sm_{name}_{nit}_zero"]), (name, nit)
+            r = sm.solve(m, s.rhs, vx=g["vx0"].copy(), use_vx_ini=True)
+            assert np.array_equal(r["vx"][:s.n_rows], g[f"sm_{name}_{nit}_warm"]), (name, nit)
+            assert r["n_iter"] == int(g[f"sm_{name}_{nit}_n_iter"])
+            sm.destroy()
+    m.destroy()
+
+
+@pytest.mark.parametrize("N", [33, 64])
+def test_smoothers_bit_exact_vs_oracle(csb, oracle, N):
+    """Sizes with several thread blocks and a ragged last block; even and odd sweep counts
+    (result in either ping-pong buffer)."""
+    s = cube_poisson(N, "neumann", with_mesh=False)
+    rng = np.random.default_rng(N)
+    vx0 = rng.standard_normal(s.n_rows)
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+    for st in SMOOTHERS.values():
+        for nit in (2, 5):
+            sm = csb.Smoother(st, nit)
+            for v0 in (None, vx0):
+                o = oracle.smoother(st, s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, nit, v0)
+                r = sm.solve(m, s.rhs, vx=None if v0 is None else v0.copy(),
+                             use_vx_ini=v0 is not None)
+                assert r["n_iter"] == o["n_iter"]
+                assert np.array_equal(r["vx"][:s.n_rows], o["vx"]), (st, nit, v0 is None)
+            sm.destroy()
+    m.destroy()
+
+
+def test_smoother_rejects_other_types(csb):
+    with pytest.raises(csb.CsbError):
+        csb.Smoother(csb.SlesItType.PCG, 2)
+    with pytest.raises(csb.CsbError):
+        csb.SlesIt(csb.SlesItType.RJ3, 3)
+
+
+# ------------------------------------------------- single-cycle V-cycle (preconditioner form)
+
+@pytest.mark.parametrize("N,bc", MGPC_CASES)
+def test_cycle_pc_matches_reference_golden(csb, N, bc):
+    """cs_multigrid_solve with n_max_cycles == 1 = _multigrid_v_cycle_pc: no convergence
+    test, ascent smoother on level 0 too, returns CS_SLES_ITERATING."""
+    g = np.load(os.path.join(GOLD, f"mgpc_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    r_norm = float(g["r_norm"])
+    m = csb.Matrix.from_system(s)
+    for name, (types, nmi) in CYCLES.items():
+        mg = _mg(csb, types, nmi)
+        mg.setup(m)
+        r = mg.solve(m, s.rhs, 1e-8, r_norm)
+        assert int(r["cvg"]) == 0
+        assert abs(r["n_iter"] - int(g[f"cyc_{name}_n_iter"])) <= 1   # coarse PCG count +-1
+        # the coarsest-level PCG stops at 1e-8 in both
+        assert rel_l2(r["vx"][:s.n_rows], g[f"cyc_{name}_vx"]) <= 1e-6, name
+        mg.destroy()
+    m.destroy()
+
+
+def test_cycle_pc_tight_vs_oracle(csb, oracle):
+    """With the coarsest level solved to 1e-14 the whole cycle agrees to rounding; also from a
+    nonzero initial vx (level-0 descent smoother starts from it)."""
+    s = cube_poisson(24, "neumann")
+    r_norm = float(np.linalg.norm(s.rhs))
+    vx0 = np.sin(0.11 * np.arange(s.n_rows))
+    m = csb.Matrix.from_system(s)
+    omg = oracle.mg_setup(s)
+    for name, (types, nmi) in CYCLES.items():
+        mg = _mg(csb, types, nmi)
+        mg.setup(m)
+        for v0 in (None, vx0):
+            o = oracle.mg_cycle_pc(omg, s.rhs, 1e-14, r_norm, types, nmi, vx0=v0)
+            r = mg.solve(m, s.rhs, 1e-14, r_norm, vx=None if v0 is None else
+                         np.concatenate([v0, np.zeros(m.n_cols_ext - s.n_rows)]),
+                         use_vx_ini=v0 is not None)
+            assert rel_l2(r["vx"][:s.n_rows], o["vx"]) <= SOL_TOL, (name, v0 is None)
+        mg.destroy()
+    oracle.mg_free(omg)
+    m.destroy()
+
+
+def test_cycle_pc_with_pcg_smoothers_vs_reference(csb, oracle):
+    """n_max_cycles == 1 with the cs_multigrid_create default PCG smoothers also takes the
+    single-cycle form in the reference (cs_multigrid.cpp:5484)."""
+    s = cube_poisson(16, "neumann")
+    r_norm = float(np.linalg.norm(s.rhs))
+    m = csb.Matrix.from_system(s)
+    omg = oracle.mg_setup(s)
+    mg = _mg(csb, (0, 0, 0), (2, 10, 500), precision_mult=(1., 1., 1.))
+    mg.setup(m)
+    o = oracle.mg_cycle_pc(omg, s.rhs, 1e-14, r_norm, (0, 0, 0), (2, 10, 500), (1., 1., 1.))
+    r = mg.solve(m, s.rhs, 1e-14, r_norm)
+    assert rel_l2(r["vx"][:s.n_rows], o["vx"]) <= 1e-9
+    mg.destroy(); oracle.mg_free(omg); m.destroy()
+
+
+# ----------------------------------------------------------- FCG + multigrid preconditioner
+
+@pytest.mark.parametrize("N,bc", MGPC_CASES)
+def test_fcg_mgpc_matches_reference_golden(csb, N, bc):
+    """The reference's production layout: cs_sles_it FCG + cs_multigrid_pc (one V-cycle per
+    iteration), for each smoother family."""
+    g = np.load(os.path.join(GOLD, f"mgpc_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    r_norm = float(g["r_norm"])
+    m = csb.Matrix.from_system(s)
+    for name, (types, nmi) in CYCLES.items():
+        c = csb.SlesIt(csb.SlesItType.FCG, 200, poly_degree=-1)
+        c.transfer_pc(_mg(csb, types, nmi))
+        r = c.solve(m, s.rhs, 1e-8, r_norm)
+        assert int(r["cvg"]) == int(g[f"fcg_{name}_cvg"]) == 1
+        assert abs(r["n_iter"] - int(g[f"fcg_{name}_n_iter"])) <= 2, name
+        ir = float(g[f"fcg_{name}_initial_residual"])
+        assert abs(r["initial_residual"] - ir) <= 1e-12 * ir
+        k = min(len(r["history"]) - 1, len(g[f"fcg_{name}_history"]), 4)
+        assert np.allclose(r["history"][1:1 + k], g[f"fcg_{name}_history"][:k], rtol=1e-5, atol=0)
+        res = np.linalg.norm(s.rhs - m.vector_multiply(r["vx"][:s.n_rows].copy()))
+        assert res <= 1.01e-8 * r_norm
+        assert rel_l2(r["vx"][:s.n_rows], g[f"fcg_{name}_vx"]) <= (1e-6 if bc == "dirichlet" else 1e-3)
+        c.destroy()
+    m.destroy()
+
+
+def test_fcg_mgpc_default_pc_tight_tolerance_solution_parity(csb, oracle):
+    """csb_multigrid_pc_create defaults (RJ3, 3 sweeps, PCG coarse): both solved to 1e-13 ->
+    solutions within the north-star tolerance; warm start with a max-iteration exit."""
+    s = cube_poisson(32, "dirichlet")
+    r_norm = float(np.sqrt(oracle.dot_xx(s.rhs)))
+    omg = oracle.mg_setup(s)
+    o = oracle.fcg_mgpc(omg, s.rhs, 200, 1e-13, r_norm)
+    m = csb.Matrix.from_system(s)
+    c = csb.SlesIt(csb.SlesItType.FCG, 200, poly_degree=-1)
+    c.transfer_pc(csb.Multigrid(pc=True))
+    r = c.solve(m, s.rhs, 1e-13, r_norm)
+    assert int(r["cvg"]) == 1 and o["cvg"] == 1
+    assert abs(r["n_iter"] - o["n_iter"]) <= 2
+    assert rel_l2(r["vx"][:s.n_rows], o["vx"]) <= SOL_TOL
+    # second solve with the same object (hierarchy kept), zero right-hand side
+    z = c.solve(m, np.zeros(s.n_rows), 1e-8, 1.0)
+    assert not z["vx"].any()
+    # warm start, 3 iterations allowed: same iterate as the oracle's
+    c3 = csb.SlesIt(csb.SlesItType.FCG, 3, poly_degree=-1)
+    c3.transfer_pc(csb.Multigrid(pc=True))
+    ow = oracle.fcg_mgpc(omg, s.rhs, 3, 1e-14, r_norm, vx0=0.5 * o["vx"])
+    w = c3.solve(m, s.rhs, 1e-14, r_norm,
+                 vx=np.concatenate([0.5 * o["vx"], np.zeros(m.n_cols_ext - s.n_rows)]),
+                 use_vx_ini=True)
+    assert (int(w["cvg"]), w["n_iter"]) == (ow["cvg"], ow["n_iter"]) == (-1, 3)
+    assert rel_l2(w["vx"][:s.n_rows], ow["vx"]) <= 1e-9
+    c.destroy(); c3.destroy(); oracle.mg_free(omg); m.destroy()
+
+
+def test_fcg_without_preconditioner_converges(csb):
+    """poly_degree < 0 and nothing transferred: identity preconditioner."""
+    s = cube_poisson(20, "dirichlet", with_mesh=False)
+    r_norm = float(np.linalg.norm(s.rhs))
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+    c = csb.SlesIt(csb.SlesItType.FCG, 2000, poly_degree=-1)
+    r = c.solve(m, s.rhs, 1e-10, r_norm)
+    assert int(r["cvg"]) == 1
+    res = np.linalg.norm(s.rhs - m.vector_multiply(r["vx"][:s.n_rows].copy()))
+    assert res <= 1.01e-10 * r_norm and abs(res - r["residual"]) <= 1e-2 * res
+    c.destroy(); m.destroy()
+
+
+def test_fcg_mgpc_128_true_residual(csb):
+    """Config-2 size (128^3): FCG + V-cycle(RJ3) converges in a few tens of iterations and the
+    reported residual is the true one."""
+    s = cube_poisson(128, "neumann")
+    r_norm = float(np.linalg.norm(s.rhs))
+    m = csb.Matrix.from_system(s)
+    c = csb.SlesIt(csb.SlesItType.FCG, 200, poly_degree=-1)
+    c.transfer_pc(csb.Multigrid(pc=True))
+    r = c.solve(m, s.rhs, 1e-8, r_norm)
+    assert int(r["cvg"]) == 1 and r["n_iter"] <= 60
+    res = np.linalg.norm(s.rhs - m.vector_multiply(r["vx"][:s.n_rows].copy()))
+    assert res <= 1.01e-8 * r_norm and abs(res - r["residual"]) <= 1e-2 * res
+    c.destroy(); m.destroy()
