@@ -1,0 +1,159 @@
+"""tests/cudasim/run_checks.py -- TEST INFRASTRUCTURE (see cuda_runtime.h in this directory).
+
+Runs in a process of its own (tests/test_cudasim.py) with the simulated library bound in
+place of libcsb200.so: the UNMODIFIED kernels of csrc/kernels.cu and the launch sequences of
+csrc/sles.cu execute on host threads and are compared with the reference-built golden
+fixtures and the oracle.  Sizes are tiny: a block of 256 CUDA threads is 256 OS threads.
+Usage: python tests/cudasim/run_checks.py [check ...]   (default: all)
+"""
+import os
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import build as simbuild  # noqa: E402
+
+os.environ["CSB_LIB"] = simbuild.build()
+# the persistent cooperative kernels cannot run here: kernel-per-phase variants
+os.environ["CSB_PCG_MODE_MULTI"] = "1"
+os.environ["CSB_MG_MODE_MULTI"] = "1"
+
+import numpy as np  # noqa: E402
+
+from code_saturne_b200 import api as csb  # noqa: E402
+from code_saturne_b200.mesh_cartesian import cube_poisson, matrix_check_coefficients  # noqa: E402
+from oracle.pyoracle import Oracle  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+SMOOTHERS = {"jacobi": 3, "l1_jacobi": 13, "r_jacobi": 14, "rj2": 15, "rj3": 16}
+CYCLES = {"rj3": ((16, 16, 0), (3, 3, 500)), "rj2": ((15, 15, 0), (2, 4, 500)),
+          "r_jacobi": ((14, 14, 0), (2, 2, 500)), "l1_jacobi": ((13, 13, 0), (2, 2, 500)),
+          "jacobi": ((3, 3, 0), (2, 3, 500))}
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def _mg(types, nmi, precision_mult=(-1., -1., 1.)):
+    mg = csb.Multigrid()
+    mg.set_solver_options(descent=types[0], ascent=types[1], coarse=types[2], n_max_cycles=1,
+                          n_max_iter_descent=nmi[0], n_max_iter_ascent=nmi[1],
+                          n_max_iter_coarse=nmi[2], precision_mult=precision_mult)
+    return mg
+
+
+def check_spmv_pcg(ora):
+    """the simulator itself, on paths the B200 runs have already validated"""
+    s = cube_poisson(8, "neumann")
+    d, xv, x = matrix_check_coefficients(s)
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, d, xv)
+    assert np.array_equal(m.vector_multiply(x), ora.spmv(s.row_index, s.col_id, d, xv, x))
+    assert np.array_equal(m.vector_multiply(x, exclude_diag=True),
+                          ora.spmv(s.row_index, s.col_id, d, xv, x, True))
+    m.destroy()
+    m = csb.Matrix.from_system(s)
+    rn = float(np.linalg.norm(s.rhs))
+    c = csb.SlesIt(csb.SlesItType.PCG, 200)
+    r = c.solve(m, s.rhs, 1e-8, rn)
+    o = ora.pcg(s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, 200, 1e-8, rn)
+    assert r["n_iter"] == o["n_iter"] and rel(r["vx"][:s.n_rows], o["vx"]) < 1e-12
+    c.destroy(); m.destroy()
+
+
+def check_smoothers(ora):
+    for N, bc in ((8, "neumann"), (12, "dirichlet")):
+        g = np.load(os.path.join(GOLD, f"mgpc_N{N}_{bc}.npz"))
+        s = cube_poisson(N, bc)
+        m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+        for name, st in SMOOTHERS.items():
+            for nit in (1, 3):
+                sm = csb.Smoother(st, nit)
+                r = sm.solve(m, s.rhs)
+                assert int(r["cvg"]) == -1 and r["residual"] == -1.0
+                assert np.array_equal(r["vx"][:s.n_rows], g[f"sm_{name}_{nit}_zero"]), (name, nit)
+                r = sm.solve(m, s.rhs, vx=g["vx0"].copy(), use_vx_ini=True)
+                assert np.array_equal(r["vx"][:s.n_rows], g[f"sm_{name}_{nit}_warm"]), (name, nit)
+                assert r["n_iter"] == int(g[f"sm_{name}_{nit}_n_iter"])
+                sm.destroy()
+        m.destroy()
+
+
+def check_cycle_pc(ora):
+    g = np.load(os.path.join(GOLD, "mgpc_N8_neumann.npz"))
+    s = cube_poisson(8, "neumann")
+    rn = float(g["r_norm"])
+    m = csb.Matrix.from_system(s)
+    for name in ("rj3", "l1_jacobi", "jacobi"):
+        types, nmi = CYCLES[name]
+        mg = _mg(types, nmi)
+        mg.setup(m)
+        r = mg.solve(m, s.rhs, 1e-8, rn)
+        assert int(r["cvg"]) == 0
+        assert abs(r["n_iter"] - int(g[f"cyc_{name}_n_iter"])) <= 1
+        assert rel(r["vx"][:s.n_rows], g[f"cyc_{name}_vx"]) <= 1e-6, name
+        mg.destroy()
+    # PCG smoothers in the single-cycle form, warm start
+    omg = ora.mg_setup(s)
+    vx0 = np.sin(0.11 * np.arange(s.n_rows))
+    mg = _mg((0, 0, 0), (2, 10, 500), (1., 1., 1.))
+    mg.setup(m)
+    o = ora.mg_cycle_pc(omg, s.rhs, 1e-14, rn, (0, 0, 0), (2, 10, 500), (1., 1., 1.), vx0=vx0)
+    r = mg.solve(m, s.rhs, 1e-14, rn, vx=vx0.copy(), use_vx_ini=True)
+    assert rel(r["vx"][:s.n_rows], o["vx"]) <= 1e-9
+    mg.destroy(); ora.mg_free(omg); m.destroy()
+
+
+def check_fcg_mgpc(ora):
+    g = np.load(os.path.join(GOLD, "mgpc_N8_neumann.npz"))
+    s = cube_poisson(8, "neumann")
+    rn = float(g["r_norm"])
+    m = csb.Matrix.from_system(s)
+    c = csb.SlesIt(csb.SlesItType.FCG, 200, poly_degree=-1)
+    c.transfer_pc(csb.Multigrid(pc=True))          # defaults = RJ3, 2 -> 3 sweeps
+    r = c.solve(m, s.rhs, 1e-8, rn)
+    assert int(r["cvg"]) == int(g["fcg_rj3_cvg"]) == 1
+    assert abs(r["n_iter"] - int(g["fcg_rj3_n_iter"])) <= 2
+    k = min(len(r["history"]) - 1, len(g["fcg_rj3_history"]), 4)
+    assert np.allclose(r["history"][1:1 + k], g["fcg_rj3_history"][:k], rtol=1e-5, atol=0)
+    assert rel(r["vx"][:s.n_rows], g["fcg_rj3_vx"]) <= 1e-6
+    z = c.solve(m, np.zeros(s.n_rows), 1e-8, 1.0)
+    assert not z["vx"].any()
+    # warm start with a max-iteration exit
+    omg = ora.mg_setup(s)
+    c3 = csb.SlesIt(csb.SlesItType.FCG, 3, poly_degree=-1)
+    c3.transfer_pc(csb.Multigrid(pc=True))
+    ow = ora.fcg_mgpc(omg, s.rhs, 3, 1e-14, rn, vx0=0.5 * g["fcg_rj3_vx"])
+    w = c3.solve(m, s.rhs, 1e-14, rn, vx=0.5 * g["fcg_rj3_vx"], use_vx_ini=True)
+    assert (int(w["cvg"]), w["n_iter"]) == (ow["cvg"], ow["n_iter"]) == (-1, 3)
+    assert rel(w["vx"][:s.n_rows], ow["vx"]) <= 1e-9
+    # copy keeps the preconditioner settings
+    c.destroy(); c3.destroy(); ora.mg_free(omg)
+    # identity preconditioner
+    c = csb.SlesIt(csb.SlesItType.FCG, 500, poly_degree=-1)
+    r = c.solve(m, s.rhs, 1e-10, rn)
+    assert int(r["cvg"]) == 1
+    res = np.linalg.norm(s.rhs - m.vector_multiply(r["vx"][:s.n_rows].copy()))
+    assert res <= 1.01e-10 * rn
+    c.destroy(); m.destroy()
+
+
+CHECKS = {"spmv_pcg": check_spmv_pcg, "smoothers": check_smoothers,
+          "cycle_pc": check_cycle_pc, "fcg_mgpc": check_fcg_mgpc}
+
+
+def main(argv):
+    csb.init(0)
+    ora = Oracle()
+    for name in (argv or list(CHECKS)):
+        t0 = time.time()
+        CHECKS[name](ora)
+        print(f"cudasim {name}: ok ({time.time() - t0:.1f} s)", flush=True)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
