@@ -413,6 +413,13 @@ bool launch_copy_gated(int n, const double *src, double *dst, const MgState *gat
 /* mirror the outer Krylov solver's state into the gate of its multigrid preconditioner */
 bool launch_gate_from_it(MgState *gate, const ItState *st);
 
+/* single-reduction PCG with a general preconditioner (cs_sles_it.cpp:1229-1415) */
+bool launch_pcg_pc_init(int n, const double *rhs, double *vx, double *rk, bool have_ax);
+bool launch_pcg_pc_update_first(int n, ItState *st, const double *dk, const double *zk,
+                                double *vx, double *rk);
+bool launch_pcg_pc_update(int n, ItState *st, const double *gk, const double *sk, double *dk,
+                          double *zk, double *rk, double *vx);
+
 /* FCG with a general preconditioner, kernel per phase (cs_sles_it.cpp:832-985) */
 bool launch_fcg_init(int n, ItState *st, const double *rhs, double *vx, double *rk,
                      double *qk, bool have_residual);

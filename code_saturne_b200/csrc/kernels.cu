@@ -1733,7 +1733,89 @@ k_fcg_update(int n, const ItState *st, const double *__restrict__ vk,
   }
 }
 
+/* Single-reduction PCG with a general preconditioner (_conjugate_gradient_sr,
+   cs_sles_it.cpp:1229-1415): the vector phases without the fused Jacobi scaling of
+   k_pcg_update_first / k_pcg_update; the preconditioner runs between them. */
+
+/* :1278-1290; rk holds A.vx on entry when have_ax */
+__global__ void __launch_bounds__(TPB)
+k_pcg_pc_init(int n, const double *__restrict__ rhs, double *__restrict__ vx,
+              double *__restrict__ rk, int have_ax)
+{
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    if (have_ax)
+      rk[i] -= rhs[i];
+    else {
+      vx[i] = 0.;
+      rk[i] = -rhs[i];
+    }
+  }
+}
+
+/* :1325-1341 */
+__global__ void __launch_bounds__(TPB)
+k_pcg_pc_update_first(int n, ItState *st, const double *__restrict__ dk,
+                      const double *__restrict__ zk, double *__restrict__ vx,
+                      double *__restrict__ rk, double *partials, unsigned *ticket)
+{
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  const double alpha = st->alpha;
+  double v[1] = {0.};
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    vx[i] += (alpha * dk[i]);
+    const double r = rk[i] + (alpha * zk[i]);
+    rk[i] = r;
+    v[0] += r*r;
+  }
+  grid_sum_finalize<1>(v, partials, ticket, [st](const double *s) {
+    st->cvg = it_cvg_test(st, st->n_iter, sqrt(s[0]));
+  });
+}
+
+/* :1388-1394 */
+__global__ void __launch_bounds__(TPB)
+k_pcg_pc_update(int n, const ItState *st, const double *__restrict__ gk,
+                const double *__restrict__ sk, double *__restrict__ dk,
+                double *__restrict__ zk, double *__restrict__ rk, double *__restrict__ vx)
+{
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  const double alpha = st->alpha, beta = st->beta;
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    const double d = gk[i] + (beta * dk[i]);
+    dk[i] = d;
+    vx[i] += alpha * d;
+    const double z = sk[i] + (beta * zk[i]);
+    zk[i] = z;
+    rk[i] += alpha * z;
+  }
+}
+
 } // anonymous namespace
+
+bool launch_pcg_pc_init(int n, const double *rhs, double *vx, double *rk, bool have_ax)
+{
+  if (n < 1) return true;
+  k_pcg_pc_init<<<vec_grid(n), TPB, 0, ctx().stream>>>(n, rhs, vx, rk, have_ax ? 1 : 0);
+  return post_launch("pcg_pc_init");
+}
+
+bool launch_pcg_pc_update_first(int n, ItState *st, const double *dk, const double *zk,
+                                double *vx, double *rk)
+{
+  Context &c = ctx();
+  const int g = vec_grid(n);
+  if (!ensure_partials(g)) return false;
+  k_pcg_pc_update_first<<<g, TPB, 0, c.stream>>>(n, st, dk, zk, vx, rk, c.partials, c.ticket);
+  return post_launch("pcg_pc_update_first");
+}
+
+bool launch_pcg_pc_update(int n, ItState *st, const double *gk, const double *sk, double *dk,
+                          double *zk, double *rk, double *vx)
+{
+  if (n < 1) return true;
+  k_pcg_pc_update<<<vec_grid(n), TPB, 0, ctx().stream>>>(n, st, gk, sk, dk, zk, rk, vx);
+  return post_launch("pcg_pc_update");
+}
 
 bool launch_l1_inv(const _csb_matrix_t *m, double *l1_inv)
 {

@@ -147,6 +147,16 @@ struct _csb_sles_it_t {
      cs_sles_it_t::_pc, src/alge/cs_sles_it_priv.h */
   csb_multigrid_t    *pc_mg = nullptr;
   bool                is_smoother = false;   /* created by csb_multigrid_smoother_create */
+  DevBuf<double>      pc_tmp;                /* polynomial preconditioner work vector */
+  /* true when the solve goes through a general preconditioner (kernel-per-phase FCG /
+     single-reduction PCG): polynomial (poly_degree >= 1), transferred multigrid, or none
+     (FCG with poly_degree < 0) -- cs_sles_it_create, cs_sles_it.cpp:4676-4690 */
+  bool general_pc() const {
+    if (is_smoother) return false;
+    if (type == CSB_SLES_FCG) return (poly_degree != 0);
+    if (type == CSB_SLES_PCG) return (poly_degree > 0 || (poly_degree < 0 && pc_mg != nullptr));
+    return false;
+  }
   /* setup data (cs_sles_it_setup_t, src/alge/cs_sles_it_priv.h) */
   const csb_matrix_t *a = nullptr;
   bool                setup_done = false;
@@ -382,9 +392,29 @@ bool mg_cycle_pc_enqueue(csb_multigrid_t *mg, double precision, double r_norm,
 int  mg_n_levels(const csb_multigrid_t *mg);
 MgState *mg_gate(csb_multigrid_t *mg);
 
-/* FCG with a general preconditioner (_flexible_conjugate_gradient, cs_sles_it.cpp:832-985;
-   pc_apply = one multigrid V-cycle, _multigrid_pc_apply cs_multigrid.cpp:1500-1600, or the
-   identity).  Per iteration: the preconditioner's launches, one SpMV with the 4 dot products
+/* x_out = M^-1 x_in for the general preconditioners of cs_sles_it:
+     multigrid   _multigrid_pc_apply (cs_multigrid.cpp:1500-1600): one V-cycle, identity for
+                 a one-level hierarchy (:1518-1541); tolerance = the outer solver's
+     polynomial  _sles_pc_poly_apply_poly (cs_sles_pc.cpp:549-610): x = r/d then `degree`
+                 times x = (r - E.x)/d, i.e. degree+1 Jacobi sweeps from zero -- the fused
+                 sweep kernel of the smoothers
+     none        cs_sles_pc_none: copy */
+bool pc_apply_enqueue(csb_sles_it_t *c, const csb_matrix_t *a, double precision,
+                      double r_norm, const double *x_in, double *x_out)
+{
+  csb_multigrid_t *mg = c->pc_mg;
+  if (mg != nullptr && mg_n_levels(mg) > 1)
+    return mg_cycle_pc_enqueue(mg, precision, r_norm, x_in, x_out, false);
+  if (mg == nullptr && c->poly_degree > 0)
+    return smoother_enqueue(a, CSB_SLES_JACOBI, (c->poly_degree > 2 ? 2 : c->poly_degree) + 1,
+                            c->ad_inv.p, x_in, x_out, false, c->pc_tmp.p, nullptr);
+  return launch_copy(a->n_rows, x_in, x_out, c->st.p);
+}
+
+bool pc_is_mg(const csb_sles_it_t *c) { return (c->pc_mg != nullptr && mg_n_levels(c->pc_mg) > 1); }
+
+/* FCG with a general preconditioner (_flexible_conjugate_gradient, cs_sles_it.cpp:832-985).
+   Per iteration: the preconditioner's launches, one SpMV with the 4 dot products
    and the scalar recurrences in its epilogue, one fused 6-vector update; Krylov scalars and
    the convergence state stay on the device, the host only polls the state every few
    iterations.  Launches issued after convergence are gated off on the device. */
@@ -396,8 +426,7 @@ bool fcg_pc_enqueue(csb_sles_it_t *c, const csb_matrix_t *a, double precision, d
   Context &cx = ctx();
   double *rk = c->work.p, *vk = rk + ws, *wk = rk + 2*ws, *dk = rk + 3*ws, *qk = rk + 4*ws;
   ItState *st = c->st.p;
-  csb_multigrid_t *mg = c->pc_mg;
-  const bool identity = (mg == nullptr || mg_n_levels(mg) == 1);   /* cs_multigrid.cpp:1518 */
+  const bool mgpc = pc_is_mg(c);
 
   if (!launch_it_state_init(st, nullptr, precision, r_norm, c->n_max_iter)) return false;
   if (vx_ini_nonzero) {
@@ -405,21 +434,64 @@ bool fcg_pc_enqueue(csb_sles_it_t *c, const csb_matrix_t *a, double precision, d
     if (!launch_spmv(EPI_STORE, sa)) return false;
   }
   if (!launch_fcg_init(n, st, rhs, vx, rk, qk, vx_ini_nonzero)) return false;
-  if (!identity && !launch_mg_state_init(mg_gate(mg), precision, r_norm, 1)) return false;
+  if (mgpc && !launch_mg_state_init(mg_gate(c->pc_mg), precision, r_norm, 1)) return false;
 
-  const int poll = identity ? 16 : 2;
+  const int poll = mgpc ? 2 : 16;
   for (int it = 0; it <= c->n_max_iter; it++) {
-    if (identity) {
-      if (!launch_copy(n, rk, vk, st)) return false;
-    }
-    else if (!mg_cycle_pc_enqueue(mg, precision, r_norm, rk, vk, false))
-      return false;
+    if (!pc_apply_enqueue(c, a, precision, r_norm, rk, vk)) return false;
     SpmvArgs sa;
     sa.m = a; sa.x = vk; sa.y = wk; sa.rk = rk; sa.qk = qk; sa.st = st;
     if (!launch_spmv(EPI_FCG_DOT4, sa)) return false;
-    if (!identity && !launch_gate_from_it(mg_gate(mg), st)) return false;
+    if (mgpc && !launch_gate_from_it(mg_gate(c->pc_mg), st)) return false;
     if (!launch_fcg_update(n, st, vk, wk, dk, qk, rk, vx)) return false;
     if ((it + 1) % poll == 0) {
+      if (!CSB_CUDA(cudaMemcpyAsync(c->h_st, st, IT_HEAD, cudaMemcpyDeviceToHost, cx.stream)))
+        return false;
+      if (!CSB_CUDA(cudaStreamSynchronize(cx.stream))) return false;
+      if (c->h_st->cvg != CSB_SLES_ITERATING) break;
+    }
+  }
+  return true;
+}
+
+/* Single-reduction PCG with a general preconditioner (_conjugate_gradient_sr,
+   cs_sles_it.cpp:1229-1415): pcg_enqueue with the fused Jacobi scaling replaced by the
+   preconditioner's launches; the SpMV epilogue (3 dots + scalar recurrences) is shared. */
+bool pcg_pc_enqueue(csb_sles_it_t *c, const csb_matrix_t *a, double precision, double r_norm,
+                    const double *rhs, double *vx, bool vx_ini_nonzero)
+{
+  const int n = a->n_rows;
+  const size_t ws = work_stride_of((size_t)a->n_cols_ext);
+  Context &cx = ctx();
+  double *rk = c->work.p, *dk = rk + ws, *gk = rk + 2*ws, *zk = rk + 3*ws, *sk = rk + 4*ws;
+  ItState *st = c->st.p;
+  const bool mgpc = pc_is_mg(c);
+
+  if (!launch_it_state_init(st, nullptr, precision, r_norm, c->n_max_iter)) return false;
+  if (vx_ini_nonzero) {
+    SpmvArgs sa; sa.m = a; sa.x = vx; sa.y = rk;
+    if (!launch_spmv(EPI_STORE, sa)) return false;
+  }
+  if (!launch_pcg_pc_init(n, rhs, vx, rk, vx_ini_nonzero)) return false;
+  if (mgpc && !launch_mg_state_init(mg_gate(c->pc_mg), precision, r_norm, 1)) return false;
+
+  if (!pc_apply_enqueue(c, a, precision, r_norm, rk, dk)) return false;
+  SpmvArgs sa;
+  sa.m = a; sa.st = st; sa.rk = rk;
+  sa.x = dk; sa.y = zk; sa.phase = 0;
+  if (!launch_spmv(EPI_PCG_DOT3, sa)) return false;
+  if (!launch_pcg_pc_update_first(n, st, dk, zk, vx, rk)) return false;
+  if (mgpc && !launch_gate_from_it(mg_gate(c->pc_mg), st)) return false;
+
+  sa.x = gk; sa.y = sk; sa.phase = 1;
+  const int poll = mgpc ? 2 : 16;
+  for (int it = 1; ; it++) {
+    if (!pc_apply_enqueue(c, a, precision, r_norm, rk, gk)) return false;
+    if (!launch_spmv(EPI_PCG_DOT3, sa)) return false;
+    if (it >= c->n_max_iter) break;     /* that was the final convergence test */
+    if (mgpc && !launch_gate_from_it(mg_gate(c->pc_mg), st)) return false;
+    if (!launch_pcg_pc_update(n, st, gk, sk, dk, zk, rk, vx)) return false;
+    if ((it % poll) == 0) {
       if (!CSB_CUDA(cudaMemcpyAsync(c->h_st, st, IT_HEAD, cudaMemcpyDeviceToHost, cx.stream)))
         return false;
       if (!CSB_CUDA(cudaStreamSynchronize(cx.stream))) return false;
@@ -450,9 +522,9 @@ csb_sles_it_create(csb_sles_it_type_t solver_type, int poly_degree, int n_max_it
   /* FCG with poly_degree < 0: the preconditioner is handed over afterwards
      (csb_sles_it_transfer_pc: one multigrid V-cycle), identity if none is */
   if (solver_type != CSB_SLES_JACOBI && poly_degree != 0
-      && !((solver_type == CSB_SLES_PCG || solver_type == CSB_SLES_FCG) && poly_degree < 0)) {
-    set_error("csb_sles_it_create: poly_degree %d: Jacobi (0), or none / transferred "
-              "(< 0, PCG and FCG only), are the preconditioners available on this path",
+      && !(solver_type == CSB_SLES_PCG || solver_type == CSB_SLES_FCG)) {
+    set_error("csb_sles_it_create: poly_degree %d: polynomial (> 0), none or transferred "
+              "(< 0) preconditioners are available with PCG and FCG only on this path",
               poly_degree);
     return nullptr;
   }
@@ -505,13 +577,15 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
   if (!c->st.alloc(1)) return;
   if (c->h_st == nullptr)
     if (!CSB_CUDA(cudaMallocHost((void **)&c->h_st, sizeof(ItState)))) return;
-  if (c->type == CSB_SLES_FCG && c->poly_degree < 0) {
-    /* general-preconditioner FCG, kernel per phase (fcg_pc_enqueue) */
+  if (c->general_pc()) {
+    /* general preconditioner: kernel per phase (fcg_pc_enqueue, pcg_pc_enqueue) */
     if (a->halo != nullptr) {
-      set_error("csb_sles_it_setup: FCG with a transferred preconditioner runs on one rank "
+      set_error("csb_sles_it_setup: polynomial / multigrid preconditioning runs on one rank "
                 "on this path");
       return;
     }
+    if (c->pc_mg == nullptr && c->poly_degree > 0
+        && !c->pc_tmp.alloc(work_stride_of((size_t)a->n_cols_ext))) return;
     if (c->pc_mg != nullptr) {
       csb_multigrid_setup(c->pc_mg, name, a, verbosity);
       if (!csb_multigrid_is_setup(c->pc_mg)) return;
@@ -588,7 +662,9 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
   bool ok = false;
   switch (c->type) {
   case CSB_SLES_PCG:
-    if (a->halo != nullptr || env_int("CSB_PCG_MODE_MULTI", 0) == 0) {
+    if (c->general_pc())
+      ok = pcg_pc_enqueue(c, a, precision, r_norm, s_rhs.d, s_vx.d, ini);
+    else if (a->halo != nullptr || env_int("CSB_PCG_MODE_MULTI", 0) == 0) {
       /* whole solve in one persistent cooperative kernel (per rank) */
       PersistentCommon P;
       P.work = c->work.p; P.work_stride = work_stride_of((size_t)a->n_cols_ext);
@@ -607,7 +683,7 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
     break;
   case CSB_SLES_FCG:
   case CSB_SLES_IPCG:
-    if (c->type == CSB_SLES_FCG && c->poly_degree < 0) {
+    if (c->general_pc()) {
       ok = fcg_pc_enqueue(c, a, precision, r_norm, s_rhs.d, s_vx.d, ini);
       break;
     }
@@ -1723,8 +1799,10 @@ csb_multigrid_t *csb_multigrid_pc_create(csb_multigrid_type_t mg_type)
 int csb_sles_it_transfer_pc(csb_sles_it_t *c, csb_multigrid_t **pc)
 {
   if (c == nullptr || pc == nullptr) return -1;
-  if (c->type != CSB_SLES_FCG || c->poly_degree >= 0) {
-    set_error("csb_sles_it_transfer_pc: needs CSB_SLES_FCG created with poly_degree < 0");
+  if ((c->type != CSB_SLES_FCG && c->type != CSB_SLES_PCG) || c->poly_degree >= 0
+      || c->is_smoother) {
+    set_error("csb_sles_it_transfer_pc: needs CSB_SLES_FCG or CSB_SLES_PCG created with "
+              "poly_degree < 0");
     return -1;
   }
   delete c->pc_mg;

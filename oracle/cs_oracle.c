@@ -1763,24 +1763,69 @@ ora_mg_cycle_pc(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt,
 }
 
 /*----------------------------------------------------------------------------
- * Flexible CG preconditioned by one multigrid V-cycle -- the reference's
- * production pressure solver (cs_sles_default.cpp: FCG + cs_multigrid_pc):
- *   _flexible_conjugate_gradient (src/alge/cs_sles_it.cpp:832-985) with
- *   pc_apply = _multigrid_pc_apply (src/alge/cs_multigrid.cpp:1500-1600);
- *   the pc tolerance is the outer solver's (cs_sles_it_solve ->
- *   cs_sles_pc_set_tolerance, _multigrid_pc_tolerance_t :1473-1481).
- * A one-level hierarchy makes the preconditioner the identity (:1518-1541).
- * out[0]=n_iter out[1]=residual out[2]=initial_residual out[3]=history count
+ * General preconditioners of cs_sles_it (cs_sles_pc_t apply functions):
+ *   none   cs_sles_pc_none            (x_out = x_in)
+ *   poly   _sles_pc_poly_apply_poly   (src/alge/cs_sles_pc.cpp:549-610): x = r/d, then
+ *          degree times x = (r - E.x)/d; cs_sles_it_create maps poly_degree 1 -> 1,
+ *          >= 2 -> 2 (cs_sles_it.cpp:4683-4690)
+ *   mg     _multigrid_pc_apply        (src/alge/cs_multigrid.cpp:1500-1600): one V-cycle,
+ *          identity for a one-level hierarchy; tolerance = the outer solver's
+ *          (_multigrid_pc_tolerance_t :1473-1481)
  *----------------------------------------------------------------------------*/
 
-int
-ora_fcg_mgpc(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt,
-             int n_max_iter, double precision, double r_norm,
-             const double *rhs, double *vx, int use_vx_ini,
-             double *out, double *history, int history_size)
+typedef struct {
+  int     kind;            /* 0 none, 1 poly, 2 multigrid */
+  int     n_rows;
+  const int *row_index, *col_id;
+  const double *d_val, *x_val;
+  int     poly_degree;
+  double *ad_inv, *w;      /* poly */
+  const ora_mg_t *mg;
+  const ora_mg_pc_opt_t *opt;
+  double  precision, r_norm;
+} ora_pc_t;
+
+static void
+_pc_init_matrix(ora_pc_t *pc, int n, const int *ri, const int *ci, const double *d,
+                const double *xv)
 {
-  const ora_grid_t *g = mg->grids[0];
-  const int n = g->n_rows;
+  pc->n_rows = n; pc->row_index = ri; pc->col_id = ci; pc->d_val = d; pc->x_val = xv;
+  pc->ad_inv = NULL; pc->w = NULL;
+  if (pc->kind == 1) {
+    pc->ad_inv = malloc(sizeof(double)*(2*(size_t)n + 1));
+    pc->w = pc->ad_inv + n;
+    for (int i = 0; i < n; i++) pc->ad_inv[i] = 1.0 / d[i];
+  }
+}
+
+static void
+_pc_apply(const ora_pc_t *pc, const double *x_in, double *x_out)
+{
+  const int n = pc->n_rows;
+  if (pc->kind == 0 || (pc->kind == 2 && pc->mg->n_levels == 1)) {
+    for (int ii = 0; ii < n; ii++) x_out[ii] = x_in[ii];
+  }
+  else if (pc->kind == 1) {
+    for (int ii = 0; ii < n; ii++) x_out[ii] = x_in[ii] * pc->ad_inv[ii];
+    for (int deg_id = 1; deg_id <= pc->poly_degree; deg_id++) {
+      ora_spmv_msr(n, pc->row_index, pc->col_id, pc->d_val, pc->x_val, 1, x_out, pc->w);
+      for (int ii = 0; ii < n; ii++)
+        x_out[ii] = (x_in[ii] - pc->w[ii]) * pc->ad_inv[ii];
+    }
+  }
+  else
+    ora_mg_cycle_pc(pc->mg, pc->opt, pc->precision, pc->r_norm, x_in, x_out, 0, NULL);
+}
+
+/* _flexible_conjugate_gradient (src/alge/cs_sles_it.cpp:832-985) with pc_apply = pc.
+   out[0]=n_iter out[1]=residual out[2]=initial_residual out[3]=history count */
+
+static int
+_fcg_pc(const ora_pc_t *pc, int n_max_iter, double precision, double r_norm,
+        const double *rhs, double *vx, int use_vx_ini,
+        double *out, double *history, int history_size)
+{
+  const int n = pc->n_rows;
   double *rk = malloc(sizeof(double)*((size_t)n*5 + 1));
   double *vk = rk + n, *wk = rk + 2*n, *dk = rk + 3*n, *qk = rk + 4*n;
 
@@ -1791,7 +1836,7 @@ ora_fcg_mgpc(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt,
   double residual = -1;
 
   if (use_vx_ini) {
-    ora_spmv_msr(n, g->row_index, g->col_id, g->d_val, g->x_val, 0, vx, rk);
+    ora_spmv_msr(n, pc->row_index, pc->col_id, pc->d_val, pc->x_val, 0, vx, rk);
     for (int ii = 0; ii < n; ii++) rk[ii] = rhs[ii] - rk[ii];
   }
   else {
@@ -1802,11 +1847,8 @@ ora_fcg_mgpc(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt,
   double rho_km1 = 0;
 
   while (cvg == ORA_ITERATING) {
-    if (mg->n_levels == 1)
-      for (int ii = 0; ii < n; ii++) vk[ii] = rk[ii];
-    else
-      ora_mg_cycle_pc(mg, opt, precision, r_norm, rk, vk, 0, NULL);
-    ora_spmv_msr(n, g->row_index, g->col_id, g->d_val, g->x_val, 0, vk, wk);
+    _pc_apply(pc, rk, vk);
+    ora_spmv_msr(n, pc->row_index, pc->col_id, pc->d_val, pc->x_val, 0, vk, wk);
 
     double alpha_k, beta_k, gamma_k;
     ora_dot_xy_yz(n, wk, vk, qk, &beta_k, &gamma_k);
@@ -1855,5 +1897,160 @@ ora_fcg_mgpc(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt,
   out[0] = n_iter; out[1] = residual; out[2] = cv.initial_residual;
   out[3] = cv.history_n;
   free(rk);
+  return cvg;
+}
+
+/* _conjugate_gradient_sr (src/alge/cs_sles_it.cpp:1229-1415): single-reduction PCG with a
+   general preconditioner; residual sign r = A.x - b.  The first iteration has its own
+   residual norm and convergence test (:1330-1345).
+   out[0]=n_iter out[1]=residual out[2]=initial_residual out[3]=history count */
+
+static int
+_pcg_sr_pc(const ora_pc_t *pc, int n_max_iter, double precision, double r_norm,
+           const double *rhs, double *vx, int use_vx_ini,
+           double *out, double *history, int history_size)
+{
+  const int n = pc->n_rows;
+  double *rk = malloc(sizeof(double)*((size_t)n*5 + 1));
+  double *dk = rk + n, *gk = rk + 2*n, *zk = rk + 3*n, *sk = rk + 4*n;
+
+  ora_cvg_t cv = {precision, r_norm, -1, n_max_iter, 0, -1,
+                  history, history_size, 0};
+  int cvg = ORA_ITERATING;
+  int n_iter = 0;
+  const int update_residual = (precision > 0.) ? 1 : 0;
+
+  if (use_vx_ini) {
+    ora_spmv_msr(n, pc->row_index, pc->col_id, pc->d_val, pc->x_val, 0, vx, rk);
+    for (int ii = 0; ii < n; ii++) rk[ii] -= rhs[ii];
+  }
+  else {
+    for (int ii = 0; ii < n; ii++) { vx[ii] = 0; rk[ii] = -rhs[ii]; }
+  }
+
+  _pc_apply(pc, rk, dk);
+  ora_spmv_msr(n, pc->row_index, pc->col_id, pc->d_val, pc->x_val, 0, dk, zk);
+
+  double ro_0 = 0, ro_1 = 0;
+  double rk_gkm1 = 0, residual = -1, rk_gk = 0, gk_sk = 0;
+
+  if (update_residual) {
+    ora_dot_xx_xy_yz(n, rk, dk, zk, &residual, &ro_0, &ro_1);
+    residual = sqrt(residual);
+  }
+  else
+    ora_dot_xy_yz(n, rk, dk, zk, &ro_0, &ro_1);
+
+  cv.initial_residual = residual;
+  cvg = _cvg_test(&cv, n_iter, residual);
+
+  if (cvg == ORA_ITERATING) {
+    n_iter = 1;
+    const double d_ro_1 = (fabs(ro_1) > DBL_MIN) ? 1. / ro_1 : 0.;
+    const double alpha = - ro_0 * d_ro_1;
+    rk_gkm1 = ro_0;
+    for (int ii = 0; ii < n; ii++) {
+      vx[ii] += (alpha * dk[ii]);
+      rk[ii] += (alpha * zk[ii]);
+    }
+    if (update_residual)
+      residual = sqrt(ora_dot_xx(n, rk));
+    cvg = _cvg_test(&cv, n_iter, residual);
+  }
+
+  while (cvg == ORA_ITERATING) {
+    _pc_apply(pc, rk, gk);
+    ora_spmv_msr(n, pc->row_index, pc->col_id, pc->d_val, pc->x_val, 0, gk, sk);
+
+    if (update_residual) {
+      ora_dot_xx_xy_yz(n, rk, gk, sk, &residual, &rk_gk, &gk_sk);
+      residual = sqrt(residual);
+    }
+    else
+      ora_dot_xy_yz(n, rk, gk, sk, &rk_gk, &gk_sk);
+
+    if (n_iter > 1)
+      cvg = _cvg_test(&cv, n_iter, residual);
+    if (cvg != ORA_ITERATING)
+      break;
+
+    n_iter += 1;
+
+    const double beta = (fabs(rk_gkm1) > DBL_MIN) ? rk_gk / rk_gkm1 : 0.;
+    rk_gkm1 = rk_gk;
+    ro_1 = gk_sk - beta*beta*ro_1;
+    ro_0 = rk_gk;
+    const double d_ro_1 = (fabs(ro_1) > DBL_MIN) ? 1. / ro_1 : 0.;
+    const double alpha = - ro_0 * d_ro_1;
+
+    for (int ii = 0; ii < n; ii++) {
+      dk[ii] = gk[ii] + (beta * dk[ii]);
+      vx[ii] += alpha * dk[ii];
+      zk[ii] = sk[ii] + (beta * zk[ii]);
+      rk[ii] += alpha * zk[ii];
+    }
+  }
+
+  out[0] = cv.n_iterations; out[1] = cv.residual; out[2] = cv.initial_residual;
+  out[3] = cv.history_n;
+  free(rk);
+  return cvg;
+}
+
+/* FCG (solver 1) or single-reduction PCG (solver 0) preconditioned by one multigrid
+   V-cycle -- FCG + cs_multigrid_pc is the reference's production pressure solver. */
+
+int
+ora_it_mgpc(int solver, const ora_mg_t *mg, const ora_mg_pc_opt_t *opt,
+            int n_max_iter, double precision, double r_norm,
+            const double *rhs, double *vx, int use_vx_ini,
+            double *out, double *history, int history_size)
+{
+  const ora_grid_t *g = mg->grids[0];
+  ora_pc_t pc;
+  memset(&pc, 0, sizeof(pc));
+  pc.kind = 2; pc.mg = mg; pc.opt = opt; pc.precision = precision; pc.r_norm = r_norm;
+  _pc_init_matrix(&pc, g->n_rows, g->row_index, g->col_id, g->d_val, g->x_val);
+  if (solver == 1)
+    return _fcg_pc(&pc, n_max_iter, precision, r_norm, rhs, vx, use_vx_ini,
+                   out, history, history_size);
+  return _pcg_sr_pc(&pc, n_max_iter, precision, r_norm, rhs, vx, use_vx_ini,
+                    out, history, history_size);
+}
+
+int
+ora_fcg_mgpc(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt,
+             int n_max_iter, double precision, double r_norm,
+             const double *rhs, double *vx, int use_vx_ini,
+             double *out, double *history, int history_size)
+{
+  return ora_it_mgpc(1, mg, opt, n_max_iter, precision, r_norm, rhs, vx, use_vx_ini,
+                     out, history, history_size);
+}
+
+/* FCG (solver 1) or single-reduction PCG (solver 0) with the polynomial preconditioner
+   (poly_degree >= 1), or with none (poly_degree < 0; FCG only -- unpreconditioned PCG is
+   ora_pcg_sr_npc, a different function in the reference). */
+
+int
+ora_it_poly(int solver, int n_rows, const int *row_index, const int *col_id,
+            const double *d_val, const double *x_val, int poly_degree,
+            int n_max_iter, double precision, double r_norm,
+            const double *rhs, double *vx, int use_vx_ini,
+            double *out, double *history, int history_size)
+{
+  ora_pc_t pc;
+  memset(&pc, 0, sizeof(pc));
+  pc.kind = (poly_degree < 0) ? 0 : 1;
+  pc.poly_degree = (poly_degree > 2) ? 2 : poly_degree;
+  _pc_init_matrix(&pc, n_rows, row_index, col_id, d_val, x_val);
+  int cvg;
+  if (solver == 1)
+    cvg = _fcg_pc(&pc, n_max_iter, precision, r_norm, rhs, vx, use_vx_ini,
+                  out, history, history_size);
+  else
+    cvg = _pcg_sr_pc(&pc, n_max_iter, precision, r_norm, rhs, vx, use_vx_ini,
+                     out, history, history_size);
+  free(pc.ad_inv);
   return cvg;
 }

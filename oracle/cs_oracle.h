@@ -154,6 +154,15 @@ int    ora_smoother(int type, int n_rows, const int *row_index, const int *col_i
 int    ora_mg_cycle_pc(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt,
                        double precision, double r_norm,
                        const double *rhs, double *vx, int use_vx_ini, double *out);
+int    ora_it_mgpc(int solver, const ora_mg_t *mg, const ora_mg_pc_opt_t *opt,
+                   int n_max_iter, double precision, double r_norm,
+                   const double *rhs, double *vx, int use_vx_ini,
+                   double *out, double *history, int history_size);
+int    ora_it_poly(int solver, int n_rows, const int *row_index, const int *col_id,
+                   const double *d_val, const double *x_val, int poly_degree,
+                   int n_max_iter, double precision, double r_norm,
+                   const double *rhs, double *vx, int use_vx_ini,
+                   double *out, double *history, int history_size);
 int    ora_fcg_mgpc(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt,
                     int n_max_iter, double precision, double r_norm,
                     const double *rhs, double *vx, int use_vx_ini,

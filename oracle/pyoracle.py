@@ -298,6 +298,40 @@ class Oracle:
                                        _dp(vx), 0 if vx0 is None else 1, _dp(out))
         return dict(cvg=cvg, n_iter=int(out[0]), vx=vx)
 
+    def it_poly(self, solver, ri, ci, d, xv, rhs, poly_degree, n_max_iter, precision, r_norm,
+                vx0=None):
+        """FCG (solver 1) / single-reduction PCG (0) with the polynomial preconditioner
+        (poly_degree >= 1) or none (< 0, FCG)."""
+        ri, ci, d, xv, rhs = _i32(ri), _i32(ci), _f64(d), _f64(xv), _f64(rhs)
+        n = len(ri) - 1
+        vx = np.zeros(n) if vx0 is None else _f64(vx0).copy()
+        out = np.zeros(4)
+        hist = np.zeros(n_max_iter + 8)
+        cvg = self.lib.ora_it_poly(C.c_int(solver), C.c_int(n), _ip(ri), _ip(ci), _dp(d), _dp(xv),
+                                   C.c_int(poly_degree), C.c_int(n_max_iter),
+                                   C.c_double(precision), C.c_double(r_norm), _dp(rhs), _dp(vx),
+                                   C.c_int(0 if vx0 is None else 1), _dp(out), _dp(hist),
+                                   C.c_int(len(hist)))
+        return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], initial_residual=out[2],
+                    history=hist[:int(out[3])].copy(), vx=vx)
+
+    def it_mgpc(self, solver, mg, rhs, n_max_iter, precision, r_norm,
+                types=(SLES_RJ3, SLES_RJ3, SLES_PCG), mg_n_max_iter=(3, 3, 500),
+                precision_mult=(-1., -1., 1.), vx0=None):
+        rhs = _f64(rhs)
+        vx = np.zeros(len(rhs)) if vx0 is None else _f64(vx0).copy()
+        opt = self._pc_opt(types, mg_n_max_iter, precision_mult)
+        out = np.zeros(4)
+        hist = np.zeros(n_max_iter + 8)
+        self.lib.ora_it_mgpc.argtypes = [C.c_int, C.POINTER(OraMg), C.POINTER(OraMgPcOpt),
+                                         C.c_int, C.c_double, C.c_double, c_dbl_p, c_dbl_p,
+                                         C.c_int, c_dbl_p, c_dbl_p, C.c_int]
+        cvg = self.lib.ora_it_mgpc(solver, mg, C.byref(opt), n_max_iter, precision, r_norm,
+                                   _dp(rhs), _dp(vx), 0 if vx0 is None else 1, _dp(out),
+                                   _dp(hist), len(hist))
+        return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], initial_residual=out[2],
+                    history=hist[:int(out[3])].copy(), vx=vx)
+
     def fcg_mgpc(self, mg, rhs, n_max_iter, precision, r_norm,
                  types=(SLES_RJ3, SLES_RJ3, SLES_PCG), mg_n_max_iter=(3, 3, 500),
                  precision_mult=(-1., -1., 1.), vx0=None):
@@ -439,9 +473,13 @@ class RefLib:
         return dict(cvg=cvg, n_iter=int(out[0]), vx=vx)
 
     def fcg_mgpc(self, h, rhs, n_max_iter, precision, r_norm, types=(16, 16, 0),
-                 mg_n_max_iter=(3, 3, 500), poly_degree=(0, 0, 0),
-                 precision_mult=(-1., -1., 1.), aggregation_limit=3, coarsening_type=0,
-                 n_levels_max=25, n_g_rows_min=30, p0p1_relax=0.95, vx0=None):
+                 mg_n_max_iter=(3, 3, 500), **kw):
+        return self.it_mgpc(h, 1, rhs, n_max_iter, precision, r_norm, types, mg_n_max_iter, **kw)
+
+    def it_mgpc(self, h, solver, rhs, n_max_iter, precision, r_norm, types=(16, 16, 0),
+                mg_n_max_iter=(3, 3, 500), poly_degree=(0, 0, 0),
+                precision_mult=(-1., -1., 1.), aggregation_limit=3, coarsening_type=0,
+                n_levels_max=25, n_g_rows_min=30, p0p1_relax=0.95, vx0=None):
         rhs = _f64(rhs)
         vx = np.zeros(len(rhs)) if vx0 is None else _f64(vx0).copy()
         iopt = np.array(list(types) + [1] + list(mg_n_max_iter) + list(poly_degree)
@@ -449,7 +487,7 @@ class RefLib:
                         dtype=np.int32)
         dopt = np.array(list(precision_mult) + [p0p1_relax], dtype=np.float64)
         out = np.zeros(5)
-        cvg = self.lib.csref_fcg_mgpc_solve(h, _ip(iopt), _dp(dopt), C.c_int(n_max_iter),
+        cvg = self.lib.csref_it_mgpc_solve(h, C.c_int(solver), _ip(iopt), _dp(dopt), C.c_int(n_max_iter),
                                             C.c_double(precision), C.c_double(r_norm),
                                             _dp(rhs), _dp(vx),
                                             C.c_int(0 if vx0 is None else 1), _dp(out))

@@ -441,13 +441,15 @@ csref_smoother_solve(void          *sys,
   return (int)cvg;
 }
 
-/* FCG preconditioned by one V-cycle (cs_multigrid_pc_create + cs_sles_it_transfer_pc),
-   the reference's production pressure solver layout.
+/* FCG (solver_type 1; the reference's production pressure solver layout) or PCG (0,
+   _conjugate_gradient_sr) preconditioned by one V-cycle (cs_multigrid_pc_create +
+   cs_sles_it_transfer_pc).
    iopt/dopt as csref_multigrid_solve ([3] n_max_cycles is forced to 1).
    out: [0] n_iter, [1] residual, [2] initial residual, [3] setup s, [4] solve s */
 int
-csref_fcg_mgpc_solve(void          *sys,
-                     const int     *iopt,
+csref_it_mgpc_solve(void          *sys,
+                    int            solver_type,
+                    const int     *iopt,
                      const double  *dopt,
                      int            n_max_iter,
                      double         precision,
@@ -458,7 +460,8 @@ csref_fcg_mgpc_solve(void          *sys,
                      double        *out)
 {
   ref_system *s = static_cast<ref_system *>(sys);
-  cs_sles_it_t *c = cs_sles_it_create(CS_SLES_FCG, -1, n_max_iter, false);
+  cs_sles_it_t *c = cs_sles_it_create((cs_sles_it_type_t)solver_type, -1,
+                                      n_max_iter, false);
   cs_sles_pc_t *pc = cs_multigrid_pc_create(CS_MULTIGRID_V_CYCLE);
   cs_multigrid_t *mg = (cs_multigrid_t *)cs_sles_pc_get_context(pc);
   cs_multigrid_set_solver_options(mg,
@@ -492,6 +495,15 @@ csref_fcg_mgpc_solve(void          *sys,
   cs_sles_it_free(ctx);
   cs_sles_it_destroy(&ctx);
   return (int)cvg;
+}
+
+int
+csref_fcg_mgpc_solve(void *sys, const int *iopt, const double *dopt, int n_max_iter,
+                     double precision, double r_norm, const double *rhs, double *vx,
+                     int use_vx_ini, double *out)
+{
+  return csref_it_mgpc_solve(sys, (int)CS_SLES_FCG, iopt, dopt, n_max_iter, precision,
+                             r_norm, rhs, vx, use_vx_ini, out);
 }
 
 /* Build the grid hierarchy with the reference's cs_grid_coarsen, following

@@ -142,7 +142,37 @@ def check_fcg_mgpc(ora):
     c.destroy(); m.destroy()
 
 
-CHECKS = {"spmv_pcg": check_spmv_pcg, "smoothers": check_smoothers,
+def check_general_pc(ora):
+    g = np.load(os.path.join(GOLD, "pc_N8_neumann.npz"))
+    s = cube_poisson(8, "neumann")
+    rn = float(g["r_norm"])
+    m = csb.Matrix.from_system(s)
+    tags = [("pcg_poly1", 0, 1), ("pcg_poly2", 0, 2), ("fcg_poly1", 1, 1), ("fcg_poly2", 1, 2),
+            ("fcg_poly-1", 1, -1), ("pcg_mgpc", 0, -1)]
+
+    def make(tag, so, deg, nmax):
+        c = csb.SlesIt(csb.SlesItType.PCG if so == 0 else csb.SlesItType.FCG, nmax,
+                       poly_degree=deg)
+        if tag == "pcg_mgpc":
+            c.transfer_pc(csb.Multigrid(pc=True))
+        return c
+
+    for tag, so, deg in tags:
+        c = make(tag, so, deg, 500)
+        r = c.solve(m, s.rhs, 1e-9, rn)
+        assert int(r["cvg"]) == int(g[f"{tag}_cvg"]) == 1, tag
+        assert abs(r["n_iter"] - int(g[f"{tag}_n_iter"])) <= 2, tag
+        assert rel(r["vx"][:s.n_rows], g[f"{tag}_vx"]) <= 1e-6, tag
+        w = make(tag, so, deg, 4)
+        rw = w.solve(m, s.rhs, 1e-12, rn, vx=0.3 * g[f"{tag}_vx"], use_vx_ini=True)
+        assert (int(rw["cvg"]), rw["n_iter"]) == (int(g[f"{tag}_warm_cvg"]),
+                                                  int(g[f"{tag}_warm_n_iter"])), tag
+        assert rel(rw["vx"][:s.n_rows], g[f"{tag}_warm_vx"]) <= 1e-9, tag
+        c.destroy(); w.destroy()
+    m.destroy()
+
+
+CHECKS = {"spmv_pcg": check_spmv_pcg, "general_pc": check_general_pc, "smoothers": check_smoothers,
           "cycle_pc": check_cycle_pc, "fcg_mgpc": check_fcg_mgpc}
 
 

@@ -227,3 +227,71 @@ def test_fcg_mgpc_128_true_residual(csb):
     res = np.linalg.norm(s.rhs - m.vector_multiply(r["vx"][:s.n_rows].copy()))
     assert res <= 1.01e-8 * r_norm and abs(res - r["residual"]) <= 1e-2 * res
     c.destroy(); m.destroy()
+
+
+# -------------------------------- cs_sles_it with general preconditioners (a14, a21)
+
+PC_TAGS = [("pcg_poly1", 0, 1), ("pcg_poly2", 0, 2), ("fcg_poly1", 1, 1), ("fcg_poly2", 1, 2),
+           ("fcg_poly-1", 1, -1)]
+
+
+@pytest.mark.parametrize("N,bc", MGPC_CASES)
+def test_general_pc_matches_reference_golden(csb, N, bc):
+    """Single-reduction PCG (_conjugate_gradient_sr) and FCG with the polynomial
+    preconditioner (degree+1 fused Jacobi sweeps from zero), FCG without preconditioner, PCG
+    preconditioned by one V-cycle: iteration counts +-2, first residuals to reduction-order
+    rounding, warm start with a max-iteration exit reproduces the same iterate."""
+    g = np.load(os.path.join(GOLD, f"pc_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    r_norm = float(g["r_norm"])
+    m = csb.Matrix.from_system(s)
+
+    def make(tag, so, deg, nmax):
+        c = csb.SlesIt(csb.SlesItType.PCG if so == 0 else csb.SlesItType.FCG, nmax,
+                       poly_degree=deg)
+        if tag == "pcg_mgpc":
+            c.transfer_pc(csb.Multigrid(pc=True))
+        return c
+
+    for tag, so, deg in PC_TAGS + [("pcg_mgpc", 0, -1)]:
+        c = make(tag, so, deg, 500)
+        r = c.solve(m, s.rhs, 1e-9, r_norm)
+        assert int(r["cvg"]) == int(g[f"{tag}_cvg"]) == 1, tag
+        assert abs(r["n_iter"] - int(g[f"{tag}_n_iter"])) <= 2, tag
+        ir = float(g[f"{tag}_initial_residual"])
+        assert abs(r["initial_residual"] - ir) <= 1e-12 * ir
+        res = np.linalg.norm(s.rhs - m.vector_multiply(r["vx"][:s.n_rows].copy()))
+        assert res <= 1.01e-9 * r_norm, tag
+        w = make(tag, so, deg, 4)
+        rw = w.solve(m, s.rhs, 1e-12, r_norm,
+                     vx=np.concatenate([0.3 * g[f"{tag}_vx"], np.zeros(m.n_cols_ext - s.n_rows)]),
+                     use_vx_ini=True)
+        assert (int(rw["cvg"]), rw["n_iter"]) == (int(g[f"{tag}_warm_cvg"]),
+                                                  int(g[f"{tag}_warm_n_iter"])), tag
+        assert rel_l2(rw["vx"][:s.n_rows], g[f"{tag}_warm_vx"]) <= 1e-9, tag
+        c.destroy(); w.destroy()
+    m.destroy()
+
+
+def test_general_pc_tight_tolerance_solution_parity(csb, oracle):
+    s = cube_poisson(32, "dirichlet")
+    r_norm = float(np.sqrt(oracle.dot_xx(s.rhs)))
+    A = (s.row_index, s.col_id, s.d_val, s.x_val)
+    m = csb.Matrix.from_system(s)
+    for so, T in ((0, csb.SlesItType.PCG), (1, csb.SlesItType.FCG)):
+        for deg in (1, 2):
+            o = oracle.it_poly(so, *A, s.rhs, deg, 2000, 1e-13, r_norm)
+            c = csb.SlesIt(T, 2000, poly_degree=deg)
+            r = c.solve(m, s.rhs, 1e-13, r_norm)
+            assert int(r["cvg"]) == 1 and o["cvg"] == 1
+            assert abs(r["n_iter"] - o["n_iter"]) <= 2
+            assert rel_l2(r["vx"][:s.n_rows], o["vx"]) <= SOL_TOL, (so, deg)
+            c.destroy()
+    omg = oracle.mg_setup(s)
+    o = oracle.it_mgpc(0, omg, s.rhs, 200, 1e-13, r_norm)
+    c = csb.SlesIt(csb.SlesItType.PCG, 200, poly_degree=-1)
+    c.transfer_pc(csb.Multigrid(pc=True))
+    r = c.solve(m, s.rhs, 1e-13, r_norm)
+    assert int(r["cvg"]) == 1 and abs(r["n_iter"] - o["n_iter"]) <= 2
+    assert rel_l2(r["vx"][:s.n_rows], o["vx"]) <= SOL_TOL
+    c.destroy(); oracle.mg_free(omg); m.destroy()

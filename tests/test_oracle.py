@@ -315,3 +315,53 @@ def test_oracle_mgpc_vs_reference_direct(oracle, reflib):
             assert a["cvg"] == b["cvg"] == -1 and np.array_equal(a["vx"], b["vx"])
         oracle.mg_free(mg)
         reflib.destroy(h)
+
+
+# ---- cs_sles_it with general preconditioners (polynomial, none, multigrid) ----
+
+PC_TAGS = [("pcg_poly1", 0, 1), ("pcg_poly2", 0, 2), ("fcg_poly1", 1, 1), ("fcg_poly2", 1, 2),
+           ("fcg_poly-1", 1, -1)]
+
+
+@pytest.mark.parametrize("N,bc", MGPC_CASES)
+def test_oracle_general_pc_matches_golden(oracle, N, bc):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"pc_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    r_norm = float(g["r_norm"])
+    A = (s.row_index, s.col_id, s.d_val, s.x_val)
+    mg = oracle.mg_setup(s)
+    runs = [(tag, lambda nmax, eps, v0, so=so, deg=deg:
+             oracle.it_poly(so, *A, s.rhs, deg, nmax, eps, r_norm, vx0=v0))
+            for tag, so, deg in PC_TAGS]
+    runs.append(("pcg_mgpc", lambda nmax, eps, v0: oracle.it_mgpc(0, mg, s.rhs, nmax, eps, r_norm,
+                                                                    vx0=v0)))
+    for tag, solve in runs:
+        r = solve(500, 1e-9, None)
+        assert r["cvg"] == int(g[f"{tag}_cvg"]) and r["n_iter"] == int(g[f"{tag}_n_iter"]), tag
+        assert r["residual"] == float(g[f"{tag}_residual"])
+        assert r["initial_residual"] == float(g[f"{tag}_initial_residual"])
+        assert np.array_equal(r["vx"], g[f"{tag}_vx"]), tag
+        w = solve(4, 1e-12, 0.3 * r["vx"])
+        assert (w["cvg"], w["n_iter"]) == (int(g[f"{tag}_warm_cvg"]), int(g[f"{tag}_warm_n_iter"]))
+        assert np.array_equal(w["vx"], g[f"{tag}_warm_vx"]), tag
+    oracle.mg_free(mg)
+
+
+def test_oracle_general_pc_vs_reference_direct(oracle, reflib):
+    s = cube_poisson(17, "neumann")
+    h = reflib.system(s)
+    r_norm = float(np.linalg.norm(s.rhs))
+    A = (s.row_index, s.col_id, s.d_val, s.x_val)
+    for tag, so, deg in PC_TAGS + [("pcg_poly3", 0, 3)]:
+        a = oracle.it_poly(so, *A, s.rhs, deg, 500, 1e-10, r_norm)
+        b = reflib.sles_it(h, so, s.rhs, 500, 1e-10, r_norm, poly_degree=deg)
+        assert (a["cvg"], a["n_iter"], a["residual"]) == (b["cvg"], b["n_iter"], b["residual"]), tag
+        assert np.array_equal(a["vx"], b["vx"]), tag
+    mg = oracle.mg_setup(s)
+    for types, nmi in ((16, 16, 0), (3, 3, 500)), ((13, 13, 0), (2, 2, 500)):
+        a = oracle.it_mgpc(0, mg, s.rhs, 200, 1e-10, r_norm, types, nmi)
+        b = reflib.it_mgpc(h, 0, s.rhs, 200, 1e-10, r_norm, types, nmi)
+        assert (a["cvg"], a["n_iter"], a["residual"]) == (b["cvg"], b["n_iter"], b["residual"])
+        assert np.array_equal(a["vx"], b["vx"])
+    oracle.mg_free(mg)
+    reflib.destroy(h)
