@@ -413,6 +413,12 @@ bool launch_copy_gated(int n, const double *src, double *dst, const MgState *gat
 /* mirror the outer Krylov solver's state into the gate of its multigrid preconditioner */
 bool launch_gate_from_it(MgState *gate, const ItState *st);
 
+/* 3x3 block Jacobi (cs_sles_it.cpp:2284-2440): block inverses (cs_math.h:540-586), one
+   sweep after vxx = E.vx with the residual of the previous iterate */
+bool launch_gauss_inverse_33(int n_blocks, const double *ad, double *ad_inv);
+bool launch_b3_jacobi_update(int n_blocks, ItState *st, const double *ad, const double *ad_inv,
+                             const double *rhs, const double *vxx, double *vx, bool first);
+
 /* single-reduction PCG with a general preconditioner (cs_sles_it.cpp:1229-1415) */
 bool launch_pcg_pc_init(int n, const double *rhs, double *vx, double *rk, bool have_ax);
 bool launch_pcg_pc_update_first(int n, ItState *st, const double *dk, const double *zk,

@@ -1817,6 +1817,107 @@ bool launch_pcg_pc_update(int n, ItState *st, const double *gk, const double *sk
   return post_launch("pcg_pc_update");
 }
 
+/*--------------------------------------------------------------------------
+ * 3x3 block Jacobi (_block_3_jacobi, src/alge/cs_sles_it.cpp:2284-2440)
+ *--------------------------------------------------------------------------*/
+
+namespace {
+
+/* cs_math_matrix_gauss_inverse<3> (src/base/cs_math.h:540-586): Gauss-Jordan on [A | I]
+   with row pivoting; the reference swaps row pointers, here a row permutation -- the same
+   rows see the same operations in the same order, so the inverse is bit-identical. */
+__global__ void __launch_bounds__(TPB)
+k_gauss_inverse_33(int n_blocks, const double *__restrict__ ad, double *__restrict__ ad_inv)
+{
+  for (int b = blockIdx.x*TPB + threadIdx.x; b < n_blocks; b += gridDim.x*TPB) {
+    double t[3][6];
+    int p[3] = {0, 1, 2};
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < 3; j++) {
+        t[i][j] = ad[(size_t)b*9 + i*3 + j];
+        t[i][j+3] = 0.;
+      }
+      t[i][i+3] = 1.;
+    }
+    for (int i = 0; i < 3; i++) {
+      for (int j = i+1; j < 3; j++) {
+        if (fabs(t[p[i]][i]) < fabs(t[p[j]][i])) {
+          const int tmp = p[j]; p[j] = p[i]; p[i] = tmp;
+        }
+      }
+      for (int j = 0; j < 3; j++) {
+        if (j != i) {
+          const double s = t[p[j]][i] / t[p[i]][i];
+          for (int k = 0; k < 6; k++)
+            t[p[j]][k] -= t[p[i]][k] * s;
+        }
+      }
+    }
+    for (int i = 0; i < 3; i++) {
+      const double s = 1. / t[p[i]][i];
+      for (int j = 0; j < 3; j++)
+        ad_inv[(size_t)b*9 + i*3 + j] = t[p[i]][3+j] * s;
+    }
+  }
+}
+
+/* One sweep after vxx = E.vx: vx = ad_inv.(rhs - vxx) (_mat_c_m_b_33,
+   cs_sles_it_priv.h:272-289) and residual^2 = sum (D.(x_new - x_old))^2
+   (cs_sles_it.cpp:2396-2410); first = 1: the simplified sweep from vx = 0 (:2338-2359). */
+__global__ void __launch_bounds__(TPB)
+k_b3_jacobi_update(int n_blocks, ItState *st, const double *__restrict__ ad,
+                   const double *__restrict__ ad_inv, const double *__restrict__ rhs,
+                   const double *__restrict__ vxx, double *__restrict__ vx, int first,
+                   double *partials, unsigned *ticket)
+{
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  double v[1] = {0.};
+  for (int ii = blockIdx.x*TPB + threadIdx.x; ii < n_blocks; ii += gridDim.x*TPB) {
+    double xo[3], aux[3], xn[3];
+    for (int k = 0; k < 3; k++) {
+      xo[k] = first ? 0. : vx[(size_t)ii*3 + k];
+      const double b = first ? 0. : vxx[(size_t)ii*3 + k];
+      aux[k] = (rhs[(size_t)ii*3 + k] - b);
+    }
+    const double *mat = ad_inv + (size_t)ii*9;
+    for (int r = 0; r < 3; r++)
+      xn[r] = mat[3*r + 0]*aux[0] + mat[3*r + 1]*aux[1] + mat[3*r + 2]*aux[2];
+    for (int k = 0; k < 3; k++) vx[(size_t)ii*3 + k] = xn[k];
+    for (int jj = 0; jj < 3; jj++) {
+      double r = 0.0;
+      for (int kk = 0; kk < 3; kk++)
+        r += ad[(size_t)ii*9 + jj*3 + kk] * (xn[kk] - xo[kk]);
+      v[0] += (r*r);
+    }
+  }
+  grid_sum_finalize<1>(v, partials, ticket, [st](const double *s) {
+    st->n_iter += 1;
+    const double residual = sqrt(s[0]);
+    if (st->n_iter == 1) st->initial_residual = residual;
+    st->cvg = it_cvg_test(st, st->n_iter, residual);
+  });
+}
+
+} // anonymous namespace
+
+bool launch_gauss_inverse_33(int n_blocks, const double *ad, double *ad_inv)
+{
+  if (n_blocks < 1) return true;
+  k_gauss_inverse_33<<<vec_grid(n_blocks*4), TPB, 0, ctx().stream>>>(n_blocks, ad, ad_inv);
+  return post_launch("gauss_inverse_33");
+}
+
+bool launch_b3_jacobi_update(int n_blocks, ItState *st, const double *ad, const double *ad_inv,
+                             const double *rhs, const double *vxx, double *vx, bool first)
+{
+  Context &c = ctx();
+  const int g = vec_grid(n_blocks*4);
+  if (!ensure_partials(g)) return false;
+  k_b3_jacobi_update<<<g, TPB, 0, c.stream>>>(n_blocks, st, ad, ad_inv, rhs, vxx, vx,
+                                              first ? 1 : 0, c.partials, c.ticket);
+  return post_launch("b3_jacobi_update");
+}
+
 bool launch_l1_inv(const _csb_matrix_t *m, double *l1_inv)
 {
   if (m->n_rows < 1) return true;

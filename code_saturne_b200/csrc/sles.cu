@@ -413,6 +413,38 @@ bool pc_apply_enqueue(csb_sles_it_t *c, const csb_matrix_t *a, double precision,
 
 bool pc_is_mg(const csb_sles_it_t *c) { return (c->pc_mg != nullptr && mg_n_levels(c->pc_mg) > 1); }
 
+/* 3x3 block Jacobi (_block_3_jacobi, cs_sles_it.cpp:2284-2440) on a CS_MATRIX_BLOCK_D
+   matrix: vxx = E.vx (k_spmv_b3, diagonal blocks excluded), then one kernel for
+   vx = D^-1.(rhs - vxx) and the residual ||D.(x_new - x_old)||, tested every sweep on the
+   device.  vxx: n_cols_ext*3 doubles. */
+bool block3_jacobi_enqueue(const csb_matrix_t *m, ItState *st, const double *ad_inv,
+                           double precision, double r_norm, int n_max_iter, const double *rhs,
+                           double *vx, bool vx_ini_nonzero, double *vxx, ItState *h_st)
+{
+  Context &c = ctx();
+  if (!launch_it_state_init(st, nullptr, precision, r_norm, n_max_iter)) return false;
+  int t = 0;
+  if (!vx_ini_nonzero) {
+    if (!launch_b3_jacobi_update(m->n_rows, st, m->d_val.p, ad_inv, rhs, vxx, vx, true))
+      return false;
+    t = 1;
+  }
+  const int poll = 16;
+  while (t < n_max_iter) {
+    t += 1;
+    if (!launch_spmv_b3(m, vx, vxx, true)) return false;
+    if (!launch_b3_jacobi_update(m->n_rows, st, m->d_val.p, ad_inv, rhs, vxx, vx, false))
+      return false;
+    if (h_st != nullptr && (t % poll) == 0) {
+      if (!CSB_CUDA(cudaMemcpyAsync(h_st, st, IT_HEAD, cudaMemcpyDeviceToHost, c.stream)))
+        return false;
+      if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return false;
+      if (h_st->cvg != CSB_SLES_ITERATING) break;
+    }
+  }
+  return true;
+}
+
 /* FCG with a general preconditioner (_flexible_conjugate_gradient, cs_sles_it.cpp:832-985).
    Per iteration: the preconditioner's launches, one SpMV with the 4 dot products
    and the scalar recurrences in its epilogue, one fused 6-vector update; Krylov scalars and
@@ -560,9 +592,23 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
   c->setup_done = false;
   const size_t n_wa = (c->type == CSB_SLES_BICGSTAB) ? 6
     : ((c->type == CSB_SLES_PCG || c->type == CSB_SLES_FCG || c->type == CSB_SLES_IPCG) ? 5 : 1);
-  if (a->db != 1 && c->type != CSB_SLES_BICGSTAB) {
+  if (a->db != 1 && c->type != CSB_SLES_BICGSTAB && !(c->type == CSB_SLES_JACOBI && a->db == 3)) {
     set_error("csb_sles_it_setup: block matrices (db %d) are solved with CSB_SLES_BICGSTAB "
-              "on this path", a->db);
+              "or, for 3x3 blocks, CSB_SLES_JACOBI on this path", a->db);
+    return;
+  }
+  if (a->db == 3 && c->type == CSB_SLES_JACOBI) {
+    /* block_nn_inverse (cs_sles_it_setup :4999, cs_sles_it_priv.cpp:174-222) */
+    if (a->halo != nullptr) { set_error("csb_sles_it_setup: block Jacobi runs on one rank"); return; }
+    if (!c->ad_inv.alloc((size_t)a->n_rows*9)) return;
+    if (!launch_gauss_inverse_33(a->n_rows, a->d_val.p, c->ad_inv.p)) return;
+    if (!c->work.alloc(work_stride_of((size_t)a->n_cols_ext*3))) return;
+    if (!c->st.alloc(1)) return;
+    if (c->h_st == nullptr)
+      if (!CSB_CUDA(cudaMallocHost((void **)&c->h_st, sizeof(ItState)))) return;
+    c->setup_done = true;
+    c->n_setups += 1;
+    c->t_setup += wall() - t0;
     return;
   }
   if (!c->ad_inv.alloc((size_t)a->n_rows*a->db)) return;
@@ -702,6 +748,11 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
     }
     break;
   case CSB_SLES_JACOBI:
+    if (a->db == 3) {
+      ok = block3_jacobi_enqueue(a, c->st.p, c->ad_inv.p, precision, r_norm, c->n_max_iter,
+                                 s_rhs.d, s_vx.d, ini, c->work.p, c->h_st);
+      break;
+    }
     ok = jacobi_enqueue(a, c->st.p, c->ad_inv.p, precision, r_norm, c->n_max_iter,
                         s_rhs.d, s_vx.d, ini, c->work.p, c->h_st);
     break;

@@ -2054,3 +2054,119 @@ ora_it_poly(int solver, int n_rows, const int *row_index, const int *col_id,
   free(pc.ad_inv);
   return cvg;
 }
+
+/*----------------------------------------------------------------------------
+ * 3x3 block Jacobi: _block_3_jacobi (src/alge/cs_sles_it.cpp:2284-2440) with
+ *   ad_inv = cs_math_matrix_gauss_inverse<3> of each diagonal block (Gauss-Jordan with
+ *            row pivoting by pointer swap, src/base/cs_math.h:540-586; called from
+ *            _setup_ad_block_nn_inv, src/alge/cs_sles_it_priv.cpp:174-222)
+ *   x = ad_inv.(rhs - E.x)  (_mat_c_m_b_33, src/alge/cs_sles_it_priv.h:272-289)
+ *   residual^2 = sum_rows (D.(x_new - x_old))^2, tested every sweep.
+ *----------------------------------------------------------------------------*/
+
+void
+ora_gauss_inverse_33(const double a[9], double b[9])
+{
+  double t[3][6];
+  double *p_a[3];
+  for (int i = 0; i < 3; i++) {
+    p_a[i] = t[i];
+    for (int j = 0; j < 3; j++) {
+      p_a[i][j] = a[i*3 + j];
+      p_a[i][j+3] = 0;
+    }
+    p_a[i][i+3] = 1;
+  }
+  for (int i = 0; i < 3; i++) {
+    for (int j = i+1; j < 3; j++) {
+      if (fabs(p_a[i][i]) < fabs(p_a[j][i])) {
+        double *tmp = p_a[j]; p_a[j] = p_a[i]; p_a[i] = tmp;
+      }
+    }
+    for (int j = 0; j < 3; j++) {
+      if (j != i) {
+        double s = p_a[j][i] / p_a[i][i];
+        for (int k = 0; k < 6; k++)
+          p_a[j][k] -= p_a[i][k] * s;
+      }
+    }
+  }
+  for (int i = 0; i < 3; i++) {
+    double s = 1. / p_a[i][i];
+    for (int j = 0; j < 3; j++)
+      b[i*3 + j] = p_a[i][3+j] * s;
+  }
+}
+
+static void
+_ora_mat_c_m_b_33(const double *mat, double *x, const double *b, const double *c)
+{
+  double aux[3];
+  for (int ii = 0; ii < 3; ii++) aux[ii] = (c[ii] - b[ii]);
+  for (int ii = 0; ii < 3; ii++)
+    x[ii] = mat[3*ii + 0]*aux[0] + mat[3*ii + 1]*aux[1] + mat[3*ii + 2]*aux[2];
+}
+
+int
+ora_block3_jacobi(int n_rows, const int *row_index, const int *col_id,
+                  const double *d_val, const double *x_val,
+                  int n_max_iter, double precision, double r_norm,
+                  const double *rhs, double *vx, int use_vx_ini,
+                  double *out, double *history, int history_size)
+{
+  const int n_blocks = n_rows;
+  const size_t n = (size_t)n_rows*3;
+  double *rk = malloc(sizeof(double)*(2*n + 9*(size_t)n_blocks + 1));
+  double *vxx = rk + n, *ad_inv = rk + 2*n;
+  const double *ad = d_val;
+  for (int i = 0; i < n_blocks; i++)
+    ora_gauss_inverse_33(d_val + 9*(size_t)i, ad_inv + 9*(size_t)i);
+
+  ora_cvg_t cv = {precision, r_norm, -1, n_max_iter, 0, -1,
+                  history, history_size, 0};
+  int cvg = ORA_ITERATING;
+  int n_iter = 0;
+  double residual = -1, res2;
+
+  if (!use_vx_ini) {
+    n_iter += 1;
+    res2 = 0.0;
+    for (int ii = 0; ii < n_blocks; ii++) {
+      for (int jj = 0; jj < 3; jj++) { rk[3*ii + jj] = 0; vxx[3*ii + jj] = 0; }
+      _ora_mat_c_m_b_33(ad_inv + 9*ii, vx + 3*ii, vxx + 3*ii, rhs + 3*ii);
+      for (int jj = 0; jj < 3; jj++) {
+        double r = 0.0;
+        for (int kk = 0; kk < 3; kk++)
+          r += ad[ii*9 + jj*3 + kk] * (vx[ii*3 + kk] - rk[ii*3 + kk]);
+        res2 += (r*r);
+      }
+    }
+    residual = sqrt(res2);
+    if (n_iter == 1) cv.initial_residual = residual;
+    cvg = _cvg_test(&cv, n_iter, residual);
+  }
+
+  while (cvg == ORA_ITERATING) {
+    n_iter += 1;
+    ora_spmv_msr_b3(n_rows, row_index, col_id, d_val, x_val, 1, vx, vxx);
+    res2 = 0.0;
+    for (int ii = 0; ii < n_blocks; ii++) {
+      for (int kk = 0; kk < 3; kk++) rk[ii*3 + kk] = vx[ii*3 + kk];
+      _ora_mat_c_m_b_33(ad_inv + 9*ii, vx + 3*ii, vxx + 3*ii, rhs + 3*ii);
+      for (int jj = 0; jj < 3; jj++) {
+        double r = 0.0;
+        for (int kk = 0; kk < 3; kk++)
+          r += ad[ii*9 + jj*3 + kk] * (vx[ii*3 + kk] - rk[ii*3 + kk]);
+        res2 += (r*r);
+      }
+    }
+    residual = sqrt(res2);
+    if (n_iter == 1) cv.initial_residual = residual;
+    cvg = _cvg_test(&cv, n_iter, residual);
+  }
+
+  out[0] = cv.n_iterations; out[1] = cv.residual; out[2] = cv.initial_residual;
+  out[3] = cv.history_n;
+  free(rk);
+  return cvg;
+}

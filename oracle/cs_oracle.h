@@ -148,6 +148,12 @@ int    ora_mg_solve(const ora_mg_t *mg, const ora_mg_opt_t *opt,
                     const double *rhs, double *vx, int use_vx_ini,
                     double *out, double *cycle_res);
 
+void   ora_gauss_inverse_33(const double a[9], double b[9]);
+int    ora_block3_jacobi(int n_rows, const int *row_index, const int *col_id,
+                         const double *d_val, const double *x_val,
+                         int n_max_iter, double precision, double r_norm,
+                         const double *rhs, double *vx, int use_vx_ini,
+                         double *out, double *history, int history_size);
 int    ora_smoother(int type, int n_rows, const int *row_index, const int *col_id,
                     const double *d_val, const double *x_val, int n_max_iter,
                     const double *rhs, double *vx, int use_vx_ini, double *out);

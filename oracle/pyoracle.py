@@ -142,6 +142,20 @@ class Oracle:
         return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], initial_residual=out[2],
                     history=hist[:int(out[3])].copy(), vx=vx)
 
+    def block3_jacobi(self, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0=None):
+        ri, ci, d, xv, rhs = _i32(ri), _i32(ci), _f64(d), _f64(xv), _f64(rhs)
+        n = len(ri) - 1
+        vx = np.zeros(3 * n) if vx0 is None else _f64(vx0).copy()
+        out = np.zeros(4)
+        hist = np.zeros(n_max_iter + 8)
+        cvg = self.lib.ora_block3_jacobi(C.c_int(n), _ip(ri), _ip(ci), _dp(d), _dp(xv),
+                                         C.c_int(n_max_iter), C.c_double(precision),
+                                         C.c_double(r_norm), _dp(rhs), _dp(vx),
+                                         C.c_int(0 if vx0 is None else 1), _dp(out), _dp(hist),
+                                         C.c_int(len(hist)))
+        return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], initial_residual=out[2],
+                    history=hist[:int(out[3])].copy(), vx=vx)
+
     def spmv_csr(self, ri, ci, val, x, exclude_diag=False):
         ri, ci, val, x = _i32(ri), _i32(ci), _f64(val), _f64(x)
         y = np.empty(len(ri) - 1)

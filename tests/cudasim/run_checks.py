@@ -65,6 +65,43 @@ def check_spmv_pcg(ora):
     c.destroy(); m.destroy()
 
 
+def check_kernel_per_phase_paths(ora):
+    """the other kernel-per-phase solvers that share k_spmv_stream's epilogues: PCG warm
+    start (EPI_PCG_INIT), Jacobi, BiCGStab, the multi-kernel V-cycle (EPI_RESIDUAL_NORM)"""
+    s = cube_poisson(8, "neumann")
+    rn = float(np.linalg.norm(s.rhs))
+    A = (s.row_index, s.col_id, s.d_val, s.x_val)
+    m = csb.Matrix.from_system(s)
+    o = ora.pcg(*A, s.rhs, 200, 1e-10, rn, vx0=0.5 * s.rhs)
+    c = csb.SlesIt(csb.SlesItType.PCG, 200)
+    r = c.solve(m, s.rhs, 1e-10, rn, vx=0.5 * s.rhs, use_vx_ini=True)
+    assert abs(r["n_iter"] - o["n_iter"]) <= 1 and rel(r["vx"][:s.n_rows], o["vx"]) < 1e-9
+    c.destroy()
+    o = ora.jacobi(*A, s.rhs, 20, 1e-12, rn)
+    c = csb.SlesIt(csb.SlesItType.JACOBI, 20)
+    r = c.solve(m, s.rhs, 1e-12, rn)
+    assert r["n_iter"] == o["n_iter"] and rel(r["vx"][:s.n_rows], o["vx"]) < 1e-13
+    c.destroy()
+    o = ora.bicgstab(*A, s.rhs, 200, 1e-10, rn)
+    c = csb.SlesIt(csb.SlesItType.BICGSTAB, 200)
+    r = c.solve(m, s.rhs, 1e-10, rn)
+    assert abs(r["n_iter"] - o["n_iter"]) <= 2 and rel(r["vx"][:s.n_rows], o["vx"]) < 1e-7
+    c.destroy()
+    omg = ora.mg_setup(s)
+    o = ora.mg_solve(omg, s.rhs, 1e-8, rn)
+    mg = csb.Multigrid()
+    mg.setup(m)
+    lv, olv = mg.levels(), ora.mg_levels(omg)
+    for a, b in zip(lv[1:], olv[1:]):
+        assert np.array_equal(a["coarse_row"], b["coarse_row"])
+        assert np.array_equal(a["x_val"], b["x_val"]) and np.array_equal(a["d_val"], b["d_val"])
+    r = mg.solve(m, s.rhs, 1e-8, rn)
+    assert int(r["cvg"]) == o["cvg"] == 1 and abs(r["n_cycles"] - o["n_cycles"]) <= 1
+    k = min(len(r["cycle_residuals"]), len(o["cycle_residuals"]), 4)
+    assert np.allclose(r["cycle_residuals"][:k], o["cycle_residuals"][:k], rtol=1e-7, atol=0)
+    mg.destroy(); ora.mg_free(omg); m.destroy()
+
+
 def check_smoothers(ora):
     for N, bc in ((8, "neumann"), (12, "dirichlet")):
         g = np.load(os.path.join(GOLD, f"mgpc_N{N}_{bc}.npz"))
@@ -172,7 +209,31 @@ def check_general_pc(ora):
     m.destroy()
 
 
-CHECKS = {"spmv_pcg": check_spmv_pcg, "general_pc": check_general_pc, "smoothers": check_smoothers,
+def check_block3_jacobi(ora):
+    from code_saturne_b200.mesh_cartesian import cube_block3_convection_diffusion
+    g = np.load(os.path.join(GOLD, "block3jac_N6.npz"))
+    ri, ci, d, xv, rhs = cube_block3_convection_diffusion(6)
+    n = len(ri) - 1
+    rn = float(g["r_norm"])
+    m = csb.Matrix.from_block(n, 3, ri, ci, d.ravel(), xv)
+    for nit in (1, 2, 7):
+        c = csb.SlesIt(csb.SlesItType.JACOBI, nit)
+        r = c.solve(m, rhs, 1e-12, rn)
+        assert (int(r["cvg"]), r["n_iter"]) == (-1, nit)
+        assert np.array_equal(r["vx"], g[f"sweeps{nit}_vx"]), nit
+        c.destroy()
+    c = csb.SlesIt(csb.SlesItType.JACOBI, 1000)
+    r = c.solve(m, rhs, 1e-8, rn)
+    assert int(r["cvg"]) == 1 and abs(r["n_iter"] - int(g["n_iter"])) <= 1
+    c.destroy()
+    c = csb.SlesIt(csb.SlesItType.JACOBI, 5)
+    w = c.solve(m, rhs, 1e-12, rn, vx=g["vx0"].copy(), use_vx_ini=True)
+    assert np.array_equal(w["vx"], g["warm_vx"])
+    c.destroy(); m.destroy()
+
+
+CHECKS = {"spmv_pcg": check_spmv_pcg, "block3_jacobi": check_block3_jacobi, "general_pc": check_general_pc,
+          "kernel_per_phase": check_kernel_per_phase_paths, "smoothers": check_smoothers,
           "cycle_pc": check_cycle_pc, "fcg_mgpc": check_fcg_mgpc}
 
 

@@ -295,3 +295,35 @@ def test_general_pc_tight_tolerance_solution_parity(csb, oracle):
     assert int(r["cvg"]) == 1 and abs(r["n_iter"] - o["n_iter"]) <= 2
     assert rel_l2(r["vx"][:s.n_rows], o["vx"]) <= SOL_TOL
     c.destroy(); oracle.mg_free(omg); m.destroy()
+
+
+# ------------------------------------------------------------ 3x3 block Jacobi (a17)
+
+@pytest.mark.parametrize("N", [6, 10])
+def test_block3_jacobi_matches_reference_golden(csb, N):
+    """_block_3_jacobi on a CS_MATRIX_BLOCK_D matrix: the iterates have no reduction in them
+    (Gauss-Jordan block inverses, block SpMV, D^-1.(rhs - E.x)) -> bit-exact for a fixed
+    number of sweeps; the residual norm to reduction-order rounding."""
+    from code_saturne_b200.mesh_cartesian import cube_block3_convection_diffusion
+    g = np.load(os.path.join(GOLD, f"block3jac_N{N}.npz"))
+    ri, ci, d, xv, rhs = cube_block3_convection_diffusion(N)
+    n = len(ri) - 1
+    r_norm = float(g["r_norm"])
+    m = csb.Matrix.from_block(n, 3, ri, ci, d.ravel(), xv)
+    for nit in (1, 2, 7):
+        c = csb.SlesIt(csb.SlesItType.JACOBI, nit)
+        r = c.solve(m, rhs, 1e-12, r_norm)
+        assert (int(r["cvg"]), r["n_iter"]) == (-1, nit)
+        assert np.array_equal(r["vx"], g[f"sweeps{nit}_vx"]), nit
+        assert abs(r["residual"] - float(g[f"sweeps{nit}_residual"])) <= 1e-13 * r["residual"]
+        c.destroy()
+    c = csb.SlesIt(csb.SlesItType.JACOBI, 1000)
+    r = c.solve(m, rhs, 1e-8, r_norm)
+    assert int(r["cvg"]) == int(g["cvg"]) == 1
+    assert abs(r["n_iter"] - int(g["n_iter"])) <= 1
+    assert rel_l2(r["vx"], g["vx"]) <= 1e-7
+    c.destroy()
+    c = csb.SlesIt(csb.SlesItType.JACOBI, 5)
+    w = c.solve(m, rhs, 1e-12, r_norm, vx=g["vx0"].copy(), use_vx_ini=True)
+    assert np.array_equal(w["vx"], g["warm_vx"])
+    c.destroy(); m.destroy()

@@ -365,3 +365,22 @@ def test_oracle_general_pc_vs_reference_direct(oracle, reflib):
         assert np.array_equal(a["vx"], b["vx"])
     oracle.mg_free(mg)
     reflib.destroy(h)
+
+
+@pytest.mark.parametrize("N", [6, 10])
+def test_oracle_block3_jacobi_matches_golden(oracle, N):
+    from code_saturne_b200.mesh_cartesian import cube_block3_convection_diffusion
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"block3jac_N{N}.npz"))
+    ri, ci, d, xv, rhs = cube_block3_convection_diffusion(N)
+    r_norm = float(g["r_norm"])
+    r = oracle.block3_jacobi(ri, ci, d.ravel(), xv, rhs, 1000, 1e-8, r_norm)
+    assert (r["cvg"], r["n_iter"]) == (int(g["cvg"]), int(g["n_iter"]))
+    assert r["residual"] == float(g["residual"])
+    assert r["initial_residual"] == float(g["initial_residual"])
+    assert np.array_equal(r["vx"], g["vx"])
+    for nit in (1, 2, 7):
+        f = oracle.block3_jacobi(ri, ci, d.ravel(), xv, rhs, nit, 1e-12, r_norm)
+        assert np.array_equal(f["vx"], g[f"sweeps{nit}_vx"])
+        assert f["residual"] == float(g[f"sweeps{nit}_residual"])
+    w = oracle.block3_jacobi(ri, ci, d.ravel(), xv, rhs, 5, 1e-12, r_norm, vx0=g["vx0"])
+    assert np.array_equal(w["vx"], g["warm_vx"]) and w["residual"] == float(g["warm_residual"])
