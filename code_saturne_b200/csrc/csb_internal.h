@@ -463,6 +463,9 @@ struct CoarseAssemblyArgs {
   double relax;
 };
 bool launch_coarse_assembly(const CoarseAssemblyArgs &a, int stages /* 1 | 2 */);
+/* relaxation parameter <= 0: plain Galerkin sums, no mesh quantities (cs_grid.cpp:5969-6090);
+   uses the matrix, f_c_row and c_f_* members of the arguments only */
+bool launch_coarse_galerkin(const CoarseAssemblyArgs &a);
 
 bool launch_halo_pack(int n_send, const int *send_list, const double *var, double *buf);
 

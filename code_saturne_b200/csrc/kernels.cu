@@ -1602,6 +1602,51 @@ k_coarse_stage_2(const CoarseAssemblyArgs a)
 /* stages: 1 = sums over fine rows (cell centres, volumes, faces, diagonal),
    2 = extra-diagonal values; ghost cell centres / volumes of a distributed
    level are synchronised between the two (cs_grid.cpp:6561-6581) */
+namespace {
+
+/* Galerkin coarse matrix, relaxation parameter <= 0: _compute_coarse_quantities_msr, scalar
+   case (src/alge/cs_grid.cpp:6040-6090).  One thread per coarse row, fine rows of the
+   aggregate in ascending order and their entries in CSR order, like the reference's
+   row-parallel lambda -> bit-identical sums. */
+__global__ void __launch_bounds__(128)
+k_coarse_galerkin(const CoarseAssemblyArgs a)
+{
+  const int ic = blockIdx.x*128 + threadIdx.x;
+  if (ic >= a.c_n_rows) return;
+  const int s_id = a.c_row_index[ic];
+  const int n_cols = a.c_row_index[ic+1] - s_id;
+  double *__restrict__ row_x_vals = a.c_x_val + s_id;
+  double d = 0.;
+  for (int ll = 0; ll < n_cols; ll++) row_x_vals[ll] = 0.;
+  const int r_s = a.c_f_row_index[ic], r_e = a.c_f_row_index[ic+1];
+  for (int r_idx = r_s; r_idx < r_e; r_idx++) {
+    const int ii = a.c_f_row_ids[r_idx];
+    d += a.f_d_val[ii];
+    const int f_s = a.f_row_index[ii], f_e = a.f_row_index[ii+1];
+    for (int jj = f_s; jj < f_e; jj++) {
+      const int jc = a.f_c_row[a.f_col_id[jj]];
+      if (jc > -1) {
+        if (ic != jc) {
+          const int k = l_id_search(n_cols, jc, a.c_col_id + s_id);
+          row_x_vals[k] += a.f_x_val[jj];
+        }
+        else
+          d += a.f_x_val[jj];
+      }
+    }
+  }
+  a.c_d_val[ic] = d;
+}
+
+} // anonymous namespace
+
+bool launch_coarse_galerkin(const CoarseAssemblyArgs &a)
+{
+  if (a.c_n_rows < 1) return true;
+  k_coarse_galerkin<<<(a.c_n_rows + 127)/128, 128, 0, ctx().stream>>>(a);
+  return post_launch("coarse_galerkin");
+}
+
 bool launch_coarse_assembly(const CoarseAssemblyArgs &a, int stages)
 {
   Context &c = ctx();

@@ -1248,10 +1248,13 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
   if (mg == nullptr || a == nullptr) { set_error("csb_multigrid_setup: null argument"); return; }
   if (mg->setup_done) mg_clear_hierarchy(mg);
 
-  if (!a->symmetric || !a->has_mesh) {
-    set_error("csb_multigrid_setup: this path needs a symmetric MSR matrix with mesh "
-              "association (cs_matrix_set_mesh_association), as the reference's "
-              "pressure solve provides");
+  /* p0p1_relax <= 0: Galerkin coarse matrices (_compute_coarse_quantities_msr,
+     cs_grid.cpp:8222-8223), which need no mesh quantities */
+  const bool galerkin = (mg->p0p1_relax <= 0.);
+  if (!a->symmetric || (!a->has_mesh && !galerkin)) {
+    set_error("csb_multigrid_setup: this path needs a symmetric MSR matrix, with mesh "
+              "association (cs_matrix_set_mesh_association) unless p0p1_relax <= 0, as the "
+              "reference's pressure solve provides");
     return;
   }
   if (mg->coarsening_type != 0 && mg->coarsening_type != 1) {
@@ -1375,13 +1378,14 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
            && f->c_f_row_ids.upload(cs.c_f_row_ids.data(), (size_t)fm->n_rows)
            && cm->row_index.upload(cs.c_row_index.data(), (size_t)c_n_rows + 1)
            && cm->col_id.upload(cs.c_col_id.data(), (size_t)c_nnz)
-           && cl->cell_face.upload(cs.c_cell_face.data(), (size_t)c_nnz)
+           && cm->d_val.alloc((size_t)c_n_rows) && cm->x_val.alloc((size_t)c_nnz);
+    if (ok && !galerkin)
+      ok = cl->cell_face.upload(cs.c_cell_face.data(), (size_t)c_nnz)
            && cl->cell_face_sgn.upload(cs.c_cell_face_sgn.data(), (size_t)c_nnz)
-           && cm->d_val.alloc((size_t)c_n_rows) && cm->x_val.alloc((size_t)c_nnz)
            && cl->cell_cen.alloc(3*c_n_cols_ext) && cl->cell_vol.alloc(c_n_cols_ext)
            && cl->face_normal.alloc(3*(size_t)cs.c_n_faces)
-           && cl->xa0.alloc((size_t)cs.c_n_faces) && cl->xa0ij.alloc(3*(size_t)cs.c_n_faces)
-           && CSB_CUDA(cudaStreamSynchronize(c.stream));  /* cs.* vectors die below */
+           && cl->xa0.alloc((size_t)cs.c_n_faces) && cl->xa0ij.alloc(3*(size_t)cs.c_n_faces);
+    ok = ok && CSB_CUDA(cudaStreamSynchronize(c.stream));  /* cs.* vectors die below */
     if (!ok) { delete cl; return; }
     cl->n_faces = cs.c_n_faces;
     cm->h_row_index.swap(cs.c_row_index);
@@ -1398,6 +1402,15 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     ca.f_c_row = f->coarse_row.p;
     ca.c_f_row_index = f->c_f_row_index.p; ca.c_f_row_ids = f->c_f_row_ids.p;
     ca.c_row_index = cm->row_index.p; ca.c_col_id = cm->col_id.p;
+    ca.c_d_val = cm->d_val.p; ca.c_x_val = cm->x_val.p;
+    if (galerkin) {
+      if (!launch_coarse_galerkin(ca)) { delete cl; return; }
+      if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) { delete cl; return; }
+      t_asm += wall() - t0;
+      matrix_plan_spmv(cm);
+      mg->levels.push_back(cl);
+      continue;
+    }
     ca.c_cell_face = cl->cell_face.p; ca.c_cell_face_sgn = cl->cell_face_sgn.p;
     if (f_level == 0) {
       ca.f_cell_face = fm->c2f.p; ca.f_cell_face_sgn = fm->c2f_sgn.p;

@@ -1342,6 +1342,109 @@ ora_grid_coarsen_finish(ora_grid_t *c, double relax_param)
 
 }
 
+/* Galerkin coarse matrix (relaxation parameter <= 0): _compute_coarse_quantities_msr, scalar
+   case (src/alge/cs_grid.cpp:5969-6090) -- d_c = sum of the fine diagonals and of the
+   fine extra-diagonal terms interior to the aggregate, x_c[k] += fine terms between two
+   aggregates (binary search of the sorted coarse column), fine rows in ascending order.
+   No mesh quantities are needed or produced. */
+static ora_grid_t *
+_grid_coarsen_galerkin(const ora_grid_t *f, const int *f_c_row_in, int c_n_rows)
+{
+  const int f_n_rows = f->n_rows;
+  const int *f_row_index = f->row_index, *f_col_id = f->col_id;
+  const double *f_d_val = f->d_val, *f_x_val = f->x_val;
+
+  ora_grid_t *c = calloc(1, sizeof(ora_grid_t));
+  c->level = f->level + 1;
+  c->coarse_row = malloc(sizeof(int)*(f_n_rows > 0 ? f_n_rows : 1));
+  memcpy(c->coarse_row, f_c_row_in, sizeof(int)*f_n_rows);
+  const int *f_c_row = c->coarse_row;
+  c->n_rows = c_n_rows;
+  c->n_cols_ext = c_n_rows;
+
+  int *c_f_row_index = calloc(c_n_rows + 1, sizeof(int));
+  int *c_f_row_ids = malloc(sizeof(int)*(f_n_rows > 0 ? f_n_rows : 1));
+  for (int ii = 0; ii < f_n_rows; ii++)
+    if (f_c_row[ii] > -1) c_f_row_index[f_c_row[ii] + 1] += 1;
+  for (int i = 0; i < c_n_rows; i++) c_f_row_index[i+1] += c_f_row_index[i];
+  {
+    int *shift = calloc(c_n_rows > 0 ? c_n_rows : 1, sizeof(int));
+    for (int ii = 0; ii < f_n_rows; ii++) {
+      int jj = f_c_row[ii];
+      if (jj > -1) c_f_row_ids[c_f_row_index[jj] + shift[jj]++] = ii;
+    }
+    free(shift);
+  }
+
+  /* coarse MSR structure (_coarse_msr_struct, :3020-3200) */
+  int *c_row_index = calloc(c_n_rows + 1, sizeof(int));
+  int c_nnz_0 = 0;
+  for (int ic = 0; ic < c_n_rows; ic++)
+    for (int r = c_f_row_index[ic]; r < c_f_row_index[ic+1]; r++) {
+      int ii = c_f_row_ids[r];
+      c_nnz_0 += f_row_index[ii+1] - f_row_index[ii];
+    }
+  int *c_col_id = malloc(sizeof(int)*(c_nnz_0 > 0 ? c_nnz_0 : 1));
+  int c_nnz = 0;
+  for (int ic = 0; ic < c_n_rows; ic++) {
+    int *l_buf = c_col_id + c_nnz;
+    int b_e = 0;
+    for (int r = c_f_row_index[ic]; r < c_f_row_index[ic+1]; r++) {
+      int ii = c_f_row_ids[r];
+      for (int jj = f_row_index[ii]; jj < f_row_index[ii+1]; jj++) {
+        int kk = f_c_row[f_col_id[jj]];
+        if (kk > -1 && kk != ic) l_buf[b_e++] = kk;
+      }
+    }
+    qsort(l_buf, b_e, sizeof(int), _cmp_int);
+    int r_count = 0;
+    if (b_e > 0) {
+      r_count = 1;
+      for (int jj = 1; jj < b_e; jj++)
+        if (l_buf[jj] > l_buf[jj-1]) l_buf[r_count++] = l_buf[jj];
+    }
+    c_nnz += r_count;
+    c_row_index[ic+1] = c_nnz;
+  }
+
+  double *c_d_val = calloc(c_n_rows > 0 ? c_n_rows : 1, sizeof(double));
+  double *c_x_val = calloc(c_nnz > 0 ? c_nnz : 1, sizeof(double));
+  for (int ic = 0; ic < c_n_rows; ic++) {
+    const int s_id = c_row_index[ic];
+    const int n_cols = c_row_index[ic+1] - s_id;
+    double *row_x_vals = c_x_val + s_id;
+    c_d_val[ic] = 0;
+    for (int r_idx = c_f_row_index[ic]; r_idx < c_f_row_index[ic+1]; r_idx++) {
+      const int ii = c_f_row_ids[r_idx];
+      c_d_val[ic] += f_d_val[ii];
+      for (int jj = f_row_index[ii]; jj < f_row_index[ii+1]; jj++) {
+        const int jc = f_c_row[f_col_id[jj]];
+        if (jc > -1) {
+          if (ic != jc) {
+            int lo = 0, hi = n_cols - 1, k = -1;
+            while (lo <= hi) {
+              int mid = (lo + hi) / 2;
+              if (c_col_id[s_id + mid] < jc) lo = mid + 1;
+              else if (c_col_id[s_id + mid] > jc) hi = mid - 1;
+              else { k = mid; break; }
+            }
+            row_x_vals[k] += f_x_val[jj];
+          }
+          else
+            c_d_val[ic] += f_x_val[jj];
+        }
+      }
+    }
+  }
+
+  free(c_f_row_index); free(c_f_row_ids);
+  c->nnz = c_nnz;
+  c->row_index = c_row_index;
+  c->col_id = c_col_id;
+  c->d_val = c_d_val; c->x_val = c_x_val;
+  return c;
+}
+
 ora_grid_t *
 ora_grid_coarsen(const ora_grid_t *f, int max_aggregation, double relax_param,
                  int n_threads)
@@ -1354,6 +1457,11 @@ ora_grid_coarsen(const ora_grid_t *f, int max_aggregation, double relax_param,
     = ora_aggregation_dx_msr(f->level, f_n_rows, f->row_index, f->col_id,
                              f->d_val, f->x_val, max_aggregation, n_threads,
                              f_c_row);
+  if (relax_param <= 0) {        /* cs_grid_coarsen, src/alge/cs_grid.cpp:8222-8223 */
+    ora_grid_t *cg = _grid_coarsen_galerkin(f, f_c_row, c_n_rows);
+    free(f_c_row);
+    return cg;
+  }
   ora_grid_t *c = ora_grid_coarsen_begin(f, f_c_row, c_n_rows, c_n_rows);
   free(f_c_row);
   ora_grid_coarsen_finish(c, relax_param);

@@ -232,7 +232,26 @@ def check_block3_jacobi(ora):
     c.destroy(); m.destroy()
 
 
-CHECKS = {"spmv_pcg": check_spmv_pcg, "block3_jacobi": check_block3_jacobi, "general_pc": check_general_pc,
+def check_galerkin(ora):
+    g = np.load(os.path.join(GOLD, "galerkin_N8_neumann.npz"))
+    s = cube_poisson(8, "neumann")
+    rn = float(g["r_norm"])
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)     # no mesh
+    mg = csb.Multigrid()
+    mg.set_coarsening_options(p0p1_relax=0.)
+    mg.setup(m)
+    lv = mg.levels()
+    assert len(lv) == int(g["n_levels"])
+    for l in range(1, len(lv)):
+        for k in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
+            assert np.array_equal(lv[l][k], g[f"l{l}_{k}"]), (l, k)
+    r = mg.solve(m, s.rhs, 1e-8, rn)
+    assert int(r["cvg"]) == 1 and abs(r["n_iter"] - int(g["mg_n_iter"])) <= 5
+    assert rel(r["vx"][:s.n_rows], g["mg_vx"]) <= 1e-6
+    mg.destroy(); m.destroy()
+
+
+CHECKS = {"spmv_pcg": check_spmv_pcg, "galerkin": check_galerkin, "block3_jacobi": check_block3_jacobi, "general_pc": check_general_pc,
           "kernel_per_phase": check_kernel_per_phase_paths, "smoothers": check_smoothers,
           "cycle_pc": check_cycle_pc, "fcg_mgpc": check_fcg_mgpc}
 

@@ -327,3 +327,57 @@ def test_block3_jacobi_matches_reference_golden(csb, N):
     w = c.solve(m, rhs, 1e-12, r_norm, vx=g["vx0"].copy(), use_vx_ini=True)
     assert np.array_equal(w["vx"], g["warm_vx"])
     c.destroy(); m.destroy()
+
+
+# ------------------------------------------- Galerkin coarse matrices (a36, p0p1_relax = 0)
+
+@pytest.mark.parametrize("N,bc", [(8, "neumann"), (12, "dirichlet")])
+def test_galerkin_hierarchy_matches_reference_golden(csb, N, bc):
+    """p0p1_relax <= 0 selects _compute_coarse_quantities_msr: no mesh association needed;
+    coarse matrices bit-exact (thread per coarse row, the reference's summation order),
+    V-cycle and FCG + V-cycle over that hierarchy within the usual tolerances."""
+    g = np.load(os.path.join(GOLD, f"galerkin_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    r_norm = float(g["r_norm"])
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)     # no mesh
+    mg = csb.Multigrid()
+    mg.set_coarsening_options(p0p1_relax=0.)
+    mg.setup(m)
+    lv = mg.levels()
+    assert len(lv) == int(g["n_levels"])
+    for l in range(1, len(lv)):
+        for k in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
+            assert np.array_equal(lv[l][k], g[f"l{l}_{k}"]), (l, k)
+    r = mg.solve(m, s.rhs, 1e-8, r_norm)
+    assert int(r["cvg"]) == int(g["mg_cvg"]) == 1
+    assert abs(r["n_iter"] - int(g["mg_n_iter"])) <= max(2, int(g["mg_n_iter"]) // 20)
+    res = np.linalg.norm(s.rhs - m.vector_multiply(r["vx"][:s.n_rows].copy()))
+    assert res <= 1.0001e-8 * r_norm
+    mg.destroy()
+    c = csb.SlesIt(csb.SlesItType.FCG, 200, poly_degree=-1)
+    pc = csb.Multigrid(pc=True)
+    pc.set_coarsening_options(p0p1_relax=0.)
+    c.transfer_pc(pc)
+    r = c.solve(m, s.rhs, 1e-8, r_norm)
+    assert int(r["cvg"]) == 1 and abs(r["n_iter"] - int(g["fcg_n_iter"])) <= 2
+    c.destroy(); m.destroy()
+
+
+def test_galerkin_vs_oracle_larger(csb, oracle):
+    s = cube_poisson(40, "neumann", with_mesh=False)
+    r_norm = float(np.linalg.norm(s.rhs))
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+    omg = oracle.mg_setup(cube_poisson(40, "neumann"), p0p1_relax=0.)
+    olv = oracle.mg_levels(omg)
+    mg = csb.Multigrid()
+    mg.set_coarsening_options(p0p1_relax=0.)
+    mg.setup(m)
+    lv = mg.levels()
+    assert [x["n_rows"] for x in lv] == [x["n_rows"] for x in olv]
+    for l in range(1, len(lv)):
+        for k in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
+            assert np.array_equal(lv[l][k], olv[l][k]), (l, k)
+    o = oracle.mg_solve(omg, s.rhs, 1e-8, r_norm)
+    r = mg.solve(m, s.rhs, 1e-8, r_norm)
+    assert int(r["cvg"]) == o["cvg"] == 1 and abs(r["n_cycles"] - o["n_cycles"]) <= 1
+    oracle.mg_free(omg); mg.destroy(); m.destroy()

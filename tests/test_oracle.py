@@ -384,3 +384,26 @@ def test_oracle_block3_jacobi_matches_golden(oracle, N):
         assert f["residual"] == float(g[f"sweeps{nit}_residual"])
     w = oracle.block3_jacobi(ri, ci, d.ravel(), xv, rhs, 5, 1e-12, r_norm, vx0=g["vx0"])
     assert np.array_equal(w["vx"], g["warm_vx"]) and w["residual"] == float(g["warm_residual"])
+
+
+@pytest.mark.parametrize("N,bc", [(8, "neumann"), (12, "dirichlet")])
+def test_oracle_galerkin_hierarchy_matches_golden(oracle, N, bc):
+    """p0p1_relax = 0: Galerkin coarse matrices (_compute_coarse_quantities_msr)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"galerkin_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    r_norm = float(g["r_norm"])
+    mg = oracle.mg_setup(s, p0p1_relax=0.)
+    lv = oracle.mg_levels(mg)
+    assert len(lv) == int(g["n_levels"])
+    for l in range(1, len(lv)):
+        for k in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
+            assert np.array_equal(lv[l][k], g[f"l{l}_{k}"]), (l, k)
+    r = oracle.mg_solve(mg, s.rhs, 1e-8, r_norm)
+    assert (r["cvg"], r["n_iter"], r["residual"]) == (int(g["mg_cvg"]), int(g["mg_n_iter"]),
+                                                      float(g["mg_residual"]))
+    assert np.array_equal(r["vx"], g["mg_vx"])
+    r = oracle.fcg_mgpc(mg, s.rhs, 200, 1e-8, r_norm)
+    assert (r["cvg"], r["n_iter"], r["residual"]) == (int(g["fcg_cvg"]), int(g["fcg_n_iter"]),
+                                                      float(g["fcg_residual"]))
+    assert np.array_equal(r["vx"], g["fcg_vx"])
+    oracle.mg_free(mg)
