@@ -164,6 +164,22 @@ def reference_main(args):
     print(json.dumps(line))
 
 
+def run_production_solver(args):
+    """Side measurement, never part of `value`: the reference's production layout (FCG
+    preconditioned by one V-cycle, scripts/fcg_mg_times.py) on the same cube, in a process of
+    its own after the headline numbers are taken; a failure there only shows up here."""
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fcg_mg_times.py"),
+                              "--cube", str(args.cube)], capture_output=True, text=True,
+                             timeout=300, cwd=ROOT)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"unavailable": (out.stderr.strip().splitlines() or ["no output"])[-1][:300]}
+    except Exception as e:
+        return {"unavailable": str(e)[:300]}
+
+
 # --------------------------------------------------------------------------- our arm
 
 def main():
@@ -178,6 +194,8 @@ def main():
     ap.add_argument("--warmup-ref", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spmv-launches", type=int, default=50)
+    ap.add_argument("--no-production-solver", action="store_true",
+                    help="skip the FCG + multigrid-preconditioner side measurement")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -383,6 +401,8 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_production_solver:
+            line["production_solver"] = run_production_solver(args)
         print(json.dumps(line))
 
     if world > 1:
