@@ -199,6 +199,7 @@ def load_library() -> C.CDLL:
     L.csb_multigrid_smoother_solve.argtypes = solve_args
     L.csb_host_aggregate_dx_msr.argtypes = [ci, ci, vp, vp, vp, vp, ci, ci, vp]
     L.csb_host_coarse_structure.argtypes = [ci, vp, vp, vp, ci, vp, vp, vp, vp, vp]
+    L.csb_host_coarsen_pairwise.argtypes = [ci, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -515,6 +516,24 @@ def host_aggregate(level, row_index, col_id, d_val, x_val, max_aggregation=3, n_
     nc = load_library().csb_host_aggregate_dx_msr(level, n, _ptr(ri), _ptr(ci), _ptr(d), _ptr(x),
                                                   max_aggregation, n_blocks, _ptr(f_c_row))
     return nc, f_c_row[:n]
+
+
+def host_coarsen_pairwise(level, row_index, col_id, d_val, x_val, aggregation_limit=4):
+    """One CS_GRID_COARSENING_SPD_PW + Galerkin coarsening step on the host (no GPU needed)."""
+    ri, ci, d, x = _i32(row_index), _i32(col_id), _f64(d_val), _f64(x_val)
+    n = len(ri) - 1
+    nnz = int(ri[-1])
+    f_c_row = np.full(max(n, 1), -2, dtype=np.int32)
+    c_ri = np.zeros(n + 1, dtype=np.int32)
+    c_ci = np.zeros(max(nnz, 1), dtype=np.int32)
+    c_d = np.zeros(max(n, 1))
+    c_x = np.zeros(max(nnz, 1))
+    nc = load_library().csb_host_coarsen_pairwise(level, n, _ptr(ri), _ptr(ci), _ptr(d), _ptr(x),
+                                                  aggregation_limit, _ptr(f_c_row), _ptr(c_ri),
+                                                  _ptr(c_ci), _ptr(c_d), _ptr(c_x))
+    c_nnz = int(c_ri[nc]) if nc > 0 else 0
+    return dict(n_rows=nc, coarse_row=f_c_row[:n], row_index=c_ri[:nc + 1], col_id=c_ci[:c_nnz],
+                d_val=c_d[:nc], x_val=c_x[:c_nnz])
 
 
 def host_coarse_structure(row_index, col_id, f_c_row, c_n_rows):

@@ -11,12 +11,15 @@
  *
  * Reference behaviour reproduced (not copied): _automatic_aggregation_dx_msr
  * (cs_grid.cpp:4282-4767), _coarse_to_fine_adjacency_msr (:2860),
- * _coarse_msr_struct (:3020), _msr_face_adjacency (:3751).
+ * _coarse_msr_struct (:3020), _msr_face_adjacency (:3751); pairwise aggregation
+ * _pairwise_msr (:1744-2020) with its recursion for aggregation limits 4 and 8
+ * (:8143-8150, :8305-8346) over host Galerkin matrices (:6040-6090).
  *============================================================================*/
 
 #include "grid_host.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <omp.h>
@@ -220,6 +223,233 @@ int aggregate_dx_msr(int level, int n_rows, const int *row_index, const int *col
         if (f_c_row[i] > -1) f_c_row[i] += shift;
   }
   return total;
+}
+
+/*----------------------------------------------------------------------------
+ * Pairwise aggregation (CS_GRID_COARSENING_SPD_PW)
+ *----------------------------------------------------------------------------*/
+
+namespace {
+
+/* Rows bucketed by their number of still-free strong neighbours ("degree"); every bucket is
+   a doubly linked list whose head is the most recently inserted row, so that the row taken
+   next -- the head of the lowest non-empty bucket -- is the one the reference's
+   _graph_m_ptr lists (cs_grid.cpp:1544-1620) would give. */
+class DegreeBuckets {
+public:
+  DegreeBuckets(int n_rows, int max_degree)
+    : head_(max_degree + 1, -1), next_(std::max(n_rows, 1), -1), prev_(std::max(n_rows, 1), -1),
+      lo_(0), hi_(max_degree) {}
+
+  int lo() const { return lo_; }
+  int hi() const { return hi_; }
+  int head(int d) const { return head_[d]; }
+  void set_empty() { lo_ = -1; hi_ = -1; }
+  void skip_empty_low() { while (lo_ < hi_ && head_[lo_] < 0) lo_++; }
+
+  /* initial fill: called for rows in DEcreasing order, so that lists start ascending */
+  void push_front_initial(int d, int row)
+  {
+    const int h = head_[d];
+    head_[d] = row;
+    next_[row] = h;
+    if (h > -1) prev_[h] = row;
+  }
+
+  void remove(int d, int row)
+  {
+    const int p = prev_[row], n = next_[row];
+    if (p > -1) {
+      next_[p] = n;
+      if (n > -1) prev_[n] = p;
+    }
+    else {
+      head_[d] = n;
+      if (n > -1) prev_[n] = -1;
+      if (n < 0) {                     /* bucket d is now empty: tighten the bounds */
+        if (d == lo_)
+          skip_empty_low();
+        else if (d == hi_) {
+          hi_ -= 1;
+          while (hi_ > lo_ && head_[hi_] < 0) hi_--;
+        }
+      }
+    }
+    prev_[row] = -1;
+    next_[row] = -1;
+  }
+
+  void insert(int d, int row)
+  {
+    const int h = head_[d];
+    if (h > -1) {
+      prev_[h] = row;
+      next_[row] = h;
+    }
+    else if (d < lo_)
+      lo_ = d;
+    else if (d > hi_) {
+      hi_ = d;
+      if (head_[lo_] < 0) lo_ = d;
+    }
+    head_[d] = row;
+  }
+
+private:
+  std::vector<int> head_, next_, prev_;
+  int lo_, hi_;
+};
+
+} // anonymous namespace
+
+int aggregate_pw_msr(int level, int n_rows, const int *row_index, const int *col_id,
+                     const double *d_val, const double *x_val, int *f_c_row)
+{
+  const double beta = 0.25;                                /* cs_grid.cpp:2049 */
+  const double dd_threshold = (level == 0) ? 5. : -1.;     /* _dd_threshold_pw, :172, :2050 */
+
+  std::vector<short> degree(std::max(n_rows, 1));
+  std::vector<double> strongest(std::max(n_rows, 1));      /* max_k(-a_ik) over a_ik < 0 */
+  std::fill(f_c_row, f_c_row + n_rows, -2);
+
+  int max_degree = -1;
+  for (int i = 0; i < n_rows; i++) {
+    const int ks = row_index[i], ke = row_index[i+1];
+    double abs_sum = 0., big = 0.;
+    for (int k = ks; k < ke; k++) {
+      const double v = x_val[k];
+      abs_sum += std::fabs(v);
+      if (v < 0) big = std::max(big, -v);
+    }
+    strongest[i] = big;
+    short deg = 0;
+    if (dd_threshold > 0 && d_val[i] > dd_threshold * abs_sum) {
+      deg = -1;                       /* strongly diagonally dominant: left out */
+      f_c_row[i] = -1;
+    }
+    else if (dd_threshold > 0) {
+      for (int k = ke - 1; k >= ks; k--)
+        if (col_id[k] < n_rows && x_val[k] < beta * abs_sum) deg++;
+    }
+    else {
+      for (int k = ke - 1; k >= ks; k--)
+        if (col_id[k] < n_rows) deg++;
+    }
+    degree[i] = deg;
+    if (max_degree < deg) max_degree = deg;
+  }
+  if (max_degree < 0) return 0;       /* every row left out (cs_grid.cpp:1850) */
+
+  DegreeBuckets buckets(n_rows, max_degree);
+  for (int i = n_rows - 1; i >= 0; i--)
+    if (degree[i] >= 0) buckets.push_front_initial(degree[i], i);
+  buckets.skip_empty_low();
+
+  int n_coarse = 0;
+  while (buckets.lo() > -1) {
+    const int i = buckets.head(buckets.lo());
+    int pair[2] = {i, -1};
+    f_c_row[i] = n_coarse;
+    /* free neighbour with the most negative coefficient, kept if strong enough */
+    int j = -1;
+    double a_min = HUGE_VAL;
+    for (int k = row_index[i]; k < row_index[i+1]; k++) {
+      const int c = col_id[k];
+      if (c < n_rows && f_c_row[c] == -2 && x_val[k] < a_min) { a_min = x_val[k]; j = c; }
+    }
+    if (row_index[i+1] > row_index[i] && !(a_min >= -beta * strongest[i])) {
+      f_c_row[j] = n_coarse;
+      pair[1] = j;
+    }
+    n_coarse++;
+
+    for (int ip = 0; ip < 2; ip++) {
+      const int r = pair[ip];
+      if (r < 0 || degree[r] < 0) continue;
+      buckets.remove(degree[r], r);
+      degree[r] = -1;
+      for (int k = row_index[r+1] - 1; k >= row_index[r]; k--) {
+        const int c = col_id[k];
+        if (c >= n_rows) continue;
+        const short dc = degree[c];
+        if (dc >= 0) {
+          buckets.remove(dc, c);
+          if (dc > 0) buckets.insert(dc - 1, c);
+          degree[c] = dc - 1;
+        }
+      }
+    }
+    if (buckets.lo() >= buckets.hi() && buckets.head(buckets.lo()) < 0)
+      buckets.set_empty();
+  }
+
+  for (int i = 0; i < n_rows; i++)
+    if (f_c_row[i] < -1) f_c_row[i] = n_coarse++;
+  return n_coarse;
+}
+
+/* Galerkin coarse values on the host, same sums in the same order as k_coarse_galerkin
+   (kernels.cu) and the reference's row-parallel lambda (cs_grid.cpp:6040-6090). */
+void galerkin_values_host(int f_n_rows, const int *f_row_index, const int *f_col_id,
+                          const double *f_d_val, const double *f_x_val, const int *f_c_row,
+                          int c_n_rows, const CoarseStructure &cs, std::vector<double> &c_d_val,
+                          std::vector<double> &c_x_val)
+{
+  (void)f_n_rows;
+  c_d_val.assign(std::max(c_n_rows, 1), 0.);
+  c_x_val.assign(std::max(cs.c_row_index[c_n_rows], 1), 0.);
+  #pragma omp parallel for schedule(static)
+  for (int ic = 0; ic < c_n_rows; ic++) {
+    const int s_id = cs.c_row_index[ic];
+    const int *cols = cs.c_col_id.data() + s_id;
+    const int n_cols = cs.c_row_index[ic+1] - s_id;
+    double *row = c_x_val.data() + s_id;
+    double d = 0.;
+    for (int r = cs.c_f_row_index[ic]; r < cs.c_f_row_index[ic+1]; r++) {
+      const int ii = cs.c_f_row_ids[r];
+      d += f_d_val[ii];
+      for (int k = f_row_index[ii]; k < f_row_index[ii+1]; k++) {
+        const int jc = f_c_row[f_col_id[k]];
+        if (jc < 0) continue;
+        if (jc != ic)
+          row[std::lower_bound(cols, cols + n_cols, jc) - cols] += f_x_val[k];
+        else
+          d += f_x_val[k];
+      }
+    }
+    c_d_val[ic] = d;
+  }
+}
+
+int coarsen_pairwise_galerkin(int level, int n_rows, const int *row_index, const int *col_id,
+                              const double *d_val, const double *x_val, int aggregation_limit,
+                              int *f_c_row, HostMsr &coarse)
+{
+  const int c_n_rows = aggregate_pw_msr(level, n_rows, row_index, col_id, d_val, x_val, f_c_row);
+  CoarseStructure cs;
+  build_coarse_structure(n_rows, row_index, col_id, f_c_row, c_n_rows, cs);
+  HostMsr c;
+  c.n_rows = c_n_rows;
+  galerkin_values_host(n_rows, row_index, col_id, d_val, x_val, f_c_row, c_n_rows, cs,
+                       c.d_val, c.x_val);
+  c.row_index.swap(cs.c_row_index);
+  c.col_id.swap(cs.c_col_id);
+  if (aggregation_limit > 2) {
+    /* pair the pairs (limit / 2), project the map back to the fine rows and keep only the
+       coarsest matrix, whose values are sums of the intermediate matrix's */
+    std::vector<int> c_cc(std::max(c_n_rows, 1));
+    HostMsr cc;
+    const int cc_n_rows
+      = coarsen_pairwise_galerkin(level + 1, c_n_rows, c.row_index.data(), c.col_id.data(),
+                                  c.d_val.data(), c.x_val.data(), aggregation_limit / 2,
+                                  c_cc.data(), cc);
+    for (int i = 0; i < n_rows; i++)
+      if (f_c_row[i] >= 0) f_c_row[i] = c_cc[f_c_row[i]];
+    coarse = std::move(cc);
+    return cc_n_rows;
+  }
+  coarse = std::move(c);
+  return c_n_rows;
 }
 
 void build_coarse_structure(int f_n_rows, const int *f_row_index, const int *f_col_id,

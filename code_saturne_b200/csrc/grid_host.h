@@ -25,6 +25,26 @@ struct CoarseStructure {
 void build_coarse_structure(int f_n_rows, const int *f_row_index, const int *f_col_id,
                             const int *f_c_row, int c_n_rows, CoarseStructure &cs);
 
+/* Fine -> coarse row map of the reference's pairwise aggregation (_pairwise_msr,
+   cs_grid.cpp:1744-2020; beta = 0.25, diagonal-dominance threshold 5 at level 0).
+   Returns the number of coarse rows. */
+int aggregate_pw_msr(int level, int n_rows, const int *row_index, const int *col_id,
+                     const double *d_val, const double *x_val, int *f_c_row);
+
+struct HostMsr {
+  int                 n_rows = 0;
+  std::vector<int>    row_index, col_id;
+  std::vector<double> d_val, x_val;
+};
+
+/* One coarsening step of CS_GRID_COARSENING_SPD_PW with Galerkin values: pairs, and for an
+   aggregation limit of 4 or 8 pairs of pairs (recursion on the intermediate Galerkin matrix,
+   cs_grid.cpp:8305-8346).  f_c_row receives the map from the fine rows to the rows of
+   `coarse`.  Returns the number of coarse rows. */
+int coarsen_pairwise_galerkin(int level, int n_rows, const int *row_index, const int *col_id,
+                              const double *d_val, const double *x_val, int aggregation_limit,
+                              int *f_c_row, HostMsr &coarse);
+
 } // namespace csb
 
 #endif

@@ -1257,8 +1257,17 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
               "reference's pressure solve provides");
     return;
   }
-  if (mg->coarsening_type != 0 && mg->coarsening_type != 1) {
-    set_error("csb_multigrid_setup: only CS_GRID_COARSENING_DEFAULT / SPD_DX are available");
+  /* cs_grid_coarsening_t (cs_grid.h): 0 default (= SPD_DX for a symmetric matrix), 1 SPD_DX,
+     3 SPD_PW (pairwise aggregation, with Galerkin coarse matrices on one rank here) */
+  const bool pairwise = (mg->coarsening_type == 3);
+  if (mg->coarsening_type != 0 && mg->coarsening_type != 1 && !pairwise) {
+    set_error("csb_multigrid_setup: only CS_GRID_COARSENING_DEFAULT / SPD_DX / SPD_PW are "
+              "available");
+    return;
+  }
+  if (pairwise && (!galerkin || a->halo != nullptr)) {
+    set_error("csb_multigrid_setup: CS_GRID_COARSENING_SPD_PW is available with Galerkin "
+              "coarse matrices (p0p1_relax <= 0) on one rank");
     return;
   }
   /* smoothers: cs_sles_it PCG + Jacobi (cs_multigrid_create defaults), or -- in the
@@ -1326,8 +1335,12 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     /* aggregation on the host */
     t0 = wall();
     f->h_coarse_row.assign((size_t)std::max(fm->n_cols_ext, 1), -1);
-    const int c_n_rows
-      = aggregate_dx_msr(f_level, fm->n_rows, fm->h_row_index.data(), fm->h_col_id.data(),
+    HostMsr pw;      /* pairwise: coarse values come out of the host recursion */
+    const int c_n_rows = pairwise
+      ? coarsen_pairwise_galerkin(f_level, fm->n_rows, fm->h_row_index.data(),
+                                  fm->h_col_id.data(), fm->h_d_val.data(), fm->h_x_val.data(),
+                                  mg->aggregation_limit, f->h_coarse_row.data(), pw)
+      : aggregate_dx_msr(f_level, fm->n_rows, fm->h_row_index.data(), fm->h_col_id.data(),
                          fm->h_d_val.data(), fm->h_x_val.data(), mg->aggregation_limit,
                          mg->n_blocks, f->h_coarse_row.data());
     t_aggr += wall() - t0;
@@ -1403,6 +1416,30 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     ca.c_f_row_index = f->c_f_row_index.p; ca.c_f_row_ids = f->c_f_row_ids.p;
     ca.c_row_index = cm->row_index.p; ca.c_col_id = cm->col_id.p;
     ca.c_d_val = cm->d_val.p; ca.c_x_val = cm->x_val.p;
+    if (pairwise) {
+      /* same structure (sorted unique coarse neighbours) whichever way it is built; the
+         values are those of the recursion (sums of the intermediate matrix's entries) */
+      if ((int)pw.row_index.size() != c_n_rows + 1 || pw.row_index[c_n_rows] != c_nnz
+          || pw.col_id.size() < (size_t)c_nnz
+          || !std::equal(cm->h_col_id.begin(), cm->h_col_id.begin() + c_nnz, pw.col_id.begin())) {
+        set_error("csb_multigrid_setup: pairwise recursion and projected structure differ");
+        delete cl; return;
+      }
+      if (!CSB_CUDA(cudaMemcpyAsync(cm->d_val.p, pw.d_val.data(), sizeof(double)*(size_t)c_n_rows,
+                                    cudaMemcpyHostToDevice, c.stream))
+          || !CSB_CUDA(cudaMemcpyAsync(cm->x_val.p, pw.x_val.data(), sizeof(double)*(size_t)c_nnz,
+                                       cudaMemcpyHostToDevice, c.stream))
+          || !CSB_CUDA(cudaStreamSynchronize(c.stream))) { delete cl; return; }
+      cm->h_d_val.swap(pw.d_val);
+      cm->h_x_val.swap(pw.x_val);
+      cm->h_x_val.resize((size_t)c_nnz);
+      cm->h_d_val.resize((size_t)c_n_rows);
+      cm->h_vals_valid = true;
+      t_asm += wall() - t0;
+      matrix_plan_spmv(cm);
+      mg->levels.push_back(cl);
+      continue;
+    }
     if (galerkin) {
       if (!launch_coarse_galerkin(ca)) { delete cl; return; }
       if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) { delete cl; return; }
@@ -1691,6 +1728,23 @@ int csb_host_aggregate_dx_msr(int level, csb_lnum_t n_rows, const csb_lnum_t *ro
 {
   return aggregate_dx_msr(level, n_rows, row_index, col_id, d_val, x_val, max_aggregation,
                           n_blocks, f_c_row);
+}
+
+int csb_host_coarsen_pairwise(int level, csb_lnum_t n_rows, const csb_lnum_t *row_index,
+                              const csb_lnum_t *col_id, const csb_real_t *d_val,
+                              const csb_real_t *x_val, int aggregation_limit,
+                              csb_lnum_t *f_c_row, csb_lnum_t *c_row_index,
+                              csb_lnum_t *c_col_id, csb_real_t *c_d_val, csb_real_t *c_x_val)
+{
+  HostMsr c;
+  const int nc = coarsen_pairwise_galerkin(level, n_rows, row_index, col_id, d_val, x_val,
+                                           aggregation_limit, f_c_row, c);
+  const int nnz = (nc > 0) ? c.row_index[nc] : 0;
+  if (c_row_index) std::copy(c.row_index.begin(), c.row_index.begin() + nc + 1, c_row_index);
+  if (c_col_id) std::copy(c.col_id.begin(), c.col_id.begin() + nnz, c_col_id);
+  if (c_d_val) std::copy(c.d_val.begin(), c.d_val.begin() + nc, c_d_val);
+  if (c_x_val) std::copy(c.x_val.begin(), c.x_val.begin() + nnz, c_x_val);
+  return nc;
 }
 
 int csb_host_coarse_structure(csb_lnum_t f_n_rows, const csb_lnum_t *f_row_index,

@@ -337,7 +337,9 @@ void csb_multigrid_set_solver_options(csb_multigrid_t    *mg,
                                       double              precision_mult_coarse);
 
 /* cs_multigrid_set_coarsening_options (src/alge/cs_multigrid.cpp:4945);
-   coarsening_type 0 (default) / 1 = CS_GRID_COARSENING_SPD_DX. */
+   coarsening_type 0 (default) / 1 = CS_GRID_COARSENING_SPD_DX; 3 = CS_GRID_COARSENING_SPD_PW
+   (pairwise aggregation; needs p0p1_relax <= 0, i.e. Galerkin coarse matrices, one rank).
+   p0p1_relax <= 0 selects Galerkin coarse matrices, which need no mesh association. */
 void csb_multigrid_set_coarsening_options(csb_multigrid_t  *mg,
                                           int               aggregation_limit,
                                           int               coarsening_type,
@@ -425,6 +427,15 @@ int  csb_host_aggregate_dx_msr(int level, csb_lnum_t n_rows, const csb_lnum_t *r
                                const csb_lnum_t *col_id, const csb_real_t *d_val,
                                const csb_real_t *x_val, int max_aggregation, int n_blocks,
                                csb_lnum_t *f_c_row);
+/* One coarsening step of CS_GRID_COARSENING_SPD_PW with Galerkin coarse values
+   (_pairwise_msr, src/alge/cs_grid.cpp:1744-2020; recursion for aggregation limits 4 and 8,
+   :8305-8346; values :6040-6090), entirely on the host.  Output arrays must hold n_rows + 1 /
+   the fine nnz / n_rows / the fine nnz entries; returns the number of coarse rows. */
+int  csb_host_coarsen_pairwise(int level, csb_lnum_t n_rows, const csb_lnum_t *row_index,
+                               const csb_lnum_t *col_id, const csb_real_t *d_val,
+                               const csb_real_t *x_val, int aggregation_limit,
+                               csb_lnum_t *f_c_row, csb_lnum_t *c_row_index,
+                               csb_lnum_t *c_col_id, csb_real_t *c_d_val, csb_real_t *c_x_val);
 int  csb_host_coarse_structure(csb_lnum_t f_n_rows, const csb_lnum_t *f_row_index,
                                const csb_lnum_t *f_col_id, const csb_lnum_t *f_c_row,
                                csb_lnum_t c_n_rows, csb_lnum_t *c_row_index,

@@ -1445,6 +1445,257 @@ _grid_coarsen_galerkin(const ora_grid_t *f, const int *f_c_row_in, int c_n_rows)
   return c;
 }
 
+/*----------------------------------------------------------------------------
+ * Pairwise aggregation (Notay), CS_GRID_COARSENING_SPD_PW:
+ *   _pairwise_msr (src/alge/cs_grid.cpp:1744-2020), single-thread form, with the bucket
+ *   lists _graph_m_ptr_remove_m / _insert_m (:1544-1620); called with beta = 0.25 and
+ *   dd_threshold = 5 at level 0, -1 below (_automatic_aggregation_pw_msr :2041-2110).
+ * Rows are taken by increasing number of remaining (strong) neighbours a_m; row i is paired
+ * with the free neighbour of most negative coefficient if it is below -beta * max_k(-a_ik).
+ *----------------------------------------------------------------------------*/
+
+typedef struct {
+  int  m_min, m_max;
+  int *m_head, *next, *prev;
+} ora_graph_m_ptr_t;
+
+static void
+_gm_remove(ora_graph_m_ptr_t *s, int _m, int elt_id)
+{
+  int s_p = s->prev[elt_id];
+  int s_n = s->next[elt_id];
+  if (s_p > -1) {
+    s->next[s_p] = s_n;
+    if (s_n > -1) s->prev[s_n] = s_p;
+  }
+  else {
+    s->m_head[_m] = s_n;
+    if (s_n > -1) s->prev[s_n] = -1;
+    if (s->m_head[_m] < 0) {
+      if (_m == s->m_min) {
+        while (s->m_min < s->m_max && s->m_head[s->m_min] < 0) s->m_min++;
+      }
+      else if (_m == s->m_max) {
+        s->m_max -= 1;
+        while (s->m_max > s->m_min) {
+          if (s->m_head[s->m_max] > -1) break;
+          else s->m_max--;
+        }
+      }
+    }
+  }
+  s->prev[elt_id] = -1;
+  s->next[elt_id] = -1;
+}
+
+static void
+_gm_insert(ora_graph_m_ptr_t *s, int _m, int elt_id)
+{
+  int s_p = s->m_head[_m];
+  if (s_p > -1) {
+    s->prev[s_p] = elt_id;
+    s->next[elt_id] = s_p;
+  }
+  else {
+    if (_m < s->m_min) s->m_min = _m;
+    else if (_m > s->m_max) {
+      s->m_max = _m;
+      if (s->m_head[s->m_min] < 0) s->m_min = _m;
+    }
+  }
+  s->m_head[_m] = elt_id;
+}
+
+int
+ora_pairwise_msr(int level, int f_n_rows, const int *row_index, const int *col_id,
+                 const double *d_val, const double *x_val, int *f_c_row)
+{
+  const double beta = 0.25;
+  const double dd_threshold = (level == 0) ? 5. : -1.;
+  const int t_s_id = 0, t_e_id = f_n_rows;
+  int c_n_rows = 0;
+
+  short *a_m = malloc(sizeof(short)*(f_n_rows > 0 ? f_n_rows : 1));
+  double *a_max = malloc(sizeof(double)*(f_n_rows > 0 ? f_n_rows : 1));
+  int *s_next = malloc(sizeof(int)*(2*(size_t)f_n_rows + 1));
+
+  int t_c_n_rows = 0;
+  for (int ii = t_s_id; ii < t_e_id; ii++) f_c_row[ii] = -2;
+
+  int m_max = -1;
+  if (dd_threshold > 0) {
+    for (int ii = t_s_id; ii < t_e_id; ii++) {
+      double sum = 0.0;
+      const int s_id = row_index[ii], e_id = row_index[ii+1];
+      a_max[ii] = 0.0;
+      for (int jj = s_id; jj < e_id; jj++) {
+        double xv = x_val[jj];
+        sum += fabs(xv);
+        if (xv < 0) a_max[ii] = (a_max[ii] > -xv) ? a_max[ii] : -xv;
+      }
+      if (d_val[ii] > dd_threshold * sum) {
+        a_m[ii] = -1;
+        f_c_row[ii] = -1;
+      }
+      else {
+        a_m[ii] = 0;
+        for (int jj = e_id-1; jj >= s_id; jj--)
+          if (col_id[jj] < f_n_rows && x_val[jj] < beta*sum) a_m[ii] += 1;
+      }
+      if (m_max < a_m[ii]) m_max = a_m[ii];
+    }
+  }
+  else {
+    for (int ii = t_s_id; ii < t_e_id; ii++) {
+      const int s_id = row_index[ii], e_id = row_index[ii+1];
+      a_max[ii] = 0.0;
+      for (int jj = s_id; jj < e_id; jj++) {
+        double xv = x_val[jj];
+        if (xv < 0) a_max[ii] = (a_max[ii] > -xv) ? a_max[ii] : -xv;
+      }
+      a_m[ii] = 0;
+      for (int jj = e_id-1; jj >= s_id; jj--)
+        if (col_id[jj] < f_n_rows) a_m[ii] += 1;
+      if (m_max < a_m[ii]) m_max = a_m[ii];
+    }
+  }
+
+  if (m_max >= 0) {
+    ora_graph_m_ptr_t s;
+    s.m_min = 0;
+    s.m_max = m_max;
+    s.m_head = malloc(sizeof(int)*(m_max + 1));
+    s.next = s_next;
+    s.prev = s.next + f_n_rows;
+    for (int ii = 0; ii < s.m_max+1; ii++) s.m_head[ii] = -1;
+    for (int ii = t_s_id; ii < t_e_id; ii++) { s.next[ii] = -1; s.prev[ii] = -1; }
+    for (int ii = t_e_id-1; ii >= t_s_id; ii--) {
+      short _m = a_m[ii];
+      if (_m >= 0) {
+        int prev_head = s.m_head[_m];
+        s.m_head[_m] = ii;
+        s.next[ii] = prev_head;
+        if (prev_head > -1) s.prev[prev_head] = ii;
+      }
+    }
+    while (s.m_min < s.m_max) {
+      if (s.m_head[s.m_min] < 0) s.m_min++;
+      else break;
+    }
+
+    while (s.m_min > -1) {
+      int ii = s.m_head[s.m_min];
+      int gg[2] = {ii, -1};
+      const int s_id = row_index[ii], e_id = row_index[ii+1];
+      f_c_row[ii] = t_c_n_rows;
+      if (e_id > s_id) {
+        int jj = -1;
+        double _a_min = HUGE_VAL;
+        for (int kk_idx = s_id; kk_idx < e_id; kk_idx++) {
+          int kk = col_id[kk_idx];
+          if (kk >= t_s_id && kk < t_e_id && f_c_row[kk] == -2) {
+            double xv = x_val[kk_idx];
+            if (xv < _a_min) { _a_min = xv; jj = kk; }
+          }
+        }
+        if (_a_min >= -beta*a_max[ii])
+          jj = -1;
+        else {
+          f_c_row[jj] = t_c_n_rows;
+          gg[1] = jj;
+        }
+      }
+      t_c_n_rows++;
+
+      for (int ip = 0; ip < 2; ip++) {
+        int i = gg[ip];
+        if (i >= t_s_id && i < t_e_id) {
+          int _m = a_m[i];
+          if (_m < 0) continue;
+          _gm_remove(&s, _m, i);
+          a_m[i] = -1;
+          for (int k = row_index[i+1]-1; k >= row_index[i]; k--) {
+            int j = col_id[k];
+            if (j < t_s_id || j >= t_e_id) continue;
+            _m = a_m[j];
+            if (_m >= 0) {
+              _gm_remove(&s, _m, j);
+              if (_m > 0) _gm_insert(&s, _m-1, j);
+              a_m[j] = _m - 1;
+            }
+          }
+        }
+      }
+
+      if (s.m_min >= s.m_max) {
+        if (s.m_head[s.m_min] < 0) { s.m_min = -1; s.m_max = -1; }
+      }
+    }
+
+    for (int ii = t_s_id; ii < t_e_id; ii++)
+      if (f_c_row[ii] < -1) f_c_row[ii] = t_c_n_rows++;
+
+    free(s.m_head);
+    c_n_rows = t_c_n_rows;
+  }
+
+  free(s_next); free(a_max); free(a_m);
+  return c_n_rows;
+}
+
+/* cs_grid_coarsen with CS_GRID_COARSENING_SPD_PW and relaxation <= 0
+   (src/alge/cs_grid.cpp:8143-8150, :8222-8223, :8305-8346): pairs, Galerkin values, and for an
+   aggregation limit > 2 a recursion on the intermediate grid (limit / 2) whose map is
+   projected back to the fine rows; only the coarsest grid is kept. */
+static ora_grid_t *
+_grid_coarsen_pw(const ora_grid_t *f, int aggregation_limit)
+{
+  int *f_c_row = malloc(sizeof(int)*(f->n_rows > 0 ? f->n_rows : 1));
+  const int c_n_rows = ora_pairwise_msr(f->level, f->n_rows, f->row_index, f->col_id,
+                                        f->d_val, f->x_val, f_c_row);
+  ora_grid_t *c = _grid_coarsen_galerkin(f, f_c_row, c_n_rows);
+  free(f_c_row);
+  if (aggregation_limit > 2) {
+    ora_grid_t *cc = _grid_coarsen_pw(c, aggregation_limit / 2);
+    for (int ii = 0; ii < f->n_rows; ii++) {
+      int ic = c->coarse_row[ii];
+      if (ic >= 0) c->coarse_row[ii] = cc->coarse_row[ic];
+    }
+    free(cc->coarse_row);
+    cc->coarse_row = c->coarse_row;
+    c->coarse_row = NULL;
+    cc->level -= 1;
+    ora_grid_free(c);
+    return cc;
+  }
+  return c;
+}
+
+ora_mg_t *
+ora_mg_setup_pw(ora_grid_t *fine, int aggregation_limit, int n_levels_max, int n_g_rows_min)
+{
+  ora_mg_t *mg = calloc(1, sizeof(ora_mg_t));
+  mg->grids = calloc(n_levels_max > 0 ? n_levels_max : 1, sizeof(ora_grid_t *));
+  mg->grids[0] = fine;
+  mg->n_levels = 1;
+  ora_grid_t *g = fine;
+  long n_g_rows = g->n_rows, n_g_rows_prev;
+  while (mg->n_levels < n_levels_max) {
+    n_g_rows_prev = n_g_rows;
+    ora_grid_t *c = _grid_coarsen_pw(g, aggregation_limit);
+    n_g_rows = c->n_rows;
+    int add = 1;
+    if (n_g_rows == 0) add = 0;
+    else if (mg->n_levels > 1) {
+      if (n_g_rows < n_g_rows_min || n_g_rows > 0.8*n_g_rows_prev) add = 0;
+    }
+    if (!add) { ora_grid_free(c); break; }
+    mg->grids[mg->n_levels++] = c;
+    g = c;
+  }
+  return mg;
+}
+
 ora_grid_t *
 ora_grid_coarsen(const ora_grid_t *f, int max_aggregation, double relax_param,
                  int n_threads)

@@ -148,6 +148,10 @@ int    ora_mg_solve(const ora_mg_t *mg, const ora_mg_opt_t *opt,
                     const double *rhs, double *vx, int use_vx_ini,
                     double *out, double *cycle_res);
 
+int    ora_pairwise_msr(int level, int f_n_rows, const int *row_index, const int *col_id,
+                        const double *d_val, const double *x_val, int *f_c_row);
+ora_mg_t *ora_mg_setup_pw(ora_grid_t *fine, int aggregation_limit, int n_levels_max,
+                          int n_g_rows_min);
 void   ora_gauss_inverse_33(const double a[9], double b[9]);
 int    ora_block3_jacobi(int n_rows, const int *row_index, const int *col_id,
                          const double *d_val, const double *x_val,

@@ -240,6 +240,21 @@ class Oracle:
         return self.lib.ora_mg_setup(g, aggregation_limit, n_levels_max, n_g_rows_min,
                                      p0p1_relax, n_threads)
 
+    def mg_setup_pw(self, s, aggregation_limit=4, n_levels_max=25, n_g_rows_min=30):
+        """CS_GRID_COARSENING_SPD_PW (pairwise aggregation) with Galerkin coarse matrices."""
+        g = self.fine_grid(s)
+        self.lib.ora_mg_setup_pw.restype = C.POINTER(OraMg)
+        self.lib.ora_mg_setup_pw.argtypes = [C.POINTER(OraGrid), C.c_int, C.c_int, C.c_int]
+        return self.lib.ora_mg_setup_pw(g, aggregation_limit, n_levels_max, n_g_rows_min)
+
+    def pairwise(self, level, ri, ci, d, xv):
+        ri, ci, d, xv = _i32(ri), _i32(ci), _f64(d), _f64(xv)
+        n = len(ri) - 1
+        f_c_row = np.empty(max(n, 1), dtype=np.int32)
+        nc = self.lib.ora_pairwise_msr(C.c_int(level), C.c_int(n), _ip(ri), _ip(ci), _dp(d),
+                                       _dp(xv), _ip(f_c_row))
+        return nc, f_c_row[:n]
+
     @staticmethod
     def mg_levels(mg):
         """Copy every level out as numpy arrays."""

@@ -251,7 +251,29 @@ def check_galerkin(ora):
     mg.destroy(); m.destroy()
 
 
-CHECKS = {"spmv_pcg": check_spmv_pcg, "galerkin": check_galerkin, "block3_jacobi": check_block3_jacobi, "general_pc": check_general_pc,
+def check_pairwise(ora):
+    g = np.load(os.path.join(GOLD, "pairwise_N8_neumann.npz"))
+    s = cube_poisson(8, "neumann")
+    rn = float(g["r_norm"])
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+    for lim in (4,):
+        mg = csb.Multigrid()
+        mg.set_coarsening_options(aggregation_limit=lim, coarsening_type=3, n_max_levels=10,
+                                  p0p1_relax=0.)
+        mg.setup(m)
+        lv = mg.levels()
+        assert len(lv) == int(g[f"lim{lim}_n_levels"])
+        for l in range(1, len(lv)):
+            for k in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
+                assert np.array_equal(lv[l][k], g[f"lim{lim}_l{l}_{k}"]), (lim, l, k)
+        r = mg.solve(m, s.rhs, 1e-8, rn)
+        n_ref = int(g[f"lim{lim}_mg_n_iter"])
+        assert int(r["cvg"]) == 1 and abs(r["n_iter"] - n_ref) <= max(2, n_ref // 20)
+        mg.destroy()
+    m.destroy()
+
+
+CHECKS = {"spmv_pcg": check_spmv_pcg, "pairwise": check_pairwise, "galerkin": check_galerkin, "block3_jacobi": check_block3_jacobi, "general_pc": check_general_pc,
           "kernel_per_phase": check_kernel_per_phase_paths, "smoothers": check_smoothers,
           "cycle_pc": check_cycle_pc, "fcg_mgpc": check_fcg_mgpc}
 

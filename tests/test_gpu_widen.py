@@ -381,3 +381,39 @@ def test_galerkin_vs_oracle_larger(csb, oracle):
     r = mg.solve(m, s.rhs, 1e-8, r_norm)
     assert int(r["cvg"]) == o["cvg"] == 1 and abs(r["n_cycles"] - o["n_cycles"]) <= 1
     oracle.mg_free(omg); mg.destroy(); m.destroy()
+
+
+# ------------------------------------------ pairwise aggregation (a30, CS_GRID_COARSENING_SPD_PW)
+
+@pytest.mark.parametrize("N,bc", [(8, "neumann"), (12, "dirichlet")])
+def test_pairwise_hierarchy_matches_reference_golden(csb, N, bc):
+    """coarsening_type 3 with Galerkin coarse matrices, aggregation limits 2 / 4 / 8: maps,
+    structures and values bit-exact against the reference; the V-cycle over each hierarchy
+    converges with the reference's iteration count (+- the usual slack)."""
+    g = np.load(os.path.join(GOLD, f"pairwise_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    r_norm = float(g["r_norm"])
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+    for lim in (2, 4, 8):
+        mg = csb.Multigrid()
+        mg.set_coarsening_options(aggregation_limit=lim, coarsening_type=3, n_max_levels=10,
+                                  p0p1_relax=0.)
+        mg.setup(m)
+        lv = mg.levels()
+        assert len(lv) == int(g[f"lim{lim}_n_levels"])
+        for l in range(1, len(lv)):
+            for k in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
+                assert np.array_equal(lv[l][k], g[f"lim{lim}_l{l}_{k}"]), (lim, l, k)
+        r = mg.solve(m, s.rhs, 1e-8, r_norm)
+        n_ref = int(g[f"lim{lim}_mg_n_iter"])
+        assert int(r["cvg"]) == int(g[f"lim{lim}_mg_cvg"]) == 1
+        assert abs(r["n_iter"] - n_ref) <= max(2, n_ref // 20)
+        res = np.linalg.norm(s.rhs - m.vector_multiply(r["vx"][:s.n_rows].copy()))
+        assert res <= 1.0001e-8 * r_norm
+        mg.destroy()
+    # the with-faces coarse values are not available with pairwise aggregation
+    mg = csb.Multigrid()
+    mg.set_coarsening_options(aggregation_limit=4, coarsening_type=3, p0p1_relax=0.95)
+    with pytest.raises(csb.CsbError):
+        mg.setup(m)
+    mg.destroy(); m.destroy()

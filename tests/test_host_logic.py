@@ -92,3 +92,39 @@ def test_host_aggregation_empty():
     ri = np.zeros(1, dtype=np.int32)
     nc, f = api.host_aggregate(0, ri, np.zeros(0, dtype=np.int32), np.zeros(0), np.zeros(0))
     assert nc == 0 and len(f) == 0
+
+
+@pytest.mark.parametrize("N,bc", [(8, "neumann"), (12, "dirichlet")])
+def test_host_pairwise_coarsening_matches_reference_golden(N, bc):
+    """csb_host_coarsen_pairwise (the host recursion csb_multigrid_setup uses for
+    CS_GRID_COARSENING_SPD_PW: _pairwise_msr + Galerkin values) level by level against the
+    reference-built fixtures: maps, structures and values bit-exact.  No GPU needed."""
+    import os
+    from code_saturne_b200 import api
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"pairwise_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    for lim in (2, 4, 8):
+        f = dict(row_index=s.row_index, col_id=s.col_id, d_val=s.d_val, x_val=s.x_val)
+        for l in range(1, int(g[f"lim{lim}_n_levels"])):
+            c = api.host_coarsen_pairwise(l - 1, f["row_index"], f["col_id"], f["d_val"],
+                                          f["x_val"], lim)
+            for k in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
+                assert np.array_equal(c[k], g[f"lim{lim}_l{l}_{k}"]), (lim, l, k)
+            f = c
+
+
+def test_host_pairwise_edge_cases():
+    from code_saturne_b200 import api
+    # a diagonal matrix: every row is left alone (level > 0) ...
+    ri = np.arange(5, dtype=np.int32) * 0
+    c = api.host_coarsen_pairwise(1, ri, np.zeros(0, np.int32), np.ones(4), np.zeros(0), 4)
+    assert c["n_rows"] == 4 and list(c["coarse_row"]) == [0, 1, 2, 3]
+    # ... and at level 0 its rows are strongly diagonally dominant: no coarse rows at all
+    c = api.host_coarsen_pairwise(0, ri, np.zeros(0, np.int32), np.ones(4), np.zeros(0), 4)
+    assert c["n_rows"] == 0 and list(c["coarse_row"]) == [-1, -1, -1, -1]
+    # two coupled rows form one pair
+    ri = np.array([0, 1, 2], dtype=np.int32)
+    ci = np.array([1, 0], dtype=np.int32)
+    c = api.host_coarsen_pairwise(1, ri, ci, np.array([2., 2.]), np.array([-1., -1.]), 2)
+    assert c["n_rows"] == 1 and list(c["coarse_row"]) == [0, 0]
+    assert c["d_val"][0] == 2. and len(c["x_val"]) == 0

@@ -407,3 +407,24 @@ def test_oracle_galerkin_hierarchy_matches_golden(oracle, N, bc):
                                                       float(g["fcg_residual"]))
     assert np.array_equal(r["vx"], g["fcg_vx"])
     oracle.mg_free(mg)
+
+
+PW_CASES = [(8, "neumann"), (12, "dirichlet")]
+
+
+@pytest.mark.parametrize("N,bc", PW_CASES)
+def test_oracle_pairwise_hierarchy_matches_golden(oracle, N, bc):
+    """CS_GRID_COARSENING_SPD_PW: pairs, pairs of pairs (limit 4), and of those (limit 8)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"pairwise_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    for lim in (2, 4, 8):
+        mg = oracle.mg_setup_pw(s, aggregation_limit=lim, n_levels_max=10)
+        lv = oracle.mg_levels(mg)
+        assert len(lv) == int(g[f"lim{lim}_n_levels"])
+        for l in range(1, len(lv)):
+            for k in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
+                assert np.array_equal(lv[l][k], g[f"lim{lim}_l{l}_{k}"]), (lim, l, k)
+        r = oracle.mg_solve(mg, s.rhs, 1e-8, float(g["r_norm"]))
+        assert (r["cvg"], r["n_iter"], r["residual"]) == (
+            int(g[f"lim{lim}_mg_cvg"]), int(g[f"lim{lim}_mg_n_iter"]), float(g[f"lim{lim}_mg_residual"]))
+        oracle.mg_free(mg)
