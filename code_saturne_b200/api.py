@@ -454,6 +454,34 @@ class Matrix:
                                                           _ptr(fun), _ptr(fs)) != 0:
             _err("csb_matrix_set_mesh_association")
 
+    def set_boundary_faces(self, b_face_cells):
+        bfc = _i32(b_face_cells)
+        if load_library().csb_matrix_set_boundary_faces(self.handle, len(bfc), _ptr(bfc)) != 0:
+            _err("csb_matrix_set_boundary_faces")
+
+    def compute_coeffs(self, rovsdt, i_visc, b_visc=None, cofbfp=None, idiffp=1, ndircp=1,
+                       thetap=1., relaxp=1., iconvp=0):
+        """cs_matrix_compute_coeffs (symmetric scalar case): fill the MSR coefficients in HBM
+        from face viscosities, boundary coefficients and the unsteady term."""
+        L = load_library()
+        L.csb_matrix_compute_coeffs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p]
+        args = [a if a is None or not isinstance(a, np.ndarray) else _f64(a)
+                for a in (cofbfp, rovsdt, i_visc, b_visc)]
+        if L.csb_matrix_compute_coeffs(self.handle, iconvp, idiffp, ndircp, float(thetap),
+                                       float(relaxp), *[_ptr(a) for a in args]) != 0:
+            _err("csb_matrix_compute_coeffs")
+
+    def get_coefficients(self):
+        """(d_val, x_val) copied back from HBM."""
+        L = load_library()
+        d, x = np.empty(self.n_rows * self.db * self.db), np.empty(max(self.nnz, 1))
+        L.csb_matrix_get_coefficients.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        if L.csb_matrix_get_coefficients(self.handle, _ptr(d), _ptr(x)) != 0:
+            _err("csb_matrix_get_coefficients")
+        return d, x[:self.nnz]
+
     def set_halo(self, halo):
         self._halo = halo
         load_library().csb_matrix_set_halo(self.handle, halo.handle if halo else None)

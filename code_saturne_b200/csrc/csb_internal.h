@@ -300,6 +300,12 @@ struct _csb_matrix_t {
   csb::DevBuf<short>       c2f_sgn;
   csb::DevBuf<double>      cell_cen, cell_vol, face_u_normal, face_surf;
   bool        has_mesh = false;
+  /* boundary faces by adjacent cell, ascending face ids (csb_matrix_set_boundary_faces):
+     what cs_matrix_compute_coeffs needs beside the mesh association */
+  csb_lnum_t  n_b_faces = 0;
+  csb::DevBuf<csb_lnum_t>  cell_b_faces_idx, cell_b_faces;
+  bool        has_b_faces = false;
+  csb::DevBuf<double>      coef_stage;   /* host inputs of csb_matrix_compute_coeffs */
   _csb_halo_t *halo = nullptr;
   /* matrix created from CSR arrays (cs_matrix_type_t CS_MATRIX_CSR): the CSR arrays are
      kept for cs_matrix_vector_multiply in CSR order (_mat_vec_p_l_csr); this object holds
@@ -359,6 +365,13 @@ bool launch_bicg_spmv_b3(int mode, const _csb_matrix_t *m, ItState *st, const do
 
 /* setup of SpMV launch geometry after (re)building a structure */
 void matrix_plan_spmv(_csb_matrix_t *m);
+
+/* MSR coefficients of a symmetric scalar diffusion system from face data
+   (_sym_coeffs_msr, cs_matrix_building.cpp:136-206, and :2243-2262) */
+bool launch_sym_coeffs_msr(const _csb_matrix_t *m, int idiffp, int ndircp, double thetap,
+                           double relaxp, const double *cofbfp, const double *rovsdt,
+                           const double *i_visc, const double *b_visc, double *d_val,
+                           double *x_val);
 
 /* ad_inv = 1/d  (cs_sles_pc.cpp:376) */
 bool launch_ad_inv(int n, const double *d, double *ad_inv);

@@ -2018,6 +2018,67 @@ bool launch_fcg_update(int n, ItState *st, const double *vk, const double *wk, d
 }
 
 /*--------------------------------------------------------------------------
+ * Matrix coefficients straight into the MSR arrays in HBM
+ * (cs_matrix_compute_coeffs, src/alge/cs_matrix_building.cpp:1948-2283, iconvp = 0):
+ * the solve's inputs become 8 bytes per face and per cell instead of the 12 bytes per
+ * entry of an uploaded matrix.
+ *--------------------------------------------------------------------------*/
+
+namespace {
+
+/* _sym_coeffs_msr (:136-206): thread per cell; interior faces in the order of the MSR row,
+   then the cell's boundary faces in ascending face id -- the order of the reference's
+   sequential boundary loop -- then relaxation and the no-Dirichlet shift (:2243-2262). */
+__global__ void __launch_bounds__(TPB)
+k_sym_coeffs_msr(int n_rows, const int *__restrict__ row_index,
+                 const int *__restrict__ cell_i_faces, const int *__restrict__ c2b_idx,
+                 const int *__restrict__ c2b, int idiffp, int ndircp, double thetap,
+                 double relaxp, const double *__restrict__ cofbfp,
+                 const double *__restrict__ rovsdt, const double *__restrict__ i_visc,
+                 const double *__restrict__ b_visc, double *__restrict__ da,
+                 double *__restrict__ ea)
+{
+  const double rf = 1. / relaxp;
+  const double epsi_p1 = 1. + 1.e-7;
+  for (int c_id = blockIdx.x*TPB + threadIdx.x; c_id < n_rows; c_id += gridDim.x*TPB) {
+    double _da = rovsdt[c_id];
+    const int ks = row_index[c_id], ke = row_index[c_id+1];
+    if (idiffp) {
+      for (int k = ks; k < ke; k++) {
+        const double _xa = -thetap*i_visc[cell_i_faces[k]];
+        ea[k] = _xa;
+        _da -= _xa;
+      }
+      if (c2b_idx != nullptr)
+        for (int b = c2b_idx[c_id]; b < c2b_idx[c_id+1]; b++) {
+          const int f_id = c2b[b];
+          _da += thetap*b_visc[f_id]*cofbfp[f_id];
+        }
+    }
+    else
+      for (int k = ks; k < ke; k++) ea[k] = 0.;
+    if (relaxp < 1) _da *= rf;
+    if (ndircp <= 0) _da *= epsi_p1;
+    da[c_id] = _da;
+  }
+}
+
+} // anonymous namespace
+
+bool launch_sym_coeffs_msr(const _csb_matrix_t *m, int idiffp, int ndircp, double thetap,
+                           double relaxp, const double *cofbfp, const double *rovsdt,
+                           const double *i_visc, const double *b_visc, double *d_val,
+                           double *x_val)
+{
+  if (m->n_rows < 1) return true;
+  k_sym_coeffs_msr<<<vec_grid(m->n_rows*4), TPB, 0, ctx().stream>>>(
+    m->n_rows, m->row_index.p, m->c2f.p,
+    m->has_b_faces ? m->cell_b_faces_idx.p : nullptr, m->cell_b_faces.p, idiffp, ndircp,
+    thetap, relaxp, cofbfp, rovsdt, i_visc, b_visc, d_val, x_val);
+  return post_launch("sym_coeffs_msr");
+}
+
+/*--------------------------------------------------------------------------
  * Halo packing (cs_halo_sync_pack, src/base/cs_halo.cpp:1739-1834;
  * _gather_full_cu, src/base/cs_halo_cuda.cu:74-160)
  *--------------------------------------------------------------------------*/

@@ -321,6 +321,111 @@ int csb_matrix_set_mesh_association(csb_matrix_t *m, csb_lnum_t n_faces,
   return ok ? 0 : -1;
 }
 
+/* Boundary faces of the mesh by adjacent cell (cs_mesh_t::b_face_cells); builds the
+   cell -> boundary faces adjacency the reference keeps in cs_mesh_adjacencies
+   (cell_b_faces_idx / cell_b_faces, src/mesh/cs_mesh_adjacencies.cpp:705-760). */
+int csb_matrix_set_boundary_faces(csb_matrix_t *m, csb_lnum_t n_b_faces,
+                                  const csb_lnum_t *b_face_cells)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (n_b_faces < 0 || (n_b_faces > 0 && b_face_cells == nullptr)) {
+    set_error("csb_matrix_set_boundary_faces: bad arguments");
+    return -1;
+  }
+  std::vector<csb_lnum_t> bfc((size_t)n_b_faces);
+  if (n_b_faces > 0
+      && !CSB_CUDA(cudaMemcpy(bfc.data(), b_face_cells, sizeof(csb_lnum_t)*(size_t)n_b_faces,
+                              cudaMemcpyDefault))) return -1;
+  std::vector<csb_lnum_t> idx((size_t)m->n_rows + 1, 0), ids((size_t)std::max(n_b_faces, 1));
+  for (csb_lnum_t f = 0; f < n_b_faces; f++) {
+    if (bfc[f] < 0 || bfc[f] >= m->n_rows) {
+      set_error("csb_matrix_set_boundary_faces: face %d is adjacent to cell %d", f, bfc[f]);
+      return -1;
+    }
+    idx[(size_t)bfc[f] + 1]++;
+  }
+  for (csb_lnum_t i = 0; i < m->n_rows; i++) idx[(size_t)i + 1] += idx[i];
+  {
+    std::vector<csb_lnum_t> fill(idx.begin(), idx.end() - 1);
+    for (csb_lnum_t f = 0; f < n_b_faces; f++) ids[(size_t)fill[bfc[f]]++] = f;   /* ascending */
+  }
+  m->n_b_faces = n_b_faces;
+  bool ok = m->cell_b_faces_idx.upload(idx.data(), idx.size())
+         && m->cell_b_faces.upload(ids.data(), (size_t)n_b_faces)
+         && CSB_CUDA(cudaStreamSynchronize(ctx().stream));
+  m->has_b_faces = ok;
+  return ok ? 0 : -1;
+}
+
+/* cs_matrix_compute_coeffs (src/alge/cs_matrix_building.cpp:1948-2283), symmetric scalar
+   case: the MSR coefficients are computed in HBM from i_visc[n_faces], b_visc / cofbfp
+   [n_b_faces] and rovsdt[n_rows] (host or device arrays). */
+int csb_matrix_compute_coeffs(csb_matrix_t *m, int iconvp, int idiffp, int ndircp,
+                              double thetap, double relaxp, const csb_real_t *cofbfp,
+                              const csb_real_t *rovsdt, const csb_real_t *i_visc,
+                              const csb_real_t *b_visc)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (iconvp != 0 || m->db != 1) {
+    set_error("csb_matrix_compute_coeffs: the symmetric scalar case (iconvp 0) is the one "
+              "available on this path");
+    return -1;
+  }
+  if (!m->has_mesh) {
+    set_error("csb_matrix_compute_coeffs: needs the mesh association "
+              "(csb_matrix_set_mesh_association)");
+    return -1;
+  }
+  if (rovsdt == nullptr || (idiffp && i_visc == nullptr)
+      || (idiffp && m->has_b_faces && m->n_b_faces > 0 && (b_visc == nullptr || cofbfp == nullptr))) {
+    set_error("csb_matrix_compute_coeffs: null coefficient array");
+    return -1;
+  }
+  Context &c = ctx();
+  /* host arrays are staged in one buffer that lives with the matrix */
+  const size_t nf = (size_t)m->n_faces, nb = (size_t)m->n_b_faces, nr = (size_t)m->n_rows;
+  const double *src[4] = {rovsdt, i_visc, b_visc, cofbfp};
+  const size_t len[4] = {nr, idiffp ? nf : 0, idiffp ? nb : 0, idiffp ? nb : 0};
+  const double *dev[4];
+  size_t need = 0;
+  for (int i = 0; i < 4; i++)
+    if (len[i] > 0 && src[i] != nullptr && !is_device_ptr(src[i])) need += len[i];
+  if (need > m->coef_stage.n && !m->coef_stage.alloc(need)) return -1;
+  size_t off = 0;
+  for (int i = 0; i < 4; i++) {
+    dev[i] = src[i];
+    if (len[i] > 0 && src[i] != nullptr && !is_device_ptr(src[i])) {
+      if (!CSB_CUDA(cudaMemcpyAsync(m->coef_stage.p + off, src[i], sizeof(double)*len[i],
+                                    cudaMemcpyHostToDevice, c.stream))) return -1;
+      dev[i] = m->coef_stage.p + off;
+      off += len[i];
+    }
+  }
+  if (!launch_sym_coeffs_msr(m, idiffp, ndircp, thetap, relaxp, dev[3], dev[0], dev[1], dev[2],
+                             m->d_val.p, m->x_val.p)) return -1;
+  if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return -1;   /* host inputs may go away */
+  m->symmetric = true;
+  m->h_vals_valid = false;
+  return 0;
+}
+
+/* The MSR coefficients as they are in HBM, copied to d_val[n_rows*db*db] / x_val[nnz]
+   (host or device); cs_matrix_get_msr_arrays (cs_matrix.cpp:6199) lends them, here they are
+   copied because they live on the device. */
+int csb_matrix_get_coefficients(const csb_matrix_t *m, csb_real_t *d_val, csb_real_t *x_val)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  Context &c = ctx();
+  bool ok = true;
+  if (d_val != nullptr)
+    ok = CSB_CUDA(cudaMemcpyAsync(d_val, m->d_val.p, sizeof(double)*(size_t)m->n_rows*m->db*m->db,
+                                  cudaMemcpyDefault, c.stream));
+  if (ok && x_val != nullptr && m->nnz > 0)
+    ok = CSB_CUDA(cudaMemcpyAsync(x_val, m->x_val.p, sizeof(double)*(size_t)m->nnz,
+                                  cudaMemcpyDefault, c.stream));
+  return (ok && CSB_CUDA(cudaStreamSynchronize(c.stream))) ? 0 : -1;
+}
+
 int csb_matrix_set_halo(csb_matrix_t *m, csb_halo_t *halo)
 {
   if (m == nullptr) { set_error("The matrix is not defined."); return -1; }

@@ -230,6 +230,16 @@ def _bounds(N, p):
     return [(N * r) // p for r in range(p + 1)]
 
 
+def cube_boundary_face_cells(N: int) -> np.ndarray:
+    """Adjacent cell of every boundary face of the N^3 cube: the six sides in the order
+    x-min, x-max, y-min, y-max, z-min, z-max, cells in increasing id inside a side (a corner
+    cell appears three times)."""
+    ids = np.arange(N * N * N, dtype=np.int32).reshape(N, N, N)      # [k, j, i]
+    sides = [ids[:, :, 0], ids[:, :, N - 1], ids[:, 0, :], ids[:, N - 1, :], ids[0, :, :],
+             ids[N - 1, :, :]]
+    return np.concatenate([x.ravel() for x in sides]).astype(np.int32)
+
+
 def cube_poisson_local(N: int, n_ranks: int, rank: int, bc: str = "neumann",
                        eps_factor: float = 1e-6):
     """The rows of cube_poisson(N, bc) owned by `rank` out of `n_ranks` bricks, in the

@@ -161,6 +161,29 @@ int  csb_matrix_set_mesh_association(csb_matrix_t      *m,
                                      const csb_real_t  *face_surf);    /* [n_faces] */
 
 /* Attach a halo (cs_matrix_structure_create_msr_shared "halo" argument). */
+/* Boundary faces by adjacent cell (cs_mesh_t::b_face_cells, n_b_faces entries): builds the
+   cell -> boundary faces adjacency of cs_mesh_adjacencies (src/mesh/cs_mesh_adjacencies.cpp:
+   705-760) used by csb_matrix_compute_coeffs. */
+int  csb_matrix_set_boundary_faces(csb_matrix_t *m, csb_lnum_t n_b_faces,
+                                   const csb_lnum_t *b_face_cells);
+
+/* cs_matrix_compute_coeffs (src/alge/cs_matrix_building.cpp:1948-2283) for the symmetric scalar
+   case (iconvp = 0 -> _sym_coeffs_msr, :136-206): the MSR coefficients are computed in HBM
+   from the face viscosities i_visc[n_faces], b_visc[n_b_faces], the implicit boundary
+   coefficient cofbfp[n_b_faces] (cs_field_bc_coeffs_t::bf) and the unsteady term
+   rovsdt[n_rows]; relaxp < 1 scales the diagonal by 1/relaxp, ndircp <= 0 applies the
+   (1 + 1e-7) shift (:2243-2262).  Arrays may be host or device pointers.  Needs the mesh
+   association (the face of every MSR entry) and, for boundary terms, the boundary faces.
+   Bit-identical to the reference's CPU result: same per-cell summation order. */
+int  csb_matrix_compute_coeffs(csb_matrix_t *m, int iconvp, int idiffp, int ndircp,
+                               double thetap, double relaxp, const csb_real_t *cofbfp,
+                               const csb_real_t *rovsdt, const csb_real_t *i_visc,
+                               const csb_real_t *b_visc);
+
+/* Copy of the MSR coefficients held in HBM (cs_matrix_get_msr_arrays, cs_matrix.cpp:6199,
+   lends the host arrays; these live on the device).  Either pointer may be NULL. */
+int  csb_matrix_get_coefficients(const csb_matrix_t *m, csb_real_t *d_val, csb_real_t *x_val);
+
 int  csb_matrix_set_halo(csb_matrix_t *m, csb_halo_t *halo);
 
 void csb_matrix_destroy(csb_matrix_t **m);

@@ -2529,3 +2529,55 @@ ora_block3_jacobi(int n_rows, const int *row_index, const int *col_id,
   free(rk);
   return cvg;
 }
+
+/*----------------------------------------------------------------------------
+ * Matrix coefficients of a symmetric scalar diffusion system, straight into MSR:
+ *   cs_matrix_compute_coeffs (src/alge/cs_matrix_building.cpp:1948-2283) with iconvp = 0 ->
+ *   _sym_coeffs_msr (:136-206): per cell, in the order of its MSR row,
+ *     x_k = -thetap * i_visc[face of entry k],  d = rovsdt - sum_k x_k
+ *   then the boundary faces in face order, d[cell] += thetap * b_visc * cofbfp
+ *   (sequential "simple" sum on the CPU), the relaxation d *= 1/relaxp (:2243-2249) and the
+ *   (1 + 1e-7) shift of the diagonal when no Dirichlet condition exists (:2256-2262).
+ * cell_i_faces = interior face id of every MSR entry (the matrix's mesh association).
+ *----------------------------------------------------------------------------*/
+
+void
+ora_matrix_compute_coeffs_sym(int n_rows, const int *row_index, const int *cell_i_faces,
+                              int n_b_faces, const int *b_face_cells,
+                              int idiffp, int ndircp, double thetap, double relaxp,
+                              const double *cofbfp, const double *rovsdt,
+                              const double *i_visc, const double *b_visc,
+                              double *da, double *ea)
+{
+  if (idiffp) {
+    for (int c_id = 0; c_id < n_rows; c_id++) {
+      double _da = rovsdt[c_id];
+      for (int cidx = row_index[c_id]; cidx < row_index[c_id+1]; cidx++) {
+        const int f_id = cell_i_faces[cidx];
+        double _xa = -thetap*i_visc[f_id];
+        ea[cidx] = _xa;
+        _da -= _xa;
+      }
+      da[c_id] = _da;
+    }
+    for (int f_id = 0; f_id < n_b_faces; f_id++) {
+      int ii = b_face_cells[f_id];
+      da[ii] += thetap*b_visc[f_id]*cofbfp[f_id];
+    }
+  }
+  else {
+    for (int c_id = 0; c_id < n_rows; c_id++) {
+      da[c_id] = rovsdt[c_id];
+      for (int cidx = row_index[c_id]; cidx < row_index[c_id+1]; cidx++)
+        ea[cidx] = 0.;
+    }
+  }
+  if (relaxp < 1) {
+    double rf = 1. / relaxp;
+    for (int i = 0; i < n_rows; i++) da[i] *= rf;
+  }
+  if (ndircp <= 0) {
+    const double epsi_p1 = 1. + 1.e-7;
+    for (int c_id = 0; c_id < n_rows; c_id++) da[c_id] *= epsi_p1;
+  }
+}

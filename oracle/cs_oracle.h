@@ -148,6 +148,12 @@ int    ora_mg_solve(const ora_mg_t *mg, const ora_mg_opt_t *opt,
                     const double *rhs, double *vx, int use_vx_ini,
                     double *out, double *cycle_res);
 
+void   ora_matrix_compute_coeffs_sym(int n_rows, const int *row_index, const int *cell_i_faces,
+                                     int n_b_faces, const int *b_face_cells,
+                                     int idiffp, int ndircp, double thetap, double relaxp,
+                                     const double *cofbfp, const double *rovsdt,
+                                     const double *i_visc, const double *b_visc,
+                                     double *da, double *ea);
 int    ora_pairwise_msr(int level, int f_n_rows, const int *row_index, const int *col_id,
                         const double *d_val, const double *x_val, int *f_c_row);
 ora_mg_t *ora_mg_setup_pw(ora_grid_t *fine, int aggregation_limit, int n_levels_max,

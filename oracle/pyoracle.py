@@ -247,6 +247,17 @@ class Oracle:
         self.lib.ora_mg_setup_pw.argtypes = [C.POINTER(OraGrid), C.c_int, C.c_int, C.c_int]
         return self.lib.ora_mg_setup_pw(g, aggregation_limit, n_levels_max, n_g_rows_min)
 
+    def matrix_compute_coeffs_sym(self, ri, c2f, b_face_cells, cofbfp, rovsdt, i_visc, b_visc,
+                                  idiffp=1, ndircp=1, thetap=1., relaxp=1.):
+        ri, c2f, bfc = _i32(ri), _i32(c2f), _i32(b_face_cells)
+        n = len(ri) - 1
+        da, ea = np.zeros(max(n, 1)), np.zeros(max(int(ri[-1]), 1))
+        self.lib.ora_matrix_compute_coeffs_sym(
+            C.c_int(n), _ip(ri), _ip(c2f), C.c_int(len(bfc)), _ip(bfc), C.c_int(idiffp),
+            C.c_int(ndircp), C.c_double(thetap), C.c_double(relaxp), _dp(_f64(cofbfp)),
+            _dp(_f64(rovsdt)), _dp(_f64(i_visc)), _dp(_f64(b_visc)), _dp(da), _dp(ea))
+        return da[:n], ea[:int(ri[-1])]
+
     def pairwise(self, level, ri, ci, d, xv):
         ri, ci, d, xv = _i32(ri), _i32(ci), _f64(d), _f64(xv)
         n = len(ri) - 1
@@ -491,6 +502,19 @@ class RefLib:
                                              C.c_int(verbosity), _dp(out))
         return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], t_setup=out[2],
                     t_solve=out[3], vx=vx)
+
+    def matrix_compute_coeffs_sym(self, h, s, b_face_cells, cofbfp, rovsdt, i_visc, b_visc,
+                                  idiffp=1, ndircp=1, thetap=1., relaxp=1.):
+        """cs_matrix_compute_coeffs (iconvp = 0) on the system's matrix; returns (d_val, x_val)."""
+        bfc = _i32(b_face_cells)
+        d, x = np.zeros(max(s.n_rows, 1)), np.zeros(max(s.nnz, 1))
+        rc = self.lib.csref_matrix_compute_coeffs_sym(
+            h, C.c_int(len(bfc)), _ip(bfc), C.c_int(idiffp), C.c_int(ndircp), C.c_double(thetap),
+            C.c_double(relaxp), _dp(_f64(cofbfp)), _dp(_f64(rovsdt)), _dp(_f64(i_visc)),
+            _dp(_f64(b_visc)), _dp(d), _dp(x))
+        if rc != 0:
+            raise RuntimeError("csref_matrix_compute_coeffs_sym: system has no mesh")
+        return d[:s.n_rows], x[:s.nnz]
 
     def smoother(self, h, stype, rhs, n_max_iter, vx0=None):
         rhs = _f64(rhs)

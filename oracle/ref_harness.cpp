@@ -41,6 +41,11 @@
 #include "base/cs_halo.h"
 #include "base/cs_timer.h"
 #include "mesh/cs_mesh.h"
+#include "mesh/cs_mesh_adjacencies.h"
+#include "mesh/cs_mesh_quantities.h"
+#include "base/cs_numbering.h"
+#include "base/cs_field.h"
+#include "alge/cs_matrix_building.h"
 #include "alge/cs_blas.h"
 #include "alge/cs_matrix.h"
 #include "alge/cs_matrix_default.h"
@@ -504,6 +509,66 @@ csref_fcg_mgpc_solve(void *sys, const int *iopt, const double *dopt, int n_max_i
 {
   return csref_it_mgpc_solve(sys, (int)CS_SLES_FCG, iopt, dopt, n_max_iter, precision,
                              r_norm, rhs, vx, use_vx_ini, out);
+}
+
+/* cs_matrix_compute_coeffs, symmetric scalar case (iconvp = 0): the reference fills the MSR
+   coefficients of the system's matrix from face viscosities, the implicit boundary
+   coefficient and the unsteady term (_sym_coeffs_msr, src/alge/cs_matrix_building.cpp:136-
+   206; relaxation, the (1 + 1e-7) shift when there is no Dirichlet condition :2243-2262).
+   The mesh globals it reads (cs_glob_mesh faces, cs_glob_mesh_adjacencies,
+   cs_glob_mesh_quantities) are set up from the system's face -> cell table.
+   d_out[n_rows], x_out[nnz] receive the MSR coefficients. */
+int
+csref_matrix_compute_coeffs_sym(void          *sys,
+                                int            n_b_faces,
+                                const int     *b_face_cells,
+                                int            idiffp,
+                                int            ndircp,
+                                double         thetap,
+                                double         relaxp,
+                                const double  *cofbfp,
+                                const double  *rovsdt,
+                                const double  *i_visc,
+                                const double  *b_visc,
+                                double        *d_out,
+                                double        *x_out)
+{
+  ref_system *s = static_cast<ref_system *>(sys);
+  cs_mesh_t *mesh = cs_glob_mesh;
+  if (mesh == nullptr || mesh->n_i_faces != s->n_faces)
+    return -1;                      /* csref_system_set_mesh first */
+
+  CS_FREE(mesh->b_face_cells);
+  mesh->n_b_faces = n_b_faces;
+  mesh->n_b_faces_all = n_b_faces;
+  CS_MALLOC(mesh->b_face_cells, (n_b_faces > 0) ? n_b_faces : 1, cs_lnum_t);
+  memcpy(mesh->b_face_cells, b_face_cells, sizeof(cs_lnum_t)*n_b_faces);
+  if (mesh->b_face_numbering != nullptr)
+    cs_numbering_destroy(&(mesh->b_face_numbering));
+  mesh->b_face_numbering = cs_numbering_create_default(n_b_faces);
+  if (mesh->i_face_numbering != nullptr)
+    cs_numbering_destroy(&(mesh->i_face_numbering));
+  mesh->i_face_numbering = cs_numbering_create_default(mesh->n_i_faces);
+
+  if (cs_glob_mesh_quantities == nullptr)
+    cs_glob_mesh_quantities = cs_mesh_quantities_create();
+  cs_mesh_adjacencies_finalize();
+  cs_mesh_adjacencies_initialize();
+  cs_mesh_adjacencies_update_mesh();
+
+  cs_field_bc_coeffs_t bc;
+  memset(&bc, 0, sizeof(bc));
+  bc.bf = const_cast<cs_real_t *>(cofbfp);
+
+  cs_matrix_compute_coeffs(s->m, nullptr, 0, idiffp, ndircp, thetap, relaxp, 0,
+                           &bc, rovsdt, nullptr, nullptr, i_visc, b_visc, nullptr);
+
+  const cs_lnum_t *ri, *ci;
+  const cs_real_t *d, *x;
+  cs_matrix_get_msr_arrays(s->m, &ri, &ci, &d, &x);
+  memcpy(d_out, d, sizeof(double)*s->n_rows);
+  memcpy(x_out, x, sizeof(double)*ri[s->n_rows]);
+  return 0;
 }
 
 /* Build the grid hierarchy with the reference's cs_grid_coarsen, following

@@ -273,7 +273,21 @@ def check_pairwise(ora):
     m.destroy()
 
 
-CHECKS = {"spmv_pcg": check_spmv_pcg, "pairwise": check_pairwise, "galerkin": check_galerkin, "block3_jacobi": check_block3_jacobi, "general_pc": check_general_pc,
+def check_compute_coeffs(ora):
+    g = np.load(os.path.join(GOLD, "coeffs_N6.npz"))
+    s = cube_poisson(6, "neumann")
+    m = csb.Matrix.from_system(s)
+    m.set_boundary_faces(g["b_face_cells"])
+    for name, kw in (("default", dict()), ("no_dirichlet", dict(ndircp=0)),
+                     ("theta_relax", dict(thetap=0.5, relaxp=0.7)),
+                     ("no_diffusion", dict(idiffp=0))):
+        m.compute_coeffs(g["rovsdt"], g["i_visc"], g["b_visc"], g["cofbfp"], **kw)
+        d, x = m.get_coefficients()
+        assert np.array_equal(d, g[f"{name}_d"]) and np.array_equal(x, g[f"{name}_x"]), name
+    m.destroy()
+
+
+CHECKS = {"spmv_pcg": check_spmv_pcg, "compute_coeffs": check_compute_coeffs, "pairwise": check_pairwise, "galerkin": check_galerkin, "block3_jacobi": check_block3_jacobi, "general_pc": check_general_pc,
           "kernel_per_phase": check_kernel_per_phase_paths, "smoothers": check_smoothers,
           "cycle_pc": check_cycle_pc, "fcg_mgpc": check_fcg_mgpc}
 

@@ -1,0 +1,49 @@
+"""Golden fixtures for the matrix coefficient build (cs_matrix_compute_coeffs, symmetric
+scalar case: _sym_coeffs_msr, cs_matrix_building.cpp:136-206, :2243-2262): MSR coefficients
+computed by the reference's own compiled CPU code (oracle/_ref/libcsref.so) from seeded face
+viscosities / boundary coefficients on the N^3 cube:
+
+    python tests/golden/make_golden_coeffs.py   -> tests/golden/coeffs_N{N}.npz
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from code_saturne_b200.mesh_cartesian import cube_boundary_face_cells, cube_poisson  # noqa: E402
+from oracle.pyoracle import RefLib  # noqa: E402
+
+OPTIONS = {"default": dict(), "no_dirichlet": dict(ndircp=0),
+           "theta_relax": dict(thetap=0.5, relaxp=0.7), "no_diffusion": dict(idiffp=0)}
+
+
+def inputs(N, s):
+    rng = np.random.default_rng(1234)
+    bfc = cube_boundary_face_cells(N)
+    return dict(b_face_cells=bfc, i_visc=0.5 + rng.random(s.n_faces),
+                b_visc=0.5 + rng.random(len(bfc)), cofbfp=rng.random(len(bfc)),
+                rovsdt=1e-3 * rng.random(s.n_rows))
+
+
+def main():
+    ref = RefLib(1)
+    for N in (6, 10):
+        s = cube_poisson(N, "neumann")
+        h = ref.system(s)
+        out = inputs(N, s)
+        for name, kw in OPTIONS.items():
+            d, x = ref.matrix_compute_coeffs_sym(h, s, out["b_face_cells"], out["cofbfp"],
+                                                 out["rovsdt"], out["i_visc"], out["b_visc"], **kw)
+            out[f"{name}_d"] = d
+            out[f"{name}_x"] = x
+        ref.destroy(h)
+        path = os.path.join(ROOT, "tests", "golden", f"coeffs_N{N}.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path))
+
+
+if __name__ == "__main__":
+    main()

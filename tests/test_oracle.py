@@ -428,3 +428,32 @@ def test_oracle_pairwise_hierarchy_matches_golden(oracle, N, bc):
         assert (r["cvg"], r["n_iter"], r["residual"]) == (
             int(g[f"lim{lim}_mg_cvg"]), int(g[f"lim{lim}_mg_n_iter"]), float(g[f"lim{lim}_mg_residual"]))
         oracle.mg_free(mg)
+
+
+COEFF_OPTIONS = {"default": dict(), "no_dirichlet": dict(ndircp=0),
+                 "theta_relax": dict(thetap=0.5, relaxp=0.7), "no_diffusion": dict(idiffp=0)}
+
+
+@pytest.mark.parametrize("N", [6, 10])
+def test_oracle_matrix_compute_coeffs_matches_golden(oracle, N):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"coeffs_N{N}.npz"))
+    s = cube_poisson(N, "neumann")
+    for name, kw in COEFF_OPTIONS.items():
+        d, x = oracle.matrix_compute_coeffs_sym(s.row_index, s.c2f, g["b_face_cells"], g["cofbfp"],
+                                                g["rovsdt"], g["i_visc"], g["b_visc"], **kw)
+        assert np.array_equal(d, g[f"{name}_d"]) and np.array_equal(x, g[f"{name}_x"]), name
+
+
+def test_oracle_matrix_compute_coeffs_vs_reference_direct(oracle, reflib):
+    from code_saturne_b200.mesh_cartesian import cube_boundary_face_cells
+    rng = np.random.default_rng(3)
+    s = cube_poisson(13, "neumann")
+    h = reflib.system(s)
+    bfc = cube_boundary_face_cells(13)
+    iv, bv = 0.1 + rng.random(s.n_faces), 0.1 + rng.random(len(bfc))
+    cb, ro = rng.random(len(bfc)), rng.random(s.n_rows)
+    for kw in COEFF_OPTIONS.values():
+        a = oracle.matrix_compute_coeffs_sym(s.row_index, s.c2f, bfc, cb, ro, iv, bv, **kw)
+        b = reflib.matrix_compute_coeffs_sym(h, s, bfc, cb, ro, iv, bv, **kw)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    reflib.destroy(h)
