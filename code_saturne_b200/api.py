@@ -460,17 +460,18 @@ class Matrix:
             _err("csb_matrix_set_boundary_faces")
 
     def compute_coeffs(self, rovsdt, i_visc, b_visc=None, cofbfp=None, idiffp=1, ndircp=1,
-                       thetap=1., relaxp=1., iconvp=0):
-        """cs_matrix_compute_coeffs (symmetric scalar case): fill the MSR coefficients in HBM
-        from face viscosities, boundary coefficients and the unsteady term."""
+                       thetap=1., relaxp=1., iconvp=0, coefbp=None, i_massflux=None,
+                       b_massflux=None, xcpp=None):
+        """cs_matrix_compute_coeffs (scalar cases): fill the MSR coefficients in HBM from
+        face viscosities / mass fluxes, boundary coefficients and the unsteady term."""
         L = load_library()
         L.csb_matrix_compute_coeffs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                                C.c_double, C.c_double, C.c_void_p, C.c_void_p,
-                                                C.c_void_p, C.c_void_p]
+                                                C.c_double, C.c_double, C.c_int] + [C.c_void_p] * 8
         args = [a if a is None or not isinstance(a, np.ndarray) else _f64(a)
-                for a in (cofbfp, rovsdt, i_visc, b_visc)]
+                for a in (coefbp, cofbfp, rovsdt, i_massflux, b_massflux, i_visc, b_visc, xcpp)]
         if L.csb_matrix_compute_coeffs(self.handle, iconvp, idiffp, ndircp, float(thetap),
-                                       float(relaxp), *[_ptr(a) for a in args]) != 0:
+                                       float(relaxp), 0 if xcpp is None else 1,
+                                       *[_ptr(a) for a in args]) != 0:
             _err("csb_matrix_compute_coeffs")
 
     def get_coefficients(self):

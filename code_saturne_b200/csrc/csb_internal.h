@@ -373,6 +373,13 @@ bool launch_sym_coeffs_msr(const _csb_matrix_t *m, int idiffp, int ndircp, doubl
                            const double *i_visc, const double *b_visc, double *d_val,
                            double *x_val);
 
+/* same for a convection-diffusion scalar (_coeffs_msr, cs_matrix_building.cpp:407-520) */
+bool launch_coeffs_msr(const _csb_matrix_t *m, int idiffp, int ndircp, double thetap,
+                       double relaxp, const double *coefbp, const double *cofbfp,
+                       const double *rovsdt, const double *i_massflux, const double *b_massflux,
+                       const double *i_visc, const double *b_visc, const double *xcpp,
+                       double *d_val, double *x_val);
+
 /* ad_inv = 1/d  (cs_sles_pc.cpp:376) */
 bool launch_ad_inv(int n, const double *d, double *ad_inv);
 bool launch_fill(int n, double v, double *x);

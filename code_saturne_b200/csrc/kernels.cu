@@ -2063,7 +2063,76 @@ k_sym_coeffs_msr(int n_rows, const int *__restrict__ row_index,
   }
 }
 
+/* _coeffs_msr<is_thermal> (:407-520), convection-diffusion scalar: upwind convective part
+   from the face mass flux (sign of the face relative to the cell from the mesh association),
+   boundary terms in ascending face id; xcpp != nullptr multiplies the convective part by Cp. */
+__global__ void __launch_bounds__(TPB)
+k_coeffs_msr(int n_rows, const int *__restrict__ row_index, const int *__restrict__ col_id,
+             const int *__restrict__ cell_i_faces, const short *__restrict__ c2f_sgn,
+             const int *__restrict__ c2b_idx, const int *__restrict__ c2b, int idiffp,
+             int ndircp, double thetap, double relaxp, const double *__restrict__ coefbp,
+             const double *__restrict__ cofbfp, const double *__restrict__ rovsdt,
+             const double *__restrict__ i_massflux, const double *__restrict__ b_massflux,
+             const double *__restrict__ i_visc, const double *__restrict__ b_visc,
+             const double *__restrict__ xcpp, double *__restrict__ da, double *__restrict__ ea)
+{
+  const double rf = 1. / relaxp;
+  const double epsi_p1 = 1. + 1.e-7;
+  const bool is_thermal = (xcpp != nullptr);
+  for (int c_id = blockIdx.x*TPB + threadIdx.x; c_id < n_rows; c_id += gridDim.x*TPB) {
+    double _da = rovsdt[c_id];
+    const int ks = row_index[c_id], ke = row_index[c_id+1];
+    for (int k = ks; k < ke; k++) {
+      const int f_id = cell_i_faces[k];
+      const double _i_massflux = i_massflux[f_id];
+      if (c2f_sgn[k] > 0) {
+        const double flui = 0.5*(_i_massflux - fabs(_i_massflux));
+        const double cpi = is_thermal ? xcpp[c_id] : 1.0;
+        const double xai = thetap*(cpi*flui - idiffp*i_visc[f_id]);
+        ea[k] = xai;
+        _da -= xai + (1.-thetap) * cpi * _i_massflux;
+      }
+      else {
+        const double fluj = -0.5*(_i_massflux + fabs(_i_massflux));
+        const double cpj = is_thermal ? xcpp[col_id[k]] : 1.0;
+        const double xaj = thetap*(cpj*fluj - idiffp*i_visc[f_id]);
+        ea[k] = xaj;
+        _da -= xaj - (1.-thetap) * cpj * _i_massflux;
+      }
+    }
+    if (c2b_idx != nullptr)
+      for (int b = c2b_idx[c_id]; b < c2b_idx[c_id+1]; b++) {
+        const int f_id = c2b[b];
+        const double _b_massflux = b_massflux[f_id];
+        const double flui = 0.5*(_b_massflux - fabs(_b_massflux));
+        const double cpi = is_thermal ? xcpp[c_id] : 1.0;
+        const double bfac =          cpi *(  flui * thetap * (coefbp[f_id] - 1.)
+                                           - (1. - thetap) * _b_massflux)
+                            + idiffp * thetap * b_visc[f_id] * cofbfp[f_id];
+        _da += bfac;
+      }
+    if (relaxp < 1) _da *= rf;
+    if (ndircp <= 0) _da *= epsi_p1;
+    da[c_id] = _da;
+  }
+}
+
 } // anonymous namespace
+
+bool launch_coeffs_msr(const _csb_matrix_t *m, int idiffp, int ndircp, double thetap,
+                       double relaxp, const double *coefbp, const double *cofbfp,
+                       const double *rovsdt, const double *i_massflux, const double *b_massflux,
+                       const double *i_visc, const double *b_visc, const double *xcpp,
+                       double *d_val, double *x_val)
+{
+  if (m->n_rows < 1) return true;
+  k_coeffs_msr<<<vec_grid(m->n_rows*4), TPB, 0, ctx().stream>>>(
+    m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, m->c2f_sgn.p,
+    m->has_b_faces ? m->cell_b_faces_idx.p : nullptr, m->cell_b_faces.p, idiffp, ndircp,
+    thetap, relaxp, coefbp, cofbfp, rovsdt, i_massflux, b_massflux, i_visc, b_visc, xcpp,
+    d_val, x_val);
+  return post_launch("coeffs_msr");
+}
 
 bool launch_sym_coeffs_msr(const _csb_matrix_t *m, int idiffp, int ndircp, double thetap,
                            double relaxp, const double *cofbfp, const double *rovsdt,

@@ -357,18 +357,18 @@ int csb_matrix_set_boundary_faces(csb_matrix_t *m, csb_lnum_t n_b_faces,
   return ok ? 0 : -1;
 }
 
-/* cs_matrix_compute_coeffs (src/alge/cs_matrix_building.cpp:1948-2283), symmetric scalar
-   case: the MSR coefficients are computed in HBM from i_visc[n_faces], b_visc / cofbfp
-   [n_b_faces] and rovsdt[n_rows] (host or device arrays). */
+/* cs_matrix_compute_coeffs (src/alge/cs_matrix_building.cpp:1948-2283), scalar cases: the
+   MSR coefficients are computed in HBM from per-face and per-cell arrays (host or device). */
 int csb_matrix_compute_coeffs(csb_matrix_t *m, int iconvp, int idiffp, int ndircp,
-                              double thetap, double relaxp, const csb_real_t *cofbfp,
-                              const csb_real_t *rovsdt, const csb_real_t *i_visc,
-                              const csb_real_t *b_visc)
+                              double thetap, double relaxp, int imucpp,
+                              const csb_real_t *coefbp, const csb_real_t *cofbfp,
+                              const csb_real_t *rovsdt, const csb_real_t *i_massflux,
+                              const csb_real_t *b_massflux, const csb_real_t *i_visc,
+                              const csb_real_t *b_visc, const csb_real_t *xcpp)
 {
   if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
-  if (iconvp != 0 || m->db != 1) {
-    set_error("csb_matrix_compute_coeffs: the symmetric scalar case (iconvp 0) is the one "
-              "available on this path");
+  if (m->db != 1) {
+    set_error("csb_matrix_compute_coeffs: scalar matrices only on this path");
     return -1;
   }
   if (!m->has_mesh) {
@@ -376,23 +376,32 @@ int csb_matrix_compute_coeffs(csb_matrix_t *m, int iconvp, int idiffp, int ndirc
               "(csb_matrix_set_mesh_association)");
     return -1;
   }
-  if (rovsdt == nullptr || (idiffp && i_visc == nullptr)
-      || (idiffp && m->has_b_faces && m->n_b_faces > 0 && (b_visc == nullptr || cofbfp == nullptr))) {
+  const bool conv = (iconvp != 0);
+  const bool diff = (idiffp != 0);
+  const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  if (imucpp == 0) xcpp = nullptr;
+  if (rovsdt == nullptr || ((diff || conv) && i_visc == nullptr)
+      || (conv && i_massflux == nullptr) || (imucpp != 0 && conv && xcpp == nullptr)
+      || (bnd && (conv || diff) && (b_visc == nullptr || cofbfp == nullptr))
+      || (bnd && conv && (b_massflux == nullptr || coefbp == nullptr))) {
     set_error("csb_matrix_compute_coeffs: null coefficient array");
     return -1;
   }
   Context &c = ctx();
   /* host arrays are staged in one buffer that lives with the matrix */
   const size_t nf = (size_t)m->n_faces, nb = (size_t)m->n_b_faces, nr = (size_t)m->n_rows;
-  const double *src[4] = {rovsdt, i_visc, b_visc, cofbfp};
-  const size_t len[4] = {nr, idiffp ? nf : 0, idiffp ? nb : 0, idiffp ? nb : 0};
-  const double *dev[4];
+  const size_t nce = (size_t)m->n_cols_ext;
+  const bool face_terms = conv || diff;
+  const double *src[8] = {rovsdt, i_visc, b_visc, cofbfp, coefbp, i_massflux, b_massflux, xcpp};
+  const size_t len[8] = {nr, face_terms ? nf : 0, face_terms ? nb : 0, face_terms ? nb : 0,
+                         conv ? nb : 0, conv ? nf : 0, conv ? nb : 0, conv ? nce : 0};
+  const double *dev[8];
   size_t need = 0;
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < 8; i++)
     if (len[i] > 0 && src[i] != nullptr && !is_device_ptr(src[i])) need += len[i];
   if (need > m->coef_stage.n && !m->coef_stage.alloc(need)) return -1;
   size_t off = 0;
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < 8; i++) {
     dev[i] = src[i];
     if (len[i] > 0 && src[i] != nullptr && !is_device_ptr(src[i])) {
       if (!CSB_CUDA(cudaMemcpyAsync(m->coef_stage.p + off, src[i], sizeof(double)*len[i],
@@ -401,10 +410,14 @@ int csb_matrix_compute_coeffs(csb_matrix_t *m, int iconvp, int idiffp, int ndirc
       off += len[i];
     }
   }
-  if (!launch_sym_coeffs_msr(m, idiffp, ndircp, thetap, relaxp, dev[3], dev[0], dev[1], dev[2],
-                             m->d_val.p, m->x_val.p)) return -1;
+  const bool ok = conv
+    ? launch_coeffs_msr(m, idiffp, ndircp, thetap, relaxp, dev[4], dev[3], dev[0], dev[5],
+                        dev[6], dev[1], dev[2], dev[7], m->d_val.p, m->x_val.p)
+    : launch_sym_coeffs_msr(m, idiffp, ndircp, thetap, relaxp, dev[3], dev[0], dev[1], dev[2],
+                            m->d_val.p, m->x_val.p);
+  if (!ok) return -1;
   if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return -1;   /* host inputs may go away */
-  m->symmetric = true;
+  m->symmetric = !conv;
   m->h_vals_valid = false;
   return 0;
 }

@@ -167,18 +167,24 @@ int  csb_matrix_set_mesh_association(csb_matrix_t      *m,
 int  csb_matrix_set_boundary_faces(csb_matrix_t *m, csb_lnum_t n_b_faces,
                                    const csb_lnum_t *b_face_cells);
 
-/* cs_matrix_compute_coeffs (src/alge/cs_matrix_building.cpp:1948-2283) for the symmetric scalar
-   case (iconvp = 0 -> _sym_coeffs_msr, :136-206): the MSR coefficients are computed in HBM
-   from the face viscosities i_visc[n_faces], b_visc[n_b_faces], the implicit boundary
-   coefficient cofbfp[n_b_faces] (cs_field_bc_coeffs_t::bf) and the unsteady term
-   rovsdt[n_rows]; relaxp < 1 scales the diagonal by 1/relaxp, ndircp <= 0 applies the
-   (1 + 1e-7) shift (:2243-2262).  Arrays may be host or device pointers.  Needs the mesh
-   association (the face of every MSR entry) and, for boundary terms, the boundary faces.
-   Bit-identical to the reference's CPU result: same per-cell summation order. */
+/* cs_matrix_compute_coeffs (src/alge/cs_matrix_building.cpp:1948-2283, same argument order
+   without the field pointer; bc_coeffs->b = coefbp, ->bf = cofbfp) for scalar variables: the
+   MSR coefficients are computed in HBM from per-face / per-cell arrays, which may be host or
+   device pointers:
+     iconvp = 0  symmetric diffusion matrix, _sym_coeffs_msr (:136-206); needs rovsdt[n_rows],
+                 i_visc[n_faces], b_visc / cofbfp[n_b_faces]
+     iconvp = 1  convection-diffusion, _coeffs_msr (:407-520): also i_massflux[n_faces],
+                 b_massflux / coefbp[n_b_faces], and xcpp[n_cols] when imucpp != 0
+   relaxp < 1 scales the diagonal by 1/relaxp, ndircp <= 0 applies the (1 + 1e-7) shift
+   (:2243-2262).  Needs the mesh association (face and face sign of every MSR entry) and, for
+   boundary terms, csb_matrix_set_boundary_faces.  Bit-identical to the reference's CPU
+   result: same per-cell summation order. */
 int  csb_matrix_compute_coeffs(csb_matrix_t *m, int iconvp, int idiffp, int ndircp,
-                               double thetap, double relaxp, const csb_real_t *cofbfp,
-                               const csb_real_t *rovsdt, const csb_real_t *i_visc,
-                               const csb_real_t *b_visc);
+                               double thetap, double relaxp, int imucpp,
+                               const csb_real_t *coefbp, const csb_real_t *cofbfp,
+                               const csb_real_t *rovsdt, const csb_real_t *i_massflux,
+                               const csb_real_t *b_massflux, const csb_real_t *i_visc,
+                               const csb_real_t *b_visc, const csb_real_t *xcpp);
 
 /* Copy of the MSR coefficients held in HBM (cs_matrix_get_msr_arrays, cs_matrix.cpp:6199,
    lends the host arrays; these live on the device).  Either pointer may be NULL. */

@@ -2581,3 +2581,71 @@ ora_matrix_compute_coeffs_sym(int n_rows, const int *row_index, const int *cell_
     for (int c_id = 0; c_id < n_rows; c_id++) da[c_id] *= epsi_p1;
   }
 }
+
+/*----------------------------------------------------------------------------
+ * Same for a convection-diffusion scalar (iconvp = 1, non-symmetric matrix):
+ *   _coeffs_msr<is_thermal> (src/alge/cs_matrix_building.cpp:407-520): upwind convective
+ *   fluxes from the face mass flux, sign of the face relative to the cell from the mesh
+ *   association; boundary faces add the convective / diffusive boundary terms in face order.
+ *   xcpp != NULL (imucpp != 0): convective part multiplied by Cp (temperature).
+ * cell_i_faces_sgn: +1 when the cell is the first cell of the face.
+ *----------------------------------------------------------------------------*/
+
+void
+ora_matrix_compute_coeffs(int n_rows, const int *row_index, const int *col_id,
+                          const int *cell_i_faces, const short *cell_i_faces_sgn,
+                          int n_b_faces, const int *b_face_cells,
+                          int iconvp, int idiffp, int ndircp, double thetap, double relaxp,
+                          const double *coefbp, const double *cofbfp, const double *rovsdt,
+                          const double *i_massflux, const double *b_massflux,
+                          const double *i_visc, const double *b_visc, const double *xcpp,
+                          double *da, double *ea)
+{
+  if (!iconvp) {
+    ora_matrix_compute_coeffs_sym(n_rows, row_index, cell_i_faces, n_b_faces, b_face_cells,
+                                  idiffp, ndircp, thetap, relaxp, cofbfp, rovsdt, i_visc,
+                                  b_visc, da, ea);
+    return;
+  }
+  const int is_thermal = (xcpp != NULL);
+  for (int c_id = 0; c_id < n_rows; c_id++) {
+    double _da = rovsdt[c_id];
+    for (int cidx = row_index[c_id]; cidx < row_index[c_id+1]; cidx++) {
+      const int f_id = cell_i_faces[cidx];
+      double _i_massflux = i_massflux[f_id];
+      if (cell_i_faces_sgn[cidx] > 0) {
+        double flui = 0.5*(_i_massflux - fabs(_i_massflux));
+        double cpi = (is_thermal) ? xcpp[c_id] : 1.0;
+        double xai = thetap*(cpi*flui - idiffp*i_visc[f_id]);
+        ea[cidx] = xai;
+        _da -= xai + (1.-thetap) * cpi * _i_massflux;
+      }
+      else {
+        double fluj = -0.5*(_i_massflux + fabs(_i_massflux));
+        double cpj = (is_thermal) ? xcpp[col_id[cidx]] : 1.0;
+        double xaj = thetap*(cpj*fluj - idiffp*i_visc[f_id]);
+        ea[cidx] = xaj;
+        _da -= xaj - (1.-thetap) * cpj * _i_massflux;
+      }
+    }
+    da[c_id] = _da;
+  }
+  for (int f_id = 0; f_id < n_b_faces; f_id++) {
+    int ii = b_face_cells[f_id];
+    double _b_massflux = b_massflux[f_id];
+    double flui = 0.5*(_b_massflux - fabs(_b_massflux));
+    double cpi = (is_thermal) ? xcpp[ii] : 1.0;
+    double bfac =          cpi *(  flui * thetap * (coefbp[f_id] - 1.)
+                                 - (1. - thetap) * _b_massflux)
+                  + idiffp * thetap * b_visc[f_id] * cofbfp[f_id];
+    da[ii] += bfac;
+  }
+  if (relaxp < 1) {
+    double rf = 1. / relaxp;
+    for (int i = 0; i < n_rows; i++) da[i] *= rf;
+  }
+  if (ndircp <= 0) {
+    const double epsi_p1 = 1. + 1.e-7;
+    for (int c_id = 0; c_id < n_rows; c_id++) da[c_id] *= epsi_p1;
+  }
+}

@@ -258,6 +258,21 @@ class Oracle:
             _dp(_f64(rovsdt)), _dp(_f64(i_visc)), _dp(_f64(b_visc)), _dp(da), _dp(ea))
         return da[:n], ea[:int(ri[-1])]
 
+    def matrix_compute_coeffs(self, s, b_face_cells, coefbp, cofbfp, rovsdt, i_massflux,
+                              b_massflux, i_visc, b_visc, xcpp=None, iconvp=1, idiffp=1,
+                              ndircp=1, thetap=1., relaxp=1.):
+        ri, ci, c2f, bfc = _i32(s.row_index), _i32(s.col_id), _i32(s.c2f), _i32(b_face_cells)
+        sgn = np.ascontiguousarray(s.c2f_sgn, dtype=np.int16)
+        n = len(ri) - 1
+        da, ea = np.zeros(max(n, 1)), np.zeros(max(int(ri[-1]), 1))
+        f = lambda a: None if a is None else _f64(a)
+        arrs = [f(a) for a in (coefbp, cofbfp, rovsdt, i_massflux, b_massflux, i_visc, b_visc, xcpp)]
+        self.lib.ora_matrix_compute_coeffs(
+            C.c_int(n), _ip(ri), _ip(ci), _ip(c2f), _sp(sgn), C.c_int(len(bfc)), _ip(bfc),
+            C.c_int(iconvp), C.c_int(idiffp), C.c_int(ndircp), C.c_double(thetap),
+            C.c_double(relaxp), *[_dp(a) for a in arrs], _dp(da), _dp(ea))
+        return da[:n], ea[:int(ri[-1])]
+
     def pairwise(self, level, ri, ci, d, xv):
         ri, ci, d, xv = _i32(ri), _i32(ci), _f64(d), _f64(xv)
         n = len(ri) - 1
@@ -514,6 +529,22 @@ class RefLib:
             _dp(_f64(b_visc)), _dp(d), _dp(x))
         if rc != 0:
             raise RuntimeError("csref_matrix_compute_coeffs_sym: system has no mesh")
+        return d[:s.n_rows], x[:s.nnz]
+
+    def matrix_compute_coeffs(self, h, s, b_face_cells, coefbp, cofbfp, rovsdt, i_massflux,
+                              b_massflux, i_visc, b_visc, xcpp=None, iconvp=1, idiffp=1,
+                              ndircp=1, thetap=1., relaxp=1.):
+        """cs_matrix_compute_coeffs, scalar cases, on the system's matrix (created with
+        symmetric=False when iconvp = 1); returns (d_val, x_val)."""
+        bfc = _i32(b_face_cells)
+        d, x = np.zeros(max(s.n_rows, 1)), np.zeros(max(s.nnz, 1))
+        f = lambda a: None if a is None else _f64(a)
+        arrs = [f(a) for a in (coefbp, cofbfp, rovsdt, i_massflux, b_massflux, i_visc, b_visc, xcpp)]
+        rc = self.lib.csref_matrix_compute_coeffs(
+            h, C.c_int(len(bfc)), _ip(bfc), C.c_int(iconvp), C.c_int(idiffp), C.c_int(ndircp),
+            C.c_double(thetap), C.c_double(relaxp), *[_dp(a) for a in arrs], _dp(d), _dp(x))
+        if rc != 0:
+            raise RuntimeError("csref_matrix_compute_coeffs: system has no mesh")
         return d[:s.n_rows], x[:s.nnz]
 
     def smoother(self, h, stype, rhs, n_max_iter, vx0=None):

@@ -511,7 +511,9 @@ csref_fcg_mgpc_solve(void *sys, const int *iopt, const double *dopt, int n_max_i
                              r_norm, rhs, vx, use_vx_ini, out);
 }
 
-/* cs_matrix_compute_coeffs, symmetric scalar case (iconvp = 0): the reference fills the MSR
+/* cs_matrix_compute_coeffs, scalar cases -- symmetric (iconvp = 0, _sym_coeffs_msr) and
+   convection-diffusion (iconvp = 1, _coeffs_msr<is_thermal>, :407-520; the system must have
+   been created non-symmetric): the reference fills the MSR
    coefficients of the system's matrix from face viscosities, the implicit boundary
    coefficient and the unsteady term (_sym_coeffs_msr, src/alge/cs_matrix_building.cpp:136-
    206; relaxation, the (1 + 1e-7) shift when there is no Dirichlet condition :2243-2262).
@@ -519,19 +521,24 @@ csref_fcg_mgpc_solve(void *sys, const int *iopt, const double *dopt, int n_max_i
    cs_glob_mesh_quantities) are set up from the system's face -> cell table.
    d_out[n_rows], x_out[nnz] receive the MSR coefficients. */
 int
-csref_matrix_compute_coeffs_sym(void          *sys,
-                                int            n_b_faces,
-                                const int     *b_face_cells,
-                                int            idiffp,
-                                int            ndircp,
-                                double         thetap,
-                                double         relaxp,
-                                const double  *cofbfp,
-                                const double  *rovsdt,
-                                const double  *i_visc,
-                                const double  *b_visc,
-                                double        *d_out,
-                                double        *x_out)
+csref_matrix_compute_coeffs(void          *sys,
+                            int            n_b_faces,
+                            const int     *b_face_cells,
+                            int            iconvp,
+                            int            idiffp,
+                            int            ndircp,
+                            double         thetap,
+                            double         relaxp,
+                            const double  *coefbp,
+                            const double  *cofbfp,
+                            const double  *rovsdt,
+                            const double  *i_massflux,
+                            const double  *b_massflux,
+                            const double  *i_visc,
+                            const double  *b_visc,
+                            const double  *xcpp,     /* NULL: imucpp = 0 */
+                            double        *d_out,
+                            double        *x_out)
 {
   ref_system *s = static_cast<ref_system *>(sys);
   cs_mesh_t *mesh = cs_glob_mesh;
@@ -559,9 +566,11 @@ csref_matrix_compute_coeffs_sym(void          *sys,
   cs_field_bc_coeffs_t bc;
   memset(&bc, 0, sizeof(bc));
   bc.bf = const_cast<cs_real_t *>(cofbfp);
+  bc.b = const_cast<cs_real_t *>(coefbp);
 
-  cs_matrix_compute_coeffs(s->m, nullptr, 0, idiffp, ndircp, thetap, relaxp, 0,
-                           &bc, rovsdt, nullptr, nullptr, i_visc, b_visc, nullptr);
+  cs_matrix_compute_coeffs(s->m, nullptr, iconvp, idiffp, ndircp, thetap, relaxp,
+                           (xcpp != nullptr) ? 1 : 0, &bc, rovsdt, i_massflux, b_massflux,
+                           i_visc, b_visc, xcpp);
 
   const cs_lnum_t *ri, *ci;
   const cs_real_t *d, *x;
@@ -569,6 +578,17 @@ csref_matrix_compute_coeffs_sym(void          *sys,
   memcpy(d_out, d, sizeof(double)*s->n_rows);
   memcpy(x_out, x, sizeof(double)*ri[s->n_rows]);
   return 0;
+}
+
+int
+csref_matrix_compute_coeffs_sym(void *sys, int n_b_faces, const int *b_face_cells, int idiffp,
+                                int ndircp, double thetap, double relaxp, const double *cofbfp,
+                                const double *rovsdt, const double *i_visc,
+                                const double *b_visc, double *d_out, double *x_out)
+{
+  return csref_matrix_compute_coeffs(sys, n_b_faces, b_face_cells, 0, idiffp, ndircp, thetap,
+                                     relaxp, nullptr, cofbfp, rovsdt, nullptr, nullptr, i_visc,
+                                     b_visc, nullptr, d_out, x_out);
 }
 
 /* Build the grid hierarchy with the reference's cs_grid_coarsen, following

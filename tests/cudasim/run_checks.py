@@ -284,7 +284,26 @@ def check_compute_coeffs(ora):
         m.compute_coeffs(g["rovsdt"], g["i_visc"], g["b_visc"], g["cofbfp"], **kw)
         d, x = m.get_coefficients()
         assert np.array_equal(d, g[f"{name}_d"]) and np.array_equal(x, g[f"{name}_x"]), name
-    m.destroy()
+    for name, kw in (("conv", dict()), ("conv_theta_relax", dict(ndircp=0, thetap=0.5, relaxp=0.7)),
+                     ("conv_only", dict(idiffp=0)), ("conv_thermal", dict(xcpp=g["xcpp"], thetap=0.5))):
+        m.compute_coeffs(g["rovsdt"], g["i_visc"], g["b_visc"], g["cofbfp"], iconvp=1,
+                         coefbp=g["coefbp"], i_massflux=g["i_massflux"],
+                         b_massflux=g["b_massflux"], **kw)
+        d, x = m.get_coefficients()
+        assert np.array_equal(d, g[f"{name}_d"]) and np.array_equal(x, g[f"{name}_x"]), name
+    # the non-symmetric matrix solves with BiCGStab straight from the device coefficients
+    m.compute_coeffs(1.0 + g["rovsdt"], g["i_visc"], g["b_visc"], g["cofbfp"], iconvp=1,
+                     coefbp=g["coefbp"], i_massflux=0.1 * g["i_massflux"],
+                     b_massflux=0.0 * g["b_massflux"])
+    d, x = m.get_coefficients()
+    rhs = np.sin(0.2 * np.arange(s.n_rows))
+    rn = float(np.linalg.norm(rhs))
+    c = csb.SlesIt(csb.SlesItType.BICGSTAB, 500)
+    r = c.solve(m, rhs, 1e-10, rn)
+    assert int(r["cvg"]) == 1
+    res = np.linalg.norm(rhs - ora.spmv(s.row_index, s.col_id, d, x, r["vx"][:s.n_rows]))
+    assert res <= 1.01e-10 * rn
+    c.destroy(); m.destroy()
 
 
 CHECKS = {"spmv_pcg": check_spmv_pcg, "compute_coeffs": check_compute_coeffs, "pairwise": check_pairwise, "galerkin": check_galerkin, "block3_jacobi": check_block3_jacobi, "general_pc": check_general_pc,

@@ -1,5 +1,6 @@
-"""Golden fixtures for the matrix coefficient build (cs_matrix_compute_coeffs, symmetric
-scalar case: _sym_coeffs_msr, cs_matrix_building.cpp:136-206, :2243-2262): MSR coefficients
+"""Golden fixtures for the matrix coefficient build (cs_matrix_compute_coeffs, scalar cases:
+symmetric _sym_coeffs_msr, cs_matrix_building.cpp:136-206, and convection-diffusion
+_coeffs_msr, :407-520; relaxation and diagonal shift :2243-2262): MSR coefficients
 computed by the reference's own compiled CPU code (oracle/_ref/libcsref.so) from seeded face
 viscosities / boundary coefficients on the N^3 cube:
 
@@ -20,12 +21,19 @@ OPTIONS = {"default": dict(), "no_dirichlet": dict(ndircp=0),
            "theta_relax": dict(thetap=0.5, relaxp=0.7), "no_diffusion": dict(idiffp=0)}
 
 
+CONV_OPTIONS = {"conv": dict(), "conv_theta_relax": dict(ndircp=0, thetap=0.5, relaxp=0.7),
+                "conv_only": dict(idiffp=0), "conv_thermal": dict(thermal=True, thetap=0.5)}
+
+
 def inputs(N, s):
     rng = np.random.default_rng(1234)
     bfc = cube_boundary_face_cells(N)
-    return dict(b_face_cells=bfc, i_visc=0.5 + rng.random(s.n_faces),
-                b_visc=0.5 + rng.random(len(bfc)), cofbfp=rng.random(len(bfc)),
-                rovsdt=1e-3 * rng.random(s.n_rows))
+    out = dict(b_face_cells=bfc, i_visc=0.5 + rng.random(s.n_faces),
+               b_visc=0.5 + rng.random(len(bfc)), cofbfp=rng.random(len(bfc)),
+               rovsdt=1e-3 * rng.random(s.n_rows))
+    out.update(i_massflux=rng.standard_normal(s.n_faces), b_massflux=rng.standard_normal(len(bfc)),
+               coefbp=rng.random(len(bfc)), xcpp=1000. + rng.random(s.n_rows))
+    return out
 
 
 def main():
@@ -37,6 +45,17 @@ def main():
         for name, kw in OPTIONS.items():
             d, x = ref.matrix_compute_coeffs_sym(h, s, out["b_face_cells"], out["cofbfp"],
                                                  out["rovsdt"], out["i_visc"], out["b_visc"], **kw)
+            out[f"{name}_d"] = d
+            out[f"{name}_x"] = x
+        ref.destroy(h)
+        h = ref.system(s, symmetric=False)
+        for name, kw in CONV_OPTIONS.items():
+            kw = dict(kw)
+            xcpp = out["xcpp"] if kw.pop("thermal", False) else None
+            d, x = ref.matrix_compute_coeffs(h, s, out["b_face_cells"], out["coefbp"],
+                                             out["cofbfp"], out["rovsdt"], out["i_massflux"],
+                                             out["b_massflux"], out["i_visc"], out["b_visc"],
+                                             xcpp=xcpp, **kw)
             out[f"{name}_d"] = d
             out[f"{name}_x"] = x
         ref.destroy(h)

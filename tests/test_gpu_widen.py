@@ -474,3 +474,38 @@ def test_matrix_compute_coeffs_large_device_inputs(csb, oracle):
     d0, x0 = oracle.matrix_compute_coeffs_sym(s.row_index, s.c2f, bfc, cb, ro, iv, bv, ndircp=0)
     assert np.array_equal(d, d0) and np.array_equal(x, x0)
     m.destroy()
+
+
+CONV_OPTIONS = {"conv": dict(), "conv_theta_relax": dict(ndircp=0, thetap=0.5, relaxp=0.7),
+                "conv_only": dict(idiffp=0), "conv_thermal": dict(thermal=True, thetap=0.5)}
+
+
+@pytest.mark.parametrize("N", [6, 10])
+def test_matrix_compute_coeffs_convection_bit_exact_vs_reference_golden(csb, oracle, N):
+    """iconvp = 1 (_coeffs_msr): upwind convection + diffusion, optional Cp weighting; the
+    non-symmetric matrix is then solved with BiCGStab on the device-resident coefficients."""
+    g = np.load(os.path.join(GOLD, f"coeffs_N{N}.npz"))
+    s = cube_poisson(N, "neumann")
+    m = csb.Matrix.from_system(s)
+    m.set_boundary_faces(g["b_face_cells"])
+    for name, kw in CONV_OPTIONS.items():
+        kw = dict(kw)
+        xcpp = g["xcpp"] if kw.pop("thermal", False) else None
+        m.compute_coeffs(g["rovsdt"], g["i_visc"], g["b_visc"], g["cofbfp"], iconvp=1,
+                         coefbp=g["coefbp"], i_massflux=g["i_massflux"],
+                         b_massflux=g["b_massflux"], xcpp=xcpp, **kw)
+        d, x = m.get_coefficients()
+        assert np.array_equal(d, g[f"{name}_d"]) and np.array_equal(x, g[f"{name}_x"]), name
+    # a diagonally dominant convection-diffusion system (small fluxes, unsteady term)
+    m.compute_coeffs(1.0 + g["rovsdt"], g["i_visc"], g["b_visc"], g["cofbfp"], iconvp=1,
+                     coefbp=g["coefbp"], i_massflux=0.1 * g["i_massflux"],
+                     b_massflux=0.0 * g["b_massflux"])
+    d, x = m.get_coefficients()
+    rhs = np.sin(0.2 * np.arange(s.n_rows))
+    r_norm = float(np.linalg.norm(rhs))
+    c = csb.SlesIt(csb.SlesItType.BICGSTAB, 500)
+    r = c.solve(m, rhs, 1e-10, r_norm)
+    assert int(r["cvg"]) == 1
+    res = np.linalg.norm(rhs - oracle.spmv(s.row_index, s.col_id, d, x, r["vx"][:s.n_rows]))
+    assert res <= 1.01e-10 * r_norm
+    c.destroy(); m.destroy()

@@ -457,3 +457,20 @@ def test_oracle_matrix_compute_coeffs_vs_reference_direct(oracle, reflib):
         b = reflib.matrix_compute_coeffs_sym(h, s, bfc, cb, ro, iv, bv, **kw)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     reflib.destroy(h)
+
+
+CONV_OPTIONS = {"conv": dict(), "conv_theta_relax": dict(ndircp=0, thetap=0.5, relaxp=0.7),
+                "conv_only": dict(idiffp=0), "conv_thermal": dict(thermal=True, thetap=0.5)}
+
+
+@pytest.mark.parametrize("N", [6, 10])
+def test_oracle_matrix_compute_coeffs_convection_matches_golden(oracle, N):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"coeffs_N{N}.npz"))
+    s = cube_poisson(N, "neumann")
+    for name, kw in CONV_OPTIONS.items():
+        kw = dict(kw)
+        xcpp = g["xcpp"] if kw.pop("thermal", False) else None
+        d, x = oracle.matrix_compute_coeffs(s, g["b_face_cells"], g["coefbp"], g["cofbfp"],
+                                            g["rovsdt"], g["i_massflux"], g["b_massflux"],
+                                            g["i_visc"], g["b_visc"], xcpp=xcpp, **kw)
+        assert np.array_equal(d, g[f"{name}_d"]) and np.array_equal(x, g[f"{name}_x"]), name
