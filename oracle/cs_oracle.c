@@ -2132,8 +2132,13 @@ ora_mg_cycle_pc(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt,
  *          (_multigrid_pc_tolerance_t :1473-1481)
  *----------------------------------------------------------------------------*/
 
+static int
+_k_cycle(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt, double trsh, int level,
+         double precision, double r_norm, const double *rhs, double *vx, int *n_equiv_iter);
+
 typedef struct {
-  int     kind;            /* 0 none, 1 poly, 2 multigrid */
+  int     kind;            /* 0 none, 1 poly, 2 multigrid V-cycle, 3 multigrid K-cycle */
+  double  trsh;            /* K-cycle threshold */
   int     n_rows;
   const int *row_index, *col_id;
   const double *d_val, *x_val;
@@ -2161,7 +2166,7 @@ static void
 _pc_apply(const ora_pc_t *pc, const double *x_in, double *x_out)
 {
   const int n = pc->n_rows;
-  if (pc->kind == 0 || (pc->kind == 2 && pc->mg->n_levels == 1)) {
+  if (pc->kind == 0 || (pc->kind >= 2 && pc->mg->n_levels == 1)) {
     for (int ii = 0; ii < n; ii++) x_out[ii] = x_in[ii];
   }
   else if (pc->kind == 1) {
@@ -2171,6 +2176,10 @@ _pc_apply(const ora_pc_t *pc, const double *x_in, double *x_out)
       for (int ii = 0; ii < n; ii++)
         x_out[ii] = (x_in[ii] - pc->w[ii]) * pc->ad_inv[ii];
     }
+  }
+  else if (pc->kind == 3) {
+    int n_equiv = 0;
+    _k_cycle(pc->mg, pc->opt, pc->trsh, 0, pc->precision, pc->r_norm, x_in, x_out, &n_equiv);
   }
   else
     ora_mg_cycle_pc(pc->mg, pc->opt, pc->precision, pc->r_norm, x_in, x_out, 0, NULL);
@@ -2648,4 +2657,141 @@ ora_matrix_compute_coeffs(int n_rows, const int *row_index, const int *col_id,
     const double epsi_p1 = 1. + 1.e-7;
     for (int c_id = 0; c_id < n_rows; c_id++) da[c_id] *= epsi_p1;
   }
+}
+
+/*----------------------------------------------------------------------------
+ * K-cycle (Notay): _multigrid_k_cycle (src/alge/cs_multigrid.cpp:4051-4480), the single
+ * cycle form used as a preconditioner (n_max_cycles == 1: no fine-level convergence test).
+ * At each level: pre-smoothing from zero, residual, restriction; the coarser problem is
+ * solved by the coarse solver (next level coarsest) or by one or two recursive K-cycles
+ * combined by a 2-step Krylov (FCG-like) acceleration -- the second step is skipped when the
+ * first reduced the residual norm below trsh (k_cycle_threshold, 0.25); then prolongation
+ * (overwrite form, cs_grid.cpp:9180-9190), new residual, post-smoothing from zero, sum.
+ * Dot products as _dot_xy_yz / _dot_xx_yy / _dot_xu_xv_xw (:2792-2901).
+ *----------------------------------------------------------------------------*/
+
+static int
+_k_cycle(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt, double trsh, int level,
+         double precision, double r_norm, const double *rhs, double *vx, int *n_equiv_iter)
+{
+  const int coarsest_level = mg->n_levels - 1;
+  const ora_grid_t *f = mg->grids[level];
+  const ora_grid_t *c = mg->grids[level+1];
+  const int f_n = f->n_rows, c_n = c->n_rows;
+  const double denom_n_g_rows_0 = 1.0 / mg->grids[0]->n_rows;
+  double sout[4];
+  int cvg = ORA_ITERATING;
+  int n_iter = 0;
+
+  double *wf = malloc(sizeof(double)*(4*(size_t)f_n + 1));
+  double *rt_lv = wf, *rb_lv = wf + f_n, *z1_lv = wf + 2*(size_t)f_n, *z2_lv = wf + 3*(size_t)f_n;
+  double *wc = malloc(sizeof(double)*(6*(size_t)c_n + 1));
+  double *vx_lv1 = wc, *rhs_lv1 = wc + c_n, *v_lv1 = wc + 2*(size_t)c_n,
+         *rt_lv1 = wc + 3*(size_t)c_n, *vx2_lv1 = wc + 4*(size_t)c_n, *w_lv1 = wc + 5*(size_t)c_n;
+
+  /* Pre-smoothing */
+  int c_cvg = _mg_level_solve(opt->type[0], opt->precision_mult[0], f, opt->n_max_iter[0],
+                              precision, r_norm, rhs, vx, 0, sout);
+  n_iter = (int)sout[0];
+  *n_equiv_iter += n_iter * f_n * denom_n_g_rows_0;
+
+  ora_spmv_msr(f_n, f->row_index, f->col_id, f->d_val, f->x_val, 0, vx, rt_lv);
+  for (int ii = 0; ii < f_n; ii++) rt_lv[ii] = rhs[ii] - rt_lv[ii];
+
+  if (c_cvg < ORA_BREAKDOWN) { free(wf); free(wc); return c_cvg; }
+
+  ora_restrict(f_n, c_n, c->coarse_row, rt_lv, rhs_lv1);
+
+  if (level == coarsest_level - 1) {
+    cvg = _mg_level_solve(opt->type[2], opt->precision_mult[2], c, opt->n_max_iter[2],
+                          precision, r_norm, rhs_lv1, vx_lv1, 0, sout);
+    n_iter = (int)sout[0];
+    *n_equiv_iter += n_iter * c_n * denom_n_g_rows_0;
+  }
+  else {
+    _k_cycle(mg, opt, trsh, level + 1, precision, r_norm, rhs_lv1, vx_lv1, &n_iter);
+    ora_spmv_msr(c_n, c->row_index, c->col_id, c->d_val, c->x_val, 0, vx_lv1, v_lv1);
+
+    double rho1 = 0, alpha1 = 0;
+    ora_dot_xy_yz(c_n, v_lv1, vx_lv1, rhs_lv1, &rho1, &alpha1);
+    const double ar1 = alpha1 / rho1;
+    for (int i = 0; i < c_n; i++) rt_lv1[i] = rhs_lv1[i] - ar1 * v_lv1[i];
+
+    double rt_lv1_norm = 1.0, r_lv1_norm = 0.0;
+    if (trsh > 0) {
+      rt_lv1_norm = ora_dot_xx(c_n, rt_lv1);
+      r_lv1_norm = ora_dot_xx(c_n, rhs_lv1);
+    }
+
+    if (rt_lv1_norm < trsh * trsh * r_lv1_norm) {
+      for (int i = 0; i < c_n; i++) vx_lv1[i] = ar1 * vx_lv1[i];
+    }
+    else {
+      for (int i = 0; i < c_n; i++) w_lv1[i] = 0.0;
+      _k_cycle(mg, opt, trsh, level + 1, precision, r_norm, rt_lv1, vx2_lv1, &n_iter);
+      ora_spmv_msr(c_n, c->row_index, c->col_id, c->d_val, c->x_val, 0, vx2_lv1, w_lv1);
+
+      double gamma = 0, beta = 0, alpha2 = 0;
+      ora_dot_xy_yz(c_n, v_lv1, vx2_lv1, w_lv1, &gamma, &beta);
+      alpha2 = ora_dot(c_n, vx2_lv1, rt_lv1);
+      const double rho2 = beta - (gamma * gamma) / rho1;
+      const double ar2 = alpha2 / rho2;
+      const double ar1_ar2 = ar1 - (gamma / rho1) * ar2;
+      for (int i = 0; i < c_n; i++)
+        vx_lv1[i] = ar1_ar2 * vx_lv1[i] + ar2 * vx2_lv1[i];
+    }
+  }
+
+  /* Ascent */
+  for (int ii = 0; ii < f_n; ii++) z2_lv[ii] = 0.0;
+  for (int ii = 0; ii < f_n; ii++) {
+    int ic = c->coarse_row[ii];
+    z1_lv[ii] = (ic >= 0) ? vx_lv1[ic] : 0;
+  }
+  ora_spmv_msr(f_n, f->row_index, f->col_id, f->d_val, f->x_val, 0, z1_lv, rb_lv);
+  for (int ii = 0; ii < f_n; ii++) rb_lv[ii] = rt_lv[ii] - rb_lv[ii];
+
+  cvg = _mg_level_solve(opt->type[1], opt->precision_mult[1], f, opt->n_max_iter[1],
+                        precision, r_norm, rb_lv, z2_lv, 1, sout);
+  n_iter = (int)sout[0];
+  *n_equiv_iter += n_iter * f_n * denom_n_g_rows_0;
+
+  for (int ii = 0; ii < f_n; ii++) vx[ii] += z1_lv[ii] + z2_lv[ii];
+
+  free(wf); free(wc);
+  return cvg;
+}
+
+/* One K-cycle from rhs (cs_multigrid_solve, CS_MULTIGRID_K_CYCLE, n_max_cycles 1: :5513-5533).
+   A one-level hierarchy cannot cycle: returns -100.  out[0] = n_equiv_iter. */
+int
+ora_mg_k_cycle(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt, double k_cycle_threshold,
+               double precision, double r_norm, const double *rhs, double *vx, double *out)
+{
+  if (mg->n_levels < 2) return -100;
+  int n_equiv_iter = 0;
+  int cvg = _k_cycle(mg, opt, k_cycle_threshold, 0, precision, r_norm, rhs, vx, &n_equiv_iter);
+  if (out != NULL) out[0] = n_equiv_iter;
+  return cvg;
+}
+
+/* FCG (solver 1) or single-reduction PCG (0) preconditioned by one K-cycle
+   (cs_multigrid_pc_create(CS_MULTIGRID_K_CYCLE), src/alge/cs_multigrid.cpp:1642-1655). */
+int
+ora_it_kpc(int solver, const ora_mg_t *mg, const ora_mg_pc_opt_t *opt, double k_cycle_threshold,
+           int n_max_iter, double precision, double r_norm,
+           const double *rhs, double *vx, int use_vx_ini,
+           double *out, double *history, int history_size)
+{
+  const ora_grid_t *g = mg->grids[0];
+  ora_pc_t pc;
+  memset(&pc, 0, sizeof(pc));
+  pc.kind = 3; pc.trsh = k_cycle_threshold;
+  pc.mg = mg; pc.opt = opt; pc.precision = precision; pc.r_norm = r_norm;
+  _pc_init_matrix(&pc, g->n_rows, g->row_index, g->col_id, g->d_val, g->x_val);
+  if (solver == 1)
+    return _fcg_pc(&pc, n_max_iter, precision, r_norm, rhs, vx, use_vx_ini,
+                   out, history, history_size);
+  return _pcg_sr_pc(&pc, n_max_iter, precision, r_norm, rhs, vx, use_vx_ini,
+                    out, history, history_size);
 }

@@ -387,6 +387,36 @@ class Oracle:
         return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], initial_residual=out[2],
                     history=hist[:int(out[3])].copy(), vx=vx)
 
+    def mg_k_cycle(self, mg, rhs, precision, r_norm, types=(SLES_JACOBI, SLES_JACOBI, SLES_PCG),
+                   n_max_iter=(2, 2, 500), precision_mult=(-1., -1., 10.), trsh=0.25):
+        rhs = _f64(rhs)
+        vx = np.zeros(len(rhs))
+        opt = self._pc_opt(types, n_max_iter, precision_mult)
+        out = np.zeros(4)
+        self.lib.ora_mg_k_cycle.argtypes = [C.POINTER(OraMg), C.POINTER(OraMgPcOpt), C.c_double,
+                                            C.c_double, C.c_double, c_dbl_p, c_dbl_p, c_dbl_p]
+        cvg = self.lib.ora_mg_k_cycle(mg, C.byref(opt), trsh, precision, r_norm, _dp(rhs),
+                                      _dp(vx), _dp(out))
+        return dict(cvg=cvg, n_iter=int(out[0]), vx=vx)
+
+    def it_kpc(self, solver, mg, rhs, n_max_iter, precision, r_norm,
+               types=(SLES_JACOBI, SLES_JACOBI, SLES_PCG), mg_n_max_iter=(2, 2, 500),
+               precision_mult=(-1., -1., 10.), trsh=0.25, vx0=None):
+        """FCG (1) / PCG (0) preconditioned by one K-cycle."""
+        rhs = _f64(rhs)
+        vx = np.zeros(len(rhs)) if vx0 is None else _f64(vx0).copy()
+        opt = self._pc_opt(types, mg_n_max_iter, precision_mult)
+        out = np.zeros(4)
+        hist = np.zeros(n_max_iter + 8)
+        self.lib.ora_it_kpc.argtypes = [C.c_int, C.POINTER(OraMg), C.POINTER(OraMgPcOpt),
+                                        C.c_double, C.c_int, C.c_double, C.c_double, c_dbl_p,
+                                        c_dbl_p, C.c_int, c_dbl_p, c_dbl_p, C.c_int]
+        cvg = self.lib.ora_it_kpc(solver, mg, C.byref(opt), trsh, n_max_iter, precision, r_norm,
+                                  _dp(rhs), _dp(vx), 0 if vx0 is None else 1, _dp(out),
+                                  _dp(hist), len(hist))
+        return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], initial_residual=out[2],
+                    history=hist[:int(out[3])].copy(), vx=vx)
+
     def fcg_mgpc(self, mg, rhs, n_max_iter, precision, r_norm,
                  types=(SLES_RJ3, SLES_RJ3, SLES_PCG), mg_n_max_iter=(3, 3, 500),
                  precision_mult=(-1., -1., 1.), vx0=None):
@@ -503,12 +533,12 @@ class RefLib:
     def multigrid(self, h, rhs, precision, r_norm, n_max_cycles=100, n_max_iter=(2, 10, 500),
                   types=(0, 0, 0), poly_degree=(0, 0, 0), precision_mult=(1., 1., 1.),
                   aggregation_limit=3, coarsening_type=0, n_levels_max=25, n_g_rows_min=30,
-                  p0p1_relax=0.95, vx0=None, verbosity=0):
+                  p0p1_relax=0.95, vx0=None, verbosity=0, mg_type=0):
         rhs = _f64(rhs)
         vx = np.zeros(len(rhs)) if vx0 is None else _f64(vx0).copy()
         iopt = np.array(list(types) + [n_max_cycles] + list(n_max_iter) + list(poly_degree)
-                        + [aggregation_limit, coarsening_type, n_levels_max, n_g_rows_min],
-                        dtype=np.int32)
+                        + [aggregation_limit, coarsening_type, n_levels_max, n_g_rows_min,
+                           mg_type], dtype=np.int32)
         dopt = np.array(list(precision_mult) + [p0p1_relax], dtype=np.float64)
         out = np.zeros(4)
         cvg = self.lib.csref_multigrid_solve(h, _ip(iopt), _dp(dopt), C.c_double(precision),
@@ -563,12 +593,12 @@ class RefLib:
     def it_mgpc(self, h, solver, rhs, n_max_iter, precision, r_norm, types=(16, 16, 0),
                 mg_n_max_iter=(3, 3, 500), poly_degree=(0, 0, 0),
                 precision_mult=(-1., -1., 1.), aggregation_limit=3, coarsening_type=0,
-                n_levels_max=25, n_g_rows_min=30, p0p1_relax=0.95, vx0=None):
+                n_levels_max=25, n_g_rows_min=30, p0p1_relax=0.95, vx0=None, mg_type=0):
         rhs = _f64(rhs)
         vx = np.zeros(len(rhs)) if vx0 is None else _f64(vx0).copy()
         iopt = np.array(list(types) + [1] + list(mg_n_max_iter) + list(poly_degree)
-                        + [aggregation_limit, coarsening_type, n_levels_max, n_g_rows_min],
-                        dtype=np.int32)
+                        + [aggregation_limit, coarsening_type, n_levels_max, n_g_rows_min,
+                           mg_type], dtype=np.int32)
         dopt = np.array(list(precision_mult) + [p0p1_relax], dtype=np.float64)
         out = np.zeros(5)
         cvg = self.lib.csref_it_mgpc_solve(h, C.c_int(solver), _ip(iopt), _dp(dopt), C.c_int(n_max_iter),

@@ -364,7 +364,8 @@ csref_sles_it_solve(void          *sys,
 /* cs_multigrid V-cycle solve (solver mode).
    iopt: [0..2] descent/ascent/coarse solver type, [3] n_max_cycles,
          [4..6] n_max_iter, [7..9] poly_degree, [10] aggregation_limit,
-         [11] coarsening_type, [12] n_max_levels, [13] min_g_rows
+         [11] coarsening_type, [12] n_max_levels, [13] min_g_rows,
+         [14] cs_multigrid_type_t (0 V-cycle, 1 K-cycle)
    dopt: [0..2] precision_mult, [3] p0p1_relax
    out : [0] n_equiv_iter, [1] residual, [2] setup s, [3] solve s */
 int
@@ -380,7 +381,7 @@ csref_multigrid_solve(void          *sys,
                       double        *out)
 {
   ref_system *s = static_cast<ref_system *>(sys);
-  cs_multigrid_t *mg = cs_multigrid_create(CS_MULTIGRID_V_CYCLE, nullptr);
+  cs_multigrid_t *mg = cs_multigrid_create((cs_multigrid_type_t)iopt[14], nullptr);
   cs_multigrid_set_solver_options(mg,
                                   (cs_sles_it_type_t)iopt[0],
                                   (cs_sles_it_type_t)iopt[1],
@@ -467,7 +468,7 @@ csref_it_mgpc_solve(void          *sys,
   ref_system *s = static_cast<ref_system *>(sys);
   cs_sles_it_t *c = cs_sles_it_create((cs_sles_it_type_t)solver_type, -1,
                                       n_max_iter, false);
-  cs_sles_pc_t *pc = cs_multigrid_pc_create(CS_MULTIGRID_V_CYCLE);
+  cs_sles_pc_t *pc = cs_multigrid_pc_create((cs_multigrid_type_t)iopt[14]);
   cs_multigrid_t *mg = (cs_multigrid_t *)cs_sles_pc_get_context(pc);
   cs_multigrid_set_solver_options(mg,
                                   (cs_sles_it_type_t)iopt[0],
