@@ -693,9 +693,10 @@ class Multigrid(_SolverBase):
 
     _solve_name = "csb_multigrid_solve"
 
-    def __init__(self, pc=False):
+    def __init__(self, pc=False, mg_type=0):
+        """mg_type: 0 V-cycle, 1 K-cycle (cs_multigrid_type_t)."""
         L = load_library()
-        self._h = L.csb_multigrid_pc_create(0) if pc else L.csb_multigrid_create(0)
+        self._h = L.csb_multigrid_pc_create(mg_type) if pc else L.csb_multigrid_create(mg_type)
         if not self._h:
             _err("csb_multigrid_create")
 

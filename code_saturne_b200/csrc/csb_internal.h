@@ -446,6 +446,12 @@ bool launch_pcg_pc_update_first(int n, ItState *st, const double *dk, const doub
 bool launch_pcg_pc_update(int n, ItState *st, const double *gk, const double *sk, double *dk,
                           double *zk, double *rk, double *vx);
 
+/* K-cycle vector steps (cs_multigrid.cpp:4300-4470): mode 0 y = b - a*x, 1 y = a*y,
+   2 y = a*y + c*x, 3 y += x + b; overwrite-form prolongation (cs_grid.cpp:9180-9190) */
+bool launch_kc_vec(int mode, int n, double a, double c, const double *x, const double *b,
+                   double *y);
+bool launch_prolong_set(int f_n_rows, const int *coarse_row, const double *c_var, double *f_var);
+
 /* FCG with a general preconditioner, kernel per phase (cs_sles_it.cpp:832-985) */
 bool launch_fcg_init(int n, ItState *st, const double *rhs, double *vx, double *rk,
                      double *qk, bool have_residual);

@@ -1987,6 +1987,62 @@ bool launch_copy_gated(int n, const double *src, double *dst, const MgState *gat
   return post_launch("copy_gated");
 }
 
+/*--------------------------------------------------------------------------
+ * K-cycle vector steps (_multigrid_k_cycle, src/alge/cs_multigrid.cpp:4300-4470)
+ *--------------------------------------------------------------------------*/
+
+namespace {
+
+/* mode 0: y = b - a*x (:4320)   1: y = a*y (:4336)   2: y = a*y + c*x (:4379)
+   3: y += x + b (:4460, vx += z1 + z2) */
+template <int MODE>
+__global__ void __launch_bounds__(TPB)
+k_kc_vec(int n, double a, double c, const double *__restrict__ x,
+         const double *__restrict__ b, double *__restrict__ y)
+{
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    if (MODE == 0) y[i] = b[i] - a * x[i];
+    else if (MODE == 1) y[i] = a * y[i];
+    else if (MODE == 2) y[i] = a * y[i] + c * x[i];
+    else y[i] += x[i] + b[i];
+  }
+}
+
+/* cs_grid_prolong_row_var, overwrite form (cs_grid.cpp:9180-9190) */
+__global__ void __launch_bounds__(TPB)
+k_prolong_set(int f_n_rows, const int *__restrict__ coarse_row,
+              const double *__restrict__ c_var, double *__restrict__ f_var)
+{
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < f_n_rows; i += gridDim.x*TPB) {
+    const int ic = coarse_row[i];
+    f_var[i] = (ic >= 0) ? c_var[ic] : 0.;
+  }
+}
+
+} // anonymous namespace
+
+bool launch_kc_vec(int mode, int n, double a, double c, const double *x, const double *b,
+                   double *y)
+{
+  if (n < 1) return true;
+  const int g = vec_grid(n);
+  cudaStream_t st = ctx().stream;
+  switch (mode) {
+  case 0: k_kc_vec<0><<<g, TPB, 0, st>>>(n, a, c, x, b, y); break;
+  case 1: k_kc_vec<1><<<g, TPB, 0, st>>>(n, a, c, x, b, y); break;
+  case 2: k_kc_vec<2><<<g, TPB, 0, st>>>(n, a, c, x, b, y); break;
+  default: k_kc_vec<3><<<g, TPB, 0, st>>>(n, a, c, x, b, y); break;
+  }
+  return post_launch("kc_vec");
+}
+
+bool launch_prolong_set(int f_n_rows, const int *coarse_row, const double *c_var, double *f_var)
+{
+  if (f_n_rows < 1) return true;
+  k_prolong_set<<<vec_grid(f_n_rows*4), TPB, 0, ctx().stream>>>(f_n_rows, coarse_row, c_var, f_var);
+  return post_launch("prolong_set");
+}
+
 bool launch_mg_accum_n(MgState *mg, int n_iter, int n_rows, double denom_n_g_rows_0)
 {
   k_mg_accum_n<<<1, 1, 0, ctx().stream>>>(mg, n_iter, n_rows, denom_n_g_rows_0);

@@ -390,6 +390,7 @@ bool bicgstab_enqueue(const csb_matrix_t *m, ItState *st, const double *ad_inv,
 bool mg_cycle_pc_enqueue(csb_multigrid_t *mg, double precision, double r_norm,
                          const double *rhs_d, double *vx_d, bool vx_ini_nonzero);
 int  mg_n_levels(const csb_multigrid_t *mg);
+bool mg_is_k_cycle(const csb_multigrid_t *mg);
 MgState *mg_gate(csb_multigrid_t *mg);
 
 /* x_out = M^-1 x_in for the general preconditioners of cs_sles_it:
@@ -468,7 +469,8 @@ bool fcg_pc_enqueue(csb_sles_it_t *c, const csb_matrix_t *a, double precision, d
   if (!launch_fcg_init(n, st, rhs, vx, rk, qk, vx_ini_nonzero)) return false;
   if (mgpc && !launch_mg_state_init(mg_gate(c->pc_mg), precision, r_norm, 1)) return false;
 
-  const int poll = mgpc ? 2 : 16;
+  /* the K-cycle reads reductions back on the host: never run it past convergence */
+  const int poll = (mgpc && mg_is_k_cycle(c->pc_mg)) ? 1 : (mgpc ? 2 : 16);
   for (int it = 0; it <= c->n_max_iter; it++) {
     if (!pc_apply_enqueue(c, a, precision, r_norm, rk, vk)) return false;
     SpmvArgs sa;
@@ -516,7 +518,7 @@ bool pcg_pc_enqueue(csb_sles_it_t *c, const csb_matrix_t *a, double precision, d
   if (mgpc && !launch_gate_from_it(mg_gate(c->pc_mg), st)) return false;
 
   sa.x = gk; sa.y = sk; sa.phase = 1;
-  const int poll = mgpc ? 2 : 16;
+  const int poll = (mgpc && mg_is_k_cycle(c->pc_mg)) ? 1 : (mgpc ? 2 : 16);
   for (int it = 1; ; it++) {
     if (!pc_apply_enqueue(c, a, precision, r_norm, rk, gk)) return false;
     if (!launch_spmv(EPI_PCG_DOT3, sa)) return false;
@@ -881,6 +883,9 @@ struct MgLevel {
   /* solve data */
   DevBuf<double>      ad_inv, rhs, vx;
   DevBuf<double>      l1_inv;                     /* L1 Jacobi smoother only */
+  DevBuf<double>      kwork;                      /* K-cycle: the 10 vectors of this level
+                                                     (mgd->rhs_vx[level*10 + k], cs_multigrid.cpp:1950) */
+  size_t              kstride = 0;
   /* geometry of this level used to coarsen it (level > 0; level 0 uses the
      matrix's mesh association) */
   DevBuf<int>         cell_face;
@@ -908,6 +913,7 @@ struct _csb_multigrid_t {
   int     n_levels_max = 25;
   unsigned long long n_g_rows_min = 30;
   double  p0p1_relax = 0.95;
+  double  k_cycle_threshold = 0.;      /* cs_multigrid.cpp:4707, :4724 */
   int     n_blocks = 1;
   csb_sles_it_type_t solver_type[3] = {CSB_SLES_PCG, CSB_SLES_PCG, CSB_SLES_PCG};
   int     n_max_cycles = 100;
@@ -954,13 +960,15 @@ _csb_sles_it_t::~_csb_sles_it_t()
 namespace {
 
 int mg_n_levels(const csb_multigrid_t *mg) { return (int)mg->levels.size(); }
+bool mg_is_k_cycle(const csb_multigrid_t *mg) { return mg->type == CSB_MULTIGRID_K_CYCLE; }
 MgState *mg_gate(csb_multigrid_t *mg) { return mg->mg_state.p; }
 
 /* One level's descent (which = 0) or ascent (1) smoother of the single-cycle form, as
    _multigrid_setup_sles builds it (cs_multigrid.cpp:2150-2175): a cs_multigrid_smoother
    when precision_mult < 0 and the type is one, cs_sles_it PCG + Jacobi otherwise. */
 bool mg_level_smooth(csb_multigrid_t *mg, int which, int level, const double *rhs_lv,
-                     double *vx_lv, bool ini, double precision, double r_norm)
+                     double *vx_lv, bool ini, double precision, double r_norm,
+                     bool count = true)   /* false: not part of n_equiv_iter */
 {
   MgLevel *f = mg->levels[level];
   MgState *ms = mg->mg_state.p;
@@ -973,10 +981,109 @@ bool mg_level_smooth(csb_multigrid_t *mg, int which, int level, const double *rh
            && launch_mg_accum_iter(ms, st, level, ratio, 0);
   }
   const double *inv = (type == CSB_SLES_L1_JACOBI) ? f->l1_inv.p : f->ad_inv.p;
-  return smoother_enqueue(f->m, type, mg->n_max_iter[which], inv, rhs_lv, vx_lv, ini,
-                          mg->aux.p, ms)
-         && launch_mg_accum_n(ms, smoother_plan(type, mg->n_max_iter[which]).n_iter,
+  if (!smoother_enqueue(f->m, type, mg->n_max_iter[which], inv, rhs_lv, vx_lv, ini,
+                        mg->aux.p, ms)) return false;
+  return !count || launch_mg_accum_n(ms, smoother_plan(type, mg->n_max_iter[which]).n_iter,
                               f->m->n_rows, 1.0 / (double)mg->levels[0]->m->n_rows);
+}
+
+/* (x.x, x.y, y.z) -- or x.y / x.x alone -- on the device, result read back: the K-cycle's
+   inner Krylov coefficients decide on the host whether a second coarse visit is needed */
+bool dots_to_host(int n, const double *x, const double *y, const double *z, int mode,
+                  double r[3])
+{
+  Context &c = ctx();
+  if (!launch_dot(n, x, y, z, mode)) return false;
+  if (!CSB_CUDA(cudaMemcpyAsync(c.red_out_h, c.red_out, 3*sizeof(double),
+                                cudaMemcpyDeviceToHost, c.stream))) return false;
+  if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return false;
+  r[0] = c.red_out_h[0]; r[1] = c.red_out_h[1]; r[2] = c.red_out_h[2];
+  return true;
+}
+
+/* _multigrid_k_cycle (cs_multigrid.cpp:4051-4480), single-cycle form: pre-smoothing from
+   zero, residual, restriction; next level solved by the coarse solver, or by one or two
+   recursive K-cycles combined by two steps of a Krylov acceleration (the second one skipped
+   when ||rt|| < trsh ||r||); overwrite prolongation, residual, post-smoothing from zero, sum.
+   Kernel per phase; the three reductions of a level visit come back to the host, which
+   takes the reference's branch. */
+bool k_cycle_enqueue(csb_multigrid_t *mg, int level, double precision, double r_norm,
+                     const double *rhs, double *vx)
+{
+  const int coarsest = (int)mg->levels.size() - 1;
+  MgLevel *f = mg->levels[level], *cl = mg->levels[level+1];
+  const csb_matrix_t *fm = f->m, *cm = cl->m;
+  const int f_n = fm->n_rows, c_n = cm->n_rows;
+  MgState *ms = mg->mg_state.p;
+  const double trsh = mg->k_cycle_threshold;
+  /* slots of mgd->rhs_vx (cs_multigrid.cpp:4192, :4262-4263, :4311-4312, :4345-4346, :4396-4398) */
+  double *rt_lv = f->kwork.p, *rb_lv = rt_lv + f->kstride, *z1_lv = rt_lv + 2*f->kstride,
+         *z2_lv = rt_lv + 3*f->kstride;
+  double *vx_lv1 = cl->kwork.p + 4*cl->kstride, *rhs_lv1 = cl->kwork.p + 5*cl->kstride,
+         *v_lv1 = cl->kwork.p + 6*cl->kstride, *rt_lv1 = cl->kwork.p + 7*cl->kstride,
+         *vx2_lv1 = cl->kwork.p + 8*cl->kstride, *w_lv1 = cl->kwork.p + 9*cl->kstride;
+
+  /* only the level-0 visit counts in n_equiv_iter: deeper visits add to a local of the
+     recursion in the reference (:4281-4282) */
+  if (!mg_level_smooth(mg, 0, level, rhs, vx, false, precision, r_norm, level == 0))
+    return false;
+  SpmvArgs sa;
+  sa.m = fm; sa.x = vx; sa.y = rt_lv; sa.b = rhs;
+  if (!launch_spmv(EPI_RESIDUAL, sa)) return false;
+  if (!launch_restrict(c_n, f->c_f_row_index.p, f->c_f_row_ids.p, rt_lv, rhs_lv1, nullptr))
+    return false;
+
+  if (level == coarsest - 1) {
+    ItState *st = mg->it_states.p + 2*coarsest;
+    if (!pcg_enqueue(cm, st, ms, cl->ad_inv.p, precision*mg->precision_mult[2], r_norm,
+                     mg->n_max_iter[2], rhs_lv1, vx_lv1, false, true, mg->aux.p, nullptr))
+      return false;
+    if (level == 0
+        && !launch_mg_accum_iter(ms, st, coarsest,
+                                 (double)c_n / (double)mg->levels[0]->m->n_rows, 0)) return false;
+  }
+  else {
+    if (!k_cycle_enqueue(mg, level + 1, precision, r_norm, rhs_lv1, vx_lv1)) return false;
+    SpmvArgs sc;
+    sc.m = cm; sc.x = vx_lv1; sc.y = v_lv1;
+    if (!launch_spmv(EPI_STORE, sc)) return false;
+    double r[3];
+    if (!dots_to_host(c_n, v_lv1, vx_lv1, rhs_lv1, 2, r)) return false;   /* _dot_xy_yz */
+    const double rho1 = r[1], alpha1 = r[2];
+    const double ar1 = alpha1 / rho1;
+    if (!launch_kc_vec(0, c_n, ar1, 0., v_lv1, rhs_lv1, rt_lv1)) return false;
+    double rt_lv1_norm = 1.0, r_lv1_norm = 0.0;
+    if (trsh > 0) {                                                         /* _dot_xx_yy */
+      if (!dots_to_host(c_n, rt_lv1, nullptr, nullptr, 1, r)) return false;
+      rt_lv1_norm = r[0];
+      if (!dots_to_host(c_n, rhs_lv1, nullptr, nullptr, 1, r)) return false;
+      r_lv1_norm = r[0];
+    }
+    if (rt_lv1_norm < trsh * trsh * r_lv1_norm) {
+      if (!launch_kc_vec(1, c_n, ar1, 0., nullptr, nullptr, vx_lv1)) return false;
+    }
+    else {
+      if (!k_cycle_enqueue(mg, level + 1, precision, r_norm, rt_lv1, vx2_lv1)) return false;
+      sc.x = vx2_lv1; sc.y = w_lv1;
+      if (!launch_spmv(EPI_STORE, sc)) return false;
+      if (!dots_to_host(c_n, v_lv1, vx2_lv1, w_lv1, 2, r)) return false;   /* _dot_xu_xv_xw */
+      const double gamma = r[1], beta = r[2];
+      if (!dots_to_host(c_n, vx2_lv1, rt_lv1, nullptr, 0, r)) return false;
+      const double alpha2 = r[0];
+      const double rho2 = beta - (gamma * gamma) / rho1;
+      const double ar2 = alpha2 / rho2;
+      const double ar1_ar2 = ar1 - (gamma / rho1) * ar2;
+      if (!launch_kc_vec(2, c_n, ar1_ar2, ar2, vx2_lv1, nullptr, vx_lv1)) return false;
+    }
+  }
+
+  if (!launch_fill(f_n, 0.0, z2_lv)) return false;
+  if (!launch_prolong_set(f_n, f->coarse_row.p, vx_lv1, z1_lv)) return false;
+  sa.x = z1_lv; sa.y = rb_lv; sa.b = rt_lv;
+  if (!launch_spmv(EPI_RESIDUAL, sa)) return false;
+  if (!mg_level_smooth(mg, 1, level, rb_lv, z2_lv, true, precision, r_norm, level == 0))
+    return false;
+  return launch_kc_vec(3, f_n, 0., 0., z1_lv, z2_lv, vx);
 }
 
 /* _multigrid_v_cycle_pc (cs_multigrid.cpp:3569-4000): one V-cycle without convergence
@@ -992,6 +1099,9 @@ bool mg_cycle_pc_enqueue(csb_multigrid_t *mg, double precision, double r_norm,
   MgState *ms = mg->mg_state.p;
   const double denom = 1.0 / (double)mg->levels[0]->m->n_rows;
   bool ok = true;
+
+  if (mg->type == CSB_MULTIGRID_K_CYCLE && n_levels > 1)
+    return k_cycle_enqueue(mg, 0, precision, r_norm, rhs_d, vx_d);   /* starts from zero */
 
   for (int level = 0; ok && level < coarsest; level++) {
     MgLevel *f = mg->levels[level], *cl = mg->levels[level+1];
@@ -1154,11 +1264,27 @@ extern "C" {
 csb_multigrid_t *csb_multigrid_create(csb_multigrid_type_t mg_type)
 {
   if (!ctx().ready) { set_error("csb_multigrid_create: csb_init not called"); return nullptr; }
-  if (mg_type != CSB_MULTIGRID_V_CYCLE) {
-    set_error("csb_multigrid_create: only the V-cycle is available on this path");
+  if (mg_type != CSB_MULTIGRID_V_CYCLE && mg_type != CSB_MULTIGRID_K_CYCLE) {
+    set_error("csb_multigrid_create: V-cycle and K-cycle are available on this path");
     return nullptr;
   }
-  return new csb_multigrid_t;
+  csb_multigrid_t *mg = new csb_multigrid_t;
+  mg->type = mg_type;
+  if (mg_type == CSB_MULTIGRID_K_CYCLE) {
+    /* cs_multigrid_create :4718-4725: pairwise aggregation up to 4 rows, Galerkin coarse
+       matrices, at most 10 levels of at least 256 rows, second inner iteration skipped when
+       the first one reduced the residual by 0.25; :4777-4788 with the device substitution
+       of :5083-5087: symmetric Gauss-Seidel (1 sweep) -> Jacobi (3 sweeps), PCG (50) */
+    mg->coarsening_type = 3;
+    mg->aggregation_limit = 4;
+    mg->n_levels_max = 10;
+    mg->n_g_rows_min = 256;
+    mg->p0p1_relax = 0.;
+    mg->k_cycle_threshold = 0.25;
+    csb_multigrid_set_solver_options(mg, CSB_SLES_JACOBI, CSB_SLES_JACOBI, CSB_SLES_PCG,
+                                     100, 3, 3, 50, -1, -1, 0, -1., -1., 1.);
+  }
+  return mg;
 }
 
 void
@@ -1287,6 +1413,15 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
       return;
     }
     if (mg->solver_type[i] == CSB_SLES_L1_JACOBI) any_l1 = true;
+  }
+  const bool kcycle = (mg->type == CSB_MULTIGRID_K_CYCLE);
+  if (kcycle && (mg->n_max_cycles != 1 || a->halo != nullptr
+                 || !is_smoother_type((int)mg->solver_type[0])
+                 || !is_smoother_type((int)mg->solver_type[1]))) {
+    set_error("csb_multigrid_setup: the K-cycle is available as a single cycle (n_max_cycles "
+              "1: the preconditioner form, csb_multigrid_pc_create) with Jacobi-family "
+              "smoothers on one rank");
+    return;
   }
   const bool dist = (a->halo != nullptr);
   csb_pcomm_t *pc = dist ? mg->pcomm : nullptr;
@@ -1500,6 +1635,10 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     if (!launch_ad_inv(m->n_rows, m->d_val.p, lv->ad_inv.p)) return;
     if (any_l1) {
       if (!lv->l1_inv.alloc((size_t)m->n_rows) || !launch_l1_inv(m, lv->l1_inv.p)) return;
+    }
+    if (kcycle) {
+      lv->kstride = work_stride_of((size_t)m->n_cols_ext);
+      if (!lv->kwork.alloc(10*lv->kstride)) return;
     }
     if (l > 0) {
       if (!lv->rhs.alloc((size_t)m->n_cols_ext) || !lv->vx.alloc((size_t)m->n_cols_ext)) return;
@@ -1882,6 +2021,7 @@ void *csb_multigrid_copy(const void *context)
   d->n_levels_max = s->n_levels_max;
   d->n_g_rows_min = s->n_g_rows_min;
   d->p0p1_relax = s->p0p1_relax;
+  d->k_cycle_threshold = s->k_cycle_threshold;
   d->n_blocks = s->n_blocks;
   d->n_max_cycles = s->n_max_cycles;
   for (int i = 0; i < 3; i++) {
@@ -1907,8 +2047,14 @@ csb_multigrid_t *csb_multigrid_pc_create(csb_multigrid_type_t mg_type)
 {
   csb_multigrid_t *mg = csb_multigrid_create(mg_type);
   if (mg == nullptr) return nullptr;
-  csb_multigrid_set_solver_options(mg, CSB_SLES_RJ3, CSB_SLES_RJ3, CSB_SLES_PCG,
-                                   1, 2, 2, 500, 0, 0, 0, -1., -1., 1.);
+  if (mg_type == CSB_MULTIGRID_K_CYCLE)
+    /* :1642-1655 (truncated Gauss-Seidel) with the device substitution of :5093-5100:
+       2 Jacobi sweeps; PCG coarse solver at 10 times the outer precision */
+    csb_multigrid_set_solver_options(mg, CSB_SLES_JACOBI, CSB_SLES_JACOBI, CSB_SLES_PCG,
+                                     1, 2, 2, 500, 0, 0, 0, -1., -1., 10.);
+  else
+    csb_multigrid_set_solver_options(mg, CSB_SLES_RJ3, CSB_SLES_RJ3, CSB_SLES_PCG,
+                                     1, 2, 2, 500, 0, 0, 0, -1., -1., 1.);
   return mg;
 }
 

@@ -57,7 +57,8 @@ typedef enum {
 
 /* cs_multigrid_type_t, src/alge/cs_multigrid.h:58-65 */
 typedef enum {
-  CSB_MULTIGRID_V_CYCLE = 0
+  CSB_MULTIGRID_V_CYCLE = 0,
+  CSB_MULTIGRID_K_CYCLE = 1    /* as a preconditioner (one cycle): csb_multigrid_pc_create */
 } csb_multigrid_type_t;
 
 typedef struct _csb_matrix_t     csb_matrix_t;      /* cs_matrix_t (MSR) */

@@ -306,7 +306,33 @@ def check_compute_coeffs(ora):
     c.destroy(); m.destroy()
 
 
-CHECKS = {"spmv_pcg": check_spmv_pcg, "compute_coeffs": check_compute_coeffs, "pairwise": check_pairwise, "galerkin": check_galerkin, "block3_jacobi": check_block3_jacobi, "general_pc": check_general_pc,
+def check_k_cycle(ora):
+    g = np.load(os.path.join(GOLD, "kcycle_N8_dirichlet.npz"))
+    s = cube_poisson(8, "dirichlet")
+    rn = float(g["r_norm"])
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+
+    def kpc():
+        pc = csb.Multigrid(pc=True, mg_type=1)
+        pc.set_coarsening_options(aggregation_limit=4, coarsening_type=3, n_max_levels=10,
+                                  min_g_rows=30, p0p1_relax=0.)
+        return pc
+
+    mg = kpc()
+    mg.setup(m)
+    r = mg.solve(m, s.rhs, 1e-8, rn)
+    assert rel(r["vx"][:s.n_rows], g["cycle_vx"]) <= 1e-6
+    assert abs(r["n_iter"] - int(g["cycle_n_iter"])) <= 1
+    mg.destroy()
+    c = csb.SlesIt(csb.SlesItType.FCG, 200, poly_degree=-1)
+    c.transfer_pc(kpc())
+    r = c.solve(m, s.rhs, 1e-8, rn)
+    assert int(r["cvg"]) == 1 and abs(r["n_iter"] - int(g["fcg_n_iter"])) <= 2
+    assert rel(r["vx"][:s.n_rows], g["fcg_vx"]) <= 1e-6
+    c.destroy(); m.destroy()
+
+
+CHECKS = {"spmv_pcg": check_spmv_pcg, "k_cycle": check_k_cycle, "compute_coeffs": check_compute_coeffs, "pairwise": check_pairwise, "galerkin": check_galerkin, "block3_jacobi": check_block3_jacobi, "general_pc": check_general_pc,
           "kernel_per_phase": check_kernel_per_phase_paths, "smoothers": check_smoothers,
           "cycle_pc": check_cycle_pc, "fcg_mgpc": check_fcg_mgpc}
 

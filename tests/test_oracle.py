@@ -474,3 +474,40 @@ def test_oracle_matrix_compute_coeffs_convection_matches_golden(oracle, N):
                                             g["rovsdt"], g["i_massflux"], g["b_massflux"],
                                             g["i_visc"], g["b_visc"], xcpp=xcpp, **kw)
         assert np.array_equal(d, g[f"{name}_d"]) and np.array_equal(x, g[f"{name}_x"]), name
+
+
+@pytest.mark.parametrize("N,bc", [(8, "dirichlet"), (12, "dirichlet")])
+def test_oracle_k_cycle_matches_golden(oracle, N, bc):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"kcycle_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    r_norm = float(g["r_norm"])
+    mg = oracle.mg_setup_pw(s, aggregation_limit=4, n_levels_max=10, n_g_rows_min=30)
+    r = oracle.mg_k_cycle(mg, s.rhs, 1e-8, r_norm)
+    assert np.array_equal(r["vx"], g["cycle_vx"]) and r["n_iter"] == int(g["cycle_n_iter"])
+    r = oracle.it_kpc(1, mg, s.rhs, 200, 1e-8, r_norm)
+    assert (r["cvg"], r["n_iter"], r["residual"]) == (int(g["fcg_cvg"]), int(g["fcg_n_iter"]),
+                                                      float(g["fcg_residual"]))
+    assert np.array_equal(r["vx"], g["fcg_vx"])
+    oracle.mg_free(mg)
+
+
+def test_oracle_k_cycle_vs_reference_direct(oracle, reflib):
+    """deeper hierarchies (both inner Krylov branches taken), pairs only, Neumann problem"""
+    for N, bc, lim in ((16, "neumann", 4), (14, "dirichlet", 2)):
+        s = cube_poisson(N, bc)
+        h = reflib.system(s)
+        r_norm = float(np.linalg.norm(s.rhs))
+        kw = dict(aggregation_limit=lim, coarsening_type=3, n_levels_max=10, n_g_rows_min=30,
+                  p0p1_relax=0., mg_type=1)
+        mg = oracle.mg_setup_pw(s, aggregation_limit=lim, n_levels_max=10, n_g_rows_min=30)
+        a = oracle.mg_k_cycle(mg, s.rhs, 1e-8, r_norm)
+        b = reflib.multigrid(h, s.rhs, 1e-8, r_norm, n_max_cycles=1, n_max_iter=(2, 2, 500),
+                             types=(3, 3, 0), precision_mult=(-1., -1., 10.), **kw)
+        assert np.array_equal(a["vx"], b["vx"]) and a["n_iter"] == b["n_iter"]
+        a = oracle.it_kpc(1, mg, s.rhs, 60, 1e-8, r_norm)
+        b = reflib.it_mgpc(h, 1, s.rhs, 60, 1e-8, r_norm, types=(3, 3, 0),
+                           mg_n_max_iter=(2, 2, 500), precision_mult=(-1., -1., 10.), **kw)
+        assert (a["cvg"], a["n_iter"], a["residual"]) == (b["cvg"], b["n_iter"], b["residual"])
+        assert np.array_equal(a["vx"], b["vx"])
+        oracle.mg_free(mg)
+        reflib.destroy(h)
