@@ -474,6 +474,19 @@ class Matrix:
                                        *[_ptr(a) for a in args]) != 0:
             _err("csb_matrix_compute_coeffs")
 
+    def compute_coeffs_vector(self, i_visc, b_visc=None, cofbfp=None, coefbp=None, fimp=None,
+                              i_massflux=None, b_massflux=None, iconvp=0, idiffp=1, ndircp=1,
+                              thetap=1., relaxp=1.):
+        """cs_matrix_compute_coeffs<3>: vector variable, 3x3 diagonal blocks."""
+        L = load_library()
+        L.csb_matrix_compute_coeffs_vector.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                       C.c_double, C.c_double] + [C.c_void_p] * 7
+        args = [a if a is None or not isinstance(a, np.ndarray) else _f64(a)
+                for a in (coefbp, cofbfp, fimp, i_massflux, b_massflux, i_visc, b_visc)]
+        if L.csb_matrix_compute_coeffs_vector(self.handle, iconvp, idiffp, ndircp, float(thetap),
+                                              float(relaxp), *[_ptr(a) for a in args]) != 0:
+            _err("csb_matrix_compute_coeffs_vector")
+
     def get_coefficients(self):
         """(d_val, x_val) copied back from HBM."""
         L = load_library()

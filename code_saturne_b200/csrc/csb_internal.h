@@ -380,6 +380,13 @@ bool launch_coeffs_msr(const _csb_matrix_t *m, int idiffp, int ndircp, double th
                        const double *i_visc, const double *b_visc, const double *xcpp,
                        double *d_val, double *x_val);
 
+/* vector variable, 3x3 diagonal blocks (_sym_coeffs_msr<3> / _coeffs_msr<3>, :250-353, :560-692) */
+bool launch_coeffs_msr_v3(const _csb_matrix_t *m, int iconvp, int idiffp, int ndircp,
+                          double thetap, double relaxp, const double *coefbp,
+                          const double *cofbfp, const double *fimp, const double *i_massflux,
+                          const double *b_massflux, const double *i_visc, const double *b_visc,
+                          double *d_val, double *x_val);
+
 /* ad_inv = 1/d  (cs_sles_pc.cpp:376) */
 bool launch_ad_inv(int n, const double *d, double *ad_inv);
 bool launch_fill(int n, double v, double *x);

@@ -2173,7 +2173,99 @@ k_coeffs_msr(int n_rows, const int *__restrict__ row_index, const int *__restric
   }
 }
 
+/* Vector variable, 3x3 diagonal blocks and scalar extra-diagonal (CS_MATRIX_BLOCK_D):
+   _sym_coeffs_msr<3> (:250-353) when iconvp = 0, _coeffs_msr<3> (:560-692) otherwise; then
+   the relaxation of all 9 block entries and the diagonal shift (:2551-2568). */
+__global__ void __launch_bounds__(TPB)
+k_coeffs_msr_v3(int n_rows, const int *__restrict__ row_index,
+                const int *__restrict__ cell_i_faces, const short *__restrict__ c2f_sgn,
+                const int *__restrict__ c2b_idx, const int *__restrict__ c2b, int iconvp,
+                int idiffp, int ndircp, double thetap, double relaxp,
+                const double *__restrict__ coefbp, const double *__restrict__ cofbfp,
+                const double *__restrict__ fimp, const double *__restrict__ i_massflux,
+                const double *__restrict__ b_massflux, const double *__restrict__ i_visc,
+                const double *__restrict__ b_visc, double *__restrict__ da,
+                double *__restrict__ ea)
+{
+  const double rf = 1. / relaxp;
+  const double epsi_p1 = 1. + 1.e-7;
+  for (int c_id = blockIdx.x*TPB + threadIdx.x; c_id < n_rows; c_id += gridDim.x*TPB) {
+    double _da[9];
+    for (int q = 0; q < 9; q++) _da[q] = (fimp != nullptr) ? fimp[(size_t)c_id*9 + q] : 0.;
+    const int ks = row_index[c_id], ke = row_index[c_id+1];
+    for (int k = ks; k < ke; k++) {
+      const int f_id = cell_i_faces[k];
+      if (!iconvp) {
+        if (idiffp) {
+          const double _xa = -thetap*i_visc[f_id];
+          ea[k] = _xa;
+          _da[0] -= _xa; _da[4] -= _xa; _da[8] -= _xa;
+        }
+        else
+          ea[k] = 0.;
+      }
+      else {
+        const double _i_massflux = i_massflux[f_id];
+        double fac;
+        if (c2f_sgn[k] > 0) {
+          const double flui = 0.5*(_i_massflux - fabs(_i_massflux));
+          const double xai = thetap*(flui - idiffp*i_visc[f_id]);
+          ea[k] = xai;
+          fac = xai + (1.-thetap) * _i_massflux;
+        }
+        else {
+          const double fluj = -0.5*(_i_massflux + fabs(_i_massflux));
+          const double xaj = thetap*(fluj - idiffp*i_visc[f_id]);
+          ea[k] = xaj;
+          fac = xaj - (1.-thetap) * _i_massflux;
+        }
+        _da[0] -= fac; _da[4] -= fac; _da[8] -= fac;
+      }
+    }
+    if (c2b_idx != nullptr && (iconvp || idiffp))
+      for (int b = c2b_idx[c_id]; b < c2b_idx[c_id+1]; b++) {
+        const int f_id = c2b[b];
+        if (!iconvp) {
+          for (int q = 0; q < 9; q++)
+            _da[q] += thetap * b_visc[f_id] * cofbfp[(size_t)f_id*9 + q];
+        }
+        else {
+          const double _b_massflux = b_massflux[f_id];
+          const double flui = 0.5*(_b_massflux - fabs(_b_massflux));
+          for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) {
+              const double d_ij = ((i == j) ? 1. : 0.);
+              const double diag = d_ij * (thetap * flui + (1. - thetap) * _b_massflux);
+              _da[3*i+j] += - diag + thetap * (  flui * coefbp[(size_t)f_id*9 + 3*i + j]
+                                               + idiffp * b_visc[f_id] * cofbfp[(size_t)f_id*9 + 3*i + j]);
+            }
+        }
+      }
+    if (relaxp < 1)
+      for (int q = 0; q < 9; q++) _da[q] *= rf;
+    if (ndircp <= 0) {
+      _da[0] = epsi_p1 * _da[0]; _da[4] = epsi_p1 * _da[4]; _da[8] = epsi_p1 * _da[8];
+    }
+    for (int q = 0; q < 9; q++) da[(size_t)c_id*9 + q] = _da[q];
+  }
+}
+
 } // anonymous namespace
+
+bool launch_coeffs_msr_v3(const _csb_matrix_t *m, int iconvp, int idiffp, int ndircp,
+                          double thetap, double relaxp, const double *coefbp,
+                          const double *cofbfp, const double *fimp, const double *i_massflux,
+                          const double *b_massflux, const double *i_visc, const double *b_visc,
+                          double *d_val, double *x_val)
+{
+  if (m->n_rows < 1) return true;
+  k_coeffs_msr_v3<<<vec_grid(m->n_rows*4), TPB, 0, ctx().stream>>>(
+    m->n_rows, m->row_index.p, m->c2f.p, m->c2f_sgn.p,
+    m->has_b_faces ? m->cell_b_faces_idx.p : nullptr, m->cell_b_faces.p, iconvp, idiffp,
+    ndircp, thetap, relaxp, coefbp, cofbfp, fimp, i_massflux, b_massflux, i_visc, b_visc,
+    d_val, x_val);
+  return post_launch("coeffs_msr_v3");
+}
 
 bool launch_coeffs_msr(const _csb_matrix_t *m, int idiffp, int ndircp, double thetap,
                        double relaxp, const double *coefbp, const double *cofbfp,

@@ -422,6 +422,62 @@ int csb_matrix_compute_coeffs(csb_matrix_t *m, int iconvp, int idiffp, int ndirc
   return 0;
 }
 
+/* cs_matrix_compute_coeffs<3> (src/alge/cs_matrix_building.cpp:2284-2600) for a vector
+   variable with scalar diffusion: 3x3 diagonal blocks, scalar extra-diagonal terms. */
+int csb_matrix_compute_coeffs_vector(csb_matrix_t *m, int iconvp, int idiffp, int ndircp,
+                                     double thetap, double relaxp, const csb_real_t *coefbp,
+                                     const csb_real_t *cofbfp, const csb_real_t *fimp,
+                                     const csb_real_t *i_massflux,
+                                     const csb_real_t *b_massflux, const csb_real_t *i_visc,
+                                     const csb_real_t *b_visc)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (m->db != 3) {
+    set_error("csb_matrix_compute_coeffs_vector: needs a matrix with 3x3 diagonal blocks");
+    return -1;
+  }
+  if (!m->has_mesh) {
+    set_error("csb_matrix_compute_coeffs_vector: needs the mesh association "
+              "(csb_matrix_set_mesh_association)");
+    return -1;
+  }
+  const bool conv = (iconvp != 0), diff = (idiffp != 0);
+  const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  if (((conv || diff) && i_visc == nullptr) || (conv && i_massflux == nullptr)
+      || (bnd && (conv || diff) && (b_visc == nullptr || cofbfp == nullptr))
+      || (bnd && conv && (b_massflux == nullptr || coefbp == nullptr))) {
+    set_error("csb_matrix_compute_coeffs_vector: null coefficient array");
+    return -1;
+  }
+  Context &c = ctx();
+  const size_t nf = (size_t)m->n_faces, nb = (size_t)m->n_b_faces, nr = (size_t)m->n_rows;
+  const bool face_terms = conv || diff;
+  const double *src[7] = {fimp, i_visc, b_visc, cofbfp, coefbp, i_massflux, b_massflux};
+  const size_t len[7] = {9*nr, face_terms ? nf : 0, face_terms ? nb : 0,
+                         face_terms ? 9*nb : 0, conv ? 9*nb : 0, conv ? nf : 0, conv ? nb : 0};
+  const double *dev[7];
+  size_t need = 0;
+  for (int i = 0; i < 7; i++)
+    if (len[i] > 0 && src[i] != nullptr && !is_device_ptr(src[i])) need += len[i];
+  if (need > m->coef_stage.n && !m->coef_stage.alloc(need)) return -1;
+  size_t off = 0;
+  for (int i = 0; i < 7; i++) {
+    dev[i] = src[i];
+    if (len[i] > 0 && src[i] != nullptr && !is_device_ptr(src[i])) {
+      if (!CSB_CUDA(cudaMemcpyAsync(m->coef_stage.p + off, src[i], sizeof(double)*len[i],
+                                    cudaMemcpyHostToDevice, c.stream))) return -1;
+      dev[i] = m->coef_stage.p + off;
+      off += len[i];
+    }
+  }
+  if (!launch_coeffs_msr_v3(m, iconvp, idiffp, ndircp, thetap, relaxp, dev[4], dev[3], dev[0],
+                            dev[5], dev[6], dev[1], dev[2], m->d_val.p, m->x_val.p)) return -1;
+  if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return -1;
+  m->symmetric = !conv;
+  m->h_vals_valid = false;
+  return 0;
+}
+
 /* The MSR coefficients as they are in HBM, copied to d_val[n_rows*db*db] / x_val[nnz]
    (host or device); cs_matrix_get_msr_arrays (cs_matrix.cpp:6199) lends them, here they are
    copied because they live on the device. */

@@ -187,6 +187,18 @@ int  csb_matrix_compute_coeffs(csb_matrix_t *m, int iconvp, int idiffp, int ndir
                                const csb_real_t *b_massflux, const csb_real_t *i_visc,
                                const csb_real_t *b_visc, const csb_real_t *xcpp);
 
+/* cs_matrix_compute_coeffs<3> (src/alge/cs_matrix_building.cpp:2284-2600) for a vector
+   variable with scalar diffusion (tensorial_diffusion 1, eb_size 1), on a matrix created with
+   csb_matrix_create_msr_block (db 3): _sym_coeffs_msr<3> (:250-353) when iconvp = 0,
+   _coeffs_msr<3> (:560-692) when iconvp = 1.  fimp[n_rows x 3 x 3] may be NULL; coefbp and
+   cofbfp hold a 3x3 block per boundary face.  Same conventions as csb_matrix_compute_coeffs. */
+int  csb_matrix_compute_coeffs_vector(csb_matrix_t *m, int iconvp, int idiffp, int ndircp,
+                                      double thetap, double relaxp, const csb_real_t *coefbp,
+                                      const csb_real_t *cofbfp, const csb_real_t *fimp,
+                                      const csb_real_t *i_massflux,
+                                      const csb_real_t *b_massflux, const csb_real_t *i_visc,
+                                      const csb_real_t *b_visc);
+
 /* Copy of the MSR coefficients held in HBM (cs_matrix_get_msr_arrays, cs_matrix.cpp:6199,
    lends the host arrays; these live on the device).  Either pointer may be NULL. */
 int  csb_matrix_get_coefficients(const csb_matrix_t *m, csb_real_t *d_val, csb_real_t *x_val);

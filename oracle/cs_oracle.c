@@ -2795,3 +2795,89 @@ ora_it_kpc(int solver, const ora_mg_t *mg, const ora_mg_pc_opt_t *opt, double k_
   return _pcg_sr_pc(&pc, n_max_iter, precision, r_norm, rhs, vx, use_vx_ini,
                     out, history, history_size);
 }
+
+/*----------------------------------------------------------------------------
+ * Same for a vector variable (3x3 diagonal blocks, scalar extra-diagonal: CS_MATRIX_BLOCK_D):
+ *   cs_matrix_compute_coeffs<3> (src/alge/cs_matrix_building.cpp:2284-2600) with scalar
+ *   diffusion (tensorial_diffusion 1, eb_size 1): _sym_coeffs_msr<3> (:250-353) when
+ *   iconvp = 0, _coeffs_msr<3> (:560-692) when iconvp = 1.  fimp (n x 3 x 3) may be NULL;
+ *   coefbp / cofbfp are 3x3 per boundary face.
+ *----------------------------------------------------------------------------*/
+
+void
+ora_matrix_compute_coeffs_v3(int n_rows, const int *row_index,
+                             const int *cell_i_faces, const short *cell_i_faces_sgn,
+                             int n_b_faces, const int *b_face_cells,
+                             int iconvp, int idiffp, int ndircp, double thetap, double relaxp,
+                             const double *coefbp, const double *cofbfp, const double *fimp,
+                             const double *i_massflux, const double *b_massflux,
+                             const double *i_visc, const double *b_visc,
+                             double *da, double *ea)
+{
+  const int stride = 3;
+  for (int c_id = 0; c_id < n_rows; c_id++) {
+    double *_da = da + 9*(size_t)c_id;
+    for (int q = 0; q < 9; q++) _da[q] = (fimp != NULL) ? fimp[9*(size_t)c_id + q] : 0.;
+    for (int cidx = row_index[c_id]; cidx < row_index[c_id+1]; cidx++) {
+      const int f_id = cell_i_faces[cidx];
+      if (!iconvp) {
+        if (idiffp) {
+          double _xa = -thetap*i_visc[f_id];
+          ea[cidx] = _xa;
+          for (int i = 0; i < stride; i++) _da[i*3+i] -= _xa;
+        }
+        else
+          ea[cidx] = 0.;
+      }
+      else {
+        double _i_massflux = i_massflux[f_id];
+        if (cell_i_faces_sgn[cidx] > 0) {
+          double flui = 0.5*(_i_massflux - fabs(_i_massflux));
+          double xai = thetap*(flui - idiffp*i_visc[f_id]);
+          ea[cidx] = xai;
+          double ifac = xai + (1.-thetap) * _i_massflux;
+          for (int i = 0; i < stride; i++) _da[i*3+i] -= ifac;
+        }
+        else {
+          double fluj = -0.5*(_i_massflux + fabs(_i_massflux));
+          double xaj = thetap*(fluj - idiffp*i_visc[f_id]);
+          ea[cidx] = xaj;
+          double jfac = xaj - (1.-thetap) * _i_massflux;
+          for (int i = 0; i < stride; i++) _da[i*3+i] -= jfac;
+        }
+      }
+    }
+  }
+  if (!iconvp) {
+    if (idiffp)
+      for (int f_id = 0; f_id < n_b_faces; f_id++) {
+        double *_da = da + 9*(size_t)b_face_cells[f_id];
+        for (int q = 0; q < 9; q++)
+          _da[q] += thetap * b_visc[f_id] * cofbfp[9*(size_t)f_id + q];
+      }
+  }
+  else {
+    for (int f_id = 0; f_id < n_b_faces; f_id++) {
+      double _b_massflux = b_massflux[f_id];
+      double *_da = da + 9*(size_t)b_face_cells[f_id];
+      double flui = 0.5*(_b_massflux - fabs(_b_massflux));
+      for (int i = 0; i < stride; i++)
+        for (int j = 0; j < stride; j++) {
+          double d_ij = ((i == j) ? 1. : 0.);
+          double diag = d_ij * (thetap * flui + (1. - thetap) * b_massflux[f_id]);
+          _da[3*i+j] += - diag + thetap * (  flui * coefbp[9*(size_t)f_id + 3*i + j]
+                                           + idiffp * b_visc[f_id] * cofbfp[9*(size_t)f_id + 3*i + j]);
+        }
+    }
+  }
+  if (relaxp < 1) {
+    double rf = 1. / relaxp;
+    for (size_t i = 0; i < 9*(size_t)n_rows; i++) da[i] *= rf;
+  }
+  if (ndircp <= 0) {
+    const double epsi_p1 = 1. + 1.e-7;
+    for (int c_id = 0; c_id < n_rows; c_id++)
+      for (int i = 0; i < stride; i++)
+        da[9*(size_t)c_id + 3*i + i] = epsi_p1 * da[9*(size_t)c_id + 3*i + i];
+  }
+}

@@ -163,6 +163,14 @@ void   ora_matrix_compute_coeffs(int n_rows, const int *row_index, const int *co
                                  const double *b_massflux, const double *i_visc,
                                  const double *b_visc, const double *xcpp,
                                  double *da, double *ea);
+void   ora_matrix_compute_coeffs_v3(int n_rows, const int *row_index,
+                                    const int *cell_i_faces, const short *cell_i_faces_sgn,
+                                    int n_b_faces, const int *b_face_cells,
+                                    int iconvp, int idiffp, int ndircp, double thetap,
+                                    double relaxp, const double *coefbp, const double *cofbfp,
+                                    const double *fimp, const double *i_massflux,
+                                    const double *b_massflux, const double *i_visc,
+                                    const double *b_visc, double *da, double *ea);
 int    ora_pairwise_msr(int level, int f_n_rows, const int *row_index, const int *col_id,
                         const double *d_val, const double *x_val, int *f_c_row);
 ora_mg_t *ora_mg_setup_pw(ora_grid_t *fine, int aggregation_limit, int n_levels_max,

@@ -273,6 +273,21 @@ class Oracle:
             C.c_double(relaxp), *[_dp(a) for a in arrs], _dp(da), _dp(ea))
         return da[:n], ea[:int(ri[-1])]
 
+    def matrix_compute_coeffs_v3(self, s, b_face_cells, coefbp, cofbfp, fimp, i_massflux,
+                                 b_massflux, i_visc, b_visc, iconvp=1, idiffp=1, ndircp=1,
+                                 thetap=1., relaxp=1.):
+        ri, c2f, bfc = _i32(s.row_index), _i32(s.c2f), _i32(b_face_cells)
+        sgn = np.ascontiguousarray(s.c2f_sgn, dtype=np.int16)
+        n = len(ri) - 1
+        da, ea = np.zeros(9 * max(n, 1)), np.zeros(max(int(ri[-1]), 1))
+        f = lambda a: None if a is None else _f64(a)
+        arrs = [f(a) for a in (coefbp, cofbfp, fimp, i_massflux, b_massflux, i_visc, b_visc)]
+        self.lib.ora_matrix_compute_coeffs_v3(
+            C.c_int(n), _ip(ri), _ip(c2f), _sp(sgn), C.c_int(len(bfc)), _ip(bfc),
+            C.c_int(iconvp), C.c_int(idiffp), C.c_int(ndircp), C.c_double(thetap),
+            C.c_double(relaxp), *[_dp(a) for a in arrs], _dp(da), _dp(ea))
+        return da[:9 * n], ea[:int(ri[-1])]
+
     def pairwise(self, level, ri, ci, d, xv):
         ri, ci, d, xv = _i32(ri), _i32(ci), _f64(d), _f64(xv)
         n = len(ri) - 1
@@ -576,6 +591,32 @@ class RefLib:
         if rc != 0:
             raise RuntimeError("csref_matrix_compute_coeffs: system has no mesh")
         return d[:s.n_rows], x[:s.nnz]
+
+    def system_block_with_mesh(self, s, db=3):
+        """Block-diagonal MSR system on the structure and mesh association of CubeSystem s
+        (coefficients zero: to be filled by matrix_compute_coeffs_v3)."""
+        h = self.system_block(s.n_rows, db, s.row_index, s.col_id,
+                              np.tile(np.eye(db).ravel(), s.n_rows), np.zeros(s.nnz), False)
+        fc, c2f = _i32(s.face_cells), _i32(s.c2f)
+        sgn = np.ascontiguousarray(s.c2f_sgn, dtype=np.int16)
+        self.lib.csref_system_set_mesh(h, C.c_int(s.n_faces), _ip(fc), _ip(c2f), _sp(sgn),
+                                       _dp(_f64(s.cell_cen)), _dp(_f64(s.cell_vol)),
+                                       _dp(_f64(s.face_u_normal)), _dp(_f64(s.face_surf)))
+        return h
+
+    def matrix_compute_coeffs_v3(self, h, s, b_face_cells, coefbp, cofbfp, fimp, i_massflux,
+                                 b_massflux, i_visc, b_visc, iconvp=1, idiffp=1, ndircp=1,
+                                 thetap=1., relaxp=1.):
+        bfc = _i32(b_face_cells)
+        d, x = np.zeros(9 * max(s.n_rows, 1)), np.zeros(max(s.nnz, 1))
+        f = lambda a: None if a is None else _f64(a)
+        arrs = [f(a) for a in (coefbp, cofbfp, fimp, i_massflux, b_massflux, i_visc, b_visc)]
+        rc = self.lib.csref_matrix_compute_coeffs_v3(
+            h, C.c_int(len(bfc)), _ip(bfc), C.c_int(iconvp), C.c_int(idiffp), C.c_int(ndircp),
+            C.c_double(thetap), C.c_double(relaxp), *[_dp(a) for a in arrs], _dp(d), _dp(x))
+        if rc != 0:
+            raise RuntimeError("csref_matrix_compute_coeffs_v3: system has no mesh")
+        return d[:9 * s.n_rows], x[:s.nnz]
 
     def smoother(self, h, stype, rhs, n_max_iter, vx0=None):
         rhs = _f64(rhs)

@@ -581,6 +581,68 @@ csref_matrix_compute_coeffs(void          *sys,
   return 0;
 }
 
+/* cs_matrix_compute_coeffs<3> (vector variable, scalar diffusion, eb_size 1) on a system
+   created with 3x3 diagonal blocks (csref_system_create_block + csref_system_set_mesh);
+   mesh globals as set by a previous csref_matrix_compute_coeffs call are rebuilt here too.
+   coefbp / cofbfp: n_b_faces x 9; fimp: n_rows x 9 or NULL; d_out: n_rows x 9. */
+int
+csref_matrix_compute_coeffs_v3(void          *sys,
+                               int            n_b_faces,
+                               const int     *b_face_cells,
+                               int            iconvp,
+                               int            idiffp,
+                               int            ndircp,
+                               double         thetap,
+                               double         relaxp,
+                               const double  *coefbp,
+                               const double  *cofbfp,
+                               const double  *fimp,
+                               const double  *i_massflux,
+                               const double  *b_massflux,
+                               const double  *i_visc,
+                               const double  *b_visc,
+                               double        *d_out,
+                               double        *x_out)
+{
+  ref_system *s = static_cast<ref_system *>(sys);
+  cs_mesh_t *mesh = cs_glob_mesh;
+  if (mesh == nullptr || mesh->n_i_faces != s->n_faces)
+    return -1;
+
+  CS_FREE(mesh->b_face_cells);
+  mesh->n_b_faces = n_b_faces;
+  mesh->n_b_faces_all = n_b_faces;
+  CS_MALLOC(mesh->b_face_cells, (n_b_faces > 0) ? n_b_faces : 1, cs_lnum_t);
+  memcpy(mesh->b_face_cells, b_face_cells, sizeof(cs_lnum_t)*n_b_faces);
+  if (mesh->b_face_numbering != nullptr)
+    cs_numbering_destroy(&(mesh->b_face_numbering));
+  mesh->b_face_numbering = cs_numbering_create_default(n_b_faces);
+  if (mesh->i_face_numbering != nullptr)
+    cs_numbering_destroy(&(mesh->i_face_numbering));
+  mesh->i_face_numbering = cs_numbering_create_default(mesh->n_i_faces);
+  if (cs_glob_mesh_quantities == nullptr)
+    cs_glob_mesh_quantities = cs_mesh_quantities_create();
+  cs_mesh_adjacencies_finalize();
+  cs_mesh_adjacencies_initialize();
+  cs_mesh_adjacencies_update_mesh();
+
+  cs_field_bc_coeffs_t bc;
+  memset(&bc, 0, sizeof(bc));
+  bc.bf = const_cast<cs_real_t *>(cofbfp);
+  bc.b = const_cast<cs_real_t *>(coefbp);
+
+  cs_matrix_compute_coeffs<3>(s->m, nullptr, iconvp, idiffp, 1, ndircp, 1, thetap, relaxp,
+                              &bc, reinterpret_cast<const cs_real_t (*)[3][3]>(fimp),
+                              i_massflux, b_massflux, i_visc, b_visc);
+
+  const cs_lnum_t *ri, *ci;
+  const cs_real_t *d, *x;
+  cs_matrix_get_msr_arrays(s->m, &ri, &ci, &d, &x);
+  memcpy(d_out, d, sizeof(double)*9*s->n_rows);
+  memcpy(x_out, x, sizeof(double)*ri[s->n_rows]);
+  return 0;
+}
+
 int
 csref_matrix_compute_coeffs_sym(void *sys, int n_b_faces, const int *b_face_cells, int idiffp,
                                 int ndircp, double thetap, double relaxp, const double *cofbfp,

@@ -274,8 +274,8 @@ def check_pairwise(ora):
 
 
 def check_compute_coeffs(ora):
-    g = np.load(os.path.join(GOLD, "coeffs_N6.npz"))
-    s = cube_poisson(6, "neumann")
+    g = np.load(os.path.join(GOLD, "coeffs_N5.npz"))
+    s = cube_poisson(5, "neumann")
     m = csb.Matrix.from_system(s)
     m.set_boundary_faces(g["b_face_cells"])
     for name, kw in (("default", dict()), ("no_dirichlet", dict(ndircp=0)),
@@ -304,6 +304,24 @@ def check_compute_coeffs(ora):
     res = np.linalg.norm(rhs - ora.spmv(s.row_index, s.col_id, d, x, r["vx"][:s.n_rows]))
     assert res <= 1.01e-10 * rn
     c.destroy(); m.destroy()
+    # vector variable: 3x3 diagonal blocks
+    mb = csb.Matrix.from_block(s.n_rows, 3, s.row_index, s.col_id,
+                               np.tile(np.eye(3).ravel(), s.n_rows), np.zeros(s.nnz))
+    mb.set_mesh_association(s.n_faces, s.c2f, s.c2f_sgn, s.cell_cen, s.cell_vol,
+                            s.face_u_normal, s.face_surf)
+    mb.set_boundary_faces(g["b_face_cells"])
+    for name, kw in (("v3_sym", dict(iconvp=0)),
+                     ("v3_sym_nofimp", dict(iconvp=0, fimp=False, ndircp=0, relaxp=0.5)),
+                     ("v3_conv", dict(iconvp=1)),
+                     ("v3_conv_theta", dict(iconvp=1, ndircp=0, thetap=0.5, relaxp=0.7)),
+                     ("v3_conv_only", dict(iconvp=1, idiffp=0, fimp=False))):
+        kw = dict(kw)
+        fimp = g["v3_fimp"] if kw.pop("fimp", True) else None
+        mb.compute_coeffs_vector(g["i_visc"], g["b_visc"], g["v3_cofbfp"], g["v3_coefbp"], fimp,
+                                 g["i_massflux"], g["b_massflux"], **kw)
+        d, x = mb.get_coefficients()
+        assert np.array_equal(d, g[f"{name}_d"]) and np.array_equal(x, g[f"{name}_x"]), name
+    mb.destroy()
 
 
 def check_k_cycle(ora):

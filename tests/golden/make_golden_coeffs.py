@@ -25,6 +25,11 @@ CONV_OPTIONS = {"conv": dict(), "conv_theta_relax": dict(ndircp=0, thetap=0.5, r
                 "conv_only": dict(idiffp=0), "conv_thermal": dict(thermal=True, thetap=0.5)}
 
 
+V3_OPTIONS = {"v3_sym": dict(iconvp=0), "v3_sym_nofimp": dict(iconvp=0, fimp=False, ndircp=0, relaxp=0.5),
+              "v3_conv": dict(iconvp=1), "v3_conv_theta": dict(iconvp=1, ndircp=0, thetap=0.5, relaxp=0.7),
+              "v3_conv_only": dict(iconvp=1, idiffp=0, fimp=False)}
+
+
 def inputs(N, s):
     rng = np.random.default_rng(1234)
     bfc = cube_boundary_face_cells(N)
@@ -38,7 +43,7 @@ def inputs(N, s):
 
 def main():
     ref = RefLib(1)
-    for N in (6, 10):
+    for N in (5, 7):
         s = cube_poisson(N, "neumann")
         h = ref.system(s)
         out = inputs(N, s)
@@ -56,6 +61,22 @@ def main():
                                              out["cofbfp"], out["rovsdt"], out["i_massflux"],
                                              out["b_massflux"], out["i_visc"], out["b_visc"],
                                              xcpp=xcpp, **kw)
+            out[f"{name}_d"] = d
+            out[f"{name}_x"] = x
+        ref.destroy(h)
+        # vector variable: 3x3 diagonal blocks (cs_matrix_compute_coeffs<3>)
+        rng = np.random.default_rng(4321)
+        nb = len(out["b_face_cells"])
+        out.update(v3_coefbp=rng.random(nb * 9), v3_cofbfp=rng.random(nb * 9),
+                   v3_fimp=rng.random(s.n_rows * 9))
+        h = ref.system_block_with_mesh(s)
+        for name, kw in V3_OPTIONS.items():
+            kw = dict(kw)
+            fimp = out["v3_fimp"] if kw.pop("fimp", True) else None
+            d, x = ref.matrix_compute_coeffs_v3(h, s, out["b_face_cells"], out["v3_coefbp"],
+                                                out["v3_cofbfp"], fimp, out["i_massflux"],
+                                                out["b_massflux"], out["i_visc"], out["b_visc"],
+                                                **kw)
             out[f"{name}_d"] = d
             out[f"{name}_x"] = x
         ref.destroy(h)
