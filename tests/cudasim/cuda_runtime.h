@@ -4,9 +4,9 @@
  * (csrc/kernels.cu, the kernel-per-phase path) and its host logic (csrc/sles.cu,
  * csrc/runtime.cu) be compiled by g++ and executed on host threads, so that kernels and
  * launch sequences can be desk-checked against the oracle in a container without a GPU
- * (tests/test_cudasim.py).  One OS thread per CUDA thread of a block, blocks one after the
- * other, __syncthreads = a barrier, __shfl_down_sync = exchange through a per-block
- * array.  It proves nothing about performance or about real concurrency on the device;
+ * (tests/test_cudasim.py).  The CUDA threads of a block are fibers run round-robin, blocks
+ * one after the other, __syncthreads = a barrier among the fibers, __shfl_down_sync = exchange
+ * through a per-block array (cudasim.cpp).  It proves nothing about performance or about real concurrency on the device;
  * the `-m gpu` tests remain the parity tests proper.  The product library is never built
  * from this header and has no CPU path.
  */

@@ -3,7 +3,7 @@
 Runs in a process of its own (tests/test_cudasim.py) with the simulated library bound in
 place of libcsb200.so: the UNMODIFIED kernels of csrc/kernels.cu and the launch sequences of
 csrc/sles.cu execute on host threads and are compared with the reference-built golden
-fixtures and the oracle.  Sizes are tiny: a block of 256 CUDA threads is 256 OS threads.
+fixtures and the oracle.  Sizes are small: everything runs on one host thread.
 Usage: python tests/cudasim/run_checks.py [check ...]   (default: all)
 """
 import os
