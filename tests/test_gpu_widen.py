@@ -203,14 +203,14 @@ def test_fcg_mgpc_default_pc_tight_tolerance_solution_parity(csb, oracle):
 
 def test_fcg_without_preconditioner_converges(csb):
     """poly_degree < 0 and nothing transferred: identity preconditioner."""
-    s = cube_poisson(20, "dirichlet", with_mesh=False)
+    s = cube_poisson(20, "neumann", with_mesh=False)
     r_norm = float(np.linalg.norm(s.rhs))
     m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
     c = csb.SlesIt(csb.SlesItType.FCG, 2000, poly_degree=-1)
     r = c.solve(m, s.rhs, 1e-10, r_norm)
-    assert int(r["cvg"]) == 1
+    assert int(r["cvg"]) == 1 and r["n_iter"] > 5
     res = np.linalg.norm(s.rhs - m.vector_multiply(r["vx"][:s.n_rows].copy()))
-    assert res <= 1.01e-10 * r_norm and abs(res - r["residual"]) <= 1e-2 * res
+    assert res <= 1.01e-10 * r_norm and abs(res - r["residual"]) <= 1e-2 * res + 1e-14 * r_norm
     c.destroy(); m.destroy()
 
 
@@ -225,7 +225,7 @@ def test_fcg_mgpc_128_true_residual(csb):
     r = c.solve(m, s.rhs, 1e-8, r_norm)
     assert int(r["cvg"]) == 1 and r["n_iter"] <= 60
     res = np.linalg.norm(s.rhs - m.vector_multiply(r["vx"][:s.n_rows].copy()))
-    assert res <= 1.01e-8 * r_norm and abs(res - r["residual"]) <= 1e-2 * res
+    assert res <= 1.01e-8 * r_norm and abs(res - r["residual"]) <= 1e-2 * res + 1e-14 * r_norm
     c.destroy(); m.destroy()
 
 
