@@ -472,6 +472,7 @@ bool launch_prolong_inc(int f_n_rows, const int *coarse_row, const double *c_var
                         double *f_var, const MgState *gate);
 bool launch_mg_state_init(MgState *mg, double precision, double r_norm, int n_max_cycles);
 bool launch_mg_cycle_begin(MgState *mg, int cycle_id);
+bool launch_mg_set_initial_residual(MgState *mg, double v);
 bool launch_mg_accum_iter(MgState *mg, const ItState *st, int level, double n_rows_ratio,
                           int take_initial_residual);
 /* same for a smoother whose sweep count is known: += n_iter * n_rows * denom */

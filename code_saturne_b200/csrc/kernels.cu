@@ -1462,6 +1462,17 @@ bool launch_mg_state_init(MgState *mg, double precision, double r_norm, int n_ma
   return post_launch("mg_state_init");
 }
 
+namespace {
+__global__ void k_mg_set_initial_residual(MgState *mg, double v) { mg->initial_residual = v; }
+}
+
+/* a cs_multigrid_smoother reports no initial residual: HUGE_VAL (cs_multigrid.cpp:3270-3276) */
+bool launch_mg_set_initial_residual(MgState *mg, double v)
+{
+  k_mg_set_initial_residual<<<1, 1, 0, ctx().stream>>>(mg, v);
+  return post_launch("mg_set_initial_residual");
+}
+
 bool launch_mg_cycle_begin(MgState *mg, int cycle_id)
 {
   k_mg_cycle_begin<<<1, 1, 0, ctx().stream>>>(mg, cycle_id);

@@ -1397,19 +1397,18 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     return;
   }
   /* smoothers: cs_sles_it PCG + Jacobi (cs_multigrid_create defaults), or -- in the
-     single-cycle (preconditioner) form, precision_mult < 0 -- the Jacobi-family
-     cs_multigrid_smoother types the reference's device settings select
+     kernel-per-phase forms (single cycle, or solver mode), precision_mult < 0 -- the
+     Jacobi-family cs_multigrid_smoother types the reference's device settings select
      (cs_multigrid_set_solver_options, cs_multigrid.cpp:5070-5090); coarse solver: PCG */
   bool any_l1 = false;
   for (int i = 0; i < 3; i++) {
     const bool pcg = (mg->solver_type[i] == CSB_SLES_PCG && mg->poly_degree[i] == 0);
     const bool smoother = (i < 2 && is_smoother_type((int)mg->solver_type[i])
-                           && mg->precision_mult[i] < 0 && mg->n_max_cycles == 1
-                           && a->halo == nullptr);
+                           && mg->precision_mult[i] < 0 && a->halo == nullptr);
     if (!pcg && !smoother) {
-      set_error("csb_multigrid_setup: smoothers must be PCG + Jacobi, or (n_max_cycles 1, "
-                "precision_mult < 0, one rank) Jacobi / L1 / relaxed / RJ2 / RJ3 smoothers; "
-                "the coarse solver PCG + Jacobi");
+      set_error("csb_multigrid_setup: smoothers must be PCG + Jacobi, or (precision_mult < 0, "
+                "one rank) Jacobi / L1 / relaxed / RJ2 / RJ3 smoothers; the coarse solver PCG "
+                "+ Jacobi");
       return;
     }
     if (mg->solver_type[i] == CSB_SLES_L1_JACOBI) any_l1 = true;
@@ -1753,7 +1752,13 @@ csb_multigrid_solve(void *context, const char *name, const csb_matrix_t *a, int 
   int cvg = CSB_SLES_ITERATING;
   int n_cycles = 0;
   const bool dist = (a->halo != nullptr);
-  const bool persistent = dist || (env_int("CSB_MG_MODE_MULTI", 0) == 0);
+  /* cs_multigrid_smoother smoothers run kernel per phase (the persistent kernel holds the
+     PCG-smoothed cycle); a smoother reports no initial residual (:3270-3276) */
+  const bool sm_descent = is_smoother_type((int)mg->solver_type[0]);
+  const bool sm_ascent = is_smoother_type((int)mg->solver_type[1]);
+  const bool persistent = dist || (env_int("CSB_MG_MODE_MULTI", 0) == 0 && !sm_descent
+                                   && !sm_ascent);
+  if (sm_descent && !launch_mg_set_initial_residual(ms, HUGE_VAL)) return CSB_SLES_BREAKDOWN;
 
   if (persistent) {
     /* the whole solve (all cycles, all levels) in one cooperative launch */
@@ -1796,11 +1801,15 @@ csb_multigrid_solve(void *context, const char *name, const csb_matrix_t *a, int 
       const bool ini = (level == 0) ? ((n_cycles > 0) || (vx_ini == vx)) : false;
       ItState *st = mg->it_states.p + 2*level;
 
-      ok = ok && pcg_enqueue(f->m, st, ms, f->ad_inv.p, precision*mg->precision_mult[0],
-                             r_norm, mg->n_max_iter[0], rhs_lv, vx_lv, ini, true,
-                             mg->aux.p, nullptr);
-      ok = ok && launch_mg_accum_iter(ms, st, level, (double)f->m->n_rows * denom,
-                                      level == 0 ? 1 : 0);
+      if (sm_descent)
+        ok = ok && mg_level_smooth(mg, 0, level, rhs_lv, vx_lv, ini, precision, r_norm);
+      else {
+        ok = ok && pcg_enqueue(f->m, st, ms, f->ad_inv.p, precision*mg->precision_mult[0],
+                               r_norm, mg->n_max_iter[0], rhs_lv, vx_lv, ini, true,
+                               mg->aux.p, nullptr);
+        ok = ok && launch_mg_accum_iter(ms, st, level, (double)f->m->n_rows * denom,
+                                        level == 0 ? 1 : 0);
+      }
       SpmvArgs sa;
       sa.m = f->m; sa.x = vx_lv; sa.y = mg->wr.p; sa.b = rhs_lv; sa.mg = ms;
       ok = ok && launch_spmv(level == 0 ? EPI_RESIDUAL_NORM : EPI_RESIDUAL, sa);
@@ -1825,7 +1834,9 @@ csb_multigrid_solve(void *context, const char *name, const csb_matrix_t *a, int 
       MgLevel *f = mg->levels[level], *cl = mg->levels[level+1];
       double *vx_lv = (level == 0) ? s_vx.d : f->vx.p;
       ok = ok && launch_prolong_inc(f->m->n_rows, f->coarse_row.p, cl->vx.p, vx_lv, ms);
-      if (level > 0) {
+      if (level > 0 && sm_ascent)
+        ok = ok && mg_level_smooth(mg, 1, level, f->rhs.p, vx_lv, true, precision, r_norm);
+      else if (level > 0) {
         ItState *st = mg->it_states.p + 2*level + 1;
         ok = ok && pcg_enqueue(f->m, st, ms, f->ad_inv.p, precision*mg->precision_mult[1],
                                r_norm, mg->n_max_iter[1], f->rhs.p, vx_lv, true, true,

@@ -2881,3 +2881,121 @@ ora_matrix_compute_coeffs_v3(int n_rows, const int *row_index,
         da[9*(size_t)c_id + 3*i + i] = epsi_p1 * da[9*(size_t)c_id + 3*i + i];
   }
 }
+
+/*----------------------------------------------------------------------------
+ * ora_mg_solve with any of the level solvers of _mg_level_solve: the V-cycle in solver
+ * mode (n_max_cycles > 1, _multigrid_v_cycle) with cs_multigrid_smoother smoothers
+ * (precision_mult < 0).  A smoother reports no initial residual: HUGE_VAL
+ * (cs_multigrid.cpp:3270-3276), so the divergence test of the cycle never fires.
+ *----------------------------------------------------------------------------*/
+
+int
+ora_mg_solve_sm(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt, int n_max_cycles,
+             double precision, double r_norm,
+             const double *rhs, double *vx, int use_vx_ini,
+             double *out, double *cycle_res)
+{
+  const int n_levels = mg->n_levels;
+  const int coarsest_level = n_levels - 1;
+  const ora_grid_t *g0 = mg->grids[0];
+  const double denom_n_g_rows_0 = 1.0 / g0->n_rows;
+
+  /* rhs_vx work arrays (cs_multigrid.cpp:1888-1935) */
+  double **rhs_l = calloc(n_levels, sizeof(double *));
+  double **vx_l = calloc(n_levels, sizeof(double *));
+  int wr_size = g0->n_rows;
+  for (int l = 1; l < n_levels; l++) {
+    int n = mg->grids[l]->n_rows;
+    rhs_l[l] = calloc(n > 0 ? n : 1, sizeof(double));
+    vx_l[l] = calloc(n > 0 ? n : 1, sizeof(double));
+    if (n > wr_size) wr_size = n;
+  }
+  vx_l[0] = vx;
+  double *wr = malloc(sizeof(double)*(wr_size > 0 ? wr_size : 1));
+
+  int cvg = ORA_ITERATING;
+  int n_equiv_iter = 0;
+  double initial_residual = -1, residual = -1;
+  int n_cycles = 0;
+  double sout[4];
+
+  for (n_cycles = 0; cvg == ORA_ITERATING; n_cycles++) {
+    const int cycle_id = n_cycles + 1;
+    const int vx_ini_nonzero = (n_cycles > 0) ? 1 : use_vx_ini;
+    int end_cycle = 0;
+    int c_cvg = ORA_ITERATING;
+    int level;
+
+    /* Descent */
+    for (level = 0; level < coarsest_level; level++) {
+      const ora_grid_t *f = mg->grids[level];
+      const ora_grid_t *c = mg->grids[level+1];
+      const double *rhs_lv = (level == 0) ? rhs : rhs_l[level];
+      double *vx_lv = vx_l[level];
+      const int ini = (level == 0) ? vx_ini_nonzero : 0;
+
+      c_cvg = _mg_level_solve(opt->type[0], opt->precision_mult[0], f, opt->n_max_iter[0],
+                              precision, r_norm, rhs_lv, vx_lv, ini, sout);
+      int n_iter = (int)sout[0];
+      if (level == 0 && cycle_id == 1) initial_residual = sout[2];
+      if (c_cvg < ORA_BREAKDOWN) { end_cycle = 1; break; }
+
+      ora_spmv_msr(f->n_rows, f->row_index, f->col_id, f->d_val, f->x_val,
+                   0, vx_lv, wr);
+      for (int ii = 0; ii < f->n_rows; ii++) wr[ii] = rhs_lv[ii] - wr[ii];
+
+      if (level == 0) {
+        double r2 = ora_dot_xx(f->n_rows, wr);
+        residual = sqrt(r2);
+        /* initial_residual is passed by value to _convergence_test (:2937,
+           :2967-2968): cycle 1 compares against itself, later cycles against
+           the level-0 smoother's initial residual of cycle 1 (:3278-3279) */
+        const double ir = (cycle_id == 1) ? residual : initial_residual;
+        if (cycle_res != NULL) cycle_res[cycle_id - 1] = residual;
+        if (residual < precision*r_norm) cvg = ORA_CONVERGED;
+        else if (cycle_id > n_max_cycles) cvg = ORA_MAX_ITERATION;
+        else if (residual > ir * 10000.0 && residual > 100.)
+          cvg = ORA_DIVERGED;
+        else if (isnan(residual) || isinf(residual)) cvg = ORA_DIVERGED;
+        if (cvg != 0) {
+          c_cvg = cvg; end_cycle = 1;
+          n_equiv_iter += n_iter * f->n_rows * denom_n_g_rows_0;
+          break;
+        }
+      }
+      n_equiv_iter += n_iter * f->n_rows * denom_n_g_rows_0;
+
+      ora_restrict(f->n_rows, c->n_rows, c->coarse_row, wr, rhs_l[level+1]);
+    }
+
+    if (!end_cycle) {
+      const ora_grid_t *c = mg->grids[coarsest_level];
+      const double *rhs_lv = (coarsest_level == 0) ? rhs : rhs_l[coarsest_level];
+      c_cvg = _mg_level_solve(opt->type[2], opt->precision_mult[2], c, opt->n_max_iter[2],
+                              precision, r_norm, rhs_lv, vx_l[coarsest_level], 0, sout);
+      n_equiv_iter += (int)sout[0] * c->n_rows * denom_n_g_rows_0;
+      if (c_cvg < ORA_BREAKDOWN) end_cycle = 1;
+    }
+
+    if (!end_cycle) {
+      for (level = coarsest_level - 1; level > -1; level--) {
+        const ora_grid_t *f = mg->grids[level];
+        const ora_grid_t *c = mg->grids[level+1];
+        ora_prolong_inc(f->n_rows, c->coarse_row, vx_l[level+1], vx_l[level]);
+        if (level > 0) {
+          c_cvg = _mg_level_solve(opt->type[1], opt->precision_mult[1], f, opt->n_max_iter[1],
+                                  precision, r_norm, rhs_l[level], vx_l[level], 1, sout);
+          n_equiv_iter += (int)sout[0] * f->n_rows * denom_n_g_rows_0;
+          if (c_cvg < ORA_BREAKDOWN) break;
+        }
+      }
+    }
+  }
+
+  out[0] = n_equiv_iter;
+  out[1] = residual;
+  out[2] = n_cycles;
+  for (int l = 1; l < n_levels; l++) { free(rhs_l[l]); free(vx_l[l]); }
+  free(rhs_l); free(vx_l); free(wr);
+  return cvg;
+}

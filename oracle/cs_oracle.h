@@ -196,6 +196,10 @@ int    ora_it_poly(int solver, int n_rows, const int *row_index, const int *col_
                    int n_max_iter, double precision, double r_norm,
                    const double *rhs, double *vx, int use_vx_ini,
                    double *out, double *history, int history_size);
+int    ora_mg_solve_sm(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt, int n_max_cycles,
+                       double precision, double r_norm,
+                       const double *rhs, double *vx, int use_vx_ini,
+                       double *out, double *cycle_res);
 int    ora_mg_k_cycle(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt, double k_cycle_threshold,
                       double precision, double r_norm, const double *rhs, double *vx,
                       double *out);

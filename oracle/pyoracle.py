@@ -402,6 +402,25 @@ class Oracle:
         return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], initial_residual=out[2],
                     history=hist[:int(out[3])].copy(), vx=vx)
 
+    def mg_solve_sm(self, mg, rhs, precision, r_norm, types=(SLES_RJ3, SLES_RJ3, SLES_PCG),
+                    n_max_iter=(3, 3, 500), precision_mult=(-1., -1., 1.), n_max_cycles=100,
+                    vx0=None):
+        """V-cycle in solver mode with cs_multigrid_smoother smoothers."""
+        rhs = _f64(rhs)
+        vx = np.zeros(len(rhs)) if vx0 is None else _f64(vx0).copy()
+        opt = self._pc_opt(types, n_max_iter, precision_mult)
+        out = np.zeros(4)
+        cyc = np.zeros(n_max_cycles + 2)
+        self.lib.ora_mg_solve_sm.argtypes = [C.POINTER(OraMg), C.POINTER(OraMgPcOpt), C.c_int,
+                                             C.c_double, C.c_double, c_dbl_p, c_dbl_p, C.c_int,
+                                             c_dbl_p, c_dbl_p]
+        cvg = self.lib.ora_mg_solve_sm(mg, C.byref(opt), n_max_cycles, precision, r_norm,
+                                       _dp(rhs), _dp(vx), 0 if vx0 is None else 1, _dp(out),
+                                       _dp(cyc))
+        nc = int(out[2])
+        return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], n_cycles=nc,
+                    cycle_residuals=cyc[:nc].copy(), vx=vx)
+
     def mg_k_cycle(self, mg, rhs, precision, r_norm, types=(SLES_JACOBI, SLES_JACOBI, SLES_PCG),
                    n_max_iter=(2, 2, 500), precision_mult=(-1., -1., 10.), trsh=0.25):
         rhs = _f64(rhs)

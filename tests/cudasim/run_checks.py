@@ -134,6 +134,20 @@ def check_cycle_pc(ora):
         assert abs(r["n_iter"] - int(g[f"cyc_{name}_n_iter"])) <= 1
         assert rel(r["vx"][:s.n_rows], g[f"cyc_{name}_vx"]) <= 1e-6, name
         mg.destroy()
+    # the V-cycle's solver mode with smoothers (cycles to convergence)
+    for name in ("rj3", "l1_jacobi"):
+        types, nmi = CYCLES[name]
+        mg = csb.Multigrid()
+        mg.set_solver_options(descent=types[0], ascent=types[1], coarse=types[2],
+                              n_max_cycles=100, n_max_iter_descent=nmi[0],
+                              n_max_iter_ascent=nmi[1], n_max_iter_coarse=nmi[2],
+                              precision_mult=(-1., -1., 1.))
+        mg.setup(m)
+        r = mg.solve(m, s.rhs, 1e-8, rn)
+        n_ref = int(g[f"vsm_{name}_n_iter"])
+        assert int(r["cvg"]) == 1 and abs(r["n_iter"] - n_ref) <= max(2, n_ref // 20), name
+        assert abs(r["residual"] - float(g[f"vsm_{name}_residual"])) <= 1e-6 * r["residual"]
+        mg.destroy()
     # PCG smoothers in the single-cycle form, warm start
     omg = ora.mg_setup(s)
     vx0 = np.sin(0.11 * np.arange(s.n_rows))

@@ -43,6 +43,11 @@ def main():
                               types=types, precision_mult=(-1., -1., 1.))
             out[f"cyc_{name}_vx"] = r["vx"]
             out[f"cyc_{name}_n_iter"] = r["n_iter"]
+            # the same smoothers in the V-cycle's solver mode (cycles to convergence)
+            r = ref.multigrid(h, s.rhs, 1e-8, r_norm, n_max_iter=nmi, types=types,
+                              precision_mult=(-1., -1., 1.))
+            for k in ("cvg", "n_iter", "residual", "vx"):
+                out[f"vsm_{name}_{k}"] = r[k]
             r = ref.fcg_mgpc(h, s.rhs, 200, 1e-8, r_norm, types, nmi)
             for k in ("cvg", "n_iter", "residual", "initial_residual", "vx"):
                 out[f"fcg_{name}_{k}"] = r[k]

@@ -108,6 +108,32 @@ def test_cycle_pc_matches_reference_golden(csb, N, bc):
     m.destroy()
 
 
+@pytest.mark.parametrize("N,bc", MGPC_CASES)
+def test_v_cycle_solver_mode_with_smoothers_matches_reference_golden(csb, N, bc):
+    """cs_multigrid V-cycle in solver mode (cycles to convergence, fine-level residual test every
+    cycle) with cs_multigrid_smoother smoothers: kernel-per-phase cycle, no reduction except
+    the residual norm and the coarsest solve."""
+    g = np.load(os.path.join(GOLD, f"mgpc_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    r_norm = float(g["r_norm"])
+    m = csb.Matrix.from_system(s)
+    for name, (types, nmi) in CYCLES.items():
+        mg = csb.Multigrid()
+        mg.set_solver_options(descent=types[0], ascent=types[1], coarse=types[2],
+                              n_max_cycles=100, n_max_iter_descent=nmi[0],
+                              n_max_iter_ascent=nmi[1], n_max_iter_coarse=nmi[2],
+                              precision_mult=(-1., -1., 1.))
+        mg.setup(m)
+        r = mg.solve(m, s.rhs, 1e-8, r_norm)
+        n_ref = int(g[f"vsm_{name}_n_iter"])
+        assert int(r["cvg"]) == int(g[f"vsm_{name}_cvg"]) == 1, name
+        assert abs(r["n_iter"] - n_ref) <= max(2, n_ref // 20), name
+        assert abs(r["residual"] - float(g[f"vsm_{name}_residual"])) <= 1e-6 * r["residual"]
+        assert rel_l2(r["vx"][:s.n_rows], g[f"vsm_{name}_vx"]) <= (1e-7 if bc == "dirichlet" else 1e-3)
+        mg.destroy()
+    m.destroy()
+
+
 def test_cycle_pc_tight_vs_oracle(csb, oracle):
     """With the coarsest level solved to 1e-14 the whole cycle agrees to rounding; also from a
     nonzero initial vx (level-0 descent smoother starts from it)."""

@@ -280,6 +280,10 @@ def test_oracle_cycle_pc_and_fcg_mgpc_match_golden(oracle, N, bc):
         assert np.array_equal(r["vx"], g[f"fcg_{name}_vx"])
         hist = g[f"fcg_{name}_history"]
         assert np.array_equal(r["history"][1:], hist)     # history[0] = initial residual
+        r = oracle.mg_solve_sm(mg, s.rhs, 1e-8, r_norm, types, nmi)      # V-cycle solver mode
+        assert (r["cvg"], r["n_iter"], r["residual"]) == (
+            int(g[f"vsm_{name}_cvg"]), int(g[f"vsm_{name}_n_iter"]), float(g[f"vsm_{name}_residual"]))
+        assert np.array_equal(r["vx"], g[f"vsm_{name}_vx"])
     oracle.mg_free(mg)
 
 
