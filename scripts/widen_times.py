@@ -83,6 +83,28 @@ def main():
         None, f"{mg.n_levels()} levels")
     mg.destroy()
 
+    # V-cycle in solver mode with RJ3 smoothers (cycles to convergence, kernel per phase)
+    g = api.Multigrid()
+    g.set_solver_options(descent=api.SlesItType.RJ3, ascent=api.SlesItType.RJ3, n_max_cycles=100,
+                         n_max_iter_descent=3, n_max_iter_ascent=3, precision_mult=(-1., -1., 1.))
+    g.setup(m)
+    out = {}
+    t = timed(lambda: out.update(g.solve(m, s.rhs, args.precision, r_norm)), max(1, args.reps // 2))
+    row(f"V-cycle solver mode, RJ3 3+3 sweeps, solve to {args.precision:g} (e2e)", t, None,
+        f"{out['n_cycles']} cycles, cvg {int(out['cvg'])}")
+    g.destroy()
+
+    # FCG + K-cycle (pairwise aggregation, Galerkin, 2 Jacobi sweeps)
+    c = api.SlesIt(api.SlesItType.FCG, 500, poly_degree=-1)
+    c.transfer_pc(api.Multigrid(pc=True, mg_type=1))
+    t0 = time.perf_counter(); c.setup(m); api.synchronize(); t_s = time.perf_counter() - t0
+    out = {}
+    t = timed(lambda: out.update(c.solve(m, s.rhs, args.precision, r_norm)), 1)
+    row("K-cycle hierarchy setup (pairwise, limit 4, Galerkin; host)", t_s)
+    row(f"FCG + K-cycle solve to {args.precision:g} (e2e)", t, None,
+        f"{out['n_iter']} iterations, cvg {int(out['cvg'])}")
+    c.destroy()
+
     for label, T, kw in (("FCG + V-cycle(RJ3)", api.SlesItType.FCG, dict(poly_degree=-1)),
                          ("PCG + V-cycle(RJ3)", api.SlesItType.PCG, dict(poly_degree=-1)),
                          ("FCG + poly(1)", api.SlesItType.FCG, dict(poly_degree=1)),
