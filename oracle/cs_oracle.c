@@ -2365,7 +2365,12 @@ _pcg_sr_pc(const ora_pc_t *pc, int n_max_iter, double precision, double r_norm,
   return cvg;
 }
 
-/* FCG (solver 1) or single-reduction PCG (solver 0) preconditioned by one multigrid
+static int
+_ipcg_pc(const ora_pc_t *pc, int n_max_iter, double precision, double r_norm,
+         const double *rhs, double *vx, int use_vx_ini,
+         double *out, double *history, int history_size);
+
+/* FCG (solver 1), IPCG (2) or single-reduction PCG (0) preconditioned by one multigrid
    V-cycle -- FCG + cs_multigrid_pc is the reference's production pressure solver. */
 
 int
@@ -2379,6 +2384,9 @@ ora_it_mgpc(int solver, const ora_mg_t *mg, const ora_mg_pc_opt_t *opt,
   memset(&pc, 0, sizeof(pc));
   pc.kind = 2; pc.mg = mg; pc.opt = opt; pc.precision = precision; pc.r_norm = r_norm;
   _pc_init_matrix(&pc, g->n_rows, g->row_index, g->col_id, g->d_val, g->x_val);
+  if (solver == 2)
+    return _ipcg_pc(&pc, n_max_iter, precision, r_norm, rhs, vx, use_vx_ini,
+                    out, history, history_size);
   if (solver == 1)
     return _fcg_pc(&pc, n_max_iter, precision, r_norm, rhs, vx, use_vx_ini,
                    out, history, history_size);
@@ -2413,7 +2421,10 @@ ora_it_poly(int solver, int n_rows, const int *row_index, const int *col_id,
   pc.poly_degree = (poly_degree > 2) ? 2 : poly_degree;
   _pc_init_matrix(&pc, n_rows, row_index, col_id, d_val, x_val);
   int cvg;
-  if (solver == 1)
+  if (solver == 2)
+    cvg = _ipcg_pc(&pc, n_max_iter, precision, r_norm, rhs, vx, use_vx_ini,
+                   out, history, history_size);
+  else if (solver == 1)
     cvg = _fcg_pc(&pc, n_max_iter, precision, r_norm, rhs, vx, use_vx_ini,
                   out, history, history_size);
   else
@@ -2789,6 +2800,9 @@ ora_it_kpc(int solver, const ora_mg_t *mg, const ora_mg_pc_opt_t *opt, double k_
   pc.kind = 3; pc.trsh = k_cycle_threshold;
   pc.mg = mg; pc.opt = opt; pc.precision = precision; pc.r_norm = r_norm;
   _pc_init_matrix(&pc, g->n_rows, g->row_index, g->col_id, g->d_val, g->x_val);
+  if (solver == 2)
+    return _ipcg_pc(&pc, n_max_iter, precision, r_norm, rhs, vx, use_vx_ini,
+                    out, history, history_size);
   if (solver == 1)
     return _fcg_pc(&pc, n_max_iter, precision, r_norm, rhs, vx, use_vx_ini,
                    out, history, history_size);
@@ -2997,5 +3011,78 @@ ora_mg_solve_sm(const ora_mg_t *mg, const ora_mg_pc_opt_t *opt, int n_max_cycles
   out[2] = n_cycles;
   for (int l = 1; l < n_levels; l++) { free(rhs_l[l]); free(vx_l[l]); }
   free(rhs_l); free(vx_l); free(wr);
+  return cvg;
+}
+
+/*----------------------------------------------------------------------------
+ * Inexact-preconditioning CG with a general preconditioner: _conjugate_gradient_ip
+ * (src/alge/cs_sles_it.cpp:1016-1203) with pc_apply = pc -- the solver the reference pairs
+ * with the K-cycle ("has to be used with IPCG (or FCG)", cs_multigrid.cpp:4030-4035).
+ *----------------------------------------------------------------------------*/
+
+static int
+_ipcg_pc(const ora_pc_t *pc, int n_max_iter, double precision, double r_norm,
+         const double *rhs, double *vx, int use_vx_ini,
+         double *out, double *history, int history_size)
+{
+  const int n = pc->n_rows;
+  double *rk = malloc(sizeof(double)*((size_t)n*5 + 1));
+  double *rkm1 = rk + n, *dk = rk + 2*n, *gk = rk + 3*n, *zk = rk + 4*n;
+
+  ora_cvg_t cv = {precision, r_norm, -1, n_max_iter, 0, -1,
+                  history, history_size, 0};
+  int cvg;
+  int n_iter = 0;
+  double ro_0, ro_1, alpha, rk_gk_m1, rkm1_gk, rk_gk, beta, residual;
+
+  if (use_vx_ini) {
+    ora_spmv_msr(n, pc->row_index, pc->col_id, pc->d_val, pc->x_val, 0, vx, rk);
+    for (int ii = 0; ii < n; ii++) rk[ii] -= rhs[ii];
+  }
+  else {
+    for (int ii = 0; ii < n; ii++) { vx[ii] = 0; rk[ii] = -rhs[ii]; }
+  }
+  _pc_apply(pc, rk, gk);
+  for (int ii = 0; ii < n; ii++) dk[ii] = gk[ii];
+
+  ora_dot_xx_xy(n, rk, gk, &residual, &rk_gk_m1);
+  residual = sqrt(residual);
+  cv.initial_residual = residual;
+  cvg = _cvg_test(&cv, n_iter, residual);
+
+  if (cvg == ORA_ITERATING) {
+    n_iter = 1;
+    ora_spmv_msr(n, pc->row_index, pc->col_id, pc->d_val, pc->x_val, 0, dk, zk);
+    ora_dot_xy_yz(n, rk, dk, zk, &ro_0, &ro_1);
+    double d_ro_1 = (fabs(ro_1) > DBL_MIN) ? 1. / ro_1 : 0.;
+    alpha = - ro_0 * d_ro_1;
+    for (int ii = 0; ii < n; ii++) vx[ii] += (alpha * dk[ii]);
+    for (int ii = 0; ii < n; ii++) { rkm1[ii] = rk[ii]; rk[ii] += (alpha * zk[ii]); }
+    residual = sqrt(ora_dot_xx(n, rk));
+    cvg = _cvg_test(&cv, n_iter, residual);
+  }
+
+  while (cvg == ORA_ITERATING) {
+    _pc_apply(pc, rk, gk);
+    ora_dot_xx_xy_yz(n, rk, gk, rkm1, &residual, &rk_gk, &rkm1_gk);
+    residual = sqrt(residual);
+    if (n_iter > 1)
+      cvg = _cvg_test(&cv, n_iter, residual);
+    if (cvg != ORA_ITERATING) break;
+    n_iter += 1;
+    beta = (fabs(rk_gk_m1) > DBL_MIN) ? (rk_gk - rkm1_gk) / rk_gk_m1 : 0.;
+    rk_gk_m1 = rk_gk;
+    for (int ii = 0; ii < n; ii++) dk[ii] = gk[ii] + (beta * dk[ii]);
+    ora_spmv_msr(n, pc->row_index, pc->col_id, pc->d_val, pc->x_val, 0, dk, zk);
+    ora_dot_xy_yz(n, rk, dk, zk, &ro_0, &ro_1);
+    double d_ro_1 = (fabs(ro_1) > DBL_MIN) ? 1. / ro_1 : 0.;
+    alpha = - ro_0 * d_ro_1;
+    for (int ii = 0; ii < n; ii++) vx[ii] += (alpha * dk[ii]);
+    for (int ii = 0; ii < n; ii++) { rkm1[ii] = rk[ii]; rk[ii] += (alpha * zk[ii]); }
+  }
+
+  out[0] = cv.n_iterations; out[1] = cv.residual; out[2] = cv.initial_residual;
+  out[3] = cv.history_n;
+  free(rk);
   return cvg;
 }
