@@ -350,7 +350,8 @@ struct SpmvArgs {
   double       *dk = nullptr;
   ItState      *st = nullptr;
   MgState      *mg = nullptr;
-  int           phase = 0;         /* PCG_DOT3: 0 = first (ro_0, ro_1), 1 = iteration */
+  int           phase = 0;         /* PCG_DOT3: 0 = first (ro_0, ro_1), 1 = iteration,
+                                      2 = IPCG step length only */
   int           smooth_mode = 0;   /* EPI_SMOOTH */
   double        w0 = 1., w1 = 0.;  /* EPI_SMOOTH relaxation weights */
   const double *qk = nullptr;      /* EPI_FCG_DOT4 */
@@ -458,6 +459,14 @@ bool launch_pcg_pc_update(int n, ItState *st, const double *gk, const double *sk
 bool launch_kc_vec(int mode, int n, double a, double c, const double *x, const double *b,
                    double *y);
 bool launch_prolong_set(int f_n_rows, const int *coarse_row, const double *c_var, double *f_var);
+
+/* IPCG with a general preconditioner (cs_sles_it.cpp:1016-1203); the step length comes out of
+   launch_spmv(EPI_PCG_DOT3) with phase = 2 */
+bool launch_ipcg_dots(int n, ItState *st, bool first, const double *rk, const double *gk,
+                      const double *rkm1, double *dk);
+bool launch_ipcg_dir(int n, ItState *st, const double *gk, double *dk);
+bool launch_ipcg_update(int n, ItState *st, bool first, const double *dk, const double *zk,
+                        double *vx, double *rk, double *rkm1);
 
 /* FCG with a general preconditioner, kernel per phase (cs_sles_it.cpp:832-985) */
 bool launch_fcg_init(int n, ItState *st, const double *rhs, double *vx, double *rk,

@@ -207,6 +207,15 @@ __device__ __forceinline__ void fcg_finalize(ItState *st, const double *s)
   st->cvg = cvg;
 }
 
+/* IPCG step length (cs_sles_it.cpp:1122-1127, :1178-1183): s = (rk.rk, rk.dk, dk.zk) */
+__device__ __forceinline__ void ipcg_finalize_alpha(ItState *st, const double *s)
+{
+  st->ro_0 = s[1];
+  st->ro_1 = s[2];
+  const double d_ro_1 = (fabs(st->ro_1) > DBL_MIN) ? 1. / st->ro_1 : 0.;
+  st->alpha = - st->ro_0 * d_ro_1;
+}
+
 /* _convergence_test, src/alge/cs_multigrid.cpp:2927-3035 */
 __device__ __forceinline__ void mg_finalize_residual(MgState *mg, const double *s)
 {
@@ -337,9 +346,12 @@ __device__ __forceinline__ void spmv_epilogue(const SpmvK &a, int r, bool active
     if (a.phase == 0)
       grid_sum_finalize<3>(v, a.partials, a.ticket,
                            [st](const double *s) { pcg_finalize_first(st, s); });
-    else
+    else if (a.phase == 1)
       grid_sum_finalize<3>(v, a.partials, a.ticket,
                            [st](const double *s) { pcg_finalize_iter(st, s); });
+    else     /* 2: IPCG, only the step length comes out of this product */
+      grid_sum_finalize<3>(v, a.partials, a.ticket,
+                           [st](const double *s) { ipcg_finalize_alpha(st, s); });
   }
 }
 
@@ -1846,7 +1858,112 @@ k_pcg_pc_update(int n, const ItState *st, const double *__restrict__ gk,
   }
 }
 
+/* Inexact-preconditioning CG with a general preconditioner (_conjugate_gradient_ip,
+   cs_sles_it.cpp:1016-1203): the reductions that follow the preconditioner.
+   first = 1 (:1090-1103): dk = gk, (rk.rk, rk.gk) -> initial residual and test, rk_gk_m1;
+   first = 0 (:1140-1163): (rk.rk, rk.gk, gk.rkm1) -> test, beta = (rk.gk - rkm1.gk)/rk_gk_m1 */
+__global__ void __launch_bounds__(TPB)
+k_ipcg_dots(int n, ItState *st, int first, const double *__restrict__ rk,
+            const double *__restrict__ gk, const double *__restrict__ rkm1,
+            double *__restrict__ dk, double *partials, unsigned *ticket)
+{
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  double v[3] = {0., 0., 0.};
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    const double r = rk[i], g = gk[i];
+    v[0] += r*r;
+    v[1] += r*g;
+    if (first) dk[i] = g;
+    else v[2] += g*rkm1[i];
+  }
+  grid_sum_finalize<3>(v, partials, ticket, [st, first](const double *s) {
+    const double residual = sqrt(s[0]);
+    if (first) {
+      st->rk_gkm1 = s[1];
+      st->initial_residual = residual;
+      const int cvg = it_cvg_test(st, 0, residual);
+      if (cvg == CSB_SLES_ITERATING) st->n_iter = 1;
+      st->cvg = cvg;
+    }
+    else {
+      int cvg = CSB_SLES_ITERATING;
+      if (st->n_iter > 1) cvg = it_cvg_test(st, st->n_iter, residual);
+      if (cvg == CSB_SLES_ITERATING) {
+        st->n_iter += 1;
+        const double rk_gk = s[1], rkm1_gk = s[2];
+        st->beta = (fabs(st->rk_gkm1) > DBL_MIN) ? (rk_gk - rkm1_gk) / st->rk_gkm1 : 0.;
+        st->rk_gkm1 = rk_gk;
+      }
+      st->cvg = cvg;
+    }
+  });
+}
+
+/* dk = gk + beta dk (:1166-1168) */
+__global__ void __launch_bounds__(TPB)
+k_ipcg_dir(int n, const ItState *st, const double *__restrict__ gk, double *__restrict__ dk)
+{
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  const double beta = st->beta;
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB)
+    dk[i] = gk[i] + (beta * dk[i]);
+}
+
+/* vx += alpha dk; rkm1 = rk; rk += alpha zk (:1129-1137, :1185-1193); first = 1 adds the
+   residual norm and convergence test that close the first iteration (:1139-1146) */
+__global__ void __launch_bounds__(TPB)
+k_ipcg_update(int n, ItState *st, int first, const double *__restrict__ dk,
+              const double *__restrict__ zk, double *__restrict__ vx,
+              double *__restrict__ rk, double *__restrict__ rkm1, double *partials,
+              unsigned *ticket)
+{
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  const double alpha = st->alpha;
+  double v[1] = {0.};
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    vx[i] += (alpha * dk[i]);
+    const double ro = rk[i];
+    rkm1[i] = ro;
+    const double r = ro + (alpha * zk[i]);
+    rk[i] = r;
+    v[0] += r*r;
+  }
+  if (first)
+    grid_sum_finalize<1>(v, partials, ticket, [st](const double *s) {
+      st->cvg = it_cvg_test(st, st->n_iter, sqrt(s[0]));
+    });
+}
+
 } // anonymous namespace
+
+bool launch_ipcg_dots(int n, ItState *st, bool first, const double *rk, const double *gk,
+                      const double *rkm1, double *dk)
+{
+  Context &c = ctx();
+  const int g = vec_grid(n);
+  if (!ensure_partials(g)) return false;
+  k_ipcg_dots<<<g, TPB, 0, c.stream>>>(n, st, first ? 1 : 0, rk, gk, rkm1, dk, c.partials,
+                                       c.ticket);
+  return post_launch("ipcg_dots");
+}
+
+bool launch_ipcg_dir(int n, ItState *st, const double *gk, double *dk)
+{
+  if (n < 1) return true;
+  k_ipcg_dir<<<vec_grid(n), TPB, 0, ctx().stream>>>(n, st, gk, dk);
+  return post_launch("ipcg_dir");
+}
+
+bool launch_ipcg_update(int n, ItState *st, bool first, const double *dk, const double *zk,
+                        double *vx, double *rk, double *rkm1)
+{
+  Context &c = ctx();
+  const int g = vec_grid(n);
+  if (!ensure_partials(g)) return false;
+  k_ipcg_update<<<g, TPB, 0, c.stream>>>(n, st, first ? 1 : 0, dk, zk, vx, rk, rkm1,
+                                         c.partials, c.ticket);
+  return post_launch("ipcg_update");
+}
 
 bool launch_pcg_pc_init(int n, const double *rhs, double *vx, double *rk, bool have_ax)
 {

@@ -153,7 +153,7 @@ struct _csb_sles_it_t {
      (FCG with poly_degree < 0) -- cs_sles_it_create, cs_sles_it.cpp:4676-4690 */
   bool general_pc() const {
     if (is_smoother) return false;
-    if (type == CSB_SLES_FCG) return (poly_degree != 0);
+    if (type == CSB_SLES_FCG || type == CSB_SLES_IPCG) return (poly_degree != 0);
     if (type == CSB_SLES_PCG) return (poly_degree > 0 || (poly_degree < 0 && pc_mg != nullptr));
     return false;
   }
@@ -488,6 +488,62 @@ bool fcg_pc_enqueue(csb_sles_it_t *c, const csb_matrix_t *a, double precision, d
   return true;
 }
 
+/* Inexact-preconditioning CG with a general preconditioner (_conjugate_gradient_ip,
+   cs_sles_it.cpp:1016-1203) -- the solver the reference pairs with the K-cycle.  Per
+   iteration: the preconditioner's launches, a 3-dot reduction (test, beta), the direction
+   update, one SpMV with the 2 dots of the step length in its epilogue, one fused update. */
+bool ipcg_pc_enqueue(csb_sles_it_t *c, const csb_matrix_t *a, double precision, double r_norm,
+                     const double *rhs, double *vx, bool vx_ini_nonzero)
+{
+  const int n = a->n_rows;
+  const size_t ws = work_stride_of((size_t)a->n_cols_ext);
+  Context &cx = ctx();
+  double *rk = c->work.p, *rkm1 = rk + ws, *dk = rk + 2*ws, *gk = rk + 3*ws, *zk = rk + 4*ws;
+  ItState *st = c->st.p;
+  const bool mgpc = pc_is_mg(c);
+
+  if (!launch_it_state_init(st, nullptr, precision, r_norm, c->n_max_iter)) return false;
+  if (vx_ini_nonzero) {
+    SpmvArgs s0; s0.m = a; s0.x = vx; s0.y = rk;
+    if (!launch_spmv(EPI_STORE, s0)) return false;
+  }
+  if (!launch_pcg_pc_init(n, rhs, vx, rk, vx_ini_nonzero)) return false;
+  if (mgpc && !launch_mg_state_init(mg_gate(c->pc_mg), precision, r_norm, 1)) return false;
+
+  SpmvArgs sa;
+  sa.m = a; sa.st = st; sa.rk = rk; sa.x = dk; sa.y = zk; sa.phase = 2;
+
+  if (!pc_apply_enqueue(c, a, precision, r_norm, rk, gk)) return false;
+  if (!launch_ipcg_dots(n, st, true, rk, gk, rkm1, dk)) return false;
+  if (!launch_spmv(EPI_PCG_DOT3, sa)) return false;
+  if (!launch_ipcg_update(n, st, true, dk, zk, vx, rk, rkm1)) return false;
+  if (mgpc && !launch_gate_from_it(mg_gate(c->pc_mg), st)) return false;
+
+  const int poll = (mgpc && mg_is_k_cycle(c->pc_mg)) ? 1 : (mgpc ? 2 : 16);
+  if (poll == 1) {
+    if (!CSB_CUDA(cudaMemcpyAsync(c->h_st, st, IT_HEAD, cudaMemcpyDeviceToHost, cx.stream)))
+      return false;
+    if (!CSB_CUDA(cudaStreamSynchronize(cx.stream))) return false;
+    if (c->h_st->cvg != CSB_SLES_ITERATING) return true;
+  }
+  for (int it = 1; ; it++) {
+    if (!pc_apply_enqueue(c, a, precision, r_norm, rk, gk)) return false;
+    if (!launch_ipcg_dots(n, st, false, rk, gk, rkm1, dk)) return false;
+    if (it >= c->n_max_iter) break;     /* that was the final convergence test */
+    if (!launch_ipcg_dir(n, st, gk, dk)) return false;
+    if (!launch_spmv(EPI_PCG_DOT3, sa)) return false;
+    if (!launch_ipcg_update(n, st, false, dk, zk, vx, rk, rkm1)) return false;
+    if (mgpc && !launch_gate_from_it(mg_gate(c->pc_mg), st)) return false;
+    if ((it % poll) == 0) {
+      if (!CSB_CUDA(cudaMemcpyAsync(c->h_st, st, IT_HEAD, cudaMemcpyDeviceToHost, cx.stream)))
+        return false;
+      if (!CSB_CUDA(cudaStreamSynchronize(cx.stream))) return false;
+      if (c->h_st->cvg != CSB_SLES_ITERATING) break;
+    }
+  }
+  return true;
+}
+
 /* Single-reduction PCG with a general preconditioner (_conjugate_gradient_sr,
    cs_sles_it.cpp:1229-1415): pcg_enqueue with the fused Jacobi scaling replaced by the
    preconditioner's launches; the SpMV epilogue (3 dots + scalar recurrences) is shared. */
@@ -556,9 +612,10 @@ csb_sles_it_create(csb_sles_it_type_t solver_type, int poly_degree, int n_max_it
   /* FCG with poly_degree < 0: the preconditioner is handed over afterwards
      (csb_sles_it_transfer_pc: one multigrid V-cycle), identity if none is */
   if (solver_type != CSB_SLES_JACOBI && poly_degree != 0
-      && !(solver_type == CSB_SLES_PCG || solver_type == CSB_SLES_FCG)) {
+      && !(solver_type == CSB_SLES_PCG || solver_type == CSB_SLES_FCG
+           || solver_type == CSB_SLES_IPCG)) {
     set_error("csb_sles_it_create: poly_degree %d: polynomial (> 0), none or transferred "
-              "(< 0) preconditioners are available with PCG and FCG only on this path",
+              "(< 0) preconditioners are available with PCG, FCG and IPCG only on this path",
               poly_degree);
     return nullptr;
   }
@@ -732,7 +789,9 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
   case CSB_SLES_FCG:
   case CSB_SLES_IPCG:
     if (c->general_pc()) {
-      ok = fcg_pc_enqueue(c, a, precision, r_norm, s_rhs.d, s_vx.d, ini);
+      ok = (c->type == CSB_SLES_IPCG)
+        ? ipcg_pc_enqueue(c, a, precision, r_norm, s_rhs.d, s_vx.d, ini)
+        : fcg_pc_enqueue(c, a, precision, r_norm, s_rhs.d, s_vx.d, ini);
       break;
     }
     {
@@ -2074,9 +2133,9 @@ csb_multigrid_t *csb_multigrid_pc_create(csb_multigrid_type_t mg_type)
 int csb_sles_it_transfer_pc(csb_sles_it_t *c, csb_multigrid_t **pc)
 {
   if (c == nullptr || pc == nullptr) return -1;
-  if ((c->type != CSB_SLES_FCG && c->type != CSB_SLES_PCG) || c->poly_degree >= 0
-      || c->is_smoother) {
-    set_error("csb_sles_it_transfer_pc: needs CSB_SLES_FCG or CSB_SLES_PCG created with "
+  if ((c->type != CSB_SLES_FCG && c->type != CSB_SLES_PCG && c->type != CSB_SLES_IPCG)
+      || c->poly_degree >= 0 || c->is_smoother) {
+    set_error("csb_sles_it_transfer_pc: needs CSB_SLES_FCG, _IPCG or _PCG created with "
               "poly_degree < 0");
     return -1;
   }

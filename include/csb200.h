@@ -310,8 +310,9 @@ int          csb_halo_set_pcomm(csb_halo_t *halo, csb_pcomm_t *c);
  * Iterative solvers (cs_sles_it_t)
  *----------------------------------------------------------------------------*/
 
-/* cs_sles_it_create (src/alge/cs_sles_it.cpp:4659): poly_degree 0 = Jacobi
-   preconditioner (the only one on this path), < 0 = none. */
+/* cs_sles_it_create (src/alge/cs_sles_it.cpp:4659): poly_degree 0 = Jacobi preconditioner,
+   1 / >= 2 = polynomial of degree 1 / 2 (PCG, FCG, IPCG; :4683-4690), < 0 = none, or the one
+   handed over with csb_sles_it_transfer_pc. */
 csb_sles_it_t *csb_sles_it_create(csb_sles_it_type_t  solver_type,
                                   int                 poly_degree,
                                   int                 n_max_iter,
@@ -503,7 +504,7 @@ int  csb_host_coarse_structure(csb_lnum_t f_n_rows, const csb_lnum_t *f_row_inde
 csb_multigrid_t *csb_multigrid_pc_create(csb_multigrid_type_t mg_type);
 
 /* The solver takes ownership of the preconditioner; *pc is set to NULL.
-   CSB_SLES_FCG created with poly_degree < 0 only; with no preconditioner transferred such
+   CSB_SLES_FCG, _IPCG or _PCG created with poly_degree < 0 only; with no preconditioner transferred such
    a solver runs unpreconditioned (identity).  Returns 0, or -1 (see csb_last_error). */
 int  csb_sles_it_transfer_pc(csb_sles_it_t *c, csb_multigrid_t **pc);
 csb_multigrid_t *csb_sles_it_get_pc(csb_sles_it_t *c);   /* cs_sles_it_get_pc */

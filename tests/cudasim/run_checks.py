@@ -199,12 +199,13 @@ def check_general_pc(ora):
     rn = float(g["r_norm"])
     m = csb.Matrix.from_system(s)
     tags = [("pcg_poly1", 0, 1), ("pcg_poly2", 0, 2), ("fcg_poly1", 1, 1), ("fcg_poly2", 1, 2),
-            ("fcg_poly-1", 1, -1), ("pcg_mgpc", 0, -1)]
+            ("fcg_poly-1", 1, -1), ("pcg_mgpc", 0, -1), ("ipcg_poly1", 2, 1),
+            ("ipcg_poly2", 2, 2), ("ipcg_mgpc", 2, -1)]
 
     def make(tag, so, deg, nmax):
-        c = csb.SlesIt(csb.SlesItType.PCG if so == 0 else csb.SlesItType.FCG, nmax,
+        c = csb.SlesIt((csb.SlesItType.PCG, csb.SlesItType.FCG, csb.SlesItType.IPCG)[so], nmax,
                        poly_degree=deg)
-        if tag == "pcg_mgpc":
+        if tag.endswith("_mgpc"):
             c.transfer_pc(csb.Multigrid(pc=True))
         return c
 

@@ -1,5 +1,5 @@
 """Golden fixtures for cs_sles_it with general preconditioners: single-reduction PCG
-(_conjugate_gradient_sr, cs_sles_it.cpp:1229-1415) and FCG (:832-985) with the polynomial
+(_conjugate_gradient_sr, cs_sles_it.cpp:1229-1415), FCG (:832-985) and IPCG (:1016-1203) with the polynomial
 preconditioner of degree 1 and 2 (cs_sles_pc.cpp:549-610), FCG without preconditioner, and
 PCG preconditioned by one V-cycle: outputs of the reference's own compiled CPU code
 (oracle/_ref/libcsref.so, OMP_NUM_THREADS=1):
@@ -39,13 +39,15 @@ def main():
                 out[f"{tag}_warm_{k}"] = w[k]
             print(N, bc, tag, "n_iter", r["n_iter"])
 
-        for sname, solver in (("pcg", ref.PCG), ("fcg", ref.FCG)):
+        for sname, solver in (("pcg", ref.PCG), ("fcg", ref.FCG), ("ipcg", ref.IPCG)):
             for deg in (1, 2) + ((-1,) if sname == "fcg" else ()):
                 record(f"{sname}_poly{deg}",
                        lambda nmax, eps, v0, solver=solver, deg=deg:
                        ref.sles_it(h, solver, s.rhs, nmax, eps, r_norm, vx0=v0, poly_degree=deg))
         record("pcg_mgpc", lambda nmax, eps, v0: ref.it_mgpc(h, ref.PCG, s.rhs, nmax, eps, r_norm,
                                                               vx0=v0))
+        record("ipcg_mgpc", lambda nmax, eps, v0: ref.it_mgpc(h, ref.IPCG, s.rhs, nmax, eps, r_norm,
+                                                               vx0=v0))
         ref.destroy(h)
         path = os.path.join(ROOT, "tests", "golden", f"pc_N{N}_{bc}.npz")
         np.savez_compressed(path, **out)

@@ -258,12 +258,12 @@ def test_fcg_mgpc_128_true_residual(csb):
 # -------------------------------- cs_sles_it with general preconditioners (a14, a21)
 
 PC_TAGS = [("pcg_poly1", 0, 1), ("pcg_poly2", 0, 2), ("fcg_poly1", 1, 1), ("fcg_poly2", 1, 2),
-           ("fcg_poly-1", 1, -1)]
+           ("fcg_poly-1", 1, -1), ("ipcg_poly1", 2, 1), ("ipcg_poly2", 2, 2)]
 
 
 @pytest.mark.parametrize("N,bc", MGPC_CASES)
 def test_general_pc_matches_reference_golden(csb, N, bc):
-    """Single-reduction PCG (_conjugate_gradient_sr) and FCG with the polynomial
+    """Single-reduction PCG (_conjugate_gradient_sr), FCG and IPCG with the polynomial
     preconditioner (degree+1 fused Jacobi sweeps from zero), FCG without preconditioner, PCG
     preconditioned by one V-cycle: iteration counts +-2, first residuals to reduction-order
     rounding, warm start with a max-iteration exit reproduces the same iterate."""
@@ -273,13 +273,13 @@ def test_general_pc_matches_reference_golden(csb, N, bc):
     m = csb.Matrix.from_system(s)
 
     def make(tag, so, deg, nmax):
-        c = csb.SlesIt(csb.SlesItType.PCG if so == 0 else csb.SlesItType.FCG, nmax,
+        c = csb.SlesIt((csb.SlesItType.PCG, csb.SlesItType.FCG, csb.SlesItType.IPCG)[so], nmax,
                        poly_degree=deg)
-        if tag == "pcg_mgpc":
+        if tag.endswith("_mgpc"):
             c.transfer_pc(csb.Multigrid(pc=True))
         return c
 
-    for tag, so, deg in PC_TAGS + [("pcg_mgpc", 0, -1)]:
+    for tag, so, deg in PC_TAGS + [("pcg_mgpc", 0, -1), ("ipcg_mgpc", 2, -1)]:
         c = make(tag, so, deg, 500)
         r = c.solve(m, s.rhs, 1e-9, r_norm)
         assert int(r["cvg"]) == int(g[f"{tag}_cvg"]) == 1, tag
@@ -304,7 +304,7 @@ def test_general_pc_tight_tolerance_solution_parity(csb, oracle):
     r_norm = float(np.sqrt(oracle.dot_xx(s.rhs)))
     A = (s.row_index, s.col_id, s.d_val, s.x_val)
     m = csb.Matrix.from_system(s)
-    for so, T in ((0, csb.SlesItType.PCG), (1, csb.SlesItType.FCG)):
+    for so, T in ((0, csb.SlesItType.PCG), (1, csb.SlesItType.FCG), (2, csb.SlesItType.IPCG)):
         for deg in (1, 2):
             o = oracle.it_poly(so, *A, s.rhs, deg, 2000, 1e-13, r_norm)
             c = csb.SlesIt(T, 2000, poly_degree=deg)

@@ -324,7 +324,7 @@ def test_oracle_mgpc_vs_reference_direct(oracle, reflib):
 # ---- cs_sles_it with general preconditioners (polynomial, none, multigrid) ----
 
 PC_TAGS = [("pcg_poly1", 0, 1), ("pcg_poly2", 0, 2), ("fcg_poly1", 1, 1), ("fcg_poly2", 1, 2),
-           ("fcg_poly-1", 1, -1)]
+           ("fcg_poly-1", 1, -1), ("ipcg_poly1", 2, 1), ("ipcg_poly2", 2, 2)]
 
 
 @pytest.mark.parametrize("N,bc", MGPC_CASES)
@@ -339,6 +339,8 @@ def test_oracle_general_pc_matches_golden(oracle, N, bc):
             for tag, so, deg in PC_TAGS]
     runs.append(("pcg_mgpc", lambda nmax, eps, v0: oracle.it_mgpc(0, mg, s.rhs, nmax, eps, r_norm,
                                                                     vx0=v0)))
+    runs.append(("ipcg_mgpc", lambda nmax, eps, v0: oracle.it_mgpc(2, mg, s.rhs, nmax, eps, r_norm,
+                                                                     vx0=v0)))
     for tag, solve in runs:
         r = solve(500, 1e-9, None)
         assert r["cvg"] == int(g[f"{tag}_cvg"]) and r["n_iter"] == int(g[f"{tag}_n_iter"]), tag
