@@ -4,9 +4,13 @@ bound with ctypes to the C-ABI of ``csrc/libcsb200.so`` (include/csb200.h).
 This is what the parity tests and bench.py call; it adds no arithmetic of its
 own.  Names and argument meaning follow the reference:
 
-* ``Matrix``            cs_matrix_t (MSR)          src/alge/cs_matrix.cpp:4518,:5451,:6328,:6405
-* ``SlesIt``            cs_sles_it_t               src/alge/cs_sles_it.cpp:4659,:4964,:5194
-* ``Multigrid``         cs_multigrid_t             src/alge/cs_multigrid.cpp:4644,:5032,:5275,:5362
+* ``Matrix``            cs_matrix_t (MSR)          src/alge/cs_matrix.cpp:4518,:5451,:6328,:6405;
+                        ``compute_coeffs`` = cs_matrix_compute_coeffs, src/alge/cs_matrix_building.cpp:1948
+* ``SlesIt``            cs_sles_it_t               src/alge/cs_sles_it.cpp:4659,:4964,:5194;
+                        ``transfer_pc`` = cs_sles_it_transfer_pc
+* ``Smoother``          cs_multigrid_smoother_*    src/alge/cs_multigrid_smoother.cpp:1726,:1825,:2008
+* ``Multigrid``         cs_multigrid_t             src/alge/cs_multigrid.cpp:4644,:5032,:5275,:5362;
+                        ``Multigrid(pc=True)`` = cs_multigrid_pc_create (:5682), V- or K-cycle
 * ``ConvergenceState``  cs_sles_convergence_state_t  src/alge/cs_sles.h:57-68
 
 The library has no CPU fallback: importing works anywhere (so that the symbol
@@ -24,7 +28,10 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "csrc", "libcsb200.so")
-if os.environ.get("CSB_LIB"):       # tuning experiments: a variant build of the same library
+# CSB_LIB: another build of the same sources -- tuning variants (-DCSB_PHASE_TRACE ...) and the
+# host-thread stand-in that tests/cudasim builds to desk-check kernels without a GPU (test
+# infrastructure only; nothing in this package builds or selects it)
+if os.environ.get("CSB_LIB"):
     LIB_PATH = os.path.abspath(os.environ["CSB_LIB"])
 HEADER_PATH = os.path.join(_ROOT, "include", "csb200.h")
 
