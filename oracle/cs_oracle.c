@@ -9,8 +9,8 @@
  * Parity status: PINNED.  Every function here is checked against the
  * reference's own compiled code (oracle/_ref/libcsref.so, built from
  * /root/reference by oracle/Makefile.ref) in tests/test_oracle.py,
- * and against the committed fixtures in tests/golden/ (generated from that
- * same reference build by tests/golden/make_golden.py).  The reference tree
+ * and / or against the committed fixtures in tests/golden/ (generated from that
+ * same reference build by the tests/golden/make_golden*.py scripts).  The reference tree
  * itself holds no golden vectors for this path.
  *
  * Arithmetic: plain IEEE double mul/add in the reference's evaluation order
