@@ -1450,9 +1450,10 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
               "available");
     return;
   }
-  if (pairwise && (!galerkin || a->halo != nullptr)) {
+  if (pairwise && (!galerkin || a->halo != nullptr || mg->n_blocks > 1)) {
     set_error("csb_multigrid_setup: CS_GRID_COARSENING_SPD_PW is available with Galerkin "
-              "coarse matrices (p0p1_relax <= 0) on one rank");
+              "coarse matrices (p0p1_relax <= 0) on one rank, one aggregation block (the "
+              "reference's single-thread pairing)");
     return;
   }
   /* smoothers: cs_sles_it PCG + Jacobi (cs_multigrid_create defaults), or -- in the
