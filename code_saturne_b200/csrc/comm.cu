@@ -192,11 +192,25 @@ void *pcomm_arena_alloc(csb_pcomm_t *c, size_t bytes)
   return p;
 }
 
-size_t pcomm_arena_mark(const csb_pcomm_t *c) { return c->arena_used; }
+/* The arena is a stack of owner segments.  An owner (a solver or a hierarchy) opens a
+   segment with pcomm_arena_mark before its allocations and closes it with
+   pcomm_arena_release.  Owners may be freed in any order: a released segment is only
+   handed out again once every segment above it has been released too, so a live
+   owner's ghost buffers and flag words (which peers keep writing) are never reused. */
+size_t pcomm_arena_mark(csb_pcomm_t *c)
+{
+  c->segs.push_back({c->arena_used, true});
+  return c->arena_used;
+}
 
 void pcomm_arena_release(csb_pcomm_t *c, size_t mark)
 {
-  if (mark <= c->arena_used) c->arena_used = mark;
+  for (size_t i = c->segs.size(); i-- > 0; )
+    if (c->segs[i].alive && c->segs[i].start == mark) { c->segs[i].alive = false; break; }
+  while (!c->segs.empty() && !c->segs.back().alive) {
+    c->arena_used = c->segs.back().start;
+    c->segs.pop_back();
+  }
 }
 
 void pcomm_host_barrier(csb_pcomm_t *c)

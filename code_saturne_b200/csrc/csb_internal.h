@@ -222,6 +222,8 @@ struct _csb_pcomm_t {
   csb::CommDev  *d = nullptr;       /* device copy */
   char          *arena = nullptr;
   size_t         arena_bytes = 0, arena_used = 0;
+  struct ArenaSeg { size_t start; bool alive; };
+  std::vector<ArenaSeg> segs;       /* owner segments, bottom to top (comm.cu) */
   CommGroup     *group = nullptr;   /* in-process ranks (host threads) */
   bool           ipc_open[csb::COMM_MAX_RANKS] = {false};
   double        *scratch = nullptr; /* 16 doubles, device */
@@ -232,7 +234,7 @@ typedef struct _csb_pcomm_t csb_pcomm_t;
 namespace csb {
 
 void  *pcomm_arena_alloc(csb_pcomm_t *c, size_t bytes);   /* zero-filled, 256-byte aligned */
-size_t pcomm_arena_mark(const csb_pcomm_t *c);
+size_t pcomm_arena_mark(csb_pcomm_t *c);      /* opens an owner segment */
 void   pcomm_arena_release(csb_pcomm_t *c, size_t mark);
 void   pcomm_host_barrier(csb_pcomm_t *c);
 /* sum of n (<= 8) doubles over all ranks, in place, result on the host */

@@ -52,6 +52,27 @@ inline bool post_launch(const char *name)
   return true;
 }
 
+/* Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute belongs to
+   the (function, device) pair and ranks may live on different devices in one process (one
+   host thread each, thread_local Context): what has been granted is remembered per thread,
+   never process-wide. */
+inline void smem_optin(const void *func, size_t bytes)
+{
+  if (bytes <= 48*1024) return;
+  struct Granted { const void *f; size_t bytes; int device; };
+  static thread_local std::vector<Granted> granted;
+  const int dev = ctx().device;
+  for (Granted &g : granted)
+    if (g.f == func && g.device == dev) {
+      if (g.bytes >= bytes) return;
+      cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      g.bytes = bytes;
+      return;
+    }
+  cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  granted.push_back({func, bytes, dev});
+}
+
 /*--------------------------------------------------------------------------
  * Reductions
  *--------------------------------------------------------------------------*/
@@ -426,14 +447,7 @@ bool spmv_dispatch(const SpmvK &k, const _csb_matrix_t *m)
   const int grid = (m->n_rows + TPB - 1) / TPB;
   if (grid < 1) return true;
   if (m->spmv_stream_ok) {
-    static bool attr_set = false;
-    static size_t attr_bytes = 0;
-    if (m->spmv_smem > 48*1024 && (!attr_set || m->spmv_smem > attr_bytes)) {
-      cudaFuncSetAttribute(k_spmv_stream<EPI>,
-                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)m->spmv_smem);
-      attr_set = true; attr_bytes = m->spmv_smem;
-    }
+    smem_optin((const void *)k_spmv_stream<EPI>, m->spmv_smem);
     k_spmv_stream<EPI><<<grid, TPB, m->spmv_smem, ctx().stream>>>(k);
   }
   else
@@ -1103,12 +1117,7 @@ bool launch_jacobi_sweep(const _csb_matrix_t *m, ItState *st, const double *rhs,
     set_error("jacobi sweep: row slab exceeds shared memory");
     return false;
   }
-  static size_t attr_bytes = 0;
-  if (m->spmv_smem > 48*1024 && m->spmv_smem > attr_bytes) {
-    cudaFuncSetAttribute(k_jacobi_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)m->spmv_smem);
-    attr_bytes = m->spmv_smem;
-  }
+  smem_optin((const void *)k_jacobi_sweep, m->spmv_smem);
   k_jacobi_sweep<<<grid, TPB, m->spmv_smem, ctx().stream>>>(k);
   return post_launch("jacobi_sweep");
 }
@@ -1298,16 +1307,8 @@ bool bicg_spmv_launch(int mode, const _csb_matrix_t *m, ItState *st, const doubl
     set_error("bicgstab spmv: row slab exceeds shared memory");
     return false;
   }
-  static size_t attr_bytes[2] = {0, 0};
-  if (m->spmv_smem > 48*1024 && m->spmv_smem > attr_bytes[mode]) {
-    if (mode == 0)
-      cudaFuncSetAttribute(k_bicg_spmv<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)m->spmv_smem);
-    else
-      cudaFuncSetAttribute(k_bicg_spmv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)m->spmv_smem);
-    attr_bytes[mode] = m->spmv_smem;
-  }
+  smem_optin(mode == 0 ? (const void *)k_bicg_spmv<0> : (const void *)k_bicg_spmv<1>,
+             m->spmv_smem);
   if (mode == 0)
     k_bicg_spmv<0><<<grid, TPB, m->spmv_smem, ctx().stream>>>(k);
   else

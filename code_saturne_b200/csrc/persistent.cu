@@ -506,6 +506,13 @@ __device__ __forceinline__ void consumer_release(const SmemView &sv, unsigned q)
  * acc_out[0..3] receives this thread's partial sums.
  *--------------------------------------------------------------------------*/
 
+/* number of staged operand vectors of an epilogue: F::NV, or f.nv() when it depends on a
+   run-time mode (EpiSmooth) */
+template <class F>
+__device__ __forceinline__ auto epi_nv(const F &f, int) -> decltype(f.nv()) { return f.nv(); }
+template <class F>
+__device__ __forceinline__ int epi_nv(const F &, long) { return F::NV; }
+
 template <bool SINGLE, bool GHOST, class F>
 __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
                                           const double *ghost, unsigned char *s_raw,
@@ -531,6 +538,7 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
         const int    *__restrict__ row_index = L.row_index;
         const int    *col_id = L.col_id;
         const double *x_val = L.x_val;
+        const int n_ops = epi_nv(f, 0);
         int k0 = __ldg(row_index + first*slab_rows);
         int k1 = __ldg(row_index + min(first*slab_rows + slab_rows, n_rows));
         for (int j = 0; j < n_my; j++) {
@@ -550,13 +558,13 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
           const unsigned ri_b = (unsigned)(((rows + 1)*4 + 15) & ~15);
           const unsigned v_b = (unsigned)((rows*8 + 15) & ~15);
           producer_acquire(sv, q);
-          mbar_expect_tx(bar, 4u*nc + 8u*nv + ri_b + (unsigned)F::NV*v_b);
+          mbar_expect_tx(bar, 4u*nc + 8u*nv + ri_b + (unsigned)n_ops*v_b);
           if (nc > 0) bulk_load(sb, col_id + ka, 4u*nc, bar);
           if (nv > 0) bulk_load(sb + off_val, x_val + kb, 8u*nv, bar);
           bulk_load(sb + off_ri, row_index + r0, ri_b, bar);
 #pragma unroll
           for (int v = 0; v < F::NV; v++)
-            bulk_load(sb + off_ops + v*ST_OP_STRIDE*8, f.src(v) + r0, v_b, bar);
+            if (v < n_ops) bulk_load(sb + off_ops + v*ST_OP_STRIDE*8, f.src(v) + r0, v_b, bar);
           k0 = k0n; k1 = k1n;
         }
       }
@@ -1749,6 +1757,457 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
   }
 }
 
+/*--------------------------------------------------------------------------
+ * Kernel 3: flexible CG preconditioned by one V-cycle per iteration -- the
+ * reference's production pressure-solver layout (cs_sles_it FCG,
+ * _flexible_conjugate_gradient cs_sles_it.cpp:832-985, with cs_multigrid_pc,
+ * _multigrid_v_cycle_pc cs_multigrid.cpp:3569-4020) and the Jacobi-family
+ * cs_multigrid_smoother smoothers its device settings select (:5070-5090;
+ * _jacobi / _relaxed_jacobi / _l1_jacobi, cs_multigrid_smoother.cpp:143-373,
+ * :804-905).  The whole solve -- every FCG iteration, every level of every
+ * cycle -- is ONE cooperative launch.
+ *
+ * A smoother sweep is one pass over the level's matrix: the (diagonal-
+ * excluded) product in CSR order with the update in the epilogue of the row
+ * sum.  Sweeps ping-pong between the level's vx and one shared buffer (tmp);
+ * the buffer a smoother starts in is chosen so that its last sweep lands in
+ * vx (no copy back): the prolongation writes vx + P.c_vx into that buffer, the
+ * first sweep from zero (elementwise) is the tail of the phase that produced
+ * its right-hand side (the FCG update at level 0, the restriction below).
+ * No reduction anywhere in the cycle except the coarsest-level PCG: per level
+ * 4 phases down (2 sweeps, residual, restriction) and 4 up (prolongation, 3
+ * sweeps) with RJ3 x 3; the levels small enough for one CTA are run by CTA 0
+ * as one block (descent, coarsest solve, ascent) between two grid barriers.
+ *--------------------------------------------------------------------------*/
+
+/* first sweep of a smoother from a zero start
+   (cs_multigrid_smoother.cpp:196-199, :322-327, :858-861) */
+__device__ __forceinline__ double smooth_first_value(int mode, double w0, double rhs, double inv)
+{
+  return (mode == SMOOTH_RELAXED) ? w0 * rhs*inv : rhs*inv;
+}
+
+/* one sweep: y = S(x, rhs, E.x), or S(x, rhs, A.x) for L1 (:205-213, :345-352, :880-887) */
+struct EpiSmooth {
+  static constexpr int NV = 4;
+  int mode;
+  double w0, w1;
+  const double *rhs, *inv, *xold, *d_val;
+  double *y;
+  __device__ __forceinline__ int nv() const
+  { return (mode == SMOOTH_JACOBI) ? 2 : (mode == SMOOTH_RELAXED) ? 3 : 4; }
+  __device__ __forceinline__ const double *src(int v) const
+  { return (v == 0) ? rhs : (v == 1) ? inv : (v == 2) ? xold : d_val; }
+  __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&)[4]) const
+  {
+    const double b = op[0], iv = op[ST_OP_STRIDE];
+    if (mode == SMOOTH_JACOBI)
+      y[r] = (b - sii) * iv;
+    else if (mode == SMOOTH_RELAXED) {
+      const double t = b - sii;
+      y[r] = w1*op[2*ST_OP_STRIDE] + w0*t*iv;
+    }
+    else {
+      const double xr = op[2*ST_OP_STRIDE];
+      const double yr = sii + op[3*ST_OP_STRIDE]*xr;
+      const double t = b - yr;
+      y[r] = xr + t*iv;
+    }
+  }
+};
+
+struct RowSmoothFirst {
+  static constexpr int NV = 2;
+  int mode;
+  double w0;
+  const double *rhs, *inv;
+  double *y;
+  __device__ __forceinline__ const double *src(int v) const { return (v == 0) ? rhs : inv; }
+  __device__ __forceinline__ void st(int i, const double *op, double (&)[4]) const
+  { y[i] = smooth_first_value(mode, w0, op[0], op[ROW_CH]); }
+};
+
+/* rk = rhs - A.vx, qk = 0 (cs_sles_it.cpp:874-900) + the preconditioner's first sweep */
+struct EpiFcgPcInit {
+  static constexpr int NV = 4;
+  int mode;
+  double w0;
+  const double *d_val, *vx, *rhs, *inv;
+  double *rk, *qk, *z0;
+  __device__ __forceinline__ const double *src(int v) const
+  { return (v == 0) ? d_val : (v == 1) ? vx : (v == 2) ? rhs : inv; }
+  __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&)[4]) const
+  {
+    const double rr = op[2*ST_OP_STRIDE] - (sii + op[0]*op[ST_OP_STRIDE]);
+    rk[r] = rr;
+    qk[r] = 0;
+    z0[r] = smooth_first_value(mode, w0, rr, op[3*ST_OP_STRIDE]);
+  }
+};
+
+struct RowFcgPcInitZero {     /* vx = 0, rk = rhs, qk = 0 (:880-893) + first sweep */
+  static constexpr int NV = 2;
+  int mode;
+  double w0;
+  const double *rhs, *inv;
+  double *vx, *rk, *qk, *z0;
+  __device__ __forceinline__ const double *src(int v) const { return (v == 0) ? rhs : inv; }
+  __device__ __forceinline__ void st(int i, const double *op, double (&)[4]) const
+  {
+    vx[i] = 0;
+    rk[i] = op[0];
+    qk[i] = 0;
+    z0[i] = smooth_first_value(mode, w0, op[0], op[ROW_CH]);
+  }
+};
+
+/* dk, vx, qk, rk updates (:939-951; first iteration :960-972) + the preconditioner's first
+   sweep from the new rk.  z0 may be vk itself: operands are read from the staged copy. */
+struct RowFcgPcUpdate {
+  static constexpr int NV = 7;
+  int mode;
+  double w0;
+  double gk_rk1, ak_rk;
+  int first;
+  const double *vk, *wk, *inv;
+  double *dk, *vx, *qk, *rk, *z0;
+  __device__ __forceinline__ const double *src(int v) const
+  {
+    return (v == 0) ? vk : (v == 1) ? dk : (v == 2) ? vx : (v == 3) ? wk : (v == 4) ? qk
+         : (v == 5) ? rk : inv;
+  }
+  __device__ __forceinline__ void st(int i, const double *op, double (&)[4]) const
+  {
+    const double d = first ? op[0] : op[0] - gk_rk1 * op[ROW_CH];
+    dk[i] = d;
+    vx[i] = op[2*ROW_CH] + ak_rk * d;
+    const double q = first ? op[3*ROW_CH] : op[3*ROW_CH] - gk_rk1 * op[4*ROW_CH];
+    qk[i] = q;
+    const double rr = op[5*ROW_CH] - ak_rk * q;
+    rk[i] = rr;
+    z0[i] = smooth_first_value(mode, w0, rr, op[6*ROW_CH]);
+  }
+};
+
+/* dst = vx + P.c_vx (cs_grid.cpp:9156-9166; rows without a coarse row keep vx) */
+template <bool SINGLE>
+__device__ __noinline__ void prolong_rows_to(int n, const int *__restrict__ coarse_row,
+                                             const double *c_vx, const double *vx, double *dst)
+{
+  constexpr int U = 4;
+  const int first = SINGLE ? threadIdx.x : blockIdx.x*PT + threadIdx.x;
+  const int step = SINGLE ? PT : gridDim.x*PT;
+  for (int base = first; base < n; base += U*step) {
+    int ic[U];
+    double v[U], c[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int i = base + u*step;
+      ic[u] = -2;
+      if (i < n) { ic[u] = __ldg(coarse_row + i); v[u] = vx[i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (ic[u] >= 0) c[u] = c_vx[ic[u]];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (ic[u] >= 0) dst[base + u*step] = v[u] + c[u];
+      else if (ic[u] == -1) dst[base + u*step] = v[u];
+    }
+  }
+}
+
+/* restriction (as restrict_rows) + the next level's first sweep from the restricted value */
+template <bool SINGLE>
+__device__ __noinline__ void restrict_rows_first(int nc, const int *__restrict__ cfi,
+                                                 const int *__restrict__ cfr, const double *wr,
+                                                 double *c_rhs, int mode, double w0,
+                                                 const double *c_inv, double *c_start)
+{
+  constexpr int U = 2, J = 4;
+  const int first = SINGLE ? threadIdx.x : blockIdx.x*PT + threadIdx.x;
+  const int step = SINGLE ? PT : gridDim.x*PT;
+  for (int base = first; base < nc; base += U*step) {
+    int rs[U], cnt[U], id[U][J];
+    double w[U][J], iv[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int ic = base + u*step;
+      rs[u] = 0; cnt[u] = 0; iv[u] = 0.;
+      if (ic < nc) {
+        rs[u] = __ldg(cfi + ic); cnt[u] = __ldg(cfi + ic + 1) - rs[u];
+        if (c_start != nullptr) iv[u] = c_inv[ic];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int j = 0; j < J; j++)
+        if (j < cnt[u]) id[u][j] = __ldg(cfr + rs[u] + j);
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int j = 0; j < J; j++)
+        if (j < cnt[u]) w[u][j] = wr[id[u][j]];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int ic = base + u*step;
+      if (ic < nc) {
+        double s = 0.;
+#pragma unroll
+        for (int j = 0; j < J; j++)
+          if (j < cnt[u]) s += w[u][j];
+        for (int q = J; q < cnt[u]; q++) s += wr[__ldg(cfr + rs[u] + q)];
+        c_rhs[ic] = s;
+        if (c_start != nullptr) c_start[ic] = smooth_first_value(mode, w0, s, iv[u]);
+      }
+    }
+  }
+}
+
+struct VcProf {
+  MgState *ms;
+  unsigned long long t_last;
+  bool lead;
+  __device__ __forceinline__ void mark(int level, int phase)
+  { if (lead) prof_mark(ms, t_last, level, phase); }
+  __device__ __forceinline__ void mark_it(int level, int kind)
+  {
+    if (lead) {
+      const unsigned long long t = global_ns();
+      if (level < PROF_LEVELS) ms->prof_it[level][kind] += t - t_last;
+      t_last = t;
+    }
+  }
+};
+
+__device__ __forceinline__ const double *smooth_inv(const MgLevelDesc &L, int mode)
+{ return (mode == SMOOTH_L1) ? L.l1_inv : L.ad_inv; }
+
+/* buffer a smoother of n sweeps must start in for its last sweep to land in vx */
+__device__ __forceinline__ double *sweep_start(int n_toggles, double *vx_lv, double *tmp)
+{ return (n_toggles & 1) ? tmp : vx_lv; }
+
+/* sweeps it0 .. n_iter-1: each reads the other buffer and writes the current one */
+template <bool SINGLE>
+__device__ __forceinline__ void vc_sweeps(const MgLevelDesc &L, const SmoothPlanDev &sp,
+                                          const double *rhs_lv, double *cur, double *oth, int it0,
+                                          const PersistentCommon &P, unsigned char *s_raw)
+{
+  const double *inv = smooth_inv(L, sp.mode);
+  for (int it = it0; it < sp.n_iter; it++) {
+    double *t = cur; cur = oth; oth = t;
+    const double wk = sp.w[it % sp.wk_m];
+    const double *gh = halo_exchange<SINGLE>(L, oth);
+    EpiSmooth f;
+    f.mode = sp.mode; f.w0 = wk; f.w1 = 1.0 - wk;
+    f.rhs = rhs_lv; f.inv = inv; f.xold = oth; f.d_val = L.d_val; f.y = cur;
+    spmv_phase<SINGLE>(L, oth, gh, s_raw, f, nullptr);
+    phase_barrier<SINGLE>(P.barrier);
+  }
+}
+
+/* one level of the descent (cs_multigrid.cpp:3660-3790): smoother from zero, residual,
+   restriction (+ first sweep of the next level unless it is the coarsest) */
+template <bool SINGLE>
+__device__ __forceinline__ void vc_descend(const FcgMgParams &S, const PersistentCommon &P,
+                                           int level, const double *rhs_lv, double *vx_lv,
+                                           bool first_done, unsigned char *s_raw, VcProf &pf)
+{
+  const MgLevelDesc &L = S.levels[level];
+  const MgLevelDesc &C = S.levels[level+1];
+  const SmoothPlanDev &sp = S.sm[0];
+  double *start = sweep_start(sp.n_iter - 1, vx_lv, S.tmp);
+  double *other = (start == vx_lv) ? S.tmp : vx_lv;
+  if (!first_done) {
+    RowSmoothFirst f;
+    f.mode = sp.mode; f.w0 = sp.w[0]; f.rhs = rhs_lv; f.inv = smooth_inv(L, sp.mode); f.y = start;
+    row_phase<SINGLE>(L.n_rows, s_raw, f, nullptr);
+    phase_barrier<SINGLE>(P.barrier);
+  }
+  vc_sweeps<SINGLE>(L, sp, rhs_lv, start, other, 1, P, s_raw);
+  pf.mark(level, MG_PROF_DESCENT);
+  {
+    const double *gh = halo_exchange<SINGLE>(L, vx_lv);
+    EpiResidual f;
+    f.d_val = L.d_val; f.vx = vx_lv; f.rhs = rhs_lv; f.wr = S.wr;
+    double acc[4];
+    spmv_phase<SINGLE>(L, vx_lv, gh, s_raw, f, acc);
+    phase_barrier<SINGLE>(P.barrier);
+  }
+  pf.mark(level, MG_PROF_RESIDUAL);
+  {
+    const bool fuse = (level + 1 < S.n_levels - 1);
+    double *c_start = fuse ? sweep_start(sp.n_iter - 1, C.vx, S.tmp) : nullptr;
+    restrict_rows_first<SINGLE>(C.n_rows, L.c_f_row_index, L.c_f_row_ids, S.wr, C.rhs, sp.mode,
+                                sp.w[0], smooth_inv(C, sp.mode), c_start);
+    phase_barrier<SINGLE>(P.barrier);
+  }
+  pf.mark(level, MG_PROF_RESTRICT);
+}
+
+/* one level of the ascent (:3880-3990): prolongation, smoother from the prolonged iterate */
+template <bool SINGLE>
+__device__ __forceinline__ void vc_ascend(const FcgMgParams &S, const PersistentCommon &P,
+                                          int level, const double *rhs_lv, double *vx_lv,
+                                          unsigned char *s_raw, VcProf &pf)
+{
+  const MgLevelDesc &L = S.levels[level];
+  const MgLevelDesc &C = S.levels[level+1];
+  const SmoothPlanDev &sp = S.sm[1];
+  double *start = sweep_start(sp.n_iter, vx_lv, S.tmp);
+  double *other = (start == vx_lv) ? S.tmp : vx_lv;
+  prolong_rows_to<SINGLE>(L.n_rows, L.coarse_row, C.vx, vx_lv, start);
+  phase_barrier<SINGLE>(P.barrier);
+  pf.mark(level, MG_PROF_PROLONG);
+  vc_sweeps<SINGLE>(L, sp, rhs_lv, start, other, 0, P, s_raw);
+  pf.mark(level, MG_PROF_ASCENT);
+}
+
+__global__ void __launch_bounds__(PT, CSB_MIN_CTAS)
+k_fcg_mg_persistent(const FcgMgParams S, const PersistentCommon P)
+{
+  unsigned char *s_raw = s_raw_base;
+  double *s_red = (double *)s_raw;
+  pipe_init(s_raw);
+  halo_counts_init(S.levels, S.n_levels, P.barrier);
+
+  const MgLevelDesc *__restrict__ LV = S.levels;
+  const MgLevelDesc &L0 = LV[0];
+  const int n = L0.n_rows;
+  const int coarsest = S.n_levels - 1;
+  double *rk = S.fwork, *vk = S.fwork + S.fstride, *wk = S.fwork + 2*S.fstride,
+         *dk = S.fwork + 3*S.fstride, *qk = S.fwork + 4*S.fstride;
+  ItState *st = S.st;
+  const bool rec = (blockIdx.x == 0 && threadIdx.x == 0);
+  VcProf pf;
+  pf.ms = S.ms; pf.lead = rec; pf.t_last = rec ? global_ns() : 0ull;
+
+  /* first level small enough for one CTA: it and everything below is CTA 0's */
+  int ls = S.n_levels;
+  for (int l = 0; l < S.n_levels; l++)
+    if (LV[l].n_rows <= S.single_rows) { ls = l; break; }
+  const int n_grid_desc = (ls < coarsest) ? ls : coarsest;   /* levels descended on the grid */
+
+  const SmoothPlanDev &sp0 = S.sm[0];
+  const double *inv0 = smooth_inv(L0, sp0.mode);
+  double *z0 = sweep_start(sp0.n_iter - 1, vk, S.tmp);
+
+  PcgResult R;
+  R.n_iter = 0; R.cvg = CSB_SLES_ITERATING; R.residual = -1.; R.initial_residual = -1.;
+  if (rec) st->n_hist = 0;
+
+  if (S.vx_ini_nonzero) {
+    const double *gh = halo_exchange<false>(L0, S.vx);
+    EpiFcgPcInit f;
+    f.mode = sp0.mode; f.w0 = sp0.w[0];
+    f.d_val = L0.d_val; f.vx = S.vx; f.rhs = S.rhs; f.inv = inv0; f.rk = rk; f.qk = qk; f.z0 = z0;
+    spmv_phase<false>(L0, S.vx, gh, s_raw, f, nullptr);
+  }
+  else {
+    RowFcgPcInitZero f;
+    f.mode = sp0.mode; f.w0 = sp0.w[0];
+    f.rhs = S.rhs; f.inv = inv0; f.vx = S.vx; f.rk = rk; f.qk = qk; f.z0 = z0;
+    row_phase<false>(n, s_raw, f, nullptr);
+  }
+  grid_barrier(P.barrier);
+  pf.mark_it(0, 0);
+
+  double rho_km1 = 0., ak_rk = 0., gk_rk1 = 0.;
+  while (R.cvg == CSB_SLES_ITERATING) {
+
+    /* ---- vk = M^-1 rk: one V-cycle from zero (_multigrid_pc_apply, :1500-1600) ---- */
+    for (int level = 0; level < n_grid_desc; level++)
+      vc_descend<false>(S, P, level, (level == 0) ? rk : LV[level].rhs,
+                        (level == 0) ? vk : LV[level].vx, true, s_raw, pf);
+    if (ls <= coarsest) {
+      if (blockIdx.x == 0) {
+        for (int level = ls; level < coarsest; level++)
+          vc_descend<true>(S, P, level, (level == 0) ? rk : LV[level].rhs,
+                           (level == 0) ? vk : LV[level].vx, true, s_raw, pf);
+        const MgLevelDesc &L = LV[coarsest];
+        pcg_run<true>(L, (coarsest == 0) ? rk : L.rhs, (coarsest == 0) ? vk : L.vx, false,
+                      S.coarse_n_max_iter, S.precision*S.coarse_precision_mult, S.r_norm, true,
+                      P, L.st_descent, s_raw);
+        __syncthreads();
+        pf.mark(coarsest, MG_PROF_COARSEST);
+        for (int level = coarsest - 1; level >= ls; level--)
+          vc_ascend<true>(S, P, level, (level == 0) ? rk : LV[level].rhs,
+                          (level == 0) ? vk : LV[level].vx, s_raw, pf);
+      }
+      grid_barrier(P.barrier);
+      /* exchanges CTA 0 did alone: every CTA takes the levels' counts from the source */
+      if (threadIdx.x == 0)
+        for (int l = ls; l <= coarsest && l < PROF_LEVELS; l++)
+          if (LV[l].dist != nullptr)
+            ((unsigned *)(s_raw_base + HALO_K_OFF))[LV[l].level_id]
+              = *(volatile unsigned *)LV[l].dist->count;
+      __syncthreads();
+    }
+    else {
+      const MgLevelDesc &L = LV[coarsest];
+      pcg_run<false>(L, L.rhs, L.vx, false, S.coarse_n_max_iter,
+                     S.precision*S.coarse_precision_mult, S.r_norm, true, P, L.st_descent,
+                     s_raw);
+      grid_barrier(P.barrier);
+      pf.mark(coarsest, MG_PROF_COARSEST);
+    }
+    for (int level = n_grid_desc - 1; level >= 0; level--)
+      vc_ascend<false>(S, P, level, (level == 0) ? rk : LV[level].rhs,
+                       (level == 0) ? vk : LV[level].vx, s_raw, pf);
+
+    /* ---- wk = A.vk and the four dot products (:908-918) ---- */
+    double v[4] = {0., 0., 0., 0.};
+    {
+      const double *gh = halo_exchange<false>(L0, vk);
+      EpiFcg f;
+      f.d_val = L0.d_val; f.vk = vk; f.rk = rk; f.qk = qk; f.wk = wk;
+      spmv_phase<false>(L0, vk, gh, s_raw, f, v);
+    }
+    all_sum<false, 4>(v, P.partials + 8*(size_t)gridDim.x, P.barrier, s_red, P.comm);
+    pf.mark_it(0, 1);
+    const double alpha_k = v[0], beta_k = v[1], gamma_k = v[2];
+    R.residual = sqrt(v[3]);
+    if (R.n_iter > 0)
+      R.cvg = it_cvg_eval(S.precision, S.r_norm, S.n_max_iter, R.initial_residual, R.n_iter,
+                          R.residual);
+    else
+      R.initial_residual = R.residual;
+    if (rec && st->n_hist < HIST_MAX) st->hist[st->n_hist++] = R.residual;
+    if (R.cvg != CSB_SLES_ITERATING) break;
+
+    double rho_k;
+    if (R.n_iter > 0) {
+      gk_rk1 = (fabs(rho_km1) > DBL_MIN) ? gamma_k / rho_km1 : 0.;
+      rho_k = beta_k - gamma_k * gk_rk1;
+    }
+    else {
+      gk_rk1 = 0.;
+      rho_k = beta_k;
+    }
+    ak_rk = (fabs(rho_k) > DBL_MIN) ? alpha_k / rho_k : 0.;
+    {
+      RowFcgPcUpdate f;
+      f.mode = sp0.mode; f.w0 = sp0.w[0];
+      f.gk_rk1 = gk_rk1; f.ak_rk = ak_rk; f.first = (R.n_iter == 0) ? 1 : 0;
+      f.vk = vk; f.wk = wk; f.inv = inv0;
+      f.dk = dk; f.vx = S.vx; f.qk = qk; f.rk = rk; f.z0 = z0;
+      row_phase<false>(n, s_raw, f, nullptr);
+    }
+    grid_barrier(P.barrier);
+    pf.mark_it(0, 2);
+    rho_km1 = rho_k;
+    R.n_iter += 1;
+  }
+
+  if (rec) {
+    st->precision = S.precision; st->r_norm = S.r_norm;
+    st->residual = R.residual; st->initial_residual = R.initial_residual;
+    st->n_iter = R.n_iter; st->n_max_iter = S.n_max_iter; st->cvg = R.cvg;
+    st->alpha = ak_rk; st->beta = gk_rk1; st->ro_0 = rho_km1; st->ro_1 = 0.; st->rk_gkm1 = 0.;
+  }
+}
+
 
 } // anonymous namespace
 
@@ -1800,7 +2259,8 @@ int persistent_grid(int which, size_t smem)
   }
   const void *k = (which == 0) ? (const void *)k_pcg_persistent
                 : (which == 2) ? (const void *)k_fcg_persistent
-                : (which == 3) ? (const void *)k_ipcg_persistent : (const void *)k_mg_persistent;
+                : (which == 3) ? (const void *)k_ipcg_persistent
+                : (which == 4) ? (const void *)k_fcg_mg_persistent : (const void *)k_mg_persistent;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   if (which == 0)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pcg_persistent, PT, smem);
@@ -1808,6 +2268,8 @@ int persistent_grid(int which, size_t smem)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fcg_persistent, PT, smem);
   else if (which == 3)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ipcg_persistent, PT, smem);
+  else if (which == 4)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fcg_mg_persistent, PT, smem);
   else
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mg_persistent, PT, smem);
   if (occ < 1) {
@@ -1987,6 +2449,24 @@ bool launch_fcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
   if (e != cudaSuccess) {
     set_error("cooperative launch of k_%s_persistent failed: %s", ipcg ? "ipcg" : "fcg",
               cudaGetErrorString(e));
+    return false;
+  }
+  return true;
+}
+
+bool launch_fcg_mg_persistent(const FcgMgParams &S, const PersistentCommon &P, int grid,
+                              size_t smem, bool cooperative)
+{
+  void *args[] = {(void *)&S, (void *)&P};
+  if (!reset_barrier(P)) return false;
+  cudaError_t e = cooperative
+    ? cudaLaunchCooperativeKernel((void *)k_fcg_mg_persistent, dim3(grid), dim3(PT), args, smem,
+                                  ctx().stream)
+    : cudaLaunchKernel((void *)k_fcg_mg_persistent, dim3(grid), dim3(PT), args, smem,
+                       ctx().stream);
+  ctx().launches += 1;
+  if (e != cudaSuccess) {
+    set_error("cooperative launch of k_fcg_mg_persistent failed: %s", cudaGetErrorString(e));
     return false;
   }
   return true;

@@ -18,6 +18,7 @@ struct MgLevelDesc {
   const double *d_val;
   const double *x_val;
   const double *ad_inv;
+  const double *l1_inv;        /* L1 Jacobi smoother only (cs_sles_it_priv.cpp:231-262) */
   double       *rhs;           /* levels > 0 */
   double       *vx;            /* levels > 0 */
   const int    *coarse_row;    /* rows of this level -> rows of the next level */
@@ -54,8 +55,37 @@ struct MgSolveParams {
   int                single_rows;  /* levels up to this size run in one CTA */
 };
 
+/* Sweep schedule of a Jacobi-family cs_multigrid_smoother (cs_multigrid_smoother.cpp:143-373,
+   :804-905): mode = SmoothMode, n_iter sweeps, relaxation weight w[it % wk_m]. */
+struct SmoothPlanDev {
+  int    mode, wk_m, n_iter;
+  double w[3];
+};
+
+/* FCG preconditioned by one V-cycle (cs_sles_it FCG + cs_multigrid_pc, the reference's
+   production pressure-solver layout), whole solve in one launch: k_fcg_mg_persistent. */
+struct FcgMgParams {
+  int                n_levels;
+  const MgLevelDesc *levels;     /* device array */
+  MgState           *ms;         /* phase timers */
+  ItState           *st;         /* FCG state, residual history */
+  const double      *rhs;
+  double            *vx;
+  int                vx_ini_nonzero;
+  int                n_max_iter;           /* FCG */
+  double             precision, r_norm;
+  SmoothPlanDev      sm[2];                /* descent, ascent smoothers */
+  int                coarse_n_max_iter;    /* coarsest-level PCG */
+  double             coarse_precision_mult;
+  int                single_rows;          /* levels up to this size run in one CTA */
+  double            *wr, *tmp;             /* residual; second sweep buffer (level-0 sized) */
+  double            *fwork;                /* FCG vectors rk vk wk dk qk */
+  size_t             fstride;
+};
+
 size_t persistent_smem_bytes(size_t max_slab_entries);
-int    persistent_grid(int which, size_t smem);   /* 0: PCG, 1: multigrid, 2: FCG, 3: IPCG kernel */
+int    persistent_grid(int which, size_t smem);   /* 0: PCG, 1: multigrid, 2: FCG, 3: IPCG,
+                                                      4: FCG + multigrid kernel */
 
 bool launch_pcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
                            bool vx_ini_nonzero, int n_max_iter, double precision,
@@ -71,6 +101,9 @@ bool launch_fcg_persistent(const MgLevelDesc &L, const double *rhs, double *vx,
                            double r_norm, const PersistentCommon &P, ItState *st,
                            int grid, size_t smem, bool single, bool cooperative,
                            bool ipcg = false);   /* true: _conjugate_gradient_ip (:1016-1203) */
+
+bool launch_fcg_mg_persistent(const FcgMgParams &S, const PersistentCommon &P, int grid,
+                              size_t smem, bool cooperative);
 
 /* y = A.x (or E.x) through the bulk-copy pipeline of the persistent kernels, as a
    stand-alone launch (cs_matrix_vector_multiply).  Returns false with no error set when

@@ -286,9 +286,21 @@ int csb_matrix_set_coefficients(csb_matrix_t *m, int symmetric,
                                 const csb_real_t *d_val, const csb_real_t *x_val)
 {
   if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (d_val == nullptr || (x_val == nullptr && m->nnz > 0)) {
+    set_error("csb_matrix_set_coefficients: null coefficient array"); return -1;
+  }
+  if (m->csr != nullptr) {
+    /* the CSR value array kept for cs_matrix_vector_multiply is not expressible in the MSR
+       arguments of this call: refuse rather than multiply with stale values */
+    set_error("csb_matrix_set_coefficients: matrix was created from CSR arrays; create it "
+              "again with csb_matrix_create_csr to change its values");
+    return -1;
+  }
   m->symmetric = (symmetric != 0);
   Context &c = ctx();
-  bool ok = CSB_CUDA(cudaMemcpyAsync(m->d_val.p, d_val, sizeof(double)*(size_t)m->n_rows,
+  /* d_val holds db x db blocks per row (CS_MATRIX_BLOCK_D: n_rows*9 values) */
+  const size_t n_d = (size_t)m->n_rows * (size_t)m->db * (size_t)m->db;
+  bool ok = CSB_CUDA(cudaMemcpyAsync(m->d_val.p, d_val, sizeof(double)*n_d,
                                      cudaMemcpyDefault, c.stream))
          && CSB_CUDA(cudaMemcpyAsync(m->x_val.p, x_val, sizeof(double)*(size_t)m->nnz,
                                      cudaMemcpyDefault, c.stream))
@@ -369,6 +381,11 @@ int csb_matrix_compute_coeffs(csb_matrix_t *m, int iconvp, int idiffp, int ndirc
   if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
   if (m->db != 1) {
     set_error("csb_matrix_compute_coeffs: scalar matrices only on this path");
+    return -1;
+  }
+  if (m->csr != nullptr) {
+    set_error("csb_matrix_compute_coeffs: matrix was created from CSR arrays (its CSR values "
+              "would go stale); use an MSR matrix");
     return -1;
   }
   if (!m->has_mesh) {

@@ -147,6 +147,7 @@ struct _csb_sles_it_t {
      cs_sles_it_t::_pc, src/alge/cs_sles_it_priv.h */
   csb_multigrid_t    *pc_mg = nullptr;
   bool                is_smoother = false;   /* created by csb_multigrid_smoother_create */
+  bool                fcg_mg_persistent = false;  /* FCG + V-cycle in one launch (setup) */
   DevBuf<double>      pc_tmp;                /* polynomial preconditioner work vector */
   /* true when the solve goes through a general preconditioner (kernel-per-phase FCG /
      single-reduction PCG): polynomial (poly_degree >= 1), transferred multigrid, or none
@@ -392,6 +393,12 @@ bool mg_cycle_pc_enqueue(csb_multigrid_t *mg, double precision, double r_norm,
 int  mg_n_levels(const csb_multigrid_t *mg);
 bool mg_is_k_cycle(const csb_multigrid_t *mg);
 MgState *mg_gate(csb_multigrid_t *mg);
+/* FCG + one V-cycle per iteration as one persistent launch (k_fcg_mg_persistent): can this
+   hierarchy run there (V-cycle, Jacobi-family cs_multigrid_smoother smoothers, PCG coarse
+   solver); shared memory / fill the kernel's parameters (defined with the multigrid below) */
+bool mg_fcg_persistent_ok(const csb_multigrid_t *mg);
+size_t mg_persistent_smem(const csb_multigrid_t *mg);
+void mg_fcg_params(csb_multigrid_t *mg, FcgMgParams &S, PersistentCommon &P);
 
 /* x_out = M^-1 x_in for the general preconditioners of cs_sles_it:
      multigrid   _multigrid_pc_apply (cs_multigrid.cpp:1500-1600): one V-cycle, identity for
@@ -694,6 +701,16 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
     if (c->pc_mg != nullptr) {
       csb_multigrid_setup(c->pc_mg, name, a, verbosity);
       if (!csb_multigrid_is_setup(c->pc_mg)) return;
+      c->fcg_mg_persistent = false;
+      if (c->type == CSB_SLES_FCG && mg_fcg_persistent_ok(c->pc_mg)
+          && env_int("CSB_FCG_MG_MODE_MULTI", 0) == 0) {
+        c->p_smem = mg_persistent_smem(c->pc_mg);
+        c->p_grid = persistent_grid(4, c->p_smem);
+        if (c->p_grid < 1) return;
+        if (!c->partials.alloc(12*(size_t)c->p_grid) || !c->barrier.alloc(2)) return;
+        if (!CSB_CUDA(cudaMemsetAsync(c->barrier.p, 0, 2*sizeof(unsigned), ctx().stream))) return;
+        c->fcg_mg_persistent = true;
+      }
     }
     c->setup_done = true;
     c->n_setups += 1;
@@ -788,6 +805,21 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
     break;
   case CSB_SLES_FCG:
   case CSB_SLES_IPCG:
+    if (c->general_pc() && c->type == CSB_SLES_FCG && c->fcg_mg_persistent) {
+      /* FCG + cs_multigrid_pc: the whole solve in one persistent cooperative kernel */
+      FcgMgParams S;
+      PersistentCommon P;
+      mg_fcg_params(c->pc_mg, S, P);
+      S.st = c->st.p;
+      S.rhs = s_rhs.d; S.vx = s_vx.d; S.vx_ini_nonzero = ini ? 1 : 0;
+      S.n_max_iter = c->n_max_iter; S.precision = precision; S.r_norm = r_norm;
+      S.single_rows = sb_rows_threshold();
+      S.fwork = c->work.p; S.fstride = work_stride_of((size_t)a->n_cols_ext);
+      P.partials = c->partials.p; P.barrier = c->barrier.p;
+      if (!launch_mg_state_init(S.ms, precision, r_norm, 1)) return CSB_SLES_BREAKDOWN;
+      ok = launch_fcg_mg_persistent(S, P, c->p_grid, c->p_smem, cx.device_share <= 1);
+      break;
+    }
     if (c->general_pc()) {
       ok = (c->type == CSB_SLES_IPCG)
         ? ipcg_pc_enqueue(c, a, precision, r_norm, s_rhs.d, s_vx.d, ini)
@@ -1021,6 +1053,40 @@ namespace {
 int mg_n_levels(const csb_multigrid_t *mg) { return (int)mg->levels.size(); }
 bool mg_is_k_cycle(const csb_multigrid_t *mg) { return mg->type == CSB_MULTIGRID_K_CYCLE; }
 MgState *mg_gate(csb_multigrid_t *mg) { return mg->mg_state.p; }
+
+bool mg_fcg_persistent_ok(const csb_multigrid_t *mg)
+{
+  if (mg->type != CSB_MULTIGRID_V_CYCLE || mg->levels.size() < 2) return false;
+  for (int i = 0; i < 2; i++)
+    if (!is_smoother_type((int)mg->solver_type[i]) || mg->precision_mult[i] >= 0
+        || mg->n_max_iter[i] < 1) return false;
+  return (mg->solver_type[2] == CSB_SLES_PCG && mg->poly_degree[2] == 0
+          && mg->levels[0]->m->halo == nullptr);
+}
+
+size_t mg_persistent_smem(const csb_multigrid_t *mg) { return mg->p_smem; }
+
+void mg_fcg_params(csb_multigrid_t *mg, FcgMgParams &S, PersistentCommon &P)
+{
+  memset(&S, 0, sizeof(S));
+  S.n_levels = (int)mg->levels.size();
+  S.levels = mg->descs.p;
+  S.ms = mg->mg_state.p;
+  for (int i = 0; i < 2; i++) {
+    const SmootherPlan p = smoother_plan((int)mg->solver_type[i], mg->n_max_iter[i]);
+    S.sm[i].mode = p.mode; S.sm[i].wk_m = p.wk_m; S.sm[i].n_iter = p.n_iter;
+    for (int k = 0; k < 3; k++) S.sm[i].w[k] = p.w[k];
+  }
+  S.coarse_n_max_iter = mg->n_max_iter[2];
+  S.coarse_precision_mult = mg->precision_mult[2];
+  S.wr = mg->wr.p;
+  S.tmp = mg->aux.p;          /* free while no level-local PCG runs */
+  /* the coarsest-level PCG works in the hierarchy's own vectors */
+  P.work = mg->aux.p;
+  P.work_stride = work_stride_of((size_t)mg->levels[0]->m->n_cols_ext);
+  P.partials = nullptr; P.barrier = nullptr;
+  P.comm = nullptr;
+}
 
 /* One level's descent (which = 0) or ascent (1) smoother of the single-cycle form, as
    _multigrid_setup_sles builds it (cs_multigrid.cpp:2150-2175): a cs_multigrid_smoother
@@ -1431,7 +1497,13 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
   csb_multigrid_t *mg = static_cast<csb_multigrid_t *>(context);
   Context &c = ctx();
   if (mg == nullptr || a == nullptr) { set_error("csb_multigrid_setup: null argument"); return; }
-  if (mg->setup_done) mg_clear_hierarchy(mg);
+  /* whatever an earlier (possibly failed) setup left behind goes first; any early return
+     below leaves the object empty again (levels, arena mark), never half built */
+  mg_clear_hierarchy(mg);
+  struct SetupGuard {
+    csb_multigrid_t *mg;
+    ~SetupGuard() { if (!mg->setup_done) mg_clear_hierarchy(mg); }
+  } setup_guard{mg};
 
   /* p0p1_relax <= 0: Galerkin coarse matrices (_compute_coarse_quantities_msr,
      cs_grid.cpp:8222-8223), which need no mesh quantities */
@@ -1722,6 +1794,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
       d.level_id = l;
       d.row_index = m->row_index.p; d.col_id = m->col_id.p;
       d.d_val = m->d_val.p; d.x_val = m->x_val.p; d.ad_inv = lv->ad_inv.p;
+      d.l1_inv = lv->l1_inv.p;
       d.rhs = lv->rhs.p; d.vx = lv->vx.p;
       d.coarse_row = lv->coarse_row.p;
       d.c_f_row_index = lv->c_f_row_index.p; d.c_f_row_ids = lv->c_f_row_ids.p;
@@ -1811,6 +1884,7 @@ csb_multigrid_solve(void *context, const char *name, const csb_matrix_t *a, int 
 
   int cvg = CSB_SLES_ITERATING;
   int n_cycles = 0;
+  double one_level_residual = -1.;
   const bool dist = (a->halo != nullptr);
   /* cs_multigrid_smoother smoothers run kernel per phase (the persistent kernel holds the
      PCG-smoothed cycle); a smoother reports no initial residual (:3270-3276) */
@@ -1908,8 +1982,22 @@ csb_multigrid_solve(void *context, const char *name, const csb_matrix_t *a, int 
 
     if (!CSB_CUDA(cudaMemcpyAsync(mg->h_mg, ms, MG_HEAD, cudaMemcpyDeviceToHost, c.stream)))
       return CSB_SLES_BREAKDOWN;
+    if (coarsest == 0) {
+      /* degenerate one-level hierarchy: no descent, hence no cycle test; the coarsest
+         solver's result is the cycle's (as k_mg_persistent does) */
+      ItState head;
+      if (!CSB_CUDA(cudaMemcpyAsync(&head, mg->it_states.p, IT_HEAD, cudaMemcpyDeviceToHost,
+                                    c.stream))
+          || !CSB_CUDA(cudaStreamSynchronize(c.stream))) return CSB_SLES_BREAKDOWN;
+      cvg = (head.cvg == CSB_SLES_ITERATING) ? CSB_SLES_MAX_ITERATION : head.cvg;
+      one_level_residual = head.residual;
+      n_cycles = 1;
+      break;
+    }
     if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return CSB_SLES_BREAKDOWN;
     cvg = mg->h_mg->cvg;
+    if (cvg == CSB_SLES_ITERATING && cycle_id > mg->n_max_cycles)
+      cvg = CSB_SLES_MAX_ITERATION;      /* never spin past the cycle budget */
     if (verbosity > 2)
       printf("     %4d  |               %6d  |  %12.4e\n", cycle_id, mg->h_mg->n_equiv_iter,
              mg->h_mg->residual / r_norm);
@@ -1921,7 +2009,7 @@ csb_multigrid_solve(void *context, const char *name, const csb_matrix_t *a, int 
   if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return CSB_SLES_BREAKDOWN;
 
   if (n_iter) *n_iter = mg->h_mg->n_equiv_iter;
-  if (residual) *residual = mg->h_mg->residual;
+  if (residual) *residual = (one_level_residual >= 0.) ? one_level_residual : mg->h_mg->residual;
   mg->n_cycles_last = n_cycles;
   mg->n_cycles_tot += n_cycles;
   mg->n_solves += 1;

@@ -21,6 +21,7 @@ os.environ["CSB_LIB"] = simbuild.build()
 # the persistent cooperative kernels cannot run here: kernel-per-phase variants
 os.environ["CSB_PCG_MODE_MULTI"] = "1"
 os.environ["CSB_MG_MODE_MULTI"] = "1"
+os.environ["CSB_FCG_MG_MODE_MULTI"] = "1"
 
 import numpy as np  # noqa: E402
 

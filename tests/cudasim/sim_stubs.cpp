@@ -19,6 +19,8 @@ bool launch_fcg_persistent(const MgLevelDesc &, const double *, double *, bool, 
                            double, const PersistentCommon &, ItState *, int, size_t, bool, bool,
                            bool)
 { return no("k_fcg_persistent"); }
+bool launch_fcg_mg_persistent(const FcgMgParams &, const PersistentCommon &, int, size_t, bool)
+{ return no("k_fcg_mg_persistent"); }
 bool launch_spmv_pipeline(const _csb_matrix_t *, const double *, double *, bool, bool *launched)
 { *launched = false; return true; }
 void plan_slabs(const std::vector<csb_lnum_t> &, int n_rows, int &slab_rows, int &n_slabs,
@@ -26,7 +28,7 @@ void plan_slabs(const std::vector<csb_lnum_t> &, int n_rows, int &slab_rows, int
 { slab_rows = 224; n_slabs = (n_rows + 223)/224; max_entries = 2432; }
 
 void  *pcomm_arena_alloc(csb_pcomm_t *, size_t) { no("peer arena"); return nullptr; }
-size_t pcomm_arena_mark(const csb_pcomm_t *) { return 0; }
+size_t pcomm_arena_mark(csb_pcomm_t *) { return 0; }
 void   pcomm_arena_release(csb_pcomm_t *, size_t) {}
 void   pcomm_host_barrier(csb_pcomm_t *) {}
 bool   pcomm_allreduce(csb_pcomm_t *, double *, int) { return no("peer all-reduce"); }
