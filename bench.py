@@ -3,18 +3,22 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--cube 256]
 
-One "step" = one cs_multigrid_solve (V-cycle, solver-mode defaults of
-cs_multigrid_define: PCG+Jacobi smoothers 2/10, PCG coarse solve) of the
-synthetic pressure system to precision 1e-8, hierarchy already set up (the
-reference times setup and solve separately too: cs_multigrid.cpp:5324-5332,
-:5583-5586; setup seconds are reported beside the headline).
+One "step" = one solve of the synthetic pressure system to precision 1e-8 with the
+reference's production pressure-solver layout: cs_sles_it FCG preconditioned by one
+cs_multigrid V-cycle per iteration (cs_multigrid_pc_create with the Jacobi-family smoother
+settings the reference itself selects for device execution, cs_multigrid.cpp:5070-5090:
+RJ3 x 3 sweeps, PCG coarse solve), hierarchy already set up (the reference times setup and
+solve separately too: cs_multigrid.cpp:5324-5332, :5583-5586; setup seconds are reported
+beside the headline).  Both arms run exactly this algorithm at the full 256^3 size; the
+V-cycle in solver mode (round 1's headline, PCG-smoothed) is reported beside it as
+`vcycle_solver`.
 
-Prints ONE JSON line (rank 0).  `value` = seconds per solve with rhs/vx resident
-in HBM; `e2e` = the same solve through the C-ABI with HOST rhs/vx buffers
-(H2D + D2H inside the timed region); `roofline` = level-0 SpMV kernel, achieved
+Prints ONE JSON line (rank 0).  `value` = seconds per solve with rhs/vx resident in HBM;
+`e2e` = the same solve through the C-ABI with HOST rhs/vx buffers (H2D + D2H inside the
+timed region); `roofline` = the dominant kernel (one launch = one whole solve): its
 algorithmic bytes / CUDA-event time against the measured HBM copy bandwidth;
-`cpu_baseline` = the reference's own CPU code (oracle/_ref/libcsref.so) on the
-box's host cores on a bounded sample.
+`cpu_baseline` = the reference's own CPU code (oracle/_ref/libcsref.so) on the box's host
+cores, one full solve of the same system.
 """
 from __future__ import annotations
 
@@ -97,87 +101,106 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# --------------------------------------------------------------------------- workload
+
+def workload_name(cube, n_rows):
+    return (f"{cube}^3 hex cube ({n_rows} cells) pressure Poisson, all-Neumann + eps; "
+            "cs_sles_it FCG + cs_multigrid_pc (one V-cycle per iteration: RJ3 x 3 sweeps down "
+            f"and up, PCG coarse solve), precision {PRECISION:g}")
+
+
+# smoother / coarse-solver settings of cs_multigrid_pc_create as the reference's own device
+# settings make them (cs_multigrid.cpp:5070-5090): cs_sles_it_type_t 16 = CS_SLES_RJ3, 0 = PCG
+PC_TYPES = (16, 16, 0)
+PC_N_MAX_ITER = (3, 3, 500)
+FCG_N_MAX_ITER = 200
+
+
 # --------------------------------------------------------------------------- reference arm
 
-def run_reference(args, sample_cube=None, quiet=False):
-    """Time the reference's own CPU implementation (cs_multigrid_setup/_solve from
-    oracle/_ref/libcsref.so) on the host cores, on a bounded sample of the workload."""
+def run_reference(args, cube, budget_s, max_steps, vcycle_too=False):
+    """Time the reference's own CPU implementation (oracle/_ref/libcsref.so: the real
+    cs_sles_it_solve / cs_multigrid code compiled from /root/reference) on all host cores,
+    on the FULL workload: whole solves of the same cube, as many as fit in budget_s
+    (at least one; the first one is the warm-up when more than one fits)."""
     from code_saturne_b200.mesh_cartesian import cube_poisson
     from oracle.pyoracle import RefLib, ref_available
     cores = os.cpu_count() or 1
-    n_cube = sample_cube or args.ref_cube
+    s = cube_poisson(cube)
+    r_norm = float(np.linalg.norm(s.rhs))
     if not ref_available():
-        # the oracle port always exists: single-threaded C restatement
+        # the oracle port always exists: single-threaded C restatement of the same algorithm
         from oracle.pyoracle import Oracle
         ora = Oracle()
-        s = cube_poisson(n_cube)
-        r_norm = float(np.linalg.norm(s.rhs))
         t0 = time.perf_counter(); mg = ora.mg_setup(s); t_setup = time.perf_counter() - t0
-        times = []
-        for i in range(max(1, min(args.steps, 2))):
-            t0 = time.perf_counter(); r = ora.mg_solve(mg, s.rhs, PRECISION, r_norm)
-            times.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        r = ora.fcg_mgpc(mg, s.rhs, FCG_N_MAX_ITER, PRECISION, r_norm)
+        t = time.perf_counter() - t0
         ora.mg_free(mg)
-        return dict(kind="port", cores=1, cube=n_cube, n_rows=s.n_rows, t_solve=min(times),
-                    t_setup=t_setup, n_cycles=r["n_cycles"], n_iter=r["n_iter"])
+        return dict(kind="port", cores=1, cube=cube, n_rows=s.n_rows, times=[t], warmup=0,
+                    t_setup=t_setup, n_iter=r["n_iter"], cvg=r["cvg"], residual=r["residual"],
+                    r_norm=r_norm)
     ref = RefLib(cores)
-    s = cube_poisson(n_cube)
     h = ref.system(s)
-    r_norm = float(np.linalg.norm(s.rhs))
-    times, setups = [], []
-    n_runs = args.warmup_ref + max(1, args.steps_ref)
-    r = None
-    for i in range(n_runs):
-        r = ref.multigrid(h, s.rhs, PRECISION, r_norm)
-        if i >= args.warmup_ref:
+
+    def one():
+        return ref.fcg_mgpc(h, s.rhs, FCG_N_MAX_ITER, PRECISION, r_norm, types=PC_TYPES,
+                            mg_n_max_iter=PC_N_MAX_ITER)
+    w0 = time.perf_counter()
+    r = one()
+    t_first = time.perf_counter() - w0          # setup + solve, what one more step costs
+    times, setups, warm = [r["t_solve"]], [r["t_setup"]], 0
+    n_more = int(min(max_steps, (budget_s - t_first) // max(t_first, 1e-3)))
+    if n_more >= 1:
+        times, setups, warm = [], [], 1
+        for _ in range(n_more):
+            r = one()
             times.append(r["t_solve"]); setups.append(r["t_setup"])
+    out = dict(kind="reference", cores=ref.n_threads, cube=cube, n_rows=s.n_rows, times=times,
+               warmup=warm, t_setup=float(np.mean(setups)), n_iter=r["n_iter"], cvg=r["cvg"],
+               residual=r["residual"], r_norm=r_norm)
+    if vcycle_too:
+        v = ref.multigrid(h, s.rhs, PRECISION, r_norm)
+        out["vcycle"] = dict(s_per_solve=v["t_solve"], setup_s=v["t_setup"],
+                             n_equiv_iter=v["n_iter"], cvg=v["cvg"])
     ref.destroy(h)
-    return dict(kind="reference", cores=ref.n_threads, cube=n_cube, n_rows=s.n_rows,
-                t_solve=float(np.mean(times)), t_setup=float(np.mean(setups)),
-                n_iter=r["n_iter"], cvg=r["cvg"], residual=r["residual"])
+    return out
+
+
+def cpu_baseline_block(b):
+    t = float(np.mean(b["times"]))
+    return {"value": t, "unit": UNIT, "cores": b["cores"], "kind": b["kind"],
+            "sample": (f"{len(b['times'])} full solve(s) of the same {b['cube']}^3 system "
+                       f"({b['n_rows']} rows) to {PRECISION:g}, same algorithm, "
+                       f"{b['cores']} OpenMP threads, {b['warmup']} warm-up solve(s); no scaling"),
+            "setup_s": b["t_setup"], "n_iter": b["n_iter"], "cvg": b["cvg"],
+            "final_residual_over_rnorm": b["residual"] / b["r_norm"]}
 
 
 def reference_main(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    b = run_reference(args)
-    scale = (args.cube ** 3) / float(b["n_rows"])
-    value = b["t_solve"] * scale
-    sample = (f"{b['cube']}^3 cube ({b['n_rows']} rows) full solve to {PRECISION:g}, "
-              f"{b['cores']} OpenMP threads; seconds scaled x{scale:g} (row count) to the "
-              f"{args.cube}^3 workload")
+    b = run_reference(args, args.cube, args.ref_budget_s, max(1, args.steps),
+                      vcycle_too=args.ref_vcycle)
+    value = float(np.mean(b["times"]))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference",
-        "n_gpus": args.gpus, "steps": args.steps_ref, "warmup": args.warmup_ref,
+        "n_gpus": args.gpus, "steps": len(b["times"]), "warmup": b["warmup"],
         "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.cube}^3 hex cube pressure Poisson, cs_multigrid V-cycle "
-                               "(PCG+Jacobi smoothers), precision 1e-8",
-                   "sample_cube": b["cube"]},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": b["cores"], "kind": b["kind"],
-                         "sample": sample, "sample_s_per_solve": b["t_solve"],
-                         "sample_setup_s": b["t_setup"], "sample_n_equiv_iter": b["n_iter"]},
+        "config": {"workload": workload_name(args.cube, b["n_rows"]),
+                   "n_iter": b["n_iter"], "setup_s": b["t_setup"],
+                   "steps_note": (f"whole solves at full size, bounded by a {args.ref_budget_s:g} s "
+                                  f"budget: {len(b['times'])} timed after {b['warmup']} warm-up "
+                                  f"(asked: {args.steps} / {args.warmup})")},
+        "cpu_baseline": cpu_baseline_block(b),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if "vcycle" in b:
+        line["vcycle_solver"] = b["vcycle"]
     print(json.dumps(line))
-
-
-def run_production_solver(args):
-    """Side measurement, never part of `value`: the reference's production layout (FCG
-    preconditioned by one V-cycle, scripts/fcg_mg_times.py) on the same cube, in a process of
-    its own after the headline numbers are taken; a failure there only shows up here."""
-    try:
-        out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fcg_mg_times.py"),
-                              "--cube", str(args.cube)], capture_output=True, text=True,
-                             timeout=300, cwd=ROOT)
-        for ln in reversed(out.stdout.strip().splitlines()):
-            if ln.startswith("{"):
-                return json.loads(ln)
-        return {"unavailable": (out.stderr.strip().splitlines() or ["no output"])[-1][:300]}
-    except Exception as e:
-        return {"unavailable": str(e)[:300]}
 
 
 # --------------------------------------------------------------------------- our arm
@@ -189,22 +212,29 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cube", type=int, default=256, help="cells per edge of the hex cube")
-    ap.add_argument("--ref-cube", type=int, default=128, help="CPU sample size (bounded)")
-    ap.add_argument("--steps-ref", type=int, default=2)
-    ap.add_argument("--warmup-ref", type=int, default=1)
+    ap.add_argument("--ref-budget-s", type=float, default=200.0,
+                    help="wall-clock budget of the reference arm's solves")
+    ap.add_argument("--ref-vcycle", action="store_true",
+                    help="reference arm: also time the V-cycle in solver mode once")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spmv-launches", type=int, default=50)
-    ap.add_argument("--no-production-solver", action="store_true",
-                    help="skip the FCG + multigrid-preconditioner side measurement")
+    ap.add_argument("--no-vcycle-solver", action="store_true",
+                    help="skip the side measurement of the PCG-smoothed V-cycle solver")
+    ap.add_argument("--solver", default="auto", choices=["auto", "fcg_mg", "vcycle"],
+                    help="headline solver (auto: FCG + V-cycle preconditioner)")
     args = ap.parse_args()
 
     if args.impl == "reference":
         reference_main(args)
         return
+    if os.environ.get("CSB_LIB"):
+        sys.exit("bench.py: CSB_LIB is set (a substitute library, test infrastructure only); "
+                 "the bench measures code_saturne_b200/csrc/libcsb200.so")
 
     import torch
     from code_saturne_b200 import api
     from code_saturne_b200.mesh_cartesian import cube_poisson
+    from code_saturne_b200 import traffic
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -218,6 +248,8 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     api.set_stream(stream.cuda_stream)
+    cores = os.cpu_count() or 1
+    n_blocks = max(1, cores // world)     # aggregation blocks = host threads of this rank
 
     # ---- synthetic input (host), matrix + hierarchy setup ------------------
     # N > 1: the SAME cube is partitioned into N bricks (what the reference's Morton-box
@@ -225,7 +257,7 @@ def main():
     # Ghost exchange and dot products run inside the persistent solver kernel over
     # NVLink peer memory; torch.distributed only bootstraps.
     t0 = time.perf_counter()
-    ro = None
+    ro = pc = None
     if world > 1:
         from code_saturne_b200.dist import RankObjects, pcomm_from_torch_dist
         from code_saturne_b200.mesh_cartesian import cube_poisson_local
@@ -246,14 +278,46 @@ def main():
         pc = pcomm_from_torch_dist(halo_desc.n_ghost)
         ro = RankObjects(s, halo_desc, gids, pc, rank)
         m = ro.matrix
-        mg = ro.multigrid()
     else:
         m = api.Matrix.from_system(s)
-        mg = api.Multigrid()
+    api.synchronize()
     t_upload = time.perf_counter() - t0
+
+    solver_kind = args.solver
+    if solver_kind == "auto":
+        solver_kind = "fcg_mg"
+
+    def make_fcg_mg():
+        c = api.SlesIt(api.SlesItType.FCG, FCG_N_MAX_ITER, poly_degree=-1)
+        mgp = api.Multigrid(pc=True)
+        mgp.set_aggregation_blocks(n_blocks)
+        if world > 1:
+            mgp.set_pcomm(pc)
+            c.set_pcomm(pc)
+        c.transfer_pc(mgp)
+        return c
+
+    def make_vcycle():
+        if world > 1:
+            mgv = ro.multigrid()
+        else:
+            mgv = api.Multigrid()
+        mgv.set_aggregation_blocks(n_blocks)
+        return mgv
+
     t0 = time.perf_counter()
-    mg.setup(m)
+    if solver_kind == "fcg_mg":
+        sol = make_fcg_mg()
+        sol.setup(m)
+        mg = sol.pc()
+    else:
+        sol = make_vcycle()
+        sol.setup(m)
+        mg = sol
+    api.synchronize()
     t_setup = time.perf_counter() - t0
+    if mg is None or mg.n_levels() < 1:
+        sys.exit("bench.py: solver setup failed: " + api.load_library().csb_last_error().decode())
     st = mg.setup_times()
     n_levels = mg.n_levels()
 
@@ -267,11 +331,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def solve_device():
-        return mg.solve(m, rhs_d, PRECISION, r_norm, vx=vx_d)
+    def solve_device(x=sol):
+        return x.solve(m, rhs_d, PRECISION, r_norm, vx=vx_d)
 
-    def solve_host():
-        return mg.solve(m, rhs_h.numpy(), PRECISION, r_norm, vx=vx_h.numpy())
+    def solve_host(x=sol):
+        return x.solve(m, rhs_h.numpy(), PRECISION, r_norm, vx=vx_h.numpy())
 
     for _ in range(args.warmup):
         r = solve_device()
@@ -303,7 +367,7 @@ def main():
         barrier()
         t_e2e = max(e0.elapsed_time(e1) * 1e-3, time.perf_counter() - w0) / args.steps
 
-        # ---- roofline: level-0 SpMV kernel, inputs (1.7 GB) >> L2 ----------
+        # ---- stand-alone level-0 SpMV kernel, inputs (1.7 GB) >> L2 --------
         x_d = torch.from_numpy(np.sin(np.arange(n_cols_ext) * 0.37)).cuda()
         y_d = torch.empty(s.n_rows, dtype=torch.float64, device="cuda")
         for _ in range(5):
@@ -317,6 +381,14 @@ def main():
         t_spmv = e0.elapsed_time(e1) * 1e-3 / args.spmv_launches
     clocks = sampler.summary()
 
+    # true residual of the last device solve (not timed)
+    m.vector_multiply(vx_d, y_d)
+    tr = torch.tensor([float(torch.sum((rhs_d - y_d) ** 2).item())], dtype=torch.float64,
+                      device="cuda")
+    if world > 1:
+        dist.all_reduce(tr)
+    true_res = float(torch.sqrt(tr[0]).item())
+
     if world > 1:
         t = torch.tensor([t_dev, t_e2e, t_spmv], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -325,38 +397,63 @@ def main():
     spmv_bytes = m.spmv_bytes()          # this rank's brick; all bricks are equal
     peak, peak_src = measured_peak_gbs()
     spmv_gbs = spmv_bytes / t_spmv / 1e9
-    # dominant kernel = k_mg_persistent, ONE launch per solve: algorithmic bytes of the
-    # cycles it ran (code_saturne_b200/traffic.py) over its CUDA-event time
-    from code_saturne_b200.traffic import cycle_bytes, level_sizes
-    info = level_sizes(mg)
-    solve_bytes = cycle_bytes(info) * int(r["n_cycles"])       # per rank
+    info = traffic.level_sizes(mg)
+    pt = mg.phase_times()                # device-side timers of the last solve
+    if solver_kind == "fcg_mg":
+        n_units = int(r["n_iter"])
+        unit_bytes = traffic.fcg_mg_iter_bytes(info, PC_N_MAX_ITER[0], PC_N_MAX_ITER[1])
+        kernel = ("k_fcg_mg_persistent (whole FCG solve, one V-cycle per iteration: all "
+                  "iterations and levels in one launch")
+        traffic_file, traffic_key = "ncu_fcg_mg_traffic.json", "dram_bytes_per_iter"
+    else:
+        n_units = int(r["n_cycles"])
+        unit_bytes = traffic.cycle_bytes(info)
+        kernel = "k_mg_persistent (whole V-cycle solve: all cycles and levels in one launch"
+        traffic_file, traffic_key = "ncu_mg_persistent_traffic.json", "dram_bytes_per_cycle"
+    solve_bytes = unit_bytes * n_units                          # per rank
     achieved = solve_bytes / t_dev / 1e9
-    # in-solve SpMV + 3 dots phase of the finest level, from the device-side timers
-    stt = mg.smoother_times()
-    n0, nnz0 = info[0]
-    t_sp = stt[0, 1] / max(int(r["n_cycles"]), 1) / 2.0
-    in_solve_spmv = ((12.0 * nnz0 + 36.0 * n0) / t_sp / 1e9) if t_sp > 0 else None
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01", "ncu_mg_persistent_traffic.json")
-    if world == 1 and args.cube == 256 and os.path.exists(tp):
-        try:      # dram__bytes_read+write of one ncu --set full capture, per cycle
-            traffic = float(json.load(open(tp))["dram_bytes_per_cycle"]) * int(r["n_cycles"])
-        except Exception:
-            traffic = None
+    dram = None
+    for rnd in ("r02", "r01"):
+        tp = os.path.join(ROOT, "profiles", rnd, traffic_file)
+        if world == 1 and args.cube == 256 and os.path.exists(tp):
+            try:      # dram__bytes_read+write of one ncu --set full capture, per unit
+                dram = float(json.load(open(tp))[traffic_key]) * n_units
+                break
+            except Exception:
+                dram = None
+
+    extra = {}
+    if world == 1 and solver_kind == "fcg_mg" and not args.no_vcycle_solver:
+        # side measurement, after the headline numbers: round 1's headline solver
+        try:
+            mgv = make_vcycle()
+            t0 = time.perf_counter(); mgv.setup(m); api.synchronize()
+            tv_setup = time.perf_counter() - t0
+            rv = solve_device(mgv)
+            barrier()
+            e0.record(stream)
+            for _ in range(2):
+                rv = solve_device(mgv)
+            e1.record(stream)
+            barrier()
+            tv = e0.elapsed_time(e1) * 1e-3 / 2
+            vb = traffic.cycle_bytes(traffic.level_sizes(mgv)) * int(rv["n_cycles"])
+            extra["vcycle_solver"] = {
+                "solver": "cs_multigrid V-cycle in solver mode (PCG+Jacobi smoothers 2/10, PCG "
+                          "coarse), k_mg_persistent: round 1's headline",
+                "s_per_solve": tv, "n_cycles": int(rv["n_cycles"]),
+                "n_equiv_iter": int(rv["n_iter"]), "cvg": int(rv["cvg"]), "setup_s": tv_setup,
+                "roofline_frac": vb / tv / 1e9 / peak, "steps": 2, "warmup": 1}
+            mgv.destroy()
+        except Exception as e:
+            extra["vcycle_solver"] = {"unavailable": str(e)[:300]}
 
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             try:
-                b = run_reference(args)
-                scale = s.n_rows / float(b["n_rows"])
-                cpu = {"value": b["t_solve"] * scale, "unit": UNIT, "cores": b["cores"],
-                       "kind": b["kind"],
-                       "sample": (f"{b['cube']}^3 cube ({b['n_rows']} rows) full solve to "
-                                  f"{PRECISION:g} with {b['cores']} OpenMP threads; seconds "
-                                  f"scaled x{scale:g} (row count) to the {args.cube}^3 workload"),
-                       "sample_s_per_solve": b["t_solve"], "sample_setup_s": b["t_setup"],
-                       "sample_n_equiv_iter": b["n_iter"]}
+                b = run_reference(args, args.cube, 0.0, 0)      # one full solve, no repeat
+                cpu = cpu_baseline_block(b)
             except Exception as e:  # the baseline is reported, never required
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
                        "sample": f"unavailable: {e}"}
@@ -365,49 +462,54 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev * 1e3,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.cube}^3 hex cube ({n_rows_global} cells) pressure Poisson, "
-                                   "cs_multigrid V-cycle (PCG+Jacobi smoothers 2/10, coarse PCG), "
-                                   f"precision {PRECISION:g}, all-Neumann + eps",
+            "config": {"workload": workload_name(args.cube, n_rows_global)
+                       if solver_kind == "fcg_mg" else
+                       f"{args.cube}^3 hex cube ({n_rows_global} cells) pressure Poisson, "
+                       "cs_multigrid V-cycle (PCG+Jacobi smoothers 2/10, coarse PCG), "
+                       f"precision {PRECISION:g}, all-Neumann + eps",
                        "rows_per_gpu": n_rows_global // world, "n_levels": n_levels,
-                       "n_cycles": int(r["n_cycles"]), "n_equiv_iter": int(r["n_iter"]),
+                       "n_iter": int(r["n_iter"]),
                        "final_residual_over_rnorm": float(r["residual"] / r_norm),
+                       "true_residual_over_rnorm": true_res / r_norm,
                        "l2_policy": "inputs (1.7 GB matrix) larger than L2; no flush needed",
                        "setup_s": t_setup, "setup_aggregation_host_s": st["aggregation"],
                        "setup_assembly_device_s": st["assembly"],
                        "setup_transfers_s": st["transfers"],
+                       "aggregation_blocks": n_blocks,
                        "matrix_upload_s": t_upload, "input_generation_s": t_gen,
                        "parallelism": "1 GPU" if world == 1 else
                        f"{world} bricks (Morton-box partition), one per GPU; ghost exchange + "
-                       "all-reduce fused in the persistent kernel over NVLink peer memory"},
+                       "all-reduce fused in the persistent kernel over NVLink peer memory; "
+                       "multi-rank coarse halos have no reference run behind them here (no MPI "
+                       "in the image): parity unpinned for _coarsen_halo"},
             "e2e": {"value": t_e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n_rows_global,
                     "d2h_bytes_per_step": 8 * n_rows_global + 4096 * world},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm",
-                         "kernel": "k_mg_persistent (whole V-cycle solve: all cycles and levels "
-                                   "in one launch" + (", per GPU)" if world > 1 else ")"),
+                         "kernel": kernel + (", per GPU)" if world > 1 else ")"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic,
+                         "frac": achieved / peak, "traffic": dram,
                          "algorithmic_bytes_per_launch": solve_bytes,
                          "ms_per_launch": t_dev * 1e3, "peak_source": peak_src,
-                         "launches_timed": args.steps},
+                         "launches_timed": args.steps,
+                         "in_kernel_phase_seconds": float(pt.sum())},
             "spmv": {"kernel": "k_spmv_stream (level-0 MSR SpMV, stand-alone"
                                + (", per GPU, incl. ghost exchange)" if world > 1 else ")"),
                      "achieved": spmv_gbs, "frac": spmv_gbs / peak, "unit": "GB/s",
-                     "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": t_spmv * 1e3,
-                     "in_solve_spmv_3dots_gbs": in_solve_spmv,
-                     "in_solve_spmv_3dots_frac": (in_solve_spmv / peak) if in_solve_spmv else None},
+                     "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": t_spmv * 1e3},
             "spmv_hbm_gbs": spmv_gbs,
             "clocks": clocks,
         }
+        if solver_kind != "fcg_mg":
+            line["config"]["n_cycles"] = int(r["n_cycles"])
+        line.update(extra)
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        if world == 1 and not args.no_production_solver:
-            line["production_solver"] = run_production_solver(args)
         print(json.dumps(line))
 
     if world > 1:
         dist.barrier()
-    mg.destroy()
+    sol.destroy()
     if ro is not None:
         ro.destroy()
         pc.destroy()

@@ -654,6 +654,18 @@ class SlesIt(_SolverBase):
             _err("csb_sles_it_transfer_pc")
         mg._h = None
 
+    def pc(self):
+        """cs_sles_it_get_pc: the transferred multigrid preconditioner (borrowed), or None."""
+        L = load_library()
+        L.csb_sles_it_get_pc.restype = C.c_void_p
+        h = L.csb_sles_it_get_pc(C.c_void_p(self._h))
+        if not h:
+            return None
+        mg = Multigrid.__new__(Multigrid)
+        mg._h = h
+        mg._borrowed = True
+        return mg
+
     def setup(self, a: Matrix, name="system", verbosity=0):
         load_library().csb_sles_it_setup(C.c_void_p(self._h), name.encode(), a.handle, verbosity)
 
@@ -825,10 +837,10 @@ class Multigrid(_SolverBase):
         load_library().csb_multigrid_log(C.c_void_p(self._h), 0)
 
     def destroy(self):
-        if self._h:
+        if self._h and not getattr(self, "_borrowed", False):
             h = C.c_void_p(self._h)
             load_library().csb_multigrid_destroy(C.byref(h))
-            self._h = None
+        self._h = None
 
     def __del__(self):
         try:

@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstddef>
 #include <algorithm>
+#include <omp.h>
 
 using namespace csb;
 
@@ -399,6 +400,7 @@ MgState *mg_gate(csb_multigrid_t *mg);
 bool mg_fcg_persistent_ok(const csb_multigrid_t *mg);
 size_t mg_persistent_smem(const csb_multigrid_t *mg);
 void mg_fcg_params(csb_multigrid_t *mg, FcgMgParams &S, PersistentCommon &P);
+bool mg_fetch_state(csb_multigrid_t *mg);     /* device-side timers -> host mirror (async) */
 
 /* x_out = M^-1 x_in for the general preconditioners of cs_sles_it:
      multigrid   _multigrid_pc_apply (cs_multigrid.cpp:1500-1600): one V-cycle, identity for
@@ -817,7 +819,8 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
       S.fwork = c->work.p; S.fstride = work_stride_of((size_t)a->n_cols_ext);
       P.partials = c->partials.p; P.barrier = c->barrier.p;
       if (!launch_mg_state_init(S.ms, precision, r_norm, 1)) return CSB_SLES_BREAKDOWN;
-      ok = launch_fcg_mg_persistent(S, P, c->p_grid, c->p_smem, cx.device_share <= 1);
+      ok = launch_fcg_mg_persistent(S, P, c->p_grid, c->p_smem, cx.device_share <= 1)
+           && mg_fetch_state(c->pc_mg);
       break;
     }
     if (c->general_pc()) {
@@ -1005,7 +1008,7 @@ struct _csb_multigrid_t {
   unsigned long long n_g_rows_min = 30;
   double  p0p1_relax = 0.95;
   double  k_cycle_threshold = 0.;      /* cs_multigrid.cpp:4707, :4724 */
-  int     n_blocks = 1;
+  int     n_blocks = 0;      /* 0: as many as OpenMP threads (the reference's behaviour) */
   csb_sles_it_type_t solver_type[3] = {CSB_SLES_PCG, CSB_SLES_PCG, CSB_SLES_PCG};
   int     n_max_cycles = 100;
   int     n_max_iter[3] = {2, 10, 500};
@@ -1065,6 +1068,12 @@ bool mg_fcg_persistent_ok(const csb_multigrid_t *mg)
 }
 
 size_t mg_persistent_smem(const csb_multigrid_t *mg) { return mg->p_smem; }
+
+bool mg_fetch_state(csb_multigrid_t *mg)
+{
+  return CSB_CUDA(cudaMemcpyAsync(mg->h_mg, mg->mg_state.p, sizeof(MgState),
+                                  cudaMemcpyDeviceToHost, ctx().stream));
+}
 
 void mg_fcg_params(csb_multigrid_t *mg, FcgMgParams &S, PersistentCommon &P)
 {
@@ -1456,7 +1465,7 @@ csb_multigrid_set_coarsening_options(csb_multigrid_t *mg, int aggregation_limit,
 
 void csb_multigrid_set_aggregation_blocks(csb_multigrid_t *mg, int n_blocks)
 {
-  if (mg != nullptr) mg->n_blocks = (n_blocks > 0) ? n_blocks : 1;
+  if (mg != nullptr) mg->n_blocks = (n_blocks > 0) ? n_blocks : 0;
 }
 
 int csb_multigrid_set_reduce_comm(csb_multigrid_t *mg, void *nccl_comm)
@@ -1522,7 +1531,14 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
               "available");
     return;
   }
-  if (pairwise && (!galerkin || a->halo != nullptr || mg->n_blocks > 1)) {
+  /* the reference confines its greedy aggregation to one block of rows per OpenMP thread
+     (cs_grid.cpp:4374-4393): unless csb_multigrid_set_aggregation_blocks fixed a count,
+     follow the thread count of this process (OMP_NUM_THREADS), as it does; pairwise
+     aggregation is the reference's single-thread pairing */
+  const bool pairwise_req = (mg->coarsening_type == 3);
+  const int n_blocks = (mg->n_blocks > 0) ? mg->n_blocks
+                     : (pairwise_req ? 1 : std::max(1, omp_get_max_threads()));
+  if (pairwise && (!galerkin || a->halo != nullptr || n_blocks > 1)) {
     set_error("csb_multigrid_setup: CS_GRID_COARSENING_SPD_PW is available with Galerkin "
               "coarse matrices (p0p1_relax <= 0) on one rank, one aggregation block (the "
               "reference's single-thread pairing)");
@@ -1608,7 +1624,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
                                   mg->aggregation_limit, f->h_coarse_row.data(), pw)
       : aggregate_dx_msr(f_level, fm->n_rows, fm->h_row_index.data(), fm->h_col_id.data(),
                          fm->h_d_val.data(), fm->h_x_val.data(), mg->aggregation_limit,
-                         mg->n_blocks, f->h_coarse_row.data());
+                         n_blocks, f->h_coarse_row.data());
     t_aggr += wall() - t0;
 
     /* stop criteria of _setup_hierarchy (cs_multigrid.cpp:2518-2529); they

@@ -66,3 +66,48 @@ def cycle_bytes(info, n_desc=2, n_asc=10):
         nc = info[l + 1][0] if l < coarsest else 0
         tot += phase_bytes(n, nnz, nc, n_desc, n_asc, l, coarsest).sum()
     return tot
+
+
+# ---------------------------------------------------------------------------------------
+# FCG preconditioned by one V-cycle with Jacobi-family smoothers (k_fcg_mg_persistent)
+# ---------------------------------------------------------------------------------------
+
+def sweep_bytes(n, nnz, mode="relaxed"):
+    """One fused smoother sweep: E (col_id, x_val, row_index), x (read once: gather and
+    staged copy are the same vector), rhs, 1/d, write; L1 adds d_val."""
+    b = 12.0 * nnz + 4.0 * (n + 1) + 32.0 * n
+    if mode == "jacobi":
+        pass                      # same arrays, x only gathered
+    elif mode == "l1":
+        b += 8.0 * n
+    return b
+
+
+def fcg_mg_phase_bytes(n, nnz, nc, n_desc, n_asc, level, coarsest, mode="relaxed"):
+    """Bytes of each phase (PHASES order) of one preconditioner V-cycle at one level.
+    The first descent sweep (from zero) is fused into the phase that produces its right-hand
+    side: 16 bytes per row (read 1/d, write) are counted with the restriction above (level
+    > 0) or with the FCG update (level 0)."""
+    out = np.zeros(6)
+    if level < coarsest:
+        out[0] = max(n_desc - 1, 0) * sweep_bytes(n, nnz, mode)
+        out[1] = 12.0 * nnz + 4.0 * (n + 1) + 32.0 * n        # d, x, rhs, wr
+        fused_first = 16.0 * nc if level + 1 < coarsest else 0.0
+        out[2] = 12.0 * n + 12.0 * nc + fused_first
+        out[4] = 20.0 * n + 8.0 * nc
+        out[5] = n_asc * sweep_bytes(n, nnz, mode)
+    return out
+
+
+def fcg_mg_iter_bytes(info, n_desc=3, n_asc=3, mode="relaxed"):
+    """Algorithmic bytes of ONE FCG iteration: the V-cycle over `info`, wk = A.vk with the 4
+    dot products (vk, rk, qk read; wk written) and the fused 6-vector update + first sweep."""
+    coarsest = len(info) - 1
+    tot = 0.0
+    for l, (n, nnz) in enumerate(info):
+        nc = info[l + 1][0] if l < coarsest else 0
+        tot += fcg_mg_phase_bytes(n, nnz, nc, n_desc, n_asc, l, coarsest, mode).sum()
+    n0, nnz0 = info[0]
+    tot += 12.0 * nnz0 + 4.0 * (n0 + 1) + 40.0 * n0           # SpMV + 4 dots
+    tot += 96.0 * n0                                          # update (7 reads, 5 writes)
+    return tot

@@ -393,7 +393,9 @@ void csb_multigrid_set_coarsening_options(csb_multigrid_t  *mg,
 
 /* Number of row blocks the greedy aggregation is confined to; restates the
    reference's per-OpenMP-thread blocks (src/alge/cs_grid.cpp:4374-4393).
-   1 (default) == reference with OMP_NUM_THREADS=1. */
+   n_blocks == reference run with that many OpenMP threads (maps are bit-identical per
+   count); 0 (default): the OpenMP thread count of this process (OMP_NUM_THREADS), which
+   is what the reference uses. */
 void csb_multigrid_set_aggregation_blocks(csb_multigrid_t *mg, int n_blocks);
 
 int  csb_multigrid_set_reduce_comm(csb_multigrid_t *mg, void *nccl_comm);

@@ -17,7 +17,7 @@ import numpy as np
 import pytest
 
 from code_saturne_b200.mesh_cartesian import cube_poisson, matrix_check_coefficients
-from conftest import golden_cases, rel_l2
+from conftest import equiv_iters_close, golden_cases, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -284,7 +284,9 @@ def test_multigrid_vs_oracle(csb, oracle, N, bc, n_blocks):
     r = mg.solve(m, s.rhs, 1e-8, r_norm)
     assert int(r["cvg"]) == o["cvg"] == 1
     assert abs(r["n_cycles"] - o["n_cycles"]) <= 1
-    assert abs(r["n_iter"] - o["n_iter"]) <= max(2, o["n_iter"] // 20)
+    assert equiv_iters_close(r["n_iter"], o["n_iter"], o["n_iter"] / o["n_cycles"])
+    if r["n_cycles"] == o["n_cycles"]:
+        assert abs(r["n_iter"] - o["n_iter"]) <= 2
     k = min(len(r["cycle_residuals"]), len(o["cycle_residuals"]), 5)
     assert np.allclose(r["cycle_residuals"][:k], o["cycle_residuals"][:k], rtol=1e-7, atol=0)
     res = np.linalg.norm(oracle.spmv(s.row_index, s.col_id, s.d_val, s.x_val,
@@ -574,8 +576,7 @@ def test_pcg_without_preconditioner_matches_oracle(csb, oracle):
     m = csb.Matrix(s.n_rows, s.row_index, s.col_id, d, s.x_val)
     c = csb.SlesIt(csb.SlesItType.PCG, 2000, poly_degree=-1)
     r = c.solve(m, s.rhs, 1e-10, r_norm)
-    # 241 unpreconditioned iterations: the count drifts with reduction-order rounding
-    assert int(r["cvg"]) == 1 == o["cvg"] and abs(r["n_iter"] - o["n_iter"]) <= max(2, o["n_iter"] // 20)
+    assert int(r["cvg"]) == 1 == o["cvg"] and abs(r["n_iter"] - o["n_iter"]) <= 2
     assert o["n_iter"] != op["n_iter"]                  # really a different algorithm
     k = min(len(r["history"]), len(o["history"]), 8)
     assert np.allclose(r["history"][:k], o["history"][:k], rtol=1e-10, atol=0)

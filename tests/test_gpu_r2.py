@@ -1,0 +1,246 @@
+"""Round-2 GPU tests, through the C-ABI.
+
+* k_fcg_mg_persistent (FCG + one V-cycle per iteration in ONE launch) against the
+  kernel-per-phase path it replaces, the oracle and the reference build;
+* parity at the benchmarked sizes (BASELINE configs 1-3: 50^3, 128^3, 256^3) against the
+  reference's own code (oracle/_ref/libcsref.so): level count, every aggregation map
+  bit-exact, cycle / iteration counts, converged solutions <= 1e-10 relative L2 at
+  precision 1e-12;
+* the fixes of round 1's review: csb_matrix_set_coefficients on block / CSR matrices, the
+  one-level hierarchy in the kernel-per-phase cycle loop, a failed setup leaving the object
+  clean.
+
+Tolerances: aggregation maps bit-exact; Krylov iteration counts +-2; cs_multigrid cycle
+counts +-1 (equivalent iterations: conftest.equiv_iters_close); solutions 1e-10 relative L2.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from code_saturne_b200.mesh_cartesian import cube_poisson
+from conftest import equiv_iters_close, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+SOL_TOL = 1e-10
+CYCLES = {"rj3": ((16, 16, 0), (3, 3, 500)), "rj2": ((15, 15, 0), (2, 4, 500)),
+          "r_jacobi": ((14, 14, 0), (2, 2, 500)), "l1_jacobi": ((13, 13, 0), (2, 2, 500)),
+          "jacobi": ((3, 3, 0), (2, 3, 500)), "jacobi_1": ((3, 3, 0), (1, 1, 500)),
+          "l1_4": ((13, 13, 0), (4, 4, 500))}
+
+
+def _pc(csb, types, nmi):
+    mg = csb.Multigrid()
+    mg.set_solver_options(descent=types[0], ascent=types[1], coarse=types[2], n_max_cycles=1,
+                          n_max_iter_descent=nmi[0], n_max_iter_ascent=nmi[1],
+                          n_max_iter_coarse=nmi[2], precision_mult=(-1., -1., 1.))
+    return mg
+
+
+def _fcg(csb, m, s, precision, r_norm, pc, multi, n_max_iter=200, **kw):
+    """FCG + multigrid preconditioner; multi: kernel per phase instead of one launch."""
+    old = os.environ.get("CSB_FCG_MG_MODE_MULTI")
+    os.environ["CSB_FCG_MG_MODE_MULTI"] = "1" if multi else "0"
+    try:
+        c = csb.SlesIt(csb.SlesItType.FCG, n_max_iter, poly_degree=-1)
+        c.transfer_pc(pc)
+        csb.launch_count(reset=True)
+        r = c.solve(m, s.rhs, precision, r_norm, **kw)
+        r["launches"] = csb.launch_count()
+        c.destroy()
+    finally:
+        if old is None:
+            os.environ.pop("CSB_FCG_MG_MODE_MULTI", None)
+        else:
+            os.environ["CSB_FCG_MG_MODE_MULTI"] = old
+    return r
+
+
+@pytest.mark.parametrize("N,bc", [(24, "neumann"), (40, "dirichlet")])
+def test_fcg_mg_persistent_matches_kernel_per_phase(csb, N, bc):
+    """Same algorithm, same per-row arithmetic; only the order of the 4 global sums differs."""
+    s = cube_poisson(N, bc)
+    r_norm = float(np.linalg.norm(s.rhs))
+    m = csb.Matrix.from_system(s)
+    for name, (types, nmi) in CYCLES.items():
+        p = _fcg(csb, m, s, 1e-12, r_norm, _pc(csb, types, nmi), multi=False)
+        q = _fcg(csb, m, s, 1e-12, r_norm, _pc(csb, types, nmi), multi=True)
+        assert int(p["cvg"]) == int(q["cvg"]) == 1, name
+        assert p["launches"] <= 3 < q["launches"], (name, p["launches"], q["launches"])
+        assert abs(p["n_iter"] - q["n_iter"]) <= 1, (name, p["n_iter"], q["n_iter"])
+        k = min(len(p["history"]), len(q["history"]), 6)
+        assert np.allclose(p["history"][:k], q["history"][:k], rtol=1e-9, atol=0), name
+        assert rel_l2(p["vx"][:s.n_rows], q["vx"][:s.n_rows]) <= SOL_TOL, name
+        res = np.linalg.norm(s.rhs - m.vector_multiply(p["vx"][:s.n_rows].copy()))
+        assert res <= 1.01e-12 * r_norm, name
+    m.destroy()
+
+
+def test_fcg_mg_persistent_warm_start_and_max_iter(csb, oracle):
+    s = cube_poisson(32, "dirichlet")
+    r_norm = float(np.sqrt(oracle.dot_xx(s.rhs)))
+    omg = oracle.mg_setup(s)
+    o = oracle.fcg_mgpc(omg, s.rhs, 200, 1e-13, r_norm)
+    ow = oracle.fcg_mgpc(omg, s.rhs, 3, 1e-14, r_norm, vx0=0.5 * o["vx"])
+    m = csb.Matrix.from_system(s)
+    vx0 = np.concatenate([0.5 * o["vx"], np.zeros(m.n_cols_ext - s.n_rows)])
+    w = _fcg(csb, m, s, 1e-14, r_norm, csb.Multigrid(pc=True), multi=False, n_max_iter=3,
+             vx=vx0, use_vx_ini=True)
+    assert (int(w["cvg"]), w["n_iter"]) == (ow["cvg"], ow["n_iter"]) == (-1, 3)
+    assert w["launches"] <= 3
+    assert rel_l2(w["vx"][:s.n_rows], ow["vx"]) <= 1e-9
+    oracle.mg_free(omg); m.destroy()
+
+
+def _reference_parity(csb, reflib, N, n_threads, vcycle=True):
+    """Hierarchy, V-cycle solver and FCG + V-cycle(RJ3) of an N^3 cube against the reference's
+    own code run with n_threads OpenMP threads (its aggregation never crosses a thread's
+    block of rows, cs_grid.cpp:4374-4393: the maps depend on the thread count)."""
+    s = cube_poisson(N, "neumann")
+    r_norm = float(np.linalg.norm(s.rhs))
+    reflib.set_threads(n_threads)
+    out = {}
+    try:
+        h = reflib.system(s)
+        rlv = reflib.hierarchy(h)
+        m = csb.Matrix.from_system(s)
+        mg = csb.Multigrid()
+        mg.set_aggregation_blocks(n_threads)
+        mg.setup(m)
+        assert mg.n_levels() == len(rlv), (mg.n_levels(), len(rlv))
+        lv = mg.levels()
+        for l in range(1, len(lv)):
+            assert lv[l]["n_rows"] == rlv[l]["n_rows"], l
+            assert np.array_equal(lv[l]["coarse_row"], rlv[l]["coarse_row"]), l
+            if lv[l]["n_rows"] < 3000000:     # assembled coarse matrices: bit-exact
+                assert np.array_equal(lv[l]["x_val"], rlv[l]["x_val"]), l
+                assert np.array_equal(lv[l]["d_val"], rlv[l]["d_val"]), l
+        del lv, rlv
+        out["n_levels"] = mg.n_levels()
+        if vcycle:
+            o = reflib.multigrid(h, s.rhs, 1e-12, r_norm)
+            r = mg.solve(m, s.rhs, 1e-12, r_norm)
+            assert int(r["cvg"]) == o["cvg"] == 1
+            assert equiv_iters_close(r["n_iter"], o["n_iter"], r["n_iter"] / r["n_cycles"]), \
+                (r["n_iter"], o["n_iter"], r["n_cycles"])
+            out["vcycle"] = (r["n_cycles"], r["n_iter"], o["n_iter"],
+                             rel_l2(r["vx"][:s.n_rows], o["vx"]))
+            assert out["vcycle"][3] <= SOL_TOL, out
+        mg.destroy()
+        o = reflib.fcg_mgpc(h, s.rhs, 200, 1e-12, r_norm)
+        pc = csb.Multigrid(pc=True)
+        pc.set_aggregation_blocks(n_threads)
+        r = _fcg(csb, m, s, 1e-12, r_norm, pc, multi=False)
+        assert int(r["cvg"]) == o["cvg"] == 1
+        assert abs(r["n_iter"] - o["n_iter"]) <= 2, (r["n_iter"], o["n_iter"])
+        out["fcg"] = (r["n_iter"], o["n_iter"], rel_l2(r["vx"][:s.n_rows], o["vx"]))
+        assert out["fcg"][2] <= SOL_TOL, out
+        assert r["launches"] <= 3
+        m.destroy()
+        reflib.destroy(h)
+    finally:
+        reflib.set_threads(1)
+    return out
+
+
+def test_reference_parity_config1_50_cube_threaded_aggregation(csb, reflib):
+    """BASELINE config 1 (50^3) with the reference on 4 threads = 4 aggregation blocks."""
+    _reference_parity(csb, reflib, 50, 4)
+
+
+def test_reference_parity_config1_50_cube_single_thread(csb, reflib):
+    _reference_parity(csb, reflib, 50, 1)
+
+
+def test_reference_parity_config2_128_cube(csb, reflib):
+    """BASELINE config 2 size, reference at OMP_NUM_THREADS=1."""
+    _reference_parity(csb, reflib, 128, 1)
+
+
+def test_reference_parity_bench_256_cube(csb, reflib):
+    """The benchmarked workload (BASELINE config 3, 256^3): the reference on all host cores,
+    this library with as many aggregation blocks."""
+    t = max(1, min(os.cpu_count() or 1, 64))
+    out = _reference_parity(csb, reflib, 256, t)
+    print("256^3 parity:", out)
+
+
+# ----------------------------------------------------------------- fixes of round 1's review
+
+def test_set_coefficients_block3_updates_whole_blocks(csb):
+    s = cube_poisson(8, "dirichlet", with_mesh=False)
+    rng = np.random.default_rng(1234)
+    n = s.n_rows
+    def blocks(seed_shift):
+        b = 0.1 * rng.standard_normal((n, 3, 3)) + seed_shift
+        return (b + np.eye(3)[None] * (4.0 + seed_shift)).reshape(-1)
+    d1, d2 = blocks(0.0), blocks(0.5)
+    x2 = s.x_val * 1.25
+    x = np.sin(0.3 * np.arange(3 * n))
+    m = csb.Matrix.from_block(n, 3, s.row_index, s.col_id, d1, s.x_val)
+    y1 = m.vector_multiply(x.copy())
+    m.set_coefficients(d2, x2, symmetric=False)
+    y2 = m.vector_multiply(x.copy())
+    f = csb.Matrix.from_block(n, 3, s.row_index, s.col_id, d2, x2)
+    yf = f.vector_multiply(x.copy())
+    assert np.array_equal(y2, yf) and not np.array_equal(y1, y2)
+    m.destroy(); f.destroy()
+
+
+def test_set_coefficients_refused_on_csr_matrix(csb):
+    s = cube_poisson(6, "dirichlet", with_mesh=False)
+    # CSR with the diagonal first in each row
+    ri = s.row_index + np.arange(s.n_rows + 1, dtype=np.int32)
+    ci = np.empty(ri[-1], dtype=np.int32); v = np.empty(ri[-1])
+    for i in range(s.n_rows):
+        k0, k1 = s.row_index[i], s.row_index[i+1]
+        ci[ri[i]] = i; v[ri[i]] = s.d_val[i]
+        ci[ri[i]+1:ri[i+1]] = s.col_id[k0:k1]; v[ri[i]+1:ri[i+1]] = s.x_val[k0:k1]
+    m = csb.Matrix.from_csr(s.n_rows, ri, ci, v)
+    with pytest.raises(csb.CsbError):
+        m.set_coefficients(s.d_val, s.x_val)
+    m.destroy()
+
+
+def test_one_level_hierarchy_kernel_per_phase_terminates(csb, oracle, monkeypatch):
+    """n_max_levels = 1: no descent, no cycle test; the coarsest solver's result is the
+    cycle's (k_mg_persistent does the same, persistent.cu)."""
+    s = cube_poisson(12, "dirichlet")
+    r_norm = float(np.linalg.norm(s.rhs))
+    m = csb.Matrix.from_system(s)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("CSB_MG_MODE_MULTI", mode)
+        mg = csb.Multigrid()
+        mg.set_coarsening_options(n_max_levels=1)
+        mg.setup(m)
+        assert mg.n_levels() == 1
+        r = mg.solve(m, s.rhs, 1e-10, r_norm)
+        assert int(r["cvg"]) == 1, mode
+        tr = np.linalg.norm(s.rhs - m.vector_multiply(r["vx"][:s.n_rows].copy()))
+        assert tr <= 1.01e-10 * r_norm and abs(tr - r["residual"]) <= 1e-2 * tr + 1e-14 * r_norm
+        res[mode] = r
+        mg.destroy()
+    assert rel_l2(res["0"]["vx"], res["1"]["vx"]) <= 1e-9
+    m.destroy()
+
+
+def test_failed_setup_leaves_multigrid_reusable(csb):
+    s = cube_poisson(10, "dirichlet")
+    r_norm = float(np.linalg.norm(s.rhs))
+    n = s.n_rows
+    d3 = np.tile(np.eye(3).reshape(-1) * 6.0, n)
+    mb = csb.Matrix.from_block(n, 3, s.row_index, s.col_id, d3, s.x_val, symmetric=True)
+    m = csb.Matrix.from_system(s)
+    mg = csb.Multigrid()
+    with pytest.raises(csb.CsbError):
+        mg.setup(mb)                      # block matrices are refused after level 0 is pushed
+    mg.setup(m)
+    fresh = csb.Multigrid()
+    fresh.setup(m)
+    assert mg.n_levels() == fresh.n_levels()
+    a, b = mg.solve(m, s.rhs, 1e-9, r_norm), fresh.solve(m, s.rhs, 1e-9, r_norm)
+    assert int(a["cvg"]) == 1 and a["n_cycles"] == b["n_cycles"]
+    assert np.array_equal(a["vx"], b["vx"])
+    mg.destroy(); fresh.destroy(); m.destroy(); mb.destroy()
