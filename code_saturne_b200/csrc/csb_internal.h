@@ -294,7 +294,7 @@ struct _csb_matrix_t {
   bool        spmv_stream_ok = true;   /* false -> scalar fallback kernel */
   /* slab plan of the bulk-copy pipeline kernel (k_spmv_pipeline), made on first use */
   mutable int    pl_state = 0;         /* 0 not planned, 1 usable, -1 not usable */
-  mutable int    pl_slab_rows = 0, pl_n_slabs = 0, pl_grid = 0;
+  mutable int    pl_slab_rows = 0, pl_n_slabs = 0, pl_grid = 0, pl_gdepth = 2;
   mutable size_t pl_smem = 0;
   /* mesh association (device) */
   csb_lnum_t  n_faces = 0;

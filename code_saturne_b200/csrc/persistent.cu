@@ -25,6 +25,7 @@
 #include "csb_internal.h"
 #include "persistent.h"
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
@@ -513,11 +514,20 @@ __device__ __forceinline__ auto epi_nv(const F &f, int) -> decltype(f.nv()) { re
 template <class F>
 __device__ __forceinline__ int epi_nv(const F &, long) { return F::NV; }
 
-template <bool SINGLE, bool GHOST, class F>
+/* GD = gather depth: register sets of x[col] values a lane keeps in flight.  2 (NG values
+   each): the gathers of the next slab overlap the sums of this one.  3 (NG3 values each,
+   levels whose rows have at most NG3 entries, e.g. the 7-point fine level): gathers are
+   issued TWO slabs ahead, so that a loaded L2 latency of ~2 slab times is covered -- with
+   one slab of look-ahead every consumer warp spends one full gather latency per slab and
+   the phase saturates at ~0.75 of the HBM rate (profiles/r02). */
+constexpr int NG3 = 8;
+
+template <bool SINGLE, bool GHOST, int GD, class F>
 __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
                                           const double *ghost, unsigned char *s_raw,
                                           const F f, double *acc_out)
 {
+  constexpr int NGS = (GD == 3) ? NG3 : NG;      /* gathers per register set */
   /* column c < n_rows: x[c]; ghost column: ghost[c - n_rows] */
   const double *xg = GHOST ? ghost - L.n_rows : x;
   const int tid = threadIdx.x;
@@ -575,11 +585,11 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
       /* Two register sets (A, B) alternate between "being gathered for the next slab" and
          "being consumed": the loop body handles two slabs, so no set is ever copied and
          every element is indexed by a compile-time constant (they stay in registers). */
-      double gA[NG], gB[NG];
-      int ksA = 0, keA = 0, ksB = 0, keB = 0;   /* entries of the lane's row, relative to the
+      double gA[NGS], gB[NGS], gC[NGS];   /* gC: GD == 3 only */
+      int ksA = 0, keA = 0, ksB = 0, keB = 0, ksC = 0, keC = 0;   /* entries of the lane's row, relative to the
                                                    start of the staged x_val */
       /* row bounds of local iteration j and the first NG gathers of the lane's row */
-      auto prefetch = [&](int j, double (&gg)[NG], int &pks, int &pke) {
+      auto prefetch = [&](int j, double (&gg)[NGS], int &pks, int &pke) {
         const unsigned q = base + (unsigned)j;
         const unsigned char *sb = sv.stages + (q % NS)*sv.stage_bytes;
         consumer_wait(sv, q);
@@ -590,7 +600,7 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
         if (tid < rows) { ks = s_ri[tid] - k0; ke = s_ri[tid + 1] - k0; }
         const int *s_col = (const int *)sb + (k0 & 3);
 #pragma unroll
-        for (int e = 0; e < NG; e++) {
+        for (int e = 0; e < NGS; e++) {
           double v = 0.;
           if (ks + e < ke) {
             const int c = s_col[ks + e];
@@ -602,7 +612,7 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
         pks = ks + (k0 & 1);        /* x_val is staged from an even entry */
         pke = ke + (k0 & 1);
       };
-      auto consume = [&](int j, const double (&gg)[NG], int ks, int ke) {
+      auto consume = [&](int j, const double (&gg)[NGS], int ks, int ke) {
         const unsigned q = base + (unsigned)j;
         const unsigned char *sb = sv.stages + (q % NS)*sv.stage_bytes;
         const int r0 = (first + j*step)*slab_rows;
@@ -610,9 +620,9 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
           const double *s_val = (const double *)(sb + off_val);
           double sii = 0.0;
 #pragma unroll
-          for (int e = 0; e < NG; e++)
+          for (int e = 0; e < NGS; e++)
             if (ks + e < ke) sii += s_val[ks + e] * gg[e];
-          if (ks + NG < ke) {
+          if (ks + NGS < ke) {
             /* row longer than the gather pipeline: the rest is gathered NT at a time
                (one L2 latency per batch, not per entry), in registers the first NG
                values no longer need */
@@ -620,7 +630,7 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
             const int k0 = ((const int *)(sb + off_ri))[0];
             const int *s_col = (const int *)sb + (k0 & 3) - (k0 & 1);
 #pragma unroll 1
-            for (int kb = ks + NG; kb < ke; kb += NT) {
+            for (int kb = ks + NGS; kb < ke; kb += NT) {
               double gt[NT];
 #pragma unroll
               for (int e = 0; e < NT; e++) {
@@ -656,12 +666,30 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
       if (tr && gA[0] == 1.2345e300) g_trace[14] += 1;      /* wait for the gathers */
       const unsigned long long tr2 = trace_now();
 #endif
-      for (int j = 0; j < n_my; j += 2) {
-        prefetch(min(j + 1, j_last), gB, ksB, keB);
-        consume(j, gA, ksA, keA);
-        if (j + 1 < n_my) {
-          prefetch(min(j + 2, j_last), gA, ksA, keA);
-          consume(j + 1, gB, ksB, keB);
+      if constexpr (GD == 3) {
+        /* three sets rotate: the set consumed at step j was gathered at step j - 2 */
+        prefetch(min(1, j_last), gB, ksB, keB);
+        for (int j = 0; j < n_my; j += 3) {
+          prefetch(min(j + 2, j_last), gC, ksC, keC);
+          consume(j, gA, ksA, keA);
+          if (j + 1 < n_my) {
+            prefetch(min(j + 3, j_last), gA, ksA, keA);
+            consume(j + 1, gB, ksB, keB);
+          }
+          if (j + 2 < n_my) {
+            prefetch(min(j + 4, j_last), gB, ksB, keB);
+            consume(j + 2, gC, ksC, keC);
+          }
+        }
+      }
+      else {
+        for (int j = 0; j < n_my; j += 2) {
+          prefetch(min(j + 1, j_last), gB, ksB, keB);
+          consume(j, gA, ksA, keA);
+          if (j + 1 < n_my) {
+            prefetch(min(j + 2, j_last), gA, ksA, keA);
+            consume(j + 1, gB, ksB, keB);
+          }
         }
       }
 #ifdef CSB_PHASE_TRACE
@@ -688,8 +716,12 @@ __device__ __forceinline__ void spmv_phase(const MgLevelDesc &L, const double *x
                                            const double *ghost, unsigned char *s_raw,
                                            const F &f, double *acc_out)
 {
-  if (ghost != nullptr) spmv_phase_g<SINGLE, true>(L, x, ghost, s_raw, f, acc_out);
-  else spmv_phase_g<SINGLE, false>(L, x, ghost, s_raw, f, acc_out);
+  if (!SINGLE && L.gather_depth == 3) {
+    if (ghost != nullptr) spmv_phase_g<false, true, 3>(L, x, ghost, s_raw, f, acc_out);
+    else spmv_phase_g<false, false, 3>(L, x, ghost, s_raw, f, acc_out);
+  }
+  else if (ghost != nullptr) spmv_phase_g<SINGLE, true, 2>(L, x, ghost, s_raw, f, acc_out);
+  else spmv_phase_g<SINGLE, false, 2>(L, x, ghost, s_raw, f, acc_out);
 }
 
 /* r = (A.vx - rhs), dk = r * ad_inv            (cs_sles_it.cpp:1502-1516) */
@@ -1547,12 +1579,12 @@ k_spmv_pipeline(const MgLevelDesc L, const double *x, double *y, int exclude_dia
   if (exclude_diag) {
     EpiStoreExDiag f;
     f.y = y;
-    spmv_phase_g<false, false>(L, x, nullptr, s_raw, f, nullptr);
+    spmv_phase<false>(L, x, nullptr, s_raw, f, nullptr);
   }
   else {
     EpiStore f;
     f.d_val = L.d_val; f.x = x; f.y = y;
-    spmv_phase_g<false, false>(L, x, nullptr, s_raw, f, nullptr);
+    spmv_phase<false>(L, x, nullptr, s_raw, f, nullptr);
   }
 }
 
@@ -2211,6 +2243,21 @@ k_fcg_mg_persistent(const FcgMgParams S, const PersistentCommon P)
 
 } // anonymous namespace
 
+int plan_gather_depth(const std::vector<csb_lnum_t> &ri, int n_rows)
+{
+  static int want = -1;
+  if (want < 0) {
+    const char *s = getenv("CSB_GATHER_DEPTH");
+    want = (s != nullptr) ? atoi(s) : ((NS >= 4) ? 3 : 2);
+  }
+  /* three register sets need a fourth stage in flight (the stage two slabs ahead must have
+     landed while the oldest one is still being summed) and rows of at most NG3 entries */
+  if (want != 3 || NS < 4 || (size_t)n_rows + 1 > ri.size()) return 2;
+  int mx = 0;
+  for (int i = 0; i < n_rows; i++) mx = std::max(mx, (int)(ri[i+1] - ri[i]));
+  return (mx <= NG3) ? 3 : 2;
+}
+
 void plan_slabs(const std::vector<csb_lnum_t> &ri, int n_rows, int &slab_rows, int &n_slabs,
                 size_t &max_entries)
 {
@@ -2371,6 +2418,7 @@ bool launch_spmv_pipeline(const _csb_matrix_t *m, const double *x, double *y, bo
     if ((size_t)m->h_row_index.size() == (size_t)m->n_rows + 1 && m->n_rows > 0) {
       size_t max_entries = 0;
       plan_slabs(m->h_row_index, m->n_rows, m->pl_slab_rows, m->pl_n_slabs, max_entries);
+      m->pl_gdepth = plan_gather_depth(m->h_row_index, m->n_rows);
       m->pl_smem = persistent_smem_bytes(max_entries);
       int optin = 0, occ = 0;
       cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device);
@@ -2393,6 +2441,7 @@ bool launch_spmv_pipeline(const _csb_matrix_t *m, const double *x, double *y, bo
   MgLevelDesc L;
   memset(&L, 0, sizeof(L));
   L.n_rows = m->n_rows; L.n_slabs = m->pl_n_slabs; L.slab_rows = m->pl_slab_rows;
+  L.gather_depth = m->pl_gdepth;
   L.row_index = m->row_index.p; L.col_id = m->col_id.p;
   L.d_val = m->d_val.p; L.x_val = m->x_val.p;
   k_spmv_pipeline<<<m->pl_grid, PT, m->pl_smem, c.stream>>>(L, x, y, exclude_diag ? 1 : 0);

@@ -13,6 +13,7 @@ struct MgLevelDesc {
   int           slab_rows;     /* <= 256 rows streamed per CTA step */
   int           n_rows_next;
   int           level_id;      /* index of the level (slot of its exchange counter) */
+  int           gather_depth;  /* 2, or 3 when no row has more than 8 entries (persistent.cu) */
   const int    *row_index;
   const int    *col_id;
   const double *d_val;
@@ -111,6 +112,9 @@ bool launch_fcg_mg_persistent(const FcgMgParams &S, const PersistentCommon &P, i
    to k_spmv_stream. */
 bool launch_spmv_pipeline(const _csb_matrix_t *m, const double *x, double *y, bool exclude_diag,
                           bool *launched);
+
+/* gather depth of the SpMV phases for a matrix with these row lengths (CSB_GATHER_DEPTH) */
+int plan_gather_depth(const std::vector<csb_lnum_t> &row_index, int n_rows);
 
 /* choose the slab height of a level so that a slab's products fit in ~40 KB */
 void plan_slabs(const std::vector<csb_lnum_t> &row_index, int n_rows, int &slab_rows,

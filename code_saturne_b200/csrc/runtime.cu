@@ -53,6 +53,8 @@ const char *csb_version(void) { return "csb200 0.1 (sm_100a, FP64)"; }
 
 const char *csb_last_error(void) { return ctx().err.c_str(); }
 
+int csb_get_device(void) { return ctx().ready ? ctx().device : -1; }
+
 int csb_init(int device_id)
 {
   Context &c = ctx();

@@ -739,6 +739,7 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
       if (!pcomm_allreduce(c->pcomm, &d.n_g_rows, 1)) return;
     }
     plan_slabs(a->h_row_index, a->n_rows, d.slab_rows, d.n_slabs, max_entries);
+    d.gather_depth = plan_gather_depth(a->h_row_index, a->n_rows);
     d.n_rows = a->n_rows;
     d.row_index = a->row_index.p; d.col_id = a->col_id.p;
     d.d_val = a->d_val.p; d.x_val = a->x_val.p; d.ad_inv = c->ad_inv.p;
@@ -1804,6 +1805,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
       const csb_matrix_t *m = lv->m;
       size_t me = 0;
       plan_slabs(m->h_row_index, m->n_rows, d.slab_rows, d.n_slabs, me);
+      d.gather_depth = plan_gather_depth(m->h_row_index, m->n_rows);
       max_entries = std::max(max_entries, me);
       d.n_rows = m->n_rows;
       d.n_rows_next = (l + 1 < n_levels) ? mg->levels[l+1]->m->n_rows : 0;

