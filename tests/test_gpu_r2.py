@@ -112,12 +112,27 @@ def _reference_parity(csb, reflib, N, n_threads, vcycle=True):
         mg.setup(m)
         assert mg.n_levels() == len(rlv), (mg.n_levels(), len(rlv))
         lv = mg.levels()
+        # With more than 4 threads the reference lists the fine rows of a coarse row in the
+        # order its threads happen to run (atomic capture, cs_grid.cpp:2930-2958): its own
+        # coarse diagonal / cell sums then vary in the last bit from run to run (x_val and
+        # the maps were identical in every run seen).  Values are compared bit for bit up
+        # to 4 threads, to 1e-14 beyond; the maps bit for bit as long as the values feeding
+        # them were.
+        exact = (n_threads <= 4)
+        bits_equal = True
         for l in range(1, len(lv)):
             assert lv[l]["n_rows"] == rlv[l]["n_rows"], l
-            assert np.array_equal(lv[l]["coarse_row"], rlv[l]["coarse_row"]), l
-            if lv[l]["n_rows"] < 3000000:     # assembled coarse matrices: bit-exact
-                assert np.array_equal(lv[l]["x_val"], rlv[l]["x_val"]), l
-                assert np.array_equal(lv[l]["d_val"], rlv[l]["d_val"]), l
+            if bits_equal:
+                assert np.array_equal(lv[l]["coarse_row"], rlv[l]["coarse_row"]), l
+            if lv[l]["n_rows"] < 3000000:
+                for k in ("x_val", "d_val"):
+                    if exact:
+                        assert np.array_equal(lv[l][k], rlv[l][k]), (l, k)
+                    else:
+                        assert lv[l][k].shape == rlv[l][k].shape, (l, k)
+                        assert np.allclose(lv[l][k], rlv[l][k], rtol=1e-14, atol=0), (l, k)
+                        bits_equal = bits_equal and np.array_equal(lv[l][k], rlv[l][k])
+        out["maps_bit_exact_through_level"] = len(lv) - 1 if bits_equal else "first differing values"
         del lv, rlv
         out["n_levels"] = mg.n_levels()
         if vcycle:
