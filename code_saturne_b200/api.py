@@ -259,7 +259,8 @@ class PComm:
     def default_sizes(n_ghost, n_levels=25):
         """(arena_bytes, window_bytes) large enough for a hierarchy whose finest level
         has n_ghost ghost rows (ghost buffers shrink ~2x per level)."""
-        return 64 * (n_ghost + 64) + 8192 * n_levels, 32 * (n_ghost + 64)
+        # + room for the merge boundary (merged right-hand side of the first merged level)
+        return 64 * (n_ghost + 64) + 8192 * n_levels + (16 << 20), 32 * (n_ghost + 64) + (1 << 20)
 
     @classmethod
     def from_handles(cls, n_ranks, rank, arena_bytes, window_bytes, all_gather):
@@ -765,6 +766,19 @@ class Multigrid(_SolverBase):
         L.csb_multigrid_get_level_halo(C.c_void_p(self._h), level, _ptr(sizes), _ptr(ranks),
                                        _ptr(si), _ptr(sl), _ptr(gi))
         return dict(ranks=ranks[:nd], send_index=si, send_list=sl[:ns], index=gi)
+
+    def set_merge_options(self, rank_stride, rows_mean_threshold=300, rows_glob_threshold=500):
+        """cs_multigrid_set_merge_options: merge coarse levels onto rank 0 (rank_stride >= the
+        number of ranks) once a level's mean rows per rank / global rows fall under the
+        thresholds."""
+        L = load_library()
+        L.csb_multigrid_set_merge_options.argtypes = [C.c_void_p, C.c_int, C.c_int,
+                                                      C.c_ulonglong]
+        L.csb_multigrid_set_merge_options(C.c_void_p(self._h), int(rank_stride),
+                                          int(rows_mean_threshold), int(rows_glob_threshold))
+
+    def merge_level(self):
+        return load_library().csb_multigrid_get_merge_level(C.c_void_p(self._h))
 
     def set_aggregation_blocks(self, n_blocks):
         load_library().csb_multigrid_set_aggregation_blocks(C.c_void_p(self._h), int(n_blocks))

@@ -163,6 +163,68 @@ k_comm_window(const CommDev *C, const HaloDev h, int stride, const T *src, T *gh
   }
 }
 
+/*--------------------------------------------------------------------------
+ * gather to rank 0 through its staging window, in chunks: sender q owns slot
+ * q - 1 of the window.  Same per-pair counters as the window exchange (a chunk
+ * is a message from q to 0: w_sent / wflag on the way, w_recv / wack back).
+ * count[q] elements of rank q land at dst + offset[q] on rank 0.
+ *--------------------------------------------------------------------------*/
+
+struct GatherArgs {
+  int       count[COMM_MAX_RANKS];
+  long long offset[COMM_MAX_RANKS];
+  int       slot_elems;                 /* elements per window slot */
+};
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+k_comm_gather(const CommDev *C, const GatherArgs g, const T *src, T *dst)
+{
+  const int t = threadIdx.x, nt = blockDim.x, me = C->rank, R = C->n_ranks;
+  CommLocal *L = C->local;
+  CommHeader *H = (CommHeader *)C->peer[me];
+  if (me != 0) {
+    CommHeader *P = (CommHeader *)C->peer[0];
+    T *slot = (T *)(C->peer[0] + C->window_off) + (size_t)(me - 1) * g.slot_elems;
+    for (int c0 = 0; c0 < g.count[me]; c0 += g.slot_elems) {
+      const int n = min(g.slot_elems, g.count[me] - c0);
+      if (t == 0) spin_until_ge(&H->wack[0], L->w_sent[0], C->timeout_ns, 8);
+      __syncthreads();
+      for (int k = t; k < n; k += nt) slot[k] = src[c0 + k];
+      __threadfence_system();
+      __syncthreads();
+      if (t == 0) {
+        const unsigned s = L->w_sent[0] + 1;
+        *(volatile unsigned *)&P->wflag[me] = s;
+        L->w_sent[0] = s;
+      }
+      __syncthreads();
+    }
+  }
+  else {
+    for (int k = t; k < g.count[0]; k += nt) dst[g.offset[0] + k] = src[k];
+    for (int q = 1; q < R; q++) {
+      CommHeader *P = (CommHeader *)C->peer[q];
+      const T *slot = (const T *)(C->peer[0] + C->window_off) + (size_t)(q - 1) * g.slot_elems;
+      for (int c0 = 0; c0 < g.count[q]; c0 += g.slot_elems) {
+        const int n = min(g.slot_elems, g.count[q] - c0);
+        if (t == 0) spin_until_ge(&H->wflag[q], L->w_recv[q] + 1, C->timeout_ns, 9);
+        __syncthreads();
+        __threadfence();
+        for (int k = t; k < n; k += nt) dst[g.offset[q] + c0 + k] = __ldcg(slot + k);
+        __threadfence_system();
+        __syncthreads();
+        if (t == 0) {
+          const unsigned r = L->w_recv[q] + 1;
+          *(volatile unsigned *)&P->wack[0] = r;
+          L->w_recv[q] = r;
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
 bool launched(const char *name)
 {
   ctx().launches += 1;
@@ -267,6 +329,57 @@ bool pcomm_mailbox(csb_pcomm_t *c, int n_nbr, const int *nbr, const long long *s
                                 cudaMemcpyDeviceToHost, cx.stream))
     && CSB_CUDA(cudaStreamSynchronize(cx.stream));
   return ok;
+}
+
+bool pcomm_allgather_count(csb_pcomm_t *c, long long mine, long long *all)
+{
+  const int R = (c != nullptr) ? c->h.n_ranks : 1, me = (c != nullptr) ? c->h.rank : 0;
+  for (int r0 = 0; r0 < R; r0 += 8) {           /* exact in doubles below 2^53 */
+    double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (me >= r0 && me < r0 + 8) v[me - r0] = (double)mine;
+    if (!pcomm_allreduce(c, v, 8)) return false;
+    for (int k = 0; k < 8 && r0 + k < R; k++) all[r0 + k] = (long long)v[k];
+  }
+  return true;
+}
+
+bool pcomm_gather_to_root(csb_pcomm_t *c, int elem_bytes, const long long *counts,
+                          const void *src_d, void *dst_d)
+{
+  if (c == nullptr) { set_error("pcomm_gather_to_root: no communicator"); return false; }
+  const int R = c->h.n_ranks;
+  GatherArgs g;
+  long long off = 0;
+  for (int r = 0; r < COMM_MAX_RANKS; r++) {
+    g.count[r] = (r < R) ? (int)counts[r] : 0;
+    g.offset[r] = off;
+    off += g.count[r];
+  }
+  const size_t slot_bytes = (R > 1) ? (c->h.window_bytes / (size_t)(R - 1)) / 256 * 256 : 0;
+  g.slot_elems = (int)(slot_bytes / (size_t)elem_bytes);
+  if (R > 1 && g.slot_elems < 1) {
+    set_error("pcomm_gather_to_root: staging window of %zu bytes is too small for %d ranks",
+              c->h.window_bytes, R);
+    return false;
+  }
+  Context &cx = ctx();
+  /* The window is shared with the neighbour exchanges: no rank may still be reading its
+     window (or a neighbour writing it) when the slots are used, nor the other way round
+     afterwards.  The all-reduce is a device-side barrier over all ranks (a rank leaves it
+     only when every rank has reached it in stream order). */
+  double sync = 0.;
+  if (!pcomm_allreduce(c, &sync, 1)) return false;
+  pcomm_host_barrier(c);
+  bool ok = true;
+  if (elem_bytes == 8)
+    k_comm_gather<double><<<1, 1024, 0, cx.stream>>>(c->d, g, (const double *)src_d,
+                                                     (double *)dst_d);
+  else if (elem_bytes == 4)
+    k_comm_gather<int><<<1, 1024, 0, cx.stream>>>(c->d, g, (const int *)src_d, (int *)dst_d);
+  else { set_error("pcomm_gather_to_root: element size %d", elem_bytes); ok = false; }
+  if (ok) ok = launched("comm_gather");
+  pcomm_host_barrier(c);
+  return ok && pcomm_allreduce(c, &sync, 1);
 }
 
 bool pcomm_window_exchange(csb_pcomm_t *c, const HaloDev &h, int elem_bytes, int stride,

@@ -185,6 +185,27 @@ struct DistLevel {
   unsigned long long timeout_ns;
 };
 
+/* Coarse levels merged onto rank 0 (cs_grid_merge_ranks, src/alge/cs_grid_rank_merge.cpp:1359;
+   gather / scatter of cs_grid_restrict_row_var / _prolong_row_var, cs_grid.cpp:9058-9085,
+   :9131-9155): what the persistent kernel needs at the merge boundary.  Every V-cycle has one
+   gather (restricted right-hand sides of the merge level, every rank -> rank 0) and one
+   scatter (the level's correction, rank 0 -> every rank); both are peer stores followed by
+   a counter in a flag word of the destination's arena. */
+struct MergeDev {
+  int        is_root, n_ranks, rank;
+  int        n_local;                          /* rows of the merge level owned by this rank */
+  int        shift[COMM_MAX_RANKS];            /* first merged row of rank r */
+  int        n_of[COMM_MAX_RANKS];             /* rows of rank r */
+  double    *stub_rhs, *stub_vx;               /* this rank's part: local buffers */
+  double    *root_rhs_dst;                     /* rank 0's merged rhs + my shift (peer) */
+  unsigned  *root_flag;                        /* rank 0's flag word for me (peer) */
+  unsigned  *flag_in;                          /* own arena: [rank of sender], [0] on others */
+  double    *peer_vx[COMM_MAX_RANKS];          /* rank 0 only: stub_vx of rank r (peer) */
+  unsigned  *peer_flag[COMM_MAX_RANKS];        /* rank 0 only: flag_in of rank r (peer) */
+  unsigned  *count;                            /* exchanges done so far (rank-private) */
+  unsigned long long timeout_ns;
+};
+
 #ifdef __CUDACC__
 /* device-side helpers shared by comm.cu and persistent.cu */
 __device__ __forceinline__ unsigned long long gtime_ns()
@@ -242,6 +263,12 @@ bool   pcomm_allreduce(csb_pcomm_t *c, double *vals, int n);
 /* send 8 values to / receive 8 values from each listed neighbour */
 bool   pcomm_mailbox(csb_pcomm_t *c, int n_nbr, const int *nbr, const long long *send,
                      long long *recv);
+/* every rank's value, on every rank (host) */
+bool   pcomm_allgather_count(csb_pcomm_t *c, long long mine, long long *all);
+/* counts[r] elements (4 or 8 bytes each) of every rank r, concatenated in rank order in
+   dst_d on rank 0 (device arrays; dst_d is ignored elsewhere); chunked through the window */
+bool   pcomm_gather_to_root(csb_pcomm_t *c, int elem_bytes, const long long *counts,
+                            const void *src_d, void *dst_d);
 /* ghost section of dst <- neighbours' send lists of src; device arrays */
 bool   pcomm_window_exchange(csb_pcomm_t *c, const HaloDev &h, int elem_bytes, int stride,
                              const void *src_d, void *ghost_dst_d);
@@ -513,6 +540,9 @@ bool launch_coarse_assembly(const CoarseAssemblyArgs &a, int stages /* 1 | 2 */)
 bool launch_coarse_galerkin(const CoarseAssemblyArgs &a);
 
 bool launch_halo_pack(int n_send, const int *send_list, const double *var, double *buf);
+/* index helpers of the coarse-level merge: 0 out = shift + i, 1 out = map[in], 2 row
+   lengths of a row index, 3 in + shift where in >= 0 */
+bool launch_merge_index(int mode, int n, int shift, const int *in, const int *map, int *out);
 
 } // namespace csb
 

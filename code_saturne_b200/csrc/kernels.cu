@@ -2439,6 +2439,35 @@ k_halo_pack(int n_send, const int *__restrict__ send_list, const double *__restr
 }
 }
 
+/*--------------------------------------------------------------------------
+ * Index helpers of the coarse-level merge (sles.cu, mg_merge_coarse_levels)
+ *--------------------------------------------------------------------------*/
+
+namespace {
+/* mode 0: out[i] = shift + i                  (merged ids of the local rows)
+   mode 1: out[i] = map[in[i]]                 (column ids -> merged ids)
+   mode 2: out[i] = in[i+1] - in[i]            (row lengths)
+   mode 3: out[i] = in[i] >= 0 ? in[i] + shift : in[i]   (coarse rows -> merged coarse rows) */
+__global__ void __launch_bounds__(TPB)
+k_merge_index(int mode, int n, int shift, const int *__restrict__ in,
+              const int *__restrict__ map, int *__restrict__ out)
+{
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    if (mode == 0) out[i] = shift + i;
+    else if (mode == 1) out[i] = map[in[i]];
+    else if (mode == 2) out[i] = in[i+1] - in[i];
+    else out[i] = (in[i] >= 0) ? in[i] + shift : in[i];
+  }
+}
+}
+
+bool launch_merge_index(int mode, int n, int shift, const int *in, const int *map, int *out)
+{
+  if (n < 1) return true;
+  k_merge_index<<<vec_grid(n), TPB, 0, ctx().stream>>>(mode, n, shift, in, map, out);
+  return post_launch("merge_index");
+}
+
 bool launch_halo_pack(int n_send, const int *send_list, const double *var, double *buf)
 {
   if (n_send < 1) return true;

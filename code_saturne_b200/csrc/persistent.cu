@@ -2069,7 +2069,9 @@ __device__ __forceinline__ void vc_descend(const FcgMgParams &S, const Persisten
   }
   pf.mark(level, MG_PROF_RESIDUAL);
   {
-    const bool fuse = (level + 1 < S.n_levels - 1);
+    /* not into the coarsest level (PCG from zero) nor across the merge boundary (the
+       level's rows of the other ranks arrive later) */
+    const bool fuse = (level + 1 < S.n_levels - 1) && (level + 1 != S.merge_level);
     double *c_start = fuse ? sweep_start(sp.n_iter - 1, C.vx, S.tmp) : nullptr;
     restrict_rows_first<SINGLE>(C.n_rows, L.c_f_row_index, L.c_f_row_ids, S.wr, C.rhs, sp.mode,
                                 sp.w[0], smooth_inv(C, sp.mode), c_start);
@@ -2096,6 +2098,64 @@ __device__ __forceinline__ void vc_ascend(const FcgMgParams &S, const Persistent
   pf.mark(level, MG_PROF_ASCENT);
 }
 
+/*--------------------------------------------------------------------------
+ * Merge boundary (coarse levels merged onto rank 0; cs_grid_restrict_row_var /
+ * cs_grid_prolong_row_var with merge_sub_size > 1, cs_grid.cpp:9058-9085,
+ * :9131-9155): exchange number k of the launch sequence.
+ *   gather : every other rank stores its rows of the merge level's rhs into
+ *            rank 0's merged rhs and publishes k; rank 0 waits for all of them
+ *   scatter: rank 0 stores each rank's rows of the level's vx into that rank's
+ *            buffer and publishes k; the others wait for it
+ * One buffer each way is enough: a rank sends gather k+1 only after scatter k
+ * has told it that rank 0 is done with the level.
+ *--------------------------------------------------------------------------*/
+
+__device__ __forceinline__ void merge_gather(const MergeDev *M, unsigned k, unsigned *bar)
+{
+  if (M->is_root) {
+    if (blockIdx.x == 0 && threadIdx.x > 0 && threadIdx.x < M->n_ranks) {
+      spin_until_ge(M->flag_in + threadIdx.x, k, M->timeout_ns, 10);
+      fence_sys();
+    }
+  }
+  else {
+    const double *src = M->stub_rhs;
+    double *dst = M->root_rhs_dst;
+    for (int i = blockIdx.x*PT + threadIdx.x; i < M->n_local; i += gridDim.x*PT) dst[i] = src[i];
+    fence_sys();
+  }
+  grid_barrier(bar);
+  if (!M->is_root && blockIdx.x == 0 && threadIdx.x == 0) {
+    fence_sys();
+    *(volatile unsigned *)M->root_flag = k;
+  }
+}
+
+__device__ __forceinline__ void merge_scatter(const MergeDev *M, const double *vx_merged,
+                                              unsigned k, unsigned *bar)
+{
+  if (M->is_root) {
+    for (int r = 1; r < M->n_ranks; r++) {
+      const double *src = vx_merged + M->shift[r];
+      double *dst = M->peer_vx[r];
+      for (int i = blockIdx.x*PT + threadIdx.x; i < M->n_of[r]; i += gridDim.x*PT) dst[i] = src[i];
+    }
+    fence_sys();
+    grid_barrier(bar);
+    if (blockIdx.x == 0 && threadIdx.x > 0 && threadIdx.x < M->n_ranks) {
+      fence_sys();
+      *(volatile unsigned *)M->peer_flag[threadIdx.x] = k;
+    }
+  }
+  else {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      spin_until_ge(M->flag_in, k, M->timeout_ns, 11);
+      fence_sys();
+    }
+    grid_barrier(bar);
+  }
+}
+
 __global__ void __launch_bounds__(PT, CSB_MIN_CTAS)
 k_fcg_mg_persistent(const FcgMgParams S, const PersistentCommon P)
 {
@@ -2115,11 +2175,20 @@ k_fcg_mg_persistent(const FcgMgParams S, const PersistentCommon P)
   VcProf pf;
   pf.ms = S.ms; pf.lead = rec; pf.t_last = rec ? global_ns() : 0ull;
 
-  /* first level small enough for one CTA: it and everything below is CTA 0's */
+  /* coarse levels merged onto rank 0: the other ranks' hierarchy ends with their part of
+     the merge level (rhs out, vx back) */
+  const MergeDev *MD = S.merge;
+  const int Lm = (MD != nullptr) ? S.merge_level : -1;
+  const bool merged_away = (MD != nullptr && !MD->is_root);
+  unsigned mk = (MD != nullptr) ? *(volatile unsigned *)MD->count : 0u;
+
+  /* first level small enough for one CTA: it and everything below is CTA 0's (never the
+     levels down to the merge boundary, whose exchanges are grid-wide) */
   int ls = S.n_levels;
-  for (int l = 0; l < S.n_levels; l++)
+  for (int l = (Lm >= 0) ? Lm + 1 : 0; l < S.n_levels; l++)
     if (LV[l].n_rows <= S.single_rows) { ls = l; break; }
-  const int n_grid_desc = (ls < coarsest) ? ls : coarsest;   /* levels descended on the grid */
+  if (merged_away) ls = S.n_levels;
+  const int n_grid_desc = merged_away ? Lm : ((ls < coarsest) ? ls : coarsest);
 
   const SmoothPlanDev &sp0 = S.sm[0];
   const double *inv0 = smooth_inv(L0, sp0.mode);
@@ -2149,18 +2218,29 @@ k_fcg_mg_persistent(const FcgMgParams S, const PersistentCommon P)
   while (R.cvg == CSB_SLES_ITERATING) {
 
     /* ---- vk = M^-1 rk: one V-cycle from zero (_multigrid_pc_apply, :1500-1600) ---- */
-    for (int level = 0; level < n_grid_desc; level++)
+    if (MD != nullptr) mk += 1;
+    for (int level = 0; level < n_grid_desc; level++) {
+      if (level == Lm) merge_gather(MD, mk, P.barrier);       /* rank 0: rows of the others */
       vc_descend<false>(S, P, level, (level == 0) ? rk : LV[level].rhs,
-                        (level == 0) ? vk : LV[level].vx, true, s_raw, pf);
-    if (ls <= coarsest) {
+                        (level == 0) ? vk : LV[level].vx, level != Lm, s_raw, pf);
+    }
+    if (merged_away) {
+      merge_gather(MD, mk, P.barrier);
+      merge_scatter(MD, nullptr, mk, P.barrier);
+      pf.mark(Lm, MG_PROF_COARSEST);          /* waiting for rank 0's coarse levels */
+    }
+    else if (ls <= coarsest) {
+      if (Lm == coarsest && coarsest >= n_grid_desc) merge_gather(MD, mk, P.barrier);
       if (blockIdx.x == 0) {
         for (int level = ls; level < coarsest; level++)
           vc_descend<true>(S, P, level, (level == 0) ? rk : LV[level].rhs,
                            (level == 0) ? vk : LV[level].vx, true, s_raw, pf);
         const MgLevelDesc &L = LV[coarsest];
+        PersistentCommon Pl = P;
+        if (L.dist == nullptr) Pl.comm = nullptr;   /* merged level: this rank alone */
         pcg_run<true>(L, (coarsest == 0) ? rk : L.rhs, (coarsest == 0) ? vk : L.vx, false,
                       S.coarse_n_max_iter, S.precision*S.coarse_precision_mult, S.r_norm, true,
-                      P, L.st_descent, s_raw);
+                      Pl, L.st_descent, s_raw);
         __syncthreads();
         pf.mark(coarsest, MG_PROF_COARSEST);
         for (int level = coarsest - 1; level >= ls; level--)
@@ -2178,15 +2258,21 @@ k_fcg_mg_persistent(const FcgMgParams S, const PersistentCommon P)
     }
     else {
       const MgLevelDesc &L = LV[coarsest];
+      if (Lm == coarsest) merge_gather(MD, mk, P.barrier);
+      PersistentCommon Pl = P;
+      if (L.dist == nullptr) Pl.comm = nullptr;     /* merged level: this rank alone */
       pcg_run<false>(L, L.rhs, L.vx, false, S.coarse_n_max_iter,
-                     S.precision*S.coarse_precision_mult, S.r_norm, true, P, L.st_descent,
+                     S.precision*S.coarse_precision_mult, S.r_norm, true, Pl, L.st_descent,
                      s_raw);
       grid_barrier(P.barrier);
       pf.mark(coarsest, MG_PROF_COARSEST);
     }
-    for (int level = n_grid_desc - 1; level >= 0; level--)
+    if (!merged_away && Lm == coarsest) merge_scatter(MD, LV[coarsest].vx, mk, P.barrier);
+    for (int level = n_grid_desc - 1; level >= 0; level--) {
       vc_ascend<false>(S, P, level, (level == 0) ? rk : LV[level].rhs,
                        (level == 0) ? vk : LV[level].vx, s_raw, pf);
+      if (!merged_away && level == Lm) merge_scatter(MD, LV[level].vx, mk, P.barrier);
+    }
 
     /* ---- wk = A.vk and the four dot products (:908-918) ---- */
     double v[4] = {0., 0., 0., 0.};
@@ -2237,6 +2323,7 @@ k_fcg_mg_persistent(const FcgMgParams S, const PersistentCommon P)
     st->residual = R.residual; st->initial_residual = R.initial_residual;
     st->n_iter = R.n_iter; st->n_max_iter = S.n_max_iter; st->cvg = R.cvg;
     st->alpha = ak_rk; st->beta = gk_rk1; st->ro_0 = rho_km1; st->ro_1 = 0.; st->rk_gkm1 = 0.;
+    if (MD != nullptr) *(volatile unsigned *)MD->count = mk;
   }
 }
 

@@ -82,6 +82,8 @@ struct FcgMgParams {
   double            *wr, *tmp;             /* residual; second sweep buffer (level-0 sized) */
   double            *fwork;                /* FCG vectors rk vk wk dk qk */
   size_t             fstride;
+  const MergeDev    *merge;                /* coarse levels merged onto rank 0, or nullptr */
+  int                merge_level;          /* first merged level (-1: none) */
 };
 
 size_t persistent_smem_bytes(size_t max_slab_entries);

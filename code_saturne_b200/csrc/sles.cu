@@ -693,11 +693,15 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
     if (!CSB_CUDA(cudaMallocHost((void **)&c->h_st, sizeof(ItState)))) return;
   if (c->general_pc()) {
     /* general preconditioner: kernel per phase (fcg_pc_enqueue, pcg_pc_enqueue) */
-    if (a->halo != nullptr) {
-      set_error("csb_sles_it_setup: polynomial / multigrid preconditioning runs on one rank "
-                "on this path");
+    const bool dist_fcg_mg = (a->halo != nullptr && c->type == CSB_SLES_FCG
+                              && c->pc_mg != nullptr && c->pcomm != nullptr);
+    if (a->halo != nullptr && !dist_fcg_mg) {
+      set_error("csb_sles_it_setup: on a partitioned matrix the general preconditioners are "
+                "available as FCG + multigrid (csb_sles_it_transfer_pc) with a peer "
+                "communicator (csb_sles_it_set_pcomm)");
       return;
     }
+    if (dist_fcg_mg) csb_multigrid_set_pcomm(c->pc_mg, c->pcomm);
     if (c->pc_mg == nullptr && c->poly_degree > 0
         && !c->pc_tmp.alloc(work_stride_of((size_t)a->n_cols_ext))) return;
     if (c->pc_mg != nullptr) {
@@ -712,6 +716,12 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
         if (!c->partials.alloc(12*(size_t)c->p_grid) || !c->barrier.alloc(2)) return;
         if (!CSB_CUDA(cudaMemsetAsync(c->barrier.p, 0, 2*sizeof(unsigned), ctx().stream))) return;
         c->fcg_mg_persistent = true;
+      }
+      if (a->halo != nullptr && !c->fcg_mg_persistent) {
+        set_error("csb_sles_it_setup: FCG + multigrid on a partitioned matrix needs the "
+                  "persistent form (V-cycle, Jacobi-family smoothers with precision_mult < 0, "
+                  "PCG coarse solver)");
+        return;
       }
     }
     c->setup_done = true;
@@ -820,8 +830,10 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
       S.fwork = c->work.p; S.fstride = work_stride_of((size_t)a->n_cols_ext);
       P.partials = c->partials.p; P.barrier = c->barrier.p;
       if (!launch_mg_state_init(S.ms, precision, r_norm, 1)) return CSB_SLES_BREAKDOWN;
-      ok = launch_fcg_mg_persistent(S, P, c->p_grid, c->p_smem, cx.device_share <= 1)
-           && mg_fetch_state(c->pc_mg);
+      if (a->halo != nullptr) pcomm_host_barrier(c->pcomm);   /* nobody inside cudaFree */
+      ok = launch_fcg_mg_persistent(S, P, c->p_grid, c->p_smem, cx.device_share <= 1);
+      if (a->halo != nullptr) pcomm_host_barrier(c->pcomm);   /* all ranks launched */
+      ok = ok && mg_fetch_state(c->pc_mg);
       break;
     }
     if (c->general_pc()) {
@@ -992,6 +1004,11 @@ struct MgLevel {
   bool                halo_owned = false;
   double              n_g_rows = 0.;        /* rows over all ranks */
   DistLevelHost       dist;
+  /* coarse-level merge: this level and the ones below live on rank 0 only */
+  bool                merged = false;       /* rank 0: rows of all ranks, no halo */
+  bool                stub = false;         /* other ranks: their part of the merge level */
+  double             *arena_rhs = nullptr;  /* rank 0, merge level: peer-writable rhs */
+  double             *arena_vx = nullptr;   /* other ranks, merge level: peer-writable vx */
   ~MgLevel() {
     if (owned) csb_matrix_destroy(&owned);
     if (halo_owned && halo) csb_halo_destroy(&halo);
@@ -1019,6 +1036,15 @@ struct _csb_multigrid_t {
   csb_pcomm_t *pcomm = nullptr;
   size_t  arena_mark = 0;
   bool    arena_used = false;
+  size_t  work_stride = 0;             /* distance between the PCG work vectors in aux */
+  /* cs_multigrid_set_merge_options (cs_multigrid.cpp:4689-4694: stride 1 = no merging) */
+  int     merge_stride = 1;
+  int     merge_mean_threshold = 300;
+  unsigned long long merge_glob_threshold = 500;
+  int     merge_level = -1;              /* set by setup */
+  MergeDev          h_merge;
+  DevBuf<MergeDev>  d_merge;
+  DevBuf<unsigned>  merge_count;
   /* setup data */
   std::vector<MgLevel *> levels;
   DevBuf<ItState>  it_states;   /* 2 per level */
@@ -1064,8 +1090,7 @@ bool mg_fcg_persistent_ok(const csb_multigrid_t *mg)
   for (int i = 0; i < 2; i++)
     if (!is_smoother_type((int)mg->solver_type[i]) || mg->precision_mult[i] >= 0
         || mg->n_max_iter[i] < 1) return false;
-  return (mg->solver_type[2] == CSB_SLES_PCG && mg->poly_degree[2] == 0
-          && mg->levels[0]->m->halo == nullptr);
+  return (mg->solver_type[2] == CSB_SLES_PCG && mg->poly_degree[2] == 0);
 }
 
 size_t mg_persistent_smem(const csb_multigrid_t *mg) { return mg->p_smem; }
@@ -1093,9 +1118,11 @@ void mg_fcg_params(csb_multigrid_t *mg, FcgMgParams &S, PersistentCommon &P)
   S.tmp = mg->aux.p;          /* free while no level-local PCG runs */
   /* the coarsest-level PCG works in the hierarchy's own vectors */
   P.work = mg->aux.p;
-  P.work_stride = work_stride_of((size_t)mg->levels[0]->m->n_cols_ext);
+  P.work_stride = mg->work_stride;
+  S.merge = (mg->merge_level >= 0) ? mg->d_merge.p : nullptr;
+  S.merge_level = mg->merge_level;
   P.partials = nullptr; P.barrier = nullptr;
-  P.comm = nullptr;
+  P.comm = (mg->levels[0]->m->halo != nullptr && mg->pcomm != nullptr) ? mg->pcomm->d : nullptr;
 }
 
 /* One level's descent (which = 0) or ascent (1) smoother of the single-cycle form, as
@@ -1282,6 +1309,7 @@ void mg_clear_hierarchy(csb_multigrid_t *mg)
   mg->wr.release();
   mg->aux.release();
   mg->it_states.release();
+  mg->merge_level = -1;
   mg->setup_done = false;
   mg->a = nullptr;
 }
@@ -1392,6 +1420,202 @@ csb_halo_t *coarsen_halo(csb_pcomm_t *pc, const csb_halo_t *fh, int f_n_rows, in
   return ch;
 }
 
+
+/* Coarse levels merged onto rank 0: cs_grid_merge_ranks (src/alge/cs_grid_rank_merge.cpp:1359)
+   as the reference triggers it (cs_grid.cpp:8355-8372), with merge_stride >= n_ranks.
+   Called when the partitioned hierarchy is complete.  For every level l >= Lm the local
+   matrices of all ranks are concatenated in rank order on rank 0 (rows of rank r first get
+   the ids shift_l[r] + i, cs_grid_rank_merge.cpp:1420-1448; ghost columns become the merged
+   ids of the rows they mirror, obtained by one exchange of the shifted ids over the level's
+   halo, :1450-1460).  Every row keeps its entries in their order, so the row sums -- and
+   with them every smoother sweep -- are those of the partitioned level, bit for bit; the
+   aggregates are the ones built before the merge (the reference aggregates the merged grid
+   again, across the former rank boundaries).  On the other ranks the hierarchy ends with a
+   stub of the merge level (their rows of its rhs / vx).  Collective. */
+bool mg_merge_coarse_levels(csb_multigrid_t *mg, csb_pcomm_t *pc, int Lm, bool galerkin)
+{
+  (void)galerkin;
+  Context &c = ctx();
+  const int R = pc->h.n_ranks, me = pc->h.rank;
+  const int nl = (int)mg->levels.size();
+  std::vector<MgLevel *> merged;
+
+  std::vector<long long> n_next(R, 0);      /* rows of level l + 1 per rank */
+  for (int l = Lm; l < nl; l++) {
+    MgLevel *lv = mg->levels[l];
+    csb_matrix_t *m = const_cast<csb_matrix_t *>(lv->m);
+    std::vector<long long> n_of(R), nnz_of(R), ext_of(R);
+    if (!pcomm_allgather_count(pc, m->n_rows, n_of.data())
+        || !pcomm_allgather_count(pc, m->nnz, nnz_of.data())) return false;
+    long long n_tot = 0, nnz_tot = 0;
+    std::vector<int> shift(R, 0);
+    for (int r = 0; r < R; r++) { shift[r] = (int)n_tot; n_tot += n_of[r]; nnz_tot += nnz_of[r]; }
+    std::vector<int> shift_next(R, 0);
+    if (l + 1 < nl) {
+      if (!pcomm_allgather_count(pc, mg->levels[l+1]->m->n_rows, n_next.data())) return false;
+      long long t = 0;
+      for (int r = 0; r < R; r++) { shift_next[r] = (int)t; t += n_next[r]; }
+    }
+
+    /* merged ids of the local rows and, through the halo, of the ghost columns */
+    DevBuf<int> new_id, col_m, row_len, cr_m;
+    const size_t nce = (size_t)std::max(m->n_cols_ext, 1);
+    if (!new_id.alloc(nce) || !col_m.alloc((size_t)std::max(m->nnz, 1))
+        || !row_len.alloc((size_t)std::max(m->n_rows, 1))
+        || !cr_m.alloc((size_t)std::max(m->n_rows, 1))) return false;
+    if (!launch_merge_index(0, m->n_rows, shift[me], nullptr, nullptr, new_id.p)) return false;
+    {
+      HaloDev hv;
+      memset(&hv, 0, sizeof(hv));
+      if (lv->halo != nullptr && !halo_dev_view(lv->halo, hv)) return false;
+      if (!pcomm_window_exchange(pc, hv, 4, 1, new_id.p, new_id.p + m->n_rows)) return false;
+    }
+    if (!launch_merge_index(1, m->nnz, 0, m->col_id.p, new_id.p, col_m.p)
+        || !launch_merge_index(2, m->n_rows, 0, m->row_index.p, nullptr, row_len.p))
+      return false;
+    if (l + 1 < nl
+        && !launch_merge_index(3, m->n_rows, shift_next[me], lv->coarse_row.p, nullptr, cr_m.p))
+      return false;
+
+    MgLevel *ml = nullptr;
+    csb_matrix_t *cm = nullptr;
+    DevBuf<int> g_len, g_cr;
+    if (me == 0) {
+      ml = new MgLevel;
+      cm = new csb_matrix_t;
+      ml->owned = cm; ml->m = cm; ml->merged = true;
+      ml->n_g_rows = (double)n_tot;
+      cm->n_rows = (csb_lnum_t)n_tot; cm->n_cols_ext = (csb_lnum_t)n_tot;
+      cm->nnz = (csb_lnum_t)nnz_tot; cm->symmetric = true;
+      merged.push_back(ml);
+      if (!cm->col_id.alloc((size_t)std::max<long long>(nnz_tot, 1))
+          || !cm->x_val.alloc((size_t)std::max<long long>(nnz_tot, 1))
+          || !cm->d_val.alloc((size_t)std::max<long long>(n_tot, 1))
+          || !cm->row_index.alloc((size_t)n_tot + 1)
+          || !g_len.alloc((size_t)std::max<long long>(n_tot, 1))
+          || !g_cr.alloc((size_t)std::max<long long>(n_tot, 1))) return false;
+    }
+    bool ok = pcomm_gather_to_root(pc, 4, n_of.data(), row_len.p, me == 0 ? g_len.p : nullptr)
+           && pcomm_gather_to_root(pc, 4, nnz_of.data(), col_m.p, me == 0 ? cm->col_id.p : nullptr)
+           && pcomm_gather_to_root(pc, 8, nnz_of.data(), m->x_val.p, me == 0 ? cm->x_val.p : nullptr)
+           && pcomm_gather_to_root(pc, 8, n_of.data(), m->d_val.p, me == 0 ? cm->d_val.p : nullptr);
+    if (ok && l + 1 < nl)
+      ok = pcomm_gather_to_root(pc, 4, n_of.data(), cr_m.p, me == 0 ? g_cr.p : nullptr);
+    if (!ok || !CSB_CUDA(cudaStreamSynchronize(c.stream))) return false;
+
+    if (me == 0) {
+      std::vector<int> h_len((size_t)n_tot);
+      if (n_tot > 0 && !CSB_CUDA(cudaMemcpy(h_len.data(), g_len.p, sizeof(int)*(size_t)n_tot,
+                                            cudaMemcpyDeviceToHost))) return false;
+      cm->h_row_index.assign((size_t)n_tot + 1, 0);
+      for (long long i = 0; i < n_tot; i++) cm->h_row_index[(size_t)i+1] = cm->h_row_index[(size_t)i] + h_len[(size_t)i];
+      if (cm->h_row_index[(size_t)n_tot] != nnz_tot) {
+        set_error("coarse level merge: gathered row lengths do not add up");
+        return false;
+      }
+      if (!CSB_CUDA(cudaMemcpy(cm->row_index.p, cm->h_row_index.data(), sizeof(int)*((size_t)n_tot+1),
+                               cudaMemcpyHostToDevice))) return false;
+      matrix_plan_spmv(cm);
+      if (l + 1 < nl) {
+        /* merged fine -> coarse map and its inverse; the fine rows of a coarse row stay in
+           ascending order (they all belong to one rank) */
+        long long nc_tot = 0;
+        for (int r = 0; r < R; r++) nc_tot += n_next[r];
+        ml->h_coarse_row.resize((size_t)std::max<long long>(n_tot, 1));
+        if (n_tot > 0 && !CSB_CUDA(cudaMemcpy(ml->h_coarse_row.data(), g_cr.p, sizeof(int)*(size_t)n_tot,
+                                              cudaMemcpyDeviceToHost))) return false;
+        std::vector<int> cfi((size_t)nc_tot + 1, 0), cfr((size_t)std::max<long long>(n_tot, 1));
+        for (long long i = 0; i < n_tot; i++) {
+          const int ic = ml->h_coarse_row[(size_t)i];
+          if (ic >= 0) cfi[(size_t)ic + 1]++;
+        }
+        for (long long i = 0; i < nc_tot; i++) cfi[(size_t)i+1] += cfi[(size_t)i];
+        {
+          std::vector<int> fill(cfi.begin(), cfi.end() - 1);
+          for (long long i = 0; i < n_tot; i++) {
+            const int ic = ml->h_coarse_row[(size_t)i];
+            if (ic >= 0) cfr[(size_t)fill[(size_t)ic]++] = (int)i;
+          }
+        }
+        if (!ml->coarse_row.upload(ml->h_coarse_row.data(), (size_t)std::max<long long>(n_tot, 1))
+            || !ml->c_f_row_index.upload(cfi.data(), (size_t)nc_tot + 1)
+            || !ml->c_f_row_ids.upload(cfr.data(), (size_t)std::max<long long>(n_tot, 1))
+            || !CSB_CUDA(cudaStreamSynchronize(c.stream))) return false;
+      }
+    }
+    if (l == Lm) {
+      /* what the kernels need at the boundary */
+      MergeDev &M = mg->h_merge;
+      memset(&M, 0, sizeof(M));
+      M.is_root = (me == 0) ? 1 : 0; M.n_ranks = R; M.rank = me;
+      M.n_local = m->n_rows;
+      for (int r = 0; r < R; r++) { M.shift[r] = shift[r]; M.n_of[r] = (int)n_of[r]; }
+      M.timeout_ns = pc->h.timeout_ns;
+    }
+  }
+
+  /* swap the levels: rank 0 continues with the merged ones, the others stop at a stub */
+  if (me == 0) {
+    for (int l = Lm; l < nl; l++) { delete mg->levels[l]; mg->levels[l] = merged[(size_t)(l - Lm)]; }
+  }
+  else {
+    for (int l = Lm + 1; l < nl; l++) delete mg->levels[l];
+    mg->levels.resize((size_t)Lm + 1);
+    mg->levels[Lm]->stub = true;
+  }
+  mg->merge_level = Lm;
+  return true;
+}
+
+/* peer buffers and flags of the merge boundary (after the levels' solve-time data) */
+bool mg_merge_build_dev(csb_multigrid_t *mg, csb_pcomm_t *pc)
+{
+  Context &c = ctx();
+  MergeDev &M = mg->h_merge;
+  const int R = M.n_ranks, me = M.rank;
+  MgLevel *lv = mg->levels[(size_t)mg->merge_level];
+  if (!mg->merge_count.alloc(1)
+      || !CSB_CUDA(cudaMemsetAsync(mg->merge_count.p, 0, sizeof(unsigned), c.stream))) return false;
+  M.count = mg->merge_count.p;
+  M.flag_in = (unsigned *)pcomm_arena_alloc(pc, sizeof(unsigned)*COMM_MAX_RANKS);
+  if (M.flag_in == nullptr) return false;
+  std::vector<int> nbr;
+  std::vector<long long> snd, rcv;
+  if (me == 0) {
+    const size_t n_tot = (size_t)std::max(lv->m->n_rows, 1);
+    lv->arena_rhs = (double *)pcomm_arena_alloc(pc, sizeof(double)*(n_tot + 2));
+    if (lv->arena_rhs == nullptr) return false;
+    for (int r = 1; r < R; r++) {
+      nbr.push_back(r);
+      snd.push_back(((char *)lv->arena_rhs - pc->arena) + 8ll*M.shift[r]);
+      snd.push_back(((char *)M.flag_in - pc->arena) + 4ll*r);
+      for (int k = 2; k < 8; k++) snd.push_back(0);
+    }
+  }
+  else {
+    lv->arena_vx = (double *)pcomm_arena_alloc(pc, sizeof(double)*((size_t)std::max(M.n_local, 1) + 2));
+    if (lv->arena_vx == nullptr) return false;
+    nbr.push_back(0);
+    snd.push_back((char *)lv->arena_vx - pc->arena);
+    snd.push_back((char *)M.flag_in - pc->arena);
+    for (int k = 2; k < 8; k++) snd.push_back(0);
+  }
+  rcv.assign(snd.size() + 8, 0);
+  if (!pcomm_mailbox(pc, (int)nbr.size(), nbr.data(), snd.data(), rcv.data())) return false;
+  if (me == 0) {
+    for (int r = 1; r < R; r++) {
+      char *base = pc->h.peer[r];
+      M.peer_vx[r] = (double *)(base + rcv[(size_t)(r-1)*8 + 0]);
+      M.peer_flag[r] = (unsigned *)(base + rcv[(size_t)(r-1)*8 + 1]);
+    }
+  }
+  else {
+    char *base = pc->h.peer[0];
+    M.root_rhs_dst = (double *)(base + rcv[0]);
+    M.root_flag = (unsigned *)(base + rcv[1]);
+  }
+  return true;
+}
 } // anonymous namespace
 
 extern "C" {
@@ -1467,6 +1691,21 @@ csb_multigrid_set_coarsening_options(csb_multigrid_t *mg, int aggregation_limit,
 void csb_multigrid_set_aggregation_blocks(csb_multigrid_t *mg, int n_blocks)
 {
   if (mg != nullptr) mg->n_blocks = (n_blocks > 0) ? n_blocks : 0;
+}
+
+void csb_multigrid_set_merge_options(csb_multigrid_t *mg, int rank_stride,
+                                     int rows_mean_threshold,
+                                     unsigned long long rows_glob_threshold)
+{
+  if (mg == nullptr) return;
+  mg->merge_stride = rank_stride;
+  mg->merge_mean_threshold = rows_mean_threshold;
+  mg->merge_glob_threshold = rows_glob_threshold;
+}
+
+int csb_multigrid_get_merge_level(const csb_multigrid_t *mg)
+{
+  return (mg != nullptr) ? mg->merge_level : -1;
 }
 
 int csb_multigrid_set_reduce_comm(csb_multigrid_t *mg, void *nccl_comm)
@@ -1553,11 +1792,10 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
   for (int i = 0; i < 3; i++) {
     const bool pcg = (mg->solver_type[i] == CSB_SLES_PCG && mg->poly_degree[i] == 0);
     const bool smoother = (i < 2 && is_smoother_type((int)mg->solver_type[i])
-                           && mg->precision_mult[i] < 0 && a->halo == nullptr);
+                           && mg->precision_mult[i] < 0);
     if (!pcg && !smoother) {
-      set_error("csb_multigrid_setup: smoothers must be PCG + Jacobi, or (precision_mult < 0, "
-                "one rank) Jacobi / L1 / relaxed / RJ2 / RJ3 smoothers; the coarse solver PCG "
-                "+ Jacobi");
+      set_error("csb_multigrid_setup: smoothers must be PCG + Jacobi, or (precision_mult < 0) "
+                "Jacobi / L1 / relaxed / RJ2 / RJ3 smoothers; the coarse solver PCG + Jacobi");
       return;
     }
     if (mg->solver_type[i] == CSB_SLES_L1_JACOBI) any_l1 = true;
@@ -1771,6 +2009,29 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
              (int)mg->levels.size() - 1, c_n_rows, c_nnz + c_n_rows);
   }
 
+  /* coarse levels merged onto rank 0 (cs_grid.cpp:8355-8372: mean rows per rank under
+     the mean threshold, or global rows under the global one) */
+  mg->merge_level = -1;
+  if (dist && mg->merge_stride > 1) {
+    const int R = pc->h.n_ranks;
+    if (mg->merge_stride < R) {
+      set_error("csb_multigrid_setup: merge rank_stride %d: only a merge of all %d ranks "
+                "onto rank 0 (rank_stride >= number of ranks) is available", mg->merge_stride, R);
+      return;
+    }
+    int Lm = -1;
+    for (int l = 1; l < (int)mg->levels.size() && Lm < 0; l++) {
+      const double g = mg->levels[l]->n_g_rows;
+      if (g / R < (double)mg->merge_mean_threshold || g < (double)mg->merge_glob_threshold)
+        Lm = l;
+    }
+    if (Lm > 0 && R > 1) {
+      const double t0 = wall();
+      if (!mg_merge_coarse_levels(mg, pc, Lm, galerkin)) return;
+      t_xfer += wall() - t0;
+    }
+  }
+
   /* solve-time data */
   const int n_levels = (int)mg->levels.size();
   size_t wr_size = 1, aux_size = 1;
@@ -1791,8 +2052,10 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     if (l > 0) {
       if (!lv->rhs.alloc((size_t)m->n_cols_ext) || !lv->vx.alloc((size_t)m->n_cols_ext)) return;
     }
-    if (dist && !build_dist_level(pc, lv->halo, lv->dist)) return;
+    if (dist && !lv->merged && !lv->stub && !build_dist_level(pc, lv->halo, lv->dist)) return;
   }
+  mg->work_stride = aux_size / 5;
+  if (mg->merge_level >= 0 && !mg_merge_build_dev(mg, pc)) return;
   if (!mg->wr.alloc(wr_size) || !mg->aux.alloc(aux_size)) return;
   if (!mg->it_states.alloc(2*(size_t)n_levels)) return;
   {
@@ -1813,13 +2076,20 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
       d.row_index = m->row_index.p; d.col_id = m->col_id.p;
       d.d_val = m->d_val.p; d.x_val = m->x_val.p; d.ad_inv = lv->ad_inv.p;
       d.l1_inv = lv->l1_inv.p;
-      d.rhs = lv->rhs.p; d.vx = lv->vx.p;
+      d.rhs = (lv->arena_rhs != nullptr) ? lv->arena_rhs : lv->rhs.p;
+      d.vx = (lv->arena_vx != nullptr) ? lv->arena_vx : lv->vx.p;
       d.coarse_row = lv->coarse_row.p;
       d.c_f_row_index = lv->c_f_row_index.p; d.c_f_row_ids = lv->c_f_row_ids.p;
       d.st_descent = mg->it_states.p + 2*l;
       d.st_ascent = mg->it_states.p + 2*l + 1;
       d.n_g_rows = dist ? lv->n_g_rows : (double)m->n_rows;
-      d.dist = dist ? lv->dist.d.p : nullptr;
+      d.dist = (dist && !lv->merged && !lv->stub) ? lv->dist.d.p : nullptr;
+    }
+    if (mg->merge_level >= 0) {
+      MgLevel *ml = mg->levels[(size_t)mg->merge_level];
+      mg->h_merge.stub_rhs = ml->rhs.p;
+      mg->h_merge.stub_vx = ml->arena_vx;
+      if (!mg->d_merge.upload(&mg->h_merge, 1)) return;
     }
     mg->p_smem = persistent_smem_bytes(max_entries);
     mg->p_grid = persistent_grid(1, mg->p_smem);
@@ -1910,6 +2180,18 @@ csb_multigrid_solve(void *context, const char *name, const csb_matrix_t *a, int 
   const bool sm_ascent = is_smoother_type((int)mg->solver_type[1]);
   const bool persistent = dist || (env_int("CSB_MG_MODE_MULTI", 0) == 0 && !sm_descent
                                    && !sm_ascent);
+  if (mg->merge_level >= 0) {
+    set_error("csb_multigrid_solve: a hierarchy with merged coarse levels "
+              "(csb_multigrid_set_merge_options) runs as the preconditioner of FCG "
+              "(csb_sles_it_transfer_pc)");
+    return CSB_SLES_BREAKDOWN;
+  }
+  if (dist && (sm_descent || sm_ascent)) {
+    set_error("csb_multigrid_solve: on a partitioned matrix the cs_multigrid_smoother "
+              "smoothers run as the preconditioner of FCG (csb_sles_it_transfer_pc); the "
+              "V-cycle in solver mode takes PCG + Jacobi smoothers");
+    return CSB_SLES_BREAKDOWN;
+  }
   if (sm_descent && !launch_mg_set_initial_residual(ms, HUGE_VAL)) return CSB_SLES_BREAKDOWN;
 
   if (persistent) {
@@ -2209,6 +2491,9 @@ void *csb_multigrid_copy(const void *context)
   }
   d->nccl_comm = s->nccl_comm;
   d->pcomm = s->pcomm;
+  d->merge_stride = s->merge_stride;
+  d->merge_mean_threshold = s->merge_mean_threshold;
+  d->merge_glob_threshold = s->merge_glob_threshold;
   return d;
 }
 

@@ -401,6 +401,20 @@ void csb_multigrid_set_coarsening_options(csb_multigrid_t  *mg,
    is what the reference uses. */
 void csb_multigrid_set_aggregation_blocks(csb_multigrid_t *mg, int n_blocks);
 
+/* cs_multigrid_set_merge_options (src/alge/cs_multigrid.cpp:6039-6051): coarse levels whose
+   mean row count per rank falls under rows_mean_threshold, or whose global row count falls
+   under rows_glob_threshold, are merged onto fewer ranks (cs_grid_merge_ranks,
+   src/alge/cs_grid_rank_merge.cpp:1359; trigger cs_grid.cpp:8355-8372).  On this path
+   rank_stride >= the number of ranks (everything onto rank 0) is available; rank_stride <= 1
+   (default, as in the reference) disables merging.  The merged levels keep the aggregates
+   built on the partitioned levels (the reference re-aggregates across the former rank
+   boundaries). */
+void csb_multigrid_set_merge_options(csb_multigrid_t *mg, int rank_stride,
+                                     int rows_mean_threshold,
+                                     unsigned long long rows_glob_threshold);
+/* level at which the last setup merged (-1: none) */
+int  csb_multigrid_get_merge_level(const csb_multigrid_t *mg);
+
 int  csb_multigrid_set_reduce_comm(csb_multigrid_t *mg, void *nccl_comm);
 /* Communicator of a distributed hierarchy: required when the matrix has a halo
    (the reference takes cs_glob_mpi_comm, src/alge/cs_multigrid.cpp:4720). */

@@ -427,6 +427,152 @@ class DistOracle:
         return dict(cvg=cvg, n_iter=n_equiv, residual=residual, n_cycles=n_cycles,
                     cycle_residuals=np.array(cyc), vx=[v[:n[0][r]] for r, v in enumerate(vx_l[0])])
 
+    # ------------------------------------------------- FCG + V-cycle preconditioner
+    SMOOTHERS = {3: ("jacobi", (1.0,)), 14: ("relaxed", (2. / 3.,)),
+                 15: ("relaxed", (1.7319, 0.5695)), 16: ("relaxed", (2.2473, 0.8573, 0.5296))}
+
+    def _spmv_e(self, l, xs):
+        """E_r . x_r (diagonal excluded) after a halo sync of x."""
+        lv = self.levels[l]
+        halo_sync(lv["halos"], xs)
+        out = []
+        for r in range(self.R):
+            ri, ci, d, xv = self._cached(l, r)
+            out.append(self.ora.spmv(ri, ci, d, xv, xs[r], exclude_diag=True))
+        return out
+
+    def smoother(self, l, stype, n_max_iter, rhs, vx, use_vx_ini):
+        """cs_multigrid_smoother _jacobi / _relaxed_jacobi (cs_multigrid_smoother.cpp:143-373)
+        over all ranks, in place in vx[r] (n_cols_ext entries)."""
+        mode, w = self.SMOOTHERS[stype]
+        n_iter = n_max_iter
+        if mode == "relaxed" and n_iter % len(w):
+            n_iter += len(w) - n_iter % len(w)        # whole schedules (:1888-1898)
+        R = self.R
+        n = [g.contents.n_rows for g in self.levels[l]["grids"]]
+        ad_inv = [1.0 / self._cached(l, r)[2] for r in range(R)]
+        it0 = 0
+        if not use_vx_ini:
+            for r in range(R):
+                b = rhs[r][:n[r]]
+                vx[r][:n[r]] = (w[0] * b * ad_inv[r]) if mode == "relaxed" else (b * ad_inv[r])
+            it0 = 1
+        for it in range(it0, n_iter):
+            wk = w[it % len(w)]
+            ex = self._spmv_e(l, vx)
+            for r in range(R):
+                b, x = rhs[r][:n[r]], vx[r][:n[r]]
+                t = b - ex[r]
+                if mode == "relaxed":
+                    vx[r][:n[r]] = (1.0 - wk) * x + wk * t * ad_inv[r]
+                else:
+                    vx[r][:n[r]] = t * ad_inv[r]
+        return n_iter
+
+    def vcycle_pc(self, rhs, vx, precision, r_norm, types=(16, 16, 0), n_max_iter=(3, 3, 500),
+                  precision_mult=(-1., -1., 1.)):
+        """_multigrid_v_cycle_pc (cs_multigrid.cpp:3569-4020) from a zero start over all
+        ranks: vx[r] (n_cols_ext of level 0) receives M^-1 rhs."""
+        R, nl = self.R, len(self.levels)
+        coarsest = nl - 1
+        n = [[g.contents.n_rows for g in lv["grids"]] for lv in self.levels]
+        nce = [[max(g.contents.n_cols_ext, g.contents.n_rows) for g in lv["grids"]]
+               for lv in self.levels]
+        rhs_l = [rhs] + [[np.zeros(nce[l][r]) for r in range(R)] for l in range(1, nl)]
+        vx_l = [vx] + [[np.zeros(nce[l][r]) for r in range(R)] for l in range(1, nl)]
+        for level in range(coarsest):
+            self.smoother(level, types[0], n_max_iter[0], rhs_l[level], vx_l[level], False)
+            y = self._spmv(level, vx_l[level])
+            wr = [rhs_l[level][r][:n[level][r]] - y[r] for r in range(R)]
+            cr = self.levels[level + 1]["coarse_row"]
+            for r in range(R):
+                c = np.zeros(n[level + 1][r])
+                self.ora.lib.ora_restrict(n[level][r], n[level + 1][r], _ip(cr[r]),
+                                          _dp(_f64(wr[r])), _dp(c))
+                rhs_l[level + 1][r][:n[level + 1][r]] = c
+        self.pcg(coarsest, rhs_l[coarsest], vx_l[coarsest], n_max_iter[2],
+                 precision * precision_mult[2], r_norm, False)
+        for level in range(coarsest - 1, -1, -1):
+            cr = self.levels[level + 1]["coarse_row"]
+            for r in range(R):
+                f = np.ascontiguousarray(vx_l[level][r][:n[level][r]])
+                self.ora.lib.ora_prolong_inc(n[level][r], _ip(cr[r]),
+                                             _dp(_f64(vx_l[level + 1][r])), _dp(f))
+                vx_l[level][r][:n[level][r]] = f
+            self.smoother(level, types[1], n_max_iter[1], rhs_l[level], vx_l[level], True)
+
+    def fcg_mgpc(self, rhs, n_max_iter, precision, r_norm, types=(16, 16, 0),
+                 mg_n_max_iter=(3, 3, 500), precision_mult=(-1., -1., 1.), vx0=None):
+        """_flexible_conjugate_gradient (cs_sles_it.cpp:832-985) preconditioned by vcycle_pc,
+        over all ranks; dot products summed per rank, then in rank order."""
+        R = self.R
+        lv = self.levels[0]
+        n = [g.contents.n_rows for g in lv["grids"]]
+        nce = [max(g.contents.n_cols_ext, g.contents.n_rows) for g in lv["grids"]]
+        ext = lambda: [np.zeros(nce[r]) for r in range(R)]
+        vx, rk, vk, wk, dk, qk = (ext() for _ in range(6))
+        if vx0 is not None:
+            for r in range(R):
+                vx[r][:n[r]] = vx0[r][:n[r]]
+            y = self._spmv(0, vx)
+            for r in range(R):
+                rk[r][:n[r]] = rhs[r][:n[r]] - y[r]
+        else:
+            for r in range(R):
+                rk[r][:n[r]] = rhs[r][:n[r]]
+        hist = []
+        cvg, n_iter, residual, initial = 0, 0, -1., -1.
+        rho_km1 = 0.
+        tiny = 2.2250738585072014e-308
+        loc = lambda v, r: v[r][:n[r]]
+        while cvg == 0:
+            for r in range(R):
+                vk[r][:] = 0.
+            self.vcycle_pc(rk, vk, precision, r_norm, types, mg_n_max_iter, precision_mult)
+            y = self._spmv(0, vk)
+            for r in range(R):
+                wk[r][:n[r]] = y[r]
+            a = b = g = rr = 0.0
+            parts = [(self.ora.dot(loc(vk, r), loc(rk, r)), self.ora.dot(loc(vk, r), loc(wk, r)),
+                      self.ora.dot(loc(vk, r), loc(qk, r)), self.ora.dot_xx(loc(rk, r)))
+                     for r in range(R)]
+            for p4 in parts:
+                a += p4[0]; b += p4[1]; g += p4[2]; rr += p4[3]
+            residual = math.sqrt(rr)
+            hist.append(residual)
+            if n_iter > 0:
+                if precision > 0 and residual < precision * r_norm:
+                    cvg = 1
+                elif n_iter >= n_max_iter:
+                    cvg = -1
+                elif residual > initial * 10000.0 and residual > 100.:
+                    cvg = -3
+            else:
+                initial = residual
+            if cvg != 0:
+                break
+            if n_iter > 0:
+                gk_rk1 = g / rho_km1 if abs(rho_km1) > tiny else 0.
+                rho_k = b - g * gk_rk1
+            else:
+                gk_rk1 = 0.
+                rho_k = b
+            ak_rk = a / rho_k if abs(rho_k) > tiny else 0.
+            for r in range(R):
+                m = n[r]
+                if n_iter > 0:
+                    dk[r][:m] = vk[r][:m] - gk_rk1 * dk[r][:m]
+                    qk[r][:m] = wk[r][:m] - gk_rk1 * qk[r][:m]
+                else:
+                    dk[r][:m] = vk[r][:m]
+                    qk[r][:m] = wk[r][:m]
+                vx[r][:m] = vx[r][:m] + ak_rk * dk[r][:m]
+                rk[r][:m] = rk[r][:m] - ak_rk * qk[r][:m]
+            rho_km1 = rho_k
+            n_iter += 1
+        return dict(cvg=cvg, n_iter=n_iter, residual=residual, initial_residual=initial,
+                    history=np.array(hist), vx=[v[:n[r]] for r, v in enumerate(vx)])
+
     def free(self):
         for l, lv in enumerate(self.levels):
             for g in lv["grids"]:

@@ -175,12 +175,89 @@ def scenario_mg(N, R, bc, precision):
     D.free()
 
 
+def scenario_fcgmg(N, R, bc, precision, merge_mean):
+    """FCG + V-cycle(RJ3) preconditioner in one persistent launch per rank, optionally with
+    the coarse levels merged onto rank 0 (merge_mean > 0: mean rows per rank under which a
+    level is merged).  The merged levels keep the partitioned aggregates and the order of
+    every row's entries, so the merged run must reproduce the partitioned algorithm."""
+    from oracle.dist_oracle import DistOracle
+    from oracle.pyoracle import Oracle
+    ora = Oracle()
+    g = cube_poisson(N, bc)
+    r_norm = float(np.sqrt(ora.dot_xx(g.rhs)))
+    parts = [cube_poisson_local(N, R, r, bc) for r in range(R)]
+    D = DistOracle([p[0] for p in parts], [p[1] for p in parts], ora)
+    nl = D.mg_setup()
+    o = D.fcg_mgpc([p[0].rhs for p in parts], 200, precision, r_norm)
+    omg = ora.mg_setup(g)
+    o1 = ora.fcg_mgpc(omg, g.rhs, 200, precision, r_norm)
+
+    def fn(rank, pc):
+        ro = build_rank(N, R, rank, pc, bc)
+        c = api.SlesIt(api.SlesItType.FCG, 200, poly_degree=-1)
+        mgp = api.Multigrid(pc=True)
+        mgp.set_aggregation_blocks(1)
+        if R > 1:
+            c.set_pcomm(pc)
+            mgp.set_pcomm(pc)
+            if merge_mean > 0:
+                mgp.set_merge_options(R, merge_mean, 0)
+        c.transfer_pc(mgp)
+        c.setup(ro.matrix)
+        api.synchronize()
+        api.launch_count(reset=True)
+        r = c.solve(ro.matrix, ro.system.rhs, precision, r_norm)
+        launches = api.launch_count()
+        r2 = c.solve(ro.matrix, ro.system.rhs, precision, r_norm)     # counters persist
+        assert np.array_equal(r["vx"][:ro.system.n_rows], r2["vx"][:ro.system.n_rows])
+        mg = c.pc()
+        out = dict(cvg=int(r["cvg"]), n_iter=r["n_iter"], residual=r["residual"],
+                   hist=r["history"], vx=r["vx"][:ro.system.n_rows].copy(),
+                   n_levels=mg.n_levels(), merge_level=mg.merge_level(), launches=launches)
+        pc.barrier()
+        c.destroy(); ro.destroy()
+        return out
+
+    res = run_ranks_in_threads(R, fn, device_of_rank_fn())
+    for r, x in enumerate(res):
+        assert x["cvg"] == o["cvg"] == 1, (x["cvg"], o["cvg"])
+        assert x["launches"] <= 3, x["launches"]
+        assert (x["n_iter"], x["residual"]) == (res[0]["n_iter"], res[0]["residual"])
+        assert abs(x["n_iter"] - o["n_iter"]) <= 1, (x["n_iter"], o["n_iter"])
+        k = min(len(x["hist"]), len(o["history"]), 6)
+        assert np.allclose(x["hist"][:k], o["history"][:k], rtol=1e-9, atol=0)
+        if merge_mean > 0 and R > 1:
+            assert x["merge_level"] >= 1, x["merge_level"]
+            assert x["n_levels"] == (nl if r == 0 else x["merge_level"] + 1), (r, x["n_levels"], nl)
+        else:
+            assert x["n_levels"] == nl and x["merge_level"] == -1
+    vx = gather_global([x["vx"] for x in res], [p[2] for p in parts], g.n_rows)
+    res_true = np.linalg.norm(ora.spmv(g.row_index, g.col_id, g.d_val, g.x_val, vx) - g.rhs)
+    assert res_true <= 1.01 * precision * r_norm, res_true / r_norm
+    vxo = gather_global(o["vx"], [p[2] for p in parts], g.n_rows)
+    erro = np.linalg.norm(vx - vxo) / np.linalg.norm(vxo)
+    err1 = np.linalg.norm(vx - o1["vx"]) / np.linalg.norm(o1["vx"])
+    tol = 1e-10 if precision <= 1e-12 else 1e-6
+    assert erro <= tol, erro
+    if bc == "dirichlet":
+        assert err1 <= tol, err1
+    print(f"OK fcgmg N={N} R={R} {bc} merge_mean={merge_mean}: levels {res[0]['n_levels']}, "
+          f"merge level {res[0]['merge_level']}, n_iter {res[0]['n_iter']} (oracle {o['n_iter']}, "
+          f"single-rank {o1['n_iter']}), rel diff vs partitioned oracle {erro:.2e}, "
+          f"vs single-rank {err1:.2e}")
+    ora.mg_free(omg)
+    D.free()
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
     if what == "comm":
         scenario_comm(int(sys.argv[2]))
     elif what == "pcg":
         scenario_pcg(int(sys.argv[2]), int(sys.argv[3]), sys.argv[4])
+    elif what == "fcgmg":
+        scenario_fcgmg(int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], float(sys.argv[5]),
+                       int(sys.argv[6]) if len(sys.argv) > 6 else 0)
     elif what == "mg":
         scenario_mg(int(sys.argv[2]), int(sys.argv[3]), sys.argv[4],
                     float(sys.argv[5]) if len(sys.argv) > 5 else 1e-8)

@@ -39,6 +39,17 @@ def test_distributed_multigrid(N, R, bc, prec):
     run("mg", N, R, bc, prec)
 
 
+@pytest.mark.parametrize("N,R,bc,prec,merge_mean", [
+    (16, 2, "dirichlet", 1e-8, 0), (24, 4, "neumann", 1e-8, 0), (32, 8, "dirichlet", 1e-13, 0),
+    (24, 1, "dirichlet", 1e-8, 0),
+    # coarse levels merged onto rank 0 (cs_grid_merge_ranks): at the first coarse level, in
+    # the middle of the hierarchy, at the coarsest level only
+    (16, 2, "dirichlet", 1e-13, 100000), (32, 4, "neumann", 1e-8, 300), (32, 8, "dirichlet", 1e-13, 200),
+    (24, 4, "dirichlet", 1e-13, 12), (40, 8, "neumann", 1e-8, 2000)])
+def test_distributed_fcg_multigrid_pc(N, R, bc, prec, merge_mean):
+    run("fcgmg", N, R, bc, prec, merge_mean)
+
+
 def _n_gpus():
     try:
         import torch

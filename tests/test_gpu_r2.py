@@ -95,7 +95,7 @@ def test_fcg_mg_persistent_warm_start_and_max_iter(csb, oracle):
     oracle.mg_free(omg); m.destroy()
 
 
-def _reference_parity(csb, reflib, N, n_threads, vcycle=True):
+def _reference_parity(csb, reflib, N, n_threads, vcycle=True, vcycle_precision=1e-12):
     """Hierarchy, V-cycle solver and FCG + V-cycle(RJ3) of an N^3 cube against the reference's
     own code run with n_threads OpenMP threads (its aggregation never crosses a thread's
     block of rows, cs_grid.cpp:4374-4393: the maps depend on the thread count)."""
@@ -136,14 +136,17 @@ def _reference_parity(csb, reflib, N, n_threads, vcycle=True):
         del lv, rlv
         out["n_levels"] = mg.n_levels()
         if vcycle:
-            o = reflib.multigrid(h, s.rhs, 1e-12, r_norm)
-            r = mg.solve(m, s.rhs, 1e-12, r_norm)
-            assert int(r["cvg"]) == o["cvg"] == 1
+            o = reflib.multigrid(h, s.rhs, vcycle_precision, r_norm)
+            r = mg.solve(m, s.rhs, vcycle_precision, r_norm)
+            assert int(r["cvg"]) == o["cvg"] == 1, (int(r["cvg"]), o["cvg"], r["n_cycles"])
             assert equiv_iters_close(r["n_iter"], o["n_iter"], r["n_iter"] / r["n_cycles"]), \
                 (r["n_iter"], o["n_iter"], r["n_cycles"])
             out["vcycle"] = (r["n_cycles"], r["n_iter"], o["n_iter"],
                              rel_l2(r["vx"][:s.n_rows], o["vx"]))
-            assert out["vcycle"][3] <= SOL_TOL, out
+            assert abs(r["residual"] - o["residual"]) <= 1e-3 * o["residual"], out
+            # solutions: 1e-10 when both are converged to 1e-12; a solve stopped at 1e-8 only
+            # determines the (eps-regularised) constant mode to ~1e-6
+            assert out["vcycle"][3] <= (SOL_TOL if vcycle_precision <= 1e-12 else 1e-5), out
         mg.destroy()
         o = reflib.fcg_mgpc(h, s.rhs, 200, 1e-12, r_norm)
         pc = csb.Multigrid(pc=True)
@@ -179,7 +182,10 @@ def test_reference_parity_bench_256_cube(csb, reflib):
     """The benchmarked workload (BASELINE config 3, 256^3): the reference on all host cores,
     this library with as many aggregation blocks."""
     t = max(1, min(os.cpu_count() or 1, 64))
-    out = _reference_parity(csb, reflib, 256, t)
+    # the PCG-smoothed V-cycle in solver mode needs ~55 cycles per 1e-8 at this size (more
+    # than its 100-cycle budget for 1e-12): it is compared at the benchmark's precision, the
+    # 1e-10 solution bar is checked with FCG + V-cycle, solved to 1e-12
+    out = _reference_parity(csb, reflib, 256, t, vcycle_precision=1e-8)
     print("256^3 parity:", out)
 
 
