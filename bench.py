@@ -220,6 +220,8 @@ def main():
     ap.add_argument("--spmv-launches", type=int, default=50)
     ap.add_argument("--no-vcycle-solver", action="store_true",
                     help="skip the side measurement of the PCG-smoothed V-cycle solver")
+    ap.add_argument("--merge-glob", type=int, default=250000,
+                    help="N > 1: merge coarse levels with fewer global rows onto rank 0 (0: off)")
     ap.add_argument("--solver", default="auto", choices=["auto", "fcg_mg", "vcycle"],
                     help="headline solver (auto: FCG + V-cycle preconditioner)")
     args = ap.parse_args()
@@ -294,6 +296,10 @@ def main():
         if world > 1:
             mgp.set_pcomm(pc)
             c.set_pcomm(pc)
+            if args.merge_glob > 0:
+                # cs_multigrid_set_merge_options: levels under this many rows (over all
+                # ranks) are latency-bound on ONE GPU already -- run them on rank 0
+                mgp.set_merge_options(world, 0, args.merge_glob)
         c.transfer_pc(mgp)
         return c
 
@@ -476,10 +482,12 @@ def main():
                        "setup_assembly_device_s": st["assembly"],
                        "setup_transfers_s": st["transfers"],
                        "aggregation_blocks": n_blocks,
+                       "merge_level": (mg.merge_level() if world > 1 else -1),
                        "matrix_upload_s": t_upload, "input_generation_s": t_gen,
                        "parallelism": "1 GPU" if world == 1 else
                        f"{world} bricks (Morton-box partition), one per GPU; ghost exchange + "
                        "all-reduce fused in the persistent kernel over NVLink peer memory; "
+                       "coarse levels merged onto rank 0 (cs_multigrid_set_merge_options); "
                        "multi-rank coarse halos have no reference run behind them here (no MPI "
                        "in the image): parity unpinned for _coarsen_halo"},
             "e2e": {"value": t_e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n_rows_global,
@@ -502,6 +510,18 @@ def main():
         }
         if solver_kind != "fcg_mg":
             line["config"]["n_cycles"] = int(r["n_cycles"])
+        else:
+            # device-side timers of the last solve on rank 0: microseconds per V-cycle and level
+            # (descent sweeps, residual, restrict, coarsest solve / wait for rank 0's merged
+            # levels, prolong, ascent sweeps) and per FCG phase
+            n_cyc = max(int(r["n_iter"]) + 1, 1)
+            itp = mg.smoother_times()
+            line["phases"] = {
+                "per_level_us_per_cycle": [[round(float(v) / n_cyc * 1e6, 1) for v in row]
+                                           for row in pt],
+                "columns": ["descent", "residual", "restrict", "coarsest", "prolong", "ascent"],
+                "fcg_spmv_4dots_us": round(float(itp[0, 1]) / n_cyc * 1e6, 1),
+                "fcg_update_us": round(float(itp[0, 2]) / max(int(r["n_iter"]), 1) * 1e6, 1)}
         line.update(extra)
         if cpu is not None:
             line["cpu_baseline"] = cpu

@@ -2073,7 +2073,7 @@ __device__ __forceinline__ void vc_descend(const FcgMgParams &S, const Persisten
        level's rows of the other ranks arrive later) */
     const bool fuse = (level + 1 < S.n_levels - 1) && (level + 1 != S.merge_level);
     double *c_start = fuse ? sweep_start(sp.n_iter - 1, C.vx, S.tmp) : nullptr;
-    restrict_rows_first<SINGLE>(C.n_rows, L.c_f_row_index, L.c_f_row_ids, S.wr, C.rhs, sp.mode,
+    restrict_rows_first<SINGLE>(L.n_rows_next, L.c_f_row_index, L.c_f_row_ids, S.wr, C.rhs, sp.mode,
                                 sp.w[0], smooth_inv(C, sp.mode), c_start);
     phase_barrier<SINGLE>(P.barrier);
   }

@@ -2071,7 +2071,10 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
       d.gather_depth = plan_gather_depth(m->h_row_index, m->n_rows);
       max_entries = std::max(max_entries, me);
       d.n_rows = m->n_rows;
+      /* rows of the next level THIS rank restricts to: at the merge boundary its own part
+         of the merged level */
       d.n_rows_next = (l + 1 < n_levels) ? mg->levels[l+1]->m->n_rows : 0;
+      if (l + 1 == mg->merge_level) d.n_rows_next = mg->h_merge.n_local;
       d.level_id = l;
       d.row_index = m->row_index.p; d.col_id = m->col_id.p;
       d.d_val = m->d_val.p; d.x_val = m->x_val.p; d.ad_inv = lv->ad_inv.p;

@@ -33,6 +33,9 @@ size_t pcomm_arena_mark(csb_pcomm_t *) { return 0; }
 void   pcomm_arena_release(csb_pcomm_t *, size_t) {}
 void   pcomm_host_barrier(csb_pcomm_t *) {}
 bool   pcomm_allreduce(csb_pcomm_t *, double *, int) { return no("peer all-reduce"); }
+bool   pcomm_allgather_count(csb_pcomm_t *, long long, long long *) { return no("peer all-gather"); }
+bool   pcomm_gather_to_root(csb_pcomm_t *, int, const long long *, const void *, void *)
+{ return no("peer gather"); }
 bool   pcomm_mailbox(csb_pcomm_t *, int, const int *, const long long *, long long *)
 { return no("peer mailbox"); }
 bool   pcomm_window_exchange(csb_pcomm_t *, const HaloDev &, int, int, const void *, void *)

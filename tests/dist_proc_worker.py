@@ -13,6 +13,59 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def fcg_mg(N, R, rank, bc, precision, merge_glob, r_norm, s, gids, pc, ro):
+    """FCG + V-cycle(RJ3) preconditioner, coarse levels under merge_glob global rows merged
+    onto rank 0, against the partitioned oracle (the merged run is the same algorithm)."""
+    import torch.distributed as dist
+    from code_saturne_b200 import api
+    from code_saturne_b200.dist import gather_global
+    from code_saturne_b200.mesh_cartesian import cube_poisson, cube_poisson_local
+    c = api.SlesIt(api.SlesItType.FCG, 200, poly_degree=-1)
+    mgp = api.Multigrid(pc=True)
+    mgp.set_aggregation_blocks(1)
+    c.set_pcomm(pc)
+    mgp.set_pcomm(pc)
+    if merge_glob > 0:
+        mgp.set_merge_options(R, 0, merge_glob)
+    c.transfer_pc(mgp)
+    c.setup(ro.matrix)
+    r = c.solve(ro.matrix, s.rhs, precision, r_norm)
+    r2 = c.solve(ro.matrix, s.rhs, precision, r_norm)
+    assert np.array_equal(r["vx"][:s.n_rows], r2["vx"][:s.n_rows])
+    mine = dict(cvg=int(r["cvg"]), n_iter=r["n_iter"], residual=r["residual"],
+                merge_level=c.pc().merge_level(), n_levels=c.pc().n_levels(),
+                vx=r["vx"][:s.n_rows].copy(), gids=gids[:s.n_rows].copy())
+    out = [None] * R
+    dist.all_gather_object(out, mine)
+    dist.barrier()
+    c.destroy(); ro.destroy(); pc.destroy()
+    if rank == 0:
+        from oracle.dist_oracle import DistOracle
+        from oracle.pyoracle import Oracle
+        ora = Oracle()
+        g = cube_poisson(N, bc)
+        parts = [cube_poisson_local(N, R, q, bc) for q in range(R)]
+        D = DistOracle([p[0] for p in parts], [p[1] for p in parts], ora)
+        D.mg_setup()
+        o = D.fcg_mgpc([p[0].rhs for p in parts], 200, precision, r_norm)
+        for x in out:
+            assert x["cvg"] == o["cvg"] == 1
+            assert (x["n_iter"], x["residual"]) == (out[0]["n_iter"], out[0]["residual"])
+            assert abs(x["n_iter"] - o["n_iter"]) <= 1, (x["n_iter"], o["n_iter"])
+        if merge_glob > 0:
+            assert out[0]["merge_level"] >= 1 and out[1]["n_levels"] == out[1]["merge_level"] + 1
+        vx = gather_global([x["vx"] for x in out], [x["gids"] for x in out], g.n_rows)
+        res_true = np.linalg.norm(ora.spmv(g.row_index, g.col_id, g.d_val, g.x_val, vx) - g.rhs)
+        assert res_true <= 1.01 * precision * r_norm, res_true / r_norm
+        vxo = gather_global(o["vx"], [p[2] for p in parts], g.n_rows)
+        err = np.linalg.norm(vx - vxo) / np.linalg.norm(vxo)
+        assert err <= 1e-6, err
+        print(f"OK proc-fcgmg N={N} R={R} {bc}: levels {out[0]['n_levels']}, merge level "
+              f"{out[0]['merge_level']}, n_iter {out[0]['n_iter']} (oracle {o['n_iter']}), "
+              f"rel diff {err:.2e}")
+        D.free()
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -22,6 +75,8 @@ def main():
 
     N, bc = int(sys.argv[1]), sys.argv[2]
     precision = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-8
+    mode = sys.argv[4] if len(sys.argv) > 4 else "mg"
+    merge_glob = int(sys.argv[5]) if len(sys.argv) > 5 else 3000
     rank, R = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -35,6 +90,10 @@ def main():
     pc = pcomm_from_torch_dist(h.n_ghost)
     assert np.array_equal(pc.allreduce_sum([rank + 1.0, 1.0]), [R * (R + 1) / 2.0, float(R)])
     ro = RankObjects(s, h, gids, pc, rank)
+    if mode == "fcgmg":
+        fcg_mg(N, R, rank, bc, precision, merge_glob, r_norm, s, gids, pc, ro)
+        dist.destroy_process_group()
+        return
     mg = ro.multigrid()
     mg.setup(ro.matrix)
     r = mg.solve(ro.matrix, s.rhs, precision, r_norm)

@@ -45,7 +45,7 @@ def test_distributed_multigrid(N, R, bc, prec):
     # coarse levels merged onto rank 0 (cs_grid_merge_ranks): at the first coarse level, in
     # the middle of the hierarchy, at the coarsest level only
     (16, 2, "dirichlet", 1e-13, 100000), (32, 4, "neumann", 1e-8, 300), (32, 8, "dirichlet", 1e-13, 200),
-    (24, 4, "dirichlet", 1e-13, 12), (40, 8, "neumann", 1e-8, 2000)])
+    (24, 4, "dirichlet", 1e-13, 25), (40, 8, "neumann", 1e-8, 2000)])
 def test_distributed_fcg_multigrid_pc(N, R, bc, prec, merge_mean):
     run("fcgmg", N, R, bc, prec, merge_mean)
 
@@ -58,9 +58,12 @@ def _n_gpus():
         return 0
 
 
-@pytest.mark.parametrize("N,R,bc", [(32, 2, "dirichlet"), (48, 4, "neumann"), (64, 8, "dirichlet")])
-def test_one_process_per_gpu_multigrid(N, R, bc):
-    """torchrun, one process per GPU, arenas mapped with cudaIpc: needs R visible GPUs."""
+@pytest.mark.parametrize("N,R,bc,mode", [(32, 2, "dirichlet", "mg"), (48, 4, "neumann", "mg"),
+                                         (64, 8, "dirichlet", "mg"), (48, 2, "dirichlet", "fcgmg"),
+                                         (64, 4, "neumann", "fcgmg"), (64, 8, "dirichlet", "fcgmg")])
+def test_one_process_per_gpu_multigrid(N, R, bc, mode):
+    """torchrun, one process per GPU, arenas mapped with cudaIpc: needs R visible GPUs.
+    mode fcgmg: FCG + V-cycle preconditioner with the coarse levels merged onto rank 0."""
     if _n_gpus() < R:
         pytest.skip(f"needs {R} GPUs")
     import socket
@@ -70,6 +73,7 @@ def test_one_process_per_gpu_multigrid(N, R, bc):
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                         f"--nproc-per-node={R}", "--master-addr", "127.0.0.1",
                         "--master-port", str(port),
-                        os.path.join(ROOT, "tests", "dist_proc_worker.py"), str(N), bc],
+                        os.path.join(ROOT, "tests", "dist_proc_worker.py"), str(N), bc, "1e-8",
+                        mode],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
-    assert p.returncode == 0 and "OK proc-mg" in p.stdout, f"{p.stdout[-2000:]}\n{p.stderr[-4000:]}"
+    assert p.returncode == 0 and "OK proc-" in p.stdout, f"{p.stdout[-2000:]}\n{p.stderr[-4000:]}"

@@ -143,7 +143,7 @@ def _reference_parity(csb, reflib, N, n_threads, vcycle=True, vcycle_precision=1
                 (r["n_iter"], o["n_iter"], r["n_cycles"])
             out["vcycle"] = (r["n_cycles"], r["n_iter"], o["n_iter"],
                              rel_l2(r["vx"][:s.n_rows], o["vx"]))
-            assert abs(r["residual"] - o["residual"]) <= 1e-3 * o["residual"], out
+            assert abs(r["residual"] - o["residual"]) <= 0.05 * o["residual"], out
             # solutions: 1e-10 when both are converged to 1e-12; a solve stopped at 1e-8 only
             # determines the (eps-regularised) constant mode to ~1e-6
             assert out["vcycle"][3] <= (SOL_TOL if vcycle_precision <= 1e-12 else 1e-5), out
