@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "csb200.h"
+#include "grid_host.h"
 
 namespace csb {
 
@@ -312,8 +313,9 @@ struct _csb_matrix_t {
   /* host mirrors of the structure and values (needed by the host-side
      aggregation, like the reference which always aggregates on the host,
      src/alge/cs_grid.cpp:8035-8041) */
-  std::vector<csb_lnum_t>  h_row_index, h_col_id;
-  std::vector<double>      h_d_val, h_x_val;
+  std::vector<csb_lnum_t>  h_row_index;
+  csb::HostVec<csb_lnum_t> h_col_id;
+  csb::HostVec<double>     h_d_val, h_x_val;
   bool        h_vals_valid = false;
   /* SpMV launch geometry */
   int         spmv_rows_per_block = 256;
@@ -321,7 +323,7 @@ struct _csb_matrix_t {
   bool        spmv_stream_ok = true;   /* false -> scalar fallback kernel */
   /* slab plan of the bulk-copy pipeline kernel (k_spmv_pipeline), made on first use */
   mutable int    pl_state = 0;         /* 0 not planned, 1 usable, -1 not usable */
-  mutable int    pl_slab_rows = 0, pl_n_slabs = 0, pl_grid = 0, pl_gdepth = 2;
+  mutable int    pl_slab_rows = 0, pl_n_slabs = 0, pl_grid = 0, pl_gdepth = 2, pl_row_len_max = 0;
   mutable size_t pl_smem = 0;
   /* mesh association (device) */
   csb_lnum_t  n_faces = 0;

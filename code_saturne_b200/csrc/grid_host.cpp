@@ -194,8 +194,8 @@ int aggregate_dx_msr(int level, int n_rows, const int *row_index, const int *col
   if (nb < 1) nb = 1;
 
   const long nnz = row_index[n_rows];
-  std::vector<short> card(std::max(n_rows, 1)), count(std::max(n_rows, 1));
-  std::vector<int> queue(std::max<long>(std::max<long>(2*nnz, n_rows), 1));
+  HostVec<short> card(std::max(n_rows, 1)), count(std::max(n_rows, 1));
+  HostVec<int> queue(std::max<long>(std::max<long>(2*nnz, n_rows), 1));
   std::vector<int> n_coarse_b(nb, 0), rs(nb), re(nb);
 
   std::fill(f_c_row, f_c_row + n_rows, -2);
@@ -392,8 +392,8 @@ int aggregate_pw_msr(int level, int n_rows, const int *row_index, const int *col
    (kernels.cu) and the reference's row-parallel lambda (cs_grid.cpp:6040-6090). */
 void galerkin_values_host(int f_n_rows, const int *f_row_index, const int *f_col_id,
                           const double *f_d_val, const double *f_x_val, const int *f_c_row,
-                          int c_n_rows, const CoarseStructure &cs, std::vector<double> &c_d_val,
-                          std::vector<double> &c_x_val)
+                          int c_n_rows, const CoarseStructure &cs, HostVec<double> &c_d_val,
+                          HostVec<double> &c_x_val)
 {
   (void)f_n_rows;
   c_d_val.assign(std::max(c_n_rows, 1), 0.);
@@ -470,47 +470,44 @@ void build_coarse_structure(int f_n_rows, const int *f_row_index, const int *f_c
     }
   }
 
-  /* sorted, unique coarse columns per coarse row: count, scan, fill */
+  /* sorted, unique coarse columns per coarse row, in one pass: every coarse row first
+     writes its columns into an oversized array (room for all entries of its fine rows, the
+     reference's c_row_index_0, cs_grid.cpp:2966-2980), sorts and deduplicates them there;
+     a scan of the counts and a parallel copy compact the rows */
   cs.c_row_index.assign((size_t)c_n_rows + 1, 0);
   const int *cfi = cs.c_f_row_index.data(), *cfr = cs.c_f_row_ids.data();
-
-  auto gather_row = [&](int c, std::vector<int> &buf) {
-    buf.clear();
+  std::vector<long> ub((size_t)c_n_rows + 1, 0);
+  #pragma omp parallel for schedule(static)
+  for (int c = 0; c < c_n_rows; c++) {
+    long n = 0;
+    for (int r = cfi[c]; r < cfi[c+1]; r++) n += f_row_index[cfr[r]+1] - f_row_index[cfr[r]];
+    ub[(size_t)c+1] = n;
+  }
+  for (int c = 0; c < c_n_rows; c++) ub[(size_t)c+1] += ub[c];
+  HostVec<int> wide((size_t)std::max<long>(ub[c_n_rows], 1));
+  #pragma omp parallel for schedule(static)
+  for (int c = 0; c < c_n_rows; c++) {
+    int *buf = wide.data() + ub[c];
+    int n = 0;
     for (int r = cfi[c]; r < cfi[c+1]; r++) {
       const int i = cfr[r];
       for (int k = f_row_index[i]; k < f_row_index[i+1]; k++) {
         const int cc = f_c_row[f_col_id[k]];
-        if (cc > -1 && cc != c) buf.push_back(cc);
+        if (cc > -1 && cc != c) buf[n++] = cc;
       }
     }
-    std::sort(buf.begin(), buf.end());
-    buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
-  };
-
-  #pragma omp parallel
-  {
-    std::vector<int> buf;
-    buf.reserve(64);
-    #pragma omp for schedule(static)
-    for (int c = 0; c < c_n_rows; c++) {
-      gather_row(c, buf);
-      cs.c_row_index[c+1] = (int)buf.size();
-    }
+    std::sort(buf, buf + n);
+    cs.c_row_index[(size_t)c+1] = (int)(std::unique(buf, buf + n) - buf);
   }
   for (int c = 0; c < c_n_rows; c++)
     cs.c_row_index[c+1] += cs.c_row_index[c];
   const int c_nnz = cs.c_row_index[c_n_rows];
   cs.c_col_id.resize(std::max(c_nnz, 1));
-  #pragma omp parallel
-  {
-    std::vector<int> buf;
-    buf.reserve(64);
-    #pragma omp for schedule(static)
-    for (int c = 0; c < c_n_rows; c++) {
-      gather_row(c, buf);
-      std::copy(buf.begin(), buf.end(), cs.c_col_id.begin() + cs.c_row_index[c]);
-    }
-  }
+  #pragma omp parallel for schedule(static)
+  for (int c = 0; c < c_n_rows; c++)
+    std::copy(wide.data() + ub[c], wide.data() + ub[c] + (cs.c_row_index[c+1] - cs.c_row_index[c]),
+              cs.c_col_id.data() + cs.c_row_index[c]);
+  { HostVec<int>().swap(wide); }
 
   /* coarse faces = upper-triangle entries numbered in (row, column) order;
      lower-triangle entries point to the same face with sign -1 */

@@ -2,9 +2,28 @@
 #ifndef CSB_GRID_HOST_H
 #define CSB_GRID_HOST_H
 
+#include <memory>
+#include <utility>
 #include <vector>
 
 namespace csb {
+
+/* std::vector whose resize() leaves new elements uninitialised: the structure arrays of a
+   16 M-row level are hundreds of megabytes, every element is written before it is read, and
+   a zero fill by one thread costs as much as the sweep that follows (first touch by the
+   OpenMP loops instead). */
+template <typename T>
+struct NoInitAlloc : std::allocator<T> {
+  template <typename U> struct rebind { using other = NoInitAlloc<U>; };
+  NoInitAlloc() = default;
+  template <typename U> NoInitAlloc(const NoInitAlloc<U> &) {}
+  template <typename U, typename... A> void construct(U *p, A &&... a)
+  {
+    if constexpr (sizeof...(A) == 0) ::new ((void *)p) U;
+    else ::new ((void *)p) U(std::forward<A>(a)...);
+  }
+};
+template <typename T> using HostVec = std::vector<T, NoInitAlloc<T>>;
 
 /* Fine -> coarse row map of the reference's DX aggregation for a symmetric
    scalar MSR matrix (-2 never remains; -1 = penalised row).  n_blocks > 1
@@ -15,10 +34,12 @@ int aggregate_dx_msr(int level, int n_rows, const int *row_index, const int *col
                      int n_blocks, int *f_c_row);
 
 struct CoarseStructure {
-  std::vector<int>   c_f_row_index, c_f_row_ids;  /* coarse -> fine rows */
-  std::vector<int>   c_row_index, c_col_id;       /* coarse MSR structure */
-  std::vector<int>   c_cell_face;                 /* per coarse entry */
-  std::vector<short> c_cell_face_sgn;
+  std::vector<int>   c_f_row_index;               /* coarse -> fine rows */
+  HostVec<int>       c_f_row_ids;
+  std::vector<int>   c_row_index;                 /* coarse MSR structure */
+  HostVec<int>       c_col_id;
+  HostVec<int>       c_cell_face;                 /* per coarse entry */
+  HostVec<short>     c_cell_face_sgn;
   int                c_n_faces = 0;
 };
 
@@ -33,8 +54,9 @@ int aggregate_pw_msr(int level, int n_rows, const int *row_index, const int *col
 
 struct HostMsr {
   int                 n_rows = 0;
-  std::vector<int>    row_index, col_id;
-  std::vector<double> d_val, x_val;
+  std::vector<int>    row_index;
+  HostVec<int>        col_id;
+  HostVec<double>     d_val, x_val;
 };
 
 /* One coarsening step of CS_GRID_COARSENING_SPD_PW with Galerkin values: pairs, and for an

@@ -475,11 +475,19 @@ __device__ __forceinline__ void pipe_init(unsigned char *s_raw)
 /* Fill number q (counted per CTA over the whole kernel) goes to stage q % NS and is the
    (q / NS)-th use of it: the producer first waits until use q/NS - 1 has been released
    by all consumer warps; consumers wait for the fill, read, then release. */
+/* The release (mbarrier arrive by the consumer warps) / acquire (mbarrier wait here) pair
+   orders the consumers' reads of a stage before the bulk copy that refills it: no proxy
+   fence per stage.  Round 1 had a fence.proxy.async here; it also waits for the producer's
+   own row_index loads in flight -- one DRAM latency per slab on the one thread every
+   consumer waits for (ncu, profiles/r02: half of the producer warp's samples on MEMBAR /
+   FENCE.VIEW.ASYNC, consumers 35 % of theirs waiting for a stage to fill) and capped the
+   SpMV phases at ~0.75 of the HBM rate; without it they run at 0.86-0.92.  One proxy fence
+   per phase, before the first bulk copy, still orders what other CTAs stored ahead of the
+   grid barrier before this phase's bulk reads. */
 __device__ __forceinline__ void producer_acquire(const SmemView &sv, unsigned q)
 {
   const unsigned u = q / NS;
   if (u > 0) mbar_wait(&sv.pipe->empty[q % NS], (u - 1) & 1u);
-  fence_proxy_async();
 }
 __device__ __forceinline__ void consumer_wait(const SmemView &sv, unsigned q)
 { mbar_wait(&sv.pipe->full[q % NS], (q / NS) & 1u); }
@@ -517,9 +525,10 @@ __device__ __forceinline__ int epi_nv(const F &, long) { return F::NV; }
 /* GD = gather depth: register sets of x[col] values a lane keeps in flight.  2 (NG values
    each): the gathers of the next slab overlap the sums of this one.  3 (NG3 values each,
    levels whose rows have at most NG3 entries, e.g. the 7-point fine level): gathers are
-   issued TWO slabs ahead, so that a loaded L2 latency of ~2 slab times is covered -- with
-   one slab of look-ahead every consumer warp spends one full gather latency per slab and
-   the phase saturates at ~0.75 of the HBM rate (profiles/r02). */
+   issued TWO slabs ahead, so that a loaded L2 latency of ~2 slab times is covered; needs a
+   fourth stage (-DCSB_STAGES=4 -DCSB_SLAB_CAP=1648).  Measured (profiles/r02): level 0
+   0.91 against 0.88 with two sets, but the smaller stages cost the denser levels more --
+   the default build keeps two sets and three stages. */
 constexpr int NG3 = 8;
 
 template <bool SINGLE, bool GHOST, int GD, class F>
@@ -545,6 +554,7 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
     if (tid >= NWC*32) {
       /* ---------------- producer ---------------- */
       if (tid == NWC*32) {
+        fence_proxy_async();
         const int    *__restrict__ row_index = L.row_index;
         const int    *col_id = L.col_id;
         const double *x_val = L.x_val;
@@ -795,6 +805,7 @@ __device__ __noinline__ void row_phase(int n, unsigned char *s_raw, const F f, d
   if (n_my > 0) {
     if (tid >= NWC*32) {
       if (tid == NWC*32) {
+        fence_proxy_async();
         for (int j = 0; j < n_my; j++) {
           const unsigned q = base + (unsigned)j;
           unsigned char *sb = sv.stages + (q % NS)*sv.stage_bytes;
@@ -1326,6 +1337,151 @@ __device__ __noinline__ PcgResult fcg_run(const MgLevelDesc &L, const double *rh
   return R;
 }
 
+/*--------------------------------------------------------------------------
+ * PCG + Jacobi on a system small enough to LIVE in shared memory (the coarsest
+ * level of a hierarchy: tens to a few hundred rows, solved to convergence in
+ * every cycle).  pcg_run<true> streams the matrix through the bulk-copy ring
+ * again for each of the ~50 iterations and pays two pipeline fills per
+ * iteration (~3 us); here matrix and vectors are loaded once and an iteration
+ * is a few __syncthreads.  Same recurrences, same per-entry arithmetic and --
+ * thread t owns rows t, t + SLAB_ROWS_MAX, ... exactly as the lanes of the
+ * streamed phases do -- the same summation order: results are bit-identical
+ * to pcg_run<true> (checked by tests/test_gpu_r2.py).  One CTA, zero start,
+ * no ghost columns.
+ *--------------------------------------------------------------------------*/
+
+__device__ __forceinline__ bool pcg_small_fits(const MgLevelDesc &L, int small_rows)
+{
+  if (L.dist != nullptr || L.n_rows > small_rows || L.n_rows < 1) return false;
+  const int n = L.n_rows;
+  const long long nnz_max = (long long)n * L.row_len_max;
+  const long long bytes = 8ll*((n + 2)/2 + (nnz_max + 1)/2) + 8ll*nnz_max + 72ll*n + 64;
+  return bytes <= (long long)dyn_smem_bytes() - SMEM_HDR;
+}
+
+__device__ __noinline__ void pcg_small(const MgLevelDesc &L, const double *rhs, double *vx,
+                                       int n_max_iter, double precision, double r_norm,
+                                       bool smoother, ItState *st, unsigned char *s_raw)
+{
+  const int n = L.n_rows, tid = threadIdx.x, slab_rows = L.slab_rows;
+  double *s_red = (double *)s_raw;
+  unsigned char *area = s_raw + SMEM_HDR;
+  int *s_ri = (int *)area;
+  for (int i = tid; i <= n; i += PT) s_ri[i] = L.row_index[i];
+  __syncthreads();
+  const int nnz = s_ri[n];
+  int *s_col = s_ri + ((n + 2) & ~1);
+  double *s_val = (double *)(s_col + ((nnz + 1) & ~1));
+  double *s_d = s_val + nnz, *s_inv = s_d + n, *s_rhs = s_inv + n, *s_vx = s_rhs + n,
+         *rk = s_vx + n, *dk = rk + n, *gk = dk + n, *zk = gk + n, *sk = zk + n;
+  for (int k = tid; k < nnz; k += PT) { s_col[k] = L.col_id[k]; s_val[k] = L.x_val[k]; }
+  for (int i = tid; i < n; i += PT) {
+    s_d[i] = L.d_val[i]; s_inv[i] = L.ad_inv[i]; s_rhs[i] = rhs[i];
+    /* vx = 0, rk = -rhs, dk = rk * ad_inv   (cs_sles_it.cpp:1502-1516, vx = 0) */
+    s_vx[i] = 0;
+    const double rr = -rhs[i];
+    rk[i] = rr;
+    dk[i] = rr * L.ad_inv[i];
+  }
+  __syncthreads();
+
+  const bool rec = (st != nullptr) && tid == 0;
+  int n_iter = 0, cvg = CSB_SLES_ITERATING;
+  double residual = -1., initial_residual = -1.;
+  if (rec) st->n_hist = 0;
+
+  /* out = A.p in CSR order, diagonal last; dots rk.rk, rk.p, p.out (:1521-1535, :1591-1600) */
+  auto spmv_dots = [&](const double *p_, double *out, double (&v)[3]) {
+    v[0] = 0.; v[1] = 0.; v[2] = 0.;
+    if (tid < slab_rows)          /* the lanes of the streamed SpMV phase own rows t + k*slab_rows */
+      for (int i = tid; i < n; i += slab_rows) {
+        double sii = 0.0;
+        for (int k = s_ri[i]; k < s_ri[i+1]; k++) sii += s_val[k] * p_[s_col[k]];
+        const double d = p_[i];
+        const double z = sii + s_d[i]*d;
+        out[i] = z;
+        const double rr = rk[i];
+        v[0] += rr*rr; v[1] += rr*d; v[2] += d*z;
+      }
+    cta_sum_bcast<3>(v, s_red);
+  };
+
+  double v[3];
+  spmv_dots(dk, zk, v);
+  double ro_0 = v[1], ro_1 = v[2], rk_gkm1 = 0., alpha = 0., beta = 0.;
+  residual = sqrt(v[0]);
+  initial_residual = residual;
+  cvg = it_cvg_eval(precision, r_norm, n_max_iter, initial_residual, 0, residual);
+  if (rec && st->n_hist < HIST_MAX) st->hist[st->n_hist++] = residual;
+
+  if (cvg == CSB_SLES_ITERATING) {
+    n_iter = 1;
+    const double d_ro_1 = (fabs(ro_1) > DBL_MIN) ? 1. / ro_1 : 0.;
+    alpha = - ro_0 * d_ro_1;
+    rk_gkm1 = ro_0;
+    double w[1] = {0.};
+    if (tid < SLAB_ROWS_MAX)
+      for (int i = tid; i < n; i += SLAB_ROWS_MAX) {            /* :1550-1558 */
+        s_vx[i] = s_vx[i] + (alpha * dk[i]);
+        const double rr = rk[i] + (alpha * zk[i]);
+        rk[i] = rr;
+        gk[i] = rr * s_inv[i];
+        w[0] += rr*rr;
+      }
+    cta_sum_bcast<1>(w, s_red);
+    residual = sqrt(w[0]);
+    cvg = it_cvg_eval(precision, r_norm, n_max_iter, initial_residual, 1, residual);
+    if (rec && st->n_hist < HIST_MAX) st->hist[st->n_hist++] = residual;
+  }
+
+  while (cvg == CSB_SLES_ITERATING) {
+    if (smoother && n_iter >= n_max_iter) break;
+    spmv_dots(gk, sk, v);
+    const double rk_gk = v[1], gk_sk = v[2];
+    residual = sqrt(v[0]);
+    if (n_iter > 1) {
+      cvg = it_cvg_eval(precision, r_norm, n_max_iter, initial_residual, n_iter, residual);
+      if (rec && st->n_hist < HIST_MAX) st->hist[st->n_hist++] = residual;
+    }
+    if (cvg != CSB_SLES_ITERATING) break;
+    n_iter += 1;
+    beta = (fabs(rk_gkm1) > DBL_MIN) ? rk_gk / rk_gkm1 : 0.;    /* :1614-1621 */
+    rk_gkm1 = rk_gk;
+    ro_1 = gk_sk - beta*beta*ro_1;
+    ro_0 = rk_gk;
+    const double d_ro_1 = (fabs(ro_1) > DBL_MIN) ? 1. / ro_1 : 0.;
+    alpha = - ro_0 * d_ro_1;
+    const bool last = (smoother && n_iter >= n_max_iter);
+    if (tid < SLAB_ROWS_MAX)
+      for (int i = tid; i < n; i += SLAB_ROWS_MAX) {            /* :1623-1631 */
+        const double d = gk[i] + (beta * dk[i]);
+        s_vx[i] = s_vx[i] + alpha * d;
+        if (!last) {
+          dk[i] = d;
+          const double z = sk[i] + (beta * zk[i]);
+          zk[i] = z;
+          const double rr = rk[i] + alpha * z;
+          rk[i] = rr;
+          gk[i] = rr * s_inv[i];
+        }
+      }
+    __syncthreads();
+  }
+
+  for (int i = tid; i < n; i += PT) vx[i] = s_vx[i];
+  if (rec) {
+    st->precision = precision; st->r_norm = r_norm;
+    st->residual = residual; st->initial_residual = initial_residual;
+    st->n_iter = n_iter; st->n_max_iter = n_max_iter; st->cvg = cvg;
+    st->alpha = alpha; st->beta = beta; st->ro_0 = ro_0; st->ro_1 = ro_1;
+    st->rk_gkm1 = rk_gkm1;
+    st->n_halo = 0;
+  }
+  /* the stage area goes back to the bulk-copy rings */
+  __syncthreads();
+  fence_proxy_async();
+}
+
 __global__ void __launch_bounds__(PT, CSB_MIN_CTAS)
 k_fcg_persistent(const MgLevelDesc L, const double *rhs, double *vx, int vx_ini_nonzero,
                  int n_max_iter, double precision, double r_norm,
@@ -1715,10 +1871,15 @@ k_mg_persistent(const MgSolveParams S, const PersistentCommon P)
       const bool single = (L.n_rows <= S.single_rows);
       PcgResult R;
       if (single) {
-        if (blockIdx.x == 0)
-          R = pcg_run<true>(L, rhs_lv, vx_lv, false, S.n_max_iter[2],
-                            S.precision*S.precision_mult[2], S.r_norm, true, P,
-                            L.st_descent, s_raw, ms->prof_it[coarsest < PROF_LEVELS ? coarsest : PROF_LEVELS-1]);
+        if (blockIdx.x == 0) {
+          if (P.comm == nullptr && pcg_small_fits(L, S.small_rows))
+            pcg_small(L, rhs_lv, vx_lv, S.n_max_iter[2], S.precision*S.precision_mult[2],
+                      S.r_norm, true, L.st_descent, s_raw);
+          else
+            R = pcg_run<true>(L, rhs_lv, vx_lv, false, S.n_max_iter[2],
+                              S.precision*S.precision_mult[2], S.r_norm, true, P,
+                              L.st_descent, s_raw, ms->prof_it[coarsest < PROF_LEVELS ? coarsest : PROF_LEVELS-1]);
+        }
         grid_barrier(P.barrier);
         R.n_iter = *((volatile int *)&L.st_descent->n_iter);
         R.cvg = *((volatile int *)&L.st_descent->cvg);
@@ -2238,9 +2399,14 @@ k_fcg_mg_persistent(const FcgMgParams S, const PersistentCommon P)
         const MgLevelDesc &L = LV[coarsest];
         PersistentCommon Pl = P;
         if (L.dist == nullptr) Pl.comm = nullptr;   /* merged level: this rank alone */
-        pcg_run<true>(L, (coarsest == 0) ? rk : L.rhs, (coarsest == 0) ? vk : L.vx, false,
-                      S.coarse_n_max_iter, S.precision*S.coarse_precision_mult, S.r_norm, true,
-                      Pl, L.st_descent, s_raw);
+        if (Pl.comm == nullptr && pcg_small_fits(L, S.small_rows))
+          pcg_small(L, (coarsest == 0) ? rk : L.rhs, (coarsest == 0) ? vk : L.vx,
+                    S.coarse_n_max_iter, S.precision*S.coarse_precision_mult, S.r_norm, true,
+                    L.st_descent, s_raw);
+        else
+          pcg_run<true>(L, (coarsest == 0) ? rk : L.rhs, (coarsest == 0) ? vk : L.vx, false,
+                        S.coarse_n_max_iter, S.precision*S.coarse_precision_mult, S.r_norm, true,
+                        Pl, L.st_descent, s_raw);
         __syncthreads();
         pf.mark(coarsest, MG_PROF_COARSEST);
         for (int level = coarsest - 1; level >= ls; level--)
@@ -2330,19 +2496,22 @@ k_fcg_mg_persistent(const FcgMgParams S, const PersistentCommon P)
 
 } // anonymous namespace
 
-int plan_gather_depth(const std::vector<csb_lnum_t> &ri, int n_rows)
+int plan_gather_depth(const std::vector<csb_lnum_t> &ri, int n_rows, int *row_len_max)
 {
   static int want = -1;
   if (want < 0) {
     const char *s = getenv("CSB_GATHER_DEPTH");
     want = (s != nullptr) ? atoi(s) : ((NS >= 4) ? 3 : 2);
   }
+  int mx = 1 << 30;
+  if ((size_t)n_rows + 1 <= ri.size()) {
+    mx = 0;
+    for (int i = 0; i < n_rows; i++) mx = std::max(mx, (int)(ri[i+1] - ri[i]));
+  }
+  if (row_len_max != nullptr) *row_len_max = mx;
   /* three register sets need a fourth stage in flight (the stage two slabs ahead must have
      landed while the oldest one is still being summed) and rows of at most NG3 entries */
-  if (want != 3 || NS < 4 || (size_t)n_rows + 1 > ri.size()) return 2;
-  int mx = 0;
-  for (int i = 0; i < n_rows; i++) mx = std::max(mx, (int)(ri[i+1] - ri[i]));
-  return (mx <= NG3) ? 3 : 2;
+  return (want == 3 && NS >= 4 && mx <= NG3) ? 3 : 2;
 }
 
 void plan_slabs(const std::vector<csb_lnum_t> &ri, int n_rows, int &slab_rows, int &n_slabs,
@@ -2505,7 +2674,7 @@ bool launch_spmv_pipeline(const _csb_matrix_t *m, const double *x, double *y, bo
     if ((size_t)m->h_row_index.size() == (size_t)m->n_rows + 1 && m->n_rows > 0) {
       size_t max_entries = 0;
       plan_slabs(m->h_row_index, m->n_rows, m->pl_slab_rows, m->pl_n_slabs, max_entries);
-      m->pl_gdepth = plan_gather_depth(m->h_row_index, m->n_rows);
+      m->pl_gdepth = plan_gather_depth(m->h_row_index, m->n_rows, &m->pl_row_len_max);
       m->pl_smem = persistent_smem_bytes(max_entries);
       int optin = 0, occ = 0;
       cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device);
@@ -2528,7 +2697,7 @@ bool launch_spmv_pipeline(const _csb_matrix_t *m, const double *x, double *y, bo
   MgLevelDesc L;
   memset(&L, 0, sizeof(L));
   L.n_rows = m->n_rows; L.n_slabs = m->pl_n_slabs; L.slab_rows = m->pl_slab_rows;
-  L.gather_depth = m->pl_gdepth;
+  L.gather_depth = m->pl_gdepth; L.row_len_max = m->pl_row_len_max;
   L.row_index = m->row_index.p; L.col_id = m->col_id.p;
   L.d_val = m->d_val.p; L.x_val = m->x_val.p;
   k_spmv_pipeline<<<m->pl_grid, PT, m->pl_smem, c.stream>>>(L, x, y, exclude_diag ? 1 : 0);

@@ -14,6 +14,7 @@ struct MgLevelDesc {
   int           n_rows_next;
   int           level_id;      /* index of the level (slot of its exchange counter) */
   int           gather_depth;  /* 2, or 3 when no row has more than 8 entries (persistent.cu) */
+  int           row_len_max;   /* longest row (entries) */
   const int    *row_index;
   const int    *col_id;
   const double *d_val;
@@ -54,6 +55,7 @@ struct MgSolveParams {
   double             precision_mult[3];
   double             precision, r_norm;
   int                single_rows;  /* levels up to this size run in one CTA */
+  int                small_rows;   /* coarsest level up to this size: shared-memory PCG */
 };
 
 /* Sweep schedule of a Jacobi-family cs_multigrid_smoother (cs_multigrid_smoother.cpp:143-373,
@@ -79,6 +81,7 @@ struct FcgMgParams {
   int                coarse_n_max_iter;    /* coarsest-level PCG */
   double             coarse_precision_mult;
   int                single_rows;          /* levels up to this size run in one CTA */
+  int                small_rows;           /* coarsest level up to this size: shared-memory PCG */
   double            *wr, *tmp;             /* residual; second sweep buffer (level-0 sized) */
   double            *fwork;                /* FCG vectors rk vk wk dk qk */
   size_t             fstride;
@@ -116,7 +119,7 @@ bool launch_spmv_pipeline(const _csb_matrix_t *m, const double *x, double *y, bo
                           bool *launched);
 
 /* gather depth of the SpMV phases for a matrix with these row lengths (CSB_GATHER_DEPTH) */
-int plan_gather_depth(const std::vector<csb_lnum_t> &row_index, int n_rows);
+int plan_gather_depth(const std::vector<csb_lnum_t> &row_index, int n_rows, int *row_len_max);
 
 /* choose the slab height of a level so that a slab's products fit in ~40 KB */
 void plan_slabs(const std::vector<csb_lnum_t> &row_index, int n_rows, int &slab_rows,

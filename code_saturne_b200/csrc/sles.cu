@@ -749,7 +749,7 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
       if (!pcomm_allreduce(c->pcomm, &d.n_g_rows, 1)) return;
     }
     plan_slabs(a->h_row_index, a->n_rows, d.slab_rows, d.n_slabs, max_entries);
-    d.gather_depth = plan_gather_depth(a->h_row_index, a->n_rows);
+    d.gather_depth = plan_gather_depth(a->h_row_index, a->n_rows, &d.row_len_max);
     d.n_rows = a->n_rows;
     d.row_index = a->row_index.p; d.col_id = a->col_id.p;
     d.d_val = a->d_val.p; d.x_val = a->x_val.p; d.ad_inv = c->ad_inv.p;
@@ -827,6 +827,7 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
       S.rhs = s_rhs.d; S.vx = s_vx.d; S.vx_ini_nonzero = ini ? 1 : 0;
       S.n_max_iter = c->n_max_iter; S.precision = precision; S.r_norm = r_norm;
       S.single_rows = sb_rows_threshold();
+      S.small_rows = env_int("CSB_PCG_SMALL_ROWS", 448);
       S.fwork = c->work.p; S.fstride = work_stride_of((size_t)a->n_cols_ext);
       P.partials = c->partials.p; P.barrier = c->barrier.p;
       if (!launch_mg_state_init(S.ms, precision, r_norm, 1)) return CSB_SLES_BREAKDOWN;
@@ -2068,7 +2069,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
       const csb_matrix_t *m = lv->m;
       size_t me = 0;
       plan_slabs(m->h_row_index, m->n_rows, d.slab_rows, d.n_slabs, me);
-      d.gather_depth = plan_gather_depth(m->h_row_index, m->n_rows);
+      d.gather_depth = plan_gather_depth(m->h_row_index, m->n_rows, &d.row_len_max);
       max_entries = std::max(max_entries, me);
       d.n_rows = m->n_rows;
       /* rows of the next level THIS rank restricts to: at the merge boundary its own part
@@ -2210,6 +2211,7 @@ csb_multigrid_solve(void *context, const char *name, const csb_matrix_t *a, int 
     }
     S.precision = precision; S.r_norm = r_norm;
     S.single_rows = sb_rows_threshold();
+    S.small_rows = env_int("CSB_PCG_SMALL_ROWS", 448);
     PersistentCommon P;
     P.work = mg->aux.p; P.work_stride = work_stride_of((size_t)a->n_cols_ext);
     P.partials = mg->partials.p; P.barrier = mg->barrier.p;

@@ -23,7 +23,7 @@ bool launch_fcg_mg_persistent(const FcgMgParams &, const PersistentCommon &, int
 { return no("k_fcg_mg_persistent"); }
 bool launch_spmv_pipeline(const _csb_matrix_t *, const double *, double *, bool, bool *launched)
 { *launched = false; return true; }
-int plan_gather_depth(const std::vector<csb_lnum_t> &, int) { return 2; }
+int plan_gather_depth(const std::vector<csb_lnum_t> &, int, int *m) { if (m) *m = 64; return 2; }
 void plan_slabs(const std::vector<csb_lnum_t> &, int n_rows, int &slab_rows, int &n_slabs,
                 size_t &max_entries)
 { slab_rows = 224; n_slabs = (n_rows + 223)/224; max_entries = 2432; }

@@ -267,3 +267,25 @@ def test_failed_setup_leaves_multigrid_reusable(csb):
     assert int(a["cvg"]) == 1 and a["n_cycles"] == b["n_cycles"]
     assert np.array_equal(a["vx"], b["vx"])
     mg.destroy(); fresh.destroy(); m.destroy(); mb.destroy()
+
+
+def test_shared_memory_coarse_pcg_is_bit_identical_to_streamed(csb, monkeypatch):
+    """pcg_small (coarsest level resident in shared memory) follows the arithmetic and the
+    summation order of the streamed single-CTA PCG: same bits, V-cycle solver and FCG."""
+    out = {}
+    for N, bc in ((20, "neumann"), (32, "dirichlet")):
+        s = cube_poisson(N, bc)
+        r_norm = float(np.linalg.norm(s.rhs))
+        m = csb.Matrix.from_system(s)
+        for small in ("0", "448"):
+            monkeypatch.setenv("CSB_PCG_SMALL_ROWS", small)
+            mg = csb.Multigrid()
+            mg.setup(m)
+            r = mg.solve(m, s.rhs, 1e-10, r_norm)
+            f = _fcg(csb, m, s, 1e-10, r_norm, csb.Multigrid(pc=True), multi=False)
+            out[(N, small)] = (r["vx"].copy(), r["n_cycles"], f["vx"].copy(), f["n_iter"])
+            mg.destroy()
+        a, b = out[(N, "0")], out[(N, "448")]
+        assert a[1] == b[1] and a[3] == b[3]
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+        m.destroy()
