@@ -387,6 +387,63 @@ def main():
         t_spmv = e0.elapsed_time(e1) * 1e-3 / args.spmv_launches
     clocks = sampler.summary()
 
+    # ---- the bar SURVEY.md 2.5 sets for the SpMV kernel (N = 1): the reference's own device
+    # kernel `_mat_vect_p_l_msr` compiled for sm_100a and its cuSPARSE sequence
+    # (oracle/ref_spmv_cuda.cu, test infrastructure), same matrix, same run, same stream
+    spmv_bar = {}
+    refcu = os.path.join(ROOT, "oracle", "_ref", "libref_spmv_cuda.so")
+    if world == 1 and os.path.exists(refcu):
+        try:
+            import ctypes as C
+            RL = C.CDLL(refcu, mode=os.RTLD_LAZY)
+            RL.csref_cusparse_msr_create.restype = C.c_void_p
+            ri_d = torch.from_numpy(np.ascontiguousarray(s.row_index, dtype=np.int32)).cuda()
+            ci_d = torch.from_numpy(np.ascontiguousarray(s.col_id, dtype=np.int32)).cuda()
+            dv_d = torch.from_numpy(np.ascontiguousarray(s.d_val)).cuda()
+            xv_d = torch.from_numpy(np.ascontiguousarray(s.x_val)).cuda()
+            y_r = torch.empty_like(y_d)
+            sp = C.c_void_p(stream.cuda_stream)
+            p = lambda t: C.c_void_p(t.data_ptr())
+            m.vector_multiply(x_d, y_d)
+
+            def timed(fn):
+                for _ in range(5):
+                    fn()
+                barrier()
+                e0.record(stream)
+                for _ in range(args.spmv_launches):
+                    fn()
+                e1.record(stream)
+                barrier()
+                return e0.elapsed_time(e1) * 1e-3 / args.spmv_launches
+
+            t_ref = timed(lambda: RL.csref_cuda_spmv_msr(s.n_rows, p(ri_d), p(ci_d), p(dv_d),
+                                                         p(xv_d), p(x_d), p(y_r), sp))
+            err_ref = float((y_r - y_d).abs().max() / y_d.abs().max())
+            h = C.c_void_p(RL.csref_cusparse_msr_create(s.n_rows, s.n_rows, int(s.nnz), p(ri_d),
+                                                        p(ci_d), p(dv_d), p(xv_d), p(x_d),
+                                                        p(y_r), sp))
+            if h:
+                t_cus = timed(lambda: RL.csref_cusparse_msr_spmv(h, p(x_d), p(y_r), sp))
+                err_cus = float((y_r - y_d).abs().max() / y_d.abs().max())
+                RL.csref_cusparse_msr_destroy(h)
+            else:
+                t_cus, err_cus = None, None
+            nb = m.spmv_bytes()
+            spmv_bar = {
+                "reference_kernel": "_mat_vect_p_l_msr (cs_matrix_spmv_cuda.cu:415-439) "
+                                    "compiled for sm_100a, 256 threads per block",
+                "reference_kernel_ms": t_ref * 1e3, "reference_kernel_gbs": nb / t_ref / 1e9,
+                "reference_kernel_max_rel_diff": err_ref,
+                "cusparse": "_mat_vect_p_l_msr_diag + cusparseSpMV(ALG_DEFAULT, beta = 1) on the "
+                            "extra-diagonal CSR part, as cs_matrix_spmv_cuda.cu:1540-1615",
+                "cusparse_ms": (t_cus * 1e3) if t_cus else None,
+                "cusparse_gbs": (nb / t_cus / 1e9) if t_cus else None,
+                "cusparse_max_rel_diff": err_cus}
+            del ri_d, ci_d, dv_d, xv_d, y_r
+        except Exception as e:        # test infrastructure: reported, never required
+            spmv_bar = {"unavailable": str(e)[:300]}
+
     # true residual of the last device solve (not timed)
     m.vector_multiply(vx_d, y_d)
     tr = torch.tensor([float(torch.sum((rhs_d - y_d) ** 2).item())], dtype=torch.float64,
@@ -501,7 +558,8 @@ def main():
                          "ms_per_launch": t_dev * 1e3, "peak_source": peak_src,
                          "launches_timed": args.steps,
                          "in_kernel_phase_seconds": float(pt.sum())},
-            "spmv": {"kernel": "k_spmv_stream (level-0 MSR SpMV, stand-alone"
+            "spmv": {"kernel": "k_spmv_pipeline (level-0 MSR SpMV, stand-alone: the bulk-copy "
+                               "pipeline of the solvers' SpMV phases"
                                + (", per GPU, incl. ghost exchange)" if world > 1 else ")"),
                      "achieved": spmv_gbs, "frac": spmv_gbs / peak, "unit": "GB/s",
                      "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": t_spmv * 1e3},
@@ -522,6 +580,7 @@ def main():
                 "columns": ["descent", "residual", "restrict", "coarsest", "prolong", "ascent"],
                 "fcg_spmv_4dots_us": round(float(itp[0, 1]) / n_cyc * 1e6, 1),
                 "fcg_update_us": round(float(itp[0, 2]) / max(int(r["n_iter"]), 1) * 1e6, 1)}
+        line["spmv"].update(spmv_bar)
         line.update(extra)
         if cpu is not None:
             line["cpu_baseline"] = cpu

@@ -22,6 +22,8 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include <omp.h>
 
 namespace csb {
@@ -455,6 +457,10 @@ int coarsen_pairwise_galerkin(int level, int n_rows, const int *row_index, const
 void build_coarse_structure(int f_n_rows, const int *f_row_index, const int *f_col_id,
                             const int *f_c_row, int c_n_rows, CoarseStructure &cs)
 {
+  const bool tm = (getenv("CSB_SETUP_TIMES") != nullptr);
+  double t_[8]; int ti_ = 0;
+  auto mark = [&]() { if (tm) t_[ti_++] = omp_get_wtime(); };
+  mark();
   /* coarse -> fine rows, ascending fine ids inside each coarse row */
   cs.c_f_row_index.assign((size_t)c_n_rows + 1, 0);
   cs.c_f_row_ids.resize(std::max(f_n_rows, 1));
@@ -470,6 +476,7 @@ void build_coarse_structure(int f_n_rows, const int *f_row_index, const int *f_c
     }
   }
 
+  mark();
   /* sorted, unique coarse columns per coarse row, in one pass: every coarse row first
      writes its columns into an oversized array (room for all entries of its fine rows, the
      reference's c_row_index_0, cs_grid.cpp:2966-2980), sorts and deduplicates them there;
@@ -484,6 +491,7 @@ void build_coarse_structure(int f_n_rows, const int *f_row_index, const int *f_c
     ub[(size_t)c+1] = n;
   }
   for (int c = 0; c < c_n_rows; c++) ub[(size_t)c+1] += ub[c];
+  mark();
   HostVec<int> wide((size_t)std::max<long>(ub[c_n_rows], 1));
   #pragma omp parallel for schedule(static)
   for (int c = 0; c < c_n_rows; c++) {
@@ -499,6 +507,7 @@ void build_coarse_structure(int f_n_rows, const int *f_row_index, const int *f_c
     std::sort(buf, buf + n);
     cs.c_row_index[(size_t)c+1] = (int)(std::unique(buf, buf + n) - buf);
   }
+  mark();
   for (int c = 0; c < c_n_rows; c++)
     cs.c_row_index[c+1] += cs.c_row_index[c];
   const int c_nnz = cs.c_row_index[c_n_rows];
@@ -508,6 +517,7 @@ void build_coarse_structure(int f_n_rows, const int *f_row_index, const int *f_c
     std::copy(wide.data() + ub[c], wide.data() + ub[c] + (cs.c_row_index[c+1] - cs.c_row_index[c]),
               cs.c_col_id.data() + cs.c_row_index[c]);
   { HostVec<int>().swap(wide); }
+  mark();
 
   /* coarse faces = upper-triangle entries numbered in (row, column) order;
      lower-triangle entries point to the same face with sign -1 */
@@ -542,6 +552,12 @@ void build_coarse_structure(int f_n_rows, const int *f_row_index, const int *f_c
       const int *p = std::lower_bound(b, e, c);
       cs.c_cell_face[k] = cs.c_cell_face[p - cs.c_col_id.data()];
     }
+  }
+  mark();
+  if (tm) {
+    fprintf(stderr, "[csb200] coarse structure %d -> %d rows:", f_n_rows, c_n_rows);
+    for (int i = 1; i < ti_; i++) fprintf(stderr, " %.3f", t_[i] - t_[i-1]);
+    fprintf(stderr, " s (c->f adjacency, bounds, gather+sort, compact, faces)\n");
   }
 }
 

@@ -609,10 +609,12 @@ bool ensure_partials(int n_blocks);
 static bool spmv_pipeline_enabled()
 {
   static int v = -1;
-  /* measured at 256^3: 0.339 ms (pipeline) vs 0.335 ms (k_spmv_stream) per launch -- a
-     stand-alone launch pays the pipeline fill once per call, so the streaming kernel
-     stays the default; CSB_SPMV_PIPELINE=1 selects the pipeline kernel */
-  if (v < 0) { const char *e = getenv("CSB_SPMV_PIPELINE"); v = (e != nullptr && atoi(e) != 0) ? 1 : 0; }
+  /* measured at 256^3 (profiles/r02): the bulk-copy pipeline kernel -- the code of the
+     solvers' SpMV phases -- runs y = A.x at ~0.88 of the measured HBM rate since its
+     producer no longer fences per stage, k_spmv_stream at 0.75: the pipeline is the
+     default, CSB_SPMV_PIPELINE=0 selects the streaming kernel (which also remains for
+     buffers the pipeline cannot take) */
+  if (v < 0) { const char *e = getenv("CSB_SPMV_PIPELINE"); v = (e != nullptr && atoi(e) == 0) ? 0 : 1; }
   return v == 1;
 }
 
