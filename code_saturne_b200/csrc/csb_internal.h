@@ -184,6 +184,11 @@ struct DistLevel {
   unsigned  *count;                        /* exchanges done so far (rank-private) */
   unsigned  *ticket;                       /* CTA arrival counter (rank-private) */
   unsigned long long timeout_ns;
+  /* overlap of the exchange with the rows that need no ghost value (persistent.cu,
+     spmv_phase_g): bit r of bmask = row r has ghost columns; bsum[r] = its parked sum */
+  const unsigned *bmask;
+  double    *bsum;
+  int        overlap;
 };
 
 /* Coarse levels merged onto rank 0 (cs_grid_merge_ranks, src/alge/cs_grid_rank_merge.cpp:1359;

@@ -306,9 +306,12 @@ __device__ __forceinline__ const double *halo_exchange(const MgLevelDesc &L, con
       for (int e = s0 + first; e < s1; e += step)
         dst[e - s0] = x[send_list[e]];
     }
-    fence_sys();
+    /* one system-scope fence per CTA, by the thread that takes the ticket: the CTA barrier
+       orders the other threads' peer stores before it (cumulativity); 256 concurrent
+       MEMBAR.SYS per CTA were a large part of the exchange's cost at 8 GPUs */
     __syncthreads();
     if (threadIdx.x == 0) {
+      fence_sys();
       bool last = true;
       if (!SINGLE) last = (atomicInc(D->ticket, n_pack - 1) == n_pack - 1);
       if (last) {
@@ -319,13 +322,25 @@ __device__ __forceinline__ const double *halo_exchange(const MgLevelDesc &L, con
       }
     }
   }
-  if (threadIdx.x < n_dom) {
+  /* the wait for the neighbours' values is the SpMV phase's (halo_wait): with
+     D->overlap it comes after the rows that need no ghost value have been summed */
+  return D->gbuf[par];
+}
+
+/* second half of the exchange started by halo_exchange: wait until every neighbour has
+   published this exchange's count */
+__device__ __forceinline__ void halo_wait(const MgLevelDesc &L)
+{
+  const DistLevel *D = L.dist;
+  unsigned *s_hk = (unsigned *)(s_raw_base + HALO_K_OFF) + L.level_id;
+  const unsigned k = *s_hk + 1;
+  if (threadIdx.x < D->n_dom) {
     spin_until_ge(D->flag_local + threadIdx.x, k, D->timeout_ns, 7);
     fence_gpu();
   }
   __syncthreads();
   if (threadIdx.x == 0) *s_hk = k;      /* read again only after further CTA barriers */
-  return D->gbuf[par];
+  __syncthreads();
 }
 
 __device__ __forceinline__ unsigned halo_count(const MgLevelDesc &L)
@@ -537,8 +552,8 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
                                           const F f, double *acc_out)
 {
   constexpr int NGS = (GD == 3) ? NG3 : NG;      /* gathers per register set */
-  /* column c < n_rows: x[c]; ghost column: ghost[c - n_rows] */
-  const double *xg = GHOST ? ghost - L.n_rows : x;
+  constexpr int PARKED = 0x40000000;             /* flag carried in the row's start offset */
+  double *bsum = GHOST ? L.dist->bsum : nullptr; /* parked row sums, by row */
   const int tid = threadIdx.x;
   const int first = SINGLE ? 0 : blockIdx.x;
   const int step = SINGLE ? 1 : gridDim.x;
@@ -549,6 +564,16 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
   const int off_val = 4*(sv.cap + 4), off_ri = off_val + 8*(sv.cap + 2),
             off_ops = off_ri + ST_RI_BYTES;
   double acc[4] = {0., 0., 0., 0.};
+
+  /* GHOST: the exchange of x has been STARTED (halo_exchange); its values are needed by the
+     rows that have ghost columns only (a few per cent: the faces of the brick).  Those rows
+     are summed over their local columns here -- ghost columns come last in a row, so this is
+     the head of the row's CSR-order sum -- and parked in bsum; everything else runs to its
+     epilogue while the neighbours' stores cross NVLink.  The wait comes after the main
+     pass, then the parked rows get their ghost terms and their epilogue (the reference's
+     overlap of halo exchange and local product, _mat_vec_p_l_dist
+     cs_matrix_spmv.cpp:3092-3112).  CSB_HALO_OVERLAP=0: wait first (same code, for A/B). */
+  if (GHOST && !L.dist->overlap) halo_wait(L);
 
   if (n_my > 0) {
     if (tid >= NWC*32) {
@@ -609,23 +634,28 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
         int ks = 0, ke = 0;
         if (tid < rows) { ks = s_ri[tid] - k0; ke = s_ri[tid + 1] - k0; }
         const int *s_col = (const int *)sb + (k0 & 3);
+        /* GHOST: the row's local entries end where its ghost columns (sorted last) begin */
+        int hg = 0;
+        if (GHOST) {
+          const int ke_all = ke;
+          while (ke > ks && s_col[ke - 1] >= n_rows) ke--;
+          hg = (ke < ke_all) ? PARKED : 0;
+        }
 #pragma unroll
         for (int e = 0; e < NGS; e++) {
           double v = 0.;
-          if (ks + e < ke) {
-            const int c = s_col[ks + e];
-            const double *px = (!GHOST || c < n_rows) ? x : xg;   /* one load, selected base */
-            v = px[c];
-          }
+          if (ks + e < ke) v = x[s_col[ks + e]];
           gg[e] = v;
         }
-        pks = ks + (k0 & 1);        /* x_val is staged from an even entry */
+        pks = (ks + (k0 & 1)) | hg;  /* x_val is staged from an even entry */
         pke = ke + (k0 & 1);
       };
       auto consume = [&](int j, const double (&gg)[NGS], int ks, int ke) {
         const unsigned q = base + (unsigned)j;
         const unsigned char *sb = sv.stages + (q % NS)*sv.stage_bytes;
         const int r0 = (first + j*step)*slab_rows;
+        const bool parked = (ks & PARKED) != 0;
+        ks &= ~PARKED;
         if (tid < min(slab_rows, n_rows - r0)) {
           const double *s_val = (const double *)(sb + off_val);
           double sii = 0.0;
@@ -645,11 +675,7 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
 #pragma unroll
               for (int e = 0; e < NT; e++) {
                 double v = 0.;
-                if (kb + e < ke) {
-                  const int c = s_col[kb + e];
-                  const double *px = (!GHOST || c < n_rows) ? x : xg;
-                  v = px[c];
-                }
+                if (kb + e < ke) v = x[s_col[kb + e]];
                 gt[e] = v;
               }
 #pragma unroll
@@ -657,7 +683,8 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
                 if (kb + e < ke) sii += s_val[kb + e] * gt[e];
             }
           }
-          f.epi(r0 + tid, sii, (const double *)(sb + off_ops) + tid, acc);
+          if (GHOST && parked) bsum[r0 + tid] = sii;
+          else f.template epi<ST_OP_STRIDE>(r0 + tid, sii, (const double *)(sb + off_ops) + tid, acc);
         }
         consumer_release(sv, q);
       };
@@ -716,6 +743,32 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
     if (tid == 0) sv.pipe->base = base + (unsigned)n_my;
     __syncthreads();
   }
+
+  if (GHOST) {
+    /* the neighbours' values (or: they were waited for before the main pass) */
+    if (L.dist->overlap) halo_wait(L);
+    /* parked rows of this CTA's slabs, in a fixed order per thread: + the ghost terms (the
+       tail of the row in CSR order), then the epilogue with operands read in place */
+    const unsigned *__restrict__ bmask = L.dist->bmask;
+    const int n_ops = epi_nv(f, 0);
+    const int tot = n_my * slab_rows;
+    for (int idx = tid; idx < tot; idx += PT) {
+      const int j = idx / slab_rows;
+      const int r = (first + j*step)*slab_rows + (idx - j*slab_rows);
+      if (r < n_rows && ((bmask[r >> 5] >> (r & 31)) & 1u)) {
+        double sii = bsum[r];
+        const int ke = L.row_index[r+1];
+        for (int k = L.row_index[r]; k < ke; k++) {
+          const int c = L.col_id[k];
+          if (c >= n_rows) sii += L.x_val[k] * ghost[c - n_rows];
+        }
+        double opv[F::NV > 0 ? F::NV : 1];
+#pragma unroll
+        for (int v = 0; v < F::NV; v++) opv[v] = (v < n_ops) ? f.src(v)[r] : 0.;
+        f.template epi<1>(r, sii, opv, acc);
+      }
+    }
+  }
   if (acc_out != nullptr) {
     acc_out[0] = acc[0]; acc_out[1] = acc[1]; acc_out[2] = acc[2]; acc_out[3] = acc[3];
   }
@@ -741,11 +794,12 @@ struct EpiInitResidual {
   double *rk, *dk;
   __device__ __forceinline__ const double *src(int v) const
   { return (v == 0) ? d_val : (v == 1) ? vx : (v == 2) ? rhs : ad_inv; }
+  template <int S>
   __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&)[4]) const
   {
-    const double rr = (sii + op[0]*op[ST_OP_STRIDE]) - op[2*ST_OP_STRIDE];
+    const double rr = (sii + op[0]*op[S]) - op[2*S];
     rk[r] = rr;
-    dk[r] = rr * op[3*ST_OP_STRIDE];
+    dk[r] = rr * op[3*S];
   }
 };
 
@@ -756,12 +810,13 @@ struct EpiDots {
   double *out;
   __device__ __forceinline__ const double *src(int v) const
   { return (v == 0) ? d_val : (v == 1) ? p : rk; }
+  template <int S>
   __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&acc)[4]) const
   {
-    const double d = op[ST_OP_STRIDE];
+    const double d = op[S];
     const double z = sii + op[0]*d;
     out[r] = z;
-    const double rr = op[2*ST_OP_STRIDE];
+    const double rr = op[2*S];
     acc[0] += rr*rr; acc[1] += rr*d; acc[2] += d*z;
   }
 };
@@ -773,10 +828,11 @@ struct EpiResidual {
   double *wr;
   __device__ __forceinline__ const double *src(int v) const
   { return (v == 0) ? d_val : (v == 1) ? vx : rhs; }
+  template <int S>
   __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&acc)[4]) const
   {
-    const double y = sii + op[0]*op[ST_OP_STRIDE];
-    const double t = op[2*ST_OP_STRIDE] - y;
+    const double y = sii + op[0]*op[S];
+    const double t = op[2*S] - y;
     wr[r] = t;
     acc[0] += t*t;
   }
@@ -1190,12 +1246,13 @@ struct EpiFcgInit {
   double *rk, *qk, *vk;
   __device__ __forceinline__ const double *src(int v) const
   { return (v == 0) ? d_val : (v == 1) ? vx : (v == 2) ? rhs : ad_inv; }
+  template <int S>
   __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&)[4]) const
   {
-    const double rr = op[2*ST_OP_STRIDE] - (sii + op[0]*op[ST_OP_STRIDE]);
+    const double rr = op[2*S] - (sii + op[0]*op[S]);
     rk[r] = rr;
     qk[r] = 0;
-    vk[r] = rr * op[3*ST_OP_STRIDE];
+    vk[r] = rr * op[3*S];
   }
 };
 
@@ -1206,13 +1263,14 @@ struct EpiFcg {
   double *wk;
   __device__ __forceinline__ const double *src(int v) const
   { return (v == 0) ? d_val : (v == 1) ? vk : (v == 2) ? rk : qk; }
+  template <int S>
   __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&acc)[4]) const
   {
-    const double v = op[ST_OP_STRIDE];
+    const double v = op[S];
     const double w = sii + op[0]*v;
     wk[r] = w;
-    const double rr = op[2*ST_OP_STRIDE];
-    acc[0] += rr*v; acc[1] += w*v; acc[2] += v*op[3*ST_OP_STRIDE]; acc[3] += rr*rr;
+    const double rr = op[2*S];
+    acc[0] += rr*v; acc[1] += w*v; acc[2] += v*op[3*S]; acc[3] += rr*rr;
   }
 };
 
@@ -1514,10 +1572,11 @@ struct EpiIpcgInit {
   double *rk, *gk, *dk;
   __device__ __forceinline__ const double *src(int v) const
   { return (v == 0) ? d_val : (v == 1) ? vx : (v == 2) ? rhs : ad_inv; }
+  template <int S>
   __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&acc)[4]) const
   {
-    const double rr = (sii + op[0]*op[ST_OP_STRIDE]) - op[2*ST_OP_STRIDE];
-    const double g = rr * op[3*ST_OP_STRIDE];
+    const double rr = (sii + op[0]*op[S]) - op[2*S];
+    const double g = rr * op[3*S];
     rk[r] = rr; gk[r] = g; dk[r] = g;
     acc[0] += rr*rr; acc[1] += rr*g;
   }
@@ -1715,14 +1774,16 @@ struct EpiStore {            /* y = E.x + d*x  (diagonal last, :2138-2142) */
   const double *d_val, *x;
   double *y;
   __device__ __forceinline__ const double *src(int v) const { return (v == 0) ? d_val : x; }
+  template <int S>
   __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&)[4]) const
-  { y[r] = sii + op[0]*op[ST_OP_STRIDE]; }
+  { y[r] = sii + op[0]*op[S]; }
 };
 
 struct EpiStoreExDiag {      /* y = E.x */
   static constexpr int NV = 0;
   double *y;
   __device__ __forceinline__ const double *src(int) const { return nullptr; }
+  template <int S>
   __device__ __forceinline__ void epi(int r, double sii, const double *, double (&)[4]) const
   { y[r] = sii; }
 };
@@ -1991,18 +2052,19 @@ struct EpiSmooth {
   { return (mode == SMOOTH_JACOBI) ? 2 : (mode == SMOOTH_RELAXED) ? 3 : 4; }
   __device__ __forceinline__ const double *src(int v) const
   { return (v == 0) ? rhs : (v == 1) ? inv : (v == 2) ? xold : d_val; }
+  template <int S>
   __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&)[4]) const
   {
-    const double b = op[0], iv = op[ST_OP_STRIDE];
+    const double b = op[0], iv = op[S];
     if (mode == SMOOTH_JACOBI)
       y[r] = (b - sii) * iv;
     else if (mode == SMOOTH_RELAXED) {
       const double t = b - sii;
-      y[r] = w1*op[2*ST_OP_STRIDE] + w0*t*iv;
+      y[r] = w1*op[2*S] + w0*t*iv;
     }
     else {
-      const double xr = op[2*ST_OP_STRIDE];
-      const double yr = sii + op[3*ST_OP_STRIDE]*xr;
+      const double xr = op[2*S];
+      const double yr = sii + op[3*S]*xr;
       const double t = b - yr;
       y[r] = xr + t*iv;
     }
@@ -2029,12 +2091,13 @@ struct EpiFcgPcInit {
   double *rk, *qk, *z0;
   __device__ __forceinline__ const double *src(int v) const
   { return (v == 0) ? d_val : (v == 1) ? vx : (v == 2) ? rhs : inv; }
+  template <int S>
   __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&)[4]) const
   {
-    const double rr = op[2*ST_OP_STRIDE] - (sii + op[0]*op[ST_OP_STRIDE]);
+    const double rr = op[2*S] - (sii + op[0]*op[S]);
     rk[r] = rr;
     qk[r] = 0;
-    z0[r] = smooth_first_value(mode, w0, rr, op[3*ST_OP_STRIDE]);
+    z0[r] = smooth_first_value(mode, w0, rr, op[3*S]);
   }
 };
 
@@ -2283,7 +2346,8 @@ __device__ __forceinline__ void merge_gather(const MergeDev *M, unsigned k, unsi
     const double *src = M->stub_rhs;
     double *dst = M->root_rhs_dst;
     for (int i = blockIdx.x*PT + threadIdx.x; i < M->n_local; i += gridDim.x*PT) dst[i] = src[i];
-    fence_sys();
+    __syncthreads();
+    if (threadIdx.x == 0) fence_sys();
   }
   grid_barrier(bar);
   if (!M->is_root && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -2301,7 +2365,8 @@ __device__ __forceinline__ void merge_scatter(const MergeDev *M, const double *v
       double *dst = M->peer_vx[r];
       for (int i = blockIdx.x*PT + threadIdx.x; i < M->n_of[r]; i += gridDim.x*PT) dst[i] = src[i];
     }
-    fence_sys();
+    __syncthreads();
+    if (threadIdx.x == 0) fence_sys();
     grid_barrier(bar);
     if (blockIdx.x == 0 && threadIdx.x > 0 && threadIdx.x < M->n_ranks) {
       fence_sys();

@@ -71,16 +71,52 @@ inline size_t work_stride_of(size_t n_cols_ext) { return (n_cols_ext + 1) & ~(si
 const size_t IT_HEAD = offsetof(ItState, hist);
 const size_t MG_HEAD = offsetof(MgState, cycle_res);
 
+/* col_id on the host (row_index always is); defined with the multigrid below */
+bool matrix_host_mirror_structure(csb_matrix_t *m);
+
 /* Ghost-exchange descriptor of one matrix/level for the persistent kernels:
    ghost buffers and flag words in the arena, the neighbours' matching
    addresses obtained through the mailbox.  Collective over all ranks. */
 struct DistLevelHost {
   DistLevel           h;
   DevBuf<unsigned>    words;      /* count, ticket */
+  DevBuf<unsigned>    bmask;      /* rows with ghost columns */
+  DevBuf<double>      bsum;       /* their parked sums */
   DevBuf<DistLevel>   d;          /* device copy */
 };
 
-bool build_dist_level(csb_pcomm_t *pc, const csb_halo_t *halo, DistLevelHost &out)
+/* rows of m that have ghost columns (one bit each); false if a row does not keep its ghost
+   columns behind its local ones (the exchange / product overlap sums the local head of such
+   rows first) */
+bool ghost_row_mask(const csb_matrix_t *m, std::vector<unsigned> &mask)
+{
+  mask.assign(((size_t)m->n_rows + 31) / 32 + 1, 0u);
+  if ((size_t)m->h_col_id.size() < (size_t)m->nnz || m->h_row_index.size() < (size_t)m->n_rows + 1) {
+    set_error("ghost_row_mask: matrix structure is not mirrored on the host");
+    return false;
+  }
+  const int *ri = m->h_row_index.data(), *ci = m->h_col_id.data();
+  bool sorted = true;
+  #pragma omp parallel for schedule(static, 4096) reduction(&&: sorted)
+  for (int i = 0; i < m->n_rows; i++) {
+    bool seen_ghost = false;
+    for (int k = ri[i]; k < ri[i+1]; k++) {
+      if (ci[k] >= m->n_rows) seen_ghost = true;
+      else if (seen_ghost) sorted = false;
+    }
+    if (seen_ghost) {
+      #pragma omp atomic
+      mask[(size_t)i >> 5] |= 1u << (i & 31);
+    }
+  }
+  if (!sorted)
+    set_error("matrix rows must list their ghost columns (ids >= n_rows) after the local "
+              "ones, as cs_matrix_t does (sorted column ids)");
+  return sorted;
+}
+
+bool build_dist_level(csb_pcomm_t *pc, const csb_halo_t *halo, const csb_matrix_t *m,
+                      DistLevelHost &out)
 {
   Context &c = ctx();
   DistLevel &D = out.h;
@@ -109,6 +145,16 @@ bool build_dist_level(csb_pcomm_t *pc, const csb_halo_t *halo, DistLevelHost &ou
   D.count = out.words.p;
   D.ticket = out.words.p + 1;
   D.timeout_ns = pc->h.timeout_ns;
+  {
+    std::vector<unsigned> mask;
+    if (!ghost_row_mask(m, mask)) return false;
+    if (!out.bmask.upload(mask.data(), mask.size())
+        || !out.bsum.alloc((size_t)std::max(m->n_rows, 1))
+        || !CSB_CUDA(cudaStreamSynchronize(c.stream))) return false;    /* mask dies here */
+    D.bmask = out.bmask.p;
+    D.bsum = out.bsum.p;
+    D.overlap = (env_int("CSB_HALO_OVERLAP", 1) != 0) ? 1 : 0;
+  }
 
   std::vector<long long> snd((size_t)nd*8 + 8, 0), rcv((size_t)nd*8 + 8, 0);
   for (int i = 0; i < nd; i++) {
@@ -744,7 +790,8 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
       if (c->arena_used) pcomm_arena_release(c->pcomm, c->arena_mark);
       c->arena_mark = pcomm_arena_mark(c->pcomm);
       c->arena_used = true;
-      if (!build_dist_level(c->pcomm, a->halo, c->dist)) return;
+      if (!matrix_host_mirror_structure(const_cast<csb_matrix_t *>(a))
+          || !build_dist_level(c->pcomm, a->halo, a, c->dist)) return;
       d.dist = c->dist.d.p;
       if (!pcomm_allreduce(c->pcomm, &d.n_g_rows, 1)) return;
     }
@@ -1314,6 +1361,20 @@ void mg_clear_hierarchy(csb_multigrid_t *mg)
   mg->setup_done = false;
   mg->a = nullptr;
 }
+
+} // anonymous namespace
+namespace {
+bool matrix_host_mirror_structure(csb_matrix_t *m)
+{
+  if (m->h_col_id.size() == (size_t)std::max<size_t>((size_t)m->nnz, 1)) return true;
+  m->h_col_id.resize(std::max<size_t>((size_t)m->nnz, 1));
+  if (m->nnz > 0 &&
+      !CSB_CUDA(cudaMemcpyAsync(m->h_col_id.data(), m->col_id.p, sizeof(int)*(size_t)m->nnz,
+                                cudaMemcpyDeviceToHost, ctx().stream))) return false;
+  return CSB_CUDA(cudaStreamSynchronize(ctx().stream));
+}
+}
+namespace {
 
 /* make sure the host mirrors of a matrix are available for aggregation */
 bool matrix_host_mirror(csb_matrix_t *m)
@@ -2053,7 +2114,9 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     if (l > 0) {
       if (!lv->rhs.alloc((size_t)m->n_cols_ext) || !lv->vx.alloc((size_t)m->n_cols_ext)) return;
     }
-    if (dist && !lv->merged && !lv->stub && !build_dist_level(pc, lv->halo, lv->dist)) return;
+    if (dist && !lv->merged && !lv->stub
+        && (!matrix_host_mirror_structure(const_cast<csb_matrix_t *>(m))
+            || !build_dist_level(pc, lv->halo, m, lv->dist))) return;
   }
   mg->work_stride = aux_size / 5;
   if (mg->merge_level >= 0 && !mg_merge_build_dev(mg, pc)) return;
