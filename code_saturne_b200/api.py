@@ -54,6 +54,11 @@ class SlesItType(enum.IntEnum):
     IPCG = 2
     JACOBI = 3
     BICGSTAB = 4
+    # process-local Gauss-Seidel family (cs_sles_it.h:64-65, :84-85)
+    P_GAUSS_SEIDEL = 8
+    P_SYM_GAUSS_SEIDEL = 9
+    TS_F_GAUSS_SEIDEL = 17
+    TS_B_GAUSS_SEIDEL = 18
     # multigrid smoothers (cs_sles_it.h:79-83)
     L1_JACOBI = 13
     R_JACOBI = 14

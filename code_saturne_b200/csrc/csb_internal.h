@@ -347,7 +347,9 @@ struct _csb_matrix_t {
      kept for cs_matrix_vector_multiply in CSR order (_mat_vec_p_l_csr); this object holds
      the MSR split (diagonal extracted) the solvers and the hierarchy work on */
   _csb_matrix_t *csr = nullptr;
-  ~_csb_matrix_t() { delete csr; }
+  /* dependency levels of the Gauss-Seidel sweeps (sles.cu), built on first use */
+  mutable struct GsPlan *gs_plan = nullptr;
+  ~_csb_matrix_t();
 };
 
 namespace csb {
@@ -427,6 +429,7 @@ bool launch_coeffs_msr_v3(const _csb_matrix_t *m, int iconvp, int idiffp, int nd
 /* ad_inv = 1/d  (cs_sles_pc.cpp:376) */
 bool launch_ad_inv(int n, const double *d, double *ad_inv);
 bool launch_fill(int n, double v, double *x);
+bool launch_fill_gated(int n, double v, double *x, const MgState *gate);
 
 /* plain reductions -> ctx().red_out[0..q) */
 bool launch_dot(int n, const double *x, const double *y, const double *z, int mode);
@@ -547,6 +550,16 @@ bool launch_coarse_assembly(const CoarseAssemblyArgs &a, int stages /* 1 | 2 */)
 bool launch_coarse_galerkin(const CoarseAssemblyArgs &a);
 
 bool launch_halo_pack(int n_send, const int *send_list, const double *var, double *buf);
+/* Gauss-Seidel update of the n rows listed in `rows` (one dependency level); mode 0 whole
+   row, 1 lower part, 2 upper part (truncated sweeps); res != NULL: d_i (new - old) per row
+   (solver form); launch_gs_chain: levels l0 .. l1-1 of a plan in one CTA */
+bool launch_gs_rows(int n, const int *rows, const _csb_matrix_t *m, const double *ad_inv,
+                    const double *rhs, double *vx, int mode, const MgState *gate,
+                    const ItState *st, double *res);
+bool launch_gs_chain(const int *rows, const int *level_start, int l0, int l1, bool backward,
+                     const _csb_matrix_t *m, const double *ad_inv, const double *rhs,
+                     double *vx, int mode, const MgState *gate, const ItState *st, double *res);
+bool launch_gs_residual(int n, ItState *st, const double *res);
 /* index helpers of the coarse-level merge: 0 out = shift + i, 1 out = map[in], 2 row
    lengths of a row index, 3 in + shift where in >= 0 */
 bool launch_merge_index(int mode, int n, int shift, const int *in, const int *map, int *out);

@@ -793,6 +793,20 @@ bool launch_fill(int n, double v, double *x)
   return post_launch("fill");
 }
 
+__global__ void __launch_bounds__(TPB)
+k_fill_gated(int n, double v, double *__restrict__ x, const MgState *gate)
+{
+  if (gate != nullptr && gate->cvg != CSB_SLES_ITERATING) return;
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) x[i] = v;
+}
+
+bool launch_fill_gated(int n, double v, double *x, const MgState *gate)
+{
+  if (n < 1) return true;
+  k_fill_gated<<<vec_grid(n), TPB, 0, ctx().stream>>>(n, v, x, gate);
+  return post_launch("fill_gated");
+}
+
 bool launch_ad_inv(int n, const double *d, double *ad_inv)
 {
   if (n < 1) return true;
@@ -2468,6 +2482,130 @@ bool launch_merge_index(int mode, int n, int shift, const int *in, const int *ma
   if (n < 1) return true;
   k_merge_index<<<vec_grid(n), TPB, 0, ctx().stream>>>(mode, n, shift, in, map, out);
   return post_launch("merge_index");
+}
+
+/*--------------------------------------------------------------------------
+ * Gauss-Seidel family: the rows of ONE dependency level (sles.cu, GsPlan).  A row's update is
+ * the reference's, term by term: vx0 = rhs; vx0 -= (a_ij * vx_j) over the row's entries in
+ * order (all of them, the lower part up to the first column > i, or the upper part from the
+ * last entry down to the first column < i); vx_i = vx0 * ad_inv_i
+ * (cs_multigrid_smoother.cpp:1095-1107, :1243-1256, :1436-1449, :1566-1579).  Rows of a level
+ * do not depend on each other, every row they read from an earlier level is final: the
+ * sequential sweep, reproduced bit for bit.  res (solver form, cs_sles_it.cpp:4003-4024,
+ * :4262-4284): r_i = d_i (vx_i_new - vx_i_old), summed in squares by k_gs_residual.
+ *--------------------------------------------------------------------------*/
+
+namespace {
+
+struct GsK {
+  const int *rows, *row_index, *col_id;
+  const double *x_val, *ad_inv, *rhs, *d_val;
+  double *vx, *res;
+  int mode;
+  const MgState *gate;
+  const ItState *st;
+};
+
+__device__ __forceinline__ void gs_row(const GsK &a, int ii)
+{
+  const int ks = a.row_index[ii], ke = a.row_index[ii+1];
+  double vx0 = a.rhs[ii];
+  if (a.mode == 0)
+    for (int jj = ks; jj < ke; jj++) vx0 -= (a.x_val[jj]*a.vx[a.col_id[jj]]);
+  else if (a.mode == 1)
+    for (int jj = ks; jj < ke; jj++) {
+      if (a.col_id[jj] > ii) break;
+      vx0 -= (a.x_val[jj]*a.vx[a.col_id[jj]]);
+    }
+  else
+    for (int jj = ke - 1; jj > ks - 1; jj--) {
+      if (a.col_id[jj] < ii) break;
+      vx0 -= (a.x_val[jj]*a.vx[a.col_id[jj]]);
+    }
+  vx0 *= a.ad_inv[ii];
+  if (a.res != nullptr) a.res[ii] = a.d_val[ii] * (vx0 - a.vx[ii]);
+  a.vx[ii] = vx0;
+}
+
+__global__ void __launch_bounds__(TPB)
+k_gs_rows(GsK a, int n)
+{
+  if (a.gate != nullptr && a.gate->cvg != CSB_SLES_ITERATING) return;
+  if (a.st != nullptr && a.st->cvg != CSB_SLES_ITERATING) return;
+  const int t = blockIdx.x*TPB + threadIdx.x;
+  if (t < n) gs_row(a, a.rows[t]);
+}
+
+/* a run of consecutive small levels in ONE CTA (levels l0 .. l1-1 in the given direction,
+   a __syncthreads between levels): coarse matrices and the first / last wavefronts of fine
+   ones, where a launch per level would be all latency */
+__global__ void __launch_bounds__(1024)
+k_gs_chain(GsK a, const int *__restrict__ level_start, int l0, int l1, int backward)
+{
+  if (a.gate != nullptr && a.gate->cvg != CSB_SLES_ITERATING) return;
+  if (a.st != nullptr && a.st->cvg != CSB_SLES_ITERATING) return;
+  for (int k = 0; k < l1 - l0; k++) {
+    const int l = backward ? l1 - 1 - k : l0 + k;
+    const int s = level_start[l], e = level_start[l+1];
+    for (int t = s + threadIdx.x; t < e; t += 1024) gs_row(a, a.rows[t]);
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(TPB)
+k_gs_residual(int n, ItState *st, const double *__restrict__ res, double *partials,
+              unsigned *ticket)
+{
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  double v[1] = {0.};
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) v[0] += (res[i]*res[i]);
+  grid_sum_finalize<1>(v, partials, ticket, [st](const double *s) {
+    st->n_iter += 1;
+    double residual = (st->precision > 0.) ? sqrt(s[0]) : -1.;   /* of the previous iterate */
+    if (st->n_iter == 1) st->initial_residual = residual;
+    st->cvg = it_cvg_test(st, st->n_iter, residual);
+  });
+}
+
+GsK gs_args(const int *rows, const _csb_matrix_t *m, const double *ad_inv, const double *rhs,
+            double *vx, int mode, const MgState *gate, const ItState *st, double *res)
+{
+  GsK a;
+  a.rows = rows; a.row_index = m->row_index.p; a.col_id = m->col_id.p; a.x_val = m->x_val.p;
+  a.ad_inv = ad_inv; a.rhs = rhs; a.d_val = m->d_val.p; a.vx = vx; a.res = res; a.mode = mode;
+  a.gate = gate; a.st = st;
+  return a;
+}
+}
+
+bool launch_gs_rows(int n, const int *rows, const _csb_matrix_t *m, const double *ad_inv,
+                    const double *rhs, double *vx, int mode, const MgState *gate,
+                    const ItState *st, double *res)
+{
+  if (n < 1) return true;
+  k_gs_rows<<<(n + TPB - 1)/TPB, TPB, 0, ctx().stream>>>(
+    gs_args(rows, m, ad_inv, rhs, vx, mode, gate, st, res), n);
+  return post_launch("gs_rows");
+}
+
+bool launch_gs_chain(const int *rows, const int *level_start, int l0, int l1, bool backward,
+                     const _csb_matrix_t *m, const double *ad_inv, const double *rhs,
+                     double *vx, int mode, const MgState *gate, const ItState *st, double *res)
+{
+  if (l1 <= l0) return true;
+  k_gs_chain<<<1, 1024, 0, ctx().stream>>>(
+    gs_args(rows, m, ad_inv, rhs, vx, mode, gate, st, res), level_start, l0, l1,
+    backward ? 1 : 0);
+  return post_launch("gs_chain");
+}
+
+bool launch_gs_residual(int n, ItState *st, const double *res)
+{
+  Context &c = ctx();
+  const int g = vec_grid(n);
+  if (!ensure_partials(g)) return false;
+  k_gs_residual<<<g, TPB, 0, c.stream>>>(n, st, res, c.partials, c.ticket);
+  return post_launch("gs_residual");
 }
 
 bool launch_halo_pack(int n_send, const int *send_list, const double *var, double *buf)

@@ -47,6 +47,9 @@ void reset_partials();
 
 using namespace csb;
 
+namespace csb { void gs_plan_free(GsPlan *p); }
+_csb_matrix_t::~_csb_matrix_t() { delete csr; if (gs_plan) csb::gs_plan_free(gs_plan); }
+
 extern "C" {
 
 const char *csb_version(void) { return "csb200 0.1 (sm_100a, FP64)"; }

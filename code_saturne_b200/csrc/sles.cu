@@ -227,6 +227,21 @@ struct _csb_sles_it_t {
   ~_csb_sles_it_t();
 };
 
+/* Dependency levels of the Gauss-Seidel sweeps of one matrix: rows sorted by level, a level's
+   rows in ascending order.  level(i) = 1 + max level(j) over the neighbours j < i of row i in
+   the SYMMETRISED structure (j in row i or i in row j), so that a row runs after every
+   lower-numbered row it reads (the values the sequential sweep has already updated) and
+   before every higher-numbered row that reads it or that it reads (the values the sequential
+   sweep has not touched yet).  Forward sweeps take the levels in ascending order, backward
+   sweeps in descending order: exactly the reference's one-thread result
+   (cs_multigrid_smoother.cpp:1053-1630, cs_sles_it.cpp:3940-4360). */
+struct GsPlan {
+  csb::DevBuf<int> rows, level_start_d;
+  std::vector<int> level_start;
+};
+
+namespace csb { void gs_plan_free(GsPlan *p) { delete p; } }
+
 namespace {
 
 int sb_rows_threshold()
@@ -238,7 +253,15 @@ int sb_rows_threshold()
 bool is_smoother_type(int t)
 {
   return (t == CSB_SLES_JACOBI || t == CSB_SLES_L1_JACOBI || t == CSB_SLES_R_JACOBI
-          || t == CSB_SLES_RJ2 || t == CSB_SLES_RJ3);
+          || t == CSB_SLES_RJ2 || t == CSB_SLES_RJ3 || t == CSB_SLES_P_GAUSS_SEIDEL
+          || t == CSB_SLES_P_SYM_GAUSS_SEIDEL || t == CSB_SLES_TS_F_GAUSS_SEIDEL
+          || t == CSB_SLES_TS_B_GAUSS_SEIDEL);
+}
+
+bool is_gs_type(int t)
+{
+  return (t == CSB_SLES_P_GAUSS_SEIDEL || t == CSB_SLES_P_SYM_GAUSS_SEIDEL
+          || t == CSB_SLES_TS_F_GAUSS_SEIDEL || t == CSB_SLES_TS_B_GAUSS_SEIDEL);
 }
 
 /* Sweep schedule of the Jacobi-family smoothers: relaxation weights
@@ -266,6 +289,138 @@ SmootherPlan smoother_plan(int type, int n_max_iter)
   return p;
 }
 
+const GsPlan *gs_plan_get(const csb_matrix_t *m)
+{
+  if (m->gs_plan != nullptr) return m->gs_plan;
+  if (m->db != 1) { set_error("Gauss-Seidel: scalar (db = 1) matrices only"); return nullptr; }
+  if (!matrix_host_mirror_structure(const_cast<csb_matrix_t *>(m))) return nullptr;
+  const int n = m->n_rows;
+  const int *ri = m->h_row_index.data();
+  const int *ci = m->h_col_id.data();
+  std::vector<int> lvl((size_t)std::max(n, 1), 0);
+  int n_lv = 0;
+  for (int i = 0; i < n; i++) {
+    int l = lvl[i];                                   /* pushed by rows j < i that hold i */
+    for (int k = ri[i]; k < ri[i+1]; k++) {
+      const int j = ci[k];
+      if (j < i && lvl[j] + 1 > l) l = lvl[j] + 1;
+    }
+    lvl[i] = l;
+    for (int k = ri[i]; k < ri[i+1]; k++) {
+      const int j = ci[k];
+      if (j > i && j < n && lvl[j] < l + 1) lvl[j] = l + 1;
+    }
+    if (l + 1 > n_lv) n_lv = l + 1;
+  }
+  GsPlan *p = new GsPlan;
+  p->level_start.assign((size_t)n_lv + 1, 0);
+  for (int i = 0; i < n; i++) p->level_start[(size_t)lvl[i] + 1]++;
+  for (int l = 0; l < n_lv; l++) p->level_start[(size_t)l + 1] += p->level_start[l];
+  std::vector<int> pos(p->level_start.begin(), p->level_start.end() - 1), rows((size_t)std::max(n, 1));
+  for (int i = 0; i < n; i++) rows[(size_t)pos[lvl[i]]++] = i;
+  if (!p->rows.upload(rows.data(), (size_t)n)
+      || !p->level_start_d.upload(p->level_start.data(), p->level_start.size())
+      || !CSB_CUDA(cudaStreamSynchronize(ctx().stream))) { delete p; return nullptr; }
+  m->gs_plan = p;
+  return p;
+}
+
+/* One sweep over all rows in dependency-level order.  Levels of more than 1024 rows take a
+   launch each; runs of smaller ones share one single-CTA launch. */
+bool gs_sweep(const csb_matrix_t *m, const GsPlan *p, bool backward, int mode,
+              const double *ad_inv, const double *rhs, double *vx, const MgState *gate,
+              const ItState *st, double *res)
+{
+  const int nl = (int)p->level_start.size() - 1;
+  const int chain_max = 1024;
+  int k = 0;
+  while (k < nl) {
+    const int l = backward ? nl - 1 - k : k;
+    const int cnt = p->level_start[l+1] - p->level_start[l];
+    if (cnt > chain_max) {
+      if (!launch_gs_rows(cnt, p->rows.p + p->level_start[l], m, ad_inv, rhs, vx, mode, gate,
+                          st, res)) return false;
+      k++;
+      continue;
+    }
+    int k1 = k + 1;
+    while (k1 < nl) {
+      const int l1 = backward ? nl - 1 - k1 : k1;
+      if (p->level_start[l1+1] - p->level_start[l1] > chain_max) break;
+      k1++;
+    }
+    const int la = backward ? nl - k1 : k, lb = backward ? nl - k : k1;   /* [la, lb) */
+    if (!launch_gs_chain(p->rows.p, p->level_start_d.p, la, lb, backward, m, ad_inv, rhs, vx,
+                         mode, gate, st, res)) return false;
+    k = k1;
+  }
+  return true;
+}
+
+/* Gauss-Seidel smoothers (fixed sweeps, no convergence test): _p_gauss_seidel_msr,
+   _p_sym_gauss_seidel_msr, _ts_f_gauss_seidel_msr, _ts_b_gauss_seidel_msr
+   (cs_multigrid_smoother.cpp:1053, :1179, :1389, :1519). */
+bool gs_smoother_enqueue(const csb_matrix_t *m, int type, int n_max_iter, const double *ad_inv,
+                         const double *rhs, double *vx, bool vx_ini_nonzero,
+                         const MgState *gate)
+{
+  const GsPlan *p = gs_plan_get(m);
+  if (p == nullptr) return false;
+  const int n = m->n_rows, n_ext = m->n_cols_ext;
+  if (type == CSB_SLES_TS_F_GAUSS_SEIDEL || type == CSB_SLES_TS_B_GAUSS_SEIDEL) {
+    /* one truncated sweep; ghost values (all values without vx_ini) are zero */
+    if (!vx_ini_nonzero) { if (!launch_fill_gated(n_ext, 0.0, vx, gate)) return false; }
+    else if (n_ext > n && !launch_fill_gated(n_ext - n, 0.0, vx + n, gate)) return false;
+    const bool fwd = (type == CSB_SLES_TS_F_GAUSS_SEIDEL);
+    return gs_sweep(m, p, !fwd, fwd ? 1 : 2, ad_inv, rhs, vx, gate, nullptr, nullptr);
+  }
+  for (int it = 0; it < n_max_iter; it++) {
+    if (it == 0 && !vx_ini_nonzero) { if (!launch_fill_gated(n_ext, 0.0, vx, gate)) return false; }
+    else if (m->halo != nullptr && csb_halo_sync_var(m->halo, vx) != 0) return false;
+    if (!gs_sweep(m, p, false, 0, ad_inv, rhs, vx, gate, nullptr, nullptr)) return false;
+    if (type == CSB_SLES_P_SYM_GAUSS_SEIDEL) {
+      if (m->halo != nullptr && csb_halo_sync_var(m->halo, vx) != 0) return false;
+      if (!gs_sweep(m, p, true, 0, ad_inv, rhs, vx, gate, nullptr, nullptr)) return false;
+    }
+  }
+  return true;
+}
+
+/* Gauss-Seidel solvers with the convergence test of cs_sles_it (_p_gauss_seidel_msr
+   cs_sles_it.cpp:3940-4110, _p_sym_gauss_seidel_msr :4124-4360): the residual of an
+   iteration is sqrt(sum (d_i (vx_i_new - vx_i_old))^2) over the forward sweep (GS) or the
+   backward sweep (symmetric GS).  res: n_rows doubles. */
+bool gs_enqueue(const csb_matrix_t *m, int type, ItState *st, const double *ad_inv,
+                double precision, double r_norm, int n_max_iter, const double *rhs,
+                double *vx, bool vx_ini_nonzero, double *res, ItState *h_st)
+{
+  const GsPlan *p = gs_plan_get(m);
+  if (p == nullptr) return false;
+  Context &c = ctx();
+  const int n = m->n_rows, n_ext = m->n_cols_ext;
+  const bool sym = (type == CSB_SLES_P_SYM_GAUSS_SEIDEL);
+  if (!launch_it_state_init(st, nullptr, precision, r_norm, n_max_iter)) return false;
+  const int poll = 4;
+  for (int it = 1; it <= n_max_iter; it++) {
+    if (it == 1 && !vx_ini_nonzero) { if (!launch_fill(n_ext, 0.0, vx)) return false; }
+    else if (m->halo != nullptr && csb_halo_sync_var(m->halo, vx) != 0) return false;
+    if (!gs_sweep(m, p, false, 0, ad_inv, rhs, vx, nullptr, st, sym ? nullptr : res))
+      return false;
+    if (sym) {
+      if (m->halo != nullptr && csb_halo_sync_var(m->halo, vx) != 0) return false;
+      if (!gs_sweep(m, p, true, 0, ad_inv, rhs, vx, nullptr, st, res)) return false;
+    }
+    if (!launch_gs_residual(n, st, res)) return false;
+    if (h_st != nullptr && (it % poll) == 0) {
+      if (!CSB_CUDA(cudaMemcpyAsync(h_st, st, IT_HEAD, cudaMemcpyDeviceToHost, c.stream)))
+        return false;
+      if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return false;
+      if (h_st->cvg != CSB_SLES_ITERATING) break;
+    }
+  }
+  return true;
+}
+
 /* Fixed number of Jacobi-family sweeps without convergence test (_jacobi, _relaxed_jacobi,
    _l1_jacobi: cs_multigrid_smoother.cpp:143-226, :244-373, :804-905).  Each sweep is ONE
    kernel: the (diagonal-excluded, or full for L1) product in CSR order with the update in
@@ -275,6 +430,8 @@ bool smoother_enqueue(const csb_matrix_t *m, int type, int n_max_iter, const dou
                       const double *rhs, double *vx, bool vx_ini_nonzero, double *tmp,
                       const MgState *gate)
 {
+  if (is_gs_type(type))
+    return gs_smoother_enqueue(m, type, n_max_iter, inv, rhs, vx, vx_ini_nonzero, gate);
   const SmootherPlan p = smoother_plan(type, n_max_iter);
   const int n = m->n_rows;
   double *vx_n = vx, *vx_np = tmp;
@@ -657,7 +814,8 @@ csb_sles_it_create(csb_sles_it_type_t solver_type, int poly_degree, int n_max_it
   if (!ctx().ready) { set_error("csb_sles_it_create: csb_init not called"); return nullptr; }
   if (solver_type != CSB_SLES_PCG && solver_type != CSB_SLES_FCG
       && solver_type != CSB_SLES_IPCG
-      && solver_type != CSB_SLES_JACOBI && solver_type != CSB_SLES_BICGSTAB) {
+      && solver_type != CSB_SLES_JACOBI && solver_type != CSB_SLES_BICGSTAB
+      && solver_type != CSB_SLES_P_GAUSS_SEIDEL && solver_type != CSB_SLES_P_SYM_GAUSS_SEIDEL) {
     set_error("csb_sles_it_create: solver type %d is not available on this path",
               (int)solver_type);
     return nullptr;
@@ -666,7 +824,7 @@ csb_sles_it_create(csb_sles_it_type_t solver_type, int poly_degree, int n_max_it
      cs_sles_it.cpp:1673-1860) */
   /* FCG with poly_degree < 0: the preconditioner is handed over afterwards
      (csb_sles_it_transfer_pc: one multigrid V-cycle), identity if none is */
-  if (solver_type != CSB_SLES_JACOBI && poly_degree != 0
+  if (solver_type != CSB_SLES_JACOBI && !is_gs_type((int)solver_type) && poly_degree != 0
       && !(solver_type == CSB_SLES_PCG || solver_type == CSB_SLES_FCG
            || solver_type == CSB_SLES_IPCG)) {
     set_error("csb_sles_it_create: poly_degree %d: polynomial (> 0), none or transferred "
@@ -706,6 +864,11 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
   c->setup_done = false;
   const size_t n_wa = (c->type == CSB_SLES_BICGSTAB) ? 6
     : ((c->type == CSB_SLES_PCG || c->type == CSB_SLES_FCG || c->type == CSB_SLES_IPCG) ? 5 : 1);
+  if (is_gs_type((int)c->type) && a->halo != nullptr) {
+    set_error("csb_sles_it_setup: the Gauss-Seidel solvers run on one rank on this path (the "
+              "smoother forms take a halo)");
+    return;
+  }
   if (a->db != 1 && c->type != CSB_SLES_BICGSTAB && !(c->type == CSB_SLES_JACOBI && a->db == 3)) {
     set_error("csb_sles_it_setup: block matrices (db %d) are solved with CSB_SLES_BICGSTAB "
               "or, for 3x3 blocks, CSB_SLES_JACOBI on this path", a->db);
@@ -917,6 +1080,14 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
     ok = bicgstab_enqueue(a, c->st.p, c->ad_inv.p, precision, r_norm, c->n_max_iter,
                           s_rhs.d, s_vx.d, ini, c->work.p, c->h_st);
     break;
+  case CSB_SLES_P_GAUSS_SEIDEL:
+  case CSB_SLES_P_SYM_GAUSS_SEIDEL:
+    ok = gs_enqueue(a, (int)c->type, c->st.p, c->ad_inv.p, precision, r_norm, c->n_max_iter,
+                    s_rhs.d, s_vx.d, ini, c->work.p, c->h_st);
+    break;
+  default:
+    set_error("csb_sles_it_solve: solver type %d", (int)c->type);
+    break;
   }
   if (!ok) return CSB_SLES_BREAKDOWN;
 
@@ -991,7 +1162,12 @@ void csb_sles_it_log(const void *context, int log_type)
                  : (c->type == CSB_SLES_L1_JACOBI) ? "L1 Jacobi"
                  : (c->type == CSB_SLES_R_JACOBI) ? "Relaxed Jacobi"
                  : (c->type == CSB_SLES_RJ2) ? "Scheduled relaxed Jacobi (M=2)"
-                 : (c->type == CSB_SLES_RJ3) ? "Scheduled relaxed Jacobi (M=3)" : "BiCGstab";
+                 : (c->type == CSB_SLES_RJ3) ? "Scheduled relaxed Jacobi (M=3)"
+                 : (c->type == CSB_SLES_P_GAUSS_SEIDEL) ? "Local Gauss-Seidel"
+                 : (c->type == CSB_SLES_P_SYM_GAUSS_SEIDEL) ? "Local symmetric Gauss-Seidel"
+                 : (c->type == CSB_SLES_TS_F_GAUSS_SEIDEL) ? "Truncated forward Gauss-Seidel"
+                 : (c->type == CSB_SLES_TS_B_GAUSS_SEIDEL) ? "Truncated backward Gauss-Seidel"
+                 : "BiCGstab";
   printf("  Solver type:                       %s (B200 device)\n"
          "  Number of setups:                  %12u\n"
          "  Number of calls:                   %12u\n"
@@ -1136,8 +1312,8 @@ bool mg_fcg_persistent_ok(const csb_multigrid_t *mg)
 {
   if (mg->type != CSB_MULTIGRID_V_CYCLE || mg->levels.size() < 2) return false;
   for (int i = 0; i < 2; i++)
-    if (!is_smoother_type((int)mg->solver_type[i]) || mg->precision_mult[i] >= 0
-        || mg->n_max_iter[i] < 1) return false;
+    if (!is_smoother_type((int)mg->solver_type[i]) || is_gs_type((int)mg->solver_type[i])
+        || mg->precision_mult[i] >= 0 || mg->n_max_iter[i] < 1) return false;
   return (mg->solver_type[2] == CSB_SLES_PCG && mg->poly_degree[2] == 0);
 }
 
@@ -1193,7 +1369,9 @@ bool mg_level_smooth(csb_multigrid_t *mg, int which, int level, const double *rh
   const double *inv = (type == CSB_SLES_L1_JACOBI) ? f->l1_inv.p : f->ad_inv.p;
   if (!smoother_enqueue(f->m, type, mg->n_max_iter[which], inv, rhs_lv, vx_lv, ini,
                         mg->aux.p, ms)) return false;
-  return !count || launch_mg_accum_n(ms, smoother_plan(type, mg->n_max_iter[which]).n_iter,
+  const int n_it = (type == CSB_SLES_TS_F_GAUSS_SEIDEL || type == CSB_SLES_TS_B_GAUSS_SEIDEL)
+    ? 1 : smoother_plan(type, mg->n_max_iter[which]).n_iter;
+  return !count || launch_mg_accum_n(ms, n_it,
                               f->m->n_rows, 1.0 / (double)mg->levels[0]->m->n_rows);
 }
 
@@ -2619,7 +2797,8 @@ csb_multigrid_smoother_create(csb_sles_it_type_t smoother_type, int poly_degree,
   if (!ctx().ready) { set_error("csb_multigrid_smoother_create: csb_init not called"); return nullptr; }
   if (!is_smoother_type((int)smoother_type)) {
     set_error("csb_multigrid_smoother_create: type %d is not a smoother available on this "
-              "path (Jacobi, L1 Jacobi, relaxed Jacobi, RJ2, RJ3)", (int)smoother_type);
+              "path (Jacobi, L1 Jacobi, relaxed Jacobi, RJ2, RJ3, local / symmetric / "
+              "truncated Gauss-Seidel)", (int)smoother_type);
     return nullptr;
   }
   csb_sles_it_t *c = new csb_sles_it_t;
@@ -2652,6 +2831,10 @@ void csb_multigrid_smoother_setup(void *context, const char *name, const csb_mat
   if (!c->work.alloc(work_stride_of((size_t)a->n_cols_ext))) return;
   /* the scheduled variants run whole schedules (:1888-1898) */
   c->n_max_iter = smoother_plan((int)c->type, c->n_max_iter).n_iter;
+  /* the truncated Gauss-Seidel sweeps are single iterations (:1497, :1627) */
+  if (c->type == CSB_SLES_TS_F_GAUSS_SEIDEL || c->type == CSB_SLES_TS_B_GAUSS_SEIDEL)
+    c->n_max_iter = 1;
+  if (is_gs_type((int)c->type) && gs_plan_get(a) == nullptr) return;
   c->setup_done = true;
   c->n_setups += 1;
   c->t_setup += wall() - t0;

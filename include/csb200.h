@@ -49,6 +49,13 @@ typedef enum {
   /* multigrid smoothers without convergence test (cs_sles_it.h:79-83,
      src/alge/cs_multigrid_smoother.cpp); created with csb_multigrid_smoother_create or
      selected through csb_multigrid_set_solver_options with precision_mult < 0 */
+  /* process-local Gauss-Seidel family (cs_multigrid_smoother.cpp:1053-1630), sequential
+     (one-thread) semantics reproduced exactly with level-scheduled sweeps: rows of one
+     dependency level are updated together, levels in order */
+  CSB_SLES_P_GAUSS_SEIDEL     = 8,   /* _p_gauss_seidel_msr      :1053 forward sweeps */
+  CSB_SLES_P_SYM_GAUSS_SEIDEL = 9,   /* _p_sym_gauss_seidel_msr  :1179 forward + backward */
+  CSB_SLES_TS_F_GAUSS_SEIDEL  = 17,  /* _ts_f_gauss_seidel_msr   :1389 one lower solve */
+  CSB_SLES_TS_B_GAUSS_SEIDEL  = 18,  /* _ts_b_gauss_seidel_msr   :1519 one upper solve */
   CSB_SLES_L1_JACOBI = 13,  /* _l1_jacobi       :804-905 */
   CSB_SLES_R_JACOBI  = 14,  /* _relaxed_jacobi  :244-373, w = 2/3 */
   CSB_SLES_RJ2       = 15,  /* scheduled relaxation {1.7319, 0.5695} */

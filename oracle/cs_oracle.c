@@ -636,6 +636,88 @@ ora_jacobi(int n_rows, const int *row_index, const int *col_id,
 }
 
 /*----------------------------------------------------------------------------
+ * Process-local Gauss-Seidel solvers with convergence test, one thread:
+ *   sym == 0: _p_gauss_seidel_msr      (src/alge/cs_sles_it.cpp:3940-4110)
+ *   sym != 0: _p_sym_gauss_seidel_msr  (src/alge/cs_sles_it.cpp:4124-4360)
+ * The residual of an iteration is sqrt(sum (d_i (vx_i_new - vx_i_old))^2) over
+ * the forward sweep (GS) or over the backward sweep (symmetric GS), rows summed
+ * in sweep order.  With precision <= 0 no residual is computed and the loop
+ * ends at n_max_iter (:4098-4101, :4349-4352).
+ * out as ora_jacobi.
+ *----------------------------------------------------------------------------*/
+
+int
+ora_gauss_seidel(int sym, int n_rows, const int *row_index, const int *col_id,
+                 const double *d_val, const double *x_val,
+                 int n_max_iter, double precision, double r_norm,
+                 const double *rhs, double *vx, int use_vx_ini,
+                 double *out, double *history, int history_size)
+{
+  const int n = n_rows;
+  double *ad_inv = malloc(sizeof(double)*(n > 0 ? n : 1));
+  for (int i = 0; i < n; i++) ad_inv[i] = 1.0 / d_val[i];
+
+  ora_cvg_t cv = {precision, r_norm, -1, n_max_iter, 0, -1,
+                  history, history_size, 0};
+  int cvg = ORA_ITERATING;
+  int n_iter = 0;
+  double residual = -1;
+
+  while (cvg == ORA_ITERATING) {
+    if (n_iter == 0 && !use_vx_ini)
+      for (int ii = 0; ii < n; ii++) vx[ii] = 0;
+    n_iter += 1;
+    double res2 = 0.0;
+    if (sym) {
+      for (int ii = 0; ii < n; ii++) {
+        double vx0 = rhs[ii];
+        for (int jj = row_index[ii]; jj < row_index[ii+1]; jj++)
+          vx0 -= (x_val[jj]*vx[col_id[jj]]);
+        vx[ii] = vx0 * ad_inv[ii];
+      }
+      for (int ii = n - 1; ii > -1; ii--) {
+        double vxm1 = vx[ii];
+        double vx0 = rhs[ii];
+        for (int jj = row_index[ii]; jj < row_index[ii+1]; jj++)
+          vx0 -= (x_val[jj]*vx[col_id[jj]]);
+        vx0 *= ad_inv[ii];
+        double r = d_val[ii] * (vx0 - vxm1);
+        res2 += (r*r);
+        vx[ii] = vx0;
+      }
+    }
+    else {
+      for (int ii = 0; ii < n; ii++) {
+        double vxm1 = vx[ii];
+        double vx0 = rhs[ii];
+        for (int jj = row_index[ii]; jj < row_index[ii+1]; jj++)
+          vx0 -= (x_val[jj]*vx[col_id[jj]]);
+        vx0 *= ad_inv[ii];
+        double r = d_val[ii] * (vx0 - vxm1);
+        res2 += (r*r);
+        vx[ii] = vx0;
+      }
+    }
+    if (precision > 0.) {
+      residual = sqrt(res2);   /* of the previous iterate */
+      if (n_iter == 1) cv.initial_residual = residual;
+      cvg = _cvg_test(&cv, n_iter, residual);
+    }
+    else if (n_iter >= n_max_iter) {
+      cv.n_iterations = n_iter;
+      cvg = ORA_MAX_ITERATION;
+    }
+  }
+
+  out[0] = cv.n_iterations;
+  out[1] = cv.residual;
+  out[2] = cv.initial_residual;
+  out[3] = cv.history_n;
+  free(ad_inv);
+  return cvg;
+}
+
+/*----------------------------------------------------------------------------
  * Block-diagonal MSR SpMV, 3x3 blocks: _b_mat_vec_p_l_msr_3
  * (src/alge/cs_matrix_spmv.cpp:2394-2455) with _dense_3_3_ax (:590-607):
  * y_i = D_i.x_i first, then += e_ij * x_j in CSR order, per component.
@@ -1931,9 +2013,68 @@ ora_smoother(int type, int n_rows, const int *row_index, const int *col_id,
              const double *rhs, double *vx, int use_vx_ini, double *out)
 {
   const int n = n_rows;
+  const int gs = (   type == ORA_SLES_P_GAUSS_SEIDEL || type == ORA_SLES_P_SYM_GAUSS_SEIDEL
+                  || type == ORA_SLES_TS_F_GAUSS_SEIDEL || type == ORA_SLES_TS_B_GAUSS_SEIDEL);
   if (   type != ORA_SLES_JACOBI && type != ORA_SLES_L1_JACOBI
-      && type != ORA_SLES_R_JACOBI && type != ORA_SLES_RJ2 && type != ORA_SLES_RJ3)
+      && type != ORA_SLES_R_JACOBI && type != ORA_SLES_RJ2 && type != ORA_SLES_RJ3 && !gs)
     return -100;
+
+  if (gs) {
+    /* Process-local Gauss-Seidel family, ONE thread (the reference's OpenMP loops over the
+       rows update vx in place, so with several threads the result depends on their timing;
+       the sequential sweep is the defined one):
+         _p_gauss_seidel_msr      cs_multigrid_smoother.cpp:1053-1160  forward sweeps
+         _p_sym_gauss_seidel_msr  :1179-1370   forward then backward sweep per iteration
+         _ts_f_gauss_seidel_msr   :1389-1500   ONE forward sweep over the lower part
+         _ts_b_gauss_seidel_msr   :1519-1630   ONE backward sweep over the upper part */
+    int n_it = 0;
+    if (type == ORA_SLES_TS_F_GAUSS_SEIDEL || type == ORA_SLES_TS_B_GAUSS_SEIDEL) {
+      if (!use_vx_ini) for (int ii = 0; ii < n; ii++) vx[ii] = 0.0;
+      if (type == ORA_SLES_TS_F_GAUSS_SEIDEL)
+        for (int ii = 0; ii < n; ii++) {
+          double vx0 = rhs[ii];
+          for (int jj = row_index[ii]; jj < row_index[ii+1]; jj++) {
+            if (col_id[jj] > ii) break;
+            vx0 -= (x_val[jj]*vx[col_id[jj]]);
+          }
+          vx0 *= 1.0 / d_val[ii];
+          vx[ii] = vx0;
+        }
+      else
+        for (int ii = n - 1; ii > -1; ii--) {
+          double vx0 = rhs[ii];
+          for (int jj = row_index[ii+1] - 1; jj > row_index[ii] - 1; jj--) {
+            if (col_id[jj] < ii) break;
+            vx0 -= (x_val[jj]*vx[col_id[jj]]);
+          }
+          vx0 *= 1.0 / d_val[ii];
+          vx[ii] = vx0;
+        }
+      n_it = 1;
+    }
+    else {
+      for (n_it = 0; n_it < n_max_iter; n_it++) {
+        if (n_it == 0 && !use_vx_ini)
+          for (int ii = 0; ii < n; ii++) vx[ii] = 0;
+        for (int ii = 0; ii < n; ii++) {
+          double vx0 = rhs[ii];
+          for (int jj = row_index[ii]; jj < row_index[ii+1]; jj++)
+            vx0 -= (x_val[jj]*vx[col_id[jj]]);
+          vx[ii] = vx0 * (1.0 / d_val[ii]);
+        }
+        if (type == ORA_SLES_P_SYM_GAUSS_SEIDEL)
+          for (int ii = n - 1; ii > -1; ii--) {
+            double vx0 = rhs[ii];
+            for (int jj = row_index[ii]; jj < row_index[ii+1]; jj++)
+              vx0 -= (x_val[jj]*vx[col_id[jj]]);
+            vx0 *= 1.0 / d_val[ii];
+            vx[ii] = vx0;
+          }
+      }
+    }
+    if (out != NULL) out[0] = n_it;
+    return ORA_MAX_ITERATION;
+  }
 
   double *tmp = malloc(sizeof(double)*(2*(size_t)n + 2));
   double *ad_inv = tmp + n;

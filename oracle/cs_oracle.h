@@ -44,6 +44,10 @@ typedef struct {
 /* cs_sles_it_type_t values used on this path (src/alge/cs_sles_it.h:55-87) */
 #define ORA_SLES_PCG        0
 #define ORA_SLES_JACOBI     3
+#define ORA_SLES_P_GAUSS_SEIDEL      8   /* cs_sles_it_type_t values (cs_sles_it.h:59-86) */
+#define ORA_SLES_P_SYM_GAUSS_SEIDEL  9
+#define ORA_SLES_TS_F_GAUSS_SEIDEL  17
+#define ORA_SLES_TS_B_GAUSS_SEIDEL  18
 #define ORA_SLES_L1_JACOBI 13
 #define ORA_SLES_R_JACOBI  14
 #define ORA_SLES_RJ2       15
@@ -97,6 +101,12 @@ int    ora_jacobi(int n_rows, const int *row_index, const int *col_id,
                   int n_max_iter, double precision, double r_norm,
                   const double *rhs, double *vx, int use_vx_ini,
                   double *out, double *history, int history_size);
+/* _p_gauss_seidel_msr (sym 0) / _p_sym_gauss_seidel_msr (sym 1), cs_sles_it.cpp:3940, :4124 */
+int    ora_gauss_seidel(int sym, int n_rows, const int *row_index, const int *col_id,
+                        const double *d_val, const double *x_val,
+                        int n_max_iter, double precision, double r_norm,
+                        const double *rhs, double *vx, int use_vx_ini,
+                        double *out, double *history, int history_size);
 void   ora_spmv_msr_b3(int n_rows, const int *row_index, const int *col_id,
                        const double *d_val, const double *x_val, int exclude_diag,
                        const double *x, double *y);

@@ -210,6 +210,12 @@ class Oracle:
         return self._solve(self.lib.ora_jacobi, ri, ci, d, xv, rhs, n_max_iter,
                            precision, r_norm, vx0)
 
+    def gauss_seidel(self, sym, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0=None):
+        """_p_gauss_seidel_msr (sym False) / _p_sym_gauss_seidel_msr (True), with convergence test."""
+        import functools
+        return self._solve(functools.partial(self.lib.ora_gauss_seidel, C.c_int(1 if sym else 0)),
+                           ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0)
+
     def bicgstab(self, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0=None):
         return self._solve(self.lib.ora_bicgstab, ri, ci, d, xv, rhs, n_max_iter,
                            precision, r_norm, vx0)

@@ -535,3 +535,63 @@ def test_oracle_matrix_compute_coeffs_vector_matches_golden(oracle, N):
                                                fimp, g["i_massflux"], g["b_massflux"], g["i_visc"],
                                                g["b_visc"], **kw)
         assert np.array_equal(d, g[f"{name}_d"]) and np.array_equal(x, g[f"{name}_x"]), name
+
+
+# ---- process-local Gauss-Seidel family (a18, GS part of a26) ----
+
+GS_SMOOTHERS = {"p_gs": 8, "p_sym_gs": 9, "ts_f_gs": 17, "ts_b_gs": 18}
+
+
+@pytest.mark.parametrize("N,bc", MGPC_CASES)
+def test_oracle_gauss_seidel_matches_golden(oracle, N, bc):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"gs_N{N}_{bc}.npz"))
+    s = cube_poisson(N, bc)
+    r_norm = float(g["r_norm"])
+    for name, st in GS_SMOOTHERS.items():
+        for nit in (1, 3):
+            r = oracle.smoother(st, s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, nit)
+            assert np.array_equal(r["vx"], g[f"sm_{name}_{nit}_zero"]), (name, nit)
+            r = oracle.smoother(st, s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, nit, g["vx0"])
+            assert np.array_equal(r["vx"], g[f"sm_{name}_{nit}_warm"]), (name, nit)
+            assert r["n_iter"] == int(g[f"sm_{name}_{nit}_n_iter"])
+    for name, sym in (("p_gs", False), ("p_sym_gs", True)):
+        for tag, v0 in (("zero", None), ("warm", g["vx0"])):
+            r = oracle.gauss_seidel(sym, s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, 400,
+                                    1e-6, r_norm, v0)
+            for k in ("cvg", "n_iter", "residual", "initial_residual"):
+                assert r[k] == g[f"it_{name}_{tag}_{k}"], (name, tag, k)
+            assert np.array_equal(r["vx"], g[f"it_{name}_{tag}_vx"])
+    mg = oracle.mg_setup(s)
+    types, nmi = (9, 9, 0), (1, 1, 500)
+    r = oracle.mg_cycle_pc(mg, s.rhs, 1e-8, r_norm, types, nmi)
+    assert np.array_equal(r["vx"], g["cyc_sgs_vx"]) and r["n_iter"] == int(g["cyc_sgs_n_iter"])
+    r = oracle.fcg_mgpc(mg, s.rhs, 200, 1e-8, r_norm, types, nmi)
+    for k in ("cvg", "n_iter", "residual", "initial_residual"):
+        assert r[k] == g[f"fcg_sgs_{k}"], k
+    assert np.array_equal(r["vx"], g["fcg_sgs_vx"])
+    oracle.mg_free(mg)
+
+
+def test_oracle_gauss_seidel_vs_reference_direct(oracle, reflib):
+    rng = np.random.default_rng(5)
+    for N, bc in ((10, "dirichlet"), (21, "neumann")):
+        s = cube_poisson(N, bc)
+        h = reflib.system(s)
+        r_norm = float(np.linalg.norm(s.rhs))
+        vx0 = rng.standard_normal(s.n_rows)
+        for st in GS_SMOOTHERS.values():
+            for nit in (1, 2, 4):
+                for v0 in (None, vx0):
+                    a = oracle.smoother(st, s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, nit, v0)
+                    b = reflib.smoother(h, st, s.rhs, nit, v0)
+                    assert a["n_iter"] == b["n_iter"] and a["cvg"] == b["cvg"]
+                    assert np.array_equal(a["vx"], b["vx"]), (N, st, nit)
+        for sym, st in ((False, 8), (True, 9)):
+            for v0 in (None, vx0):
+                a = oracle.gauss_seidel(sym, s.row_index, s.col_id, s.d_val, s.x_val, s.rhs, 150,
+                                        1e-6, r_norm, v0)
+                b = reflib.sles_it(h, st, s.rhs, 150, 1e-6, r_norm, v0)
+                assert (a["cvg"], a["n_iter"], a["residual"], a["initial_residual"]) == (
+                    b["cvg"], b["n_iter"], b["residual"], b["initial_residual"])
+                assert np.array_equal(a["vx"], b["vx"])
+        reflib.destroy(h)
