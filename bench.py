@@ -558,8 +558,8 @@ def main():
                          "ms_per_launch": t_dev * 1e3, "peak_source": peak_src,
                          "launches_timed": args.steps,
                          "in_kernel_phase_seconds": float(pt.sum())},
-            "spmv": {"kernel": "k_spmv_pipeline (level-0 MSR SpMV, stand-alone: the bulk-copy "
-                               "pipeline of the solvers' SpMV phases"
+            "spmv": {"kernel": api.load_library().csb_spmv_kernel_name().decode()
+                               + " (level-0 MSR SpMV, stand-alone, csb_matrix_vector_multiply"
                                + (", per GPU, incl. ghost exchange)" if world > 1 else ")"),
                      "achieved": spmv_gbs, "frac": spmv_gbs / peak, "unit": "GB/s",
                      "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": t_spmv * 1e3},

@@ -89,6 +89,7 @@ def load_library() -> C.CDLL:
     vp, ci, cd, cs = C.c_void_p, C.c_int, C.c_double, C.c_size_t
     L.csb_last_error.restype = C.c_char_p
     L.csb_version.restype = C.c_char_p
+    L.csb_spmv_kernel_name.restype = C.c_char_p
     L.csb_init.argtypes = [ci]
     L.csb_set_stream.argtypes = [vp]
     L.csb_malloc_device.restype = vp

@@ -396,9 +396,18 @@ struct SpmvArgs {
 };
 
 bool launch_spmv(SpmvEpilogue epi, const SpmvArgs &a);
+const char *spmv_kernel_name();
 bool launch_spmv_csr_exdiag(const _csb_matrix_t *m, const double *x, double *y);
 bool launch_spmv_b3(const _csb_matrix_t *m, const double *x, double *y, bool exclude_diag);
 bool launch_ad_inv_block(int n_rows, int db, const double *d_val, double *ad_inv);
+/* block-diagonal MSR of any block size (thread per row component); mode -1 store, 0 / 1 the
+   BiCGStab products with their dots */
+bool launch_spmv_bn(int mode, const _csb_matrix_t *m, ItState *st, const double *x, double *y,
+                    const double *b, bool exclude_diag);
+bool launch_block_nn_inverse(int n_blocks, int db, const double *ad, double *ad_inv);
+bool launch_bn_jacobi_update(int n_blocks, int db, ItState *st, const double *ad,
+                             const double *ad_inv, const double *rhs, const double *vxx,
+                             double *vx, bool first);
 bool launch_bicg_spmv_b3(int mode, const _csb_matrix_t *m, ItState *st, const double *x,
                          double *y, const double *b);
 

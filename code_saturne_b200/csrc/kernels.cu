@@ -22,6 +22,7 @@
 #include "persistent.h"
 
 #include <cfloat>
+#include <cstring>
 #include <cmath>
 
 namespace csb {
@@ -569,6 +570,83 @@ bool launch_bicg_spmv_b3(int mode, const _csb_matrix_t *m, ItState *st, const do
   return post_launch("bicg_spmv_b3");
 }
 
+/*--------------------------------------------------------------------------
+ * Block-diagonal MSR of any block size 2..9 (CS_MATRIX_BLOCK_D): _b_mat_vec_p_l_msr_generic
+ * and _b_mat_vec_p_l_msr_6 (cs_matrix_spmv.cpp:2308-2380, :2478-2545).  Thread per (block
+ * row, component): the db threads of a row read the same e_ij (broadcast) and db consecutive
+ * x, so the accesses coalesce whatever the block size; a component's sum is the reference's,
+ * term by term: (D_i.x_i)_k (_dense_b_ax :560-576 starts from 0., _dense_6_6_ax :622-670 from
+ * the first product) FIRST, then += e_ij * x_j,k in CSR order.
+ * MODE as k_spmv_b3.  Algorithmic bytes: 12 nnz + 4 n + 8 db^2 n (D) + 8 db n (x) + 8 db n (y).
+ *--------------------------------------------------------------------------*/
+
+template <int MODE>
+__global__ void __launch_bounds__(TPB)
+k_spmv_bn(int n_rows, int db, const int *__restrict__ row_index,
+          const int *__restrict__ col_id, const double *__restrict__ d_val,
+          const double *__restrict__ x_val, const double *__restrict__ x,
+          double *__restrict__ y, const double *__restrict__ b, ItState *st,
+          double *partials, unsigned *ticket)
+{
+  if (MODE >= 0 && st->cvg != CSB_SLES_ITERATING) return;
+  const long long t = (long long)blockIdx.x*TPB + threadIdx.x;
+  double v[2] = {0., 0.};
+  if (t < (long long)n_rows*db) {
+    const int ii = (int)(t / db), kk = (int)(t - (long long)ii*db);
+    double yk = 0.;
+    if (d_val != nullptr) {
+      const double *a = d_val + (size_t)ii*db*db + (size_t)kk*db;
+      const double *xi = x + (size_t)ii*db;
+      if (db == 6) {
+        yk = a[0]*xi[0];
+        for (int j = 1; j < 6; j++) yk += a[j]*xi[j];
+      }
+      else
+        for (int j = 0; j < db; j++) yk += a[j]*xi[j];
+    }
+    const int ks = row_index[ii], ke = row_index[ii+1];
+    for (int jj = ks; jj < ke; jj++)
+      yk += (x_val[jj]*x[(size_t)col_id[jj]*db + kk]);
+    y[t] = yk;
+    if (MODE == 0) v[0] = yk*b[t];
+    else if (MODE == 1) { v[0] = yk*yk; v[1] = yk*b[t]; }
+  }
+  if (MODE == 0)
+    grid_sum_finalize<2>(v, partials, ticket, [st](const double *s) {
+      st->gamma = st->beta / s[0];          /* cs_sles_it.cpp:2830-2832 */
+    });
+  else if (MODE == 1)
+    grid_sum_finalize<2>(v, partials, ticket, [st](const double *s) {
+      const double ro_1 = s[0], ro_0 = s[1]; /* cs_sles_it.cpp:2847-2855 */
+      if (fabs(ro_1) < 1.e-30) { st->cvg = CSB_SLES_BREAKDOWN; return; }
+      double d_ro_1 = (fabs(ro_1) > DBL_MIN) ? 1. / ro_1 : 0.;
+      st->alpha = ro_0 * d_ro_1;
+    });
+}
+
+/* mode -1: y = A.x (or E.x); 0 / 1: the two BiCGStab products with their dot products */
+bool launch_spmv_bn(int mode, const _csb_matrix_t *m, ItState *st, const double *x, double *y,
+                    const double *b, bool exclude_diag)
+{
+  const long long nt = (long long)m->n_rows*m->db;
+  const int grid = (int)((nt + TPB - 1) / TPB);
+  if (grid < 1) return true;
+  Context &c = ctx();
+  if (mode >= 0 && !ensure_partials(grid)) return false;
+  const double *d = exclude_diag ? nullptr : m->d_val.p;
+  if (mode < 0)
+    k_spmv_bn<-1><<<grid, TPB, 0, c.stream>>>(m->n_rows, m->db, m->row_index.p, m->col_id.p, d,
+                                              m->x_val.p, x, y, nullptr, nullptr, nullptr,
+                                              nullptr);
+  else if (mode == 0)
+    k_spmv_bn<0><<<grid, TPB, 0, c.stream>>>(m->n_rows, m->db, m->row_index.p, m->col_id.p, d,
+                                             m->x_val.p, x, y, b, st, c.partials, c.ticket);
+  else
+    k_spmv_bn<1><<<grid, TPB, 0, c.stream>>>(m->n_rows, m->db, m->row_index.p, m->col_id.p, d,
+                                             m->x_val.p, x, y, b, st, c.partials, c.ticket);
+  return post_launch("spmv_bn");
+}
+
 /* point Jacobi of a block matrix: ad_inv[i] = 1 / ad[i*db + i%db]  (cs_sles_pc.cpp:383-388) */
 __global__ void __launch_bounds__(TPB)
 k_ad_inv_block(int n, int db, const double *__restrict__ d, double *__restrict__ ad_inv)
@@ -606,16 +684,103 @@ void matrix_plan_spmv(_csb_matrix_t *m)
 
 bool ensure_partials(int n_blocks);
 
-static bool spmv_pipeline_enabled()
+/*--------------------------------------------------------------------------
+ * Stand-alone y = A.x, a thread per row with everything in registers (k_spmv_rows).
+ * Measured on the 256^3 cube (profiles/r02): on B200 the row-per-thread access pattern is
+ * served by L1 (a warp's 32 rows are ~2.7 KB of contiguous col_id / x_val; every 128-byte
+ * line is consumed by neighbouring lanes within a few instructions), and 2048 resident
+ * threads per SM with 3 x 8 independent loads each keep more bytes in flight than the
+ * shared-memory staged kernels did -- the reference's own `_mat_vect_p_l_msr`
+ * (cs_matrix_spmv_cuda.cu:415-439) ran at 0.98 of the measured copy rate, the bulk-copy
+ * pipeline at 0.90, k_spmv_stream at 0.75.  This kernel keeps that access pattern and adds:
+ * batches of 8 entries whose index / value loads, then gathers, are all issued before the
+ * first use (the compiler cannot hoist them out of a variable-trip loop by itself);
+ * optionally streaming (evict-first) loads of the matrix so that x stays in L2; the CPU path's
+ * arithmetic (no FMA, CSR order, diagonal last) so that y is bit-identical to the oracle.
+ *--------------------------------------------------------------------------*/
+
+namespace {
+
+/* matrix entries are read once: STREAM selects ld.global.cs (evict-first) for them so that
+   x keeps its place in L2; measured against plain read-only loads (CSB_SPMV_ROWS_CS) */
+template <bool STREAM> __device__ __forceinline__ int ld_mat(const int *p)
+{ return STREAM ? __ldcs(p) : __ldg(p); }
+template <bool STREAM> __device__ __forceinline__ double ld_mat(const double *p)
+{ return STREAM ? __ldcs(p) : __ldg(p); }
+
+template <bool EXDIAG, bool STREAM, int B, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
+k_spmv_rows(int n_rows, const int *__restrict__ row_index, const int *__restrict__ col_id,
+            const double *__restrict__ d_val, const double *__restrict__ x_val,
+            const double *__restrict__ x, double *__restrict__ y)
+{
+  const int ii = blockIdx.x*TPB + threadIdx.x;
+  if (ii >= n_rows) return;
+  const int ks = __ldg(row_index + ii), ke = __ldg(row_index + ii + 1);
+  double dx = 0.0;
+  if (!EXDIAG) dx = ld_mat<STREAM>(d_val + ii) * __ldg(x + ii);
+  double sii = 0.0;
+  int k = ks;
+  for (; k + B <= ke; k += B) {
+    int c[B]; double v[B], g[B];
+#pragma unroll
+    for (int j = 0; j < B; j++) { c[j] = ld_mat<STREAM>(col_id + k + j); v[j] = ld_mat<STREAM>(x_val + k + j); }
+#pragma unroll
+    for (int j = 0; j < B; j++) g[j] = __ldg(x + c[j]);
+#pragma unroll
+    for (int j = 0; j < B; j++) sii += v[j] * g[j];
+  }
+  if (k < ke) {
+    int c[B]; double v[B], g[B];
+#pragma unroll
+    for (int j = 0; j < B - 1; j++) {
+      const bool p = (k + j < ke);
+      c[j] = p ? ld_mat<STREAM>(col_id + k + j) : ii;
+      v[j] = p ? ld_mat<STREAM>(x_val + k + j) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < B - 1; j++) g[j] = __ldg(x + c[j]);
+#pragma unroll
+    for (int j = 0; j < B - 1; j++) if (k + j < ke) sii += v[j] * g[j];
+  }
+  y[ii] = EXDIAG ? sii : sii + dx;
+}
+
+template <bool EXDIAG, bool STREAM, int B, int MINB>
+void rows_launch(int grid, const _csb_matrix_t *m, const SpmvK &k)
+{
+  k_spmv_rows<EXDIAG, STREAM, B, MINB><<<grid, TPB, 0, ctx().stream>>>(
+    m->n_rows, k.row_index, k.col_id, m->d_val.p, k.x_val, k.x, k.y);
+}
+
+int env_flag(const char *name, int dflt)
+{
+  const char *e = getenv(name);
+  return (e != nullptr) ? atoi(e) : dflt;
+}
+
+/* 0 rows (default), 1 bulk-copy pipeline, 2 streaming kernel */
+int spmv_kernel_choice()
 {
   static int v = -1;
-  /* measured at 256^3 (profiles/r02): the bulk-copy pipeline kernel -- the code of the
-     solvers' SpMV phases -- runs y = A.x at ~0.88 of the measured HBM rate since its
-     producer no longer fences per stage, k_spmv_stream at 0.75: the pipeline is the
-     default, CSB_SPMV_PIPELINE=0 selects the streaming kernel (which also remains for
-     buffers the pipeline cannot take) */
-  if (v < 0) { const char *e = getenv("CSB_SPMV_PIPELINE"); v = (e != nullptr && atoi(e) == 0) ? 0 : 1; }
-  return v == 1;
+  if (v < 0) {
+    const char *e = getenv("CSB_SPMV_KERNEL");
+    v = 0;
+    if (e != nullptr && strcmp(e, "pipeline") == 0) v = 1;
+    if (e != nullptr && strcmp(e, "stream") == 0) v = 2;
+    /* earlier switch, still honoured */
+    const char *o = getenv("CSB_SPMV_PIPELINE");
+    if (e == nullptr && o != nullptr) v = (atoi(o) == 0) ? 2 : 1;
+  }
+  return v;
+}
+
+} // anonymous namespace
+
+const char *spmv_kernel_name()
+{
+  const int v = spmv_kernel_choice();
+  return v == 0 ? "k_spmv_rows" : (v == 1 ? "k_spmv_pipeline" : "k_spmv_stream");
 }
 
 bool launch_spmv(SpmvEpilogue epi, const SpmvArgs &a)
@@ -633,7 +798,27 @@ bool launch_spmv(SpmvEpilogue epi, const SpmvArgs &a)
   if (epi == EPI_RESIDUAL_NORM || epi == EPI_PCG_DOT3 || epi == EPI_FCG_DOT4)
     if (!ensure_partials((m->n_rows + TPB - 1) / TPB)) return false;
   k.partials = ctx().partials; k.ticket = ctx().ticket;   /* after a possible regrow */
-  if (epi == EPI_STORE && spmv_pipeline_enabled()) {
+  if (epi == EPI_STORE && spmv_kernel_choice() == 0) {
+    const int grid = (m->n_rows + TPB - 1)/TPB;
+    if (grid < 1) return true;
+    /* measured variants (profiles/r02/spmv_rows_variants.md): batches of 8 entries at 48
+       registers (5 CTAs per SM) or batches of 4 capped at 32 registers (8 CTAs per SM) */
+    static const int cs = env_flag("CSB_SPMV_ROWS_CS", 0);
+    static const int b4 = env_flag("CSB_SPMV_ROWS_B4", 0);
+    const int v = (a.exclude_diag ? 4 : 0) + (cs ? 2 : 0) + (b4 ? 1 : 0);
+    switch (v) {
+    case 0: rows_launch<false, false, 8, 5>(grid, m, k); break;
+    case 1: rows_launch<false, false, 4, 8>(grid, m, k); break;
+    case 2: rows_launch<false, true, 8, 5>(grid, m, k); break;
+    case 3: rows_launch<false, true, 4, 8>(grid, m, k); break;
+    case 4: rows_launch<true, false, 8, 5>(grid, m, k); break;
+    case 5: rows_launch<true, false, 4, 8>(grid, m, k); break;
+    case 6: rows_launch<true, true, 8, 5>(grid, m, k); break;
+    default: rows_launch<true, true, 4, 8>(grid, m, k); break;
+    }
+    return post_launch("spmv_rows");
+  }
+  if (epi == EPI_STORE && spmv_kernel_choice() == 1) {
     /* bulk-copy pipeline with producer / consumer warps (persistent.cu); the streaming
        kernel below remains for buffers the pipeline cannot take */
     bool launched = false;
@@ -1310,6 +1495,7 @@ bool bicg_spmv_launch(int mode, const _csb_matrix_t *m, ItState *st, const doubl
                       double *y, const double *b)
 {
   if (m->db == 3) return launch_bicg_spmv_b3(mode, m, st, x, y, b);
+  if (m->db > 1) return launch_spmv_bn(mode, m, st, x, y, b, false);
   SpmvK k;
   k.n_rows = m->n_rows; k.row_index = m->row_index.p; k.col_id = m->col_id.p;
   k.d_val = m->d_val.p; k.x_val = m->x_val.p; k.x = x; k.y = y; k.b = b;
@@ -2088,6 +2274,117 @@ k_b3_jacobi_update(int n_blocks, ItState *st, const double *__restrict__ ad,
   });
 }
 
+/* cs_math_matrix_gauss_inverse<6> (cs_math.h:540-586), the block inverse of 6x6 diagonal
+   blocks (_setup_ad_block_nn_inv, cs_sles_it_priv.cpp:205-214) */
+__global__ void __launch_bounds__(64)
+k_gauss_inverse_66(int n_blocks, const double *__restrict__ ad, double *__restrict__ ad_inv)
+{
+  for (int b = blockIdx.x*64 + threadIdx.x; b < n_blocks; b += gridDim.x*64) {
+    double t[6][12];
+    int p[6] = {0, 1, 2, 3, 4, 5};
+    for (int i = 0; i < 6; i++) {
+      for (int j = 0; j < 6; j++) {
+        t[i][j] = ad[(size_t)b*36 + i*6 + j];
+        t[i][j+6] = 0.;
+      }
+      t[i][i+6] = 1.;
+    }
+    for (int i = 0; i < 6; i++) {
+      for (int j = i+1; j < 6; j++) {
+        if (fabs(t[p[i]][i]) < fabs(t[p[j]][i])) {
+          const int tmp = p[j]; p[j] = p[i]; p[i] = tmp;
+        }
+      }
+      for (int j = 0; j < 6; j++) {
+        if (j != i) {
+          const double s = t[p[j]][i] / t[p[i]][i];
+          for (int k = 0; k < 12; k++)
+            t[p[j]][k] -= t[p[i]][k] * s;
+        }
+      }
+    }
+    for (int i = 0; i < 6; i++) {
+      const double s = 1. / t[p[i]][i];
+      for (int j = 0; j < 6; j++)
+        ad_inv[(size_t)b*36 + i*6 + j] = t[p[i]][6+j] * s;
+    }
+  }
+}
+
+/* _fact_lu (cs_sles_it_priv.cpp:118-160): what _setup_ad_block_nn_inv stores in ad_inv for
+   block sizes other than 3 and 6 -- the LU factors, which _block_jacobi then applies with
+   _mat_c_m_b as if they were the inverse.  Reproduced as it is: the results are the
+   reference's for every block size. */
+__global__ void __launch_bounds__(TPB)
+k_fact_lu(int n_blocks, int db, const double *__restrict__ ad, double *__restrict__ ad_inv)
+{
+  for (int b = blockIdx.x*TPB + threadIdx.x; b < n_blocks; b += gridDim.x*TPB) {
+    double *ai = ad_inv + (size_t)db*db*b;
+    const double *a = ad + (size_t)db*db*b;
+    ai[0] = a[0];
+    for (int ii = 1; ii < db; ii++) {
+      ai[ii] = a[ii];
+      ai[ii*db] = a[ii*db]/a[0];
+    }
+    for (int ii = 1; ii < db - 1; ii++) {
+      ai[ii + ii*db] = a[ii + ii*db];
+      for (int kk = 0; kk < ii; kk++)
+        ai[ii + ii*db] -= ai[ii*db + kk]*ai[kk*db + ii];
+      for (int jj = ii + 1; jj < db; jj++) {
+        ai[ii*db + jj] = a[ii*db + jj];
+        ai[jj*db + ii] = a[jj*db + ii] / ai[ii*db + ii];
+        for (int kk = 0; kk < ii; kk++) {
+          ai[ii*db + jj] -= ai[ii*db + kk]*ai[kk*db + jj];
+          ai[jj*db + ii] -= ai[jj*db + kk]*ai[kk*db + ii]/ai[ii*db + ii];
+        }
+      }
+    }
+    ai[db*db - 1] = a[db*db - 1];
+    for (int kk = 0; kk < db - 1; kk++)
+      ai[db*db - 1] -= ai[(db-1)*db + kk]*ai[kk*db + db - 1];
+  }
+}
+
+/* _block_jacobi sweep (cs_sles_it.cpp:2460-2620) after vxx = E.vx: vx = mat.(rhs - vxx)
+   (_mat_c_m_b, cs_sles_it_priv.h:302-322: x = 0; x += aux_j * mat_ij) and
+   residual^2 = sum (D.(x_new - x_old))^2; first = 1: the simplified sweep from vx = 0. */
+__global__ void __launch_bounds__(TPB)
+k_bn_jacobi_update(int n_blocks, int db, ItState *st, const double *__restrict__ ad,
+                   const double *__restrict__ ad_inv, const double *__restrict__ rhs,
+                   const double *__restrict__ vxx, double *__restrict__ vx, int first,
+                   double *partials, unsigned *ticket)
+{
+  if (st->cvg != CSB_SLES_ITERATING) return;
+  double v[1] = {0.};
+  for (int ii = blockIdx.x*TPB + threadIdx.x; ii < n_blocks; ii += gridDim.x*TPB) {
+    double xo[9], aux[9], xn[9];
+    for (int k = 0; k < db; k++) {
+      xo[k] = first ? 0. : vx[(size_t)ii*db + k];
+      const double b = first ? 0. : vxx[(size_t)ii*db + k];
+      aux[k] = (rhs[(size_t)ii*db + k] - b);
+    }
+    const double *mat = ad_inv + (size_t)ii*db*db;
+    for (int r = 0; r < db; r++) {
+      double x = 0;
+      for (int j = 0; j < db; j++) x += aux[j]*mat[r*db + j];
+      xn[r] = x;
+    }
+    for (int k = 0; k < db; k++) vx[(size_t)ii*db + k] = xn[k];
+    for (int jj = 0; jj < db; jj++) {
+      double r = 0.0;
+      for (int kk = 0; kk < db; kk++)
+        r += ad[(size_t)ii*db*db + jj*db + kk] * (xn[kk] - xo[kk]);
+      v[0] += (r*r);
+    }
+  }
+  grid_sum_finalize<1>(v, partials, ticket, [st](const double *s) {
+    st->n_iter += 1;
+    const double residual = sqrt(s[0]);
+    if (st->n_iter == 1) st->initial_residual = residual;
+    st->cvg = it_cvg_test(st, st->n_iter, residual);
+  });
+}
+
 } // anonymous namespace
 
 bool launch_gauss_inverse_33(int n_blocks, const double *ad, double *ad_inv)
@@ -2106,6 +2403,33 @@ bool launch_b3_jacobi_update(int n_blocks, ItState *st, const double *ad, const 
   k_b3_jacobi_update<<<g, TPB, 0, c.stream>>>(n_blocks, st, ad, ad_inv, rhs, vxx, vx,
                                               first ? 1 : 0, c.partials, c.ticket);
   return post_launch("b3_jacobi_update");
+}
+
+/* block "inverse" of cs_sles_it_setup for block Jacobi with db != 3: Gauss-Jordan inverse for
+   6x6 blocks, LU factors otherwise (_setup_ad_block_nn_inv, cs_sles_it_priv.cpp:178-222) */
+bool launch_block_nn_inverse(int n_blocks, int db, const double *ad, double *ad_inv)
+{
+  if (n_blocks < 1) return true;
+  if (db == 3) return launch_gauss_inverse_33(n_blocks, ad, ad_inv);
+  if (db == 6) {
+    int g = (n_blocks + 63)/64; if (g > 65535) g = 65535;
+    k_gauss_inverse_66<<<g, 64, 0, ctx().stream>>>(n_blocks, ad, ad_inv);
+  }
+  else
+    k_fact_lu<<<vec_grid(n_blocks*4), TPB, 0, ctx().stream>>>(n_blocks, db, ad, ad_inv);
+  return post_launch("block_nn_inverse");
+}
+
+bool launch_bn_jacobi_update(int n_blocks, int db, ItState *st, const double *ad,
+                             const double *ad_inv, const double *rhs, const double *vxx,
+                             double *vx, bool first)
+{
+  Context &c = ctx();
+  const int g = vec_grid(n_blocks*4);
+  if (!ensure_partials(g)) return false;
+  k_bn_jacobi_update<<<g, TPB, 0, c.stream>>>(n_blocks, db, st, ad, ad_inv, rhs, vxx, vx,
+                                              first ? 1 : 0, c.partials, c.ticket);
+  return post_launch("bn_jacobi_update");
 }
 
 bool launch_l1_inv(const _csb_matrix_t *m, double *l1_inv)

@@ -53,6 +53,7 @@ _csb_matrix_t::~_csb_matrix_t() { delete csr; if (gs_plan) csb::gs_plan_free(gs_
 extern "C" {
 
 const char *csb_version(void) { return "csb200 0.1 (sm_100a, FP64)"; }
+const char *csb_spmv_kernel_name(void) { return csb::spmv_kernel_name(); }
 
 const char *csb_last_error(void) { return ctx().err.c_str(); }
 
@@ -213,8 +214,8 @@ csb_matrix_create_msr_block(csb_lnum_t n_rows, csb_lnum_t n_cols_ext, int db_siz
     return csb_matrix_create_msr(n_rows, n_cols_ext, row_index, col_id, d_val, x_val, symmetric);
   Context &c = ctx();
   if (!c.ready) { set_error("csb_matrix_create_msr_block: csb_init not called"); return nullptr; }
-  if (db_size != 3) {
-    set_error("csb_matrix_create_msr_block: diagonal block size %d (1 and 3 are available)",
+  if (db_size < 2 || db_size > 9) {     /* DB_SIZE_MAX, cs_sles_it_priv.h:92 */
+    set_error("csb_matrix_create_msr_block: diagonal block size %d (1 to 9 are available)",
               db_size);
     return nullptr;
   }
@@ -557,10 +558,11 @@ static int _spmv_api(const csb_matrix_t *m, csb_real_t *x, csb_real_t *y, bool e
     if (!ty.alloc((size_t)m->n_rows*m->db)) return -1;
     y_d = ty.p;
   }
-  if (m->db == 3) {
+  if (m->db > 1) {
     if (m->halo != nullptr) { set_error("block matrices: no halo on this path yet"); return -1; }
-    if (!launch_spmv_b3(m, x_d, y_d, exdiag)) return -1;
-    if (!yd && !CSB_CUDA(cudaMemcpyAsync(y, y_d, sizeof(double)*(size_t)m->n_rows*3,
+    if (m->db == 3) { if (!launch_spmv_b3(m, x_d, y_d, exdiag)) return -1; }
+    else if (!launch_spmv_bn(-1, m, nullptr, x_d, y_d, nullptr, exdiag)) return -1;
+    if (!yd && !CSB_CUDA(cudaMemcpyAsync(y, y_d, sizeof(double)*(size_t)m->n_rows*m->db,
                                          cudaMemcpyDeviceToHost, c.stream))) return -1;
     if ((!xd || !yd) && !CSB_CUDA(cudaStreamSynchronize(c.stream))) return -1;
     return 0;

@@ -567,6 +567,7 @@ bool bicgstab_enqueue(const csb_matrix_t *m, ItState *st, const double *ad_inv,
   if (!launch_it_state_init(st, nullptr, precision, r_norm, n_max_iter)) return false;
   if (vx_ini_nonzero) {
     if (m->db == 3) { if (!launch_spmv_b3(m, vx, res0, false)) return false; }
+    else if (m->db > 1) { if (!launch_spmv_bn(-1, m, nullptr, vx, res0, nullptr, false)) return false; }
     else {
       SpmvArgs a; a.m = m; a.x = vx; a.y = res0;
       if (!launch_spmv(EPI_STORE, a)) return false;
@@ -637,17 +638,22 @@ bool block3_jacobi_enqueue(const csb_matrix_t *m, ItState *st, const double *ad_
   Context &c = ctx();
   if (!launch_it_state_init(st, nullptr, precision, r_norm, n_max_iter)) return false;
   int t = 0;
+  const int db = m->db;
+  auto update = [&](bool first) {
+    return (db == 3)
+      ? launch_b3_jacobi_update(m->n_rows, st, m->d_val.p, ad_inv, rhs, vxx, vx, first)
+      : launch_bn_jacobi_update(m->n_rows, db, st, m->d_val.p, ad_inv, rhs, vxx, vx, first);
+  };
   if (!vx_ini_nonzero) {
-    if (!launch_b3_jacobi_update(m->n_rows, st, m->d_val.p, ad_inv, rhs, vxx, vx, true))
-      return false;
+    if (!update(true)) return false;
     t = 1;
   }
   const int poll = 16;
   while (t < n_max_iter) {
     t += 1;
-    if (!launch_spmv_b3(m, vx, vxx, true)) return false;
-    if (!launch_b3_jacobi_update(m->n_rows, st, m->d_val.p, ad_inv, rhs, vxx, vx, false))
-      return false;
+    if (db == 3) { if (!launch_spmv_b3(m, vx, vxx, true)) return false; }
+    else if (!launch_spmv_bn(-1, m, nullptr, vx, vxx, nullptr, true)) return false;
+    if (!update(false)) return false;
     if (h_st != nullptr && (t % poll) == 0) {
       if (!CSB_CUDA(cudaMemcpyAsync(h_st, st, IT_HEAD, cudaMemcpyDeviceToHost, c.stream)))
         return false;
@@ -869,17 +875,18 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
               "smoother forms take a halo)");
     return;
   }
-  if (a->db != 1 && c->type != CSB_SLES_BICGSTAB && !(c->type == CSB_SLES_JACOBI && a->db == 3)) {
+  if (a->db != 1 && c->type != CSB_SLES_BICGSTAB && c->type != CSB_SLES_JACOBI) {
     set_error("csb_sles_it_setup: block matrices (db %d) are solved with CSB_SLES_BICGSTAB "
-              "or, for 3x3 blocks, CSB_SLES_JACOBI on this path", a->db);
+              "or CSB_SLES_JACOBI (block Jacobi) on this path", a->db);
     return;
   }
-  if (a->db == 3 && c->type == CSB_SLES_JACOBI) {
-    /* block_nn_inverse (cs_sles_it_setup :4999, cs_sles_it_priv.cpp:174-222) */
+  if (a->db > 1 && c->type == CSB_SLES_JACOBI) {
+    /* block_nn_inverse (cs_sles_it_setup :4999, cs_sles_it_priv.cpp:174-222): Gauss-Jordan
+       inverses of 3x3 and 6x6 blocks, LU factors for the other sizes */
     if (a->halo != nullptr) { set_error("csb_sles_it_setup: block Jacobi runs on one rank"); return; }
-    if (!c->ad_inv.alloc((size_t)a->n_rows*9)) return;
-    if (!launch_gauss_inverse_33(a->n_rows, a->d_val.p, c->ad_inv.p)) return;
-    if (!c->work.alloc(work_stride_of((size_t)a->n_cols_ext*3))) return;
+    if (!c->ad_inv.alloc((size_t)a->n_rows*a->db*a->db)) return;
+    if (!launch_block_nn_inverse(a->n_rows, a->db, a->d_val.p, c->ad_inv.p)) return;
+    if (!c->work.alloc(work_stride_of((size_t)a->n_cols_ext*a->db))) return;
     if (!c->st.alloc(1)) return;
     if (c->h_st == nullptr)
       if (!CSB_CUDA(cudaMallocHost((void **)&c->h_st, sizeof(ItState)))) return;
@@ -1068,7 +1075,8 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
     }
     break;
   case CSB_SLES_JACOBI:
-    if (a->db == 3) {
+    if (a->db > 1) {
+      /* _block_3_jacobi for 3x3 blocks, _block_jacobi otherwise (cs_sles_it.cpp:5058-5064) */
       ok = block3_jacobi_enqueue(a, c->st.p, c->ad_inv.p, precision, r_norm, c->n_max_iter,
                                  s_rhs.d, s_vx.d, ini, c->work.p, c->h_st);
       break;

@@ -399,3 +399,28 @@ def cube_block3_convection_diffusion(N: int, seed: int = 1234):
     g = np.arange(3 * n, dtype=np.float64)
     rhs = np.sin(0.013 * g + 0.4) * h ** 3
     return s.row_index, s.col_id, d_val, x_val, rhs
+
+
+def cube_block_convection_diffusion(N: int, db: int, seed: int = 4321):
+    """The system of cube_block3_convection_diffusion with db x db diagonal blocks (any block
+    size of CS_MATRIX_BLOCK_D: 6 for symmetric tensors, others for the generic code paths).
+    Returns (row_index, col_id, d_val[n,db,db], x_val, rhs[db*n])."""
+    s = cube_poisson(N, "dirichlet", with_mesh=False)
+    n = s.n_rows
+    ri = s.row_index.astype(np.int64)
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(ri))
+    cols = s.col_id.astype(np.int64)
+    h = 1.0 / N
+    lo, hi = np.minimum(rows, cols), np.maximum(rows, cols)
+    phi = 0.6 * h * np.cos(0.37 * lo + 0.11 * hi)
+    x_val = -h + np.where(cols > rows, 0.5, -0.5) * phi
+    row_sum = np.zeros(n)
+    np.add.at(row_sum, rows, -x_val)
+    rng = np.random.default_rng(seed + db)
+    d_val = np.zeros((n, db, db))
+    for k in range(db):
+        d_val[:, k, k] = row_sum + (0.05 + 0.02 * k) * h + (6 - np.diff(ri)) * 2.0 * h
+    d_val += 0.02 * h * rng.standard_normal((n, db, db))
+    g = np.arange(db * n, dtype=np.float64)
+    rhs = np.sin(0.013 * g + 0.4) * h ** 3
+    return s.row_index, s.col_id, d_val, x_val, rhs

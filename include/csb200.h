@@ -88,6 +88,9 @@ int          csb_get_device(void);
 void         csb_finalize(void);
 const char  *csb_last_error(void);
 const char  *csb_version(void);
+/* name of the kernel csb_matrix_vector_multiply launches for scalar MSR matrices (k_spmv_rows
+   by default; CSB_SPMV_KERNEL=pipeline|stream selects the others) */
+const char  *csb_spmv_kernel_name(void);
 
 /* Use an externally owned cudaStream_t (passed as void *) for all work;
    NULL restores the library's own stream

@@ -754,6 +754,49 @@ ora_spmv_msr_b3(int n_rows, const int *row_index, const int *col_id,
 }
 
 /*----------------------------------------------------------------------------
+ * Block-diagonal MSR SpMV, any block size: _b_mat_vec_p_l_msr_generic
+ * (src/alge/cs_matrix_spmv.cpp:2308-2380) with _dense_b_ax (:560-576, sums from 0.), and for
+ * 6x6 blocks _b_mat_vec_p_l_msr_6 (:2478-2545) with _dense_6_6_ax (:622-670, sums from the
+ * first product); selected by block size like _b_mat_vec_p_l_msr (:2562-2580).
+ *----------------------------------------------------------------------------*/
+
+void
+ora_spmv_msr_bn(int n_rows, int db, const int *row_index, const int *col_id,
+                const double *d_val, const double *x_val, int exclude_diag,
+                const double *x, double *y)
+{
+  if (db == 3) {
+    ora_spmv_msr_b3(n_rows, row_index, col_id, d_val, x_val, exclude_diag, x, y);
+    return;
+  }
+  const int db2 = db*db;
+  for (int ii = 0; ii < n_rows; ii++) {
+    const int *restrict c = col_id + row_index[ii];
+    const double *restrict m_row = x_val + row_index[ii];
+    const int n_cols = row_index[ii+1] - row_index[ii];
+    if (!exclude_diag) {
+      for (int kk = 0; kk < db; kk++) {
+        const double *a = d_val + (size_t)ii*db2 + kk*db;
+        if (db == 6)
+          y[ii*6 + kk] =   a[0]*x[ii*6]     + a[1]*x[ii*6 + 1] + a[2]*x[ii*6 + 2]
+                         + a[3]*x[ii*6 + 3] + a[4]*x[ii*6 + 4] + a[5]*x[ii*6 + 5];
+        else {
+          y[ii*db + kk] = 0.;
+          for (int jj = 0; jj < db; jj++)
+            y[ii*db + kk] += a[jj] * x[ii*db + jj];
+        }
+      }
+    }
+    else {
+      for (int kk = 0; kk < db; kk++) y[ii*db + kk] = 0.;
+    }
+    for (int jj = 0; jj < n_cols; jj++)
+      for (int kk = 0; kk < db; kk++)
+        y[ii*db + kk] += (m_row[jj]*x[c[jj]*db + kk]);
+  }
+}
+
+/*----------------------------------------------------------------------------
  * BiCGStab + Jacobi preconditioner: _bi_cgstab (src/alge/cs_sles_it.cpp:2693-2880)
  * with pc_apply = x*ad_inv (src/alge/cs_sles_pc.cpp:502-535).
  * db = 1 (scalar) or 3 (block-diagonal matrix: vectors of n_rows*3, point
@@ -776,7 +819,7 @@ ora_bicgstab_b(int n_rows, int db, const int *row_index, const int *col_id,
 
 #define ORA_SPMV(xx, yy) \
   do { if (db == 1) ora_spmv_msr(n_rows, row_index, col_id, d_val, x_val, 0, xx, yy); \
-       else ora_spmv_msr_b3(n_rows, row_index, col_id, d_val, x_val, 0, xx, yy); } while (0)
+       else ora_spmv_msr_bn(n_rows, db, row_index, col_id, d_val, x_val, 0, xx, yy); } while (0)
 
   ora_cvg_t cv = {precision, r_norm, -1, n_max_iter, 0, -1,
                   history, history_size, 0};
@@ -2677,6 +2720,152 @@ ora_block3_jacobi(int n_rows, const int *row_index, const int *col_id,
         double r = 0.0;
         for (int kk = 0; kk < 3; kk++)
           r += ad[ii*9 + jj*3 + kk] * (vx[ii*3 + kk] - rk[ii*3 + kk]);
+        res2 += (r*r);
+      }
+    }
+    residual = sqrt(res2);
+    if (n_iter == 1) cv.initial_residual = residual;
+    cvg = _cvg_test(&cv, n_iter, residual);
+  }
+
+  out[0] = cv.n_iterations; out[1] = cv.residual; out[2] = cv.initial_residual;
+  out[3] = cv.history_n;
+  free(rk);
+  return cvg;
+}
+
+/*----------------------------------------------------------------------------
+ * Block Jacobi for block sizes other than 3: _block_jacobi (src/alge/cs_sles_it.cpp:2460-2620).
+ * Setup (_setup_ad_block_nn_inv, cs_sles_it_priv.cpp:178-222): 6x6 blocks get their
+ * Gauss-Jordan inverse (cs_math_matrix_gauss_inverse<6>, cs_math.h:540-586); every other size
+ * gets the LU factors of _fact_lu (:118-160) -- which the sweep then applies with _mat_c_m_b
+ * (cs_sles_it_priv.h:302-322) as it does an inverse.  Restated as it is.
+ *----------------------------------------------------------------------------*/
+
+static void
+_ora_gauss_inverse_n(int n, const double *a, double *b)
+{
+  double t[9][18];
+  double *p_a[9];
+  for (int i = 0; i < n; i++) {
+    p_a[i] = t[i];
+    for (int j = 0; j < n; j++) { p_a[i][j] = a[i*n + j]; p_a[i][j+n] = 0; }
+    p_a[i][i+n] = 1;
+  }
+  for (int i = 0; i < n; i++) {
+    for (int j = i+1; j < n; j++) {
+      if (fabs(p_a[i][i]) < fabs(p_a[j][i])) {
+        double *tmp = p_a[j]; p_a[j] = p_a[i]; p_a[i] = tmp;
+      }
+    }
+    for (int j = 0; j < n; j++) {
+      if (j != i) {
+        double s = p_a[j][i] / p_a[i][i];
+        for (int k = 0; k < 2*n; k++) p_a[j][k] -= p_a[i][k] * s;
+      }
+    }
+  }
+  for (int i = 0; i < n; i++) {
+    double s = 1. / p_a[i][i];
+    for (int j = 0; j < n; j++) b[i*n + j] = p_a[i][n+j] * s;
+  }
+}
+
+static void
+_ora_fact_lu(int db_size, const double *_ad, double *_ad_inv)
+{
+  _ad_inv[0] = _ad[0];
+  for (int ii = 1; ii < db_size; ii++) {
+    _ad_inv[ii] = _ad[ii];
+    _ad_inv[ii*db_size] = _ad[ii*db_size]/_ad[0];
+  }
+  for (int ii = 1; ii < db_size - 1; ii++) {
+    _ad_inv[ii + ii*db_size] = _ad[ii + ii*db_size];
+    for (int kk = 0; kk < ii; kk++)
+      _ad_inv[ii + ii*db_size] -= _ad_inv[ii*db_size + kk]*_ad_inv[kk*db_size + ii];
+    for (int jj = ii + 1; jj < db_size; jj++) {
+      _ad_inv[ii*db_size + jj] = _ad[ii*db_size + jj];
+      _ad_inv[jj*db_size + ii] = _ad[jj*db_size + ii] / _ad_inv[ii*db_size + ii];
+      for (int kk = 0; kk < ii; kk++) {
+        _ad_inv[ii*db_size + jj] -= _ad_inv[ii*db_size + kk]*_ad_inv[kk*db_size + jj];
+        _ad_inv[jj*db_size + ii] -=  _ad_inv[jj*db_size + kk]*_ad_inv[kk*db_size + ii]
+                                    /_ad_inv[ii*db_size + ii];
+      }
+    }
+  }
+  _ad_inv[db_size*db_size - 1] = _ad[db_size*db_size - 1];
+  for (int kk = 0; kk < db_size - 1; kk++)
+    _ad_inv[db_size*db_size - 1] -=  _ad_inv[(db_size-1)*db_size + kk]
+                                    *_ad_inv[kk*db_size + db_size - 1];
+}
+
+static void
+_ora_mat_c_m_b(const double *mat, int db_size, double *x, const double *b, const double *c)
+{
+  double aux[9];
+  for (int ii = 0; ii < db_size; ii++) aux[ii] = (c[ii] - b[ii]);
+  for (int ii = 0; ii < db_size; ii++) {
+    x[ii] = 0;
+    for (int jj = 0; jj < db_size; jj++) x[ii] += aux[jj]*mat[ii*db_size + jj];
+  }
+}
+
+int
+ora_block_jacobi(int n_rows, int db, const int *row_index, const int *col_id,
+                 const double *d_val, const double *x_val,
+                 int n_max_iter, double precision, double r_norm,
+                 const double *rhs, double *vx, int use_vx_ini,
+                 double *out, double *history, int history_size)
+{
+  if (db == 3)
+    return ora_block3_jacobi(n_rows, row_index, col_id, d_val, x_val, n_max_iter, precision,
+                             r_norm, rhs, vx, use_vx_ini, out, history, history_size);
+  const int n_blocks = n_rows, db2 = db*db;
+  const size_t n = (size_t)n_rows*db;
+  double *rk = malloc(sizeof(double)*(2*n + db2*(size_t)n_blocks + 1));
+  double *vxx = rk + n, *ad_inv = rk + 2*n;
+  const double *ad = d_val;
+  for (int i = 0; i < n_blocks; i++) {
+    if (db == 6) _ora_gauss_inverse_n(6, d_val + db2*(size_t)i, ad_inv + db2*(size_t)i);
+    else _ora_fact_lu(db, d_val + db2*(size_t)i, ad_inv + db2*(size_t)i);
+  }
+
+  ora_cvg_t cv = {precision, r_norm, -1, n_max_iter, 0, -1,
+                  history, history_size, 0};
+  int cvg = ORA_ITERATING;
+  int n_iter = 0;
+  double residual = -1, res2;
+
+  if (!use_vx_ini) {
+    n_iter += 1;
+    res2 = 0.0;
+    for (int ii = 0; ii < n_blocks; ii++) {
+      double _vxx[9];
+      for (int jj = 0; jj < db; jj++) { rk[db*ii + jj] = 0; _vxx[jj] = 0; }
+      _ora_mat_c_m_b(ad_inv + db2*ii, db, vx + db*ii, _vxx, rhs + db*ii);
+      for (int jj = 0; jj < db; jj++) {
+        double r = 0.0;
+        for (int kk = 0; kk < db; kk++)
+          r += ad[ii*db2 + jj*db + kk] * (vx[ii*db + kk] - rk[ii*db + kk]);
+        res2 += (r*r);
+      }
+    }
+    residual = sqrt(res2);
+    if (n_iter == 1) cv.initial_residual = residual;
+    cvg = _cvg_test(&cv, n_iter, residual);
+  }
+
+  while (cvg == ORA_ITERATING) {
+    n_iter += 1;
+    ora_spmv_msr_bn(n_rows, db, row_index, col_id, d_val, x_val, 1, vx, vxx);
+    res2 = 0.0;
+    for (int ii = 0; ii < n_blocks; ii++) {
+      for (int kk = 0; kk < db; kk++) rk[ii*db + kk] = vx[ii*db + kk];
+      _ora_mat_c_m_b(ad_inv + db2*ii, db, vx + db*ii, vxx + db*ii, rhs + db*ii);
+      for (int jj = 0; jj < db; jj++) {
+        double r = 0.0;
+        for (int kk = 0; kk < db; kk++)
+          r += ad[ii*db2 + jj*db + kk] * (vx[ii*db + kk] - rk[ii*db + kk]);
         res2 += (r*r);
       }
     }

@@ -110,6 +110,14 @@ int    ora_gauss_seidel(int sym, int n_rows, const int *row_index, const int *co
 void   ora_spmv_msr_b3(int n_rows, const int *row_index, const int *col_id,
                        const double *d_val, const double *x_val, int exclude_diag,
                        const double *x, double *y);
+void   ora_spmv_msr_bn(int n_rows, int db, const int *row_index, const int *col_id,
+                       const double *d_val, const double *x_val, int exclude_diag,
+                       const double *x, double *y);
+int    ora_block_jacobi(int n_rows, int db, const int *row_index, const int *col_id,
+                        const double *d_val, const double *x_val,
+                        int n_max_iter, double precision, double r_norm,
+                        const double *rhs, double *vx, int use_vx_ini,
+                        double *out, double *history, int history_size);
 int    ora_bicgstab_b(int n_rows, int db, const int *row_index, const int *col_id,
                       const double *d_val, const double *x_val,
                       int n_max_iter, double precision, double r_norm,

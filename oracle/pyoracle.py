@@ -156,6 +156,37 @@ class Oracle:
         return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], initial_residual=out[2],
                     history=hist[:int(out[3])].copy(), vx=vx)
 
+    def spmv_bn(self, db, ri, ci, d, x_val, x, exclude_diag=False):
+        """_b_mat_vec_p_l_msr_generic / _6 / _3 by block size."""
+        ri, ci, d, x_val, x = _i32(ri), _i32(ci), _f64(d), _f64(x_val), _f64(x)
+        n = len(ri) - 1
+        y = np.empty(db * n)
+        self.lib.ora_spmv_msr_bn(C.c_int(n), C.c_int(db), _ip(ri), _ip(ci), _dp(d), _dp(x_val),
+                                 C.c_int(int(exclude_diag)), _dp(x), _dp(y))
+        return y
+
+    def _solve_b(self, fn, db, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0):
+        ri, ci, d, xv, rhs = _i32(ri), _i32(ci), _f64(d), _f64(xv), _f64(rhs)
+        n = len(ri) - 1
+        vx = np.zeros(db * n) if vx0 is None else _f64(vx0).copy()
+        out = np.zeros(4)
+        hist = np.zeros(n_max_iter + 8)
+        cvg = fn(C.c_int(n), C.c_int(db), _ip(ri), _ip(ci), _dp(d), _dp(xv),
+                 C.c_int(n_max_iter), C.c_double(precision), C.c_double(r_norm), _dp(rhs),
+                 _dp(vx), C.c_int(0 if vx0 is None else 1), _dp(out), _dp(hist),
+                 C.c_int(len(hist)))
+        return dict(cvg=cvg, n_iter=int(out[0]), residual=out[1], initial_residual=out[2],
+                    history=hist[:int(out[3])].copy(), vx=vx)
+
+    def bicgstab_bn(self, db, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0=None):
+        return self._solve_b(self.lib.ora_bicgstab_b, db, ri, ci, d, xv, rhs, n_max_iter,
+                             precision, r_norm, vx0)
+
+    def block_jacobi(self, db, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0=None):
+        """_block_jacobi (cs_sles_it.cpp:2460) / _block_3_jacobi by block size."""
+        return self._solve_b(self.lib.ora_block_jacobi, db, ri, ci, d, xv, rhs, n_max_iter,
+                             precision, r_norm, vx0)
+
     def spmv_csr(self, ri, ci, val, x, exclude_diag=False):
         ri, ci, val, x = _i32(ri), _i32(ci), _f64(val), _f64(x)
         y = np.empty(len(ri) - 1)

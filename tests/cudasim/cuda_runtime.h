@@ -62,6 +62,7 @@ inline void __syncthreads() { cudasim::syncthreads(); }
 inline void __threadfence() { __sync_synchronize(); }
 inline double __shfl_down_sync(unsigned, double v, unsigned delta) { return cudasim::shfl_down(v, delta); }
 template <typename T> inline T __ldg(const T *p) { return *p; }
+template <typename T> inline T __ldcs(const T *p) { return *p; }
 template <typename T> inline T __ldcg(const T *p) { return *(const volatile T *)p; }
 inline unsigned atomicInc(unsigned *p, unsigned limit)
 {

@@ -595,3 +595,52 @@ def test_oracle_gauss_seidel_vs_reference_direct(oracle, reflib):
                     b["cvg"], b["n_iter"], b["residual"], b["initial_residual"])
                 assert np.array_equal(a["vx"], b["vx"])
         reflib.destroy(h)
+
+
+# ---- block-diagonal matrices of any block size (a4 _6 / _generic, a17 _block_jacobi) ----
+
+BLOCKN_CASES = [(6, 6), (2, 7), (4, 5), (9, 4)]       # (db, N)
+
+
+@pytest.mark.parametrize("db,N", BLOCKN_CASES)
+def test_oracle_blockn_matches_golden(oracle, db, N):
+    from code_saturne_b200.mesh_cartesian import cube_block_convection_diffusion
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"blockn_db{db}_N{N}.npz"))
+    ri, ci, d, xv, rhs = cube_block_convection_diffusion(N, db)
+    r_norm = float(g["r_norm"])
+    assert np.array_equal(oracle.spmv_bn(db, ri, ci, d.ravel(), xv, g["x"]), g["y"])
+    assert np.array_equal(oracle.spmv_bn(db, ri, ci, d.ravel(), xv, g["x"], True), g["y_exdiag"])
+    for nit in (1, 2, 4):
+        f = oracle.block_jacobi(db, ri, ci, d.ravel(), xv, rhs, nit, 1e-12, r_norm)
+        assert np.array_equal(f["vx"], g[f"jac{nit}_vx"]), nit
+        assert f["residual"] == float(g[f"jac{nit}_residual"])
+    w = oracle.block_jacobi(db, ri, ci, d.ravel(), xv, rhs, 3, 1e-12, r_norm, vx0=g["x"])
+    assert np.array_equal(w["vx"], g["jac_warm_vx"]) and w["residual"] == float(g["jac_warm_residual"])
+    r = oracle.block_jacobi(db, ri, ci, d.ravel(), xv, rhs, 500, 1e-8, r_norm)
+    assert (r["cvg"], r["n_iter"], r["residual"]) == (int(g["jac_cvg"]), int(g["jac_n_iter"]),
+                                                      float(g["jac_residual"]))
+    b = oracle.bicgstab_bn(db, ri, ci, d.ravel(), xv, rhs, 500, 1e-10, r_norm)
+    assert (b["cvg"], b["n_iter"], b["residual"], b["initial_residual"]) == (
+        int(g["bicg_cvg"]), int(g["bicg_n_iter"]), float(g["bicg_residual"]),
+        float(g["bicg_initial_residual"]))
+    assert np.array_equal(b["vx"], g["bicg_vx"])
+
+
+def test_oracle_blockn_vs_reference_direct(oracle, reflib):
+    from code_saturne_b200.mesh_cartesian import cube_block_convection_diffusion
+    for db, N in ((5, 6), (6, 8), (8, 5)):
+        ri, ci, d, xv, rhs = cube_block_convection_diffusion(N, db, seed=77)
+        n = len(ri) - 1
+        h = reflib.system_block(n, db, ri, ci, d.ravel(), xv, False)
+        x = np.sin(0.21 * np.arange(db * n))
+        assert np.array_equal(oracle.spmv_bn(db, ri, ci, d.ravel(), xv, x), reflib.spmv(h, x, db * n))
+        r_norm = float(np.linalg.norm(rhs))
+        for nit in (1, 3):
+            a = oracle.block_jacobi(db, ri, ci, d.ravel(), xv, rhs, nit, 1e-12, r_norm)
+            b = reflib.sles_it(h, reflib.JACOBI, rhs, nit, 1e-12, r_norm)
+            assert np.array_equal(a["vx"], b["vx"]) and a["residual"] == b["residual"]
+        a = oracle.bicgstab_bn(db, ri, ci, d.ravel(), xv, rhs, 300, 1e-9, r_norm)
+        b = reflib.sles_it(h, reflib.BICGSTAB, rhs, 300, 1e-9, r_norm)
+        assert (a["cvg"], a["n_iter"], a["residual"]) == (b["cvg"], b["n_iter"], b["residual"])
+        assert np.array_equal(a["vx"], b["vx"])
+        reflib.destroy(h)
