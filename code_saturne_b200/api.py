@@ -54,6 +54,7 @@ class SlesItType(enum.IntEnum):
     IPCG = 2
     JACOBI = 3
     BICGSTAB = 4
+    GCR = 6
     # process-local Gauss-Seidel family (cs_sles_it.h:64-65, :84-85)
     P_GAUSS_SEIDEL = 8
     P_SYM_GAUSS_SEIDEL = 9
@@ -154,6 +155,11 @@ def load_library() -> C.CDLL:
     L.csb_sles_it_create.restype = vp
     L.csb_sles_it_create.argtypes = [ci, ci, ci, ci]
     L.csb_sles_it_set_reduce_comm.argtypes = [vp, vp]
+    L.csb_sles_it_set_fallback_threshold.argtypes = [vp, ci, ci]
+    L.csb_sles_it_set_fallback_threshold.restype = None
+    L.csb_sles_it_set_restart_interval.argtypes = [vp, ci]
+    L.csb_sles_it_set_restart_interval.restype = None
+    L.csb_sles_it_used_fallback.argtypes = [vp]
     L.csb_sles_it_setup.argtypes = [vp, C.c_char_p, vp, ci]
     L.csb_sles_it_setup.restype = None
     solve_args = [vp, C.c_char_p, vp, ci, cd, cd, C.POINTER(ci), C.POINTER(cd), vp, vp, vp,
@@ -652,6 +658,17 @@ class SlesIt(_SolverBase):
 
     def set_pcomm(self, pcomm):
         load_library().csb_sles_it_set_pcomm(C.c_void_p(self._h), pcomm.handle)
+
+    def set_fallback_threshold(self, threshold, n_iter_max):
+        """cs_sles_it_set_fallback_threshold: fall back to GCR below this convergence state."""
+        load_library().csb_sles_it_set_fallback_threshold(C.c_void_p(self._h), int(threshold),
+                                                          int(n_iter_max))
+
+    def set_restart_interval(self, interval):
+        load_library().csb_sles_it_set_restart_interval(C.c_void_p(self._h), int(interval))
+
+    def used_fallback(self):
+        return bool(load_library().csb_sles_it_used_fallback(C.c_void_p(self._h)))
 
     def transfer_pc(self, mg: "Multigrid"):
         """cs_sles_it_transfer_pc: the solver takes ownership of the multigrid preconditioner

@@ -2463,7 +2463,7 @@ bool launch_copy_gated(int n, const double *src, double *dst, const MgState *gat
 namespace {
 
 /* mode 0: y = b - a*x (:4320)   1: y = a*y (:4336)   2: y = a*y + c*x (:4379)
-   3: y += x + b (:4460, vx += z1 + z2) */
+   3: y += x + b (:4460, vx += z1 + z2)   4: y -= a*x*c   5: y = x*b (GCR, sles.cu) */
 template <int MODE>
 __global__ void __launch_bounds__(TPB)
 k_kc_vec(int n, double a, double c, const double *__restrict__ x,
@@ -2473,7 +2473,9 @@ k_kc_vec(int n, double a, double c, const double *__restrict__ x,
     if (MODE == 0) y[i] = b[i] - a * x[i];
     else if (MODE == 1) y[i] = a * y[i];
     else if (MODE == 2) y[i] = a * y[i] + c * x[i];
-    else y[i] += x[i] + b[i];
+    else if (MODE == 3) y[i] += x[i] + b[i];
+    else if (MODE == 4) y[i] -= a * x[i] * c;            /* GCR solution update (:3471) */
+    else y[i] = x[i] * b[i];                             /* Jacobi preconditioner: rk * ad_inv */
   }
 }
 
@@ -2500,7 +2502,9 @@ bool launch_kc_vec(int mode, int n, double a, double c, const double *x, const d
   case 0: k_kc_vec<0><<<g, TPB, 0, st>>>(n, a, c, x, b, y); break;
   case 1: k_kc_vec<1><<<g, TPB, 0, st>>>(n, a, c, x, b, y); break;
   case 2: k_kc_vec<2><<<g, TPB, 0, st>>>(n, a, c, x, b, y); break;
-  default: k_kc_vec<3><<<g, TPB, 0, st>>>(n, a, c, x, b, y); break;
+  case 3: k_kc_vec<3><<<g, TPB, 0, st>>>(n, a, c, x, b, y); break;
+  case 4: k_kc_vec<4><<<g, TPB, 0, st>>>(n, a, c, x, b, y); break;
+  default: k_kc_vec<5><<<g, TPB, 0, st>>>(n, a, c, x, b, y); break;
   }
   return post_launch("kc_vec");
 }

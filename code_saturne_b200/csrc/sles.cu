@@ -212,6 +212,14 @@ struct _csb_sles_it_t {
   DevBuf<double>      work;
   DevBuf<ItState>     st;
   ItState            *h_st = nullptr;     /* pinned mirror */
+  /* GCR (restart_interval, cs_sles_it.cpp:4699) and the fallback solver
+     (fallback_cvg / fallback_n_max_iter / fallback, cs_sles_it.cpp:4736-4749) */
+  int                 restart_interval = 20;
+  int                 fallback_cvg = CSB_SLES_DIVERGED;
+  int                 fallback_n_max_iter = 0;
+  _csb_sles_it_t     *fallback = nullptr;
+  bool                fallback_last = false;
+  const _csb_sles_it_t *shared = nullptr;  /* cs_sles_it_set_shareable: setup data of another context */
   /* persistent-kernel launch data */
   MgLevelDesc         desc;
   DevBuf<double>      partials;
@@ -592,6 +600,132 @@ bool bicgstab_enqueue(const csb_matrix_t *m, ItState *st, const double *ad_inv,
   return true;
 }
 
+bool dots_to_host(int n, const double *x, const double *y, const double *z, int mode,
+                  double r[3]);
+
+/* y = A.x for any diagonal block size */
+bool spmv_any(const csb_matrix_t *m, const double *x, double *y)
+{
+  if (m->db == 3) return launch_spmv_b3(m, x, y, false);
+  if (m->db > 1) return launch_spmv_bn(-1, m, nullptr, x, y, nullptr, false);
+  SpmvArgs a; a.m = m; a.x = x; a.y = y;
+  return launch_spmv(EPI_STORE, a);
+}
+
+/* _convergence_test (cs_sles_it.cpp:243-325) on the host, for the solvers whose scalars are
+   read back every iteration */
+int it_cvg_test_host(ItState *st, int n_iter, double residual)
+{
+  st->residual = residual;
+  st->n_iter = n_iter;
+  if (st->n_hist < HIST_MAX) st->hist[st->n_hist++] = residual;
+  if (st->precision > 0 && residual < st->precision * st->r_norm) return CSB_SLES_CONVERGED;
+  else if (n_iter >= st->n_max_iter) return CSB_SLES_MAX_ITERATION;
+  else if (residual > st->initial_residual * 10000.0 && residual > 100.) return CSB_SLES_DIVERGED;
+  if (std::isnan(residual) || std::isinf(residual)) return CSB_SLES_DIVERGED;
+  return CSB_SLES_ITERATING;
+}
+
+/* Preconditioned GCR with restart (_gcr, cs_sles_it.cpp:3272-3480): the solver the reference
+   falls back to on a device when BiCGStab breaks down (:5383-5385), and a solver type of its
+   own.  Host-driven: the projection coefficients of the modified Gram-Schmidt loop, the step
+   lengths and the residual norm are read back (every one of them decides what the next
+   launch does, as in the reference), the small triangular system Gamma is inverted on the
+   host exactly as there; every vector operation is the reference's expression.
+   ad_inv: Jacobi preconditioner (NULL: none).  work: (1 + 2*restart) vectors of stride ws. */
+bool gcr_enqueue(const csb_matrix_t *m, ItState *st, ItState *h, const double *ad_inv,
+                 int restart, double precision, double r_norm, int n_max_iter,
+                 const double *rhs, double *vx, bool vx_ini_nonzero, double *work)
+{
+  Context &cx = ctx();
+  const int n = m->n_rows*m->db;
+  const size_t ws = work_stride_of((size_t)m->n_cols_ext*m->db);
+  double *rk = work, *zk = work + ws, *ck = work + ws*(1 + (size_t)restart);
+  std::vector<double> alpha((size_t)restart), gkj((size_t)(restart + 1)*restart/2),
+                      gkj_inv((size_t)(restart + 1)*restart/2);
+  memset(h, 0, sizeof(ItState));
+  h->precision = precision; h->r_norm = r_norm; h->n_max_iter = n_max_iter;
+  h->residual = -1.; h->initial_residual = -1.;
+  int cvg = CSB_SLES_ITERATING;
+  unsigned n_restart = 0;
+  bool have_vx = vx_ini_nonzero;
+  double r[3];
+
+  while (cvg == CSB_SLES_ITERATING) {
+    int n_c_iter = 0;
+    if (have_vx) {
+      if (!spmv_any(m, vx, rk)) return false;                       /* rk = A.x0 - rhs */
+      if (!launch_kc_vec(2, n, 1.0, -1.0, rhs, nullptr, rk)) return false;
+    }
+    else {
+      if (!launch_fill(m->n_cols_ext*m->db, 0.0, vx)) return false;
+      if (!launch_fill(n, 0.0, rk)) return false;
+      if (!launch_kc_vec(2, n, 1.0, -1.0, rhs, nullptr, rk)) return false;
+      have_vx = true;
+    }
+    if (!dots_to_host(n, rk, nullptr, nullptr, 1, r)) return false;
+    double residual = sqrt(r[0]);
+    if (n_restart == 0) h->initial_residual = residual;
+
+    while (cvg == CSB_SLES_ITERATING && n_c_iter < restart) {
+      double *zk_n = zk + (size_t)n_c_iter*ws, *ck_n = ck + (size_t)n_c_iter*ws;
+      if (ad_inv != nullptr) { if (!launch_kc_vec(5, n, 0., 0., rk, ad_inv, zk_n)) return false; }
+      else if (!launch_copy(n, rk, zk_n, nullptr)) return false;
+      if (!spmv_any(m, zk_n, ck_n)) return false;
+      for (int jj = 0; jj < n_c_iter; jj++) {
+        const double *ck_j = ck + (size_t)jj*ws;
+        const int ii_jn = (n_c_iter + 1)*n_c_iter/2 + jj;
+        if (!dots_to_host(n, ck_j, ck_n, nullptr, 0, r)) return false;
+        gkj[ii_jn] = r[0];
+        if (!launch_kc_vec(2, n, 1.0, -gkj[ii_jn], ck_j, nullptr, ck_n)) return false;
+      }
+      const int iter_shift = (n_c_iter + 1)*n_c_iter/2 + n_c_iter;
+      if (!dots_to_host(n, ck_n, nullptr, nullptr, 1, r)) return false;
+      gkj[iter_shift] = sqrt(r[0]);
+      if (fabs(gkj[iter_shift]) > 0) {
+        const double scale = 1. / gkj[iter_shift];
+        if (!launch_kc_vec(1, n, scale, 0., nullptr, nullptr, ck_n)) return false;
+        if (!dots_to_host(n, ck_n, rk, nullptr, 0, r)) return false;
+        alpha[n_c_iter] = r[0];
+      }
+      else
+        alpha[n_c_iter] = 0.;
+      if (!launch_kc_vec(2, n, 1.0, -alpha[n_c_iter], ck_n, nullptr, rk)) return false;
+      if (!dots_to_host(n, rk, nullptr, nullptr, 1, r)) return false;
+      residual = sqrt(r[0]);
+      n_c_iter += 1;
+      cvg = it_cvg_test_host(h, (int)(n_restart*(unsigned)restart) + n_c_iter, residual);
+      if (cvg != CSB_SLES_ITERATING) break;
+    }
+
+    /* inversion of Gamma (:3424-3449) */
+    if (n_c_iter == 1 && !(fabs(alpha[0]) > 0))
+      gkj_inv[0] = 1.0;
+    else {
+      std::fill(gkj_inv.begin(), gkj_inv.end(), 0.0);
+      for (int kk = 0; kk < n_c_iter; kk++) {
+        for (int ii = 0; ii < kk; ii++)
+          for (int jj = 0; jj < kk; jj++)
+            gkj_inv[(kk + 1)*kk/2 + ii]
+              += ((ii <= jj) ? gkj_inv[(jj + 1)*jj/2 + ii] : 0.0) * gkj[(kk + 1)*kk/2 + jj];
+        for (int jj = 0; jj < kk; jj++)
+          gkj_inv[(kk + 1)*kk/2 + jj] /= - gkj[(kk + 1)*kk/2 + kk];
+        gkj_inv[(kk + 1)*kk/2 + kk] = 1.0 / gkj[(kk + 1)*kk/2 + kk];
+      }
+    }
+    /* the solution (:3453-3468) */
+    for (int kk = 0; kk < n_c_iter; kk++)
+      for (int jj = 0; jj <= kk; jj++)
+        if (!launch_kc_vec(4, n, alpha[kk], gkj_inv[(kk + 1)*kk/2 + jj], zk + (size_t)jj*ws,
+                           nullptr, vx)) return false;
+    n_restart += 1;
+  }
+  h->cvg = cvg;
+  /* the common tail of csb_sles_it_solve reads the device state */
+  return CSB_CUDA(cudaMemcpyAsync(st, h, sizeof(ItState), cudaMemcpyHostToDevice, cx.stream))
+      && CSB_CUDA(cudaStreamSynchronize(cx.stream));
+}
+
 /* _multigrid_v_cycle_pc as a sequence of launches (defined with the multigrid below) */
 bool mg_cycle_pc_enqueue(csb_multigrid_t *mg, double precision, double r_norm,
                          const double *rhs_d, double *vx_d, bool vx_ini_nonzero);
@@ -821,6 +955,7 @@ csb_sles_it_create(csb_sles_it_type_t solver_type, int poly_degree, int n_max_it
   if (solver_type != CSB_SLES_PCG && solver_type != CSB_SLES_FCG
       && solver_type != CSB_SLES_IPCG
       && solver_type != CSB_SLES_JACOBI && solver_type != CSB_SLES_BICGSTAB
+      && solver_type != CSB_SLES_GCR
       && solver_type != CSB_SLES_P_GAUSS_SEIDEL && solver_type != CSB_SLES_P_SYM_GAUSS_SEIDEL) {
     set_error("csb_sles_it_create: solver type %d is not available on this path",
               (int)solver_type);
@@ -831,6 +966,7 @@ csb_sles_it_create(csb_sles_it_type_t solver_type, int poly_degree, int n_max_it
   /* FCG with poly_degree < 0: the preconditioner is handed over afterwards
      (csb_sles_it_transfer_pc: one multigrid V-cycle), identity if none is */
   if (solver_type != CSB_SLES_JACOBI && !is_gs_type((int)solver_type) && poly_degree != 0
+      && !(solver_type == CSB_SLES_GCR && poly_degree < 0)       /* GCR without preconditioner */
       && !(solver_type == CSB_SLES_PCG || solver_type == CSB_SLES_FCG
            || solver_type == CSB_SLES_IPCG)) {
     set_error("csb_sles_it_create: poly_degree %d: polynomial (> 0), none or transferred "
@@ -843,7 +979,40 @@ csb_sles_it_create(csb_sles_it_type_t solver_type, int poly_degree, int n_max_it
   c->poly_degree = poly_degree;
   c->n_max_iter = n_max_iter;
   c->update_stats = (update_stats != 0);
+  /* fallback mechanism (cs_sles_it_create, cs_sles_it.cpp:4736-4749) */
+  c->fallback_cvg = (solver_type == CSB_SLES_BICGSTAB) ? CSB_SLES_MAX_ITERATION
+                                                       : CSB_SLES_DIVERGED;
+  c->fallback_n_max_iter = n_max_iter;
   return c;
+}
+
+/* cs_sles_it_set_fallback_threshold (cs_sles_it.cpp:5791-5797): the solve switches to the
+   fallback solver (GCR on a device, :5383-5385) when its convergence state is < threshold */
+void csb_sles_it_set_fallback_threshold(csb_sles_it_t *c, csb_sles_convergence_state_t threshold,
+                                        int n_iter_max)
+{
+  if (c == nullptr) return;
+  c->fallback_cvg = (int)threshold;
+  c->fallback_n_max_iter = n_iter_max;
+  /* a fallback context made by an earlier solve would keep its own limit */
+  delete c->fallback;
+  c->fallback = nullptr;
+  c->fallback_last = false;
+}
+
+/* cs_sles_it_set_restart_interval (cs_sles_it.cpp:5810-5817) */
+void csb_sles_it_set_restart_interval(csb_sles_it_t *c, int interval)
+{
+  if (c == nullptr || interval < 1) return;
+  c->restart_interval = interval;
+  c->setup_done = false;
+}
+
+/* 1 when the last csb_sles_it_solve of this context went through its fallback solver */
+int csb_sles_it_used_fallback(const csb_sles_it_t *c)
+{
+  return (c != nullptr && c->fallback != nullptr && c->fallback->n_solves > 0
+          && c->fallback_last) ? 1 : 0;
 }
 
 int csb_sles_it_set_reduce_comm(csb_sles_it_t *c, void *nccl_comm)
@@ -868,16 +1037,18 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
   double t0 = wall();
   c->a = a;
   c->setup_done = false;
-  const size_t n_wa = (c->type == CSB_SLES_BICGSTAB) ? 6
+  const size_t n_wa = (c->type == CSB_SLES_GCR) ? 1 + 2*(size_t)c->restart_interval
+    : (c->type == CSB_SLES_BICGSTAB) ? 6
     : ((c->type == CSB_SLES_PCG || c->type == CSB_SLES_FCG || c->type == CSB_SLES_IPCG) ? 5 : 1);
   if (is_gs_type((int)c->type) && a->halo != nullptr) {
     set_error("csb_sles_it_setup: the Gauss-Seidel solvers run on one rank on this path (the "
               "smoother forms take a halo)");
     return;
   }
-  if (a->db != 1 && c->type != CSB_SLES_BICGSTAB && c->type != CSB_SLES_JACOBI) {
-    set_error("csb_sles_it_setup: block matrices (db %d) are solved with CSB_SLES_BICGSTAB "
-              "or CSB_SLES_JACOBI (block Jacobi) on this path", a->db);
+  if (a->db != 1 && c->type != CSB_SLES_BICGSTAB && c->type != CSB_SLES_JACOBI
+      && c->type != CSB_SLES_GCR) {
+    set_error("csb_sles_it_setup: block matrices (db %d) are solved with CSB_SLES_BICGSTAB, "
+              "CSB_SLES_GCR or CSB_SLES_JACOBI (block Jacobi) on this path", a->db);
     return;
   }
   if (a->db > 1 && c->type == CSB_SLES_JACOBI) {
@@ -987,7 +1158,6 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
                   const csb_real_t *rhs, csb_real_t *vx_ini, csb_real_t *vx,
                   size_t aux_size, void *aux_vectors)
 {
-  (void)aux_size; (void)aux_vectors;
   csb_sles_it_t *c = static_cast<csb_sles_it_t *>(context);
   Context &cx = ctx();
   cx.err.clear();
@@ -1088,6 +1258,11 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
     ok = bicgstab_enqueue(a, c->st.p, c->ad_inv.p, precision, r_norm, c->n_max_iter,
                           s_rhs.d, s_vx.d, ini, c->work.p, c->h_st);
     break;
+  case CSB_SLES_GCR:
+    ok = gcr_enqueue(a, c->st.p, c->h_st, (c->poly_degree < 0) ? nullptr : c->ad_inv.p,
+                     c->restart_interval, precision, r_norm, c->n_max_iter, s_rhs.d, s_vx.d,
+                     ini, c->work.p);
+    break;
   case CSB_SLES_P_GAUSS_SEIDEL:
   case CSB_SLES_P_SYM_GAUSS_SEIDEL:
     ok = gs_enqueue(a, (int)c->type, c->st.p, c->ad_inv.p, precision, r_norm, c->n_max_iter,
@@ -1118,6 +1293,26 @@ csb_sles_it_solve(void *context, const char *name, const csb_matrix_t *a, int ve
   c->n_iterations_last = n_it;
   c->n_iterations_tot += n_it;
   c->t_solve += wall() - t0;
+
+  /* _fallback (cs_sles_it.cpp:4464-4528, call site :5383-5418): GCR on a device, from zero
+     unless the first solver merely broke down, its iterations added to the count */
+  c->fallback_last = false;
+  if (cvg < c->fallback_cvg && c->type != CSB_SLES_GCR && !c->is_smoother) {
+    if (c->fallback == nullptr) {
+      c->fallback = csb_sles_it_create(CSB_SLES_GCR, 0, c->fallback_n_max_iter,
+                                       c->update_stats ? 1 : 0);
+      if (c->fallback == nullptr) return (csb_sles_convergence_state_t)cvg;
+    }
+    int fb_iter = 0;
+    csb_real_t *fb_ini = (cvg < CSB_SLES_BREAKDOWN) ? nullptr : vx;
+    const csb_sles_convergence_state_t fcvg
+      = csb_sles_it_solve(c->fallback, name, a, verbosity, precision, r_norm, &fb_iter,
+                          residual, rhs, fb_ini, vx, aux_size, aux_vectors);
+    csb_sles_it_free(c->fallback);
+    if (n_iter) *n_iter = fb_iter + n_it;
+    c->fallback_last = true;
+    return fcvg;
+  }
   return (csb_sles_convergence_state_t)cvg;
 }
 
@@ -1308,6 +1503,7 @@ _csb_sles_it_t::~_csb_sles_it_t()
 {
   if (h_st) cudaFreeHost(h_st);
   delete pc_mg;
+  delete fallback;
 }
 
 namespace {

@@ -46,6 +46,8 @@ typedef enum {
   CSB_SLES_IPCG     = 2,   /* inexact-preconditioning CG, cs_sles_it.cpp:1016-1203 */
   CSB_SLES_JACOBI   = 3,
   CSB_SLES_BICGSTAB = 4,
+  CSB_SLES_GCR      = 6,   /* preconditioned GCR with restart, cs_sles_it.cpp:3272-3480; also the
+                              fallback solver on a device (:5383-5385) */
   /* multigrid smoothers without convergence test (cs_sles_it.h:79-83,
      src/alge/cs_multigrid_smoother.cpp); created with csb_multigrid_smoother_create or
      selected through csb_multigrid_set_solver_options with precision_mult < 0 */
@@ -330,6 +332,20 @@ csb_sles_it_t *csb_sles_it_create(csb_sles_it_type_t  solver_type,
                                   int                 poly_degree,
                                   int                 n_max_iter,
                                   int                 update_stats);
+
+/* cs_sles_it_set_fallback_threshold (src/alge/cs_sles_it.cpp:5791): when a solve ends in a
+   state < threshold, csb_sles_it_solve runs the fallback solver -- GCR + the same Jacobi
+   preconditioner, the reference's choice on a device (:5383-5385) -- from the current vx, or
+   from zero when the first solver diverged (_fallback :4464-4528), and returns its state, the
+   iteration counts added.  Defaults as cs_sles_it_create (:4736-4749):
+   CSB_SLES_MAX_ITERATION for BiCGStab (it falls back on breakdown and divergence),
+   CSB_SLES_DIVERGED (never) for the other solvers; n_iter_max = the solver's own. */
+void csb_sles_it_set_fallback_threshold(csb_sles_it_t *c, csb_sles_convergence_state_t threshold,
+                                        int n_iter_max);
+/* cs_sles_it_set_restart_interval (src/alge/cs_sles_it.cpp:5810): GCR restart, default 20 */
+void csb_sles_it_set_restart_interval(csb_sles_it_t *c, int interval);
+/* 1 if the last csb_sles_it_solve of this context went through the fallback solver */
+int  csb_sles_it_used_fallback(const csb_sles_it_t *c);
 
 /* Global-sum communicator for dot products (cs_sles_it_set_mpi_reduce_comm,
    src/alge/cs_sles_it.cpp:5669): ncclComm_t as void *, NULL = single rank. */

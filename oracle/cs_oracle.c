@@ -2735,6 +2735,111 @@ ora_block3_jacobi(int n_rows, const int *row_index, const int *col_id,
 }
 
 /*----------------------------------------------------------------------------
+ * Preconditioned GCR with restart: _gcr (src/alge/cs_sles_it.cpp:3272-3480), Jacobi
+ * preconditioner (jacobi != 0: pc_apply = x*ad_inv, point Jacobi for block matrices) or none.
+ * It is also the solver cs_sles_it_solve falls back to on a device (:5383-5385).
+ * restart = c->restart_interval (20 by default, :4699).
+ *----------------------------------------------------------------------------*/
+
+int
+ora_gcr(int n_rows, int db, const int *row_index, const int *col_id,
+        const double *d_val, const double *x_val, int jacobi, int restart,
+        int n_max_iter, double precision, double r_norm,
+        const double *rhs, double *vx, int use_vx_ini,
+        double *out, double *history, int history_size)
+{
+  const int n = n_rows*db;
+  const size_t wa = (size_t)n;
+  const int n_k = restart;
+  double *rk = malloc(sizeof(double)*(wa*(2 + 2*(size_t)n_k) + 1));
+  double *zk = rk + wa, *ck = rk + wa*(1 + (size_t)n_k), *ad_inv = rk + wa*(1 + 2*(size_t)n_k);
+  double *alpha = malloc(sizeof(double)*n_k);
+  double *gkj = malloc(sizeof(double)*((n_k + 1)*n_k/2));
+  double *gkj_inv = malloc(sizeof(double)*((n_k + 1)*n_k/2));
+  for (int i = 0; i < n; i++) ad_inv[i] = 1.0 / d_val[(size_t)i*db + (i % db)];
+
+#define ORA_SPMV_G(xx, yy) \
+  do { if (db == 1) ora_spmv_msr(n_rows, row_index, col_id, d_val, x_val, 0, xx, yy); \
+       else ora_spmv_msr_bn(n_rows, db, row_index, col_id, d_val, x_val, 0, xx, yy); } while (0)
+
+  ora_cvg_t cv = {precision, r_norm, -1, n_max_iter, 0, -1, history, history_size, 0};
+  int cvg = ORA_ITERATING;
+  unsigned n_restart = 0;
+  int have_vx = use_vx_ini;
+
+  while (cvg == ORA_ITERATING) {
+    int n_c_iter = 0;
+    if (have_vx) {
+      ORA_SPMV_G(vx, rk);
+      for (int ii = 0; ii < n; ii++) rk[ii] -= rhs[ii];
+    }
+    else {
+      for (int ii = 0; ii < n; ii++) { vx[ii] = 0; rk[ii] = -rhs[ii]; }
+      have_vx = 1;
+    }
+    double residual = sqrt(ora_dot_xx(n, rk));
+    if (n_restart == 0) cv.initial_residual = residual;
+
+    while (cvg == ORA_ITERATING && n_c_iter < n_k) {
+      double *zk_n = zk + n_c_iter*wa, *ck_n = ck + n_c_iter*wa;
+      if (jacobi) for (int ii = 0; ii < n; ii++) zk_n[ii] = rk[ii]*ad_inv[ii];
+      else for (int ii = 0; ii < n; ii++) zk_n[ii] = rk[ii];
+      ORA_SPMV_G(zk_n, ck_n);
+      for (int jj = 0; jj < n_c_iter; jj++) {
+        double *ck_j = ck + jj*wa;
+        int ii_jn = (n_c_iter + 1)*n_c_iter/2 + jj;
+        gkj[ii_jn] = ora_dot(n, ck_j, ck_n);
+        for (int ii = 0; ii < n; ii++) ck_n[ii] += - gkj[ii_jn] * ck_j[ii];
+      }
+      const int iter_shift = (n_c_iter+1)*n_c_iter/2 + n_c_iter;
+      gkj[iter_shift] = sqrt(ora_dot(n, ck_n, ck_n));
+      if (fabs(gkj[iter_shift]) > 0) {
+        double scale = 1. / gkj[iter_shift];
+        for (int ii = 0; ii < n; ii++) ck_n[ii] *= scale;
+        alpha[n_c_iter] = ora_dot(n, ck_n, rk);
+      }
+      else
+        alpha[n_c_iter] = 0.;
+      for (int ii = 0; ii < n; ii++) rk[ii] += - alpha[n_c_iter] * ck_n[ii];
+      residual = sqrt(ora_dot_xx(n, rk));
+      n_c_iter += 1;
+      cvg = _cvg_test(&cv, (int)(n_restart*n_k) + n_c_iter, residual);
+      if (cvg != ORA_ITERATING) break;
+    }
+
+    if (n_c_iter == 1 && !(fabs(alpha[0]) > 0))
+      gkj_inv[0] = 1.0;
+    else {
+      int n_g_inv = (n_k + 1)*n_k/2;
+      for (int jj = 0; jj < n_g_inv; jj++) gkj_inv[jj] = 0.0;
+      for (int kk = 0; kk < n_c_iter; kk++) {
+        for (int ii = 0; ii < kk; ii++)
+          for (int jj = 0; jj < kk; jj++)
+            gkj_inv[(kk + 1)*kk/2 + ii]
+              +=   ((ii <= jj) ? gkj_inv[(jj + 1)*jj/2 + ii] : 0.0)
+                 * gkj[(kk + 1)*kk/2 + jj];
+        for (int jj = 0; jj < kk; jj++)
+          gkj_inv[(kk + 1)*kk/2 + jj] /= - gkj[(kk + 1)*kk/2 + kk];
+        gkj_inv[(kk + 1)*kk/2 + kk] = 1.0 / gkj[(kk + 1)*kk/2 + kk];
+      }
+    }
+    for (int kk = 0; kk < n_c_iter; kk++)
+      for (int jj = 0; jj <= kk; jj++) {
+        const double *zk_j = zk + jj*wa;
+        for (int ii = 0; ii < n; ii++)
+          vx[ii] -= alpha[kk] * zk_j[ii] * gkj_inv[(kk + 1)*kk/2 + jj];
+      }
+    n_restart += 1;
+  }
+#undef ORA_SPMV_G
+
+  out[0] = cv.n_iterations; out[1] = cv.residual; out[2] = cv.initial_residual;
+  out[3] = cv.history_n;
+  free(rk); free(alpha); free(gkj); free(gkj_inv);
+  return cvg;
+}
+
+/*----------------------------------------------------------------------------
  * Block Jacobi for block sizes other than 3: _block_jacobi (src/alge/cs_sles_it.cpp:2460-2620).
  * Setup (_setup_ad_block_nn_inv, cs_sles_it_priv.cpp:178-222): 6x6 blocks get their
  * Gauss-Jordan inverse (cs_math_matrix_gauss_inverse<6>, cs_math.h:540-586); every other size

@@ -113,6 +113,12 @@ void   ora_spmv_msr_b3(int n_rows, const int *row_index, const int *col_id,
 void   ora_spmv_msr_bn(int n_rows, int db, const int *row_index, const int *col_id,
                        const double *d_val, const double *x_val, int exclude_diag,
                        const double *x, double *y);
+/* _gcr (cs_sles_it.cpp:3272-3480): Jacobi-preconditioned (jacobi != 0) GCR with restart */
+int    ora_gcr(int n_rows, int db, const int *row_index, const int *col_id,
+               const double *d_val, const double *x_val, int jacobi, int restart,
+               int n_max_iter, double precision, double r_norm,
+               const double *rhs, double *vx, int use_vx_ini,
+               double *out, double *history, int history_size);
 int    ora_block_jacobi(int n_rows, int db, const int *row_index, const int *col_id,
                         const double *d_val, const double *x_val,
                         int n_max_iter, double precision, double r_norm,

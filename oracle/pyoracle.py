@@ -182,6 +182,16 @@ class Oracle:
         return self._solve_b(self.lib.ora_bicgstab_b, db, ri, ci, d, xv, rhs, n_max_iter,
                              precision, r_norm, vx0)
 
+    def gcr(self, db, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0=None, jacobi=True,
+            restart=20):
+        """_gcr (cs_sles_it.cpp:3272), the fallback solver on a device."""
+        import functools
+
+        def fn(n, dbc, *rest):
+            return self.lib.ora_gcr(n, dbc, *rest[:4], C.c_int(int(jacobi)), C.c_int(restart),
+                                    *rest[4:])
+        return self._solve_b(fn, db, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0)
+
     def block_jacobi(self, db, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0=None):
         """_block_jacobi (cs_sles_it.cpp:2460) / _block_3_jacobi by block size."""
         return self._solve_b(self.lib.ora_block_jacobi, db, ri, ci, d, xv, rhs, n_max_iter,

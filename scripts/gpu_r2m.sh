@@ -1,0 +1,8 @@
+#!/bin/bash
+TAG=${1:-r02m}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+echo "== pytest blockn + parity spmv"; timeout -k 5 900 python -m pytest tests/test_gpu_blockn.py tests/test_gpu_parity.py -m gpu -q 2>&1 | tail -6 | tee $OUT/pytest.log
+echo "== spmv variants"; timeout -k 5 600 python scripts/spmv_variants.py 2>&1 | tee $OUT/spmv_rows_variants.md
+echo "== gs timing"; timeout -k 5 600 python scripts/gs_times.py 2>&1 | tail -20 | tee $OUT/gs_times.md
+ls $OUT

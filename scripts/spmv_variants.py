@@ -47,7 +47,7 @@ def child(cube, launches):
     if os.environ.get("SPMV_REF") == "1":
         p = os.path.join(ROOT, "oracle", "_ref", "libref_spmv_cuda.so")
         if os.path.exists(p):
-            RL = C.CDLL(p)
+            RL = C.CDLL(p, mode=os.RTLD_LAZY)
             t = lambda a: C.c_void_p(a.data_ptr())
             ri = torch.from_numpy(s.row_index).cuda(); ci = torch.from_numpy(s.col_id).cuda()
             dv = torch.from_numpy(s.d_val).cuda(); xv = torch.from_numpy(s.x_val).cuda()
@@ -81,6 +81,7 @@ if __name__ == "__main__":
             o = json.loads(r.stdout.strip().splitlines()[-1])
         except Exception:
             print(f"| {name} | failed: {r.stderr[-200:]} | | |")
+            first = False
             continue
         gbs = o["bytes"] / o["ms"] / 1e6
         print(f"| {name} | {o['ms']:.4f} | {gbs:.0f} | {gbs / a.peak:.3f} |")

@@ -644,3 +644,32 @@ def test_oracle_blockn_vs_reference_direct(oracle, reflib):
         assert (a["cvg"], a["n_iter"], a["residual"]) == (b["cvg"], b["n_iter"], b["residual"])
         assert np.array_equal(a["vx"], b["vx"])
         reflib.destroy(h)
+
+
+# ---- GCR (the fallback solver on a device), a22 ----
+
+def test_oracle_gcr_matches_golden(oracle):
+    from code_saturne_b200.mesh_cartesian import cube_block3_convection_diffusion
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "gcr.npz"))
+    s = cube_poisson(12, "dirichlet")
+    A = (1, s.row_index, s.col_id, s.d_val, s.x_val)
+    rn = float(g["s_r_norm"])
+    for tag, jac, v0, nmi, prec in (("jac_zero", True, None, 200, 1e-10),
+                                    ("jac_warm", True, g["s_vx0"], 200, 1e-10),
+                                    ("npc_warm", False, g["s_vx0"], 200, 1e-10),
+                                    ("jac_27", True, g["s_vx0"], 27, 1e-14)):
+        r = oracle.gcr(*A, s.rhs, nmi, prec, rn, v0, jacobi=jac)
+        for k in ("cvg", "n_iter", "residual", "initial_residual"):
+            assert r[k] == g[f"s_{tag}_{k}"], (tag, k)
+        assert np.array_equal(r["vx"], g[f"s_{tag}_vx"]), tag
+    ri, ci, d, xv, rhs = cube_block3_convection_diffusion(8)
+    r = oracle.gcr(3, ri, ci, d.ravel(), xv, rhs, 200, 1e-10, float(g["b3_r_norm"]))
+    assert (r["cvg"], r["n_iter"], r["residual"]) == (int(g["b3_gcr_cvg"]), int(g["b3_gcr_n_iter"]),
+                                                      float(g["b3_gcr_residual"]))
+    assert np.array_equal(r["vx"], g["b3_gcr_vx"])
+    # the fallback sequence: BiCGStab stopped after 3 iterations, GCR from its iterate
+    b = oracle.bicgstab_bn(3, ri, ci, d.ravel(), xv, rhs, 3, 1e-10, float(g["b3_r_norm"]))
+    assert (b["cvg"], b["n_iter"]) == (int(g["b3_fb_first_cvg"]), int(g["b3_fb_first_n_iter"]))
+    f = oracle.gcr(3, ri, ci, d.ravel(), xv, rhs, 200, 1e-10, float(g["b3_r_norm"]), vx0=b["vx"])
+    assert (f["cvg"], f["n_iter"]) == (int(g["b3_fb200_cvg"]), int(g["b3_fb200_n_iter"]))
+    assert np.array_equal(f["vx"], g["b3_fb200_vx"])
