@@ -281,7 +281,9 @@ def main():
         ro = RankObjects(s, halo_desc, gids, pc, rank)
         m = ro.matrix
     else:
-        m = api.Matrix.from_system(s)
+        # the host arrays are lent to the matrix (csb_matrix_share_host_arrays), the way the
+        # reference's cs_matrix_t shares its caller's arrays: level 0 is aggregated from them
+        m = api.Matrix.from_system(s, share_host=True)
     api.synchronize()
     t_upload = time.perf_counter() - t0
 
@@ -321,9 +323,22 @@ def main():
         sol.setup(m)
         mg = sol
     api.synchronize()
-    t_setup = time.perf_counter() - t0
+    t_setup_first = time.perf_counter() - t0
     if mg is None or mg.n_levels() < 1:
         sys.exit("bench.py: solver setup failed: " + api.load_library().csb_last_error().decode())
+    # The reference frees and rebuilds the hierarchy at every pressure solve, so
+    # the setup that matters is the repeated one: free, set up again on the same matrix.  The
+    # first one also page-locks the host pool's blocks, which later setups reuse.
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    sol.free()
+    sol.setup(m)
+    api.synchronize()
+    t_setup = time.perf_counter() - t0
+    mg = sol.pc() if solver_kind == "fcg_mg" else sol
+    if mg is None or mg.n_levels() < 1:
+        sys.exit("bench.py: repeated setup failed: " + api.load_library().csb_last_error().decode())
     st = mg.setup_times()
     n_levels = mg.n_levels()
 
@@ -535,7 +550,11 @@ def main():
                        "final_residual_over_rnorm": float(r["residual"] / r_norm),
                        "true_residual_over_rnorm": true_res / r_norm,
                        "l2_policy": "inputs (1.7 GB matrix) larger than L2; no flush needed",
-                       "setup_s": t_setup, "setup_aggregation_host_s": st["aggregation"],
+                       "setup_s": t_setup, "setup_first_s": t_setup_first,
+                       "setup_note": "setup_s = hierarchy freed and rebuilt on the same matrix "
+                                     "(what each pressure solve pays); setup_first_s also "
+                                     "page-locks the host pool",
+                       "setup_aggregation_host_s": st["aggregation"],
                        "setup_assembly_device_s": st["assembly"],
                        "setup_transfers_s": st["transfers"],
                        "aggregation_blocks": n_blocks,

@@ -110,6 +110,8 @@ def load_library() -> C.CDLL:
     L.csb_matrix_create_msr.restype = vp
     L.csb_matrix_create_msr.argtypes = [ci, ci, vp, vp, vp, vp, ci]
     L.csb_matrix_set_coefficients.argtypes = [vp, ci, vp, vp]
+    L.csb_matrix_share_host_arrays.argtypes = [vp, vp, vp, vp]
+    L.csb_host_pool_trim.restype = None
     L.csb_matrix_set_mesh_association.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp]
     L.csb_matrix_set_halo.argtypes = [vp, vp]
     L.csb_matrix_destroy.argtypes = [C.POINTER(vp)]
@@ -444,14 +446,24 @@ class Matrix:
         return self
 
     @classmethod
-    def from_system(cls, s, with_mesh=True):
-        """Build from a mesh_cartesian.CubeSystem (host arrays)."""
+    def from_system(cls, s, with_mesh=True, share_host=False):
+        """Build from a mesh_cartesian.CubeSystem (host arrays).  share_host: lend the
+        system's host arrays to the matrix (csb_matrix_share_host_arrays; s must outlive it)."""
         m = cls(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val, True,
                 n_cols_ext=s.meta.get("n_cols_ext", s.n_rows))
         if with_mesh and s.n_faces > 0:
             m.set_mesh_association(s.n_faces, s.c2f, s.c2f_sgn, s.cell_cen, s.cell_vol,
                                    s.face_u_normal, s.face_surf)
+        if share_host:
+            m.share_host_arrays(s.col_id, s.d_val, s.x_val)
         return m
+
+    def share_host_arrays(self, col_id, d_val, x_val):
+        """csb_matrix_share_host_arrays: the arrays are kept alive with this object."""
+        ci, d, xv = _i32(col_id), _f64(d_val), _f64(x_val)
+        self._lent = (ci, d, xv)
+        if load_library().csb_matrix_share_host_arrays(self.handle, _ptr(ci), _ptr(d), _ptr(xv)) != 0:
+            _err("csb_matrix_share_host_arrays")
 
     @property
     def handle(self):

@@ -322,6 +322,17 @@ struct _csb_matrix_t {
   csb::HostVec<csb_lnum_t> h_col_id;
   csb::HostVec<double>     h_d_val, h_x_val;
   bool        h_vals_valid = false;
+  /* host arrays lent by the caller (csb_matrix_share_host_arrays): same content as the device
+     arrays, valid until the values change or the matrix is destroyed; they stand in for the
+     mirrors above, so that the setup of a hierarchy reads level 0 where it already is */
+  const csb_lnum_t *b_col_id = nullptr;
+  const double     *b_d_val = nullptr, *b_x_val = nullptr;
+  const csb_lnum_t *host_col_id() const { return b_col_id != nullptr ? b_col_id : h_col_id.data(); }
+  const double     *host_d_val() const { return b_d_val != nullptr ? b_d_val : h_d_val.data(); }
+  const double     *host_x_val() const { return b_x_val != nullptr ? b_x_val : h_x_val.data(); }
+  bool host_structure_ready() const {
+    return b_col_id != nullptr || h_col_id.size() == (size_t)(nnz > 0 ? nnz : 1);
+  }
   /* SpMV launch geometry */
   int         spmv_rows_per_block = 256;
   size_t      spmv_smem = 0;           /* bytes of staged products per block */

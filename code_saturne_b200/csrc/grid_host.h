@@ -2,6 +2,7 @@
 #ifndef CSB_GRID_HOST_H
 #define CSB_GRID_HOST_H
 
+#include <cstddef>
 #include <memory>
 #include <utility>
 #include <vector>
@@ -10,13 +11,24 @@ namespace csb {
 
 /* std::vector whose resize() leaves new elements uninitialised: the structure arrays of a
    16 M-row level are hundreds of megabytes, every element is written before it is read, and
-   a zero fill by one thread costs as much as the sweep that follows (first touch by the
-   OpenMP loops instead). */
+   a zero fill by one thread costs as much as the sweep that follows.
+   Storage comes from the library's host pool (runtime.cu): page-locked blocks that are
+   cached when a hierarchy is freed and handed out again by the next setup -- the reference
+   rebuilds the hierarchy at every pressure solve, and a block that is already pinned and
+   already faulted in moves to and from the device at the full PCIe rate. */
+extern "C" void *csb_host_pool_alloc(size_t bytes);
+extern "C" void  csb_host_pool_free(void *p, size_t bytes);
+
 template <typename T>
-struct NoInitAlloc : std::allocator<T> {
+struct NoInitAlloc {
+  using value_type = T;
   template <typename U> struct rebind { using other = NoInitAlloc<U>; };
   NoInitAlloc() = default;
   template <typename U> NoInitAlloc(const NoInitAlloc<U> &) {}
+  T *allocate(size_t n) { return static_cast<T *>(csb_host_pool_alloc(n*sizeof(T))); }
+  void deallocate(T *p, size_t n) { csb_host_pool_free(p, n*sizeof(T)); }
+  template <typename U> bool operator==(const NoInitAlloc<U> &) const { return true; }
+  template <typename U> bool operator!=(const NoInitAlloc<U> &) const { return false; }
   template <typename U, typename... A> void construct(U *p, A &&... a)
   {
     if constexpr (sizeof...(A) == 0) ::new ((void *)p) U;

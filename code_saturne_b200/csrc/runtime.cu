@@ -5,6 +5,10 @@
 #include "csb_internal.h"
 
 #include <cstdarg>
+#include <map>
+#include <mutex>
+#include <new>
+#include <unordered_map>
 
 namespace csb {
 
@@ -49,6 +53,99 @@ using namespace csb;
 
 namespace csb { void gs_plan_free(GsPlan *p); }
 _csb_matrix_t::~_csb_matrix_t() { delete csr; if (gs_plan) csb::gs_plan_free(gs_plan); }
+
+/*--------------------------------------------------------------------------
+ * Host pool: page-locked blocks for the host side of the hierarchy setup (HostVec,
+ * grid_host.h).  Blocks of at least POOL_MIN bytes are cudaHostAlloc'ed, rounded up to 2 MiB,
+ * and cached on free (best fit on reuse, a block at most 1.5 times the request); smaller
+ * requests go to malloc.  The cache is bounded (CSB_HOST_POOL_MAX_MB, default 16384): beyond
+ * it freed blocks are returned to the driver.  Before csb_init (or without a device) the pool
+ * falls back to malloc -- it is host memory either way.
+ *--------------------------------------------------------------------------*/
+
+namespace {
+struct HostPool {
+  std::mutex mtx;
+  std::multimap<size_t, void *> cache;                 /* free pinned blocks by size */
+  std::unordered_map<void *, size_t> live;             /* pinned blocks in use -> block size */
+  size_t cached_bytes = 0, max_cached = 0;
+  bool   enabled = true;
+  HostPool() {
+    const char *e = getenv("CSB_HOST_POOL_MAX_MB");
+    max_cached = (size_t)(e != nullptr ? atoll(e) : 16384) << 20;
+    const char *d = getenv("CSB_HOST_POOL");
+    if (d != nullptr && atoi(d) == 0) enabled = false;
+  }
+  ~HostPool() { /* blocks are released with the process: the CUDA context may be gone */ }
+};
+HostPool &host_pool() { static HostPool *p = new HostPool; return *p; }
+const size_t POOL_MIN = 1u << 20, POOL_GRAIN = 2u << 20;
+}
+
+extern "C" void *csb_host_pool_alloc(size_t bytes)
+{
+  if (bytes == 0) bytes = 1;
+  HostPool &hp = host_pool();
+  if (bytes < POOL_MIN || !hp.enabled || !csb::ctx().ready) {
+    void *p = malloc(bytes);
+    if (p == nullptr) throw std::bad_alloc();
+    return p;
+  }
+  const size_t want = (bytes + POOL_GRAIN - 1)/POOL_GRAIN*POOL_GRAIN;
+  {
+    std::lock_guard<std::mutex> lk(hp.mtx);
+    auto it = hp.cache.lower_bound(want);
+    if (it != hp.cache.end() && it->first <= want + want/2) {
+      void *p = it->second;
+      const size_t sz = it->first;
+      hp.cache.erase(it);
+      hp.cached_bytes -= sz;
+      hp.live[p] = sz;
+      return p;
+    }
+  }
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess || p == nullptr) {
+    cudaGetLastError();
+    p = malloc(bytes);                                 /* not registered in live: freed by free */
+    if (p == nullptr) throw std::bad_alloc();
+    return p;
+  }
+  std::lock_guard<std::mutex> lk(hp.mtx);
+  hp.live[p] = want;
+  return p;
+}
+
+extern "C" void csb_host_pool_free(void *p, size_t bytes)
+{
+  (void)bytes;
+  if (p == nullptr) return;
+  HostPool &hp = host_pool();
+  size_t sz = 0;
+  {
+    std::lock_guard<std::mutex> lk(hp.mtx);
+    auto it = hp.live.find(p);
+    if (it == hp.live.end()) { free(p); return; }
+    sz = it->second;
+    hp.live.erase(it);
+    if (hp.cached_bytes + sz <= hp.max_cached) {
+      hp.cache.emplace(sz, p);
+      hp.cached_bytes += sz;
+      return;
+    }
+  }
+  cudaFreeHost(p);
+}
+
+/* release the cached blocks (csb_finalize; also callable to trim host memory) */
+extern "C" void csb_host_pool_trim(void)
+{
+  HostPool &hp = host_pool();
+  std::lock_guard<std::mutex> lk(hp.mtx);
+  for (auto &kv : hp.cache) cudaFreeHost(kv.second);
+  hp.cache.clear();
+  hp.cached_bytes = 0;
+}
 
 extern "C" {
 
@@ -205,6 +302,29 @@ csb_matrix_create_msr(csb_lnum_t n_rows, csb_lnum_t n_cols_ext,
   return m;
 }
 
+/* Host arrays lent to the matrix: the reference's matrices share the caller's arrays
+   (cs_matrix_set_coefficients keeps pointers unless told to copy, src/alge/cs_matrix.cpp:5451);
+   here the device holds the working copy and the host arrays, when lent, serve the host side
+   of the hierarchy setup (aggregation of level 0) without a 1.3 GB device-to-host copy. */
+int csb_matrix_share_host_arrays(csb_matrix_t *m, const csb_lnum_t *col_id,
+                                 const csb_real_t *d_val, const csb_real_t *x_val)
+{
+  if (m == nullptr) { set_error("csb_matrix_share_host_arrays: null matrix"); return -1; }
+  if (m->db != 1 || m->csr != nullptr) {
+    set_error("csb_matrix_share_host_arrays: scalar MSR matrices only");
+    return -1;
+  }
+  if ((col_id != nullptr && is_device_ptr(col_id)) || (d_val != nullptr && is_device_ptr(d_val))
+      || (x_val != nullptr && is_device_ptr(x_val))) {
+    set_error("csb_matrix_share_host_arrays: host pointers expected");
+    return -1;
+  }
+  m->b_col_id = col_id;
+  m->b_d_val = d_val;
+  m->b_x_val = x_val;
+  return 0;
+}
+
 csb_matrix_t *
 csb_matrix_create_msr_block(csb_lnum_t n_rows, csb_lnum_t n_cols_ext, int db_size,
                             const csb_lnum_t *row_index, const csb_lnum_t *col_id,
@@ -312,6 +432,7 @@ int csb_matrix_set_coefficients(csb_matrix_t *m, int symmetric,
                                      cudaMemcpyDefault, c.stream))
          && CSB_CUDA(cudaStreamSynchronize(c.stream));
   m->h_vals_valid = false;
+  m->b_d_val = nullptr; m->b_x_val = nullptr;   /* lent host values are stale now */
   return ok ? 0 : -1;
 }
 
@@ -442,6 +563,7 @@ int csb_matrix_compute_coeffs(csb_matrix_t *m, int iconvp, int idiffp, int ndirc
   if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return -1;   /* host inputs may go away */
   m->symmetric = !conv;
   m->h_vals_valid = false;
+  m->b_d_val = nullptr; m->b_x_val = nullptr;   /* lent host values are stale now */
   return 0;
 }
 
@@ -498,6 +620,7 @@ int csb_matrix_compute_coeffs_vector(csb_matrix_t *m, int iconvp, int idiffp, in
   if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return -1;
   m->symmetric = !conv;
   m->h_vals_valid = false;
+  m->b_d_val = nullptr; m->b_x_val = nullptr;   /* lent host values are stale now */
   return 0;
 }
 

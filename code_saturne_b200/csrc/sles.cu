@@ -91,11 +91,11 @@ struct DistLevelHost {
 bool ghost_row_mask(const csb_matrix_t *m, std::vector<unsigned> &mask)
 {
   mask.assign(((size_t)m->n_rows + 31) / 32 + 1, 0u);
-  if ((size_t)m->h_col_id.size() < (size_t)m->nnz || m->h_row_index.size() < (size_t)m->n_rows + 1) {
+  if (!m->host_structure_ready() || m->h_row_index.size() < (size_t)m->n_rows + 1) {
     set_error("ghost_row_mask: matrix structure is not mirrored on the host");
     return false;
   }
-  const int *ri = m->h_row_index.data(), *ci = m->h_col_id.data();
+  const int *ri = m->h_row_index.data(), *ci = m->host_col_id();
   bool sorted = true;
   #pragma omp parallel for schedule(static, 4096) reduction(&&: sorted)
   for (int i = 0; i < m->n_rows; i++) {
@@ -304,7 +304,7 @@ const GsPlan *gs_plan_get(const csb_matrix_t *m)
   if (!matrix_host_mirror_structure(const_cast<csb_matrix_t *>(m))) return nullptr;
   const int n = m->n_rows;
   const int *ri = m->h_row_index.data();
-  const int *ci = m->h_col_id.data();
+  const int *ci = m->host_col_id();
   std::vector<int> lvl((size_t)std::max(n, 1), 0);
   int n_lv = 0;
   for (int i = 0; i < n; i++) {
@@ -1748,7 +1748,7 @@ void mg_clear_hierarchy(csb_multigrid_t *mg)
 namespace {
 bool matrix_host_mirror_structure(csb_matrix_t *m)
 {
-  if (m->h_col_id.size() == (size_t)std::max<size_t>((size_t)m->nnz, 1)) return true;
+  if (m->host_structure_ready()) return true;
   m->h_col_id.resize(std::max<size_t>((size_t)m->nnz, 1));
   if (m->nnz > 0 &&
       !CSB_CUDA(cudaMemcpyAsync(m->h_col_id.data(), m->col_id.p, sizeof(int)*(size_t)m->nnz,
@@ -1762,13 +1762,13 @@ namespace {
 bool matrix_host_mirror(csb_matrix_t *m)
 {
   Context &c = ctx();
-  if (m->h_col_id.size() != (size_t)m->nnz) {
+  if (!m->host_structure_ready()) {
     m->h_col_id.resize(std::max<size_t>((size_t)m->nnz, 1));
     if (m->nnz > 0 &&
         !CSB_CUDA(cudaMemcpyAsync(m->h_col_id.data(), m->col_id.p, sizeof(int)*(size_t)m->nnz,
                                   cudaMemcpyDeviceToHost, c.stream))) return false;
   }
-  if (!m->h_vals_valid) {
+  if (!m->h_vals_valid && (m->b_d_val == nullptr || m->b_x_val == nullptr)) {
     m->h_d_val.resize(std::max<size_t>((size_t)m->n_rows, 1));
     m->h_x_val.resize(std::max<size_t>((size_t)m->nnz, 1));
     if (m->n_rows > 0 &&
@@ -2303,10 +2303,10 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     HostMsr pw;      /* pairwise: coarse values come out of the host recursion */
     const int c_n_rows = pairwise
       ? coarsen_pairwise_galerkin(f_level, fm->n_rows, fm->h_row_index.data(),
-                                  fm->h_col_id.data(), fm->h_d_val.data(), fm->h_x_val.data(),
+                                  fm->host_col_id(), fm->host_d_val(), fm->host_x_val(),
                                   mg->aggregation_limit, f->h_coarse_row.data(), pw)
-      : aggregate_dx_msr(f_level, fm->n_rows, fm->h_row_index.data(), fm->h_col_id.data(),
-                         fm->h_d_val.data(), fm->h_x_val.data(), mg->aggregation_limit,
+      : aggregate_dx_msr(f_level, fm->n_rows, fm->h_row_index.data(), fm->host_col_id(),
+                         fm->host_d_val(), fm->host_x_val(), mg->aggregation_limit,
                          n_blocks, f->h_coarse_row.data());
     t_aggr += wall() - t0;
 
@@ -2337,7 +2337,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
 
     t0 = wall();
     CoarseStructure cs;
-    build_coarse_structure(fm->n_rows, fm->h_row_index.data(), fm->h_col_id.data(),
+    build_coarse_structure(fm->n_rows, fm->h_row_index.data(), fm->host_col_id(),
                            f->h_coarse_row.data(), c_n_rows, cs);
     t_aggr += wall() - t0;
     const int c_nnz = cs.c_row_index[c_n_rows];

@@ -41,7 +41,7 @@ class RankObjects:
     def __init__(self, system, halo_desc, gids, pcomm, rank):
         self.system, self.halo_desc, self.gids = system, halo_desc, gids
         self.rank, self.pcomm = rank, pcomm
-        self.matrix = api.Matrix.from_system(system)
+        self.matrix = api.Matrix.from_system(system, share_host=True)   # system outlives it
         self.halo = None
         if pcomm is not None and pcomm.n_ranks > 1:
             self.halo = api.Halo(halo_desc, rank, pcomm=pcomm)

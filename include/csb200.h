@@ -129,6 +129,17 @@ csb_matrix_t *csb_matrix_create_msr(csb_lnum_t         n_rows,
                                     const csb_real_t  *x_val,
                                     int                symmetric);
 
+/* Lend the host copies of the matrix arrays (same content as given to csb_matrix_create_msr).
+   They must stay valid and unchanged until the matrix is destroyed, its values are replaced
+   (csb_matrix_set_coefficients / _compute_coeffs drop the lent values) or this is called
+   again with NULL.  The reference's cs_matrix_t shares the caller's arrays the same way
+   (src/alge/cs_matrix.cpp:5451); here they spare csb_multigrid_setup the device-to-host copy
+   of level 0 for the host-side aggregation.  Returns 0. */
+int csb_matrix_share_host_arrays(csb_matrix_t *m, const csb_lnum_t *col_id,
+                                 const csb_real_t *d_val, const csb_real_t *x_val);
+/* Give the cached page-locked blocks of the host pool (hierarchy setup) back to the system */
+void csb_host_pool_trim(void);
+
 /* MSR with db_size x db_size diagonal blocks and scalar extra-diagonal entries (fill type
    CS_MATRIX_BLOCK_D: cs_matrix_transfer_coefficients_msr with db_size = 3, eb_size = 1; the
    velocity systems).  d_val: n_rows*db_size*db_size, row-major blocks; vectors hold db_size

@@ -25,6 +25,9 @@ def child(cube, launches):
     from code_saturne_b200 import api
     from code_saturne_b200.mesh_cartesian import cube_poisson
     api.init(0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    api.set_stream(stream.cuda_stream)        # the library launches on this stream
     s = cube_poisson(cube, "neumann", with_mesh=False)
     m = api.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
     x = torch.from_numpy(np.sin(np.arange(s.n_rows) * 0.37)).cuda()
@@ -35,10 +38,10 @@ def child(cube, launches):
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(stream)
         for _ in range(launches):
             fn()
-        e1.record()
+        e1.record(stream)
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / launches
 

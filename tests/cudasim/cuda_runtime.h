@@ -85,6 +85,8 @@ inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
 template <typename T> inline cudaError_t cudaMallocHost(T **p, size_t n) { return cudaMalloc((void **)p, n); }
 inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+#define cudaHostAllocPortable 1u
+inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { return cudaMalloc(p, n); }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }

@@ -289,3 +289,35 @@ def test_shared_memory_coarse_pcg_is_bit_identical_to_streamed(csb, monkeypatch)
         assert a[1] == b[1] and a[3] == b[3]
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
         m.destroy()
+
+
+def test_shared_host_arrays_give_the_same_hierarchy(csb):
+    """csb_matrix_share_host_arrays: level 0 is aggregated from the caller's arrays instead of
+    a device-to-host mirror; the hierarchy and the solve are identical, a value update drops
+    the lent values, and setups after the first reuse the host pool's blocks."""
+    s = cube_poisson(20, "neumann")
+    r_norm = float(np.linalg.norm(s.rhs))
+    out = []
+    for share in (False, True, True):
+        m = csb.Matrix.from_system(s, share_host=share)
+        mg = csb.Multigrid()
+        mg.set_aggregation_blocks(1)
+        mg.setup(m)
+        lv = mg.levels()
+        r = mg.solve(m, s.rhs, 1e-8, r_norm)
+        out.append((lv, r))
+        if share:
+            m.set_coefficients(s.d_val * 2.0, s.x_val * 2.0)      # lent values dropped
+            mg.setup(m)
+            r2 = mg.solve(m, 2.0 * s.rhs, 1e-8, 2.0 * r_norm)
+            assert r2["n_cycles"] == r["n_cycles"]
+            assert np.allclose(r2["vx"][:s.n_rows], r["vx"][:s.n_rows], rtol=1e-12, atol=0)
+        mg.destroy()
+        m.destroy()
+    for lv, r in out[1:]:
+        assert len(lv) == len(out[0][0])
+        for a, b in zip(lv[1:], out[0][0][1:]):
+            for k in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
+                assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(r["vx"], out[0][1]["vx"]) and r["n_cycles"] == out[0][1]["n_cycles"]
+    csb.load_library().csb_host_pool_trim()
