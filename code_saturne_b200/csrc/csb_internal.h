@@ -34,6 +34,7 @@ struct Context {
   long long     launches = 0;
   int           partials_blocks = 0;    /* capacity of `partials` in CTAs */
   int           device_share = 1;       /* ranks sharing this device (in-process groups) */
+  bool          pool_ok = false;        /* stream-ordered allocator usable (dev_alloc) */
   std::string   err;
 };
 
@@ -56,6 +57,15 @@ enum { MG_PROF_DESCENT = 0, MG_PROF_RESIDUAL, MG_PROF_RESTRICT, MG_PROF_COARSEST
 /* true if p is a device (or managed) pointer */
 bool is_device_ptr(const void *p);
 
+/* Device memory of the library's objects: the stream-ordered allocator of the device's default
+   memory pool (cudaMallocAsync / cudaFreeAsync on the library's stream, release threshold
+   raised at csb_init so that freed blocks stay in the pool).  A hierarchy has ~12 arrays per
+   level; with cudaMalloc / cudaFree a repeated setup spent ~0.25 s of its 0.55 s in the driver
+   (profiles/r02/setup_trace_256_v1.log) -- the reference rebuilds its hierarchy at every
+   pressure solve.  CSB_DEV_POOL=0 goes back to cudaMalloc.  NULL + set_error on failure. */
+void *dev_alloc(size_t bytes);
+void  dev_free(void *p);
+
 /* RAII device buffer */
 template <typename T>
 struct DevBuf {
@@ -70,9 +80,10 @@ struct DevBuf {
     n = count;
     if (count == 0) count = 1;
     /* 64 bytes of slack: bulk copies (cp.async.bulk) read whole 16-byte units */
-    return CSB_CUDA(cudaMalloc((void **)&p, count * sizeof(T) + 64));
+    p = static_cast<T *>(dev_alloc(count * sizeof(T) + 64));
+    return p != nullptr;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() { if (p) dev_free(p); p = nullptr; n = 0; }
   /* copy from host or device pointer */
   bool upload(const T *src, size_t count) {
     if (!alloc(count)) return false;

@@ -107,6 +107,9 @@ constexpr int PIPE_OFF = BAR_TGT_OFF + 16;            /* PipeState */
 __device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 
+/* longer than any peer-flag timeout (CSB_SPIN_TIMEOUT_S, default 10 s): the peer wait reports first */
+constexpr unsigned long long GRID_BARRIER_TIMEOUT_NS = 120ull*1000000000ull;
+
 __device__ __forceinline__ void grid_barrier(unsigned *bar)
 {
   __syncthreads();
@@ -116,10 +119,24 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar)
     *tgt = target;
     fence_gpu();                     /* release: this CTA's stores (bar.sync-cumulative) */
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" :: "l"(bar) : "memory");
-    unsigned seen;
-    do {
+    unsigned seen, n_poll = 0;
+    unsigned long long t0 = 0;
+    for (;;) {
       asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
-    } while ((int)(seen - target) < 0);
+      if ((int)(seen - target) >= 0) break;
+      /* a CTA that never arrives (a fault elsewhere, a peer rank that died inside its own
+         wait) must not hang the device: after GRID_BARRIER_TIMEOUT_NS the kernel traps and
+         the launch returns an error, like the peer-flag waits (spin_until_ge) */
+      if ((++n_poll & 0x3FFFu) == 0) {
+        const unsigned long long now = gtime_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > GRID_BARRIER_TIMEOUT_NS) {
+          printf("[csb200] grid barrier timeout (block %d): have %u, expect %u\n",
+                 blockIdx.x, seen, target);
+          __trap();
+        }
+      }
+    }
     fence_gpu();                     /* acquire */
   }
   __syncthreads();

@@ -5,6 +5,7 @@
 #include "csb_internal.h"
 
 #include <cstdarg>
+#include <cstdint>
 #include <map>
 #include <mutex>
 #include <new>
@@ -81,6 +82,67 @@ struct HostPool {
 HostPool &host_pool() { static HostPool *p = new HostPool; return *p; }
 const size_t POOL_MIN = 1u << 20, POOL_GRAIN = 2u << 20;
 }
+
+namespace csb {
+
+namespace {
+bool dev_pool_enabled()
+{
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("CSB_DEV_POOL"); v = (e != nullptr && atoi(e) == 0) ? 0 : 1; }
+  return v == 1;
+}
+/* blocks that came from the stream-ordered allocator, with the stream they belong to */
+std::mutex g_dev_mtx;
+std::unordered_map<void *, cudaStream_t> g_dev_async;
+}
+
+void *dev_alloc(size_t bytes)
+{
+  Context &c = ctx();
+  void *p = nullptr;
+#ifndef CUDASIM
+  if (dev_pool_enabled() && c.ready && c.pool_ok) {
+    if (cudaMallocAsync(&p, bytes, c.stream) == cudaSuccess && p != nullptr
+        && (reinterpret_cast<uintptr_t>(p) & 255u) == 0) {
+      std::lock_guard<std::mutex> lk(g_dev_mtx);
+      g_dev_async[p] = c.stream;
+      return p;
+    }
+    cudaGetLastError();
+    if (p != nullptr) { cudaFreeAsync(p, c.stream); p = nullptr; }
+  }
+#endif
+  if (!CSB_CUDA(cudaMalloc(&p, bytes))) return nullptr;
+  return p;
+}
+
+void dev_free(void *p)
+{
+  if (p == nullptr) return;
+  cudaStream_t s = nullptr;
+  bool async = false;
+  {
+    std::lock_guard<std::mutex> lk(g_dev_mtx);
+    auto it = g_dev_async.find(p);
+    if (it != g_dev_async.end()) { s = it->second; async = true; g_dev_async.erase(it); }
+  }
+#ifndef CUDASIM
+  if (async) {
+    /* on the stream the block was allocated on; work enqueued on another stream since
+       (csb_set_stream) is waited for first.  If the allocation stream is gone (csb_finalize
+       before the object's destruction) cudaFree takes the block */
+    Context &c = ctx();
+    if (c.ready && c.stream != s) cudaStreamSynchronize(c.stream);
+    if (cudaFreeAsync(p, s) == cudaSuccess) return;
+    cudaGetLastError();
+  }
+#endif
+  (void)async; (void)s;
+  cudaFree(p);
+}
+
+} // namespace csb
 
 extern "C" void *csb_host_pool_alloc(size_t bytes)
 {
@@ -179,6 +241,20 @@ int csb_init(int device_id)
   if (!CSB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking))) return -1;
   if (!CSB_CUDA(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking))) return -1;
   c.stream = c.own_stream;
+#ifndef CUDASIM
+  {
+    /* stream-ordered allocator (dev_alloc): keep freed blocks in the device's default pool */
+    int pools = 0;
+    cudaMemPool_t mp;
+    if (cudaDeviceGetAttribute(&pools, cudaDevAttrMemoryPoolsSupported, device_id) == cudaSuccess
+        && pools != 0 && cudaDeviceGetDefaultMemPool(&mp, device_id) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      if (cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr) == cudaSuccess)
+        c.pool_ok = true;
+    }
+    cudaGetLastError();
+  }
+#endif
   if (!CSB_CUDA(cudaEventCreateWithFlags(&c.ev_a, cudaEventDisableTiming))) return -1;
   if (!CSB_CUDA(cudaEventCreateWithFlags(&c.ev_b, cudaEventDisableTiming))) return -1;
   if (!CSB_CUDA(cudaMalloc((void **)&c.ticket, sizeof(unsigned)))) return -1;
@@ -214,6 +290,8 @@ int csb_set_stream(void *cuda_stream)
 {
   Context &c = ctx();
   if (!c.ready) { set_error("csb_set_stream: csb_init not called"); return -1; }
+  /* blocks of the stream-ordered allocator are handed from the old stream to the new one */
+  if (c.stream != nullptr) cudaStreamSynchronize(c.stream);
   c.stream = (cuda_stream != nullptr) ? (cudaStream_t)cuda_stream : c.own_stream;
   return 0;
 }

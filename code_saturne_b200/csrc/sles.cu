@@ -37,6 +37,18 @@ int env_int(const char *name, int dflt)
   return (s != nullptr) ? atoi(s) : dflt;
 }
 
+/* CSB_SETUP_TRACE=1: wall-clock marks of the setup stages on stderr (tuning aid) */
+struct SetupTrace {
+  bool on; double t_last;
+  SetupTrace() : on(env_int("CSB_SETUP_TRACE", 0) != 0), t_last(wall()) {}
+  void mark(const char *what, int level = -1) {
+    if (!on) return;
+    const double t = wall();
+    fprintf(stderr, "[csb200 setup] %-28s level %2d  %8.2f ms\n", what, level, (t - t_last)*1e3);
+    t_last = t;
+  }
+};
+
 /* stage a host vector on the device when needed */
 struct StagedVec {
   double         *d = nullptr;
@@ -1091,8 +1103,11 @@ void csb_sles_it_setup(void *context, const char *name, const csb_matrix_t *a, i
     if (dist_fcg_mg) csb_multigrid_set_pcomm(c->pc_mg, c->pcomm);
     if (c->pc_mg == nullptr && c->poly_degree > 0
         && !c->pc_tmp.alloc(work_stride_of((size_t)a->n_cols_ext))) return;
+    SetupTrace tr;
     if (c->pc_mg != nullptr) {
+      tr.mark("sles_it: ad_inv, work");
       csb_multigrid_setup(c->pc_mg, name, a, verbosity);
+      tr.mark("sles_it: multigrid setup");
       if (!csb_multigrid_is_setup(c->pc_mg)) return;
       c->fcg_mg_persistent = false;
       if (c->type == CSB_SLES_FCG && mg_fcg_persistent_ok(c->pc_mg)
@@ -1320,9 +1335,11 @@ void csb_sles_it_free(void *context)
 {
   csb_sles_it_t *c = static_cast<csb_sles_it_t *>(context);
   if (c == nullptr) return;
+  SetupTrace tr;
   c->ad_inv.release();
   c->work.release();
   if (c->pc_mg != nullptr) csb_multigrid_free(c->pc_mg);
+  tr.mark("csb_sles_it_free");
   if (c->arena_used && c->pcomm != nullptr) {
     pcomm_arena_release(c->pcomm, c->arena_mark);
     c->arena_used = false;
@@ -2267,6 +2284,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
 
   const double t_start = wall();
   double t_aggr = 0, t_asm = 0, t_xfer = 0;
+  SetupTrace tr;
 
   MgLevel *l0 = new MgLevel;
   l0->m = a;
@@ -2296,6 +2314,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     double t0 = wall();
     if (!matrix_host_mirror(fm)) return;
     t_xfer += wall() - t0;
+    tr.mark("host mirror", f_level);
 
     /* aggregation on the host */
     t0 = wall();
@@ -2309,6 +2328,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
                          fm->host_d_val(), fm->host_x_val(), mg->aggregation_limit,
                          n_blocks, f->h_coarse_row.data());
     t_aggr += wall() - t0;
+    tr.mark("aggregation", f_level);
 
     /* stop criteria of _setup_hierarchy (cs_multigrid.cpp:2518-2529); they
        only depend on the (global) row count, so the rejected level is never
@@ -2340,6 +2360,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     build_coarse_structure(fm->n_rows, fm->h_row_index.data(), fm->host_col_id(),
                            f->h_coarse_row.data(), c_n_rows, cs);
     t_aggr += wall() - t0;
+    tr.mark("coarse structure (host)", f_level);
     const int c_nnz = cs.c_row_index[c_n_rows];
 
     t0 = wall();
@@ -2369,6 +2390,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     cm->h_row_index.swap(cs.c_row_index);
     cm->h_col_id.swap(cs.c_col_id);
     t_xfer += wall() - t0;
+    tr.mark("alloc + upload", f_level);
 
     /* floating-point assembly on the device */
     t0 = wall();
@@ -2443,9 +2465,11 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     if (!launch_coarse_assembly(ca, 2)) { delete cl; return; }
     if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) { delete cl; return; }
     t_asm += wall() - t0;
+    tr.mark("coarse values (device)", f_level);
 
     matrix_plan_spmv(cm);
     mg->levels.push_back(cl);
+    tr.mark("plan spmv", f_level);
 
     if (verbosity > 2)
       printf("   building level %2d grid\n     number of rows:      %10d\n"
@@ -2500,6 +2524,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
         && (!matrix_host_mirror_structure(const_cast<csb_matrix_t *>(m))
             || !build_dist_level(pc, lv->halo, m, lv->dist))) return;
   }
+  tr.mark("per-level solve data");
   mg->work_stride = aux_size / 5;
   if (mg->merge_level >= 0 && !mg_merge_build_dev(mg, pc)) return;
   if (!mg->wr.alloc(wr_size) || !mg->aux.alloc(aux_size)) return;
@@ -2540,6 +2565,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
       mg->h_merge.stub_vx = ml->arena_vx;
       if (!mg->d_merge.upload(&mg->h_merge, 1)) return;
     }
+    tr.mark("slab plans");
     mg->p_smem = persistent_smem_bytes(max_entries);
     mg->p_grid = persistent_grid(1, mg->p_smem);
     if (mg->p_grid < 1) return;
@@ -2553,6 +2579,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     if (!CSB_CUDA(cudaMallocHost((void **)&mg->h_mg, sizeof(MgState)))) return;
   if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) return;
 
+  tr.mark("descriptors, state");
   mg->setup_done = true;
   mg->n_setups += 1;
   mg->t_setup[0] = wall() - t_start;

@@ -66,6 +66,50 @@ def fcg_mg(N, R, rank, bc, precision, merge_glob, r_norm, s, gids, pc, ro):
         D.free()
 
 
+def nccl_halo(N, R, rank, bc, s, h, gids):
+    """cs_halo_sync_var over the reference-shaped NCCL path (csb_comm_init_rank +
+    csb_halo_create(nccl_comm): pack kernel, grouped ncclSend / ncclRecv; cs_halo.cpp:518-587)
+    and the distributed SpMV that runs on it, against the global product."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from code_saturne_b200 import api
+    from code_saturne_b200.mesh_cartesian import cube_poisson
+    from oracle.pyoracle import Oracle
+    L = api.load_library()
+    uid = (C.c_char * 128)()
+    if rank == 0:
+        assert L.csb_comm_get_unique_id(C.cast(uid, C.c_void_p)) == 0, L.csb_last_error()
+    box = [bytes(uid)]
+    dist.broadcast_object_list(box, src=0)
+    uid = (C.c_char * 128).from_buffer_copy(box[0])
+    comm = L.csb_comm_init_rank(C.cast(uid, C.c_void_p), R, rank)
+    assert comm, L.csb_last_error()
+    halo = api.Halo(h, rank, nccl_comm=comm)
+    m = api.Matrix.from_system(s)
+    m.set_halo(halo)
+    n_ext = s.meta.get("n_cols_ext", s.n_rows)
+    g = cube_poisson(N, bc)
+    xg = np.sin(0.37 * np.arange(g.n_rows) + 0.2)
+    x = torch.zeros(n_ext, dtype=torch.float64, device="cuda")
+    x[:s.n_rows] = torch.from_numpy(xg[gids[:s.n_rows]]).cuda()
+    halo.sync_var(x)
+    api.synchronize()
+    assert np.array_equal(x.cpu().numpy(), xg[gids[:n_ext]]), "ghost values after the NCCL exchange"
+    x[s.n_rows:] = 0.
+    y = torch.empty(s.n_rows, dtype=torch.float64, device="cuda")
+    m.vector_multiply(x, y)                      # syncs the halo first, like the reference
+    api.synchronize()
+    yg = Oracle().spmv(g.row_index, g.col_id, g.d_val, g.x_val, xg)
+    assert np.array_equal(y.cpu().numpy(), yg[gids[:s.n_rows]]), "distributed SpMV over NCCL"
+    ok = [None] * R
+    dist.all_gather_object(ok, True)
+    m.destroy(); halo.destroy()
+    L.csb_comm_destroy(C.c_void_p(comm))
+    if rank == 0:
+        print(f"OK proc-nccl N={N} R={R} {bc}: halo exchange and SpMV over ncclSend/ncclRecv bit-exact")
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -87,6 +131,10 @@ def main():
     rr = torch.tensor([float(np.dot(s.rhs, s.rhs))], dtype=torch.float64, device="cuda")
     dist.all_reduce(rr)
     r_norm = float(torch.sqrt(rr[0]).item())
+    if mode == "nccl":
+        nccl_halo(N, R, rank, bc, s, h, gids)
+        dist.destroy_process_group()
+        return
     pc = pcomm_from_torch_dist(h.n_ghost)
     assert np.array_equal(pc.allreduce_sum([rank + 1.0, 1.0]), [R * (R + 1) / 2.0, float(R)])
     ro = RankObjects(s, h, gids, pc, rank)

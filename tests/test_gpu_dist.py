@@ -60,10 +60,12 @@ def _n_gpus():
 
 @pytest.mark.parametrize("N,R,bc,mode", [(32, 2, "dirichlet", "mg"), (48, 4, "neumann", "mg"),
                                          (64, 8, "dirichlet", "mg"), (48, 2, "dirichlet", "fcgmg"),
-                                         (64, 4, "neumann", "fcgmg"), (64, 8, "dirichlet", "fcgmg")])
+                                         (64, 4, "neumann", "fcgmg"), (64, 8, "dirichlet", "fcgmg"),
+                                         (24, 2, "neumann", "nccl"), (32, 8, "dirichlet", "nccl")])
 def test_one_process_per_gpu_multigrid(N, R, bc, mode):
     """torchrun, one process per GPU, arenas mapped with cudaIpc: needs R visible GPUs.
-    mode fcgmg: FCG + V-cycle preconditioner with the coarse levels merged onto rank 0."""
+    mode fcgmg: FCG + V-cycle preconditioner with the coarse levels merged onto rank 0;
+    mode nccl: the halo exchange and SpMV over the NCCL send / receive path of halo.cu."""
     if _n_gpus() < R:
         pytest.skip(f"needs {R} GPUs")
     import socket
