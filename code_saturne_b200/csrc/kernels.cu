@@ -1703,15 +1703,38 @@ bool launch_mg_accum_iter(MgState *mg, const ItState *st, int level, double n_ro
 }
 
 /*--------------------------------------------------------------------------
- * Coarse level assembly: one thread per coarse row, same loop order as the
- * reference's row-parallel host/device lambdas
- * (src/alge/cs_grid.cpp:6347-6435, :6446-6530, :6848-6895), so values are
- * bit-identical to the CPU path (compiled with -fmad=false).
+ * Coarse level assembly (cs_grid.cpp _compute_coarse_quantities_msr_with_faces :6226-6990,
+ * _compute_coarse_quantities_msr :5969-6090).
+ *
+ * What must be reproduced is a set of ORDERED sums: every coarse face (an upper entry of a
+ * coarse row) adds up the fine faces between its two aggregates in the order "fine rows of the
+ * aggregate ascending, entries of a fine row in CSR order", and the coarse diagonal adds up the
+ * fine diagonal and every fine entry in that same order.  The reference walks this order with
+ * one thread per coarse row and updates the face arrays as it goes.
+ *
+ * Here a WARP owns a coarse row and splits the work by what is parallel in it:
+ *   stage:  the entries of the aggregate are enumerated in the canonical order -- fine rows
+ *           one after the other, the lanes of the warp taking the entries of a row side by
+ *           side -- and each lane computes ITS entry's target (the coarse row's entry it
+ *           falls into, by binary search) and the values it contributes; target and values
+ *           go to a shared-memory stage in canonical position;
+ *   fold:   a lane owns a coarse ENTRY (lane k: entries k, k + 32, ...) and adds up, in
+ *           canonical position order, the staged contributions aimed at it -- registers only,
+ *           one store per coarse face, no read-modify-write of the face arrays, no atomics;
+ *           one more lane runs the sequential chain of the diagonal over the same stage.
+ * Aggregates larger than the stage are folded in several rounds (accumulators live in
+ * registers across rounds).  The sums are the reference's, term by term (built with
+ * -fmad=false), so the coarse matrices stay bit-identical to the CPU path.
  *--------------------------------------------------------------------------*/
 
 namespace {
 
-__device__ __forceinline__ int l_id_search(int size, int id, const int *__restrict__ a)
+constexpr int CA_WARPS = 4;          /* coarse rows per CTA */
+constexpr int CA_STAGE = 128;        /* staged contributions per round and warp */
+constexpr int CA_OWN = 4;            /* coarse entries a lane can own: rows up to 128 entries */
+
+/* position of id in the sorted row a[0..size), -1 if absent */
+__device__ __forceinline__ int sorted_find(int size, int id, const int *__restrict__ a)
 {
   int lo = 0, hi = size - 1;
   while (lo <= hi) {
@@ -1724,144 +1747,308 @@ __device__ __forceinline__ int l_id_search(int size, int id, const int *__restri
   return -1;
 }
 
-__global__ void __launch_bounds__(128)
-k_coarse_stage_1(const CoarseAssemblyArgs a)
+struct CaStage {
+  int    target[CA_STAGE];           /* coarse entry (offset in its row); -1 none, -2 diagonal */
+  double w[CA_STAGE];                /* value added to the diagonal chain / Galerkin value */
+  double v[7][CA_STAGE];             /* face normal (3), xa0, xa0ij (3) */
+};
+
+/* Fold of one round: lane `lane` owns the coarse entries lane, lane + 32, ... of its row
+   (those that are faces) and gathers the staged contributions aimed at them, in order. */
+__device__ __forceinline__ void ca_fold7(const CaStage &S, int n_staged, int lane,
+                                         const bool is_face[CA_OWN], double acc[CA_OWN][7])
 {
-  const int ii_c = blockIdx.x*blockDim.x + threadIdx.x;
-  if (ii_c >= a.c_n_rows) return;
+#pragma unroll
+  for (int o = 0; o < CA_OWN; o++) {
+    if (!is_face[o]) continue;
+    const int k = lane + 32*o;
+    for (int p = 0; p < n_staged; p++) {
+      if (S.target[p] == k) {
+#pragma unroll
+        for (int q = 0; q < 7; q++) acc[o][q] += S.v[q][p];
+      }
+    }
+  }
+}
 
-  const int c_s_idx = a.c_row_index[ii_c];
-  const int n_c_cols = a.c_row_index[ii_c+1] - c_s_idx;
+/* Sums over the fine rows of every aggregate: cell centre and volume, the diagonal chain, and
+   (faces) the coarse face normals, xa0 and xa0ij.  Rows with more than 32*CA_OWN entries are
+   left to k_coarse_sums_wide. */
+__global__ void __launch_bounds__(CA_WARPS*32)
+k_coarse_sums(const CoarseAssemblyArgs a, int wide_limit, int *wide_rows, int *n_wide)
+{
+  __shared__ CaStage s_stage[CA_WARPS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int crow = blockIdx.x*CA_WARPS + wid;
+  if (crow >= a.c_n_rows) return;                 /* whole warp */
+  CaStage &S = s_stage[wid];
 
-  double cen0 = 0., cen1 = 0., cen2 = 0., vol = 0., dsum = 0.;
+  const int c_beg = a.c_row_index[crow];
+  const int c_len = a.c_row_index[crow+1] - c_beg;
+  const int *__restrict__ c_cols = a.c_col_id + c_beg;
+  if (c_len > wide_limit) {                       /* rare: handled by the wide kernel */
+    if (lane == 0) wide_rows[atomicAdd(n_wide, 1)] = crow;
+    return;
+  }
+  bool is_face[CA_OWN];
+  double acc[CA_OWN][7];
+#pragma unroll
+  for (int o = 0; o < CA_OWN; o++) {
+    const int k = lane + 32*o;
+    is_face[o] = (k < c_len && c_cols[k] > crow);   /* faces are the upper entries */
+#pragma unroll
+    for (int q = 0; q < 7; q++) acc[o][q] = 0.;
+  }
+  double diag = 0.;                               /* lane 31: the coarse diagonal chain */
 
-  const int r_s = a.c_f_row_index[ii_c], r_e = a.c_f_row_index[ii_c+1];
-  for (int r_idx = r_s; r_idx < r_e; r_idx++) {
-    const int ii = a.c_f_row_ids[r_idx];
-    const double fv = a.f_cell_vol[ii];
-    const double fc0 = a.f_cell_cen[ii*3], fc1 = a.f_cell_cen[ii*3+1],
-                 fc2 = a.f_cell_cen[ii*3+2];
-    cen0 += fc0*fv; cen1 += fc1*fv; cen2 += fc2*fv;
+  const int r_beg = a.c_f_row_index[crow], r_end = a.c_f_row_index[crow+1];
+  int n_staged = 0;
+  for (int r = r_beg; r < r_end; r++) {
+    const int frow = a.c_f_row_ids[r];
+    const int e_beg = a.f_row_index[frow], e_end = a.f_row_index[frow+1];
+    const double xi0 = a.f_cell_cen[frow*3], xi1 = a.f_cell_cen[frow*3+1],
+                 xi2 = a.f_cell_cen[frow*3+2];
+    /* the fine diagonal opens the row's part of the chain */
+    int e = e_beg - 1;                            /* -1: the diagonal marker */
+    while (e < e_end) {
+      const int room = CA_STAGE - n_staged;
+      const int n_now = min(room, e_end - e);
+      const int mine = e + lane;
+      for (int q = mine; q < e + n_now; q += 32) {
+        const int p = n_staged + (q - e);
+        if (q < e_beg) { S.target[p] = -2; S.w[p] = a.f_d_val[frow]; continue; }
+        const int fcol = a.f_col_id[q];
+        const int ccol = a.f_c_row[fcol];
+        const double fx = a.f_x_val[q];
+        S.w[p] = fx;
+        int tgt = -1;
+        if (ccol > crow) {
+          tgt = sorted_find(c_len, ccol, c_cols);
+          const int ff = a.f_cell_face[q];
+          const int sg = a.f_cell_face_sgn[q];
+          if (a.f_level == 0) {
+            const double ss = sg * a.f_face_surf[ff];
+            S.v[0][p] = ss * a.f_face_u_normal[ff*3];
+            S.v[1][p] = ss * a.f_face_u_normal[ff*3+1];
+            S.v[2][p] = ss * a.f_face_u_normal[ff*3+2];
+            S.v[3][p] = fx;
+            S.v[4][p] = fx * (a.f_cell_cen[fcol*3]   - xi0);
+            S.v[5][p] = fx * (a.f_cell_cen[fcol*3+1] - xi1);
+            S.v[6][p] = fx * (a.f_cell_cen[fcol*3+2] - xi2);
+          }
+          else {
+            S.v[0][p] = sg * a.f_face_normal[ff*3];
+            S.v[1][p] = sg * a.f_face_normal[ff*3+1];
+            S.v[2][p] = sg * a.f_face_normal[ff*3+2];
+            S.v[3][p] = a.f_xa0[ff];
+            S.v[4][p] = sg * a.f_xa0ij[ff*3];
+            S.v[5][p] = sg * a.f_xa0ij[ff*3+1];
+            S.v[6][p] = sg * a.f_xa0ij[ff*3+2];
+          }
+        }
+        S.target[p] = tgt;
+      }
+      n_staged += n_now;
+      e += n_now;
+      if (n_staged == CA_STAGE) {                 /* stage full: fold it */
+        __syncwarp();
+        ca_fold7(S, n_staged, lane, is_face, acc);
+        if (lane == 31) for (int p = 0; p < n_staged; p++) diag += S.w[p];
+        __syncwarp();
+        n_staged = 0;
+      }
+    }
+  }
+  __syncwarp();
+  ca_fold7(S, n_staged, lane, is_face, acc);
+  if (lane == 31) {
+    for (int p = 0; p < n_staged; p++) diag += S.w[p];
+    a.c_d_val[crow] = diag;
+  }
+#pragma unroll
+  for (int o = 0; o < CA_OWN; o++) {
+    if (!is_face[o]) continue;
+    const int face = a.c_cell_face[c_beg + lane + 32*o];
+    a.c_face_normal[3*(size_t)face]   = acc[o][0];
+    a.c_face_normal[3*(size_t)face+1] = acc[o][1];
+    a.c_face_normal[3*(size_t)face+2] = acc[o][2];
+    a.c_xa0[face] = acc[o][3];
+    a.c_xa0ij[3*(size_t)face]   = acc[o][4];
+    a.c_xa0ij[3*(size_t)face+1] = acc[o][5];
+    a.c_xa0ij[3*(size_t)face+2] = acc[o][6];
+  }
+  /* cell centre and volume: four short chains over the fine rows, one lane each (the stage
+     is reused for the exchange: every lane must be done reading it) */
+  __syncwarp();
+  if (lane < 4) {
+    double sum = 0.;
+    for (int r = r_beg; r < r_end; r++) {
+      const int frow = a.c_f_row_ids[r];
+      const double fv = a.f_cell_vol[frow];
+      if (lane < 3) sum += a.f_cell_cen[frow*3 + lane]*fv;
+      else sum += fv;
+    }
+    S.w[lane] = sum;
+  }
+  __syncwarp();
+  if (lane < 3) a.c_cell_cen[crow*3 + lane] = S.w[lane] / S.w[3];
+  else if (lane == 3) a.c_cell_vol[crow] = S.w[3];
+}
+
+/* Same sums for the coarse rows with more entries than a warp's lanes can own: one thread per
+   row walks the canonical order and adds into the face arrays (zeroed by the launcher) -- a
+   handful of rows at most on the hierarchies of this path. */
+__global__ void __launch_bounds__(64)
+k_coarse_sums_wide(const CoarseAssemblyArgs a, const int *__restrict__ wide_rows,
+                   const int *__restrict__ n_wide)
+{
+  const int t = blockIdx.x*64 + threadIdx.x;
+  if (t >= *n_wide) return;
+  const int crow = wide_rows[t];
+  const int c_beg = a.c_row_index[crow];
+  const int c_len = a.c_row_index[crow+1] - c_beg;
+  const int *__restrict__ c_cols = a.c_col_id + c_beg;
+  for (int k = 0; k < c_len; k++)
+    if (c_cols[k] > crow) {
+      const int face = a.c_cell_face[c_beg + k];
+      for (int q = 0; q < 3; q++) { a.c_face_normal[3*(size_t)face+q] = 0.; a.c_xa0ij[3*(size_t)face+q] = 0.; }
+      a.c_xa0[face] = 0.;
+    }
+  double diag = 0., vol = 0., cen[3] = {0., 0., 0.};
+  for (int r = a.c_f_row_index[crow]; r < a.c_f_row_index[crow+1]; r++) {
+    const int frow = a.c_f_row_ids[r];
+    const double fv = a.f_cell_vol[frow];
+    const double xi[3] = {a.f_cell_cen[frow*3], a.f_cell_cen[frow*3+1], a.f_cell_cen[frow*3+2]};
+    for (int q = 0; q < 3; q++) cen[q] += xi[q]*fv;
     vol += fv;
-    dsum += a.f_d_val[ii];
-
-    const int f_s = a.f_row_index[ii], f_e = a.f_row_index[ii+1];
-    for (int f_idx = f_s; f_idx < f_e; f_idx++) {
-      const int jj = a.f_col_id[f_idx];
-      const int jj_c = a.f_c_row[jj];
-      const double fx = a.f_x_val[f_idx];
-      dsum += fx;
-
-      if (jj_c > -1 && jj_c != ii_c && jj_c > ii_c) {
-        const int k = l_id_search(n_c_cols, jj_c, a.c_col_id + c_s_idx);
-        const int c_face_id = a.c_cell_face[c_s_idx + k];
-        const int sgn = a.f_cell_face_sgn[f_idx];
-        const int f_face_id = a.f_cell_face[f_idx];
-        double *nrm = a.c_face_normal + 3*(size_t)c_face_id;
-        double *xij = a.c_xa0ij + 3*(size_t)c_face_id;
+    diag += a.f_d_val[frow];
+    for (int e = a.f_row_index[frow]; e < a.f_row_index[frow+1]; e++) {
+      const int fcol = a.f_col_id[e];
+      const int ccol = a.f_c_row[fcol];
+      const double fx = a.f_x_val[e];
+      diag += fx;
+      if (ccol > crow) {
+        const int face = a.c_cell_face[c_beg + sorted_find(c_len, ccol, c_cols)];
+        const int ff = a.f_cell_face[e];
+        const int sg = a.f_cell_face_sgn[e];
+        double *fn = a.c_face_normal + 3*(size_t)face, *fxij = a.c_xa0ij + 3*(size_t)face;
         if (a.f_level == 0) {
-          const double sgn_surf = sgn * a.f_face_surf[f_face_id];
-          nrm[0] += sgn_surf * a.f_face_u_normal[f_face_id*3];
-          nrm[1] += sgn_surf * a.f_face_u_normal[f_face_id*3+1];
-          nrm[2] += sgn_surf * a.f_face_u_normal[f_face_id*3+2];
-          a.c_xa0[c_face_id] += fx;
-          xij[0] += fx * (a.f_cell_cen[jj*3]   - fc0);
-          xij[1] += fx * (a.f_cell_cen[jj*3+1] - fc1);
-          xij[2] += fx * (a.f_cell_cen[jj*3+2] - fc2);
+          const double ss = sg * a.f_face_surf[ff];
+          for (int q = 0; q < 3; q++) fn[q] += ss * a.f_face_u_normal[ff*3+q];
+          a.c_xa0[face] += fx;
+          for (int q = 0; q < 3; q++) fxij[q] += fx * (a.f_cell_cen[fcol*3+q] - xi[q]);
         }
         else {
-          nrm[0] += sgn * a.f_face_normal[f_face_id*3];
-          nrm[1] += sgn * a.f_face_normal[f_face_id*3+1];
-          nrm[2] += sgn * a.f_face_normal[f_face_id*3+2];
-          a.c_xa0[c_face_id] += a.f_xa0[f_face_id];
-          xij[0] += sgn * a.f_xa0ij[f_face_id*3];
-          xij[1] += sgn * a.f_xa0ij[f_face_id*3+1];
-          xij[2] += sgn * a.f_xa0ij[f_face_id*3+2];
+          for (int q = 0; q < 3; q++) fn[q] += sg * a.f_face_normal[ff*3+q];
+          a.c_xa0[face] += a.f_xa0[ff];
+          for (int q = 0; q < 3; q++) fxij[q] += sg * a.f_xa0ij[ff*3+q];
         }
       }
     }
   }
-  a.c_cell_cen[ii_c*3]   = cen0 / vol;
-  a.c_cell_cen[ii_c*3+1] = cen1 / vol;
-  a.c_cell_cen[ii_c*3+2] = cen2 / vol;
-  a.c_cell_vol[ii_c] = vol;
-  a.c_d_val[ii_c] = dsum;
+  for (int q = 0; q < 3; q++) a.c_cell_cen[crow*3+q] = cen[q] / vol;
+  a.c_cell_vol[crow] = vol;
+  a.c_d_val[crow] = diag;
 }
 
-__global__ void __launch_bounds__(128)
-k_coarse_stage_2(const CoarseAssemblyArgs a)
+/* Extra-diagonal values from the face quantities (cs_grid.cpp:6848-6895): a thread per coarse
+   ENTRY computes its value (they are independent of one another); the diagonal then takes
+   them off in entry order, one lane per row walking the values its warp has just written. */
+__global__ void __launch_bounds__(CA_WARPS*32)
+k_coarse_values(const CoarseAssemblyArgs a)
 {
-  const int ic = blockIdx.x*blockDim.x + threadIdx.x;
-  if (ic >= a.c_n_rows) return;
-  const double ci0 = a.c_cell_cen[ic*3], ci1 = a.c_cell_cen[ic*3+1],
-               ci2 = a.c_cell_cen[ic*3+2];
-  double d = a.c_d_val[ic];
-  const int s = a.c_row_index[ic], e = a.c_row_index[ic+1];
-  for (int r_idx = s; r_idx < e; r_idx++) {
-    const int jc = a.c_col_id[r_idx];
-    const int c_face_id = a.c_cell_face[r_idx];
-    const double sgn = (double)a.c_cell_face_sgn[r_idx];
-    const double *nrm = a.c_face_normal + 3*(size_t)c_face_id;
-    const double *xij = a.c_xa0ij + 3*(size_t)c_face_id;
-    const double n0 = nrm[0], n1 = nrm[1], n2 = nrm[2];
-    const double dsigjg
-      = sgn * (  (a.c_cell_cen[jc*3]   - ci0)*n0
-               + (a.c_cell_cen[jc*3+1] - ci1)*n1
-               + (a.c_cell_cen[jc*3+2] - ci2)*n2);
-    const double xa0 = a.c_xa0[c_face_id];
-    double c_x_val_c = xa0;
-    if (fabs(dsigjg) > 1e-12) {          /* cs_math_epzero */
-      const double dsxaij = xij[0]*n0 + xij[1]*n1 + xij[2]*n2;
-      const double agij = dsxaij/dsigjg;
-      if (agij >= c_x_val_c && agij <= 0.)
-        c_x_val_c = agij;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int crow = blockIdx.x*CA_WARPS + wid;
+  if (crow >= a.c_n_rows) return;
+  const double xi0 = a.c_cell_cen[crow*3], xi1 = a.c_cell_cen[crow*3+1],
+               xi2 = a.c_cell_cen[crow*3+2];
+  const int beg = a.c_row_index[crow], end = a.c_row_index[crow+1];
+  for (int k = beg + lane; k < end; k += 32) {
+    const int ccol = a.c_col_id[k];
+    const int face = a.c_cell_face[k];
+    const double sg = (double)a.c_cell_face_sgn[k];
+    const double n0 = a.c_face_normal[3*(size_t)face], n1 = a.c_face_normal[3*(size_t)face+1],
+                 n2 = a.c_face_normal[3*(size_t)face+2];
+    const double dist_n
+      = sg * (  (a.c_cell_cen[ccol*3]   - xi0)*n0
+              + (a.c_cell_cen[ccol*3+1] - xi1)*n1
+              + (a.c_cell_cen[ccol*3+2] - xi2)*n2);
+    const double xa0 = a.c_xa0[face];
+    double val = xa0;
+    if (fabs(dist_n) > 1e-12) {          /* cs_math_epzero */
+      const double flux_n = a.c_xa0ij[3*(size_t)face]*n0 + a.c_xa0ij[3*(size_t)face+1]*n1
+                          + a.c_xa0ij[3*(size_t)face+2]*n2;
+      const double ratio = flux_n/dist_n;
+      if (ratio >= val && ratio <= 0.) val = ratio;
     }
-    c_x_val_c = a.relax*c_x_val_c + (1. - a.relax)*xa0;
-    a.c_x_val[r_idx] = c_x_val_c;
-    d -= c_x_val_c;
+    a.c_x_val[k] = a.relax*val + (1. - a.relax)*xa0;
   }
-  a.c_d_val[ic] = d;
+  __syncwarp();
+  if (lane == 0) {
+    double d = a.c_d_val[crow];
+    for (int k = beg; k < end; k++) d -= a.c_x_val[k];
+    a.c_d_val[crow] = d;
+  }
 }
 
-} // anonymous namespace
-
-/* stages: 1 = sums over fine rows (cell centres, volumes, faces, diagonal),
-   2 = extra-diagonal values; ghost cell centres / volumes of a distributed
-   level are synchronised between the two (cs_grid.cpp:6561-6581) */
-namespace {
-
-/* Galerkin coarse matrix, relaxation parameter <= 0: _compute_coarse_quantities_msr, scalar
-   case (src/alge/cs_grid.cpp:6040-6090).  One thread per coarse row, fine rows of the
-   aggregate in ascending order and their entries in CSR order, like the reference's
-   row-parallel lambda -> bit-identical sums. */
-__global__ void __launch_bounds__(128)
+/* Galerkin coarse matrix, relaxation parameter <= 0 (_compute_coarse_quantities_msr, scalar
+   case, cs_grid.cpp:6040-6090): the same stage / fold, one value per contribution; entries
+   inside the aggregate join the diagonal chain. */
+__global__ void __launch_bounds__(CA_WARPS*32)
 k_coarse_galerkin(const CoarseAssemblyArgs a)
 {
-  const int ic = blockIdx.x*128 + threadIdx.x;
-  if (ic >= a.c_n_rows) return;
-  const int s_id = a.c_row_index[ic];
-  const int n_cols = a.c_row_index[ic+1] - s_id;
-  double *__restrict__ row_x_vals = a.c_x_val + s_id;
-  double d = 0.;
-  for (int ll = 0; ll < n_cols; ll++) row_x_vals[ll] = 0.;
-  const int r_s = a.c_f_row_index[ic], r_e = a.c_f_row_index[ic+1];
-  for (int r_idx = r_s; r_idx < r_e; r_idx++) {
-    const int ii = a.c_f_row_ids[r_idx];
-    d += a.f_d_val[ii];
-    const int f_s = a.f_row_index[ii], f_e = a.f_row_index[ii+1];
-    for (int jj = f_s; jj < f_e; jj++) {
-      const int jc = a.f_c_row[a.f_col_id[jj]];
-      if (jc > -1) {
-        if (ic != jc) {
-          const int k = l_id_search(n_cols, jc, a.c_col_id + s_id);
-          row_x_vals[k] += a.f_x_val[jj];
+  __shared__ int    s_target[CA_WARPS][CA_STAGE];
+  __shared__ double s_w[CA_WARPS][CA_STAGE];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int crow = blockIdx.x*CA_WARPS + wid;
+  if (crow >= a.c_n_rows) return;
+  int *tg = s_target[wid];
+  double *w = s_w[wid];
+  const int c_beg = a.c_row_index[crow];
+  const int c_len = a.c_row_index[crow+1] - c_beg;
+  const int *__restrict__ c_cols = a.c_col_id + c_beg;
+  /* a lane's coarse entries: k = lane, lane + 32, ...; the sums live in c_x_val between
+     rounds, so a row may have any number of entries */
+  for (int k = lane; k < c_len; k += 32) a.c_x_val[c_beg + k] = 0.;
+  double diag = 0.;
+  int n_staged = 0;
+  const int r_beg = a.c_f_row_index[crow], r_end = a.c_f_row_index[crow+1];
+  for (int r = r_beg; r < r_end; r++) {
+    const int frow = a.c_f_row_ids[r];
+    const int e_beg = a.f_row_index[frow], e_end = a.f_row_index[frow+1];
+    int e = e_beg - 1;                            /* -1: the fine diagonal opens the row */
+    while (e < e_end) {
+      const int n_now = min(CA_STAGE - n_staged, e_end - e);
+      for (int q = e + lane; q < e + n_now; q += 32) {
+        const int p = n_staged + (q - e);
+        if (q < e_beg) { tg[p] = -2; w[p] = a.f_d_val[frow]; continue; }
+        const int ccol = a.f_c_row[a.f_col_id[q]];
+        w[p] = a.f_x_val[q];
+        tg[p] = (ccol < 0) ? -1 : ((ccol == crow) ? -2 : sorted_find(c_len, ccol, c_cols));
+      }
+      n_staged += n_now;
+      e += n_now;
+      if (n_staged == CA_STAGE) {
+        __syncwarp();
+        for (int k = lane; k < c_len; k += 32) {
+          double sum = a.c_x_val[c_beg + k];
+          for (int p = 0; p < n_staged; p++) if (tg[p] == k) sum += w[p];
+          a.c_x_val[c_beg + k] = sum;
         }
-        else
-          d += a.f_x_val[jj];
+        if (lane == 31) for (int p = 0; p < n_staged; p++) if (tg[p] == -2) diag += w[p];
+        __syncwarp();
+        n_staged = 0;
       }
     }
   }
-  a.c_d_val[ic] = d;
+  __syncwarp();
+  for (int k = lane; k < c_len; k += 32) {
+    double sum = a.c_x_val[c_beg + k];
+    for (int p = 0; p < n_staged; p++) if (tg[p] == k) sum += w[p];
+    a.c_x_val[c_beg + k] = sum;
+  }
+  if (lane == 31) for (int p = 0; p < n_staged; p++) if (tg[p] == -2) diag += w[p];
+  if (lane == 31) a.c_d_val[crow] = diag;
 }
 
 } // anonymous namespace
@@ -1869,29 +2056,44 @@ k_coarse_galerkin(const CoarseAssemblyArgs a)
 bool launch_coarse_galerkin(const CoarseAssemblyArgs &a)
 {
   if (a.c_n_rows < 1) return true;
-  k_coarse_galerkin<<<(a.c_n_rows + 127)/128, 128, 0, ctx().stream>>>(a);
+  k_coarse_galerkin<<<(a.c_n_rows + CA_WARPS - 1)/CA_WARPS, CA_WARPS*32, 0, ctx().stream>>>(a);
   return post_launch("coarse_galerkin");
 }
 
+/* stages: 1 = sums over fine rows (cell centres, volumes, faces, diagonal),
+   2 = extra-diagonal values; ghost cell centres / volumes of a distributed
+   level are synchronised between the two (cs_grid.cpp:6561-6581) */
 bool launch_coarse_assembly(const CoarseAssemblyArgs &a, int stages)
 {
   Context &c = ctx();
   if (a.c_n_rows < 1) return true;
-  const int grid = (a.c_n_rows + 127) / 128;
-  if (!(stages & 1)) {
-    k_coarse_stage_2<<<grid, 128, 0, c.stream>>>(a);
-    return post_launch("coarse_stage_2");
+  const int grid = (a.c_n_rows + CA_WARPS - 1)/CA_WARPS;
+  if (stages & 1) {
+    /* list of the rows too wide for a warp (normally empty): n_wide, then the row ids */
+    int *wide = static_cast<int *>(dev_alloc(sizeof(int)*((size_t)a.c_n_rows + 1)));
+    if (wide == nullptr) return false;
+    bool ok = CSB_CUDA(cudaMemsetAsync(wide, 0, sizeof(int), c.stream));
+    if (ok) {
+      /* CSB_CA_WIDE_LIMIT: test hook, sends rows with more entries than this to the wide kernel */
+      static const int lim = env_flag("CSB_CA_WIDE_LIMIT", 32*CA_OWN);
+      k_coarse_sums<<<grid, CA_WARPS*32, 0, c.stream>>>(a, lim < 32*CA_OWN ? lim : 32*CA_OWN,
+                                                         wide + 1, wide);
+      ok = post_launch("coarse_sums");
+    }
+    if (ok) {
+      /* at most the rows with more than 128 entries; the grid covers them all, threads
+         beyond *n_wide return at once */
+      k_coarse_sums_wide<<<(a.c_n_rows + 63)/64, 64, 0, c.stream>>>(a, wide + 1, wide);
+      ok = post_launch("coarse_sums_wide");
+    }
+    dev_free(wide);
+    if (!ok) return false;
   }
-  if (a.c_n_faces > 0) {
-    if (!CSB_CUDA(cudaMemsetAsync(a.c_face_normal, 0, sizeof(double)*3*(size_t)a.c_n_faces, c.stream))) return false;
-    if (!CSB_CUDA(cudaMemsetAsync(a.c_xa0, 0, sizeof(double)*(size_t)a.c_n_faces, c.stream))) return false;
-    if (!CSB_CUDA(cudaMemsetAsync(a.c_xa0ij, 0, sizeof(double)*3*(size_t)a.c_n_faces, c.stream))) return false;
+  if (stages & 2) {
+    k_coarse_values<<<grid, CA_WARPS*32, 0, c.stream>>>(a);
+    return post_launch("coarse_values");
   }
-  k_coarse_stage_1<<<grid, 128, 0, c.stream>>>(a);
-  if (!post_launch("coarse_stage_1")) return false;
-  if (!(stages & 2)) return true;
-  k_coarse_stage_2<<<grid, 128, 0, c.stream>>>(a);
-  return post_launch("coarse_stage_2");
+  return true;
 }
 
 /*--------------------------------------------------------------------------

@@ -52,6 +52,7 @@ void  launch(unsigned grid, unsigned block, size_t smem, const std::function<voi
 void *dyn_smem();
 void  syncthreads();
 double shfl_down(double v, unsigned delta);
+void  warp_yield();
 }
 #define threadIdx (cudasim::t_threadIdx)
 #define blockIdx  (cudasim::t_blockIdx)
@@ -61,6 +62,10 @@ double shfl_down(double v, unsigned delta);
 inline void __syncthreads() { cudasim::syncthreads(); }
 inline void __threadfence() { __sync_synchronize(); }
 inline double __shfl_down_sync(unsigned, double v, unsigned delta) { return cudasim::shfl_down(v, delta); }
+/* __syncwarp: one yield -- with ascending round-robin every lane of the warp has reached the
+   same yield before any lane passes it (warps keep uniform control flow around their syncs) */
+inline void __syncwarp(unsigned = 0xffffffffu) { cudasim::warp_yield(); }
+inline int atomicAdd(int *p, int v) { const int o = *p; *p += v; return o; }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 template <typename T> inline T __ldcs(const T *p) { return *p; }
 template <typename T> inline T __ldcg(const T *p) { return *(const volatile T *)p; }

@@ -131,6 +131,11 @@ void syncthreads()
   if (g_blockDim.x > 1) yield(AT_BARRIER);
 }
 
+void warp_yield()
+{
+  if (g_blockDim.x > 1) yield(AT_SHFL);
+}
+
 double shfl_down(double v, unsigned delta)
 {
   if (g_blockDim.x == 1) return v;

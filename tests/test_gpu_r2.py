@@ -321,3 +321,42 @@ def test_shared_host_arrays_give_the_same_hierarchy(csb):
                 assert np.array_equal(a[k], b[k]), k
         assert np.array_equal(r["vx"], out[0][1]["vx"]) and r["n_cycles"] == out[0][1]["n_cycles"]
     csb.load_library().csb_host_pool_trim()
+
+
+_WIDE_SCRIPT = r"""
+import sys
+import numpy as np
+sys.path.insert(0, {root!r})
+from code_saturne_b200 import api
+from code_saturne_b200.mesh_cartesian import cube_poisson
+from oracle.pyoracle import Oracle
+api.init(0)
+ora = Oracle()
+s = cube_poisson(20, "neumann")
+m = api.Matrix.from_system(s)
+mg = api.Multigrid()
+mg.set_aggregation_blocks(1)
+mg.setup(m)
+omg = ora.mg_setup(s)
+lv, olv = mg.levels(), ora.mg_levels(omg)
+assert len(lv) == len(olv)
+for a, b in zip(lv[1:], olv[1:]):
+    for k in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
+        assert np.array_equal(a[k], b[k]), k
+print("WIDE-OK", len(lv))
+"""
+
+
+@pytest.mark.parametrize("limit", [0, 9])
+def test_coarse_assembly_wide_row_kernel_is_bit_exact(limit):
+    """Coarse rows with more entries than a warp's lanes own go to k_coarse_sums_wide; the cube
+    hierarchies never have such rows, so the limit is lowered (CSB_CA_WIDE_LIMIT, read once per
+    process): all rows (0) or the longer ones (9) take that kernel, the matrices stay those of
+    the oracle."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CSB_CA_WIDE_LIMIT=str(limit))
+    p = subprocess.run([sys.executable, "-c", _WIDE_SCRIPT.format(root=root)], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "WIDE-OK" in p.stdout, p.stdout[-2000:] + p.stderr[-3000:]
