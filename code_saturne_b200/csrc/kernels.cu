@@ -539,8 +539,21 @@ k_spmv_b3(int n_rows, const int *__restrict__ row_index, const int *__restrict__
     });
 }
 
+bool launch_spmv_bn(int mode, const _csb_matrix_t *m, ItState *st, const double *x, double *y,
+                    const double *b, bool exclude_diag);
+
+/* 3x3 blocks through the thread-per-component kernel (k_spmv_bn) instead of the
+   thread-per-block-row one: chosen by measurement (profiles/r02/config4_times.md) */
+static bool b3_by_component()
+{
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("CSB_SPMV_B3_BN"); v = (e != nullptr) ? (atoi(e) != 0) : 0; }
+  return v != 0;
+}
+
 bool launch_spmv_b3(const _csb_matrix_t *m, const double *x, double *y, bool exclude_diag)
 {
+  if (b3_by_component()) return launch_spmv_bn(-1, m, nullptr, x, y, nullptr, exclude_diag);
   const int grid = (m->n_rows + TPB - 1) / TPB;
   if (grid < 1) return true;
   k_spmv_b3<-1><<<grid, TPB, 0, ctx().stream>>>(m->n_rows, m->row_index.p, m->col_id.p,
@@ -555,6 +568,7 @@ bool ensure_partials(int n_blocks);
 bool launch_bicg_spmv_b3(int mode, const _csb_matrix_t *m, ItState *st, const double *x,
                          double *y, const double *b)
 {
+  if (b3_by_component()) return launch_spmv_bn(mode, m, st, x, y, b, false);
   const int grid = (m->n_rows + TPB - 1) / TPB;
   if (grid < 1) return true;
   if (!ensure_partials(grid)) return false;
@@ -597,9 +611,9 @@ k_spmv_bn(int n_rows, int db, const int *__restrict__ row_index,
     if (d_val != nullptr) {
       const double *a = d_val + (size_t)ii*db*db + (size_t)kk*db;
       const double *xi = x + (size_t)ii*db;
-      if (db == 6) {
+      if (db == 6 || db == 3) {                 /* _dense_6_6_ax / _dense_3_3_ax: no leading 0. */
         yk = a[0]*xi[0];
-        for (int j = 1; j < 6; j++) yk += a[j]*xi[j];
+        for (int j = 1; j < db; j++) yk += a[j]*xi[j];
       }
       else
         for (int j = 0; j < db; j++) yk += a[j]*xi[j];

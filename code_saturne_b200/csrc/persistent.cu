@@ -563,14 +563,20 @@ __device__ __forceinline__ int epi_nv(const F &, long) { return F::NV; }
    the default build keeps two sets and three stages. */
 constexpr int NG3 = 8;
 
-template <bool SINGLE, bool GHOST, int GD, class F>
+/* GHOST: 0 no ghost columns; 1 the exchange is waited for first and ghost columns are
+   gathered in line, from the ghost buffer (the default: measured faster, see sles.cu
+   build_dist_level); 2 rows with ghost columns are parked and finished after the wait
+   (the overlapped form, CSB_HALO_OVERLAP=1) */
+template <bool SINGLE, int GHOST, int GD, class F>
 __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
                                           const double *ghost, unsigned char *s_raw,
                                           const F f, double *acc_out)
 {
   constexpr int NGS = (GD == 3) ? NG3 : NG;      /* gathers per register set */
   constexpr int PARKED = 0x40000000;             /* flag carried in the row's start offset */
-  double *bsum = GHOST ? L.dist->bsum : nullptr; /* parked row sums, by row */
+  double *bsum = (GHOST == 2) ? L.dist->bsum : nullptr; /* parked row sums, by row */
+  /* in-line form: column c < n_rows reads x[c], a ghost column ghost[c - n_rows] */
+  const double *xg = (GHOST == 1) ? ghost - L.n_rows : x;
   const int tid = threadIdx.x;
   const int first = SINGLE ? 0 : blockIdx.x;
   const int step = SINGLE ? 1 : gridDim.x;
@@ -589,8 +595,9 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
      epilogue while the neighbours' stores cross NVLink.  The wait comes after the main
      pass, then the parked rows get their ghost terms and their epilogue (the reference's
      overlap of halo exchange and local product, _mat_vec_p_l_dist
-     cs_matrix_spmv.cpp:3092-3112).  CSB_HALO_OVERLAP=0: wait first (same code, for A/B). */
-  if (GHOST && !L.dist->overlap) halo_wait(L);
+     cs_matrix_spmv.cpp:3092-3112).  That is GHOST == 2; GHOST == 1 waits first and reads the
+     ghost columns in line. */
+  if (GHOST == 1) halo_wait(L);
 
   if (n_my > 0) {
     if (tid >= NWC*32) {
@@ -653,7 +660,7 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
         const int *s_col = (const int *)sb + (k0 & 3);
         /* GHOST: the row's local entries end where its ghost columns (sorted last) begin */
         int hg = 0;
-        if (GHOST) {
+        if (GHOST == 2) {
           const int ke_all = ke;
           while (ke > ks && s_col[ke - 1] >= n_rows) ke--;
           hg = (ke < ke_all) ? PARKED : 0;
@@ -661,7 +668,11 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
 #pragma unroll
         for (int e = 0; e < NGS; e++) {
           double v = 0.;
-          if (ks + e < ke) v = x[s_col[ks + e]];
+          if (ks + e < ke) {
+            const int c = s_col[ks + e];
+            const double *px = (GHOST != 1 || c < n_rows) ? x : xg;   /* one load, selected base */
+            v = px[c];
+          }
           gg[e] = v;
         }
         pks = (ks + (k0 & 1)) | hg;  /* x_val is staged from an even entry */
@@ -692,7 +703,11 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
 #pragma unroll
               for (int e = 0; e < NT; e++) {
                 double v = 0.;
-                if (kb + e < ke) v = x[s_col[kb + e]];
+                if (kb + e < ke) {
+                  const int c = s_col[kb + e];
+                  const double *px = (GHOST != 1 || c < n_rows) ? x : xg;
+                  v = px[c];
+                }
                 gt[e] = v;
               }
 #pragma unroll
@@ -700,7 +715,7 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
                 if (kb + e < ke) sii += s_val[kb + e] * gt[e];
             }
           }
-          if (GHOST && parked) bsum[r0 + tid] = sii;
+          if (GHOST == 2 && parked) bsum[r0 + tid] = sii;
           else f.template epi<ST_OP_STRIDE>(r0 + tid, sii, (const double *)(sb + off_ops) + tid, acc);
         }
         consumer_release(sv, q);
@@ -761,9 +776,9 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
     __syncthreads();
   }
 
-  if (GHOST) {
-    /* the neighbours' values (or: they were waited for before the main pass) */
-    if (L.dist->overlap) halo_wait(L);
+  if (GHOST == 2) {
+    /* the neighbours' values */
+    halo_wait(L);
     /* parked rows of this CTA's slabs, in a fixed order per thread: + the ghost terms (the
        tail of the row in CSR order), then the epilogue with operands read in place */
     const unsigned *__restrict__ bmask = L.dist->bmask;
@@ -796,12 +811,15 @@ __device__ __forceinline__ void spmv_phase(const MgLevelDesc &L, const double *x
                                            const double *ghost, unsigned char *s_raw,
                                            const F &f, double *acc_out)
 {
+  const int gm = (ghost == nullptr) ? 0 : (L.dist->overlap ? 2 : 1);
   if (!SINGLE && L.gather_depth == 3) {
-    if (ghost != nullptr) spmv_phase_g<false, true, 3>(L, x, ghost, s_raw, f, acc_out);
-    else spmv_phase_g<false, false, 3>(L, x, ghost, s_raw, f, acc_out);
+    if (gm == 2) spmv_phase_g<false, 2, 3>(L, x, ghost, s_raw, f, acc_out);
+    else if (gm == 1) spmv_phase_g<false, 1, 3>(L, x, ghost, s_raw, f, acc_out);
+    else spmv_phase_g<false, 0, 3>(L, x, ghost, s_raw, f, acc_out);
   }
-  else if (ghost != nullptr) spmv_phase_g<SINGLE, true, 2>(L, x, ghost, s_raw, f, acc_out);
-  else spmv_phase_g<SINGLE, false, 2>(L, x, ghost, s_raw, f, acc_out);
+  else if (gm == 2) spmv_phase_g<SINGLE, 2, 2>(L, x, ghost, s_raw, f, acc_out);
+  else if (gm == 1) spmv_phase_g<SINGLE, 1, 2>(L, x, ghost, s_raw, f, acc_out);
+  else spmv_phase_g<SINGLE, 0, 2>(L, x, ghost, s_raw, f, acc_out);
 }
 
 /* r = (A.vx - rhs), dk = r * ad_inv            (cs_sles_it.cpp:1502-1516) */

@@ -165,7 +165,14 @@ bool build_dist_level(csb_pcomm_t *pc, const csb_halo_t *halo, const csb_matrix_
         || !CSB_CUDA(cudaStreamSynchronize(c.stream))) return false;    /* mask dies here */
     D.bmask = out.bmask.p;
     D.bsum = out.bsum.p;
-    D.overlap = (env_int("CSB_HALO_OVERLAP", 1) != 0) ? 1 : 0;
+    /* Two forms of the SpMV phase on a partitioned level (persistent.cu, spmv_phase_g):
+       the exchange is waited for first and ghost columns are read in line (default), or the
+       rows with ghost columns are parked while the peer stores are in flight and finished
+       in a fix-up pass after the wait (CSB_HALO_OVERLAP=1).  Measured on B200 pairs over
+       NVLink (profiles/r02/scale_v2_overlap_ab.md): the neighbours' stores land within a few
+       microseconds, about what the fix-up pass costs, so the overlapped form does not pay
+       on this fabric; both are kept and tested. */
+    D.overlap = (env_int("CSB_HALO_OVERLAP", 0) != 0) ? 1 : 0;
   }
 
   std::vector<long long> snd((size_t)nd*8 + 8, 0), rcv((size_t)nd*8 + 8, 0);

@@ -112,6 +112,9 @@ _sync_device_matrix(b200_ctx_t *x, const cs_matrix_t *a)
       bft_error(__FILE__, __LINE__, 0, "cs_sles_b200: %s", csb_last_error());
     x->a_host = a; x->d_val = d_val; x->x_val = x_val;
     x->n_value_updates += 1;
+    /* the matrix's own arrays serve the host side of the hierarchy setup (level 0 is
+       aggregated from them: no device-to-host copy); they live as long as the coefficients */
+    csb_matrix_share_host_arrays(x->a_dev, col_id, d_val, x_val);
     return;
   }
 
@@ -120,6 +123,7 @@ _sync_device_matrix(b200_ctx_t *x, const cs_matrix_t *a)
   if (x->a_dev == nullptr)
     bft_error(__FILE__, __LINE__, 0, "cs_sles_b200: %s", csb_last_error());
   x->n_uploads += 1;
+  csb_matrix_share_host_arrays(x->a_dev, col_id, d_val, x_val);
 
   /* geometry for the P0/P1 relaxation of the coarse matrices (cs_grid.cpp:6606-6990) */
   const cs_lnum_t *c2f_idx, *c2f;

@@ -50,6 +50,16 @@ def test_distributed_fcg_multigrid_pc(N, R, bc, prec, merge_mean):
     run("fcgmg", N, R, bc, prec, merge_mean)
 
 
+@pytest.mark.parametrize("what,args", [
+    ("pcg", (24, 4, "neumann")), ("mg", (24, 4, "neumann", 1e-8)),
+    ("fcgmg", (32, 8, "dirichlet", 1e-13, 0)), ("fcgmg", (32, 4, "neumann", 1e-8, 300))])
+def test_distributed_solvers_with_overlapped_exchange(monkeypatch, what, args):
+    """CSB_HALO_OVERLAP=1: boundary rows parked while the peer stores are in flight, fix-up pass
+    after the wait (_mat_vec_p_l_dist's overlap; off by default because it measured slower)."""
+    monkeypatch.setenv("CSB_HALO_OVERLAP", "1")
+    run(what, *args)
+
+
 def _n_gpus():
     try:
         import torch
