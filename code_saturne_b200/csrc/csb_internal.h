@@ -427,6 +427,10 @@ bool launch_ad_inv_block(int n_rows, int db, const double *d_val, double *ad_inv
 bool launch_spmv_bn(int mode, const _csb_matrix_t *m, ItState *st, const double *x, double *y,
                     const double *b, bool exclude_diag);
 bool launch_block_nn_inverse(int n_blocks, int db, const double *ad, double *ad_inv);
+/* _block_relaxed_jacobi sweep (cs_multigrid_smoother.cpp:626-790); first: the sweep from zero */
+bool launch_bn_relaxed_update(int n_blocks, int db, double wk, const double *ad_inv,
+                              const double *rhs, const double *vxx, const double *vx_np,
+                              double *vx_n, bool first);
 bool launch_bn_jacobi_update(int n_blocks, int db, ItState *st, const double *ad,
                              const double *ad_inv, const double *rhs, const double *vxx,
                              double *vx, bool first);

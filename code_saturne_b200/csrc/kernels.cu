@@ -2621,6 +2621,45 @@ bool launch_b3_jacobi_update(int n_blocks, ItState *st, const double *ad, const 
   return post_launch("b3_jacobi_update");
 }
 
+namespace {
+/* _block_relaxed_jacobi (cs_multigrid_smoother.cpp:626-790), one thread per (block row,
+   component): vx_n = (1 - w) vx_np + w (ad_inv_row . (rhs - vxx)), first = 1: the sweep from
+   zero, vx_n = w (rhs . ad_inv_row) */
+__global__ void __launch_bounds__(TPB)
+k_bn_relaxed_update(long long n, int db, double wk, const double *__restrict__ ad_inv,
+                    const double *__restrict__ rhs, const double *__restrict__ vxx,
+                    const double *__restrict__ vx_np, double *__restrict__ vx_n, int first)
+{
+  const long long t = (long long)blockIdx.x*TPB + threadIdx.x;
+  if (t >= n) return;
+  const long long ii = t / db;
+  const int jj = (int)(t - ii*db);
+  const double *inv = ad_inv + (size_t)db*db*ii + (size_t)db*jj;
+  const double *b = rhs + (size_t)db*ii;
+  double v = 0;
+  if (first) {
+    for (int kk = 0; kk < db; kk++) v += b[kk] * inv[kk];
+    vx_n[t] = wk * v;
+  }
+  else {
+    const double *e = vxx + (size_t)db*ii;
+    for (int kk = 0; kk < db; kk++) v += inv[kk] * (b[kk] - e[kk]);
+    vx_n[t] = (1.0 - wk)*vx_np[t] + wk*v;
+  }
+}
+}
+
+bool launch_bn_relaxed_update(int n_blocks, int db, double wk, const double *ad_inv,
+                              const double *rhs, const double *vxx, const double *vx_np,
+                              double *vx_n, bool first)
+{
+  const long long n = (long long)n_blocks*db;
+  if (n < 1) return true;
+  k_bn_relaxed_update<<<(unsigned)((n + TPB - 1)/TPB), TPB, 0, ctx().stream>>>(
+    n, db, wk, ad_inv, rhs, vxx, vx_np, vx_n, first ? 1 : 0);
+  return post_launch("bn_relaxed_update");
+}
+
 /* block "inverse" of cs_sles_it_setup for block Jacobi with db != 3: Gauss-Jordan inverse for
    6x6 blocks, LU factors otherwise (_setup_ad_block_nn_inv, cs_sles_it_priv.cpp:178-222) */
 bool launch_block_nn_inverse(int n_blocks, int db, const double *ad, double *ad_inv)

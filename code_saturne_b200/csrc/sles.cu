@@ -448,6 +448,52 @@ bool gs_enqueue(const csb_matrix_t *m, int type, ItState *st, const double *ad_i
   return true;
 }
 
+/* cs_multigrid_smoother on a block-diagonal matrix (db > 1): _block_3_jacobi / _block_jacobi
+   (cs_multigrid_smoother.cpp:390-500, :507-620: the solver forms' sweep without the residual)
+   and _block_relaxed_jacobi (:626-790) for R_JACOBI / RJ2 / RJ3.  inv: the block_nn_inverse
+   of the setup.  work: two vectors of ws doubles (vx_tmp, vxx). */
+bool block_smoother_enqueue(const csb_matrix_t *m, int type, int n_max_iter, const double *inv,
+                            const double *rhs, double *vx, bool vx_ini_nonzero, double *work,
+                            size_t ws, ItState *st)
+{
+  const int db = m->db, nb = m->n_rows;
+  double *vx_tmp = work, *vxx = work + ws;
+  auto e_product = [&](const double *x) {
+    return (db == 3) ? launch_spmv_b3(m, x, vxx, true)
+                     : launch_spmv_bn(-1, m, nullptr, x, vxx, nullptr, true);
+  };
+  if (type == CSB_SLES_JACOBI) {
+    for (int it = 0; it < n_max_iter; it++) {
+      /* the sweep kernels of the solver form, their convergence test made void (a fresh
+         state per sweep: iteration 1 of 2 never stops and never diverges) */
+      if (!launch_it_state_init(st, nullptr, 0., 1., 2)) return false;
+      const bool first = (it == 0 && !vx_ini_nonzero);
+      if (!first && !e_product(vx)) return false;
+      const bool ok = (db == 3)
+        ? launch_b3_jacobi_update(nb, st, m->d_val.p, inv, rhs, vxx, vx, first)
+        : launch_bn_jacobi_update(nb, db, st, m->d_val.p, inv, rhs, vxx, vx, first);
+      if (!ok) return false;
+    }
+    return true;
+  }
+  const SmootherPlan p = smoother_plan(type, n_max_iter);
+  double *vx_n = vx, *vx_np = vx_tmp;
+  int iter_ini = 0;
+  if (!vx_ini_nonzero) {
+    if (!launch_bn_relaxed_update(nb, db, p.w[0], inv, rhs, nullptr, nullptr, vx_n, true))
+      return false;
+    iter_ini = 1;
+  }
+  for (int it = iter_ini; it < p.n_iter; it++) {
+    const double wk = p.w[it % p.wk_m];
+    double *t = vx_n; vx_n = vx_np; vx_np = t;
+    if (!e_product(vx_np)) return false;
+    if (!launch_bn_relaxed_update(nb, db, wk, inv, rhs, vxx, vx_np, vx_n, false)) return false;
+  }
+  if (vx_n != vx && !launch_copy(nb*db, vx_n, vx, nullptr)) return false;
+  return true;
+}
+
 /* Fixed number of Jacobi-family sweeps without convergence test (_jacobi, _relaxed_jacobi,
    _l1_jacobi: cs_multigrid_smoother.cpp:143-226, :244-373, :804-905).  Each sweep is ONE
    kernel: the (diagonal-excluded, or full for L1) product in CSR order with the update in
@@ -3059,8 +3105,27 @@ void csb_multigrid_smoother_setup(void *context, const char *name, const csb_mat
   const double t0 = wall();
   c->a = a;
   c->setup_done = false;
-  if (a->db != 1 || a->halo != nullptr) {
-    set_error("csb_multigrid_smoother_setup: scalar matrices on one rank on this path");
+  if (a->halo != nullptr) {
+    set_error("csb_multigrid_smoother_setup: one rank on this path");
+    return;
+  }
+  if (a->db != 1) {
+    /* block-diagonal matrices: block Jacobi and block relaxed Jacobi
+       (cs_multigrid_smoother_setup :1880-1960); L1 Jacobi has no block form there either */
+    if (c->type != CSB_SLES_JACOBI && c->type != CSB_SLES_R_JACOBI && c->type != CSB_SLES_RJ2
+        && c->type != CSB_SLES_RJ3) {
+      set_error("csb_multigrid_smoother_setup: smoother type %d is not available for a diagonal "
+                "block size of %d (Jacobi, relaxed Jacobi, RJ2, RJ3 are)", (int)c->type, a->db);
+      return;
+    }
+    if (!c->ad_inv.alloc((size_t)a->n_rows*a->db*a->db)) return;
+    if (!launch_block_nn_inverse(a->n_rows, a->db, a->d_val.p, c->ad_inv.p)) return;
+    if (!c->work.alloc(2*work_stride_of((size_t)a->n_cols_ext*a->db))) return;
+    if (!c->st.alloc(1)) return;
+    c->n_max_iter = smoother_plan((int)c->type, c->n_max_iter).n_iter;
+    c->setup_done = true;
+    c->n_setups += 1;
+    c->t_setup += wall() - t0;
     return;
   }
   if (!c->ad_inv.alloc((size_t)a->n_rows)) return;
@@ -3107,12 +3172,17 @@ csb_multigrid_smoother_solve(void *context, const char *name, const csb_matrix_t
   const double t0 = wall();
   const bool ini = (vx_ini == vx);
   StagedVec s_rhs, s_vx;
-  if (!s_rhs.init(const_cast<double *>(rhs), (size_t)a->n_rows, true, c->stage_rhs))
+  if (!s_rhs.init(const_cast<double *>(rhs), (size_t)a->n_rows*a->db, true, c->stage_rhs))
     return CSB_SLES_BREAKDOWN;
-  if (!s_vx.init(vx, (size_t)a->n_cols_ext, ini, c->stage_vx)) return CSB_SLES_BREAKDOWN;
-  if (!smoother_enqueue(a, (int)c->type, c->n_max_iter, c->ad_inv.p, s_rhs.d, s_vx.d, ini,
-                        c->work.p, nullptr)) return CSB_SLES_BREAKDOWN;
-  if (!s_vx.copy_back((size_t)a->n_rows)) return CSB_SLES_BREAKDOWN;
+  if (!s_vx.init(vx, (size_t)a->n_cols_ext*a->db, ini, c->stage_vx)) return CSB_SLES_BREAKDOWN;
+  if (a->db != 1) {
+    if (!block_smoother_enqueue(a, (int)c->type, c->n_max_iter, c->ad_inv.p, s_rhs.d, s_vx.d,
+                                ini, c->work.p, work_stride_of((size_t)a->n_cols_ext*a->db),
+                                c->st.p)) return CSB_SLES_BREAKDOWN;
+  }
+  else if (!smoother_enqueue(a, (int)c->type, c->n_max_iter, c->ad_inv.p, s_rhs.d, s_vx.d, ini,
+                             c->work.p, nullptr)) return CSB_SLES_BREAKDOWN;
+  if (!s_vx.copy_back((size_t)a->n_rows*a->db)) return CSB_SLES_BREAKDOWN;
   if (!CSB_CUDA(cudaStreamSynchronize(cx.stream))) return CSB_SLES_BREAKDOWN;
   if (n_iter) *n_iter = c->n_max_iter;
   c->n_solves += 1;

@@ -2986,6 +2986,95 @@ ora_block_jacobi(int n_rows, int db, const int *row_index, const int *col_id,
 }
 
 /*----------------------------------------------------------------------------
+ * cs_multigrid_smoother on block-diagonal matrices (fixed sweeps, no residual):
+ *   type 3 (Jacobi): _block_3_jacobi (cs_multigrid_smoother.cpp:390-500) for 3x3 blocks,
+ *                    _block_jacobi (:507-620) otherwise;
+ *   types 14 / 15 / 16 (R_JACOBI, RJ2, RJ3): _block_relaxed_jacobi (:626-790);
+ * ad_inv = the block_nn_inverse of cs_multigrid_smoother_setup (:1844-1866 ->
+ * _setup_ad_block_nn_inv): Gauss-Jordan inverse for 3x3 and 6x6, LU factors otherwise.
+ * out[0] = n_iter.
+ *----------------------------------------------------------------------------*/
+
+int
+ora_smoother_block(int type, int n_rows, int db, const int *row_index, const int *col_id,
+                   const double *d_val, const double *x_val, int n_max_iter,
+                   const double *rhs, double *vx, int use_vx_ini, double *out)
+{
+  const int n_blocks = n_rows, db2 = db*db;
+  const size_t n = (size_t)n_rows*db;
+  if (type != ORA_SLES_JACOBI && type != ORA_SLES_R_JACOBI && type != ORA_SLES_RJ2
+      && type != ORA_SLES_RJ3)
+    return -100;
+  double *tmp = malloc(sizeof(double)*(2*n + db2*(size_t)n_blocks + 1));
+  double *vxx = tmp + n, *ad_inv = tmp + 2*n;
+  for (int i = 0; i < n_blocks; i++) {
+    if (db == 3) ora_gauss_inverse_33(d_val + 9*(size_t)i, ad_inv + 9*(size_t)i);
+    else if (db == 6) _ora_gauss_inverse_n(6, d_val + db2*(size_t)i, ad_inv + db2*(size_t)i);
+    else _ora_fact_lu(db, d_val + db2*(size_t)i, ad_inv + db2*(size_t)i);
+  }
+  int n_iter = 0;
+
+  if (type == ORA_SLES_JACOBI) {
+    int iter_ini = 0;
+    if (!use_vx_ini) {
+      for (int ii = 0; ii < n_blocks; ii++) {
+        double _vxx[9];
+        for (int jj = 0; jj < db; jj++) _vxx[jj] = 0;
+        if (db == 3) _ora_mat_c_m_b_33(ad_inv + 9*ii, vx + 3*ii, _vxx, rhs + 3*ii);
+        else _ora_mat_c_m_b(ad_inv + db2*ii, db, vx + db*ii, _vxx, rhs + db*ii);
+      }
+      iter_ini = 1;
+    }
+    for (n_iter = iter_ini; n_iter < n_max_iter; n_iter++) {
+      ora_spmv_msr_bn(n_rows, db, row_index, col_id, d_val, x_val, 1, vx, vxx);
+      for (int ii = 0; ii < n_blocks; ii++) {
+        if (db == 3) _ora_mat_c_m_b_33(ad_inv + 9*ii, vx + 3*ii, vxx + 3*ii, rhs + 3*ii);
+        else _ora_mat_c_m_b(ad_inv + db2*ii, db, vx + db*ii, vxx + db*ii, rhs + db*ii);
+      }
+    }
+  }
+  else {
+    int wk_m = 1;
+    double w[3] = {2./3., 1.0, 1.0};
+    if (type == ORA_SLES_RJ2) { w[0] = 1.7319; w[1] = 0.5695; wk_m = 2; }
+    if (type == ORA_SLES_RJ3) { w[0] = 2.2473; w[1] = 0.8573; w[2] = 0.5296; wk_m = 3; }
+    if (n_max_iter % wk_m) n_max_iter += wk_m - (n_max_iter % wk_m);   /* setup, :1893-1898 */
+    double *vx_n = vx, *vx_np = tmp;
+    int iter_ini = 0;
+    if (!use_vx_ini) {
+      const double wk = w[0];
+      for (size_t r = 0; r < n; r++) {
+        const size_t ii = r / db, jj = r % db;
+        const double *_ad_inv = ad_inv + db2*ii + db*jj, *_rhs = rhs + db*ii;
+        double _vx = 0;
+        for (int kk = 0; kk < db; kk++) _vx += _rhs[kk] * _ad_inv[kk];
+        vx_n[r] = wk * _vx;
+      }
+      iter_ini = 1;
+    }
+    for (n_iter = iter_ini; n_iter < n_max_iter; n_iter++) {
+      const double wk = w[n_iter % wk_m];
+      const double o_m_wk = 1.0 - wk;
+      double *t = vx_n; vx_n = vx_np; vx_np = t;
+      ora_spmv_msr_bn(n_rows, db, row_index, col_id, d_val, x_val, 1, vx_np, vxx);
+      for (size_t r = 0; r < n; r++) {
+        const size_t ii = r / db, jj = r % db;
+        const double *_ad_inv = ad_inv + db2*ii + db*jj, *_rhs = rhs + db*ii,
+                     *_vxx = vxx + db*ii;
+        double _vx = 0;
+        for (int kk = 0; kk < db; kk++) _vx += _ad_inv[kk] * (_rhs[kk] - _vxx[kk]);
+        vx_n[r] = o_m_wk*vx_np[r] + wk*_vx;
+      }
+    }
+    if (vx_n != vx)
+      for (size_t r = 0; r < n; r++) vx[r] = vx_n[r];
+  }
+  if (out != NULL) out[0] = n_iter;
+  free(tmp);
+  return ORA_MAX_ITERATION;
+}
+
+/*----------------------------------------------------------------------------
  * Matrix coefficients of a symmetric scalar diffusion system, straight into MSR:
  *   cs_matrix_compute_coeffs (src/alge/cs_matrix_building.cpp:1948-2283) with iconvp = 0 ->
  *   _sym_coeffs_msr (:136-206): per cell, in the order of its MSR row,

@@ -119,6 +119,11 @@ int    ora_gcr(int n_rows, int db, const int *row_index, const int *col_id,
                int n_max_iter, double precision, double r_norm,
                const double *rhs, double *vx, int use_vx_ini,
                double *out, double *history, int history_size);
+/* cs_multigrid_smoother on block-diagonal matrices: block Jacobi (type 3), block relaxed
+   Jacobi (14, 15, 16); cs_multigrid_smoother.cpp:390-790 */
+int    ora_smoother_block(int type, int n_rows, int db, const int *row_index, const int *col_id,
+                          const double *d_val, const double *x_val, int n_max_iter,
+                          const double *rhs, double *vx, int use_vx_ini, double *out);
 int    ora_block_jacobi(int n_rows, int db, const int *row_index, const int *col_id,
                         const double *d_val, const double *x_val,
                         int n_max_iter, double precision, double r_norm,

@@ -192,6 +192,17 @@ class Oracle:
                                     *rest[4:])
         return self._solve_b(fn, db, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0)
 
+    def smoother_block(self, stype, db, ri, ci, d, xv, rhs, n_max_iter, vx0=None):
+        """cs_multigrid_smoother on a block-diagonal matrix (block Jacobi / block relaxed Jacobi)."""
+        ri, ci, d, xv, rhs = _i32(ri), _i32(ci), _f64(d), _f64(xv), _f64(rhs)
+        n = len(ri) - 1
+        vx = np.zeros(db * n) if vx0 is None else _f64(vx0).copy()
+        out = np.zeros(2)
+        cvg = self.lib.ora_smoother_block(C.c_int(stype), C.c_int(n), C.c_int(db), _ip(ri), _ip(ci),
+                                          _dp(d), _dp(xv), C.c_int(n_max_iter), _dp(rhs), _dp(vx),
+                                          C.c_int(0 if vx0 is None else 1), _dp(out))
+        return dict(cvg=cvg, n_iter=int(out[0]), vx=vx)
+
     def block_jacobi(self, db, ri, ci, d, xv, rhs, n_max_iter, precision, r_norm, vx0=None):
         """_block_jacobi (cs_sles_it.cpp:2460) / _block_3_jacobi by block size."""
         return self._solve_b(self.lib.ora_block_jacobi, db, ri, ci, d, xv, rhs, n_max_iter,

@@ -1,7 +1,9 @@
 """Golden fixtures for block-diagonal (CS_MATRIX_BLOCK_D) matrices with block sizes other
-than 3: the SpMV (_b_mat_vec_p_l_msr_6 / _generic, cs_matrix_spmv.cpp:2478, :2308), block
-Jacobi (_block_jacobi, cs_sles_it.cpp:2460, with the block_nn_inverse of
-cs_sles_it_priv.cpp:178-222) and BiCGStab + point Jacobi: outputs of the reference's own
+than 3 (and 3 for the smoothers): the SpMV (_b_mat_vec_p_l_msr_6 / _generic,
+cs_matrix_spmv.cpp:2478, :2308), block Jacobi (_block_jacobi, cs_sles_it.cpp:2460, with the
+block_nn_inverse of cs_sles_it_priv.cpp:178-222), BiCGStab + point Jacobi, and the block forms
+of the multigrid smoothers (_block_3_jacobi, _block_jacobi, _block_relaxed_jacobi,
+cs_multigrid_smoother.cpp:390-790): outputs of the reference's own
 compiled CPU code (oracle/_ref/libcsref.so, OMP_NUM_THREADS=1):
 
     python tests/golden/make_golden_blockn.py   -> tests/golden/blockn_db{db}_N{N}.npz
@@ -17,7 +19,7 @@ sys.path.insert(0, ROOT)
 from code_saturne_b200.mesh_cartesian import cube_block_convection_diffusion  # noqa: E402
 from oracle.pyoracle import RefLib  # noqa: E402
 
-CASES = [(6, 6), (2, 7), (4, 5), (9, 4)]       # (db, N)
+CASES = [(6, 6), (2, 7), (4, 5), (9, 4), (3, 6)]       # (db, N)
 
 
 def main():
@@ -44,6 +46,13 @@ def main():
         b = ref.sles_it(h, ref.BICGSTAB, rhs, 500, 1e-10, r_norm)
         for k in ("cvg", "n_iter", "residual", "initial_residual", "vx"):
             out[f"bicg_{k}"] = b[k]
+        # cs_multigrid_smoother on the block matrix: block Jacobi (3), block relaxed Jacobi (14-16)
+        for st in (3, 14, 15, 16):
+            for nit in (1, 3):
+                out[f"sm{st}_{nit}_zero"] = ref.smoother(h, st, rhs, nit)["vx"]
+                w = ref.smoother(h, st, rhs, nit, x)
+                out[f"sm{st}_{nit}_warm"] = w["vx"]
+                out[f"sm{st}_{nit}_n_iter"] = w["n_iter"]
         print(db, N, "jacobi", r["cvg"], r["n_iter"], "bicgstab", b["cvg"], b["n_iter"])
         ref.destroy(h)
         path = os.path.join(ROOT, "tests", "golden", f"blockn_db{db}_N{N}.npz")

@@ -87,3 +87,26 @@ def test_blockn_vs_oracle_larger(csb, oracle, db, N):
     assert rel_l2(r["vx"], o["vx"]) <= 1e-8
     c.destroy()
     m.destroy()
+
+
+@pytest.mark.parametrize("db,N", CASES + [(3, 6)])
+def test_block_smoothers_bit_exact_vs_reference_golden(csb, db, N):
+    """cs_multigrid_smoother on block-diagonal matrices (the block variants of a26): block
+    Jacobi and block relaxed Jacobi (R_JACOBI, RJ2, RJ3) -- per-row arithmetic, no reduction."""
+    g = np.load(os.path.join(GOLD, f"blockn_db{db}_N{N}.npz"))
+    ri, ci, d, xv, rhs = cube_block_convection_diffusion(N, db)
+    n = len(ri) - 1
+    m = csb.Matrix.from_block(n, db, ri, ci, d.ravel(), xv)
+    for st in (3, 14, 15, 16):
+        for nit in (1, 3):
+            sm = csb.Smoother(st, nit)
+            r = sm.solve(m, rhs)
+            assert int(r["cvg"]) == -1
+            assert np.array_equal(r["vx"], g[f"sm{st}_{nit}_zero"]), (st, nit)
+            r = sm.solve(m, rhs, vx=g["x"].copy(), use_vx_ini=True)
+            assert np.array_equal(r["vx"], g[f"sm{st}_{nit}_warm"]), (st, nit)
+            assert r["n_iter"] == int(g[f"sm{st}_{nit}_n_iter"])
+            sm.destroy()
+    with pytest.raises(csb.CsbError):
+        csb.Smoother(csb.SlesItType.L1_JACOBI, 2).solve(m, rhs)      # no block form (reference: error)
+    m.destroy()

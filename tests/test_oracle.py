@@ -673,3 +673,18 @@ def test_oracle_gcr_matches_golden(oracle):
     f = oracle.gcr(3, ri, ci, d.ravel(), xv, rhs, 200, 1e-10, float(g["b3_r_norm"]), vx0=b["vx"])
     assert (f["cvg"], f["n_iter"]) == (int(g["b3_fb200_cvg"]), int(g["b3_fb200_n_iter"]))
     assert np.array_equal(f["vx"], g["b3_fb200_vx"])
+
+
+@pytest.mark.parametrize("db,N", BLOCKN_CASES + [(3, 6)])
+def test_oracle_block_smoothers_match_golden(oracle, db, N):
+    """Block forms of the multigrid smoothers (a26): block Jacobi, block relaxed Jacobi."""
+    from code_saturne_b200.mesh_cartesian import cube_block_convection_diffusion
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"blockn_db{db}_N{N}.npz"))
+    ri, ci, d, xv, rhs = cube_block_convection_diffusion(N, db)
+    for st in (3, 14, 15, 16):
+        for nit in (1, 3):
+            r = oracle.smoother_block(st, db, ri, ci, d.ravel(), xv, rhs, nit)
+            assert np.array_equal(r["vx"], g[f"sm{st}_{nit}_zero"]), (st, nit)
+            r = oracle.smoother_block(st, db, ri, ci, d.ravel(), xv, rhs, nit, g["x"])
+            assert np.array_equal(r["vx"], g[f"sm{st}_{nit}_warm"]), (st, nit)
+            assert r["n_iter"] == int(g[f"sm{st}_{nit}_n_iter"])
