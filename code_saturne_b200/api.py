@@ -107,6 +107,9 @@ def load_library() -> C.CDLL:
     L.csb_matrix_create_msr_block.argtypes = [ci, ci, ci, vp, vp, vp, vp, ci]
     L.csb_matrix_create_csr.restype = vp
     L.csb_matrix_create_csr.argtypes = [ci, ci, vp, vp, vp, ci]
+    L.csb_matrix_create_native.restype = vp
+    L.csb_matrix_create_native.argtypes = [ci, ci, ci, vp, vp, vp, ci]
+    L.csb_matrix_set_coefficients_native.argtypes = [vp, vp, vp]
     L.csb_matrix_create_msr.restype = vp
     L.csb_matrix_create_msr.argtypes = [ci, ci, vp, vp, vp, vp, ci]
     L.csb_matrix_set_coefficients.argtypes = [vp, ci, vp, vp]
@@ -446,6 +449,44 @@ class Matrix:
         return self
 
     @classmethod
+    def from_native(cls, n_rows, edges, da, xa, n_cols_ext=None):
+        """csb_matrix_create_native: the matrix of a caller holding face-based arrays
+        (cs_matrix_set_coefficients(edges, da, xa)); symmetric, one value per edge."""
+        L = load_library()
+        self = cls.__new__(cls)
+        self.n_rows = int(n_rows)
+        self.n_cols_ext = int(n_cols_ext if n_cols_ext is not None else n_rows)
+        e = np.ascontiguousarray(edges, dtype=np.int32).reshape(-1, 2)
+        d, x = _f64(np.asarray(da)), _f64(np.asarray(xa))
+        self.n_edges = len(e)
+        self._h = L.csb_matrix_create_native(self.n_rows, self.n_cols_ext, self.n_edges, _ptr(e),
+                                             _ptr(d), _ptr(x), 1)
+        if not self._h:
+            _err("csb_matrix_create_native")
+        self.nnz = int(L.csb_matrix_get_n_entries(self._h)) - self.n_rows
+        self._halo = None
+        return self
+
+    @classmethod
+    def from_system_native(cls, s, da=None, xa=None, with_mesh=True):
+        """The same system as from_system, entered through its face arrays."""
+        if da is None or xa is None:
+            xa = np.zeros(max(s.n_faces, 1))
+            up = np.asarray(s.c2f_sgn) > 0
+            xa[np.asarray(s.c2f)[up]] = np.asarray(s.x_val)[up]
+            da, xa = s.d_val, xa[:s.n_faces]
+        m = cls.from_native(s.n_rows, s.face_cells, da, xa)
+        if with_mesh and s.n_faces > 0:
+            m.set_mesh_association(s.n_faces, None, None, s.cell_cen, s.cell_vol,
+                                   s.face_u_normal, s.face_surf)
+        return m
+
+    def set_coefficients_native(self, da, xa):
+        d, x = _f64(np.asarray(da)), _f64(np.asarray(xa))
+        if load_library().csb_matrix_set_coefficients_native(self.handle, _ptr(d), _ptr(x)) != 0:
+            _err("csb_matrix_set_coefficients_native")
+
+    @classmethod
     def from_system(cls, s, with_mesh=True, share_host=False):
         """Build from a mesh_cartesian.CubeSystem (host arrays).  share_host: lend the
         system's host arrays to the matrix (csb_matrix_share_host_arrays; s must outlive it)."""
@@ -477,8 +518,8 @@ class Matrix:
 
     def set_mesh_association(self, n_faces, c2f, c2f_sgn, cell_cen, cell_vol, face_u_normal,
                              face_surf):
-        c2f = _i32(c2f)
-        sgn = np.ascontiguousarray(c2f_sgn, dtype=np.int16)
+        c2f = None if c2f is None else _i32(c2f)
+        sgn = None if c2f_sgn is None else np.ascontiguousarray(c2f_sgn, dtype=np.int16)
         cen, vol = _f64(cell_cen), _f64(cell_vol)
         fun, fs = _f64(face_u_normal), _f64(face_surf)
         if load_library().csb_matrix_set_mesh_association(self.handle, int(n_faces), _ptr(c2f),

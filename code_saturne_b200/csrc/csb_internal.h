@@ -365,6 +365,15 @@ struct _csb_matrix_t {
   bool        has_b_faces = false;
   csb::DevBuf<double>      coef_stage;   /* host inputs of csb_matrix_compute_coeffs */
   _csb_halo_t *halo = nullptr;
+  /* matrix mapped from native (face-based) arrays (csb_matrix_create_native): the faces and
+     their values stay with the matrix, c2f / c2f_sgn above are the entry -> face map; the
+     hierarchy is then built like the reference builds it for such a matrix (face-order
+     aggregation and sums, cs_grid.cpp:3997, :5144) */
+  bool        from_native = false;
+  csb::DevBuf<csb_lnum_t>  face_cell;
+  csb::DevBuf<double>      xa;
+  csb::HostVec<csb_lnum_t> h_face_cell;
+  csb::HostVec<double>     h_xa;
   /* matrix created from CSR arrays (cs_matrix_type_t CS_MATRIX_CSR): the CSR arrays are
      kept for cs_matrix_vector_multiply in CSR order (_mat_vec_p_l_csr); this object holds
      the MSR split (diagonal extracted) the solvers and the hierarchy work on */
@@ -583,6 +592,33 @@ bool launch_coarse_assembly(const CoarseAssemblyArgs &a, int stages /* 1 | 2 */)
 /* relaxation parameter <= 0: plain Galerkin sums, no mesh quantities (cs_grid.cpp:5969-6090);
    uses the matrix, f_c_row and c_f_* members of the arguments only */
 bool launch_coarse_galerkin(const CoarseAssemblyArgs &a);
+
+/* coarse level of a matrix mapped from native (face-based) arrays: the sums of
+   _compute_coarse_cell_quantities / _compute_coarse_quantities_native (cs_grid.cpp:4778,
+   :5144-5558) run in FACE order there; here a thread owns a coarse face (a fine row, a
+   coarse row) and takes its contributions in ascending face order */
+struct NativeCoarseArgs {
+  int  f_level;
+  int  f_n_rows, c_n_rows, c_n_faces;
+  const int *f_row_index, *f_col_id;
+  const double *f_d_val, *f_x_val;
+  const int *f_cell_face;                /* fine entry -> fine face */
+  const int *f_face_cell;                /* fine faces, 2 cells each */
+  const int *f_c_row;
+  const int *c_f_row_index, *c_f_row_ids;
+  const int *c_row_index, *c_cell_face;  /* coarse entry -> coarse face */
+  const int *c_face_cell;
+  const double *f_cell_cen, *f_cell_vol;
+  const double *f_face_u_normal, *f_face_surf;   /* level 0 */
+  const double *f_face_normal, *f_xa0, *f_xa0ij; /* level > 0 */
+  double *c_cell_cen, *c_cell_vol, *c_face_normal, *c_xa0, *c_xa0ij, *c_xa;
+  double *w1;                            /* f_n_rows values of scratch */
+  double *c_d_val, *c_x_val;
+  double relax;
+};
+bool launch_coarse_native(const NativeCoarseArgs &a);
+/* x_val[k] = xa[c2f[k]] (cs_matrix_set_coefficients from edges, symmetric, unique faces) */
+bool launch_native_to_msr(int nnz, const int *c2f, const double *xa, double *x_val);
 
 bool launch_halo_pack(int n_send, const int *send_list, const double *var, double *buf);
 /* Gauss-Seidel update of the n rows listed in `rows` (one dependency level); mode 0 whole

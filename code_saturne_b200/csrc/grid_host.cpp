@@ -561,4 +561,163 @@ void build_coarse_structure(int f_n_rows, const int *f_row_index, const int *f_c
   }
 }
 
+/*----------------------------------------------------------------------------
+ * Matrices mapped from native (face-based) arrays: the entry of a caller that holds
+ * edges, da, xa (cs_matrix_set_coefficients, cs_matrix.cpp:5315).  The reference then
+ * aggregates over the face list when it runs one thread (_automatic_aggregation_fc,
+ * cs_grid.cpp:3997-4263), numbers the coarse faces in the order the fine faces reach them
+ * (_coarsen_face_cell, :637-788) and sums the coarse values in face order
+ * (_compute_coarse_quantities_native, :5144-5558; on the device here, kernels.cu).
+ *----------------------------------------------------------------------------*/
+
+/* MSR structure of a face list: both directions of every face, columns ascending in each
+   row, and for every entry its face and side (+1: the row is the face's first cell).
+   What cs_matrix_structure_create(CS_MATRIX_MSR) + _matrix_from_native's entry -> face
+   map give (cs_grid.cpp:7146-7186).  Returns false when two faces join the same cells. */
+bool msr_structure_from_faces(int n_rows, int n_faces, const int *face_cell,
+                              std::vector<int> &row_index, HostVec<int> &col_id,
+                              HostVec<int> &c2f, HostVec<short> &c2f_sgn)
+{
+  row_index.assign((size_t)n_rows + 1, 0);
+  for (int f = 0; f < n_faces; f++) {
+    const int a = face_cell[2*f], b = face_cell[2*f+1];
+    if (a < n_rows) row_index[(size_t)a+1]++;
+    if (b < n_rows) row_index[(size_t)b+1]++;
+  }
+  for (int i = 0; i < n_rows; i++) row_index[(size_t)i+1] += row_index[i];
+  const int nnz = row_index[n_rows];
+  col_id.resize(std::max(nnz, 1));
+  c2f.resize(std::max(nnz, 1));
+  c2f_sgn.resize(std::max(nnz, 1));
+  /* (column, signed face) pairs are dropped in face order, then every row is sorted by
+     column; the face rides along in the upper half of a 64-bit key */
+  HostVec<int64_t> key((size_t)std::max(nnz, 1));
+  {
+    std::vector<int> fill(row_index.begin(), row_index.end() - 1);
+    for (int f = 0; f < n_faces; f++) {
+      const int a = face_cell[2*f], b = face_cell[2*f+1];
+      if (a < n_rows) key[(size_t)fill[a]++] = ((int64_t)b << 32) | (uint32_t)(2*f);
+      if (b < n_rows) key[(size_t)fill[b]++] = ((int64_t)a << 32) | (uint32_t)(2*f + 1);
+    }
+  }
+  bool unique = true;
+  #pragma omp parallel for schedule(static) reduction(&&:unique)
+  for (int i = 0; i < n_rows; i++) {
+    int64_t *b = key.data() + row_index[i], *e = key.data() + row_index[(size_t)i+1];
+    std::sort(b, e);
+    for (int64_t *p = b; p < e; p++) {
+      const size_t k = (size_t)(p - key.data());
+      col_id[k] = (int)(*p >> 32);
+      const uint32_t fs = (uint32_t)(*p & 0xffffffff);
+      c2f[k] = (int)(fs >> 1);
+      c2f_sgn[k] = (fs & 1u) ? (short)-1 : (short)1;
+      if (p > b && col_id[k] == col_id[k-1]) unique = false;
+    }
+  }
+  return unique;
+}
+
+/* Face-list form of the DX aggregation.  The faces still worth trying are kept in one
+   queue compacted in place behind the read position (a face is re-queued at or before the
+   slot it was read from).  f_c_cell: n_cols_ext entries, all written. */
+int aggregate_fc(int level, int n_rows, int n_cols_ext, int n_faces, const int *face_cell,
+                 const double *da, const double *xa, int max_aggregation, int *f_c_cell)
+{
+  const int n_ext = std::max(n_cols_ext, 1);
+  HostVec<int> queue((size_t)std::max(n_faces, 1)), n_nei((size_t)n_ext), n_in((size_t)n_ext);
+  for (int i = 0; i < n_cols_ext; i++) { f_c_cell[i] = -2; n_nei[i] = -1; n_in[i] = 1; }
+  for (int f = 0; f < n_faces; f++) {
+    queue[f] = f;
+    n_nei[face_cell[2*f]] += 1;
+    n_nei[face_cell[2*f+1]] += 1;
+  }
+  if (level == 0) {
+    /* cells whose diagonal dwarfs their extra-diagonal mass stay out (threshold 1e4) */
+    HostVec<double> mass((size_t)n_ext);
+    for (int i = 0; i < n_cols_ext; i++) mass[i] = 0.;
+    for (int f = 0; f < n_faces; f++) {
+      const double v = std::fabs(xa[f]);
+      mass[face_cell[2*f]] += v;
+      mass[face_cell[2*f+1]] += v;
+    }
+    for (int i = 0; i < n_rows; i++)
+      if (da[i] > 1e4 * mass[i]) f_c_cell[i] = -1;
+  }
+
+  int n_coarse = 0, q_len = n_faces, limit = 1;
+  for (int pass = 1; pass <= 10; pass++) {
+    limit = std::min(limit + 1, max_aggregation);
+    const int bonus = pass;
+    const int n_try = q_len;
+    q_len = 0;
+    for (int q = 0; q < n_try; q++) {
+      const int f = queue[q];
+      const int i = face_cell[2*f], j = face_cell[2*f+1];
+      if (i >= n_rows || j >= n_rows) continue;          /* never across a rank boundary */
+      const int ci = f_c_cell[i], cj = f_c_cell[j];
+      if (!(ci < -1 || cj < -1)) continue;
+      bool merged = false;
+      const double inv = (double)((n_nei[i] + bonus) * (n_nei[j] + bonus)) / (da[i] * da[j]);
+      const double crit = inv * (xa[f] * xa[f]);
+      if (crit > 1. - 1.e-6) {
+        if (ci > -1 && cj < -1) {
+          if (n_in[ci] < limit + 1) { f_c_cell[j] = ci; n_in[ci] += 1; merged = true; }
+        }
+        else if (ci < -1 && cj > -1) {
+          if (n_in[cj] < limit + 1) { f_c_cell[i] = cj; n_in[cj] += 1; merged = true; }
+        }
+        else if (ci < -1 && cj < -1) {
+          f_c_cell[i] = n_coarse; f_c_cell[j] = n_coarse;
+          n_in[n_coarse] += 1;
+          n_coarse++;
+          merged = true;
+        }
+      }
+      if (!merged && (f_c_cell[i] < -1 || f_c_cell[j] < -1)) queue[q_len++] = f;
+    }
+    long pending = 0;
+    #pragma omp parallel for reduction(+:pending) schedule(static)
+    for (int i = 0; i < n_rows; i++)
+      if (f_c_cell[i] < -1) pending++;
+    if (pending == 0 || ((long)n_coarse + pending) * 8 < n_rows || q_len == 0) break;
+  }
+  for (int i = 0; i < n_rows; i++)
+    if (f_c_cell[i] < -1) f_c_cell[i] = n_coarse++;
+  return n_coarse;
+}
+
+/* Coarse faces of the native path: the coarse MSR structure of `cs` (sorted coarse
+   neighbours, build_coarse_structure) is kept, its faces are renumbered in the order in
+   which the fine faces first reach them; c_face_cell[2*cf] < c_face_cell[2*cf+1]. */
+void number_coarse_faces_native(int f_n_faces, const int *f_face_cell, const int *f_c_row,
+                                int c_n_rows, CoarseStructure &cs, HostVec<int> &c_face_cell)
+{
+  const int c_nnz = cs.c_row_index[c_n_rows];
+  int *face = cs.c_cell_face.data();
+  short *sgn = cs.c_cell_face_sgn.data();
+  #pragma omp parallel for schedule(static)
+  for (int k = 0; k < c_nnz; k++) face[k] = -1;
+  c_face_cell.resize((size_t)std::max(c_nnz, 2));     /* 2 x (nnz / 2) faces */
+  int n = 0;
+  auto entry = [&cs](int row, int col) {
+    const int *b = cs.c_col_id.data() + cs.c_row_index[row];
+    const int *e = cs.c_col_id.data() + cs.c_row_index[(size_t)row+1];
+    return (int)(std::lower_bound(b, e, col) - cs.c_col_id.data());
+  };
+  for (int f = 0; f < f_n_faces; f++) {
+    int ic = f_c_row[f_face_cell[2*f]], jc = f_c_row[f_face_cell[2*f+1]];
+    if (ic == jc || ic < 0 || jc < 0 || ic >= c_n_rows || jc >= c_n_rows) continue;
+    if (ic > jc) std::swap(ic, jc);
+    const int k = entry(ic, jc);
+    if (face[k] > -1) continue;
+    const int k2 = entry(jc, ic);
+    face[k] = n; sgn[k] = 1;
+    face[k2] = n; sgn[k2] = -1;
+    c_face_cell[2*(size_t)n] = ic;
+    c_face_cell[2*(size_t)n+1] = jc;
+    n++;
+  }
+  cs.c_n_faces = n;
+}
+
 } // namespace csb

@@ -58,6 +58,15 @@ struct CoarseStructure {
 void build_coarse_structure(int f_n_rows, const int *f_row_index, const int *f_col_id,
                             const int *f_c_row, int c_n_rows, CoarseStructure &cs);
 
+/* Matrices mapped from native (face-based) arrays (grid_host.cpp, last section) */
+bool msr_structure_from_faces(int n_rows, int n_faces, const int *face_cell,
+                              std::vector<int> &row_index, HostVec<int> &col_id,
+                              HostVec<int> &c2f, HostVec<short> &c2f_sgn);
+int aggregate_fc(int level, int n_rows, int n_cols_ext, int n_faces, const int *face_cell,
+                 const double *da, const double *xa, int max_aggregation, int *f_c_cell);
+void number_coarse_faces_native(int f_n_faces, const int *f_face_cell, const int *f_c_row,
+                                int c_n_rows, CoarseStructure &cs, HostVec<int> &c_face_cell);
+
 /* Fine -> coarse row map of the reference's pairwise aggregation (_pairwise_msr,
    cs_grid.cpp:1744-2020; beta = 0.25, diagonal-dominance threshold 5 at level 0).
    Returns the number of coarse rows. */

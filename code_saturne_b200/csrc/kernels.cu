@@ -22,6 +22,7 @@
 #include "persistent.h"
 
 #include <cfloat>
+#include <climits>
 #include <cstring>
 #include <cmath>
 
@@ -2072,6 +2073,184 @@ bool launch_coarse_galerkin(const CoarseAssemblyArgs &a)
   if (a.c_n_rows < 1) return true;
   k_coarse_galerkin<<<(a.c_n_rows + CA_WARPS - 1)/CA_WARPS, CA_WARPS*32, 0, ctx().stream>>>(a);
   return post_launch("coarse_galerkin");
+}
+
+/*----------------------------------------------------------------------------
+ * Coarse level of a matrix mapped from native (face-based) arrays.
+ *
+ * The reference sums in face order: every coarse face adds up its fine faces by ascending
+ * fine face id, every fine cell its faces by ascending face id, every coarse cell its
+ * coarse faces by ascending coarse face id (cs_grid.cpp:5303-5372, :5479-5486, :5527-5534).
+ * Nothing here is sorted or staged: a thread finds the next face of its set by scanning
+ * the few entries it owns for the smallest face id above the last one it took, so the
+ * order is the reference's whatever the entry order is.
+ *----------------------------------------------------------------------------*/
+
+namespace {
+
+__global__ void k_native_cells(NativeCoarseArgs a)
+{
+  const int ic = blockIdx.x*blockDim.x + threadIdx.x;
+  if (ic >= a.c_n_rows) return;
+  double vol = 0., cx = 0., cy = 0., cz = 0.;
+  for (int r = a.c_f_row_index[ic]; r < a.c_f_row_index[ic+1]; r++) {
+    const int ii = a.c_f_row_ids[r];
+    const double v = a.f_cell_vol[ii];
+    vol += v;
+    cx += v*a.f_cell_cen[3*(size_t)ii];
+    cy += v*a.f_cell_cen[3*(size_t)ii+1];
+    cz += v*a.f_cell_cen[3*(size_t)ii+2];
+  }
+  a.c_cell_vol[ic] = vol;
+  a.c_cell_cen[3*(size_t)ic]   = cx / vol;
+  a.c_cell_cen[3*(size_t)ic+1] = cy / vol;
+  a.c_cell_cen[3*(size_t)ic+2] = cz / vol;
+}
+
+/* non-differential part of a fine row: diagonal plus its faces' values in face order */
+__global__ void k_native_w1(NativeCoarseArgs a)
+{
+  const int ii = blockIdx.x*blockDim.x + threadIdx.x;
+  if (ii >= a.f_n_rows) return;
+  const int s = a.f_row_index[ii], e = a.f_row_index[ii+1];
+  double w = a.f_d_val[ii];
+  int last = -1;
+  while (true) {
+    int best = INT_MAX, bk = -1;
+    for (int k = s; k < e; k++) {
+      const int f = a.f_cell_face[k];
+      if (f > last && f < best) { best = f; bk = k; }
+    }
+    if (bk < 0) break;
+    w += a.f_x_val[bk];
+    last = best;
+  }
+  a.w1[ii] = w;
+}
+
+__global__ void k_native_faces(NativeCoarseArgs a)
+{
+  const int cf = blockIdx.x*blockDim.x + threadIdx.x;
+  if (cf >= a.c_n_faces) return;
+  const int ic = a.c_face_cell[2*(size_t)cf], jc = a.c_face_cell[2*(size_t)cf+1];
+  double xa0 = 0., nx = 0., ny = 0., nz = 0., ax = 0., ay = 0., az = 0.;
+  int last = -1;
+  while (true) {
+    /* next fine face between the two aggregates */
+    int best = INT_MAX, bk = -1;
+    for (int r = a.c_f_row_index[ic]; r < a.c_f_row_index[ic+1]; r++) {
+      const int ii = a.c_f_row_ids[r];
+      for (int k = a.f_row_index[ii]; k < a.f_row_index[ii+1]; k++) {
+        if (a.f_c_row[a.f_col_id[k]] != jc) continue;
+        const int f = a.f_cell_face[k];
+        if (f > last && f < best) { best = f; bk = k; }
+      }
+    }
+    if (bk < 0) break;
+    last = best;
+    const size_t f = (size_t)best;
+    const int c0 = a.f_face_cell[2*f], c1 = a.f_face_cell[2*f+1];
+    const double sgn = (a.f_c_row[c0] == ic) ? 1. : -1.;
+    if (a.f_level == 0) {
+      const double v = a.f_x_val[bk];                       /* f_xa0 = xa */
+      const double sx = sgn * (a.f_cell_cen[3*(size_t)c1]   - a.f_cell_cen[3*(size_t)c0]);
+      const double sy = sgn * (a.f_cell_cen[3*(size_t)c1+1] - a.f_cell_cen[3*(size_t)c0+1]);
+      const double sz = sgn * (a.f_cell_cen[3*(size_t)c1+2] - a.f_cell_cen[3*(size_t)c0+2]);
+      xa0 += v;
+      const double sgn_surf = sgn*a.f_face_surf[f];
+      nx += a.f_face_u_normal[3*f]   * sgn_surf;
+      ny += a.f_face_u_normal[3*f+1] * sgn_surf;
+      nz += a.f_face_u_normal[3*f+2] * sgn_surf;
+      ax += v * sx;
+      ay += v * sy;
+      az += v * sz;
+    }
+    else {
+      xa0 += a.f_xa0[f];
+      nx += sgn*a.f_face_normal[3*f];
+      ny += sgn*a.f_face_normal[3*f+1];
+      nz += sgn*a.f_face_normal[3*f+2];
+      ax += sgn*a.f_xa0ij[3*f];
+      ay += sgn*a.f_xa0ij[3*f+1];
+      az += sgn*a.f_xa0ij[3*f+2];
+    }
+  }
+  a.c_xa0[cf] = xa0;
+  a.c_face_normal[3*(size_t)cf] = nx; a.c_face_normal[3*(size_t)cf+1] = ny;
+  a.c_face_normal[3*(size_t)cf+2] = nz;
+  a.c_xa0ij[3*(size_t)cf] = ax; a.c_xa0ij[3*(size_t)cf+1] = ay; a.c_xa0ij[3*(size_t)cf+2] = az;
+
+  /* P1-interpolated value, clipped to [xa0, 0], relaxed towards the P0 value */
+  const double *ci = a.c_cell_cen + 3*(size_t)ic, *cj = a.c_cell_cen + 3*(size_t)jc;
+  const double dsigjg = (cj[0] - ci[0])*nx + (cj[1] - ci[1])*ny + (cj[2] - ci[2])*nz;
+  const double dsxaij = ax*nx + ay*ny + az*nz;
+  double x = xa0;
+  if (fabs(dsigjg) > 1.e-12) {
+    const double agij = dsxaij/dsigjg;
+    x = (agij < xa0 || agij > 0.) ? xa0 : agij;
+  }
+  a.c_xa[cf] = a.relax*x + (1. - a.relax)*xa0;
+}
+
+/* coarse diagonal (fine rows ascending, then the coarse faces ascending) and the MSR values */
+__global__ void k_native_diag(NativeCoarseArgs a)
+{
+  const int ic = blockIdx.x*blockDim.x + threadIdx.x;
+  if (ic >= a.c_n_rows) return;
+  double d = 0.;
+  for (int r = a.c_f_row_index[ic]; r < a.c_f_row_index[ic+1]; r++) {
+    const double w = a.w1[a.c_f_row_ids[r]];
+    if (w > 0.) d += w;
+  }
+  const int s = a.c_row_index[ic], e = a.c_row_index[ic+1];
+  int last = -1;
+  while (true) {
+    int best = INT_MAX, bk = -1;
+    for (int k = s; k < e; k++) {
+      const int f = a.c_cell_face[k];
+      if (f > last && f < best) { best = f; bk = k; }
+    }
+    if (bk < 0) break;
+    const double x = a.c_xa[best];
+    d -= x;
+    a.c_x_val[bk] = x;
+    last = best;
+  }
+  a.c_d_val[ic] = d;
+}
+
+__global__ void k_native_to_msr(int nnz, const int *c2f, const double *xa, double *x_val)
+{
+  const int k = blockIdx.x*blockDim.x + threadIdx.x;
+  if (k < nnz) x_val[k] = xa[c2f[k]];
+}
+
+} // anonymous namespace
+
+bool launch_coarse_native(const NativeCoarseArgs &a)
+{
+  Context &c = ctx();
+  if (a.c_n_rows < 1) return true;
+  const int nt = 128;
+  k_native_cells<<<(a.c_n_rows + nt - 1)/nt, nt, 0, c.stream>>>(a);
+  if (!post_launch("native_cells")) return false;
+  if (a.f_n_rows > 0) {
+    k_native_w1<<<(a.f_n_rows + nt - 1)/nt, nt, 0, c.stream>>>(a);
+    if (!post_launch("native_w1")) return false;
+  }
+  if (a.c_n_faces > 0) {
+    k_native_faces<<<(a.c_n_faces + nt - 1)/nt, nt, 0, c.stream>>>(a);
+    if (!post_launch("native_faces")) return false;
+  }
+  k_native_diag<<<(a.c_n_rows + nt - 1)/nt, nt, 0, c.stream>>>(a);
+  return post_launch("native_diag");
+}
+
+bool launch_native_to_msr(int nnz, const int *c2f, const double *xa, double *x_val)
+{
+  if (nnz < 1) return true;
+  k_native_to_msr<<<(nnz + 255)/256, 256, 0, ctx().stream>>>(nnz, c2f, xa, x_val);
+  return post_launch("native_to_msr");
 }
 
 /* stages: 1 = sums over fine rows (cell centres, volumes, faces, diagonal),

@@ -380,6 +380,77 @@ csb_matrix_create_msr(csb_lnum_t n_rows, csb_lnum_t n_cols_ext,
   return m;
 }
 
+/* Matrix mapped from native (face-based) arrays: cs_matrix_structure_create(CS_MATRIX_MSR,
+   n_rows, n_cols_ext, n_edges, edges) + cs_matrix_set_coefficients(m, symmetric, 1, 1,
+   n_edges, edges, da, xa) (src/alge/cs_matrix.cpp:4328, :5315).  The MSR structure is built
+   on the host (sorted columns), the values are placed on the device; the faces and their
+   values stay with the matrix: csb_multigrid_setup then follows the reference's path for
+   such a matrix (cs_grid_create_from_shared, cs_grid.cpp:7485-7491). */
+csb_matrix_t *
+csb_matrix_create_native(csb_lnum_t n_rows, csb_lnum_t n_cols_ext, csb_lnum_t n_edges,
+                         const csb_lnum_t *edges, const csb_real_t *da, const csb_real_t *xa,
+                         int symmetric)
+{
+  Context &c = ctx();
+  if (!c.ready) { set_error("csb_matrix_create_native: csb_init not called"); return nullptr; }
+  if (n_rows < 0 || n_cols_ext < n_rows || n_edges < 0 || da == nullptr
+      || (n_edges > 0 && (edges == nullptr || xa == nullptr))) {
+    set_error("csb_matrix_create_native: invalid arguments"); return nullptr;
+  }
+  if (!symmetric) {
+    set_error("csb_matrix_create_native: symmetric matrices only (one value per face)");
+    return nullptr;
+  }
+  csb_matrix_t *m = new csb_matrix_t;
+  m->n_rows = n_rows;
+  m->n_cols_ext = n_cols_ext;
+  m->symmetric = true;
+  m->from_native = true;
+  m->n_faces = n_edges;
+  m->h_face_cell.resize(2*(size_t)std::max(n_edges, 1));
+  m->h_xa.resize((size_t)std::max(n_edges, 1));
+  m->h_d_val.resize((size_t)std::max(n_rows, 1));
+  bool ok = true;
+  if (n_edges > 0)
+    ok = CSB_CUDA(cudaMemcpy(m->h_face_cell.data(), edges, sizeof(csb_lnum_t)*2*(size_t)n_edges,
+                             cudaMemcpyDefault))
+      && CSB_CUDA(cudaMemcpy(m->h_xa.data(), xa, sizeof(double)*(size_t)n_edges,
+                             cudaMemcpyDefault));
+  if (ok && n_rows > 0)
+    ok = CSB_CUDA(cudaMemcpy(m->h_d_val.data(), da, sizeof(double)*(size_t)n_rows,
+                             cudaMemcpyDefault));
+  if (!ok) { delete m; return nullptr; }
+  for (csb_lnum_t f = 0; f < n_edges; f++) {
+    const csb_lnum_t a = m->h_face_cell[2*(size_t)f], b = m->h_face_cell[2*(size_t)f+1];
+    if (a < 0 || b < 0 || a >= n_cols_ext || b >= n_cols_ext || a == b) {
+      set_error("csb_matrix_create_native: edge %d joins cells %d and %d", f, a, b);
+      delete m; return nullptr;
+    }
+  }
+  csb::HostVec<csb_lnum_t> c2f;
+  csb::HostVec<short> c2f_sgn;
+  if (!csb::msr_structure_from_faces(n_rows, n_edges, m->h_face_cell.data(), m->h_row_index,
+                                     m->h_col_id, c2f, c2f_sgn)) {
+    set_error("csb_matrix_create_native: two edges join the same pair of cells (values to be "
+              "added by the caller first)");
+    delete m; return nullptr;
+  }
+  m->nnz = m->h_row_index[n_rows];
+  ok = m->row_index.upload(m->h_row_index.data(), (size_t)n_rows + 1)
+    && m->col_id.upload(m->h_col_id.data(), (size_t)m->nnz)
+    && m->c2f.upload(c2f.data(), (size_t)m->nnz)
+    && m->c2f_sgn.upload(c2f_sgn.data(), (size_t)m->nnz)
+    && m->face_cell.upload(m->h_face_cell.data(), 2*(size_t)n_edges)
+    && m->xa.upload(m->h_xa.data(), (size_t)n_edges)
+    && m->d_val.upload(m->h_d_val.data(), (size_t)n_rows)
+    && m->x_val.alloc((size_t)m->nnz)
+    && csb::launch_native_to_msr(m->nnz, m->c2f.p, m->xa.p, m->x_val.p)
+    && CSB_CUDA(cudaStreamSynchronize(c.stream));
+  if (!ok) { delete m; return nullptr; }
+  matrix_plan_spmv(m);
+  return m;
+}
+
 /* Host arrays lent to the matrix: the reference's matrices share the caller's arrays
    (cs_matrix_set_coefficients keeps pointers unless told to copy, src/alge/cs_matrix.cpp:5451);
    here the device holds the working copy and the host arrays, when lent, serve the host side
@@ -500,6 +571,11 @@ int csb_matrix_set_coefficients(csb_matrix_t *m, int symmetric,
               "again with csb_matrix_create_csr to change its values");
     return -1;
   }
+  if (m->from_native) {
+    set_error("csb_matrix_set_coefficients: matrix was created from native arrays; use "
+              "csb_matrix_set_coefficients_native(da, xa)");
+    return -1;
+  }
   m->symmetric = (symmetric != 0);
   Context &c = ctx();
   /* d_val holds db x db blocks per row (CS_MATRIX_BLOCK_D: n_rows*9 values) */
@@ -514,6 +590,36 @@ int csb_matrix_set_coefficients(csb_matrix_t *m, int symmetric,
   return ok ? 0 : -1;
 }
 
+/* New values on the same edges (cs_matrix_set_coefficients called again with the edges the
+   structure was built from) */
+int csb_matrix_set_coefficients_native(csb_matrix_t *m, const csb_real_t *da,
+                                       const csb_real_t *xa)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (!m->from_native || da == nullptr || (xa == nullptr && m->n_faces > 0)) {
+    set_error("csb_matrix_set_coefficients_native: needs a matrix made by "
+              "csb_matrix_create_native and both arrays");
+    return -1;
+  }
+  Context &c = ctx();
+  bool ok = CSB_CUDA(cudaMemcpy(m->h_d_val.data(), da, sizeof(double)*(size_t)m->n_rows,
+                                cudaMemcpyDefault))
+         && (m->n_faces == 0
+             || CSB_CUDA(cudaMemcpy(m->h_xa.data(), xa, sizeof(double)*(size_t)m->n_faces,
+                                    cudaMemcpyDefault)))
+         && CSB_CUDA(cudaMemcpyAsync(m->d_val.p, m->h_d_val.data(),
+                                     sizeof(double)*(size_t)m->n_rows, cudaMemcpyHostToDevice,
+                                     c.stream))
+         && (m->n_faces == 0
+             || CSB_CUDA(cudaMemcpyAsync(m->xa.p, m->h_xa.data(),
+                                         sizeof(double)*(size_t)m->n_faces,
+                                         cudaMemcpyHostToDevice, c.stream)))
+         && csb::launch_native_to_msr(m->nnz, m->c2f.p, m->xa.p, m->x_val.p)
+         && CSB_CUDA(cudaStreamSynchronize(c.stream));
+  m->h_vals_valid = false;
+  return ok ? 0 : -1;
+}
+
 int csb_matrix_set_mesh_association(csb_matrix_t *m, csb_lnum_t n_faces,
                                     const csb_lnum_t *c2f, const short *c2f_sgn,
                                     const csb_real_t *cell_cen, const csb_real_t *cell_vol,
@@ -521,14 +627,21 @@ int csb_matrix_set_mesh_association(csb_matrix_t *m, csb_lnum_t n_faces,
                                     const csb_real_t *face_surf)
 {
   if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
-  if (c2f == nullptr || c2f_sgn == nullptr || cell_cen == nullptr || cell_vol == nullptr
-      || face_u_normal == nullptr || face_surf == nullptr) {
+  /* a matrix mapped from native arrays already knows the face of every entry */
+  const bool own_c2f = (m->from_native && c2f == nullptr && c2f_sgn == nullptr);
+  if (m->from_native && (!own_c2f || n_faces != m->n_faces)) {
+    set_error("csb_matrix_set_mesh_association: matrix created from %d edges: pass that face "
+              "count and NULL for c2f / c2f_sgn", m->n_faces);
+    return -1;
+  }
+  if ((!own_c2f && (c2f == nullptr || c2f_sgn == nullptr)) || cell_cen == nullptr
+      || cell_vol == nullptr || face_u_normal == nullptr || face_surf == nullptr) {
     set_error("csb_matrix_set_mesh_association: all arrays are required");
     return -1;
   }
   m->n_faces = n_faces;
-  bool ok = m->c2f.upload(c2f, (size_t)m->nnz)
-         && m->c2f_sgn.upload(c2f_sgn, (size_t)m->nnz)
+  bool ok = (own_c2f || (m->c2f.upload(c2f, (size_t)m->nnz)
+                         && m->c2f_sgn.upload(c2f_sgn, (size_t)m->nnz)))
          && m->cell_cen.upload(cell_cen, 3*(size_t)m->n_cols_ext)
          && m->cell_vol.upload(cell_vol, (size_t)m->n_cols_ext)
          && m->face_u_normal.upload(face_u_normal, 3*(size_t)n_faces)

@@ -1496,6 +1496,13 @@ struct MgLevel {
   DevBuf<short>       cell_face_sgn;
   DevBuf<double>      cell_cen, cell_vol, face_normal, xa0, xa0ij;
   int                 n_faces = 0;
+  /* hierarchy of a matrix mapped from native arrays: the level's faces (2 cells each,
+     numbered like _coarsen_face_cell numbers them) and their values; host copies feed the
+     face-list aggregation of the next step */
+  DevBuf<int>         face_cell;
+  DevBuf<double>      xa;
+  HostVec<int>        h_face_cell;
+  HostVec<double>     h_xa;
   /* distributed hierarchy */
   csb_halo_t         *halo = nullptr;       /* this level's halo (owned when level > 0) */
   bool                halo_owned = false;
@@ -2324,6 +2331,17 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     return;
   }
   const bool dist = (a->halo != nullptr);
+  /* matrix mapped from native arrays (cs_grid_create_from_shared: use_faces, use_xa,
+     cs_grid.cpp:7485-7491): coarse values by the face-order sums of
+     _compute_coarse_quantities_native; with one aggregation block (the reference running
+     one thread) the aggregation is the face-list one, _automatic_aggregation_fc
+     (cs_grid.cpp:8106-8122); with Galerkin values only level 0 still has faces (:8055) */
+  const bool native = (a->from_native && !galerkin);
+  if (a->from_native && (dist || pairwise || a->n_rows != a->n_cols_ext)) {
+    set_error("csb_multigrid_setup: a matrix created from native arrays is handled on one "
+              "rank, with the DX aggregation");
+    return;
+  }
   csb_pcomm_t *pc = dist ? mg->pcomm : nullptr;
   if (dist && (pc == nullptr || a->halo->pcomm != pc)) {
     set_error("csb_multigrid_setup: a matrix with a halo needs csb_multigrid_set_pcomm and "
@@ -2364,8 +2382,15 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     csb_matrix_t *fm = const_cast<csb_matrix_t *>(f->m);
     const int f_level = (int)mg->levels.size() - 1;
 
+    /* faces of this level when the hierarchy follows a native matrix */
+    const bool f_faces = a->from_native && (native || f_level == 0);
+    const bool use_fc = f_faces && n_blocks == 1;
+    const int f_n_faces = (f_level == 0) ? fm->n_faces : f->n_faces;
+    const int *f_h_face_cell = (f_level == 0) ? fm->h_face_cell.data() : f->h_face_cell.data();
+    const double *f_h_xa = (f_level == 0) ? fm->h_xa.data() : f->h_xa.data();
+
     double t0 = wall();
-    if (!matrix_host_mirror(fm)) return;
+    if (use_fc ? !matrix_host_mirror_structure(fm) : !matrix_host_mirror(fm)) return;
     t_xfer += wall() - t0;
     tr.mark("host mirror", f_level);
 
@@ -2377,6 +2402,10 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
       ? coarsen_pairwise_galerkin(f_level, fm->n_rows, fm->h_row_index.data(),
                                   fm->host_col_id(), fm->host_d_val(), fm->host_x_val(),
                                   mg->aggregation_limit, f->h_coarse_row.data(), pw)
+      : use_fc
+      ? aggregate_fc(f_level, fm->n_rows, fm->n_cols_ext, f_n_faces, f_h_face_cell,
+                     fm->h_d_val.data(), f_h_xa, mg->aggregation_limit,
+                     f->h_coarse_row.data())
       : aggregate_dx_msr(f_level, fm->n_rows, fm->h_row_index.data(), fm->host_col_id(),
                          fm->host_d_val(), fm->host_x_val(), mg->aggregation_limit,
                          n_blocks, f->h_coarse_row.data());
@@ -2412,6 +2441,10 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     CoarseStructure cs;
     build_coarse_structure(fm->n_rows, fm->h_row_index.data(), fm->host_col_id(),
                            f->h_coarse_row.data(), c_n_rows, cs);
+    HostVec<int> c_h_face_cell;
+    if (native)
+      number_coarse_faces_native(f_n_faces, f_h_face_cell, f->h_coarse_row.data(), c_n_rows,
+                                 cs, c_h_face_cell);
     t_aggr += wall() - t0;
     tr.mark("coarse structure (host)", f_level);
     const int c_nnz = cs.c_row_index[c_n_rows];
@@ -2437,9 +2470,13 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
            && cl->cell_cen.alloc(3*c_n_cols_ext) && cl->cell_vol.alloc(c_n_cols_ext)
            && cl->face_normal.alloc(3*(size_t)cs.c_n_faces)
            && cl->xa0.alloc((size_t)cs.c_n_faces) && cl->xa0ij.alloc(3*(size_t)cs.c_n_faces);
+    if (ok && native)
+      ok = cl->face_cell.upload(c_h_face_cell.data(), 2*(size_t)cs.c_n_faces)
+           && cl->xa.alloc((size_t)cs.c_n_faces);
     ok = ok && CSB_CUDA(cudaStreamSynchronize(c.stream));  /* cs.* vectors die below */
     if (!ok) { delete cl; return; }
     cl->n_faces = cs.c_n_faces;
+    if (native) cl->h_face_cell.swap(c_h_face_cell);
     cm->h_row_index.swap(cs.c_row_index);
     cm->h_col_id.swap(cs.c_col_id);
     t_xfer += wall() - t0;
@@ -2484,6 +2521,55 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
       if (!launch_coarse_galerkin(ca)) { delete cl; return; }
       if (!CSB_CUDA(cudaStreamSynchronize(c.stream))) { delete cl; return; }
       t_asm += wall() - t0;
+      matrix_plan_spmv(cm);
+      mg->levels.push_back(cl);
+      continue;
+    }
+    if (native) {
+      /* face-order sums (_compute_coarse_cell_quantities, _compute_coarse_quantities_native,
+         _matrix_from_native), then the host copies the next face-list aggregation reads */
+      NativeCoarseArgs na;
+      na.f_level = f_level;
+      na.f_n_rows = fm->n_rows; na.c_n_rows = c_n_rows; na.c_n_faces = cl->n_faces;
+      na.f_row_index = fm->row_index.p; na.f_col_id = fm->col_id.p;
+      na.f_d_val = fm->d_val.p; na.f_x_val = fm->x_val.p;
+      na.f_c_row = f->coarse_row.p;
+      na.c_f_row_index = f->c_f_row_index.p; na.c_f_row_ids = f->c_f_row_ids.p;
+      na.c_row_index = cm->row_index.p; na.c_cell_face = cl->cell_face.p;
+      na.c_face_cell = cl->face_cell.p;
+      if (f_level == 0) {
+        na.f_cell_face = fm->c2f.p; na.f_face_cell = fm->face_cell.p;
+        na.f_cell_cen = fm->cell_cen.p; na.f_cell_vol = fm->cell_vol.p;
+        na.f_face_u_normal = fm->face_u_normal.p; na.f_face_surf = fm->face_surf.p;
+        na.f_face_normal = nullptr; na.f_xa0 = nullptr; na.f_xa0ij = nullptr;
+      }
+      else {
+        na.f_cell_face = f->cell_face.p; na.f_face_cell = f->face_cell.p;
+        na.f_cell_cen = f->cell_cen.p; na.f_cell_vol = f->cell_vol.p;
+        na.f_face_u_normal = nullptr; na.f_face_surf = nullptr;
+        na.f_face_normal = f->face_normal.p; na.f_xa0 = f->xa0.p; na.f_xa0ij = f->xa0ij.p;
+      }
+      na.c_cell_cen = cl->cell_cen.p; na.c_cell_vol = cl->cell_vol.p;
+      na.c_face_normal = cl->face_normal.p; na.c_xa0 = cl->xa0.p; na.c_xa0ij = cl->xa0ij.p;
+      na.c_xa = cl->xa.p;
+      na.c_d_val = cm->d_val.p; na.c_x_val = cm->x_val.p;
+      na.relax = mg->p0p1_relax;
+      DevBuf<double> w1;
+      if (!w1.alloc((size_t)fm->n_rows)) { delete cl; return; }
+      na.w1 = w1.p;
+      cl->h_xa.resize((size_t)std::max(cl->n_faces, 1));
+      cm->h_d_val.resize((size_t)std::max(c_n_rows, 1));
+      if (!launch_coarse_native(na)
+          || (cl->n_faces > 0
+              && !CSB_CUDA(cudaMemcpyAsync(cl->h_xa.data(), cl->xa.p,
+                                           sizeof(double)*(size_t)cl->n_faces,
+                                           cudaMemcpyDeviceToHost, c.stream)))
+          || !CSB_CUDA(cudaMemcpyAsync(cm->h_d_val.data(), cm->d_val.p,
+                                       sizeof(double)*(size_t)c_n_rows,
+                                       cudaMemcpyDeviceToHost, c.stream))
+          || !CSB_CUDA(cudaStreamSynchronize(c.stream))) { delete cl; return; }
+      t_asm += wall() - t0;
+      tr.mark("coarse values (device, face order)", f_level);
       matrix_plan_spmv(cm);
       mg->levels.push_back(cl);
       continue;

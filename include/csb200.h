@@ -168,6 +168,31 @@ csb_matrix_t *csb_matrix_create_csr(csb_lnum_t         n_rows,
                                     const csb_real_t  *val,
                                     int                symmetric);
 
+/* Matrix "mapped from native arrays": what a caller that holds face-based coefficients does
+   in the reference -- cs_matrix_structure_create(CS_MATRIX_MSR, n_rows, n_cols_ext, n_edges,
+   edges, ...) + cs_matrix_set_coefficients(m, symmetric, 1, 1, n_edges, edges, da, xa)
+   (src/alge/cs_matrix.cpp:4328, :5315).  edges[n_edges][2] (host), da[n_rows], xa[n_edges]
+   (symmetric: one value per edge; host or device).  Two edges may not join the same pair of
+   cells.  The result is an MSR matrix like the others (sorted columns) that also keeps the
+   edges and their values: cs_matrix_is_mapped_from_native (cs_matrix.cpp:5722) is true for
+   it in the reference, and csb_multigrid_setup then builds the hierarchy the way the
+   reference does for such a matrix (cs_grid_create_from_shared, src/alge/cs_grid.cpp:7485-7491):
+   face-list aggregation _automatic_aggregation_fc (:3997-4263) when one aggregation block is
+   used, coarse faces numbered by _coarsen_face_cell (:637-788), coarse values summed in face
+   order by _compute_coarse_cell_quantities / _compute_coarse_quantities_native (:4778,
+   :5144-5558) and turned into MSR by _matrix_from_native (:7105).  For the geometry call
+   csb_matrix_set_mesh_association with n_faces = n_edges and NULL c2f / c2f_sgn. */
+csb_matrix_t *csb_matrix_create_native(csb_lnum_t         n_rows,
+                                       csb_lnum_t         n_cols_ext,
+                                       csb_lnum_t         n_edges,
+                                       const csb_lnum_t  *edges,
+                                       const csb_real_t  *da,
+                                       const csb_real_t  *xa,
+                                       int                symmetric);
+/* new values on the same edges */
+int  csb_matrix_set_coefficients_native(csb_matrix_t *m, const csb_real_t *da,
+                                        const csb_real_t *xa);
+
 /* Replace coefficient values only (cs_matrix_set_coefficients on an existing
    structure, src/alge/cs_matrix.cpp:5315). */
 int  csb_matrix_set_coefficients(csb_matrix_t      *m,

@@ -1190,6 +1190,7 @@ ora_grid_free(ora_grid_t *g)
   free(g->coarse_row); free(g->cell_face); free(g->cell_face_sgn);
   free(g->cell_cen); free(g->cell_vol); free(g->face_normal);
   free(g->face_u_normal); free(g->face_surf); free(g->xa0); free(g->xa0ij);
+  free(g->face_cell); free(g->xa);
   free(g);
 }
 
@@ -1568,6 +1569,14 @@ _grid_coarsen_galerkin(const ora_grid_t *f, const int *f_c_row_in, int c_n_rows)
   c->col_id = c_col_id;
   c->d_val = c_d_val; c->x_val = c_x_val;
   return c;
+}
+
+/* the same for a given fine -> coarse map (cs_oracle_native.c: level 0 of a matrix mapped
+   from native arrays is aggregated over its face list even when the values are Galerkin) */
+ora_grid_t *
+ora_grid_coarsen_galerkin_map(const ora_grid_t *f, const int *f_c_row, int c_n_rows)
+{
+  return _grid_coarsen_galerkin(f, f_c_row, c_n_rows);
 }
 
 /*----------------------------------------------------------------------------

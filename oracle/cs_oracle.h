@@ -28,6 +28,8 @@ typedef struct {
   double  *face_u_normal, *face_surf;  /* level 0 */
   double  *xa0, *xa0ij;     /* level > 0 */
   int      n_cols_ext;      /* n_rows + ghost rows (== n_rows on one rank) */
+  int     *face_cell;       /* hierarchy of a matrix mapped from native arrays   */
+  double  *xa;              /* (cs_oracle_native.c): faces and per-face values    */
 } ora_grid_t;
 
 typedef struct {
@@ -166,6 +168,22 @@ void        ora_grid_free(ora_grid_t *g);
 ora_mg_t   *ora_mg_setup(ora_grid_t *fine, int aggregation_limit, int n_levels_max,
                          int n_g_rows_min, double p0p1_relax, int n_threads);
 void        ora_mg_free(ora_mg_t *mg, int free_fine);
+
+/* matrix mapped from native (face-based) arrays: cs_oracle_native.c */
+ora_grid_t *ora_grid_coarsen_galerkin_map(const ora_grid_t *f, const int *f_c_row, int c_n_rows);
+int    ora_aggregation_fc(int level, int f_n_cells, int f_n_cells_ext, int f_n_faces,
+                          const int *face_cell, const double *da, const double *xa,
+                          int max_aggregation, int *f_c_cell);
+int    ora_coarsen_face_cell(int f_n_faces, const int *f_face_cell, const int *coarse_row,
+                             int c_n_cells, int *coarse_face, int *c_face_cell);
+ora_grid_t *ora_grid_create_fine_native(int n_rows, int n_faces, const int *face_cell,
+                                        const double *da, const double *xa,
+                                        const double *cell_cen, const double *cell_vol,
+                                        const double *face_u_normal, const double *face_surf);
+ora_grid_t *ora_grid_coarsen_native(const ora_grid_t *f, int max_aggregation,
+                                    double relax_param, int n_threads);
+ora_mg_t   *ora_mg_setup_native(ora_grid_t *fine, int aggregation_limit, int n_levels_max,
+                                int n_g_rows_min, double p0p1_relax, int n_threads);
 
 void   ora_restrict(int f_n_rows, int c_n_rows, const int *coarse_row,
                     const double *f_var, double *c_var);

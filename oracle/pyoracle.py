@@ -46,8 +46,8 @@ def _f64(a):
 def build_oracle(force: bool = False) -> str:
     """Compile oracle/cs_oracle.c into oracle/libcs_oracle.so (gcc, seconds)."""
     so = os.path.join(_HERE, "libcs_oracle.so")
-    src = os.path.join(_HERE, "cs_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("cs_oracle.c", "cs_oracle_native.c", "cs_oracle.h")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(map(os.path.getmtime, srcs)):
         subprocess.check_call(["make", "-f", "oracle/Makefile"], cwd=_ROOT,
                               stdout=subprocess.DEVNULL)
     return so
@@ -67,7 +67,7 @@ class OraGrid(C.Structure):
                 ("cell_cen", c_dbl_p), ("cell_vol", c_dbl_p),
                 ("face_normal", c_dbl_p), ("face_u_normal", c_dbl_p),
                 ("face_surf", c_dbl_p), ("xa0", c_dbl_p), ("xa0ij", c_dbl_p),
-                ("n_cols_ext", C.c_int)]
+                ("n_cols_ext", C.c_int), ("face_cell", c_int_p), ("xa", c_dbl_p)]
 
 
 class OraMg(C.Structure):
@@ -93,6 +93,15 @@ def _np_from(ptr, n, dtype):
     if n <= 0 or not ptr:
         return np.zeros(0, dtype=dtype)
     return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+def native_arrays(s):
+    """(da, xa) of a symmetric CubeSystem in native form: xa[f] = the value of the MSR entry
+    (face_cells[f][0], face_cells[f][1]) (sign +1 side of the mesh association)."""
+    xa = np.zeros(max(s.n_faces, 1))
+    up = np.asarray(s.c2f_sgn) > 0
+    xa[np.asarray(s.c2f)[up]] = np.asarray(s.x_val)[up]
+    return np.array(s.d_val, dtype=np.float64), xa[:s.n_faces]
 
 
 class Oracle:
@@ -297,6 +306,29 @@ class Oracle:
         g = self.fine_grid(s)
         return self.lib.ora_mg_setup(g, aggregation_limit, n_levels_max, n_g_rows_min,
                                      p0p1_relax, n_threads)
+
+    def mg_setup_native(self, s, aggregation_limit=3, n_levels_max=25, n_g_rows_min=30,
+                        p0p1_relax=0.95, n_threads=1, da=None, xa=None):
+        """Hierarchy of the matrix mapped from native arrays (cs_oracle_native.c)."""
+        if da is None or xa is None:
+            da, xa = native_arrays(s)
+        self.lib.ora_grid_create_fine_native.restype = C.POINTER(OraGrid)
+        self.lib.ora_mg_setup_native.restype = C.POINTER(OraMg)
+        g = self.lib.ora_grid_create_fine_native(
+            C.c_int(s.n_rows), C.c_int(s.n_faces), _ip(_i32(s.face_cells)), _dp(_f64(da)),
+            _dp(_f64(xa)), _dp(_f64(s.cell_cen)), _dp(_f64(s.cell_vol)),
+            _dp(_f64(s.face_u_normal)), _dp(_f64(s.face_surf)))
+        return self.lib.ora_mg_setup_native(g, C.c_int(aggregation_limit), C.c_int(n_levels_max),
+                                            C.c_int(n_g_rows_min), C.c_double(p0p1_relax),
+                                            C.c_int(n_threads))
+
+    def aggregation_fc(self, level, n_rows, face_cells, da, xa, max_aggregation=3):
+        fc = _i32(face_cells)
+        f_c = np.empty(max(n_rows, 1), dtype=np.int32)
+        nc = self.lib.ora_aggregation_fc(C.c_int(level), C.c_int(n_rows), C.c_int(n_rows),
+                                         C.c_int(len(fc)), _ip(fc), _dp(_f64(da)), _dp(_f64(xa)),
+                                         C.c_int(max_aggregation), _ip(f_c))
+        return nc, f_c[:n_rows]
 
     def mg_setup_pw(self, s, aggregation_limit=4, n_levels_max=25, n_g_rows_min=30):
         """CS_GRID_COARSENING_SPD_PW (pairwise aggregation) with Galerkin coarse matrices."""
@@ -565,6 +597,18 @@ class RefLib:
             self.lib.csref_system_set_mesh(h, C.c_int(s.n_faces), _ip(fc), _ip(c2f), _sp(sgn),
                                            _dp(cen), _dp(vol), _dp(fun), _dp(fs))
         return h
+
+    def system_native(self, s, da=None, xa=None):
+        """MSR matrix mapped from native (face-based) arrays: cs_matrix_set_coefficients with
+        edges = s.face_cells, da, xa[n_faces] (symmetric); geometry attached."""
+        fc = _i32(s.face_cells)
+        if da is None or xa is None:
+            da, xa = native_arrays(s)
+        self.lib.csref_system_create_native.restype = C.c_void_p
+        return C.c_void_p(self.lib.csref_system_create_native(
+            C.c_int(s.n_rows), C.c_int(s.n_faces), _ip(fc), _dp(_f64(da)), _dp(_f64(xa)),
+            _dp(_f64(s.cell_cen)), _dp(_f64(s.cell_vol)), _dp(_f64(s.face_u_normal)),
+            _dp(_f64(s.face_surf))))
 
     def system_block(self, n_rows, db, ri, ci, d_val, x_val, symmetric=False):
         """MSR matrix with db x db diagonal blocks (d_val: n_rows*db*db) built by the reference."""

@@ -232,6 +232,64 @@ csref_system_create_csr(int            n_rows,
   return s;
 }
 
+/* MSR matrix "mapped from native" (cs_matrix_structure_create(CS_MATRIX_MSR, faces) +
+   cs_matrix_set_coefficients(edges, da, xa), cs_matrix.cpp:4328, :5315): the entry of a
+   caller that holds face-based arrays.  cs_grid_create_from_shared then takes its
+   use_faces / use_xa branch (cs_grid.cpp:7485-7491), so cs_grid_coarsen runs
+   _automatic_aggregation_fc (one thread) or _automatic_aggregation_dx_msr, then
+   _coarsen_face_cell, _compute_coarse_cell_quantities, _compute_coarse_quantities_native
+   and _matrix_from_native.  da, xa and the geometry are kept (the matrix maps them). */
+struct ref_native_arrays {
+  cs_lnum_2_t *face_cells; cs_real_t *da, *xa;
+};
+static std::vector<std::pair<void *, ref_native_arrays>> g_native;
+
+void *
+csref_system_create_native(int            n_rows,
+                           int            n_faces,
+                           const int     *face_cells,
+                           const double  *da,
+                           const double  *xa,
+                           const double  *cell_cen,
+                           const double  *cell_vol,
+                           const double  *face_u_normal,
+                           const double  *face_surf)
+{
+  ref_system *s = new ref_system;
+  s->n_rows = n_rows;
+  s->n_faces = n_faces;
+  s->symmetric = true;
+  ref_native_arrays na;
+  CS_MALLOC(na.face_cells, n_faces > 0 ? n_faces : 1, cs_lnum_2_t);
+  CS_MALLOC(na.da, n_rows, cs_real_t);
+  CS_MALLOC(na.xa, n_faces > 0 ? n_faces : 1, cs_real_t);
+  memcpy(na.face_cells, face_cells, sizeof(cs_lnum_2_t)*n_faces);
+  memcpy(na.da, da, sizeof(cs_real_t)*n_rows);
+  memcpy(na.xa, xa, sizeof(cs_real_t)*n_faces);
+  s->ms = cs_matrix_structure_create(CS_MATRIX_MSR, n_rows, n_rows, n_faces,
+                                     na.face_cells, nullptr, nullptr);
+  s->m = cs_matrix_create(s->ms);
+  cs_matrix_set_coefficients(s->m, true, 1, 1, n_faces, na.face_cells, na.da, na.xa);
+
+  CS_MALLOC(s->cell_cen, n_rows, cs_real_3_t);
+  CS_MALLOC(s->cell_vol, n_rows, cs_real_t);
+  CS_MALLOC(s->face_u_normal, n_faces > 0 ? n_faces : 1, cs_nreal_3_t);
+  CS_MALLOC(s->face_surf, n_faces > 0 ? n_faces : 1, cs_real_t);
+  memcpy(s->cell_cen, cell_cen, sizeof(cs_real_3_t)*n_rows);
+  memcpy(s->cell_vol, cell_vol, sizeof(cs_real_t)*n_rows);
+  for (cs_lnum_t i = 0; i < n_faces; i++) {
+    for (int k = 0; k < 3; k++)
+      s->face_u_normal[i][k] = face_u_normal[i*3+k];
+    s->face_surf[i] = face_surf[i];
+  }
+  cs_matrix_set_mesh_association(s->m, nullptr, nullptr, nullptr,
+                                 s->cell_cen, s->cell_vol,
+                                 s->face_u_normal, s->face_surf);
+  _set_glob_mesh_faces(s, face_cells);
+  g_native.push_back({s, na});
+  return s;
+}
+
 /* Copy the CSR arrays out; returns the number of entries (call with null pointers
    first to size the buffers). */
 int
@@ -294,6 +352,15 @@ csref_system_destroy(void *sys)
   if (s == nullptr) return;
   cs_matrix_destroy(&(s->m));
   cs_matrix_structure_destroy(&(s->ms));
+  for (size_t i = 0; i < g_native.size(); i++) {
+    if (g_native[i].first == sys) {
+      CS_FREE(g_native[i].second.face_cells);
+      CS_FREE(g_native[i].second.da);
+      CS_FREE(g_native[i].second.xa);
+      g_native.erase(g_native.begin() + i);
+      break;
+    }
+  }
   CS_FREE(s->row_index); CS_FREE(s->col_id);
   CS_FREE(s->c2f); CS_FREE(s->c2f_sgn);
   CS_FREE(s->cell_cen); CS_FREE(s->cell_vol);

@@ -267,6 +267,45 @@ def check_galerkin(ora):
     mg.destroy(); m.destroy()
 
 
+def check_native(ora):
+    """matrix mapped from native arrays: face-list aggregation, face-order coarse values
+    (oracle/cs_oracle_native.c is pinned bit for bit to the reference, tests/test_oracle.py)"""
+    from oracle.pyoracle import native_arrays
+    for N, bc, blocks, perturb, relax in ((8, "neumann", 1, False, 0.95),
+                                          (12, "dirichlet", 1, True, 0.95),
+                                          (12, "neumann", 3, True, 0.95),
+                                          (12, "neumann", 1, True, 0.)):
+        s = cube_poisson(N, bc)
+        da, xa = native_arrays(s)
+        if perturb:
+            rng = np.random.default_rng(1234)
+            xa = xa * (1 + 0.3 * rng.random(len(xa)))
+            da = np.zeros(s.n_rows)
+            np.add.at(da, s.face_cells[:, 0], -xa)
+            np.add.at(da, s.face_cells[:, 1], -xa)
+            da += 1e-3 * np.abs(xa).mean()
+        omg = ora.mg_setup_native(s, n_threads=blocks, da=da, xa=xa, p0p1_relax=relax)
+        lo = ora.mg_levels(omg)
+        m = csb.Matrix.from_system_native(s, da, xa)
+        assert np.array_equal(m.get_coefficients()[1], lo[0]["x_val"])
+        mg = csb.Multigrid()
+        mg.set_aggregation_blocks(blocks)
+        mg.set_coarsening_options(p0p1_relax=relax)
+        mg.setup(m)
+        lv = mg.levels()
+        assert len(lv) == len(lo), (len(lv), len(lo))
+        for l in range(1, len(lv)):
+            for k in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
+                assert np.array_equal(lv[l][k], lo[l][k]), (N, bc, blocks, relax, l, k)
+        rn = float(np.linalg.norm(s.rhs))
+        r = mg.solve(m, s.rhs, 1e-8, rn)
+        o = ora.mg_solve(omg, s.rhs, 1e-8, rn)
+        assert int(r["cvg"]) == 1 and abs(r["n_iter"] - o["n_iter"]) <= 2, (r["n_iter"], o["n_iter"])
+        assert rel(r["vx"][:s.n_rows], o["vx"]) <= 1e-6
+        ora.mg_free(omg)
+        mg.destroy(); m.destroy()
+
+
 def check_pairwise(ora):
     g = np.load(os.path.join(GOLD, "pairwise_N8_neumann.npz"))
     s = cube_poisson(8, "neumann")
@@ -366,7 +405,7 @@ def check_k_cycle(ora):
     c.destroy(); m.destroy()
 
 
-CHECKS = {"spmv_pcg": check_spmv_pcg, "k_cycle": check_k_cycle, "compute_coeffs": check_compute_coeffs, "pairwise": check_pairwise, "galerkin": check_galerkin, "block3_jacobi": check_block3_jacobi, "general_pc": check_general_pc,
+CHECKS = {"spmv_pcg": check_spmv_pcg, "native": check_native, "k_cycle": check_k_cycle, "compute_coeffs": check_compute_coeffs, "pairwise": check_pairwise, "galerkin": check_galerkin, "block3_jacobi": check_block3_jacobi, "general_pc": check_general_pc,
           "kernel_per_phase": check_kernel_per_phase_paths, "smoothers": check_smoothers,
           "cycle_pc": check_cycle_pc, "fcg_mgpc": check_fcg_mgpc}
 

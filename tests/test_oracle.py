@@ -4,6 +4,7 @@ code and (2) that code directly when oracle/_ref/libcsref.so is present.
 Integer/index data must match bit-exactly; floating-point data too, since the
 restatement keeps the reference's evaluation order."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -688,3 +689,86 @@ def test_oracle_block_smoothers_match_golden(oracle, db, N):
             r = oracle.smoother_block(st, db, ri, ci, d.ravel(), xv, rhs, nit, g["x"])
             assert np.array_equal(r["vx"], g[f"sm{st}_{nit}_warm"]), (st, nit)
             assert r["n_iter"] == int(g[f"sm{st}_{nit}_n_iter"])
+
+
+# ----------------- matrix mapped from native (face-based) arrays: a29, a35 (cs_oracle_native.c)
+
+def _native_cases():
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_native import CASES
+    return sorted(CASES.items())
+
+
+@pytest.mark.parametrize("name,case", _native_cases())
+def test_oracle_native_hierarchy_matches_golden(oracle, name, case):
+    """_automatic_aggregation_fc / _coarsen_face_cell / _compute_coarse_quantities_native /
+    _matrix_from_native restated: every level bit-exact against the reference's own run, and
+    the V-cycle over that hierarchy reproduces its iterates."""
+    from make_golden_native import native_system
+    N, bc, nt, perturb, relax = case
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"native_{name}.npz"))
+    s, da, xa = native_system(N, bc, perturb)
+    assert np.array_equal(da, g["da"]) and np.array_equal(xa, g["xa"])
+    mg = oracle.mg_setup_native(s, n_threads=nt, da=da, xa=xa, p0p1_relax=relax)
+    lv = oracle.mg_levels(mg)
+    assert len(lv) == int(g["n_levels"])
+    for k in ("row_index", "col_id", "x_val"):
+        assert np.array_equal(lv[0][k], g[f"l0_{k}"]), k
+    for l in range(1, len(lv)):
+        for k in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
+            assert np.array_equal(lv[l][k], g[f"l{l}_{k}"]), (l, k)
+    r = oracle.mg_solve(mg, s.rhs, 1e-8, float(g["r_norm"]))
+    assert (r["cvg"], r["n_iter"]) == (int(g["mg_cvg"]), int(g["mg_n_iter"]))
+    if nt == 1:       # the dot products of a several-thread reference run sum in another order
+        assert r["residual"] == float(g["mg_residual"])
+        assert np.array_equal(r["vx"], g["mg_vx"])
+    else:
+        assert np.allclose(r["vx"], g["mg_vx"], rtol=0, atol=1e-12 * np.abs(g["mg_vx"]).max())
+    oracle.mg_free(mg)
+
+
+@pytest.mark.parametrize("N,bc,nt", [(20, "neumann", 1), (24, "dirichlet", 1), (20, "dirichlet", 4)])
+def test_oracle_native_hierarchy_matches_reference(oracle, N, bc, nt):
+    """the same against the reference library run here (larger cubes, perturbed faces)"""
+    from oracle.pyoracle import RefLib, ref_available
+    from make_golden_native import native_system
+    if not ref_available():
+        pytest.skip("oracle/_ref/libcsref.so not built (needs /root/reference)")
+    s, da, xa = native_system(N, bc, True)
+    ref = RefLib(nt)
+    h = ref.system_native(s, da, xa)
+    lr = ref.hierarchy(h)
+    ref.destroy(h)
+    ref.set_threads(1)
+    mg = oracle.mg_setup_native(s, n_threads=nt, da=da, xa=xa)
+    lo = oracle.mg_levels(mg)
+    assert [x["n_rows"] for x in lo] == [x["n_rows"] for x in lr]
+    for a, b in zip(lo, lr):
+        for k in ("coarse_row", "row_index", "col_id", "d_val", "x_val", "cell_cen", "cell_vol"):
+            assert np.array_equal(a[k], b[k]), (a["n_rows"], k)
+    oracle.mg_free(mg)
+
+
+def test_oracle_aggregation_fc_properties(oracle):
+    """face-list aggregation: every row mapped, aggregates within the limit, penalised rows
+    (diagonal above 1e4 x the extra-diagonal mass) left out at level 0"""
+    from oracle.pyoracle import native_arrays
+    s = cube_poisson(9, "neumann")
+    da, xa = native_arrays(s)
+    da = da.copy()
+    da[[5, 77]] = 1e6
+    nc, f_c = oracle.aggregation_fc(0, s.n_rows, s.face_cells, da, xa, 3)
+    assert f_c[5] == -1 and f_c[77] == -1
+    kept = f_c[f_c >= 0]
+    assert kept.size == s.n_rows - 2 and kept.max() == nc - 1
+    assert np.bincount(kept).max() <= 4 and np.bincount(kept).min() >= 1
+    nc1, f_c1 = oracle.aggregation_fc(1, s.n_rows, s.face_cells, da, xa, 3)
+    assert (f_c1 >= 0).all()          # no penalisation below level 0
+    # no faces at all: at level 0 every row is penalised (no extra-diagonal mass), below
+    # level 0 every row becomes a coarse row of its own
+    nc0, f_c0 = oracle.aggregation_fc(0, 4, np.zeros((0, 2), dtype=np.int32), np.ones(4),
+                                      np.zeros(0), 3)
+    assert nc0 == 0 and (f_c0 == -1).all()
+    nc0, f_c0 = oracle.aggregation_fc(1, 4, np.zeros((0, 2), dtype=np.int32), np.ones(4),
+                                      np.zeros(0), 3)
+    assert nc0 == 4 and np.array_equal(f_c0, np.arange(4))
