@@ -107,6 +107,22 @@ def load_library() -> C.CDLL:
     L.csb_matrix_create_msr_block.argtypes = [ci, ci, ci, vp, vp, vp, vp, ci]
     L.csb_matrix_create_csr.restype = vp
     L.csb_matrix_create_csr.argtypes = [ci, ci, vp, vp, vp, ci]
+    cll = C.c_longlong
+    L.csb_matrix_assembler_create.restype = vp
+    L.csb_matrix_assembler_create.argtypes = [vp, ci]
+    L.csb_matrix_assembler_destroy.argtypes = [C.POINTER(vp)]
+    L.csb_matrix_assembler_add_g_ids.argtypes = [vp, ci, vp, vp]
+    L.csb_matrix_assembler_compute.argtypes = [vp]
+    L.csb_matrix_assembler_get_n_rows.argtypes = [vp]
+    L.csb_matrix_assembler_get_structure.argtypes = [vp, vp, vp]
+    L.csb_matrix_create_from_assembler.restype = vp
+    L.csb_matrix_create_from_assembler.argtypes = [vp]
+    L.csb_matrix_assembler_values_init.restype = vp
+    L.csb_matrix_assembler_values_init.argtypes = [vp, vp, ci, ci]
+    L.csb_matrix_assembler_values_add_g.argtypes = [vp, ci, vp, vp, vp]
+    L.csb_matrix_assembler_values_done.argtypes = [vp]
+    L.csb_matrix_assembler_values_add_declared.argtypes = [vp, vp]
+    L.csb_matrix_assembler_values_finalize.argtypes = [C.POINTER(vp)]
     L.csb_matrix_create_native.restype = vp
     L.csb_matrix_create_native.argtypes = [ci, ci, ci, vp, vp, vp, ci]
     L.csb_matrix_set_coefficients_native.argtypes = [vp, vp, vp]
@@ -391,6 +407,95 @@ def _i32(a):
 
 def _f64(a):
     return a if not isinstance(a, np.ndarray) else np.ascontiguousarray(a, dtype=np.float64)
+
+
+class MatrixAssembler:
+    """cs_matrix_assembler_t on one rank (MSR target): declare (row, column) global-id pairs,
+    compute the structure, create the matrix, add coefficient values."""
+
+    def __init__(self, l_range):
+        L = load_library()
+        lr = np.array(l_range, dtype=np.uint64)
+        self._h = L.csb_matrix_assembler_create(_ptr(lr), 1)
+        if not self._h:
+            _err("csb_matrix_assembler_create")
+        self._mav = None
+
+    @property
+    def handle(self):
+        return C.c_void_p(self._h)
+
+    def add_g_ids(self, rows, cols):
+        r = np.ascontiguousarray(rows, dtype=np.uint64)
+        c = np.ascontiguousarray(cols, dtype=np.uint64)
+        if load_library().csb_matrix_assembler_add_g_ids(self.handle, len(r), _ptr(r), _ptr(c)) != 0:
+            _err("csb_matrix_assembler_add_g_ids")
+
+    def compute(self):
+        if load_library().csb_matrix_assembler_compute(self.handle) != 0:
+            _err("csb_matrix_assembler_compute")
+
+    def structure(self):
+        L = load_library()
+        n = L.csb_matrix_assembler_get_n_rows(self.handle)
+        nnz = L.csb_matrix_assembler_get_structure(self.handle, None, None)
+        if nnz < 0:
+            _err("csb_matrix_assembler_get_structure")
+        ri = np.zeros(n + 1, dtype=np.int32)
+        ci = np.zeros(max(nnz, 1), dtype=np.int32)
+        L.csb_matrix_assembler_get_structure(self.handle, _ptr(ri), _ptr(ci))
+        return ri, ci[:nnz]
+
+    def create_matrix(self):
+        """cs_matrix_create_from_assembler(CS_MATRIX_MSR, ma): values zero"""
+        L = load_library()
+        h = L.csb_matrix_create_from_assembler(self.handle)
+        if not h:
+            _err("csb_matrix_create_from_assembler")
+        m = Matrix.__new__(Matrix)
+        m._h = h
+        m.n_rows = m.n_cols_ext = int(L.csb_matrix_get_n_rows(h))
+        m.nnz = int(L.csb_matrix_get_n_entries(h)) - m.n_rows
+        m._halo = None
+        return m
+
+    def values_init(self, m):
+        L = load_library()
+        self._mav = L.csb_matrix_assembler_values_init(m.handle, self.handle, 1, 1)
+        if not self._mav:
+            _err("csb_matrix_assembler_values_init")
+
+    def values_add_g(self, rows, cols, vals):
+        r = np.ascontiguousarray(rows, dtype=np.uint64)
+        c = np.ascontiguousarray(cols, dtype=np.uint64)
+        v = _f64(np.asarray(vals))
+        if load_library().csb_matrix_assembler_values_add_g(C.c_void_p(self._mav), len(r), _ptr(r),
+                                                            _ptr(c), _ptr(v)) != 0:
+            _err("csb_matrix_assembler_values_add_g")
+
+    def values_add_declared(self, vals):
+        """vals[k] for the k-th declared pair; numpy array or a device tensor"""
+        v = _f64(vals) if isinstance(vals, np.ndarray) else vals
+        if load_library().csb_matrix_assembler_values_add_declared(C.c_void_p(self._mav),
+                                                                   _ptr(v)) != 0:
+            _err("csb_matrix_assembler_values_add_declared")
+
+    def values_done(self):
+        if load_library().csb_matrix_assembler_values_done(C.c_void_p(self._mav)) != 0:
+            _err("csb_matrix_assembler_values_done")
+
+    def values_finalize(self):
+        h = C.c_void_p(self._mav)
+        r = load_library().csb_matrix_assembler_values_finalize(C.byref(h))
+        self._mav = None
+        if r != 0:
+            _err("csb_matrix_assembler_values_finalize")
+
+    def destroy(self):
+        if self._h:
+            h = C.c_void_p(self._h)
+            load_library().csb_matrix_assembler_destroy(C.byref(h))
+            self._h = None
 
 
 class Matrix:

@@ -620,6 +620,12 @@ bool launch_coarse_native(const NativeCoarseArgs &a);
 /* x_val[k] = xa[c2f[k]] (cs_matrix_set_coefficients from edges, symmetric, unique faces) */
 bool launch_native_to_msr(int nnz, const int *c2f, const double *xa, double *x_val);
 
+/* matrix assembler (assembler.cu): slot s < n_rows is the diagonal of row s, slot
+   n_rows + k the extra-diagonal entry k; every slot adds val[src[j]] for j in
+   [index[s], index[s+1]) to its current value, in that order */
+bool launch_assembler_fold(int n_rows, int nnz, const int *index, const int *src,
+                           const double *val, double *d_val, double *x_val);
+
 bool launch_halo_pack(int n_send, const int *send_list, const double *var, double *buf);
 /* Gauss-Seidel update of the n rows listed in `rows` (one dependency level); mode 0 whole
    row, 1 lower part, 2 upper part (truncated sweeps); res != NULL: d_i (new - old) per row

@@ -2246,6 +2246,34 @@ bool launch_coarse_native(const NativeCoarseArgs &a)
   return post_launch("native_diag");
 }
 
+namespace {
+/* a thread per slot: sums of a few terms each (a row's diagonal gets one term per pair
+   declared on that row), read through the plan in arrival order */
+__global__ void k_assembler_fold(int n_rows, int n_slots, const int *__restrict__ index,
+                                 const int *__restrict__ src, const double *__restrict__ val,
+                                 double *d_val, double *x_val)
+{
+  const int s = blockIdx.x*blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  const int b = index[s], e = index[s+1];
+  if (b == e) return;
+  double *out = (s < n_rows) ? d_val + s : x_val + (s - n_rows);
+  double acc = *out;
+  for (int j = b; j < e; j++) acc += val[src[j]];
+  *out = acc;
+}
+} // anonymous namespace
+
+bool launch_assembler_fold(int n_rows, int nnz, const int *index, const int *src,
+                           const double *val, double *d_val, double *x_val)
+{
+  const long n_slots = (long)n_rows + (long)nnz;
+  if (n_slots < 1) return true;
+  k_assembler_fold<<<(unsigned)((n_slots + 255)/256), 256, 0, ctx().stream>>>(
+    n_rows, (int)n_slots, index, src, val, d_val, x_val);
+  return post_launch("assembler_fold");
+}
+
 bool launch_native_to_msr(int nnz, const int *c2f, const double *xa, double *x_val)
 {
   if (nnz < 1) return true;

@@ -29,6 +29,7 @@ extern "C" {
 
 typedef int    csb_lnum_t;   /* cs_lnum_t */
 typedef double csb_real_t;   /* cs_real_t */
+typedef unsigned long long csb_gnum_t;   /* cs_gnum_t (64-bit global ids) */
 
 /* cs_sles_convergence_state_t, src/alge/cs_sles.h:57-68 */
 typedef enum {
@@ -192,6 +193,54 @@ csb_matrix_t *csb_matrix_create_native(csb_lnum_t         n_rows,
 /* new values on the same edges */
 int  csb_matrix_set_coefficients_native(csb_matrix_t *m, const csb_real_t *da,
                                         const csb_real_t *xa);
+
+/*----------------------------------------------------------------------------
+ * Matrix assembler (cs_matrix_assembler_t, src/alge/cs_matrix_assembler.cpp): matrices whose
+ * graph is a list of (row, column) global-id pairs rather than the mesh faces -- CDO systems,
+ * internal coupling.  One rank: every id inside l_range.
+ *
+ *   ma = csb_matrix_assembler_create(l_range, 1);            cs_matrix_assembler_create :2366
+ *   csb_matrix_assembler_add_g_ids(ma, n, rows, cols); ...   _add_g_ids :2673
+ *   csb_matrix_assembler_compute(ma);                        _compute :2734
+ *   m = csb_matrix_create_from_assembler(ma);                cs_matrix_structure_create_from_assembler
+ *   mav = csb_matrix_assembler_values_init(m, ma, 1, 1);     cs_matrix.cpp:5635
+ *   csb_matrix_assembler_values_add_g(mav, n, rows, cols, vals); ...   :3276
+ *   csb_matrix_assembler_values_finalize(&mav);              :3119
+ *
+ * Every entry is the sum of its coefficients in arrival order, starting from zero: the
+ * reference's one-thread result bit for bit (_msr_assembler_values_add, cs_matrix.cpp:2422).
+ * The matrix is non-symmetric as far as its flag goes (_set_fill_info(matrix, false, ...)).
+ *----------------------------------------------------------------------------*/
+typedef struct _csb_matrix_assembler_t        csb_matrix_assembler_t;
+typedef struct _csb_matrix_assembler_values_t csb_matrix_assembler_values_t;
+
+csb_matrix_assembler_t *csb_matrix_assembler_create(const csb_gnum_t l_range[2],
+                                                    int separate_diag /* must be 1: MSR */);
+void        csb_matrix_assembler_destroy(csb_matrix_assembler_t **ma);
+int         csb_matrix_assembler_add_g_ids(csb_matrix_assembler_t *ma, csb_lnum_t n,
+                                           const csb_gnum_t *row_g_id,
+                                           const csb_gnum_t *col_g_id);
+int         csb_matrix_assembler_compute(csb_matrix_assembler_t *ma);
+csb_lnum_t  csb_matrix_assembler_get_n_rows(const csb_matrix_assembler_t *ma);
+/* cs_matrix_assembler_get_row_index / _get_col_ids (:2900, :2926) as copies; returns the
+   number of extra-diagonal entries (-1 before _compute); either pointer may be NULL */
+csb_lnum_t  csb_matrix_assembler_get_structure(const csb_matrix_assembler_t *ma,
+                                               csb_lnum_t *row_index, csb_lnum_t *col_id);
+csb_matrix_t *csb_matrix_create_from_assembler(const csb_matrix_assembler_t *ma);
+csb_matrix_assembler_values_t *
+csb_matrix_assembler_values_init(csb_matrix_t *m, const csb_matrix_assembler_t *ma,
+                                 int diag_block_size, int extra_diag_block_size);
+int  csb_matrix_assembler_values_add_g(csb_matrix_assembler_values_t *mav, csb_lnum_t n,
+                                       const csb_gnum_t *row_g_id, const csb_gnum_t *col_g_id,
+                                       const csb_real_t *val);
+/* cs_matrix_assembler_values_done (:3510): fold what was added so far into the matrix */
+int  csb_matrix_assembler_values_done(csb_matrix_assembler_values_t *mav);
+/* Coefficients of ALL the pairs declared with csb_matrix_assembler_add_g_ids, in declaration
+   order (val[k] for the k-th pair; host or device array): the re-assembly of a time loop that
+   adds the same ids at every step, as ONE kernel over a plan kept in HBM. */
+int  csb_matrix_assembler_values_add_declared(csb_matrix_assembler_values_t *mav,
+                                              const csb_real_t *val);
+int  csb_matrix_assembler_values_finalize(csb_matrix_assembler_values_t **mav);
 
 /* Replace coefficient values only (cs_matrix_set_coefficients on an existing
    structure, src/alge/cs_matrix.cpp:5315). */

@@ -169,6 +169,15 @@ ora_mg_t   *ora_mg_setup(ora_grid_t *fine, int aggregation_limit, int n_levels_m
                          int n_g_rows_min, double p0p1_relax, int n_threads);
 void        ora_mg_free(ora_mg_t *mg, int free_fine);
 
+/* matrix assembler on one rank, MSR target: cs_oracle_assembler.c */
+int    ora_assembler_structure(int n_rows, int n, const long long *row_g_id,
+                               const long long *col_g_id, long long l_range_0,
+                               int *row_index, int *col_id);
+int    ora_assembler_values_add(int n_rows, const int *row_index, const int *col_id, int n,
+                                const long long *row_g_id, const long long *col_g_id,
+                                long long l_range_0, const double *val, double *d_val,
+                                double *x_val);
+
 /* matrix mapped from native (face-based) arrays: cs_oracle_native.c */
 ora_grid_t *ora_grid_coarsen_galerkin_map(const ora_grid_t *f, const int *f_c_row, int c_n_rows);
 int    ora_aggregation_fc(int level, int f_n_cells, int f_n_cells_ext, int f_n_faces,

@@ -46,7 +46,7 @@ def _f64(a):
 def build_oracle(force: bool = False) -> str:
     """Compile oracle/cs_oracle.c into oracle/libcs_oracle.so (gcc, seconds)."""
     so = os.path.join(_HERE, "libcs_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("cs_oracle.c", "cs_oracle_native.c", "cs_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("cs_oracle.c", "cs_oracle_native.c", "cs_oracle_assembler.c", "cs_oracle.h")]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(map(os.path.getmtime, srcs)):
         subprocess.check_call(["make", "-f", "oracle/Makefile"], cwd=_ROOT,
                               stdout=subprocess.DEVNULL)
@@ -321,6 +321,26 @@ class Oracle:
         return self.lib.ora_mg_setup_native(g, C.c_int(aggregation_limit), C.c_int(n_levels_max),
                                             C.c_int(n_g_rows_min), C.c_double(p0p1_relax),
                                             C.c_int(n_threads))
+
+    def assembler(self, n_rows, rows, cols, batches, l0=0):
+        """Structure from the declared (rows, cols) pairs, then the values of `batches`
+        (list of (rows, cols, vals)) added in order; returns (row_index, col_id, d_val, x_val)."""
+        i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+        lp = lambda a: a.ctypes.data_as(C.POINTER(C.c_longlong))
+        rows, cols = i64(rows), i64(cols)
+        ri = np.zeros(n_rows + 1, dtype=np.int32)
+        ci = np.zeros(max(len(rows), 1), dtype=np.int32)
+        nnz = self.lib.ora_assembler_structure(C.c_int(n_rows), C.c_int(len(rows)), lp(rows),
+                                               lp(cols), C.c_longlong(l0), _ip(ri), _ip(ci))
+        ci = ci[:nnz].copy()
+        d, x = np.zeros(n_rows), np.zeros(max(nnz, 1))
+        for br, bc, bv in batches:
+            br, bc, bv = i64(br), i64(bc), _f64(bv)
+            miss = self.lib.ora_assembler_values_add(C.c_int(n_rows), _ip(ri), _ip(ci),
+                                                     C.c_int(len(br)), lp(br), lp(bc),
+                                                     C.c_longlong(l0), _dp(bv), _dp(d), _dp(x))
+            assert miss == 0
+        return ri, ci, d, x[:nnz]
 
     def aggregation_fc(self, level, n_rows, face_cells, da, xa, max_aggregation=3):
         fc = _i32(face_cells)
@@ -609,6 +629,27 @@ class RefLib:
             C.c_int(s.n_rows), C.c_int(s.n_faces), _ip(fc), _dp(_f64(da)), _dp(_f64(xa)),
             _dp(_f64(s.cell_cen)), _dp(_f64(s.cell_vol)), _dp(_f64(s.face_u_normal)),
             _dp(_f64(s.face_surf))))
+
+    def assembler(self, n_rows, rows, cols, batches, l0=0):
+        """The reference's cs_matrix_assembler on one rank: structure from the declared pairs,
+        MSR matrix, values of `batches` added with cs_matrix_assembler_values_add_g in order.
+        Returns (handle, row_index, col_id, d_val, x_val); the handle is a system usable with
+        spmv / sles_it / destroy."""
+        u64 = lambda a: np.ascontiguousarray(a, dtype=np.uint64)
+        up = lambda a: a.ctypes.data_as(C.POINTER(C.c_ulonglong))
+        rows, cols = u64(rows), u64(cols)
+        self.lib.csref_assembler_system_create.restype = C.c_void_p
+        h = C.c_void_p(self.lib.csref_assembler_system_create(
+            C.c_ulonglong(l0), C.c_int(n_rows), C.c_int(len(rows)), up(rows), up(cols)))
+        for br, bc, bv in batches:
+            br, bc, bv = u64(br), u64(bc), _f64(bv)
+            self.lib.csref_assembler_values_add(h, C.c_int(len(br)), up(br), up(bc), _dp(bv))
+        nnz = self.lib.csref_assembler_values_finalize(h)
+        ri = np.zeros(n_rows + 1, dtype=np.int32)
+        ci = np.zeros(max(nnz, 1), dtype=np.int32)
+        d, x = np.zeros(n_rows), np.zeros(max(nnz, 1))
+        self.lib.csref_get_msr_arrays(h, _ip(ri), _ip(ci), _dp(d), _dp(x))
+        return h, ri, ci[:nnz], d, x[:nnz]
 
     def system_block(self, n_rows, db, ri, ci, d_val, x_val, symmetric=False):
         """MSR matrix with db x db diagonal blocks (d_val: n_rows*db*db) built by the reference."""

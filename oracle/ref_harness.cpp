@@ -46,6 +46,7 @@
 #include "base/cs_numbering.h"
 #include "base/cs_field.h"
 #include "alge/cs_matrix_building.h"
+#include "alge/cs_matrix_assembler.h"
 #include "alge/cs_blas.h"
 #include "alge/cs_matrix.h"
 #include "alge/cs_matrix_default.h"
@@ -290,6 +291,82 @@ csref_system_create_native(int            n_rows,
   return s;
 }
 
+/* Matrix built through the reference's assembler on one rank
+   (cs_matrix_assembler_create / _add_g_ids / _compute, cs_matrix_assembler.cpp:2366, :2673,
+   :2734; cs_matrix_create_from_assembler; cs_matrix_assembler_values_init / _add_g /
+   _finalize, cs_matrix.cpp:5635, cs_matrix_assembler.cpp:3276, :3119). */
+struct ref_assembler {
+  cs_matrix_assembler_t *ma; cs_matrix_assembler_values_t *mav;
+};
+static std::vector<std::pair<void *, ref_assembler>> g_assemblers;
+
+void *
+csref_assembler_system_create(unsigned long long        l0,
+                              int                       n_rows,
+                              int                       n,
+                              const unsigned long long *row_g_id,
+                              const unsigned long long *col_g_id)
+{
+  ref_system *s = new ref_system;
+  s->n_rows = n_rows;
+  s->symmetric = false;
+  cs_gnum_t l_range[2] = {(cs_gnum_t)l0, (cs_gnum_t)(l0 + n_rows)};
+  ref_assembler ra;
+  ra.ma = cs_matrix_assembler_create(l_range, true);
+  cs_matrix_assembler_add_g_ids(ra.ma, n, (const cs_gnum_t *)row_g_id,
+                                (const cs_gnum_t *)col_g_id);
+  cs_matrix_assembler_compute(ra.ma);
+  s->m = cs_matrix_create_from_assembler(CS_MATRIX_MSR, ra.ma);
+  ra.mav = cs_matrix_assembler_values_init(s->m, 1, 1);
+  g_assemblers.push_back({s, ra});
+  return s;
+}
+
+static ref_assembler *_find_assembler(void *sys)
+{
+  for (size_t i = 0; i < g_assemblers.size(); i++)
+    if (g_assemblers[i].first == sys) return &(g_assemblers[i].second);
+  return nullptr;
+}
+
+void
+csref_assembler_values_add(void                     *sys,
+                           int                       n,
+                           const unsigned long long *row_g_id,
+                           const unsigned long long *col_g_id,
+                           const double             *val)
+{
+  ref_assembler *ra = _find_assembler(sys);
+  cs_matrix_assembler_values_add_g(ra->mav, n, (const cs_gnum_t *)row_g_id,
+                                   (const cs_gnum_t *)col_g_id, val);
+}
+
+/* returns the number of extra-diagonal entries */
+int
+csref_assembler_values_finalize(void *sys)
+{
+  ref_system *s = static_cast<ref_system *>(sys);
+  ref_assembler *ra = _find_assembler(sys);
+  cs_matrix_assembler_values_finalize(&(ra->mav));
+  const cs_lnum_t *ri, *ci; const cs_real_t *d, *x;
+  cs_matrix_get_msr_arrays(s->m, &ri, &ci, &d, &x);
+  return ri[s->n_rows];
+}
+
+/* MSR arrays of any system (copies) */
+void
+csref_get_msr_arrays(void *sys, int *row_index, int *col_id, double *d_val, double *x_val)
+{
+  ref_system *s = static_cast<ref_system *>(sys);
+  const cs_lnum_t *ri, *ci; const cs_real_t *d, *x;
+  cs_matrix_get_msr_arrays(s->m, &ri, &ci, &d, &x);
+  const cs_lnum_t n = s->n_rows, nnz = ri[n];
+  if (row_index) memcpy(row_index, ri, sizeof(cs_lnum_t)*(n+1));
+  if (col_id) memcpy(col_id, ci, sizeof(cs_lnum_t)*nnz);
+  if (d_val) memcpy(d_val, d, sizeof(cs_real_t)*n);
+  if (x_val) memcpy(x_val, x, sizeof(cs_real_t)*nnz);
+}
+
 /* Copy the CSR arrays out; returns the number of entries (call with null pointers
    first to size the buffers). */
 int
@@ -351,7 +428,17 @@ csref_system_destroy(void *sys)
   ref_system *s = static_cast<ref_system *>(sys);
   if (s == nullptr) return;
   cs_matrix_destroy(&(s->m));
-  cs_matrix_structure_destroy(&(s->ms));
+  if (s->ms != nullptr)
+    cs_matrix_structure_destroy(&(s->ms));
+  for (size_t i = 0; i < g_assemblers.size(); i++) {
+    if (g_assemblers[i].first == sys) {
+      if (g_assemblers[i].second.mav != nullptr)
+        cs_matrix_assembler_values_finalize(&(g_assemblers[i].second.mav));
+      cs_matrix_assembler_destroy(&(g_assemblers[i].second.ma));
+      g_assemblers.erase(g_assemblers.begin() + i);
+      break;
+    }
+  }
   for (size_t i = 0; i < g_native.size(); i++) {
     if (g_native[i].first == sys) {
       CS_FREE(g_native[i].second.face_cells);

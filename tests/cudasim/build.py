@@ -1,7 +1,7 @@
 """tests/cudasim/build.py -- TEST INFRASTRUCTURE (see cuda_runtime.h in this directory).
 
 Builds tests/cudasim/_build/libcsb200_sim.so from the UNMODIFIED product sources
-csrc/kernels.cu, csrc/sles.cu, csrc/runtime.cu and csrc/grid_host.cpp with g++ against the
+csrc/kernels.cu, csrc/sles.cu, csrc/runtime.cu, csrc/assembler.cu and csrc/grid_host.cpp with g++ against the
 stand-in cuda_runtime.h of this directory.  The only source transformation is syntactic:
 
   kernel<<<grid, block, smem, stream>>>(args);   ->  cudasim::launch(grid, block, smem, [&]{ kernel(args); });
@@ -69,7 +69,7 @@ def transform(src: str) -> str:
 
 def build(force=False) -> str:
     os.makedirs(OUT, exist_ok=True)
-    srcs = [os.path.join(CSRC, f) for f in ("kernels.cu", "sles.cu", "runtime.cu")]
+    srcs = [os.path.join(CSRC, f) for f in ("kernels.cu", "sles.cu", "runtime.cu", "assembler.cu")]
     deps = srcs + [os.path.join(CSRC, f) for f in ("grid_host.cpp", "csb_internal.h",
                                                     "persistent.h", "grid_host.h")] \
         + [os.path.join(HERE, f) for f in ("cuda_runtime.h", "cudasim.cpp", "sim_stubs.cpp",

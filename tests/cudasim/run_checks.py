@@ -306,6 +306,36 @@ def check_native(ora):
         mg.destroy(); m.destroy()
 
 
+def check_assembler(ora):
+    """matrix assembler: structure and values (sums in arrival order) against the reference's
+    fixtures; the declared-sequence plan; SpMV on the assembled matrix"""
+    sys.path.insert(0, GOLD)
+    from make_golden_assembler import CASES, assembler_input
+    for N, (l0, seed) in CASES.items():
+        g = np.load(os.path.join(GOLD, f"assembler_N{N}.npz"))
+        n, rows, cols, vals, batches = assembler_input(N, l0, seed)
+        ma = csb.MatrixAssembler((l0, l0 + n))
+        ma.add_g_ids(rows[:100], cols[:100]); ma.add_g_ids(rows[100:], cols[100:])
+        ma.compute()
+        ri, ci = ma.structure()
+        assert np.array_equal(ri, g["row_index"]) and np.array_equal(ci, g["col_id"])
+        m = ma.create_matrix()
+        ma.values_init(m)
+        for b in batches:
+            ma.values_add_g(*b)
+        ma.values_finalize()
+        d, x = m.get_coefficients()
+        assert np.array_equal(d, g["d_val"]) and np.array_equal(x, g["x_val"])
+        xv = np.sin(np.arange(n) * 0.37)
+        assert np.array_equal(m.vector_multiply(xv.copy()), g["y"])
+        ma.values_init(m)
+        ma.values_add_declared(vals)
+        ma.values_finalize()
+        d, x = m.get_coefficients()
+        assert np.array_equal(d, g["d_val_declared"]) and np.array_equal(x, g["x_val_declared"])
+        m.destroy(); ma.destroy()
+
+
 def check_pairwise(ora):
     g = np.load(os.path.join(GOLD, "pairwise_N8_neumann.npz"))
     s = cube_poisson(8, "neumann")
@@ -405,7 +435,7 @@ def check_k_cycle(ora):
     c.destroy(); m.destroy()
 
 
-CHECKS = {"spmv_pcg": check_spmv_pcg, "native": check_native, "k_cycle": check_k_cycle, "compute_coeffs": check_compute_coeffs, "pairwise": check_pairwise, "galerkin": check_galerkin, "block3_jacobi": check_block3_jacobi, "general_pc": check_general_pc,
+CHECKS = {"spmv_pcg": check_spmv_pcg, "native": check_native, "assembler": check_assembler, "k_cycle": check_k_cycle, "compute_coeffs": check_compute_coeffs, "pairwise": check_pairwise, "galerkin": check_galerkin, "block3_jacobi": check_block3_jacobi, "general_pc": check_general_pc,
           "kernel_per_phase": check_kernel_per_phase_paths, "smoothers": check_smoothers,
           "cycle_pc": check_cycle_pc, "fcg_mgpc": check_fcg_mgpc}
 

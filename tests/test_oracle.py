@@ -772,3 +772,40 @@ def test_oracle_aggregation_fc_properties(oracle):
     nc0, f_c0 = oracle.aggregation_fc(1, 4, np.zeros((0, 2), dtype=np.int32), np.ones(4),
                                       np.zeros(0), 3)
     assert nc0 == 4 and np.array_equal(f_c0, np.arange(4))
+
+
+# ------------------------------ matrix assembler, one rank, MSR (f4; cs_oracle_assembler.c)
+
+def _assembler_cases():
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_assembler import CASES
+    return sorted(CASES.items())
+
+
+@pytest.mark.parametrize("N,case", _assembler_cases())
+def test_oracle_assembler_matches_golden(oracle, N, case):
+    """structure (sorted unique columns, diagonal apart) and values (every entry the sum of its
+    coefficients in arrival order) bit-exact against the reference's assembler"""
+    from make_golden_assembler import assembler_input
+    l0, seed = case
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"assembler_N{N}.npz"))
+    n, rows, cols, vals, batches = assembler_input(N, l0, seed)
+    ri, ci, d, x = oracle.assembler(n, rows, cols, batches, l0)
+    for a, k in ((ri, "row_index"), (ci, "col_id"), (d, "d_val"), (x, "x_val")):
+        assert np.array_equal(a, g[k]), k
+    assert np.array_equal(oracle.spmv(ri, ci, d, x, np.sin(np.arange(n) * 0.37)), g["y"])
+    ri, ci, d, x = oracle.assembler(n, rows, cols, [(rows, cols, vals)], l0)
+    assert np.array_equal(d, g["d_val_declared"]) and np.array_equal(x, g["x_val_declared"])
+
+
+def test_oracle_assembler_matches_reference_live(oracle):
+    from oracle.pyoracle import RefLib, ref_available
+    from make_golden_assembler import assembler_input
+    if not ref_available():
+        pytest.skip("oracle/_ref/libcsref.so not built (needs /root/reference)")
+    ref = RefLib(1)
+    n, rows, cols, vals, batches = assembler_input(18, 77, 9)
+    h, ri, ci, d, x = ref.assembler(n, rows, cols, batches, 77)
+    ref.destroy(h)
+    ri2, ci2, d2, x2 = oracle.assembler(n, rows, cols, batches, 77)
+    assert all(np.array_equal(a, b) for a, b in ((ri, ri2), (ci, ci2), (d, d2), (x, x2)))
