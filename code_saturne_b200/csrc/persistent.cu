@@ -101,6 +101,14 @@ constexpr int PIPE_OFF = BAR_TGT_OFF + 16;            /* PipeState */
  * same sequence of barriers).
  *--------------------------------------------------------------------------*/
 
+/* rows in flight per thread in the transfer operators (independent gather chains) */
+#ifndef CSB_PROLONG_U
+#define CSB_PROLONG_U 4
+#endif
+#ifndef CSB_RESTRICT_U
+#define CSB_RESTRICT_U 2
+#endif
+
 /* Release / acquire fences of the message-passing patterns below.  __threadfence() is a
    sequentially-consistent fence (SASS MEMBAR.SC + ERRBAR); everything here is "publish data,
    then a flag / read the flag, then the data", for which acq_rel (MEMBAR.ALL) is enough. */
@@ -1015,7 +1023,7 @@ template <bool SINGLE>
 __device__ __noinline__ void prolong_rows(int n, const int *__restrict__ coarse_row,
                                           const double *c_vx, double *vx)
 {
-  constexpr int U = 4;
+  constexpr int U = CSB_PROLONG_U;
   const int first = SINGLE ? threadIdx.x : blockIdx.x*PT + threadIdx.x;
   const int step = SINGLE ? PT : gridDim.x*PT;
   for (int base = first; base < n; base += U*step) {
@@ -1045,7 +1053,7 @@ __device__ __noinline__ void restrict_rows(int nc, const int *__restrict__ cfi,
                                            const int *__restrict__ cfr,
                                            const double *wr, double *c_rhs)
 {
-  constexpr int U = 2, J = 4;
+  constexpr int U = CSB_RESTRICT_U, J = 4;
   const int first = SINGLE ? threadIdx.x : blockIdx.x*PT + threadIdx.x;
   const int step = SINGLE ? PT : gridDim.x*PT;
   for (int base = first; base < nc; base += U*step) {
@@ -2185,7 +2193,7 @@ template <bool SINGLE>
 __device__ __noinline__ void prolong_rows_to(int n, const int *__restrict__ coarse_row,
                                              const double *c_vx, const double *vx, double *dst)
 {
-  constexpr int U = 4;
+  constexpr int U = CSB_PROLONG_U;
   const int first = SINGLE ? threadIdx.x : blockIdx.x*PT + threadIdx.x;
   const int step = SINGLE ? PT : gridDim.x*PT;
   for (int base = first; base < n; base += U*step) {
@@ -2215,7 +2223,7 @@ __device__ __noinline__ void restrict_rows_first(int nc, const int *__restrict__
                                                  double *c_rhs, int mode, double w0,
                                                  const double *c_inv, double *c_start)
 {
-  constexpr int U = 2, J = 4;
+  constexpr int U = CSB_RESTRICT_U, J = 4;
   const int first = SINGLE ? threadIdx.x : blockIdx.x*PT + threadIdx.x;
   const int step = SINGLE ? PT : gridDim.x*PT;
   for (int base = first; base < nc; base += U*step) {

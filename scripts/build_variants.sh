@@ -11,6 +11,6 @@ for spec in "$@"; do
     -Xcompiler -fPIC -Iinclude -I$HERE -ccbin /usr/bin/g++ $defs -c $HERE/persistent.cu -o /tmp/persistent_$tag.o
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ \
     -o $HERE/libcsb200_$tag.so /tmp/persistent_$tag.o $HERE/kernels.o $HERE/runtime.o $HERE/sles.o \
-    $HERE/halo.o $HERE/comm.o $HERE/grid_host.o -Xcompiler -fopenmp -lgomp -ldl
+    $HERE/halo.o $HERE/comm.o $HERE/assembler.o $HERE/grid_host.o -Xcompiler -fopenmp -lgomp -ldl
   echo "built $HERE/libcsb200_$tag.so ($defs)"
 done
