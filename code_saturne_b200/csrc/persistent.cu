@@ -103,10 +103,10 @@ constexpr int PIPE_OFF = BAR_TGT_OFF + 16;            /* PipeState */
 
 /* rows in flight per thread in the transfer operators (independent gather chains) */
 #ifndef CSB_PROLONG_U
-#define CSB_PROLONG_U 4
+#define CSB_PROLONG_U 8
 #endif
 #ifndef CSB_RESTRICT_U
-#define CSB_RESTRICT_U 2
+#define CSB_RESTRICT_U 6
 #endif
 
 /* Release / acquire fences of the message-passing patterns below.  __threadfence() is a
