@@ -575,10 +575,13 @@ constexpr int NG3 = 8;
    gathered in line, from the ghost buffer (the default: measured faster, see sles.cu
    build_dist_level); 2 rows with ghost columns are parked and finished after the wait
    (the overlapped form, CSB_HALO_OVERLAP=1) */
-template <bool SINGLE, int GHOST, int GD, class F>
-__device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
-                                          const double *ghost, unsigned char *s_raw,
-                                          const F f, double *acc_out)
+/* NOVAL: the matrix is a 0/1 matrix given by its structure alone (the restriction: rows of the
+   next level, columns = this level's rows, cs_grid.cpp:9025-9030): no value array is staged
+   and a row sum is the sum of the gathered x values in CSR order. */
+template <bool SINGLE, int GHOST, int GD, bool NOVAL, class F>
+__device__ __noinline__ void spmv_phase_gv(const MgLevelDesc &L, const double *x,
+                                           const double *ghost, unsigned char *s_raw,
+                                           const F f, double *acc_out)
 {
   constexpr int NGS = (GD == 3) ? NG3 : NG;      /* gathers per register set */
   constexpr int PARKED = 0x40000000;             /* flag carried in the row's start offset */
@@ -635,9 +638,9 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
           const unsigned ri_b = (unsigned)(((rows + 1)*4 + 15) & ~15);
           const unsigned v_b = (unsigned)((rows*8 + 15) & ~15);
           producer_acquire(sv, q);
-          mbar_expect_tx(bar, 4u*nc + 8u*nv + ri_b + (unsigned)n_ops*v_b);
+          mbar_expect_tx(bar, 4u*nc + (NOVAL ? 0u : 8u*nv) + ri_b + (unsigned)n_ops*v_b);
           if (nc > 0) bulk_load(sb, col_id + ka, 4u*nc, bar);
-          if (nv > 0) bulk_load(sb + off_val, x_val + kb, 8u*nv, bar);
+          if (!NOVAL && nv > 0) bulk_load(sb + off_val, x_val + kb, 8u*nv, bar);
           bulk_load(sb + off_ri, row_index + r0, ri_b, bar);
 #pragma unroll
           for (int v = 0; v < F::NV; v++)
@@ -697,7 +700,7 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
           double sii = 0.0;
 #pragma unroll
           for (int e = 0; e < NGS; e++)
-            if (ks + e < ke) sii += s_val[ks + e] * gg[e];
+            if (ks + e < ke) sii += NOVAL ? gg[e] : s_val[ks + e] * gg[e];
           if (ks + NGS < ke) {
             /* row longer than the gather pipeline: the rest is gathered NT at a time
                (one L2 latency per batch, not per entry), in registers the first NG
@@ -720,7 +723,7 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
               }
 #pragma unroll
               for (int e = 0; e < NT; e++)
-                if (kb + e < ke) sii += s_val[kb + e] * gt[e];
+                if (kb + e < ke) sii += NOVAL ? gt[e] : s_val[kb + e] * gt[e];
             }
           }
           if (GHOST == 2 && parked) bsum[r0 + tid] = sii;
@@ -812,6 +815,14 @@ __device__ __noinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
   if (acc_out != nullptr) {
     acc_out[0] = acc[0]; acc_out[1] = acc[1]; acc_out[2] = acc[2]; acc_out[3] = acc[3];
   }
+}
+
+template <bool SINGLE, int GHOST, int GD, class F>
+__device__ __forceinline__ void spmv_phase_g(const MgLevelDesc &L, const double *x,
+                                             const double *ghost, unsigned char *s_raw,
+                                             const F &f, double *acc_out)
+{
+  spmv_phase_gv<SINGLE, GHOST, GD, false>(L, x, ghost, s_raw, f, acc_out);
 }
 
 template <bool SINGLE, class F>
@@ -2264,6 +2275,25 @@ __device__ __noinline__ void restrict_rows_first(int nc, const int *__restrict__
   }
 }
 
+/* restriction through the slab pipeline: the 0/1 matrix (c_f_row_index, c_f_row_ids) times the
+   residual, + the next level's first sweep from the restricted value (operand: its inverse
+   diagonal) */
+struct EpiRestrictFirst {
+  static constexpr int NV = 1;
+  int mode;
+  double w0;
+  const double *c_inv;
+  double *c_rhs, *c_start;
+  __device__ __forceinline__ int nv() const { return (c_start != nullptr) ? 1 : 0; }
+  __device__ __forceinline__ const double *src(int) const { return c_inv; }
+  template <int S>
+  __device__ __forceinline__ void epi(int r, double sii, const double *op, double (&)[4]) const
+  {
+    c_rhs[r] = sii;
+    if (c_start != nullptr) c_start[r] = smooth_first_value(mode, w0, sii, op[0]);
+  }
+};
+
 struct VcProf {
   MgState *ms;
   unsigned long long t_last;
@@ -2340,8 +2370,19 @@ __device__ __forceinline__ void vc_descend(const FcgMgParams &S, const Persisten
        level's rows of the other ranks arrive later) */
     const bool fuse = (level + 1 < S.n_levels - 1) && (level + 1 != S.merge_level);
     double *c_start = fuse ? sweep_start(sp.n_iter - 1, C.vx, S.tmp) : nullptr;
-    restrict_rows_first<SINGLE>(L.n_rows_next, L.c_f_row_index, L.c_f_row_ids, S.wr, C.rhs, sp.mode,
-                                sp.w[0], smooth_inv(C, sp.mode), c_start);
+    if (L.r_n_slabs > 0) {
+      MgLevelDesc R;
+      R.n_rows = L.n_rows_next; R.n_slabs = L.r_n_slabs; R.slab_rows = L.r_slab_rows;
+      R.row_index = L.c_f_row_index; R.col_id = L.c_f_row_ids; R.x_val = nullptr;
+      R.dist = nullptr;
+      EpiRestrictFirst f;
+      f.mode = sp.mode; f.w0 = sp.w[0]; f.c_inv = smooth_inv(C, sp.mode);
+      f.c_rhs = C.rhs; f.c_start = c_start;
+      spmv_phase_gv<SINGLE, 0, 2, true>(R, S.wr, nullptr, s_raw, f, nullptr);
+    }
+    else
+      restrict_rows_first<SINGLE>(L.n_rows_next, L.c_f_row_index, L.c_f_row_ids, S.wr, C.rhs,
+                                  sp.mode, sp.w[0], smooth_inv(C, sp.mode), c_start);
     phase_barrier<SINGLE>(P.barrier);
   }
   pf.mark(level, MG_PROF_RESTRICT);

@@ -15,6 +15,9 @@ struct MgLevelDesc {
   int           level_id;      /* index of the level (slot of its exchange counter) */
   int           gather_depth;  /* 2, or 3 when no row has more than 8 entries (persistent.cu) */
   int           row_len_max;   /* longest row (entries) */
+  int           r_slab_rows;   /* slab plan of the restriction to the next level (rows = rows of
+                                  the next level, entries = this level's rows); 0: none */
+  int           r_n_slabs;
   const int    *row_index;
   const int    *col_id;
   const double *d_val;

@@ -271,6 +271,14 @@ namespace csb { void gs_plan_free(GsPlan *p) { delete p; } }
 
 namespace {
 
+/* restriction through the bulk-copy ring of the persistent kernel (CSB_RESTRICT_RING=0: the
+   register-batched gather form) */
+bool restrict_ring_enabled()
+{
+  static int v = env_int("CSB_RESTRICT_RING", 1);
+  return v != 0;
+}
+
 int sb_rows_threshold()
 {
   static int v = env_int("CSB_SB_ROWS", 512);   /* measured: 796-row level faster on the grid, 263-row level in one CTA */
@@ -1484,6 +1492,8 @@ struct MgLevel {
   DevBuf<int>         coarse_row;                 /* this level's rows -> next level */
   DevBuf<int>         c_f_row_index, c_f_row_ids; /* next level rows -> this level's rows */
   std::vector<int>    h_coarse_row;
+  int                 r_slab_rows = 0, r_n_slabs = 0;   /* slab plan of (c_f_row_index, c_f_row_ids) */
+  size_t              r_max_entries = 0;
   /* solve data */
   DevBuf<double>      ad_inv, rhs, vx;
   DevBuf<double>      l1_inv;                     /* L1 Jacobi smoother only */
@@ -2441,6 +2451,10 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     CoarseStructure cs;
     build_coarse_structure(fm->n_rows, fm->h_row_index.data(), fm->host_col_id(),
                            f->h_coarse_row.data(), c_n_rows, cs);
+    /* the restriction as a 0/1 CSR matrix (coarse rows x fine rows): same slab pipeline as the
+       matrix products in the persistent kernel */
+    if (restrict_ring_enabled())
+      plan_slabs(cs.c_f_row_index, c_n_rows, f->r_slab_rows, f->r_n_slabs, f->r_max_entries);
     HostVec<int> c_h_face_cell;
     if (native)
       number_coarse_faces_native(f_n_faces, f_h_face_cell, f->h_coarse_row.data(), c_n_rows,
@@ -2680,6 +2694,8 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
       plan_slabs(m->h_row_index, m->n_rows, d.slab_rows, d.n_slabs, me);
       d.gather_depth = plan_gather_depth(m->h_row_index, m->n_rows, &d.row_len_max);
       max_entries = std::max(max_entries, me);
+      max_entries = std::max(max_entries, lv->r_max_entries);
+      d.r_slab_rows = lv->r_slab_rows; d.r_n_slabs = lv->r_n_slabs;
       d.n_rows = m->n_rows;
       /* rows of the next level THIS rank restricts to: at the merge boundary its own part
          of the merged level */
