@@ -652,6 +652,19 @@ class Matrix:
                                        *[_ptr(a) for a in args]) != 0:
             _err("csb_matrix_compute_coeffs")
 
+    def diffusion_potential(self, pvar, i_visc, b_visc=None, cofaf=None, cofbf=None, init=1, inc=1,
+                            diverg=None):
+        """cs_diffusion_potential without flux reconstruction on this matrix's mesh."""
+        L = load_library()
+        L.csb_diffusion_potential.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
+        div = np.zeros(self.n_rows) if diverg is None else _f64(np.asarray(diverg)).copy()
+        args = [a if a is None or not isinstance(a, np.ndarray) else _f64(a)
+                for a in (pvar, cofaf, cofbf, i_visc, b_visc)]
+        if L.csb_diffusion_potential(self.handle, int(init), int(inc), *[_ptr(a) for a in args],
+                                     _ptr(div)) != 0:
+            _err("csb_diffusion_potential")
+        return div
+
     def compute_coeffs_vector(self, i_visc, b_visc=None, cofbfp=None, coefbp=None, fimp=None,
                               i_massflux=None, b_massflux=None, iconvp=0, idiffp=1, ndircp=1,
                               thetap=1., relaxp=1.):

@@ -620,6 +620,9 @@ bool launch_coarse_native(const NativeCoarseArgs &a);
 /* x_val[k] = xa[c2f[k]] (cs_matrix_set_coefficients from edges, symmetric, unique faces) */
 bool launch_native_to_msr(int nnz, const int *c2f, const double *xa, double *x_val);
 
+bool launch_diffusion_potential(const _csb_matrix_t *m, int init, int inc, const double *pvar,
+                                const double *cofaf, const double *cofbf, const double *i_visc,
+                                const double *b_visc, double *diverg);
 /* matrix assembler (assembler.cu): slot s < n_rows is the diagonal of row s, slot
    n_rows + k the extra-diagonal entry k; every slot adds val[src[j]] for j in
    [index[s], index[s+1]) to its current value, in that order */

@@ -2274,6 +2274,65 @@ bool launch_assembler_fold(int n_rows, int nnz, const int *index, const int *src
   return post_launch("assembler_fold");
 }
 
+namespace {
+/* cs_diffusion_potential without flux reconstruction (cs_convection_diffusion.cpp:8869-8889,
+   :8975-8982): the reference scatters face fluxes to the two cells in face order; a thread owns a
+   cell and takes its interior faces by ascending face id (the next one is the smallest face id
+   above the last one among the row's entries), then its boundary faces (stored ascending) --
+   the same additions in the same order, no atomics. */
+__global__ void k_diffusion_potential(int n_rows, const int *__restrict__ row_index,
+                                      const int *__restrict__ col_id,
+                                      const int *__restrict__ c2f,
+                                      const short *__restrict__ c2f_sgn,
+                                      const int *__restrict__ cell_b_faces_idx,
+                                      const int *__restrict__ cell_b_faces, int init, int inc,
+                                      const double *__restrict__ pvar,
+                                      const double *__restrict__ cofaf,
+                                      const double *__restrict__ cofbf,
+                                      const double *__restrict__ i_visc,
+                                      const double *__restrict__ b_visc, double *diverg)
+{
+  const int c = blockIdx.x*blockDim.x + threadIdx.x;
+  if (c >= n_rows) return;
+  const int s = row_index[c], e = row_index[c+1];
+  const double pc = pvar[c];
+  double d = (init >= 1) ? 0. : diverg[c];
+  int last = -1;
+  while (true) {
+    int best = INT_MAX, bk = -1;
+    for (int k = s; k < e; k++) {
+      const int f = c2f[k];
+      if (f > last && f < best) { best = f; bk = k; }
+    }
+    if (bk < 0) break;
+    last = best;
+    const double pj = pvar[col_id[bk]];
+    if (c2f_sgn[bk] > 0) d += i_visc[best]*(pc - pj);      /* this cell is the face's first */
+    else d += -(i_visc[best]*(pj - pc));
+  }
+  if (cell_b_faces_idx != nullptr)
+    for (int k = cell_b_faces_idx[c]; k < cell_b_faces_idx[c+1]; k++) {
+      const int f = cell_b_faces[k];
+      const double flux_d = inc*cofaf[f] + cofbf[f]*pc;
+      d += b_visc[f]*flux_d;
+    }
+  diverg[c] = d;
+}
+} // anonymous namespace
+
+bool launch_diffusion_potential(const _csb_matrix_t *m, int init, int inc, const double *pvar,
+                                const double *cofaf, const double *cofbf, const double *i_visc,
+                                const double *b_visc, double *diverg)
+{
+  if (m->n_rows < 1) return true;
+  const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  k_diffusion_potential<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
+    m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, m->c2f_sgn.p,
+    bnd ? m->cell_b_faces_idx.p : nullptr, bnd ? m->cell_b_faces.p : nullptr, init, inc, pvar,
+    cofaf, cofbf, i_visc, b_visc, diverg);
+  return post_launch("diffusion_potential");
+}
+
 bool launch_native_to_msr(int nnz, const int *c2f, const double *xa, double *x_val)
 {
   if (nnz < 1) return true;

@@ -651,6 +651,58 @@ int csb_matrix_set_mesh_association(csb_matrix_t *m, csb_lnum_t n_faces,
   return ok ? 0 : -1;
 }
 
+/* cs_diffusion_potential (src/alge/cs_convection_diffusion.cpp:8743-8990), no flux
+   reconstruction: diverg (+)= divergence of the diffusive flux of pvar over the mesh the matrix
+   is associated with.  Arrays may be host or device pointers; diverg on the host is copied in
+   (init = 0) and out. */
+int csb_diffusion_potential(const csb_matrix_t *m, int init, int inc, const csb_real_t *pvar,
+                            const csb_real_t *cofaf, const csb_real_t *cofbf,
+                            const csb_real_t *i_visc, const csb_real_t *b_visc,
+                            csb_real_t *diverg)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (!m->has_mesh || m->db != 1 || m->halo != nullptr) {
+    set_error("csb_diffusion_potential: needs a scalar matrix with its mesh association "
+              "(csb_matrix_set_mesh_association) on one rank");
+    return -1;
+  }
+  if (init < 0) { set_error("csb_diffusion_potential: invalid value of init"); return -1; }
+  const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  if (pvar == nullptr || diverg == nullptr || (m->n_faces > 0 && i_visc == nullptr)
+      || (bnd && (cofaf == nullptr || cofbf == nullptr || b_visc == nullptr))) {
+    set_error("csb_diffusion_potential: null array");
+    return -1;
+  }
+  Context &c = ctx();
+  const size_t nr = (size_t)m->n_rows, nf = (size_t)m->n_faces, nb = bnd ? (size_t)m->n_b_faces : 0;
+  const double *src[6] = {pvar, i_visc, cofaf, cofbf, b_visc, diverg};
+  const size_t len[6] = {nr, nf, nb, nb, nb, nr};
+  const double *dev[6];
+  csb::DevBuf<double> stage;
+  size_t need = 0;
+  for (int i = 0; i < 6; i++)
+    if (len[i] > 0 && !is_device_ptr(src[i])) need += len[i];
+  if (need > 0 && !stage.alloc(need)) return -1;
+  size_t off = 0;
+  for (int i = 0; i < 6; i++) {
+    dev[i] = src[i];
+    if (len[i] > 0 && !is_device_ptr(src[i])) {
+      if ((i < 5 || init == 0)
+          && !CSB_CUDA(cudaMemcpyAsync(stage.p + off, src[i], sizeof(double)*len[i],
+                                       cudaMemcpyHostToDevice, c.stream))) return -1;
+      dev[i] = stage.p + off;
+      off += len[i];
+    }
+  }
+  double *d_div = const_cast<double *>(dev[5]);
+  if (!csb::launch_diffusion_potential(m, init, inc, dev[0], dev[2], dev[3], dev[1], dev[4], d_div))
+    return -1;
+  if (d_div != diverg
+      && !CSB_CUDA(cudaMemcpyAsync(diverg, d_div, sizeof(double)*nr, cudaMemcpyDeviceToHost,
+                                   c.stream))) return -1;
+  return CSB_CUDA(cudaStreamSynchronize(c.stream)) ? 0 : -1;
+}
+
 /* Boundary faces of the mesh by adjacent cell (cs_mesh_t::b_face_cells); builds the
    cell -> boundary faces adjacency the reference keeps in cs_mesh_adjacencies
    (cell_b_faces_idx / cell_b_faces, src/mesh/cs_mesh_adjacencies.cpp:705-760). */

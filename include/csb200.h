@@ -299,6 +299,20 @@ int  csb_matrix_compute_coeffs_vector(csb_matrix_t *m, int iconvp, int idiffp, i
                                       const csb_real_t *b_massflux, const csb_real_t *i_visc,
                                       const csb_real_t *b_visc);
 
+/* cs_diffusion_potential (src/alge/cs_convection_diffusion.cpp:8743-8990; the explicit
+   right-hand-side operator of the pressure correction) without
+   flux reconstruction (eqp->ircflu = 0; on an orthogonal mesh the reconstructed branch adds
+   exact zeros): init >= 1 zeroes diverg first, then
+     diverg[c0] += i_visc[f] (pvar[c0] - pvar[c1]),  diverg[c1] -= the same   (interior faces)
+     diverg[c]  += b_visc[f] (inc cofaf[f] + cofbf[f] pvar[c])                 (boundary faces)
+   summed per cell in the reference's order (ascending interior face ids, then ascending
+   boundary face ids): bit-identical to its one-thread result.  Uses the mesh association of m
+   (face of every entry) and csb_matrix_set_boundary_faces; host or device pointers. */
+int  csb_diffusion_potential(const csb_matrix_t *m, int init, int inc, const csb_real_t *pvar,
+                             const csb_real_t *cofaf, const csb_real_t *cofbf,
+                             const csb_real_t *i_visc, const csb_real_t *b_visc,
+                             csb_real_t *diverg);
+
 /* Copy of the MSR coefficients held in HBM (cs_matrix_get_msr_arrays, cs_matrix.cpp:6199,
    lends the host arrays; these live on the device).  Either pointer may be NULL. */
 int  csb_matrix_get_coefficients(const csb_matrix_t *m, csb_real_t *d_val, csb_real_t *x_val);

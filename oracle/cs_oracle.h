@@ -169,6 +169,12 @@ ora_mg_t   *ora_mg_setup(ora_grid_t *fine, int aggregation_limit, int n_levels_m
                          int n_g_rows_min, double p0p1_relax, int n_threads);
 void        ora_mg_free(ora_mg_t *mg, int free_fine);
 
+/* cs_diffusion_potential without flux reconstruction: cs_oracle_rhs.c */
+void   ora_diffusion_potential(int n_cells, int n_i_faces, const int *i_face_cells,
+                               int n_b_faces, const int *b_face_cells, int init, int inc,
+                               const double *pvar, const double *cofaf, const double *cofbf,
+                               const double *i_visc, const double *b_visc, double *diverg);
+
 /* matrix assembler on one rank, MSR target: cs_oracle_assembler.c */
 int    ora_assembler_structure(int n_rows, int n, const long long *row_g_id,
                                const long long *col_g_id, long long l_range_0,

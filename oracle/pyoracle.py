@@ -46,7 +46,7 @@ def _f64(a):
 def build_oracle(force: bool = False) -> str:
     """Compile oracle/cs_oracle.c into oracle/libcs_oracle.so (gcc, seconds)."""
     so = os.path.join(_HERE, "libcs_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("cs_oracle.c", "cs_oracle_native.c", "cs_oracle_assembler.c", "cs_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("cs_oracle.c", "cs_oracle_native.c", "cs_oracle_assembler.c", "cs_oracle_rhs.c", "cs_oracle.h")]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(map(os.path.getmtime, srcs)):
         subprocess.check_call(["make", "-f", "oracle/Makefile"], cwd=_ROOT,
                               stdout=subprocess.DEVNULL)
@@ -341,6 +341,17 @@ class Oracle:
                                                      C.c_longlong(l0), _dp(bv), _dp(d), _dp(x))
             assert miss == 0
         return ri, ci, d, x[:nnz]
+
+    def diffusion_potential(self, s, b_face_cells, pvar, cofaf, cofbf, i_visc, b_visc, init=1,
+                            inc=1, diverg=None):
+        div = np.zeros(s.n_rows) if diverg is None else _f64(diverg).copy()
+        fc, bfc = _i32(s.face_cells), _i32(b_face_cells)
+        self.lib.ora_diffusion_potential.restype = None
+        self.lib.ora_diffusion_potential(
+            C.c_int(s.n_rows), C.c_int(len(fc)), _ip(fc), C.c_int(len(bfc)), _ip(bfc),
+            C.c_int(init), C.c_int(inc), _dp(_f64(pvar)), _dp(_f64(cofaf)), _dp(_f64(cofbf)),
+            _dp(_f64(i_visc)), _dp(_f64(b_visc)), _dp(div))
+        return div
 
     def aggregation_fc(self, level, n_rows, face_cells, da, xa, max_aggregation=3):
         fc = _i32(face_cells)
@@ -650,6 +661,18 @@ class RefLib:
         d, x = np.zeros(n_rows), np.zeros(max(nnz, 1))
         self.lib.csref_get_msr_arrays(h, _ip(ri), _ip(ci), _dp(d), _dp(x))
         return h, ri, ci[:nnz], d, x[:nnz]
+
+    def diffusion_potential(self, h, s, b_face_cells, b_geo, i_face_cog, pvar, cofaf, cofbf,
+                            i_visc, b_visc, init=1, inc=1, diverg=None):
+        """cs_diffusion_potential without flux reconstruction on the system's mesh."""
+        div = np.zeros(s.n_rows) if diverg is None else _f64(diverg).copy()
+        bfc = _i32(b_face_cells)
+        r = self.lib.csref_diffusion_potential(
+            h, _ip(_i32(s.face_cells)), C.c_int(len(bfc)), _ip(bfc), _dp(_f64(b_geo)),
+            _dp(_f64(i_face_cog)), C.c_int(init), C.c_int(inc), _dp(_f64(pvar)), _dp(_f64(cofaf)),
+            _dp(_f64(cofbf)), _dp(_f64(i_visc)), _dp(_f64(b_visc)), _dp(div))
+        assert r == 0
+        return div
 
     def system_block(self, n_rows, db, ri, ci, d_val, x_val, symmetric=False):
         """MSR matrix with db x db diagonal blocks (d_val: n_rows*db*db) built by the reference."""

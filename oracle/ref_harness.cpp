@@ -47,6 +47,9 @@
 #include "base/cs_field.h"
 #include "alge/cs_matrix_building.h"
 #include "alge/cs_matrix_assembler.h"
+#include "alge/cs_convection_diffusion.h"
+#include "base/cs_parameters.h"
+#include "base/cs_boundary_conditions_set_coeffs.h"
 #include "alge/cs_blas.h"
 #include "alge/cs_matrix.h"
 #include "alge/cs_matrix_default.h"
@@ -813,6 +816,105 @@ csref_matrix_compute_coeffs_sym(void *sys, int n_b_faces, const int *b_face_cell
   return csref_matrix_compute_coeffs(sys, n_b_faces, b_face_cells, 0, idiffp, ndircp, thetap,
                                      relaxp, nullptr, cofbfp, rovsdt, nullptr, nullptr, i_visc,
                                      b_visc, nullptr, d_out, x_out);
+}
+
+/* cs_diffusion_potential (src/alge/cs_convection_diffusion.cpp:8743-8990) without flux
+   reconstruction (eqp->ircflu = 0) on the mesh of a system with mesh association: the
+   divergence of the diffusive flux of pvar, interior faces then boundary faces
+   (flux_diff = inc*af + bf*pvar, cs_boundary_conditions_set_coeffs.cpp:172-185).
+   Boundary geometry (b_geo: per boundary face its unit normal [3], centre [3], distance to
+   the cell centre [1]) and i_face_cog feed the reference's boundary reconstruction
+   (cs_gradient_boundary_iprime_lsq_s), whose result is multiplied by diipb = 0 here.
+   diverg: n_rows values, read (init = 0) and written. */
+int
+csref_diffusion_potential(void          *sys,
+                          const int     *face_cells,
+                          int            n_b_faces,
+                          const int     *b_face_cells,
+                          const double  *b_geo,        /* 7 per boundary face */
+                          const double  *i_face_cog,   /* 3 per interior face */
+                          int            init,
+                          int            inc,
+                          const double  *pvar,
+                          const double  *cofaf,
+                          const double  *cofbf,
+                          const double  *i_visc,
+                          const double  *b_visc,
+                          double        *diverg)
+{
+  ref_system *s = static_cast<ref_system *>(sys);
+  _set_glob_mesh_faces(s, face_cells);
+  cs_mesh_t *mesh = cs_glob_mesh;
+  const cs_lnum_t n_cells = s->n_rows, n_i_faces = s->n_faces;
+
+  CS_FREE(mesh->b_face_cells);
+  mesh->n_b_faces = n_b_faces;
+  mesh->n_b_faces_all = n_b_faces;
+  CS_MALLOC(mesh->b_face_cells, (n_b_faces > 0) ? n_b_faces : 1, cs_lnum_t);
+  memcpy(mesh->b_face_cells, b_face_cells, sizeof(cs_lnum_t)*n_b_faces);
+  if (mesh->b_face_numbering != nullptr)
+    cs_numbering_destroy(&(mesh->b_face_numbering));
+  mesh->b_face_numbering = cs_numbering_create_default(n_b_faces);
+  if (mesh->i_face_numbering != nullptr)
+    cs_numbering_destroy(&(mesh->i_face_numbering));
+  mesh->i_face_numbering = cs_numbering_create_default(n_i_faces);
+
+  if (cs_glob_mesh_quantities == nullptr)
+    cs_glob_mesh_quantities = cs_mesh_quantities_create();
+  cs_mesh_quantities_t *mq = cs_glob_mesh_quantities;
+  cs_mesh_adjacencies_finalize();
+  cs_mesh_adjacencies_initialize();
+  cs_mesh_adjacencies_update_mesh();
+
+  /* geometry of an orthogonal mesh: II' = JJ' = 0 */
+  std::vector<cs_real_t> b_dist(n_b_faces > 0 ? n_b_faces : 1), i_dist(n_i_faces > 0 ? n_i_faces : 1, 1.);
+  std::vector<cs_nreal_t> b_un(3*(n_b_faces > 0 ? n_b_faces : 1));
+  std::vector<cs_real_t> b_cog(3*(n_b_faces > 0 ? n_b_faces : 1));
+  std::vector<cs_rreal_t> zero_b(3*(n_b_faces > 0 ? n_b_faces : 1), 0.),
+                          zero_i(3*(n_i_faces > 0 ? n_i_faces : 1), 0.);
+  for (cs_lnum_t f = 0; f < n_b_faces; f++) {
+    for (int k = 0; k < 3; k++) {
+      b_un[3*f+k] = b_geo[7*f+k];
+      b_cog[3*f+k] = b_geo[7*f+3+k];
+    }
+    b_dist[f] = b_geo[7*f+6];
+  }
+  mq->cell_cen = (cs_real_3_t *)s->cell_cen;
+  mq->b_face_u_normal = (cs_nreal_3_t *)b_un.data();
+  mq->b_dist = b_dist.data();
+  mq->i_dist = i_dist.data();
+  mq->i_face_cog = (cs_real_3_t *)const_cast<double *>(i_face_cog);
+  mq->b_face_cog = (cs_real_3_t *)b_cog.data();
+  mq->i_face_surf = s->face_surf;
+  mq->diipb = (cs_rreal_3_t *)zero_b.data();
+  mq->diipf = (cs_rreal_3_t *)zero_i.data();
+  mq->djjpf = (cs_rreal_3_t *)zero_i.data();
+
+  cs_equation_param_t eqp = cs_parameters_equation_param_default();
+  eqp.ircflu = 0;
+  eqp.verbosity = 0;
+
+  cs_field_bc_coeffs_t bc;
+  memset(&bc, 0, sizeof(bc));
+  std::vector<cs_real_t> a(n_b_faces > 0 ? n_b_faces : 1, 0.), b(n_b_faces > 0 ? n_b_faces : 1, 1.);
+  bc.a = a.data(); bc.b = b.data();
+  bc.af = const_cast<cs_real_t *>(cofaf);
+  bc.bf = const_cast<cs_real_t *>(cofbf);
+
+  std::vector<cs_real_t> _pvar(pvar, pvar + n_cells), visel(n_cells > 0 ? n_cells : 1, 1.);
+  std::vector<cs_real_t> _div(n_cells > 0 ? n_cells : 1, 0.);
+  if (!init) memcpy(_div.data(), diverg, sizeof(cs_real_t)*n_cells);
+
+  cs_diffusion_potential(nullptr, &eqp, mesh, mq, init, inc, 0, nullptr, _pvar.data(), &bc,
+                         i_visc, b_visc, visel.data(), _div.data());
+  memcpy(diverg, _div.data(), sizeof(cs_real_t)*n_cells);
+
+  /* the quantities point to this call's arrays */
+  mq->cell_cen = nullptr; mq->b_face_u_normal = nullptr; mq->b_dist = nullptr;
+  mq->i_dist = nullptr; mq->i_face_cog = nullptr; mq->b_face_cog = nullptr;
+  mq->i_face_surf = nullptr; mq->diipb = nullptr; mq->diipf = nullptr; mq->djjpf = nullptr;
+  CS_FREE(bc.val_f); CS_FREE(bc.flux_diff);
+  return 0;
 }
 
 /* Build the grid hierarchy with the reference's cs_grid_coarsen, following

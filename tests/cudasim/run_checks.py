@@ -336,6 +336,24 @@ def check_assembler(ora):
         m.destroy(); ma.destroy()
 
 
+def check_rhs(ora):
+    """cs_diffusion_potential without reconstruction: per-cell gathers in face order against
+    the reference's fixtures"""
+    sys.path.insert(0, GOLD)
+    from make_golden_rhs import CASES, rhs_input
+    for N in CASES:
+        g = np.load(os.path.join(GOLD, f"rhs_N{N}.npz"))
+        s, bfc, _, _, f = rhs_input(N)
+        for native in (False, True):
+            m = csb.Matrix.from_system_native(s) if native else csb.Matrix.from_system(s)
+            m.set_boundary_faces(bfc)
+            for init, inc in ((1, 1), (0, 1), (1, 0)):
+                d = m.diffusion_potential(f["pvar"], f["i_visc"], f["b_visc"], f["cofaf"], f["cofbf"],
+                                          init=init, inc=inc, diverg=f["div0"])
+                assert np.array_equal(d, g[f"div_init{init}_inc{inc}"]), (N, native, init, inc)
+            m.destroy()
+
+
 def check_pairwise(ora):
     g = np.load(os.path.join(GOLD, "pairwise_N8_neumann.npz"))
     s = cube_poisson(8, "neumann")
@@ -435,7 +453,7 @@ def check_k_cycle(ora):
     c.destroy(); m.destroy()
 
 
-CHECKS = {"spmv_pcg": check_spmv_pcg, "native": check_native, "assembler": check_assembler, "k_cycle": check_k_cycle, "compute_coeffs": check_compute_coeffs, "pairwise": check_pairwise, "galerkin": check_galerkin, "block3_jacobi": check_block3_jacobi, "general_pc": check_general_pc,
+CHECKS = {"spmv_pcg": check_spmv_pcg, "rhs": check_rhs, "native": check_native, "assembler": check_assembler, "k_cycle": check_k_cycle, "compute_coeffs": check_compute_coeffs, "pairwise": check_pairwise, "galerkin": check_galerkin, "block3_jacobi": check_block3_jacobi, "general_pc": check_general_pc,
           "kernel_per_phase": check_kernel_per_phase_paths, "smoothers": check_smoothers,
           "cycle_pc": check_cycle_pc, "fcg_mgpc": check_fcg_mgpc}
 

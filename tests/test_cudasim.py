@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("check", ["spmv_pcg", "smoothers", "cycle_pc", "fcg_mgpc", "general_pc",
-                                   "kernel_per_phase", "block3_jacobi", "galerkin", "pairwise", "compute_coeffs", "k_cycle", "native", "assembler"])
+                                   "kernel_per_phase", "block3_jacobi", "galerkin", "pairwise", "compute_coeffs", "k_cycle", "native", "assembler", "rhs"])
 def test_cudasim(check):
     env = dict(os.environ)
     env.pop("CSB_LIB", None)

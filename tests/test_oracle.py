@@ -809,3 +809,43 @@ def test_oracle_assembler_matches_reference_live(oracle):
     ref.destroy(h)
     ri2, ci2, d2, x2 = oracle.assembler(n, rows, cols, batches, 77)
     assert all(np.array_equal(a, b) for a, b in ((ri, ri2), (ci, ci2), (d, d2), (x, x2)))
+
+
+# ------------------- cs_diffusion_potential without reconstruction (f2; cs_oracle_rhs.c)
+
+@pytest.mark.parametrize("N", [5, 9])
+def test_oracle_diffusion_potential_matches_golden(oracle, N):
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_rhs import rhs_input
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"rhs_N{N}.npz"))
+    s, bfc, _, _, f = rhs_input(N)
+    for init, inc in ((1, 1), (0, 1), (1, 0)):
+        d = oracle.diffusion_potential(s, bfc, f["pvar"], f["cofaf"], f["cofbf"], f["i_visc"],
+                                       f["b_visc"], init=init, inc=inc, diverg=f["div0"])
+        assert np.array_equal(d, g[f"div_init{init}_inc{inc}"]), (init, inc)
+
+
+def test_oracle_diffusion_potential_matches_reference_live(oracle):
+    from oracle.pyoracle import RefLib, ref_available
+    from make_golden_rhs import rhs_input
+    if not ref_available():
+        pytest.skip("oracle/_ref/libcsref.so not built (needs /root/reference)")
+    ref = RefLib(4)          # the face loops follow the mesh numbering, not the thread count
+    s, bfc, b_geo, ifc, f = rhs_input(14, seed=11)
+    h = ref.system(s)
+    r = ref.diffusion_potential(h, s, bfc, b_geo, ifc, f["pvar"], f["cofaf"], f["cofbf"],
+                                f["i_visc"], f["b_visc"])
+    ref.destroy(h)
+    ref.set_threads(1)
+    o = oracle.diffusion_potential(s, bfc, f["pvar"], f["cofaf"], f["cofbf"], f["i_visc"],
+                                   f["b_visc"])
+    assert np.array_equal(r, o)
+    # a Poisson matrix applied to pvar is this operator with the matrix's own face values
+    xa = np.zeros(s.n_faces)
+    up = np.asarray(s.c2f_sgn) > 0
+    xa[np.asarray(s.c2f)[up]] = np.asarray(s.x_val)[up]
+    zb = np.zeros(len(bfc))
+    d = oracle.diffusion_potential(s, bfc, f["pvar"], zb, zb, -xa, zb)
+    y = oracle.spmv(s.row_index, s.col_id, s.d_val * 0., s.x_val, f["pvar"])
+    rowsum = np.add.reduceat(np.append(s.x_val, 0.), s.row_index[:-1])
+    assert np.allclose(d, y - rowsum * f["pvar"], rtol=0, atol=1e-12)
