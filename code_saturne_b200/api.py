@@ -665,6 +665,36 @@ class Matrix:
             _err("csb_diffusion_potential")
         return div
 
+    def set_face_geometry(self, i_dist, diipf, djjpf, b_face_u_normal, b_dist):
+        L = load_library()
+        L.csb_matrix_set_face_geometry.argtypes = [C.c_void_p] * 6
+        a = [_f64(np.asarray(x)) for x in (i_dist, diipf, djjpf, b_face_u_normal, b_dist)]
+        if L.csb_matrix_set_face_geometry(self.handle, *[_ptr(x) for x in a]) != 0:
+            _err("csb_matrix_set_face_geometry")
+
+    def gradient_lsq(self, pvar, coefa=None, coefb=None, inc=1):
+        """least-squares cell gradient (cs_gradient_scalar_synced_input, CS_GRADIENT_LSQ)"""
+        L = load_library()
+        L.csb_gradient_scalar_lsq.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+        grad = np.zeros(3 * self.n_rows)
+        a = [x if x is None or not isinstance(x, np.ndarray) else _f64(x) for x in (pvar, coefa, coefb)]
+        if L.csb_gradient_scalar_lsq(self.handle, int(inc), *[_ptr(x) for x in a], _ptr(grad)) != 0:
+            _err("csb_gradient_scalar_lsq")
+        return grad.reshape(-1, 3)
+
+    def diffusion_potential_rc(self, pvar, coefa, coefb, cofaf, cofbf, i_visc, b_visc, visel,
+                               irecmf=0, init=1, inc=1, diverg=None):
+        """cs_diffusion_potential with flux reconstruction (least-squares gradient)"""
+        L = load_library()
+        L.csb_diffusion_potential_rc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 9
+        div = np.zeros(self.n_rows) if diverg is None else _f64(np.asarray(diverg)).copy()
+        a = [x if x is None or not isinstance(x, np.ndarray) else _f64(x)
+             for x in (pvar, coefa, coefb, cofaf, cofbf, i_visc, b_visc, visel)]
+        if L.csb_diffusion_potential_rc(self.handle, int(irecmf), int(init), int(inc),
+                                        *[_ptr(x) for x in a], _ptr(div)) != 0:
+            _err("csb_diffusion_potential_rc")
+        return div
+
     def compute_coeffs_vector(self, i_visc, b_visc=None, cofbfp=None, coefbp=None, fimp=None,
                               i_massflux=None, b_massflux=None, iconvp=0, idiffp=1, ndircp=1,
                               thetap=1., relaxp=1.):

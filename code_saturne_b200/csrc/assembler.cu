@@ -232,6 +232,10 @@ csb_matrix_assembler_values_init(csb_matrix_t *m, const csb_matrix_assembler_t *
     set_error("csb_matrix_assembler_values_init: scalar coefficients only");
     return nullptr;
   }
+  if ((size_t)m->n_rows + (size_t)m->nnz > 0x7fffffffULL) {
+    set_error("csb_matrix_assembler_values_init: more than 2^31 matrix entries");
+    return nullptr;
+  }
   if (!CSB_CUDA(cudaMemsetAsync(m->d_val.p, 0, sizeof(double)*(size_t)std::max(m->n_rows, 1), c.stream))
       || !CSB_CUDA(cudaMemsetAsync(m->x_val.p, 0, sizeof(double)*(size_t)std::max(m->nnz, 1), c.stream)))
     return nullptr;

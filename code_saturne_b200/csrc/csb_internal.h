@@ -369,6 +369,13 @@ struct _csb_matrix_t {
      their values stay with the matrix, c2f / c2f_sgn above are the entry -> face map; the
      hierarchy is then built like the reference builds it for such a matrix (face-order
      aggregation and sums, cs_grid.cpp:3997, :5144) */
+  /* face geometry of a non-orthogonal mesh (csb_matrix_set_face_geometry) and the cached
+     least-squares cocg matrices of the cell gradient (single precision like the reference's,
+     cs_gradient_priv.h:54) */
+  csb::DevBuf<double>      i_dist, diipf, djjpf, b_face_u_normal, b_dist;
+  bool        has_face_geo = false;
+  mutable csb::DevBuf<float> cocg_lsq;
+  mutable bool cocg_valid = false;
   bool        from_native = false;
   csb::DevBuf<csb_lnum_t>  face_cell;
   csb::DevBuf<double>      xa;
@@ -623,6 +630,15 @@ bool launch_native_to_msr(int nnz, const int *c2f, const double *xa, double *x_v
 bool launch_diffusion_potential(const _csb_matrix_t *m, int init, int inc, const double *pvar,
                                 const double *cofaf, const double *cofbf, const double *i_visc,
                                 const double *b_visc, double *diverg);
+/* least-squares cell gradient (cs_gradient.cpp:2501-2680, :2695-2900) and the reconstructed
+   form of cs_diffusion_potential (cs_convection_diffusion.cpp:8895-8982) */
+bool launch_lsq_cocg(const _csb_matrix_t *m, float *cocg);
+bool launch_lsq_gradient(const _csb_matrix_t *m, const float *cocg, int inc, const double *pvar,
+                         const double *coefa, const double *coefb, double *grad);
+bool launch_diffusion_potential_rc(const _csb_matrix_t *m, int irecmf, int init, int inc,
+                                   const double *pvar, const double *grad, const double *cofaf,
+                                   const double *cofbf, const double *i_visc,
+                                   const double *b_visc, const double *visel, double *diverg);
 /* matrix assembler (assembler.cu): slot s < n_rows is the diagonal of row s, slot
    n_rows + k the extra-diagonal entry k; every slot adds val[src[j]] for j in
    [index[s], index[s+1]) to its current value, in that order */

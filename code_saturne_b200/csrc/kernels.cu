@@ -2333,6 +2333,254 @@ bool launch_diffusion_potential(const _csb_matrix_t *m, int init, int inc, const
   return post_launch("diffusion_potential");
 }
 
+namespace {
+
+/* cocg of the least-squares gradient, one cell per thread: sum of dc (x) dc / |dc|^2 over the
+   cell's neighbours in adjacency (= MSR) order, then of n (x) n over its boundary faces,
+   ACCUMULATED IN SINGLE PRECISION like the reference's cs_cocg_t (each term is a double
+   expression added to the float), inverted by the float Gauss-Jordan elimination with row
+   pivoting of cs_math_matrix_gauss_inverse (cs_math.h:542-590). */
+__global__ void k_lsq_cocg(int n_rows, const int *__restrict__ row_index,
+                           const int *__restrict__ col_id, const double *__restrict__ cell_cen,
+                           const int *__restrict__ cell_b_faces_idx,
+                           const int *__restrict__ cell_b_faces,
+                           const double *__restrict__ b_un, float *cocg)
+{
+  const int c = blockIdx.x*blockDim.x + threadIdx.x;
+  if (c >= n_rows) return;
+  float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const double cx = cell_cen[3*(size_t)c], cy = cell_cen[3*(size_t)c+1], cz = cell_cen[3*(size_t)c+2];
+  for (int k = row_index[c]; k < row_index[c+1]; k++) {
+    const size_t j = (size_t)col_id[k];
+    const double d0 = cell_cen[3*j] - cx, d1 = cell_cen[3*j+1] - cy, d2 = cell_cen[3*j+2] - cz;
+    const double ddc = 1. / (d0*d0 + d1*d1 + d2*d2);
+    g[0] = (float)((double)g[0] + d0 * d0 * ddc);
+    g[1] = (float)((double)g[1] + d1 * d1 * ddc);
+    g[2] = (float)((double)g[2] + d2 * d2 * ddc);
+    g[3] = (float)((double)g[3] + d0 * d1 * ddc);
+    g[4] = (float)((double)g[4] + d1 * d2 * ddc);
+    g[5] = (float)((double)g[5] + d0 * d2 * ddc);
+  }
+  if (cell_b_faces_idx != nullptr)
+    for (int k = cell_b_faces_idx[c]; k < cell_b_faces_idx[c+1]; k++) {
+      const double *d = b_un + 3*(size_t)cell_b_faces[k];
+      g[0] = (float)((double)g[0] + d[0] * d[0]);
+      g[1] = (float)((double)g[1] + d[1] * d[1]);
+      g[2] = (float)((double)g[2] + d[2] * d[2]);
+      g[3] = (float)((double)g[3] + d[0] * d[1]);
+      g[4] = (float)((double)g[4] + d[1] * d[2]);
+      g[5] = (float)((double)g[5] + d[0] * d[2]);
+    }
+  /* rows are exchanged through their index, like the pointer swaps of the reference */
+  float t[3][6] = {{g[0], g[3], g[5], 1.f, 0.f, 0.f},
+                   {g[3], g[1], g[4], 0.f, 1.f, 0.f},
+                   {g[5], g[4], g[2], 0.f, 0.f, 1.f}};
+  int p[3] = {0, 1, 2};
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    for (int j = i+1; j < 3; j++) {
+      float pii = 0.f, pji = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        if (p[i] == r) pii = t[r][i];
+        if (p[j] == r) pji = t[r][i];
+      }
+      if (fabsf(pii) < fabsf(pji)) { const int tmp = p[j]; p[j] = p[i]; p[i] = tmp; }
+    }
+    float ri[6];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+      if (p[i] == r) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) ri[k] = t[r][k];
+      }
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      if (j != i) {
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+          if (p[j] == r) {
+            const float sc = t[r][i] / ri[i];
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+              const float prod = ri[k] * sc;
+              t[r][k] = t[r][k] - prod;
+            }
+          }
+      }
+    }
+  }
+  float b[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+      if (p[i] == r) {
+        const float sc = 1.f / t[r][i];
+#pragma unroll
+        for (int j = 0; j < 3; j++) b[i][j] = t[r][3+j] * sc;
+      }
+  float *o = cocg + 6*(size_t)c;
+  o[0] = b[0][0]; o[1] = b[1][1]; o[2] = b[2][2];
+  o[3] = b[0][1]; o[4] = b[1][2]; o[5] = b[0][2];
+}
+
+/* the gradient itself: right-hand side gathered per cell in the reference's scatter order
+   (interior faces by ascending id -- both cells of a face add the SAME vector dc * pfac
+   computed in the face's orientation -- then boundary faces), times the cell's cocg */
+__global__ void k_lsq_gradient(int n_rows, const int *__restrict__ row_index,
+                               const int *__restrict__ col_id, const int *__restrict__ c2f,
+                               const short *__restrict__ c2f_sgn,
+                               const double *__restrict__ cell_cen,
+                               const int *__restrict__ cell_b_faces_idx,
+                               const int *__restrict__ cell_b_faces,
+                               const double *__restrict__ b_un,
+                               const double *__restrict__ b_dist,
+                               const float *__restrict__ cocg, int inc,
+                               const double *__restrict__ pvar,
+                               const double *__restrict__ coefa,
+                               const double *__restrict__ coefb, double *grad)
+{
+  const int c = blockIdx.x*blockDim.x + threadIdx.x;
+  if (c >= n_rows) return;
+  const int s = row_index[c], e = row_index[c+1];
+  const double pc = pvar[c];
+  double r0 = 0., r1 = 0., r2 = 0.;
+  int last = -1;
+  while (true) {
+    int best = INT_MAX, bk = -1;
+    for (int k = s; k < e; k++) {
+      const int f = c2f[k];
+      if (f > last && f < best) { best = f; bk = k; }
+    }
+    if (bk < 0) break;
+    last = best;
+    const int o = col_id[bk];
+    const bool first = (c2f_sgn[bk] > 0);
+    const size_t ii = (size_t)(first ? c : o), jj = (size_t)(first ? o : c);
+    const double d0 = cell_cen[3*jj] - cell_cen[3*ii], d1 = cell_cen[3*jj+1] - cell_cen[3*ii+1],
+                 d2 = cell_cen[3*jj+2] - cell_cen[3*ii+2];
+    const double pfac = (pvar[jj] - pvar[ii]) / (d0*d0 + d1*d1 + d2*d2);
+    r0 += d0 * pfac; r1 += d1 * pfac; r2 += d2 * pfac;
+  }
+  if (cell_b_faces_idx != nullptr)
+    for (int k = cell_b_faces_idx[c]; k < cell_b_faces_idx[c+1]; k++) {
+      const int f = cell_b_faces[k];
+      const double val_f = inc*coefa[f] + coefb[f]*pc;
+      const double ddif = 1. / b_dist[f];
+      const double pfac = (val_f - pc) * ddif;
+      r0 += b_un[3*(size_t)f] * pfac; r1 += b_un[3*(size_t)f+1] * pfac; r2 += b_un[3*(size_t)f+2] * pfac;
+    }
+  const float *g = cocg + 6*(size_t)c;
+  grad[3*(size_t)c]   = g[0]*r0 + g[3]*r1 + g[5]*r2;
+  grad[3*(size_t)c+1] = g[3]*r0 + g[1]*r1 + g[4]*r2;
+  grad[3*(size_t)c+2] = g[5]*r0 + g[4]*r1 + g[2]*r2;
+}
+
+/* cs_diffusion_potential with flux reconstruction (:8921-8961): the face flux is computed in
+   the face's orientation by both of its cells, identically */
+__global__ void k_diffusion_potential_rc(int n_rows, const int *__restrict__ row_index,
+                                         const int *__restrict__ col_id,
+                                         const int *__restrict__ c2f,
+                                         const short *__restrict__ c2f_sgn,
+                                         const int *__restrict__ cell_b_faces_idx,
+                                         const int *__restrict__ cell_b_faces,
+                                         const double *__restrict__ diipf,
+                                         const double *__restrict__ djjpf,
+                                         const double *__restrict__ i_dist,
+                                         const double *__restrict__ i_face_surf, int irecmf,
+                                         int init, int inc, const double *__restrict__ pvar,
+                                         const double *__restrict__ grad,
+                                         const double *__restrict__ cofaf,
+                                         const double *__restrict__ cofbf,
+                                         const double *__restrict__ i_visc,
+                                         const double *__restrict__ b_visc,
+                                         const double *__restrict__ visel, double *diverg)
+{
+  const int c = blockIdx.x*blockDim.x + threadIdx.x;
+  if (c >= n_rows) return;
+  const int s = row_index[c], e = row_index[c+1];
+  double d = (init >= 1) ? 0. : diverg[c];
+  int last = -1;
+  while (true) {
+    int best = INT_MAX, bk = -1;
+    for (int k = s; k < e; k++) {
+      const int f = c2f[k];
+      if (f > last && f < best) { best = f; bk = k; }
+    }
+    if (bk < 0) break;
+    last = best;
+    const size_t f = (size_t)best;
+    const int o = col_id[bk];
+    const bool first = (c2f_sgn[bk] > 0);
+    const size_t c0 = (size_t)(first ? c : o), c1 = (size_t)(first ? o : c);
+    const double *g0 = grad + 3*c0, *g1 = grad + 3*c1;
+    const double *ip = diipf + 3*f, *jp = djjpf + 3*f;
+    double flux = i_visc[f]*(pvar[c0] - pvar[c1]);
+    if (irecmf == 0) {
+      const double dijx = ip[0] - jp[0], dijy = ip[1] - jp[1], dijz = ip[2] - jp[2];
+      const double dpxf = 0.5*(visel[c0]*g0[0] + visel[c1]*g1[0]);
+      const double dpyf = 0.5*(visel[c0]*g0[1] + visel[c1]*g1[1]);
+      const double dpzf = 0.5*(visel[c0]*g0[2] + visel[c1]*g1[2]);
+      flux += (dpxf*dijx + dpyf*dijy + dpzf*dijz) * i_face_surf[f]/i_dist[f];
+    }
+    else
+      flux += i_visc[f] * (  (g0[0]*ip[0] + g0[1]*ip[1] + g0[2]*ip[2])
+                           - (g1[0]*jp[0] + g1[1]*jp[1] + g1[2]*jp[2]));
+    if (first) d += flux;
+    else d += -flux;
+  }
+  if (cell_b_faces_idx != nullptr) {
+    const double pc = pvar[c];
+    for (int k = cell_b_faces_idx[c]; k < cell_b_faces_idx[c+1]; k++) {
+      const int f = cell_b_faces[k];
+      const double flux_d = inc*cofaf[f] + cofbf[f]*pc;
+      d += b_visc[f]*flux_d;
+    }
+  }
+  diverg[c] = d;
+}
+
+} // anonymous namespace
+
+bool launch_lsq_cocg(const _csb_matrix_t *m, float *cocg)
+{
+  if (m->n_rows < 1) return true;
+  const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  k_lsq_cocg<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
+    m->n_rows, m->row_index.p, m->col_id.p, m->cell_cen.p,
+    bnd ? m->cell_b_faces_idx.p : nullptr, bnd ? m->cell_b_faces.p : nullptr,
+    m->b_face_u_normal.p, cocg);
+  return post_launch("lsq_cocg");
+}
+
+bool launch_lsq_gradient(const _csb_matrix_t *m, const float *cocg, int inc, const double *pvar,
+                         const double *coefa, const double *coefb, double *grad)
+{
+  if (m->n_rows < 1) return true;
+  const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  k_lsq_gradient<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
+    m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, m->c2f_sgn.p, m->cell_cen.p,
+    bnd ? m->cell_b_faces_idx.p : nullptr, bnd ? m->cell_b_faces.p : nullptr,
+    m->b_face_u_normal.p, m->b_dist.p, cocg, inc, pvar, coefa, coefb, grad);
+  return post_launch("lsq_gradient");
+}
+
+bool launch_diffusion_potential_rc(const _csb_matrix_t *m, int irecmf, int init, int inc,
+                                   const double *pvar, const double *grad, const double *cofaf,
+                                   const double *cofbf, const double *i_visc,
+                                   const double *b_visc, const double *visel, double *diverg)
+{
+  if (m->n_rows < 1) return true;
+  const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  k_diffusion_potential_rc<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
+    m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, m->c2f_sgn.p,
+    bnd ? m->cell_b_faces_idx.p : nullptr, bnd ? m->cell_b_faces.p : nullptr, m->diipf.p,
+    m->djjpf.p, m->i_dist.p, m->face_surf.p, irecmf, init, inc, pvar, grad, cofaf, cofbf,
+    i_visc, b_visc, visel, diverg);
+  return post_launch("diffusion_potential_rc");
+}
+
 bool launch_native_to_msr(int nnz, const int *c2f, const double *xa, double *x_val)
 {
   if (nnz < 1) return true;

@@ -648,6 +648,7 @@ int csb_matrix_set_mesh_association(csb_matrix_t *m, csb_lnum_t n_faces,
          && m->face_surf.upload(face_surf, (size_t)n_faces)
          && CSB_CUDA(cudaStreamSynchronize(ctx().stream));
   m->has_mesh = ok;
+  m->cocg_valid = false;
   return ok ? 0 : -1;
 }
 
@@ -697,6 +698,144 @@ int csb_diffusion_potential(const csb_matrix_t *m, int init, int inc, const csb_
   double *d_div = const_cast<double *>(dev[5]);
   if (!csb::launch_diffusion_potential(m, init, inc, dev[0], dev[2], dev[3], dev[1], dev[4], d_div))
     return -1;
+  if (d_div != diverg
+      && !CSB_CUDA(cudaMemcpyAsync(diverg, d_div, sizeof(double)*nr, cudaMemcpyDeviceToHost,
+                                   c.stream))) return -1;
+  return CSB_CUDA(cudaStreamSynchronize(c.stream)) ? 0 : -1;
+}
+
+namespace {
+/* device views of arrays that may live on the host: host ones are copied into `stage` */
+bool stage_arrays(int n, const double *const *src, const size_t *len, const bool *copy_in,
+                  const double **dev, csb::DevBuf<double> &stage)
+{
+  size_t need = 0;
+  for (int i = 0; i < n; i++)
+    if (len[i] > 0 && src[i] != nullptr && !is_device_ptr(src[i])) need += len[i];
+  if (need > 0 && !stage.alloc(need)) return false;
+  size_t off = 0;
+  for (int i = 0; i < n; i++) {
+    dev[i] = src[i];
+    if (len[i] > 0 && src[i] != nullptr && !is_device_ptr(src[i])) {
+      if (copy_in[i]
+          && !CSB_CUDA(cudaMemcpyAsync(stage.p + off, src[i], sizeof(double)*len[i],
+                                       cudaMemcpyHostToDevice, ctx().stream))) return false;
+      dev[i] = stage.p + off;
+      off += len[i];
+    }
+  }
+  return true;
+}
+
+bool ensure_cocg(const csb_matrix_t *m)
+{
+  if (m->cocg_valid) return true;
+  if (!m->cocg_lsq.alloc(6*(size_t)std::max(m->n_rows, 1))) return false;
+  if (!csb::launch_lsq_cocg(m, m->cocg_lsq.p)) return false;
+  m->cocg_valid = true;
+  return true;
+}
+} // anonymous namespace
+
+/* Face geometry of a non-orthogonal mesh, as cs_mesh_quantities_t holds it
+   (src/mesh/cs_mesh_quantities.h:101-125): i_dist[n_faces], diipf / djjpf [n_faces][3] (II',
+   JJ'), b_face_u_normal[n_b_faces][3], b_dist[n_b_faces].  II' of the boundary faces is taken
+   as zero.  Needs csb_matrix_set_mesh_association and csb_matrix_set_boundary_faces first. */
+int csb_matrix_set_face_geometry(csb_matrix_t *m, const csb_real_t *i_dist,
+                                 const csb_real_t *diipf, const csb_real_t *djjpf,
+                                 const csb_real_t *b_face_u_normal, const csb_real_t *b_dist)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (!m->has_mesh) {
+    set_error("csb_matrix_set_face_geometry: csb_matrix_set_mesh_association first");
+    return -1;
+  }
+  const size_t nf = (size_t)m->n_faces, nb = m->has_b_faces ? (size_t)m->n_b_faces : 0;
+  if ((nf > 0 && (i_dist == nullptr || diipf == nullptr || djjpf == nullptr))
+      || (nb > 0 && (b_face_u_normal == nullptr || b_dist == nullptr))) {
+    set_error("csb_matrix_set_face_geometry: null array");
+    return -1;
+  }
+  const bool ok = m->i_dist.upload(i_dist, nf) && m->diipf.upload(diipf, 3*nf)
+               && m->djjpf.upload(djjpf, 3*nf) && m->b_face_u_normal.upload(b_face_u_normal, 3*nb)
+               && m->b_dist.upload(b_dist, nb) && CSB_CUDA(cudaStreamSynchronize(ctx().stream));
+  m->has_face_geo = ok;
+  m->cocg_valid = false;
+  return ok ? 0 : -1;
+}
+
+/* cs_gradient_scalar_synced_input with CS_GRADIENT_LSQ, standard neighbourhood, no weighting,
+   no limiter (src/alge/cs_gradient.cpp:9651, _lsq_scalar_gradient :2695-2900): grad[n_rows][3].
+   Boundary face values are inc*coefa + coefb*pvar(cell) (II' = 0 at the boundary).  The cocg
+   matrices are computed on first use and kept with the matrix. */
+int csb_gradient_scalar_lsq(const csb_matrix_t *m, int inc, const csb_real_t *pvar,
+                            const csb_real_t *coefa, const csb_real_t *coefb, csb_real_t *grad)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (!m->has_face_geo || m->db != 1 || m->halo != nullptr) {
+    set_error("csb_gradient_scalar_lsq: needs a scalar matrix on one rank with its mesh "
+              "association, boundary faces and csb_matrix_set_face_geometry");
+    return -1;
+  }
+  const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  if (pvar == nullptr || grad == nullptr || (bnd && (coefa == nullptr || coefb == nullptr))) {
+    set_error("csb_gradient_scalar_lsq: null array");
+    return -1;
+  }
+  Context &c = ctx();
+  const size_t nr = (size_t)m->n_rows, nb = bnd ? (size_t)m->n_b_faces : 0;
+  const double *src[4] = {pvar, coefa, coefb, grad};
+  const size_t len[4] = {nr, nb, nb, 3*nr};
+  const bool in[4] = {true, true, true, false};
+  const double *dev[4];
+  csb::DevBuf<double> stage;
+  if (!ensure_cocg(m) || !stage_arrays(4, src, len, in, dev, stage)) return -1;
+  double *d_grad = const_cast<double *>(dev[3]);
+  if (!csb::launch_lsq_gradient(m, m->cocg_lsq.p, inc, dev[0], dev[1], dev[2], d_grad)) return -1;
+  if (d_grad != grad
+      && !CSB_CUDA(cudaMemcpyAsync(grad, d_grad, sizeof(double)*3*nr, cudaMemcpyDeviceToHost,
+                                   c.stream))) return -1;
+  return CSB_CUDA(cudaStreamSynchronize(c.stream)) ? 0 : -1;
+}
+
+/* cs_diffusion_potential WITH flux reconstruction (eqp->ircflu = 1, imrgra = 1;
+   src/alge/cs_convection_diffusion.cpp:8895-8982): the least-squares gradient of pvar, then the
+   face fluxes with the non-orthogonality term -- irecmf = 0: 0.5 (visel grad)_I+J . (II' - JJ')
+   S/d, irecmf = 1: i_visc (grad_I . II' - grad_J . JJ'). */
+int csb_diffusion_potential_rc(const csb_matrix_t *m, int irecmf, int init, int inc,
+                               const csb_real_t *pvar, const csb_real_t *coefa,
+                               const csb_real_t *coefb, const csb_real_t *cofaf,
+                               const csb_real_t *cofbf, const csb_real_t *i_visc,
+                               const csb_real_t *b_visc, const csb_real_t *visel,
+                               csb_real_t *diverg)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (!m->has_face_geo || m->db != 1 || m->halo != nullptr) {
+    set_error("csb_diffusion_potential_rc: needs a scalar matrix on one rank with its mesh "
+              "association, boundary faces and csb_matrix_set_face_geometry");
+    return -1;
+  }
+  if (init < 0) { set_error("csb_diffusion_potential_rc: invalid value of init"); return -1; }
+  const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  if (pvar == nullptr || diverg == nullptr || visel == nullptr
+      || (m->n_faces > 0 && i_visc == nullptr)
+      || (bnd && (coefa == nullptr || coefb == nullptr || cofaf == nullptr || cofbf == nullptr
+                  || b_visc == nullptr))) {
+    set_error("csb_diffusion_potential_rc: null array");
+    return -1;
+  }
+  Context &c = ctx();
+  const size_t nr = (size_t)m->n_rows, nf = (size_t)m->n_faces, nb = bnd ? (size_t)m->n_b_faces : 0;
+  const double *src[9] = {pvar, coefa, coefb, cofaf, cofbf, i_visc, b_visc, visel, diverg};
+  const size_t len[9] = {nr, nb, nb, nb, nb, nf, nb, nr, nr};
+  const bool in[9] = {true, true, true, true, true, true, true, true, init == 0};
+  const double *dev[9];
+  csb::DevBuf<double> stage, grad;
+  if (!ensure_cocg(m) || !stage_arrays(9, src, len, in, dev, stage) || !grad.alloc(3*nr)) return -1;
+  double *d_div = const_cast<double *>(dev[8]);
+  if (!csb::launch_lsq_gradient(m, m->cocg_lsq.p, inc, dev[0], dev[1], dev[2], grad.p)
+      || !csb::launch_diffusion_potential_rc(m, irecmf, init, inc, dev[0], grad.p, dev[3], dev[4],
+                                             dev[5], dev[6], dev[7], d_div)) return -1;
   if (d_div != diverg
       && !CSB_CUDA(cudaMemcpyAsync(diverg, d_div, sizeof(double)*nr, cudaMemcpyDeviceToHost,
                                    c.stream))) return -1;
@@ -756,6 +895,11 @@ int csb_matrix_compute_coeffs(csb_matrix_t *m, int iconvp, int idiffp, int ndirc
   if (m->csr != nullptr) {
     set_error("csb_matrix_compute_coeffs: matrix was created from CSR arrays (its CSR values "
               "would go stale); use an MSR matrix");
+    return -1;
+  }
+  if (m->from_native) {
+    set_error("csb_matrix_compute_coeffs: matrix was created from native arrays (its face "
+              "values would go stale); use csb_matrix_set_coefficients_native");
     return -1;
   }
   if (!m->has_mesh) {

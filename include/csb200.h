@@ -313,6 +313,31 @@ int  csb_diffusion_potential(const csb_matrix_t *m, int init, int inc, const csb
                              const csb_real_t *i_visc, const csb_real_t *b_visc,
                              csb_real_t *diverg);
 
+/* Reconstruction on non-orthogonal meshes.
+   csb_matrix_set_face_geometry: the face quantities cs_mesh_quantities_t holds
+   (src/mesh/cs_mesh_quantities.h:101-125): i_dist[n_faces], diipf / djjpf[n_faces][3] (II',
+   JJ'), b_face_u_normal[n_b_faces][3], b_dist[n_b_faces]; II' of boundary faces is taken as
+   zero.  After csb_matrix_set_mesh_association and csb_matrix_set_boundary_faces.
+   csb_gradient_scalar_lsq: cs_gradient_scalar_synced_input with CS_GRADIENT_LSQ (imrgra = 1),
+   standard neighbourhood, no weighting, no limiter (src/alge/cs_gradient.cpp:9651;
+   _lsq_scalar_gradient :2695-2900, cocg _compute_cell_cocg_lsq :2501-2680 -- kept in single
+   precision and inverted by the float Gauss-Jordan elimination like the reference's
+   cs_cocg_t); grad[n_rows][3]; boundary face value inc*coefa + coefb*pvar.
+   csb_diffusion_potential_rc: cs_diffusion_potential with eqp->ircflu = 1 (:8895-8982), irecmf
+   as cs_glob_velocity_pressure_param->irecmf (0 or 1).
+   All bit-identical to the reference's one-thread results; host or device pointers. */
+int  csb_matrix_set_face_geometry(csb_matrix_t *m, const csb_real_t *i_dist,
+                                  const csb_real_t *diipf, const csb_real_t *djjpf,
+                                  const csb_real_t *b_face_u_normal, const csb_real_t *b_dist);
+int  csb_gradient_scalar_lsq(const csb_matrix_t *m, int inc, const csb_real_t *pvar,
+                             const csb_real_t *coefa, const csb_real_t *coefb, csb_real_t *grad);
+int  csb_diffusion_potential_rc(const csb_matrix_t *m, int irecmf, int init, int inc,
+                                const csb_real_t *pvar, const csb_real_t *coefa,
+                                const csb_real_t *coefb, const csb_real_t *cofaf,
+                                const csb_real_t *cofbf, const csb_real_t *i_visc,
+                                const csb_real_t *b_visc, const csb_real_t *visel,
+                                csb_real_t *diverg);
+
 /* Copy of the MSR coefficients held in HBM (cs_matrix_get_msr_arrays, cs_matrix.cpp:6199,
    lends the host arrays; these live on the device).  Either pointer may be NULL. */
 int  csb_matrix_get_coefficients(const csb_matrix_t *m, csb_real_t *d_val, csb_real_t *x_val);

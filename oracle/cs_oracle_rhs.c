@@ -8,12 +8,23 @@
  * variable: interior faces in face order, then boundary faces in face order with
  * flux_diff = inc*af + bf*pvar (cs_boundary_conditions_set_coeffs.cpp:172-185).
  * On an orthogonal mesh (II' = JJ' = 0) the reconstructed branch (:8895-8972) adds
- * exact zeros, so this is also its result there.  The gradient reconstruction of
- * non-orthogonal meshes (cs_gradient.cpp) is not restated.
+ * exact zeros, so this is also its result there.
+ *
+ * ora_gradient_lsq / ora_diffusion_potential_rc: the reconstructed branch and the cell
+ * gradient it needs -- least squares over the face neighbours (imrgra = 1, CS_GRADIENT_LSQ,
+ * standard neighbourhood, no weighting, no limiter): _lsq_scalar_gradient
+ * (src/alge/cs_gradient.cpp:2695-2900) with the cocg matrices of _compute_cell_cocg_lsq
+ * (:2501-2680), which the reference keeps in SINGLE precision (cs_cocg_t = float,
+ * cs_gradient_priv.h:54) and inverts with the float instance of
+ * cs_math_matrix_gauss_inverse (src/base/cs_math.h:542-590): restated as such.  II' of the
+ * boundary faces is taken as zero (boundary face value = inc*a + b*pvar).
  *
  * Pinned bit for bit against oracle/_ref/libcsref.so (csref_diffusion_potential
  * drives the reference's real function), tests/test_oracle.py.
  *============================================================================*/
+
+#include <math.h>
+#include <stdlib.h>
 
 #include "cs_oracle.h"
 
@@ -28,6 +39,144 @@ ora_diffusion_potential(int n_cells, int n_i_faces, const int *i_face_cells, int
   for (int f = 0; f < n_i_faces; f++) {
     const int c0 = i_face_cells[2*f], c1 = i_face_cells[2*f+1];
     const double flux = i_visc[f]*(pvar[c0] - pvar[c1]);
+    if (c0 < n_cells) diverg[c0] += flux;
+    if (c1 < n_cells) diverg[c1] += -flux;
+  }
+  for (int f = 0; f < n_b_faces; f++) {
+    const int c0 = b_face_cells[f];
+    const double flux_d = inc*cofaf[f] + cofbf[f]*pvar[c0];
+    diverg[c0] += b_visc[f]*flux_d;
+  }
+}
+
+/* cs_math_6_gauss_inverse_in_place<float> (cs_math.h:598-615, :542-590) */
+static void
+_gauss_inverse_6f(float a[6])
+{
+  float t[3][6] = {{a[0], a[3], a[5], 1, 0, 0},
+                   {a[3], a[1], a[4], 0, 1, 0},
+                   {a[5], a[4], a[2], 0, 0, 1}};
+  float *p_a[3] = {t[0], t[1], t[2]};
+  for (int i = 0; i < 3; i++) {
+    for (int j = i+1; j < 3; j++) {
+      if (fabsf(p_a[i][i]) < fabsf(p_a[j][i])) {
+        float *tmp = p_a[j]; p_a[j] = p_a[i]; p_a[i] = tmp;
+      }
+    }
+    for (int j = 0; j < 3; j++) {
+      if (j != i) {
+        const float s = p_a[j][i] / p_a[i][i];
+        for (int k = 0; k < 6; k++) {
+          const float prod = p_a[i][k] * s;
+          p_a[j][k] = p_a[j][k] - prod;
+        }
+      }
+    }
+  }
+  float b[3][3];
+  for (int i = 0; i < 3; i++) {
+    const float s = 1.f / p_a[i][i];
+    for (int j = 0; j < 3; j++) b[i][j] = p_a[i][3+j] * s;
+  }
+  a[0] = b[0][0]; a[1] = b[1][1]; a[2] = b[2][2];
+  a[3] = b[0][1]; a[4] = b[1][2]; a[5] = b[0][2];
+}
+
+/* (row_index, col_id): the cell -> cells adjacency in the order of cs_mesh_adjacencies
+   (= the MSR structure); cell_b_faces: boundary faces by cell, ascending.  b_face_u_normal: 3
+   per boundary face; grad: 3 per cell */
+void
+ora_gradient_lsq(int n_cells, const int *row_index, const int *col_id, int n_i_faces,
+                 const int *i_face_cells, int n_b_faces, const int *b_face_cells,
+                 const double *cell_cen, const double *b_face_u_normal, const double *b_dist,
+                 int inc, const double *pvar, const double *coefa, const double *coefb,
+                 double *grad)
+{
+  float *cocg = calloc(6*(size_t)(n_cells > 0 ? n_cells : 1), sizeof(float));
+  double *rhsv = calloc(3*(size_t)(n_cells > 0 ? n_cells : 1), sizeof(double));
+  for (int c = 0; c < n_cells; c++) {
+    float *g = cocg + 6*(size_t)c;
+    for (int k = row_index[c]; k < row_index[c+1]; k++) {
+      const int c1 = col_id[k];
+      const double dc[3] = {cell_cen[3*c1] - cell_cen[3*c], cell_cen[3*c1+1] - cell_cen[3*c+1],
+                            cell_cen[3*c1+2] - cell_cen[3*c+2]};
+      const double ddc = 1. / (dc[0]*dc[0] + dc[1]*dc[1] + dc[2]*dc[2]);
+      g[0] += dc[0] * dc[0] * ddc;
+      g[1] += dc[1] * dc[1] * ddc;
+      g[2] += dc[2] * dc[2] * ddc;
+      g[3] += dc[0] * dc[1] * ddc;
+      g[4] += dc[1] * dc[2] * ddc;
+      g[5] += dc[0] * dc[2] * ddc;
+    }
+  }
+  for (int f = 0; f < n_b_faces; f++) {       /* ascending faces = every cell's c2b order */
+    float *g = cocg + 6*(size_t)b_face_cells[f];
+    const double *d = b_face_u_normal + 3*(size_t)f;
+    g[0] += d[0] * d[0];
+    g[1] += d[1] * d[1];
+    g[2] += d[2] * d[2];
+    g[3] += d[0] * d[1];
+    g[4] += d[1] * d[2];
+    g[5] += d[0] * d[2];
+  }
+  for (int c = 0; c < n_cells; c++) _gauss_inverse_6f(cocg + 6*(size_t)c);
+
+  for (int f = 0; f < n_i_faces; f++) {
+    const int ii = i_face_cells[2*f], jj = i_face_cells[2*f+1];
+    const double dc[3] = {cell_cen[3*jj] - cell_cen[3*ii], cell_cen[3*jj+1] - cell_cen[3*ii+1],
+                          cell_cen[3*jj+2] - cell_cen[3*ii+2]};
+    const double pfac = (pvar[jj] - pvar[ii]) / (dc[0]*dc[0] + dc[1]*dc[1] + dc[2]*dc[2]);
+    for (int ll = 0; ll < 3; ll++) {
+      const double fctb = dc[ll] * pfac;
+      if (ii < n_cells) rhsv[3*ii+ll] += fctb;
+      if (jj < n_cells) rhsv[3*jj+ll] += fctb;
+    }
+  }
+  for (int f = 0; f < n_b_faces; f++) {
+    const int c = b_face_cells[f];
+    const double val_f = inc*coefa[f] + coefb[f]*pvar[c];
+    const double ddif = 1. / b_dist[f];
+    const double pfac = (val_f - pvar[c]) * ddif;
+    for (int ll = 0; ll < 3; ll++) rhsv[3*c+ll] += b_face_u_normal[3*f+ll] * pfac;
+  }
+  for (int c = 0; c < n_cells; c++) {
+    const float *g = cocg + 6*(size_t)c;
+    const double *r = rhsv + 3*(size_t)c;
+    grad[3*c]   = g[0]*r[0] + g[3]*r[1] + g[5]*r[2];
+    grad[3*c+1] = g[3]*r[0] + g[1]*r[1] + g[4]*r[2];
+    grad[3*c+2] = g[5]*r[0] + g[4]*r[1] + g[2]*r[2];
+  }
+  free(cocg); free(rhsv);
+}
+
+/* cs_diffusion_potential with flux reconstruction (:8895-8982); i_geo: per interior face II'
+   [3], JJ' [3], distance of the cell centres [1]; irecmf as
+   cs_glob_velocity_pressure_param->irecmf */
+void
+ora_diffusion_potential_rc(int n_cells, int n_i_faces, const int *i_face_cells, int n_b_faces,
+                           const int *b_face_cells, const double *i_geo,
+                           const double *i_face_surf, int irecmf, int init, int inc,
+                           const double *pvar, const double *grad, const double *cofaf,
+                           const double *cofbf, const double *i_visc, const double *b_visc,
+                           const double *visel, double *diverg)
+{
+  if (init >= 1)
+    for (int i = 0; i < n_cells; i++) diverg[i] = 0.;
+  for (int f = 0; f < n_i_faces; f++) {
+    const int c0 = i_face_cells[2*f], c1 = i_face_cells[2*f+1];
+    const double *ip = i_geo + 7*(size_t)f, *jp = ip + 3;
+    const double *g0 = grad + 3*(size_t)c0, *g1 = grad + 3*(size_t)c1;
+    double flux = i_visc[f]*(pvar[c0] - pvar[c1]);
+    if (irecmf == 0) {
+      const double dijx = ip[0] - jp[0], dijy = ip[1] - jp[1], dijz = ip[2] - jp[2];
+      const double dpxf = 0.5*(visel[c0]*g0[0] + visel[c1]*g1[0]);
+      const double dpyf = 0.5*(visel[c0]*g0[1] + visel[c1]*g1[1]);
+      const double dpzf = 0.5*(visel[c0]*g0[2] + visel[c1]*g1[2]);
+      flux += (dpxf*dijx + dpyf*dijy + dpzf*dijz) * i_face_surf[f]/ip[6];
+    }
+    else
+      flux += i_visc[f] * (  (g0[0]*ip[0] + g0[1]*ip[1] + g0[2]*ip[2])
+                           - (g1[0]*jp[0] + g1[1]*jp[1] + g1[2]*jp[2]));
     if (c0 < n_cells) diverg[c0] += flux;
     if (c1 < n_cells) diverg[c1] += -flux;
   }

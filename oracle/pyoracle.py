@@ -353,6 +353,29 @@ class Oracle:
             _dp(_f64(i_visc)), _dp(_f64(b_visc)), _dp(div))
         return div
 
+    def gradient_lsq(self, s, b_face_cells, b_un, b_dist, pvar, coefa, coefb, inc=1):
+        grad = np.zeros(3 * s.n_rows)
+        fc, bfc = _i32(s.face_cells), _i32(b_face_cells)
+        self.lib.ora_gradient_lsq.restype = None
+        self.lib.ora_gradient_lsq(
+            C.c_int(s.n_rows), _ip(_i32(s.row_index)), _ip(_i32(s.col_id)), C.c_int(len(fc)),
+            _ip(fc), C.c_int(len(bfc)), _ip(bfc), _dp(_f64(s.cell_cen)), _dp(_f64(b_un)),
+            _dp(_f64(b_dist)), C.c_int(inc), _dp(_f64(pvar)), _dp(_f64(coefa)), _dp(_f64(coefb)),
+            _dp(grad))
+        return grad.reshape(-1, 3)
+
+    def diffusion_potential_rc(self, s, b_face_cells, i_geo, grad, pvar, cofaf, cofbf, i_visc,
+                               b_visc, visel, irecmf=0, init=1, inc=1, diverg=None):
+        div = np.zeros(s.n_rows) if diverg is None else _f64(diverg).copy()
+        fc, bfc = _i32(s.face_cells), _i32(b_face_cells)
+        self.lib.ora_diffusion_potential_rc.restype = None
+        self.lib.ora_diffusion_potential_rc(
+            C.c_int(s.n_rows), C.c_int(len(fc)), _ip(fc), C.c_int(len(bfc)), _ip(bfc),
+            _dp(_f64(i_geo)), _dp(_f64(s.face_surf)), C.c_int(irecmf), C.c_int(init), C.c_int(inc),
+            _dp(_f64(pvar)), _dp(_f64(grad)), _dp(_f64(cofaf)), _dp(_f64(cofbf)),
+            _dp(_f64(i_visc)), _dp(_f64(b_visc)), _dp(_f64(visel)), _dp(div))
+        return div
+
     def aggregation_fc(self, level, n_rows, face_cells, da, xa, max_aggregation=3):
         fc = _i32(face_cells)
         f_c = np.empty(max(n_rows, 1), dtype=np.int32)
@@ -673,6 +696,24 @@ class RefLib:
             _dp(_f64(cofbf)), _dp(_f64(i_visc)), _dp(_f64(b_visc)), _dp(div))
         assert r == 0
         return div
+
+    def diffusion_potential_rc(self, h, s, b_face_cells, b_geo, i_face_cog, i_geo, pvar, coefa,
+                               coefb, cofaf, cofbf, i_visc, b_visc, visel, irecmf=0, init=1,
+                               inc=1, diverg=None):
+        """cs_diffusion_potential WITH flux reconstruction (LSQ gradient) on the geometry given;
+        returns (diverg, grad)."""
+        div = np.zeros(s.n_rows) if diverg is None else _f64(diverg).copy()
+        grad = np.zeros(3 * s.n_rows)
+        bfc = _i32(b_face_cells)
+        keep = [_f64(x) for x in (b_geo, i_face_cog, i_geo, pvar, coefa, coefb, cofaf, cofbf,
+                                  i_visc, b_visc, visel)]
+        r = self.lib.csref_diffusion_potential_rc(
+            h, _ip(_i32(s.face_cells)), C.c_int(len(bfc)), _ip(bfc), _dp(keep[0]), _dp(keep[1]),
+            _dp(keep[2]), C.c_int(irecmf), C.c_int(init), C.c_int(inc), _dp(keep[3]), _dp(keep[4]),
+            _dp(keep[5]), _dp(keep[6]), _dp(keep[7]), _dp(keep[8]), _dp(keep[9]), _dp(keep[10]),
+            _dp(div), _dp(grad))
+        assert r == 0
+        return div, grad.reshape(-1, 3)
 
     def system_block(self, n_rows, db, ri, ci, d_val, x_val, symmetric=False):
         """MSR matrix with db x db diagonal blocks (d_val: n_rows*db*db) built by the reference."""

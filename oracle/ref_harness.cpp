@@ -49,6 +49,8 @@
 #include "alge/cs_matrix_assembler.h"
 #include "alge/cs_convection_diffusion.h"
 #include "base/cs_parameters.h"
+#include "base/cs_velocity_pressure.h"
+#include "alge/cs_gradient.h"
 #include "base/cs_boundary_conditions_set_coeffs.h"
 #include "alge/cs_blas.h"
 #include "alge/cs_matrix.h"
@@ -910,6 +912,133 @@ csref_diffusion_potential(void          *sys,
   memcpy(diverg, _div.data(), sizeof(cs_real_t)*n_cells);
 
   /* the quantities point to this call's arrays */
+  mq->cell_cen = nullptr; mq->b_face_u_normal = nullptr; mq->b_dist = nullptr;
+  mq->i_dist = nullptr; mq->i_face_cog = nullptr; mq->b_face_cog = nullptr;
+  mq->i_face_surf = nullptr; mq->diipb = nullptr; mq->diipf = nullptr; mq->djjpf = nullptr;
+  CS_FREE(bc.val_f); CS_FREE(bc.flux_diff);
+  return 0;
+}
+
+/* The same operator WITH flux reconstruction (eqp->ircflu = 1, cs_convection_diffusion.cpp:
+   8895-8972) and the least-squares cell gradient it calls (imrgra = 1: CS_GRADIENT_LSQ,
+   standard neighbourhood; _lsq_scalar_gradient cs_gradient.cpp:2695-2900, cocg
+   _compute_cell_cocg_lsq :2501-2680).  The geometry is whatever the caller passes: i_geo holds
+   per interior face II' [3], JJ' [3] and the distance of the cell centres [1]; cell centres are
+   those of the system; II' of the boundary faces stays zero (boundary values are then the cell
+   values through the BC coefficients a = coefa, b = coefb).  irecmf selects the reconstruction
+   formula (cs_glob_velocity_pressure_param->irecmf).  grad_out (3 per cell, may be NULL)
+   receives the gradient of pvar computed by cs_gradient_scalar_synced_input with the same
+   arguments cs_diffusion_potential uses. */
+int
+csref_diffusion_potential_rc(void          *sys,
+                             const int     *face_cells,
+                             int            n_b_faces,
+                             const int     *b_face_cells,
+                             const double  *b_geo,        /* 7 per boundary face */
+                             const double  *i_face_cog,   /* 3 per interior face */
+                             const double  *i_geo,        /* 7 per interior face */
+                             int            irecmf,
+                             int            init,
+                             int            inc,
+                             const double  *pvar,
+                             const double  *coefa,
+                             const double  *coefb,
+                             const double  *cofaf,
+                             const double  *cofbf,
+                             const double  *i_visc,
+                             const double  *b_visc,
+                             const double  *visel,
+                             double        *diverg,
+                             double        *grad_out)
+{
+  ref_system *s = static_cast<ref_system *>(sys);
+  _set_glob_mesh_faces(s, face_cells);
+  cs_mesh_t *mesh = cs_glob_mesh;
+  const cs_lnum_t n_cells = s->n_rows, n_i_faces = s->n_faces;
+
+  CS_FREE(mesh->b_face_cells);
+  mesh->n_b_faces = n_b_faces;
+  mesh->n_b_faces_all = n_b_faces;
+  CS_MALLOC(mesh->b_face_cells, (n_b_faces > 0) ? n_b_faces : 1, cs_lnum_t);
+  memcpy(mesh->b_face_cells, b_face_cells, sizeof(cs_lnum_t)*n_b_faces);
+  if (mesh->b_face_numbering != nullptr)
+    cs_numbering_destroy(&(mesh->b_face_numbering));
+  mesh->b_face_numbering = cs_numbering_create_default(n_b_faces);
+  if (mesh->i_face_numbering != nullptr)
+    cs_numbering_destroy(&(mesh->i_face_numbering));
+  mesh->i_face_numbering = cs_numbering_create_default(n_i_faces);
+  cs_mesh_update_b_cells(mesh);
+
+  if (cs_glob_mesh_quantities == nullptr)
+    cs_glob_mesh_quantities = cs_mesh_quantities_create();
+  cs_mesh_quantities_t *mq = cs_glob_mesh_quantities;
+  cs_mesh_adjacencies_finalize();
+  cs_mesh_adjacencies_initialize();
+  cs_mesh_adjacencies_update_mesh();
+  cs_gradient_free_quantities();
+
+  const cs_lnum_t nb1 = (n_b_faces > 0) ? n_b_faces : 1, ni1 = (n_i_faces > 0) ? n_i_faces : 1;
+  std::vector<cs_real_t> b_dist(nb1), i_dist(ni1), b_cog(3*nb1);
+  std::vector<cs_nreal_t> b_un(3*nb1);
+  std::vector<cs_rreal_t> zero_b(3*nb1, 0.), diipf(3*ni1), djjpf(3*ni1);
+  for (cs_lnum_t f = 0; f < n_b_faces; f++) {
+    for (int k = 0; k < 3; k++) {
+      b_un[3*f+k] = b_geo[7*f+k];
+      b_cog[3*f+k] = b_geo[7*f+3+k];
+    }
+    b_dist[f] = b_geo[7*f+6];
+  }
+  for (cs_lnum_t f = 0; f < n_i_faces; f++) {
+    for (int k = 0; k < 3; k++) {
+      diipf[3*f+k] = i_geo[7*f+k];
+      djjpf[3*f+k] = i_geo[7*f+3+k];
+    }
+    i_dist[f] = i_geo[7*f+6];
+  }
+  mq->cell_cen = (cs_real_3_t *)s->cell_cen;
+  mq->b_face_u_normal = (cs_nreal_3_t *)b_un.data();
+  mq->b_dist = b_dist.data();
+  mq->i_dist = i_dist.data();
+  mq->i_face_cog = (cs_real_3_t *)const_cast<double *>(i_face_cog);
+  mq->b_face_cog = (cs_real_3_t *)b_cog.data();
+  mq->i_face_surf = s->face_surf;
+  mq->diipb = (cs_rreal_3_t *)zero_b.data();
+  mq->diipf = (cs_rreal_3_t *)diipf.data();
+  mq->djjpf = (cs_rreal_3_t *)djjpf.data();
+
+  cs_equation_param_t eqp = cs_parameters_equation_param_default();
+  eqp.ircflu = 1;
+  eqp.imrgra = 1;          /* least squares, standard neighbourhood */
+  eqp.imligr = -1;         /* no gradient limiter */
+  eqp.iwgrec = 0;
+  eqp.verbosity = 0;
+  cs_velocity_pressure_param_t *vp = cs_get_glob_velocity_pressure_param();
+  const int irecmf_prev = vp->irecmf;
+  vp->irecmf = irecmf;
+
+  cs_field_bc_coeffs_t bc;
+  memset(&bc, 0, sizeof(bc));
+  bc.a = const_cast<cs_real_t *>(coefa); bc.b = const_cast<cs_real_t *>(coefb);
+  bc.af = const_cast<cs_real_t *>(cofaf); bc.bf = const_cast<cs_real_t *>(cofbf);
+
+  std::vector<cs_real_t> _pvar(pvar, pvar + n_cells), _visel(visel, visel + n_cells);
+  std::vector<cs_real_t> _div(n_cells > 0 ? n_cells : 1, 0.);
+  if (!init) memcpy(_div.data(), diverg, sizeof(cs_real_t)*n_cells);
+
+  cs_diffusion_potential(nullptr, &eqp, mesh, mq, init, inc, 0, nullptr, _pvar.data(), &bc,
+                         i_visc, b_visc, _visel.data(), _div.data());
+  memcpy(diverg, _div.data(), sizeof(cs_real_t)*n_cells);
+
+  if (grad_out != nullptr) {
+    /* bc.val_f was filled by cs_diffusion_potential's update of the face values */
+    cs_gradient_scalar_synced_input("csref", CS_GRADIENT_LSQ, CS_HALO_STANDARD, inc, eqp.nswrgr,
+                                    0, 1, 0, (cs_gradient_limit_t)(eqp.imligr), eqp.epsrgr,
+                                    eqp.climgr, nullptr, &bc, _pvar.data(), nullptr,
+                                    (cs_real_3_t *)grad_out, nullptr);
+  }
+
+  vp->irecmf = irecmf_prev;
+  cs_gradient_free_quantities();
   mq->cell_cen = nullptr; mq->b_face_u_normal = nullptr; mq->b_dist = nullptr;
   mq->i_dist = nullptr; mq->i_face_cog = nullptr; mq->b_face_cog = nullptr;
   mq->i_face_surf = nullptr; mq->diipb = nullptr; mq->diipf = nullptr; mq->djjpf = nullptr;

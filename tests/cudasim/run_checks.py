@@ -352,6 +352,24 @@ def check_rhs(ora):
                                           init=init, inc=inc, diverg=f["div0"])
                 assert np.array_equal(d, g[f"div_init{init}_inc{inc}"]), (N, native, init, inc)
             m.destroy()
+    # non-orthogonal variant: least-squares gradient and the reconstructed branch
+    from make_golden_rhs import rc_input
+    for N in CASES:
+        g = np.load(os.path.join(GOLD, f"rhs_rc_N{N}.npz"))
+        s, bfc, b_geo, _, i_geo, f = rc_input(N)
+        m = csb.Matrix.from_system(s)
+        m.set_boundary_faces(bfc)
+        m.set_face_geometry(i_geo[:, 6], i_geo[:, :3], i_geo[:, 3:6], b_geo[:, :3], b_geo[:, 6])
+        assert np.array_equal(m.gradient_lsq(f["pvar"], f["coefa"], f["coefb"]), g["grad"])
+        for irecmf in (0, 1):
+            d = m.diffusion_potential_rc(f["pvar"], f["coefa"], f["coefb"], f["cofaf"], f["cofbf"],
+                                         f["i_visc"], f["b_visc"], f["visel"], irecmf=irecmf)
+            assert np.array_equal(d, g[f"div_irecmf{irecmf}"]), (N, irecmf)
+        d = m.diffusion_potential_rc(f["pvar"], f["coefa"], f["coefb"], f["cofaf"], f["cofbf"],
+                                     f["i_visc"], f["b_visc"], f["visel"], irecmf=0, init=0, inc=0,
+                                     diverg=f["div0"])
+        assert np.array_equal(d, g["div_init0_inc0"])
+        m.destroy()
 
 
 def check_pairwise(ora):

@@ -2,7 +2,10 @@
 (src/alge/cs_convection_diffusion.cpp:8743-8990, eqp->ircflu = 0) on the cube mesh: outputs of
 the reference's own compiled CPU code (oracle/_ref/libcsref.so, csref_diffusion_potential):
 
-    python tests/golden/make_golden_rhs.py   -> tests/golden/rhs_N{N}.npz
+    python tests/golden/make_golden_rhs.py   -> tests/golden/rhs_N{N}.npz, rhs_rc_N{N}.npz
+
+rhs_rc_*: the same operator WITH flux reconstruction (eqp->ircflu = 1, least-squares gradient,
+csref_diffusion_potential_rc) on a non-orthogonal variant of the cube.
 """
 import os
 import sys
@@ -37,9 +40,47 @@ def rhs_input(N, seed=3):
     return s, bfc, b_geo, i_face_cog, f
 
 
+def rc_input(N, seed=5):
+    """the same cube made non-orthogonal: perturbed cell centres, seeded II' / JJ' vectors and
+    centre distances per interior face, boundary distances, BC coefficients a / b and a cell
+    viscosity -- the reference uses these arrays as they are (no consistency check), so every
+    term of the reconstruction is exercised"""
+    s, bfc, b_geo, i_face_cog, f = rhs_input(N)
+    rng = np.random.default_rng(seed)
+    nf, nb, n, h = s.n_faces, len(bfc), s.n_rows, 1.0 / N
+    i_geo = np.hstack([0.1 * h * rng.standard_normal((nf, 3)), 0.1 * h * rng.standard_normal((nf, 3)),
+                       h * (1 + 0.2 * rng.random((nf, 1)))])
+    s.cell_cen = (s.cell_cen.reshape(-1, 3) + 0.15 * h * rng.standard_normal((n, 3))).ravel().copy()
+    f["coefa"] = rng.standard_normal(nb)
+    f["coefb"] = rng.random(nb)
+    f["visel"] = rng.random(n) + 0.5
+    b_geo = b_geo.copy()
+    b_geo[:, 6] *= (1 + 0.2 * rng.random(nb))
+    return s, bfc, b_geo, i_face_cog, i_geo, f
+
+
 def main():
     from oracle.pyoracle import RefLib
     ref = RefLib(1)
+    for N in CASES:
+        s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
+        h = ref.system(s)
+        out = {}
+        for irecmf in (0, 1):
+            d, g = ref.diffusion_potential_rc(h, s, bfc, b_geo, ifc, i_geo, f["pvar"], f["coefa"],
+                                              f["coefb"], f["cofaf"], f["cofbf"], f["i_visc"],
+                                              f["b_visc"], f["visel"], irecmf=irecmf)
+            out[f"div_irecmf{irecmf}"] = d
+            out["grad"] = g
+        d, _ = ref.diffusion_potential_rc(h, s, bfc, b_geo, ifc, i_geo, f["pvar"], f["coefa"],
+                                          f["coefb"], f["cofaf"], f["cofbf"], f["i_visc"],
+                                          f["b_visc"], f["visel"], irecmf=0, init=0, inc=0,
+                                          diverg=f["div0"])
+        out["div_init0_inc0"] = d
+        ref.destroy(h)
+        path = os.path.join(ROOT, "tests", "golden", f"rhs_rc_N{N}.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path))
     for N in CASES:
         s, bfc, b_geo, ifc, f = rhs_input(N)
         h = ref.system(s)

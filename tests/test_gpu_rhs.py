@@ -65,3 +65,72 @@ def test_diffusion_potential_errors(csb):
     with pytest.raises(csb.CsbError):
         m.diffusion_potential(f["pvar"], f["i_visc"], f["b_visc"], f["cofaf"], f["cofbf"], init=-1)
     m.destroy()
+
+
+# ------------------- reconstruction on a non-orthogonal mesh: LSQ gradient + reconstructed flux
+
+from make_golden_rhs import rc_input  # noqa: E402
+
+
+def _rc_matrix(csb, s, bfc, b_geo, i_geo):
+    m = csb.Matrix.from_system(s)
+    m.set_boundary_faces(bfc)
+    m.set_face_geometry(i_geo[:, 6], i_geo[:, :3], i_geo[:, 3:6], b_geo[:, :3], b_geo[:, 6])
+    return m
+
+
+@pytest.mark.parametrize("N", CASES)
+def test_gradient_lsq_and_reconstructed_flux_match_reference_golden(csb, N):
+    """cs_gradient_scalar_synced_input (CS_GRADIENT_LSQ; single-precision cocg matrices inverted
+    by the float Gauss-Jordan elimination, as in the reference) and cs_diffusion_potential with
+    eqp->ircflu = 1, both reconstruction formulas: bit-identical"""
+    g = np.load(os.path.join(GOLD, f"rhs_rc_N{N}.npz"))
+    s, bfc, b_geo, _, i_geo, f = rc_input(N)
+    m = _rc_matrix(csb, s, bfc, b_geo, i_geo)
+    assert np.array_equal(m.gradient_lsq(f["pvar"], f["coefa"], f["coefb"]), g["grad"])
+    for irecmf in (0, 1):
+        d = m.diffusion_potential_rc(f["pvar"], f["coefa"], f["coefb"], f["cofaf"], f["cofbf"],
+                                     f["i_visc"], f["b_visc"], f["visel"], irecmf=irecmf)
+        assert np.array_equal(d, g[f"div_irecmf{irecmf}"]), irecmf
+    d = m.diffusion_potential_rc(f["pvar"], f["coefa"], f["coefb"], f["cofaf"], f["cofbf"],
+                                 f["i_visc"], f["b_visc"], f["visel"], irecmf=0, init=0, inc=0,
+                                 diverg=f["div0"])
+    assert np.array_equal(d, g["div_init0_inc0"])
+    m.destroy()
+
+
+def test_gradient_lsq_vs_oracle_larger_and_linear_field(csb, oracle):
+    """40^3 non-orthogonal cube against the oracle (bit-exact), cocg cache reused across calls
+    and rebuilt after a geometry change; a linear field's gradient is reproduced"""
+    s, bfc, b_geo, _, i_geo, f = rc_input(40, seed=17)
+    m = _rc_matrix(csb, s, bfc, b_geo, i_geo)
+    for k in range(2):
+        p = f["pvar"] * (1 + k)
+        go = oracle.gradient_lsq(s, bfc, b_geo[:, :3], b_geo[:, 6], p, f["coefa"], f["coefb"])
+        assert np.array_equal(m.gradient_lsq(p, f["coefa"], f["coefb"]), go)
+    do = oracle.diffusion_potential_rc(s, bfc, i_geo, go, p, f["cofaf"], f["cofbf"], f["i_visc"],
+                                       f["b_visc"], f["visel"], irecmf=1)
+    d = m.diffusion_potential_rc(p, f["coefa"], f["coefb"], f["cofaf"], f["cofbf"], f["i_visc"],
+                                 f["b_visc"], f["visel"], irecmf=1)
+    assert np.array_equal(d, do)
+    cen = s.cell_cen.reshape(-1, 3)
+    a = np.array([0.7, -1.3, 2.1])
+    lin = cen @ a + 0.4
+    vf = lin[bfc] + b_geo[:, 6] * (b_geo[:, :3] @ a)
+    grad = m.gradient_lsq(lin, vf, np.zeros(len(bfc)))
+    assert np.abs(grad - a).max() < 5e-6 * np.abs(a).max()
+    # new boundary distances: the cached cocg matrices do not depend on them, the gradient does
+    b2 = b_geo.copy(); b2[:, 6] *= 1.5
+    m.set_face_geometry(i_geo[:, 6], i_geo[:, :3], i_geo[:, 3:6], b2[:, :3], b2[:, 6])
+    go = oracle.gradient_lsq(s, bfc, b2[:, :3], b2[:, 6], f["pvar"], f["coefa"], f["coefb"])
+    assert np.array_equal(m.gradient_lsq(f["pvar"], f["coefa"], f["coefb"]), go)
+    m.destroy()
+
+
+def test_reconstruction_needs_geometry(csb):
+    s, bfc, _, _, _, f = rc_input(5)
+    m = csb.Matrix.from_system(s)
+    m.set_boundary_faces(bfc)
+    with pytest.raises(csb.CsbError):
+        m.gradient_lsq(f["pvar"], f["coefa"], f["coefb"])
+    m.destroy()

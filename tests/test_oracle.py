@@ -849,3 +849,39 @@ def test_oracle_diffusion_potential_matches_reference_live(oracle):
     y = oracle.spmv(s.row_index, s.col_id, s.d_val * 0., s.x_val, f["pvar"])
     rowsum = np.add.reduceat(np.append(s.x_val, 0.), s.row_index[:-1])
     assert np.allclose(d, y - rowsum * f["pvar"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("N", [5, 9])
+def test_oracle_gradient_lsq_and_reconstructed_flux_match_golden(oracle, N):
+    """least-squares gradient (float cocg, float Gauss-Jordan inverse) and the reconstructed
+    branch of cs_diffusion_potential, both formulas: bit-exact against the reference"""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_rhs import rc_input
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"rhs_rc_N{N}.npz"))
+    s, bfc, b_geo, _, i_geo, f = rc_input(N)
+    grad = oracle.gradient_lsq(s, bfc, b_geo[:, :3], b_geo[:, 6], f["pvar"], f["coefa"], f["coefb"])
+    assert np.array_equal(grad, g["grad"])
+    for irecmf in (0, 1):
+        d = oracle.diffusion_potential_rc(s, bfc, i_geo, grad, f["pvar"], f["cofaf"], f["cofbf"],
+                                          f["i_visc"], f["b_visc"], f["visel"], irecmf=irecmf)
+        assert np.array_equal(d, g[f"div_irecmf{irecmf}"]), irecmf
+    grad0 = oracle.gradient_lsq(s, bfc, b_geo[:, :3], b_geo[:, 6], f["pvar"], f["coefa"],
+                                f["coefb"], inc=0)
+    d = oracle.diffusion_potential_rc(s, bfc, i_geo, grad0, f["pvar"], f["cofaf"], f["cofbf"],
+                                      f["i_visc"], f["b_visc"], f["visel"], irecmf=0, init=0, inc=0,
+                                      diverg=f["div0"])
+    assert np.array_equal(d, g["div_init0_inc0"])
+
+
+def test_oracle_gradient_lsq_is_exact_for_linear_fields(oracle):
+    """property: a least-squares gradient reproduces the gradient of a linear field (to the
+    single precision of its cocg matrices) when the boundary values are those of the field"""
+    from make_golden_rhs import rc_input
+    s, bfc, b_geo, _, _, _ = rc_input(8)
+    cen = s.cell_cen.reshape(-1, 3)
+    a = np.array([0.7, -1.3, 2.1])
+    p = cen @ a + 0.4
+    # boundary value of the field at distance b_dist along the normal from the cell centre
+    vf = p[bfc] + b_geo[:, 6] * (b_geo[:, :3] @ a)
+    grad = oracle.gradient_lsq(s, bfc, b_geo[:, :3], b_geo[:, 6], p, vf, np.zeros(len(bfc)))
+    assert np.abs(grad - a).max() < 5e-6 * np.abs(a).max()
