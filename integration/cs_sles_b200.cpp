@@ -43,6 +43,7 @@ struct b200_ctx_t {                       /* cs_sles_t "context" */
   const cs_lnum_t     *row_index = nullptr;   /* structure the image was built from */
   const cs_lnum_t     *col_id = nullptr;
   const cs_real_t     *d_val = nullptr, *x_val = nullptr;
+  const cs_real_t     *da = nullptr, *xa = nullptr;   /* matrix mapped from native arrays */
   cs_lnum_t            n_rows = 0, n_cols = 0;
   int                  n_uploads = 0, n_value_updates = 0;
 };
@@ -84,6 +85,7 @@ _drop_device_matrix(b200_ctx_t *x)
   if (x->halo_dev != nullptr) csb_halo_destroy(&x->halo_dev);
   x->a_host = nullptr;
   x->row_index = nullptr; x->col_id = nullptr; x->d_val = nullptr; x->x_val = nullptr;
+  x->da = nullptr; x->xa = nullptr;
 }
 
 /* cs_matrix_t -> csb_matrix_t.  Arrays are borrowed from the matrix and copied to HBM;
@@ -104,8 +106,48 @@ _sync_device_matrix(b200_ctx_t *x, const cs_matrix_t *a)
   const cs_lnum_t n_rows = cs_matrix_get_n_rows(a), n_cols = cs_matrix_get_n_columns(a);
   const int symmetric = cs_matrix_is_symmetric(a) ? 1 : 0;
 
+  /* A matrix mapped from native (face-based) arrays -- cs_matrix_set_coefficients(edges, da,
+     xa), cs_matrix_is_mapped_from_native (src/alge/cs_matrix.cpp:5315, :5722): the reference
+     builds its multigrid hierarchy from the faces (cs_grid_create_from_shared,
+     src/alge/cs_grid.cpp:7485-7491), so does the device matrix made by
+     csb_matrix_create_native.  The edges are the mesh's interior faces, as cs_multigrid_setup
+     itself takes them (src/alge/cs_multigrid.cpp:5283, :5312). */
+  if (cs_matrix_is_mapped_from_native(a) && symmetric && cs_glob_mesh != nullptr
+      && cs_matrix_get_halo(a) == nullptr) {
+    const cs_real_t *da = cs_matrix_get_diagonal(a), *xa = cs_matrix_get_extra_diagonal(a);
+    if (x->a_dev != nullptr && x->row_index == row_index && x->col_id == col_id
+        && x->n_rows == n_rows && x->n_cols == n_cols && x->xa != nullptr) {
+      if (x->a_host == a && x->da == da && x->xa == xa)
+        return;
+      if (csb_matrix_set_coefficients_native(x->a_dev, da, xa) != 0)
+        bft_error(__FILE__, __LINE__, 0, "cs_sles_b200: %s", csb_last_error());
+      x->a_host = a; x->da = da; x->xa = xa;
+      x->n_value_updates += 1;
+      return;
+    }
+    _drop_device_matrix(x);
+    x->a_dev = csb_matrix_create_native(n_rows, n_cols, cs_glob_mesh->n_i_faces,
+                                        (const csb_lnum_t *)cs_glob_mesh->i_face_cells, da, xa, 1);
+    if (x->a_dev == nullptr)
+      bft_error(__FILE__, __LINE__, 0, "cs_sles_b200: %s", csb_last_error());
+    x->n_uploads += 1;
+    const cs_real_3_t *cen;
+    const cs_nreal_3_t *f_u_normal;
+    const cs_real_t *vol, *f_surf;
+    cs_matrix_get_mesh_association(a, nullptr, nullptr, nullptr, &cen, &vol, &f_u_normal, &f_surf);
+    if (cen != nullptr
+        && csb_matrix_set_mesh_association(x->a_dev, cs_glob_mesh->n_i_faces, nullptr, nullptr,
+                                           (const cs_real_t *)cen, vol,
+                                           (const cs_real_t *)f_u_normal, f_surf) != 0)
+      bft_error(__FILE__, __LINE__, 0, "cs_sles_b200: %s", csb_last_error());
+    x->a_host = a;
+    x->row_index = row_index; x->col_id = col_id; x->da = da; x->xa = xa;
+    x->n_rows = n_rows; x->n_cols = n_cols;
+    return;
+  }
+
   if (x->a_dev != nullptr && x->row_index == row_index && x->col_id == col_id
-      && x->n_rows == n_rows && x->n_cols == n_cols) {
+      && x->n_rows == n_rows && x->n_cols == n_cols && x->xa == nullptr) {
     if (x->a_host == a && x->d_val == d_val && x->x_val == x_val)
       return;                               /* same object, same arrays: nothing to move */
     if (csb_matrix_set_coefficients(x->a_dev, symmetric, d_val, x_val) != 0)

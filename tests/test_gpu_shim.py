@@ -52,6 +52,37 @@ def test_registry_roundtrip_matches_reference_solvers(csb, refb):
     refb.destroy(h)
 
 
+def test_registry_native_matrix_follows_the_reference_face_path(csb, refb):
+    """A cs_matrix_t the reference built with cs_matrix_set_coefficients(edges, da, xa)
+    ("mapped from native"): the binding creates the device matrix from the faces, and the
+    hierarchy is the reference's face-list one (1 thread: _automatic_aggregation_fc +
+    _compute_coarse_quantities_native) -- same cycle counts, same solution."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_native import native_system
+    s, da, xa = native_system(24, "dirichlet", True)
+    r_norm = float(np.linalg.norm(s.rhs))
+    h = refb.system_native(s, da, xa)
+    o = refb.multigrid(h, s.rhs, 1e-12, r_norm)
+    r = refb.b200_sles_solve(h, refb.MULTIGRID, s.rhs, 100, 1e-12, r_norm)
+    assert r["cvg"] == o["cvg"] == 1
+    assert equiv_iters_close(r["n_iter"], o["n_iter"], 6)
+    assert rel_l2(r["vx"], o["vx"]) <= 1e-10
+    assert r["uploads"] == 1 and r["value_updates"] == 0
+    o = refb.fcg_mgpc(h, s.rhs, 200, 1e-13, r_norm)
+    r = refb.b200_sles_solve(h, refb.FCG_MG, s.rhs, 200, 1e-13, r_norm)
+    assert r["cvg"] == o["cvg"] == 1 and abs(r["n_iter"] - o["n_iter"]) <= 2
+    assert rel_l2(r["vx"], o["vx"]) <= 1e-10
+    # the MSR-built matrix of the same system gives another hierarchy (the MSR aggregation):
+    # the two entries are really different paths
+    h2 = refb.system(s, d_val=da, x_val=xa[np.asarray(s.c2f)])
+    o2 = refb.fcg_mgpc(h2, s.rhs, 200, 1e-13, r_norm)
+    assert rel_l2(o2["vx"], o["vx"]) <= 1e-9
+    refb.destroy(h2)
+    refb.destroy(h)
+
+
 def test_registry_reuses_device_matrix_and_frees(csb, refb):
     """Second solve of the same cs_matrix_t: no second upload; after cs_sles_free the next
     solve goes through setup (and one upload) again; warm start through vx_ini_0 = false."""
@@ -68,3 +99,4 @@ def test_registry_reuses_device_matrix_and_frees(csb, refb):
     assert w["cvg"] == 1 and w["n_iter"] <= 1
     refb.destroy(h)
     refb.finalize()                                  # destroy callbacks of every system
+
