@@ -672,6 +672,14 @@ class Matrix:
         if L.csb_matrix_set_face_geometry(self.handle, *[_ptr(x) for x in a]) != 0:
             _err("csb_matrix_set_face_geometry")
 
+    def set_boundary_iprime(self, diipb):
+        """II' of the boundary faces (cs_mesh_quantities_t::diipb); None resets it to zero"""
+        L = load_library()
+        L.csb_matrix_set_boundary_iprime.argtypes = [C.c_void_p, C.c_void_p]
+        d = None if diipb is None else _f64(np.asarray(diipb))
+        if L.csb_matrix_set_boundary_iprime(self.handle, _ptr(d)) != 0:
+            _err("csb_matrix_set_boundary_iprime")
+
     def gradient_lsq(self, pvar, coefa=None, coefb=None, inc=1):
         """least-squares cell gradient (cs_gradient_scalar_synced_input, CS_GRADIENT_LSQ)"""
         L = load_library()

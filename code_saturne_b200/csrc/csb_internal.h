@@ -374,6 +374,8 @@ struct _csb_matrix_t {
      cs_gradient_priv.h:54) */
   csb::DevBuf<double>      i_dist, diipf, djjpf, b_face_u_normal, b_dist;
   bool        has_face_geo = false;
+  csb::DevBuf<double>      diipb;        /* II' of the boundary faces (csb_matrix_set_boundary_iprime) */
+  bool        has_diipb = false;
   mutable csb::DevBuf<float> cocg_lsq;
   mutable bool cocg_valid = false;
   bool        from_native = false;
@@ -633,12 +635,19 @@ bool launch_diffusion_potential(const _csb_matrix_t *m, int init, int inc, const
 /* least-squares cell gradient (cs_gradient.cpp:2501-2680, :2695-2900) and the reconstructed
    form of cs_diffusion_potential (cs_convection_diffusion.cpp:8895-8982) */
 bool launch_lsq_cocg(const _csb_matrix_t *m, float *cocg);
+/* val_ip: values at I' of the boundary faces (launch_b_iprime_lsq,
+   cs_gradient_boundary.cpp:197-640) when the matrix holds II' of its boundary faces, else
+   nullptr (I' = I) */
+bool launch_b_iprime_lsq(const _csb_matrix_t *m, const double *pvar, const double *coefa,
+                         const double *coefb, double *val_ip);
 bool launch_lsq_gradient(const _csb_matrix_t *m, const float *cocg, int inc, const double *pvar,
-                         const double *coefa, const double *coefb, double *grad);
+                         const double *coefa, const double *coefb, const double *val_ip,
+                         double *grad);
 bool launch_diffusion_potential_rc(const _csb_matrix_t *m, int irecmf, int init, int inc,
                                    const double *pvar, const double *grad, const double *cofaf,
                                    const double *cofbf, const double *i_visc,
-                                   const double *b_visc, const double *visel, double *diverg);
+                                   const double *b_visc, const double *visel,
+                                   const double *val_ip, double *diverg);
 /* matrix assembler (assembler.cu): slot s < n_rows is the diagonal of row s, slot
    n_rows + k the extra-diagonal entry k; every slot adds val[src[j]] for j in
    [index[s], index[s+1]) to its current value, in that order */

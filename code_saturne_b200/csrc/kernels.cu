@@ -2344,7 +2344,8 @@ __global__ void k_lsq_cocg(int n_rows, const int *__restrict__ row_index,
                            const int *__restrict__ col_id, const double *__restrict__ cell_cen,
                            const int *__restrict__ cell_b_faces_idx,
                            const int *__restrict__ cell_b_faces,
-                           const double *__restrict__ b_un, float *cocg)
+                           const double *__restrict__ b_un, const double *__restrict__ b_dist,
+                           const double *__restrict__ diipb, float *cocg)
 {
   const int c = blockIdx.x*blockDim.x + threadIdx.x;
   if (c >= n_rows) return;
@@ -2363,7 +2364,14 @@ __global__ void k_lsq_cocg(int n_rows, const int *__restrict__ row_index,
   }
   if (cell_b_faces_idx != nullptr)
     for (int k = cell_b_faces_idx[c]; k < cell_b_faces_idx[c+1]; k++) {
-      const double *d = b_un + 3*(size_t)cell_b_faces[k];
+      /* direction n + II'/b_dist (cs_gradient.cpp:2632-2636); n alone when II' = 0 */
+      const size_t f = (size_t)cell_b_faces[k];
+      double d[3] = {b_un[3*f], b_un[3*f+1], b_un[3*f+2]};
+      if (diipb != nullptr) {
+        const double unddij = 1. / b_dist[f];
+        d[0] = d[0] + unddij*diipb[3*f]; d[1] = d[1] + unddij*diipb[3*f+1];
+        d[2] = d[2] + unddij*diipb[3*f+2];
+      }
       g[0] = (float)((double)g[0] + d[0] * d[0]);
       g[1] = (float)((double)g[1] + d[1] * d[1]);
       g[2] = (float)((double)g[2] + d[2] * d[2]);
@@ -2439,7 +2447,9 @@ __global__ void k_lsq_gradient(int n_rows, const int *__restrict__ row_index,
                                const float *__restrict__ cocg, int inc,
                                const double *__restrict__ pvar,
                                const double *__restrict__ coefa,
-                               const double *__restrict__ coefb, double *grad)
+                               const double *__restrict__ coefb,
+                               const double *__restrict__ diipb,
+                               const double *__restrict__ val_ip, double *grad)
 {
   const int c = blockIdx.x*blockDim.x + threadIdx.x;
   if (c >= n_rows) return;
@@ -2466,15 +2476,110 @@ __global__ void k_lsq_gradient(int n_rows, const int *__restrict__ row_index,
   if (cell_b_faces_idx != nullptr)
     for (int k = cell_b_faces_idx[c]; k < cell_b_faces_idx[c+1]; k++) {
       const int f = cell_b_faces[k];
-      const double val_f = inc*coefa[f] + coefb[f]*pc;
+      /* face value from the value at I' (_compute_bc_flux_grad,
+         cs_boundary_conditions_set_coeffs.cpp:168-170); I' = I when II' = 0 */
+      const double val_f = inc*coefa[f] + coefb[f]*(val_ip != nullptr ? val_ip[f] : pc);
       const double ddif = 1. / b_dist[f];
+      double d0 = b_un[3*(size_t)f], d1 = b_un[3*(size_t)f+1], d2 = b_un[3*(size_t)f+2];
+      if (diipb != nullptr) {
+        d0 = d0 + ddif*diipb[3*(size_t)f]; d1 = d1 + ddif*diipb[3*(size_t)f+1];
+        d2 = d2 + ddif*diipb[3*(size_t)f+2];
+      }
       const double pfac = (val_f - pc) * ddif;
-      r0 += b_un[3*(size_t)f] * pfac; r1 += b_un[3*(size_t)f+1] * pfac; r2 += b_un[3*(size_t)f+2] * pfac;
+      r0 += d0 * pfac; r1 += d1 * pfac; r2 += d2 * pfac;
     }
   const float *g = cocg + 6*(size_t)c;
   grad[3*(size_t)c]   = g[0]*r0 + g[3]*r1 + g[5]*r2;
   grad[3*(size_t)c+1] = g[3]*r0 + g[1]*r1 + g[4]*r2;
   grad[3*(size_t)c+2] = g[5]*r0 + g[4]*r1 + g[2]*r2;
+}
+
+/* cs_gradient_boundary_iprime_lsq_s (cs_gradient_boundary.cpp:197-640; no limiter, no
+   hydrostatic term, no weighting, standard neighbourhood): value of pvar at I' of the boundary
+   faces.  The local least-squares system of a face depends on its cell only, so one thread
+   per cell builds it once (neighbours in adjacency order, then the cell's boundary faces in
+   ascending order with the direction n + (1 - b) II'/b_dist; cocg in single precision, its
+   cofactors in float arithmetic, the solve in double, :560-582) and serves the cell's faces;
+   faces with |II'|^2 < 1e-6 b_dist^2 take the cell value (:285-291).  coefa enters without
+   inc, as in the reference. */
+__global__ void k_b_iprime_lsq(int n_rows, const int *__restrict__ row_index,
+                               const int *__restrict__ col_id,
+                               const double *__restrict__ cell_cen,
+                               const int *__restrict__ cell_b_faces_idx,
+                               const int *__restrict__ cell_b_faces,
+                               const double *__restrict__ b_un,
+                               const double *__restrict__ b_dist,
+                               const double *__restrict__ diipb,
+                               const double *__restrict__ pvar,
+                               const double *__restrict__ coefa,
+                               const double *__restrict__ coefb, double *val_ip)
+{
+  const int c = blockIdx.x*blockDim.x + threadIdx.x;
+  if (c >= n_rows) return;
+  const int bs = cell_b_faces_idx[c], be = cell_b_faces_idx[c+1];
+  if (bs >= be) return;
+  const double var_i = pvar[c];
+  bool any = false;
+  for (int k = bs; k < be; k++) {
+    const size_t f = (size_t)cell_b_faces[k];
+    const double *ip = diipb + 3*f;
+    const double bd = b_dist[f];
+    if (ip[0]*ip[0] + ip[1]*ip[1] + ip[2]*ip[2] < (bd*bd) * (1e-3 * 1e-3)) val_ip[f] = var_i;
+    else any = true;
+  }
+  if (!any) return;
+  float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  double r0 = 0., r1 = 0., r2 = 0.;
+  const double cx = cell_cen[3*(size_t)c], cy = cell_cen[3*(size_t)c+1], cz = cell_cen[3*(size_t)c+2];
+  for (int k = row_index[c]; k < row_index[c+1]; k++) {
+    const size_t j = (size_t)col_id[k];
+    const double d0 = cell_cen[3*j] - cx, d1 = cell_cen[3*j+1] - cy, d2 = cell_cen[3*j+2] - cz;
+    const double ddc = 1. / (d0*d0 + d1*d1 + d2*d2);
+    g[0] = (float)((double)g[0] + d0 * d0 * ddc);
+    g[1] = (float)((double)g[1] + d1 * d1 * ddc);
+    g[2] = (float)((double)g[2] + d2 * d2 * ddc);
+    g[3] = (float)((double)g[3] + d0 * d1 * ddc);
+    g[4] = (float)((double)g[4] + d1 * d2 * ddc);
+    g[5] = (float)((double)g[5] + d0 * d2 * ddc);
+    double pfac = pvar[j] - var_i;
+    pfac *= ddc;
+    r0 += d0 * pfac; r1 += d1 * pfac; r2 += d2 * pfac;
+  }
+  for (int k = bs; k < be; k++) {
+    const size_t f = (size_t)cell_b_faces[k];
+    const double a = coefa[f], b = coefb[f];
+    const double ddif = 1. / b_dist[f];
+    const double umcbdd = (1. - b) * ddif;
+    const double d0 = b_un[3*f] + umcbdd * diipb[3*f], d1 = b_un[3*f+1] + umcbdd * diipb[3*f+1],
+                 d2 = b_un[3*f+2] + umcbdd * diipb[3*f+2];
+    g[0] = (float)((double)g[0] + d0 * d0);
+    g[1] = (float)((double)g[1] + d1 * d1);
+    g[2] = (float)((double)g[2] + d2 * d2);
+    g[3] = (float)((double)g[3] + d0 * d1);
+    g[4] = (float)((double)g[4] + d1 * d2);
+    g[5] = (float)((double)g[5] + d0 * d2);
+    double pfac = (a + (b-1.)*var_i);
+    pfac *= ddif;
+    r0 += d0 * pfac; r1 += d1 * pfac; r2 += d2 * pfac;
+  }
+  const double a00 = (double)(g[1]*g[2] - g[4]*g[4]);
+  const double a01 = (double)(g[4]*g[5] - g[3]*g[2]);
+  const double a02 = (double)(g[3]*g[4] - g[1]*g[5]);
+  const double a11 = (double)(g[0]*g[2] - g[5]*g[5]);
+  const double a12 = (double)(g[3]*g[5] - g[0]*g[4]);
+  const double a22 = (double)(g[0]*g[1] - g[3]*g[3]);
+  const double det_inv = 1. / (g[0]*a00 + g[3]*a01 + g[5]*a02);
+  const double gx = (a00 * r0 + a01 * r1 + a02 * r2) * det_inv;
+  const double gy = (a01 * r0 + a11 * r1 + a12 * r2) * det_inv;
+  const double gz = (a02 * r0 + a12 * r1 + a22 * r2) * det_inv;
+  for (int k = bs; k < be; k++) {
+    const size_t f = (size_t)cell_b_faces[k];
+    const double *ip = diipb + 3*f;
+    const double bd = b_dist[f];
+    if (ip[0]*ip[0] + ip[1]*ip[1] + ip[2]*ip[2] < (bd*bd) * (1e-3 * 1e-3)) continue;
+    const double grad_dot_diipb = gx*ip[0] + gy*ip[1] + gz*ip[2];
+    val_ip[f] = var_i + grad_dot_diipb;
+  }
 }
 
 /* cs_diffusion_potential with flux reconstruction (:8921-8961): the face flux is computed in
@@ -2495,7 +2600,8 @@ __global__ void k_diffusion_potential_rc(int n_rows, const int *__restrict__ row
                                          const double *__restrict__ cofbf,
                                          const double *__restrict__ i_visc,
                                          const double *__restrict__ b_visc,
-                                         const double *__restrict__ visel, double *diverg)
+                                         const double *__restrict__ visel,
+                                         const double *__restrict__ val_ip, double *diverg)
 {
   const int c = blockIdx.x*blockDim.x + threadIdx.x;
   if (c >= n_rows) return;
@@ -2534,7 +2640,7 @@ __global__ void k_diffusion_potential_rc(int n_rows, const int *__restrict__ row
     const double pc = pvar[c];
     for (int k = cell_b_faces_idx[c]; k < cell_b_faces_idx[c+1]; k++) {
       const int f = cell_b_faces[k];
-      const double flux_d = inc*cofaf[f] + cofbf[f]*pc;
+      const double flux_d = inc*cofaf[f] + cofbf[f]*(val_ip != nullptr ? val_ip[f] : pc);
       d += b_visc[f]*flux_d;
     }
   }
@@ -2550,26 +2656,40 @@ bool launch_lsq_cocg(const _csb_matrix_t *m, float *cocg)
   k_lsq_cocg<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
     m->n_rows, m->row_index.p, m->col_id.p, m->cell_cen.p,
     bnd ? m->cell_b_faces_idx.p : nullptr, bnd ? m->cell_b_faces.p : nullptr,
-    m->b_face_u_normal.p, cocg);
+    m->b_face_u_normal.p, m->b_dist.p, (bnd && m->has_diipb) ? m->diipb.p : nullptr, cocg);
   return post_launch("lsq_cocg");
 }
 
+bool launch_b_iprime_lsq(const _csb_matrix_t *m, const double *pvar, const double *coefa,
+                         const double *coefb, double *val_ip)
+{
+  if (m->n_rows < 1 || !m->has_b_faces || m->n_b_faces < 1) return true;
+  k_b_iprime_lsq<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
+    m->n_rows, m->row_index.p, m->col_id.p, m->cell_cen.p, m->cell_b_faces_idx.p,
+    m->cell_b_faces.p, m->b_face_u_normal.p, m->b_dist.p, m->diipb.p, pvar, coefa, coefb,
+    val_ip);
+  return post_launch("b_iprime_lsq");
+}
+
 bool launch_lsq_gradient(const _csb_matrix_t *m, const float *cocg, int inc, const double *pvar,
-                         const double *coefa, const double *coefb, double *grad)
+                         const double *coefa, const double *coefb, const double *val_ip,
+                         double *grad)
 {
   if (m->n_rows < 1) return true;
   const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
   k_lsq_gradient<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
     m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, m->c2f_sgn.p, m->cell_cen.p,
     bnd ? m->cell_b_faces_idx.p : nullptr, bnd ? m->cell_b_faces.p : nullptr,
-    m->b_face_u_normal.p, m->b_dist.p, cocg, inc, pvar, coefa, coefb, grad);
+    m->b_face_u_normal.p, m->b_dist.p, cocg, inc, pvar, coefa, coefb,
+    (bnd && m->has_diipb) ? m->diipb.p : nullptr, val_ip, grad);
   return post_launch("lsq_gradient");
 }
 
 bool launch_diffusion_potential_rc(const _csb_matrix_t *m, int irecmf, int init, int inc,
                                    const double *pvar, const double *grad, const double *cofaf,
                                    const double *cofbf, const double *i_visc,
-                                   const double *b_visc, const double *visel, double *diverg)
+                                   const double *b_visc, const double *visel,
+                                   const double *val_ip, double *diverg)
 {
   if (m->n_rows < 1) return true;
   const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
@@ -2577,7 +2697,7 @@ bool launch_diffusion_potential_rc(const _csb_matrix_t *m, int irecmf, int init,
     m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, m->c2f_sgn.p,
     bnd ? m->cell_b_faces_idx.p : nullptr, bnd ? m->cell_b_faces.p : nullptr, m->diipf.p,
     m->djjpf.p, m->i_dist.p, m->face_surf.p, irecmf, init, inc, pvar, grad, cofaf, cofbf,
-    i_visc, b_visc, visel, diverg);
+    i_visc, b_visc, visel, val_ip, diverg);
   return post_launch("diffusion_potential_rc");
 }
 

@@ -739,8 +739,9 @@ bool ensure_cocg(const csb_matrix_t *m)
 
 /* Face geometry of a non-orthogonal mesh, as cs_mesh_quantities_t holds it
    (src/mesh/cs_mesh_quantities.h:101-125): i_dist[n_faces], diipf / djjpf [n_faces][3] (II',
-   JJ'), b_face_u_normal[n_b_faces][3], b_dist[n_b_faces].  II' of the boundary faces is taken
-   as zero.  Needs csb_matrix_set_mesh_association and csb_matrix_set_boundary_faces first. */
+   JJ'), b_face_u_normal[n_b_faces][3], b_dist[n_b_faces].  II' of the boundary faces is zero
+   until csb_matrix_set_boundary_iprime gives it.  Needs csb_matrix_set_mesh_association and
+   csb_matrix_set_boundary_faces first. */
 int csb_matrix_set_face_geometry(csb_matrix_t *m, const csb_real_t *i_dist,
                                  const csb_real_t *diipf, const csb_real_t *djjpf,
                                  const csb_real_t *b_face_u_normal, const csb_real_t *b_dist)
@@ -760,13 +761,35 @@ int csb_matrix_set_face_geometry(csb_matrix_t *m, const csb_real_t *i_dist,
                && m->djjpf.upload(djjpf, 3*nf) && m->b_face_u_normal.upload(b_face_u_normal, 3*nb)
                && m->b_dist.upload(b_dist, nb) && CSB_CUDA(cudaStreamSynchronize(ctx().stream));
   m->has_face_geo = ok;
+  m->has_diipb = false;          /* II' of the boundary faces is given after the geometry */
   m->cocg_valid = false;
   return ok ? 0 : -1;
 }
 
+/* II' of the boundary faces (cs_mesh_quantities_t::diipb, [n_b_faces][3]); NULL takes it back
+   to zero.  With it the boundary face values of the gradient and of the reconstructed flux use
+   the value at I' (cs_gradient_boundary_iprime_lsq_s, cs_gradient_boundary.cpp:197-640, through
+   cs_boundary_conditions_update_bc_coeff_face_values,
+   src/base/cs_boundary_conditions_set_coeffs.cpp:125-195), and the boundary directions of the
+   least-squares system are n + II'/b_dist (cs_gradient.cpp:2632-2636, :2880-2885). */
+int csb_matrix_set_boundary_iprime(csb_matrix_t *m, const csb_real_t *diipb)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (!m->has_face_geo) {
+    set_error("csb_matrix_set_boundary_iprime: csb_matrix_set_face_geometry first");
+    return -1;
+  }
+  m->cocg_valid = false;
+  const size_t nb = m->has_b_faces ? (size_t)m->n_b_faces : 0;
+  if (diipb == nullptr || nb == 0) { m->has_diipb = false; return 0; }
+  m->has_diipb = m->diipb.upload(diipb, 3*nb) && CSB_CUDA(cudaStreamSynchronize(ctx().stream));
+  return m->has_diipb ? 0 : -1;
+}
+
 /* cs_gradient_scalar_synced_input with CS_GRADIENT_LSQ, standard neighbourhood, no weighting,
    no limiter (src/alge/cs_gradient.cpp:9651, _lsq_scalar_gradient :2695-2900): grad[n_rows][3].
-   Boundary face values are inc*coefa + coefb*pvar(cell) (II' = 0 at the boundary).  The cocg
+   Boundary face values are inc*coefa + coefb*(value at I'), the cell value when II' = 0 at the
+   boundary.  The cocg
    matrices are computed on first use and kept with the matrix. */
 int csb_gradient_scalar_lsq(const csb_matrix_t *m, int inc, const csb_real_t *pvar,
                             const csb_real_t *coefa, const csb_real_t *coefb, csb_real_t *grad)
@@ -788,10 +811,14 @@ int csb_gradient_scalar_lsq(const csb_matrix_t *m, int inc, const csb_real_t *pv
   const size_t len[4] = {nr, nb, nb, 3*nr};
   const bool in[4] = {true, true, true, false};
   const double *dev[4];
-  csb::DevBuf<double> stage;
+  csb::DevBuf<double> stage, val_ip;
   if (!ensure_cocg(m) || !stage_arrays(4, src, len, in, dev, stage)) return -1;
   double *d_grad = const_cast<double *>(dev[3]);
-  if (!csb::launch_lsq_gradient(m, m->cocg_lsq.p, inc, dev[0], dev[1], dev[2], d_grad)) return -1;
+  const bool ip = (bnd && m->has_diipb);
+  if (ip && (!val_ip.alloc(nb) || !csb::launch_b_iprime_lsq(m, dev[0], dev[1], dev[2], val_ip.p)))
+    return -1;
+  if (!csb::launch_lsq_gradient(m, m->cocg_lsq.p, inc, dev[0], dev[1], dev[2],
+                                ip ? val_ip.p : nullptr, d_grad)) return -1;
   if (d_grad != grad
       && !CSB_CUDA(cudaMemcpyAsync(grad, d_grad, sizeof(double)*3*nr, cudaMemcpyDeviceToHost,
                                    c.stream))) return -1;
@@ -830,12 +857,16 @@ int csb_diffusion_potential_rc(const csb_matrix_t *m, int irecmf, int init, int 
   const size_t len[9] = {nr, nb, nb, nb, nb, nf, nb, nr, nr};
   const bool in[9] = {true, true, true, true, true, true, true, true, init == 0};
   const double *dev[9];
-  csb::DevBuf<double> stage, grad;
+  csb::DevBuf<double> stage, grad, val_ip;
   if (!ensure_cocg(m) || !stage_arrays(9, src, len, in, dev, stage) || !grad.alloc(3*nr)) return -1;
   double *d_div = const_cast<double *>(dev[8]);
-  if (!csb::launch_lsq_gradient(m, m->cocg_lsq.p, inc, dev[0], dev[1], dev[2], grad.p)
+  const bool ip = (bnd && m->has_diipb);
+  if (ip && (!val_ip.alloc(nb) || !csb::launch_b_iprime_lsq(m, dev[0], dev[1], dev[2], val_ip.p)))
+    return -1;
+  const double *d_ip = ip ? val_ip.p : nullptr;
+  if (!csb::launch_lsq_gradient(m, m->cocg_lsq.p, inc, dev[0], dev[1], dev[2], d_ip, grad.p)
       || !csb::launch_diffusion_potential_rc(m, irecmf, init, inc, dev[0], grad.p, dev[3], dev[4],
-                                             dev[5], dev[6], dev[7], d_div)) return -1;
+                                             dev[5], dev[6], dev[7], d_ip, d_div)) return -1;
   if (d_div != diverg
       && !CSB_CUDA(cudaMemcpyAsync(diverg, d_div, sizeof(double)*nr, cudaMemcpyDeviceToHost,
                                    c.stream))) return -1;

@@ -316,19 +316,29 @@ int  csb_diffusion_potential(const csb_matrix_t *m, int init, int inc, const csb
 /* Reconstruction on non-orthogonal meshes.
    csb_matrix_set_face_geometry: the face quantities cs_mesh_quantities_t holds
    (src/mesh/cs_mesh_quantities.h:101-125): i_dist[n_faces], diipf / djjpf[n_faces][3] (II',
-   JJ'), b_face_u_normal[n_b_faces][3], b_dist[n_b_faces]; II' of boundary faces is taken as
-   zero.  After csb_matrix_set_mesh_association and csb_matrix_set_boundary_faces.
+   JJ'), b_face_u_normal[n_b_faces][3], b_dist[n_b_faces].  After
+   csb_matrix_set_mesh_association and csb_matrix_set_boundary_faces.
+   csb_matrix_set_boundary_iprime: II' of the boundary faces (cs_mesh_quantities_t::diipb,
+   [n_b_faces][3]; zero until given, NULL resets it; to be called after
+   csb_matrix_set_face_geometry).  With it the value of the variable at I' of every boundary
+   face is reconstructed like cs_gradient_boundary_iprime_lsq_s
+   (src/alge/cs_gradient_boundary.cpp:197-640; no limiter: eqp->imligr < 0), face values are
+   inc*coefa + coefb*val_ip and boundary fluxes inc*cofaf + cofbf*val_ip
+   (cs_boundary_conditions_update_bc_coeff_face_values,
+   src/base/cs_boundary_conditions_set_coeffs.cpp:125-195), and the boundary directions of the
+   least-squares system become n + II'/b_dist (cs_gradient.cpp:2632-2636, :2880-2885).
    csb_gradient_scalar_lsq: cs_gradient_scalar_synced_input with CS_GRADIENT_LSQ (imrgra = 1),
    standard neighbourhood, no weighting, no limiter (src/alge/cs_gradient.cpp:9651;
    _lsq_scalar_gradient :2695-2900, cocg _compute_cell_cocg_lsq :2501-2680 -- kept in single
    precision and inverted by the float Gauss-Jordan elimination like the reference's
-   cs_cocg_t); grad[n_rows][3]; boundary face value inc*coefa + coefb*pvar.
+   cs_cocg_t); grad[n_rows][3]; boundary face value inc*coefa + coefb*(pvar at I').
    csb_diffusion_potential_rc: cs_diffusion_potential with eqp->ircflu = 1 (:8895-8982), irecmf
    as cs_glob_velocity_pressure_param->irecmf (0 or 1).
    All bit-identical to the reference's one-thread results; host or device pointers. */
 int  csb_matrix_set_face_geometry(csb_matrix_t *m, const csb_real_t *i_dist,
                                   const csb_real_t *diipf, const csb_real_t *djjpf,
                                   const csb_real_t *b_face_u_normal, const csb_real_t *b_dist);
+int  csb_matrix_set_boundary_iprime(csb_matrix_t *m, const csb_real_t *diipb);
 int  csb_gradient_scalar_lsq(const csb_matrix_t *m, int inc, const csb_real_t *pvar,
                              const csb_real_t *coefa, const csb_real_t *coefb, csb_real_t *grad);
 int  csb_diffusion_potential_rc(const csb_matrix_t *m, int irecmf, int init, int inc,

@@ -187,6 +187,28 @@ void   ora_diffusion_potential_rc(int n_cells, int n_i_faces, const int *i_face_
                                   const double *cofbf, const double *i_visc,
                                   const double *b_visc, const double *visel, double *diverg);
 
+/* forms with II' of the boundary faces (diipb, 3 per boundary face; NULL = the plain forms):
+   value at I' per boundary face (cs_gradient_boundary_iprime_lsq_s), then the gradient and
+   the boundary flux with it */
+void   ora_b_iprime_lsq(int n_cells, const int *row_index, const int *col_id, int n_b_faces,
+                        const int *b_face_cells, const double *cell_cen,
+                        const double *b_face_u_normal, const double *b_dist,
+                        const double *diipb, const double *pvar, const double *coefa,
+                        const double *coefb, double *val_ip);
+void   ora_gradient_lsq_b(int n_cells, const int *row_index, const int *col_id, int n_i_faces,
+                          const int *i_face_cells, int n_b_faces, const int *b_face_cells,
+                          const double *cell_cen, const double *b_face_u_normal,
+                          const double *b_dist, const double *diipb, const double *val_ip,
+                          int inc, const double *pvar, const double *coefa,
+                          const double *coefb, double *grad);
+void   ora_diffusion_potential_rc_b(int n_cells, int n_i_faces, const int *i_face_cells,
+                                    int n_b_faces, const int *b_face_cells, const double *i_geo,
+                                    const double *i_face_surf, const double *val_ip, int irecmf,
+                                    int init, int inc, const double *pvar, const double *grad,
+                                    const double *cofaf, const double *cofbf,
+                                    const double *i_visc, const double *b_visc,
+                                    const double *visel, double *diverg);
+
 /* matrix assembler on one rank, MSR target: cs_oracle_assembler.c */
 int    ora_assembler_structure(int n_rows, int n, const long long *row_g_id,
                                const long long *col_g_id, long long l_range_0,

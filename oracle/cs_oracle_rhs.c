@@ -16,8 +16,16 @@
  * (src/alge/cs_gradient.cpp:2695-2900) with the cocg matrices of _compute_cell_cocg_lsq
  * (:2501-2680), which the reference keeps in SINGLE precision (cs_cocg_t = float,
  * cs_gradient_priv.h:54) and inverts with the float instance of
- * cs_math_matrix_gauss_inverse (src/base/cs_math.h:542-590): restated as such.  II' of the
- * boundary faces is taken as zero (boundary face value = inc*a + b*pvar).
+ * cs_math_matrix_gauss_inverse (src/base/cs_math.h:542-590): restated as such.
+ *
+ * The *_b forms take II' of the boundary faces (cs_mesh_quantities_t::diipb): the value at I'
+ * of every boundary face is reconstructed by cs_gradient_boundary_iprime_lsq_s
+ * (src/alge/cs_gradient_boundary.cpp:197-640; no limiter, no hydrostatic term, no weighting),
+ * the face values follow _compute_bc_flux_grad<true>
+ * (src/base/cs_boundary_conditions_set_coeffs.cpp:125-195: val_f = inc*a + b*val_ip,
+ * flux_diff = inc*af + bf*val_ip), and the boundary directions of the cell gradient become
+ * n + II'/b_dist (cs_gradient.cpp:2632-2648, :2875-2900).  With diipb NULL they are the plain
+ * forms (II' = 0: val_ip = pvar of the cell).
  *
  * Pinned bit for bit against oracle/_ref/libcsref.so (csref_diffusion_potential
  * drives the reference's real function), tests/test_oracle.py.
@@ -82,15 +90,113 @@ _gauss_inverse_6f(float a[6])
   a[3] = b[0][1]; a[4] = b[1][2]; a[5] = b[0][2];
 }
 
+/* direction of a boundary face in the least-squares system, B_DIRECTION_LSQ = CS_IPRIME_F_LSQ
+   (cs_gradient.h:55): n + II'/b_dist (cs_gradient.cpp:2632-2636, :2880-2885) */
+static void
+_b_direction(int f, const double *b_face_u_normal, const double *b_dist, const double *diipb,
+             double d[3])
+{
+  if (diipb == NULL) {
+    for (int ll = 0; ll < 3; ll++) d[ll] = b_face_u_normal[3*(size_t)f+ll];
+    return;
+  }
+  const double ddif = 1. / b_dist[f];
+  for (int ll = 0; ll < 3; ll++)
+    d[ll] = b_face_u_normal[3*(size_t)f+ll] + ddif*diipb[3*(size_t)f+ll];
+}
+
+/* cs_gradient_boundary_iprime_lsq_s (src/alge/cs_gradient_boundary.cpp:197-640) with
+   clip_coeff < 0 (no limiter: eqp->imligr < 0), hyd_p_flag 0, c_weight NULL, standard
+   neighbourhood: value of pvar at I' of every boundary face from a least-squares gradient local
+   to the face's cell -- neighbours in adjacency order, then the cell's boundary faces in
+   ascending order with the BC-aware direction n + (1 - b) II'/b_dist; cocg accumulated in
+   SINGLE precision (cs_cocg_t), its cofactors computed in float, the solve in double (:560-582).
+   Note coefa enters WITHOUT inc (:505, :541). */
+void
+ora_b_iprime_lsq(int n_cells, const int *row_index, const int *col_id, int n_b_faces,
+                 const int *b_face_cells, const double *cell_cen,
+                 const double *b_face_u_normal, const double *b_dist, const double *diipb,
+                 const double *pvar, const double *coefa, const double *coefb, double *val_ip)
+{
+  /* cell -> boundary faces, ascending (cs_mesh_adjacencies.cpp:705-760) */
+  int *idx = calloc((size_t)n_cells + 2, sizeof(int));
+  int *ids = malloc(sizeof(int)*(size_t)(n_b_faces > 0 ? n_b_faces : 1));
+  for (int f = 0; f < n_b_faces; f++) idx[b_face_cells[f] + 2]++;
+  for (int c = 0; c < n_cells; c++) idx[c+2] += idx[c+1];
+  for (int f = 0; f < n_b_faces; f++) ids[idx[b_face_cells[f] + 1]++] = f;
+
+  const double eps_r_2 = 1e-3 * 1e-3;
+  for (int f_id = 0; f_id < n_b_faces; f_id++) {
+    const int c_id = b_face_cells[f_id];
+    const double *ip = diipb + 3*(size_t)f_id;
+    if (ip[0]*ip[0] + ip[1]*ip[1] + ip[2]*ip[2] < (b_dist[f_id]*b_dist[f_id]) * eps_r_2) {
+      val_ip[f_id] = pvar[c_id];
+      continue;
+    }
+    float cocg[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    double rhs[3] = {0., 0., 0.};
+    const double var_i = pvar[c_id];
+    for (int k = row_index[c_id]; k < row_index[c_id+1]; k++) {
+      const int c1 = col_id[k];
+      double dc[3];
+      for (int ll = 0; ll < 3; ll++)
+        dc[ll] = cell_cen[3*(size_t)c1+ll] - cell_cen[3*(size_t)c_id+ll];
+      const double ddc = 1. / (dc[0]*dc[0] + dc[1]*dc[1] + dc[2]*dc[2]);
+      cocg[0] += dc[0]*dc[0]*ddc;
+      cocg[1] += dc[1]*dc[1]*ddc;
+      cocg[2] += dc[2]*dc[2]*ddc;
+      cocg[3] += dc[0]*dc[1]*ddc;
+      cocg[4] += dc[1]*dc[2]*ddc;
+      cocg[5] += dc[0]*dc[2]*ddc;
+      double pfac = pvar[c1] - var_i;
+      pfac *= ddc;
+      for (int ll = 0; ll < 3; ll++) rhs[ll] += dc[ll] * pfac;
+    }
+    for (int k = idx[c_id]; k < idx[c_id+1]; k++) {
+      const int f = ids[k];
+      const double a = coefa[f], b = coefb[f];
+      const double ddif = 1. / b_dist[f];
+      const double umcbdd = (1. - b) * ddif;
+      double dif[3];
+      for (int ll = 0; ll < 3; ll++)
+        dif[ll] = b_face_u_normal[3*(size_t)f+ll] + umcbdd * diipb[3*(size_t)f+ll];
+      cocg[0] += dif[0]*dif[0];
+      cocg[1] += dif[1]*dif[1];
+      cocg[2] += dif[2]*dif[2];
+      cocg[3] += dif[0]*dif[1];
+      cocg[4] += dif[1]*dif[2];
+      cocg[5] += dif[0]*dif[2];
+      double pfac = (a + (b-1.)*var_i);
+      pfac *= ddif;
+      for (int ll = 0; ll < 3; ll++) rhs[ll] += dif[ll] * pfac;
+    }
+    /* cofactors: float operands, float arithmetic (the products are cs_cocg_t * cs_cocg_t) */
+    const double a00 = cocg[1]*cocg[2] - cocg[4]*cocg[4];
+    const double a01 = cocg[4]*cocg[5] - cocg[3]*cocg[2];
+    const double a02 = cocg[3]*cocg[4] - cocg[1]*cocg[5];
+    const double a11 = cocg[0]*cocg[2] - cocg[5]*cocg[5];
+    const double a12 = cocg[3]*cocg[5] - cocg[0]*cocg[4];
+    const double a22 = cocg[0]*cocg[1] - cocg[3]*cocg[3];
+    const double det_inv = 1. / (cocg[0]*a00 + cocg[3]*a01 + cocg[5]*a02);
+    double g[3];
+    g[0] = (a00 * rhs[0] + a01 * rhs[1] + a02 * rhs[2]) * det_inv;
+    g[1] = (a01 * rhs[0] + a11 * rhs[1] + a12 * rhs[2]) * det_inv;
+    g[2] = (a02 * rhs[0] + a12 * rhs[1] + a22 * rhs[2]) * det_inv;
+    const double grad_dot_diipb = g[0]*ip[0] + g[1]*ip[1] + g[2]*ip[2];
+    val_ip[f_id] = var_i + grad_dot_diipb;
+  }
+  free(idx); free(ids);
+}
+
 /* (row_index, col_id): the cell -> cells adjacency in the order of cs_mesh_adjacencies
    (= the MSR structure); cell_b_faces: boundary faces by cell, ascending.  b_face_u_normal: 3
    per boundary face; grad: 3 per cell */
 void
-ora_gradient_lsq(int n_cells, const int *row_index, const int *col_id, int n_i_faces,
-                 const int *i_face_cells, int n_b_faces, const int *b_face_cells,
-                 const double *cell_cen, const double *b_face_u_normal, const double *b_dist,
-                 int inc, const double *pvar, const double *coefa, const double *coefb,
-                 double *grad)
+ora_gradient_lsq_b(int n_cells, const int *row_index, const int *col_id, int n_i_faces,
+                   const int *i_face_cells, int n_b_faces, const int *b_face_cells,
+                   const double *cell_cen, const double *b_face_u_normal, const double *b_dist,
+                   const double *diipb, const double *val_ip, int inc, const double *pvar,
+                   const double *coefa, const double *coefb, double *grad)
 {
   float *cocg = calloc(6*(size_t)(n_cells > 0 ? n_cells : 1), sizeof(float));
   double *rhsv = calloc(3*(size_t)(n_cells > 0 ? n_cells : 1), sizeof(double));
@@ -111,7 +217,8 @@ ora_gradient_lsq(int n_cells, const int *row_index, const int *col_id, int n_i_f
   }
   for (int f = 0; f < n_b_faces; f++) {       /* ascending faces = every cell's c2b order */
     float *g = cocg + 6*(size_t)b_face_cells[f];
-    const double *d = b_face_u_normal + 3*(size_t)f;
+    double d[3];
+    _b_direction(f, b_face_u_normal, b_dist, diipb, d);
     g[0] += d[0] * d[0];
     g[1] += d[1] * d[1];
     g[2] += d[2] * d[2];
@@ -134,10 +241,12 @@ ora_gradient_lsq(int n_cells, const int *row_index, const int *col_id, int n_i_f
   }
   for (int f = 0; f < n_b_faces; f++) {
     const int c = b_face_cells[f];
-    const double val_f = inc*coefa[f] + coefb[f]*pvar[c];
+    const double val_f = inc*coefa[f] + coefb[f]*(val_ip != NULL ? val_ip[f] : pvar[c]);
     const double ddif = 1. / b_dist[f];
+    double dif[3];
+    _b_direction(f, b_face_u_normal, b_dist, diipb, dif);
     const double pfac = (val_f - pvar[c]) * ddif;
-    for (int ll = 0; ll < 3; ll++) rhsv[3*c+ll] += b_face_u_normal[3*f+ll] * pfac;
+    for (int ll = 0; ll < 3; ll++) rhsv[3*c+ll] += dif[ll] * pfac;
   }
   for (int c = 0; c < n_cells; c++) {
     const float *g = cocg + 6*(size_t)c;
@@ -149,16 +258,28 @@ ora_gradient_lsq(int n_cells, const int *row_index, const int *col_id, int n_i_f
   free(cocg); free(rhsv);
 }
 
+void
+ora_gradient_lsq(int n_cells, const int *row_index, const int *col_id, int n_i_faces,
+                 const int *i_face_cells, int n_b_faces, const int *b_face_cells,
+                 const double *cell_cen, const double *b_face_u_normal, const double *b_dist,
+                 int inc, const double *pvar, const double *coefa, const double *coefb,
+                 double *grad)
+{
+  ora_gradient_lsq_b(n_cells, row_index, col_id, n_i_faces, i_face_cells, n_b_faces,
+                     b_face_cells, cell_cen, b_face_u_normal, b_dist, NULL, NULL, inc, pvar,
+                     coefa, coefb, grad);
+}
+
 /* cs_diffusion_potential with flux reconstruction (:8895-8982); i_geo: per interior face II'
    [3], JJ' [3], distance of the cell centres [1]; irecmf as
    cs_glob_velocity_pressure_param->irecmf */
 void
-ora_diffusion_potential_rc(int n_cells, int n_i_faces, const int *i_face_cells, int n_b_faces,
-                           const int *b_face_cells, const double *i_geo,
-                           const double *i_face_surf, int irecmf, int init, int inc,
-                           const double *pvar, const double *grad, const double *cofaf,
-                           const double *cofbf, const double *i_visc, const double *b_visc,
-                           const double *visel, double *diverg)
+ora_diffusion_potential_rc_b(int n_cells, int n_i_faces, const int *i_face_cells,
+                             int n_b_faces, const int *b_face_cells, const double *i_geo,
+                             const double *i_face_surf, const double *val_ip, int irecmf,
+                             int init, int inc, const double *pvar, const double *grad,
+                             const double *cofaf, const double *cofbf, const double *i_visc,
+                             const double *b_visc, const double *visel, double *diverg)
 {
   if (init >= 1)
     for (int i = 0; i < n_cells; i++) diverg[i] = 0.;
@@ -182,7 +303,20 @@ ora_diffusion_potential_rc(int n_cells, int n_i_faces, const int *i_face_cells, 
   }
   for (int f = 0; f < n_b_faces; f++) {
     const int c0 = b_face_cells[f];
-    const double flux_d = inc*cofaf[f] + cofbf[f]*pvar[c0];
+    const double flux_d = inc*cofaf[f] + cofbf[f]*(val_ip != NULL ? val_ip[f] : pvar[c0]);
     diverg[c0] += b_visc[f]*flux_d;
   }
+}
+
+void
+ora_diffusion_potential_rc(int n_cells, int n_i_faces, const int *i_face_cells, int n_b_faces,
+                           const int *b_face_cells, const double *i_geo,
+                           const double *i_face_surf, int irecmf, int init, int inc,
+                           const double *pvar, const double *grad, const double *cofaf,
+                           const double *cofbf, const double *i_visc, const double *b_visc,
+                           const double *visel, double *diverg)
+{
+  ora_diffusion_potential_rc_b(n_cells, n_i_faces, i_face_cells, n_b_faces, b_face_cells, i_geo,
+                               i_face_surf, NULL, irecmf, init, inc, pvar, grad, cofaf, cofbf,
+                               i_visc, b_visc, visel, diverg);
 }

@@ -353,25 +353,45 @@ class Oracle:
             _dp(_f64(i_visc)), _dp(_f64(b_visc)), _dp(div))
         return div
 
-    def gradient_lsq(self, s, b_face_cells, b_un, b_dist, pvar, coefa, coefb, inc=1):
+    def b_iprime_lsq(self, s, b_face_cells, b_un, b_dist, diipb, pvar, coefa, coefb):
+        """value of pvar at I' of every boundary face (cs_gradient_boundary_iprime_lsq_s)"""
+        bfc = _i32(b_face_cells)
+        val_ip = np.zeros(max(len(bfc), 1))
+        self.lib.ora_b_iprime_lsq.restype = None
+        self.lib.ora_b_iprime_lsq(
+            C.c_int(s.n_rows), _ip(_i32(s.row_index)), _ip(_i32(s.col_id)), C.c_int(len(bfc)),
+            _ip(bfc), _dp(_f64(s.cell_cen)), _dp(_f64(b_un)), _dp(_f64(b_dist)),
+            _dp(_f64(diipb)), _dp(_f64(pvar)), _dp(_f64(coefa)), _dp(_f64(coefb)), _dp(val_ip))
+        return val_ip[:len(bfc)]
+
+    def gradient_lsq(self, s, b_face_cells, b_un, b_dist, pvar, coefa, coefb, inc=1, diipb=None):
+        """diipb (II' of the boundary faces) given: face values from the values at I'"""
         grad = np.zeros(3 * s.n_rows)
         fc, bfc = _i32(s.face_cells), _i32(b_face_cells)
-        self.lib.ora_gradient_lsq.restype = None
-        self.lib.ora_gradient_lsq(
+        val_ip = dip = None
+        if diipb is not None:
+            dip = _f64(diipb)
+            val_ip = self.b_iprime_lsq(s, bfc, b_un, b_dist, dip, pvar, coefa, coefb)
+        self.lib.ora_gradient_lsq_b.restype = None
+        self.lib.ora_gradient_lsq_b(
             C.c_int(s.n_rows), _ip(_i32(s.row_index)), _ip(_i32(s.col_id)), C.c_int(len(fc)),
             _ip(fc), C.c_int(len(bfc)), _ip(bfc), _dp(_f64(s.cell_cen)), _dp(_f64(b_un)),
-            _dp(_f64(b_dist)), C.c_int(inc), _dp(_f64(pvar)), _dp(_f64(coefa)), _dp(_f64(coefb)),
-            _dp(grad))
+            _dp(_f64(b_dist)), (None if dip is None else _dp(dip)),
+            (None if val_ip is None else _dp(val_ip)), C.c_int(inc), _dp(_f64(pvar)),
+            _dp(_f64(coefa)), _dp(_f64(coefb)), _dp(grad))
         return grad.reshape(-1, 3)
 
     def diffusion_potential_rc(self, s, b_face_cells, i_geo, grad, pvar, cofaf, cofbf, i_visc,
-                               b_visc, visel, irecmf=0, init=1, inc=1, diverg=None):
+                               b_visc, visel, irecmf=0, init=1, inc=1, diverg=None, val_ip=None):
+        """val_ip: values at I' of the boundary faces (b_iprime_lsq) when II' is not zero"""
         div = np.zeros(s.n_rows) if diverg is None else _f64(diverg).copy()
         fc, bfc = _i32(s.face_cells), _i32(b_face_cells)
-        self.lib.ora_diffusion_potential_rc.restype = None
-        self.lib.ora_diffusion_potential_rc(
+        vip = None if val_ip is None else _f64(val_ip)
+        self.lib.ora_diffusion_potential_rc_b.restype = None
+        self.lib.ora_diffusion_potential_rc_b(
             C.c_int(s.n_rows), C.c_int(len(fc)), _ip(fc), C.c_int(len(bfc)), _ip(bfc),
-            _dp(_f64(i_geo)), _dp(_f64(s.face_surf)), C.c_int(irecmf), C.c_int(init), C.c_int(inc),
+            _dp(_f64(i_geo)), _dp(_f64(s.face_surf)), (None if vip is None else _dp(vip)),
+            C.c_int(irecmf), C.c_int(init), C.c_int(inc),
             _dp(_f64(pvar)), _dp(_f64(grad)), _dp(_f64(cofaf)), _dp(_f64(cofbf)),
             _dp(_f64(i_visc)), _dp(_f64(b_visc)), _dp(_f64(visel)), _dp(div))
         return div
@@ -699,7 +719,7 @@ class RefLib:
 
     def diffusion_potential_rc(self, h, s, b_face_cells, b_geo, i_face_cog, i_geo, pvar, coefa,
                                coefb, cofaf, cofbf, i_visc, b_visc, visel, irecmf=0, init=1,
-                               inc=1, diverg=None):
+                               inc=1, diverg=None, diipb=None):
         """cs_diffusion_potential WITH flux reconstruction (LSQ gradient) on the geometry given;
         returns (diverg, grad)."""
         div = np.zeros(s.n_rows) if diverg is None else _f64(diverg).copy()
@@ -709,7 +729,8 @@ class RefLib:
                                   i_visc, b_visc, visel)]
         r = self.lib.csref_diffusion_potential_rc(
             h, _ip(_i32(s.face_cells)), C.c_int(len(bfc)), _ip(bfc), _dp(keep[0]), _dp(keep[1]),
-            _dp(keep[2]), C.c_int(irecmf), C.c_int(init), C.c_int(inc), _dp(keep[3]), _dp(keep[4]),
+            _dp(keep[2]), (None if diipb is None else _dp(_f64(diipb))), C.c_int(irecmf),
+            C.c_int(init), C.c_int(inc), _dp(keep[3]), _dp(keep[4]),
             _dp(keep[5]), _dp(keep[6]), _dp(keep[7]), _dp(keep[8]), _dp(keep[9]), _dp(keep[10]),
             _dp(div), _dp(grad))
         assert r == 0

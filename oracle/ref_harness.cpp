@@ -937,6 +937,7 @@ csref_diffusion_potential_rc(void          *sys,
                              const double  *b_geo,        /* 7 per boundary face */
                              const double  *i_face_cog,   /* 3 per interior face */
                              const double  *i_geo,        /* 7 per interior face */
+                             const double  *diipb,        /* 3 per boundary face, or NULL */
                              int            irecmf,
                              int            init,
                              int            inc,
@@ -981,6 +982,8 @@ csref_diffusion_potential_rc(void          *sys,
   std::vector<cs_real_t> b_dist(nb1), i_dist(ni1), b_cog(3*nb1);
   std::vector<cs_nreal_t> b_un(3*nb1);
   std::vector<cs_rreal_t> zero_b(3*nb1, 0.), diipf(3*ni1), djjpf(3*ni1);
+  if (diipb != nullptr)
+    for (cs_lnum_t k = 0; k < 3*n_b_faces; k++) zero_b[k] = diipb[k];
   for (cs_lnum_t f = 0; f < n_b_faces; f++) {
     for (int k = 0; k < 3; k++) {
       b_un[3*f+k] = b_geo[7*f+k];

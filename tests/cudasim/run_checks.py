@@ -370,6 +370,27 @@ def check_rhs(ora):
                                      diverg=f["div0"])
         assert np.array_equal(d, g["div_init0_inc0"])
         m.destroy()
+    # II' of the boundary faces not zero: values at I' (cs_gradient_boundary_iprime_lsq_s)
+    from make_golden_rhs import diipb_input
+    for N in CASES:
+        g = np.load(os.path.join(GOLD, f"rhs_rcb_N{N}.npz"))
+        s, bfc, b_geo, _, i_geo, f = rc_input(N)
+        m = csb.Matrix.from_system(s)
+        m.set_boundary_faces(bfc)
+        m.set_face_geometry(i_geo[:, 6], i_geo[:, :3], i_geo[:, 3:6], b_geo[:, :3], b_geo[:, 6])
+        g0 = m.gradient_lsq(f["pvar"], f["coefa"], f["coefb"])       # cocg cached with II' = 0
+        m.set_boundary_iprime(diipb_input(N, len(bfc)))
+        for inc in (1, 0):
+            gr = m.gradient_lsq(f["pvar"], f["coefa"], f["coefb"], inc=inc)
+            assert np.array_equal(gr, g[f"grad_inc{inc}"].reshape(-1, 3)), (N, inc)
+            for irecmf in (0, 1):
+                d = m.diffusion_potential_rc(f["pvar"], f["coefa"], f["coefb"], f["cofaf"],
+                                             f["cofbf"], f["i_visc"], f["b_visc"], f["visel"],
+                                             irecmf=irecmf, inc=inc)
+                assert np.array_equal(d, g[f"div_irecmf{irecmf}_inc{inc}"]), (N, irecmf, inc)
+        m.set_boundary_iprime(None)
+        assert np.array_equal(m.gradient_lsq(f["pvar"], f["coefa"], f["coefb"]), g0)
+        m.destroy()
 
 
 def check_pairwise(ora):

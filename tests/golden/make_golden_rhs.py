@@ -2,10 +2,13 @@
 (src/alge/cs_convection_diffusion.cpp:8743-8990, eqp->ircflu = 0) on the cube mesh: outputs of
 the reference's own compiled CPU code (oracle/_ref/libcsref.so, csref_diffusion_potential):
 
-    python tests/golden/make_golden_rhs.py   -> tests/golden/rhs_N{N}.npz, rhs_rc_N{N}.npz
+    python tests/golden/make_golden_rhs.py   -> tests/golden/rhs_N{N}.npz, rhs_rc_N{N}.npz,
+                                                rhs_rcb_N{N}.npz
 
 rhs_rc_*: the same operator WITH flux reconstruction (eqp->ircflu = 1, least-squares gradient,
 csref_diffusion_potential_rc) on a non-orthogonal variant of the cube.
+rhs_rcb_*: the same with II' of the boundary faces not zero (cs_mesh_quantities_t::diipb): the
+boundary values go through cs_gradient_boundary_iprime_lsq_s.
 """
 import os
 import sys
@@ -59,9 +62,40 @@ def rc_input(N, seed=5):
     return s, bfc, b_geo, i_face_cog, i_geo, f
 
 
+def diipb_input(N, n_b_faces, seed=11):
+    """seeded II' of the boundary faces; every 7th face keeps I' = I and every 11th (from 3) is
+    below the reference's 1e-3 b_dist threshold, so both of its short cuts are taken"""
+    rng = np.random.default_rng(seed)
+    diipb = 0.2 / N * rng.standard_normal((n_b_faces, 3))
+    diipb[::7] = 0.0
+    diipb[3::11] *= 1e-4
+    return diipb
+
+
 def main():
     from oracle.pyoracle import RefLib
     ref = RefLib(1)
+    for N in CASES:
+        s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
+        diipb = diipb_input(N, len(bfc))
+        h = ref.system(s)
+        out = {}
+        for irecmf in (0, 1):
+            for inc in (1, 0):
+                d, g = ref.diffusion_potential_rc(h, s, bfc, b_geo, ifc, i_geo, f["pvar"],
+                                                  f["coefa"], f["coefb"], f["cofaf"], f["cofbf"],
+                                                  f["i_visc"], f["b_visc"], f["visel"],
+                                                  irecmf=irecmf, inc=inc, diipb=diipb)
+                out[f"div_irecmf{irecmf}_inc{inc}"] = d
+                out[f"grad_inc{inc}"] = g
+        d0, _ = ref.diffusion_potential_rc(h, s, bfc, b_geo, ifc, i_geo, f["pvar"], f["coefa"],
+                                           f["coefb"], f["cofaf"], f["cofbf"], f["i_visc"],
+                                           f["b_visc"], f["visel"], irecmf=0)
+        assert not np.array_equal(d0, out["div_irecmf0_inc1"])      # II' does change the result
+        ref.destroy(h)
+        path = os.path.join(ROOT, "tests", "golden", f"rhs_rcb_N{N}.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path))
     for N in CASES:
         s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
         h = ref.system(s)

@@ -127,6 +127,53 @@ def test_gradient_lsq_vs_oracle_larger_and_linear_field(csb, oracle):
     m.destroy()
 
 
+@pytest.mark.parametrize("N", CASES)
+def test_boundary_iprime_reconstruction_matches_reference_golden(csb, N):
+    """II' of the boundary faces not zero (csb_matrix_set_boundary_iprime): the values at I' of
+    cs_gradient_boundary_iprime_lsq_s feed the face values of the gradient and the boundary
+    fluxes; gradient and divergence bit-identical to the reference (both formulas, inc 0 / 1);
+    resetting II' gives the plain result back (cocg cache invalidated both ways)"""
+    from make_golden_rhs import diipb_input
+    g = np.load(os.path.join(GOLD, f"rhs_rcb_N{N}.npz"))
+    s, bfc, b_geo, _, i_geo, f = rc_input(N)
+    m = _rc_matrix(csb, s, bfc, b_geo, i_geo)
+    g0 = m.gradient_lsq(f["pvar"], f["coefa"], f["coefb"])
+    m.set_boundary_iprime(diipb_input(N, len(bfc)))
+    for inc in (1, 0):
+        gr = m.gradient_lsq(f["pvar"], f["coefa"], f["coefb"], inc=inc)
+        assert np.array_equal(gr, g[f"grad_inc{inc}"].reshape(-1, 3)), inc
+        for irecmf in (0, 1):
+            d = m.diffusion_potential_rc(f["pvar"], f["coefa"], f["coefb"], f["cofaf"], f["cofbf"],
+                                         f["i_visc"], f["b_visc"], f["visel"], irecmf=irecmf,
+                                         inc=inc)
+            assert np.array_equal(d, g[f"div_irecmf{irecmf}_inc{inc}"]), (irecmf, inc)
+    m.set_boundary_iprime(None)
+    assert np.array_equal(m.gradient_lsq(f["pvar"], f["coefa"], f["coefb"]), g0)
+    m.destroy()
+
+
+def test_boundary_iprime_vs_oracle_larger(csb, oracle):
+    """40^3 non-orthogonal cube with boundary II' against the oracle, bit-exact"""
+    from make_golden_rhs import diipb_input
+    s, bfc, b_geo, _, i_geo, f = rc_input(40, seed=17)
+    diipb = diipb_input(40, len(bfc), seed=23)
+    m = _rc_matrix(csb, s, bfc, b_geo, i_geo)
+    m.set_boundary_iprime(diipb)
+    vip = oracle.b_iprime_lsq(s, bfc, b_geo[:, :3], b_geo[:, 6], diipb, f["pvar"], f["coefa"],
+                              f["coefb"])
+    go = oracle.gradient_lsq(s, bfc, b_geo[:, :3], b_geo[:, 6], f["pvar"], f["coefa"],
+                             f["coefb"], diipb=diipb)
+    assert np.array_equal(m.gradient_lsq(f["pvar"], f["coefa"], f["coefb"]), go)
+    for irecmf in (0, 1):
+        do = oracle.diffusion_potential_rc(s, bfc, i_geo, go, f["pvar"], f["cofaf"], f["cofbf"],
+                                           f["i_visc"], f["b_visc"], f["visel"], irecmf=irecmf,
+                                           val_ip=vip)
+        d = m.diffusion_potential_rc(f["pvar"], f["coefa"], f["coefb"], f["cofaf"], f["cofbf"],
+                                     f["i_visc"], f["b_visc"], f["visel"], irecmf=irecmf)
+        assert np.array_equal(d, do), irecmf
+    m.destroy()
+
+
 def test_reconstruction_needs_geometry(csb):
     s, bfc, _, _, _, f = rc_input(5)
     m = csb.Matrix.from_system(s)

@@ -873,6 +873,33 @@ def test_oracle_gradient_lsq_and_reconstructed_flux_match_golden(oracle, N):
     assert np.array_equal(d, g["div_init0_inc0"])
 
 
+@pytest.mark.parametrize("N", [5, 9])
+def test_oracle_boundary_iprime_reconstruction_matches_golden(oracle, N):
+    """II' of the boundary faces not zero: cs_gradient_boundary_iprime_lsq_s values at I' feed
+    the face values of the gradient and the boundary fluxes (both irecmf formulas, inc 0 / 1):
+    bit-exact against the reference"""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_rhs import diipb_input, rc_input
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"rhs_rcb_N{N}.npz"))
+    s, bfc, b_geo, _, i_geo, f = rc_input(N)
+    diipb = diipb_input(N, len(bfc))
+    vip = oracle.b_iprime_lsq(s, bfc, b_geo[:, :3], b_geo[:, 6], diipb, f["pvar"], f["coefa"],
+                              f["coefb"])
+    # the two short cuts of the reference: I' = I gives the cell value
+    assert np.array_equal(vip[::7], f["pvar"][bfc][::7])
+    assert np.array_equal(vip[3::11], f["pvar"][bfc][3::11])
+    assert not np.array_equal(vip[1::7], f["pvar"][bfc][1::7])
+    for inc in (1, 0):
+        grad = oracle.gradient_lsq(s, bfc, b_geo[:, :3], b_geo[:, 6], f["pvar"], f["coefa"],
+                                   f["coefb"], inc=inc, diipb=diipb)
+        assert np.array_equal(grad, g[f"grad_inc{inc}"].reshape(-1, 3)), inc
+        for irecmf in (0, 1):
+            d = oracle.diffusion_potential_rc(s, bfc, i_geo, grad, f["pvar"], f["cofaf"],
+                                              f["cofbf"], f["i_visc"], f["b_visc"], f["visel"],
+                                              irecmf=irecmf, inc=inc, val_ip=vip)
+            assert np.array_equal(d, g[f"div_irecmf{irecmf}_inc{inc}"]), (irecmf, inc)
+
+
 def test_oracle_gradient_lsq_is_exact_for_linear_fields(oracle):
     """property: a least-squares gradient reproduces the gradient of a linear field (to the
     single precision of its cocg matrices) when the boundary values are those of the field"""
