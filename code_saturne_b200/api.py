@@ -680,6 +680,32 @@ class Matrix:
         if L.csb_matrix_set_boundary_iprime(self.handle, _ptr(d)) != 0:
             _err("csb_matrix_set_boundary_iprime")
 
+    def set_green_geometry(self, weight, dofij, b_face_surf, corr_grad_lin=None):
+        """quantities of the Green-Gauss reconstruction (imrgra = 4)"""
+        L = load_library()
+        L.csb_matrix_set_green_geometry.argtypes = [C.c_void_p] * 5
+        a = [None if x is None else _f64(np.asarray(x))
+             for x in (weight, dofij, b_face_surf, corr_grad_lin)]
+        if L.csb_matrix_set_green_geometry(self.handle, *[_ptr(x) for x in a]) != 0:
+            _err("csb_matrix_set_green_geometry")
+
+    def set_gradient_type(self, imrgra):
+        L = load_library()
+        L.csb_matrix_set_gradient_type.argtypes = [C.c_void_p, C.c_int]
+        if L.csb_matrix_set_gradient_type(self.handle, int(imrgra)) != 0:
+            _err("csb_matrix_set_gradient_type")
+
+    def gradient(self, imrgra, pvar, coefa=None, coefb=None, inc=1):
+        """cs_gradient_scalar_synced_input for imrgra 1 (LSQ) or 4 (Green-Gauss, LSQ face values)"""
+        L = load_library()
+        L.csb_gradient_scalar.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4
+        grad = np.zeros(3 * self.n_rows)
+        a = [x if x is None or not isinstance(x, np.ndarray) else _f64(x) for x in (pvar, coefa, coefb)]
+        if L.csb_gradient_scalar(self.handle, int(imrgra), int(inc), *[_ptr(x) for x in a],
+                                 _ptr(grad)) != 0:
+            _err("csb_gradient_scalar")
+        return grad.reshape(-1, 3)
+
     def gradient_lsq(self, pvar, coefa=None, coefb=None, inc=1):
         """least-squares cell gradient (cs_gradient_scalar_synced_input, CS_GRADIENT_LSQ)"""
         L = load_library()

@@ -376,6 +376,12 @@ struct _csb_matrix_t {
   bool        has_face_geo = false;
   csb::DevBuf<double>      diipb;        /* II' of the boundary faces (csb_matrix_set_boundary_iprime) */
   bool        has_diipb = false;
+  /* Green-Gauss reconstruction (csb_matrix_set_green_geometry): face weights, OF vectors,
+     boundary face surfaces, optional warped-face correction matrices; imrgra = the gradient
+     csb_diffusion_potential_rc uses (1: least squares, 4: Green-Gauss with LSQ face values) */
+  csb::DevBuf<double>      g_weight, dofij, b_face_surf, corr_grad_lin;
+  bool        has_green_geo = false, has_corr_grad_lin = false;
+  int         imrgra = 1;
   mutable csb::DevBuf<float> cocg_lsq;
   mutable bool cocg_valid = false;
   bool        from_native = false;
@@ -643,6 +649,11 @@ bool launch_b_iprime_lsq(const _csb_matrix_t *m, const double *pvar, const doubl
 bool launch_lsq_gradient(const _csb_matrix_t *m, const float *cocg, int inc, const double *pvar,
                          const double *coefa, const double *coefb, const double *val_ip,
                          double *grad);
+/* second half of the Green-Gauss gradient with least-squares face values (imrgra = 4,
+   _reconstruct_scalar_gradient cs_gradient.cpp:4167): r_grad = the least-squares gradient */
+bool launch_green_reconstruct(const _csb_matrix_t *m, int inc, const double *pvar,
+                              const double *coefa, const double *coefb, const double *val_ip,
+                              const double *r_grad, double *grad);
 bool launch_diffusion_potential_rc(const _csb_matrix_t *m, int irecmf, int init, int inc,
                                    const double *pvar, const double *grad, const double *cofaf,
                                    const double *cofbf, const double *i_visc,

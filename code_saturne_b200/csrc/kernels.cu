@@ -2582,6 +2582,91 @@ __global__ void k_b_iprime_lsq(int n_rows, const int *__restrict__ row_index,
   }
 }
 
+/* _reconstruct_scalar_gradient (cs_gradient.cpp:4167-4540, the branch without hydrostatic
+   pressure :4428-4506; no cell weighting, no disabled cell): the second half of the
+   Green-Gauss gradient with least-squares face values (imrgra = 4, CS_GRADIENT_GREEN_LSQ).
+   One thread per cell gathers its faces in the reference's scatter order (interior faces by
+   ascending id, then boundary faces): (pfac + rfac) S n with the face weight and the OF vector,
+   divided by the cell volume, then the warped-face correction when corr_grad_lin is given. */
+__global__ void k_green_reconstruct(int n_rows, const int *__restrict__ row_index,
+                                    const int *__restrict__ col_id,
+                                    const int *__restrict__ c2f,
+                                    const short *__restrict__ c2f_sgn,
+                                    const int *__restrict__ cell_b_faces_idx,
+                                    const int *__restrict__ cell_b_faces,
+                                    const double *__restrict__ weight,
+                                    const double *__restrict__ dofij,
+                                    const double *__restrict__ i_face_surf,
+                                    const double *__restrict__ i_face_u_normal,
+                                    const double *__restrict__ b_face_surf,
+                                    const double *__restrict__ b_un,
+                                    const double *__restrict__ cell_vol,
+                                    const double *__restrict__ corr_grad_lin, int inc,
+                                    const double *__restrict__ pvar,
+                                    const double *__restrict__ coefa,
+                                    const double *__restrict__ coefb,
+                                    const double *__restrict__ val_ip,
+                                    const double *__restrict__ r_grad, double *grad)
+{
+  const int c = blockIdx.x*blockDim.x + threadIdx.x;
+  if (c >= n_rows) return;
+  const int s = row_index[c], e = row_index[c+1];
+  const double pc = pvar[c];
+  double g0 = 0., g1 = 0., g2 = 0.;
+  int last = -1;
+  while (true) {
+    int best = INT_MAX, bk = -1;
+    for (int k = s; k < e; k++) {
+      const int f = c2f[k];
+      if (f > last && f < best) { best = f; bk = k; }
+    }
+    if (bk < 0) break;
+    last = best;
+    const size_t f = (size_t)best;
+    const int o = col_id[bk];
+    const bool first = (c2f_sgn[bk] > 0);
+    const size_t c1 = (size_t)(first ? c : o), c2 = (size_t)(first ? o : c);
+    const double ktpond = weight[f];
+    const double d_var = pvar[c2] - pvar[c1];
+    const double *of = dofij + 3*f, *ra = r_grad + 3*c1, *rb = r_grad + 3*c2;
+    const double rfac = 0.5 * (  of[0]*(ra[0]+rb[0])
+                               + of[1]*(ra[1]+rb[1])
+                               + of[2]*(ra[2]+rb[2]));
+    const double *n = i_face_u_normal + 3*f;
+    if (first) {
+      const double pfaci = (1.0-ktpond) * d_var;
+      const double pf = (pfaci + rfac) * i_face_surf[f];
+      g0 += pf * n[0]; g1 += pf * n[1]; g2 += pf * n[2];
+    }
+    else {
+      const double pfacj = -ktpond * d_var;
+      const double pf = (pfacj + rfac) * i_face_surf[f];
+      g0 += -(pf * n[0]); g1 += -(pf * n[1]); g2 += -(pf * n[2]);
+    }
+  }
+  if (cell_b_faces_idx != nullptr)
+    for (int k = cell_b_faces_idx[c]; k < cell_b_faces_idx[c+1]; k++) {
+      const size_t f = (size_t)cell_b_faces[k];
+      const double val_f = inc*coefa[f] + coefb[f]*(val_ip != nullptr ? val_ip[f] : pc);
+      const double pfac = (val_f - pc) * b_face_surf[f];
+      g0 += pfac * b_un[3*f]; g1 += pfac * b_un[3*f+1]; g2 += pfac * b_un[3*f+2];
+    }
+  const double dvol = 1. / cell_vol[c];
+  g0 *= dvol; g1 *= dvol; g2 *= dvol;
+  if (corr_grad_lin != nullptr) {
+    const double *m = corr_grad_lin + 9*(size_t)c;
+    double r[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      double a = 0.;
+      a += m[3*i] * g0; a += m[3*i+1] * g1; a += m[3*i+2] * g2;
+      r[i] = a;
+    }
+    g0 = r[0]; g1 = r[1]; g2 = r[2];
+  }
+  grad[3*(size_t)c] = g0; grad[3*(size_t)c+1] = g1; grad[3*(size_t)c+2] = g2;
+}
+
 /* cs_diffusion_potential with flux reconstruction (:8921-8961): the face flux is computed in
    the face's orientation by both of its cells, identically */
 __global__ void k_diffusion_potential_rc(int n_rows, const int *__restrict__ row_index,
@@ -2683,6 +2768,21 @@ bool launch_lsq_gradient(const _csb_matrix_t *m, const float *cocg, int inc, con
     m->b_face_u_normal.p, m->b_dist.p, cocg, inc, pvar, coefa, coefb,
     (bnd && m->has_diipb) ? m->diipb.p : nullptr, val_ip, grad);
   return post_launch("lsq_gradient");
+}
+
+bool launch_green_reconstruct(const _csb_matrix_t *m, int inc, const double *pvar,
+                              const double *coefa, const double *coefb, const double *val_ip,
+                              const double *r_grad, double *grad)
+{
+  if (m->n_rows < 1) return true;
+  const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  k_green_reconstruct<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
+    m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, m->c2f_sgn.p,
+    bnd ? m->cell_b_faces_idx.p : nullptr, bnd ? m->cell_b_faces.p : nullptr, m->g_weight.p,
+    m->dofij.p, m->face_surf.p, m->face_u_normal.p, m->b_face_surf.p, m->b_face_u_normal.p,
+    m->cell_vol.p, m->has_corr_grad_lin ? m->corr_grad_lin.p : nullptr, inc, pvar, coefa, coefb,
+    val_ip, r_grad, grad);
+  return post_launch("green_reconstruct");
 }
 
 bool launch_diffusion_potential_rc(const _csb_matrix_t *m, int irecmf, int init, int inc,

@@ -762,6 +762,8 @@ int csb_matrix_set_face_geometry(csb_matrix_t *m, const csb_real_t *i_dist,
                && m->b_dist.upload(b_dist, nb) && CSB_CUDA(cudaStreamSynchronize(ctx().stream));
   m->has_face_geo = ok;
   m->has_diipb = false;          /* II' of the boundary faces is given after the geometry */
+  m->has_green_geo = false;      /* and so are the Green-Gauss quantities */
+  m->imrgra = 1;
   m->cocg_valid = false;
   return ok ? 0 : -1;
 }
@@ -786,6 +788,72 @@ int csb_matrix_set_boundary_iprime(csb_matrix_t *m, const csb_real_t *diipb)
   return m->has_diipb ? 0 : -1;
 }
 
+/* Quantities of the Green-Gauss reconstruction (_reconstruct_scalar_gradient,
+   cs_gradient.cpp:4167-4540), as cs_mesh_quantities_t holds them: weight[n_faces] (interior
+   face weighting factor), dofij[n_faces][3] (OF vectors), b_face_surf[n_b_faces] and,
+   optionally, corr_grad_lin[n_rows][3][3] (the warped-face correction the reference applies
+   when CS_BAD_CELLS_WARPED_CORRECTION is set, its default; NULL: no correction).  Interior
+   normals, surfaces and cell volumes are those of the mesh association. */
+int csb_matrix_set_green_geometry(csb_matrix_t *m, const csb_real_t *weight,
+                                  const csb_real_t *dofij, const csb_real_t *b_face_surf,
+                                  const csb_real_t *corr_grad_lin)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (!m->has_face_geo) {
+    set_error("csb_matrix_set_green_geometry: csb_matrix_set_face_geometry first");
+    return -1;
+  }
+  const size_t nf = (size_t)m->n_faces, nb = m->has_b_faces ? (size_t)m->n_b_faces : 0;
+  if ((nf > 0 && (weight == nullptr || dofij == nullptr)) || (nb > 0 && b_face_surf == nullptr)) {
+    set_error("csb_matrix_set_green_geometry: null array");
+    return -1;
+  }
+  m->has_green_geo = m->g_weight.upload(weight, nf) && m->dofij.upload(dofij, 3*nf)
+                  && m->b_face_surf.upload(b_face_surf, nb);
+  m->has_corr_grad_lin = false;
+  if (m->has_green_geo && corr_grad_lin != nullptr) {
+    m->has_corr_grad_lin = m->corr_grad_lin.upload(corr_grad_lin, 9*(size_t)m->n_rows);
+    if (!m->has_corr_grad_lin) m->has_green_geo = false;
+  }
+  if (!CSB_CUDA(cudaStreamSynchronize(ctx().stream))) m->has_green_geo = false;
+  return m->has_green_geo ? 0 : -1;
+}
+
+/* Gradient csb_diffusion_potential_rc reconstructs with: eqp->imrgra, whose default is
+   cs_glob_space_disc->imrgra = 4 in the reference (cs_parameters.cpp:470);
+   cs_gradient_type_by_imrgra (cs_gradient.cpp:10317): 1 = CS_GRADIENT_LSQ (the initial value
+   here), 4 = CS_GRADIENT_GREEN_LSQ; the other types are not built. */
+int csb_matrix_set_gradient_type(csb_matrix_t *m, int imrgra)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (imrgra != 1 && imrgra != 4) {
+    set_error("csb_matrix_set_gradient_type: imrgra = %d is not built (1: least squares, "
+              "4: Green-Gauss with least-squares face values)", imrgra);
+    return -1;
+  }
+  if (imrgra == 4 && !m->has_green_geo) {
+    set_error("csb_matrix_set_gradient_type: imrgra = 4 needs csb_matrix_set_green_geometry");
+    return -1;
+  }
+  m->imrgra = imrgra;
+  return 0;
+}
+
+namespace {
+/* least-squares gradient into `out`, or -- imrgra 4 -- into a work array followed by the
+   Green-Gauss reconstruction into `out` */
+bool gradient_enqueue(const csb_matrix_t *m, int imrgra, int inc, const double *pvar,
+                      const double *coefa, const double *coefb, const double *val_ip,
+                      double *out, csb::DevBuf<double> &work)
+{
+  if (imrgra != 4)
+    return csb::launch_lsq_gradient(m, m->cocg_lsq.p, inc, pvar, coefa, coefb, val_ip, out);
+  return work.alloc(3*(size_t)std::max(m->n_rows, 1))
+      && csb::launch_lsq_gradient(m, m->cocg_lsq.p, inc, pvar, coefa, coefb, val_ip, work.p)
+      && csb::launch_green_reconstruct(m, inc, pvar, coefa, coefb, val_ip, work.p, out);
+}
+} // anonymous namespace
+
 /* cs_gradient_scalar_synced_input with CS_GRADIENT_LSQ, standard neighbourhood, no weighting,
    no limiter (src/alge/cs_gradient.cpp:9651, _lsq_scalar_gradient :2695-2900): grad[n_rows][3].
    Boundary face values are inc*coefa + coefb*(value at I'), the cell value when II' = 0 at the
@@ -794,15 +862,33 @@ int csb_matrix_set_boundary_iprime(csb_matrix_t *m, const csb_real_t *diipb)
 int csb_gradient_scalar_lsq(const csb_matrix_t *m, int inc, const csb_real_t *pvar,
                             const csb_real_t *coefa, const csb_real_t *coefb, csb_real_t *grad)
 {
+  return csb_gradient_scalar(m, 1, inc, pvar, coefa, coefb, grad);
+}
+
+/* cs_gradient_scalar_synced_input for the gradient type of imrgra (1: CS_GRADIENT_LSQ,
+   4: CS_GRADIENT_GREEN_LSQ = the least-squares gradient, then _reconstruct_scalar_gradient,
+   cs_gradient.cpp:7697-7797) */
+int csb_gradient_scalar(const csb_matrix_t *m, int imrgra, int inc, const csb_real_t *pvar,
+                        const csb_real_t *coefa, const csb_real_t *coefb, csb_real_t *grad)
+{
   if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
   if (!m->has_face_geo || m->db != 1 || m->halo != nullptr) {
-    set_error("csb_gradient_scalar_lsq: needs a scalar matrix on one rank with its mesh "
+    set_error("csb_gradient_scalar: needs a scalar matrix on one rank with its mesh "
               "association, boundary faces and csb_matrix_set_face_geometry");
+    return -1;
+  }
+  if (imrgra != 1 && imrgra != 4) {
+    set_error("csb_gradient_scalar: imrgra = %d is not built (1: least squares, 4: Green-Gauss "
+              "with least-squares face values)", imrgra);
+    return -1;
+  }
+  if (imrgra == 4 && !m->has_green_geo) {
+    set_error("csb_gradient_scalar: imrgra = 4 needs csb_matrix_set_green_geometry");
     return -1;
   }
   const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
   if (pvar == nullptr || grad == nullptr || (bnd && (coefa == nullptr || coefb == nullptr))) {
-    set_error("csb_gradient_scalar_lsq: null array");
+    set_error("csb_gradient_scalar: null array");
     return -1;
   }
   Context &c = ctx();
@@ -811,14 +897,14 @@ int csb_gradient_scalar_lsq(const csb_matrix_t *m, int inc, const csb_real_t *pv
   const size_t len[4] = {nr, nb, nb, 3*nr};
   const bool in[4] = {true, true, true, false};
   const double *dev[4];
-  csb::DevBuf<double> stage, val_ip;
+  csb::DevBuf<double> stage, val_ip, work;
   if (!ensure_cocg(m) || !stage_arrays(4, src, len, in, dev, stage)) return -1;
   double *d_grad = const_cast<double *>(dev[3]);
   const bool ip = (bnd && m->has_diipb);
   if (ip && (!val_ip.alloc(nb) || !csb::launch_b_iprime_lsq(m, dev[0], dev[1], dev[2], val_ip.p)))
     return -1;
-  if (!csb::launch_lsq_gradient(m, m->cocg_lsq.p, inc, dev[0], dev[1], dev[2],
-                                ip ? val_ip.p : nullptr, d_grad)) return -1;
+  if (!gradient_enqueue(m, imrgra, inc, dev[0], dev[1], dev[2], ip ? val_ip.p : nullptr, d_grad,
+                        work)) return -1;
   if (d_grad != grad
       && !CSB_CUDA(cudaMemcpyAsync(grad, d_grad, sizeof(double)*3*nr, cudaMemcpyDeviceToHost,
                                    c.stream))) return -1;
@@ -857,14 +943,14 @@ int csb_diffusion_potential_rc(const csb_matrix_t *m, int irecmf, int init, int 
   const size_t len[9] = {nr, nb, nb, nb, nb, nf, nb, nr, nr};
   const bool in[9] = {true, true, true, true, true, true, true, true, init == 0};
   const double *dev[9];
-  csb::DevBuf<double> stage, grad, val_ip;
+  csb::DevBuf<double> stage, grad, val_ip, work;
   if (!ensure_cocg(m) || !stage_arrays(9, src, len, in, dev, stage) || !grad.alloc(3*nr)) return -1;
   double *d_div = const_cast<double *>(dev[8]);
   const bool ip = (bnd && m->has_diipb);
   if (ip && (!val_ip.alloc(nb) || !csb::launch_b_iprime_lsq(m, dev[0], dev[1], dev[2], val_ip.p)))
     return -1;
   const double *d_ip = ip ? val_ip.p : nullptr;
-  if (!csb::launch_lsq_gradient(m, m->cocg_lsq.p, inc, dev[0], dev[1], dev[2], d_ip, grad.p)
+  if (!gradient_enqueue(m, m->imrgra, inc, dev[0], dev[1], dev[2], d_ip, grad.p, work)
       || !csb::launch_diffusion_potential_rc(m, irecmf, init, inc, dev[0], grad.p, dev[3], dev[4],
                                              dev[5], dev[6], dev[7], d_ip, d_div)) return -1;
   if (d_div != diverg

@@ -339,6 +339,22 @@ int  csb_matrix_set_face_geometry(csb_matrix_t *m, const csb_real_t *i_dist,
                                   const csb_real_t *diipf, const csb_real_t *djjpf,
                                   const csb_real_t *b_face_u_normal, const csb_real_t *b_dist);
 int  csb_matrix_set_boundary_iprime(csb_matrix_t *m, const csb_real_t *diipb);
+/* Green-Gauss gradient with least-squares face values (imrgra = 4, CS_GRADIENT_GREEN_LSQ: the
+   default of cs_glob_space_disc, src/base/cs_parameters.cpp:470): the least-squares gradient,
+   then _reconstruct_scalar_gradient (src/alge/cs_gradient.cpp:7697-7797, :4167-4540; no
+   hydrostatic term, no cell weighting, no disabled cell).
+   csb_matrix_set_green_geometry: weight[n_faces], dofij[n_faces][3] (OF), b_face_surf[n_b_faces]
+   of cs_mesh_quantities_t and, optionally, corr_grad_lin[n_rows][3][3] (warped-face correction,
+   CS_BAD_CELLS_WARPED_CORRECTION: on by default in the reference; NULL = off); after
+   csb_matrix_set_face_geometry.
+   csb_matrix_set_gradient_type: eqp->imrgra for csb_diffusion_potential_rc (1, the initial
+   value, or 4).  csb_gradient_scalar: the gradient alone for imrgra 1 or 4. */
+int  csb_matrix_set_green_geometry(csb_matrix_t *m, const csb_real_t *weight,
+                                   const csb_real_t *dofij, const csb_real_t *b_face_surf,
+                                   const csb_real_t *corr_grad_lin);
+int  csb_matrix_set_gradient_type(csb_matrix_t *m, int imrgra);
+int  csb_gradient_scalar(const csb_matrix_t *m, int imrgra, int inc, const csb_real_t *pvar,
+                         const csb_real_t *coefa, const csb_real_t *coefb, csb_real_t *grad);
 int  csb_gradient_scalar_lsq(const csb_matrix_t *m, int inc, const csb_real_t *pvar,
                              const csb_real_t *coefa, const csb_real_t *coefb, csb_real_t *grad);
 int  csb_diffusion_potential_rc(const csb_matrix_t *m, int irecmf, int init, int inc,

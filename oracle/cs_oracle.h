@@ -209,6 +209,18 @@ void   ora_diffusion_potential_rc_b(int n_cells, int n_i_faces, const int *i_fac
                                     const double *i_visc, const double *b_visc,
                                     const double *visel, double *diverg);
 
+/* Green-Gauss gradient with least-squares face values (imrgra = 4): reconstruction pass over
+   the least-squares gradient r_grad (_reconstruct_scalar_gradient) */
+void   ora_gradient_green_reconstruct(int n_cells, int n_i_faces, const int *i_face_cells,
+                                      int n_b_faces, const int *b_face_cells,
+                                      const double *weight, const double *dofij,
+                                      const double *i_face_surf, const double *i_face_u_normal,
+                                      const double *b_face_surf, const double *b_face_u_normal,
+                                      const double *cell_vol, const double *val_ip, int inc,
+                                      const double *pvar, const double *coefa,
+                                      const double *coefb, const double *r_grad,
+                                      const double *corr_grad_lin, double *grad);
+
 /* matrix assembler on one rank, MSR target: cs_oracle_assembler.c */
 int    ora_assembler_structure(int n_rows, int n, const long long *row_g_id,
                                const long long *col_g_id, long long l_range_0,

@@ -320,3 +320,68 @@ ora_diffusion_potential_rc(int n_cells, int n_i_faces, const int *i_face_cells, 
                                i_face_surf, NULL, irecmf, init, inc, pvar, grad, cofaf, cofbf,
                                i_visc, b_visc, visel, diverg);
 }
+
+/* Green-Gauss gradient with least-squares face values (imrgra = 4, CS_GRADIENT_GREEN_LSQ, the
+   default of cs_glob_space_disc; cs_gradient.cpp:7697-7797): r_grad is the least-squares
+   gradient above, then _reconstruct_scalar_gradient (:4167-4540, branch without hydrostatic
+   pressure :4428-4506; no cell weighting, no disabled cell, no warped-face correction):
+   interior faces in face order add (pfac + rfac) S n to both cells with the face weight
+   (cs_mesh_quantities_t::weight) and the OF vector (dofij), boundary faces add
+   (val_f - var) S n, then the sums are divided by the cell volume and, when corr_grad_lin
+   (cs_mesh_quantities_t::corr_grad_lin, 3x3 per cell) is given, multiplied by it -- the
+   warped-face correction CS_BAD_CELLS_WARPED_CORRECTION, on by default in the reference.
+   val_ip: values at I' of the boundary faces, or NULL (II' = 0). */
+void
+ora_gradient_green_reconstruct(int n_cells, int n_i_faces, const int *i_face_cells,
+                               int n_b_faces, const int *b_face_cells, const double *weight,
+                               const double *dofij, const double *i_face_surf,
+                               const double *i_face_u_normal, const double *b_face_surf,
+                               const double *b_face_u_normal, const double *cell_vol,
+                               const double *val_ip, int inc, const double *pvar,
+                               const double *coefa, const double *coefb, const double *r_grad,
+                               const double *corr_grad_lin, double *grad)
+{
+  for (int i = 0; i < 3*n_cells; i++) grad[i] = 0.;
+  for (int f = 0; f < n_i_faces; f++) {
+    const int c1 = i_face_cells[2*f], c2 = i_face_cells[2*f+1];
+    const double ktpond = weight[f];
+    const double d_var = pvar[c2] - pvar[c1];
+    const double pfaci = (1.0-ktpond) * d_var;
+    const double pfacj =     -ktpond  * d_var;
+    const double *o = dofij + 3*(size_t)f, *g1 = r_grad + 3*(size_t)c1, *g2 = r_grad + 3*(size_t)c2;
+    const double rfac = 0.5 * (  o[0]*(g1[0]+g2[0])
+                               + o[1]*(g1[1]+g2[1])
+                               + o[2]*(g1[2]+g2[2]));
+    const double _pfaci = (pfaci + rfac) * i_face_surf[f];
+    const double _pfacj = (pfacj + rfac) * i_face_surf[f];
+    for (int j = 0; j < 3; j++) {
+      const double rhsv1 =   _pfaci * i_face_u_normal[3*(size_t)f+j];
+      const double rhsv2 = - _pfacj * i_face_u_normal[3*(size_t)f+j];
+      if (c1 < n_cells) grad[3*(size_t)c1+j] += rhsv1;
+      if (c2 < n_cells) grad[3*(size_t)c2+j] += rhsv2;
+    }
+  }
+  for (int f = 0; f < n_b_faces; f++) {
+    const int c = b_face_cells[f];
+    const double val_f = inc*coefa[f] + coefb[f]*(val_ip != NULL ? val_ip[f] : pvar[c]);
+    const double pfac = (val_f - pvar[c]) * b_face_surf[f];
+    for (int j = 0; j < 3; j++)
+      grad[3*(size_t)c+j] += pfac * b_face_u_normal[3*(size_t)f+j];
+  }
+  for (int c = 0; c < n_cells; c++) {
+    const double dvol = 1. / cell_vol[c];
+    grad[3*(size_t)c]   *= dvol;
+    grad[3*(size_t)c+1] *= dvol;
+    grad[3*(size_t)c+2] *= dvol;
+    if (corr_grad_lin != NULL) {     /* CS_BAD_CELLS_WARPED_CORRECTION (:4519-4530) */
+      double gradpa[3];
+      for (int i = 0; i < 3; i++) {
+        gradpa[i] = grad[3*(size_t)c+i];
+        grad[3*(size_t)c+i] = 0.;
+      }
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+          grad[3*(size_t)c+i] += corr_grad_lin[9*(size_t)c+3*i+j] * gradpa[j];
+    }
+  }
+}

@@ -381,6 +381,28 @@ class Oracle:
             _dp(_f64(coefa)), _dp(_f64(coefb)), _dp(grad))
         return grad.reshape(-1, 3)
 
+    def gradient_green_lsq(self, s, b_face_cells, b_un, b_dist, g_geo, b_face_surf, pvar, coefa,
+                           coefb, inc=1, diipb=None, corr_grad_lin=None):
+        """imrgra = 4: the least-squares gradient, then the Green-Gauss reconstruction pass;
+        g_geo: weight [1] and OF vector [3] per interior face"""
+        r_grad = self.gradient_lsq(s, b_face_cells, b_un, b_dist, pvar, coefa, coefb, inc=inc,
+                                   diipb=diipb)
+        fc, bfc = _i32(s.face_cells), _i32(b_face_cells)
+        vip = None
+        if diipb is not None:
+            vip = self.b_iprime_lsq(s, bfc, b_un, b_dist, diipb, pvar, coefa, coefb)
+        gg = _f64(g_geo).reshape(-1, 4)
+        grad = np.zeros(3 * s.n_rows)
+        self.lib.ora_gradient_green_reconstruct.restype = None
+        self.lib.ora_gradient_green_reconstruct(
+            C.c_int(s.n_rows), C.c_int(len(fc)), _ip(fc), C.c_int(len(bfc)), _ip(bfc),
+            _dp(_f64(gg[:, 0])), _dp(_f64(gg[:, 1:4])), _dp(_f64(s.face_surf)),
+            _dp(_f64(s.face_u_normal)), _dp(_f64(b_face_surf)), _dp(_f64(b_un)),
+            _dp(_f64(s.cell_vol)), (None if vip is None else _dp(_f64(vip))), C.c_int(inc),
+            _dp(_f64(pvar)), _dp(_f64(coefa)), _dp(_f64(coefb)), _dp(_f64(r_grad)),
+            (None if corr_grad_lin is None else _dp(_f64(corr_grad_lin))), _dp(grad))
+        return grad.reshape(-1, 3)
+
     def diffusion_potential_rc(self, s, b_face_cells, i_geo, grad, pvar, cofaf, cofbf, i_visc,
                                b_visc, visel, irecmf=0, init=1, inc=1, diverg=None, val_ip=None):
         """val_ip: values at I' of the boundary faces (b_iprime_lsq) when II' is not zero"""
@@ -719,7 +741,8 @@ class RefLib:
 
     def diffusion_potential_rc(self, h, s, b_face_cells, b_geo, i_face_cog, i_geo, pvar, coefa,
                                coefb, cofaf, cofbf, i_visc, b_visc, visel, irecmf=0, init=1,
-                               inc=1, diverg=None, diipb=None):
+                               inc=1, diverg=None, diipb=None, imrgra=1, g_geo=None,
+                               b_face_surf=None, corr_grad_lin=None):
         """cs_diffusion_potential WITH flux reconstruction (LSQ gradient) on the geometry given;
         returns (diverg, grad)."""
         div = np.zeros(s.n_rows) if diverg is None else _f64(diverg).copy()
@@ -729,7 +752,10 @@ class RefLib:
                                   i_visc, b_visc, visel)]
         r = self.lib.csref_diffusion_potential_rc(
             h, _ip(_i32(s.face_cells)), C.c_int(len(bfc)), _ip(bfc), _dp(keep[0]), _dp(keep[1]),
-            _dp(keep[2]), (None if diipb is None else _dp(_f64(diipb))), C.c_int(irecmf),
+            _dp(keep[2]), (None if diipb is None else _dp(_f64(diipb))), C.c_int(imrgra),
+            (None if g_geo is None else _dp(_f64(g_geo))),
+            (None if b_face_surf is None else _dp(_f64(b_face_surf))),
+            (None if corr_grad_lin is None else _dp(_f64(corr_grad_lin))), C.c_int(irecmf),
             C.c_int(init), C.c_int(inc), _dp(keep[3]), _dp(keep[4]),
             _dp(keep[5]), _dp(keep[6]), _dp(keep[7]), _dp(keep[8]), _dp(keep[9]), _dp(keep[10]),
             _dp(div), _dp(grad))

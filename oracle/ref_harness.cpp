@@ -938,6 +938,14 @@ csref_diffusion_potential_rc(void          *sys,
                              const double  *i_face_cog,   /* 3 per interior face */
                              const double  *i_geo,        /* 7 per interior face */
                              const double  *diipb,        /* 3 per boundary face, or NULL */
+                             int            imrgra,       /* 1: LSQ, 4: Green-Gauss with LSQ
+                                                             face values (global default) */
+                             const double  *g_geo,        /* imrgra 4: weight [1], OF [3] per
+                                                             interior face */
+                             const double  *b_face_surf,  /* imrgra 4: per boundary face */
+                             const double  *corr_grad_lin, /* imrgra 4: 3x3 per cell (warped
+                                                             face correction), or NULL: the
+                                                             correction is switched off */
                              int            irecmf,
                              int            init,
                              int            inc,
@@ -1009,9 +1017,36 @@ csref_diffusion_potential_rc(void          *sys,
   mq->diipf = (cs_rreal_3_t *)diipf.data();
   mq->djjpf = (cs_rreal_3_t *)djjpf.data();
 
+  /* quantities of the Green-Gauss reconstruction (_reconstruct_scalar_gradient,
+     cs_gradient.cpp:4167): face weights, OF vectors, boundary surfaces; interior normals,
+     surfaces and cell volumes are those of the system's mesh association */
+  std::vector<cs_real_t> weight(ni1, 0.5), dofij(3*ni1, 0.), b_surf(nb1, 0.);
+  int no_disable = 0;
+  if (imrgra == 4) {
+    for (cs_lnum_t f = 0; f < n_i_faces; f++) {
+      weight[f] = g_geo[4*f];
+      for (int k = 0; k < 3; k++) dofij[3*f+k] = g_geo[4*f+1+k];
+    }
+    for (cs_lnum_t f = 0; f < n_b_faces; f++) b_surf[f] = b_face_surf[f];
+    mq->weight = weight.data();
+    mq->dofij = (cs_real_3_t *)dofij.data();
+    mq->b_face_surf = b_surf.data();
+    mq->i_face_u_normal = s->face_u_normal;
+    mq->cell_vol = s->cell_vol;
+    mq->has_disable_flag = 0;
+    mq->c_disable_flag = &no_disable;
+    mq->corr_grad_lin = (cs_real_33_t *)const_cast<double *>(corr_grad_lin);
+  }
+  const unsigned mq_flag_prev = cs_glob_mesh_quantities_flag;
+  if (corr_grad_lin == nullptr)
+    cs_glob_mesh_quantities_flag &= ~((unsigned)CS_BAD_CELLS_WARPED_CORRECTION);
+  else
+    cs_glob_mesh_quantities_flag |= CS_BAD_CELLS_WARPED_CORRECTION;
+
   cs_equation_param_t eqp = cs_parameters_equation_param_default();
   eqp.ircflu = 1;
-  eqp.imrgra = 1;          /* least squares, standard neighbourhood */
+  eqp.imrgra = imrgra;     /* 1: least squares, standard neighbourhood; 4: Green-Gauss with
+                              least-squares face values */
   eqp.imligr = -1;         /* no gradient limiter */
   eqp.iwgrec = 0;
   eqp.verbosity = 0;
@@ -1034,7 +1069,9 @@ csref_diffusion_potential_rc(void          *sys,
 
   if (grad_out != nullptr) {
     /* bc.val_f was filled by cs_diffusion_potential's update of the face values */
-    cs_gradient_scalar_synced_input("csref", CS_GRADIENT_LSQ, CS_HALO_STANDARD, inc, eqp.nswrgr,
+    cs_gradient_scalar_synced_input("csref",
+                                    (imrgra == 4) ? CS_GRADIENT_GREEN_LSQ : CS_GRADIENT_LSQ,
+                                    CS_HALO_STANDARD, inc, eqp.nswrgr,
                                     0, 1, 0, (cs_gradient_limit_t)(eqp.imligr), eqp.epsrgr,
                                     eqp.climgr, nullptr, &bc, _pvar.data(), nullptr,
                                     (cs_real_3_t *)grad_out, nullptr);
@@ -1045,6 +1082,10 @@ csref_diffusion_potential_rc(void          *sys,
   mq->cell_cen = nullptr; mq->b_face_u_normal = nullptr; mq->b_dist = nullptr;
   mq->i_dist = nullptr; mq->i_face_cog = nullptr; mq->b_face_cog = nullptr;
   mq->i_face_surf = nullptr; mq->diipb = nullptr; mq->diipf = nullptr; mq->djjpf = nullptr;
+  mq->weight = nullptr; mq->dofij = nullptr; mq->b_face_surf = nullptr;
+  mq->i_face_u_normal = nullptr; mq->cell_vol = nullptr; mq->c_disable_flag = nullptr;
+  mq->corr_grad_lin = nullptr;
+  cs_glob_mesh_quantities_flag = mq_flag_prev;
   CS_FREE(bc.val_f); CS_FREE(bc.flux_diff);
   return 0;
 }

@@ -391,6 +391,29 @@ def check_rhs(ora):
         m.set_boundary_iprime(None)
         assert np.array_equal(m.gradient_lsq(f["pvar"], f["coefa"], f["coefb"]), g0)
         m.destroy()
+    # imrgra = 4: Green-Gauss gradient with least-squares face values
+    from make_golden_rhs import green_input
+    for N in CASES:
+        g = np.load(os.path.join(GOLD, f"rhs_green_N{N}.npz"))
+        s, bfc, b_geo, _, i_geo, f = rc_input(N)
+        g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
+        m = csb.Matrix.from_system(s)
+        m.set_boundary_faces(bfc)
+        m.set_face_geometry(i_geo[:, 6], i_geo[:, :3], i_geo[:, 3:6], b_geo[:, :3], b_geo[:, 6])
+        for tag, diipb, corr in (("plain", None, None), ("full", diipb_input(N, len(bfc)), cgl)):
+            m.set_green_geometry(g_geo[:, 0], g_geo[:, 1:4], b_surf, corr)
+            m.set_boundary_iprime(diipb)
+            m.set_gradient_type(4)
+            for inc in (1, 0):
+                gr = m.gradient(4, f["pvar"], f["coefa"], f["coefb"], inc=inc)
+                assert np.array_equal(gr, g[f"{tag}_grad_inc{inc}"].reshape(-1, 3)), (N, tag, inc)
+                for irecmf in (0, 1):
+                    d = m.diffusion_potential_rc(f["pvar"], f["coefa"], f["coefb"], f["cofaf"],
+                                                 f["cofbf"], f["i_visc"], f["b_visc"], f["visel"],
+                                                 irecmf=irecmf, inc=inc)
+                    assert np.array_equal(d, g[f"{tag}_div_irecmf{irecmf}_inc{inc}"]), \
+                        (N, tag, irecmf, inc)
+        m.destroy()
 
 
 def check_pairwise(ora):

@@ -3,12 +3,15 @@
 the reference's own compiled CPU code (oracle/_ref/libcsref.so, csref_diffusion_potential):
 
     python tests/golden/make_golden_rhs.py   -> tests/golden/rhs_N{N}.npz, rhs_rc_N{N}.npz,
-                                                rhs_rcb_N{N}.npz
+                                                rhs_rcb_N{N}.npz, rhs_green_N{N}.npz
 
 rhs_rc_*: the same operator WITH flux reconstruction (eqp->ircflu = 1, least-squares gradient,
 csref_diffusion_potential_rc) on a non-orthogonal variant of the cube.
 rhs_rcb_*: the same with II' of the boundary faces not zero (cs_mesh_quantities_t::diipb): the
 boundary values go through cs_gradient_boundary_iprime_lsq_s.
+rhs_green_*: eqp->imrgra = 4, the reference's default gradient (CS_GRADIENT_GREEN_LSQ: the
+least-squares gradient, then _reconstruct_scalar_gradient), with and without boundary II' and
+the warped-face correction matrices.
 """
 import os
 import sys
@@ -72,9 +75,41 @@ def diipb_input(N, n_b_faces, seed=11):
     return diipb
 
 
+def green_input(N, n_faces, n_b_faces, n_rows, seed=29):
+    """seeded quantities of the Green-Gauss reconstruction: per interior face the weight and
+    the OF vector (g_geo [n_faces][4]), boundary face surfaces, warped-face correction matrices
+    (identity + 5 %)"""
+    rng = np.random.default_rng(seed)
+    h = 1.0 / N
+    g_geo = np.hstack([0.3 + 0.4 * rng.random((n_faces, 1)),
+                       0.1 * h * rng.standard_normal((n_faces, 3))])
+    b_surf = h * h * (1 + 0.1 * rng.random(n_b_faces))
+    cgl = (np.eye(3)[None] + 0.05 * rng.standard_normal((n_rows, 3, 3))).reshape(-1)
+    return g_geo, b_surf, cgl
+
+
 def main():
     from oracle.pyoracle import RefLib
     ref = RefLib(1)
+    for N in CASES:
+        s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
+        g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
+        h = ref.system(s)
+        out = {}
+        for tag, diipb, corr in (("plain", None, None), ("full", diipb_input(N, len(bfc)), cgl)):
+            for irecmf in (0, 1):
+                for inc in (1, 0):
+                    d, g = ref.diffusion_potential_rc(
+                        h, s, bfc, b_geo, ifc, i_geo, f["pvar"], f["coefa"], f["coefb"],
+                        f["cofaf"], f["cofbf"], f["i_visc"], f["b_visc"], f["visel"],
+                        irecmf=irecmf, inc=inc, diipb=diipb, imrgra=4, g_geo=g_geo,
+                        b_face_surf=b_surf, corr_grad_lin=corr)
+                    out[f"{tag}_div_irecmf{irecmf}_inc{inc}"] = d
+                    out[f"{tag}_grad_inc{inc}"] = g
+        ref.destroy(h)
+        path = os.path.join(ROOT, "tests", "golden", f"rhs_green_N{N}.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path))
     for N in CASES:
         s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
         diipb = diipb_input(N, len(bfc))

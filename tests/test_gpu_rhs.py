@@ -174,6 +174,65 @@ def test_boundary_iprime_vs_oracle_larger(csb, oracle):
     m.destroy()
 
 
+@pytest.mark.parametrize("N", CASES)
+def test_green_lsq_gradient_matches_reference_golden(csb, N):
+    """imrgra = 4, the reference's default gradient (CS_GRADIENT_GREEN_LSQ: least-squares
+    gradient, then _reconstruct_scalar_gradient) and cs_diffusion_potential reconstructed with
+    it; plain, and with boundary II' + warped-face correction matrices: bit-identical"""
+    from make_golden_rhs import diipb_input, green_input
+    g = np.load(os.path.join(GOLD, f"rhs_green_N{N}.npz"))
+    s, bfc, b_geo, _, i_geo, f = rc_input(N)
+    g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
+    m = _rc_matrix(csb, s, bfc, b_geo, i_geo)
+    with pytest.raises(csb.CsbError):
+        m.set_gradient_type(4)                      # Green-Gauss quantities not given yet
+    with pytest.raises(csb.CsbError):
+        m.gradient(0, f["pvar"], f["coefa"], f["coefb"])      # iterative gradient: not built
+    for tag, diipb, corr in (("plain", None, None), ("full", diipb_input(N, len(bfc)), cgl)):
+        m.set_green_geometry(g_geo[:, 0], g_geo[:, 1:4], b_surf, corr)
+        m.set_boundary_iprime(diipb)
+        m.set_gradient_type(4)
+        for inc in (1, 0):
+            gr = m.gradient(4, f["pvar"], f["coefa"], f["coefb"], inc=inc)
+            assert np.array_equal(gr, g[f"{tag}_grad_inc{inc}"].reshape(-1, 3)), (tag, inc)
+            for irecmf in (0, 1):
+                d = m.diffusion_potential_rc(f["pvar"], f["coefa"], f["coefb"], f["cofaf"],
+                                             f["cofbf"], f["i_visc"], f["b_visc"], f["visel"],
+                                             irecmf=irecmf, inc=inc)
+                assert np.array_equal(d, g[f"{tag}_div_irecmf{irecmf}_inc{inc}"]), (tag, irecmf, inc)
+    m.set_gradient_type(1)                          # back to least squares
+    m.set_boundary_iprime(None)
+    g1 = np.load(os.path.join(GOLD, f"rhs_rc_N{N}.npz"))
+    d = m.diffusion_potential_rc(f["pvar"], f["coefa"], f["coefb"], f["cofaf"], f["cofbf"],
+                                 f["i_visc"], f["b_visc"], f["visel"], irecmf=0)
+    assert np.array_equal(d, g1["div_irecmf0"])
+    m.destroy()
+
+
+def test_green_lsq_gradient_vs_oracle_larger(csb, oracle):
+    """40^3 non-orthogonal cube, imrgra = 4 with boundary II' and the warped-face correction,
+    against the oracle: bit-exact"""
+    from make_golden_rhs import diipb_input, green_input
+    s, bfc, b_geo, _, i_geo, f = rc_input(40, seed=17)
+    g_geo, b_surf, cgl = green_input(40, s.n_faces, len(bfc), s.n_rows, seed=31)
+    diipb = diipb_input(40, len(bfc), seed=23)
+    m = _rc_matrix(csb, s, bfc, b_geo, i_geo)
+    m.set_green_geometry(g_geo[:, 0], g_geo[:, 1:4], b_surf, cgl)
+    m.set_boundary_iprime(diipb)
+    m.set_gradient_type(4)
+    go = oracle.gradient_green_lsq(s, bfc, b_geo[:, :3], b_geo[:, 6], g_geo, b_surf, f["pvar"],
+                                   f["coefa"], f["coefb"], diipb=diipb, corr_grad_lin=cgl)
+    assert np.array_equal(m.gradient(4, f["pvar"], f["coefa"], f["coefb"]), go)
+    vip = oracle.b_iprime_lsq(s, bfc, b_geo[:, :3], b_geo[:, 6], diipb, f["pvar"], f["coefa"],
+                              f["coefb"])
+    do = oracle.diffusion_potential_rc(s, bfc, i_geo, go, f["pvar"], f["cofaf"], f["cofbf"],
+                                       f["i_visc"], f["b_visc"], f["visel"], irecmf=0, val_ip=vip)
+    d = m.diffusion_potential_rc(f["pvar"], f["coefa"], f["coefb"], f["cofaf"], f["cofbf"],
+                                 f["i_visc"], f["b_visc"], f["visel"], irecmf=0)
+    assert np.array_equal(d, do)
+    m.destroy()
+
+
 def test_reconstruction_needs_geometry(csb):
     s, bfc, _, _, _, f = rc_input(5)
     m = csb.Matrix.from_system(s)

@@ -900,6 +900,50 @@ def test_oracle_boundary_iprime_reconstruction_matches_golden(oracle, N):
             assert np.array_equal(d, g[f"div_irecmf{irecmf}_inc{inc}"]), (irecmf, inc)
 
 
+@pytest.mark.parametrize("N", [5, 9])
+def test_oracle_green_lsq_gradient_matches_golden(oracle, N):
+    """imrgra = 4 (the reference's default gradient): least-squares gradient, then the
+    Green-Gauss reconstruction pass; plain, and with boundary II' + warped-face correction:
+    gradient and reconstructed divergence bit-exact against the reference"""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_rhs import diipb_input, green_input, rc_input
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"rhs_green_N{N}.npz"))
+    s, bfc, b_geo, _, i_geo, f = rc_input(N)
+    g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
+    for tag, diipb, corr in (("plain", None, None), ("full", diipb_input(N, len(bfc)), cgl)):
+        vip = None
+        if diipb is not None:
+            vip = oracle.b_iprime_lsq(s, bfc, b_geo[:, :3], b_geo[:, 6], diipb, f["pvar"],
+                                      f["coefa"], f["coefb"])
+        for inc in (1, 0):
+            grad = oracle.gradient_green_lsq(s, bfc, b_geo[:, :3], b_geo[:, 6], g_geo, b_surf,
+                                             f["pvar"], f["coefa"], f["coefb"], inc=inc,
+                                             diipb=diipb, corr_grad_lin=corr)
+            assert np.array_equal(grad, g[f"{tag}_grad_inc{inc}"].reshape(-1, 3)), (tag, inc)
+            for irecmf in (0, 1):
+                d = oracle.diffusion_potential_rc(s, bfc, i_geo, grad, f["pvar"], f["cofaf"],
+                                                  f["cofbf"], f["i_visc"], f["b_visc"],
+                                                  f["visel"], irecmf=irecmf, inc=inc, val_ip=vip)
+                assert np.array_equal(d, g[f"{tag}_div_irecmf{irecmf}_inc{inc}"]), (tag, irecmf, inc)
+
+
+def test_oracle_green_lsq_gradient_is_exact_for_linear_fields(oracle):
+    """property: on the orthogonal cube (OF = 0, weight 1/2) the Green-Gauss gradient of a
+    linear field is its gradient when the boundary values are those of the field"""
+    from make_golden_rhs import rhs_input
+    N = 8
+    s, bfc, b_geo, _, _ = rhs_input(N)
+    h = 1.0 / N
+    cen = s.cell_cen.reshape(-1, 3)
+    a = np.array([0.7, -1.3, 2.1])
+    p = cen @ a + 0.4
+    vf = p[bfc] + b_geo[:, 6] * (b_geo[:, :3] @ a)
+    g_geo = np.hstack([np.full((s.n_faces, 1), 0.5), np.zeros((s.n_faces, 3))])
+    grad = oracle.gradient_green_lsq(s, bfc, b_geo[:, :3], b_geo[:, 6], g_geo,
+                                     np.full(len(bfc), h * h), p, vf, np.zeros(len(bfc)))
+    assert np.abs(grad - a).max() < 1e-12 * np.abs(a).max() * N
+
+
 def test_oracle_gradient_lsq_is_exact_for_linear_fields(oracle):
     """property: a least-squares gradient reproduces the gradient of a linear field (to the
     single precision of its cocg matrices) when the boundary values are those of the field"""
