@@ -665,6 +665,32 @@ class Matrix:
             _err("csb_diffusion_potential")
         return div
 
+    def divergence(self, i_massflux, b_massflux=None, init=1, diverg=None):
+        """cs_divergence on this matrix's mesh"""
+        L = load_library()
+        L.csb_divergence.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3
+        div = np.zeros(self.n_rows) if diverg is None else _f64(np.asarray(diverg)).copy()
+        a = [x if x is None or not isinstance(x, np.ndarray) else _f64(x)
+             for x in (i_massflux, b_massflux)]
+        if L.csb_divergence(self.handle, int(init), *[_ptr(x) for x in a], _ptr(div)) != 0:
+            _err("csb_divergence")
+        return div
+
+    def face_diffusion_potential(self, n_faces, n_b_faces, pvar, cofaf, cofbf, i_visc, b_visc,
+                                 coefa=None, coefb=None, visel=None, ircflu=0, init=1, inc=1,
+                                 massflux=None):
+        """cs_face_diffusion_potential; returns (i_massflux, b_massflux)"""
+        L = load_library()
+        L.csb_face_diffusion_potential.argtypes = [C.c_void_p] + [C.c_int] * 3 + [C.c_void_p] * 10
+        im = np.zeros(max(n_faces, 1)) if massflux is None else _f64(np.asarray(massflux[0])).copy()
+        bm = np.zeros(max(n_b_faces, 1)) if massflux is None else _f64(np.asarray(massflux[1])).copy()
+        a = [x if x is None or not isinstance(x, np.ndarray) else _f64(x)
+             for x in (pvar, coefa, coefb, cofaf, cofbf, i_visc, b_visc, visel)]
+        if L.csb_face_diffusion_potential(self.handle, int(ircflu), int(init), int(inc),
+                                          *[_ptr(x) for x in a], _ptr(im), _ptr(bm)) != 0:
+            _err("csb_face_diffusion_potential")
+        return im[:n_faces], bm[:n_b_faces]
+
     def set_face_geometry(self, i_dist, diipf, djjpf, b_face_u_normal, b_dist):
         L = load_library()
         L.csb_matrix_set_face_geometry.argtypes = [C.c_void_p] * 6

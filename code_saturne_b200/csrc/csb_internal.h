@@ -649,6 +649,16 @@ bool launch_b_iprime_lsq(const _csb_matrix_t *m, const double *pvar, const doubl
 bool launch_lsq_gradient(const _csb_matrix_t *m, const float *cocg, int inc, const double *pvar,
                          const double *coefa, const double *coefb, const double *val_ip,
                          double *grad);
+/* cs_divergence (cs_divergence.cpp:1224) and cs_face_diffusion_potential
+   (cs_convection_diffusion.cpp:8075; grad nullptr: no reconstruction) */
+bool launch_divergence(const _csb_matrix_t *m, int init, const double *i_massflux,
+                       const double *b_massflux, double *diverg);
+bool launch_face_diffusion_potential(const _csb_matrix_t *m, int init, int inc,
+                                     const double *pvar, const double *grad,
+                                     const double *cofaf, const double *cofbf,
+                                     const double *i_visc, const double *b_visc,
+                                     const double *visel, const double *val_ip,
+                                     double *i_massflux, double *b_massflux);
 /* second half of the Green-Gauss gradient with least-squares face values (imrgra = 4,
    _reconstruct_scalar_gradient cs_gradient.cpp:4167): r_grad = the least-squares gradient */
 bool launch_green_reconstruct(const _csb_matrix_t *m, int inc, const double *pvar,

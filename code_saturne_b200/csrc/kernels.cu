@@ -2667,6 +2667,91 @@ __global__ void k_green_reconstruct(int n_rows, const int *__restrict__ row_inde
   grad[3*(size_t)c] = g0; grad[3*(size_t)c+1] = g1; grad[3*(size_t)c+2] = g2;
 }
 
+/* cs_divergence (src/alge/cs_divergence.cpp:1224-1290): diverg[c] (+)= sum of the cell's
+   interior face fluxes in ascending face order (+ the flux when the cell is the face's first,
+   - otherwise), then of its boundary face fluxes: the reference's scatter in face order, as a
+   gather */
+__global__ void k_divergence(int n_rows, const int *__restrict__ row_index,
+                             const int *__restrict__ c2f, const short *__restrict__ c2f_sgn,
+                             const int *__restrict__ cell_b_faces_idx,
+                             const int *__restrict__ cell_b_faces, int init,
+                             const double *__restrict__ i_massflux,
+                             const double *__restrict__ b_massflux, double *diverg)
+{
+  const int c = blockIdx.x*blockDim.x + threadIdx.x;
+  if (c >= n_rows) return;
+  const int s = row_index[c], e = row_index[c+1];
+  double d = (init >= 1) ? 0. : diverg[c];
+  int last = -1;
+  while (true) {
+    int best = INT_MAX, bk = -1;
+    for (int k = s; k < e; k++) {
+      const int f = c2f[k];
+      if (f > last && f < best) { best = f; bk = k; }
+    }
+    if (bk < 0) break;
+    last = best;
+    if (c2f_sgn[bk] > 0) d += i_massflux[best];
+    else d += -i_massflux[best];
+  }
+  if (cell_b_faces_idx != nullptr)
+    for (int k = cell_b_faces_idx[c]; k < cell_b_faces_idx[c+1]; k++)
+      d += b_massflux[cell_b_faces[k]];
+  diverg[c] = d;
+}
+
+/* cs_face_diffusion_potential (cs_convection_diffusion.cpp:8075-8310): the face fluxes
+   themselves.  Every interior face has exactly one MSR entry with a positive sign, in the row
+   of its first cell: the thread of that cell computes the face's flux (grad nullptr:
+   eqp->ircflu = 0, :8236-8246; else the reconstructed form :8254-8296, always the II' - JJ'
+   formula) and adds it to i_massflux[f]; it also serves the cell's boundary faces (:8298-8303).
+   No two threads touch the same face. */
+__global__ void k_face_diffusion_potential(int n_rows, const int *__restrict__ row_index,
+                                           const int *__restrict__ col_id,
+                                           const int *__restrict__ c2f,
+                                           const short *__restrict__ c2f_sgn,
+                                           const int *__restrict__ cell_b_faces_idx,
+                                           const int *__restrict__ cell_b_faces,
+                                           const double *__restrict__ diipf,
+                                           const double *__restrict__ djjpf,
+                                           const double *__restrict__ i_dist,
+                                           const double *__restrict__ i_face_surf, int init,
+                                           int inc, const double *__restrict__ pvar,
+                                           const double *__restrict__ grad,
+                                           const double *__restrict__ cofaf,
+                                           const double *__restrict__ cofbf,
+                                           const double *__restrict__ i_visc,
+                                           const double *__restrict__ b_visc,
+                                           const double *__restrict__ visel,
+                                           const double *__restrict__ val_ip,
+                                           double *i_massflux, double *b_massflux)
+{
+  const int c = blockIdx.x*blockDim.x + threadIdx.x;
+  if (c >= n_rows) return;
+  const double pc = pvar[c];
+  for (int k = row_index[c]; k < row_index[c+1]; k++) {
+    if (c2f_sgn[k] <= 0) continue;
+    const size_t f = (size_t)c2f[k], c1 = (size_t)col_id[k];
+    double flux = i_visc[f]*(pc - pvar[c1]);
+    if (grad != nullptr) {
+      const double *g0 = grad + 3*(size_t)c, *g1 = grad + 3*c1;
+      const double *ip = diipf + 3*f, *jp = djjpf + 3*f;
+      const double dpxf = 0.5*(visel[c]*g0[0] + visel[c1]*g1[0]);
+      const double dpyf = 0.5*(visel[c]*g0[1] + visel[c1]*g1[1]);
+      const double dpzf = 0.5*(visel[c]*g0[2] + visel[c1]*g1[2]);
+      const double dijx = ip[0] - jp[0], dijy = ip[1] - jp[1], dijz = ip[2] - jp[2];
+      flux = flux + (dpxf*dijx + dpyf*dijy + dpzf*dijz) * i_face_surf[f]/i_dist[f];
+    }
+    i_massflux[f] = ((init >= 1) ? 0. : i_massflux[f]) + flux;
+  }
+  if (cell_b_faces_idx != nullptr)
+    for (int k = cell_b_faces_idx[c]; k < cell_b_faces_idx[c+1]; k++) {
+      const int f = cell_b_faces[k];
+      const double flux_d = inc*cofaf[f] + cofbf[f]*(val_ip != nullptr ? val_ip[f] : pc);
+      b_massflux[f] = ((init >= 1) ? 0. : b_massflux[f]) + b_visc[f]*flux_d;
+    }
+}
+
 /* cs_diffusion_potential with flux reconstruction (:8921-8961): the face flux is computed in
    the face's orientation by both of its cells, identically */
 __global__ void k_diffusion_potential_rc(int n_rows, const int *__restrict__ row_index,
@@ -2768,6 +2853,34 @@ bool launch_lsq_gradient(const _csb_matrix_t *m, const float *cocg, int inc, con
     m->b_face_u_normal.p, m->b_dist.p, cocg, inc, pvar, coefa, coefb,
     (bnd && m->has_diipb) ? m->diipb.p : nullptr, val_ip, grad);
   return post_launch("lsq_gradient");
+}
+
+bool launch_divergence(const _csb_matrix_t *m, int init, const double *i_massflux,
+                       const double *b_massflux, double *diverg)
+{
+  if (m->n_rows < 1) return true;
+  const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  k_divergence<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
+    m->n_rows, m->row_index.p, m->c2f.p, m->c2f_sgn.p, bnd ? m->cell_b_faces_idx.p : nullptr,
+    bnd ? m->cell_b_faces.p : nullptr, init, i_massflux, b_massflux, diverg);
+  return post_launch("divergence");
+}
+
+bool launch_face_diffusion_potential(const _csb_matrix_t *m, int init, int inc,
+                                     const double *pvar, const double *grad,
+                                     const double *cofaf, const double *cofbf,
+                                     const double *i_visc, const double *b_visc,
+                                     const double *visel, const double *val_ip,
+                                     double *i_massflux, double *b_massflux)
+{
+  if (m->n_rows < 1) return true;
+  const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  k_face_diffusion_potential<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
+    m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, m->c2f_sgn.p,
+    bnd ? m->cell_b_faces_idx.p : nullptr, bnd ? m->cell_b_faces.p : nullptr, m->diipf.p,
+    m->djjpf.p, m->i_dist.p, m->face_surf.p, init, inc, pvar, grad, cofaf, cofbf, i_visc,
+    b_visc, visel, val_ip, i_massflux, b_massflux);
+  return post_launch("face_diffusion_potential");
 }
 
 bool launch_green_reconstruct(const _csb_matrix_t *m, int inc, const double *pvar,

@@ -959,6 +959,103 @@ int csb_diffusion_potential_rc(const csb_matrix_t *m, int irecmf, int init, int 
   return CSB_CUDA(cudaStreamSynchronize(c.stream)) ? 0 : -1;
 }
 
+/* cs_divergence (src/alge/cs_divergence.cpp:1224-1290): init >= 1 zeroes diverg, then every
+   cell adds the mass fluxes of its interior faces (signed by the face's orientation) in
+   ascending face order and those of its boundary faces: bit-identical to the reference's
+   one-thread result.  Host or device pointers. */
+int csb_divergence(const csb_matrix_t *m, int init, const csb_real_t *i_massflux,
+                   const csb_real_t *b_massflux, csb_real_t *diverg)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (!m->has_mesh || m->db != 1 || m->halo != nullptr) {
+    set_error("csb_divergence: needs a scalar matrix on one rank with its mesh association");
+    return -1;
+  }
+  if (init < 0) { set_error("csb_divergence: invalid value of init"); return -1; }
+  const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  if (diverg == nullptr || (m->n_faces > 0 && i_massflux == nullptr)
+      || (bnd && b_massflux == nullptr)) {
+    set_error("csb_divergence: null array");
+    return -1;
+  }
+  Context &c = ctx();
+  const size_t nr = (size_t)m->n_rows, nf = (size_t)m->n_faces, nb = bnd ? (size_t)m->n_b_faces : 0;
+  const double *src[3] = {i_massflux, b_massflux, diverg};
+  const size_t len[3] = {nf, nb, nr};
+  const bool in[3] = {true, true, init == 0};
+  const double *dev[3];
+  csb::DevBuf<double> stage;
+  if (!stage_arrays(3, src, len, in, dev, stage)) return -1;
+  double *d_div = const_cast<double *>(dev[2]);
+  if (!csb::launch_divergence(m, init, dev[0], dev[1], d_div)) return -1;
+  if (d_div != diverg
+      && !CSB_CUDA(cudaMemcpyAsync(diverg, d_div, sizeof(double)*nr, cudaMemcpyDeviceToHost,
+                                   c.stream))) return -1;
+  return CSB_CUDA(cudaStreamSynchronize(c.stream)) ? 0 : -1;
+}
+
+/* cs_face_diffusion_potential (src/alge/cs_convection_diffusion.cpp:8075-8310): the face mass
+   fluxes of the diffusion of pvar -- what the pressure correction adds to the mass flux after
+   the solve.  ircflu = 0: i_massflux[f] += i_visc (pvar_I - pvar_J), b_massflux[f] += b_visc
+   (inc cofaf + cofbf pvar_I); coefa, coefb, visel are not read.  ircflu = 1: the reconstructed
+   form with the gradient of csb_matrix_set_gradient_type and the value at I' of the boundary
+   faces.  init >= 1 starts from zero.  Bit-identical to the reference. */
+int csb_face_diffusion_potential(const csb_matrix_t *m, int ircflu, int init, int inc,
+                                 const csb_real_t *pvar, const csb_real_t *coefa,
+                                 const csb_real_t *coefb, const csb_real_t *cofaf,
+                                 const csb_real_t *cofbf, const csb_real_t *i_visc,
+                                 const csb_real_t *b_visc, const csb_real_t *visel,
+                                 csb_real_t *i_massflux, csb_real_t *b_massflux)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (!m->has_mesh || m->db != 1 || m->halo != nullptr || (ircflu && !m->has_face_geo)) {
+    set_error("csb_face_diffusion_potential: needs a scalar matrix on one rank with its mesh "
+              "association%s", ircflu ? ", boundary faces and csb_matrix_set_face_geometry" : "");
+    return -1;
+  }
+  if (init != 0 && init < 1) {
+    set_error("csb_face_diffusion_potential: invalid value of init");
+    return -1;
+  }
+  const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  if (pvar == nullptr || (m->n_faces > 0 && (i_visc == nullptr || i_massflux == nullptr))
+      || (bnd && (cofaf == nullptr || cofbf == nullptr || b_visc == nullptr
+                  || b_massflux == nullptr))
+      || (ircflu && (visel == nullptr || (bnd && (coefa == nullptr || coefb == nullptr))))) {
+    set_error("csb_face_diffusion_potential: null array");
+    return -1;
+  }
+  Context &c = ctx();
+  const size_t nr = (size_t)m->n_rows, nf = (size_t)m->n_faces, nb = bnd ? (size_t)m->n_b_faces : 0;
+  const double *src[10] = {pvar, ircflu ? coefa : nullptr, ircflu ? coefb : nullptr, cofaf, cofbf,
+                           i_visc, b_visc, ircflu ? visel : nullptr, i_massflux, b_massflux};
+  const size_t len[10] = {nr, nb, nb, nb, nb, nf, nb, nr, nf, nb};
+  const bool in[10] = {true, true, true, true, true, true, true, true, init == 0, init == 0};
+  const double *dev[10];
+  csb::DevBuf<double> stage, grad, val_ip, work;
+  if (!stage_arrays(10, src, len, in, dev, stage)) return -1;
+  const double *d_grad = nullptr, *d_ip = nullptr;
+  if (ircflu) {
+    if (!ensure_cocg(m) || !grad.alloc(3*nr)) return -1;
+    const bool ip = (bnd && m->has_diipb);
+    if (ip && (!val_ip.alloc(nb) || !csb::launch_b_iprime_lsq(m, dev[0], dev[1], dev[2], val_ip.p)))
+      return -1;
+    d_ip = ip ? val_ip.p : nullptr;
+    if (!gradient_enqueue(m, m->imrgra, inc, dev[0], dev[1], dev[2], d_ip, grad.p, work)) return -1;
+    d_grad = grad.p;
+  }
+  double *d_im = const_cast<double *>(dev[8]), *d_bm = const_cast<double *>(dev[9]);
+  if (!csb::launch_face_diffusion_potential(m, init, inc, dev[0], d_grad, dev[3], dev[4], dev[5],
+                                            dev[6], dev[7], d_ip, d_im, d_bm)) return -1;
+  if (d_im != i_massflux && nf > 0
+      && !CSB_CUDA(cudaMemcpyAsync(i_massflux, d_im, sizeof(double)*nf, cudaMemcpyDeviceToHost,
+                                   c.stream))) return -1;
+  if (d_bm != b_massflux && nb > 0
+      && !CSB_CUDA(cudaMemcpyAsync(b_massflux, d_bm, sizeof(double)*nb, cudaMemcpyDeviceToHost,
+                                   c.stream))) return -1;
+  return CSB_CUDA(cudaStreamSynchronize(c.stream)) ? 0 : -1;
+}
+
 /* Boundary faces of the mesh by adjacent cell (cs_mesh_t::b_face_cells); builds the
    cell -> boundary faces adjacency the reference keeps in cs_mesh_adjacencies
    (cell_b_faces_idx / cell_b_faces, src/mesh/cs_mesh_adjacencies.cpp:705-760). */

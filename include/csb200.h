@@ -364,6 +364,26 @@ int  csb_diffusion_potential_rc(const csb_matrix_t *m, int irecmf, int init, int
                                 const csb_real_t *b_visc, const csb_real_t *visel,
                                 csb_real_t *diverg);
 
+/* The other two face operators of the pressure correction.
+   csb_divergence: cs_divergence (src/alge/cs_divergence.cpp:1224-1290), diverg[n_rows] (+)= the
+   signed sum of the face mass fluxes i_massflux[n_faces], b_massflux[n_b_faces] of every cell,
+   in the reference's order (ascending interior faces, then boundary faces).
+   csb_face_diffusion_potential: cs_face_diffusion_potential
+   (src/alge/cs_convection_diffusion.cpp:8075-8310), the face fluxes cs_diffusion_potential
+   sums, kept per face: ircflu = 0 without reconstruction (coefa, coefb, visel may be NULL),
+   ircflu = 1 with it (gradient of csb_matrix_set_gradient_type, values at I' of the boundary
+   faces); init >= 1 starts from zero, init = 0 adds to the arrays given.
+   Both bit-identical to the reference; host or device pointers; csb_divergence of the fluxes
+   of csb_face_diffusion_potential equals csb_diffusion_potential[_rc] (irecmf 0). */
+int  csb_divergence(const csb_matrix_t *m, int init, const csb_real_t *i_massflux,
+                    const csb_real_t *b_massflux, csb_real_t *diverg);
+int  csb_face_diffusion_potential(const csb_matrix_t *m, int ircflu, int init, int inc,
+                                  const csb_real_t *pvar, const csb_real_t *coefa,
+                                  const csb_real_t *coefb, const csb_real_t *cofaf,
+                                  const csb_real_t *cofbf, const csb_real_t *i_visc,
+                                  const csb_real_t *b_visc, const csb_real_t *visel,
+                                  csb_real_t *i_massflux, csb_real_t *b_massflux);
+
 /* Copy of the MSR coefficients held in HBM (cs_matrix_get_msr_arrays, cs_matrix.cpp:6199,
    lends the host arrays; these live on the device).  Either pointer may be NULL. */
 int  csb_matrix_get_coefficients(const csb_matrix_t *m, csb_real_t *d_val, csb_real_t *x_val);

@@ -221,6 +221,19 @@ void   ora_gradient_green_reconstruct(int n_cells, int n_i_faces, const int *i_f
                                       const double *coefb, const double *r_grad,
                                       const double *corr_grad_lin, double *grad);
 
+/* cs_divergence and cs_face_diffusion_potential (grad NULL: no reconstruction) */
+void   ora_divergence(int n_cells, int n_i_faces, const int *i_face_cells, int n_b_faces,
+                      const int *b_face_cells, int init, const double *i_massflux,
+                      const double *b_massflux, double *diverg);
+void   ora_face_diffusion_potential(int n_cells, int n_i_faces, const int *i_face_cells,
+                                    int n_b_faces, const int *b_face_cells, const double *i_geo,
+                                    const double *i_face_surf, const double *val_ip, int init,
+                                    int inc, const double *pvar, const double *grad,
+                                    const double *cofaf, const double *cofbf,
+                                    const double *i_visc, const double *b_visc,
+                                    const double *visel, double *i_massflux,
+                                    double *b_massflux);
+
 /* matrix assembler on one rank, MSR target: cs_oracle_assembler.c */
 int    ora_assembler_structure(int n_rows, int n, const long long *row_g_id,
                                const long long *col_g_id, long long l_range_0,

@@ -385,3 +385,62 @@ ora_gradient_green_reconstruct(int n_cells, int n_i_faces, const int *i_face_cel
     }
   }
 }
+
+/* cs_divergence (src/alge/cs_divergence.cpp:1224-1290): signed sums of the face mass fluxes,
+   interior faces in face order then boundary faces */
+void
+ora_divergence(int n_cells, int n_i_faces, const int *i_face_cells, int n_b_faces,
+               const int *b_face_cells, int init, const double *i_massflux,
+               const double *b_massflux, double *diverg)
+{
+  if (init >= 1)
+    for (int i = 0; i < n_cells; i++) diverg[i] = 0.;
+  for (int f = 0; f < n_i_faces; f++) {
+    const int ii = i_face_cells[2*f], jj = i_face_cells[2*f+1];
+    if (ii < n_cells) diverg[ii] += i_massflux[f];
+    if (jj < n_cells) diverg[jj] += -i_massflux[f];
+  }
+  for (int f = 0; f < n_b_faces; f++) diverg[b_face_cells[f]] += b_massflux[f];
+}
+
+/* cs_face_diffusion_potential (src/alge/cs_convection_diffusion.cpp:8075-8310): the face
+   fluxes cs_diffusion_potential sums, kept per face.  grad NULL: eqp->ircflu = 0 (:8236-8246,
+   boundary flux from the cell value); else the reconstructed form (:8254-8296, always the
+   II' - JJ' formula) with the boundary flux from val_ip (NULL: the cell value). */
+void
+ora_face_diffusion_potential(int n_cells, int n_i_faces, const int *i_face_cells,
+                             int n_b_faces, const int *b_face_cells, const double *i_geo,
+                             const double *i_face_surf, const double *val_ip, int init,
+                             int inc, const double *pvar, const double *grad,
+                             const double *cofaf, const double *cofbf, const double *i_visc,
+                             const double *b_visc, const double *visel, double *i_massflux,
+                             double *b_massflux)
+{
+  (void)n_cells;
+  if (init >= 1) {
+    for (int f = 0; f < n_i_faces; f++) i_massflux[f] = 0.;
+    for (int f = 0; f < n_b_faces; f++) b_massflux[f] = 0.;
+  }
+  for (int f = 0; f < n_i_faces; f++) {
+    const int c0 = i_face_cells[2*f], c1 = i_face_cells[2*f+1];
+    if (grad == NULL) {
+      i_massflux[f] += i_visc[f]*(pvar[c0] - pvar[c1]);
+      continue;
+    }
+    const double *ip = i_geo + 7*(size_t)f, *jp = ip + 3;
+    const double *g0 = grad + 3*(size_t)c0, *g1 = grad + 3*(size_t)c1;
+    const double dpxf = 0.5*(visel[c0]*g0[0] + visel[c1]*g1[0]);
+    const double dpyf = 0.5*(visel[c0]*g0[1] + visel[c1]*g1[1]);
+    const double dpzf = 0.5*(visel[c0]*g0[2] + visel[c1]*g1[2]);
+    const double dijx = ip[0] - jp[0], dijy = ip[1] - jp[1], dijz = ip[2] - jp[2];
+    const double f_mass_flux =   i_visc[f]*(pvar[c0] - pvar[c1])
+                               + (dpxf*dijx + dpyf*dijy + dpzf*dijz) * i_face_surf[f]/ip[6];
+    i_massflux[f] += f_mass_flux;
+  }
+  for (int f = 0; f < n_b_faces; f++) {
+    const int c0 = b_face_cells[f];
+    const double flux_d
+      = inc*cofaf[f] + cofbf[f]*((grad != NULL && val_ip != NULL) ? val_ip[f] : pvar[c0]);
+    b_massflux[f] += b_visc[f]*flux_d;
+  }
+}

@@ -418,6 +418,31 @@ class Oracle:
             _dp(_f64(i_visc)), _dp(_f64(b_visc)), _dp(_f64(visel)), _dp(div))
         return div
 
+    def divergence(self, s, b_face_cells, i_massflux, b_massflux, init=1, diverg=None):
+        div = np.zeros(s.n_rows) if diverg is None else _f64(diverg).copy()
+        fc, bfc = _i32(s.face_cells), _i32(b_face_cells)
+        self.lib.ora_divergence.restype = None
+        self.lib.ora_divergence(C.c_int(s.n_rows), C.c_int(len(fc)), _ip(fc), C.c_int(len(bfc)),
+                                _ip(bfc), C.c_int(init), _dp(_f64(i_massflux)),
+                                _dp(_f64(b_massflux)), _dp(div))
+        return div
+
+    def face_diffusion_potential(self, s, b_face_cells, pvar, cofaf, cofbf, i_visc, b_visc,
+                                 i_geo=None, grad=None, visel=None, val_ip=None, init=1, inc=1,
+                                 massflux=None):
+        """grad None: eqp->ircflu = 0; returns (i_massflux, b_massflux)"""
+        fc, bfc = _i32(s.face_cells), _i32(b_face_cells)
+        im = np.zeros(max(len(fc), 1)) if massflux is None else _f64(massflux[0]).copy()
+        bm = np.zeros(max(len(bfc), 1)) if massflux is None else _f64(massflux[1]).copy()
+        opt = lambda a: None if a is None else _dp(_f64(a))
+        self.lib.ora_face_diffusion_potential.restype = None
+        self.lib.ora_face_diffusion_potential(
+            C.c_int(s.n_rows), C.c_int(len(fc)), _ip(fc), C.c_int(len(bfc)), _ip(bfc), opt(i_geo),
+            _dp(_f64(s.face_surf)), opt(val_ip), C.c_int(init), C.c_int(inc), _dp(_f64(pvar)),
+            opt(grad), _dp(_f64(cofaf)), _dp(_f64(cofbf)), _dp(_f64(i_visc)), _dp(_f64(b_visc)),
+            opt(visel), _dp(im), _dp(bm))
+        return im[:len(fc)], bm[:len(bfc)]
+
     def aggregation_fc(self, level, n_rows, face_cells, da, xa, max_aggregation=3):
         fc = _i32(face_cells)
         f_c = np.empty(max(n_rows, 1), dtype=np.int32)
@@ -742,7 +767,7 @@ class RefLib:
     def diffusion_potential_rc(self, h, s, b_face_cells, b_geo, i_face_cog, i_geo, pvar, coefa,
                                coefb, cofaf, cofbf, i_visc, b_visc, visel, irecmf=0, init=1,
                                inc=1, diverg=None, diipb=None, imrgra=1, g_geo=None,
-                               b_face_surf=None, corr_grad_lin=None):
+                               b_face_surf=None, corr_grad_lin=None, ircflu=1, massflux=None):
         """cs_diffusion_potential WITH flux reconstruction (LSQ gradient) on the geometry given;
         returns (diverg, grad)."""
         div = np.zeros(s.n_rows) if diverg is None else _f64(diverg).copy()
@@ -758,9 +783,21 @@ class RefLib:
             (None if corr_grad_lin is None else _dp(_f64(corr_grad_lin))), C.c_int(irecmf),
             C.c_int(init), C.c_int(inc), _dp(keep[3]), _dp(keep[4]),
             _dp(keep[5]), _dp(keep[6]), _dp(keep[7]), _dp(keep[8]), _dp(keep[9]), _dp(keep[10]),
-            _dp(div), _dp(grad))
+            _dp(div), _dp(grad), C.c_int(ircflu),
+            (None if massflux is None else _dp(massflux[0])),
+            (None if massflux is None else _dp(massflux[1])))
         assert r == 0
         return div, grad.reshape(-1, 3)
+
+    def divergence(self, h, s, b_face_cells, i_massflux, b_massflux, init=1, diverg=None):
+        """cs_divergence on the system's faces"""
+        div = np.zeros(s.n_rows) if diverg is None else _f64(diverg).copy()
+        bfc = _i32(b_face_cells)
+        r = self.lib.csref_divergence(h, _ip(_i32(s.face_cells)), C.c_int(len(bfc)), _ip(bfc),
+                                      C.c_int(init), _dp(_f64(i_massflux)), _dp(_f64(b_massflux)),
+                                      _dp(div))
+        assert r == 0
+        return div
 
     def system_block(self, n_rows, db, ri, ci, d_val, x_val, symmetric=False):
         """MSR matrix with db x db diagonal blocks (d_val: n_rows*db*db) built by the reference."""

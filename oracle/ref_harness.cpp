@@ -48,6 +48,7 @@
 #include "alge/cs_matrix_building.h"
 #include "alge/cs_matrix_assembler.h"
 #include "alge/cs_convection_diffusion.h"
+#include "alge/cs_divergence.h"
 #include "base/cs_parameters.h"
 #include "base/cs_velocity_pressure.h"
 #include "alge/cs_gradient.h"
@@ -958,7 +959,10 @@ csref_diffusion_potential_rc(void          *sys,
                              const double  *b_visc,
                              const double  *visel,
                              double        *diverg,
-                             double        *grad_out)
+                             double        *grad_out,
+                             int            ircflu,       /* eqp->ircflu: 1 = reconstruct */
+                             double        *i_massflux,   /* both non-NULL: call */
+                             double        *b_massflux)   /* cs_face_diffusion_potential */
 {
   ref_system *s = static_cast<ref_system *>(sys);
   _set_glob_mesh_faces(s, face_cells);
@@ -1044,7 +1048,7 @@ csref_diffusion_potential_rc(void          *sys,
     cs_glob_mesh_quantities_flag |= CS_BAD_CELLS_WARPED_CORRECTION;
 
   cs_equation_param_t eqp = cs_parameters_equation_param_default();
-  eqp.ircflu = 1;
+  eqp.ircflu = ircflu;
   eqp.imrgra = imrgra;     /* 1: least squares, standard neighbourhood; 4: Green-Gauss with
                               least-squares face values */
   eqp.imligr = -1;         /* no gradient limiter */
@@ -1063,11 +1067,18 @@ csref_diffusion_potential_rc(void          *sys,
   std::vector<cs_real_t> _div(n_cells > 0 ? n_cells : 1, 0.);
   if (!init) memcpy(_div.data(), diverg, sizeof(cs_real_t)*n_cells);
 
-  cs_diffusion_potential(nullptr, &eqp, mesh, mq, init, inc, 0, nullptr, _pvar.data(), &bc,
-                         i_visc, b_visc, _visel.data(), _div.data());
-  memcpy(diverg, _div.data(), sizeof(cs_real_t)*n_cells);
+  if (i_massflux != nullptr && b_massflux != nullptr)
+    /* the face-flux sibling (cs_convection_diffusion.cpp:8075-8310): same BC update and
+       gradient, fluxes kept per face; always the irecmf = 0 formula */
+    cs_face_diffusion_potential(nullptr, &eqp, mesh, mq, init, inc, 0, nullptr, _pvar.data(), &bc,
+                                i_visc, b_visc, _visel.data(), i_massflux, b_massflux);
+  else {
+    cs_diffusion_potential(nullptr, &eqp, mesh, mq, init, inc, 0, nullptr, _pvar.data(), &bc,
+                           i_visc, b_visc, _visel.data(), _div.data());
+    memcpy(diverg, _div.data(), sizeof(cs_real_t)*n_cells);
+  }
 
-  if (grad_out != nullptr) {
+  if (grad_out != nullptr && ircflu) {
     /* bc.val_f was filled by cs_diffusion_potential's update of the face values */
     cs_gradient_scalar_synced_input("csref",
                                     (imrgra == 4) ? CS_GRADIENT_GREEN_LSQ : CS_GRADIENT_LSQ,
@@ -1087,6 +1098,36 @@ csref_diffusion_potential_rc(void          *sys,
   mq->corr_grad_lin = nullptr;
   cs_glob_mesh_quantities_flag = mq_flag_prev;
   CS_FREE(bc.val_f); CS_FREE(bc.flux_diff);
+  return 0;
+}
+
+/* cs_divergence (src/alge/cs_divergence.cpp:1224-1290): diverg[c] (+)= the signed sum of the
+   face mass fluxes of the cell, the reference's real function on the system's faces */
+int
+csref_divergence(void          *sys,
+                 const int     *face_cells,
+                 int            n_b_faces,
+                 const int     *b_face_cells,
+                 int            init,
+                 const double  *i_massflux,
+                 const double  *b_massflux,
+                 double        *diverg)
+{
+  ref_system *s = static_cast<ref_system *>(sys);
+  _set_glob_mesh_faces(s, face_cells);
+  cs_mesh_t *mesh = cs_glob_mesh;
+  CS_FREE(mesh->b_face_cells);
+  mesh->n_b_faces = n_b_faces;
+  mesh->n_b_faces_all = n_b_faces;
+  CS_MALLOC(mesh->b_face_cells, (n_b_faces > 0) ? n_b_faces : 1, cs_lnum_t);
+  memcpy(mesh->b_face_cells, b_face_cells, sizeof(cs_lnum_t)*n_b_faces);
+  if (mesh->b_face_numbering != nullptr)
+    cs_numbering_destroy(&(mesh->b_face_numbering));
+  mesh->b_face_numbering = cs_numbering_create_default(n_b_faces);
+  if (mesh->i_face_numbering != nullptr)
+    cs_numbering_destroy(&(mesh->i_face_numbering));
+  mesh->i_face_numbering = cs_numbering_create_default(s->n_faces);
+  cs_divergence(mesh, init, i_massflux, b_massflux, diverg);
   return 0;
 }
 

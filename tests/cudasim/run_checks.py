@@ -391,8 +391,31 @@ def check_rhs(ora):
         m.set_boundary_iprime(None)
         assert np.array_equal(m.gradient_lsq(f["pvar"], f["coefa"], f["coefb"]), g0)
         m.destroy()
+    # cs_face_diffusion_potential + cs_divergence
+    from make_golden_rhs import FACE_CASES, FACE_INIT_INC, face_input, green_input
+    for N in CASES:
+        g = np.load(os.path.join(GOLD, f"rhs_face_N{N}.npz"))
+        s, bfc, b_geo, _, i_geo, f = rc_input(N)
+        g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
+        mf0 = face_input(s, len(bfc))
+        m = csb.Matrix.from_system(s)
+        m.set_boundary_faces(bfc)
+        m.set_face_geometry(i_geo[:, 6], i_geo[:, :3], i_geo[:, 3:6], b_geo[:, :3], b_geo[:, 6])
+        m.set_green_geometry(g_geo[:, 0], g_geo[:, 1:4], b_surf, cgl)
+        m.set_boundary_iprime(diipb_input(N, len(bfc)))
+        for ircflu, imrgra in FACE_CASES:
+            m.set_gradient_type(imrgra)
+            for init, inc in FACE_INIT_INC:
+                im, bm = m.face_diffusion_potential(
+                    s.n_faces, len(bfc), f["pvar"], f["cofaf"], f["cofbf"], f["i_visc"], f["b_visc"],
+                    coefa=f["coefa"], coefb=f["coefb"], visel=f["visel"], ircflu=ircflu, init=init,
+                    inc=inc, massflux=mf0)
+                tag = f"rc{ircflu}_g{imrgra}_init{init}_inc{inc}"
+                assert np.array_equal(im, g["i_" + tag]) and np.array_equal(bm, g["b_" + tag]), (N, tag)
+                d = m.divergence(im, bm, init=init, diverg=f["div0"])
+                assert np.array_equal(d, g["div_" + tag]), (N, tag)
+        m.destroy()
     # imrgra = 4: Green-Gauss gradient with least-squares face values
-    from make_golden_rhs import green_input
     for N in CASES:
         g = np.load(os.path.join(GOLD, f"rhs_green_N{N}.npz"))
         s, bfc, b_geo, _, i_geo, f = rc_input(N)

@@ -3,7 +3,8 @@
 the reference's own compiled CPU code (oracle/_ref/libcsref.so, csref_diffusion_potential):
 
     python tests/golden/make_golden_rhs.py   -> tests/golden/rhs_N{N}.npz, rhs_rc_N{N}.npz,
-                                                rhs_rcb_N{N}.npz, rhs_green_N{N}.npz
+                                                rhs_rcb_N{N}.npz, rhs_green_N{N}.npz,
+                                                rhs_face_N{N}.npz
 
 rhs_rc_*: the same operator WITH flux reconstruction (eqp->ircflu = 1, least-squares gradient,
 csref_diffusion_potential_rc) on a non-orthogonal variant of the cube.
@@ -12,6 +13,8 @@ boundary values go through cs_gradient_boundary_iprime_lsq_s.
 rhs_green_*: eqp->imrgra = 4, the reference's default gradient (CS_GRADIENT_GREEN_LSQ: the
 least-squares gradient, then _reconstruct_scalar_gradient), with and without boundary II' and
 the warped-face correction matrices.
+rhs_face_*: cs_face_diffusion_potential (the per-face fluxes; eqp->ircflu 0 and 1, imrgra 1 and
+4, boundary II' given) and cs_divergence of those fluxes.
 """
 import os
 import sys
@@ -88,9 +91,43 @@ def green_input(N, n_faces, n_b_faces, n_rows, seed=29):
     return g_geo, b_surf, cgl
 
 
+FACE_CASES = ((0, 1), (1, 1), (1, 4))            # (ircflu, imrgra)
+FACE_INIT_INC = ((1, 1), (0, 1), (1, 0))
+
+
+def face_input(s, n_b_faces, seed=41):
+    """seeded previous content of (i_massflux, b_massflux) for the init = 0 calls"""
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal(s.n_faces), rng.standard_normal(n_b_faces)
+
+
 def main():
     from oracle.pyoracle import RefLib
     ref = RefLib(1)
+    for N in CASES:
+        s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
+        g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
+        diipb = diipb_input(N, len(bfc))
+        mf0 = face_input(s, len(bfc))
+        h = ref.system(s)
+        out = {}
+        for ircflu, imrgra in FACE_CASES:
+            for init, inc in FACE_INIT_INC:
+                mf = (mf0[0].copy(), mf0[1].copy())
+                ref.diffusion_potential_rc(h, s, bfc, b_geo, ifc, i_geo, f["pvar"], f["coefa"],
+                                           f["coefb"], f["cofaf"], f["cofbf"], f["i_visc"],
+                                           f["b_visc"], f["visel"], init=init, inc=inc,
+                                           diipb=diipb, imrgra=imrgra, g_geo=g_geo,
+                                           b_face_surf=b_surf, corr_grad_lin=cgl, ircflu=ircflu,
+                                           massflux=mf)
+                tag = f"rc{ircflu}_g{imrgra}_init{init}_inc{inc}"
+                out["i_" + tag], out["b_" + tag] = mf
+                out["div_" + tag] = ref.divergence(h, s, bfc, mf[0], mf[1], init=init,
+                                                   diverg=f["div0"])
+        ref.destroy(h)
+        path = os.path.join(ROOT, "tests", "golden", f"rhs_face_N{N}.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path))
     for N in CASES:
         s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
         g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)

@@ -233,6 +233,64 @@ def test_green_lsq_gradient_vs_oracle_larger(csb, oracle):
     m.destroy()
 
 
+@pytest.mark.parametrize("N", CASES)
+def test_face_diffusion_potential_and_divergence_match_reference_golden(csb, N):
+    """cs_face_diffusion_potential (per-face fluxes: ircflu 0 / 1, imrgra 1 / 4, boundary II',
+    init 0 / 1, inc 0 / 1) and cs_divergence of them: bit-identical to the reference; the
+    divergence of the fluxes equals csb_diffusion_potential_rc (irecmf 0)"""
+    from make_golden_rhs import (FACE_CASES, FACE_INIT_INC, diipb_input, face_input, green_input)
+    g = np.load(os.path.join(GOLD, f"rhs_face_N{N}.npz"))
+    s, bfc, b_geo, _, i_geo, f = rc_input(N)
+    g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
+    mf0 = face_input(s, len(bfc))
+    m = _rc_matrix(csb, s, bfc, b_geo, i_geo)
+    m.set_green_geometry(g_geo[:, 0], g_geo[:, 1:4], b_surf, cgl)
+    m.set_boundary_iprime(diipb_input(N, len(bfc)))
+    for ircflu, imrgra in FACE_CASES:
+        m.set_gradient_type(imrgra)
+        for init, inc in FACE_INIT_INC:
+            im, bm = m.face_diffusion_potential(
+                s.n_faces, len(bfc), f["pvar"], f["cofaf"], f["cofbf"], f["i_visc"], f["b_visc"],
+                coefa=f["coefa"], coefb=f["coefb"], visel=f["visel"], ircflu=ircflu, init=init,
+                inc=inc, massflux=mf0)
+            tag = f"rc{ircflu}_g{imrgra}_init{init}_inc{inc}"
+            assert np.array_equal(im, g["i_" + tag]) and np.array_equal(bm, g["b_" + tag]), tag
+            d = m.divergence(im, bm, init=init, diverg=f["div0"])
+            assert np.array_equal(d, g["div_" + tag]), tag
+            if init == 1 and ircflu:
+                d2 = m.diffusion_potential_rc(f["pvar"], f["coefa"], f["coefb"], f["cofaf"],
+                                              f["cofbf"], f["i_visc"], f["b_visc"], f["visel"],
+                                              irecmf=0, inc=inc)
+                assert np.array_equal(d, d2), tag
+    with pytest.raises(csb.CsbError):
+        m.divergence(g["i_rc0_g1_init1_inc1"], None)                 # boundary fluxes missing
+    with pytest.raises(csb.CsbError):
+        m.face_diffusion_potential(s.n_faces, len(bfc), f["pvar"], f["cofaf"], f["cofbf"],
+                                   f["i_visc"], f["b_visc"], ircflu=1)   # coefa / coefb / visel
+    m.destroy()
+
+
+def test_face_fluxes_without_reconstruction_need_no_geometry(csb, oracle):
+    """ircflu = 0 on the plain cube (mesh association and boundary faces only), device-resident
+    arrays; 40^3 against the oracle, and divergence(fluxes) == csb_diffusion_potential"""
+    import torch
+    N = 40
+    s, bfc, _, _, f = rhs_input(N)
+    m = csb.Matrix.from_system(s)
+    m.set_boundary_faces(bfc)
+    t = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in f.items()}
+    im, bm = m.face_diffusion_potential(s.n_faces, len(bfc), t["pvar"], t["cofaf"], t["cofbf"],
+                                        t["i_visc"], t["b_visc"])
+    imo, bmo = oracle.face_diffusion_potential(s, bfc, f["pvar"], f["cofaf"], f["cofbf"],
+                                               f["i_visc"], f["b_visc"])
+    assert np.array_equal(im, imo) and np.array_equal(bm, bmo)
+    d = m.divergence(im, bm)
+    assert np.array_equal(d, oracle.divergence(s, bfc, imo, bmo))
+    assert np.array_equal(d, m.diffusion_potential(f["pvar"], f["i_visc"], f["b_visc"], f["cofaf"],
+                                                   f["cofbf"]))
+    m.destroy()
+
+
 def test_reconstruction_needs_geometry(csb):
     s, bfc, _, _, _, f = rc_input(5)
     m = csb.Matrix.from_system(s)

@@ -944,6 +944,47 @@ def test_oracle_green_lsq_gradient_is_exact_for_linear_fields(oracle):
     assert np.abs(grad - a).max() < 1e-12 * np.abs(a).max() * N
 
 
+@pytest.mark.parametrize("N", [5, 9])
+def test_oracle_face_diffusion_potential_and_divergence_match_golden(oracle, N):
+    """cs_face_diffusion_potential (per-face fluxes, ircflu 0 / 1, imrgra 1 / 4, boundary II')
+    and cs_divergence of them: bit-exact against the reference; the divergence of the fluxes is
+    cs_diffusion_potential's result (irecmf 0)"""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_rhs import (FACE_CASES, FACE_INIT_INC, diipb_input, face_input, green_input,
+                                 rc_input)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"rhs_face_N{N}.npz"))
+    s, bfc, b_geo, _, i_geo, f = rc_input(N)
+    g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
+    diipb = diipb_input(N, len(bfc))
+    mf0 = face_input(s, len(bfc))
+    bun, bd = b_geo[:, :3], b_geo[:, 6]
+    vip = oracle.b_iprime_lsq(s, bfc, bun, bd, diipb, f["pvar"], f["coefa"], f["coefb"])
+    for ircflu, imrgra in FACE_CASES:
+        for init, inc in FACE_INIT_INC:
+            kw = {}
+            if ircflu:
+                if imrgra == 4:
+                    grad = oracle.gradient_green_lsq(s, bfc, bun, bd, g_geo, b_surf, f["pvar"],
+                                                     f["coefa"], f["coefb"], inc=inc, diipb=diipb,
+                                                     corr_grad_lin=cgl)
+                else:
+                    grad = oracle.gradient_lsq(s, bfc, bun, bd, f["pvar"], f["coefa"], f["coefb"],
+                                               inc=inc, diipb=diipb)
+                kw = dict(i_geo=i_geo, grad=grad, visel=f["visel"], val_ip=vip)
+            im, bm = oracle.face_diffusion_potential(s, bfc, f["pvar"], f["cofaf"], f["cofbf"],
+                                                     f["i_visc"], f["b_visc"], init=init, inc=inc,
+                                                     massflux=mf0, **kw)
+            tag = f"rc{ircflu}_g{imrgra}_init{init}_inc{inc}"
+            assert np.array_equal(im, g["i_" + tag]) and np.array_equal(bm, g["b_" + tag]), tag
+            d = oracle.divergence(s, bfc, im, bm, init=init, diverg=f["div0"])
+            assert np.array_equal(d, g["div_" + tag]), tag
+            if init == 1 and ircflu:
+                d2 = oracle.diffusion_potential_rc(s, bfc, i_geo, grad, f["pvar"], f["cofaf"],
+                                                   f["cofbf"], f["i_visc"], f["b_visc"],
+                                                   f["visel"], irecmf=0, inc=inc, val_ip=vip)
+                assert np.array_equal(d, d2), tag
+
+
 def test_oracle_gradient_lsq_is_exact_for_linear_fields(oracle):
     """property: a least-squares gradient reproduces the gradient of a linear field (to the
     single precision of its cocg matrices) when the boundary values are those of the field"""
