@@ -691,6 +691,54 @@ class Matrix:
             _err("csb_face_diffusion_potential")
         return im[:n_faces], bm[:n_b_faces]
 
+    def set_face_cog(self, i_face_cog, b_face_cog):
+        """face centres, for the hydrostatic pressure treatment"""
+        L = load_library()
+        L.csb_matrix_set_face_cog.argtypes = [C.c_void_p] * 3
+        a = [_f64(np.asarray(x)) for x in (i_face_cog, b_face_cog)]
+        if L.csb_matrix_set_face_cog(self.handle, *[_ptr(x) for x in a]) != 0:
+            _err("csb_matrix_set_face_cog")
+
+    def gradient_hyd(self, imrgra, f_ext, pvar, coefa=None, coefb=None, inc=1, hyd_p_flag=1):
+        """cs_gradient_scalar_synced_input with the hydrostatic pressure treatment"""
+        L = load_library()
+        L.csb_gradient_scalar_hyd.argtypes = [C.c_void_p] + [C.c_int] * 3 + [C.c_void_p] * 5
+        grad = np.zeros(3 * self.n_rows)
+        a = [x if x is None or not isinstance(x, np.ndarray) else _f64(x)
+             for x in (f_ext, pvar, coefa, coefb)]
+        if L.csb_gradient_scalar_hyd(self.handle, int(imrgra), int(inc), int(hyd_p_flag),
+                                     *[_ptr(x) for x in a], _ptr(grad)) != 0:
+            _err("csb_gradient_scalar_hyd")
+        return grad.reshape(-1, 3)
+
+    def diffusion_potential_hyd(self, frcxt, pvar, coefa, coefb, cofaf, cofbf, i_visc, b_visc,
+                                visel, irecmf=0, init=1, inc=1, iphydp=1, diverg=None):
+        """cs_diffusion_potential with flux reconstruction, iphydp / frcxt given"""
+        L = load_library()
+        L.csb_diffusion_potential_hyd.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 10
+        div = np.zeros(self.n_rows) if diverg is None else _f64(np.asarray(diverg)).copy()
+        a = [x if x is None or not isinstance(x, np.ndarray) else _f64(x)
+             for x in (frcxt, pvar, coefa, coefb, cofaf, cofbf, i_visc, b_visc, visel)]
+        if L.csb_diffusion_potential_hyd(self.handle, int(irecmf), int(init), int(inc),
+                                         int(iphydp), *[_ptr(x) for x in a], _ptr(div)) != 0:
+            _err("csb_diffusion_potential_hyd")
+        return div
+
+    def face_diffusion_potential_hyd(self, n_faces, n_b_faces, frcxt, pvar, coefa, coefb, cofaf,
+                                     cofbf, i_visc, b_visc, visel, ircflu=1, init=1, inc=1,
+                                     iphydp=1, massflux=None):
+        L = load_library()
+        L.csb_face_diffusion_potential_hyd.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 11
+        im = np.zeros(max(n_faces, 1)) if massflux is None else _f64(np.asarray(massflux[0])).copy()
+        bm = np.zeros(max(n_b_faces, 1)) if massflux is None else _f64(np.asarray(massflux[1])).copy()
+        a = [x if x is None or not isinstance(x, np.ndarray) else _f64(x)
+             for x in (frcxt, pvar, coefa, coefb, cofaf, cofbf, i_visc, b_visc, visel)]
+        if L.csb_face_diffusion_potential_hyd(self.handle, int(ircflu), int(init), int(inc),
+                                              int(iphydp), *[_ptr(x) for x in a], _ptr(im),
+                                              _ptr(bm)) != 0:
+            _err("csb_face_diffusion_potential_hyd")
+        return im[:n_faces], bm[:n_b_faces]
+
     def set_face_geometry(self, i_dist, diipf, djjpf, b_face_u_normal, b_dist):
         L = load_library()
         L.csb_matrix_set_face_geometry.argtypes = [C.c_void_p] * 6

@@ -380,6 +380,9 @@ struct _csb_matrix_t {
      boundary face surfaces, optional warped-face correction matrices; imrgra = the gradient
      csb_diffusion_potential_rc uses (1: least squares, 4: Green-Gauss with LSQ face values) */
   csb::DevBuf<double>      g_weight, dofij, b_face_surf, corr_grad_lin;
+  /* face centres (csb_matrix_set_face_cog): the hydrostatic pressure treatment needs them */
+  csb::DevBuf<double>      i_face_cog, b_face_cog;
+  bool        has_face_cog = false;
   bool        has_green_geo = false, has_corr_grad_lin = false;
   int         imrgra = 1;
   mutable csb::DevBuf<float> cocg_lsq;
@@ -641,14 +644,17 @@ bool launch_diffusion_potential(const _csb_matrix_t *m, int init, int inc, const
 /* least-squares cell gradient (cs_gradient.cpp:2501-2680, :2695-2900) and the reconstructed
    form of cs_diffusion_potential (cs_convection_diffusion.cpp:8895-8982) */
 bool launch_lsq_cocg(const _csb_matrix_t *m, float *cocg);
-/* val_ip: values at I' of the boundary faces (launch_b_iprime_lsq,
-   cs_gradient_boundary.cpp:197-640) when the matrix holds II' of its boundary faces, else
-   nullptr (I' = I) */
-bool launch_b_iprime_lsq(const _csb_matrix_t *m, const double *pvar, const double *coefa,
-                         const double *coefb, double *val_ip);
+/* launch_b_iprime_lsq: values at I' of the boundary faces (cs_gradient_boundary.cpp:197-640)
+   and the face values derived from them (val_f, may be nullptr); needed when the matrix holds
+   II' of its boundary faces or when f_ext is given (hyd_p_flag = 1: exterior force
+   [n_rows][3], needs the face centres of csb_matrix_set_face_cog).  The gradient kernels take
+   val_f, or nullptr for inc*coefa + coefb*pvar. */
+bool launch_b_iprime_lsq(const _csb_matrix_t *m, int inc, const double *pvar,
+                         const double *coefa, const double *coefb, const double *f_ext,
+                         double *val_ip, double *val_f);
 bool launch_lsq_gradient(const _csb_matrix_t *m, const float *cocg, int inc, const double *pvar,
-                         const double *coefa, const double *coefb, const double *val_ip,
-                         double *grad);
+                         const double *coefa, const double *coefb, const double *val_f,
+                         const double *f_ext, double *grad);
 /* cs_divergence (cs_divergence.cpp:1224) and cs_face_diffusion_potential
    (cs_convection_diffusion.cpp:8075; grad nullptr: no reconstruction) */
 bool launch_divergence(const _csb_matrix_t *m, int init, const double *i_massflux,
@@ -662,8 +668,8 @@ bool launch_face_diffusion_potential(const _csb_matrix_t *m, int init, int inc,
 /* second half of the Green-Gauss gradient with least-squares face values (imrgra = 4,
    _reconstruct_scalar_gradient cs_gradient.cpp:4167): r_grad = the least-squares gradient */
 bool launch_green_reconstruct(const _csb_matrix_t *m, int inc, const double *pvar,
-                              const double *coefa, const double *coefb, const double *val_ip,
-                              const double *r_grad, double *grad);
+                              const double *coefa, const double *coefb, const double *val_f,
+                              const double *f_ext, const double *r_grad, double *grad);
 bool launch_diffusion_potential_rc(const _csb_matrix_t *m, int irecmf, int init, int inc,
                                    const double *pvar, const double *grad, const double *cofaf,
                                    const double *cofbf, const double *i_visc,

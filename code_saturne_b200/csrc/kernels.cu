@@ -2335,6 +2335,12 @@ bool launch_diffusion_potential(const _csb_matrix_t *m, int init, int inc, const
 
 namespace {
 
+/* (xb - xa) . xc, cs_math_3_distance_dot_product (cs_math.h:171-176) */
+__device__ __forceinline__ double ddp3(const double *xa, const double *xb, const double *xc)
+{
+  return ((xb[0] - xa[0])*xc[0]+(xb[1] - xa[1])*xc[1]+(xb[2] - xa[2])*xc[2]);
+}
+
 /* cocg of the least-squares gradient, one cell per thread: sum of dc (x) dc / |dc|^2 over the
    cell's neighbours in adjacency (= MSR) order, then of n (x) n over its boundary faces,
    ACCUMULATED IN SINGLE PRECISION like the reference's cs_cocg_t (each term is a double
@@ -2449,7 +2455,10 @@ __global__ void k_lsq_gradient(int n_rows, const int *__restrict__ row_index,
                                const double *__restrict__ coefa,
                                const double *__restrict__ coefb,
                                const double *__restrict__ diipb,
-                               const double *__restrict__ val_ip, double *grad)
+                               const double *__restrict__ val_f,
+                               const double *__restrict__ i_face_cog,
+                               const double *__restrict__ b_face_cog,
+                               const double *__restrict__ f_ext, double *grad)
 {
   const int c = blockIdx.x*blockDim.x + threadIdx.x;
   if (c >= n_rows) return;
@@ -2470,7 +2479,17 @@ __global__ void k_lsq_gradient(int n_rows, const int *__restrict__ row_index,
     const size_t ii = (size_t)(first ? c : o), jj = (size_t)(first ? o : c);
     const double d0 = cell_cen[3*jj] - cell_cen[3*ii], d1 = cell_cen[3*jj+1] - cell_cen[3*ii+1],
                  d2 = cell_cen[3*jj+2] - cell_cen[3*ii+2];
-    const double pfac = (pvar[jj] - pvar[ii]) / (d0*d0 + d1*d1 + d2*d2);
+    double pfac;
+    if (f_ext == nullptr)
+      pfac = (pvar[jj] - pvar[ii]) / (d0*d0 + d1*d1 + d2*d2);
+    else {                  /* _lsq_scalar_gradient_hyd_p (cs_gradient.cpp:3420-3445) */
+      const double dvarij = pvar[jj] - pvar[ii];
+      const double *cog = i_face_cog + 3*(size_t)best;
+      pfac =   dvarij
+             + ddp3(cog, cell_cen + 3*ii, f_ext + 3*ii)
+             - ddp3(cog, cell_cen + 3*jj, f_ext + 3*jj);
+      pfac /= (d0*d0 + d1*d1 + d2*d2);
+    }
     r0 += d0 * pfac; r1 += d1 * pfac; r2 += d2 * pfac;
   }
   if (cell_b_faces_idx != nullptr)
@@ -2478,107 +2497,162 @@ __global__ void k_lsq_gradient(int n_rows, const int *__restrict__ row_index,
       const int f = cell_b_faces[k];
       /* face value from the value at I' (_compute_bc_flux_grad,
          cs_boundary_conditions_set_coeffs.cpp:168-170); I' = I when II' = 0 */
-      const double val_f = inc*coefa[f] + coefb[f]*(val_ip != nullptr ? val_ip[f] : pc);
+      const double vf = (val_f != nullptr) ? val_f[f] : inc*coefa[f] + coefb[f]*pc;
       const double ddif = 1. / b_dist[f];
       double d0 = b_un[3*(size_t)f], d1 = b_un[3*(size_t)f+1], d2 = b_un[3*(size_t)f+2];
       if (diipb != nullptr) {
         d0 = d0 + ddif*diipb[3*(size_t)f]; d1 = d1 + ddif*diipb[3*(size_t)f+1];
         d2 = d2 + ddif*diipb[3*(size_t)f+2];
       }
-      const double pfac = (val_f - pc) * ddif;
+      double pfac;
+      if (f_ext == nullptr)
+        pfac = (vf - pc) * ddif;
+      else {                /* (:3505-3527; no porosity term) */
+        const double if_dot_fext = ddp3(cell_cen + 3*(size_t)c, b_face_cog + 3*(size_t)f,
+                                        f_ext + 3*(size_t)c);
+        pfac = ddif * (vf - pc - 0. - if_dot_fext);
+      }
       r0 += d0 * pfac; r1 += d1 * pfac; r2 += d2 * pfac;
     }
   const float *g = cocg + 6*(size_t)c;
-  grad[3*(size_t)c]   = g[0]*r0 + g[3]*r1 + g[5]*r2;
-  grad[3*(size_t)c+1] = g[3]*r0 + g[1]*r1 + g[4]*r2;
-  grad[3*(size_t)c+2] = g[5]*r0 + g[4]*r1 + g[2]*r2;
+  if (f_ext == nullptr) {
+    grad[3*(size_t)c]   = g[0]*r0 + g[3]*r1 + g[5]*r2;
+    grad[3*(size_t)c+1] = g[3]*r0 + g[1]*r1 + g[4]*r2;
+    grad[3*(size_t)c+2] = g[5]*r0 + g[4]*r1 + g[2]*r2;
+  }
+  else {
+    const double *fx = f_ext + 3*(size_t)c;
+    grad[3*(size_t)c]   = g[0]*r0 + g[3]*r1 + g[5]*r2 + fx[0];
+    grad[3*(size_t)c+1] = g[3]*r0 + g[1]*r1 + g[4]*r2 + fx[1];
+    grad[3*(size_t)c+2] = g[5]*r0 + g[4]*r1 + g[2]*r2 + fx[2];
+  }
 }
 
 /* cs_gradient_boundary_iprime_lsq_s (cs_gradient_boundary.cpp:197-640; no limiter, no
-   hydrostatic term, no weighting, standard neighbourhood): value of pvar at I' of the boundary
-   faces.  The local least-squares system of a face depends on its cell only, so one thread
+   weighting, standard neighbourhood): value of pvar at I' of the boundary faces, and the face
+   values _compute_bc_flux_grad derives from them (cs_boundary_conditions_set_coeffs.cpp:
+   168-192).  The local least-squares system of a face depends on its cell only, so one thread
    per cell builds it once (neighbours in adjacency order, then the cell's boundary faces in
    ascending order with the direction n + (1 - b) II'/b_dist; cocg in single precision, its
    cofactors in float arithmetic, the solve in double, :560-582) and serves the cell's faces;
-   faces with |II'|^2 < 1e-6 b_dist^2 take the cell value (:285-291).  coefa enters without
-   inc, as in the reference. */
+   faces with |II'|^2 < 1e-6 b_dist^2 take the cell value (:285-291).  coefa enters the local
+   system without inc, as in the reference.
+   f_ext != nullptr: hyd_p_flag = 1 -- the interior differences gain (I - F).f_I - (J - F).f_J
+   with F the centre of the shared face (c2f = cell_i_faces), the boundary terms
+   (b - 1) (F_b - I).f_I, f_I is added to the local gradient, and val_f gains b (F_b - I').f_I.
+   diipb == nullptr: II' = 0 (every face takes the cell value).  val_f may be nullptr. */
 __global__ void k_b_iprime_lsq(int n_rows, const int *__restrict__ row_index,
-                               const int *__restrict__ col_id,
+                               const int *__restrict__ col_id, const int *__restrict__ c2f,
                                const double *__restrict__ cell_cen,
                                const int *__restrict__ cell_b_faces_idx,
                                const int *__restrict__ cell_b_faces,
                                const double *__restrict__ b_un,
                                const double *__restrict__ b_dist,
                                const double *__restrict__ diipb,
+                               const double *__restrict__ i_face_cog,
+                               const double *__restrict__ b_face_cog,
+                               const double *__restrict__ f_ext, int inc,
                                const double *__restrict__ pvar,
                                const double *__restrict__ coefa,
-                               const double *__restrict__ coefb, double *val_ip)
+                               const double *__restrict__ coefb, double *val_ip, double *val_f)
 {
   const int c = blockIdx.x*blockDim.x + threadIdx.x;
   if (c >= n_rows) return;
   const int bs = cell_b_faces_idx[c], be = cell_b_faces_idx[c+1];
   if (bs >= be) return;
   const double var_i = pvar[c];
+  const double cen[3] = {cell_cen[3*(size_t)c], cell_cen[3*(size_t)c+1], cell_cen[3*(size_t)c+2]};
+  double fx[3] = {0., 0., 0.};
+  if (f_ext != nullptr) {
+    fx[0] = f_ext[3*(size_t)c]; fx[1] = f_ext[3*(size_t)c+1]; fx[2] = f_ext[3*(size_t)c+2];
+  }
   bool any = false;
+  if (diipb != nullptr)
+    for (int k = bs; k < be; k++) {
+      const size_t f = (size_t)cell_b_faces[k];
+      const double *ip = diipb + 3*f;
+      const double bd = b_dist[f];
+      if (!(ip[0]*ip[0] + ip[1]*ip[1] + ip[2]*ip[2] < (bd*bd) * (1e-3 * 1e-3))) any = true;
+    }
+  double gx = 0., gy = 0., gz = 0.;
+  if (any) {
+    float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    double r0 = 0., r1 = 0., r2 = 0.;
+    for (int k = row_index[c]; k < row_index[c+1]; k++) {
+      const size_t j = (size_t)col_id[k];
+      const double cj[3] = {cell_cen[3*j], cell_cen[3*j+1], cell_cen[3*j+2]};
+      const double d0 = cj[0] - cen[0], d1 = cj[1] - cen[1], d2 = cj[2] - cen[2];
+      const double ddc = 1. / (d0*d0 + d1*d1 + d2*d2);
+      g[0] = (float)((double)g[0] + d0 * d0 * ddc);
+      g[1] = (float)((double)g[1] + d1 * d1 * ddc);
+      g[2] = (float)((double)g[2] + d2 * d2 * ddc);
+      g[3] = (float)((double)g[3] + d0 * d1 * ddc);
+      g[4] = (float)((double)g[4] + d1 * d2 * ddc);
+      g[5] = (float)((double)g[5] + d0 * d2 * ddc);
+      double pfac = pvar[j] - var_i;
+      if (f_ext != nullptr) {
+        const double *cog = i_face_cog + 3*(size_t)c2f[k];
+        const double dot_i = ddp3(cog, cen, fx);
+        const double dot_j = ddp3(cog, cj, f_ext + 3*j);
+        pfac += dot_i - dot_j;
+      }
+      pfac *= ddc;
+      r0 += d0 * pfac; r1 += d1 * pfac; r2 += d2 * pfac;
+    }
+    for (int k = bs; k < be; k++) {
+      const size_t f = (size_t)cell_b_faces[k];
+      const double a = coefa[f], b = coefb[f];
+      const double ddif = 1. / b_dist[f];
+      const double umcbdd = (1. - b) * ddif;
+      const double d0 = b_un[3*f] + umcbdd * diipb[3*f], d1 = b_un[3*f+1] + umcbdd * diipb[3*f+1],
+                   d2 = b_un[3*f+2] + umcbdd * diipb[3*f+2];
+      g[0] = (float)((double)g[0] + d0 * d0);
+      g[1] = (float)((double)g[1] + d1 * d1);
+      g[2] = (float)((double)g[2] + d2 * d2);
+      g[3] = (float)((double)g[3] + d0 * d1);
+      g[4] = (float)((double)g[4] + d1 * d2);
+      g[5] = (float)((double)g[5] + d0 * d2);
+      double pfac = (a + (b-1.)*var_i);
+      if (f_ext != nullptr) {
+        const double dot = ddp3(cen, b_face_cog + 3*f, fx);
+        pfac += (b-1.) * dot;
+      }
+      pfac *= ddif;
+      r0 += d0 * pfac; r1 += d1 * pfac; r2 += d2 * pfac;
+    }
+    const double a00 = (double)(g[1]*g[2] - g[4]*g[4]);
+    const double a01 = (double)(g[4]*g[5] - g[3]*g[2]);
+    const double a02 = (double)(g[3]*g[4] - g[1]*g[5]);
+    const double a11 = (double)(g[0]*g[2] - g[5]*g[5]);
+    const double a12 = (double)(g[3]*g[5] - g[0]*g[4]);
+    const double a22 = (double)(g[0]*g[1] - g[3]*g[3]);
+    const double det_inv = 1. / (g[0]*a00 + g[3]*a01 + g[5]*a02);
+    gx = (a00 * r0 + a01 * r1 + a02 * r2) * det_inv;
+    gy = (a01 * r0 + a11 * r1 + a12 * r2) * det_inv;
+    gz = (a02 * r0 + a12 * r1 + a22 * r2) * det_inv;
+    if (f_ext != nullptr) { gx += fx[0]; gy += fx[1]; gz += fx[2]; }
+  }
   for (int k = bs; k < be; k++) {
     const size_t f = (size_t)cell_b_faces[k];
-    const double *ip = diipb + 3*f;
-    const double bd = b_dist[f];
-    if (ip[0]*ip[0] + ip[1]*ip[1] + ip[2]*ip[2] < (bd*bd) * (1e-3 * 1e-3)) val_ip[f] = var_i;
-    else any = true;
-  }
-  if (!any) return;
-  float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  double r0 = 0., r1 = 0., r2 = 0.;
-  const double cx = cell_cen[3*(size_t)c], cy = cell_cen[3*(size_t)c+1], cz = cell_cen[3*(size_t)c+2];
-  for (int k = row_index[c]; k < row_index[c+1]; k++) {
-    const size_t j = (size_t)col_id[k];
-    const double d0 = cell_cen[3*j] - cx, d1 = cell_cen[3*j+1] - cy, d2 = cell_cen[3*j+2] - cz;
-    const double ddc = 1. / (d0*d0 + d1*d1 + d2*d2);
-    g[0] = (float)((double)g[0] + d0 * d0 * ddc);
-    g[1] = (float)((double)g[1] + d1 * d1 * ddc);
-    g[2] = (float)((double)g[2] + d2 * d2 * ddc);
-    g[3] = (float)((double)g[3] + d0 * d1 * ddc);
-    g[4] = (float)((double)g[4] + d1 * d2 * ddc);
-    g[5] = (float)((double)g[5] + d0 * d2 * ddc);
-    double pfac = pvar[j] - var_i;
-    pfac *= ddc;
-    r0 += d0 * pfac; r1 += d1 * pfac; r2 += d2 * pfac;
-  }
-  for (int k = bs; k < be; k++) {
-    const size_t f = (size_t)cell_b_faces[k];
-    const double a = coefa[f], b = coefb[f];
-    const double ddif = 1. / b_dist[f];
-    const double umcbdd = (1. - b) * ddif;
-    const double d0 = b_un[3*f] + umcbdd * diipb[3*f], d1 = b_un[3*f+1] + umcbdd * diipb[3*f+1],
-                 d2 = b_un[3*f+2] + umcbdd * diipb[3*f+2];
-    g[0] = (float)((double)g[0] + d0 * d0);
-    g[1] = (float)((double)g[1] + d1 * d1);
-    g[2] = (float)((double)g[2] + d2 * d2);
-    g[3] = (float)((double)g[3] + d0 * d1);
-    g[4] = (float)((double)g[4] + d1 * d2);
-    g[5] = (float)((double)g[5] + d0 * d2);
-    double pfac = (a + (b-1.)*var_i);
-    pfac *= ddif;
-    r0 += d0 * pfac; r1 += d1 * pfac; r2 += d2 * pfac;
-  }
-  const double a00 = (double)(g[1]*g[2] - g[4]*g[4]);
-  const double a01 = (double)(g[4]*g[5] - g[3]*g[2]);
-  const double a02 = (double)(g[3]*g[4] - g[1]*g[5]);
-  const double a11 = (double)(g[0]*g[2] - g[5]*g[5]);
-  const double a12 = (double)(g[3]*g[5] - g[0]*g[4]);
-  const double a22 = (double)(g[0]*g[1] - g[3]*g[3]);
-  const double det_inv = 1. / (g[0]*a00 + g[3]*a01 + g[5]*a02);
-  const double gx = (a00 * r0 + a01 * r1 + a02 * r2) * det_inv;
-  const double gy = (a01 * r0 + a11 * r1 + a12 * r2) * det_inv;
-  const double gz = (a02 * r0 + a12 * r1 + a22 * r2) * det_inv;
-  for (int k = bs; k < be; k++) {
-    const size_t f = (size_t)cell_b_faces[k];
-    const double *ip = diipb + 3*f;
-    const double bd = b_dist[f];
-    if (ip[0]*ip[0] + ip[1]*ip[1] + ip[2]*ip[2] < (bd*bd) * (1e-3 * 1e-3)) continue;
-    const double grad_dot_diipb = gx*ip[0] + gy*ip[1] + gz*ip[2];
-    val_ip[f] = var_i + grad_dot_diipb;
+    double ip[3] = {0., 0., 0.};
+    double vip = var_i;
+    if (diipb != nullptr) {
+      ip[0] = diipb[3*f]; ip[1] = diipb[3*f+1]; ip[2] = diipb[3*f+2];
+      const double bd = b_dist[f];
+      if (!(ip[0]*ip[0] + ip[1]*ip[1] + ip[2]*ip[2] < (bd*bd) * (1e-3 * 1e-3))) {
+        const double grad_dot_diipb = gx*ip[0] + gy*ip[1] + gz*ip[2];
+        vip = var_i + grad_dot_diipb;
+      }
+    }
+    val_ip[f] = vip;
+    if (val_f != nullptr) {
+      double vf = inc * coefa[f] + coefb[f] * vip;
+      if (f_ext != nullptr) {
+        const double vec_iprime[3] = {cen[0] + ip[0], cen[1] + ip[1], cen[2] + ip[2]};
+        vf += coefb[f] * ddp3(vec_iprime, b_face_cog + 3*f, fx);
+      }
+      val_f[f] = vf;
+    }
   }
 }
 
@@ -2605,7 +2679,10 @@ __global__ void k_green_reconstruct(int n_rows, const int *__restrict__ row_inde
                                     const double *__restrict__ pvar,
                                     const double *__restrict__ coefa,
                                     const double *__restrict__ coefb,
-                                    const double *__restrict__ val_ip,
+                                    const double *__restrict__ val_f,
+                                    const double *__restrict__ cell_cen,
+                                    const double *__restrict__ i_face_cog,
+                                    const double *__restrict__ f_ext,
                                     const double *__restrict__ r_grad, double *grad)
 {
   const int c = blockIdx.x*blockDim.x + threadIdx.x;
@@ -2629,17 +2706,48 @@ __global__ void k_green_reconstruct(int n_rows, const int *__restrict__ row_inde
     const double ktpond = weight[f];
     const double d_var = pvar[c2] - pvar[c1];
     const double *of = dofij + 3*f, *ra = r_grad + 3*c1, *rb = r_grad + 3*c2;
-    const double rfac = 0.5 * (  of[0]*(ra[0]+rb[0])
-                               + of[1]*(ra[1]+rb[1])
-                               + of[2]*(ra[2]+rb[2]));
     const double *n = i_face_u_normal + 3*f;
+    double pfaci, pfacj, rfac;
+    if (f_ext == nullptr) {
+      rfac = 0.5 * (  of[0]*(ra[0]+rb[0])
+                    + of[1]*(ra[1]+rb[1])
+                    + of[2]*(ra[2]+rb[2]));
+      pfaci = (1.0-ktpond) * d_var;
+      pfacj = -ktpond * d_var;
+    }
+    else {                /* hydrostatic branch (cs_gradient.cpp:4318-4398; no porosity) */
+      const double *f1 = f_ext + 3*c1, *f2 = f_ext + 3*c2, *cog = i_face_cog + 3*f;
+      double fexd[3], d_oi[3], d_oj[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        fexd[k] = 0.5 * (f1[k] + f2[k]);
+        d_oi[k] = cog[k] - cell_cen[3*c1+k];
+        d_oj[k] = cog[k] - cell_cen[3*c2+k];
+      }
+      pfaci =  ktpond
+                 * (  d_oi[0]*f1[0]
+                    + d_oi[1]*f1[1]
+                    + d_oi[2]*f1[2]
+                    + 0.)
+            +  (1.0 - ktpond)
+                 * (  d_oj[0]*f2[0]
+                    + d_oj[1]*f2[1]
+                    + d_oj[2]*f2[2]
+                    + 0.);
+      pfacj = pfaci;
+      pfaci += (1.0-ktpond) * d_var;
+      pfacj -=      ktpond  * d_var;
+      rfac =   - ktpond         * (d_oi[0]*fexd[0] + d_oi[1]*fexd[1] + d_oi[2]*fexd[2])
+           -  (1.0 - ktpond)    * (d_oj[0]*fexd[0] + d_oj[1]*fexd[1] + d_oj[2]*fexd[2])
+           + (  of[0] * (ra[0]+rb[0])
+              + of[1] * (ra[1]+rb[1])
+              + of[2] * (ra[2]+rb[2])) * 0.5;
+    }
     if (first) {
-      const double pfaci = (1.0-ktpond) * d_var;
       const double pf = (pfaci + rfac) * i_face_surf[f];
       g0 += pf * n[0]; g1 += pf * n[1]; g2 += pf * n[2];
     }
     else {
-      const double pfacj = -ktpond * d_var;
       const double pf = (pfacj + rfac) * i_face_surf[f];
       g0 += -(pf * n[0]); g1 += -(pf * n[1]); g2 += -(pf * n[2]);
     }
@@ -2647,8 +2755,8 @@ __global__ void k_green_reconstruct(int n_rows, const int *__restrict__ row_inde
   if (cell_b_faces_idx != nullptr)
     for (int k = cell_b_faces_idx[c]; k < cell_b_faces_idx[c+1]; k++) {
       const size_t f = (size_t)cell_b_faces[k];
-      const double val_f = inc*coefa[f] + coefb[f]*(val_ip != nullptr ? val_ip[f] : pc);
-      const double pfac = (val_f - pc) * b_face_surf[f];
+      const double vf = (val_f != nullptr) ? val_f[f] : inc*coefa[f] + coefb[f]*pc;
+      const double pfac = (vf - pc) * b_face_surf[f];
       g0 += pfac * b_un[3*f]; g1 += pfac * b_un[3*f+1]; g2 += pfac * b_un[3*f+2];
     }
   const double dvol = 1. / cell_vol[c];
@@ -2830,20 +2938,21 @@ bool launch_lsq_cocg(const _csb_matrix_t *m, float *cocg)
   return post_launch("lsq_cocg");
 }
 
-bool launch_b_iprime_lsq(const _csb_matrix_t *m, const double *pvar, const double *coefa,
-                         const double *coefb, double *val_ip)
+bool launch_b_iprime_lsq(const _csb_matrix_t *m, int inc, const double *pvar,
+                         const double *coefa, const double *coefb, const double *f_ext,
+                         double *val_ip, double *val_f)
 {
   if (m->n_rows < 1 || !m->has_b_faces || m->n_b_faces < 1) return true;
   k_b_iprime_lsq<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
-    m->n_rows, m->row_index.p, m->col_id.p, m->cell_cen.p, m->cell_b_faces_idx.p,
-    m->cell_b_faces.p, m->b_face_u_normal.p, m->b_dist.p, m->diipb.p, pvar, coefa, coefb,
-    val_ip);
+    m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, m->cell_cen.p, m->cell_b_faces_idx.p,
+    m->cell_b_faces.p, m->b_face_u_normal.p, m->b_dist.p, m->has_diipb ? m->diipb.p : nullptr,
+    m->i_face_cog.p, m->b_face_cog.p, f_ext, inc, pvar, coefa, coefb, val_ip, val_f);
   return post_launch("b_iprime_lsq");
 }
 
 bool launch_lsq_gradient(const _csb_matrix_t *m, const float *cocg, int inc, const double *pvar,
-                         const double *coefa, const double *coefb, const double *val_ip,
-                         double *grad)
+                         const double *coefa, const double *coefb, const double *val_f,
+                         const double *f_ext, double *grad)
 {
   if (m->n_rows < 1) return true;
   const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
@@ -2851,7 +2960,8 @@ bool launch_lsq_gradient(const _csb_matrix_t *m, const float *cocg, int inc, con
     m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, m->c2f_sgn.p, m->cell_cen.p,
     bnd ? m->cell_b_faces_idx.p : nullptr, bnd ? m->cell_b_faces.p : nullptr,
     m->b_face_u_normal.p, m->b_dist.p, cocg, inc, pvar, coefa, coefb,
-    (bnd && m->has_diipb) ? m->diipb.p : nullptr, val_ip, grad);
+    (bnd && m->has_diipb) ? m->diipb.p : nullptr, val_f, m->i_face_cog.p, m->b_face_cog.p,
+    f_ext, grad);
   return post_launch("lsq_gradient");
 }
 
@@ -2884,8 +2994,8 @@ bool launch_face_diffusion_potential(const _csb_matrix_t *m, int init, int inc,
 }
 
 bool launch_green_reconstruct(const _csb_matrix_t *m, int inc, const double *pvar,
-                              const double *coefa, const double *coefb, const double *val_ip,
-                              const double *r_grad, double *grad)
+                              const double *coefa, const double *coefb, const double *val_f,
+                              const double *f_ext, const double *r_grad, double *grad)
 {
   if (m->n_rows < 1) return true;
   const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
@@ -2894,7 +3004,7 @@ bool launch_green_reconstruct(const _csb_matrix_t *m, int inc, const double *pva
     bnd ? m->cell_b_faces_idx.p : nullptr, bnd ? m->cell_b_faces.p : nullptr, m->g_weight.p,
     m->dofij.p, m->face_surf.p, m->face_u_normal.p, m->b_face_surf.p, m->b_face_u_normal.p,
     m->cell_vol.p, m->has_corr_grad_lin ? m->corr_grad_lin.p : nullptr, inc, pvar, coefa, coefb,
-    val_ip, r_grad, grad);
+    val_f, m->cell_cen.p, m->i_face_cog.p, f_ext, r_grad, grad);
   return post_launch("green_reconstruct");
 }
 

@@ -840,19 +840,82 @@ int csb_matrix_set_gradient_type(csb_matrix_t *m, int imrgra)
 }
 
 namespace {
-/* least-squares gradient into `out`, or -- imrgra 4 -- into a work array followed by the
-   Green-Gauss reconstruction into `out` */
-bool gradient_enqueue(const csb_matrix_t *m, int imrgra, int inc, const double *pvar,
-                      const double *coefa, const double *coefb, const double *val_ip,
-                      double *out, csb::DevBuf<double> &work)
+/* work arrays of one gradient: values at I' and face values of the boundary faces (when the
+   matrix holds II' of its boundary faces or the hydrostatic treatment is on), the
+   least-squares gradient the Green-Gauss pass reconstructs from, the staged exterior force */
+struct GradWork {
+  csb::DevBuf<double> val_ip, val_f, work, fext;
+  const double *d_ip = nullptr;     /* for the boundary fluxes; nullptr: the cell value */
+};
+
+/* hyd_p_flag as the reference reads it: 1 = on, 0 and 2 = off (cs_gradient.cpp:9678-9679) */
+bool hyd_check(const csb_matrix_t *m, const char *who, int hyd_p_flag, const double *f_ext)
 {
+  if (hyd_p_flag < 0 || hyd_p_flag > 2) {
+    set_error("%s: invalid hydrostatic pressure flag %d", who, hyd_p_flag);
+    return false;
+  }
+  if (hyd_p_flag == 1 && (f_ext == nullptr || !m->has_face_cog)) {
+    set_error("%s: the hydrostatic pressure treatment needs the exterior force and "
+              "csb_matrix_set_face_cog", who);
+    return false;
+  }
+  return true;
+}
+
+/* boundary values, then the least-squares gradient into `out`, or -- imrgra 4 -- into a work
+   array followed by the Green-Gauss reconstruction into `out`; f_ext (host or device,
+   [n_rows][3]) non-null = hyd_p_flag 1 */
+bool gradient_run(const csb_matrix_t *m, int imrgra, int inc, const double *f_ext,
+                  const double *pvar, const double *coefa, const double *coefb, double *out,
+                  GradWork &w)
+{
+  const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  const size_t nr = (size_t)m->n_rows, nb = bnd ? (size_t)m->n_b_faces : 0;
+  const double *d_fext = f_ext;
+  if (f_ext != nullptr && !is_device_ptr(f_ext)) {
+    if (!w.fext.alloc(3*std::max(nr, (size_t)1))
+        || !CSB_CUDA(cudaMemcpyAsync(w.fext.p, f_ext, sizeof(double)*3*nr, cudaMemcpyHostToDevice,
+                                     ctx().stream))) return false;
+    d_fext = w.fext.p;
+  }
+  const double *d_vf = nullptr;
+  w.d_ip = nullptr;
+  if (bnd && (m->has_diipb || d_fext != nullptr)) {
+    if (!w.val_ip.alloc(nb) || !w.val_f.alloc(nb)
+        || !csb::launch_b_iprime_lsq(m, inc, pvar, coefa, coefb, d_fext, w.val_ip.p, w.val_f.p))
+      return false;
+    d_vf = w.val_f.p;
+    if (m->has_diipb) w.d_ip = w.val_ip.p;
+  }
   if (imrgra != 4)
-    return csb::launch_lsq_gradient(m, m->cocg_lsq.p, inc, pvar, coefa, coefb, val_ip, out);
-  return work.alloc(3*(size_t)std::max(m->n_rows, 1))
-      && csb::launch_lsq_gradient(m, m->cocg_lsq.p, inc, pvar, coefa, coefb, val_ip, work.p)
-      && csb::launch_green_reconstruct(m, inc, pvar, coefa, coefb, val_ip, work.p, out);
+    return csb::launch_lsq_gradient(m, m->cocg_lsq.p, inc, pvar, coefa, coefb, d_vf, d_fext, out);
+  return w.work.alloc(3*std::max(nr, (size_t)1))
+      && csb::launch_lsq_gradient(m, m->cocg_lsq.p, inc, pvar, coefa, coefb, d_vf, d_fext,
+                                  w.work.p)
+      && csb::launch_green_reconstruct(m, inc, pvar, coefa, coefb, d_vf, d_fext, w.work.p, out);
 }
 } // anonymous namespace
+
+/* Face centres (cs_mesh_quantities_t::i_face_cog [n_faces][3], b_face_cog [n_b_faces][3]): read
+   by the hydrostatic pressure treatment only (hyd_p_flag = 1). */
+int csb_matrix_set_face_cog(csb_matrix_t *m, const csb_real_t *i_face_cog,
+                            const csb_real_t *b_face_cog)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (!m->has_mesh) {
+    set_error("csb_matrix_set_face_cog: csb_matrix_set_mesh_association first");
+    return -1;
+  }
+  const size_t nf = (size_t)m->n_faces, nb = m->has_b_faces ? (size_t)m->n_b_faces : 0;
+  if ((nf > 0 && i_face_cog == nullptr) || (nb > 0 && b_face_cog == nullptr)) {
+    set_error("csb_matrix_set_face_cog: null array");
+    return -1;
+  }
+  m->has_face_cog = m->i_face_cog.upload(i_face_cog, 3*nf) && m->b_face_cog.upload(b_face_cog, 3*nb)
+                 && CSB_CUDA(cudaStreamSynchronize(ctx().stream));
+  return m->has_face_cog ? 0 : -1;
+}
 
 /* cs_gradient_scalar_synced_input with CS_GRADIENT_LSQ, standard neighbourhood, no weighting,
    no limiter (src/alge/cs_gradient.cpp:9651, _lsq_scalar_gradient :2695-2900): grad[n_rows][3].
@@ -871,7 +934,20 @@ int csb_gradient_scalar_lsq(const csb_matrix_t *m, int inc, const csb_real_t *pv
 int csb_gradient_scalar(const csb_matrix_t *m, int imrgra, int inc, const csb_real_t *pvar,
                         const csb_real_t *coefa, const csb_real_t *coefb, csb_real_t *grad)
 {
+  return csb_gradient_scalar_hyd(m, imrgra, inc, 0, nullptr, pvar, coefa, coefb, grad);
+}
+
+/* the same with the hydrostatic pressure treatment of cs_gradient_scalar_synced_input
+   (hyd_p_flag = 1, exterior force f_ext [n_rows][3]: _lsq_scalar_gradient_hyd_p
+   cs_gradient.cpp:3230-3560, the hydrostatic branch of _reconstruct_scalar_gradient
+   :4314-4424) and of the boundary face values (cs_gradient_boundary.cpp:285-640 with
+   hyd_p_flag, cs_boundary_conditions_set_coeffs.cpp:176-192) */
+int csb_gradient_scalar_hyd(const csb_matrix_t *m, int imrgra, int inc, int hyd_p_flag,
+                            const csb_real_t *f_ext, const csb_real_t *pvar,
+                            const csb_real_t *coefa, const csb_real_t *coefb, csb_real_t *grad)
+{
   if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (!hyd_check(m, "csb_gradient_scalar", hyd_p_flag, f_ext)) return -1;
   if (!m->has_face_geo || m->db != 1 || m->halo != nullptr) {
     set_error("csb_gradient_scalar: needs a scalar matrix on one rank with its mesh "
               "association, boundary faces and csb_matrix_set_face_geometry");
@@ -897,14 +973,12 @@ int csb_gradient_scalar(const csb_matrix_t *m, int imrgra, int inc, const csb_re
   const size_t len[4] = {nr, nb, nb, 3*nr};
   const bool in[4] = {true, true, true, false};
   const double *dev[4];
-  csb::DevBuf<double> stage, val_ip, work;
+  csb::DevBuf<double> stage;
+  GradWork gw;
   if (!ensure_cocg(m) || !stage_arrays(4, src, len, in, dev, stage)) return -1;
   double *d_grad = const_cast<double *>(dev[3]);
-  const bool ip = (bnd && m->has_diipb);
-  if (ip && (!val_ip.alloc(nb) || !csb::launch_b_iprime_lsq(m, dev[0], dev[1], dev[2], val_ip.p)))
-    return -1;
-  if (!gradient_enqueue(m, imrgra, inc, dev[0], dev[1], dev[2], ip ? val_ip.p : nullptr, d_grad,
-                        work)) return -1;
+  if (!gradient_run(m, imrgra, inc, (hyd_p_flag == 1) ? f_ext : nullptr, dev[0], dev[1], dev[2],
+                    d_grad, gw)) return -1;
   if (d_grad != grad
       && !CSB_CUDA(cudaMemcpyAsync(grad, d_grad, sizeof(double)*3*nr, cudaMemcpyDeviceToHost,
                                    c.stream))) return -1;
@@ -922,7 +996,22 @@ int csb_diffusion_potential_rc(const csb_matrix_t *m, int irecmf, int init, int 
                                const csb_real_t *b_visc, const csb_real_t *visel,
                                csb_real_t *diverg)
 {
+  return csb_diffusion_potential_hyd(m, irecmf, init, inc, 0, nullptr, pvar, coefa, coefb, cofaf,
+                                     cofbf, i_visc, b_visc, visel, diverg);
+}
+
+/* the same with iphydp and frcxt [n_rows][3] in the reference's positions
+   (cs_diffusion_potential's argument list): iphydp = 1 is what cs_pressure_correction hands
+   over by default (iphydr = 1, src/base/cs_pressure_correction.cpp:2113-2127) */
+int csb_diffusion_potential_hyd(const csb_matrix_t *m, int irecmf, int init, int inc,
+                                int iphydp, const csb_real_t *frcxt, const csb_real_t *pvar,
+                                const csb_real_t *coefa, const csb_real_t *coefb,
+                                const csb_real_t *cofaf, const csb_real_t *cofbf,
+                                const csb_real_t *i_visc, const csb_real_t *b_visc,
+                                const csb_real_t *visel, csb_real_t *diverg)
+{
   if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (!hyd_check(m, "csb_diffusion_potential", iphydp, frcxt)) return -1;
   if (!m->has_face_geo || m->db != 1 || m->halo != nullptr) {
     set_error("csb_diffusion_potential_rc: needs a scalar matrix on one rank with its mesh "
               "association, boundary faces and csb_matrix_set_face_geometry");
@@ -943,16 +1032,14 @@ int csb_diffusion_potential_rc(const csb_matrix_t *m, int irecmf, int init, int 
   const size_t len[9] = {nr, nb, nb, nb, nb, nf, nb, nr, nr};
   const bool in[9] = {true, true, true, true, true, true, true, true, init == 0};
   const double *dev[9];
-  csb::DevBuf<double> stage, grad, val_ip, work;
+  csb::DevBuf<double> stage, grad;
+  GradWork gw;
   if (!ensure_cocg(m) || !stage_arrays(9, src, len, in, dev, stage) || !grad.alloc(3*nr)) return -1;
   double *d_div = const_cast<double *>(dev[8]);
-  const bool ip = (bnd && m->has_diipb);
-  if (ip && (!val_ip.alloc(nb) || !csb::launch_b_iprime_lsq(m, dev[0], dev[1], dev[2], val_ip.p)))
-    return -1;
-  const double *d_ip = ip ? val_ip.p : nullptr;
-  if (!gradient_enqueue(m, m->imrgra, inc, dev[0], dev[1], dev[2], d_ip, grad.p, work)
+  if (!gradient_run(m, m->imrgra, inc, (iphydp == 1) ? frcxt : nullptr, dev[0], dev[1], dev[2],
+                    grad.p, gw)
       || !csb::launch_diffusion_potential_rc(m, irecmf, init, inc, dev[0], grad.p, dev[3], dev[4],
-                                             dev[5], dev[6], dev[7], d_ip, d_div)) return -1;
+                                             dev[5], dev[6], dev[7], gw.d_ip, d_div)) return -1;
   if (d_div != diverg
       && !CSB_CUDA(cudaMemcpyAsync(diverg, d_div, sizeof(double)*nr, cudaMemcpyDeviceToHost,
                                    c.stream))) return -1;
@@ -1007,7 +1094,23 @@ int csb_face_diffusion_potential(const csb_matrix_t *m, int ircflu, int init, in
                                  const csb_real_t *b_visc, const csb_real_t *visel,
                                  csb_real_t *i_massflux, csb_real_t *b_massflux)
 {
+  return csb_face_diffusion_potential_hyd(m, ircflu, init, inc, 0, nullptr, pvar, coefa, coefb,
+                                          cofaf, cofbf, i_visc, b_visc, visel, i_massflux,
+                                          b_massflux);
+}
+
+/* the same with iphydp and frcxt in the reference's positions; they only matter when
+   ircflu = 1 (gradient and values at I') */
+int csb_face_diffusion_potential_hyd(const csb_matrix_t *m, int ircflu, int init, int inc,
+                                     int iphydp, const csb_real_t *frcxt,
+                                     const csb_real_t *pvar, const csb_real_t *coefa,
+                                     const csb_real_t *coefb, const csb_real_t *cofaf,
+                                     const csb_real_t *cofbf, const csb_real_t *i_visc,
+                                     const csb_real_t *b_visc, const csb_real_t *visel,
+                                     csb_real_t *i_massflux, csb_real_t *b_massflux)
+{
   if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (ircflu && !hyd_check(m, "csb_face_diffusion_potential", iphydp, frcxt)) return -1;
   if (!m->has_mesh || m->db != 1 || m->halo != nullptr || (ircflu && !m->has_face_geo)) {
     set_error("csb_face_diffusion_potential: needs a scalar matrix on one rank with its mesh "
               "association%s", ircflu ? ", boundary faces and csb_matrix_set_face_geometry" : "");
@@ -1032,16 +1135,15 @@ int csb_face_diffusion_potential(const csb_matrix_t *m, int ircflu, int init, in
   const size_t len[10] = {nr, nb, nb, nb, nb, nf, nb, nr, nf, nb};
   const bool in[10] = {true, true, true, true, true, true, true, true, init == 0, init == 0};
   const double *dev[10];
-  csb::DevBuf<double> stage, grad, val_ip, work;
+  csb::DevBuf<double> stage, grad;
+  GradWork gw;
   if (!stage_arrays(10, src, len, in, dev, stage)) return -1;
   const double *d_grad = nullptr, *d_ip = nullptr;
   if (ircflu) {
     if (!ensure_cocg(m) || !grad.alloc(3*nr)) return -1;
-    const bool ip = (bnd && m->has_diipb);
-    if (ip && (!val_ip.alloc(nb) || !csb::launch_b_iprime_lsq(m, dev[0], dev[1], dev[2], val_ip.p)))
-      return -1;
-    d_ip = ip ? val_ip.p : nullptr;
-    if (!gradient_enqueue(m, m->imrgra, inc, dev[0], dev[1], dev[2], d_ip, grad.p, work)) return -1;
+    if (!gradient_run(m, m->imrgra, inc, (iphydp == 1) ? frcxt : nullptr, dev[0], dev[1], dev[2],
+                      grad.p, gw)) return -1;
+    d_ip = gw.d_ip;
     d_grad = grad.p;
   }
   double *d_im = const_cast<double *>(dev[8]), *d_bm = const_cast<double *>(dev[9]);

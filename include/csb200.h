@@ -384,6 +384,36 @@ int  csb_face_diffusion_potential(const csb_matrix_t *m, int ircflu, int init, i
                                   const csb_real_t *b_visc, const csb_real_t *visel,
                                   csb_real_t *i_massflux, csb_real_t *b_massflux);
 
+/* Hydrostatic pressure treatment (hyd_p_flag / iphydp = 1 with the exterior force f_ext / frcxt
+   [n_rows][3]; cs_glob_velocity_pressure_param->iphydr = 1 is the reference's default and
+   cs_pressure_correction hands it to these operators, src/base/cs_pressure_correction.cpp:
+   2113-2127).  The *_hyd entry points carry the two arguments in the reference's positions;
+   the plain ones are the same calls with the flag off.  What changes: the least-squares
+   gradient (_lsq_scalar_gradient_hyd_p, src/alge/cs_gradient.cpp:3230-3560), the Green-Gauss
+   pass (:4314-4424), the values at I' and the face values of the boundary faces
+   (src/alge/cs_gradient_boundary.cpp:285-640, src/base/cs_boundary_conditions_set_coeffs.cpp:
+   176-192).  Needs the face centres: csb_matrix_set_face_cog (i_face_cog[n_faces][3],
+   b_face_cog[n_b_faces][3] of cs_mesh_quantities_t).  Flag values 0 and 2 switch it off, as in
+   the reference.  No porosity terms.  Bit-identical to the reference's one-thread results. */
+int  csb_matrix_set_face_cog(csb_matrix_t *m, const csb_real_t *i_face_cog,
+                             const csb_real_t *b_face_cog);
+int  csb_gradient_scalar_hyd(const csb_matrix_t *m, int imrgra, int inc, int hyd_p_flag,
+                             const csb_real_t *f_ext, const csb_real_t *pvar,
+                             const csb_real_t *coefa, const csb_real_t *coefb, csb_real_t *grad);
+int  csb_diffusion_potential_hyd(const csb_matrix_t *m, int irecmf, int init, int inc,
+                                 int iphydp, const csb_real_t *frcxt, const csb_real_t *pvar,
+                                 const csb_real_t *coefa, const csb_real_t *coefb,
+                                 const csb_real_t *cofaf, const csb_real_t *cofbf,
+                                 const csb_real_t *i_visc, const csb_real_t *b_visc,
+                                 const csb_real_t *visel, csb_real_t *diverg);
+int  csb_face_diffusion_potential_hyd(const csb_matrix_t *m, int ircflu, int init, int inc,
+                                      int iphydp, const csb_real_t *frcxt,
+                                      const csb_real_t *pvar, const csb_real_t *coefa,
+                                      const csb_real_t *coefb, const csb_real_t *cofaf,
+                                      const csb_real_t *cofbf, const csb_real_t *i_visc,
+                                      const csb_real_t *b_visc, const csb_real_t *visel,
+                                      csb_real_t *i_massflux, csb_real_t *b_massflux);
+
 /* Copy of the MSR coefficients held in HBM (cs_matrix_get_msr_arrays, cs_matrix.cpp:6199,
    lends the host arrays; these live on the device).  Either pointer may be NULL. */
 int  csb_matrix_get_coefficients(const csb_matrix_t *m, csb_real_t *d_val, csb_real_t *x_val);

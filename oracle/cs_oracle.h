@@ -221,6 +221,34 @@ void   ora_gradient_green_reconstruct(int n_cells, int n_i_faces, const int *i_f
                                       const double *coefb, const double *r_grad,
                                       const double *corr_grad_lin, double *grad);
 
+/* hydrostatic pressure treatment (hyd_p_flag = 1, exterior force f_ext [n_cells][3]): values at
+   I' and face values of the boundary faces, least-squares gradient, Green-Gauss pass */
+void   ora_b_face_values_hyd(int n_cells, const int *row_index, const int *col_id,
+                             const int *c2f, int n_b_faces, const int *b_face_cells,
+                             const double *cell_cen, const double *b_face_u_normal,
+                             const double *b_dist, const double *diipb,
+                             const double *i_face_cog, const double *b_face_cog,
+                             const double *f_ext, int inc, const double *pvar,
+                             const double *coefa, const double *coefb, double *val_ip,
+                             double *val_f);
+void   ora_gradient_lsq_hyd(int n_cells, const int *row_index, const int *col_id, int n_i_faces,
+                            const int *i_face_cells, int n_b_faces, const int *b_face_cells,
+                            const double *cell_cen, const double *b_face_u_normal,
+                            const double *b_dist, const double *diipb, const double *i_face_cog,
+                            const double *b_face_cog, const double *f_ext, const double *val_f,
+                            const double *pvar, double *grad);
+void   ora_gradient_green_reconstruct_hyd(int n_cells, int n_i_faces, const int *i_face_cells,
+                                          int n_b_faces, const int *b_face_cells,
+                                          const double *weight, const double *dofij,
+                                          const double *i_face_surf,
+                                          const double *i_face_u_normal,
+                                          const double *b_face_surf,
+                                          const double *b_face_u_normal, const double *cell_vol,
+                                          const double *cell_cen, const double *i_face_cog,
+                                          const double *f_ext, const double *val_f,
+                                          const double *pvar, const double *r_grad,
+                                          const double *corr_grad_lin, double *grad);
+
 /* cs_divergence and cs_face_diffusion_potential (grad NULL: no reconstruction) */
 void   ora_divergence(int n_cells, int n_i_faces, const int *i_face_cells, int n_b_faces,
                       const int *b_face_cells, int init, const double *i_massflux,

@@ -444,3 +444,268 @@ ora_face_diffusion_potential(int n_cells, int n_i_faces, const int *i_face_cells
     b_massflux[f] += b_visc[f]*flux_d;
   }
 }
+
+/*----------------------------------------------------------------------------
+ * Hydrostatic pressure treatment (hyd_p_flag = 1: cs_glob_velocity_pressure_param->iphydr = 1,
+ * the reference's default, hands iphydp = 1 and the exterior force f_ext [n_cells][3] to
+ * cs_diffusion_potential, src/base/cs_pressure_correction.cpp:2113-2127).
+ *----------------------------------------------------------------------------*/
+
+/* (xb - xa) . xc, cs_math_3_distance_dot_product (cs_math.h:171-176) */
+static inline double
+_ddp(const double *xa, const double *xb, const double *xc)
+{
+  return ((xb[0] - xa[0])*xc[0]+(xb[1] - xa[1])*xc[1]+(xb[2] - xa[2])*xc[2]);
+}
+
+/* Values at I' (cs_gradient_boundary_iprime_lsq_s with hyd_p_flag = 1,
+   cs_gradient_boundary.cpp:285-640: the interior differences gain (I - F).f_I - (J - F).f_J
+   with F the centre of the shared face, the boundary terms (b - 1) (F_b - I).f_I, and f_I is
+   added to the local gradient) and the face values of _compute_bc_flux_grad
+   (cs_boundary_conditions_set_coeffs.cpp:168-192: val_f = inc a + b val_ip + b (F_b - I').f_I).
+   c2f: interior face of every adjacency entry (cs_mesh_adjacencies cell_i_faces).  diipb: 3 per
+   boundary face (zeros allowed). */
+void
+ora_b_face_values_hyd(int n_cells, const int *row_index, const int *col_id, const int *c2f,
+                      int n_b_faces, const int *b_face_cells, const double *cell_cen,
+                      const double *b_face_u_normal, const double *b_dist, const double *diipb,
+                      const double *i_face_cog, const double *b_face_cog, const double *f_ext,
+                      int inc, const double *pvar, const double *coefa, const double *coefb,
+                      double *val_ip, double *val_f)
+{
+  int *idx = calloc((size_t)n_cells + 2, sizeof(int));
+  int *ids = malloc(sizeof(int)*(size_t)(n_b_faces > 0 ? n_b_faces : 1));
+  for (int f = 0; f < n_b_faces; f++) idx[b_face_cells[f] + 2]++;
+  for (int c = 0; c < n_cells; c++) idx[c+2] += idx[c+1];
+  for (int f = 0; f < n_b_faces; f++) ids[idx[b_face_cells[f] + 1]++] = f;
+
+  const double eps_r_2 = 1e-3 * 1e-3;
+  for (int f_id = 0; f_id < n_b_faces; f_id++) {
+    const int c_id = b_face_cells[f_id];
+    const double *ip = diipb + 3*(size_t)f_id;
+    const double *cen = cell_cen + 3*(size_t)c_id, *fx = f_ext + 3*(size_t)c_id;
+    const double var_i = pvar[c_id];
+    double vip = var_i;
+    if (!(ip[0]*ip[0] + ip[1]*ip[1] + ip[2]*ip[2] < (b_dist[f_id]*b_dist[f_id]) * eps_r_2)) {
+      float cocg[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      double rhs[3] = {0., 0., 0.};
+      for (int k = row_index[c_id]; k < row_index[c_id+1]; k++) {
+        const int c1 = col_id[k];
+        const double *cen1 = cell_cen + 3*(size_t)c1;
+        double dc[3];
+        for (int ll = 0; ll < 3; ll++) dc[ll] = cen1[ll] - cen[ll];
+        const double ddc = 1. / (dc[0]*dc[0] + dc[1]*dc[1] + dc[2]*dc[2]);
+        cocg[0] += dc[0]*dc[0]*ddc;
+        cocg[1] += dc[1]*dc[1]*ddc;
+        cocg[2] += dc[2]*dc[2]*ddc;
+        cocg[3] += dc[0]*dc[1]*ddc;
+        cocg[4] += dc[1]*dc[2]*ddc;
+        cocg[5] += dc[0]*dc[2]*ddc;
+        double pfac = pvar[c1] - var_i;
+        const double *cog = i_face_cog + 3*(size_t)c2f[k];
+        const double dot_i = _ddp(cog, cen, fx);
+        const double dot_j = _ddp(cog, cen1, f_ext + 3*(size_t)c1);
+        pfac += dot_i - dot_j;
+        pfac *= ddc;
+        for (int ll = 0; ll < 3; ll++) rhs[ll] += dc[ll] * pfac;
+      }
+      for (int k = idx[c_id]; k < idx[c_id+1]; k++) {
+        const int f = ids[k];
+        const double a = coefa[f], b = coefb[f];
+        const double ddif = 1. / b_dist[f];
+        const double umcbdd = (1. - b) * ddif;
+        double dif[3];
+        for (int ll = 0; ll < 3; ll++)
+          dif[ll] = b_face_u_normal[3*(size_t)f+ll] + umcbdd * diipb[3*(size_t)f+ll];
+        cocg[0] += dif[0]*dif[0];
+        cocg[1] += dif[1]*dif[1];
+        cocg[2] += dif[2]*dif[2];
+        cocg[3] += dif[0]*dif[1];
+        cocg[4] += dif[1]*dif[2];
+        cocg[5] += dif[0]*dif[2];
+        double pfac = (a + (b-1.)*var_i);
+        const double dot = _ddp(cen, b_face_cog + 3*(size_t)f, fx);
+        pfac += (b-1.) * dot;
+        pfac *= ddif;
+        for (int ll = 0; ll < 3; ll++) rhs[ll] += dif[ll] * pfac;
+      }
+      const double a00 = cocg[1]*cocg[2] - cocg[4]*cocg[4];
+      const double a01 = cocg[4]*cocg[5] - cocg[3]*cocg[2];
+      const double a02 = cocg[3]*cocg[4] - cocg[1]*cocg[5];
+      const double a11 = cocg[0]*cocg[2] - cocg[5]*cocg[5];
+      const double a12 = cocg[3]*cocg[5] - cocg[0]*cocg[4];
+      const double a22 = cocg[0]*cocg[1] - cocg[3]*cocg[3];
+      const double det_inv = 1. / (cocg[0]*a00 + cocg[3]*a01 + cocg[5]*a02);
+      double g[3];
+      g[0] = (a00 * rhs[0] + a01 * rhs[1] + a02 * rhs[2]) * det_inv;
+      g[1] = (a01 * rhs[0] + a11 * rhs[1] + a12 * rhs[2]) * det_inv;
+      g[2] = (a02 * rhs[0] + a12 * rhs[1] + a22 * rhs[2]) * det_inv;
+      g[0] += fx[0]; g[1] += fx[1]; g[2] += fx[2];
+      vip = var_i + (g[0]*ip[0] + g[1]*ip[1] + g[2]*ip[2]);
+    }
+    val_ip[f_id] = vip;
+    double vf = inc * coefa[f_id] + coefb[f_id] * vip;
+    const double vec_iprime[3] = {cen[0] + ip[0], cen[1] + ip[1], cen[2] + ip[2]};
+    vf += coefb[f_id] * _ddp(vec_iprime, b_face_cog + 3*(size_t)f_id, fx);
+    val_f[f_id] = vf;
+  }
+  free(idx); free(ids);
+}
+
+/* _lsq_scalar_gradient_hyd_p (cs_gradient.cpp:3230-3560, scatter form = the one-thread path);
+   val_f from ora_b_face_values_hyd; diipb may be NULL */
+void
+ora_gradient_lsq_hyd(int n_cells, const int *row_index, const int *col_id, int n_i_faces,
+                     const int *i_face_cells, int n_b_faces, const int *b_face_cells,
+                     const double *cell_cen, const double *b_face_u_normal,
+                     const double *b_dist, const double *diipb, const double *i_face_cog,
+                     const double *b_face_cog, const double *f_ext, const double *val_f,
+                     const double *pvar, double *grad)
+{
+  float *cocg = calloc(6*(size_t)(n_cells > 0 ? n_cells : 1), sizeof(float));
+  double *rhsv = calloc(3*(size_t)(n_cells > 0 ? n_cells : 1), sizeof(double));
+  for (int c = 0; c < n_cells; c++) {
+    float *g = cocg + 6*(size_t)c;
+    for (int k = row_index[c]; k < row_index[c+1]; k++) {
+      const int c1 = col_id[k];
+      const double dc[3] = {cell_cen[3*c1] - cell_cen[3*c], cell_cen[3*c1+1] - cell_cen[3*c+1],
+                            cell_cen[3*c1+2] - cell_cen[3*c+2]};
+      const double ddc = 1. / (dc[0]*dc[0] + dc[1]*dc[1] + dc[2]*dc[2]);
+      g[0] += dc[0] * dc[0] * ddc;
+      g[1] += dc[1] * dc[1] * ddc;
+      g[2] += dc[2] * dc[2] * ddc;
+      g[3] += dc[0] * dc[1] * ddc;
+      g[4] += dc[1] * dc[2] * ddc;
+      g[5] += dc[0] * dc[2] * ddc;
+    }
+  }
+  for (int f = 0; f < n_b_faces; f++) {
+    float *g = cocg + 6*(size_t)b_face_cells[f];
+    double d[3];
+    _b_direction(f, b_face_u_normal, b_dist, diipb, d);
+    g[0] += d[0] * d[0];
+    g[1] += d[1] * d[1];
+    g[2] += d[2] * d[2];
+    g[3] += d[0] * d[1];
+    g[4] += d[1] * d[2];
+    g[5] += d[0] * d[2];
+  }
+  for (int c = 0; c < n_cells; c++) _gauss_inverse_6f(cocg + 6*(size_t)c);
+
+  for (int f = 0; f < n_i_faces; f++) {
+    const int ii = i_face_cells[2*f], jj = i_face_cells[2*f+1];
+    const double *ci = cell_cen + 3*(size_t)ii, *cj = cell_cen + 3*(size_t)jj;
+    const double dc[3] = {cj[0] - ci[0], cj[1] - ci[1], cj[2] - ci[2]};
+    const double dvarij = pvar[jj] - pvar[ii];
+    const double *cog = i_face_cog + 3*(size_t)f;
+    double pfac =   dvarij
+                  + _ddp(cog, ci, f_ext + 3*(size_t)ii)
+                  - _ddp(cog, cj, f_ext + 3*(size_t)jj);
+    pfac /= (dc[0]*dc[0] + dc[1]*dc[1] + dc[2]*dc[2]);
+    for (int ll = 0; ll < 3; ll++) {
+      const double fctb = dc[ll] * pfac;
+      if (ii < n_cells) rhsv[3*ii+ll] += fctb;
+      if (jj < n_cells) rhsv[3*jj+ll] += fctb;
+    }
+  }
+  for (int f = 0; f < n_b_faces; f++) {
+    const int c = b_face_cells[f];
+    const double poro = 0.;
+    const double if_dot_fext = _ddp(cell_cen + 3*(size_t)c, b_face_cog + 3*(size_t)f,
+                                    f_ext + 3*(size_t)c);
+    const double ddif = 1. / b_dist[f];
+    double dif[3];
+    _b_direction(f, b_face_u_normal, b_dist, diipb, dif);
+    const double pfac = ddif * (val_f[f] - pvar[c] - poro - if_dot_fext);
+    for (int ll = 0; ll < 3; ll++) rhsv[3*c+ll] += dif[ll] * pfac;
+  }
+  for (int c = 0; c < n_cells; c++) {
+    const float *g = cocg + 6*(size_t)c;
+    const double *r = rhsv + 3*(size_t)c, *fx = f_ext + 3*(size_t)c;
+    grad[3*c]   = g[0]*r[0] + g[3]*r[1] + g[5]*r[2] + fx[0];
+    grad[3*c+1] = g[3]*r[0] + g[1]*r[1] + g[4]*r[2] + fx[1];
+    grad[3*c+2] = g[5]*r[0] + g[4]*r[1] + g[2]*r[2] + fx[2];
+  }
+  free(cocg); free(rhsv);
+}
+
+/* _reconstruct_scalar_gradient, branch with hydrostatic pressure (cs_gradient.cpp:4314-4424) */
+void
+ora_gradient_green_reconstruct_hyd(int n_cells, int n_i_faces, const int *i_face_cells,
+                                   int n_b_faces, const int *b_face_cells,
+                                   const double *weight, const double *dofij,
+                                   const double *i_face_surf, const double *i_face_u_normal,
+                                   const double *b_face_surf, const double *b_face_u_normal,
+                                   const double *cell_vol, const double *cell_cen,
+                                   const double *i_face_cog, const double *f_ext,
+                                   const double *val_f, const double *pvar,
+                                   const double *r_grad, const double *corr_grad_lin,
+                                   double *grad)
+{
+  for (int i = 0; i < 3*n_cells; i++) grad[i] = 0.;
+  for (int f = 0; f < n_i_faces; f++) {
+    const int c1 = i_face_cells[2*f], c2 = i_face_cells[2*f+1];
+    const double ktpond = weight[f];
+    const double poro[2] = {0., 0.};
+    const double *f1 = f_ext + 3*(size_t)c1, *f2 = f_ext + 3*(size_t)c2;
+    const double *cog = i_face_cog + 3*(size_t)f;
+    double fexd[3], d_oi[3], d_oj[3];
+    for (int k = 0; k < 3; k++) {
+      fexd[k] = 0.5 * (f1[k] + f2[k]);
+      d_oi[k] = cog[k] - cell_cen[3*(size_t)c1+k];
+      d_oj[k] = cog[k] - cell_cen[3*(size_t)c2+k];
+    }
+    double pfaci
+      =  ktpond
+           * (  d_oi[0]*f1[0]
+              + d_oi[1]*f1[1]
+              + d_oi[2]*f1[2]
+              + poro[0])
+      +  (1.0 - ktpond)
+           * (  d_oj[0]*f2[0]
+              + d_oj[1]*f2[1]
+              + d_oj[2]*f2[2]
+              + poro[1]);
+    double pfacj = pfaci;
+    const double d_var = pvar[c2] - pvar[c1];
+    pfaci += (1.0-ktpond) * d_var;
+    pfacj -=      ktpond  * d_var;
+    const double *o = dofij + 3*(size_t)f, *g1 = r_grad + 3*(size_t)c1, *g2 = r_grad + 3*(size_t)c2;
+    const double rfac =
+             - weight[f]      * (d_oi[0]*fexd[0] + d_oi[1]*fexd[1] + d_oi[2]*fexd[2])
+         -  (1.0 - weight[f]) * (d_oj[0]*fexd[0] + d_oj[1]*fexd[1] + d_oj[2]*fexd[2])
+         + (  o[0] * (g1[0]+g2[0])
+            + o[1] * (g1[1]+g2[1])
+            + o[2] * (g1[2]+g2[2])) * 0.5;
+    const double _pfaci = (pfaci + rfac) * i_face_surf[f];
+    const double _pfacj = (pfacj + rfac) * i_face_surf[f];
+    for (int j = 0; j < 3; j++) {
+      const double rhsv1 =   _pfaci * i_face_u_normal[3*(size_t)f+j];
+      const double rhsv2 = - _pfacj * i_face_u_normal[3*(size_t)f+j];
+      if (c1 < n_cells) grad[3*(size_t)c1+j] += rhsv1;
+      if (c2 < n_cells) grad[3*(size_t)c2+j] += rhsv2;
+    }
+  }
+  for (int f = 0; f < n_b_faces; f++) {
+    const int c = b_face_cells[f];
+    const double pfac = (val_f[f] - pvar[c]) * b_face_surf[f];
+    for (int j = 0; j < 3; j++)
+      grad[3*(size_t)c+j] += pfac * b_face_u_normal[3*(size_t)f+j];
+  }
+  for (int c = 0; c < n_cells; c++) {
+    const double dvol = 1. / cell_vol[c];
+    grad[3*(size_t)c]   *= dvol;
+    grad[3*(size_t)c+1] *= dvol;
+    grad[3*(size_t)c+2] *= dvol;
+    if (corr_grad_lin != NULL) {
+      double gradpa[3];
+      for (int i = 0; i < 3; i++) {
+        gradpa[i] = grad[3*(size_t)c+i];
+        grad[3*(size_t)c+i] = 0.;
+      }
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+          grad[3*(size_t)c+i] += corr_grad_lin[9*(size_t)c+3*i+j] * gradpa[j];
+    }
+  }
+}

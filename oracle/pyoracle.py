@@ -418,6 +418,42 @@ class Oracle:
             _dp(_f64(i_visc)), _dp(_f64(b_visc)), _dp(_f64(visel)), _dp(div))
         return div
 
+    def gradient_hyd(self, imrgra, s, b_face_cells, b_un, b_dist, i_face_cog, b_face_cog, f_ext,
+                     pvar, coefa, coefb, inc=1, diipb=None, g_geo=None, b_face_surf=None,
+                     corr_grad_lin=None):
+        """hyd_p_flag = 1 (exterior force f_ext): returns (grad, val_ip); imrgra 1 or 4"""
+        fc, bfc = _i32(s.face_cells), _i32(b_face_cells)
+        nb = len(bfc)
+        dip = np.zeros(3 * max(nb, 1)) if diipb is None else _f64(diipb)
+        vip, vf = np.zeros(max(nb, 1)), np.zeros(max(nb, 1))
+        ri, ci = _i32(s.row_index), _i32(s.col_id)
+        cen, fx = _f64(s.cell_cen), _f64(f_ext)
+        icog, bcog, bun, bd = _f64(i_face_cog), _f64(b_face_cog), _f64(b_un), _f64(b_dist)
+        p = _f64(pvar)
+        self.lib.ora_b_face_values_hyd.restype = None
+        self.lib.ora_b_face_values_hyd(
+            C.c_int(s.n_rows), _ip(ri), _ip(ci), _ip(_i32(s.c2f)), C.c_int(nb), _ip(bfc), _dp(cen),
+            _dp(bun), _dp(bd), _dp(dip), _dp(icog), _dp(bcog), _dp(fx), C.c_int(inc), _dp(p),
+            _dp(_f64(coefa)), _dp(_f64(coefb)), _dp(vip), _dp(vf))
+        r_grad = np.zeros(3 * s.n_rows)
+        self.lib.ora_gradient_lsq_hyd.restype = None
+        self.lib.ora_gradient_lsq_hyd(
+            C.c_int(s.n_rows), _ip(ri), _ip(ci), C.c_int(len(fc)), _ip(fc), C.c_int(nb), _ip(bfc),
+            _dp(cen), _dp(bun), _dp(bd), (None if diipb is None else _dp(dip)), _dp(icog),
+            _dp(bcog), _dp(fx), _dp(vf), _dp(p), _dp(r_grad))
+        if imrgra != 4:
+            return r_grad.reshape(-1, 3), vip[:nb]
+        gg = _f64(g_geo).reshape(-1, 4)
+        grad = np.zeros(3 * s.n_rows)
+        self.lib.ora_gradient_green_reconstruct_hyd.restype = None
+        self.lib.ora_gradient_green_reconstruct_hyd(
+            C.c_int(s.n_rows), C.c_int(len(fc)), _ip(fc), C.c_int(nb), _ip(bfc),
+            _dp(_f64(gg[:, 0])), _dp(_f64(gg[:, 1:4])), _dp(_f64(s.face_surf)),
+            _dp(_f64(s.face_u_normal)), _dp(_f64(b_face_surf)), _dp(bun), _dp(_f64(s.cell_vol)),
+            _dp(cen), _dp(icog), _dp(fx), _dp(vf), _dp(p), _dp(r_grad),
+            (None if corr_grad_lin is None else _dp(_f64(corr_grad_lin))), _dp(grad))
+        return grad.reshape(-1, 3), vip[:nb]
+
     def divergence(self, s, b_face_cells, i_massflux, b_massflux, init=1, diverg=None):
         div = np.zeros(s.n_rows) if diverg is None else _f64(diverg).copy()
         fc, bfc = _i32(s.face_cells), _i32(b_face_cells)
@@ -767,7 +803,8 @@ class RefLib:
     def diffusion_potential_rc(self, h, s, b_face_cells, b_geo, i_face_cog, i_geo, pvar, coefa,
                                coefb, cofaf, cofbf, i_visc, b_visc, visel, irecmf=0, init=1,
                                inc=1, diverg=None, diipb=None, imrgra=1, g_geo=None,
-                               b_face_surf=None, corr_grad_lin=None, ircflu=1, massflux=None):
+                               b_face_surf=None, corr_grad_lin=None, ircflu=1, massflux=None,
+                               frcxt=None):
         """cs_diffusion_potential WITH flux reconstruction (LSQ gradient) on the geometry given;
         returns (diverg, grad)."""
         div = np.zeros(s.n_rows) if diverg is None else _f64(diverg).copy()
@@ -785,7 +822,8 @@ class RefLib:
             _dp(keep[5]), _dp(keep[6]), _dp(keep[7]), _dp(keep[8]), _dp(keep[9]), _dp(keep[10]),
             _dp(div), _dp(grad), C.c_int(ircflu),
             (None if massflux is None else _dp(massflux[0])),
-            (None if massflux is None else _dp(massflux[1])))
+            (None if massflux is None else _dp(massflux[1])),
+            (None if frcxt is None else _dp(_f64(frcxt))))
         assert r == 0
         return div, grad.reshape(-1, 3)
 

@@ -962,7 +962,9 @@ csref_diffusion_potential_rc(void          *sys,
                              double        *grad_out,
                              int            ircflu,       /* eqp->ircflu: 1 = reconstruct */
                              double        *i_massflux,   /* both non-NULL: call */
-                             double        *b_massflux)   /* cs_face_diffusion_potential */
+                             double        *b_massflux,   /* cs_face_diffusion_potential */
+                             const double  *frcxt)        /* non-NULL: iphydp = 1 with this
+                                                             exterior force, 3 per cell */
 {
   ref_system *s = static_cast<ref_system *>(sys);
   _set_glob_mesh_faces(s, face_cells);
@@ -1067,13 +1069,21 @@ csref_diffusion_potential_rc(void          *sys,
   std::vector<cs_real_t> _div(n_cells > 0 ? n_cells : 1, 0.);
   if (!init) memcpy(_div.data(), diverg, sizeof(cs_real_t)*n_cells);
 
+  /* hydrostatic pressure treatment (iphydr = 1, the default of
+     cs_glob_velocity_pressure_param): the exterior force enters the gradient and the face
+     values */
+  std::vector<cs_real_t> frcxt_v;
+  if (frcxt != nullptr) frcxt_v.assign(frcxt, frcxt + 3*(size_t)n_cells);
+  const int iphydp = (frcxt != nullptr) ? 1 : 0;
+  cs_real_3_t *_frcxt = (frcxt != nullptr) ? (cs_real_3_t *)frcxt_v.data() : nullptr;
+
   if (i_massflux != nullptr && b_massflux != nullptr)
     /* the face-flux sibling (cs_convection_diffusion.cpp:8075-8310): same BC update and
        gradient, fluxes kept per face; always the irecmf = 0 formula */
-    cs_face_diffusion_potential(nullptr, &eqp, mesh, mq, init, inc, 0, nullptr, _pvar.data(), &bc,
-                                i_visc, b_visc, _visel.data(), i_massflux, b_massflux);
+    cs_face_diffusion_potential(nullptr, &eqp, mesh, mq, init, inc, iphydp, _frcxt, _pvar.data(),
+                                &bc, i_visc, b_visc, _visel.data(), i_massflux, b_massflux);
   else {
-    cs_diffusion_potential(nullptr, &eqp, mesh, mq, init, inc, 0, nullptr, _pvar.data(), &bc,
+    cs_diffusion_potential(nullptr, &eqp, mesh, mq, init, inc, iphydp, _frcxt, _pvar.data(), &bc,
                            i_visc, b_visc, _visel.data(), _div.data());
     memcpy(diverg, _div.data(), sizeof(cs_real_t)*n_cells);
   }
@@ -1083,8 +1093,8 @@ csref_diffusion_potential_rc(void          *sys,
     cs_gradient_scalar_synced_input("csref",
                                     (imrgra == 4) ? CS_GRADIENT_GREEN_LSQ : CS_GRADIENT_LSQ,
                                     CS_HALO_STANDARD, inc, eqp.nswrgr,
-                                    0, 1, 0, (cs_gradient_limit_t)(eqp.imligr), eqp.epsrgr,
-                                    eqp.climgr, nullptr, &bc, _pvar.data(), nullptr,
+                                    iphydp, 1, 0, (cs_gradient_limit_t)(eqp.imligr), eqp.epsrgr,
+                                    eqp.climgr, _frcxt, &bc, _pvar.data(), nullptr,
                                     (cs_real_3_t *)grad_out, nullptr);
   }
 

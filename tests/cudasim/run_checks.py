@@ -415,6 +415,37 @@ def check_rhs(ora):
                 d = m.divergence(im, bm, init=init, diverg=f["div0"])
                 assert np.array_equal(d, g["div_" + tag]), (N, tag)
         m.destroy()
+    # hydrostatic pressure treatment (iphydp = 1 with an exterior force)
+    from make_golden_rhs import HYD_CASES, hyd_input
+    for N in CASES:
+        g = np.load(os.path.join(GOLD, f"rhs_hyd_N{N}.npz"))
+        s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
+        g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
+        fx = hyd_input(s.n_rows)
+        mf0 = face_input(s, len(bfc))
+        m = csb.Matrix.from_system(s)
+        m.set_boundary_faces(bfc)
+        m.set_face_geometry(i_geo[:, 6], i_geo[:, :3], i_geo[:, 3:6], b_geo[:, :3], b_geo[:, 6])
+        m.set_green_geometry(g_geo[:, 0], g_geo[:, 1:4], b_surf, cgl)
+        m.set_face_cog(ifc, b_geo[:, 3:6])
+        for bt, imrgra in HYD_CASES:
+            m.set_boundary_iprime(diipb_input(N, len(bfc)) if bt == "b" else None)
+            m.set_gradient_type(imrgra)
+            for inc in (1, 0):
+                gr = m.gradient_hyd(imrgra, fx, f["pvar"], f["coefa"], f["coefb"], inc=inc)
+                assert np.array_equal(gr, g[f"{bt}{imrgra}_grad_inc{inc}"]), (N, bt, imrgra, inc)
+                for irecmf in (0, 1):
+                    d = m.diffusion_potential_hyd(fx, f["pvar"], f["coefa"], f["coefb"], f["cofaf"],
+                                                  f["cofbf"], f["i_visc"], f["b_visc"], f["visel"],
+                                                  irecmf=irecmf, inc=inc)
+                    assert np.array_equal(d, g[f"{bt}{imrgra}_div_irecmf{irecmf}_inc{inc}"]), \
+                        (N, bt, imrgra, irecmf, inc)
+            im, bm = m.face_diffusion_potential_hyd(
+                s.n_faces, len(bfc), fx, f["pvar"], f["coefa"], f["coefb"], f["cofaf"], f["cofbf"],
+                f["i_visc"], f["b_visc"], f["visel"], init=0, massflux=mf0)
+            assert np.array_equal(im, g[f"{bt}{imrgra}_i_massflux"]), (N, bt, imrgra)
+            assert np.array_equal(bm, g[f"{bt}{imrgra}_b_massflux"]), (N, bt, imrgra)
+        m.destroy()
     # imrgra = 4: Green-Gauss gradient with least-squares face values
     for N in CASES:
         g = np.load(os.path.join(GOLD, f"rhs_green_N{N}.npz"))

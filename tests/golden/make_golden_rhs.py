@@ -4,7 +4,7 @@ the reference's own compiled CPU code (oracle/_ref/libcsref.so, csref_diffusion_
 
     python tests/golden/make_golden_rhs.py   -> tests/golden/rhs_N{N}.npz, rhs_rc_N{N}.npz,
                                                 rhs_rcb_N{N}.npz, rhs_green_N{N}.npz,
-                                                rhs_face_N{N}.npz
+                                                rhs_face_N{N}.npz, rhs_hyd_N{N}.npz
 
 rhs_rc_*: the same operator WITH flux reconstruction (eqp->ircflu = 1, least-squares gradient,
 csref_diffusion_potential_rc) on a non-orthogonal variant of the cube.
@@ -15,6 +15,8 @@ least-squares gradient, then _reconstruct_scalar_gradient), with and without bou
 the warped-face correction matrices.
 rhs_face_*: cs_face_diffusion_potential (the per-face fluxes; eqp->ircflu 0 and 1, imrgra 1 and
 4, boundary II' given) and cs_divergence of those fluxes.
+rhs_hyd_*: the hydrostatic pressure treatment (iphydp = 1 with a seeded exterior force: what
+cs_pressure_correction hands over by default), imrgra 1 and 4, with and without boundary II'.
 """
 import os
 import sys
@@ -91,6 +93,14 @@ def green_input(N, n_faces, n_b_faces, n_rows, seed=29):
     return g_geo, b_surf, cgl
 
 
+HYD_CASES = (("b", 1), ("b", 4), ("p", 4))        # (boundary II' given / plain, imrgra)
+
+
+def hyd_input(n_rows, seed=43):
+    """seeded exterior force per cell"""
+    return np.random.default_rng(seed).standard_normal((n_rows, 3))
+
+
 FACE_CASES = ((0, 1), (1, 1), (1, 4))            # (ircflu, imrgra)
 FACE_INIT_INC = ((1, 1), (0, 1), (1, 0))
 
@@ -104,6 +114,34 @@ def face_input(s, n_b_faces, seed=41):
 def main():
     from oracle.pyoracle import RefLib
     ref = RefLib(1)
+    for N in CASES:
+        s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
+        g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
+        fx = hyd_input(s.n_rows)
+        mf0 = face_input(s, len(bfc))
+        h = ref.system(s)
+        out = {}
+        for bt, imrgra in HYD_CASES:
+            diipb = diipb_input(N, len(bfc)) if bt == "b" else None
+            kw = dict(diipb=diipb, imrgra=imrgra, g_geo=g_geo, b_face_surf=b_surf,
+                      corr_grad_lin=cgl, frcxt=fx)
+            for irecmf in (0, 1):
+                for inc in (1, 0):
+                    d, g = ref.diffusion_potential_rc(
+                        h, s, bfc, b_geo, ifc, i_geo, f["pvar"], f["coefa"], f["coefb"],
+                        f["cofaf"], f["cofbf"], f["i_visc"], f["b_visc"], f["visel"],
+                        irecmf=irecmf, inc=inc, **kw)
+                    out[f"{bt}{imrgra}_div_irecmf{irecmf}_inc{inc}"] = d
+                    out[f"{bt}{imrgra}_grad_inc{inc}"] = g
+            mf = (mf0[0].copy(), mf0[1].copy())
+            ref.diffusion_potential_rc(h, s, bfc, b_geo, ifc, i_geo, f["pvar"], f["coefa"],
+                                       f["coefb"], f["cofaf"], f["cofbf"], f["i_visc"],
+                                       f["b_visc"], f["visel"], init=0, ircflu=1, massflux=mf, **kw)
+            out[f"{bt}{imrgra}_i_massflux"], out[f"{bt}{imrgra}_b_massflux"] = mf
+        ref.destroy(h)
+        path = os.path.join(ROOT, "tests", "golden", f"rhs_hyd_N{N}.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path))
     for N in CASES:
         s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
         g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)

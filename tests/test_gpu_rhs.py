@@ -291,6 +291,72 @@ def test_face_fluxes_without_reconstruction_need_no_geometry(csb, oracle):
     m.destroy()
 
 
+@pytest.mark.parametrize("N", CASES)
+def test_hydrostatic_treatment_matches_reference_golden(csb, N):
+    """iphydp = 1 with an exterior force (what cs_pressure_correction hands over by default):
+    gradient (imrgra 1 / 4), reconstructed divergence (both formulas, inc 0 / 1) and face
+    fluxes, with and without boundary II': bit-identical to the reference; flag 0 / 2 = off"""
+    from make_golden_rhs import (HYD_CASES, diipb_input, face_input, green_input, hyd_input)
+    g = np.load(os.path.join(GOLD, f"rhs_hyd_N{N}.npz"))
+    s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
+    g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
+    fx = hyd_input(s.n_rows)
+    mf0 = face_input(s, len(bfc))
+    m = _rc_matrix(csb, s, bfc, b_geo, i_geo)
+    m.set_green_geometry(g_geo[:, 0], g_geo[:, 1:4], b_surf, cgl)
+    with pytest.raises(csb.CsbError):
+        m.gradient_hyd(1, fx, f["pvar"], f["coefa"], f["coefb"])         # face centres missing
+    m.set_face_cog(ifc, b_geo[:, 3:6])
+    for bt, imrgra in HYD_CASES:
+        m.set_boundary_iprime(diipb_input(N, len(bfc)) if bt == "b" else None)
+        m.set_gradient_type(imrgra)
+        for inc in (1, 0):
+            gr = m.gradient_hyd(imrgra, fx, f["pvar"], f["coefa"], f["coefb"], inc=inc)
+            assert np.array_equal(gr, g[f"{bt}{imrgra}_grad_inc{inc}"]), (bt, imrgra, inc)
+            for irecmf in (0, 1):
+                d = m.diffusion_potential_hyd(fx, f["pvar"], f["coefa"], f["coefb"], f["cofaf"],
+                                              f["cofbf"], f["i_visc"], f["b_visc"], f["visel"],
+                                              irecmf=irecmf, inc=inc)
+                assert np.array_equal(d, g[f"{bt}{imrgra}_div_irecmf{irecmf}_inc{inc}"]), \
+                    (bt, imrgra, irecmf, inc)
+        im, bm = m.face_diffusion_potential_hyd(
+            s.n_faces, len(bfc), fx, f["pvar"], f["coefa"], f["coefb"], f["cofaf"], f["cofbf"],
+            f["i_visc"], f["b_visc"], f["visel"], init=0, massflux=mf0)
+        assert np.array_equal(im, g[f"{bt}{imrgra}_i_massflux"]), (bt, imrgra)
+        assert np.array_equal(bm, g[f"{bt}{imrgra}_b_massflux"]), (bt, imrgra)
+    for flag in (0, 2):                              # off, like the reference reads 0 and 2
+        assert np.array_equal(m.gradient_hyd(4, fx, f["pvar"], f["coefa"], f["coefb"],
+                                             hyd_p_flag=flag),
+                              m.gradient(4, f["pvar"], f["coefa"], f["coefb"]))
+    m.destroy()
+
+
+def test_hydrostatic_treatment_vs_oracle_larger(csb, oracle):
+    """40^3, iphydp = 1, imrgra 4, boundary II', device-resident force: bit-exact vs the oracle"""
+    import torch
+    from make_golden_rhs import diipb_input, green_input, hyd_input
+    s, bfc, b_geo, ifc, i_geo, f = rc_input(40, seed=17)
+    g_geo, b_surf, cgl = green_input(40, s.n_faces, len(bfc), s.n_rows, seed=31)
+    diipb = diipb_input(40, len(bfc), seed=23)
+    fx = hyd_input(s.n_rows, seed=47)
+    m = _rc_matrix(csb, s, bfc, b_geo, i_geo)
+    m.set_green_geometry(g_geo[:, 0], g_geo[:, 1:4], b_surf, cgl)
+    m.set_face_cog(ifc, b_geo[:, 3:6])
+    m.set_boundary_iprime(diipb)
+    m.set_gradient_type(4)
+    go, vip = oracle.gradient_hyd(4, s, bfc, b_geo[:, :3], b_geo[:, 6], ifc, b_geo[:, 3:6], fx,
+                                  f["pvar"], f["coefa"], f["coefb"], diipb=diipb, g_geo=g_geo,
+                                  b_face_surf=b_surf, corr_grad_lin=cgl)
+    fx_d = torch.from_numpy(np.ascontiguousarray(fx)).cuda()
+    assert np.array_equal(m.gradient_hyd(4, fx_d, f["pvar"], f["coefa"], f["coefb"]), go)
+    do = oracle.diffusion_potential_rc(s, bfc, i_geo, go, f["pvar"], f["cofaf"], f["cofbf"],
+                                       f["i_visc"], f["b_visc"], f["visel"], irecmf=1, val_ip=vip)
+    d = m.diffusion_potential_hyd(fx_d, f["pvar"], f["coefa"], f["coefb"], f["cofaf"], f["cofbf"],
+                                  f["i_visc"], f["b_visc"], f["visel"], irecmf=1)
+    assert np.array_equal(d, do)
+    m.destroy()
+
+
 def test_reconstruction_needs_geometry(csb):
     s, bfc, _, _, _, f = rc_input(5)
     m = csb.Matrix.from_system(s)

@@ -985,6 +985,36 @@ def test_oracle_face_diffusion_potential_and_divergence_match_golden(oracle, N):
                 assert np.array_equal(d, d2), tag
 
 
+@pytest.mark.parametrize("N", [5, 9])
+def test_oracle_hydrostatic_treatment_matches_golden(oracle, N):
+    """iphydp = 1 with an exterior force: values at I' / face values, least-squares gradient,
+    Green-Gauss pass, reconstructed divergence: bit-exact against the reference"""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_rhs import HYD_CASES, diipb_input, green_input, hyd_input, rc_input
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"rhs_hyd_N{N}.npz"))
+    s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
+    g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
+    fx = hyd_input(s.n_rows)
+    for bt, imrgra in HYD_CASES:
+        diipb = diipb_input(N, len(bfc)) if bt == "b" else None
+        for inc in (1, 0):
+            grad, vip = oracle.gradient_hyd(imrgra, s, bfc, b_geo[:, :3], b_geo[:, 6], ifc,
+                                            b_geo[:, 3:6], fx, f["pvar"], f["coefa"], f["coefb"],
+                                            inc=inc, diipb=diipb, g_geo=g_geo, b_face_surf=b_surf,
+                                            corr_grad_lin=cgl)
+            assert np.array_equal(grad, g[f"{bt}{imrgra}_grad_inc{inc}"]), (bt, imrgra, inc)
+            for irecmf in (0, 1):
+                d = oracle.diffusion_potential_rc(s, bfc, i_geo, grad, f["pvar"], f["cofaf"],
+                                                  f["cofbf"], f["i_visc"], f["b_visc"],
+                                                  f["visel"], irecmf=irecmf, inc=inc, val_ip=vip)
+                assert np.array_equal(d, g[f"{bt}{imrgra}_div_irecmf{irecmf}_inc{inc}"])
+    # a zero force takes the other code path to the same mathematical gradient
+    z, _ = oracle.gradient_hyd(1, s, bfc, b_geo[:, :3], b_geo[:, 6], ifc, b_geo[:, 3:6],
+                               np.zeros((s.n_rows, 3)), f["pvar"], f["coefa"], f["coefb"])
+    p = oracle.gradient_lsq(s, bfc, b_geo[:, :3], b_geo[:, 6], f["pvar"], f["coefa"], f["coefb"])
+    assert np.abs(z - p).max() <= 1e-12 * np.abs(p).max()
+
+
 def test_oracle_gradient_lsq_is_exact_for_linear_fields(oracle):
     """property: a least-squares gradient reproduces the gradient of a linear field (to the
     single precision of its cocg matrices) when the boundary values are those of the field"""
