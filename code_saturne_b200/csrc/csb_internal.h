@@ -356,6 +356,10 @@ struct _csb_matrix_t {
   csb_lnum_t  n_faces = 0;
   csb::DevBuf<csb_lnum_t>  c2f;
   csb::DevBuf<short>       c2f_sgn;
+  /* entries of every row in ascending face order (kernels.cu face_order(); 0: not built yet,
+     1: usable, -1: rows too long, the kernels scan) */
+  mutable csb::DevBuf<unsigned char> fperm;
+  mutable int fperm_state = 0;
   csb::DevBuf<double>      cell_cen, cell_vol, face_u_normal, face_surf;
   bool        has_mesh = false;
   /* boundary faces by adjacent cell, ascending face ids (csb_matrix_set_boundary_faces):

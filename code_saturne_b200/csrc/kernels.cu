@@ -2275,6 +2275,55 @@ bool launch_assembler_fold(int n_rows, int nnz, const int *index, const int *src
 }
 
 namespace {
+/* The face operators below gather per cell in ascending face order (the order of the
+   reference's scatter loops).  fperm[row_index[c] + t] = position, within row c, of the entry
+   with the t-th smallest face id (255 = no more entries), built once per mesh association by
+   k_face_order; without it (rows longer than 255 entries) the next face is found by a scan of
+   the row. */
+struct FaceOrder {
+  const int *c2f;
+  const unsigned char *fperm;
+  int s, e, t, last;
+  __device__ FaceOrder(const int *c2f_, const unsigned char *fperm_, int s_, int e_)
+    : c2f(c2f_), fperm(fperm_), s(s_), e(e_), t(0), last(-1) {}
+  /* next face of the row: its id and the row entry that holds it */
+  __device__ bool next(int &face, int &bk)
+  {
+    if (fperm != nullptr) {
+      if (s + t >= e) return false;
+      const unsigned int p = fperm[s + t];
+      if (p == 255u) return false;
+      t++;
+      bk = s + (int)p;
+      face = c2f[bk];
+      return true;
+    }
+    int best = INT_MAX;
+    bk = -1;
+    for (int k = s; k < e; k++) {
+      const int f = c2f[k];
+      if (f > last && f < best) { best = f; bk = k; }
+    }
+    if (bk < 0) return false;
+    last = best;
+    face = best;
+    return true;
+  }
+};
+
+__global__ void k_face_order(int n_rows, const int *__restrict__ row_index,
+                             const int *__restrict__ c2f, unsigned char *fperm, int *too_long)
+{
+  const int c = blockIdx.x*blockDim.x + threadIdx.x;
+  if (c >= n_rows) return;
+  const int s = row_index[c], e = row_index[c+1];
+  if (e - s > 255) { *too_long = 1; return; }
+  FaceOrder fo(c2f, nullptr, s, e);
+  int t = 0, face, bk;
+  while (fo.next(face, bk)) fperm[s + t++] = (unsigned char)(bk - s);
+  for (; s + t < e; t++) fperm[s + t] = 255;        /* entries repeating a face id */
+}
+
 /* cs_diffusion_potential without flux reconstruction (cs_convection_diffusion.cpp:8869-8889,
    :8975-8982): the reference scatters face fluxes to the two cells in face order; a thread owns a
    cell and takes its interior faces by ascending face id (the next one is the smallest face id
@@ -2283,6 +2332,7 @@ namespace {
 __global__ void k_diffusion_potential(int n_rows, const int *__restrict__ row_index,
                                       const int *__restrict__ col_id,
                                       const int *__restrict__ c2f,
+                                      const unsigned char *__restrict__ fperm,
                                       const short *__restrict__ c2f_sgn,
                                       const int *__restrict__ cell_b_faces_idx,
                                       const int *__restrict__ cell_b_faces, int init, int inc,
@@ -2297,15 +2347,10 @@ __global__ void k_diffusion_potential(int n_rows, const int *__restrict__ row_in
   const int s = row_index[c], e = row_index[c+1];
   const double pc = pvar[c];
   double d = (init >= 1) ? 0. : diverg[c];
-  int last = -1;
+  FaceOrder fo(c2f, fperm, s, e);
   while (true) {
-    int best = INT_MAX, bk = -1;
-    for (int k = s; k < e; k++) {
-      const int f = c2f[k];
-      if (f > last && f < best) { best = f; bk = k; }
-    }
-    if (bk < 0) break;
-    last = best;
+    int best, bk;
+    if (!fo.next(best, bk)) break;
     const double pj = pvar[col_id[bk]];
     if (c2f_sgn[bk] > 0) d += i_visc[best]*(pc - pj);      /* this cell is the face's first */
     else d += -(i_visc[best]*(pj - pc));
@@ -2320,14 +2365,37 @@ __global__ void k_diffusion_potential(int n_rows, const int *__restrict__ row_in
 }
 } // anonymous namespace
 
+/* face-order permutation of the matrix's rows, built on first use after a mesh association
+   (nullptr: not available, the kernels scan) */
+static const unsigned char *face_order(const _csb_matrix_t *m)
+{
+  if (m->fperm_state == 1) return m->fperm.p;
+  if (m->fperm_state < 0 || m->n_rows < 1 || m->nnz < 1) return nullptr;
+  m->fperm_state = -1;
+  DevBuf<int> flag;
+  int h_flag = 1;
+  if (!flag.alloc(1) || !m->fperm.alloc((size_t)m->nnz)
+      || cudaMemsetAsync(flag.p, 0, sizeof(int), ctx().stream) != cudaSuccess) return nullptr;
+  k_face_order<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(m->n_rows, m->row_index.p,
+                                                                m->c2f.p, m->fperm.p, flag.p);
+  if (!post_launch("face_order")
+      || cudaMemcpyAsync(&h_flag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream)
+         != cudaSuccess
+      || cudaStreamSynchronize(ctx().stream) != cudaSuccess) return nullptr;
+  if (h_flag != 0) return nullptr;
+  m->fperm_state = 1;
+  return m->fperm.p;
+}
+
 bool launch_diffusion_potential(const _csb_matrix_t *m, int init, int inc, const double *pvar,
                                 const double *cofaf, const double *cofbf, const double *i_visc,
                                 const double *b_visc, double *diverg)
 {
   if (m->n_rows < 1) return true;
   const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  const unsigned char *fperm = face_order(m);
   k_diffusion_potential<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
-    m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, m->c2f_sgn.p,
+    m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, fperm, m->c2f_sgn.p,
     bnd ? m->cell_b_faces_idx.p : nullptr, bnd ? m->cell_b_faces.p : nullptr, init, inc, pvar,
     cofaf, cofbf, i_visc, b_visc, diverg);
   return post_launch("diffusion_potential");
@@ -2444,6 +2512,7 @@ __global__ void k_lsq_cocg(int n_rows, const int *__restrict__ row_index,
    computed in the face's orientation -- then boundary faces), times the cell's cocg */
 __global__ void k_lsq_gradient(int n_rows, const int *__restrict__ row_index,
                                const int *__restrict__ col_id, const int *__restrict__ c2f,
+                               const unsigned char *__restrict__ fperm,
                                const short *__restrict__ c2f_sgn,
                                const double *__restrict__ cell_cen,
                                const int *__restrict__ cell_b_faces_idx,
@@ -2465,15 +2534,10 @@ __global__ void k_lsq_gradient(int n_rows, const int *__restrict__ row_index,
   const int s = row_index[c], e = row_index[c+1];
   const double pc = pvar[c];
   double r0 = 0., r1 = 0., r2 = 0.;
-  int last = -1;
+  FaceOrder fo(c2f, fperm, s, e);
   while (true) {
-    int best = INT_MAX, bk = -1;
-    for (int k = s; k < e; k++) {
-      const int f = c2f[k];
-      if (f > last && f < best) { best = f; bk = k; }
-    }
-    if (bk < 0) break;
-    last = best;
+    int best, bk;
+    if (!fo.next(best, bk)) break;
     const int o = col_id[bk];
     const bool first = (c2f_sgn[bk] > 0);
     const size_t ii = (size_t)(first ? c : o), jj = (size_t)(first ? o : c);
@@ -2665,6 +2729,7 @@ __global__ void k_b_iprime_lsq(int n_rows, const int *__restrict__ row_index,
 __global__ void k_green_reconstruct(int n_rows, const int *__restrict__ row_index,
                                     const int *__restrict__ col_id,
                                     const int *__restrict__ c2f,
+                                    const unsigned char *__restrict__ fperm,
                                     const short *__restrict__ c2f_sgn,
                                     const int *__restrict__ cell_b_faces_idx,
                                     const int *__restrict__ cell_b_faces,
@@ -2690,15 +2755,10 @@ __global__ void k_green_reconstruct(int n_rows, const int *__restrict__ row_inde
   const int s = row_index[c], e = row_index[c+1];
   const double pc = pvar[c];
   double g0 = 0., g1 = 0., g2 = 0.;
-  int last = -1;
+  FaceOrder fo(c2f, fperm, s, e);
   while (true) {
-    int best = INT_MAX, bk = -1;
-    for (int k = s; k < e; k++) {
-      const int f = c2f[k];
-      if (f > last && f < best) { best = f; bk = k; }
-    }
-    if (bk < 0) break;
-    last = best;
+    int best, bk;
+    if (!fo.next(best, bk)) break;
     const size_t f = (size_t)best;
     const int o = col_id[bk];
     const bool first = (c2f_sgn[bk] > 0);
@@ -2780,7 +2840,8 @@ __global__ void k_green_reconstruct(int n_rows, const int *__restrict__ row_inde
    - otherwise), then of its boundary face fluxes: the reference's scatter in face order, as a
    gather */
 __global__ void k_divergence(int n_rows, const int *__restrict__ row_index,
-                             const int *__restrict__ c2f, const short *__restrict__ c2f_sgn,
+                             const int *__restrict__ c2f,
+                             const unsigned char *__restrict__ fperm, const short *__restrict__ c2f_sgn,
                              const int *__restrict__ cell_b_faces_idx,
                              const int *__restrict__ cell_b_faces, int init,
                              const double *__restrict__ i_massflux,
@@ -2790,15 +2851,10 @@ __global__ void k_divergence(int n_rows, const int *__restrict__ row_index,
   if (c >= n_rows) return;
   const int s = row_index[c], e = row_index[c+1];
   double d = (init >= 1) ? 0. : diverg[c];
-  int last = -1;
+  FaceOrder fo(c2f, fperm, s, e);
   while (true) {
-    int best = INT_MAX, bk = -1;
-    for (int k = s; k < e; k++) {
-      const int f = c2f[k];
-      if (f > last && f < best) { best = f; bk = k; }
-    }
-    if (bk < 0) break;
-    last = best;
+    int best, bk;
+    if (!fo.next(best, bk)) break;
     if (c2f_sgn[bk] > 0) d += i_massflux[best];
     else d += -i_massflux[best];
   }
@@ -2865,6 +2921,7 @@ __global__ void k_face_diffusion_potential(int n_rows, const int *__restrict__ r
 __global__ void k_diffusion_potential_rc(int n_rows, const int *__restrict__ row_index,
                                          const int *__restrict__ col_id,
                                          const int *__restrict__ c2f,
+                                         const unsigned char *__restrict__ fperm,
                                          const short *__restrict__ c2f_sgn,
                                          const int *__restrict__ cell_b_faces_idx,
                                          const int *__restrict__ cell_b_faces,
@@ -2885,15 +2942,10 @@ __global__ void k_diffusion_potential_rc(int n_rows, const int *__restrict__ row
   if (c >= n_rows) return;
   const int s = row_index[c], e = row_index[c+1];
   double d = (init >= 1) ? 0. : diverg[c];
-  int last = -1;
+  FaceOrder fo(c2f, fperm, s, e);
   while (true) {
-    int best = INT_MAX, bk = -1;
-    for (int k = s; k < e; k++) {
-      const int f = c2f[k];
-      if (f > last && f < best) { best = f; bk = k; }
-    }
-    if (bk < 0) break;
-    last = best;
+    int best, bk;
+    if (!fo.next(best, bk)) break;
     const size_t f = (size_t)best;
     const int o = col_id[bk];
     const bool first = (c2f_sgn[bk] > 0);
@@ -2956,8 +3008,9 @@ bool launch_lsq_gradient(const _csb_matrix_t *m, const float *cocg, int inc, con
 {
   if (m->n_rows < 1) return true;
   const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  const unsigned char *fperm = face_order(m);
   k_lsq_gradient<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
-    m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, m->c2f_sgn.p, m->cell_cen.p,
+    m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, fperm, m->c2f_sgn.p, m->cell_cen.p,
     bnd ? m->cell_b_faces_idx.p : nullptr, bnd ? m->cell_b_faces.p : nullptr,
     m->b_face_u_normal.p, m->b_dist.p, cocg, inc, pvar, coefa, coefb,
     (bnd && m->has_diipb) ? m->diipb.p : nullptr, val_f, m->i_face_cog.p, m->b_face_cog.p,
@@ -2970,8 +3023,9 @@ bool launch_divergence(const _csb_matrix_t *m, int init, const double *i_massflu
 {
   if (m->n_rows < 1) return true;
   const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  const unsigned char *fperm = face_order(m);
   k_divergence<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
-    m->n_rows, m->row_index.p, m->c2f.p, m->c2f_sgn.p, bnd ? m->cell_b_faces_idx.p : nullptr,
+    m->n_rows, m->row_index.p, m->c2f.p, fperm, m->c2f_sgn.p, bnd ? m->cell_b_faces_idx.p : nullptr,
     bnd ? m->cell_b_faces.p : nullptr, init, i_massflux, b_massflux, diverg);
   return post_launch("divergence");
 }
@@ -2999,8 +3053,9 @@ bool launch_green_reconstruct(const _csb_matrix_t *m, int inc, const double *pva
 {
   if (m->n_rows < 1) return true;
   const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  const unsigned char *fperm = face_order(m);
   k_green_reconstruct<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
-    m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, m->c2f_sgn.p,
+    m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, fperm, m->c2f_sgn.p,
     bnd ? m->cell_b_faces_idx.p : nullptr, bnd ? m->cell_b_faces.p : nullptr, m->g_weight.p,
     m->dofij.p, m->face_surf.p, m->face_u_normal.p, m->b_face_surf.p, m->b_face_u_normal.p,
     m->cell_vol.p, m->has_corr_grad_lin ? m->corr_grad_lin.p : nullptr, inc, pvar, coefa, coefb,
@@ -3016,8 +3071,9 @@ bool launch_diffusion_potential_rc(const _csb_matrix_t *m, int irecmf, int init,
 {
   if (m->n_rows < 1) return true;
   const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  const unsigned char *fperm = face_order(m);
   k_diffusion_potential_rc<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
-    m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, m->c2f_sgn.p,
+    m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, fperm, m->c2f_sgn.p,
     bnd ? m->cell_b_faces_idx.p : nullptr, bnd ? m->cell_b_faces.p : nullptr, m->diipf.p,
     m->djjpf.p, m->i_dist.p, m->face_surf.p, irecmf, init, inc, pvar, grad, cofaf, cofbf,
     i_visc, b_visc, visel, val_ip, diverg);

@@ -649,6 +649,7 @@ int csb_matrix_set_mesh_association(csb_matrix_t *m, csb_lnum_t n_faces,
          && CSB_CUDA(cudaStreamSynchronize(ctx().stream));
   m->has_mesh = ok;
   m->cocg_valid = false;
+  m->fperm_state = 0;
   return ok ? 0 : -1;
 }
 
