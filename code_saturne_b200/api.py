@@ -769,6 +769,17 @@ class Matrix:
         if L.csb_matrix_set_gradient_type(self.handle, int(imrgra)) != 0:
             _err("csb_matrix_set_gradient_type")
 
+    def set_gradient_sweeps(self, nswrgr=100, epsrgr=1e-4):
+        L = load_library()
+        L.csb_matrix_set_gradient_sweeps.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        if L.csb_matrix_set_gradient_sweeps(self.handle, int(nswrgr), float(epsrgr)) != 0:
+            _err("csb_matrix_set_gradient_sweeps")
+
+    def gradient_sweeps(self):
+        L = load_library()
+        L.csb_matrix_get_gradient_sweeps.argtypes = [C.c_void_p]
+        return int(L.csb_matrix_get_gradient_sweeps(self.handle))
+
     def gradient(self, imrgra, pvar, coefa=None, coefb=None, inc=1):
         """cs_gradient_scalar_synced_input for imrgra 1 (LSQ) or 4 (Green-Gauss, LSQ face values)"""
         L = load_library()

@@ -389,6 +389,13 @@ struct _csb_matrix_t {
   bool        has_face_cog = false;
   bool        has_green_geo = false, has_corr_grad_lin = false;
   int         imrgra = 1;
+  /* iterative Green-Gauss gradient (imrgra = 0): eqp->nswrgr, eqp->epsrgr (defaults of
+     cs_parameters.cpp:380, :394), cached cocg_it, sweeps of the last call */
+  int         nswrgr = 100;
+  double      epsrgr = 1.e-4;
+  mutable csb::DevBuf<double> cocg_it;
+  mutable bool cocg_it_valid = false;
+  mutable int  n_grad_sweeps = 0;
   mutable csb::DevBuf<float> cocg_lsq;
   mutable bool cocg_valid = false;
   bool        from_native = false;
@@ -659,6 +666,15 @@ bool launch_b_iprime_lsq(const _csb_matrix_t *m, int inc, const double *pvar,
 bool launch_lsq_gradient(const _csb_matrix_t *m, const float *cocg, int inc, const double *pvar,
                          const double *coefa, const double *coefb, const double *val_f,
                          const double *f_ext, double *grad);
+/* iterative Green-Gauss gradient (imrgra = 0): cocg_it [n_rows][3][3]; one sweep (r_grad
+   nullptr: the initial non-reconstructed gradient into out, else rhs / V into out); the update
+   grad += cocg_it . rhs */
+bool launch_cocg_it(const _csb_matrix_t *m, double *cocg_it);
+bool launch_green_iter_sweep(const _csb_matrix_t *m, int inc, const double *pvar,
+                             const double *coefa, const double *coefb, const double *r_grad,
+                             double *out);
+bool launch_green_iter_update(const _csb_matrix_t *m, const double *cocg_it, const double *rhs,
+                              double *grad);
 /* cs_divergence (cs_divergence.cpp:1224) and cs_face_diffusion_potential
    (cs_convection_diffusion.cpp:8075; grad nullptr: no reconstruction) */
 bool launch_divergence(const _csb_matrix_t *m, int init, const double *i_massflux,

@@ -2916,6 +2916,153 @@ __global__ void k_face_diffusion_potential(int n_rows, const int *__restrict__ r
     }
 }
 
+/* Iterative Green-Gauss gradient (imrgra = 0, CS_GRADIENT_GREEN_ITER; cs_gradient.cpp:
+   _compute_cell_cocg_it :1776-1860, _initialize_scalar_gradient :1329-1590,
+   _iterative_scalar_gradient :1891-2300, branches without hydrostatic pressure, no weighting).
+   One thread per cell gathers its faces in the reference's scatter order.
+   k_cocg_it: identity - 0.5 S OF (x) n / V summed over the cell's interior faces, inverted by
+   Cramer's rule (cs_math.h:1587-1610). */
+__global__ void k_cocg_it(int n_rows, const int *__restrict__ row_index,
+                          const int *__restrict__ c2f, const unsigned char *__restrict__ fperm,
+                          const short *__restrict__ c2f_sgn, const double *__restrict__ dofij,
+                          const double *__restrict__ i_face_surf,
+                          const double *__restrict__ i_face_u_normal,
+                          const double *__restrict__ cell_vol, double *cocg_it)
+{
+  const int c = blockIdx.x*blockDim.x + threadIdx.x;
+  if (c >= n_rows) return;
+  const int s = row_index[c], e = row_index[c+1];
+  double a[3][3] = {{1.0, 0.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 0.0, 1.0}};
+  const double dvol = (cell_vol[c] > 0) ? 1. / cell_vol[c] : 0.;
+  FaceOrder fo(c2f, fperm, s, e);
+  while (true) {
+    int best, bk;
+    if (!fo.next(best, bk)) break;
+    const size_t f = (size_t)best;
+    const bool first = (c2f_sgn[bk] > 0);
+    const double pfac0 = -0.5 * i_face_surf[f];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const double pfac = pfac0 * dofij[3*f+i];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const double vecfac = pfac*i_face_u_normal[3*f+j];
+        if (first) a[i][j] += vecfac * dvol;
+        else a[i][j] += -vecfac * dvol;
+      }
+    }
+  }
+  const double a00 = a[1][1]*a[2][2] - a[2][1]*a[1][2];
+  const double a01 = a[2][1]*a[0][2] - a[0][1]*a[2][2];
+  const double a02 = a[0][1]*a[1][2] - a[1][1]*a[0][2];
+  const double a10 = a[2][0]*a[1][2] - a[1][0]*a[2][2];
+  const double a11 = a[0][0]*a[2][2] - a[2][0]*a[0][2];
+  const double a12 = a[1][0]*a[0][2] - a[0][0]*a[1][2];
+  const double a20 = a[1][0]*a[2][1] - a[2][0]*a[1][1];
+  const double a21 = a[2][0]*a[0][1] - a[0][0]*a[2][1];
+  const double a22 = a[0][0]*a[1][1] - a[1][0]*a[0][1];
+  const double det_inv = 1. / (a[0][0]*a00 + a[1][0]*a01 + a[2][0]*a02);
+  double *o = cocg_it + 9*(size_t)c;
+  o[0] = a00 * det_inv; o[1] = a01 * det_inv; o[2] = a02 * det_inv;
+  o[3] = a10 * det_inv; o[4] = a11 * det_inv; o[5] = a12 * det_inv;
+  o[6] = a20 * det_inv; o[7] = a21 * det_inv; o[8] = a22 * det_inv;
+}
+
+/* sweep 0 (r_grad == nullptr): the non-reconstructed Green-Gauss gradient, out = grad;
+   later sweeps: out = rhs / V with rhs = -grad V + the reconstructed face values
+   (0.5 OF.(grad_I + grad_J) at interior faces, b II'.grad_I at boundary faces) */
+__global__ void k_green_iter_sweep(int n_rows, const int *__restrict__ row_index,
+                                   const int *__restrict__ col_id,
+                                   const int *__restrict__ c2f,
+                                   const unsigned char *__restrict__ fperm,
+                                   const short *__restrict__ c2f_sgn,
+                                   const int *__restrict__ cell_b_faces_idx,
+                                   const int *__restrict__ cell_b_faces,
+                                   const double *__restrict__ weight,
+                                   const double *__restrict__ dofij,
+                                   const double *__restrict__ i_face_surf,
+                                   const double *__restrict__ i_face_u_normal,
+                                   const double *__restrict__ b_face_surf,
+                                   const double *__restrict__ b_un,
+                                   const double *__restrict__ cell_vol,
+                                   const double *__restrict__ diipb, double inc,
+                                   const double *__restrict__ pvar,
+                                   const double *__restrict__ coefa,
+                                   const double *__restrict__ coefb,
+                                   const double *__restrict__ r_grad, double *out)
+{
+  const int c = blockIdx.x*blockDim.x + threadIdx.x;
+  if (c >= n_rows) return;
+  const int s = row_index[c], e = row_index[c+1];
+  const double pc = pvar[c];
+  double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+  if (r_grad != nullptr) {
+    const double *g = r_grad + 3*(size_t)c;
+    const double vol = cell_vol[c];
+    g0 = -g[0] * vol; g1 = -g[1] * vol; g2 = -g[2] * vol;
+  }
+  FaceOrder fo(c2f, fperm, s, e);
+  while (true) {
+    int best, bk;
+    if (!fo.next(best, bk)) break;
+    const size_t f = (size_t)best;
+    const int o = col_id[bk];
+    const bool first = (c2f_sgn[bk] > 0);
+    const size_t c1 = (size_t)(first ? c : o), c2 = (size_t)(first ? o : c);
+    const double ktpond = weight[f];
+    const double *n = i_face_u_normal + 3*f;
+    double pf;
+    if (r_grad == nullptr) {
+      if (first) pf = (1.0-ktpond) * (pvar[c2]-pvar[c1]) * i_face_surf[f];
+      else pf = -ktpond * (pvar[c2]-pvar[c1]) * i_face_surf[f];
+    }
+    else {
+      const double *of = dofij + 3*f, *ra = r_grad + 3*c1, *rb = r_grad + 3*c2;
+      pf = 0.5 * (  of[0] * (ra[0]+rb[0])
+                  + of[1] * (ra[1]+rb[1])
+                  + of[2] * (ra[2]+rb[2]));
+      if (first) pf += (1.0-ktpond) * (pvar[c2] - pvar[c1]);
+      else pf -= ktpond * (pvar[c2] - pvar[c1]);
+      pf *= i_face_surf[f];
+    }
+    if (first) { g0 += pf * n[0]; g1 += pf * n[1]; g2 += pf * n[2]; }
+    else { g0 += -pf * n[0]; g1 += -pf * n[1]; g2 += -pf * n[2]; }
+  }
+  if (cell_b_faces_idx != nullptr)
+    for (int k = cell_b_faces_idx[c]; k < cell_b_faces_idx[c+1]; k++) {
+      const size_t f = (size_t)cell_b_faces[k];
+      double pfac;
+      if (r_grad == nullptr)
+        pfac = inc*coefa[f] + (coefb[f]-1.0)*pc;
+      else {
+        const double *g = r_grad + 3*(size_t)c;
+        double ip0 = 0., ip1 = 0., ip2 = 0.;
+        if (diipb != nullptr) { ip0 = diipb[3*f]; ip1 = diipb[3*f+1]; ip2 = diipb[3*f+2]; }
+        pfac =   coefa[f] * inc
+               + coefb[f] * (ip0 * g[0] + ip1 * g[1] + ip2 * g[2]);
+        pfac += (coefb[f] -1.0) * pc;
+      }
+      pfac *= b_face_surf[f];
+      g0 += pfac * b_un[3*f]; g1 += pfac * b_un[3*f+1]; g2 += pfac * b_un[3*f+2];
+    }
+  const double dvol = 1. / cell_vol[c];
+  g0 *= dvol; g1 *= dvol; g2 *= dvol;
+  out[3*(size_t)c] = g0; out[3*(size_t)c+1] = g1; out[3*(size_t)c+2] = g2;
+}
+
+/* grad += cocg_it^T-style product of the scaled right-hand side (:2252-2260) */
+__global__ void k_green_iter_update(int n_rows, const double *__restrict__ cocg_it,
+                                    const double *__restrict__ rhs, double *grad)
+{
+  const int c = blockIdx.x*blockDim.x + threadIdx.x;
+  if (c >= n_rows) return;
+  const double *a = cocg_it + 9*(size_t)c, *r = rhs + 3*(size_t)c;
+  double *g = grad + 3*(size_t)c;
+  g[0] += r[0] * a[0] + r[1] * a[3] + r[2] * a[6];
+  g[1] += r[0] * a[1] + r[1] * a[4] + r[2] * a[7];
+  g[2] += r[0] * a[2] + r[1] * a[5] + r[2] * a[8];
+}
+
 /* cs_diffusion_potential with flux reconstruction (:8921-8961): the face flux is computed in
    the face's orientation by both of its cells, identically */
 __global__ void k_diffusion_potential_rc(int n_rows, const int *__restrict__ row_index,
@@ -3016,6 +3163,41 @@ bool launch_lsq_gradient(const _csb_matrix_t *m, const float *cocg, int inc, con
     (bnd && m->has_diipb) ? m->diipb.p : nullptr, val_f, m->i_face_cog.p, m->b_face_cog.p,
     f_ext, grad);
   return post_launch("lsq_gradient");
+}
+
+bool launch_cocg_it(const _csb_matrix_t *m, double *cocg_it)
+{
+  if (m->n_rows < 1) return true;
+  const unsigned char *fperm = face_order(m);
+  k_cocg_it<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
+    m->n_rows, m->row_index.p, m->c2f.p, fperm, m->c2f_sgn.p, m->dofij.p, m->face_surf.p,
+    m->face_u_normal.p, m->cell_vol.p, cocg_it);
+  return post_launch("cocg_it");
+}
+
+bool launch_green_iter_sweep(const _csb_matrix_t *m, int inc, const double *pvar,
+                             const double *coefa, const double *coefb, const double *r_grad,
+                             double *out)
+{
+  if (m->n_rows < 1) return true;
+  const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  const unsigned char *fperm = face_order(m);
+  k_green_iter_sweep<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
+    m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, fperm, m->c2f_sgn.p,
+    bnd ? m->cell_b_faces_idx.p : nullptr, bnd ? m->cell_b_faces.p : nullptr, m->g_weight.p,
+    m->dofij.p, m->face_surf.p, m->face_u_normal.p, m->b_face_surf.p, m->b_face_u_normal.p,
+    m->cell_vol.p, (bnd && m->has_diipb) ? m->diipb.p : nullptr, (double)inc, pvar, coefa, coefb,
+    r_grad, out);
+  return post_launch("green_iter_sweep");
+}
+
+bool launch_green_iter_update(const _csb_matrix_t *m, const double *cocg_it, const double *rhs,
+                              double *grad)
+{
+  if (m->n_rows < 1) return true;
+  k_green_iter_update<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(m->n_rows, cocg_it, rhs,
+                                                                       grad);
+  return post_launch("green_iter_update");
 }
 
 bool launch_divergence(const _csb_matrix_t *m, int init, const double *i_massflux,

@@ -649,6 +649,7 @@ int csb_matrix_set_mesh_association(csb_matrix_t *m, csb_lnum_t n_faces,
          && CSB_CUDA(cudaStreamSynchronize(ctx().stream));
   m->has_mesh = ok;
   m->cocg_valid = false;
+  m->cocg_it_valid = false;
   m->fperm_state = 0;
   return ok ? 0 : -1;
 }
@@ -809,6 +810,7 @@ int csb_matrix_set_green_geometry(csb_matrix_t *m, const csb_real_t *weight,
     set_error("csb_matrix_set_green_geometry: null array");
     return -1;
   }
+  m->cocg_it_valid = false;
   m->has_green_geo = m->g_weight.upload(weight, nf) && m->dofij.upload(dofij, 3*nf)
                   && m->b_face_surf.upload(b_face_surf, nb);
   m->has_corr_grad_lin = false;
@@ -827,17 +829,36 @@ int csb_matrix_set_green_geometry(csb_matrix_t *m, const csb_real_t *weight,
 int csb_matrix_set_gradient_type(csb_matrix_t *m, int imrgra)
 {
   if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
-  if (imrgra != 1 && imrgra != 4) {
-    set_error("csb_matrix_set_gradient_type: imrgra = %d is not built (1: least squares, "
-              "4: Green-Gauss with least-squares face values)", imrgra);
+  if (imrgra != 0 && imrgra != 1 && imrgra != 4) {
+    set_error("csb_matrix_set_gradient_type: imrgra = %d is not built (0: iterative "
+              "Green-Gauss, 1: least squares, 4: Green-Gauss with least-squares face values)",
+              imrgra);
     return -1;
   }
-  if (imrgra == 4 && !m->has_green_geo) {
-    set_error("csb_matrix_set_gradient_type: imrgra = 4 needs csb_matrix_set_green_geometry");
+  if (imrgra != 1 && !m->has_green_geo) {
+    set_error("csb_matrix_set_gradient_type: imrgra = %d needs csb_matrix_set_green_geometry",
+              imrgra);
     return -1;
   }
   m->imrgra = imrgra;
   return 0;
+}
+
+/* eqp->nswrgr and eqp->epsrgr of the iterative gradient (imrgra = 0): at most nswrgr - 1
+   reconstruction sweeps, stopped when the increment falls under epsrgr times the norm of the
+   initial gradient (defaults 100, 1e-4: cs_parameters.cpp:380, :394) */
+int csb_matrix_set_gradient_sweeps(csb_matrix_t *m, int nswrgr, double epsrgr)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  m->nswrgr = nswrgr;
+  m->epsrgr = epsrgr;
+  return 0;
+}
+
+/* sweeps the last iterative gradient on this matrix took (the reference's n_sweeps) */
+int csb_matrix_get_gradient_sweeps(const csb_matrix_t *m)
+{
+  return (m != nullptr) ? m->n_grad_sweeps : -1;
 }
 
 namespace {
@@ -861,6 +882,18 @@ bool hyd_check(const csb_matrix_t *m, const char *who, int hyd_p_flag, const dou
               "csb_matrix_set_face_cog", who);
     return false;
   }
+  return true;
+}
+
+/* sum of the squares of x on the device, read back */
+bool sum_sq_to_host(size_t n, const double *x, double *r)
+{
+  Context &c = ctx();
+  if (!csb::launch_dot((int)n, x, nullptr, nullptr, 1)
+      || !CSB_CUDA(cudaMemcpyAsync(c.red_out_h, c.red_out, sizeof(double), cudaMemcpyDeviceToHost,
+                                   c.stream))
+      || !CSB_CUDA(cudaStreamSynchronize(c.stream))) return false;
+  *r = c.red_out_h[0];
   return true;
 }
 
@@ -888,6 +921,33 @@ bool gradient_run(const csb_matrix_t *m, int imrgra, int inc, const double *f_ex
       return false;
     d_vf = w.val_f.p;
     if (m->has_diipb) w.d_ip = w.val_ip.p;
+  }
+  if (imrgra == 0) {
+    /* iterative Green-Gauss (_initialize_scalar_gradient + _iterative_scalar_gradient,
+       cs_gradient.cpp:1329, :1891): one reduction comes back to the host per sweep, like the
+       reference's global sum, for the convergence test */
+    if (!m->cocg_it_valid) {
+      if (!m->cocg_it.alloc(9*std::max(nr, (size_t)1)) || !csb::launch_cocg_it(m, m->cocg_it.p))
+        return false;
+      m->cocg_it_valid = true;
+    }
+    m->n_grad_sweeps = 0;
+    if (!csb::launch_green_iter_sweep(m, inc, pvar, coefa, coefb, nullptr, out)) return false;
+    if (m->nswrgr < 1 || nr < 1) return true;
+    double ss = 0.;
+    if (!sum_sq_to_host(3*nr, out, &ss)) return false;
+    const double rnorm = std::sqrt(ss);
+    if (rnorm <= 1.e-12) return true;                                  /* cs_math_epzero */
+    if (!w.work.alloc(3*nr)) return false;
+    int n_sweeps;
+    for (n_sweeps = 1; n_sweeps < m->nswrgr; n_sweeps++) {
+      if (!csb::launch_green_iter_sweep(m, inc, pvar, coefa, coefb, out, w.work.p)
+          || !sum_sq_to_host(3*nr, w.work.p, &ss)
+          || !csb::launch_green_iter_update(m, m->cocg_it.p, w.work.p, out)) return false;
+      if (std::sqrt(ss) < m->epsrgr*rnorm) break;
+    }
+    m->n_grad_sweeps = n_sweeps;
+    return true;
   }
   if (imrgra != 4)
     return csb::launch_lsq_gradient(m, m->cocg_lsq.p, inc, pvar, coefa, coefb, d_vf, d_fext, out);
@@ -954,13 +1014,18 @@ int csb_gradient_scalar_hyd(const csb_matrix_t *m, int imrgra, int inc, int hyd_
               "association, boundary faces and csb_matrix_set_face_geometry");
     return -1;
   }
-  if (imrgra != 1 && imrgra != 4) {
-    set_error("csb_gradient_scalar: imrgra = %d is not built (1: least squares, 4: Green-Gauss "
-              "with least-squares face values)", imrgra);
+  if (imrgra != 0 && imrgra != 1 && imrgra != 4) {
+    set_error("csb_gradient_scalar: imrgra = %d is not built (0: iterative Green-Gauss, 1: least "
+              "squares, 4: Green-Gauss with least-squares face values)", imrgra);
     return -1;
   }
-  if (imrgra == 4 && !m->has_green_geo) {
-    set_error("csb_gradient_scalar: imrgra = 4 needs csb_matrix_set_green_geometry");
+  if (imrgra != 1 && !m->has_green_geo) {
+    set_error("csb_gradient_scalar: imrgra = %d needs csb_matrix_set_green_geometry", imrgra);
+    return -1;
+  }
+  if (imrgra == 0 && hyd_p_flag == 1) {
+    set_error("csb_gradient_scalar: the hydrostatic pressure treatment of the iterative "
+              "gradient (imrgra = 0) is not built");
     return -1;
   }
   const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
@@ -1013,6 +1078,11 @@ int csb_diffusion_potential_hyd(const csb_matrix_t *m, int irecmf, int init, int
 {
   if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
   if (!hyd_check(m, "csb_diffusion_potential", iphydp, frcxt)) return -1;
+  if (m->imrgra == 0 && iphydp == 1) {
+    set_error("csb_diffusion_potential: the hydrostatic pressure treatment of the iterative "
+              "gradient (imrgra = 0) is not built");
+    return -1;
+  }
   if (!m->has_face_geo || m->db != 1 || m->halo != nullptr) {
     set_error("csb_diffusion_potential_rc: needs a scalar matrix on one rank with its mesh "
               "association, boundary faces and csb_matrix_set_face_geometry");
@@ -1112,6 +1182,11 @@ int csb_face_diffusion_potential_hyd(const csb_matrix_t *m, int ircflu, int init
 {
   if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
   if (ircflu && !hyd_check(m, "csb_face_diffusion_potential", iphydp, frcxt)) return -1;
+  if (ircflu && m->imrgra == 0 && iphydp == 1) {
+    set_error("csb_face_diffusion_potential: the hydrostatic pressure treatment of the "
+              "iterative gradient (imrgra = 0) is not built");
+    return -1;
+  }
   if (!m->has_mesh || m->db != 1 || m->halo != nullptr || (ircflu && !m->has_face_geo)) {
     set_error("csb_face_diffusion_potential: needs a scalar matrix on one rank with its mesh "
               "association%s", ircflu ? ", boundary faces and csb_matrix_set_face_geometry" : "");

@@ -353,6 +353,15 @@ int  csb_matrix_set_green_geometry(csb_matrix_t *m, const csb_real_t *weight,
                                    const csb_real_t *dofij, const csb_real_t *b_face_surf,
                                    const csb_real_t *corr_grad_lin);
 int  csb_matrix_set_gradient_type(csb_matrix_t *m, int imrgra);
+/* imrgra = 0, the iterative Green-Gauss gradient (CS_GRADIENT_GREEN_ITER:
+   _initialize_scalar_gradient src/alge/cs_gradient.cpp:1329-1590, _iterative_scalar_gradient
+   :1891-2300, cocg_it :1776-1860; without the hydrostatic treatment), is accepted by
+   csb_matrix_set_gradient_type and csb_gradient_scalar too; it needs the quantities of
+   csb_matrix_set_green_geometry.  csb_matrix_set_gradient_sweeps: eqp->nswrgr, eqp->epsrgr
+   (defaults 100, 1e-4); csb_matrix_get_gradient_sweeps: sweeps of the last call (the
+   reference's n_sweeps; one reduction per sweep is read by the host for the test). */
+int  csb_matrix_set_gradient_sweeps(csb_matrix_t *m, int nswrgr, double epsrgr);
+int  csb_matrix_get_gradient_sweeps(const csb_matrix_t *m);
 int  csb_gradient_scalar(const csb_matrix_t *m, int imrgra, int inc, const csb_real_t *pvar,
                          const csb_real_t *coefa, const csb_real_t *coefb, csb_real_t *grad);
 int  csb_gradient_scalar_lsq(const csb_matrix_t *m, int inc, const csb_real_t *pvar,

@@ -249,6 +249,16 @@ void   ora_gradient_green_reconstruct_hyd(int n_cells, int n_i_faces, const int 
                                           const double *pvar, const double *r_grad,
                                           const double *corr_grad_lin, double *grad);
 
+/* iterative Green-Gauss gradient (imrgra = 0); returns the number of sweeps */
+int    ora_gradient_green_iter(int n_cells, int n_i_faces, const int *i_face_cells,
+                               int n_b_faces, const int *b_face_cells, const double *weight,
+                               const double *dofij, const double *i_face_surf,
+                               const double *i_face_u_normal, const double *b_face_surf,
+                               const double *b_face_u_normal, const double *cell_vol,
+                               const double *diipb, int nswrgp, double epsrgp, int inc,
+                               const double *pvar, const double *coefa, const double *coefb,
+                               double *grad);
+
 /* cs_divergence and cs_face_diffusion_potential (grad NULL: no reconstruction) */
 void   ora_divergence(int n_cells, int n_i_faces, const int *i_face_cells, int n_b_faces,
                       const int *b_face_cells, int init, const double *i_massflux,

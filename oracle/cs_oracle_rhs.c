@@ -709,3 +709,142 @@ ora_gradient_green_reconstruct_hyd(int n_cells, int n_i_faces, const int *i_face
     }
   }
 }
+
+/* Iterative Green-Gauss gradient (imrgra = 0, CS_GRADIENT_GREEN_ITER; no hydrostatic term, no
+   weighting): _initialize_scalar_gradient (cs_gradient.cpp:1329-1590, the non-reconstructed
+   Green-Gauss gradient), then _iterative_scalar_gradient (:1891-2300): sweeps
+   rhs = -grad V + sum over faces of the reconstructed face values, grad += cocg_it (rhs / V),
+   until ||rhs / V|| < epsrgp ||grad_0|| or nswrgp - 1 sweeps; cocg_it from
+   _compute_cell_cocg_it (:1776-1860) with the Cramer inverse (cs_math.h:1587-1610).
+   diipb may be NULL (zeros).  Returns the number of sweeps done (the reference's n_sweeps). */
+int
+ora_gradient_green_iter(int n_cells, int n_i_faces, const int *i_face_cells, int n_b_faces,
+                        const int *b_face_cells, const double *weight, const double *dofij,
+                        const double *i_face_surf, const double *i_face_u_normal,
+                        const double *b_face_surf, const double *b_face_u_normal,
+                        const double *cell_vol, const double *diipb, int nswrgp, double epsrgp,
+                        int inc_i, const double *pvar, const double *coefa,
+                        const double *coefb, double *grad)
+{
+  const double inc = inc_i;
+  const size_t n3 = 3*(size_t)(n_cells > 0 ? n_cells : 1);
+  for (int i = 0; i < 3*n_cells; i++) grad[i] = 0.0;
+  for (int f = 0; f < n_i_faces; f++) {
+    const int ii = i_face_cells[2*f], jj = i_face_cells[2*f+1];
+    const double ktpond = weight[f];
+    const double pfaci = (1.0-ktpond) * (pvar[jj]-pvar[ii]) * i_face_surf[f];
+    const double pfacj =     -ktpond  * (pvar[jj]-pvar[ii]) * i_face_surf[f];
+    const double *n = i_face_u_normal + 3*(size_t)f;
+    for (int j = 0; j < 3; j++) {
+      const double fctb_ii =  pfaci * n[j];
+      const double fctb_jj = -pfacj * n[j];
+      if (ii < n_cells) grad[3*(size_t)ii+j] += fctb_ii;
+      if (jj < n_cells) grad[3*(size_t)jj+j] += fctb_jj;
+    }
+  }
+  for (int f = 0; f < n_b_faces; f++) {
+    const int ii = b_face_cells[f];
+    double pfac = inc*coefa[f] + (coefb[f]-1.0)*pvar[ii];
+    pfac *= b_face_surf[f];
+    for (int j = 0; j < 3; j++) grad[3*(size_t)ii+j] += pfac * b_face_u_normal[3*(size_t)f+j];
+  }
+  for (int c = 0; c < n_cells; c++) {
+    const double dvol = 1. / cell_vol[c];
+    for (int j = 0; j < 3; j++) grad[3*(size_t)c+j] *= dvol;
+  }
+  if (nswrgp < 1) return 0;
+
+  /* cocg_it */
+  double *cocg = malloc(sizeof(double)*3*n3);
+  for (int c = 0; c < n_cells; c++) {
+    double *a = cocg + 9*(size_t)c;
+    a[0] = 1.0; a[1] = 0.0; a[2] = 0.0; a[3] = 0.0; a[4] = 1.0; a[5] = 0.0;
+    a[6] = 0.0; a[7] = 0.0; a[8] = 1.0;
+  }
+  for (int f = 0; f < n_i_faces; f++) {
+    const int c1 = i_face_cells[2*f], c2 = i_face_cells[2*f+1];
+    const double dvol1 = (cell_vol[c1] > 0) ? 1. / cell_vol[c1] : 0.;
+    const double dvol2 = (cell_vol[c2] > 0) ? 1. / cell_vol[c2] : 0.;
+    const double pfac0 = -0.5 * i_face_surf[f];
+    for (int i = 0; i < 3; i++) {
+      const double pfac = pfac0 * dofij[3*(size_t)f+i];
+      for (int j = 0; j < 3; j++) {
+        const double vecfac = pfac*i_face_u_normal[3*(size_t)f+j];
+        if (c1 < n_cells) cocg[9*(size_t)c1+3*i+j] +=  vecfac * dvol1;
+        if (c2 < n_cells) cocg[9*(size_t)c2+3*i+j] += -vecfac * dvol2;
+      }
+    }
+  }
+  for (int c = 0; c < n_cells; c++) {
+    double (*a)[3] = (double (*)[3])(cocg + 9*(size_t)c);
+    const double a00 = a[1][1]*a[2][2] - a[2][1]*a[1][2];
+    const double a01 = a[2][1]*a[0][2] - a[0][1]*a[2][2];
+    const double a02 = a[0][1]*a[1][2] - a[1][1]*a[0][2];
+    const double a10 = a[2][0]*a[1][2] - a[1][0]*a[2][2];
+    const double a11 = a[0][0]*a[2][2] - a[2][0]*a[0][2];
+    const double a12 = a[1][0]*a[0][2] - a[0][0]*a[1][2];
+    const double a20 = a[1][0]*a[2][1] - a[2][0]*a[1][1];
+    const double a21 = a[2][0]*a[0][1] - a[0][0]*a[2][1];
+    const double a22 = a[0][0]*a[1][1] - a[1][0]*a[0][1];
+    const double det_inv = 1. / (a[0][0]*a00 + a[1][0]*a01 + a[2][0]*a02);
+    a[0][0] = a00 * det_inv; a[0][1] = a01 * det_inv; a[0][2] = a02 * det_inv;
+    a[1][0] = a10 * det_inv; a[1][1] = a11 * det_inv; a[1][2] = a12 * det_inv;
+    a[2][0] = a20 * det_inv; a[2][1] = a21 * det_inv; a[2][2] = a22 * det_inv;
+  }
+
+  double s = 0;
+  for (int i = 0; i < 3*n_cells; i++) s += grad[i]*grad[i];
+  const double rnorm = sqrt(s);
+  if (rnorm <= 1.e-12) { free(cocg); return 0; }
+
+  double *rhs = malloc(sizeof(double)*n3);
+  int n_sweeps;
+  for (n_sweeps = 1; n_sweeps < nswrgp; n_sweeps++) {
+    for (int c = 0; c < n_cells; c++)
+      for (int j = 0; j < 3; j++) rhs[3*(size_t)c+j] = -grad[3*(size_t)c+j] * cell_vol[c];
+    for (int f = 0; f < n_i_faces; f++) {
+      const int c1 = i_face_cells[2*f], c2 = i_face_cells[2*f+1];
+      const double *o = dofij + 3*(size_t)f, *g1 = grad + 3*(size_t)c1, *g2 = grad + 3*(size_t)c2;
+      double pfaci = 0.5 * (  o[0] * (g1[0]+g2[0])
+                            + o[1] * (g1[1]+g2[1])
+                            + o[2] * (g1[2]+g2[2]));
+      double pfacj = pfaci;
+      const double ktpond = weight[f];
+      pfaci += (1.0-ktpond) * (pvar[c2] - pvar[c1]);
+      pfacj -=      ktpond  * (pvar[c2] - pvar[c1]);
+      pfaci *= i_face_surf[f];
+      pfacj *= i_face_surf[f];
+      for (int j = 0; j < 3; j++) {
+        const double fctb_ii =  pfaci * i_face_u_normal[3*(size_t)f+j];
+        const double fctb_jj = -pfacj * i_face_u_normal[3*(size_t)f+j];
+        if (c1 < n_cells) rhs[3*(size_t)c1+j] += fctb_ii;
+        if (c2 < n_cells) rhs[3*(size_t)c2+j] += fctb_jj;
+      }
+    }
+    for (int f = 0; f < n_b_faces; f++) {
+      const int c = b_face_cells[f];
+      const double *g = grad + 3*(size_t)c;
+      const double ip[3] = {diipb ? diipb[3*(size_t)f] : 0., diipb ? diipb[3*(size_t)f+1] : 0.,
+                            diipb ? diipb[3*(size_t)f+2] : 0.};
+      double pfac =   coefa[f] * inc
+                    + coefb[f] * (ip[0] * g[0] + ip[1] * g[1] + ip[2] * g[2]);
+      pfac += (coefb[f] -1.0) * pvar[c];
+      pfac *= b_face_surf[f];
+      for (int ll = 0; ll < 3; ll++) rhs[3*(size_t)c+ll] += pfac * b_face_u_normal[3*(size_t)f+ll];
+    }
+    double l2 = 0.;
+    for (int c = 0; c < n_cells; c++) {
+      const double dvol = 1. / cell_vol[c];
+      double *r = rhs + 3*(size_t)c, *g = grad + 3*(size_t)c;
+      const double *a = cocg + 9*(size_t)c;
+      r[0] *= dvol; r[1] *= dvol; r[2] *= dvol;
+      l2 += r[0]*r[0] + r[1]*r[1] + r[2]*r[2];
+      g[0] += r[0] * a[0] + r[1] * a[3] + r[2] * a[6];
+      g[1] += r[0] * a[1] + r[1] * a[4] + r[2] * a[7];
+      g[2] += r[0] * a[2] + r[1] * a[5] + r[2] * a[8];
+    }
+    if (sqrt(l2) < epsrgp*rnorm) break;
+  }
+  free(cocg); free(rhs);
+  return n_sweeps;
+}

@@ -418,6 +418,22 @@ class Oracle:
             _dp(_f64(i_visc)), _dp(_f64(b_visc)), _dp(_f64(visel)), _dp(div))
         return div
 
+    def gradient_green_iter(self, s, b_face_cells, b_un, g_geo, b_face_surf, pvar, coefa, coefb,
+                            inc=1, diipb=None, nswrgr=100, epsrgr=1e-4):
+        """imrgra = 0: iterative Green-Gauss gradient; returns (grad, n_sweeps)"""
+        fc, bfc = _i32(s.face_cells), _i32(b_face_cells)
+        gg = _f64(g_geo).reshape(-1, 4)
+        grad = np.zeros(3 * s.n_rows)
+        self.lib.ora_gradient_green_iter.restype = C.c_int
+        n = self.lib.ora_gradient_green_iter(
+            C.c_int(s.n_rows), C.c_int(len(fc)), _ip(fc), C.c_int(len(bfc)), _ip(bfc),
+            _dp(_f64(gg[:, 0])), _dp(_f64(gg[:, 1:4])), _dp(_f64(s.face_surf)),
+            _dp(_f64(s.face_u_normal)), _dp(_f64(b_face_surf)), _dp(_f64(b_un)),
+            _dp(_f64(s.cell_vol)), (None if diipb is None else _dp(_f64(diipb))),
+            C.c_int(nswrgr), C.c_double(epsrgr), C.c_int(inc), _dp(_f64(pvar)),
+            _dp(_f64(coefa)), _dp(_f64(coefb)), _dp(grad))
+        return grad.reshape(-1, 3), int(n)
+
     def gradient_hyd(self, imrgra, s, b_face_cells, b_un, b_dist, i_face_cog, b_face_cog, f_ext,
                      pvar, coefa, coefb, inc=1, diipb=None, g_geo=None, b_face_surf=None,
                      corr_grad_lin=None):

@@ -940,7 +940,9 @@ csref_diffusion_potential_rc(void          *sys,
                              const double  *i_geo,        /* 7 per interior face */
                              const double  *diipb,        /* 3 per boundary face, or NULL */
                              int            imrgra,       /* 1: LSQ, 4: Green-Gauss with LSQ
-                                                             face values (global default) */
+                                                             face values (global default),
+                                                             0: iterative Green-Gauss (needs
+                                                             the quantities of 4 as well) */
                              const double  *g_geo,        /* imrgra 4: weight [1], OF [3] per
                                                              interior face */
                              const double  *b_face_surf,  /* imrgra 4: per boundary face */
@@ -1028,7 +1030,7 @@ csref_diffusion_potential_rc(void          *sys,
      surfaces and cell volumes are those of the system's mesh association */
   std::vector<cs_real_t> weight(ni1, 0.5), dofij(3*ni1, 0.), b_surf(nb1, 0.);
   int no_disable = 0;
-  if (imrgra == 4) {
+  if (imrgra == 4 || imrgra == 0) {
     for (cs_lnum_t f = 0; f < n_i_faces; f++) {
       weight[f] = g_geo[4*f];
       for (int k = 0; k < 3; k++) dofij[3*f+k] = g_geo[4*f+1+k];
@@ -1091,7 +1093,8 @@ csref_diffusion_potential_rc(void          *sys,
   if (grad_out != nullptr && ircflu) {
     /* bc.val_f was filled by cs_diffusion_potential's update of the face values */
     cs_gradient_scalar_synced_input("csref",
-                                    (imrgra == 4) ? CS_GRADIENT_GREEN_LSQ : CS_GRADIENT_LSQ,
+                                    (imrgra == 4) ? CS_GRADIENT_GREEN_LSQ
+                                    : ((imrgra == 0) ? CS_GRADIENT_GREEN_ITER : CS_GRADIENT_LSQ),
                                     CS_HALO_STANDARD, inc, eqp.nswrgr,
                                     iphydp, 1, 0, (cs_gradient_limit_t)(eqp.imligr), eqp.epsrgr,
                                     eqp.climgr, _frcxt, &bc, _pvar.data(), nullptr,

@@ -446,6 +446,38 @@ def check_rhs(ora):
             assert np.array_equal(im, g[f"{bt}{imrgra}_i_massflux"]), (N, bt, imrgra)
             assert np.array_equal(bm, g[f"{bt}{imrgra}_b_massflux"]), (N, bt, imrgra)
         m.destroy()
+    # imrgra = 0: iterative Green-Gauss gradient
+    for N in CASES:
+        g = np.load(os.path.join(GOLD, f"rhs_iter_N{N}.npz"))
+        s, bfc, b_geo, _, i_geo, f = rc_input(N)
+        g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
+        m = csb.Matrix.from_system(s)
+        m.set_boundary_faces(bfc)
+        m.set_face_geometry(i_geo[:, 6], i_geo[:, :3], i_geo[:, 3:6], b_geo[:, :3], b_geo[:, 6])
+        m.set_green_geometry(g_geo[:, 0], g_geo[:, 1:4], b_surf, cgl)
+        m.set_gradient_type(0)
+        for bt in ("p", "b"):
+            diipb = diipb_input(N, len(bfc)) if bt == "b" else None
+            m.set_boundary_iprime(diipb)
+            for inc in (1, 0):
+                gr = m.gradient(0, f["pvar"], f["coefa"], f["coefb"], inc=inc)
+                assert np.array_equal(gr, g[f"{bt}_grad_inc{inc}"]), (N, bt, inc)
+                _, ns = ora.gradient_green_iter(s, bfc, b_geo[:, :3], g_geo, b_surf, f["pvar"],
+                                                f["coefa"], f["coefb"], inc=inc, diipb=diipb)
+                assert m.gradient_sweeps() == ns, (N, bt, inc, m.gradient_sweeps(), ns)
+                for irecmf in (0, 1):
+                    d = m.diffusion_potential_rc(f["pvar"], f["coefa"], f["coefb"], f["cofaf"],
+                                                 f["cofbf"], f["i_visc"], f["b_visc"], f["visel"],
+                                                 irecmf=irecmf, inc=inc)
+                    assert np.array_equal(d, g[f"{bt}_div_irecmf{irecmf}_inc{inc}"]), \
+                        (N, bt, irecmf, inc)
+        for nsw in (1, 3):                   # sweep limit: no sweep at all, two sweeps
+            m.set_gradient_sweeps(nsw, 1e-4)
+            go, ns = ora.gradient_green_iter(s, bfc, b_geo[:, :3], g_geo, b_surf, f["pvar"],
+                                             f["coefa"], f["coefb"], diipb=diipb, nswrgr=nsw)
+            assert np.array_equal(m.gradient(0, f["pvar"], f["coefa"], f["coefb"]), go), (N, nsw)
+            assert m.gradient_sweeps() == ns == nsw
+        m.destroy()
     # imrgra = 4: Green-Gauss gradient with least-squares face values
     for N in CASES:
         g = np.load(os.path.join(GOLD, f"rhs_green_N{N}.npz"))

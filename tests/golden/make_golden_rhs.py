@@ -4,7 +4,8 @@ the reference's own compiled CPU code (oracle/_ref/libcsref.so, csref_diffusion_
 
     python tests/golden/make_golden_rhs.py   -> tests/golden/rhs_N{N}.npz, rhs_rc_N{N}.npz,
                                                 rhs_rcb_N{N}.npz, rhs_green_N{N}.npz,
-                                                rhs_face_N{N}.npz, rhs_hyd_N{N}.npz
+                                                rhs_face_N{N}.npz, rhs_hyd_N{N}.npz,
+                                                rhs_iter_N{N}.npz
 
 rhs_rc_*: the same operator WITH flux reconstruction (eqp->ircflu = 1, least-squares gradient,
 csref_diffusion_potential_rc) on a non-orthogonal variant of the cube.
@@ -17,6 +18,8 @@ rhs_face_*: cs_face_diffusion_potential (the per-face fluxes; eqp->ircflu 0 and 
 4, boundary II' given) and cs_divergence of those fluxes.
 rhs_hyd_*: the hydrostatic pressure treatment (iphydp = 1 with a seeded exterior force: what
 cs_pressure_correction hands over by default), imrgra 1 and 4, with and without boundary II'.
+rhs_iter_*: imrgra = 0, the iterative Green-Gauss gradient (default nswrgr 100, epsrgr 1e-4),
+with and without boundary II'.
 """
 import os
 import sys
@@ -114,6 +117,26 @@ def face_input(s, n_b_faces, seed=41):
 def main():
     from oracle.pyoracle import RefLib
     ref = RefLib(1)
+    for N in CASES:
+        s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
+        g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
+        h = ref.system(s)
+        out = {}
+        for bt in ("p", "b"):
+            diipb = diipb_input(N, len(bfc)) if bt == "b" else None
+            for irecmf in (0, 1):
+                for inc in (1, 0):
+                    d, g = ref.diffusion_potential_rc(
+                        h, s, bfc, b_geo, ifc, i_geo, f["pvar"], f["coefa"], f["coefb"],
+                        f["cofaf"], f["cofbf"], f["i_visc"], f["b_visc"], f["visel"],
+                        irecmf=irecmf, inc=inc, diipb=diipb, imrgra=0, g_geo=g_geo,
+                        b_face_surf=b_surf, corr_grad_lin=cgl)
+                    out[f"{bt}_div_irecmf{irecmf}_inc{inc}"] = d
+                    out[f"{bt}_grad_inc{inc}"] = g
+        ref.destroy(h)
+        path = os.path.join(ROOT, "tests", "golden", f"rhs_iter_N{N}.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path))
     for N in CASES:
         s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
         g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)

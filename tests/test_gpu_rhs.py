@@ -357,6 +357,61 @@ def test_hydrostatic_treatment_vs_oracle_larger(csb, oracle):
     m.destroy()
 
 
+@pytest.mark.parametrize("N", CASES)
+def test_iterative_green_gauss_matches_reference_golden(csb, oracle, N):
+    """imrgra = 0 (CS_GRADIENT_GREEN_ITER): gradient and reconstructed divergence bit-identical
+    to the reference, same number of sweeps as the pinned oracle; sweep limits honoured; the
+    hydrostatic form is refused"""
+    from make_golden_rhs import diipb_input, green_input, hyd_input
+    g = np.load(os.path.join(GOLD, f"rhs_iter_N{N}.npz"))
+    s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
+    g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
+    m = _rc_matrix(csb, s, bfc, b_geo, i_geo)
+    m.set_green_geometry(g_geo[:, 0], g_geo[:, 1:4], b_surf, cgl)
+    m.set_gradient_type(0)
+    for bt in ("p", "b"):
+        diipb = diipb_input(N, len(bfc)) if bt == "b" else None
+        m.set_boundary_iprime(diipb)
+        for inc in (1, 0):
+            gr = m.gradient(0, f["pvar"], f["coefa"], f["coefb"], inc=inc)
+            assert np.array_equal(gr, g[f"{bt}_grad_inc{inc}"]), (bt, inc)
+            _, ns = oracle.gradient_green_iter(s, bfc, b_geo[:, :3], g_geo, b_surf, f["pvar"],
+                                               f["coefa"], f["coefb"], inc=inc, diipb=diipb)
+            assert m.gradient_sweeps() == ns, (bt, inc)
+            for irecmf in (0, 1):
+                d = m.diffusion_potential_rc(f["pvar"], f["coefa"], f["coefb"], f["cofaf"],
+                                             f["cofbf"], f["i_visc"], f["b_visc"], f["visel"],
+                                             irecmf=irecmf, inc=inc)
+                assert np.array_equal(d, g[f"{bt}_div_irecmf{irecmf}_inc{inc}"]), (bt, irecmf, inc)
+    for nsw in (1, 3):
+        m.set_gradient_sweeps(nsw, 1e-4)
+        go, ns = oracle.gradient_green_iter(s, bfc, b_geo[:, :3], g_geo, b_surf, f["pvar"],
+                                            f["coefa"], f["coefb"], diipb=diipb, nswrgr=nsw)
+        assert np.array_equal(m.gradient(0, f["pvar"], f["coefa"], f["coefb"]), go), nsw
+        assert m.gradient_sweeps() == ns == nsw
+    m.set_face_cog(ifc, b_geo[:, 3:6])
+    with pytest.raises(csb.CsbError):
+        m.gradient_hyd(0, hyd_input(s.n_rows), f["pvar"], f["coefa"], f["coefb"])
+    m.destroy()
+
+
+def test_iterative_green_gauss_vs_oracle_larger(csb, oracle):
+    """40^3, imrgra = 0 with boundary II': bit-exact against the oracle, same sweep count"""
+    from make_golden_rhs import diipb_input, green_input
+    s, bfc, b_geo, _, i_geo, f = rc_input(40, seed=17)
+    g_geo, b_surf, cgl = green_input(40, s.n_faces, len(bfc), s.n_rows, seed=31)
+    diipb = diipb_input(40, len(bfc), seed=23)
+    m = _rc_matrix(csb, s, bfc, b_geo, i_geo)
+    m.set_green_geometry(g_geo[:, 0], g_geo[:, 1:4], b_surf, cgl)
+    m.set_boundary_iprime(diipb)
+    m.set_gradient_type(0)
+    go, ns = oracle.gradient_green_iter(s, bfc, b_geo[:, :3], g_geo, b_surf, f["pvar"],
+                                        f["coefa"], f["coefb"], diipb=diipb)
+    assert np.array_equal(m.gradient(0, f["pvar"], f["coefa"], f["coefb"]), go)
+    assert m.gradient_sweeps() == ns and 2 <= ns < 99
+    m.destroy()
+
+
 def test_reconstruction_needs_geometry(csb):
     s, bfc, _, _, _, f = rc_input(5)
     m = csb.Matrix.from_system(s)

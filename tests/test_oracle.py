@@ -1015,6 +1015,35 @@ def test_oracle_hydrostatic_treatment_matches_golden(oracle, N):
     assert np.abs(z - p).max() <= 1e-12 * np.abs(p).max()
 
 
+@pytest.mark.parametrize("N", [5, 9])
+def test_oracle_iterative_green_gauss_matches_golden(oracle, N):
+    """imrgra = 0: initial Green-Gauss gradient + reconstruction sweeps to the reference's
+    convergence test (5 to 13 sweeps here): gradient and reconstructed divergence bit-exact"""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_rhs import diipb_input, green_input, rc_input
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"rhs_iter_N{N}.npz"))
+    s, bfc, b_geo, _, i_geo, f = rc_input(N)
+    g_geo, b_surf, _ = green_input(N, s.n_faces, len(bfc), s.n_rows)
+    sweeps = set()
+    for bt in ("p", "b"):
+        diipb = diipb_input(N, len(bfc)) if bt == "b" else None
+        vip = None
+        if diipb is not None:
+            vip = oracle.b_iprime_lsq(s, bfc, b_geo[:, :3], b_geo[:, 6], diipb, f["pvar"],
+                                      f["coefa"], f["coefb"])
+        for inc in (1, 0):
+            grad, ns = oracle.gradient_green_iter(s, bfc, b_geo[:, :3], g_geo, b_surf, f["pvar"],
+                                                  f["coefa"], f["coefb"], inc=inc, diipb=diipb)
+            sweeps.add(ns)
+            assert np.array_equal(grad, g[f"{bt}_grad_inc{inc}"]), (bt, inc)
+            for irecmf in (0, 1):
+                d = oracle.diffusion_potential_rc(s, bfc, i_geo, grad, f["pvar"], f["cofaf"],
+                                                  f["cofbf"], f["i_visc"], f["b_visc"],
+                                                  f["visel"], irecmf=irecmf, inc=inc, val_ip=vip)
+                assert np.array_equal(d, g[f"{bt}_div_irecmf{irecmf}_inc{inc}"]), (bt, irecmf, inc)
+    assert min(sweeps) >= 2 and max(sweeps) < 99            # really iterated, really converged
+
+
 def test_oracle_gradient_lsq_is_exact_for_linear_fields(oracle):
     """property: a least-squares gradient reproduces the gradient of a linear field (to the
     single precision of its cocg matrices) when the boundary values are those of the field"""
