@@ -570,6 +570,11 @@ bool launch_pcg_pc_update(int n, ItState *st, const double *gk, const double *sk
    2 y = a*y + c*x, 3 y += x + b; overwrite-form prolongation (cs_grid.cpp:9180-9190) */
 bool launch_kc_vec(int mode, int n, double a, double c, const double *x, const double *b,
                    double *y);
+/* the modes 0..2 with a (and c) read from device memory; the K-cycle's inner Krylov
+   coefficients computed on the device from ctx().red_out (kernels.cu k_kc_scalars) */
+bool launch_kc_vec_d(int mode, int n, const double *pa, const double *pc, const double *x,
+                     const double *b, double *y);
+bool launch_kc_scalars(int mode, double *sc);
 bool launch_prolong_set(int f_n_rows, const int *coarse_row, const double *c_var, double *f_var);
 
 /* IPCG with a general preconditioner (cs_sles_it.cpp:1016-1203); the step length comes out of

@@ -3929,6 +3929,44 @@ k_kc_vec(int n, double a, double c, const double *__restrict__ x,
   }
 }
 
+/* the same vector operations with their coefficients read from device memory (the K-cycle's
+   inner Krylov coefficients stay on the device, see k_kc_scalars) */
+template <int MODE>
+__global__ void __launch_bounds__(TPB)
+k_kc_vec_d(int n, const double *__restrict__ pa, const double *__restrict__ pc,
+           const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ y)
+{
+  const double a = *pa, c = (pc != nullptr) ? *pc : 0.;
+  for (int i = blockIdx.x*TPB + threadIdx.x; i < n; i += gridDim.x*TPB) {
+    if (MODE == 0) y[i] = b[i] - a * x[i];
+    else if (MODE == 1) y[i] = a * y[i];
+    else y[i] = a * y[i] + c * x[i];
+  }
+}
+
+/* Coefficients of the two-step Krylov acceleration of a K-cycle level visit
+   (_multigrid_k_cycle, cs_multigrid.cpp:4300-4400) from the reductions left in red[0..2]:
+   sc = {rho1, ar1, |rt|^2, |r|^2, gamma, beta, ar1_ar2, ar2} */
+__global__ void k_kc_scalars(int mode, const double *__restrict__ red, double *sc)
+{
+  if (mode == 0) {                    /* after (v.v, v.vx, vx.rhs) */
+    const double rho1 = red[1], alpha1 = red[2];
+    sc[0] = rho1;
+    sc[1] = alpha1 / rho1;
+  }
+  else if (mode == 1) sc[2] = red[0];
+  else if (mode == 2) sc[3] = red[0];
+  else if (mode == 3) { sc[4] = red[1]; sc[5] = red[2]; }      /* gamma, beta */
+  else {                              /* after vx2.rt */
+    const double alpha2 = red[0];
+    const double rho1 = sc[0], ar1 = sc[1], gamma = sc[4], beta = sc[5];
+    const double rho2 = beta - (gamma * gamma) / rho1;
+    const double ar2 = alpha2 / rho2;
+    sc[6] = ar1 - (gamma / rho1) * ar2;
+    sc[7] = ar2;
+  }
+}
+
 /* cs_grid_prolong_row_var, overwrite form (cs_grid.cpp:9180-9190) */
 __global__ void __launch_bounds__(TPB)
 k_prolong_set(int f_n_rows, const int *__restrict__ coarse_row,
@@ -3957,6 +3995,26 @@ bool launch_kc_vec(int mode, int n, double a, double c, const double *x, const d
   default: k_kc_vec<5><<<g, TPB, 0, st>>>(n, a, c, x, b, y); break;
   }
   return post_launch("kc_vec");
+}
+
+bool launch_kc_vec_d(int mode, int n, const double *pa, const double *pc, const double *x,
+                     const double *b, double *y)
+{
+  if (n < 1) return true;
+  const int g = vec_grid(n);
+  cudaStream_t st = ctx().stream;
+  switch (mode) {
+  case 0: k_kc_vec_d<0><<<g, TPB, 0, st>>>(n, pa, pc, x, b, y); break;
+  case 1: k_kc_vec_d<1><<<g, TPB, 0, st>>>(n, pa, pc, x, b, y); break;
+  default: k_kc_vec_d<2><<<g, TPB, 0, st>>>(n, pa, pc, x, b, y); break;
+  }
+  return post_launch("kc_vec_d");
+}
+
+bool launch_kc_scalars(int mode, double *sc)
+{
+  k_kc_scalars<<<1, 1, 0, ctx().stream>>>(mode, ctx().red_out, sc);
+  return post_launch("kc_scalars");
 }
 
 bool launch_prolong_set(int f_n_rows, const int *coarse_row, const double *c_var, double *f_var)

@@ -1540,6 +1540,7 @@ struct _csb_multigrid_t {
   unsigned long long n_g_rows_min = 30;
   double  p0p1_relax = 0.95;
   double  k_cycle_threshold = 0.;      /* cs_multigrid.cpp:4707, :4724 */
+  csb::DevBuf<double> kc_scal;         /* K-cycle: 8 device scalars per level (k_kc_scalars) */
   int     n_blocks = 0;      /* 0: as many as OpenMP threads (the reference's behaviour) */
   csb_sles_it_type_t solver_type[3] = {CSB_SLES_PCG, CSB_SLES_PCG, CSB_SLES_PCG};
   int     n_max_cycles = 100;
@@ -1666,8 +1667,8 @@ bool mg_level_smooth(csb_multigrid_t *mg, int which, int level, const double *rh
                               f->m->n_rows, 1.0 / (double)mg->levels[0]->m->n_rows);
 }
 
-/* (x.x, x.y, y.z) -- or x.y / x.x alone -- on the device, result read back: the K-cycle's
-   inner Krylov coefficients decide on the host whether a second coarse visit is needed */
+/* (x.x, x.y, y.z) -- or x.y / x.x alone -- on the device, result read back (GCR's
+   Gram-Schmidt coefficients, declared above) */
 bool dots_to_host(int n, const double *x, const double *y, const double *z, int mode,
                   double r[3])
 {
@@ -1684,8 +1685,10 @@ bool dots_to_host(int n, const double *x, const double *y, const double *z, int 
    zero, residual, restriction; next level solved by the coarse solver, or by one or two
    recursive K-cycles combined by two steps of a Krylov acceleration (the second one skipped
    when ||rt|| < trsh ||r||); overwrite prolongation, residual, post-smoothing from zero, sum.
-   Kernel per phase; the three reductions of a level visit come back to the host, which
-   takes the reference's branch. */
+   Kernel per phase; the inner Krylov coefficients are computed and consumed on the device
+   (k_kc_scalars, k_kc_vec_d); one read per level visit -- the two norms of the threshold
+   test -- comes back to the host, which takes the reference's branch (none with a zero
+   threshold). */
 bool k_cycle_enqueue(csb_multigrid_t *mg, int level, double precision, double r_norm,
                      const double *rhs, double *vx)
 {
@@ -1726,33 +1729,34 @@ bool k_cycle_enqueue(csb_multigrid_t *mg, int level, double precision, double r_
     SpmvArgs sc;
     sc.m = cm; sc.x = vx_lv1; sc.y = v_lv1;
     if (!launch_spmv(EPI_STORE, sc)) return false;
-    double r[3];
-    if (!dots_to_host(c_n, v_lv1, vx_lv1, rhs_lv1, 2, r)) return false;   /* _dot_xy_yz */
-    const double rho1 = r[1], alpha1 = r[2];
-    const double ar1 = alpha1 / rho1;
-    if (!launch_kc_vec(0, c_n, ar1, 0., v_lv1, rhs_lv1, rt_lv1)) return false;
+    /* the coefficients of the inner Krylov steps stay on the device (ks, 8 doubles of this
+       level visit): only the two norms of the threshold test come back, in one read */
+    double *ks = mg->kc_scal.p + 8*(size_t)level;
+    if (!launch_dot(c_n, v_lv1, vx_lv1, rhs_lv1, 2) || !launch_kc_scalars(0, ks)) /* _dot_xy_yz */
+      return false;
+    if (!launch_kc_vec_d(0, c_n, ks + 1, nullptr, v_lv1, rhs_lv1, rt_lv1)) return false;
     double rt_lv1_norm = 1.0, r_lv1_norm = 0.0;
     if (trsh > 0) {                                                         /* _dot_xx_yy */
-      if (!dots_to_host(c_n, rt_lv1, nullptr, nullptr, 1, r)) return false;
-      rt_lv1_norm = r[0];
-      if (!dots_to_host(c_n, rhs_lv1, nullptr, nullptr, 1, r)) return false;
-      r_lv1_norm = r[0];
+      Context &c = ctx();
+      if (!launch_dot(c_n, rt_lv1, nullptr, nullptr, 1) || !launch_kc_scalars(1, ks)
+          || !launch_dot(c_n, rhs_lv1, nullptr, nullptr, 1) || !launch_kc_scalars(2, ks)
+          || !CSB_CUDA(cudaMemcpyAsync(c.red_out_h, ks + 2, 2*sizeof(double),
+                                       cudaMemcpyDeviceToHost, c.stream))
+          || !CSB_CUDA(cudaStreamSynchronize(c.stream))) return false;
+      rt_lv1_norm = c.red_out_h[0];
+      r_lv1_norm = c.red_out_h[1];
     }
     if (rt_lv1_norm < trsh * trsh * r_lv1_norm) {
-      if (!launch_kc_vec(1, c_n, ar1, 0., nullptr, nullptr, vx_lv1)) return false;
+      if (!launch_kc_vec_d(1, c_n, ks + 1, nullptr, nullptr, nullptr, vx_lv1)) return false;
     }
     else {
       if (!k_cycle_enqueue(mg, level + 1, precision, r_norm, rt_lv1, vx2_lv1)) return false;
       sc.x = vx2_lv1; sc.y = w_lv1;
       if (!launch_spmv(EPI_STORE, sc)) return false;
-      if (!dots_to_host(c_n, v_lv1, vx2_lv1, w_lv1, 2, r)) return false;   /* _dot_xu_xv_xw */
-      const double gamma = r[1], beta = r[2];
-      if (!dots_to_host(c_n, vx2_lv1, rt_lv1, nullptr, 0, r)) return false;
-      const double alpha2 = r[0];
-      const double rho2 = beta - (gamma * gamma) / rho1;
-      const double ar2 = alpha2 / rho2;
-      const double ar1_ar2 = ar1 - (gamma / rho1) * ar2;
-      if (!launch_kc_vec(2, c_n, ar1_ar2, ar2, vx2_lv1, nullptr, vx_lv1)) return false;
+      if (!launch_dot(c_n, v_lv1, vx2_lv1, w_lv1, 2) || !launch_kc_scalars(3, ks)  /* _dot_xu_xv_xw */
+          || !launch_dot(c_n, vx2_lv1, rt_lv1, nullptr, 0) || !launch_kc_scalars(4, ks))
+        return false;
+      if (!launch_kc_vec_d(2, c_n, ks + 6, ks + 7, vx2_lv1, nullptr, vx_lv1)) return false;
     }
   }
 
@@ -2669,6 +2673,7 @@ void csb_multigrid_setup(void *context, const char *name, const csb_matrix_t *a,
     if (kcycle) {
       lv->kstride = work_stride_of((size_t)m->n_cols_ext);
       if (!lv->kwork.alloc(10*lv->kstride)) return;
+      if (l == 0 && !mg->kc_scal.alloc(8*(size_t)n_levels)) return;
     }
     if (l > 0) {
       if (!lv->rhs.alloc((size_t)m->n_cols_ext) || !lv->vx.alloc((size_t)m->n_cols_ext)) return;
