@@ -639,6 +639,8 @@ int csb_matrix_set_mesh_association(csb_matrix_t *m, csb_lnum_t n_faces,
     set_error("csb_matrix_set_mesh_association: all arrays are required");
     return -1;
   }
+  if (m->has_mesh && n_faces != m->n_faces)      /* per-face geometry no longer matches */
+    m->has_face_geo = m->has_green_geo = m->has_diipb = m->has_face_cog = false;
   m->n_faces = n_faces;
   bool ok = (own_c2f || (m->c2f.upload(c2f, (size_t)m->nnz)
                          && m->c2f_sgn.upload(c2f_sgn, (size_t)m->nnz)))
@@ -1261,6 +1263,11 @@ int csb_matrix_set_boundary_faces(csb_matrix_t *m, csb_lnum_t n_b_faces,
   {
     std::vector<csb_lnum_t> fill(idx.begin(), idx.end() - 1);
     for (csb_lnum_t f = 0; f < n_b_faces; f++) ids[(size_t)fill[bfc[f]]++] = f;   /* ascending */
+  }
+  if (n_b_faces != m->n_b_faces || !m->has_b_faces) {
+    /* per-boundary-face geometry given earlier no longer matches: to be given again */
+    m->has_face_geo = m->has_green_geo = m->has_diipb = m->has_face_cog = false;
+    m->cocg_valid = false;
   }
   m->n_b_faces = n_b_faces;
   bool ok = m->cell_b_faces_idx.upload(idx.data(), idx.size())
