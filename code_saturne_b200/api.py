@@ -769,6 +769,13 @@ class Matrix:
         if L.csb_matrix_set_gradient_type(self.handle, int(imrgra)) != 0:
             _err("csb_matrix_set_gradient_type")
 
+    def set_gradient_limiter(self, imligr=-1, climgr=-1., b_rc_clip_factor=1.):
+        L = load_library()
+        L.csb_matrix_set_gradient_limiter.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+        if L.csb_matrix_set_gradient_limiter(self.handle, int(imligr), float(climgr),
+                                             float(b_rc_clip_factor)) != 0:
+            _err("csb_matrix_set_gradient_limiter")
+
     def set_gradient_sweeps(self, nswrgr=100, epsrgr=1e-4):
         L = load_library()
         L.csb_matrix_set_gradient_sweeps.argtypes = [C.c_void_p, C.c_int, C.c_double]

@@ -393,6 +393,10 @@ struct _csb_matrix_t {
      cs_parameters.cpp:380, :394), cached cocg_it, sweeps of the last call */
   int         nswrgr = 100;
   double      epsrgr = 1.e-4;
+  /* gradient limiter: eqp->imligr (-1: none), eqp->climgr, eqp->b_rc_clip_factor (the
+     limiter of the values at I' of the boundary faces, on when imligr >= 0) */
+  int         imligr = -1;
+  double      climgr = -1., b_rc_clip_factor = 1.;
   mutable csb::DevBuf<double> cocg_it;
   mutable bool cocg_it_valid = false;
   mutable int  n_grad_sweeps = 0;
@@ -667,7 +671,12 @@ bool launch_lsq_cocg(const _csb_matrix_t *m, float *cocg);
    val_f, or nullptr for inc*coefa + coefb*pvar. */
 bool launch_b_iprime_lsq(const _csb_matrix_t *m, int inc, const double *pvar,
                          const double *coefa, const double *coefb, const double *f_ext,
-                         double *val_ip, double *val_f);
+                         double clip_coeff, double *val_ip, double *val_f);
+/* gradient limiter (_scalar_gradient_clipping, cs_gradient.cpp:808-1215; clip_mode 0 / 1 / 2)
+   applied to grad in place; val_f nullptr: inc*coefa + coefb*pvar; work: 2 n_rows doubles */
+bool launch_gradient_clip(const _csb_matrix_t *m, int clip_mode, double climgp, int inc,
+                          const double *pvar, const double *coefa, const double *coefb,
+                          const double *val_f, double *grad, double *work);
 bool launch_lsq_gradient(const _csb_matrix_t *m, const float *cocg, int inc, const double *pvar,
                          const double *coefa, const double *coefb, const double *val_f,
                          const double *f_ext, double *grad);

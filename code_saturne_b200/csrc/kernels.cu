@@ -2615,7 +2615,7 @@ __global__ void k_b_iprime_lsq(int n_rows, const int *__restrict__ row_index,
                                const double *__restrict__ diipb,
                                const double *__restrict__ i_face_cog,
                                const double *__restrict__ b_face_cog,
-                               const double *__restrict__ f_ext, int inc,
+                               const double *__restrict__ f_ext, double clip_coeff, int inc,
                                const double *__restrict__ pvar,
                                const double *__restrict__ coefa,
                                const double *__restrict__ coefb, double *val_ip, double *val_f)
@@ -2639,11 +2639,16 @@ __global__ void k_b_iprime_lsq(int n_rows, const int *__restrict__ row_index,
       if (!(ip[0]*ip[0] + ip[1]*ip[1] + ip[2]*ip[2] < (bd*bd) * (1e-3 * 1e-3))) any = true;
     }
   double gx = 0., gy = 0., gz = 0.;
+  /* bounds of the simple limiter (:612-628; clip_coeff < 0: none): the cell's, its neighbours'
+     and its boundary faces' unreconstructed values */
+  double var_min = var_i, var_max = var_i;
   if (any) {
     float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     double r0 = 0., r1 = 0., r2 = 0.;
     for (int k = row_index[c]; k < row_index[c+1]; k++) {
       const size_t j = (size_t)col_id[k];
+      var_min = fmin(var_min, pvar[j]);
+      var_max = fmax(var_max, pvar[j]);
       const double cj[3] = {cell_cen[3*j], cell_cen[3*j+1], cell_cen[3*j+2]};
       const double d0 = cj[0] - cen[0], d1 = cj[1] - cen[1], d2 = cj[2] - cen[2];
       const double ddc = 1. / (d0*d0 + d1*d1 + d2*d2);
@@ -2683,6 +2688,14 @@ __global__ void k_b_iprime_lsq(int n_rows, const int *__restrict__ row_index,
       }
       pfac *= ddif;
       r0 += d0 * pfac; r1 += d1 * pfac; r2 += d2 * pfac;
+      const double var_f = a + b*var_i;
+      var_min = fmin(var_min, var_f);
+      var_max = fmax(var_max, var_f);
+    }
+    if (clip_coeff >= 0 && (clip_coeff < 1. || clip_coeff > 1.)) {
+      const double d_min = var_min - var_i, d_max = var_max - var_i;
+      var_min = var_i + d_min*clip_coeff;
+      var_max = var_i + d_max*clip_coeff;
     }
     const double a00 = (double)(g[1]*g[2] - g[4]*g[4]);
     const double a01 = (double)(g[4]*g[5] - g[3]*g[2]);
@@ -2706,6 +2719,10 @@ __global__ void k_b_iprime_lsq(int n_rows, const int *__restrict__ row_index,
       if (!(ip[0]*ip[0] + ip[1]*ip[1] + ip[2]*ip[2] < (bd*bd) * (1e-3 * 1e-3))) {
         const double grad_dot_diipb = gx*ip[0] + gy*ip[1] + gz*ip[2];
         vip = var_i + grad_dot_diipb;
+        if (clip_coeff >= 0) {
+          if (vip < var_min) vip = var_min;
+          if (vip > var_max) vip = var_max;
+        }
       }
     }
     val_ip[f] = vip;
@@ -3063,6 +3080,107 @@ __global__ void k_green_iter_update(int n_rows, const double *__restrict__ cocg_
   g[2] += r[0] * a[2] + r[1] * a[5] + r[2] * a[8];
 }
 
+/* _scalar_gradient_clipping (cs_gradient.cpp:808-1215), standard neighbourhood.
+   k_grad_clip_factor -- mode 0 (CS_GRADIENT_LIMIT_CELL): factor of the cell from its own
+   gradient; 1 (_FACE): the same with the mean gradient of the two cells, written to `factor`
+   for k_grad_clip_face_min (the smallest factor of the cell and its neighbours,
+   _gradient_update_face_clip_factor :691-758); 2 (_CELL_RC): values reconstructed at I' / J'
+   of the cell's interior faces kept within climgp times the range of the neighbouring cell
+   values and boundary face values.  Maxima and minima only: no summation order to keep. */
+__global__ void k_grad_clip_factor(int mode, int n_rows, const int *__restrict__ row_index,
+                                   const int *__restrict__ col_id, const int *__restrict__ c2f,
+                                   const short *__restrict__ c2f_sgn,
+                                   const int *__restrict__ cell_b_faces_idx,
+                                   const int *__restrict__ cell_b_faces,
+                                   const double *__restrict__ cell_cen,
+                                   const double *__restrict__ diipf,
+                                   const double *__restrict__ djjpf, double climgp, int inc,
+                                   const double *__restrict__ pvar,
+                                   const double *__restrict__ coefa,
+                                   const double *__restrict__ coefb,
+                                   const double *__restrict__ val_f,
+                                   const double *__restrict__ grad, double *out)
+{
+  const int c = blockIdx.x*blockDim.x + threadIdx.x;
+  if (c >= n_rows) return;
+  const int s = row_index[c], e = row_index[c+1];
+  const double pc = pvar[c];
+  const double g0 = grad[3*(size_t)c], g1 = grad[3*(size_t)c+1], g2 = grad[3*(size_t)c+2];
+  if (mode == 0 || mode == 1) {
+    double denum = 0, denom = 0;
+    for (int k = s; k < e; k++) {
+      const size_t j = (size_t)col_id[k];
+      const double d0 = cell_cen[3*(size_t)c] - cell_cen[3*j],
+                   d1 = cell_cen[3*(size_t)c+1] - cell_cen[3*j+1],
+                   d2 = cell_cen[3*(size_t)c+2] - cell_cen[3*j+2];
+      double dist1;
+      if (mode == 0)
+        dist1 = fabs(d0*g0 + d1*g1 + d2*g2);
+      else {
+        const double m0 = g0 + grad[3*j], m1 = g1 + grad[3*j+1], m2 = g2 + grad[3*j+2];
+        dist1 = 0.5 * fabs(d0*m0 + d1*m1 + d2*m2);
+      }
+      const double dvar = fabs(pc - pvar[j]);
+      denum = fmax(denum, dist1);
+      denom = fmax(denom, dvar);
+    }
+    double factor1 = 1.;
+    if (denum > climgp * denom) factor1 = climgp * denom/denum;
+    out[c] = factor1;
+    return;
+  }
+  double v_min = pc, v_max = pc;
+  for (int k = s; k < e; k++) {
+    const double pj = pvar[col_id[k]];
+    v_min = fmin(v_min, pj);
+    v_max = fmax(v_max, pj);
+  }
+  if (cell_b_faces_idx != nullptr)
+    for (int k = cell_b_faces_idx[c]; k < cell_b_faces_idx[c+1]; k++) {
+      const int f = cell_b_faces[k];
+      const double vf = (val_f != nullptr) ? val_f[f] : inc*coefa[f] + coefb[f]*pc;
+      v_min = fmin(v_min, vf);
+      v_max = fmax(v_max, vf);
+    }
+  v_min = (v_min - pc) * climgp;
+  v_max = (v_max - pc) * climgp;
+  double ccf = 1.;
+  for (int k = s; k < e; k++) {
+    const double *dkkpf = ((c2f_sgn[k] > 0) ? diipf : djjpf) + 3*(size_t)c2f[k];
+    double sub_factor = 1.;
+    const double v_r = dkkpf[0]*g0 + dkkpf[1]*g1 + dkkpf[2]*g2;
+    if (v_r < v_min)
+      sub_factor = fabs(v_min) / fabs(v_r);
+    else if (v_r > v_max)
+      sub_factor = fabs(v_max) / fabs(v_r);
+    ccf = fmin(ccf, sub_factor);
+  }
+  out[c] = ccf;
+}
+
+__global__ void k_grad_clip_face_min(int n_rows, const int *__restrict__ row_index,
+                                     const int *__restrict__ col_id,
+                                     const double *__restrict__ factor, double *clip_factor)
+{
+  const int c = blockIdx.x*blockDim.x + threadIdx.x;
+  if (c >= n_rows) return;
+  double l_min_factor = factor[c];
+  for (int k = row_index[c]; k < row_index[c+1]; k++)
+    l_min_factor = fmin(l_min_factor, factor[col_id[k]]);
+  clip_factor[c] = fmin(1., l_min_factor);
+}
+
+__global__ void k_grad_clip_apply(int n_rows, const double *__restrict__ clip_factor,
+                                  double *grad)
+{
+  const int c = blockIdx.x*blockDim.x + threadIdx.x;
+  if (c >= n_rows) return;
+  const double factor1 = clip_factor[c];
+  if (factor1 < 1) {
+    grad[3*(size_t)c] *= factor1; grad[3*(size_t)c+1] *= factor1; grad[3*(size_t)c+2] *= factor1;
+  }
+}
+
 /* cs_diffusion_potential with flux reconstruction (:8921-8961): the face flux is computed in
    the face's orientation by both of its cells, identically */
 __global__ void k_diffusion_potential_rc(int n_rows, const int *__restrict__ row_index,
@@ -3139,13 +3257,13 @@ bool launch_lsq_cocg(const _csb_matrix_t *m, float *cocg)
 
 bool launch_b_iprime_lsq(const _csb_matrix_t *m, int inc, const double *pvar,
                          const double *coefa, const double *coefb, const double *f_ext,
-                         double *val_ip, double *val_f)
+                         double clip_coeff, double *val_ip, double *val_f)
 {
   if (m->n_rows < 1 || !m->has_b_faces || m->n_b_faces < 1) return true;
   k_b_iprime_lsq<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(
     m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, m->cell_cen.p, m->cell_b_faces_idx.p,
     m->cell_b_faces.p, m->b_face_u_normal.p, m->b_dist.p, m->has_diipb ? m->diipb.p : nullptr,
-    m->i_face_cog.p, m->b_face_cog.p, f_ext, inc, pvar, coefa, coefb, val_ip, val_f);
+    m->i_face_cog.p, m->b_face_cog.p, f_ext, clip_coeff, inc, pvar, coefa, coefb, val_ip, val_f);
   return post_launch("b_iprime_lsq");
 }
 
@@ -3198,6 +3316,30 @@ bool launch_green_iter_update(const _csb_matrix_t *m, const double *cocg_it, con
   k_green_iter_update<<<(m->n_rows + 127)/128, 128, 0, ctx().stream>>>(m->n_rows, cocg_it, rhs,
                                                                        grad);
   return post_launch("green_iter_update");
+}
+
+/* gradient limiter applied to grad in place; work: 2 n_rows doubles */
+bool launch_gradient_clip(const _csb_matrix_t *m, int clip_mode, double climgp, int inc,
+                          const double *pvar, const double *coefa, const double *coefb,
+                          const double *val_f, double *grad, double *work)
+{
+  if (m->n_rows < 1 || clip_mode < 0 || climgp < 0) return true;
+  const bool bnd = (m->has_b_faces && m->n_b_faces > 0);
+  const int g = (m->n_rows + 127)/128;
+  double *clip_factor = work, *factor = work + m->n_rows;
+  k_grad_clip_factor<<<g, 128, 0, ctx().stream>>>(
+    clip_mode, m->n_rows, m->row_index.p, m->col_id.p, m->c2f.p, m->c2f_sgn.p,
+    bnd ? m->cell_b_faces_idx.p : nullptr, bnd ? m->cell_b_faces.p : nullptr, m->cell_cen.p,
+    m->diipf.p, m->djjpf.p, climgp, inc, pvar, coefa, coefb, val_f, grad,
+    (clip_mode == 1) ? factor : clip_factor);
+  if (!post_launch("grad_clip_factor")) return false;
+  if (clip_mode == 1) {
+    k_grad_clip_face_min<<<g, 128, 0, ctx().stream>>>(m->n_rows, m->row_index.p, m->col_id.p,
+                                                      factor, clip_factor);
+    if (!post_launch("grad_clip_face_min")) return false;
+  }
+  k_grad_clip_apply<<<g, 128, 0, ctx().stream>>>(m->n_rows, clip_factor, grad);
+  return post_launch("grad_clip_apply");
 }
 
 bool launch_divergence(const _csb_matrix_t *m, int init, const double *i_massflux,

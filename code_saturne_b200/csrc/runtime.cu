@@ -857,6 +857,26 @@ int csb_matrix_set_gradient_sweeps(csb_matrix_t *m, int nswrgr, double epsrgr)
   return 0;
 }
 
+/* Gradient limiter: eqp->imligr (-1 none -- the default --, 0 CS_GRADIENT_LIMIT_CELL, 1 _FACE,
+   2 _CELL_RC; _scalar_gradient_clipping, cs_gradient.cpp:808-1215, standard neighbourhood),
+   eqp->climgr (its factor; < 0: none) and eqp->b_rc_clip_factor (limiter of the values at I'
+   of the boundary faces, cs_gradient_boundary.cpp:612-628, active when imligr >= 0; the
+   reference's default is 1) */
+int csb_matrix_set_gradient_limiter(csb_matrix_t *m, int imligr, double climgr,
+                                    double b_rc_clip_factor)
+{
+  if (m == nullptr) { set_error("The matrix is not defined."); return -1; }
+  if (imligr < -1 || imligr > 2) {
+    set_error("csb_matrix_set_gradient_limiter: imligr = %d (-1: none, 0: cell, 1: face, "
+              "2: cell, values at I' / J')", imligr);
+    return -1;
+  }
+  m->imligr = imligr;
+  m->climgr = climgr;
+  m->b_rc_clip_factor = b_rc_clip_factor;
+  return 0;
+}
+
 /* sweeps the last iterative gradient on this matrix took (the reference's n_sweeps) */
 int csb_matrix_get_gradient_sweeps(const csb_matrix_t *m)
 {
@@ -868,7 +888,7 @@ namespace {
    matrix holds II' of its boundary faces or the hydrostatic treatment is on), the
    least-squares gradient the Green-Gauss pass reconstructs from, the staged exterior force */
 struct GradWork {
-  csb::DevBuf<double> val_ip, val_f, work, fext;
+  csb::DevBuf<double> val_ip, val_f, work, fext, clip;
   const double *d_ip = nullptr;     /* for the boundary fluxes; nullptr: the cell value */
 };
 
@@ -899,6 +919,10 @@ bool sum_sq_to_host(size_t n, const double *x, double *r)
   return true;
 }
 
+bool gradient_compute(const csb_matrix_t *m, int imrgra, int inc, const double *d_fext,
+                      const double *d_vf, const double *pvar, const double *coefa,
+                      const double *coefb, double *out, GradWork &w);
+
 /* boundary values, then the least-squares gradient into `out`, or -- imrgra 4 -- into a work
    array followed by the Green-Gauss reconstruction into `out`; f_ext (host or device,
    [n_rows][3]) non-null = hyd_p_flag 1 */
@@ -919,11 +943,27 @@ bool gradient_run(const csb_matrix_t *m, int imrgra, int inc, const double *f_ex
   w.d_ip = nullptr;
   if (bnd && (m->has_diipb || d_fext != nullptr)) {
     if (!w.val_ip.alloc(nb) || !w.val_f.alloc(nb)
-        || !csb::launch_b_iprime_lsq(m, inc, pvar, coefa, coefb, d_fext, w.val_ip.p, w.val_f.p))
+        || !csb::launch_b_iprime_lsq(m, inc, pvar, coefa, coefb, d_fext,
+                                     (m->imligr < 0) ? -1. : m->b_rc_clip_factor, w.val_ip.p,
+                                     w.val_f.p))
       return false;
     d_vf = w.val_f.p;
     if (m->has_diipb) w.d_ip = w.val_ip.p;
   }
+  if (!gradient_compute(m, imrgra, inc, d_fext, d_vf, pvar, coefa, coefb, out, w)) return false;
+  /* limiter of the cell gradient, whatever its type (cs_gradient.cpp:7812-7822) */
+  if (m->imligr >= 0 && m->climgr >= 0 && nr > 0)
+    return w.clip.alloc(2*nr)
+        && csb::launch_gradient_clip(m, m->imligr, m->climgr, inc, pvar, coefa, coefb, d_vf, out,
+                                     w.clip.p);
+  return true;
+}
+
+bool gradient_compute(const csb_matrix_t *m, int imrgra, int inc, const double *d_fext,
+                      const double *d_vf, const double *pvar, const double *coefa,
+                      const double *coefb, double *out, GradWork &w)
+{
+  const size_t nr = (size_t)m->n_rows;
   if (imrgra == 0) {
     /* iterative Green-Gauss (_initialize_scalar_gradient + _iterative_scalar_gradient,
        cs_gradient.cpp:1329, :1891): one reduction comes back to the host per sweep, like the

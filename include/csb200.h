@@ -360,6 +360,13 @@ int  csb_matrix_set_gradient_type(csb_matrix_t *m, int imrgra);
    csb_matrix_set_green_geometry.  csb_matrix_set_gradient_sweeps: eqp->nswrgr, eqp->epsrgr
    (defaults 100, 1e-4); csb_matrix_get_gradient_sweeps: sweeps of the last call (the
    reference's n_sweeps; one reduction per sweep is read by the host for the test). */
+/* csb_matrix_set_gradient_limiter: eqp->imligr (-1 none, the default; 0 / 1 / 2 =
+   CS_GRADIENT_LIMIT_CELL / _FACE / _CELL_RC: _scalar_gradient_clipping, :808-1215, standard
+   neighbourhood), eqp->climgr and eqp->b_rc_clip_factor (limiter of the values at I' of the
+   boundary faces, src/alge/cs_gradient_boundary.cpp:612-628, active when imligr >= 0;
+   reference default 1).  Applies to every gradient type and to the operators built on them. */
+int  csb_matrix_set_gradient_limiter(csb_matrix_t *m, int imligr, double climgr,
+                                     double b_rc_clip_factor);
 int  csb_matrix_set_gradient_sweeps(csb_matrix_t *m, int nswrgr, double epsrgr);
 int  csb_matrix_get_gradient_sweeps(const csb_matrix_t *m);
 int  csb_gradient_scalar(const csb_matrix_t *m, int imrgra, int inc, const csb_real_t *pvar,

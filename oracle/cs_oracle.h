@@ -193,8 +193,8 @@ void   ora_diffusion_potential_rc(int n_cells, int n_i_faces, const int *i_face_
 void   ora_b_iprime_lsq(int n_cells, const int *row_index, const int *col_id, int n_b_faces,
                         const int *b_face_cells, const double *cell_cen,
                         const double *b_face_u_normal, const double *b_dist,
-                        const double *diipb, const double *pvar, const double *coefa,
-                        const double *coefb, double *val_ip);
+                        const double *diipb, double clip_coeff, const double *pvar,
+                        const double *coefa, const double *coefb, double *val_ip);
 void   ora_gradient_lsq_b(int n_cells, const int *row_index, const int *col_id, int n_i_faces,
                           const int *i_face_cells, int n_b_faces, const int *b_face_cells,
                           const double *cell_cen, const double *b_face_u_normal,
@@ -228,9 +228,9 @@ void   ora_b_face_values_hyd(int n_cells, const int *row_index, const int *col_i
                              const double *cell_cen, const double *b_face_u_normal,
                              const double *b_dist, const double *diipb,
                              const double *i_face_cog, const double *b_face_cog,
-                             const double *f_ext, int inc, const double *pvar,
-                             const double *coefa, const double *coefb, double *val_ip,
-                             double *val_f);
+                             const double *f_ext, double clip_coeff, int inc,
+                             const double *pvar, const double *coefa, const double *coefb,
+                             double *val_ip, double *val_f);
 void   ora_gradient_lsq_hyd(int n_cells, const int *row_index, const int *col_id, int n_i_faces,
                             const int *i_face_cells, int n_b_faces, const int *b_face_cells,
                             const double *cell_cen, const double *b_face_u_normal,
@@ -248,6 +248,12 @@ void   ora_gradient_green_reconstruct_hyd(int n_cells, int n_i_faces, const int 
                                           const double *f_ext, const double *val_f,
                                           const double *pvar, const double *r_grad,
                                           const double *corr_grad_lin, double *grad);
+
+/* gradient limiter (eqp->imligr 0 / 1 / 2 with the factor climgr), applied to grad in place */
+void   ora_gradient_clip(int n_cells, const int *row_index, const int *col_id, const int *c2f,
+                         const short *c2f_sgn, int n_b_faces, const int *b_face_cells,
+                         const double *cell_cen, const double *i_geo, int clip_mode,
+                         double climgp, const double *pvar, const double *val_f, double *grad);
 
 /* iterative Green-Gauss gradient (imrgra = 0); returns the number of sweeps */
 int    ora_gradient_green_iter(int n_cells, int n_i_faces, const int *i_face_cells,

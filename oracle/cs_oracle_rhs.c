@@ -90,6 +90,28 @@ _gauss_inverse_6f(float a[6])
   a[3] = b[0][1]; a[4] = b[1][2]; a[5] = b[0][2];
 }
 
+/* simple limiter of the value at I' (cs_gradient_boundary.cpp:612-628): kept between the
+   smallest and largest of the cell's, its neighbours' and its boundary faces' unreconstructed
+   values, the bounds stretched around the cell value by clip_coeff; none if clip_coeff < 0
+   (b_rc_clip_factor, on with eqp->imligr >= 0) */
+static double
+_clip_ip(double var_ip, double var_i, double var_min, double var_max, double clip_coeff)
+{
+  if (clip_coeff >= 0) {
+    if (clip_coeff < 1. || clip_coeff > 1.) {
+      const double d_min = var_min - var_i;
+      const double d_max = var_max - var_i;
+      var_min = var_i + d_min*clip_coeff;
+      var_max = var_i + d_max*clip_coeff;
+    }
+    if (var_ip < var_min)
+      var_ip = var_min;
+    if (var_ip > var_max)
+      var_ip = var_max;
+  }
+  return var_ip;
+}
+
 /* direction of a boundary face in the least-squares system, B_DIRECTION_LSQ = CS_IPRIME_F_LSQ
    (cs_gradient.h:55): n + II'/b_dist (cs_gradient.cpp:2632-2636, :2880-2885) */
 static void
@@ -116,7 +138,8 @@ void
 ora_b_iprime_lsq(int n_cells, const int *row_index, const int *col_id, int n_b_faces,
                  const int *b_face_cells, const double *cell_cen,
                  const double *b_face_u_normal, const double *b_dist, const double *diipb,
-                 const double *pvar, const double *coefa, const double *coefb, double *val_ip)
+                 double clip_coeff, const double *pvar, const double *coefa,
+                 const double *coefb, double *val_ip)
 {
   /* cell -> boundary faces, ascending (cs_mesh_adjacencies.cpp:705-760) */
   int *idx = calloc((size_t)n_cells + 2, sizeof(int));
@@ -136,8 +159,11 @@ ora_b_iprime_lsq(int n_cells, const int *row_index, const int *col_id, int n_b_f
     float cocg[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     double rhs[3] = {0., 0., 0.};
     const double var_i = pvar[c_id];
+    double var_min = var_i, var_max = var_i;
     for (int k = row_index[c_id]; k < row_index[c_id+1]; k++) {
       const int c1 = col_id[k];
+      var_min = fmin(var_min, pvar[c1]);
+      var_max = fmax(var_max, pvar[c1]);
       double dc[3];
       for (int ll = 0; ll < 3; ll++)
         dc[ll] = cell_cen[3*(size_t)c1+ll] - cell_cen[3*(size_t)c_id+ll];
@@ -169,6 +195,9 @@ ora_b_iprime_lsq(int n_cells, const int *row_index, const int *col_id, int n_b_f
       double pfac = (a + (b-1.)*var_i);
       pfac *= ddif;
       for (int ll = 0; ll < 3; ll++) rhs[ll] += dif[ll] * pfac;
+      const double var_f = a + b*var_i;        /* unreconstructed value, for the limiter */
+      var_min = fmin(var_min, var_f);
+      var_max = fmax(var_max, var_f);
     }
     /* cofactors: float operands, float arithmetic (the products are cs_cocg_t * cs_cocg_t) */
     const double a00 = cocg[1]*cocg[2] - cocg[4]*cocg[4];
@@ -183,7 +212,7 @@ ora_b_iprime_lsq(int n_cells, const int *row_index, const int *col_id, int n_b_f
     g[1] = (a01 * rhs[0] + a11 * rhs[1] + a12 * rhs[2]) * det_inv;
     g[2] = (a02 * rhs[0] + a12 * rhs[1] + a22 * rhs[2]) * det_inv;
     const double grad_dot_diipb = g[0]*ip[0] + g[1]*ip[1] + g[2]*ip[2];
-    val_ip[f_id] = var_i + grad_dot_diipb;
+    val_ip[f_id] = _clip_ip(var_i + grad_dot_diipb, var_i, var_min, var_max, clip_coeff);
   }
   free(idx); free(ids);
 }
@@ -470,8 +499,8 @@ ora_b_face_values_hyd(int n_cells, const int *row_index, const int *col_id, cons
                       int n_b_faces, const int *b_face_cells, const double *cell_cen,
                       const double *b_face_u_normal, const double *b_dist, const double *diipb,
                       const double *i_face_cog, const double *b_face_cog, const double *f_ext,
-                      int inc, const double *pvar, const double *coefa, const double *coefb,
-                      double *val_ip, double *val_f)
+                      double clip_coeff, int inc, const double *pvar, const double *coefa,
+                      const double *coefb, double *val_ip, double *val_f)
 {
   int *idx = calloc((size_t)n_cells + 2, sizeof(int));
   int *ids = malloc(sizeof(int)*(size_t)(n_b_faces > 0 ? n_b_faces : 1));
@@ -489,8 +518,11 @@ ora_b_face_values_hyd(int n_cells, const int *row_index, const int *col_id, cons
     if (!(ip[0]*ip[0] + ip[1]*ip[1] + ip[2]*ip[2] < (b_dist[f_id]*b_dist[f_id]) * eps_r_2)) {
       float cocg[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       double rhs[3] = {0., 0., 0.};
+      double var_min = var_i, var_max = var_i;
       for (int k = row_index[c_id]; k < row_index[c_id+1]; k++) {
         const int c1 = col_id[k];
+        var_min = fmin(var_min, pvar[c1]);
+        var_max = fmax(var_max, pvar[c1]);
         const double *cen1 = cell_cen + 3*(size_t)c1;
         double dc[3];
         for (int ll = 0; ll < 3; ll++) dc[ll] = cen1[ll] - cen[ll];
@@ -528,6 +560,9 @@ ora_b_face_values_hyd(int n_cells, const int *row_index, const int *col_id, cons
         pfac += (b-1.) * dot;
         pfac *= ddif;
         for (int ll = 0; ll < 3; ll++) rhs[ll] += dif[ll] * pfac;
+        const double var_f = a + b*var_i;
+        var_min = fmin(var_min, var_f);
+        var_max = fmax(var_max, var_f);
       }
       const double a00 = cocg[1]*cocg[2] - cocg[4]*cocg[4];
       const double a01 = cocg[4]*cocg[5] - cocg[3]*cocg[2];
@@ -541,7 +576,8 @@ ora_b_face_values_hyd(int n_cells, const int *row_index, const int *col_id, cons
       g[1] = (a01 * rhs[0] + a11 * rhs[1] + a12 * rhs[2]) * det_inv;
       g[2] = (a02 * rhs[0] + a12 * rhs[1] + a22 * rhs[2]) * det_inv;
       g[0] += fx[0]; g[1] += fx[1]; g[2] += fx[2];
-      vip = var_i + (g[0]*ip[0] + g[1]*ip[1] + g[2]*ip[2]);
+      vip = _clip_ip(var_i + (g[0]*ip[0] + g[1]*ip[1] + g[2]*ip[2]), var_i, var_min, var_max,
+                     clip_coeff);
     }
     val_ip[f_id] = vip;
     double vf = inc * coefa[f_id] + coefb[f_id] * vip;
@@ -847,4 +883,95 @@ ora_gradient_green_iter(int n_cells, int n_i_faces, const int *i_face_cells, int
   }
   free(cocg); free(rhs);
   return n_sweeps;
+}
+
+/* _scalar_gradient_clipping (cs_gradient.cpp:808-1215), standard neighbourhood: the limiter of
+   the cell gradient, after any gradient type.  clip_mode 0 (CS_GRADIENT_LIMIT_CELL): the
+   variation |IJ.grad_I| is kept under climgp times the largest |var_I - var_J| of the cell;
+   1 (_FACE): the same with the mean gradient of the two cells, then the smallest factor of
+   the cell and its neighbours (_gradient_update_face_clip_factor :691-758); 2 (_CELL_RC): the
+   values reconstructed at I' / J' of the cell's interior faces stay within climgp times the
+   range of the neighbouring values and boundary face values.  c2f / c2f_sgn: face and
+   orientation of every adjacency entry; i_geo: II' [3], JJ' [3], distance per interior face. */
+void
+ora_gradient_clip(int n_cells, const int *row_index, const int *col_id, const int *c2f,
+                  const short *c2f_sgn, int n_b_faces, const int *b_face_cells,
+                  const double *cell_cen, const double *i_geo, int clip_mode, double climgp,
+                  const double *pvar, const double *val_f, double *grad)
+{
+  if (clip_mode < 0 || climgp < 0) return;
+  double *clip_factor = malloc(sizeof(double)*(size_t)(n_cells > 0 ? n_cells : 1));
+  double *factor = malloc(sizeof(double)*(size_t)(n_cells > 0 ? n_cells : 1));
+  if (clip_mode == 0 || clip_mode == 1) {
+    for (int c1 = 0; c1 < n_cells; c1++) {
+      double denum = 0, denom = 0;
+      const double *g1 = grad + 3*(size_t)c1;
+      for (int k = row_index[c1]; k < row_index[c1+1]; k++) {
+        const int c2 = col_id[k];
+        const double *g2 = grad + 3*(size_t)c2;
+        double dist[3];
+        for (int j = 0; j < 3; j++) dist[j] = cell_cen[3*(size_t)c1+j] - cell_cen[3*(size_t)c2+j];
+        double dist1;
+        if (clip_mode == 0)
+          dist1 = fabs(dist[0]*g1[0] + dist[1]*g1[1] + dist[2]*g1[2]);
+        else {
+          const double gradm[3] = {g1[0] + g2[0], g1[1] + g2[1], g1[2] + g2[2]};
+          dist1 = 0.5 * fabs(dist[0]*gradm[0] + dist[1]*gradm[1] + dist[2]*gradm[2]);
+        }
+        const double dvar = fabs(pvar[c1] - pvar[c2]);
+        denum = fmax(denum, dist1);
+        denom = fmax(denom, dvar);
+      }
+      double factor1 = 1.;
+      if (denum > climgp * denom) factor1 = climgp * denom/denum;
+      factor[c1] = factor1;
+      clip_factor[c1] = (clip_mode == 0) ? factor1 : 1;
+    }
+    if (clip_mode == 1)
+      for (int c1 = 0; c1 < n_cells; c1++) {
+        double l_min_factor = factor[c1];
+        for (int k = row_index[c1]; k < row_index[c1+1]; k++)
+          l_min_factor = fmin(l_min_factor, factor[col_id[k]]);
+        clip_factor[c1] = fmin(clip_factor[c1], l_min_factor);
+      }
+  }
+  else {
+    double *v_min = malloc(sizeof(double)*(size_t)(n_cells > 0 ? n_cells : 1));
+    double *v_max = malloc(sizeof(double)*(size_t)(n_cells > 0 ? n_cells : 1));
+    for (int c1 = 0; c1 < n_cells; c1++) {
+      v_min[c1] = pvar[c1]; v_max[c1] = pvar[c1];
+      for (int k = row_index[c1]; k < row_index[c1+1]; k++) {
+        v_min[c1] = fmin(v_min[c1], pvar[col_id[k]]);
+        v_max[c1] = fmax(v_max[c1], pvar[col_id[k]]);
+      }
+    }
+    for (int f = 0; f < n_b_faces; f++) {
+      const int c1 = b_face_cells[f];
+      v_min[c1] = fmin(v_min[c1], val_f[f]);
+      v_max[c1] = fmax(v_max[c1], val_f[f]);
+    }
+    for (int c1 = 0; c1 < n_cells; c1++) {
+      const double vmin = (v_min[c1] - pvar[c1]) * climgp, vmax = (v_max[c1] - pvar[c1]) * climgp;
+      const double *g = grad + 3*(size_t)c1;
+      double ccf = 1.;
+      for (int k = row_index[c1]; k < row_index[c1+1]; k++) {
+        const double *dkkpf = i_geo + 7*(size_t)c2f[k] + ((c2f_sgn[k] > 0) ? 0 : 3);
+        double sub_factor = 1.;
+        const double v_r = dkkpf[0]*g[0] + dkkpf[1]*g[1] + dkkpf[2]*g[2];
+        if (v_r < vmin)
+          sub_factor = fabs(vmin) / fabs(v_r);
+        else if (v_r > vmax)
+          sub_factor = fabs(vmax) / fabs(v_r);
+        ccf = fmin(ccf, sub_factor);
+      }
+      clip_factor[c1] = ccf;
+    }
+    free(v_min); free(v_max);
+  }
+  for (int c = 0; c < n_cells; c++) {
+    const double factor1 = clip_factor[c];
+    if (factor1 < 1)
+      for (int j = 0; j < 3; j++) grad[3*(size_t)c+j] *= factor1;
+  }
+  free(clip_factor); free(factor);
 }

@@ -353,7 +353,8 @@ class Oracle:
             _dp(_f64(i_visc)), _dp(_f64(b_visc)), _dp(div))
         return div
 
-    def b_iprime_lsq(self, s, b_face_cells, b_un, b_dist, diipb, pvar, coefa, coefb):
+    def b_iprime_lsq(self, s, b_face_cells, b_un, b_dist, diipb, pvar, coefa, coefb,
+                     clip_coeff=-1.):
         """value of pvar at I' of every boundary face (cs_gradient_boundary_iprime_lsq_s)"""
         bfc = _i32(b_face_cells)
         val_ip = np.zeros(max(len(bfc), 1))
@@ -361,17 +362,32 @@ class Oracle:
         self.lib.ora_b_iprime_lsq(
             C.c_int(s.n_rows), _ip(_i32(s.row_index)), _ip(_i32(s.col_id)), C.c_int(len(bfc)),
             _ip(bfc), _dp(_f64(s.cell_cen)), _dp(_f64(b_un)), _dp(_f64(b_dist)),
-            _dp(_f64(diipb)), _dp(_f64(pvar)), _dp(_f64(coefa)), _dp(_f64(coefb)), _dp(val_ip))
+            _dp(_f64(diipb)), C.c_double(clip_coeff), _dp(_f64(pvar)), _dp(_f64(coefa)),
+            _dp(_f64(coefb)), _dp(val_ip))
         return val_ip[:len(bfc)]
 
-    def gradient_lsq(self, s, b_face_cells, b_un, b_dist, pvar, coefa, coefb, inc=1, diipb=None):
+    def gradient_clip(self, s, b_face_cells, i_geo, imligr, climgr, pvar, val_f, grad):
+        """_scalar_gradient_clipping applied to a copy of grad; val_f: boundary face values"""
+        bfc = _i32(b_face_cells)
+        g = _f64(grad).reshape(-1).copy()
+        self.lib.ora_gradient_clip.restype = None
+        self.lib.ora_gradient_clip(
+            C.c_int(s.n_rows), _ip(_i32(s.row_index)), _ip(_i32(s.col_id)), _ip(_i32(s.c2f)),
+            np.ascontiguousarray(s.c2f_sgn, dtype=np.int16).ctypes.data_as(C.c_void_p),
+            C.c_int(len(bfc)), _ip(bfc), _dp(_f64(s.cell_cen)), _dp(_f64(i_geo)),
+            C.c_int(imligr), C.c_double(climgr), _dp(_f64(pvar)), _dp(_f64(val_f)), _dp(g))
+        return g.reshape(-1, 3)
+
+    def gradient_lsq(self, s, b_face_cells, b_un, b_dist, pvar, coefa, coefb, inc=1, diipb=None,
+                     clip_coeff=-1.):
         """diipb (II' of the boundary faces) given: face values from the values at I'"""
         grad = np.zeros(3 * s.n_rows)
         fc, bfc = _i32(s.face_cells), _i32(b_face_cells)
         val_ip = dip = None
         if diipb is not None:
             dip = _f64(diipb)
-            val_ip = self.b_iprime_lsq(s, bfc, b_un, b_dist, dip, pvar, coefa, coefb)
+            val_ip = self.b_iprime_lsq(s, bfc, b_un, b_dist, dip, pvar, coefa, coefb,
+                                       clip_coeff=clip_coeff)
         self.lib.ora_gradient_lsq_b.restype = None
         self.lib.ora_gradient_lsq_b(
             C.c_int(s.n_rows), _ip(_i32(s.row_index)), _ip(_i32(s.col_id)), C.c_int(len(fc)),
@@ -382,15 +398,16 @@ class Oracle:
         return grad.reshape(-1, 3)
 
     def gradient_green_lsq(self, s, b_face_cells, b_un, b_dist, g_geo, b_face_surf, pvar, coefa,
-                           coefb, inc=1, diipb=None, corr_grad_lin=None):
+                           coefb, inc=1, diipb=None, corr_grad_lin=None, clip_coeff=-1.):
         """imrgra = 4: the least-squares gradient, then the Green-Gauss reconstruction pass;
         g_geo: weight [1] and OF vector [3] per interior face"""
         r_grad = self.gradient_lsq(s, b_face_cells, b_un, b_dist, pvar, coefa, coefb, inc=inc,
-                                   diipb=diipb)
+                                   diipb=diipb, clip_coeff=clip_coeff)
         fc, bfc = _i32(s.face_cells), _i32(b_face_cells)
         vip = None
         if diipb is not None:
-            vip = self.b_iprime_lsq(s, bfc, b_un, b_dist, diipb, pvar, coefa, coefb)
+            vip = self.b_iprime_lsq(s, bfc, b_un, b_dist, diipb, pvar, coefa, coefb,
+                                    clip_coeff=clip_coeff)
         gg = _f64(g_geo).reshape(-1, 4)
         grad = np.zeros(3 * s.n_rows)
         self.lib.ora_gradient_green_reconstruct.restype = None
@@ -436,8 +453,8 @@ class Oracle:
 
     def gradient_hyd(self, imrgra, s, b_face_cells, b_un, b_dist, i_face_cog, b_face_cog, f_ext,
                      pvar, coefa, coefb, inc=1, diipb=None, g_geo=None, b_face_surf=None,
-                     corr_grad_lin=None):
-        """hyd_p_flag = 1 (exterior force f_ext): returns (grad, val_ip); imrgra 1 or 4"""
+                     corr_grad_lin=None, clip_coeff=-1., with_val_f=False):
+        """hyd_p_flag = 1 (exterior force f_ext): returns (grad, val_ip[, val_f]); imrgra 1 or 4"""
         fc, bfc = _i32(s.face_cells), _i32(b_face_cells)
         nb = len(bfc)
         dip = np.zeros(3 * max(nb, 1)) if diipb is None else _f64(diipb)
@@ -449,7 +466,8 @@ class Oracle:
         self.lib.ora_b_face_values_hyd.restype = None
         self.lib.ora_b_face_values_hyd(
             C.c_int(s.n_rows), _ip(ri), _ip(ci), _ip(_i32(s.c2f)), C.c_int(nb), _ip(bfc), _dp(cen),
-            _dp(bun), _dp(bd), _dp(dip), _dp(icog), _dp(bcog), _dp(fx), C.c_int(inc), _dp(p),
+            _dp(bun), _dp(bd), _dp(dip), _dp(icog), _dp(bcog), _dp(fx), C.c_double(clip_coeff),
+            C.c_int(inc), _dp(p),
             _dp(_f64(coefa)), _dp(_f64(coefb)), _dp(vip), _dp(vf))
         r_grad = np.zeros(3 * s.n_rows)
         self.lib.ora_gradient_lsq_hyd.restype = None
@@ -458,6 +476,8 @@ class Oracle:
             _dp(cen), _dp(bun), _dp(bd), (None if diipb is None else _dp(dip)), _dp(icog),
             _dp(bcog), _dp(fx), _dp(vf), _dp(p), _dp(r_grad))
         if imrgra != 4:
+            if with_val_f:
+                return r_grad.reshape(-1, 3), vip[:nb], vf[:nb]
             return r_grad.reshape(-1, 3), vip[:nb]
         gg = _f64(g_geo).reshape(-1, 4)
         grad = np.zeros(3 * s.n_rows)
@@ -468,6 +488,8 @@ class Oracle:
             _dp(_f64(s.face_u_normal)), _dp(_f64(b_face_surf)), _dp(bun), _dp(_f64(s.cell_vol)),
             _dp(cen), _dp(icog), _dp(fx), _dp(vf), _dp(p), _dp(r_grad),
             (None if corr_grad_lin is None else _dp(_f64(corr_grad_lin))), _dp(grad))
+        if with_val_f:
+            return grad.reshape(-1, 3), vip[:nb], vf[:nb]
         return grad.reshape(-1, 3), vip[:nb]
 
     def divergence(self, s, b_face_cells, i_massflux, b_massflux, init=1, diverg=None):
@@ -820,7 +842,7 @@ class RefLib:
                                coefb, cofaf, cofbf, i_visc, b_visc, visel, irecmf=0, init=1,
                                inc=1, diverg=None, diipb=None, imrgra=1, g_geo=None,
                                b_face_surf=None, corr_grad_lin=None, ircflu=1, massflux=None,
-                               frcxt=None):
+                               frcxt=None, imligr=-1, climgr=-1.):
         """cs_diffusion_potential WITH flux reconstruction (LSQ gradient) on the geometry given;
         returns (diverg, grad)."""
         div = np.zeros(s.n_rows) if diverg is None else _f64(diverg).copy()
@@ -839,7 +861,7 @@ class RefLib:
             _dp(div), _dp(grad), C.c_int(ircflu),
             (None if massflux is None else _dp(massflux[0])),
             (None if massflux is None else _dp(massflux[1])),
-            (None if frcxt is None else _dp(_f64(frcxt))))
+            (None if frcxt is None else _dp(_f64(frcxt))), C.c_int(imligr), C.c_double(climgr))
         assert r == 0
         return div, grad.reshape(-1, 3)
 

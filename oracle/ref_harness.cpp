@@ -965,8 +965,11 @@ csref_diffusion_potential_rc(void          *sys,
                              int            ircflu,       /* eqp->ircflu: 1 = reconstruct */
                              double        *i_massflux,   /* both non-NULL: call */
                              double        *b_massflux,   /* cs_face_diffusion_potential */
-                             const double  *frcxt)        /* non-NULL: iphydp = 1 with this
+                             const double  *frcxt,        /* non-NULL: iphydp = 1 with this
                                                              exterior force, 3 per cell */
+                             int            imligr,       /* gradient limiter: -1 none, 0 cell,
+                                                             1 face, 2 cell at I'/J' */
+                             double         climgr)       /* its factor (< 0: none) */
 {
   ref_system *s = static_cast<ref_system *>(sys);
   _set_glob_mesh_faces(s, face_cells);
@@ -1055,7 +1058,11 @@ csref_diffusion_potential_rc(void          *sys,
   eqp.ircflu = ircflu;
   eqp.imrgra = imrgra;     /* 1: least squares, standard neighbourhood; 4: Green-Gauss with
                               least-squares face values */
-  eqp.imligr = -1;         /* no gradient limiter */
+  eqp.imligr = imligr;     /* gradient limiter (-1: none); with one the values at I' of the
+                              boundary faces are clipped too (b_rc_clip_factor = 1) */
+  eqp.climgr = climgr;
+  if (imligr == CS_GRADIENT_LIMIT_CELL_RC)
+    cs_mesh_adjacencies_update_cell_i_faces();
   eqp.iwgrec = 0;
   eqp.verbosity = 0;
   cs_velocity_pressure_param_t *vp = cs_get_glob_velocity_pressure_param();

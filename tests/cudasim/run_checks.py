@@ -478,6 +478,34 @@ def check_rhs(ora):
             assert np.array_equal(m.gradient(0, f["pvar"], f["coefa"], f["coefb"]), go), (N, nsw)
             assert m.gradient_sweeps() == ns == nsw
         m.destroy()
+    # gradient limiter (imligr 0 / 1 / 2) on every gradient type
+    from make_golden_rhs import CLIP_CASES
+    for N in CASES:
+        g = np.load(os.path.join(GOLD, f"rhs_clip_N{N}.npz"))
+        s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
+        g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
+        fx = hyd_input(s.n_rows)
+        m = csb.Matrix.from_system(s)
+        m.set_boundary_faces(bfc)
+        m.set_face_geometry(i_geo[:, 6], i_geo[:, :3], i_geo[:, 3:6], b_geo[:, :3], b_geo[:, 6])
+        m.set_green_geometry(g_geo[:, 0], g_geo[:, 1:4], b_surf, cgl)
+        m.set_face_cog(ifc, b_geo[:, 3:6])
+        m.set_boundary_iprime(diipb_input(N, len(bfc)))
+        for imligr, climgr, imrgra, hyd in CLIP_CASES:
+            m.set_gradient_type(imrgra)
+            m.set_gradient_limiter(imligr, climgr)
+            tag = f"l{imligr}_c{climgr}_g{imrgra}_h{int(hyd)}"
+            if hyd:
+                gr = m.gradient_hyd(imrgra, fx, f["pvar"], f["coefa"], f["coefb"])
+                d = m.diffusion_potential_hyd(fx, f["pvar"], f["coefa"], f["coefb"], f["cofaf"],
+                                              f["cofbf"], f["i_visc"], f["b_visc"], f["visel"])
+            else:
+                gr = m.gradient(imrgra, f["pvar"], f["coefa"], f["coefb"])
+                d = m.diffusion_potential_rc(f["pvar"], f["coefa"], f["coefb"], f["cofaf"],
+                                             f["cofbf"], f["i_visc"], f["b_visc"], f["visel"])
+            assert np.array_equal(gr, g["grad_" + tag]), (N, tag)
+            assert np.array_equal(d, g["div_" + tag]), (N, tag)
+        m.destroy()
     # imrgra = 4: Green-Gauss gradient with least-squares face values
     for N in CASES:
         g = np.load(os.path.join(GOLD, f"rhs_green_N{N}.npz"))

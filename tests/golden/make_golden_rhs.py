@@ -5,7 +5,7 @@ the reference's own compiled CPU code (oracle/_ref/libcsref.so, csref_diffusion_
     python tests/golden/make_golden_rhs.py   -> tests/golden/rhs_N{N}.npz, rhs_rc_N{N}.npz,
                                                 rhs_rcb_N{N}.npz, rhs_green_N{N}.npz,
                                                 rhs_face_N{N}.npz, rhs_hyd_N{N}.npz,
-                                                rhs_iter_N{N}.npz
+                                                rhs_iter_N{N}.npz, rhs_clip_N{N}.npz
 
 rhs_rc_*: the same operator WITH flux reconstruction (eqp->ircflu = 1, least-squares gradient,
 csref_diffusion_potential_rc) on a non-orthogonal variant of the cube.
@@ -20,6 +20,9 @@ rhs_hyd_*: the hydrostatic pressure treatment (iphydp = 1 with a seeded exterior
 cs_pressure_correction hands over by default), imrgra 1 and 4, with and without boundary II'.
 rhs_iter_*: imrgra = 0, the iterative Green-Gauss gradient (default nswrgr 100, epsrgr 1e-4),
 with and without boundary II'.
+rhs_clip_*: the gradient limiter (eqp->imligr 0 / 1 / 2 with factors climgr 0.3 and 1.5; the
+values at I' of the boundary faces are limited too), gradient types 0 / 1 / 4, one case with
+the hydrostatic treatment.
 """
 import os
 import sys
@@ -104,6 +107,11 @@ def hyd_input(n_rows, seed=43):
     return np.random.default_rng(seed).standard_normal((n_rows, 3))
 
 
+# (imligr, climgr, imrgra, hydrostatic)
+CLIP_CASES = tuple((l, c, g, False) for l in (0, 1, 2) for c in (0.3, 1.5) for g in (0, 1, 4)) \
+    + ((1, 1.0, 4, True), (2, 0.3, 1, True))
+
+
 FACE_CASES = ((0, 1), (1, 1), (1, 4))            # (ircflu, imrgra)
 FACE_INIT_INC = ((1, 1), (0, 1), (1, 0))
 
@@ -117,6 +125,25 @@ def face_input(s, n_b_faces, seed=41):
 def main():
     from oracle.pyoracle import RefLib
     ref = RefLib(1)
+    for N in CASES:
+        s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
+        g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
+        diipb = diipb_input(N, len(bfc))
+        fx = hyd_input(s.n_rows)
+        h = ref.system(s)
+        out = {}
+        for imligr, climgr, imrgra, hyd in CLIP_CASES:
+            d, g = ref.diffusion_potential_rc(
+                h, s, bfc, b_geo, ifc, i_geo, f["pvar"], f["coefa"], f["coefb"], f["cofaf"],
+                f["cofbf"], f["i_visc"], f["b_visc"], f["visel"], irecmf=0, inc=1, diipb=diipb,
+                imrgra=imrgra, g_geo=g_geo, b_face_surf=b_surf, corr_grad_lin=cgl, imligr=imligr,
+                climgr=climgr, frcxt=(fx if hyd else None))
+            tag = f"l{imligr}_c{climgr}_g{imrgra}_h{int(hyd)}"
+            out["grad_" + tag], out["div_" + tag] = g, d
+        ref.destroy(h)
+        path = os.path.join(ROOT, "tests", "golden", f"rhs_clip_N{N}.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path))
     for N in CASES:
         s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
         g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)

@@ -1044,6 +1044,50 @@ def test_oracle_iterative_green_gauss_matches_golden(oracle, N):
     assert min(sweeps) >= 2 and max(sweeps) < 99            # really iterated, really converged
 
 
+@pytest.mark.parametrize("N", [5, 9])
+def test_oracle_gradient_limiter_matches_golden(oracle, N):
+    """eqp->imligr 0 / 1 / 2 (cell, face, I'/J' limiters) on every gradient type, with the
+    limiter of the boundary values at I': limited gradient and divergence bit-exact"""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_rhs import (CLIP_CASES, diipb_input, green_input, hyd_input, rc_input)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"rhs_clip_N{N}.npz"))
+    s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
+    g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
+    diipb = diipb_input(N, len(bfc))
+    fx = hyd_input(s.n_rows)
+    bun, bd = b_geo[:, :3], b_geo[:, 6]
+    n_clipped = 0
+    for imligr, climgr, imrgra, hyd in CLIP_CASES:
+        if hyd:
+            go, vip, vf = oracle.gradient_hyd(imrgra, s, bfc, bun, bd, ifc, b_geo[:, 3:6], fx,
+                                              f["pvar"], f["coefa"], f["coefb"], diipb=diipb,
+                                              g_geo=g_geo, b_face_surf=b_surf, corr_grad_lin=cgl,
+                                              clip_coeff=1., with_val_f=True)
+        else:
+            vip = oracle.b_iprime_lsq(s, bfc, bun, bd, diipb, f["pvar"], f["coefa"], f["coefb"],
+                                      clip_coeff=1.)
+            vf = f["coefa"] + f["coefb"] * vip
+            if imrgra == 4:
+                go = oracle.gradient_green_lsq(s, bfc, bun, bd, g_geo, b_surf, f["pvar"],
+                                               f["coefa"], f["coefb"], diipb=diipb,
+                                               corr_grad_lin=cgl, clip_coeff=1.)
+            elif imrgra == 1:
+                go = oracle.gradient_lsq(s, bfc, bun, bd, f["pvar"], f["coefa"], f["coefb"],
+                                         diipb=diipb, clip_coeff=1.)
+            else:
+                go, _ = oracle.gradient_green_iter(s, bfc, bun, g_geo, b_surf, f["pvar"],
+                                                   f["coefa"], f["coefb"], diipb=diipb)
+        gc = oracle.gradient_clip(s, bfc, i_geo, imligr, climgr, f["pvar"], vf, go)
+        n_clipped += int((gc != go).any(axis=1).sum())
+        tag = f"l{imligr}_c{climgr}_g{imrgra}_h{int(hyd)}"
+        assert np.array_equal(gc, g["grad_" + tag]), tag
+        d = oracle.diffusion_potential_rc(s, bfc, i_geo, gc, f["pvar"], f["cofaf"], f["cofbf"],
+                                          f["i_visc"], f["b_visc"], f["visel"], irecmf=0,
+                                          val_ip=vip)
+        assert np.array_equal(d, g["div_" + tag]), tag
+    assert n_clipped > 100                              # the limiters really act here
+
+
 def test_oracle_gradient_lsq_is_exact_for_linear_fields(oracle):
     """property: a least-squares gradient reproduces the gradient of a linear field (to the
     single precision of its cocg matrices) when the boundary values are those of the field"""
