@@ -2624,7 +2624,7 @@ __global__ void k_b_iprime_lsq(int n_rows, const int *__restrict__ row_index,
   if (c >= n_rows) return;
   const int bs = cell_b_faces_idx[c], be = cell_b_faces_idx[c+1];
   if (bs >= be) return;
-  const double var_i = pvar[c];
+  const double p_c = pvar[c];
   const double cen[3] = {cell_cen[3*(size_t)c], cell_cen[3*(size_t)c+1], cell_cen[3*(size_t)c+2]};
   double fx[3] = {0., 0., 0.};
   if (f_ext != nullptr) {
@@ -2641,7 +2641,7 @@ __global__ void k_b_iprime_lsq(int n_rows, const int *__restrict__ row_index,
   double gx = 0., gy = 0., gz = 0.;
   /* bounds of the simple limiter (:612-628; clip_coeff < 0: none): the cell's, its neighbours'
      and its boundary faces' unreconstructed values */
-  double var_min = var_i, var_max = var_i;
+  double var_min = p_c, var_max = p_c;
   if (any) {
     float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     double r0 = 0., r1 = 0., r2 = 0.;
@@ -2651,51 +2651,51 @@ __global__ void k_b_iprime_lsq(int n_rows, const int *__restrict__ row_index,
       var_max = fmax(var_max, pvar[j]);
       const double cj[3] = {cell_cen[3*j], cell_cen[3*j+1], cell_cen[3*j+2]};
       const double d0 = cj[0] - cen[0], d1 = cj[1] - cen[1], d2 = cj[2] - cen[2];
-      const double ddc = 1. / (d0*d0 + d1*d1 + d2*d2);
-      g[0] = (float)((double)g[0] + d0 * d0 * ddc);
-      g[1] = (float)((double)g[1] + d1 * d1 * ddc);
-      g[2] = (float)((double)g[2] + d2 * d2 * ddc);
-      g[3] = (float)((double)g[3] + d0 * d1 * ddc);
-      g[4] = (float)((double)g[4] + d1 * d2 * ddc);
-      g[5] = (float)((double)g[5] + d0 * d2 * ddc);
-      double pfac = pvar[j] - var_i;
+      const double inv_d2 = 1. / (d0*d0 + d1*d1 + d2*d2);
+      g[0] = (float)((double)g[0] + d0 * d0 * inv_d2);
+      g[1] = (float)((double)g[1] + d1 * d1 * inv_d2);
+      g[2] = (float)((double)g[2] + d2 * d2 * inv_d2);
+      g[3] = (float)((double)g[3] + d0 * d1 * inv_d2);
+      g[4] = (float)((double)g[4] + d1 * d2 * inv_d2);
+      g[5] = (float)((double)g[5] + d0 * d2 * inv_d2);
+      double t = pvar[j] - p_c;
       if (f_ext != nullptr) {
         const double *cog = i_face_cog + 3*(size_t)c2f[k];
         const double dot_i = ddp3(cog, cen, fx);
         const double dot_j = ddp3(cog, cj, f_ext + 3*j);
-        pfac += dot_i - dot_j;
+        t += dot_i - dot_j;
       }
-      pfac *= ddc;
-      r0 += d0 * pfac; r1 += d1 * pfac; r2 += d2 * pfac;
+      t *= inv_d2;
+      r0 += d0 * t; r1 += d1 * t; r2 += d2 * t;
     }
     for (int k = bs; k < be; k++) {
       const size_t f = (size_t)cell_b_faces[k];
       const double a = coefa[f], b = coefb[f];
-      const double ddif = 1. / b_dist[f];
-      const double umcbdd = (1. - b) * ddif;
-      const double d0 = b_un[3*f] + umcbdd * diipb[3*f], d1 = b_un[3*f+1] + umcbdd * diipb[3*f+1],
-                   d2 = b_un[3*f+2] + umcbdd * diipb[3*f+2];
+      const double inv_d = 1. / b_dist[f];
+      const double s_ip = (1. - b) * inv_d;
+      const double d0 = b_un[3*f] + s_ip * diipb[3*f], d1 = b_un[3*f+1] + s_ip * diipb[3*f+1],
+                   d2 = b_un[3*f+2] + s_ip * diipb[3*f+2];
       g[0] = (float)((double)g[0] + d0 * d0);
       g[1] = (float)((double)g[1] + d1 * d1);
       g[2] = (float)((double)g[2] + d2 * d2);
       g[3] = (float)((double)g[3] + d0 * d1);
       g[4] = (float)((double)g[4] + d1 * d2);
       g[5] = (float)((double)g[5] + d0 * d2);
-      double pfac = (a + (b-1.)*var_i);
+      double t = (a + (b-1.)*p_c);
       if (f_ext != nullptr) {
         const double dot = ddp3(cen, b_face_cog + 3*f, fx);
-        pfac += (b-1.) * dot;
+        t += (b-1.) * dot;
       }
-      pfac *= ddif;
-      r0 += d0 * pfac; r1 += d1 * pfac; r2 += d2 * pfac;
-      const double var_f = a + b*var_i;
-      var_min = fmin(var_min, var_f);
-      var_max = fmax(var_max, var_f);
+      t *= inv_d;
+      r0 += d0 * t; r1 += d1 * t; r2 += d2 * t;
+      const double p_face = a + b*p_c;
+      var_min = fmin(var_min, p_face);
+      var_max = fmax(var_max, p_face);
     }
     if (clip_coeff >= 0 && (clip_coeff < 1. || clip_coeff > 1.)) {
-      const double d_min = var_min - var_i, d_max = var_max - var_i;
-      var_min = var_i + d_min*clip_coeff;
-      var_max = var_i + d_max*clip_coeff;
+      const double d_min = var_min - p_c, d_max = var_max - p_c;
+      var_min = p_c + d_min*clip_coeff;
+      var_max = p_c + d_max*clip_coeff;
     }
     const double a00 = (double)(g[1]*g[2] - g[4]*g[4]);
     const double a01 = (double)(g[4]*g[5] - g[3]*g[2]);
@@ -2703,22 +2703,22 @@ __global__ void k_b_iprime_lsq(int n_rows, const int *__restrict__ row_index,
     const double a11 = (double)(g[0]*g[2] - g[5]*g[5]);
     const double a12 = (double)(g[3]*g[5] - g[0]*g[4]);
     const double a22 = (double)(g[0]*g[1] - g[3]*g[3]);
-    const double det_inv = 1. / (g[0]*a00 + g[3]*a01 + g[5]*a02);
-    gx = (a00 * r0 + a01 * r1 + a02 * r2) * det_inv;
-    gy = (a01 * r0 + a11 * r1 + a12 * r2) * det_inv;
-    gz = (a02 * r0 + a12 * r1 + a22 * r2) * det_inv;
+    const double inv_det = 1. / (g[0]*a00 + g[3]*a01 + g[5]*a02);
+    gx = (a00 * r0 + a01 * r1 + a02 * r2) * inv_det;
+    gy = (a01 * r0 + a11 * r1 + a12 * r2) * inv_det;
+    gz = (a02 * r0 + a12 * r1 + a22 * r2) * inv_det;
     if (f_ext != nullptr) { gx += fx[0]; gy += fx[1]; gz += fx[2]; }
   }
   for (int k = bs; k < be; k++) {
     const size_t f = (size_t)cell_b_faces[k];
     double ip[3] = {0., 0., 0.};
-    double vip = var_i;
+    double vip = p_c;
     if (diipb != nullptr) {
       ip[0] = diipb[3*f]; ip[1] = diipb[3*f+1]; ip[2] = diipb[3*f+2];
       const double bd = b_dist[f];
       if (!(ip[0]*ip[0] + ip[1]*ip[1] + ip[2]*ip[2] < (bd*bd) * (1e-3 * 1e-3))) {
-        const double grad_dot_diipb = gx*ip[0] + gy*ip[1] + gz*ip[2];
-        vip = var_i + grad_dot_diipb;
+        const double shift = gx*ip[0] + gy*ip[1] + gz*ip[2];
+        vip = p_c + shift;
         if (clip_coeff >= 0) {
           if (vip < var_min) vip = var_min;
           if (vip > var_max) vip = var_max;
@@ -2729,8 +2729,8 @@ __global__ void k_b_iprime_lsq(int n_rows, const int *__restrict__ row_index,
     if (val_f != nullptr) {
       double vf = inc * coefa[f] + coefb[f] * vip;
       if (f_ext != nullptr) {
-        const double vec_iprime[3] = {cen[0] + ip[0], cen[1] + ip[1], cen[2] + ip[2]};
-        vf += coefb[f] * ddp3(vec_iprime, b_face_cog + 3*f, fx);
+        const double x_ip[3] = {cen[0] + ip[0], cen[1] + ip[1], cen[2] + ip[2]};
+        vf += coefb[f] * ddp3(x_ip, b_face_cog + 3*f, fx);
       }
       val_f[f] = vf;
     }
@@ -2780,52 +2780,52 @@ __global__ void k_green_reconstruct(int n_rows, const int *__restrict__ row_inde
     const int o = col_id[bk];
     const bool first = (c2f_sgn[bk] > 0);
     const size_t c1 = (size_t)(first ? c : o), c2 = (size_t)(first ? o : c);
-    const double ktpond = weight[f];
-    const double d_var = pvar[c2] - pvar[c1];
+    const double w_face = weight[f];
+    const double dp = pvar[c2] - pvar[c1];
     const double *of = dofij + 3*f, *ra = r_grad + 3*c1, *rb = r_grad + 3*c2;
     const double *n = i_face_u_normal + 3*f;
-    double pfaci, pfacj, rfac;
+    double t_first, t_second, t_rec;
     if (f_ext == nullptr) {
-      rfac = 0.5 * (  of[0]*(ra[0]+rb[0])
+      t_rec = 0.5 * (  of[0]*(ra[0]+rb[0])
                     + of[1]*(ra[1]+rb[1])
                     + of[2]*(ra[2]+rb[2]));
-      pfaci = (1.0-ktpond) * d_var;
-      pfacj = -ktpond * d_var;
+      t_first = (1.0-w_face) * dp;
+      t_second = -w_face * dp;
     }
     else {                /* hydrostatic branch (cs_gradient.cpp:4318-4398; no porosity) */
       const double *f1 = f_ext + 3*c1, *f2 = f_ext + 3*c2, *cog = i_face_cog + 3*f;
-      double fexd[3], d_oi[3], d_oj[3];
+      double f_mid[3], r_first[3], r_second[3];
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        fexd[k] = 0.5 * (f1[k] + f2[k]);
-        d_oi[k] = cog[k] - cell_cen[3*c1+k];
-        d_oj[k] = cog[k] - cell_cen[3*c2+k];
+        f_mid[k] = 0.5 * (f1[k] + f2[k]);
+        r_first[k] = cog[k] - cell_cen[3*c1+k];
+        r_second[k] = cog[k] - cell_cen[3*c2+k];
       }
-      pfaci =  ktpond
-                 * (  d_oi[0]*f1[0]
-                    + d_oi[1]*f1[1]
-                    + d_oi[2]*f1[2]
+      t_first =  w_face
+                 * (  r_first[0]*f1[0]
+                    + r_first[1]*f1[1]
+                    + r_first[2]*f1[2]
                     + 0.)
-            +  (1.0 - ktpond)
-                 * (  d_oj[0]*f2[0]
-                    + d_oj[1]*f2[1]
-                    + d_oj[2]*f2[2]
+            +  (1.0 - w_face)
+                 * (  r_second[0]*f2[0]
+                    + r_second[1]*f2[1]
+                    + r_second[2]*f2[2]
                     + 0.);
-      pfacj = pfaci;
-      pfaci += (1.0-ktpond) * d_var;
-      pfacj -=      ktpond  * d_var;
-      rfac =   - ktpond         * (d_oi[0]*fexd[0] + d_oi[1]*fexd[1] + d_oi[2]*fexd[2])
-           -  (1.0 - ktpond)    * (d_oj[0]*fexd[0] + d_oj[1]*fexd[1] + d_oj[2]*fexd[2])
+      t_second = t_first;
+      t_first += (1.0-w_face) * dp;
+      t_second -=      w_face  * dp;
+      t_rec =   - w_face         * (r_first[0]*f_mid[0] + r_first[1]*f_mid[1] + r_first[2]*f_mid[2])
+           -  (1.0 - w_face)    * (r_second[0]*f_mid[0] + r_second[1]*f_mid[1] + r_second[2]*f_mid[2])
            + (  of[0] * (ra[0]+rb[0])
               + of[1] * (ra[1]+rb[1])
               + of[2] * (ra[2]+rb[2])) * 0.5;
     }
     if (first) {
-      const double pf = (pfaci + rfac) * i_face_surf[f];
+      const double pf = (t_first + t_rec) * i_face_surf[f];
       g0 += pf * n[0]; g1 += pf * n[1]; g2 += pf * n[2];
     }
     else {
-      const double pf = (pfacj + rfac) * i_face_surf[f];
+      const double pf = (t_second + t_rec) * i_face_surf[f];
       g0 += -(pf * n[0]); g1 += -(pf * n[1]); g2 += -(pf * n[2]);
     }
   }
@@ -2833,11 +2833,11 @@ __global__ void k_green_reconstruct(int n_rows, const int *__restrict__ row_inde
     for (int k = cell_b_faces_idx[c]; k < cell_b_faces_idx[c+1]; k++) {
       const size_t f = (size_t)cell_b_faces[k];
       const double vf = (val_f != nullptr) ? val_f[f] : inc*coefa[f] + coefb[f]*pc;
-      const double pfac = (vf - pc) * b_face_surf[f];
-      g0 += pfac * b_un[3*f]; g1 += pfac * b_un[3*f+1]; g2 += pfac * b_un[3*f+2];
+      const double t_b = (vf - pc) * b_face_surf[f];
+      g0 += t_b * b_un[3*f]; g1 += t_b * b_un[3*f+1]; g2 += t_b * b_un[3*f+2];
     }
-  const double dvol = 1. / cell_vol[c];
-  g0 *= dvol; g1 *= dvol; g2 *= dvol;
+  const double inv_vol = 1. / cell_vol[c];
+  g0 *= inv_vol; g1 *= inv_vol; g2 *= inv_vol;
   if (corr_grad_lin != nullptr) {
     const double *m = corr_grad_lin + 9*(size_t)c;
     double r[3];
@@ -2950,22 +2950,22 @@ __global__ void k_cocg_it(int n_rows, const int *__restrict__ row_index,
   if (c >= n_rows) return;
   const int s = row_index[c], e = row_index[c+1];
   double a[3][3] = {{1.0, 0.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 0.0, 1.0}};
-  const double dvol = (cell_vol[c] > 0) ? 1. / cell_vol[c] : 0.;
+  const double inv_vol = (cell_vol[c] > 0) ? 1. / cell_vol[c] : 0.;
   FaceOrder fo(c2f, fperm, s, e);
   while (true) {
     int best, bk;
     if (!fo.next(best, bk)) break;
     const size_t f = (size_t)best;
     const bool first = (c2f_sgn[bk] > 0);
-    const double pfac0 = -0.5 * i_face_surf[f];
+    const double half_s = -0.5 * i_face_surf[f];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-      const double pfac = pfac0 * dofij[3*f+i];
+      const double t_i = half_s * dofij[3*f+i];
 #pragma unroll
       for (int j = 0; j < 3; j++) {
-        const double vecfac = pfac*i_face_u_normal[3*f+j];
-        if (first) a[i][j] += vecfac * dvol;
-        else a[i][j] += -vecfac * dvol;
+        const double t_ij = t_i*i_face_u_normal[3*f+j];
+        if (first) a[i][j] += t_ij * inv_vol;
+        else a[i][j] += -t_ij * inv_vol;
       }
     }
   }
@@ -2978,11 +2978,11 @@ __global__ void k_cocg_it(int n_rows, const int *__restrict__ row_index,
   const double a20 = a[1][0]*a[2][1] - a[2][0]*a[1][1];
   const double a21 = a[2][0]*a[0][1] - a[0][0]*a[2][1];
   const double a22 = a[0][0]*a[1][1] - a[1][0]*a[0][1];
-  const double det_inv = 1. / (a[0][0]*a00 + a[1][0]*a01 + a[2][0]*a02);
+  const double inv_det = 1. / (a[0][0]*a00 + a[1][0]*a01 + a[2][0]*a02);
   double *o = cocg_it + 9*(size_t)c;
-  o[0] = a00 * det_inv; o[1] = a01 * det_inv; o[2] = a02 * det_inv;
-  o[3] = a10 * det_inv; o[4] = a11 * det_inv; o[5] = a12 * det_inv;
-  o[6] = a20 * det_inv; o[7] = a21 * det_inv; o[8] = a22 * det_inv;
+  o[0] = a00 * inv_det; o[1] = a01 * inv_det; o[2] = a02 * inv_det;
+  o[3] = a10 * inv_det; o[4] = a11 * inv_det; o[5] = a12 * inv_det;
+  o[6] = a20 * inv_det; o[7] = a21 * inv_det; o[8] = a22 * inv_det;
 }
 
 /* sweep 0 (r_grad == nullptr): the non-reconstructed Green-Gauss gradient, out = grad;
@@ -3026,20 +3026,20 @@ __global__ void k_green_iter_sweep(int n_rows, const int *__restrict__ row_index
     const int o = col_id[bk];
     const bool first = (c2f_sgn[bk] > 0);
     const size_t c1 = (size_t)(first ? c : o), c2 = (size_t)(first ? o : c);
-    const double ktpond = weight[f];
+    const double w_face = weight[f];
     const double *n = i_face_u_normal + 3*f;
     double pf;
     if (r_grad == nullptr) {
-      if (first) pf = (1.0-ktpond) * (pvar[c2]-pvar[c1]) * i_face_surf[f];
-      else pf = -ktpond * (pvar[c2]-pvar[c1]) * i_face_surf[f];
+      if (first) pf = (1.0-w_face) * (pvar[c2]-pvar[c1]) * i_face_surf[f];
+      else pf = -w_face * (pvar[c2]-pvar[c1]) * i_face_surf[f];
     }
     else {
       const double *of = dofij + 3*f, *ra = r_grad + 3*c1, *rb = r_grad + 3*c2;
       pf = 0.5 * (  of[0] * (ra[0]+rb[0])
                   + of[1] * (ra[1]+rb[1])
                   + of[2] * (ra[2]+rb[2]));
-      if (first) pf += (1.0-ktpond) * (pvar[c2] - pvar[c1]);
-      else pf -= ktpond * (pvar[c2] - pvar[c1]);
+      if (first) pf += (1.0-w_face) * (pvar[c2] - pvar[c1]);
+      else pf -= w_face * (pvar[c2] - pvar[c1]);
       pf *= i_face_surf[f];
     }
     if (first) { g0 += pf * n[0]; g1 += pf * n[1]; g2 += pf * n[2]; }
@@ -3048,22 +3048,22 @@ __global__ void k_green_iter_sweep(int n_rows, const int *__restrict__ row_index
   if (cell_b_faces_idx != nullptr)
     for (int k = cell_b_faces_idx[c]; k < cell_b_faces_idx[c+1]; k++) {
       const size_t f = (size_t)cell_b_faces[k];
-      double pfac;
+      double t_b;
       if (r_grad == nullptr)
-        pfac = inc*coefa[f] + (coefb[f]-1.0)*pc;
+        t_b = inc*coefa[f] + (coefb[f]-1.0)*pc;
       else {
         const double *g = r_grad + 3*(size_t)c;
         double ip0 = 0., ip1 = 0., ip2 = 0.;
         if (diipb != nullptr) { ip0 = diipb[3*f]; ip1 = diipb[3*f+1]; ip2 = diipb[3*f+2]; }
-        pfac =   coefa[f] * inc
+        t_b =   coefa[f] * inc
                + coefb[f] * (ip0 * g[0] + ip1 * g[1] + ip2 * g[2]);
-        pfac += (coefb[f] -1.0) * pc;
+        t_b += (coefb[f] -1.0) * pc;
       }
-      pfac *= b_face_surf[f];
-      g0 += pfac * b_un[3*f]; g1 += pfac * b_un[3*f+1]; g2 += pfac * b_un[3*f+2];
+      t_b *= b_face_surf[f];
+      g0 += t_b * b_un[3*f]; g1 += t_b * b_un[3*f+1]; g2 += t_b * b_un[3*f+2];
     }
-  const double dvol = 1. / cell_vol[c];
-  g0 *= dvol; g1 *= dvol; g2 *= dvol;
+  const double inv_vol = 1. / cell_vol[c];
+  g0 *= inv_vol; g1 *= inv_vol; g2 *= inv_vol;
   out[3*(size_t)c] = g0; out[3*(size_t)c+1] = g1; out[3*(size_t)c+2] = g2;
 }
 
@@ -3107,26 +3107,26 @@ __global__ void k_grad_clip_factor(int mode, int n_rows, const int *__restrict__
   const double pc = pvar[c];
   const double g0 = grad[3*(size_t)c], g1 = grad[3*(size_t)c+1], g2 = grad[3*(size_t)c+2];
   if (mode == 0 || mode == 1) {
-    double denum = 0, denom = 0;
+    double g_var = 0, p_var = 0;
     for (int k = s; k < e; k++) {
       const size_t j = (size_t)col_id[k];
       const double d0 = cell_cen[3*(size_t)c] - cell_cen[3*j],
                    d1 = cell_cen[3*(size_t)c+1] - cell_cen[3*j+1],
                    d2 = cell_cen[3*(size_t)c+2] - cell_cen[3*j+2];
-      double dist1;
+      double gv;
       if (mode == 0)
-        dist1 = fabs(d0*g0 + d1*g1 + d2*g2);
+        gv = fabs(d0*g0 + d1*g1 + d2*g2);
       else {
         const double m0 = g0 + grad[3*j], m1 = g1 + grad[3*j+1], m2 = g2 + grad[3*j+2];
-        dist1 = 0.5 * fabs(d0*m0 + d1*m1 + d2*m2);
+        gv = 0.5 * fabs(d0*m0 + d1*m1 + d2*m2);
       }
-      const double dvar = fabs(pc - pvar[j]);
-      denum = fmax(denum, dist1);
-      denom = fmax(denom, dvar);
+      const double pv = fabs(pc - pvar[j]);
+      g_var = fmax(g_var, gv);
+      p_var = fmax(p_var, pv);
     }
-    double factor1 = 1.;
-    if (denum > climgp * denom) factor1 = climgp * denom/denum;
-    out[c] = factor1;
+    double lim = 1.;
+    if (g_var > climgp * p_var) lim = climgp * p_var/g_var;
+    out[c] = lim;
     return;
   }
   double v_min = pc, v_max = pc;
@@ -3144,18 +3144,18 @@ __global__ void k_grad_clip_factor(int mode, int n_rows, const int *__restrict__
     }
   v_min = (v_min - pc) * climgp;
   v_max = (v_max - pc) * climgp;
-  double ccf = 1.;
+  double lim_c = 1.;
   for (int k = s; k < e; k++) {
-    const double *dkkpf = ((c2f_sgn[k] > 0) ? diipf : djjpf) + 3*(size_t)c2f[k];
-    double sub_factor = 1.;
-    const double v_r = dkkpf[0]*g0 + dkkpf[1]*g1 + dkkpf[2]*g2;
-    if (v_r < v_min)
-      sub_factor = fabs(v_min) / fabs(v_r);
-    else if (v_r > v_max)
-      sub_factor = fabs(v_max) / fabs(v_r);
-    ccf = fmin(ccf, sub_factor);
+    const double *off = ((c2f_sgn[k] > 0) ? diipf : djjpf) + 3*(size_t)c2f[k];
+    double lim_f = 1.;
+    const double dv = off[0]*g0 + off[1]*g1 + off[2]*g2;
+    if (dv < v_min)
+      lim_f = fabs(v_min) / fabs(dv);
+    else if (dv > v_max)
+      lim_f = fabs(v_max) / fabs(dv);
+    lim_c = fmin(lim_c, lim_f);
   }
-  out[c] = ccf;
+  out[c] = lim_c;
 }
 
 __global__ void k_grad_clip_face_min(int n_rows, const int *__restrict__ row_index,
@@ -3164,10 +3164,10 @@ __global__ void k_grad_clip_face_min(int n_rows, const int *__restrict__ row_ind
 {
   const int c = blockIdx.x*blockDim.x + threadIdx.x;
   if (c >= n_rows) return;
-  double l_min_factor = factor[c];
+  double lim = factor[c];
   for (int k = row_index[c]; k < row_index[c+1]; k++)
-    l_min_factor = fmin(l_min_factor, factor[col_id[k]]);
-  clip_factor[c] = fmin(1., l_min_factor);
+    lim = fmin(lim, factor[col_id[k]]);
+  clip_factor[c] = fmin(1., lim);
 }
 
 __global__ void k_grad_clip_apply(int n_rows, const double *__restrict__ clip_factor,
@@ -3175,9 +3175,9 @@ __global__ void k_grad_clip_apply(int n_rows, const double *__restrict__ clip_fa
 {
   const int c = blockIdx.x*blockDim.x + threadIdx.x;
   if (c >= n_rows) return;
-  const double factor1 = clip_factor[c];
-  if (factor1 < 1) {
-    grad[3*(size_t)c] *= factor1; grad[3*(size_t)c+1] *= factor1; grad[3*(size_t)c+2] *= factor1;
+  const double lim = clip_factor[c];
+  if (lim < 1) {
+    grad[3*(size_t)c] *= lim; grad[3*(size_t)c+1] *= lim; grad[3*(size_t)c+2] *= lim;
   }
 }
 
