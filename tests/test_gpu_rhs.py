@@ -412,43 +412,6 @@ def test_iterative_green_gauss_vs_oracle_larger(csb, oracle):
     m.destroy()
 
 
-@pytest.mark.parametrize("N", CASES)
-def test_gradient_limiter_matches_reference_golden(csb, N):
-    """eqp->imligr 0 / 1 / 2 (cell, face and I'/J' limiters; factors 0.3 and 1.5) on gradient
-    types 0 / 1 / 4, with the limiter of the boundary values at I', two cases with the
-    hydrostatic treatment: limited gradient and divergence bit-identical to the reference;
-    switching the limiter off gives the plain result back"""
-    from make_golden_rhs import CLIP_CASES, diipb_input, green_input, hyd_input
-    g = np.load(os.path.join(GOLD, f"rhs_clip_N{N}.npz"))
-    s, bfc, b_geo, ifc, i_geo, f = rc_input(N)
-    g_geo, b_surf, cgl = green_input(N, s.n_faces, len(bfc), s.n_rows)
-    fx = hyd_input(s.n_rows)
-    m = _rc_matrix(csb, s, bfc, b_geo, i_geo)
-    m.set_green_geometry(g_geo[:, 0], g_geo[:, 1:4], b_surf, cgl)
-    m.set_face_cog(ifc, b_geo[:, 3:6])
-    m.set_boundary_iprime(diipb_input(N, len(bfc)))
-    plain = m.gradient(4, f["pvar"], f["coefa"], f["coefb"])
-    for imligr, climgr, imrgra, hyd in CLIP_CASES:
-        m.set_gradient_type(imrgra)
-        m.set_gradient_limiter(imligr, climgr)
-        tag = f"l{imligr}_c{climgr}_g{imrgra}_h{int(hyd)}"
-        if hyd:
-            gr = m.gradient_hyd(imrgra, fx, f["pvar"], f["coefa"], f["coefb"])
-            d = m.diffusion_potential_hyd(fx, f["pvar"], f["coefa"], f["coefb"], f["cofaf"],
-                                          f["cofbf"], f["i_visc"], f["b_visc"], f["visel"])
-        else:
-            gr = m.gradient(imrgra, f["pvar"], f["coefa"], f["coefb"])
-            d = m.diffusion_potential_rc(f["pvar"], f["coefa"], f["coefb"], f["cofaf"],
-                                         f["cofbf"], f["i_visc"], f["b_visc"], f["visel"])
-        assert np.array_equal(gr, g["grad_" + tag]), tag
-        assert np.array_equal(d, g["div_" + tag]), tag
-    with pytest.raises(csb.CsbError):
-        m.set_gradient_limiter(3, 1.0)
-    m.set_gradient_limiter(-1, -1.)
-    assert np.array_equal(m.gradient(4, f["pvar"], f["coefa"], f["coefb"]), plain)
-    m.destroy()
-
-
 def test_reconstruction_needs_geometry(csb):
     s, bfc, _, _, _, f = rc_input(5)
     m = csb.Matrix.from_system(s)

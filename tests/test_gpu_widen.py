@@ -537,61 +537,6 @@ def test_matrix_compute_coeffs_convection_bit_exact_vs_reference_golden(csb, ora
     c.destroy(); m.destroy()
 
 
-# ------------------------------------------------------ K-cycle
-
-def _kpc(csb, min_g_rows=30, limit=4):
-    pc = csb.Multigrid(pc=True, mg_type=1)           # cs_multigrid_pc_create(CS_MULTIGRID_K_CYCLE)
-    pc.set_coarsening_options(aggregation_limit=limit, coarsening_type=3, n_max_levels=10,
-                              min_g_rows=min_g_rows, p0p1_relax=0.)
-    return pc
-
-
-@pytest.mark.parametrize("N,bc", [(8, "dirichlet"), (12, "dirichlet")])
-def test_k_cycle_matches_reference_golden(csb, N, bc):
-    """One K-cycle (pairwise aggregation, Galerkin, 2 Jacobi sweeps, inner 2-step Krylov with
-    the 0.25 threshold) and FCG preconditioned by it."""
-    g = np.load(os.path.join(GOLD, f"kcycle_N{N}_{bc}.npz"))
-    s = cube_poisson(N, bc)
-    r_norm = float(g["r_norm"])
-    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
-    mg = _kpc(csb)
-    mg.setup(m)
-    r = mg.solve(m, s.rhs, 1e-8, r_norm)
-    assert rel_l2(r["vx"][:s.n_rows], g["cycle_vx"]) <= 1e-6       # coarse PCG stops at 1e-7
-    assert abs(r["n_iter"] - int(g["cycle_n_iter"])) <= 1
-    mg.destroy()
-    c = csb.SlesIt(csb.SlesItType.FCG, 200, poly_degree=-1)
-    c.transfer_pc(_kpc(csb))
-    r = c.solve(m, s.rhs, 1e-8, r_norm)
-    assert int(r["cvg"]) == int(g["fcg_cvg"]) == 1
-    assert abs(r["n_iter"] - int(g["fcg_n_iter"])) <= 2
-    res = np.linalg.norm(s.rhs - m.vector_multiply(r["vx"][:s.n_rows].copy()))
-    assert res <= 1.01e-8 * r_norm
-    assert rel_l2(r["vx"][:s.n_rows], g["fcg_vx"]) <= 1e-6
-    c.destroy(); m.destroy()
-
-
-def test_k_cycle_deep_hierarchy_vs_oracle(csb, oracle):
-    """24^3, pairs only (limit 2): 9 levels, both branches of the inner iteration occur."""
-    s = cube_poisson(24, "dirichlet", with_mesh=False)
-    r_norm = float(np.linalg.norm(s.rhs))
-    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
-    omg = oracle.mg_setup_pw(cube_poisson(24, "dirichlet"), aggregation_limit=2, n_levels_max=10,
-                             n_g_rows_min=30)
-    mg = _kpc(csb, limit=2)
-    mg.setup(m)
-    o = oracle.mg_k_cycle(omg, s.rhs, 1e-13, r_norm)
-    r = mg.solve(m, s.rhs, 1e-13, r_norm)
-    assert rel_l2(r["vx"][:s.n_rows], o["vx"]) <= 1e-9
-    mg.destroy()
-    c = csb.SlesIt(csb.SlesItType.FCG, 200, poly_degree=-1)
-    c.transfer_pc(_kpc(csb, limit=2))
-    r = c.solve(m, s.rhs, 1e-10, r_norm)
-    o = oracle.it_kpc(1, omg, s.rhs, 200, 1e-10, r_norm)
-    assert int(r["cvg"]) == o["cvg"] == 1 and abs(r["n_iter"] - o["n_iter"]) <= 2
-    c.destroy(); oracle.mg_free(omg); m.destroy()
-
-
 V3_OPTIONS = {"v3_sym": dict(iconvp=0), "v3_sym_nofimp": dict(iconvp=0, fimp=False, ndircp=0, relaxp=0.5),
               "v3_conv": dict(iconvp=1), "v3_conv_theta": dict(iconvp=1, ndircp=0, thetap=0.5, relaxp=0.7),
               "v3_conv_only": dict(iconvp=1, idiffp=0, fimp=False)}
