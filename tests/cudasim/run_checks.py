@@ -478,6 +478,10 @@ def check_rhs(ora):
             assert np.array_equal(m.gradient(0, f["pvar"], f["coefa"], f["coefb"]), go), (N, nsw)
             assert m.gradient_sweeps() == ns == nsw
         m.destroy()
+    # irregular mesh: arbitrary face orientation / order, unordered boundary faces
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from irregular_mesh import check_device_against_oracle
+    check_device_against_oracle(csb, ora)
     # gradient limiter (imligr 0 / 1 / 2) on every gradient type
     from make_golden_rhs import CLIP_CASES
     for N in CASES:

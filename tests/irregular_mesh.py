@@ -1,0 +1,156 @@
+"""An irregular mesh for the face-operator parity tests (test infrastructure): cells are random
+points, interior faces join each cell to a few of its nearest neighbours with an arbitrary
+orientation (the first cell of a face may have the higher id) and in a shuffled order, boundary
+faces are attached to random cells in no particular order, several to some cells.  Rows have 1
+to ~10 entries, so nothing of the 6-entry regularity of the hex cube is left.  All geometric
+quantities are seeded random numbers of a plausible size: the reference uses them as they are.
+"""
+import numpy as np
+
+from code_saturne_b200.mesh_cartesian import CubeSystem
+
+
+def irregular_system(n=300, k=3, seed=7):
+    rng = np.random.default_rng(seed)
+    cen = rng.random((n, 3))
+    pairs = set()
+    for c in range(n):
+        d = np.linalg.norm(cen - cen[c], axis=1)
+        d[c] = np.inf
+        for j in np.argsort(d)[:k]:
+            pairs.add((min(c, int(j)), max(c, int(j))))
+    faces = np.array(sorted(pairs), dtype=np.int32)
+    rng.shuffle(faces)                                  # arbitrary face order
+    flip = rng.random(len(faces)) < 0.5                 # arbitrary orientation
+    faces[flip] = faces[flip][:, ::-1]
+    nf = len(faces)
+    # MSR structure: both cells of a face get an entry, rows sorted by column
+    rows = np.concatenate([faces[:, 0], faces[:, 1]])
+    cols = np.concatenate([faces[:, 1], faces[:, 0]])
+    fid = np.concatenate([np.arange(nf), np.arange(nf)])
+    sgn = np.concatenate([np.ones(nf, dtype=np.int16), -np.ones(nf, dtype=np.int16)])
+    order = np.lexsort((cols, rows))
+    rows, cols, fid, sgn = rows[order], cols[order], fid[order], sgn[order]
+    row_index = np.zeros(n + 1, dtype=np.int32)
+    np.add.at(row_index, rows + 1, 1)
+    row_index = np.cumsum(row_index).astype(np.int32)
+    h = n ** (-1.0 / 3.0)
+    x_val = -(0.5 + rng.random(len(cols))) * h
+    d_val = np.zeros(n)
+    np.add.at(d_val, rows, -x_val)
+    d_val += 0.1 * h
+    nrm = rng.standard_normal((nf, 3))
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    s = CubeSystem(N=0, n_rows=n, n_faces=nf, row_index=row_index, col_id=cols.astype(np.int32),
+                   d_val=d_val, x_val=x_val, face_cells=faces, c2f=fid.astype(np.int32),
+                   c2f_sgn=sgn, cell_cen=cen.copy(), cell_vol=h ** 3 * (0.5 + rng.random(n)),
+                   face_u_normal=nrm, face_surf=h * h * (0.5 + rng.random(nf)),
+                   rhs=rng.standard_normal(n))
+    # boundary faces: about n/2, unordered, up to three on one cell
+    nb = n // 2
+    bfc = rng.integers(0, n, nb).astype(np.int32)
+    bfc[: nb // 10] = bfc[nb // 10: 2 * (nb // 10)]      # repeated cells
+    rng.shuffle(bfc)
+    bn = rng.standard_normal((nb, 3))
+    bn /= np.linalg.norm(bn, axis=1)[:, None]
+    b_geo = np.hstack([bn, cen[bfc] + 0.5 * h * bn, h * (0.4 + 0.2 * rng.random((nb, 1)))])
+    i_face_cog = 0.5 * (cen[faces[:, 0]] + cen[faces[:, 1]]) + 0.05 * h * rng.standard_normal((nf, 3))
+    i_geo = np.hstack([0.1 * h * rng.standard_normal((nf, 3)), 0.1 * h * rng.standard_normal((nf, 3)),
+                       h * (1 + 0.2 * rng.random((nf, 1)))])
+    g_geo = np.hstack([0.3 + 0.4 * rng.random((nf, 1)), 0.1 * h * rng.standard_normal((nf, 3))])
+    f = dict(pvar=rng.standard_normal(n), i_visc=rng.random(nf) + 0.5, b_visc=rng.random(nb) + 0.5,
+             cofaf=rng.standard_normal(nb), cofbf=rng.random(nb), coefa=rng.standard_normal(nb),
+             coefb=rng.random(nb), visel=rng.random(n) + 0.5, div0=rng.standard_normal(n),
+             frcxt=rng.standard_normal((n, 3)))
+    diipb = 0.2 * h * rng.standard_normal((nb, 3))
+    diipb[::7] = 0.0
+    geo = dict(b_geo=b_geo, i_face_cog=i_face_cog, i_geo=i_geo, g_geo=g_geo,
+               b_surf=h * h * (0.5 + rng.random(nb)),
+               cgl=(np.eye(3)[None] + 0.05 * rng.standard_normal((n, 3, 3))).reshape(-1),
+               diipb=diipb)
+    return s, bfc, geo, f
+
+
+def irregular_cases():
+    """(imrgra, hydrostatic, imligr, climgr)"""
+    return ((0, False, -1, -1.), (1, False, -1, -1.), (1, True, -1, -1.), (4, False, -1, -1.),
+            (4, True, -1, -1.), (4, True, 1, 0.5), (1, False, 2, 0.5))
+
+
+def oracle_operators(ora, s, bfc, G, f, imrgra, hyd, imligr, climgr):
+    """gradient (limited if asked), reconstructed divergence (irecmf 0) and values at I' of the
+    boundary faces from the oracle"""
+    bun, bd = G["b_geo"][:, :3], G["b_geo"][:, 6]
+    clip = 1. if imligr >= 0 else -1.
+    if hyd:
+        go, vip, vf = ora.gradient_hyd(imrgra, s, bfc, bun, bd, G["i_face_cog"], G["b_geo"][:, 3:6],
+                                       f["frcxt"], f["pvar"], f["coefa"], f["coefb"],
+                                       diipb=G["diipb"], g_geo=G["g_geo"], b_face_surf=G["b_surf"],
+                                       corr_grad_lin=G["cgl"], clip_coeff=clip, with_val_f=True)
+    else:
+        vip = ora.b_iprime_lsq(s, bfc, bun, bd, G["diipb"], f["pvar"], f["coefa"], f["coefb"],
+                               clip_coeff=clip)
+        vf = f["coefa"] + f["coefb"] * vip
+        if imrgra == 4:
+            go = ora.gradient_green_lsq(s, bfc, bun, bd, G["g_geo"], G["b_surf"], f["pvar"],
+                                        f["coefa"], f["coefb"], diipb=G["diipb"],
+                                        corr_grad_lin=G["cgl"], clip_coeff=clip)
+        elif imrgra == 1:
+            go = ora.gradient_lsq(s, bfc, bun, bd, f["pvar"], f["coefa"], f["coefb"],
+                                  diipb=G["diipb"], clip_coeff=clip)
+        else:
+            go, _ = ora.gradient_green_iter(s, bfc, bun, G["g_geo"], G["b_surf"], f["pvar"],
+                                            f["coefa"], f["coefb"], diipb=G["diipb"])
+    if imligr >= 0:
+        go = ora.gradient_clip(s, bfc, G["i_geo"], imligr, climgr, f["pvar"], vf, go)
+    do = ora.diffusion_potential_rc(s, bfc, G["i_geo"], go, f["pvar"], f["cofaf"], f["cofbf"],
+                                    f["i_visc"], f["b_visc"], f["visel"], irecmf=0, val_ip=vip)
+    return go, do, vip
+
+
+def device_matrix(csb, s, bfc, G):
+    """device matrix of the irregular mesh with every geometric quantity given"""
+    m = csb.Matrix.from_system(s)
+    m.set_boundary_faces(bfc)
+    m.set_face_geometry(G["i_geo"][:, 6], G["i_geo"][:, :3], G["i_geo"][:, 3:6], G["b_geo"][:, :3],
+                        G["b_geo"][:, 6])
+    m.set_green_geometry(G["g_geo"][:, 0], G["g_geo"][:, 1:4], G["b_surf"], G["cgl"])
+    m.set_face_cog(G["i_face_cog"], G["b_geo"][:, 3:6])
+    m.set_boundary_iprime(G["diipb"])
+    return m
+
+
+def check_device_against_oracle(csb, ora):
+    """every case of irregular_cases() plus the face fluxes and their divergence"""
+    s, bfc, G, f = irregular_system()
+    m = device_matrix(csb, s, bfc, G)
+    for imrgra, hyd, imligr, climgr in irregular_cases():
+        go, do, vip = oracle_operators(ora, s, bfc, G, f, imrgra, hyd, imligr, climgr)
+        m.set_gradient_type(imrgra)
+        m.set_gradient_limiter(imligr, climgr)
+        if hyd:
+            gr = m.gradient_hyd(imrgra, f["frcxt"], f["pvar"], f["coefa"], f["coefb"])
+            d = m.diffusion_potential_hyd(f["frcxt"], f["pvar"], f["coefa"], f["coefb"],
+                                          f["cofaf"], f["cofbf"], f["i_visc"], f["b_visc"],
+                                          f["visel"])
+        else:
+            gr = m.gradient(imrgra, f["pvar"], f["coefa"], f["coefb"])
+            d = m.diffusion_potential_rc(f["pvar"], f["coefa"], f["coefb"], f["cofaf"], f["cofbf"],
+                                         f["i_visc"], f["b_visc"], f["visel"])
+        assert np.array_equal(gr, go), (imrgra, hyd, imligr)
+        assert np.array_equal(d, do), (imrgra, hyd, imligr)
+        if not hyd:
+            im, bm = m.face_diffusion_potential(s.n_faces, len(bfc), f["pvar"], f["cofaf"],
+                                                f["cofbf"], f["i_visc"], f["b_visc"],
+                                                coefa=f["coefa"], coefb=f["coefb"],
+                                                visel=f["visel"], ircflu=1)
+            imo, bmo = ora.face_diffusion_potential(s, bfc, f["pvar"], f["cofaf"], f["cofbf"],
+                                                    f["i_visc"], f["b_visc"], i_geo=G["i_geo"],
+                                                    grad=go, visel=f["visel"], val_ip=vip)
+            assert np.array_equal(im, imo) and np.array_equal(bm, bmo), (imrgra, imligr)
+            assert np.array_equal(m.divergence(im, bm), d), (imrgra, imligr)
+    m.set_gradient_limiter(-1, -1.)
+    d0 = m.diffusion_potential(f["pvar"], f["i_visc"], f["b_visc"], f["cofaf"], f["cofbf"])
+    assert np.array_equal(d0, ora.diffusion_potential(s, bfc, f["pvar"], f["cofaf"], f["cofbf"],
+                                                      f["i_visc"], f["b_visc"]))
+    m.destroy()

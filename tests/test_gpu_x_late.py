@@ -121,3 +121,15 @@ def test_gradient_limiter_matches_reference_golden(csb, N):
     m.set_gradient_limiter(-1, -1.)
     assert np.array_equal(m.gradient(4, f["pvar"], f["coefa"], f["coefb"]), plain)
     m.destroy()
+
+
+# ------------------------------------------------------------------- irregular mesh
+
+def test_face_operators_on_irregular_mesh_vs_oracle(csb, oracle):
+    """rows of 3 to 7 entries, arbitrary face orientation and order, unordered boundary faces
+    (tests/irregular_mesh.py; the oracle is pinned to the reference on this very mesh in
+    tests/test_oracle.py): gradients 0 / 1 / 4, hydrostatic treatment, limiters, reconstructed
+    divergence, face fluxes and their divergence, all bit-exact"""
+    sys.path.insert(0, os.path.dirname(__file__))
+    from irregular_mesh import check_device_against_oracle
+    check_device_against_oracle(csb, oracle)

@@ -1088,6 +1088,33 @@ def test_oracle_gradient_limiter_matches_golden(oracle, N):
     assert n_clipped > 100                              # the limiters really act here
 
 
+def test_oracle_face_operators_on_irregular_mesh_match_reference(oracle):
+    """an irregular mesh (tests/irregular_mesh.py: rows of 3 to 7 entries, arbitrary face
+    orientation and order, unordered boundary faces, several per cell): gradient types
+    0 / 1 / 4, hydrostatic treatment, limiters, reconstructed divergence and face fluxes of the
+    oracle against the reference run live (oracle/_ref), bit for bit"""
+    sys.path.insert(0, os.path.dirname(__file__))
+    from irregular_mesh import irregular_cases, irregular_system, oracle_operators
+    from oracle.pyoracle import RefLib, ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    ref = RefLib(1)
+    s, bfc, G, f = irregular_system()
+    assert np.diff(s.row_index).min() < 6 < np.diff(s.row_index).max()
+    h = ref.system(s)
+    for imrgra, hyd, imligr, climgr in irregular_cases():
+        d, g = ref.diffusion_potential_rc(
+            h, s, bfc, G["b_geo"], G["i_face_cog"], G["i_geo"], f["pvar"], f["coefa"], f["coefb"],
+            f["cofaf"], f["cofbf"], f["i_visc"], f["b_visc"], f["visel"], irecmf=0, inc=1,
+            diipb=G["diipb"], imrgra=imrgra, g_geo=G["g_geo"], b_face_surf=G["b_surf"],
+            corr_grad_lin=G["cgl"], frcxt=(f["frcxt"] if hyd else None), imligr=imligr,
+            climgr=climgr)
+        go, do, _ = oracle_operators(oracle, s, bfc, G, f, imrgra, hyd, imligr, climgr)
+        assert np.array_equal(g, go), (imrgra, hyd, imligr)
+        assert np.array_equal(d, do), (imrgra, hyd, imligr)
+    ref.destroy(h)
+
+
 def test_oracle_gradient_lsq_is_exact_for_linear_fields(oracle):
     """property: a least-squares gradient reproduces the gradient of a linear field (to the
     single precision of its cocg matrices) when the boundary values are those of the field"""
