@@ -101,6 +101,10 @@ def check_kernel_per_phase_paths(ora):
     k = min(len(r["cycle_residuals"]), len(o["cycle_residuals"]), 4)
     assert np.allclose(r["cycle_residuals"][:k], o["cycle_residuals"][:k], rtol=1e-7, atol=0)
     mg.destroy(); ora.mg_free(omg); m.destroy()
+    # the same on an irregular system (rows of 3 to 9 entries, arbitrary face order)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from irregular_mesh import check_multigrid_against_oracle
+    check_multigrid_against_oracle(csb, ora, n=600, k=4)
 
 
 def check_smoothers(ora):

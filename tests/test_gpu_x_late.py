@@ -133,3 +133,13 @@ def test_face_operators_on_irregular_mesh_vs_oracle(csb, oracle):
     sys.path.insert(0, os.path.dirname(__file__))
     from irregular_mesh import check_device_against_oracle
     check_device_against_oracle(csb, oracle)
+
+
+def test_multigrid_on_irregular_mesh_vs_oracle(csb, oracle):
+    """the hot path beyond the hex cube: hierarchy of an irregular system (3000 rows of 4 to 10
+    entries) bit-exact against the oracle -- itself pinned to the reference on this system in
+    tests/test_oracle.py --, V-cycle solve: cycles +-1, first residuals, solution"""
+    sys.path.insert(0, os.path.dirname(__file__))
+    from irregular_mesh import check_multigrid_against_oracle
+    check_multigrid_against_oracle(csb, oracle)
+

@@ -1115,6 +1115,35 @@ def test_oracle_face_operators_on_irregular_mesh_match_reference(oracle):
     ref.destroy(h)
 
 
+@pytest.mark.parametrize("n,k", [(300, 3), (3000, 4)])
+def test_oracle_multigrid_on_irregular_mesh_matches_reference(oracle, n, k):
+    """the hot path beyond the hex cube: hierarchy (aggregation maps, coarse structures and
+    values) and the V-cycle solve of the oracle on the irregular system against the reference
+    run live (oracle/_ref), bit for bit"""
+    sys.path.insert(0, os.path.dirname(__file__))
+    from irregular_mesh import irregular_system
+    from oracle.pyoracle import RefLib, ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    ref = RefLib(1)
+    s, _, _, _ = irregular_system(n=n, k=k)
+    h = ref.system(s)
+    lv_ref = ref.hierarchy(h)
+    mg = oracle.mg_setup(s)
+    lv = oracle.mg_levels(mg)
+    assert [g["n_rows"] for g in lv] == [g["n_rows"] for g in lv_ref] and len(lv) >= 3
+    for l in range(1, len(lv)):
+        for key in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
+            assert np.array_equal(lv[l][key], lv_ref[l][key]), (l, key)
+    r_norm = float(np.linalg.norm(s.rhs))
+    a = ref.multigrid(h, s.rhs, 1e-8, r_norm)
+    r = oracle.mg_solve(mg, s.rhs, 1e-8, r_norm)
+    assert a["cvg"] == r["cvg"] == 1 and a["n_iter"] == r["n_iter"]
+    assert np.array_equal(a["vx"], r["vx"])
+    oracle.mg_free(mg)
+    ref.destroy(h)
+
+
 def test_oracle_gradient_lsq_is_exact_for_linear_fields(oracle):
     """property: a least-squares gradient reproduces the gradient of a linear field (to the
     single precision of its cocg matrices) when the boundary values are those of the field"""
