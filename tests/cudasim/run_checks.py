@@ -103,8 +103,9 @@ def check_kernel_per_phase_paths(ora):
     mg.destroy(); ora.mg_free(omg); m.destroy()
     # the same on an irregular system (rows of 3 to 9 entries, arbitrary face order)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from irregular_mesh import check_multigrid_against_oracle
+    from irregular_mesh import check_multigrid_against_oracle, check_solvers_against_oracle
     check_multigrid_against_oracle(csb, ora, n=600, k=4)
+    check_solvers_against_oracle(csb, ora, n=600, k=4)
 
 
 def check_smoothers(ora):

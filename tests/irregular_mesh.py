@@ -181,3 +181,39 @@ def check_multigrid_against_oracle(csb, ora, n=3000, k=4):
     # only; one cycle apart (a residual at the threshold): by the last cycle's correction
     assert err <= (1e-8 if r["n_cycles"] == o["n_cycles"] else 1e-4), err
     mg.destroy(); ora.mg_free(omg); m.destroy()
+
+
+def check_solvers_against_oracle(csb, ora, n=3000, k=4):
+    """SpMV (bit-exact), PCG + Jacobi, Gauss-Seidel / RJ3 smoothers (bit-exact) and the
+    production layout FCG + one V-cycle per iteration on the irregular system, against the
+    oracle (iteration counts +-2, solutions to the solver tolerance)"""
+    s, _, _, _ = irregular_system(n=n, k=k)
+    A = (s.row_index, s.col_id, s.d_val, s.x_val)
+    rn = float(np.linalg.norm(s.rhs))
+    m = csb.Matrix.from_system(s)
+    x = np.sin(np.arange(s.n_rows) * 0.37)
+    assert np.array_equal(m.vector_multiply(x.copy()), ora.spmv(*A, x))
+    o = ora.pcg(*A, s.rhs, 500, 1e-10, rn)
+    c = csb.SlesIt(csb.SlesItType.PCG, 500)
+    r = c.solve(m, s.rhs, 1e-10, rn)
+    assert int(r["cvg"]) == o["cvg"] == 1 and abs(r["n_iter"] - o["n_iter"]) <= 2
+    assert np.linalg.norm(r["vx"][:s.n_rows] - o["vx"]) <= 1e-8 * np.linalg.norm(o["vx"])
+    c.destroy()
+    for st in (8, 9, 16):                     # P_GS, P_SYM_GS, RJ3: per-row arithmetic
+        sm = csb.Smoother(st, 3)
+        r = sm.solve(m, s.rhs)
+        assert np.array_equal(r["vx"][:s.n_rows], ora.smoother(st, *A, s.rhs, 3)["vx"]), st
+        sm.destroy()
+    omg = ora.mg_setup(s)
+    o = ora.fcg_mgpc(omg, s.rhs, 200, 1e-8, rn)
+    c = csb.SlesIt(csb.SlesItType.FCG, 200, poly_degree=-1)
+    pc = csb.Multigrid(pc=True)
+    pc.set_aggregation_blocks(1)
+    c.transfer_pc(pc)
+    r = c.solve(m, s.rhs, 1e-8, rn)
+    assert int(r["cvg"]) == o["cvg"] == 1 and abs(r["n_iter"] - o["n_iter"]) <= 2
+    res = np.linalg.norm(s.rhs - m.vector_multiply(r["vx"][:s.n_rows].copy()))
+    assert res <= 1.01e-8 * rn
+    err = np.linalg.norm(r["vx"][:s.n_rows] - o["vx"]) / np.linalg.norm(o["vx"])
+    assert err <= (1e-8 if r["n_iter"] == o["n_iter"] else 1e-4), err
+    c.destroy(); ora.mg_free(omg); m.destroy()

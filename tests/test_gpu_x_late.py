@@ -143,3 +143,12 @@ def test_multigrid_on_irregular_mesh_vs_oracle(csb, oracle):
     from irregular_mesh import check_multigrid_against_oracle
     check_multigrid_against_oracle(csb, oracle)
 
+
+def test_solvers_on_irregular_mesh_vs_oracle(csb, oracle):
+    """SpMV and smoothers bit-exact, PCG and the production layout FCG + cs_multigrid_pc
+    (k_fcg_mg_persistent) on the irregular system: iteration counts +-2, true residual under
+    the threshold, solution to the solver tolerance"""
+    sys.path.insert(0, os.path.dirname(__file__))
+    from irregular_mesh import check_solvers_against_oracle
+    check_solvers_against_oracle(csb, oracle)
+

@@ -1144,6 +1144,39 @@ def test_oracle_multigrid_on_irregular_mesh_matches_reference(oracle, n, k):
     ref.destroy(h)
 
 
+def test_oracle_solvers_on_irregular_mesh_match_reference(oracle):
+    """SpMV, PCG, FCG, BiCGStab, Gauss-Seidel / RJ3 smoothers and FCG + cs_multigrid_pc of the
+    oracle on the irregular system (3000 rows of 4 to 10 entries) against the reference run
+    live: iterates and iteration counts bit for bit"""
+    sys.path.insert(0, os.path.dirname(__file__))
+    from irregular_mesh import irregular_system
+    from oracle.pyoracle import RefLib, ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    ref = RefLib(1)
+    s, _, _, _ = irregular_system(n=3000, k=4)
+    A = (s.row_index, s.col_id, s.d_val, s.x_val)
+    rn = float(np.linalg.norm(s.rhs))
+    h = ref.system(s)
+    x = np.sin(np.arange(s.n_rows) * 0.37)
+    assert np.array_equal(ref.spmv(h, x, s.n_rows), oracle.spmv(*A, x))
+    for code, fn in ((ref.PCG, oracle.pcg), (ref.FCG, oracle.fcg), (ref.BICGSTAB, oracle.bicgstab)):
+        a = ref.sles_it(h, code, s.rhs, 500, 1e-10, rn)
+        r = fn(*A, s.rhs, 500, 1e-10, rn)
+        assert a["cvg"] == r["cvg"] == 1 and a["n_iter"] == r["n_iter"], code
+        assert np.array_equal(a["vx"], r["vx"]), code
+    for st in (8, 9, 16):
+        assert np.array_equal(ref.smoother(h, st, s.rhs, 3)["vx"],
+                              oracle.smoother(st, *A, s.rhs, 3)["vx"]), st
+    mg = oracle.mg_setup(s)
+    a = ref.fcg_mgpc(h, s.rhs, 200, 1e-8, rn)
+    r = oracle.fcg_mgpc(mg, s.rhs, 200, 1e-8, rn)
+    assert a["cvg"] == r["cvg"] == 1 and a["n_iter"] == r["n_iter"]
+    assert np.array_equal(a["vx"], r["vx"])
+    oracle.mg_free(mg)
+    ref.destroy(h)
+
+
 def test_oracle_gradient_lsq_is_exact_for_linear_fields(oracle):
     """property: a least-squares gradient reproduces the gradient of a linear field (to the
     single precision of its cocg matrices) when the boundary values are those of the field"""
