@@ -827,7 +827,7 @@ int csb_matrix_set_green_geometry(csb_matrix_t *m, const csb_real_t *weight,
 /* Gradient csb_diffusion_potential_rc reconstructs with: eqp->imrgra, whose default is
    cs_glob_space_disc->imrgra = 4 in the reference (cs_parameters.cpp:470);
    cs_gradient_type_by_imrgra (cs_gradient.cpp:10317): 1 = CS_GRADIENT_LSQ (the initial value
-   here), 4 = CS_GRADIENT_GREEN_LSQ; the other types are not built. */
+   here), 4 = CS_GRADIENT_GREEN_LSQ, 0 = CS_GRADIENT_GREEN_ITER; the other types are not built. */
 int csb_matrix_set_gradient_type(csb_matrix_t *m, int imrgra)
 {
   if (m == nullptr) { set_error("The matrix is not defined."); return -1; }

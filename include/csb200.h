@@ -322,13 +322,14 @@ int  csb_diffusion_potential(const csb_matrix_t *m, int init, int inc, const csb
    [n_b_faces][3]; zero until given, NULL resets it; to be called after
    csb_matrix_set_face_geometry).  With it the value of the variable at I' of every boundary
    face is reconstructed like cs_gradient_boundary_iprime_lsq_s
-   (src/alge/cs_gradient_boundary.cpp:197-640; no limiter: eqp->imligr < 0), face values are
+   (src/alge/cs_gradient_boundary.cpp:197-640; its limiter: csb_matrix_set_gradient_limiter), face values are
    inc*coefa + coefb*val_ip and boundary fluxes inc*cofaf + cofbf*val_ip
    (cs_boundary_conditions_update_bc_coeff_face_values,
    src/base/cs_boundary_conditions_set_coeffs.cpp:125-195), and the boundary directions of the
    least-squares system become n + II'/b_dist (cs_gradient.cpp:2632-2636, :2880-2885).
    csb_gradient_scalar_lsq: cs_gradient_scalar_synced_input with CS_GRADIENT_LSQ (imrgra = 1),
-   standard neighbourhood, no weighting, no limiter (src/alge/cs_gradient.cpp:9651;
+   standard neighbourhood, no weighting (src/alge/cs_gradient.cpp:9651; limiters: see
+   csb_matrix_set_gradient_limiter;
    _lsq_scalar_gradient :2695-2900, cocg _compute_cell_cocg_lsq :2501-2680 -- kept in single
    precision and inverted by the float Gauss-Jordan elimination like the reference's
    cs_cocg_t); grad[n_rows][3]; boundary face value inc*coefa + coefb*(pvar at I').

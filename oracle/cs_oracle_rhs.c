@@ -128,7 +128,7 @@ _b_direction(int f, const double *b_face_u_normal, const double *b_dist, const d
 }
 
 /* cs_gradient_boundary_iprime_lsq_s (src/alge/cs_gradient_boundary.cpp:197-640) with
-   clip_coeff < 0 (no limiter: eqp->imligr < 0), hyd_p_flag 0, c_weight NULL, standard
+   its simple limiter (clip_coeff; < 0: none, as with eqp->imligr < 0), hyd_p_flag 0, c_weight NULL, standard
    neighbourhood: value of pvar at I' of every boundary face from a least-squares gradient local
    to the face's cell -- neighbours in adjacency order, then the cell's boundary faces in
    ascending order with the BC-aware direction n + (1 - b) II'/b_dist; cocg accumulated in
