@@ -276,6 +276,9 @@ def check_native(ora):
     """matrix mapped from native arrays: face-list aggregation, face-order coarse values
     (oracle/cs_oracle_native.c is pinned bit for bit to the reference, tests/test_oracle.py)"""
     from oracle.pyoracle import native_arrays
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from irregular_mesh import check_native_against_oracle
+    check_native_against_oracle(csb, ora, n=600, k=4)      # faces in arbitrary orientation / order
     for N, bc, blocks, perturb, relax in ((8, "neumann", 1, False, 0.95),
                                           (12, "dirichlet", 1, True, 0.95),
                                           (12, "neumann", 3, True, 0.95),

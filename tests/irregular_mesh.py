@@ -217,3 +217,26 @@ def check_solvers_against_oracle(csb, ora, n=3000, k=4):
     err = np.linalg.norm(r["vx"][:s.n_rows] - o["vx"]) / np.linalg.norm(o["vx"])
     assert err <= (1e-8 if r["n_iter"] == o["n_iter"] else 1e-4), err
     c.destroy(); ora.mg_free(omg); m.destroy()
+
+
+def check_native_against_oracle(csb, ora, n=3000, k=4):
+    """the same system entered through its face arrays (cs_matrix_set_coefficients from edges:
+    face-list aggregation, first-seen coarse faces, face-order coarse values): level-0 MSR
+    matrix and hierarchy bit-exact against the oracle"""
+    from oracle.pyoracle import native_arrays
+    s, _, _, _ = irregular_system(n=n, k=k)
+    da, xa = native_arrays(s)
+    m = csb.Matrix.from_system_native(s, da, xa)
+    d0, x0 = m.get_coefficients()
+    assert np.array_equal(d0, s.d_val) and np.array_equal(x0, s.x_val)
+    mg = csb.Multigrid()
+    mg.set_aggregation_blocks(1)
+    mg.setup(m)
+    omg = ora.mg_setup_native(s, n_threads=1, da=da, xa=xa)
+    lv, olv = mg.levels(), ora.mg_levels(omg)
+    assert [a["n_rows"] for a in lv] == [b["n_rows"] for b in olv] and len(lv) >= 3
+    assert np.array_equal(lv[0]["row_index"], s.row_index) and np.array_equal(lv[0]["col_id"], s.col_id)
+    for a, b in zip(lv[1:], olv[1:]):
+        for key in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
+            assert np.array_equal(a[key], b[key]), key
+    mg.destroy(); ora.mg_free(omg); m.destroy()

@@ -152,3 +152,11 @@ def test_solvers_on_irregular_mesh_vs_oracle(csb, oracle):
     from irregular_mesh import check_solvers_against_oracle
     check_solvers_against_oracle(csb, oracle)
 
+
+def test_native_entry_on_irregular_mesh_vs_oracle(csb, oracle):
+    """the irregular system entered through its face arrays: level-0 MSR matrix and hierarchy
+    (face-list aggregation, face-order coarse values) bit-exact against the oracle"""
+    sys.path.insert(0, os.path.dirname(__file__))
+    from irregular_mesh import check_native_against_oracle
+    check_native_against_oracle(csb, oracle)
+

@@ -749,6 +749,30 @@ def test_oracle_native_hierarchy_matches_reference(oracle, N, bc, nt):
     oracle.mg_free(mg)
 
 
+def test_oracle_native_hierarchy_on_irregular_mesh_matches_reference(oracle):
+    """the face-array entry on the irregular system (faces in arbitrary orientation and order):
+    face-list aggregation, first-seen coarse faces, face-order coarse values -- the oracle's
+    hierarchy against the reference run live, bit for bit"""
+    sys.path.insert(0, os.path.dirname(__file__))
+    from irregular_mesh import irregular_system
+    from oracle.pyoracle import RefLib, native_arrays, ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    s, _, _, _ = irregular_system(n=3000, k=4)
+    da, xa = native_arrays(s)
+    ref = RefLib(1)
+    h = ref.system_native(s, da, xa)
+    lr = ref.hierarchy(h)
+    ref.destroy(h)
+    mg = oracle.mg_setup_native(s, n_threads=1, da=da, xa=xa)
+    lo = oracle.mg_levels(mg)
+    assert [x["n_rows"] for x in lo] == [x["n_rows"] for x in lr] and len(lo) >= 4
+    for a, b in zip(lo, lr):
+        for k in ("coarse_row", "row_index", "col_id", "d_val", "x_val", "cell_cen", "cell_vol"):
+            assert np.array_equal(a[k], b[k]), (a["n_rows"], k)
+    oracle.mg_free(mg)
+
+
 def test_oracle_aggregation_fc_properties(oracle):
     """face-list aggregation: every row mapped, aggregates within the limit, penalised rows
     (diagonal above 1e4 x the extra-diagonal mass) left out at level 0"""
