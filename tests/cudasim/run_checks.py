@@ -616,6 +616,9 @@ def check_compute_coeffs(ora):
 
 
 def check_k_cycle(ora):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from irregular_mesh import check_coeffs_and_k_cycle_against_oracle
+    check_coeffs_and_k_cycle_against_oracle(csb, ora, n=600, k=4)
     g = np.load(os.path.join(GOLD, "kcycle_N8_dirichlet.npz"))
     s = cube_poisson(8, "dirichlet")
     rn = float(g["r_norm"])

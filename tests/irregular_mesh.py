@@ -240,3 +240,60 @@ def check_native_against_oracle(csb, ora, n=3000, k=4):
         for key in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
             assert np.array_equal(a[key], b[key]), key
     mg.destroy(); ora.mg_free(omg); m.destroy()
+
+
+def check_coeffs_and_k_cycle_against_oracle(csb, ora, n=3000, k=4):
+    """cs_matrix_compute_coeffs on the device (symmetric and convection forms: bit-exact) and
+    the K-cycle preconditioner over the pairwise hierarchy of the irregular system (one cycle:
+    solution to the coarse solver's tolerance; FCG + K-cycle: iteration counts +-2)"""
+    s, bfc, _, _ = irregular_system(n=n, k=k)
+    rn = float(np.linalg.norm(s.rhs))
+    rng = np.random.default_rng(3)
+    iv, bv = 0.1 + rng.random(s.n_faces), 0.1 + rng.random(len(bfc))
+    cb, cf, ro = rng.random(len(bfc)), rng.random(len(bfc)), rng.random(s.n_rows)
+    imf, bmf = rng.standard_normal(s.n_faces), rng.standard_normal(len(bfc))
+    m = csb.Matrix.from_system(s)
+    m.set_boundary_faces(bfc)
+    for kw in (dict(), dict(ndircp=0), dict(thetap=0.5, relaxp=0.7), dict(idiffp=0)):
+        m.compute_coeffs(ro, iv, bv, cf, **kw)
+        d, x = m.get_coefficients()
+        do, xo = ora.matrix_compute_coeffs_sym(s.row_index, s.c2f, bfc, cf, ro, iv, bv, **kw)
+        assert np.array_equal(d, do) and np.array_equal(x, xo), kw
+    for kw in (dict(), dict(ndircp=0, thetap=0.5, relaxp=0.7), dict(idiffp=0)):
+        m.compute_coeffs(ro, iv, bv, cf, iconvp=1, coefbp=cb, i_massflux=imf, b_massflux=bmf, **kw)
+        d, x = m.get_coefficients()
+        do, xo = ora.matrix_compute_coeffs(s, bfc, cb, cf, ro, imf, bmf, iv, bv, **kw)
+        assert np.array_equal(d, do) and np.array_equal(x, xo), kw
+    m.destroy()
+
+    m = csb.Matrix(s.n_rows, s.row_index, s.col_id, s.d_val, s.x_val)
+
+    def kpc(lim):
+        pc = csb.Multigrid(pc=True, mg_type=1)
+        pc.set_coarsening_options(aggregation_limit=lim, coarsening_type=3, n_max_levels=10,
+                                  min_g_rows=30, p0p1_relax=0.)
+        return pc
+
+    for lim in (2, 4):
+        omg = ora.mg_setup_pw(s, aggregation_limit=lim, n_levels_max=10, n_g_rows_min=30)
+        mg = kpc(lim)
+        mg.setup(m)
+        lv, olv = mg.levels(), ora.mg_levels(omg)
+        assert [a["n_rows"] for a in lv] == [b["n_rows"] for b in olv]
+        for a, b in zip(lv[1:], olv[1:]):
+            for key in ("coarse_row", "row_index", "col_id", "d_val", "x_val"):
+                assert np.array_equal(a[key], b[key]), (lim, key)
+        o = ora.mg_k_cycle(omg, s.rhs, 1e-8, rn)
+        r = mg.solve(m, s.rhs, 1e-8, rn)
+        err = np.linalg.norm(r["vx"][:s.n_rows] - o["vx"]) / np.linalg.norm(o["vx"])
+        assert err <= 1e-6, (lim, err)
+        mg.destroy()
+        c = csb.SlesIt(csb.SlesItType.FCG, 60, poly_degree=-1)
+        c.transfer_pc(kpc(lim))
+        r = c.solve(m, s.rhs, 1e-8, rn)
+        o = ora.it_kpc(1, omg, s.rhs, 60, 1e-8, rn)
+        assert int(r["cvg"]) == o["cvg"] == 1 and abs(r["n_iter"] - o["n_iter"]) <= 2, lim
+        res = np.linalg.norm(s.rhs - m.vector_multiply(r["vx"][:s.n_rows].copy()))
+        assert res <= 1.01e-8 * rn
+        c.destroy(); ora.mg_free(omg)
+    m.destroy()

@@ -160,3 +160,12 @@ def test_native_entry_on_irregular_mesh_vs_oracle(csb, oracle):
     from irregular_mesh import check_native_against_oracle
     check_native_against_oracle(csb, oracle)
 
+
+def test_coefficient_build_and_k_cycle_on_irregular_mesh_vs_oracle(csb, oracle):
+    """cs_matrix_compute_coeffs (symmetric and convection forms) bit-exact, pairwise hierarchies
+    bit-exact, the K-cycle and FCG + K-cycle on the irregular system against the oracle (pinned
+    to the reference on this system in tests/test_oracle.py)"""
+    sys.path.insert(0, os.path.dirname(__file__))
+    from irregular_mesh import check_coeffs_and_k_cycle_against_oracle
+    check_coeffs_and_k_cycle_against_oracle(csb, oracle)
+

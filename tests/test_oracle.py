@@ -773,6 +773,50 @@ def test_oracle_native_hierarchy_on_irregular_mesh_matches_reference(oracle):
     oracle.mg_free(mg)
 
 
+def test_oracle_k_cycle_and_coefficient_build_on_irregular_mesh_match_reference(oracle):
+    """pairwise aggregation (limits 2 and 4: 8 and 4 levels), the K-cycle and FCG + K-cycle,
+    and cs_matrix_compute_coeffs (symmetric and convection forms) of the oracle on the
+    irregular system against the reference run live, bit for bit"""
+    sys.path.insert(0, os.path.dirname(__file__))
+    from irregular_mesh import irregular_system
+    from oracle.pyoracle import RefLib, ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    ref = RefLib(1)
+    s, bfc, _, _ = irregular_system(n=3000, k=4)
+    rn = float(np.linalg.norm(s.rhs))
+    h = ref.system(s)
+    for lim in (2, 4):
+        kw = dict(aggregation_limit=lim, coarsening_type=3, n_levels_max=10, n_g_rows_min=30,
+                  p0p1_relax=0., mg_type=1)
+        mg = oracle.mg_setup_pw(s, aggregation_limit=lim, n_levels_max=10, n_g_rows_min=30)
+        a = oracle.mg_k_cycle(mg, s.rhs, 1e-8, rn)
+        b = ref.multigrid(h, s.rhs, 1e-8, rn, n_max_cycles=1, n_max_iter=(2, 2, 500),
+                          types=(3, 3, 0), precision_mult=(-1., -1., 10.), **kw)
+        assert np.array_equal(a["vx"], b["vx"]) and a["n_iter"] == b["n_iter"], lim
+        a = oracle.it_kpc(1, mg, s.rhs, 60, 1e-8, rn)
+        b = ref.it_mgpc(h, 1, s.rhs, 60, 1e-8, rn, types=(3, 3, 0), mg_n_max_iter=(2, 2, 500),
+                        precision_mult=(-1., -1., 10.), **kw)
+        assert (a["cvg"], a["n_iter"]) == (b["cvg"], b["n_iter"]) == (1, a["n_iter"]), lim
+        assert np.array_equal(a["vx"], b["vx"]), lim
+        oracle.mg_free(mg)
+    rng = np.random.default_rng(3)
+    iv, bv = 0.1 + rng.random(s.n_faces), 0.1 + rng.random(len(bfc))
+    cb, cf, ro = rng.random(len(bfc)), rng.random(len(bfc)), rng.random(s.n_rows)
+    for kw in COEFF_OPTIONS.values():
+        a = oracle.matrix_compute_coeffs_sym(s.row_index, s.c2f, bfc, cf, ro, iv, bv, **kw)
+        b = ref.matrix_compute_coeffs_sym(h, s, bfc, cf, ro, iv, bv, **kw)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), kw
+    ref.destroy(h)
+    h = ref.system(s, symmetric=False)
+    imf, bmf = rng.standard_normal(s.n_faces), rng.standard_normal(len(bfc))
+    for kw in (dict(), dict(ndircp=0, thetap=0.5, relaxp=0.7), dict(idiffp=0)):
+        a = oracle.matrix_compute_coeffs(s, bfc, cb, cf, ro, imf, bmf, iv, bv, **kw)
+        b = ref.matrix_compute_coeffs(h, s, bfc, cb, cf, ro, imf, bmf, iv, bv, **kw)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), kw
+    ref.destroy(h)
+
+
 def test_oracle_aggregation_fc_properties(oracle):
     """face-list aggregation: every row mapped, aggregates within the limit, penalised rows
     (diagonal above 1e4 x the extra-diagonal mass) left out at level 0"""
