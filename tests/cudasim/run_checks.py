@@ -231,6 +231,9 @@ def check_general_pc(ora):
 
 
 def check_block3_jacobi(ora):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from irregular_mesh import check_block3_against_oracle
+    check_block3_against_oracle(csb, ora)
     from code_saturne_b200.mesh_cartesian import cube_block3_convection_diffusion
     g = np.load(os.path.join(GOLD, "block3jac_N6.npz"))
     ri, ci, d, xv, rhs = cube_block3_convection_diffusion(6)

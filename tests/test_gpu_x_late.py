@@ -169,3 +169,13 @@ def test_coefficient_build_and_k_cycle_on_irregular_mesh_vs_oracle(csb, oracle):
     from irregular_mesh import check_coeffs_and_k_cycle_against_oracle
     check_coeffs_and_k_cycle_against_oracle(csb, oracle)
 
+
+def test_block3_on_irregular_mesh_vs_oracle(csb, oracle):
+    """3x3-block SpMV bit-exact and BiCGStab + Jacobi on a non-symmetric block system over the
+    irregular graph: early residual history to 1e-9, true residual under the threshold, count
+    within 15 % (BiCGStab amplifies rounding differences exponentially on this system: see
+    tests/irregular_mesh.py)"""
+    sys.path.insert(0, os.path.dirname(__file__))
+    from irregular_mesh import check_block3_against_oracle
+    check_block3_against_oracle(csb, oracle)
+
